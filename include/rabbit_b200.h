@@ -1,0 +1,254 @@
+/* rabbit_b200.h — C ABI of the B200-native V-PCC reconstruction / smoothing / metrics hot path.
+ *
+ * This is the drop-in boundary beneath the reference's C++ entry points.  The
+ * reference (mic-rud/RABBIT-Transcoding, a fork of MPEG TMC2 v15) has no FFI for this path: its
+ * boundary is a set of C++ member functions of pcc::PCCCodec / pcc::PCCMetrics.  Every entry point
+ * below names the reference function(s) whose *body* it replaces (paths relative to
+ * /root/reference/source/lib).  INTEGRATION.md shows the reference-side shim that marshals the
+ * reference's containers (PCCContext / PCCFrameContext / PCCPatch / PCCVideo / PCCPointSet3) into
+ * these flat calls.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.  Pointers named "host or device" are
+ *    resolved with cudaMemcpyDefault (UVA), so pinned host, pageable host and device memory all work.
+ *  - every call returns an rb200_status; nothing here calls exit().  The reference's behaviour
+ *    (printf + exit(code), PCCPatch.cpp:237-245, PCCMetrics.cpp:342-346) is restored by the C++ shim.
+ *  - all work is enqueued on the context's CUDA stream (rb200_set_stream); calls that return data to
+ *    the host synchronise that stream themselves.
+ *  - one context per GPU, not re-entrant (the reference's PCCCodec keeps per-instance scratch too,
+ *    PccLibCommon/include/PCCCodec.h:415-423).
+ */
+#ifndef RABBIT_B200_H
+#define RABBIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB200_ABI_VERSION 1
+
+typedef enum rb200_status {
+  RB200_OK                   = 0,
+  RB200_ERR_INVALID          = 1, /* bad argument / inconsistent sizes                                  */
+  RB200_ERR_UNSUPPORTED      = 2, /* a reference mode this build does not implement (fails loudly)      */
+  RB200_ERR_CUDA             = 3, /* CUDA runtime error; see rb200_error_string                         */
+  RB200_ERR_NOMEM            = 4,
+  RB200_ERR_STATE            = 5, /* call order violated (e.g. smoothing before reconstruction)         */
+  RB200_ERR_TIE_OVERFLOW     = 6, /* metrics: a nearest-distance tie set exceeded 30 (PCCMetrics.cpp:88) */
+  RB200_ERR_PATCH_OUT_OF_CANVAS = 180 /* PccLibCommon/source/PCCPatch.cpp:237-245 exits with this code */
+} rb200_status;
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch table rows.  One row per patch per frame; fields are the PCCPatch members the path reads
+ * (PccLibCommon/include/PCCPatch.h:353-408), already resolved by PCCDecoder::createPatchFrameDataStructure
+ * (PccLibDecoder/source/PCCDecoder.cpp:869-1238).  setViewId (PCCPatch.cpp:111-137) is applied by the
+ * caller: axes and projection mode are stored explicitly.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rb200_patch {
+  int32_t u0, v0;           /* canvas position, in occupancyResolution blocks (u0_, v0_)               */
+  int32_t size_u0, size_v0; /* patch size in blocks (sizeU0_, sizeV0_)                                  */
+  int32_t u1, v1, d1;       /* tangent / bitangent / normal shift (u1_, v1_, d1_)                       */
+  int32_t normal_axis, tangent_axis, bitangent_axis; /* 0..2                                           */
+  int32_t projection_mode;  /* 0: d + d1, 1: max(d1 - d, 0)   (PCCPatch.h:177-186)                      */
+  int32_t orientation;      /* PATCH_ORIENTATION_* 0..8       (PCCPatch.cpp:192-251)                    */
+  int32_t lod_x, lod_y;     /* levelOfDetailX_/Y_                                                       */
+  int32_t axis_of_additional_plane; /* 0, or 1..3 for 45-degree planes (PCCCodec.cpp:2503-2524)         */
+  int32_t size2d_x_px, size2d_y_px; /* getPatchSize2DX/YInPixel, used by size quantisation :571-597     */
+} rb200_patch;
+
+/* PCCEomPatch (PCCPatch.h:439-451): members are indices into eom_members[] */
+typedef struct rb200_eom_patch {
+  int32_t u0, v0;               /* in blocks                                                            */
+  int32_t member_begin, member_count; /* memberPatches_ = eom_members[member_begin .. +member_count)    */
+  int32_t eom_count;            /* eomCount_ (only summed into TotalNumberOfEOMPoints, :854)            */
+} rb200_eom_patch;
+
+/* PCCRawPointsPatch (PCCPatch.h:453-…), non-auxiliary-video case of PCCCodec.cpp:894-949 */
+typedef struct rb200_raw_patch {
+  int32_t u0, v0, size_u0, size_v0; /* in blocks of occupancy_resolution                                */
+  int32_t u1, v1, d1;               /* offsets added to the X / Y / Z planes                            */
+  int32_t num_points;               /* numberOfRawPoints_                                               */
+} rb200_raw_patch;
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-GOF parameters: the fields of GeneratePointCloudParameters (PCCCodec.h:62-100) that the path
+ * reads, the decoder switches of PCCDecoderParameters.cpp:114-157, and the atlas geometry.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rb200_params {
+  int32_t width, height;            /* atlas frame size (single tile: tile == atlas)                    */
+  int32_t occupancy_resolution;     /* block size R (16)                                                */
+  int32_t occupancy_precision;      /* p: occupancy video is (W/p)x(H/p)                                */
+  int32_t threshold_lossy_om;       /* oi.getLossyOccupancyCompressionThreshold(), PCCDecoder.cpp:364   */
+  int32_t map_count_minus1;         /* 0 or 1                                                           */
+  int32_t absolute_d1;
+  int32_t remove_duplicate_points;
+  int32_t enhanced_occupancy_map_code;
+  int32_t eom_fix_bit_count;
+  int32_t enable_size_quantization;
+  int32_t log2_quantizer_x, log2_quantizer_y;
+  int32_t patch_precedence_reverse; /* bDecoder && asps.patchPrecedenceOrderFlag, PCCCodec.cpp:627-629  */
+  int32_t use_additional_points_patch; /* raw patches in the geometry video                             */
+  int32_t total_raw_points_known;   /* tile.getTotalNumberOfRawPoints() is set by the caller's syntax layer */
+  int32_t single_map_pixel_interleaving; /* UNSUPPORTED (status 2) when non-zero                        */
+  int32_t point_local_reconstruction;    /* UNSUPPORTED when non-zero                                   */
+  int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
+  int32_t multiple_streams;         /* layout only: caller still hands geometry as [F][M][H][W]         */
+  int32_t attribute_count;          /* 0: colours become 127 (PCCCodec.cpp:1327-1330)                   */
+  int32_t attribute_rgb444;         /* 1: copyRGB16ToRGB8 instead of convertYUV16ToRGB8                 */
+  int32_t geometry_bitdepth_3d;     /* geometryBitDepth3D_ (10 / 11)                                    */
+  /* geometry smoothing SEI (PCCDecoder.cpp:707-722) + decoder switch applyGeoSmoothingType             */
+  int32_t flag_geometry_smoothing;
+  int32_t grid_smoothing;
+  int32_t grid_size;
+  int32_t apply_geo_smoothing;      /* params_.applyGeoSmoothingType_ != 0                              */
+  int32_t attr_transfer_filter_type;/* params_.attrTransferFilterType_: 0 none, 1 transferColors16bitBP */
+  /* attribute smoothing SEI (PCCDecoder.cpp:754-775) + decoder switch applyAttrSmoothingType           */
+  int32_t flag_color_smoothing;
+  int32_t apply_attr_smoothing;
+  int32_t reserved0;
+  double  threshold_smoothing;
+  double  threshold_color_smoothing;
+  double  threshold_color_difference;
+  double  threshold_color_variation;
+} rb200_params;
+
+/* Decoded video planes of one GOF (what PCCVideoDecoder leaves in PCCContext, PCCContext.h:48-50).
+ * host or device pointers. */
+typedef struct rb200_frames {
+  const uint8_t*  occupancy; /* [F][H/p][W/p]      channel 0 of PCCVideoOccupancyMap frame f             */
+  const uint16_t* geometry;  /* [F][M][H][W]       channel 0 of geometry frame f*M+m (PCCCodec.cpp:613)   */
+  const uint16_t* attribute; /* [F][M][3][H][W]    4:4:4 16-bit attribute frame f*M+m; NULL if none       */
+} rb200_frames;
+
+/* Patch tables of one GOF.  host pointers.  *_offset arrays have F+1 entries. */
+typedef struct rb200_atlas {
+  const rb200_patch*     patches;
+  const int32_t*         patch_offset;
+  const rb200_eom_patch* eom_patches;   /* may be NULL */
+  const int32_t*         eom_offset;    /* may be NULL */
+  const int32_t*         eom_members;   /* may be NULL */
+  const rb200_raw_patch* raw_patches;   /* may be NULL */
+  const int32_t*         raw_offset;    /* may be NULL */
+} rb200_atlas;
+
+/* Host-side destination of rb200_download_frame.  Any pointer may be NULL (skipped).  Byte layouts are
+ * the reference's own std::vector element layouts so the shim can memcpy straight into PCCPointSet3
+ * (PCCPointSet.h:520-531, PCCMath.h:449-455). */
+typedef struct rb200_cloud_host {
+  int16_t*  positions;      /* [N][3]   positions_                                                       */
+  uint16_t* colors16;       /* [N][3]   colors16bit_                                                     */
+  uint8_t*  colors;         /* [N][3]   colors_   (valid after rb200_convert_rgb8)                       */
+  uint16_t* boundary_types; /* [N]      boundaryPointTypes_                                              */
+  uint32_t* partition;      /* [N]      partition[] (patch index; EOM/raw points: patch count)           */
+  uint32_t* point_to_pixel; /* [N][3]   tile.getPointToPixel(): x, y, layer                              */
+} rb200_cloud_host;
+
+typedef struct rb200_frame_counts {
+  int64_t total, regular, eom, raw; /* setTotalNumberOf{Regular,EOM,Raw}Points, PCCCodec.cpp:841,886,948 */
+  int64_t smoothed;                 /* points moved by geometry smoothing (type 3)                       */
+  int64_t recolored;                /* points changed by colour smoothing                                */
+} rb200_frame_counts;
+
+typedef struct rb200_ctx rb200_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int         rb200_abi_version(void);
+int         rb200_create(int cuda_device, rb200_ctx** out);
+void        rb200_destroy(rb200_ctx* ctx);
+const char* rb200_error_string(const rb200_ctx* ctx); /* last error text of this context            */
+int         rb200_set_stream(rb200_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = own stream */);
+int         rb200_synchronize(rb200_ctx* ctx);
+
+/* ---- frame ingest: replaces PCCImage::set / PCCVideo containers on the path (PCCImage.h:97-138) --- */
+int rb200_gof_begin(rb200_ctx* ctx, const rb200_params* params, int n_frames);
+int rb200_gof_upload(rb200_ctx* ctx, const rb200_frames* frames, const rb200_atlas* atlas);
+
+/* ---- reconstruction: PCCCodec::generateOccupancyMap (PCCCodec.cpp:1584-1606) +
+ *      generateBlockToPatchFromOccupancyMapVideo (:1725-1763) + generatePointCloud (:517-978, incl.
+ *      generatePoints :327-515, EOM :669-779/:846-891, raw :894-949, identifyBoundaryPoints :266-325) +
+ *      colorPointCloud (:1308-1449), for every frame of the GOF in one batched launch sequence. ------ */
+int rb200_reconstruct(rb200_ctx* ctx);
+
+/* ---- PCCCodec::smoothPointCloudPostprocess (:52-147) + smoothPointCloudGrid/gridFiltering (:1000-1104) */
+int rb200_smooth_geometry(rb200_ctx* ctx);
+
+/* ---- PCCPointSet3::transferColors16bitBP as called at PCCDecoder.cpp:447-465 (PCCPointSet.cpp:1126-1485) */
+int rb200_transfer_colors(rb200_ctx* ctx);
+
+/* ---- PCCCodec::colorSmoothing (:149-236) + gridFilteringColor / smoothPointCloudColorLC (:1182-1306) */
+int rb200_smooth_color(rb200_ctx* ctx);
+
+/* ---- PCCPointSet3::convertYUV16ToRGB8 / copyRGB16ToRGB8 (PCCPointSet.h:121-166) ------------------ */
+int rb200_convert_rgb8(rb200_ctx* ctx);
+
+/* ---- the decoder's whole per-frame sequence (PCCDecoder.cpp:330-508) governed by params ---------- */
+int rb200_decode_gof(rb200_ctx* ctx);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+int rb200_frame_counts_get(rb200_ctx* ctx, rb200_frame_counts* out /* [n_frames] */);
+int rb200_download_frame(rb200_ctx* ctx, int frame, const rb200_cloud_host* dst);
+/* block-to-patch map (tile.getBlockToPatch(), value = patch index + 1, 0 = none), [H/R][W/R] uint32 */
+int rb200_download_block_to_patch(rb200_ctx* ctx, int frame, uint32_t* dst);
+/* full-resolution occupancy map (tile.getOccupancyMap()), [H][W] uint8, after EOM marks */
+int rb200_download_occupancy(rb200_ctx* ctx, int frame, uint8_t* dst);
+
+/* ---- metrics: PCCMetrics::compute (PccLibMetrics/source/PCCMetrics.cpp:334-385) ------------------ */
+typedef struct rb200_metrics_params { /* PCCMetricsParameters fields the path reads */
+  int32_t compute_c2c, compute_c2p, compute_color, compute_hausdorff;
+  int32_t drop_duplicates;  /* 0 keep, 1 drop, 2 average colours (default 2)                            */
+  int32_t neighbors_proc;   /* 0 first NN, 1/2 average of the tie set (default 1)                       */
+  float   resolution;       /* PSNR peak (1023 vox10, 2047 vox11)                                       */
+  int32_t reserved;
+} rb200_metrics_params;
+
+typedef struct rb200_cloud_view { /* host or device pointers */
+  const int16_t* positions; /* [n][3]                                                                  */
+  const uint8_t* colors;    /* [n][3] RGB8 or NULL                                                      */
+  const float*   normals;   /* [n][3] or NULL (D2 needs them on the source, PCCMetrics.cpp:371-375)      */
+  int64_t        count;
+} rb200_cloud_view;
+
+/* One direction A->B of QualityMetrics::compute (PCCMetrics.cpp:75-231): the double accumulators and
+ * the float results derived from them exactly as :204-226 does. */
+typedef struct rb200_quality {
+  double  sse_c2c, sse_c2p, sse_color[3], max_c2c, max_c2p;
+  int64_t num;
+  float   c2c_mse, c2c_psnr, c2p_mse, c2p_psnr, c2c_hausdorff, c2c_hausdorff_psnr, c2p_hausdorff,
+      c2p_hausdorff_psnr, color_mse[3], color_psnr[3];
+} rb200_quality;
+
+typedef struct rb200_metrics_result {
+  rb200_quality q1, q2, qf;   /* quality1_ (src->rec), quality2_ (rec->src), qualityF_ (:299-332)        */
+  int64_t source_points, source_after_dedup, rec_points, rec_after_dedup;
+  int32_t tie_overflow;       /* >0: some tie set was larger than 30 (reference result order-dependent)  */
+  int32_t reserved;
+} rb200_metrics_result;
+
+/* metrics for n_pairs (source, reconstruction[, source-with-normals]) pairs in one batched launch
+ * sequence.  reconstruct[i].positions == NULL means "frame i of the GOF resident in this context". */
+int rb200_metrics(rb200_ctx* ctx, const rb200_metrics_params* params, int n_pairs,
+                  const rb200_cloud_view* sources, const rb200_cloud_view* reconstructs,
+                  rb200_metrics_result* results /* [n_pairs] */);
+
+/* PCCPointSet3::removeDuplicate(out, dropDuplicates) (PCCPointSet.cpp:169-218): lexicographic sort +
+ * merge.  Returns the number of output points; out_* may be NULL to only count. */
+int rb200_remove_duplicates(rb200_ctx* ctx, const rb200_cloud_view* in, int drop_duplicates,
+                            int16_t* out_positions, uint8_t* out_colors, int64_t* out_count);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+typedef struct rb200_launch_stats {
+  int64_t kernel_launches;    /* number of this library's kernels launched since the last reset        */
+  int64_t h2d_bytes, d2h_bytes;
+} rb200_launch_stats;
+int rb200_stats_get(rb200_ctx* ctx, rb200_launch_stats* out, int reset);
+/* per-kernel CUDA-event timing: enable, run, then read name/ms pairs (for bench.py's roofline) */
+int rb200_timing_enable(rb200_ctx* ctx, int enable);
+int rb200_timing_get(rb200_ctx* ctx, int index, char* name, int name_cap, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RABBIT_B200_H */

@@ -1,0 +1,206 @@
+"""oracle/checker.py — Python front-end of the CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Two back-ends with the same interface:
+  * `Reference`  : oracle/_ref/librabbit_ref.so — the UNMODIFIED reference sources compiled from
+                   /root/reference by oracle/Makefile (`make ref`), driven by oracle/ref_harness.cpp.
+  * `Port`       : oracle/liboracle.so — the plain-C restatement (oracle/oracle_*.c), pinned against
+                   `Reference` by tests/test_oracle_vs_reference.py and against tests/golden/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  The product package never does.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+import rabbit_transcoding_b200 as rb  # noqa: E402
+
+abi = rb.abi
+REF_LIB = os.path.join(_HERE, "_ref", "librabbit_ref.so")
+PORT_LIB = os.path.join(_HERE, "liboracle.so")
+STAGES = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
+
+
+def have_reference():
+    return os.path.exists(REF_LIB)
+
+
+def have_port():
+    return os.path.exists(PORT_LIB)
+
+
+class _Run:
+    """result handle of one GOF run"""
+
+    def __init__(self, backend, handle, n_frames):
+        self._b, self._h, self.n_frames = backend, handle, n_frames
+
+    def __del__(self):
+        if self._h:
+            self._b._lib_call("gof_free", self._h)
+            self._h = None
+
+    def counts(self, f):
+        c = abi.FrameCounts()
+        self._b._lib_call("gof_counts", self._h, f, C.byref(c))
+        return c
+
+    def cloud(self, f, stage):
+        s = STAGES.index(stage) if isinstance(stage, str) else stage
+        n = self._b._lib_call("gof_count", self._h, f, s)
+        if n < 0:
+            raise KeyError(f"stage {stage} not kept")
+        npart = self._b._lib_call("gof_partition_size", self._h, f)
+        np2p = self._b._lib_call("gof_point_to_pixel_size", self._h, f)
+        out = dict(positions=np.zeros((n, 3), np.int16), colors16=np.zeros((n, 3), np.uint16),
+                   colors=np.zeros((n, 3), np.uint8), boundary_types=np.zeros(n, np.uint16),
+                   partition=np.zeros(npart, np.uint32), point_to_pixel=np.zeros((np2p, 3), np.uint32))
+        h = abi.CloudHost(*[abi.ptr(out[k]) for k, _ in abi.CloudHost._fields_])
+        self._b._lib_call("gof_fetch", self._h, f, s, C.byref(h))
+        return out
+
+    def md5(self, f, canonical=False):
+        d = (C.c_uint8 * 16)()
+        self._b._lib_call("gof_md5", self._h, f, 1 if canonical else 0, d)
+        return bytes(d).hex()
+
+    def block_to_patch(self, f, params):
+        a = np.zeros((params.height // params.occupancy_resolution, params.width // params.occupancy_resolution), np.uint32)
+        self._b._lib_call("gof_block_to_patch", self._h, f, abi.ptr(a))
+        return a
+
+    def occupancy(self, f, params):
+        a = np.zeros((params.height, params.width), np.uint8)
+        self._b._lib_call("gof_occupancy", self._h, f, abi.ptr(a))
+        return a
+
+    def time_ms(self, f, which):
+        return self._b._lib_call("gof_time_ms", self._h, f, which)
+
+
+class _Backend:
+    prefix = None
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (cd oracle && make {'ref' if 'ref' in path else 'port'})")
+        self.lib = C.CDLL(path)
+        p = self.prefix
+        L = self.lib
+        getattr(L, p + "gof_run").restype = C.c_void_p
+        getattr(L, p + "gof_run").argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Frames),
+                                              C.POINTER(abi.Atlas), C.c_uint32, C.c_int, C.c_int, C.c_int]
+        getattr(L, p + "gof_free").argtypes = [C.c_void_p]
+        getattr(L, p + "gof_free").restype = None
+        for n in ("gof_count", "gof_partition_size", "gof_point_to_pixel_size"):
+            getattr(L, p + n).restype = C.c_int64
+        getattr(L, p + "gof_count").argtypes = [C.c_void_p, C.c_int, C.c_int]
+        getattr(L, p + "gof_partition_size").argtypes = [C.c_void_p, C.c_int]
+        getattr(L, p + "gof_point_to_pixel_size").argtypes = [C.c_void_p, C.c_int]
+        getattr(L, p + "gof_fetch").argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.CloudHost)]
+        getattr(L, p + "gof_counts").argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.FrameCounts)]
+        getattr(L, p + "gof_counts").restype = None
+        getattr(L, p + "gof_md5").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        getattr(L, p + "gof_md5").restype = None
+        getattr(L, p + "gof_block_to_patch").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        getattr(L, p + "gof_occupancy").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        getattr(L, p + "gof_time_ms").argtypes = [C.c_void_p, C.c_int, C.c_int]
+        getattr(L, p + "gof_time_ms").restype = C.c_double
+        getattr(L, p + "metrics").argtypes = [C.POINTER(abi.MetricsParams), C.POINTER(abi.CloudView),
+                                              C.POINTER(abi.CloudView), C.POINTER(abi.CloudView),
+                                              C.POINTER(abi.MetricsResult), C.POINTER(C.c_double)]
+        getattr(L, p + "remove_duplicates").argtypes = [C.POINTER(abi.CloudView), C.c_int, C.c_void_p, C.c_void_p]
+        getattr(L, p + "remove_duplicates").restype = C.c_int64
+        getattr(L, p + "knn").argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+
+    def _lib_call(self, name, *a):
+        return getattr(self.lib, self.prefix + name)(*a)
+
+    def run_gof(self, gof, keep=("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8"),
+                threads=1, canonical_md5=False, quiet=True, params=None):
+        mask = 0
+        for k in keep:
+            mask |= 1 << STAGES.index(k)
+        p = params if params is not None else gof.params
+        fr, at = gof.frames_struct(), gof.atlas_struct()
+        h = self._lib_call("gof_run", C.byref(p), gof.n_frames, C.byref(fr), C.byref(at), mask, threads,
+                           1 if canonical_md5 else 0, 1 if quiet else 0)
+        if not h:
+            raise RuntimeError("oracle run failed")
+        return _Run(self, h, gof.n_frames)
+
+    @staticmethod
+    def view(positions, colors=None, normals=None):
+        positions = np.ascontiguousarray(positions, np.int16)
+        keep = [positions]
+        v = abi.CloudView()
+        v.positions = abi.ptr(positions)
+        v.count = positions.shape[0]
+        if colors is not None:
+            colors = np.ascontiguousarray(colors, np.uint8)
+            keep.append(colors)
+            v.colors = abi.ptr(colors)
+        if normals is not None:
+            normals = np.ascontiguousarray(normals, np.float32)
+            keep.append(normals)
+            v.normals = abi.ptr(normals)
+        v._keep = keep
+        return v
+
+    def metrics(self, mparams, src, rec, normals=None):
+        """src / rec / normals: dict(positions, colors[, normals]); returns (MetricsResult, ms)"""
+        vs = self.view(src["positions"], src.get("colors"))
+        vr = self.view(rec["positions"], rec.get("colors"))
+        vn = self.view(normals["positions"], None, normals["normals"]) if normals is not None else None
+        out = abi.MetricsResult()
+        ms = C.c_double(0)
+        self._lib_call("metrics", C.byref(mparams), C.byref(vs), C.byref(vr), C.byref(vn) if vn is not None else None,
+                       C.byref(out), C.byref(ms))
+        return out, ms.value
+
+    def remove_duplicates(self, positions, colors, drop=2):
+        v = self.view(positions, colors)
+        n = positions.shape[0]
+        op = np.zeros((n, 3), np.int16)
+        oc = np.zeros((n, 3), np.uint8)
+        m = self._lib_call("remove_duplicates", C.byref(v), drop, abi.ptr(op), abi.ptr(oc) if colors is not None else None)
+        return op[:m].copy(), (oc[:m].copy() if colors is not None else None)
+
+    def knn(self, cloud, queries, k):
+        cloud = np.ascontiguousarray(cloud, np.int16)
+        queries = np.ascontiguousarray(queries, np.int16)
+        idx = np.zeros((len(queries), k), np.int64)
+        dist = np.zeros((len(queries), k), np.float64)
+        self._lib_call("knn", abi.ptr(cloud), len(cloud), abi.ptr(queries), len(queries), k, abi.ptr(idx), abi.ptr(dist))
+        return idx, dist
+
+
+class Reference(_Backend):
+    prefix = "ref_"
+
+    def __init__(self):
+        super().__init__(REF_LIB)
+
+
+class Port(_Backend):
+    prefix = "orc_"
+
+    def __init__(self):
+        super().__init__(PORT_LIB)
+
+
+def default_metrics_params(resolution=1023.0, c2p=True):
+    """PCCMetricsParameters defaults (PccLibMetrics/source/PCCMetricsParameters.cpp)"""
+    m = abi.MetricsParams()
+    m.compute_c2c = 1
+    m.compute_c2p = 1 if c2p else 0
+    m.compute_color = 1
+    m.compute_hausdorff = 0
+    m.drop_duplicates = 2
+    m.neighbors_proc = 1
+    m.resolution = resolution
+    return m

@@ -1,0 +1,525 @@
+"""Deterministic synthetic "decoded V-PCC GOF" generator.
+
+Produces exactly what PCCDecoder holds after the three video sub-bitstreams are decoded and before the
+per-frame reconstruction loop starts (PccLibDecoder/source/PCCDecoder.cpp:330): occupancy / geometry D0,D1 /
+4:4:4 16-bit attribute frames, the per-frame patch tables, and the GeneratePointCloudParameters.  All
+integer, seeded; the CUDA path, the CPU restatement and the unmodified reference consume the same arrays.
+
+Shape: a closed surface made of a union of ellipsoids ("humanoid": torso, head, limbs) inside a 2^bitdepth
+cube, projected orthographically on the 6 axis-aligned planes (view ids 0..5 of PCCPatch::setViewId,
+PCCPatch.cpp:111-137), segmented by dominant normal, cut into patches on 16x16 blocks and packed into a
+W-wide atlas with an occupancy-aware first-fit, as the encoder does.  Coding noise (+-1 on a fraction of the
+depth samples) creates smoothing candidates.  The noise-free voxels with RGB + analytic normals form the
+"source" cloud for the metrics.
+"""
+import numpy as np
+
+from . import abi
+
+# PCCPatch::setViewId: viewId -> (normal, tangent, bitangent, projectionMode)
+VIEW_AXES = {0: (0, 2, 1, 0), 1: (1, 2, 0, 0), 2: (2, 0, 1, 0), 3: (0, 2, 1, 1), 4: (1, 2, 0, 1), 5: (2, 0, 1, 1)}
+_SWITCHED = (1, 3, 5, 7, 8)  # orientations that swap U and V on the canvas (PCCPatch.h isPatchDimensionSwitched)
+
+
+def default_params(width, height, bitdepth=10, occupancy_precision=4):
+    """CTC C2 lossy defaults: cfg/common/ctc-common.cfg:22,25,57-60, Rec-1 (PCCDecoderParameters.cpp:125-134)."""
+    p = abi.Params()
+    p.width, p.height = width, height
+    p.occupancy_resolution = 16
+    p.occupancy_precision = occupancy_precision
+    p.threshold_lossy_om = 0
+    p.map_count_minus1 = 1
+    p.absolute_d1 = 1
+    p.remove_duplicate_points = 1
+    p.geometry_bitdepth_3d = bitdepth
+    p.attribute_count = 1
+    p.attribute_rgb444 = 0
+    p.flag_geometry_smoothing = 1
+    p.grid_smoothing = 1
+    p.grid_size = 8
+    p.threshold_smoothing = 64.0
+    p.apply_geo_smoothing = 1
+    p.attr_transfer_filter_type = 1
+    p.flag_color_smoothing = 1
+    p.apply_attr_smoothing = 1
+    p.threshold_color_smoothing = 10.0
+    p.threshold_color_difference = 10.0
+    p.threshold_color_variation = 6.0
+    return p
+
+
+class SyntheticGOF:
+    """Container of one generated GOF (host numpy arrays + the C structs pointing at them)."""
+
+    def __init__(self):
+        self.params = None
+        self.n_frames = 0
+        self.occupancy = None   # u8  [F][H/p][W/p]
+        self.geometry = None    # u16 [F][M][H][W]
+        self.attribute = None   # u16 [F][M][3][H][W]
+        self.patches = None     # PATCH_DTYPE [total]
+        self.patch_offset = None
+        self.eom_patches = None
+        self.eom_offset = None
+        self.eom_members = None
+        self.raw_patches = None
+        self.raw_offset = None
+        self.sources = []       # per frame: dict(positions i16[n,3], colors u8[n,3], normals f32[n,3])
+
+    def frames_struct(self):
+        f = abi.Frames()
+        f.occupancy = abi.ptr(self.occupancy)
+        f.geometry = abi.ptr(self.geometry)
+        f.attribute = abi.ptr(self.attribute) if self.attribute is not None else None
+        return f
+
+    def atlas_struct(self):
+        a = abi.Atlas()
+        a.patches = abi.ptr(self.patches)
+        a.patch_offset = abi.ptr(self.patch_offset)
+        a.eom_patches = abi.ptr(self.eom_patches) if self.eom_patches is not None else None
+        a.eom_offset = abi.ptr(self.eom_offset) if self.eom_offset is not None else None
+        a.eom_members = abi.ptr(self.eom_members) if self.eom_members is not None else None
+        a.raw_patches = abi.ptr(self.raw_patches) if self.raw_patches is not None else None
+        a.raw_offset = abi.ptr(self.raw_offset) if self.raw_offset is not None else None
+        return a
+
+    def input_bytes(self):
+        n = self.occupancy.nbytes + self.geometry.nbytes + self.patches.nbytes
+        if self.attribute is not None:
+            n += self.attribute.nbytes
+        return n
+
+
+def _humanoid(cube, scale, rng, t):
+    """list of (centre[3], radii[3]) in voxel units; t = frame phase for motion"""
+    s = cube * scale
+    cx, cz = cube * 0.5, cube * 0.5
+    sway = 0.01 * cube * np.sin(0.37 * t)
+    step = 0.015 * cube * np.sin(0.61 * t + 0.5)
+    parts = [
+        ((cx + sway, 0.56 * cube, cz), (0.19 * s, 0.26 * s, 0.13 * s)),                     # torso
+        ((cx + sway, 0.56 * cube + 0.36 * s, cz + step * 0.2), (0.09 * s, 0.11 * s, 0.10 * s)),   # head
+        ((cx - 0.26 * s + sway, 0.60 * cube, cz + step), (0.06 * s, 0.24 * s, 0.06 * s)),    # arm L
+        ((cx + 0.26 * s + sway, 0.60 * cube, cz - step), (0.06 * s, 0.24 * s, 0.06 * s)),    # arm R
+        ((cx - 0.10 * s, 0.56 * cube - 0.50 * s, cz - step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg L
+        ((cx + 0.10 * s, 0.56 * cube - 0.50 * s, cz + step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg R
+        ((cx, 0.56 * cube - 0.18 * s, cz), (0.17 * s, 0.12 * s, 0.12 * s)),                 # hips
+    ]
+    jit = rng.uniform(-0.004, 0.004, size=(len(parts), 3)) * cube
+    return [(np.array(c) + j, np.array(r)) for (c, r), j in zip(parts, jit)]
+
+
+def _view_depth(parts, cube, normal, tangent, bitangent, mode):
+    """orthographic depth map along `normal`; image axes (v=bitangent rows, u=tangent cols).
+    returns depth (float, nan where empty), part index map."""
+    depth = np.full((cube, cube), np.nan, dtype=np.float64)
+    owner = np.full((cube, cube), -1, dtype=np.int32)
+    for k, (c, r) in enumerate(parts):
+        u_lo, u_hi = int(max(0, np.floor(c[tangent] - r[tangent]))), int(min(cube, np.ceil(c[tangent] + r[tangent]) + 1))
+        v_lo, v_hi = int(max(0, np.floor(c[bitangent] - r[bitangent]))), int(min(cube, np.ceil(c[bitangent] + r[bitangent]) + 1))
+        if u_hi <= u_lo or v_hi <= v_lo:
+            continue
+        uu = (np.arange(u_lo, u_hi) - c[tangent]) / r[tangent]
+        vv = (np.arange(v_lo, v_hi) - c[bitangent]) / r[bitangent]
+        q = 1.0 - uu[None, :] ** 2 - vv[:, None] ** 2
+        inside = q > 0
+        h = np.sqrt(np.where(inside, q, 0.0)) * r[normal]
+        d = c[normal] - h if mode == 0 else c[normal] + h
+        sub = depth[v_lo:v_hi, u_lo:u_hi]
+        osub = owner[v_lo:v_hi, u_lo:u_hi]
+        if mode == 0:
+            better = inside & (np.isnan(sub) | (d < sub))
+        else:
+            better = inside & (np.isnan(sub) | (d > sub))
+        sub[better] = d[better]
+        osub[better] = k
+    return depth, owner
+
+
+def _split_rects(mask, max_blocks, rng, R=16):
+    """cut the occupied area of `mask` into block-aligned rectangles (patch bounding boxes)."""
+    out = []
+    ys, xs = np.nonzero(mask)
+    if len(ys) == 0:
+        return out
+    stack = [(xs.min(), ys.min(), xs.max() + 1, ys.max() + 1)]
+    while stack:
+        x0, y0, x1, y1 = stack.pop()
+        sub = mask[y0:y1, x0:x1]
+        if not sub.any():
+            continue
+        yy, xx = np.nonzero(sub)
+        x0, x1, y0, y1 = x0 + xx.min(), x0 + xx.max() + 1, y0 + yy.min(), y0 + yy.max() + 1
+        w, h = x1 - x0, y1 - y0
+        lim = int(rng.integers(max(2, max_blocks // 2), max_blocks + 1)) * R
+        if w <= lim and h <= lim:
+            out.append((x0, y0, x1, y1))
+            continue
+        if w >= h:
+            cut = x0 + int(rng.integers(max(1, w // (3 * R)), max(2, 2 * w // (3 * R) + 1))) * R
+            cut = min(max(cut, x0 + R), x1 - 1)
+            stack.append((x0, y0, cut, y1))
+            stack.append((cut, y0, x1, y1))
+        else:
+            cut = y0 + int(rng.integers(max(1, h // (3 * R)), max(2, 2 * h // (3 * R) + 1))) * R
+            cut = min(max(cut, y0 + R), y1 - 1)
+            stack.append((x0, y0, x1, cut))
+            stack.append((x0, cut, x1, y1))
+    return out
+
+
+def _correlate_valid(grid, cm):
+    """number of colliding blocks for every placement of `cm` inside `grid` ('valid' correlation)"""
+    from scipy.signal import correlate2d
+    return correlate2d(grid.astype(np.int32), cm.astype(np.int32), mode="valid")
+
+
+def _patch2canvas_arrays(orient, U, V, su, sv):
+    """vectorised PCCPatch::patch2Canvas (PCCPatch.cpp:192-251) relative to the patch origin, pixel units.
+    U,V patch-local pixel coords; su, sv = patch size in pixels (sizeU0*R, sizeV0*R)."""
+    if orient == 0:
+        return U, V
+    if orient == 1:
+        return sv - 1 - V, U
+    if orient == 2:
+        return su - 1 - U, sv - 1 - V
+    if orient == 3:
+        return V, su - 1 - U
+    if orient == 4:
+        return su - 1 - U, V
+    if orient == 5:
+        return sv - 1 - V, su - 1 - U
+    if orient == 6:
+        return U, sv - 1 - V
+    if orient in (7, 8):
+        return V, U
+    raise ValueError(orient)
+
+
+def _yuv16_field(P, rng_noise, amp):
+    """smooth 3-D colour field -> 16-bit YUV (8-bit content << 8), P float [...,3]"""
+    x, y, z = P[..., 0], P[..., 1], P[..., 2]
+    Y = 120 + 70 * np.sin(x * 0.021 + 0.3) * np.cos(y * 0.013) + 30 * np.sin(z * 0.05)
+    Cb = 128 + 50 * np.sin(y * 0.017 + z * 0.011)
+    Cr = 128 + 50 * np.cos(x * 0.015 - y * 0.009)
+    yuv = np.stack([Y, Cb, Cr], axis=-1)
+    if rng_noise is not None and amp > 0:
+        yuv = yuv + rng_noise.normal(0, amp, size=yuv.shape)
+    return np.clip(np.rint(yuv * 256.0), 0, 65535).astype(np.uint16)
+
+
+def yuv16_to_rgb8(c16):
+    """PCCPointSet3::convertYUV16ToRGB8 (PCCPointSet.h:133-166) in numpy float64 (source-cloud colours)."""
+    c = c16.astype(np.float64)
+    w = 1.0 / 65535.0
+    y1 = np.clip(w * c[..., 0], 0, 1)
+    u1 = np.clip(w * (c[..., 1] - 32768.0), -0.5, 0.5)
+    v1 = np.clip(w * (c[..., 2] - 32768.0), -0.5, 0.5)
+    r = y1 + 1.57480 * v1
+    g = y1 - 0.18733 * u1 - 0.46813 * v1
+    b = y1 + 1.85563 * u1
+
+    def rnd(a):  # C round(): half away from zero
+        return np.clip(np.where(a >= 0, np.floor(a * 255 + 0.5), np.ceil(a * 255 - 0.5)), 0, 255)
+    return np.stack([rnd(r), rnd(g), rnd(b)], axis=-1).astype(np.uint8)
+
+
+def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, scale=1.0, seed=0x0AB817,
+                 noise_fraction=0.10, color_noise=6.0, max_patch_blocks=12, orientations=(0, 8),
+                 eom=False, raw_points=0, map_count=2, precedence_reverse=False, min_height_blocks=0,
+                 with_sources=True, color_smoothing=True, geometry_smoothing=True, transfer_filter=1,
+                 height_blocks=None, absolute_d1=True):
+    """Generate one GOF.  `scale` sizes the body relative to the cube (1.0 ~ vox10-like point counts at
+    bitdepth 10: ~0.4 M occupied pixels, ~0.8 M points).  `height_blocks` forces the atlas height (all
+    frames of a GOF share W x H as the video does); otherwise H = tallest packing over the GOF."""
+    R = 16
+    cube = 1 << bitdepth
+    p_occ = 1 if eom else occupancy_precision
+    Wb = width // R
+    M = map_count
+    frames = []
+    for f in range(n_frames):
+        rng = np.random.default_rng([seed, f])
+        parts = _humanoid(cube, scale, rng, float(f))
+        # ---- per-view depth maps and normal-based segmentation ----
+        views = []
+        for vid, (nrm, tan, bit, mode) in VIEW_AXES.items():
+            depth, owner = _view_depth(parts, cube, nrm, tan, bit, mode)
+            valid = owner >= 0
+            dz = np.rint(np.where(valid, depth, 0)).astype(np.int64)
+            # surface normal of the owning ellipsoid at the hit point
+            vv, uu = np.mgrid[0:cube, 0:cube]
+            cen = np.array([pt[0] for pt in parts])
+            rad = np.array([pt[1] for pt in parts])
+            ow = np.where(valid, owner, 0)
+            pos = np.zeros((cube, cube, 3))
+            pos[..., nrm] = np.where(valid, depth, 0)
+            pos[..., tan] = uu
+            pos[..., bit] = vv
+            g = (pos - cen[ow]) / (rad[ow] ** 2)
+            gn = np.linalg.norm(g, axis=-1, keepdims=True)
+            g = g / np.maximum(gn, 1e-12)
+            dom = (np.abs(g[..., nrm]) >= np.abs(g[..., tan]) - 1e-9) & (np.abs(g[..., nrm]) >= np.abs(g[..., bit]) - 1e-9)
+            sel = valid & dom
+            views.append(dict(vid=vid, nrm=nrm, tan=tan, bit=bit, mode=mode, depth=dz, valid=valid, sel=sel,
+                              normal=g.astype(np.float32)))
+        # ---- cut into patches ----
+        plist = []
+        for vw in views:
+            for (x0, y0, x1, y1) in _split_rects(vw["sel"], max_patch_blocks, rng, R):
+                x0a, y0a = (x0 // R) * R if rng.random() < 0.5 else x0, (y0 // R) * R if rng.random() < 0.5 else y0
+                su0, sv0 = -(-(x1 - x0a) // R), -(-(y1 - y0a) // R)
+                # keep the patch inside the cube image
+                if x0a + su0 * R > cube:
+                    x0a = cube - su0 * R
+                if y0a + sv0 * R > cube:
+                    y0a = cube - sv0 * R
+                m = np.zeros((sv0 * R, su0 * R), bool)
+                m[:, :] = vw["sel"][y0a:y0a + sv0 * R, x0a:x0a + su0 * R]
+                # a pixel belongs to this patch only inside the cut rectangle
+                yy, xx = np.mgrid[0:sv0 * R, 0:su0 * R]
+                m &= (xx + x0a >= x0) & (xx + x0a < x1) & (yy + y0a >= y0) & (yy + y0a < y1)
+                if not m.any():
+                    continue
+                plist.append(dict(view=vw, u1=x0a, v1=y0a, su0=su0, sv0=sv0, mask=m))
+        order = rng.permutation(len(plist))
+        # biggest first, like the encoder's packing order
+        order = sorted(order, key=lambda i: -(plist[i]["su0"] * plist[i]["sv0"]))
+        plist = [plist[i] for i in order]
+        for pt in plist:
+            pt["orient"] = int(orientations[int(rng.integers(0, len(orientations)))])
+        frames.append(dict(parts=parts, views=views, patches=plist, rng=rng))
+
+    # ---- packing: occupancy-aware first fit on the block grid ----
+    Hb_needed = 0
+    for fr in frames:
+        rows_cap = 4 * (cube // R) + 64
+        grid = np.zeros((rows_cap, Wb), bool)
+        for pt in fr["patches"]:
+            su0, sv0, o = pt["su0"], pt["sv0"], pt["orient"]
+            bm = pt["mask"].reshape(sv0, R, su0, R).any(axis=(1, 3))  # [sv0][su0] occupied blocks (patch space)
+            VB, UB = np.mgrid[0:sv0, 0:su0]
+            xb, yb = _patch2canvas_arrays(o, UB, VB, su0, sv0)
+            cw, ch = (sv0, su0) if o in _SWITCHED else (su0, sv0)
+            cm = np.zeros((ch, cw), bool)
+            cm[yb, xb] = bm
+            if cw > Wb:
+                raise ValueError("patch wider than the atlas")
+            placed = False
+            # first position in raster order where no occupied block collides (encoder-style packing)
+            top = 0
+            while not placed and top < rows_cap - ch:
+                bot = min(rows_cap, top + ch + 64)
+                hit = _correlate_valid(grid[top:bot], cm)
+                ys, xs = np.nonzero(hit == 0)
+                if len(ys):
+                    y, x = int(ys[0]) + top, int(xs[0])
+                    grid[y:y + ch, x:x + cw] |= cm
+                    pt["u0"], pt["v0"] = x, y
+                    placed = True
+                else:
+                    top += 64
+            if not placed:
+                raise RuntimeError("packing failed")
+        used = np.nonzero(grid.any(axis=1))[0]
+        fr["Hb"] = int(used.max()) + 1 if len(used) else 1
+        Hb_needed = max(Hb_needed, fr["Hb"])
+
+    # extra room for EOM / raw rectangles
+    eom_rows = raw_rows = 0
+    if eom:
+        eom_rows = 0  # fixed after counting below
+    if raw_points:
+        raw_rows = -(-(3 * raw_points) // (Wb * R * R))
+    Hb = max(Hb_needed, min_height_blocks)
+
+    # ---- rasterise frames ----
+    gof = SyntheticGOF()
+    per_frame = []
+    max_eom_rows = 0
+    for f, fr in enumerate(frames):
+        rng = fr["rng"]
+        plist = fr["patches"]
+        recs = np.zeros(len(plist), abi.PATCH_DTYPE)
+        pix = []  # per patch: canvas x,y, D0, D1, P0, P1 (noise-free and coded), normals
+        for i, pt in enumerate(plist):
+            vw = pt["view"]
+            su, sv = pt["su0"] * R, pt["sv0"] * R
+            yy, xx = np.nonzero(pt["mask"])
+            gu, gv = xx + pt["u1"], yy + pt["v1"]
+            dep = vw["depth"][gv, gu]
+            if vw["mode"] == 0:
+                d1 = int(dep.min())
+                d0 = dep - d1
+            else:
+                d1 = int(dep.max())
+                d0 = d1 - dep
+            recs[i] = (pt["u0"], pt["v0"], pt["su0"], pt["sv0"], pt["u1"], pt["v1"], d1, vw["nrm"], vw["tan"],
+                       vw["bit"], vw["mode"], pt["orient"], 1, 1, 0, su, sv)
+            pix.append(dict(u=xx, v=yy, d0=d0.astype(np.int64), nrm=vw["normal"][gv, gu]))
+        per_frame.append(dict(recs=recs, pix=pix))
+    # EOM needs the per-frame extra-point count to size the atlas: computed in the loop below; reserve rows lazily
+    H_extra_rows = 0
+
+    def build_frame(f, Hb_total, want_arrays):
+        fr, pf = frames[f], per_frame[f]
+        rng = np.random.default_rng([seed, f, 7])
+        W, H = width, Hb_total * R
+        occ_full = np.zeros((H, W), np.uint8)
+        geo = np.zeros((M, H, W), np.uint16)
+        att = np.zeros((M, 3, H, W), np.uint16)
+        src_pos, src_col, src_nrm = [], [], []
+        eom_extra = 0
+        for i, pt in enumerate(fr["patches"]):
+            rec, px = pf["recs"][i], pf["pix"][i]
+            su, sv = pt["su0"] * R, pt["sv0"] * R
+            cx, cy = _patch2canvas_arrays(pt["orient"], px["u"], px["v"], su, sv)
+            cx, cy = cx + pt["u0"] * R, cy + pt["v0"] * R
+            n = len(cx)
+            d0 = px["d0"].copy()
+            # far layer within surfaceThickness 4 (cfg/common/ctc-common.cfg:25): thicker where the surface is steep
+            steep = 1.0 - np.abs(px["nrm"][:, rec["normal_axis"]])
+            delta = np.minimum(4, np.floor(steep * 6 + rng.random(n) * 1.5)).astype(np.int64)
+            d1v = d0 + delta
+            # noise-free points -> source cloud
+            if with_sources:
+                for dv in (d0, d1v):
+                    P = np.zeros((n, 3), np.int64)
+                    P[:, rec["normal_axis"]] = (dv + rec["d1"]) if rec["projection_mode"] == 0 else np.maximum(rec["d1"] - dv, 0)
+                    P[:, rec["tangent_axis"]] = px["u"] + rec["u1"]
+                    P[:, rec["bitangent_axis"]] = px["v"] + rec["v1"]
+                    src_pos.append(P)
+                    src_nrm.append(px["nrm"])
+            # coding noise
+            nz = rng.random(n) < noise_fraction
+            d0c = np.maximum(d0 + np.where(nz, rng.integers(-1, 2, n), 0), 0)
+            nz1 = rng.random(n) < noise_fraction
+            d1c = np.maximum(d1v + np.where(nz1, rng.integers(-1, 2, n), 0), d0c)
+            occv = np.ones(n, np.int64)
+            if eom:
+                diff = d1c - d0c
+                bits = np.maximum(diff - 1, 0)
+                symbol = (rng.integers(0, 1 << 16, n) % (1 << bits)).astype(np.int64)
+                occv = np.where(diff > 1, (1 << bits) - symbol, 1)
+                eom_extra += int(sum(bin(int(s)).count("1") for s in symbol[diff > 1]))
+            if want_arrays:
+                occ_full[cy, cx] = occv
+                geo[0][cy, cx] = d0c
+                if M > 1:
+                    geo[1][cy, cx] = d1c if absolute_d1 else (d1c - d0c)
+                for m, dv in enumerate((d0c, d1c)[:M]):
+                    P = np.zeros((n, 3), np.float64)
+                    P[:, rec["normal_axis"]] = (dv + rec["d1"]) if rec["projection_mode"] == 0 else np.maximum(rec["d1"] - dv, 0)
+                    P[:, rec["tangent_axis"]] = px["u"] + rec["u1"]
+                    P[:, rec["bitangent_axis"]] = px["v"] + rec["v1"]
+                    c16 = _yuv16_field(P, rng, color_noise)
+                    for c in range(3):
+                        att[m][c][cy, cx] = c16[:, c]
+        out = dict(eom_extra=eom_extra)
+        if want_arrays:
+            # low-resolution occupancy video + padding of the dilated pixels (geometry/attribute dilation as the
+            # encoder does): every pixel that the upsampled occupancy turns on must carry plausible values.
+            p = p_occ
+            if p > 1:
+                occ_lo = occ_full.reshape(H // p, p, W // p, p).max(axis=(1, 3))
+                up = np.repeat(np.repeat(occ_lo, p, axis=0), p, axis=1)
+                pad = (up != 0) & (occ_full == 0)
+                if pad.any():
+                    # nearest valid sample inside the same p x p cell (cell-wise max works as a fill)
+                    for arr in [geo[m] for m in range(M)] + [att[m][c] for m in range(M) for c in range(3)]:
+                        cell = arr.reshape(H // p, p, W // p, p).max(axis=(1, 3))
+                        fill = np.repeat(np.repeat(cell, p, axis=0), p, axis=1)
+                        arr[pad] = fill[pad]
+            else:
+                occ_lo = occ_full
+            out.update(occ=occ_lo, geo=geo, att=att)
+        if with_sources and src_pos:
+            P = np.concatenate(src_pos)
+            N = np.concatenate(src_nrm)
+            key = (P[:, 0] << 32) | (P[:, 1] << 16) | P[:, 2]
+            _, first = np.unique(key, return_index=True)
+            first = rng.permutation(first)  # PLY order shuffled by the seed
+            P, N = P[first], N[first]
+            out["source"] = dict(positions=P.astype(np.int16), normals=N.astype(np.float32),
+                                 colors=yuv16_to_rgb8(_yuv16_field(P.astype(np.float64), None, 0)))
+        return out
+
+    if eom:
+        extra = max(build_frame(f, Hb, False)["eom_extra"] for f in range(n_frames))
+        H_extra_rows += -(-extra // (Wb * R * R)) + 1
+    eom_v0 = Hb
+    raw_v0 = Hb + H_extra_rows
+    if raw_points:
+        H_extra_rows += raw_rows
+    Hb_total = Hb + H_extra_rows
+    if height_blocks is not None:
+        if height_blocks < Hb_total:
+            raise ValueError(f"height_blocks {height_blocks} < needed {Hb_total}")
+        Hb_total = height_blocks
+    H = Hb_total * R
+
+    occs, geos, atts, srcs = [], [], [], []
+    raw_recs, raw_off = [], [0]
+    eom_recs, eom_off, eom_mem = [], [0], []
+    poff = [0]
+    allp = []
+    for f in range(n_frames):
+        b = build_frame(f, Hb_total, True)
+        rngx = np.random.default_rng([seed, f, 11])
+        if eom:
+            # EOM extra points are coloured from attribute frame 0 at synthetic addresses of the EOM rectangle
+            rows = slice(eom_v0 * R, (eom_v0 + max(1, H_extra_rows - (raw_rows if raw_points else 0))) * R)
+            b["att"][0][:, rows, :] = rngx.integers(0, 65536, size=b["att"][0][:, rows, :].shape, dtype=np.uint16)
+            npat = len(frames[f]["patches"])
+            members = list(rngx.permutation(npat)) if npat else []
+            eom_recs.append((0, eom_v0, len(eom_mem), len(members), b["eom_extra"]))
+            eom_mem += [int(m) for m in members]
+        eom_off.append(len(eom_recs))
+        if raw_points:
+            nraw = raw_points
+            rows = slice(raw_v0 * R, (raw_v0 + raw_rows) * R)
+            vals = rngx.integers(0, cube, size=3 * nraw).astype(np.uint16)
+            flat = np.zeros(raw_rows * R * width, np.uint16)
+            flat[:3 * nraw] = vals
+            b["geo"][0][rows, :] = flat.reshape(raw_rows * R, width)
+            b["att"][0][:, rows, :] = rngx.integers(0, 65536, size=b["att"][0][:, rows, :].shape, dtype=np.uint16)
+            raw_recs.append((0, raw_v0, Wb, raw_rows, 0, 0, 0, nraw))
+        raw_off.append(len(raw_recs))
+        occs.append(b["occ"])
+        geos.append(b["geo"])
+        atts.append(b["att"])
+        srcs.append(b.get("source"))
+        allp.append(per_frame[f]["recs"])
+        poff.append(poff[-1] + len(per_frame[f]["recs"]))
+
+    params = default_params(width, H, bitdepth, p_occ)
+    params.map_count_minus1 = M - 1
+    params.absolute_d1 = 1 if absolute_d1 else 0
+    params.patch_precedence_reverse = 1 if precedence_reverse else 0
+    params.flag_color_smoothing = params.apply_attr_smoothing = 1 if color_smoothing else 0
+    params.flag_geometry_smoothing = params.apply_geo_smoothing = 1 if geometry_smoothing else 0
+    params.attr_transfer_filter_type = transfer_filter
+    if eom:
+        # lossless-style variant (cfg/common/ctc-common-lossless-geometry-attribute.cfg): no smoothing
+        params.enhanced_occupancy_map_code = 1
+        params.eom_fix_bit_count = 2
+        params.remove_duplicate_points = 0
+    if raw_points:
+        params.use_additional_points_patch = 1
+    gof.params = params
+    gof.n_frames = n_frames
+    gof.occupancy = np.ascontiguousarray(np.stack(occs))
+    gof.geometry = np.ascontiguousarray(np.stack(geos))
+    gof.attribute = np.ascontiguousarray(np.stack(atts))
+    gof.patches = np.ascontiguousarray(np.concatenate(allp)) if allp else np.zeros(0, abi.PATCH_DTYPE)
+    gof.patch_offset = np.array(poff, np.int32)
+    if eom:
+        gof.eom_patches = np.array(eom_recs, dtype=abi.EOM_DTYPE)
+        gof.eom_offset = np.array(eom_off, np.int32)
+        gof.eom_members = np.array(eom_mem if eom_mem else [0], np.int32)
+    if raw_points:
+        gof.raw_patches = np.array(raw_recs, dtype=abi.RAW_DTYPE)
+        gof.raw_offset = np.array(raw_off, np.int32)
+    gof.sources = srcs
+    return gof
