@@ -1,0 +1,167 @@
+"""Host-side mirror of the reference's PCCCodec entry points for the hot path, over the C ABI.
+
+The method names and argument meaning follow the reference (PccLibCommon/include/PCCCodec.h:160-183 and the
+decoder's frame loop, PccLibDecoder/source/PCCDecoder.cpp:330-508) so the parity tests read like the
+reference's own call sequence:
+
+    codec = PCCCodecB200(device=0)
+    codec.beginGof(params, n_frames); codec.uploadFrames(frames, atlas)
+    codec.generatePointCloud()            # generateOccupancyMap + generateBlockToPatch... + generatePointCloud
+                                          #   + colorPointCloud for every frame of the GOF
+    codec.smoothPointCloudPostprocess()   # PCCCodec.cpp:52-147
+    codec.transferColors16bitBP()         # PCCPointSet.cpp:1126-1485 as called at PCCDecoder.cpp:447-465
+    codec.colorSmoothing()                # PCCCodec.cpp:149-236
+    codec.convertYUV16ToRGB8()            # PCCPointSet.h:133-166
+    cloud = codec.getPointCloud(f)        # dict of numpy arrays in PCCPointSet3 layouts
+
+Error behaviour: the reference prints and exits; here every non-zero status raises `RabbitError` carrying the
+status code (180 for a patch outside the canvas, as PCCPatch.cpp:237-245 exits with).
+There is no CPU fallback: constructing a codec without the CUDA library or without a GPU raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class RabbitError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"rabbit_b200 status {status}: {message}")
+        self.status = status
+
+
+class PCCCodecB200:
+    def __init__(self, device=0, stream=None):
+        self._lib = abi.load_library()
+        if self._lib.rb200_abi_version() != 1:
+            raise RuntimeError("rabbit_b200 ABI version mismatch")
+        h = C.c_void_p()
+        st = self._lib.rb200_create(device, C.byref(h))
+        if st != abi.RB200_OK:
+            raise RabbitError(st, "rb200_create failed (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.n_frames = 0
+        self.params = None
+        self._keep = None
+        if stream is not None:
+            self.setStream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != abi.RB200_OK:
+            raise RabbitError(st, self._lib.rb200_error_string(self._h).decode())
+
+    # ---- plumbing ----
+    def setStream(self, cuda_stream):
+        self._check(self._lib.rb200_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def synchronize(self):
+        self._check(self._lib.rb200_synchronize(self._h))
+
+    def beginGof(self, params, n_frames):
+        self._check(self._lib.rb200_gof_begin(self._h, C.byref(params), n_frames))
+        self.params, self.n_frames = params, n_frames
+
+    def uploadFrames(self, frames, atlas, keep=None):
+        """frames: abi.Frames (host or device pointers), atlas: abi.Atlas (host pointers)"""
+        self._keep = keep
+        self._check(self._lib.rb200_gof_upload(self._h, C.byref(frames), C.byref(atlas)))
+
+    def uploadGof(self, gof):
+        self.beginGof(gof.params, gof.n_frames)
+        self.uploadFrames(gof.frames_struct(), gof.atlas_struct(), keep=gof)
+
+    # ---- the reference's entry points ----
+    def generatePointCloud(self):
+        self._check(self._lib.rb200_reconstruct(self._h))
+
+    def smoothPointCloudPostprocess(self):
+        self._check(self._lib.rb200_smooth_geometry(self._h))
+
+    def transferColors16bitBP(self):
+        self._check(self._lib.rb200_transfer_colors(self._h))
+
+    def colorSmoothing(self):
+        self._check(self._lib.rb200_smooth_color(self._h))
+
+    def convertYUV16ToRGB8(self):
+        self._check(self._lib.rb200_convert_rgb8(self._h))
+
+    def decodeGof(self):
+        """whole per-frame sequence of PCCDecoder.cpp:330-508 for the resident GOF"""
+        self._check(self._lib.rb200_decode_gof(self._h))
+
+    # ---- results ----
+    def frameCounts(self):
+        arr = (abi.FrameCounts * self.n_frames)()
+        self._check(self._lib.rb200_frame_counts_get(self._h, arr))
+        return list(arr)
+
+    def getPointCloud(self, f, counts=None, fields=("positions", "colors16", "colors", "boundary_types", "partition",
+                                                     "point_to_pixel")):
+        counts = counts or self.frameCounts()
+        n = counts[f].total
+        shapes = dict(positions=((n, 3), np.int16), colors16=((n, 3), np.uint16), colors=((n, 3), np.uint8),
+                      boundary_types=((n,), np.uint16), partition=((n,), np.uint32), point_to_pixel=((n, 3), np.uint32))
+        out = {k: np.zeros(*shapes[k]) for k in fields}
+        h = abi.CloudHost(*[abi.ptr(out[k]) if k in out else None for k, _ in abi.CloudHost._fields_])
+        self._check(self._lib.rb200_download_frame(self._h, f, C.byref(h)))
+        return out
+
+    def getBlockToPatch(self, f):
+        p = self.params
+        a = np.zeros((p.height // p.occupancy_resolution, p.width // p.occupancy_resolution), np.uint32)
+        self._check(self._lib.rb200_download_block_to_patch(self._h, f, abi.ptr(a)))
+        return a
+
+    def getOccupancyMap(self, f):
+        p = self.params
+        a = np.zeros((p.height, p.width), np.uint8)
+        self._check(self._lib.rb200_download_occupancy(self._h, f, abi.ptr(a)))
+        return a
+
+    # ---- instrumentation ----
+    def stats(self, reset=False):
+        s = abi.LaunchStats()
+        self._check(self._lib.rb200_stats_get(self._h, C.byref(s), 1 if reset else 0))
+        return s
+
+    def enableTiming(self, on=True):
+        self._check(self._lib.rb200_timing_enable(self._h, 1 if on else 0))
+
+    def timings(self):
+        out = {}
+        i = 0
+        name = C.create_string_buffer(64)
+        ms = C.c_double()
+        n = abi.i64()
+        while self._lib.rb200_timing_get(self._h, i, name, 64, C.byref(ms), C.byref(n)) == abi.RB200_OK:
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
+
+class Decoder:
+    """Convenience wrapper: one call = the decoder's reconstruction + post-processing of a GOF."""
+
+    def __init__(self, device=0):
+        self.codec = PCCCodecB200(device)
+
+    def decode_gof(self, gof, fields=("positions", "colors16", "colors", "boundary_types", "partition",
+                                      "point_to_pixel")):
+        self.codec.uploadGof(gof)
+        self.codec.decodeGof()
+        counts = self.codec.frameCounts()
+        return [self.codec.getPointCloud(f, counts, fields) for f in range(gof.n_frames)]

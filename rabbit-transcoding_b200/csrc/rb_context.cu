@@ -1,0 +1,603 @@
+// rb_context.cu — context lifetime, frame ingest, downloads, instrumentation (C ABI plumbing).
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "rb_common.cuh"
+
+int rb_fail( rb200_ctx* c, int code, const char* fmt, ... ) {
+  char    buf[512];
+  va_list ap;
+  va_start( ap, fmt );
+  vsnprintf( buf, sizeof( buf ), fmt, ap );
+  va_end( ap );
+  if ( c ) { c->err = buf; }
+  return code;
+}
+
+int rb_cuda( rb200_ctx* c, cudaError_t e, const char* what ) {
+  return rb_fail( c, RB200_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString( e ), what );
+}
+
+void rb_timing_begin( rb200_ctx* c, const char* name ) {
+  if ( !c->timing ) { return; }
+  RbTimingEntry t;
+  t.name = name;
+  cudaEventCreate( &t.a );
+  cudaEventCreate( &t.b );
+  cudaEventRecord( t.a, c->stream );
+  c->timing_events.push_back( t );
+}
+void rb_timing_end( rb200_ctx* c ) {
+  if ( !c->timing ) { return; }
+  cudaEventRecord( c->timing_events.back().b, c->stream );
+}
+
+void* rb_pinned( rb200_ctx* c, size_t bytes ) {
+  if ( bytes > c->h_pinned_cap ) {
+    if ( c->h_pinned ) { cudaFreeHost( c->h_pinned ); }
+    c->h_pinned     = nullptr;
+    c->h_pinned_cap = 0;
+    if ( cudaMallocHost( &c->h_pinned, bytes + 4096 ) != cudaSuccess ) { return nullptr; }
+    c->h_pinned_cap = bytes + 4096;
+  }
+  return c->h_pinned;
+}
+
+static void rb_timing_resolve( rb200_ctx* c ) {
+  if ( c->timing_events.empty() ) { return; }
+  cudaStreamSynchronize( c->stream );
+  for ( auto& t : c->timing_events ) {
+    float ms = 0.f;
+    cudaEventElapsedTime( &ms, t.a, t.b );
+    size_t k = 0;
+    for ( ; k < c->timing_names.size(); k++ ) {
+      if ( c->timing_names[k] == t.name ) { break; }
+    }
+    if ( k == c->timing_names.size() ) {
+      c->timing_names.push_back( t.name );
+      c->timing_ms.push_back( 0 );
+      c->timing_n.push_back( 0 );
+    }
+    c->timing_ms[k] += ms;
+    c->timing_n[k] += 1;
+    cudaEventDestroy( t.a );
+    cudaEventDestroy( t.b );
+  }
+  c->timing_events.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack kernels: device SoA records -> the reference's std::vector element layouts (PCCPointSet.h:520-531)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_positions( const short4* __restrict__ pos, int64_t n, int16_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  short4 p       = pos[i];
+  out[i * 3 + 0] = p.x;
+  out[i * 3 + 1] = p.y;
+  out[i * 3 + 2] = p.z;
+}
+__global__ void k_pack_types( const short4* __restrict__ pos, int64_t n, uint16_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  out[i] = (uint16_t)pos[i].w;
+}
+__global__ void k_pack_colors16( const ushort4* __restrict__ col, int64_t n, uint16_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  ushort4 p      = col[i];
+  out[i * 3 + 0] = p.x;
+  out[i * 3 + 1] = p.y;
+  out[i * 3 + 2] = p.z;
+}
+__global__ void k_pack_rgb( const uchar4* __restrict__ rgb, int64_t n, uint8_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  uchar4 p       = rgb[i];
+  out[i * 3 + 0] = p.x;
+  out[i * 3 + 1] = p.y;
+  out[i * 3 + 2] = p.z;
+}
+__global__ void k_pack_pixels( const uint32_t* __restrict__ pix,
+                               const ushort4* __restrict__ col,
+                               int64_t n,
+                               uint32_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  uint32_t p     = pix[i];
+  out[i * 3 + 0] = p & 0xFFFFu;
+  out[i * 3 + 1] = p >> 16;
+  out[i * 3 + 2] = col[i].w;
+}
+__global__ void k_expand_bitmap( const uint32_t* __restrict__ bm, int W, int H, int words, uint8_t* __restrict__ out ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= (int64_t)W * H ) { return; }
+  int y = (int)( i / W ), x = (int)( i % W );
+  out[i] = ( bm[(size_t)y * words + ( x >> 5 )] >> ( x & 31 ) ) & 1u;
+}
+
+extern "C" {
+
+int rb200_abi_version( void ) { return RB200_ABI_VERSION; }
+
+int rb200_create( int device, rb200_ctx** out ) {
+  if ( !out ) { return RB200_ERR_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  if ( cudaGetDeviceCount( &n ) != cudaSuccess || n <= 0 ) { return RB200_ERR_CUDA; }  // no CPU fallback
+  if ( device < 0 || device >= n ) { return RB200_ERR_INVALID; }
+  if ( cudaSetDevice( device ) != cudaSuccess ) { return RB200_ERR_CUDA; }
+  rb200_ctx* c = new rb200_ctx;
+  c->device    = device;
+  if ( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) != cudaSuccess ) {
+    delete c;
+    return RB200_ERR_CUDA;
+  }
+  c->own_stream = true;
+  *out          = c;
+  return RB200_OK;
+}
+
+void rb200_destroy( rb200_ctx* c ) {
+  if ( !c ) { return; }
+  cudaSetDevice( c->device );
+  cudaStreamSynchronize( c->stream );
+  RbBuf* bufs[] = {&c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
+                   &c->d_wi_count, &c->d_wi_base, &c->d_wi_eom_count, &c->d_wi_eom_base, &c->d_eom_order,
+                   &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
+                   &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
+                   &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
+                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off};
+  for ( auto* b : bufs ) { b->release(); }
+  for ( auto& b : c->d_scratch ) { b.release(); }
+  if ( c->h_pinned ) { cudaFreeHost( c->h_pinned ); }
+  for ( auto& t : c->timing_events ) {
+    cudaEventDestroy( t.a );
+    cudaEventDestroy( t.b );
+  }
+  if ( c->own_stream ) { cudaStreamDestroy( c->stream ); }
+  delete c;
+}
+
+const char* rb200_error_string( const rb200_ctx* c ) { return c ? c->err.c_str() : "null context"; }
+
+int rb200_set_stream( rb200_ctx* c, void* s ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  cudaSetDevice( c->device );
+  cudaStreamSynchronize( c->stream );
+  if ( s == nullptr ) {
+    if ( !c->own_stream ) {
+      RB_CUDA( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+      c->own_stream = true;
+    }
+  } else {
+    if ( c->own_stream ) { cudaStreamDestroy( c->stream ); }
+    c->own_stream = false;
+    c->stream     = (cudaStream_t)s;
+  }
+  return RB200_OK;
+}
+
+int rb200_synchronize( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  return RB200_OK;
+}
+
+int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
+  if ( !c || !p || nFrames <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_begin: bad arguments" ); }
+  cudaSetDevice( c->device );
+  const int R = p->occupancy_resolution, pr = p->occupancy_precision;
+  if ( p->width <= 0 || p->height <= 0 || R != 16 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "occupancy_resolution must be 16 (got %d)", R );
+  }
+  if ( !( pr == 1 || pr == 2 || pr == 4 || pr == 8 || pr == 16 ) ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "occupancy_precision %d unsupported", pr );
+  }
+  if ( p->width % R || p->height % R || p->width > 65535 || p->height > 65535 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "atlas %dx%d must be a multiple of %d and < 65536", p->width, p->height, R );
+  }
+  if ( p->single_map_pixel_interleaving || p->point_local_reconstruction || p->pbf_enable ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED,
+                    "singleMapPixelInterleaving / pointLocalReconstruction / PBF (PCCCodec.cpp:350-496,541-554) "
+                    "are not implemented in this build" );
+  }
+  if ( p->map_count_minus1 < 0 || p->map_count_minus1 > 1 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "map_count_minus1 must be 0 or 1" );
+  }
+  if ( p->flag_geometry_smoothing && p->apply_geo_smoothing && !p->grid_smoothing ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothPointCloud (PCCCodec.cpp:1106-1157) is not implemented" );
+  }
+  if ( p->geometry_bitdepth_3d < 1 || p->geometry_bitdepth_3d > 14 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "geometry_bitdepth_3d out of range" );
+  }
+  c->P       = *p;
+  c->F       = nFrames;
+  c->W       = p->width;
+  c->H       = p->height;
+  c->R       = R;
+  c->prec    = pr;
+  c->oW      = c->W / pr;
+  c->oH      = c->H / pr;
+  c->Wb      = c->W / R;
+  c->Hb      = c->H / R;
+  c->M       = p->map_count_minus1 + 1;
+  c->bmWords = ( c->W + 31 ) / 32;
+  c->have_gof = true;
+  c->uploaded = c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+  const size_t F = nFrames;
+  RB_CUDA( c->d_occ_video.ensure( F * c->oW * c->oH ) );
+  RB_CUDA( c->d_geometry.ensure( F * c->M * (size_t)c->W * c->H * 2 ) );
+  if ( p->attribute_count > 0 ) { RB_CUDA( c->d_attribute.ensure( F * c->M * 3 * (size_t)c->W * c->H * 2 ) ); }
+  RB_CUDA( c->d_bitmap.ensure( F * (size_t)c->H * c->bmWords * 4 ) );
+  RB_CUDA( c->d_b2p.ensure( F * (size_t)c->Wb * c->Hb * 4 ) );
+  RB_CUDA( c->d_frame_info.ensure( F * sizeof( RbFrameInfo ) ) );
+  RB_CUDA( c->d_frame_off.ensure( ( F + 1 ) * 8 ) );
+  c->h_frame_off.assign( F + 1, 0 );
+  c->h_counts.assign( F, rb200_frame_counts{} );
+  return RB200_OK;
+}
+
+// PCCPatch::patchBlock2CanvasBlock footprint check (PCCPatch.cpp:253-308): every patch block must land
+// inside the canvas, otherwise the reference exits 180 (PCCPatch.cpp:237-245).
+static bool patch_inside( const rb200_patch& p, int Wb, int Hb ) {
+  const bool sw = ( p.orientation == 1 || p.orientation == 3 || p.orientation == 5 || p.orientation == 7 ||
+                    p.orientation == 8 );
+  const int  cw = sw ? p.size_v0 : p.size_u0, ch = sw ? p.size_u0 : p.size_v0;
+  return p.u0 >= 0 && p.v0 >= 0 && p.size_u0 >= 0 && p.size_v0 >= 0 && p.u0 + cw <= Wb && p.v0 + ch <= Hb;
+}
+
+int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* at ) {
+  if ( !c || !fr || !at ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: null argument" ); }
+  if ( !c->have_gof ) { return rb_fail( c, RB200_ERR_STATE, "gof_upload before gof_begin" ); }
+  cudaSetDevice( c->device );
+  const size_t F = c->F;
+  if ( !fr->occupancy || !fr->geometry || ( c->P.attribute_count > 0 && !fr->attribute ) || !at->patch_offset ) {
+    return rb_fail( c, RB200_ERR_INVALID, "gof_upload: missing plane or patch table" );
+  }
+  // ---- patch tables (host) ----
+  const int nPatches = at->patch_offset[F];
+  if ( nPatches < 0 || at->patch_offset[0] != 0 || ( nPatches > 0 && !at->patches ) ) {
+    return rb_fail( c, RB200_ERR_INVALID, "gof_upload: bad patch offsets" );
+  }
+  c->h_patches.assign( at->patches, at->patches + nPatches );
+  c->h_patch_off.assign( at->patch_offset, at->patch_offset + F + 1 );
+  std::vector<RbPatch> dp( nPatches );
+  for ( size_t f = 0; f < F; f++ ) {
+    if ( c->h_patch_off[f + 1] < c->h_patch_off[f] ) { return rb_fail( c, RB200_ERR_INVALID, "patch offsets not monotone" ); }
+    if ( c->h_patch_off[f + 1] - c->h_patch_off[f] > 32000 ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "more than 32000 patches in a frame" );
+    }
+    for ( int i = c->h_patch_off[f]; i < c->h_patch_off[f + 1]; i++ ) {
+      const rb200_patch& s = c->h_patches[i];
+      if ( s.orientation < 0 || s.orientation > 8 || s.normal_axis < 0 || s.normal_axis > 2 || s.tangent_axis < 0 ||
+           s.tangent_axis > 2 || s.bitangent_axis < 0 || s.bitangent_axis > 2 || s.axis_of_additional_plane < 0 ||
+           s.axis_of_additional_plane > 3 ) {
+        return rb_fail( c, RB200_ERR_INVALID, "frame %zu patch %d: bad orientation / axes", f, i - c->h_patch_off[f] );
+      }
+      if ( !patch_inside( s, c->Wb, c->Hb ) ) {
+        return rb_fail( c, RB200_ERR_PATCH_OUT_OF_CANVAS,
+                        "patch2Canvas (x,y) is out of boundary : frame %zu patch %d canvassize %dx%d", f,
+                        i - c->h_patch_off[f], c->W, c->H );
+      }
+      RbPatch& d       = dp[i];
+      d.u0             = s.u0;
+      d.v0             = s.v0;
+      d.su0            = s.size_u0;
+      d.sv0            = s.size_v0;
+      d.u1             = s.u1;
+      d.v1             = s.v1;
+      d.d1             = s.d1;
+      d.s2dx           = s.size2d_x_px;
+      d.s2dy           = s.size2d_y_px;
+      d.frame_patch    = (int16_t)( i - c->h_patch_off[f] );
+      d.pad0           = 0;
+      d.frame          = (int32_t)f;
+      d.normal_axis    = (int8_t)s.normal_axis;
+      d.tangent_axis   = (int8_t)s.tangent_axis;
+      d.bitangent_axis = (int8_t)s.bitangent_axis;
+      d.mode           = (int8_t)s.projection_mode;
+      d.orient         = (int8_t)s.orientation;
+      d.lodx           = (int8_t)s.lod_x;
+      d.lody           = (int8_t)s.lod_y;
+      d.addplane       = (int8_t)s.axis_of_additional_plane;
+    }
+  }
+  // work items: patch blocks in the reference's emission order (PCCCodec.cpp:628-650):
+  // patch index order (reversed under patchPrecedenceOrderFlag, :629), then v0, then u0.
+  std::vector<int32_t> wiPatch, wiLocal, frameWiOff( F + 1, 0 );
+  for ( size_t f = 0; f < F; f++ ) {
+    frameWiOff[f] = (int32_t)wiPatch.size();
+    const int b = c->h_patch_off[f], e = c->h_patch_off[f + 1];
+    for ( int k = 0; k < e - b; k++ ) {
+      const int i  = c->P.patch_precedence_reverse ? ( e - 1 - k ) : ( b + k );
+      const int nb = c->h_patches[i].size_u0 * c->h_patches[i].size_v0;
+      for ( int j = 0; j < nb; j++ ) {
+        wiPatch.push_back( i );
+        wiLocal.push_back( j );
+      }
+    }
+  }
+  frameWiOff[F] = (int32_t)wiPatch.size();
+  c->nWI        = (int64_t)wiPatch.size();
+
+  // EOM / raw tables
+  c->h_eom.clear();
+  c->h_eom_off.assign( F + 1, 0 );
+  c->h_eom_members.clear();
+  if ( c->P.enhanced_occupancy_map_code && at->eom_patches && at->eom_offset ) {
+    const int n = at->eom_offset[F];
+    c->h_eom.assign( at->eom_patches, at->eom_patches + n );
+    c->h_eom_off.assign( at->eom_offset, at->eom_offset + F + 1 );
+    int nm = 0;
+    for ( auto& e : c->h_eom ) { nm = std::max( nm, e.member_begin + e.member_count ); }
+    if ( nm > 0 ) {
+      if ( !at->eom_members ) { return rb_fail( c, RB200_ERR_INVALID, "eom_members missing" ); }
+      c->h_eom_members.assign( at->eom_members, at->eom_members + nm );
+    }
+  }
+  c->h_raw.clear();
+  c->h_raw_off.assign( F + 1, 0 );
+  if ( c->P.use_additional_points_patch && at->raw_patches && at->raw_offset ) {
+    const int n = at->raw_offset[F];
+    c->h_raw.assign( at->raw_patches, at->raw_patches + n );
+    c->h_raw_off.assign( at->raw_offset, at->raw_offset + F + 1 );
+    for ( auto& r : c->h_raw ) {
+      if ( r.u0 < 0 || r.v0 < 0 || r.u0 + r.size_u0 > c->Wb || r.v0 + r.size_v0 > c->Hb ||
+           (int64_t)r.num_points > (int64_t)r.size_u0 * r.size_v0 * c->R * c->R ) {
+        return rb_fail( c, RB200_ERR_INVALID, "raw patch outside the canvas or too small for its points" );
+      }
+    }
+  }
+
+  // ---- device copies ----
+  const size_t occBytes = F * (size_t)c->oW * c->oH;
+  const size_t geoBytes = F * c->M * (size_t)c->W * c->H * 2;
+  const size_t attBytes = c->P.attribute_count > 0 ? F * c->M * 3 * (size_t)c->W * c->H * 2 : 0;
+  RB_CUDA( cudaMemcpyAsync( c->d_occ_video.p, fr->occupancy, occBytes, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fr->geometry, geoBytes, cudaMemcpyDefault, c->stream ) );
+  if ( attBytes ) { RB_CUDA( cudaMemcpyAsync( c->d_attribute.p, fr->attribute, attBytes, cudaMemcpyDefault, c->stream ) ); }
+  c->stats.h2d_bytes += (int64_t)( occBytes + geoBytes + attBytes );
+  RB_CUDA( c->d_patches.ensure( std::max<size_t>( 1, nPatches ) * sizeof( RbPatch ) ) );
+  RB_CUDA( c->d_wi_patch.ensure( std::max<int64_t>( 1, c->nWI ) * 4 ) );
+  RB_CUDA( c->d_wi_local.ensure( std::max<int64_t>( 1, c->nWI ) * 4 ) );
+  RB_CUDA( c->d_wi_count.ensure( ( c->nWI + 1 ) * 4 ) );
+  RB_CUDA( c->d_wi_base.ensure( ( c->nWI + 1 ) * 8 ) );
+  RB_CUDA( c->d_frame_wi_off.ensure( ( F + 1 ) * 4 ) );
+  // the small tables go through one pinned staging block so the copies are truly asynchronous
+  const size_t tb = nPatches * sizeof( RbPatch ) + c->nWI * 8 + ( F + 1 ) * 4;
+  char*        st = (char*)rb_pinned( c, tb + 64 );
+  if ( !st ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned staging allocation failed" ); }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );  // staging block may still be in flight from a previous GOF
+  size_t o = 0;
+  if ( nPatches ) { memcpy( st + o, dp.data(), nPatches * sizeof( RbPatch ) ); }
+  RB_CUDA( cudaMemcpyAsync( c->d_patches.p, st + o, nPatches * sizeof( RbPatch ), cudaMemcpyHostToDevice, c->stream ) );
+  o += nPatches * sizeof( RbPatch );
+  if ( c->nWI ) {
+    memcpy( st + o, wiPatch.data(), c->nWI * 4 );
+    RB_CUDA( cudaMemcpyAsync( c->d_wi_patch.p, st + o, c->nWI * 4, cudaMemcpyHostToDevice, c->stream ) );
+    o += c->nWI * 4;
+    memcpy( st + o, wiLocal.data(), c->nWI * 4 );
+    RB_CUDA( cudaMemcpyAsync( c->d_wi_local.p, st + o, c->nWI * 4, cudaMemcpyHostToDevice, c->stream ) );
+    o += c->nWI * 4;
+  }
+  memcpy( st + o, frameWiOff.data(), ( F + 1 ) * 4 );
+  RB_CUDA( cudaMemcpyAsync( c->d_frame_wi_off.p, st + o, ( F + 1 ) * 4, cudaMemcpyHostToDevice, c->stream ) );
+  c->stats.h2d_bytes += (int64_t)tb;
+  c->uploaded      = true;
+  c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+  return RB200_OK;
+}
+
+int rb200_reconstruct( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  if ( !c->uploaded ) { return rb_fail( c, RB200_ERR_STATE, "reconstruct before gof_upload" ); }
+  cudaSetDevice( c->device );
+  int r = rb_reconstruct_impl( c );
+  if ( r == RB200_OK ) {
+    c->reconstructed = true;
+    c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+  }
+  return r;
+}
+
+int rb200_smooth_geometry( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "smooth_geometry before reconstruct" ); }
+  cudaSetDevice( c->device );
+  int r = rb_smooth_geometry_impl( c );
+  if ( r == RB200_OK ) { c->geo_smoothed = true; }
+  return r;
+}
+
+int rb200_transfer_colors( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  if ( !c->geo_smoothed ) { return rb_fail( c, RB200_ERR_STATE, "transfer_colors before smooth_geometry" ); }
+  cudaSetDevice( c->device );
+  int r = rb_transfer_colors_impl( c );
+  if ( r == RB200_OK ) { c->colors_transferred = true; }
+  return r;
+}
+
+int rb200_smooth_color( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "smooth_color before reconstruct" ); }
+  cudaSetDevice( c->device );
+  int r = rb_smooth_color_impl( c );
+  if ( r == RB200_OK ) { c->color_smoothed = true; }
+  return r;
+}
+
+int rb200_convert_rgb8( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "convert_rgb8 before reconstruct" ); }
+  cudaSetDevice( c->device );
+  int r = rb_convert_rgb8_impl( c );
+  if ( r == RB200_OK ) { c->rgb_done = true; }
+  return r;
+}
+
+// The decoder's per-frame sequence, PCCDecoder.cpp:330-508, for the whole GOF.
+int rb200_decode_gof( rb200_ctx* c ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  int r = rb200_reconstruct( c );
+  if ( r ) { return r; }
+  const rb200_params& p = c->P;
+  if ( p.apply_geo_smoothing && p.flag_geometry_smoothing ) {  // :434
+    if ( p.grid_smoothing ) {
+      r = rb200_smooth_geometry( c );  // :437
+      if ( r ) { return r; }
+    }
+    if ( p.attribute_count > 0 && p.attr_transfer_filter_type != 0 ) {  // :439-465
+      if ( p.attr_transfer_filter_type != 1 ) {
+        return rb_fail( c, RB200_ERR_UNSUPPORTED, "attrTransferFilterType %d not implemented (only 0 and 1)",
+                        p.attr_transfer_filter_type );
+      }
+      if ( !c->geo_smoothed ) { c->geo_smoothed = true; }
+      r = rb200_transfer_colors( c );
+      if ( r ) { return r; }
+    }
+  }
+  if ( p.attribute_count > 0 ) {
+    if ( p.apply_attr_smoothing && p.flag_color_smoothing ) {  // :496-499
+      r = rb200_smooth_color( c );
+      if ( r ) { return r; }
+    }
+    r = rb200_convert_rgb8( c );  // :500-507
+    if ( r ) { return r; }
+  }
+  return RB200_OK;
+}
+
+int rb200_frame_counts_get( rb200_ctx* c, rb200_frame_counts* out ) {
+  if ( !c || !out ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "frame_counts before reconstruct" ); }
+  cudaSetDevice( c->device );
+  RbFrameInfo* hi = (RbFrameInfo*)rb_pinned( c, c->F * sizeof( RbFrameInfo ) );
+  if ( !hi ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( hi, c->d_frame_info.p, c->F * sizeof( RbFrameInfo ), cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.d2h_bytes += c->F * sizeof( RbFrameInfo );
+  for ( int f = 0; f < c->F; f++ ) {
+    c->h_counts[f].smoothed  = hi[f].smoothed;
+    c->h_counts[f].recolored = hi[f].recolored;
+    out[f]                   = c->h_counts[f];
+  }
+  return RB200_OK;
+}
+
+int rb200_download_frame( rb200_ctx* c, int f, const rb200_cloud_host* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  cudaSetDevice( c->device );
+  const int64_t b = c->h_frame_off[f], n = c->h_frame_off[f + 1] - b;
+  if ( n == 0 ) { return RB200_OK; }
+  RB_CUDA( c->d_pack.ensure( (size_t)n * 12 ) );
+  const int T = 256, G = rb_div_up( n, T );
+  if ( dst->positions ) {
+    RB_LAUNCH( "pack_positions", k_pack_positions, G, T, 0, c->d_pos.as<short4>() + b, n, c->d_pack.as<int16_t>() );
+    RB_CUDA( cudaMemcpyAsync( dst->positions, c->d_pack.p, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->stats.d2h_bytes += n * 6;
+  }
+  if ( dst->boundary_types ) {
+    RB_LAUNCH( "pack_types", k_pack_types, G, T, 0, c->d_pos.as<short4>() + b, n, c->d_pack.as<uint16_t>() );
+    RB_CUDA( cudaMemcpyAsync( dst->boundary_types, c->d_pack.p, n * 2, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->stats.d2h_bytes += n * 2;
+  }
+  if ( dst->colors16 ) {
+    RB_LAUNCH( "pack_colors16", k_pack_colors16, G, T, 0, c->d_col.as<ushort4>() + b, n, c->d_pack.as<uint16_t>() );
+    RB_CUDA( cudaMemcpyAsync( dst->colors16, c->d_pack.p, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->stats.d2h_bytes += n * 6;
+  }
+  if ( dst->colors ) {
+    if ( c->rgb_done ) {
+      RB_LAUNCH( "pack_rgb", k_pack_rgb, G, T, 0, c->d_rgb.as<uchar4>() + b, n, c->d_pack.as<uint8_t>() );
+      RB_CUDA( cudaMemcpyAsync( dst->colors, c->d_pack.p, n * 3, cudaMemcpyDeviceToHost, c->stream ) );
+      RB_CUDA( cudaStreamSynchronize( c->stream ) );
+      c->stats.d2h_bytes += n * 3;
+    } else {
+      memset( dst->colors, 0, n * 3 );  // colorPointCloud's fillColor(0), PCCCodec.cpp:1319
+    }
+  }
+  if ( dst->partition ) {
+    RB_CUDA( cudaMemcpyAsync( dst->partition, c->d_part.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->stats.d2h_bytes += n * 4;
+  }
+  if ( dst->point_to_pixel ) {
+    RB_LAUNCH( "pack_pixels", k_pack_pixels, G, T, 0, c->d_pix.as<uint32_t>() + b, c->d_col.as<ushort4>() + b, n,
+               c->d_pack.as<uint32_t>() );
+    RB_CUDA( cudaMemcpyAsync( dst->point_to_pixel, c->d_pack.p, n * 12, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->stats.d2h_bytes += n * 12;
+  }
+  return RB200_OK;
+}
+
+int rb200_download_block_to_patch( rb200_ctx* c, int f, uint32_t* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  cudaSetDevice( c->device );
+  const size_t n = (size_t)c->Wb * c->Hb;
+  RB_CUDA( cudaMemcpyAsync( dst, c->d_b2p.as<uint32_t>() + f * n, n * 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.d2h_bytes += n * 4;
+  return RB200_OK;
+}
+
+int rb200_download_occupancy( rb200_ctx* c, int f, uint8_t* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  cudaSetDevice( c->device );
+  const size_t n = (size_t)c->W * c->H;
+  RB_CUDA( c->d_pack.ensure( n ) );
+  RB_LAUNCH( "expand_bitmap", k_expand_bitmap, rb_div_up( n, 256 ), 256, 0,
+             c->d_bitmap.as<uint32_t>() + (size_t)f * c->H * c->bmWords, c->W, c->H, c->bmWords, c->d_pack.as<uint8_t>() );
+  RB_CUDA( cudaMemcpyAsync( dst, c->d_pack.p, n, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.d2h_bytes += n;
+  return RB200_OK;
+}
+
+int rb200_stats_get( rb200_ctx* c, rb200_launch_stats* out, int reset ) {
+  if ( !c || !out ) { return RB200_ERR_INVALID; }
+  *out = c->stats;
+  if ( reset ) { c->stats = rb200_launch_stats{}; }
+  return RB200_OK;
+}
+
+int rb200_timing_enable( rb200_ctx* c, int enable ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  cudaSetDevice( c->device );
+  rb_timing_resolve( c );
+  c->timing = enable != 0;
+  if ( enable ) {
+    c->timing_names.clear();
+    c->timing_ms.clear();
+    c->timing_n.clear();
+  }
+  return RB200_OK;
+}
+
+int rb200_timing_get( rb200_ctx* c, int index, char* name, int cap, double* ms, int64_t* n ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  cudaSetDevice( c->device );
+  rb_timing_resolve( c );
+  if ( index < 0 || index >= (int)c->timing_names.size() ) { return RB200_ERR_INVALID; }
+  if ( name && cap > 0 ) {
+    strncpy( name, c->timing_names[index].c_str(), cap - 1 );
+    name[cap - 1] = 0;
+  }
+  if ( ms ) { *ms = c->timing_ms[index]; }
+  if ( n ) { *n = c->timing_n[index]; }
+  return RB200_OK;
+}
+
+}  // extern "C"

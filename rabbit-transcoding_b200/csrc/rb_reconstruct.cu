@@ -1,0 +1,962 @@
+// rb_reconstruct.cu — patch-to-3D reprojection of a whole GOF (sm_100a).
+//
+// Restates, as batched data-parallel kernels, the reference functions
+//   PCCCodec::generateOccupancyMap                       PccLibCommon/source/PCCCodec.cpp:1584-1606
+//   PCCCodec::generateBlockToPatchFromOccupancyMapVideo  :1725-1763
+//   PCCCodec::generatePointCloud (+ generatePoints)      :517-978 (:327-515)
+//   PCCCodec::identifyBoundaryPoints                     :266-325
+//   PCCCodec::colorPointCloud (single-stream branch)     :1308-1449
+//   PCCPatch::generatePoint / patch2Canvas / patchBlock2CanvasBlock   PCCPatch.h:177-207, PCCPatch.cpp:192-308
+//
+// Design (B200, HBM-bound integer work, no tensor cores):
+//  * unit of work = one 16x16 patch block, in the reference's emission order (patch -> v0 -> u0); one warp per
+//    block, lane l owns the 8 consecutive patch-local pixels (v1 = l/2, u1 = 8*(l%2)..+7), so lane order ==
+//    emission order and an in-warp shuffle scan gives each point its ordered output slot;
+//  * every HBM read of a frame plane is a 16-byte vector load of 8 consecutive canvas pixels (two lanes = one
+//    32-byte sector); the canvas tile is staged in shared memory and re-addressed through the patch
+//    orientation there, so rotated / mirrored patches cost no uncoalesced traffic;
+//  * occupancy lives as a 1-bit-per-pixel bitmap (L2-resident, 1/16 of a byte map); the 3x3 / 5x5 boundary
+//    stencils are bit tests on 20 staged row masks per tile;
+//  * count -> exclusive scan -> emit keeps the point order of the reference exactly (ordered MD5 parity).
+#include "rb_common.cuh"
+
+namespace {
+
+struct ReprojArgs {
+  const RbPatch*  patches;
+  const int32_t*  wi_patch;
+  const int32_t*  wi_local;
+  int64_t         nWI;
+  const uint8_t*  occ_video;
+  const uint16_t* geo;
+  const uint16_t* attr;
+  const uint32_t* bitmap;
+  const uint32_t* b2p;
+  int             W, H, oW, oH, Wb, Hb, M, prec, bmWords;
+  int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
+  int32_t*        wi_count;
+  int32_t*        wi_eom_count;
+  const int64_t*  wi_base;
+  const int64_t*  wi_eom_base;
+  const int32_t*  frame_wi_off;
+  const int64_t*  frame_off;
+  short4*         pos;
+  ushort4*        col;
+  uint32_t*       pix;
+  uint32_t*       part;
+  RbFrameInfo*    finfo;
+  short4*         eom_stage;
+};
+
+// PCCPatch::patch2Canvas restricted to one 16x16 block (PCCPatch.cpp:192-251)
+__device__ __forceinline__ void tile_coord( int orient, int u1, int v1, int& tx, int& ty ) {
+  switch ( orient ) {
+    default:
+    case 0: tx = u1; ty = v1; break;
+    case 1: tx = 15 - v1; ty = u1; break;
+    case 2: tx = 15 - u1; ty = 15 - v1; break;
+    case 3: tx = v1; ty = 15 - u1; break;
+    case 4: tx = 15 - u1; ty = v1; break;
+    case 5: tx = 15 - v1; ty = 15 - u1; break;
+    case 6: tx = u1; ty = 15 - v1; break;
+    case 7:
+    case 8: tx = v1; ty = u1; break;
+  }
+}
+
+// PCCPatch::patchBlock2CanvasBlock (PCCPatch.cpp:253-308); patches are validated inside the canvas at upload
+__device__ __forceinline__ void canvas_block( const RbPatch& p, int ub, int vb, int& bx, int& by ) {
+  switch ( p.orient ) {
+    default:
+    case 0: bx = ub + p.u0; by = vb + p.v0; break;
+    case 1: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ub + p.v0; break;
+    case 2: bx = ( p.su0 - 1 - ub ) + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
+    case 3: bx = vb + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
+    case 4: bx = ( p.su0 - 1 - ub ) + p.u0; by = vb + p.v0; break;
+    case 5: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
+    case 6: bx = ub + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
+    case 7:
+    case 8: bx = vb + p.u0; by = ub + p.v0; break;
+  }
+}
+
+// PCCPatch::generateNormalCoordinate (PCCPatch.h:177-186); the double temporaries are always integral
+__device__ __forceinline__ int normal_coord( const RbPatch& p, int depth ) {
+  return p.mode == 0 ? depth + p.d1 : max( p.d1 - depth, 0 );
+}
+
+__device__ __forceinline__ void set_axis( int16_t ( &P )[3], int axis, int v ) {
+  if ( axis == 0 ) {
+    P[0] = (int16_t)v;
+  } else if ( axis == 1 ) {
+    P[1] = (int16_t)v;
+  } else {
+    P[2] = (int16_t)v;
+  }
+}
+__device__ __forceinline__ int get_axis( const int16_t ( &P )[3], int axis ) {
+  return axis == 0 ? P[0] : ( axis == 1 ? P[1] : P[2] );
+}
+
+// PCCCodec::inverseRotatePosition45DegreeOnAxis (PCCCodec.cpp:2503-2524) followed by addPoint( PCCVector3D )
+// (PCCPointSet.h:419-426: truncation to int16).  The reference adds a size_t, so a negative intermediate wraps
+// to a huge double whose int16 cast yields 0 on x86-64; mirrored here.
+__device__ __forceinline__ int16_t half_trunc( int v ) { return v < 0 ? (int16_t)0 : (int16_t)( v / 2 ); }
+__device__ __forceinline__ void   inverse_rotate45( int axis, int lod, int16_t ( &P )[3] ) {
+  const int s = ( 1 << ( lod - 1 ) ) - 1;
+  const int x = P[0], y = P[1], z = P[2];
+  if ( axis == 1 ) {
+    P[0] = half_trunc( x - z + s );
+    P[2] = half_trunc( x + z - s );
+  } else if ( axis == 2 ) {
+    P[2] = half_trunc( z - y + s );
+    P[1] = half_trunc( z + y - s );
+  } else if ( axis == 3 ) {
+    P[1] = half_trunc( y - x + s );
+    P[0] = half_trunc( y + x - s );
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K0: occupancy video -> full-resolution bitmap.  generateOccupancyMap (:1584-1606) and the upsampling
+// loop of generatePointCloud (:557-570): O[v][u] = video[v/p][u/p] > threshold (EOM: raw symbol != 0).
+// One thread per 32-pixel word.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_occupancy_bitmap( const uint8_t* __restrict__ video, uint32_t* __restrict__ bitmap, int F, int W,
+                                    int H, int oW, int oH, int prec, int words, int threshold, int eom ) {
+  const int64_t total = (int64_t)F * H * words;
+  int64_t       i     = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= total ) { return; }
+  const int      w    = (int)( i % words );
+  const int      y    = (int)( ( i / words ) % H );
+  const int      f    = (int)( i / ( (int64_t)words * H ) );
+  const uint8_t* row  = video + ( (size_t)f * oH + y / prec ) * oW;
+  uint32_t       bits = 0;
+  const int      x0   = w * 32;
+  const uint32_t run  = prec >= 32 ? 0xFFFFFFFFu : ( ( 1u << prec ) - 1u );
+  for ( int s = 0; s * prec < 32; s++ ) {
+    const int x = x0 + s * prec;
+    if ( x >= W ) { break; }
+    const int v  = row[x / prec];
+    const int on = eom ? ( v != 0 ) : ( v > threshold );
+    if ( on ) { bits |= run << ( s * prec ); }
+  }
+  if ( x0 + 32 > W ) { bits &= ( 1u << ( W - x0 ) ) - 1u; }
+  bitmap[i] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: block-to-patch (:1725-1763): the highest patch index with an occupied pixel in the block wins.
+// One thread per patch block; 16 row-word tests.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_block_to_patch( const RbPatch* __restrict__ patches, const int32_t* __restrict__ wi_patch,
+                                  const int32_t* __restrict__ wi_local, int64_t nWI,
+                                  const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ b2p, int H, int Wb,
+                                  int Hb, int words ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= nWI ) { return; }
+  const RbPatch p  = patches[wi_patch[i]];
+  const int     lb = wi_local[i];
+  int           bx, by;
+  canvas_block( p, lb % p.su0, lb / p.su0, bx, by );
+  const uint32_t* bm  = bitmap + ( (size_t)p.frame * H + by * 16 ) * words + ( bx >> 1 );
+  const uint32_t  m   = ( bx & 1 ) ? 0xFFFF0000u : 0x0000FFFFu;
+  uint32_t        any = 0;
+#pragma unroll
+  for ( int r = 0; r < 16; r++ ) { any |= bm[(size_t)r * words] & m; }
+  if ( any ) { atomicMax( &b2p[( (size_t)p.frame * Hb + by ) * Wb + bx], (uint32_t)p.frame_patch + 1u ); }
+}
+
+// size quantisation (:571-597): pixels of an owned block beyond the quantised patch size are cleared
+__global__ void k_size_quantization( const RbPatch* __restrict__ patches, const int32_t* __restrict__ wi_patch,
+                                     const int32_t* __restrict__ wi_local, int64_t nWI, uint32_t* __restrict__ bitmap,
+                                     const uint32_t* __restrict__ b2p, int H, int Wb, int Hb, int words, int log2qx,
+                                     int log2qy ) {
+  const int64_t i    = blockIdx.x;
+  const RbPatch p    = patches[wi_patch[i]];
+  const int     lb   = wi_local[i];
+  const int     ub   = lb % p.su0, vb = lb / p.su0;
+  int           bx, by;
+  canvas_block( p, ub, vb, bx, by );
+  if ( b2p[( (size_t)p.frame * Hb + by ) * Wb + bx] != (uint32_t)p.frame_patch + 1u ) { return; }
+  const int sx = ( p.s2dx >> log2qx ) << log2qx, sy = ( p.s2dy >> log2qy ) << log2qy;
+  const int u1 = threadIdx.x & 15, v1 = threadIdx.x >> 4;
+  const int u = ub * 16 + u1, v = vb * 16 + v1;
+  if ( u >= sx || v >= sy ) {
+    int tx, ty;
+    tile_coord( p.orient, u1, v1, tx, ty );
+    const int x = bx * 16 + tx, y = by * 16 + ty;
+    atomicAnd( &bitmap[( (size_t)p.frame * H + y ) * words + ( x >> 5 )], ~( 1u << ( x & 31 ) ) );
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 / K4: the per-pixel reprojection, as a counting pass (EMIT=false) and an emitting pass (EMIT=true).
+// 8 warps per CTA, one 16x16 patch block per warp.
+// ---------------------------------------------------------------------------------------------------
+constexpr int WARPS = 8;
+
+struct TileSmem {
+  uint16_t g[2][256];     // geometry D0 / D1 tile
+  uint16_t a[2][3][256];  // attribute tiles
+  uint32_t rows[20];      // occupancy bits of canvas rows Y0-2..Y0+17, bit k <-> x = X0-2+k
+  uint32_t pad[4];
+};
+
+template <bool EMIT, bool EOM>
+__global__ void __launch_bounds__( WARPS * 32 ) k_reproject( const ReprojArgs a ) {
+  __shared__ __align__( 16 ) TileSmem sm[WARPS];
+  const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t wi   = (int64_t)blockIdx.x * WARPS + wq;
+  if ( wi >= a.nWI ) { return; }
+  TileSmem&     S  = sm[wq];
+  const RbPatch p  = a.patches[a.wi_patch[wi]];
+  const int     lb = a.wi_local[wi];
+  const int     ub = lb % p.su0, vb = lb / p.su0;
+  int           bx, by;
+  canvas_block( p, ub, vb, bx, by );
+  const int  f     = p.frame;
+  const bool owned = a.b2p[( (size_t)f * a.Hb + by ) * a.Wb + bx] == (uint32_t)p.frame_patch + 1u;  // :650
+  if ( !owned ) {
+    if ( !EMIT && lane == 0 ) {
+      a.wi_count[wi] = 0;
+      if ( EOM ) { a.wi_eom_count[wi] = 0; }
+    }
+    return;
+  }
+  const int X0 = bx * 16, Y0 = by * 16;
+  // ---- stage occupancy row masks ----
+  if ( lane < 20 ) {
+    const int y    = Y0 - 2 + lane;
+    uint32_t  bits = 0xFFFFFu;  // outside the image: treated as occupied, borders are handled explicitly
+    if ( y >= 0 && y < a.H ) {
+      const uint32_t* row = a.bitmap + ( (size_t)f * a.H + y ) * a.bmWords;
+      const int       xs  = X0 - 2;  // first x of the window (may be -2)
+      // assemble bits xs..xs+19 from up to two words
+      uint64_t  win = 0;
+      const int w0  = ( xs < 0 ) ? -1 : ( xs >> 5 );
+      uint32_t  lo  = ( w0 >= 0 ) ? row[w0] : 0u;
+      uint32_t  hi  = ( w0 + 1 < a.bmWords ) ? row[w0 + 1] : 0u;
+      win           = ( (uint64_t)hi << 32 ) | lo;
+      const int sh  = ( xs < 0 ) ? ( xs + 32 ) : ( xs & 31 );
+      bits          = (uint32_t)( win >> sh ) & 0xFFFFFu;
+      // pixels outside [0,W) read as occupied
+      if ( xs < 0 ) { bits |= 0x3u; }
+      if ( xs + 20 > a.W ) { bits |= ( 0xFFFFFu << ( a.W - xs ) ) & 0xFFFFFu; }
+    }
+    S.rows[lane] = bits;
+  }
+  // ---- stage geometry (and attribute) tiles: 16-byte loads, two lanes per 32-byte sector ----
+  {
+    const int    r = lane >> 1, h = lane & 1;
+    const size_t o = (size_t)( Y0 + r ) * a.W + X0 + 8 * h;
+    const size_t plane = (size_t)a.W * a.H;
+    for ( int m = 0; m < a.M; m++ ) {
+      const uint4 v = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * a.M + m ) * plane + o );
+      *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = v;
+    }
+    if ( EMIT && a.attr_count > 0 ) {
+      for ( int m = 0; m < a.M; m++ ) {
+#pragma unroll
+        for ( int ch = 0; ch < 3; ch++ ) {
+          const uint4 v = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * a.M + m ) * 3 + ch ) * plane + o );
+          *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = v;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  const int v1 = lane >> 1, ubase = 8 * ( lane & 1 );
+  // ---- pass A: per-pixel point counts (4 bits per pixel: regular; EOM extras separately) ----
+  uint32_t cnt4 = 0, eom4 = 0;
+#pragma unroll
+  for ( int j = 0; j < 8; j++ ) {
+    int tx, ty;
+    tile_coord( p.orient, ubase + j, v1, tx, ty );
+    const uint32_t occ = ( S.rows[ty + 2] >> ( tx + 2 ) ) & 1u;
+    if ( !occ ) { continue; }
+    const int d0 = S.g[0][ty * 16 + tx];
+    const int g1 = ( a.M > 1 ) ? S.g[1][ty * 16 + tx] : 0;
+    int       c  = 1, e = 0;
+    if ( EOM ) {
+      // :686-714 eomCode from the D1-D0 difference and the occupancy symbol
+      const int sym = a.occ_video[( (size_t)f * a.oH + ( Y0 + ty ) / a.prec ) * a.oW + ( X0 + tx ) / a.prec];
+      uint32_t  code;
+      if ( a.M > 1 ) {
+        const int diff = a.absolute_d1 ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
+        if ( diff == 1 ) {
+          code = 1;
+        } else if ( diff > 1 ) {
+          const uint32_t top = 1u << ( ( diff - 1 ) & 31 );
+          code               = ( ( ( top - (uint32_t)sym ) & 0xFFFFu ) | top ) & 0xFFFFu;
+        } else {
+          code = 0;
+        }
+      } else {
+        code = ( ( 1u << ( a.eom_fix_bits & 31 ) ) - (uint32_t)sym ) & 0xFFFFu;
+      }
+      if ( code == 0 ) {
+        if ( !a.remove_dup ) { c = 2; }
+      } else {
+        const int nb = __popc( code & 0x3FFu );
+        if ( a.M > 1 && nb > 0 ) {
+          c = 2;
+          e = nb - 1;
+        } else {
+          e = nb;
+        }
+      }
+    } else if ( a.M > 1 ) {
+      // :497-512 far layer; :794-795 duplicate removal compares the int16 points
+      const int16_t n0 = (int16_t)normal_coord( p, d0 );
+      int16_t       n1;
+      if ( a.absolute_d1 ) {
+        n1 = (int16_t)normal_coord( p, g1 );
+      } else {
+        n1 = (int16_t)( p.mode == 0 ? (int)n0 + g1 : (int)n0 - g1 );
+      }
+      c = ( a.remove_dup && n1 == n0 ) ? 1 : 2;
+    }
+    cnt4 |= (uint32_t)c << ( 4 * j );
+    eom4 |= (uint32_t)e << ( 4 * j );
+  }
+  int myCount = 0, myEom = 0;
+#pragma unroll
+  for ( int j = 0; j < 8; j++ ) {
+    myCount += ( cnt4 >> ( 4 * j ) ) & 15;
+    myEom += ( eom4 >> ( 4 * j ) ) & 15;
+  }
+  // ---- ordered in-warp exclusive scan (lane order == emission order v1, u1) ----
+  int incl = myCount, inclE = myEom;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const int t  = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+    const int tE = __shfl_up_sync( 0xFFFFFFFFu, inclE, d );
+    if ( lane >= d ) {
+      incl += t;
+      inclE += tE;
+    }
+  }
+  if ( !EMIT ) {
+    if ( lane == 31 ) {
+      a.wi_count[wi] = incl;
+      if ( EOM ) { a.wi_eom_count[wi] = inclE; }
+    }
+    return;
+  }
+
+  // ---- pass B: emit ----
+  const int64_t base  = a.frame_off[f] + ( a.wi_base[wi] - a.wi_base[a.frame_wi_off[f]] ) + ( incl - myCount );
+  int64_t       ebase = 0;
+  if ( EOM ) { ebase = a.wi_eom_base[wi] + ( inclE - myEom ); }
+  int     k = 0, ke = 0;
+  int     maxc = 0;
+#pragma unroll
+  for ( int j = 0; j < 8; j++ ) {
+    const int c = ( cnt4 >> ( 4 * j ) ) & 15;
+    if ( c == 0 ) { continue; }
+    int       tx, ty;
+    const int u1 = ubase + j;
+    tile_coord( p.orient, u1, v1, tx, ty );
+    const int x = X0 + tx, y = Y0 + ty;
+    const int u = ub * 16 + u1, v = vb * 16 + v1;
+    const int d0 = S.g[0][ty * 16 + tx];
+    const int g1 = ( a.M > 1 ) ? S.g[1][ty * 16 + tx] : 0;
+    // PCCPatch::generatePoint (PCCPatch.h:201-207)
+    int16_t P0[3] = {0, 0, 0};
+    set_axis( P0, p.normal_axis, normal_coord( p, d0 ) );
+    set_axis( P0, p.tangent_axis, u * p.lodx + p.u1 );
+    set_axis( P0, p.bitangent_axis, v * p.lody + p.v1 );
+    // boundary classification (identifyBoundaryPoints, :266-325) on the staged row masks
+    int btype = 0;
+    if ( a.classify ) {
+      const int      r  = ty + 2, kx = tx + 2;
+      const uint32_t m3 = 7u << ( kx - 1 ), m5 = 31u << ( kx - 2 );
+      if ( x == 0 || y == 0 || x == a.W - 1 || y == a.H - 1 ) {
+        btype = 1;
+      } else if ( ( S.rows[r - 1] & m3 ) != m3 || ( S.rows[r] & m3 ) != m3 || ( S.rows[r + 1] & m3 ) != m3 ) {
+        btype = 1;
+      } else if ( ( S.rows[r - 2] & m5 ) != m5 || ( S.rows[r - 1] & m5 ) != m5 || ( S.rows[r] & m5 ) != m5 ||
+                  ( S.rows[r + 1] & m5 ) != m5 || ( S.rows[r + 2] & m5 ) != m5 ) {
+        btype = 1;
+      } else if ( x == 1 || y == 1 || x == a.W - 2 || y == a.H - 2 ) {
+        btype = 1;
+      }
+    }
+    const uint32_t pixv = (uint32_t)x | ( (uint32_t)y << 16 );
+    // layer 0
+    {
+      int16_t Q[3] = {P0[0], P0[1], P0[2]};
+      if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
+      const int64_t o = base + k;
+      a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
+      ushort4 cv      = make_ushort4( 0, 0, 0, 0 );
+      if ( a.attr_count > 0 ) { cv = make_ushort4( S.a[0][0][ty * 16 + tx], S.a[0][1][ty * 16 + tx], S.a[0][2][ty * 16 + tx], 0 ); }
+      a.col[o]  = cv;
+      a.pix[o]  = pixv;
+      a.part[o] = (uint32_t)p.frame_patch;
+      maxc      = max( maxc, max( (int)Q[0], max( (int)Q[1], (int)Q[2] ) ) );
+      k++;
+    }
+    if ( !EOM ) {
+      if ( c > 1 ) {
+        int16_t P1[3] = {P0[0], P0[1], P0[2]};
+        if ( a.absolute_d1 ) {
+          set_axis( P1, p.normal_axis, normal_coord( p, g1 ) );  // generatePoint( u, v, frame1 ), :503
+        } else {
+          const int n0 = get_axis( P0, p.normal_axis );
+          set_axis( P1, p.normal_axis, p.mode == 0 ? n0 + g1 : n0 - g1 );  // :505-509
+        }
+        if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, P1 ); }
+        const int64_t o = base + k;
+        a.pos[o]        = make_short4( P1[0], P1[1], P1[2], (short)btype );
+        ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
+        if ( a.attr_count > 0 ) {
+          cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
+        }
+        a.col[o]  = cv;
+        a.pix[o]  = pixv;
+        a.part[o] = (uint32_t)p.frame_patch;
+        maxc      = max( maxc, max( (int)P1[0], max( (int)P1[1], (int)P1[2] ) ) );
+        k++;
+      }
+    } else {
+      // EOM branch (:669-779): recompute the code, emit the in-place D1 and stage the extra points
+      const int sym = a.occ_video[( (size_t)f * a.oH + y / a.prec ) * a.oW + x / a.prec];
+      uint32_t  code;
+      if ( a.M > 1 ) {
+        const int diff = a.absolute_d1 ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
+        if ( diff == 1 ) {
+          code = 1;
+        } else if ( diff > 1 ) {
+          const uint32_t top = 1u << ( ( diff - 1 ) & 31 );
+          code               = ( ( ( top - (uint32_t)sym ) & 0xFFFFu ) | top ) & 0xFFFFu;
+        } else {
+          code = 0;
+        }
+      } else {
+        code = ( ( 1u << ( a.eom_fix_bits & 31 ) ) - (uint32_t)sym ) & 0xFFFFu;
+      }
+      const int n0 = get_axis( P0, p.normal_axis );
+      if ( code == 0 ) {
+        if ( c > 1 ) {  // !removeDuplicatePoints: D1 == D0 (:717-732)
+          int16_t Q[3] = {P0[0], P0[1], P0[2]};
+          if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
+          const int64_t o = base + k;
+          a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
+          ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
+          if ( a.attr_count > 0 && a.M > 1 ) {
+            cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
+          } else if ( a.attr_count > 0 ) {
+            cv = make_ushort4( 0, 0, 0, 1 );
+          }
+          a.col[o]  = cv;
+          a.pix[o]  = pixv;
+          a.part[o] = (uint32_t)p.frame_patch;
+          k++;
+        }
+      } else {
+        const uint32_t low   = code & 0x3FFu;
+        const int      d1pos = 31 - __clz( low | 0u );  // highest set bit among bits 0..9 (:736-738); -1 if none
+        for ( int i = 0; i < 10; i++ ) {
+          if ( !( low & ( 1u << i ) ) ) { continue; }
+          int16_t Q[3] = {P0[0], P0[1], P0[2]};
+          set_axis( Q, p.normal_axis, p.mode == 0 ? n0 + ( i + 1 ) : n0 - ( i + 1 ) );  // :741-748
+          if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
+          if ( ( code == 1 || i == d1pos ) && a.M > 1 ) {  // in-place D1 (:749-762)
+            const int64_t o = base + k;
+            a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
+            ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
+            if ( a.attr_count > 0 ) {
+              cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
+            }
+            a.col[o]  = cv;
+            a.pix[o]  = pixv;
+            a.part[o] = (uint32_t)p.frame_patch;
+            maxc      = max( maxc, max( (int)Q[0], max( (int)Q[1], (int)Q[2] ) ) );
+            k++;
+          } else {  // eomPointsPerPatch[patchIndex].push_back (:763-771)
+            a.eom_stage[ebase + ke] = make_short4( Q[0], Q[1], Q[2], 0 );
+            ke++;
+          }
+        }
+      }
+    }
+  }
+  // per-frame max coordinate, feeds the geometry-smoothing grid width (:68-79)
+#pragma unroll
+  for ( int d = 16; d > 0; d >>= 1 ) { maxc = max( maxc, __shfl_xor_sync( 0xFFFFFFFFu, maxc, d ) ); }
+  if ( lane == 0 && maxc > 0 ) { atomicMax( &a.finfo[f].max_coord, maxc ); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan of int32 counts into int64 bases (n+1 outputs); single CTA, n is O(1e5)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__( 1024 ) k_scan_counts( const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out ) {
+  __shared__ int64_t warpSum[32];
+  const int          t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int64_t      chunk = ( n + 1023 ) / 1024;
+  const int64_t      b = min( n, (int64_t)t * chunk ), e = min( n, b + chunk );
+  int64_t            s = 0;
+  for ( int64_t i = b; i < e; i++ ) { s += in[i]; }
+  int64_t incl = s;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const int64_t v = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+    if ( lane >= d ) { incl += v; }
+  }
+  if ( lane == 31 ) { warpSum[w] = incl; }
+  __syncthreads();
+  if ( w == 0 ) {
+    int64_t x = warpSum[lane], y = x;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+      const int64_t v = __shfl_up_sync( 0xFFFFFFFFu, y, d );
+      if ( lane >= d ) { y += v; }
+    }
+    warpSum[lane] = y - x;
+  }
+  __syncthreads();
+  int64_t run = warpSum[w] + ( incl - s );
+  for ( int64_t i = b; i < e; i++ ) {
+    out[i] = run;
+    run += in[i];
+  }
+  if ( t == 1023 ) { out[n] = run; }
+}
+
+struct FrameLayout {
+  int64_t off, regular, eom, raw;
+};
+
+// EOM segments: (EOM patch, member) pairs in the reference's append order (:849-882)
+struct EomSeg {
+  int32_t frame;
+  int32_t patch;       // global patch index whose staged EOM points are copied
+  int32_t eom_patch;   // index of the EOM patch inside the frame (restarts the synthetic pixel counter)
+  int32_t first_in_eom_patch;
+  int32_t u0, v0;      // EOM patch origin in pixels
+  int32_t pad[2];
+};
+
+// per-patch staged EOM range = [wi_eom_base[firstWI(patch)], wi_eom_base[firstWI(patch)+nblocks))
+__global__ void k_eom_segment_sizes( const EomSeg* __restrict__ segs, int nSeg, const int32_t* __restrict__ patch_first_wi,
+                                     const int32_t* __restrict__ patch_nblk, const int64_t* __restrict__ wi_eom_base,
+                                     int32_t* __restrict__ seg_size ) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= nSeg ) { return; }
+  const int     q = segs[i].patch;
+  const int64_t b = wi_eom_base[patch_first_wi[q]], e = wi_eom_base[patch_first_wi[q] + patch_nblk[q]];
+  seg_size[i]     = (int32_t)( e - b );
+}
+
+// frame layout: offsets of every frame in the GOF arena = regular + eom + raw points, in that order (:841-949)
+__global__ void k_frame_layout( int F, const int32_t* __restrict__ frame_wi_off, const int64_t* __restrict__ wi_base,
+                                const EomSeg* __restrict__ segs, const int32_t* __restrict__ seg_size, int nSeg,
+                                const int32_t* __restrict__ raw_per_frame, FrameLayout* __restrict__ out,
+                                int64_t* __restrict__ frame_off, RbFrameInfo* __restrict__ finfo ) {
+  if ( blockIdx.x != 0 || threadIdx.x != 0 ) { return; }
+  int64_t run = 0;
+  int     s   = 0;
+  for ( int f = 0; f < F; f++ ) {
+    FrameLayout L;
+    L.off     = run;
+    L.regular = wi_base[frame_wi_off[f + 1]] - wi_base[frame_wi_off[f]];
+    L.eom     = 0;
+    while ( s < nSeg && segs[s].frame == f ) {
+      L.eom += seg_size[s];
+      s++;
+    }
+    L.raw        = raw_per_frame ? raw_per_frame[f] : 0;
+    out[f]       = L;
+    frame_off[f] = run;
+    run += L.regular + L.eom + L.raw;
+    RbFrameInfo z{};
+    finfo[f] = z;
+  }
+  frame_off[F] = run;
+}
+
+// EOM append (:846-891): one CTA per segment; synthetic pixel addresses, occupancy marks, colours from
+// attribute frame 0 at those addresses (colorPointCloud, :1365-1422 with f = 0)
+__global__ void k_eom_append( const EomSeg* __restrict__ segs, const int32_t* __restrict__ seg_size,
+                              const int64_t* __restrict__ seg_dst,  // offset of the segment inside its frame's EOM range
+                              const int64_t* __restrict__ seg_pix,  // running totalPointCount inside the EOM patch
+                              const int32_t* __restrict__ patch_first_wi, const int64_t* __restrict__ wi_eom_base,
+                              const short4* __restrict__ stage, const FrameLayout* __restrict__ layout,
+                              const int32_t* __restrict__ patch_count_of_frame, const uint16_t* __restrict__ attr,
+                              uint32_t* __restrict__ bitmap, int W, int H, int Wb, int M, int words, int attr_count,
+                              short4* __restrict__ pos, ushort4* __restrict__ col, uint32_t* __restrict__ pix,
+                              uint32_t* __restrict__ part, RbFrameInfo* __restrict__ finfo ) {
+  const int     s = blockIdx.x;
+  const EomSeg  g = segs[s];
+  const int     n = seg_size[s];
+  const int64_t src = wi_eom_base[patch_first_wi[g.patch]];
+  const int64_t dst = layout[g.frame].off + layout[g.frame].regular + seg_dst[s];
+  int           maxc = 0;
+  for ( int i = threadIdx.x; i < n; i += blockDim.x ) {
+    const int64_t t   = seg_pix[s] + i;  // totalPointCount (:862-869)
+    const int64_t blk = t / 256, inb = t - blk * 256;
+    const int     uu  = (int)( blk % Wb ) * 16 + (int)( inb % 16 ) + g.u0;
+    const int     vv  = (int)( blk / Wb ) * 16 + (int)( inb / 16 ) + g.v0;
+    short4        P   = stage[src + i];
+    P.w               = 0;
+    pos[dst + i]      = P;
+    ushort4 cv        = make_ushort4( 0, 0, 0, 0 );
+    if ( attr_count > 0 && uu < W && vv < H ) {
+      const size_t plane = (size_t)W * H;
+      const size_t o     = (size_t)vv * W + uu;
+      const size_t fb    = ( (size_t)g.frame * M ) * 3 * plane;
+      cv                 = make_ushort4( attr[fb + o], attr[fb + plane + o], attr[fb + 2 * plane + o], 0 );
+    }
+    col[dst + i]  = cv;
+    pix[dst + i]  = (uint32_t)uu | ( (uint32_t)vv << 16 );
+    part[dst + i] = (uint32_t)patch_count_of_frame[g.frame];  // partition = patches.size() (:843,877)
+    if ( uu < W && vv < H ) { atomicOr( &bitmap[( (size_t)g.frame * H + vv ) * words + ( uu >> 5 )], 1u << ( uu & 31 ) ); }  // :880
+    maxc = max( maxc, max( (int)P.x, max( (int)P.y, (int)P.z ) ) );
+  }
+  if ( maxc > 0 ) { atomicMax( &finfo[g.frame].max_coord, maxc ); }
+}
+
+// raw (missed-point) patches inside the geometry video (:894-949) + their colours (:1365-1422, f = 0)
+struct RawDesc {
+  int32_t frame, u0, v0, sizeU, sizeV, u1, v1, d1, n;
+  int32_t pad;
+  int64_t dst;  // offset inside the frame's raw range
+};
+__global__ void k_raw_points( const RawDesc* __restrict__ descs, const FrameLayout* __restrict__ layout,
+                              const int32_t* __restrict__ patch_count_of_frame, const uint16_t* __restrict__ geo,
+                              const uint16_t* __restrict__ attr, int W, int H, int M, int attr_count,
+                              short4* __restrict__ pos, ushort4* __restrict__ col, uint32_t* __restrict__ pix,
+                              uint32_t* __restrict__ part, RbFrameInfo* __restrict__ finfo ) {
+  const RawDesc d     = descs[blockIdx.y];
+  const size_t  plane = (size_t)W * H;
+  const uint16_t* g   = geo + ( (size_t)d.frame * M ) * plane;
+  const int64_t dst   = layout[d.frame].off + layout[d.frame].regular + layout[d.frame].eom + d.dst;
+  int           maxc  = 0;
+  for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x ) {
+    int16_t Q[3];
+    for ( int k = 0; k < 3; k++ ) {
+      const int64_t t = (int64_t)k * d.n + i;  // numRawPointsAdded (:913-928): X || Y || Z runs
+      const int     u = (int)( t % d.sizeU ), v = (int)( t / d.sizeU );
+      const int     val = g[(size_t)( d.v0 + v ) * W + d.u0 + u];
+      Q[k]              = (int16_t)( val + ( k == 0 ? d.u1 : ( k == 1 ? d.v1 : d.d1 ) ) );
+    }
+    const int u = i % d.sizeU, v = i / d.sizeU;  // :930-941
+    const int x = d.u0 + u, y = d.v0 + v;
+    pos[dst + i] = make_short4( Q[0], Q[1], Q[2], 0 );
+    ushort4 cv   = make_ushort4( 0, 0, 0, 0 );
+    if ( attr_count > 0 ) {
+      const size_t fb = ( (size_t)d.frame * M ) * 3 * plane, o = (size_t)y * W + x;
+      cv              = make_ushort4( attr[fb + o], attr[fb + plane + o], attr[fb + 2 * plane + o], 0 );
+    }
+    col[dst + i]  = cv;
+    pix[dst + i]  = (uint32_t)x | ( (uint32_t)y << 16 );
+    part[dst + i] = (uint32_t)patch_count_of_frame[d.frame];
+    maxc          = max( maxc, max( (int)Q[0], max( (int)Q[1], (int)Q[2] ) ) );
+  }
+  if ( maxc > 0 ) { atomicMax( &finfo[d.frame].max_coord, maxc ); }
+}
+
+// boundary classification as a separate pass (:953-973) — needed when EOM marks changed the occupancy map
+// after the regular points were emitted.  Covers regular + EOM points (not raw points).
+__global__ void k_classify_points( const FrameLayout* __restrict__ layout, int F, const uint32_t* __restrict__ bitmap,
+                                   int W, int H, int words, const uint32_t* __restrict__ pix, short4* __restrict__ pos ) {
+  const int          f = blockIdx.y;
+  const FrameLayout  L = layout[f];
+  const int64_t      n = L.regular + L.eom;
+  const uint32_t*    bm = bitmap + (size_t)f * H * words;
+  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) {
+    const uint32_t pv = pix[L.off + i];
+    const int      x = pv & 0xFFFF, y = pv >> 16;
+    auto occ = [&]( int xx, int yy ) -> int {
+      if ( xx < 0 || yy < 0 || xx >= W || yy >= H ) { return 1; }
+      return ( bm[(size_t)yy * words + ( xx >> 5 )] >> ( xx & 31 ) ) & 1;
+    };
+    if ( x >= W || y >= H || !occ( x, y ) ) { continue; }
+    int t = 0;
+    if ( x == 0 || y == 0 || x == W - 1 || y == H - 1 ) {
+      t = 1;
+    } else {
+      for ( int dy = -1; dy <= 1 && !t; dy++ ) {
+        for ( int dx = -1; dx <= 1; dx++ ) {
+          if ( !occ( x + dx, y + dy ) ) { t = 1; break; }
+        }
+      }
+      if ( !t ) {
+        for ( int dy = -2; dy <= 2 && !t; dy++ ) {
+          for ( int dx = -2; dx <= 2; dx++ ) {
+            if ( !occ( x + dx, y + dy ) ) { t = 1; break; }
+          }
+        }
+      }
+      if ( !t && ( x == 1 || y == 1 || x == W - 2 || y == H - 2 ) ) { t = 1; }
+    }
+    if ( t ) { pos[L.off + i].w = 1; }
+  }
+}
+
+}  // namespace
+
+int rb_reconstruct_impl( rb200_ctx* c ) {
+  const rb200_params& P = c->P;
+  const int           F = c->F;
+  const bool          eom = P.enhanced_occupancy_map_code != 0;
+  const int64_t       nWI = c->nWI;
+  RB_CUDA( cudaMemsetAsync( c->d_b2p.p, 0, (size_t)F * c->Wb * c->Hb * 4, c->stream ) );
+  {
+    const int64_t total = (int64_t)F * c->H * c->bmWords;
+    RB_LAUNCH( "occupancy_bitmap", k_occupancy_bitmap, rb_div_up( total, 256 ), 256, 0, c->d_occ_video.as<uint8_t>(),
+               c->d_bitmap.as<uint32_t>(), F, c->W, c->H, c->oW, c->oH, c->prec, c->bmWords, P.threshold_lossy_om,
+               eom ? 1 : 0 );
+  }
+  if ( nWI > 0 ) {
+    RB_LAUNCH( "block_to_patch", k_block_to_patch, rb_div_up( nWI, 256 ), 256, 0, c->d_patches.as<RbPatch>(),
+               c->d_wi_patch.as<int32_t>(), c->d_wi_local.as<int32_t>(), nWI, c->d_bitmap.as<uint32_t>(),
+               c->d_b2p.as<uint32_t>(), c->H, c->Wb, c->Hb, c->bmWords );
+    if ( P.enable_size_quantization ) {
+      RB_LAUNCH( "size_quantization", k_size_quantization, (unsigned)nWI, 256, 0, c->d_patches.as<RbPatch>(),
+                 c->d_wi_patch.as<int32_t>(), c->d_wi_local.as<int32_t>(), nWI, c->d_bitmap.as<uint32_t>(),
+                 c->d_b2p.as<uint32_t>(), c->H, c->Wb, c->Hb, c->bmWords, P.log2_quantizer_x, P.log2_quantizer_y );
+    }
+  }
+  // geometry smoothing is only signalled through flagGeometrySmoothing_ (:953)
+  const bool classify = P.flag_geometry_smoothing != 0;
+
+  ReprojArgs a{};
+  a.patches      = c->d_patches.as<RbPatch>();
+  a.wi_patch     = c->d_wi_patch.as<int32_t>();
+  a.wi_local     = c->d_wi_local.as<int32_t>();
+  a.nWI          = nWI;
+  a.occ_video    = c->d_occ_video.as<uint8_t>();
+  a.geo          = c->d_geometry.as<uint16_t>();
+  a.attr         = c->d_attribute.as<uint16_t>();
+  a.bitmap       = c->d_bitmap.as<uint32_t>();
+  a.b2p          = c->d_b2p.as<uint32_t>();
+  a.W            = c->W;
+  a.H            = c->H;
+  a.oW           = c->oW;
+  a.oH           = c->oH;
+  a.Wb           = c->Wb;
+  a.Hb           = c->Hb;
+  a.M            = c->M;
+  a.prec         = c->prec;
+  a.bmWords      = c->bmWords;
+  a.absolute_d1  = P.absolute_d1;
+  a.remove_dup   = P.remove_duplicate_points;
+  a.eom_fix_bits = P.eom_fix_bit_count;
+  a.classify     = ( classify && !eom ) ? 1 : 0;  // with EOM the marks (:880) come first, classification after
+  a.attr_count   = P.attribute_count;
+  a.bitdepth3d   = P.geometry_bitdepth_3d;
+  a.wi_count     = c->d_wi_count.as<int32_t>();
+  a.frame_wi_off = c->d_frame_wi_off.as<int32_t>();
+  a.frame_off    = c->d_frame_off.as<int64_t>();
+  a.finfo        = c->d_frame_info.as<RbFrameInfo>();
+  if ( eom ) {
+    RB_CUDA( c->d_wi_eom_count.ensure( ( nWI + 1 ) * 4 ) );
+    RB_CUDA( c->d_wi_eom_base.ensure( ( nWI + 1 ) * 8 ) );
+    a.wi_eom_count = c->d_wi_eom_count.as<int32_t>();
+  }
+  const int G = rb_div_up( nWI, WARPS );
+  if ( nWI > 0 ) {
+    auto kCount = eom ? k_reproject<false, true> : k_reproject<false, false>;
+    RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
+  }
+  RB_LAUNCH( "scan_counts", k_scan_counts, 1, 1024, 0, c->d_wi_count.as<int32_t>(), nWI, c->d_wi_base.as<int64_t>() );
+  if ( eom ) {
+    RB_LAUNCH( "scan_counts", k_scan_counts, 1, 1024, 0, c->d_wi_eom_count.as<int32_t>(), nWI,
+               c->d_wi_eom_base.as<int64_t>() );
+  }
+  a.wi_base     = c->d_wi_base.as<int64_t>();
+  a.wi_eom_base = c->d_wi_eom_base.as<int64_t>();
+
+  // ---- host-side tables for EOM segments / raw patches / per-frame patch counts ----
+  std::vector<EomSeg>  segs;
+  std::vector<int32_t> patchFirstWI( c->h_patches.size() + 1, 0 ), patchNblk( c->h_patches.size() + 1, 0 );
+  std::vector<int32_t> patchCountOfFrame( F, 0 ), rawPerFrame( F, 0 );
+  std::vector<RawDesc> raws;
+  {
+    // first work item of every patch (work items are laid out per frame in emission order)
+    int64_t wi = 0;
+    for ( int f = 0; f < F; f++ ) {
+      const int b = c->h_patch_off[f], e = c->h_patch_off[f + 1];
+      patchCountOfFrame[f] = e - b;
+      for ( int k = 0; k < e - b; k++ ) {
+        const int i     = P.patch_precedence_reverse ? ( e - 1 - k ) : ( b + k );
+        patchFirstWI[i] = (int32_t)wi;
+        patchNblk[i]    = c->h_patches[i].size_u0 * c->h_patches[i].size_v0;
+        wi += patchNblk[i];
+      }
+    }
+  }
+  if ( eom ) {
+    for ( int f = 0; f < F; f++ ) {
+      const int pb = c->h_patch_off[f], np = c->h_patch_off[f + 1] - pb;
+      for ( int j = c->h_eom_off[f]; j < c->h_eom_off[f + 1]; j++ ) {
+        const rb200_eom_patch& e = c->h_eom[j];
+        for ( int k = 0; k < e.member_count; k++ ) {
+          int m = c->h_eom_members[e.member_begin + k];
+          if ( P.patch_precedence_reverse ) { m = np - m - 1; }  // :857-859
+          if ( m < 0 || m >= np ) { return rb_fail( c, RB200_ERR_INVALID, "EOM member patch %d out of range", m ); }
+          EomSeg s{};
+          s.frame              = f;
+          s.patch              = pb + m;
+          s.eom_patch          = j - c->h_eom_off[f];
+          s.first_in_eom_patch = ( k == 0 );
+          s.u0                 = e.u0 * c->R;
+          s.v0                 = e.v0 * c->R;
+          segs.push_back( s );
+        }
+      }
+    }
+  }
+  if ( P.use_additional_points_patch ) {
+    for ( int f = 0; f < F; f++ ) {
+      int64_t run = 0;
+      for ( int j = c->h_raw_off[f]; j < c->h_raw_off[f + 1]; j++ ) {
+        const rb200_raw_patch& r = c->h_raw[j];
+        RawDesc                d{};
+        d.frame = f;
+        d.u0    = r.u0 * c->R;
+        d.v0    = r.v0 * c->R;
+        d.sizeU = r.size_u0 * c->R;
+        d.sizeV = r.size_v0 * c->R;
+        d.u1    = r.u1;
+        d.v1    = r.v1;
+        d.d1    = r.d1;
+        d.n     = r.num_points;
+        d.dst   = run;
+        run += r.num_points;
+        raws.push_back( d );
+      }
+      rawPerFrame[f] = (int32_t)run;
+    }
+  }
+  const int nSeg = (int)segs.size();
+  // scratch layout: [segs][segSize][patchFirstWI][patchNblk][patchCountOfFrame][rawPerFrame][layout][raws]
+  const size_t szSegs = nSeg * sizeof( EomSeg ), szSegSize = ( nSeg + 1 ) * 4, szPf = patchFirstWI.size() * 4,
+               szPc = F * 4, szLayout = F * sizeof( FrameLayout ), szRaw = raws.size() * sizeof( RawDesc );
+  auto   al   = []( size_t x ) { return ( x + 255 ) & ~size_t( 255 ); };
+  size_t o    = 0;
+  const size_t oSegs = o; o += al( szSegs );
+  const size_t oSegSize = o; o += al( szSegSize );
+  const size_t oPfw = o; o += al( szPf );
+  const size_t oPnb = o; o += al( szPf );
+  const size_t oPc = o; o += al( szPc );
+  const size_t oRpf = o; o += al( szPc );
+  const size_t oLayout = o; o += al( szLayout );
+  const size_t oRaw = o; o += al( szRaw );
+  const size_t oSegDst = o; o += al( ( nSeg + 1 ) * 8 );
+  const size_t oSegPix = o; o += al( ( nSeg + 1 ) * 8 );
+  RB_CUDA( c->d_scratch[0].ensure( o + 256 ) );
+  char* dS = c->d_scratch[0].as<char>();
+  {
+    std::vector<char> hs( o, 0 );
+    if ( nSeg ) { memcpy( hs.data() + oSegs, segs.data(), szSegs ); }
+    memcpy( hs.data() + oPfw, patchFirstWI.data(), szPf );
+    memcpy( hs.data() + oPnb, patchNblk.data(), szPf );
+    memcpy( hs.data() + oPc, patchCountOfFrame.data(), szPc );
+    memcpy( hs.data() + oRpf, rawPerFrame.data(), szPc );
+    if ( !raws.empty() ) { memcpy( hs.data() + oRaw, raws.data(), szRaw ); }
+    RB_CUDA( cudaMemcpyAsync( dS, hs.data(), o, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );  // hs is a stack-lifetime pageable buffer
+    c->stats.h2d_bytes += (int64_t)o;
+  }
+  if ( nSeg ) {
+    RB_LAUNCH( "eom_segment_sizes", k_eom_segment_sizes, rb_div_up( nSeg, 128 ), 128, 0, (const EomSeg*)( dS + oSegs ), nSeg,
+               (const int32_t*)( dS + oPfw ), (const int32_t*)( dS + oPnb ), c->d_wi_eom_base.as<int64_t>(),
+               (int32_t*)( dS + oSegSize ) );
+  }
+  RB_LAUNCH( "frame_layout", k_frame_layout, 1, 32, 0, F, c->d_frame_wi_off.as<int32_t>(), c->d_wi_base.as<int64_t>(),
+             (const EomSeg*)( dS + oSegs ), (const int32_t*)( dS + oSegSize ), nSeg, (const int32_t*)( dS + oRpf ),
+             (FrameLayout*)( dS + oLayout ), c->d_frame_off.as<int64_t>(), c->d_frame_info.as<RbFrameInfo>() );
+
+  // ---- read the layout back (the caller needs the counts; the arena may need to grow) ----
+  const size_t rbBytes = szLayout + ( nSeg + 1 ) * 4;
+  char*        hp      = (char*)rb_pinned( c, rbBytes + 64 );
+  if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( hp, dS + oLayout, szLayout, cudaMemcpyDeviceToHost, c->stream ) );
+  if ( nSeg ) { RB_CUDA( cudaMemcpyAsync( hp + szLayout, dS + oSegSize, nSeg * 4, cudaMemcpyDeviceToHost, c->stream ) ); }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.d2h_bytes += (int64_t)rbBytes;
+  const FrameLayout* L = (const FrameLayout*)hp;
+  int64_t            total = 0;
+  for ( int f = 0; f < F; f++ ) {
+    c->h_frame_off[f]      = L[f].off;
+    c->h_counts[f]         = rb200_frame_counts{};
+    c->h_counts[f].regular = L[f].regular;
+    c->h_counts[f].eom     = 0;  // filled below: TotalNumberOfEOMPoints is the sum of eomCount_ (:854,886)
+    c->h_counts[f].raw     = L[f].raw;
+    c->h_counts[f].total   = L[f].regular + L[f].eom + L[f].raw;
+    total                  = L[f].off + c->h_counts[f].total;
+  }
+  c->h_frame_off[F] = total;
+  if ( eom ) {
+    for ( int f = 0; f < F; f++ ) {
+      int64_t s = 0;
+      for ( int j = c->h_eom_off[f]; j < c->h_eom_off[f + 1]; j++ ) { s += c->h_eom[j].eom_count; }
+      c->h_counts[f].eom = s;
+    }
+  }
+  const size_t cap = (size_t)std::max<int64_t>( total, 1 );
+  RB_CUDA( c->d_pos.ensure( cap * 8 ) );
+  RB_CUDA( c->d_col.ensure( cap * 8 ) );
+  RB_CUDA( c->d_pix.ensure( cap * 4 ) );
+  RB_CUDA( c->d_part.ensure( cap * 4 ) );
+  RB_CUDA( c->d_rgb.ensure( cap * 4 ) );
+  a.pos  = c->d_pos.as<short4>();
+  a.col  = c->d_col.as<ushort4>();
+  a.pix  = c->d_pix.as<uint32_t>();
+  a.part = c->d_part.as<uint32_t>();
+  if ( eom ) {
+    // staged EOM extras (per patch, emission order)
+    int64_t* hb = (int64_t*)rb_pinned( c, 64 );
+    RB_CUDA( cudaMemcpyAsync( hb, c->d_wi_eom_base.as<int64_t>() + nWI, 8, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    const int64_t nStage = *hb;
+    RB_CUDA( c->d_scratch[1].ensure( (size_t)std::max<int64_t>( nStage, 1 ) * 8 ) );
+    a.eom_stage = c->d_scratch[1].as<short4>();
+    // re-read: the pinned block was reused, restore the segment sizes view
+    RB_CUDA( cudaMemcpyAsync( hp, dS + oLayout, szLayout, cudaMemcpyDeviceToHost, c->stream ) );
+    if ( nSeg ) { RB_CUDA( cudaMemcpyAsync( hp + szLayout, dS + oSegSize, nSeg * 4, cudaMemcpyDeviceToHost, c->stream ) ); }
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  if ( nWI > 0 ) {
+    auto kEmit = eom ? k_reproject<true, true> : k_reproject<true, false>;
+    RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
+  }
+  if ( eom && nSeg ) {
+    // per-segment destination offset inside the frame's EOM range and synthetic pixel counter (resets per EOM patch)
+    const int32_t*       segSize = (const int32_t*)( hp + szLayout );
+    std::vector<int64_t> segDst( nSeg + 1, 0 ), segPix( nSeg + 1, 0 );
+    int64_t              runF = 0, runP = 0;
+    for ( int s = 0; s < nSeg; s++ ) {
+      if ( s == 0 || segs[s].frame != segs[s - 1].frame ) { runF = 0; }
+      if ( segs[s].first_in_eom_patch ) { runP = 0; }
+      segDst[s] = runF;
+      segPix[s] = runP;
+      runF += segSize[s];
+      runP += segSize[s];
+    }
+    RB_CUDA( cudaMemcpyAsync( dS + oSegDst, segDst.data(), nSeg * 8, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaMemcpyAsync( dS + oSegPix, segPix.data(), nSeg * 8, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    RB_LAUNCH( "eom_append", k_eom_append, nSeg, 256, 0, (const EomSeg*)( dS + oSegs ), (const int32_t*)( dS + oSegSize ),
+               (const int64_t*)( dS + oSegDst ), (const int64_t*)( dS + oSegPix ), (const int32_t*)( dS + oPfw ),
+               c->d_wi_eom_base.as<int64_t>(), c->d_scratch[1].as<short4>(), (const FrameLayout*)( dS + oLayout ),
+               (const int32_t*)( dS + oPc ), c->d_attribute.as<uint16_t>(), c->d_bitmap.as<uint32_t>(), c->W, c->H, c->Wb,
+               c->M, c->bmWords, P.attribute_count, a.pos, a.col, a.pix, a.part, c->d_frame_info.as<RbFrameInfo>() );
+  }
+  if ( !raws.empty() ) {
+    RB_LAUNCH( "raw_points", k_raw_points, dim3( 64, (unsigned)raws.size() ), 256, 0, (const RawDesc*)( dS + oRaw ),
+               (const FrameLayout*)( dS + oLayout ), (const int32_t*)( dS + oPc ), c->d_geometry.as<uint16_t>(),
+               c->d_attribute.as<uint16_t>(), c->W, c->H, c->M, P.attribute_count, a.pos, a.col, a.pix, a.part,
+               c->d_frame_info.as<RbFrameInfo>() );
+  }
+  if ( classify && eom ) {
+    RB_LAUNCH( "classify_points", k_classify_points, dim3( 256, F ), 256, 0, (const FrameLayout*)( dS + oLayout ), F,
+               c->d_bitmap.as<uint32_t>(), c->W, c->H, c->bmWords, a.pix, a.pos );
+  }
+  return RB200_OK;
+}
