@@ -1,7 +1,7 @@
 """ctypes mirror of include/rabbit_b200.h and loader of the CUDA library.
 
 The structures here are field-for-field the C structs of include/rabbit_b200.h; they are also what the
-test-only checkers (oracle/liboracle.so, oracle/_ref/librabbit_ref.so) consume, so the CUDA path, the CPU
+test-only CPU checkers consume, so the CUDA path, the CPU
 restatement and the unmodified reference all see byte-identical inputs.
 
 There is NO CPU fallback: `load_library()` raises if librabbit_b200.so is missing.
