@@ -53,7 +53,7 @@ typedef struct rb200_patch {
   int32_t u1, v1, d1;       /* tangent / bitangent / normal shift (u1_, v1_, d1_)                       */
   int32_t normal_axis, tangent_axis, bitangent_axis; /* 0..2                                           */
   int32_t projection_mode;  /* 0: d + d1, 1: max(d1 - d, 0)   (PCCPatch.h:177-186)                      */
-  int32_t orientation;      /* PATCH_ORIENTATION_* 0..8       (PCCPatch.cpp:192-251)                    */
+  int32_t orientation;      /* enum PCCPatchOrientation 0..8  (PCCBitstreamCommon.h:120-130)            */
   int32_t lod_x, lod_y;     /* levelOfDetailX_/Y_                                                       */
   int32_t axis_of_additional_plane; /* 0, or 1..3 for 45-degree planes (PCCCodec.cpp:2503-2524)         */
   int32_t size2d_x_px, size2d_y_px; /* getPatchSize2DX/YInPixel, used by size quantisation :571-597     */

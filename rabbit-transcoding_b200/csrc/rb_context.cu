@@ -242,7 +242,8 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
 // PCCPatch::patchBlock2CanvasBlock footprint check (PCCPatch.cpp:253-308): every patch block must land
 // inside the canvas, otherwise the reference exits 180 (PCCPatch.cpp:237-245).
 static bool patch_inside( const rb200_patch& p, int Wb, int Hb ) {
-  const bool sw = ( p.orientation == 1 || p.orientation == 3 || p.orientation == 5 || p.orientation == 7 ||
+  // SWAP, ROT90, ROT270, MROT90, MROT270 exchange U and V on the canvas (PCCBitstreamCommon.h:120-130)
+  const bool sw = ( p.orientation == 1 || p.orientation == 2 || p.orientation == 4 || p.orientation == 6 ||
                     p.orientation == 8 );
   const int  cw = sw ? p.size_v0 : p.size_u0, ch = sw ? p.size_u0 : p.size_v0;
   return p.u0 >= 0 && p.v0 >= 0 && p.size_u0 >= 0 && p.size_v0 >= 0 && p.u0 + cw <= Wb && p.v0 + ch <= Hb;

@@ -50,17 +50,17 @@ struct ReprojArgs {
 
 // PCCPatch::patch2Canvas restricted to one 16x16 block (PCCPatch.cpp:192-251)
 __device__ __forceinline__ void tile_coord( int orient, int u1, int v1, int& tx, int& ty ) {
-  switch ( orient ) {
+  switch ( orient ) {  // enum PCCPatchOrientation, PccLibBitstreamCommon/include/PCCBitstreamCommon.h:120-130
     default:
-    case 0: tx = u1; ty = v1; break;
-    case 1: tx = 15 - v1; ty = u1; break;
-    case 2: tx = 15 - u1; ty = 15 - v1; break;
-    case 3: tx = v1; ty = 15 - u1; break;
-    case 4: tx = 15 - u1; ty = v1; break;
-    case 5: tx = 15 - v1; ty = 15 - u1; break;
-    case 6: tx = u1; ty = 15 - v1; break;
-    case 7:
-    case 8: tx = v1; ty = u1; break;
+    case 0: tx = u1; ty = v1; break;            // DEFAULT
+    case 1: tx = v1; ty = u1; break;            // SWAP
+    case 2: tx = 15 - v1; ty = u1; break;       // ROT90
+    case 3: tx = 15 - u1; ty = 15 - v1; break;  // ROT180
+    case 4: tx = v1; ty = 15 - u1; break;       // ROT270
+    case 5: tx = 15 - u1; ty = v1; break;       // MIRROR
+    case 6: tx = 15 - v1; ty = 15 - u1; break;  // MROT90
+    case 7: tx = u1; ty = 15 - v1; break;       // MROT180
+    case 8: tx = v1; ty = u1; break;            // MROT270
   }
 }
 
@@ -69,13 +69,13 @@ __device__ __forceinline__ void canvas_block( const RbPatch& p, int ub, int vb, 
   switch ( p.orient ) {
     default:
     case 0: bx = ub + p.u0; by = vb + p.v0; break;
-    case 1: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ub + p.v0; break;
-    case 2: bx = ( p.su0 - 1 - ub ) + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
-    case 3: bx = vb + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
-    case 4: bx = ( p.su0 - 1 - ub ) + p.u0; by = vb + p.v0; break;
-    case 5: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
-    case 6: bx = ub + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
-    case 7:
+    case 1: bx = vb + p.u0; by = ub + p.v0; break;
+    case 2: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ub + p.v0; break;
+    case 3: bx = ( p.su0 - 1 - ub ) + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
+    case 4: bx = vb + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
+    case 5: bx = ( p.su0 - 1 - ub ) + p.u0; by = vb + p.v0; break;
+    case 6: bx = ( p.sv0 - 1 - vb ) + p.u0; by = ( p.su0 - 1 - ub ) + p.v0; break;
+    case 7: bx = ub + p.u0; by = ( p.sv0 - 1 - vb ) + p.v0; break;
     case 8: bx = vb + p.u0; by = ub + p.v0; break;
   }
 }
@@ -138,7 +138,10 @@ __global__ void k_occupancy_bitmap( const uint8_t* __restrict__ video, uint32_t*
     const int x = x0 + s * prec;
     if ( x >= W ) { break; }
     const int v  = row[x / prec];
-    const int on = eom ? ( v != 0 ) : ( v > threshold );
+    // generateOccupancyMap thresholds the video sample IN PLACE once per full-resolution pixel (:1597-1600), i.e.
+    // p*p times per sample: with threshold >= 1 and p > 1 the second visit sees the already binarised 0/1 and
+    // clears it, so the re-upsampled map of generatePointCloud (:557-570) is empty.  Reproduced, not "fixed".
+    const int on = eom ? ( v != 0 ) : ( ( prec == 1 || threshold == 0 ) ? ( v > threshold ) : 0 );
     if ( on ) { bits |= run << ( s * prec ); }
   }
   if ( x0 + 32 > W ) { bits &= ( 1u << ( W - x0 ) ) - 1u; }

@@ -18,7 +18,9 @@ from . import abi
 
 # PCCPatch::setViewId: viewId -> (normal, tangent, bitangent, projectionMode)
 VIEW_AXES = {0: (0, 2, 1, 0), 1: (1, 2, 0, 0), 2: (2, 0, 1, 0), 3: (0, 2, 1, 1), 4: (1, 2, 0, 1), 5: (2, 0, 1, 1)}
-_SWITCHED = (1, 3, 5, 7, 8)  # orientations that swap U and V on the canvas (PCCPatch.h isPatchDimensionSwitched)
+# enum PCCPatchOrientation (PCCBitstreamCommon.h:120-130): 0 DEFAULT 1 SWAP 2 ROT90 3 ROT180 4 ROT270 5 MIRROR
+# 6 MROT90 7 MROT180 8 MROT270; these exchange U and V on the canvas (PCCPatch.h:63-70):
+_SWITCHED = (1, 2, 4, 6, 8)
 
 
 def default_params(width, height, bitdepth=10, occupancy_precision=4):
@@ -180,20 +182,20 @@ def _patch2canvas_arrays(orient, U, V, su, sv):
     U,V patch-local pixel coords; su, sv = patch size in pixels (sizeU0*R, sizeV0*R)."""
     if orient == 0:
         return U, V
-    if orient == 1:
-        return sv - 1 - V, U
-    if orient == 2:
-        return su - 1 - U, sv - 1 - V
-    if orient == 3:
-        return V, su - 1 - U
-    if orient == 4:
-        return su - 1 - U, V
-    if orient == 5:
-        return sv - 1 - V, su - 1 - U
-    if orient == 6:
-        return U, sv - 1 - V
-    if orient in (7, 8):
+    if orient in (1, 8):
         return V, U
+    if orient == 2:
+        return sv - 1 - V, U
+    if orient == 3:
+        return su - 1 - U, sv - 1 - V
+    if orient == 4:
+        return V, su - 1 - U
+    if orient == 5:
+        return su - 1 - U, V
+    if orient == 6:
+        return sv - 1 - V, su - 1 - U
+    if orient == 7:
+        return U, sv - 1 - V
     raise ValueError(orient)
 
 
@@ -226,7 +228,7 @@ def yuv16_to_rgb8(c16):
 
 
 def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, scale=1.0, seed=0x0AB817,
-                 noise_fraction=0.10, color_noise=6.0, max_patch_blocks=12, orientations=(0, 8),
+                 noise_fraction=0.10, color_noise=6.0, max_patch_blocks=12, orientations=(0, 1),
                  eom=False, raw_points=0, map_count=2, precedence_reverse=False, min_height_blocks=0,
                  with_sources=True, color_smoothing=True, geometry_smoothing=True, transfer_filter=1,
                  height_blocks=None, absolute_d1=True):
@@ -322,8 +324,8 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
                     top += 64
             if not placed:
                 raise RuntimeError("packing failed")
-        used = np.nonzero(grid.any(axis=1))[0]
-        fr["Hb"] = int(used.max()) + 1 if len(used) else 1
+        # the whole bounding box of every patch must lie inside the canvas (PCCPatch.cpp:237-245 exits otherwise)
+        fr["Hb"] = max([1] + [pt["v0"] + (pt["su0"] if pt["orient"] in _SWITCHED else pt["sv0"]) for pt in fr["patches"]])
         Hb_needed = max(Hb_needed, fr["Hb"])
 
     # extra room for EOM / raw rectangles

@@ -37,17 +37,30 @@ def test_relative_d1_keep_duplicates(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, what="reld1")
 
 
-def test_lossy_threshold_and_size_quantization(rb, codec, checker_backend):
-    g = small(rb, seed=16)
+def _lossy(rb, precision):
+    g = small(rb, seed=16, occupancy_precision=precision)
     rng = np.random.default_rng(5)
-    g.occupancy[...] = np.where(g.occupancy != 0, rng.integers(1, 9, g.occupancy.shape), rng.integers(0, 3, g.occupancy.shape)).astype(np.uint8)
+    g.occupancy[...] = np.where(g.occupancy != 0, rng.integers(1, 9, g.occupancy.shape),
+                                rng.integers(0, 3, g.occupancy.shape)).astype(np.uint8)
     g.params.threshold_lossy_om = 2
+    return g
+
+
+def test_lossy_threshold_and_size_quantization(rb, codec, checker_backend):
+    g = _lossy(rb, 1)
     g.params.enable_size_quantization = 1
     g.params.log2_quantizer_x = 2
     g.params.log2_quantizer_y = 3
     g.patches["size2d_x_px"] -= 5
     g.patches["size2d_y_px"] -= 3
-    run_stages(codec, g, checker_backend, what="lossy")
+    ref = run_stages(codec, g, checker_backend, what="lossy")
+    assert ref.counts(0).total > 1000
+
+
+def test_lossy_threshold_quirk_precision4(rb, codec, checker_backend):
+    # PCCCodec.cpp:1597-1600 binarises the sample in place p*p times: threshold >= 1 with p > 1 empties the frame
+    ref = run_stages(codec, _lossy(rb, 4), checker_backend, what="lossyquirk")
+    assert ref.counts(0).total == 0
 
 
 def test_eom(rb, codec, checker_backend):
