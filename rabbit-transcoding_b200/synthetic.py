@@ -100,13 +100,13 @@ def _humanoid(cube, scale, rng, t):
     sway = 0.01 * cube * np.sin(0.37 * t)
     step = 0.015 * cube * np.sin(0.61 * t + 0.5)
     parts = [
-        ((cx + sway, 0.56 * cube, cz), (0.19 * s, 0.26 * s, 0.13 * s)),                     # torso
-        ((cx + sway, 0.56 * cube + 0.36 * s, cz + step * 0.2), (0.09 * s, 0.11 * s, 0.10 * s)),   # head
+        ((cx + sway, 0.63 * cube, cz), (0.19 * s, 0.26 * s, 0.13 * s)),                     # torso
+        ((cx + sway, 0.63 * cube + 0.36 * s, cz + step * 0.2), (0.09 * s, 0.11 * s, 0.10 * s)),   # head
         ((cx - 0.26 * s + sway, 0.60 * cube, cz + step), (0.06 * s, 0.24 * s, 0.06 * s)),    # arm L
         ((cx + 0.26 * s + sway, 0.60 * cube, cz - step), (0.06 * s, 0.24 * s, 0.06 * s)),    # arm R
-        ((cx - 0.10 * s, 0.56 * cube - 0.50 * s, cz - step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg L
-        ((cx + 0.10 * s, 0.56 * cube - 0.50 * s, cz + step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg R
-        ((cx, 0.56 * cube - 0.18 * s, cz), (0.17 * s, 0.12 * s, 0.12 * s)),                 # hips
+        ((cx - 0.10 * s, 0.63 * cube - 0.50 * s, cz - step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg L
+        ((cx + 0.10 * s, 0.63 * cube - 0.50 * s, cz + step), (0.08 * s, 0.30 * s, 0.08 * s)),  # leg R
+        ((cx, 0.63 * cube - 0.18 * s, cz), (0.17 * s, 0.12 * s, 0.12 * s)),                 # hips
     ]
     jit = rng.uniform(-0.004, 0.004, size=(len(parts), 3)) * cube
     return [(np.array(c) + j, np.array(r)) for (c, r), j in zip(parts, jit)]
@@ -248,7 +248,7 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
         views = []
         for vid, (nrm, tan, bit, mode) in VIEW_AXES.items():
             depth, owner = _view_depth(parts, cube, nrm, tan, bit, mode)
-            valid = owner >= 0
+            valid = (owner >= 0) & (np.rint(np.nan_to_num(depth, nan=-1.0)) >= 0) & (np.rint(np.nan_to_num(depth, nan=-1.0)) <= cube - 1)
             dz = np.rint(np.where(valid, depth, 0)).astype(np.int64)
             # surface normal of the owning ellipsoid at the hit point
             vv, uu = np.mgrid[0:cube, 0:cube]

@@ -64,7 +64,7 @@ def test_lossy_threshold_quirk_precision4(rb, codec, checker_backend):
 
 
 def test_eom(rb, codec, checker_backend):
-    g = small(rb, eom=True, seed=17)
+    g = small(rb, eom=True, seed=17, geometry_smoothing=False, color_smoothing=False)  # lossless-style cfg
     run_stages(codec, g, checker_backend, stages=("reconstruct", "rgb8"), what="eom")
 
 
