@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of RABBIT's V-PCC transcode loop on B200 ("Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (oracle/_ref), rank 0 only
+
+A *step* is one pass of the post-video-decode path over one synthetic 32-frame vox10 GOF per GPU
+(BASELINE.json configs[1]): reconstruction (occupancy -> block-to-patch -> reprojection of near/far layers ->
+boundary types -> attribute fetch), grid geometry smoothing, attribute re-transfer for the moved points,
+colour smoothing, YUV16 -> RGB8, and (when --metrics) the D1/D2/colour metrics against the source clouds.
+
+`value`  : whole-job Mpts/s with the decoded frames already resident in HBM (rb200_decode_gof only).
+`e2e`    : the same metric through the reference-facing call sequence with HOST buffers: pinned H2D upload of
+           the decoded planes + patch tables, decode, D2H of positions + RGB8 of every frame, inside the timer.
+`roofline`: the dominant kernel of the step (per-kernel CUDA events on the launching stream), algorithmic
+           bytes per launch / its average duration, against MEASURED_PEAKS.json.
+`cpu_baseline`: the unmodified reference (oracle/_ref/librabbit_ref.so) on this box's host cores, same GOF.
+
+Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reconstructed_points_throughput"
+UNIT = "Mpts/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--frames", type=int, default=32, help="frames per GOF per GPU")
+    ap.add_argument("--workload", default="vox10", choices=("vox10", "vox11", "tiny"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-metrics", action="store_true", help="skip the D1/D2 metrics leg")
+    ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = auto)")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: generator arguments (synthetic.generate_gof) — vox10: ~0.84 M points / frame, atlas 1280x1280
+    "vox10": dict(bitdepth=10, width=1280, scale=0.68, height_blocks=80),
+    "vox11": dict(bitdepth=11, width=2560, scale=0.62, height_blocks=176),
+    "tiny": dict(bitdepth=8, width=256, scale=0.9, height_blocks=32),
+}
+
+
+def make_gof(rb, args, rank, world, frames=None):
+    kw = dict(WORKLOADS[args.workload])
+    kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=1 if rb.abi.HAVE_TRANSFER else 0)
+    ncpu = os.cpu_count() or 1
+    workers = max(1, min(frames or args.frames, ncpu // max(1, world)))
+    return rb.synthetic.generate_gof_parallel(frames or args.frames, workers=workers, **kw)
+
+
+class ClockSampler:
+    """samples SM clock + throttle reasons of one GPU every 100 ms during the timed regions (NVML)"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self._on = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            if self._on.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.1)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def on(self):
+        self._on.set()
+
+    def off(self):
+        self._on.clear()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1)
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(name, g, n_points, n_type1, n_moved):
+    """SURVEY.md §8d algorithmic bytes of ONE launch of kernel `name` over the whole GOF (F frames)."""
+    p = g.params
+    F, W, H, M, pr = g.n_frames, p.width, p.height, p.map_count_minus1 + 1, p.occupancy_precision
+    geo = F * W * H * 2 * M
+    occ = F * (W // pr) * (H // pr)
+    N = n_points
+    table = {
+        # one pass over the geometry luma + occupancy; counts only
+        "reproject_count": geo + occ,
+        # B_rep: geometry + occupancy + attribute gather (6 B) + 26 B of outputs per point
+        "reproject_emit": geo + occ + N * 6 + N * (6 + 6 + 2 + 4 + 8),
+        "occupancy_bitmap": occ + F * H * ((W + 31) // 32) * 4,
+        # B_geo split over its passes (pos+type 8 B, partition 4 B)
+        "mark_cells": N * 8,
+        "geo_accumulate": N * 12,
+        "geo_filter": N * 8 + n_moved * 8,
+        "col_accumulate": N * (8 + 6 + 4),
+        "col_scatter_lum": N * (8 + 2) + N * 2,
+        "col_filter": N * (8 + 6) + n_type1 * 6,
+        "to_rgb8": N * (6 + 3),
+    }
+    return table.get(name)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rabbit_transcoding_b200 as rb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t0 = time.time()
+    gof = make_gof(rb, args, rank, world)
+    t_gen = time.time() - t0
+
+    # pinned host copies of the decoded planes (what the video decoders hand over)
+    def pin(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t
+    pinned = dict(occupancy=pin(gof.occupancy), geometry=pin(gof.geometry), attribute=pin(gof.attribute))
+    gof.occupancy, gof.geometry, gof.attribute = (pinned[k].numpy() for k in ("occupancy", "geometry", "attribute"))
+
+    codec = rb.codec.PCCCodecB200(device=local)
+    stream = torch.cuda.current_stream()
+    codec.setStream(stream.cuda_stream)
+    clocks = ClockSampler(local)
+    clocks.start()
+
+    # ---------------- leg 1: inputs resident in HBM ----------------
+    codec.uploadGof(gof)
+    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 0):
+        codec.decodeGof()
+    counts = codec.frameCounts()
+    n_points = sum(c.total for c in counts)
+    n_moved = sum(c.smoothed for c in counts)
+    codec.stats(reset=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.on()
+    e0.record(stream)
+    for _ in range(args.steps):
+        codec.decodeGof()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks.off()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = codec.stats(reset=True).kernel_launches
+    all_points = sum_over_ranks(n_points)
+    value = all_points * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---------------- leg 2: end to end from host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        out = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
+                   colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
+
+        def e2e_step():
+            codec.uploadGof(gof)
+            codec.decodeGof()
+            return codec.getGof(fields=("positions", "colors"), out=out)
+        for _ in range(2):
+            e2e_step()
+        codec.stats(reset=True)
+        barrier()
+        torch.cuda.synchronize()
+        clocks.on()
+        e0.record(stream)
+        for _ in range(args.steps):
+            _, n_got = e2e_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        clocks.off()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        st = codec.stats(reset=True)
+        assert n_got == n_points
+        e2e = {"value": all_points * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": st.h2d_bytes // args.steps, "d2h_bytes_per_step": st.d2h_bytes // args.steps,
+               "ms_per_step": ms_e2e / args.steps}
+
+    # ---------------- leg 3: per-kernel events -> roofline of the dominant kernel ----------------
+    codec.uploadGof(gof)
+    codec.decodeGof()
+    cloud = codec.getGof(fields=("boundary_types",))[0]
+    n_type1 = int((cloud["boundary_types"] == 1).sum()) + n_moved
+    codec.enableTiming(True)
+    for _ in range(max(2, min(args.steps, 5))):
+        codec.decodeGof()
+    timings = codec.timings()
+    codec.enableTiming(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    kernels = {}
+    for name, (ms, n) in timings.items():
+        b = algorithmic_bytes(name, gof, n_points, n_type1, n_moved)
+        avg = ms / max(n, 1)
+        kernels[name] = {"ms_per_launch": round(avg, 4), "launches_per_step": n / max(2, min(args.steps, 5)),
+                         "algorithmic_bytes": b, "gbs": (round(b / (avg * 1e-3) / 1e9, 1) if b and avg > 0 else None)}
+    step_kernel_ms = sum(ms for ms, _ in timings.values()) / max(2, min(args.steps, 5))
+    dom = max(timings.items(), key=lambda kv: kv[1][0])[0] if timings else None
+    roofline = None
+    if dom:
+        k = kernels[dom]
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peak, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": (round(k["gbs"] / peak, 4) if k["gbs"] else None), "traffic": traffic,
+                    "algorithmic_bytes": k["algorithmic_bytes"], "ms_per_launch": k["ms_per_launch"],
+                    "share_of_step_kernel_time": round(timings[dom][0] / max(1e-9, sum(ms for ms, _ in timings.values())), 3)}
+    clocks.stop()
+
+    # ---------------- leg 4 (rank 0, N=1): the reference's CPU path on the same GOF ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(rb, gof, threads=1, max_frames=min(gof.n_frames, 32))
+
+    if rank == 0:
+        p = gof.params
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i16/u16 (+f64 filters)", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.workload} {gof.n_frames}-frame GOF per GPU, C2RA r3 shape: "
+                                   f"atlas {p.width}x{p.height}, 2 maps, p={p.occupancy_precision}, "
+                                   "reconstruction + grid geometry smoothing + colour smoothing + RGB8",
+                       "frames_per_gpu": gof.n_frames, "points_per_frame": n_points // gof.n_frames,
+                       "points_moved_per_frame": n_moved // gof.n_frames,
+                       "attr_transfer_filter_type": int(p.attr_transfer_filter_type),
+                       "l2_policy": f"inputs larger than L2 ({gof.input_bytes() >> 20} MiB of planes per GPU per step)",
+                       "sharding": "one GOF per GPU, no data-path collective"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
+            "generate_s": round(t_gen, 1),
+        }
+        print(json.dumps(line), flush=True)
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference(rb, gof, threads, max_frames):
+    """times the unmodified reference (oracle/_ref) on the first `max_frames` frames of `gof` (bounded sample)."""
+    from oracle import checker
+    if not checker.have_reference():
+        return {"unavailable": "oracle/_ref/librabbit_ref.so not built"}
+    chk = checker.Reference()
+    sub = rb.synthetic.slice_gof(gof, 0, max_frames)
+    t0 = time.time()
+    run = chk.run_gof(sub, keep=(), threads=threads)
+    wall = time.time() - t0
+    pts = sum(run.counts(f).total for f in range(sub.n_frames))
+    rec_ms = sum(run.time_ms(f, 0) for f in range(sub.n_frames))
+    post_ms = sum(run.time_ms(f, 1) for f in range(sub.n_frames))
+    return {"value": round(pts / wall / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{sub.n_frames} frames of the same GOF, {pts} points, {wall:.1f} s wall "
+                      f"(reconstruction {rec_ms / 1e3:.1f} s + post-processing {post_ms / 1e3:.1f} s of CPU time)",
+            "wall_s": round(wall, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import rabbit_transcoding_b200 as rb
+    from oracle import checker
+    if not checker.have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librabbit_ref.so not built"}))
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample per step: one frame per host thread, capped at the GOF size
+    nf = args.ref_frames or max(1, min(args.frames, threads))
+    gof = make_gof(rb, args, 0, 1, frames=nf)
+    chk = checker.Reference()
+    for _ in range(max(0, min(args.warmup, 1))):
+        chk.run_gof(gof, keep=(), threads=threads)
+    steps = max(1, min(args.steps, 3))
+    pts = 0
+    t0 = time.time()
+    for _ in range(steps):
+        run = chk.run_gof(gof, keep=(), threads=threads)
+        pts += sum(run.counts(f).total for f in range(gof.n_frames))
+    wall = time.time() - t0
+    v = round(pts / wall / 1e6, 4)
+    p = gof.params
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(0, min(args.warmup, 1)), "ms_per_step": round(wall * 1e3 / steps, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i16/u16 (+f64 filters)", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.workload} GOF, C2RA r3 shape: atlas {p.width}x{p.height}, 2 maps, "
+                                   f"p={p.occupancy_precision}, reconstruction + grid geometry smoothing + colour "
+                                   "smoothing + RGB8", "frames_per_step": gof.n_frames,
+                       "attr_transfer_filter_type": int(p.attr_transfer_filter_type)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{gof.n_frames} frames per step, frame-parallel over {threads} host threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

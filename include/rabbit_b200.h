@@ -190,6 +190,8 @@ int rb200_decode_gof(rb200_ctx* ctx);
 /* ---- results ---------------------------------------------------------------------------------- */
 int rb200_frame_counts_get(rb200_ctx* ctx, rb200_frame_counts* out /* [n_frames] */);
 int rb200_download_frame(rb200_ctx* ctx, int frame, const rb200_cloud_host* dst);
+/* all frames of the GOF back to back in frame order (frame f = counts[f].total points): one packed copy per field */
+int rb200_download_gof(rb200_ctx* ctx, const rb200_cloud_host* dst);
 /* block-to-patch map (tile.getBlockToPatch(), value = patch index + 1, 0 = none), [H/R][W/R] uint32 */
 int rb200_download_block_to_patch(rb200_ctx* ctx, int frame, uint32_t* dst);
 /* full-resolution occupancy map (tile.getOccupancyMap()), [H][W] uint8, after EOM marks */

@@ -121,10 +121,14 @@ EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
     "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_reconstruct", "rb200_smooth_geometry",
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_decode_gof",
-    "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_block_to_patch",
+    "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof", "rb200_download_block_to_patch",
     "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_stats_get",
     "rb200_timing_enable", "rb200_timing_get",
 ]
+
+# stages of the path that this build implements on the GPU (bench.py / tests pick their configs from these)
+HAVE_TRANSFER = False  # rb200_transfer_colors (PCCPointSet3::transferColors16bitBP)
+HAVE_METRICS = False   # rb200_metrics / rb200_remove_duplicates
 
 _lib = None
 
@@ -154,6 +158,7 @@ def load_library(path=None):
         getattr(lib, n).argtypes = [C.c_void_p]
     lib.rb200_frame_counts_get.argtypes = [C.c_void_p, C.POINTER(FrameCounts)]
     lib.rb200_download_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(CloudHost)]
+    lib.rb200_download_gof.argtypes = [C.c_void_p, C.POINTER(CloudHost)]
     lib.rb200_download_block_to_patch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.rb200_download_occupancy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.rb200_metrics.argtypes = [C.c_void_p, C.POINTER(MetricsParams), C.c_int, C.POINTER(CloudView),

@@ -120,6 +120,26 @@ class PCCCodecB200:
         self._check(self._lib.rb200_download_frame(self._h, f, C.byref(h)))
         return out
 
+    def getGof(self, counts=None, fields=("positions", "colors"), out=None):
+        """all frames back to back (one packed D2H copy per field); `out` may hold preallocated (pinned) arrays"""
+        counts = counts or self.frameCounts()
+        n = sum(c.total for c in counts)
+        shapes = dict(positions=(3, np.int16), colors16=(3, np.uint16), colors=(3, np.uint8),
+                      boundary_types=(0, np.uint16), partition=(0, np.uint32), point_to_pixel=(3, np.uint32))
+        res = {}
+        for k in fields:
+            w, dt = shapes[k]
+            if out is not None and k in out:
+                buf = out[k]
+                if buf.shape[0] < n:
+                    raise ValueError(f"getGof: out[{k!r}] holds {buf.shape[0]} points, {n} needed")
+                res[k] = buf
+            else:
+                res[k] = np.zeros((n, w) if w else (n,), dt)
+        h = abi.CloudHost(*[abi.ptr(res[k]) if k in res else None for k, _ in abi.CloudHost._fields_])
+        self._check(self._lib.rb200_download_gof(self._h, C.byref(h)))
+        return res, n
+
     def getBlockToPatch(self, f):
         p = self.params
         a = np.zeros((p.height // p.occupancy_resolution, p.width // p.occupancy_resolution), np.uint32)

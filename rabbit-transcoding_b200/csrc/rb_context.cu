@@ -488,38 +488,36 @@ int rb200_frame_counts_get( rb200_ctx* c, rb200_frame_counts* out ) {
   return RB200_OK;
 }
 
-int rb200_download_frame( rb200_ctx* c, int f, const rb200_cloud_host* dst ) {
-  if ( !c || !dst ) { return RB200_ERR_INVALID; }
-  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
-  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
-  cudaSetDevice( c->device );
-  const int64_t b = c->h_frame_off[f], n = c->h_frame_off[f + 1] - b;
+// packs the points [b, b+n) of the GOF arena into the reference's std::vector layouts and copies them out;
+// every requested field gets its own slice of the staging buffer so one synchronisation covers them all
+static int download_range( rb200_ctx* c, int64_t b, int64_t n, const rb200_cloud_host* dst ) {
   if ( n == 0 ) { return RB200_OK; }
-  RB_CUDA( c->d_pack.ensure( (size_t)n * 12 ) );
+  auto         al = []( size_t x ) { return ( x + 255 ) & ~size_t( 255 ); };
+  const size_t oPos = 0, oTyp = oPos + ( dst->positions ? al( n * 6 ) : 0 ), oC16 = oTyp + ( dst->boundary_types ? al( n * 2 ) : 0 ),
+               oRgb = oC16 + ( dst->colors16 ? al( n * 6 ) : 0 ), oPix = oRgb + ( dst->colors && c->rgb_done ? al( n * 3 ) : 0 ),
+               total = oPix + ( dst->point_to_pixel ? al( n * 12 ) : 0 );
+  RB_CUDA( c->d_pack.ensure( total + 256 ) );
+  char*     pk = c->d_pack.as<char>();
   const int T = 256, G = rb_div_up( n, T );
   if ( dst->positions ) {
-    RB_LAUNCH( "pack_positions", k_pack_positions, G, T, 0, c->d_pos.as<short4>() + b, n, c->d_pack.as<int16_t>() );
-    RB_CUDA( cudaMemcpyAsync( dst->positions, c->d_pack.p, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    RB_LAUNCH( "pack_positions", k_pack_positions, G, T, 0, c->d_pos.as<short4>() + b, n, (int16_t*)( pk + oPos ) );
+    RB_CUDA( cudaMemcpyAsync( dst->positions, pk + oPos, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 6;
   }
   if ( dst->boundary_types ) {
-    RB_LAUNCH( "pack_types", k_pack_types, G, T, 0, c->d_pos.as<short4>() + b, n, c->d_pack.as<uint16_t>() );
-    RB_CUDA( cudaMemcpyAsync( dst->boundary_types, c->d_pack.p, n * 2, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    RB_LAUNCH( "pack_types", k_pack_types, G, T, 0, c->d_pos.as<short4>() + b, n, (uint16_t*)( pk + oTyp ) );
+    RB_CUDA( cudaMemcpyAsync( dst->boundary_types, pk + oTyp, n * 2, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 2;
   }
   if ( dst->colors16 ) {
-    RB_LAUNCH( "pack_colors16", k_pack_colors16, G, T, 0, c->d_col.as<ushort4>() + b, n, c->d_pack.as<uint16_t>() );
-    RB_CUDA( cudaMemcpyAsync( dst->colors16, c->d_pack.p, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    RB_LAUNCH( "pack_colors16", k_pack_colors16, G, T, 0, c->d_col.as<ushort4>() + b, n, (uint16_t*)( pk + oC16 ) );
+    RB_CUDA( cudaMemcpyAsync( dst->colors16, pk + oC16, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 6;
   }
   if ( dst->colors ) {
     if ( c->rgb_done ) {
-      RB_LAUNCH( "pack_rgb", k_pack_rgb, G, T, 0, c->d_rgb.as<uchar4>() + b, n, c->d_pack.as<uint8_t>() );
-      RB_CUDA( cudaMemcpyAsync( dst->colors, c->d_pack.p, n * 3, cudaMemcpyDeviceToHost, c->stream ) );
-      RB_CUDA( cudaStreamSynchronize( c->stream ) );
+      RB_LAUNCH( "pack_rgb", k_pack_rgb, G, T, 0, c->d_rgb.as<uchar4>() + b, n, (uint8_t*)( pk + oRgb ) );
+      RB_CUDA( cudaMemcpyAsync( dst->colors, pk + oRgb, n * 3, cudaMemcpyDeviceToHost, c->stream ) );
       c->stats.d2h_bytes += n * 3;
     } else {
       memset( dst->colors, 0, n * 3 );  // colorPointCloud's fillColor(0), PCCCodec.cpp:1319
@@ -527,17 +525,31 @@ int rb200_download_frame( rb200_ctx* c, int f, const rb200_cloud_host* dst ) {
   }
   if ( dst->partition ) {
     RB_CUDA( cudaMemcpyAsync( dst->partition, c->d_part.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
     c->stats.d2h_bytes += n * 4;
   }
   if ( dst->point_to_pixel ) {
     RB_LAUNCH( "pack_pixels", k_pack_pixels, G, T, 0, c->d_pix.as<uint32_t>() + b, c->d_col.as<ushort4>() + b, n,
-               c->d_pack.as<uint32_t>() );
-    RB_CUDA( cudaMemcpyAsync( dst->point_to_pixel, c->d_pack.p, n * 12, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+               (uint32_t*)( pk + oPix ) );
+    RB_CUDA( cudaMemcpyAsync( dst->point_to_pixel, pk + oPix, n * 12, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 12;
   }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
   return RB200_OK;
+}
+
+int rb200_download_frame( rb200_ctx* c, int f, const rb200_cloud_host* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  cudaSetDevice( c->device );
+  return download_range( c, c->h_frame_off[f], c->h_frame_off[f + 1] - c->h_frame_off[f], dst );
+}
+
+int rb200_download_gof( rb200_ctx* c, const rb200_cloud_host* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  cudaSetDevice( c->device );
+  return download_range( c, 0, c->h_frame_off[c->F], dst );
 }
 
 int rb200_download_block_to_patch( rb200_ctx* c, int f, uint32_t* dst ) {

@@ -231,7 +231,7 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
                  noise_fraction=0.10, color_noise=6.0, max_patch_blocks=12, orientations=(0, 1),
                  eom=False, raw_points=0, map_count=2, precedence_reverse=False, min_height_blocks=0,
                  with_sources=True, color_smoothing=True, geometry_smoothing=True, transfer_filter=1,
-                 height_blocks=None, absolute_d1=True):
+                 height_blocks=None, absolute_d1=True, frame_offset=0):
     """Generate one GOF.  `scale` sizes the body relative to the cube (1.0 ~ vox10-like point counts at
     bitdepth 10: ~0.4 M occupied pixels, ~0.8 M points).  `height_blocks` forces the atlas height (all
     frames of a GOF share W x H as the video does); otherwise H = tallest packing over the GOF."""
@@ -241,9 +241,10 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
     Wb = width // R
     M = map_count
     frames = []
+    fo = frame_offset  # frame f of this call is frame fo + f of the sequence (seeds and motion phase)
     for f in range(n_frames):
-        rng = np.random.default_rng([seed, f])
-        parts = _humanoid(cube, scale, rng, float(f))
+        rng = np.random.default_rng([seed, fo + f])
+        parts = _humanoid(cube, scale, rng, float(fo + f))
         # ---- per-view depth maps and normal-based segmentation ----
         views = []
         for vid, (nrm, tan, bit, mode) in VIEW_AXES.items():
@@ -366,7 +367,7 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
 
     def build_frame(f, Hb_total, want_arrays):
         fr, pf = frames[f], per_frame[f]
-        rng = np.random.default_rng([seed, f, 7])
+        rng = np.random.default_rng([seed, fo + f, 7])
         W, H = width, Hb_total * R
         occ_full = np.zeros((H, W), np.uint8)
         geo = np.zeros((M, H, W), np.uint16)
@@ -468,7 +469,7 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
     allp = []
     for f in range(n_frames):
         b = build_frame(f, Hb_total, True)
-        rngx = np.random.default_rng([seed, f, 11])
+        rngx = np.random.default_rng([seed, fo + f, 11])
         if eom:
             # EOM extra points are coloured from attribute frame 0 at synthetic addresses of the EOM rectangle
             rows = slice(eom_v0 * R, (eom_v0 + max(1, H_extra_rows - (raw_rows if raw_points else 0))) * R)
@@ -525,3 +526,83 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
         gof.raw_offset = np.array(raw_off, np.int32)
     gof.sources = srcs
     return gof
+
+
+def concat_gofs(gofs):
+    """join GOFs of identical parameters / atlas size into one (frames in list order)"""
+    g0 = gofs[0]
+    out = SyntheticGOF()
+    out.params = g0.params
+    for g in gofs[1:]:
+        if bytes(g.params) != bytes(g0.params):
+            raise ValueError("concat_gofs: parameter mismatch (fix the atlas height with height_blocks)")
+    out.n_frames = sum(g.n_frames for g in gofs)
+    out.occupancy = np.concatenate([g.occupancy for g in gofs])
+    out.geometry = np.concatenate([g.geometry for g in gofs])
+    out.attribute = np.concatenate([g.attribute for g in gofs])
+    out.patches = np.concatenate([g.patches for g in gofs])
+
+    def cat_off(name):
+        offs, base = [0], 0
+        for g in gofs:
+            o = getattr(g, name)
+            offs += [int(x) + base for x in o[1:]]
+            base += int(o[-1])
+        return np.array(offs, np.int32)
+    out.patch_offset = cat_off("patch_offset")
+    if g0.eom_patches is not None:
+        recs, mem, base = [], [], 0
+        for g in gofs:
+            r = g.eom_patches.copy()
+            r["member_begin"] += base
+            base += len(g.eom_members)
+            recs.append(r)
+            mem.append(g.eom_members)
+        out.eom_patches = np.concatenate(recs)
+        out.eom_members = np.concatenate(mem)
+        out.eom_offset = cat_off("eom_offset")
+    if g0.raw_patches is not None:
+        out.raw_patches = np.concatenate([g.raw_patches for g in gofs])
+        out.raw_offset = cat_off("raw_offset")
+    out.sources = [s for g in gofs for s in g.sources]
+    return out
+
+
+def slice_gof(g, begin, end):
+    """frames [begin, end) of a GOF as a new GOF (views, no plane copies)"""
+    out = SyntheticGOF()
+    out.params = g.params
+    out.n_frames = end - begin
+    out.occupancy, out.geometry, out.attribute = g.occupancy[begin:end], g.geometry[begin:end], g.attribute[begin:end]
+
+    def cut(off, recs):
+        o = off[begin:end + 1]
+        return np.ascontiguousarray(recs[o[0]:o[-1]]), (o - o[0]).astype(np.int32)
+    out.patches, out.patch_offset = cut(g.patch_offset, g.patches)
+    if g.eom_patches is not None:
+        out.eom_patches, out.eom_offset = cut(g.eom_offset, g.eom_patches)
+        out.eom_members = g.eom_members
+    if g.raw_patches is not None:
+        out.raw_patches, out.raw_offset = cut(g.raw_offset, g.raw_patches)
+    out.sources = g.sources[begin:end]
+    return out
+
+
+def _gen_one(kw):
+    return generate_gof(**kw)
+
+
+def generate_gof_parallel(n_frames, workers=None, **kw):
+    """generate_gof frame by frame in worker processes (same result as one call with a fixed `height_blocks`)"""
+    import multiprocessing as mp
+    import os
+    if "height_blocks" not in kw or kw["height_blocks"] is None:
+        raise ValueError("generate_gof_parallel needs a fixed height_blocks")
+    workers = workers or min(n_frames, os.cpu_count() or 1)
+    jobs = [dict(kw, n_frames=1, frame_offset=kw.get("frame_offset", 0) + f) for f in range(n_frames)]
+    if workers <= 1:
+        parts = [_gen_one(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_gen_one, jobs)
+    return concat_gofs(parts)
