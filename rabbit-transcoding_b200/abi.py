@@ -128,7 +128,7 @@ EXPORTED_SYMBOLS = [
 
 # stages of the path that this build implements on the GPU (bench.py / tests pick their configs from these)
 HAVE_TRANSFER = False  # rb200_transfer_colors (PCCPointSet3::transferColors16bitBP)
-HAVE_METRICS = False   # rb200_metrics / rb200_remove_duplicates
+HAVE_METRICS = True    # rb200_metrics / rb200_remove_duplicates
 
 _lib = None
 

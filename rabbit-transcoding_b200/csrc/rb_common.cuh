@@ -151,7 +151,7 @@ void* rb_pinned( rb200_ctx* c, size_t bytes );
     rb_timing_end( c );                                                                  \
     c->stats.kernel_launches++;                                                          \
     cudaError_t e__ = cudaGetLastError();                                                \
-    if ( e__ != cudaSuccess ) { return rb_cuda( c, e__, "launch " name ); }              \
+    if ( e__ != cudaSuccess ) { return rb_cuda( c, e__, name ); }                \
   } while ( 0 )
 
 static inline int rb_div_up( int64_t a, int64_t b ) { return (int)( ( a + b - 1 ) / b ); }
@@ -162,3 +162,4 @@ int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
+void rb_metrics_release( rb200_ctx* c );

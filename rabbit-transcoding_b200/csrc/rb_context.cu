@@ -151,6 +151,7 @@ void rb200_destroy( rb200_ctx* c ) {
                    &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off};
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }
+  rb_metrics_release( c );
   if ( c->h_pinned ) { cudaFreeHost( c->h_pinned ); }
   for ( auto& t : c->timing_events ) {
     cudaEventDestroy( t.a );
