@@ -240,6 +240,12 @@ int rb200_metrics(rb200_ctx* ctx, const rb200_metrics_params* params, int n_pair
 int rb200_remove_duplicates(rb200_ctx* ctx, const rb200_cloud_view* in, int drop_duplicates,
                             int16_t* out_positions, uint8_t* out_colors, int64_t* out_count);
 
+/* ---- PCCKdTree::search (PccLibCommon/source/PCCKdTree.cpp:61-66): k nearest neighbours of every query in `cloud`
+ *      in nanoflann's result order (ties in tree-traversal order), k = 1..8.  host or device pointers.
+ *      out_idx / out_dist are [nq][k]; missing entries (cloud smaller than k) are -1. ------------------------------- */
+int rb200_kdtree_search(rb200_ctx* ctx, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, int k,
+                        int64_t* out_idx, double* out_dist);
+
 /* ---- instrumentation --------------------------------------------------------------------------- */
 typedef struct rb200_launch_stats {
   int64_t kernel_launches;    /* number of this library's kernels launched since the last reset        */

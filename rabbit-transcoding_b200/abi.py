@@ -122,12 +122,12 @@ EXPORTED_SYMBOLS = [
     "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_reconstruct", "rb200_smooth_geometry",
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof", "rb200_download_block_to_patch",
-    "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_stats_get",
+    "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_stats_get",
     "rb200_timing_enable", "rb200_timing_get",
 ]
 
 # stages of the path that this build implements on the GPU (bench.py / tests pick their configs from these)
-HAVE_TRANSFER = False  # rb200_transfer_colors (PCCPointSet3::transferColors16bitBP)
+HAVE_TRANSFER = True   # rb200_transfer_colors (PCCPointSet3::transferColors16bitBP)
 HAVE_METRICS = True    # rb200_metrics / rb200_remove_duplicates
 
 _lib = None
@@ -165,6 +165,7 @@ def load_library(path=None):
                                   C.POINTER(CloudView), C.POINTER(MetricsResult)]
     lib.rb200_remove_duplicates.argtypes = [C.c_void_p, C.POINTER(CloudView), C.c_int, C.c_void_p, C.c_void_p,
                                             C.POINTER(i64)]
+    lib.rb200_kdtree_search.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_int, C.c_void_p, C.c_void_p]
     lib.rb200_stats_get.argtypes = [C.c_void_p, C.POINTER(LaunchStats), C.c_int]
     lib.rb200_timing_enable.argtypes = [C.c_void_p, C.c_int]
     lib.rb200_timing_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double),

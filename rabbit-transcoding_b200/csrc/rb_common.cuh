@@ -163,3 +163,7 @@ int rb_transfer_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
 void rb_metrics_release( rb200_ctx* c );
+void rb_transfer_release( rb200_ctx* c );
+// exclusive scan of n uint32 (in == out allowed); `sums` needs rb_scan_scratch_bytes( n ) bytes
+size_t rb_scan_scratch_bytes( int64_t n );
+int    rb_scan_u32( rb200_ctx* c, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums );

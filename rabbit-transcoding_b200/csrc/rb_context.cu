@@ -152,6 +152,7 @@ void rb200_destroy( rb200_ctx* c ) {
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }
   rb_metrics_release( c );
+  rb_transfer_release( c );
   if ( c->h_pinned ) { cudaFreeHost( c->h_pinned ); }
   for ( auto& t : c->timing_events ) {
     cudaEventDestroy( t.a );

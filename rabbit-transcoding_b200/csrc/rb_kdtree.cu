@@ -1,0 +1,557 @@
+// rb_kdtree.cu — builds, on the GPU, exactly the kd-trees nanoflann would build on the CPU (see rb_kdtree.cuh).
+//
+// Restates KDTreeSingleIndexAdaptor::buildIndex / computeBoundingBox / divideTree / middleSplit_ / planeSplit /
+// computeMinMax (dependencies/nanoflann/nanoflann.hpp:858-866, 1009-1181) for a FOREST of trees (one per cloud of a
+// GOF) in two phases:
+//  * level-parallel phase for nodes with more than KD_SMALL points: every level is a handful of passes over the
+//    element records of all trees (per-node min/max and counts with warp-aggregated atomics, then the two Hoare
+//    passes of planeSplit as "rank the misplaced elements with one prefix sum, swap the i-th misplaced element from
+//    the left with the i-th misplaced element from the right");
+//  * serial phase for subtrees of at most KD_SMALL points: one thread per subtree runs the sequential algorithm on a
+//    bank-conflict-free shared-memory copy of its records.
+// A final pass fills divlow / divhigh from the children's tight boxes (divideTree :1080-1081).
+#include <algorithm>
+
+#include "rb_common.cuh"
+#include "rb_kdtree.cuh"
+#include "rb_kdtree_build.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void atomic_minmax16( KdNode* n, int axis, int mn, int mx ) {
+  // int16 pairs are updated through their containing 32-bit words
+  auto upd = [&]( int16_t* base, int v, bool isMin ) {
+    int16_t*  p    = base + axis;
+    uint32_t* w    = (uint32_t*)( (uintptr_t)p & ~(uintptr_t)3 );
+    const int sh   = ( (uintptr_t)p & 2 ) ? 16 : 0;
+    uint32_t  old  = *w;
+    for ( ;; ) {
+      const int cur = (int16_t)( ( old >> sh ) & 0xFFFFu );
+      if ( isMin ? ( v >= cur ) : ( v <= cur ) ) { break; }
+      const uint32_t neu = ( old & ~( 0xFFFFu << sh ) ) | ( ( (uint32_t)(uint16_t)v ) << sh );
+      const uint32_t got = atomicCAS( w, old, neu );
+      if ( got == old ) { break; }
+      old = got;
+    }
+  };
+  upd( n->tmin, mn, true );
+  upd( n->tmax, mx, false );
+}
+
+// records from positions (all clouds of the forest are concatenated; tree t owns [off[t], off[t+1]))
+__global__ void k_kd_init( const short4* __restrict__ pos, const int64_t* __restrict__ off, int nTrees, int64_t E, int ox, int oy,
+                           int oz, uint64_t* __restrict__ rec, uint32_t* __restrict__ nid, uint32_t* __restrict__ err ) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( e >= E ) { return; }
+  int lo = 0, hi = nTrees - 1;
+  while ( lo < hi ) {
+    const int mid = ( lo + hi + 1 ) >> 1;
+    if ( off[mid] <= e ) {
+      lo = mid;
+    } else {
+      hi = mid - 1;
+    }
+  }
+  const short4 p = pos[e];
+  const int    x = p.x - ox, y = p.y - oy, z = p.z - oz;
+  if ( (unsigned)x > 4095u || (unsigned)y > 4095u || (unsigned)z > 4095u ) { atomicOr( err, 1u ); }
+  rec[e] = (uint64_t)( x & 0xFFF ) | ( (uint64_t)( y & 0xFFF ) << 12 ) | ( (uint64_t)( z & 0xFFF ) << 24 ) |
+           ( (uint64_t)( e - off[lo] ) << 36 );
+  nid[e] = (uint32_t)lo + 1u;
+}
+
+__global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restrict__ off, int nTrees ) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( t >= nTrees ) { return; }
+  KdNode n{};
+  n.left  = (uint32_t)off[t];
+  n.right = (uint32_t)off[t + 1];
+  for ( int k = 0; k < 3; k++ ) {
+    n.tmin[k] = 32767;
+    n.tmax[k] = -32768;
+  }
+  n.state      = 0;
+  nodes[t + 1] = n;
+  if ( t == 0 ) {
+    KdNode z{};
+    nodes[0] = z;
+  }
+}
+
+// per-node tight bounding box of the nodes of this level (computeMinMax for all three axes at once)
+__global__ void k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, KdNode* __restrict__ nodes,
+                            int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
+  const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  uint32_t      node = 0;
+  int           c[3] = {0, 0, 0};
+  bool          on   = false;
+  if ( e < E ) {
+    node = nid[e];
+    on   = node >= lvlBegin && node < lvlEnd;
+    if ( on ) {
+      const uint64_t r = rec[e];
+      c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
+    }
+  }
+  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
+  if ( !on ) { return; }
+  const uint32_t peers = __match_any_sync( act, node );
+  const int      lane = threadIdx.x & 31, leader = __ffs( peers ) - 1;
+  int            mn[3] = {c[0], c[1], c[2]}, mx[3] = {c[0], c[1], c[2]};
+  if ( peers == act && act == 0xFFFFFFFFu ) {  // whole warp in one node: shuffle reduction
+#pragma unroll
+    for ( int k = 0; k < 3; k++ ) {
+#pragma unroll
+      for ( int d = 16; d > 0; d >>= 1 ) {
+        mn[k] = min( mn[k], __shfl_xor_sync( 0xFFFFFFFFu, mn[k], d ) );
+        mx[k] = max( mx[k], __shfl_xor_sync( 0xFFFFFFFFu, mx[k], d ) );
+      }
+    }
+    if ( lane == 0 ) {
+      for ( int k = 0; k < 3; k++ ) { atomic_minmax16( &nodes[node], k, mn[k], mx[k] ); }
+    }
+    return;
+  }
+  // mixed warp: reduce inside every peer group through the leader
+  for ( uint32_t m = peers & ~( 1u << leader ); m; m &= m - 1 ) {
+    const int src = __ffs( m ) - 1;
+#pragma unroll
+    for ( int k = 0; k < 3; k++ ) {
+      const int v = __shfl_sync( peers, c[k], src );
+      mn[k] = min( mn[k], v );
+      mx[k] = max( mx[k], v );
+    }
+  }
+  if ( lane == leader ) {
+    for ( int k = 0; k < 3; k++ ) { atomic_minmax16( &nodes[node], k, mn[k], mx[k] ); }
+  }
+}
+
+// middleSplit_ (nanoflann.hpp:1103-1142) for one node: cut axis and cut value
+__device__ __forceinline__ void kd_choose_split( KdNode& n, int o[3] ) {
+  int max_span = n.hi[0] - n.lo[0];
+  for ( int i = 1; i < 3; i++ ) { max_span = max( max_span, n.hi[i] - n.lo[i] ); }
+  int cutfeat = 0, max_spread = -1;
+  for ( int i = 0; i < 3; i++ ) {
+    const int span = n.hi[i] - n.lo[i];
+    if ( (double)span > ( 1.0 - 0.00001 ) * (double)max_span ) {  // span > (1 - EPS) * max_span in double
+      const int spread = n.tmax[i] - n.tmin[i];
+      if ( spread > max_spread ) {
+        cutfeat    = i;
+        max_spread = spread;
+      }
+    }
+  }
+  // split_val = (bbox.low + bbox.high) / 2 is an int division of the ABSOLUTE coordinates (truncation toward zero)
+  const int split = ( ( n.lo[cutfeat] + o[cutfeat] ) + ( n.hi[cutfeat] + o[cutfeat] ) ) / 2 - o[cutfeat];
+  int       cut;
+  if ( split < n.tmin[cutfeat] ) {
+    cut = n.tmin[cutfeat];
+  } else if ( split > n.tmax[cutfeat] ) {
+    cut = n.tmax[cutfeat];
+  } else {
+    cut = split;
+  }
+  n.cutfeat = (int8_t)cutfeat;
+  n.cutval  = (int16_t)cut;
+}
+
+// the nodes of this level: leaf / small root / split decision
+__global__ void k_kd_split( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, int small, int ox, int oy, int oz,
+                            uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters, int isRoot ) {
+  const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= lvlEnd ) { return; }
+  KdNode& n = nodes[i];
+  if ( isRoot ) {  // a root: divideTree( 0, N, root_bbox ) starts from the tight box
+    for ( int k = 0; k < 3; k++ ) {
+      n.lo[k] = n.tmin[k];
+      n.hi[k] = n.tmax[k];
+    }
+  }
+  const uint32_t count = n.right - n.left;
+  if ( count <= (uint32_t)small ) {
+    n.state                                = 2;
+    smallRoots[atomicAdd( &counters[1], 1u )] = i;
+    return;
+  }
+  int o[3] = {ox, oy, oz};
+  kd_choose_split( n, o );
+  n.lt = n.le = 0;
+  n.state     = 1;
+  atomicAdd( &counters[2], 1u );  // big nodes of this level
+}
+
+// lim1 / lim2 of planeSplit: elements < cutval and <= cutval
+__global__ void k_kd_count( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, KdNode* __restrict__ nodes,
+                            int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
+  const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  uint32_t      node = 0;
+  bool          on = false, lt = false, le = false;
+  if ( e < E ) {
+    node = nid[e];
+    if ( node >= lvlBegin && node < lvlEnd ) {
+      const KdNode& n = nodes[node];
+      if ( n.state == 1 ) {
+        on          = true;
+        const int v = kd_coord( rec[e], n.cutfeat );
+        lt          = v < n.cutval;
+        le          = v <= n.cutval;
+      }
+    }
+  }
+  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
+  if ( !on ) { return; }
+  const uint32_t peers = __match_any_sync( act, node );
+  const uint32_t bl = __ballot_sync( act, lt ), be = __ballot_sync( act, le );
+  if ( ( threadIdx.x & 31 ) == __ffs( peers ) - 1 ) {
+    const uint32_t a = __popc( bl & peers ), b = __popc( be & peers );
+    if ( a ) { atomicAdd( &nodes[node].lt, a ); }
+    if ( b ) { atomicAdd( &nodes[node].le, b ); }
+  }
+}
+
+// misplaced-element flags of one Hoare pass.  pass 0: [0, count) split at lim1 by (v < cutval);
+// pass 1: [lim1, count) split at lim2 by (v <= cutval)
+__global__ void k_kd_flag( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes,
+                           int64_t E, uint32_t lvlBegin, uint32_t lvlEnd, int pass, uint32_t* __restrict__ flags ) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( e > E ) { return; }
+  uint32_t f = 0;
+  if ( e < E ) {
+    const uint32_t node = nid[e];
+    if ( node >= lvlBegin && node < lvlEnd ) {
+      const KdNode& n = nodes[node];
+      if ( n.state == 1 ) {
+        const uint32_t p = (uint32_t)e - n.left;
+        const int      v = kd_coord( rec[e], n.cutfeat );
+        if ( pass == 0 ) {
+          const bool in = v < n.cutval;
+          f             = ( p < n.lt ) ? !in : in;
+        } else if ( p >= n.lt ) {
+          const bool in = v <= n.cutval;
+          f             = ( p < n.le ) ? !in : in;
+        }
+      }
+    }
+  }
+  flags[e] = f;
+}
+
+// pair lists: the i-th misplaced element from the left (ascending position) meets the i-th misplaced element
+// from the right (descending position) — exactly the swaps of the two-pointer loop (:1154-1181)
+__global__ void k_kd_pairs( const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E, uint32_t lvlBegin,
+                            uint32_t lvlEnd, int pass, const uint32_t* __restrict__ scan, const uint32_t* __restrict__ flags_unused,
+                            uint32_t* __restrict__ pairL, uint32_t* __restrict__ pairR ) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( e >= E ) { return; }
+  if ( scan[e + 1] == scan[e] ) { return; }
+  const KdNode&  n     = nodes[nid[e]];
+  const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
+  const uint32_t lim   = pass == 0 ? n.left + n.lt : n.left + n.le;
+  const uint32_t m     = ( scan[n.right] - scan[begin] ) >> 1;  // misplaced on each side
+  const uint32_t r     = scan[e] - scan[begin];
+  if ( (uint32_t)e < lim ) {
+    pairL[begin + r] = (uint32_t)e;
+  } else {
+    pairR[begin + ( m - 1 - ( r - m ) )] = (uint32_t)e;
+  }
+}
+
+__global__ void k_kd_swap( uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E,
+                           uint32_t lvlBegin, uint32_t lvlEnd, int pass, const uint32_t* __restrict__ scan,
+                           const uint32_t* __restrict__ pairL, const uint32_t* __restrict__ pairR ) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( e >= E ) { return; }
+  const uint32_t node = nid[e];
+  if ( node < lvlBegin || node >= lvlEnd ) { return; }
+  const KdNode& n = nodes[node];
+  if ( n.state != 1 ) { return; }
+  const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
+  if ( (uint32_t)e < begin ) { return; }
+  const uint32_t m = ( scan[n.right] - scan[begin] ) >> 1;
+  const uint32_t k = (uint32_t)e - begin;
+  if ( k >= m ) { return; }
+  const uint32_t a = pairL[begin + k], b = pairR[begin + k];
+  const uint64_t ra = rec[a], rb = rec[b];
+  rec[a] = rb;
+  rec[b] = ra;
+}
+
+// children of the split nodes of this level (divideTree :1070-1078)
+__global__ void k_kd_children( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, uint32_t* __restrict__ counters,
+                               uint32_t nodeCap ) {
+  const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= lvlEnd ) { return; }
+  KdNode& n = nodes[i];
+  if ( n.state != 1 ) { return; }
+  const uint32_t count = n.right - n.left;
+  uint32_t       idx;  // :1137-1139
+  if ( n.lt > count / 2 ) {
+    idx = n.lt;
+  } else if ( n.le < count / 2 ) {
+    idx = n.le;
+  } else {
+    idx = count / 2;
+  }
+  const uint32_t c1 = atomicAdd( &counters[0], 2u );
+  if ( c1 + 2 > nodeCap ) {
+    counters[3] = 1;  // node pool exhausted
+    n.state     = 3;
+    n.child1    = 0;
+    return;
+  }
+  n.child1 = c1;
+  KdNode a{}, b{};
+  a.left  = n.left;
+  a.right = n.left + idx;
+  b.left  = n.left + idx;
+  b.right = n.right;
+  for ( int k = 0; k < 3; k++ ) {
+    a.lo[k] = b.lo[k] = n.lo[k];
+    a.hi[k] = b.hi[k] = n.hi[k];
+    a.tmin[k] = b.tmin[k] = 32767;
+    a.tmax[k] = b.tmax[k] = -32768;
+  }
+  a.hi[n.cutfeat] = n.cutval;  // left_bbox[cutfeat].high = cutval
+  b.lo[n.cutfeat] = n.cutval;  // right_bbox[cutfeat].low = cutval
+  nodes[c1]       = a;
+  nodes[c1 + 1]   = b;
+}
+
+__global__ void k_kd_assign( uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E, uint32_t lvlBegin,
+                             uint32_t lvlEnd ) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( e >= E ) { return; }
+  const uint32_t node = nid[e];
+  if ( node < lvlBegin || node >= lvlEnd ) { return; }
+  const KdNode& n = nodes[node];
+  if ( n.state != 1 || n.child1 == 0 ) { return; }
+  nid[e] = ( (uint32_t)e < nodes[n.child1].right ) ? n.child1 : n.child1 + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// serial phase: one thread per subtree of <= SMALL elements, records staged in shared memory.
+// element i of thread t sits at sm[i * BS + t] (consecutive threads -> consecutive banks)
+// ---------------------------------------------------------------------------------------------------
+template <int SMALL, int BS>
+__global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec, KdNode* __restrict__ nodes,
+                                                     const uint32_t* __restrict__ smallRoots, uint32_t nRoots,
+                                                     uint32_t* __restrict__ counters, uint32_t nodeCap, int ox, int oy, int oz ) {
+  extern __shared__ uint64_t sm[];
+  const uint32_t t = blockIdx.x * BS + threadIdx.x;
+  if ( t >= nRoots ) { return; }
+  const uint32_t rootId = smallRoots[t];
+  const uint32_t base = nodes[rootId].left, total = nodes[rootId].right - base;
+  uint64_t*      S = sm + threadIdx.x;
+#define EL( i ) S[( i ) * BS]
+  for ( uint32_t i = 0; i < total; i++ ) { EL( i ) = rec[base + i]; }
+  uint32_t stack[SMALL + 2];
+  uint8_t  dstack[SMALL + 2];
+  int      sp  = 0;
+  stack[sp]    = rootId;
+  dstack[sp++] = 0;
+  int o[3]     = {ox, oy, oz};
+  int maxDepth = 0;
+  while ( sp > 0 ) {
+    const uint32_t id    = stack[--sp];
+    const int      depth = dstack[sp];
+    maxDepth             = max( maxDepth, depth );
+    KdNode         n  = nodes[id];
+    const uint32_t l = n.left - base, r = n.right - base, count = r - l;
+    // tight box (computeMinMax on every axis; also what the node hands back up)
+    for ( int k = 0; k < 3; k++ ) {
+      int mn = 32767, mx = -32768;
+      for ( uint32_t i = l; i < r; i++ ) {
+        const int v = kd_coord( EL( i ), k );
+        mn = min( mn, v ), mx = max( mx, v );
+      }
+      n.tmin[k] = (int16_t)mn;
+      n.tmax[k] = (int16_t)mx;
+    }
+    if ( count <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
+      n.child1  = 0;
+      n.state   = 3;
+      nodes[id] = n;
+      continue;
+    }
+    kd_choose_split( n, o );
+    const int axis = n.cutfeat, cut = n.cutval;
+    // planeSplit (:1154-1181), indices relative to the node
+    uint32_t left = 0, right = count - 1;
+    for ( ;; ) {
+      while ( left <= right && kd_coord( EL( l + left ), axis ) < cut ) { ++left; }
+      while ( right && left <= right && kd_coord( EL( l + right ), axis ) >= cut ) { --right; }
+      if ( left > right || !right ) { break; }
+      const uint64_t x = EL( l + left );
+      EL( l + left )   = EL( l + right );
+      EL( l + right )  = x;
+      ++left;
+      --right;
+    }
+    const uint32_t lim1 = left;
+    right               = count - 1;
+    for ( ;; ) {
+      while ( left <= right && kd_coord( EL( l + left ), axis ) <= cut ) { ++left; }
+      while ( right && left <= right && kd_coord( EL( l + right ), axis ) > cut ) { --right; }
+      if ( left > right || !right ) { break; }
+      const uint64_t x = EL( l + left );
+      EL( l + left )   = EL( l + right );
+      EL( l + right )  = x;
+      ++left;
+      --right;
+    }
+    const uint32_t lim2 = left;
+    uint32_t       idx;
+    if ( lim1 > count / 2 ) {
+      idx = lim1;
+    } else if ( lim2 < count / 2 ) {
+      idx = lim2;
+    } else {
+      idx = count / 2;
+    }
+    const uint32_t c1 = atomicAdd( &counters[0], 2u );
+    if ( c1 + 2 > nodeCap ) {
+      counters[3] = 1;
+      n.child1    = 0;
+      n.state     = 3;
+      nodes[id]   = n;
+      continue;
+    }
+    n.child1 = c1;
+    n.state  = 1;
+    n.lt     = lim1;
+    n.le     = lim2;
+    nodes[id] = n;
+    KdNode a{}, b{};
+    a.left  = n.left;
+    a.right = n.left + idx;
+    b.left  = n.left + idx;
+    b.right = n.right;
+    for ( int k = 0; k < 3; k++ ) {
+      a.lo[k] = b.lo[k] = n.lo[k];
+      a.hi[k] = b.hi[k] = n.hi[k];
+    }
+    a.hi[axis]    = (int16_t)cut;
+    b.lo[axis]    = (int16_t)cut;
+    nodes[c1]     = a;
+    nodes[c1 + 1] = b;
+    stack[sp]     = c1 + 1;
+    dstack[sp++]  = (uint8_t)( depth + 1 );
+    stack[sp]     = c1;
+    dstack[sp++]  = (uint8_t)( depth + 1 );
+  }
+  for ( uint32_t i = 0; i < total; i++ ) { rec[base + i] = EL( i ); }
+  atomicMax( &counters[4], (uint32_t)maxDepth );
+#undef EL
+}
+
+// divlow / divhigh from the children's tight boxes (divideTree :1080-1081); depth bookkeeping
+__global__ void k_kd_finalize( KdNode* __restrict__ nodes, uint32_t nNodes ) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= nNodes || i == 0 ) { return; }
+  KdNode& n = nodes[i];
+  if ( n.child1 == 0 ) { return; }
+  n.divlow  = nodes[n.child1].tmax[n.cutfeat];
+  n.divhigh = nodes[n.child1 + 1].tmin[n.cutfeat];
+}
+
+}  // namespace
+
+int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* dOff, const std::vector<int64_t>& hOff, int ox,
+                 int oy, int oz ) {
+  const int     nTrees = (int)hOff.size() - 1;
+  const int64_t E      = hOff[nTrees];
+  if ( E <= 0 || nTrees <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "kd build: empty forest" ); }
+  if ( E >= ( 1ll << 31 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: more than 2^31 points" ); }
+  for ( int t = 0; t < nTrees; t++ ) {
+    if ( hOff[t + 1] - hOff[t] <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "kd build: empty cloud %d", t ); }
+    if ( hOff[t + 1] - hOff[t] >= ( 1ll << 28 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: cloud too large" ); }
+  }
+  const uint32_t nodeCap = (uint32_t)std::min<int64_t>( 2 * E + nTrees + 16, ( E * 3 ) / 4 + 64ll * nTrees + 4096 );
+  RB_CUDA( B.rec.ensure( (size_t)E * 8 ) );
+  RB_CUDA( B.nid.ensure( (size_t)E * 4 ) );
+  RB_CUDA( B.nodes.ensure( (size_t)nodeCap * sizeof( KdNode ) ) );
+  RB_CUDA( B.flags.ensure( (size_t)( E + 8 ) * 4 ) );
+  RB_CUDA( B.pairL.ensure( (size_t)E * 4 ) );
+  RB_CUDA( B.pairR.ensure( (size_t)E * 4 ) );
+  RB_CUDA( B.sums.ensure( rb_scan_scratch_bytes( E + 1 ) ) );
+  RB_CUDA( B.smallRoots.ensure( (size_t)( E + nTrees ) * 4 ) );
+  RB_CUDA( B.counters.ensure( 64 ) );
+  uint64_t* rec      = B.rec.as<uint64_t>();
+  uint32_t* nid      = B.nid.as<uint32_t>();
+  KdNode*   nodes    = B.nodes.as<KdNode>();
+  uint32_t* flags    = B.flags.as<uint32_t>();
+  uint32_t* counters = B.counters.as<uint32_t>();
+  uint32_t* h        = (uint32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  // counters: [0] next free node, [1] small roots, [2] big nodes of the level, [3] pool exhausted, [4] depth, [5] range error
+  h[0] = (uint32_t)nTrees + 1;
+  h[1] = h[2] = h[3] = h[4] = h[5] = 0;
+  RB_CUDA( cudaMemcpyAsync( counters, h, 32, cudaMemcpyHostToDevice, c->stream ) );
+  const int G = rb_div_up( E, TPB );
+  RB_LAUNCH( "kd_init", k_kd_init, G, TPB, 0, pos, dOff, nTrees, E, ox, oy, oz, rec, nid, counters + 5 );
+  RB_LAUNCH( "kd_roots", k_kd_roots, rb_div_up( nTrees, 128 ), 128, 0, nodes, dOff, nTrees );
+  uint32_t lvlBegin = 1, lvlEnd = (uint32_t)nTrees + 1;
+  int      level = 0;
+  bool     roots = true;
+  for ( ;; level++ ) {
+    if ( level > 200 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree deeper than 200 levels" ); }
+    const uint32_t nLvl = lvlEnd - lvlBegin;
+    RB_LAUNCH( "kd_stats", k_kd_stats, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd );
+    RB_CUDA( cudaMemsetAsync( counters + 2, 0, 4, c->stream ) );
+    RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KD_SMALL, ox, oy, oz,
+               B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0 );
+    roots = false;
+    RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    if ( h[5] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: coordinate range of the clouds exceeds 4096" ); }
+    if ( h[2] == 0 ) { break; }  // no node of this level is large enough for the level-parallel phase
+    RB_LAUNCH( "kd_count", k_kd_count, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd );
+    for ( int pass = 0; pass < 2; pass++ ) {
+      RB_LAUNCH( "kd_flag", k_kd_flag, rb_div_up( E + 1, TPB ), TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd, pass, flags );
+      int r = rb_scan_u32( c, flags, flags, E + 1, B.sums.as<uint32_t>() );
+      if ( r ) { return r; }
+      RB_LAUNCH( "kd_pairs", k_kd_pairs, G, TPB, 0, nid, nodes, E, lvlBegin, lvlEnd, pass, flags, nullptr, B.pairL.as<uint32_t>(),
+                 B.pairR.as<uint32_t>() );
+      RB_LAUNCH( "kd_swap", k_kd_swap, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd, pass, flags, B.pairL.as<uint32_t>(),
+                 B.pairR.as<uint32_t>() );
+    }
+    const uint32_t before = h[0];
+    RB_LAUNCH( "kd_children", k_kd_children, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, counters, nodeCap );
+    RB_LAUNCH( "kd_assign", k_kd_assign, G, TPB, 0, nid, nodes, E, lvlBegin, lvlEnd );
+    lvlBegin = before;
+    lvlEnd   = before + 2 * h[2];
+    if ( lvlEnd > nodeCap ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
+  }
+  const uint32_t nRoots = h[1];
+  if ( nRoots ) {
+    constexpr int BS = 64;
+    const size_t  smem = (size_t)KD_SMALL * BS * 8;
+    static bool   attr = false;
+    if ( !attr ) {
+      RB_CUDA( cudaFuncSetAttribute( k_kd_serial<KD_SMALL, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+      attr = true;
+    }
+    RB_LAUNCH( "kd_serial", ( k_kd_serial<KD_SMALL, BS> ), rb_div_up( nRoots, BS ), BS, smem, rec, nodes,
+               B.smallRoots.as<uint32_t>(), nRoots, counters, nodeCap, ox, oy, oz );
+  }
+  RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  if ( h[3] ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
+  const uint32_t nNodes = h[0];
+  RB_LAUNCH( "kd_finalize", k_kd_finalize, rb_div_up( nNodes, TPB ), TPB, 0, nodes, nNodes );
+  if ( level + (int)h[4] + 2 >= KD_STACK ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree depth %d exceeds the traversal stack", level + (int)h[4] );
+  }
+  B.forest.rec   = rec;
+  B.forest.nodes = nodes;
+  B.forest.ox    = ox;
+  B.forest.oy    = oy;
+  B.forest.oz    = oz;
+  B.nNodes       = nNodes;
+  B.nTrees       = nTrees;
+  B.levels       = level + (int)h[4];
+  return RB200_OK;
+}

@@ -1,0 +1,25 @@
+// rb_kdtree_build.cuh — host-side handle of a kd forest build (see rb_kdtree.cu)
+#pragma once
+#include <vector>
+
+#include "rb_common.cuh"
+#include "rb_kdtree.cuh"
+
+constexpr int KD_SMALL = 128;  // subtrees of at most this many points are built by one thread in shared memory
+
+struct RbKdBuild {
+  RbBuf    rec, nid, nodes, flags, pairL, pairR, sums, smallRoots, counters;
+  KdForest forest{};
+  uint32_t nNodes = 0;
+  int      nTrees = 0;
+  int      levels = 0;
+  void     release() {
+    RbBuf* b[] = {&rec, &nid, &nodes, &flags, &pairL, &pairR, &sums, &smallRoots, &counters};
+    for ( auto* x : b ) { x->release(); }
+  }
+};
+
+// Builds one tree per cloud.  pos: concatenated points (device), dOff: [nTrees + 1] offsets on the device, hOff: the
+// same on the host, (ox, oy, oz): origin subtracted from the coordinates (all relative coordinates must be < 4096).
+int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* dOff, const std::vector<int64_t>& hOff, int ox,
+                 int oy, int oz );

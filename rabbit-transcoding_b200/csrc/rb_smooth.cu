@@ -584,8 +584,3 @@ int rb_convert_rgb8_impl( rb200_ctx* c ) {
              c->P.attribute_rgb444, c->P.attribute_count );
   return RB200_OK;
 }
-
-int rb_transfer_colors_impl( rb200_ctx* c ) {
-  return rb_fail( c, RB200_ERR_UNSUPPORTED,
-                  "transferColors16bitBP (PCCPointSet.cpp:1126-1485) is not implemented yet in this build" );
-}

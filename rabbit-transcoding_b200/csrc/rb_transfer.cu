@@ -1,0 +1,520 @@
+// rb_transfer.cu — attribute re-transfer after geometry smoothing, for every frame of the GOF (sm_100a).
+//
+// Restates PCCPointSet3::transferColors16bitBP (PccLibCommon/source/PCCPointSet.cpp:1126-1485) exactly as the decoder
+// calls it (PccLibDecoder/source/PCCDecoder.cpp:447-465): filterType 1, searchRange 0, 8 forward / 1 backward
+// neighbours, distance-weighted averages with offsets 4, skipAvgIfIdenticalSourcePointPresentFwd, and all four
+// distance / colour thresholds disabled (1000 >= 512 and 256000 >= 131072 turn them into DBL_MAX, :1153-1156).
+// Only the points that geometry smoothing moved (boundary type 3) change colour:
+//   forward : 8-NN of the moved point in the PRE-smoothing cloud -> refinedColors1 (identical position: that colour;
+//             otherwise the 1/(d^2+4)-weighted mean), and those 8 source points become "partSource" (:1165-1265);
+//   backward: every partSource point looks up its 1-NN in the SMOOTHED cloud; if the colours are within 40 per
+//             channel it becomes a candidate of that target (:1275-1293); candidates are std::sort-ed by distance;
+//   result  : round( sum c / (sqrt(d^2)+4) / sum 1/(sqrt(d^2)+4) ) over the candidates, or refinedColors1 when
+//             there is none / the attribute is RGB444 (:1319-1483 with fixWeight, w = 0, searchRange 0).
+// Which 8 points tie at the 8th distance, and which of several equidistant targets is "the" 1-NN, is decided by
+// nanoflann's traversal order: both searches run on the emulated trees of rb_kdtree.cu.  std::sort's order of
+// equal-distance candidates (it is not stable beyond 16 elements) is reproduced with libstdc++'s introsort.
+#include <algorithm>
+
+#include "rb_common.cuh"
+#include "rb_kdtree.cuh"
+#include "rb_kdtree_build.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int KF  = 8;  // numNeighborsColorTransferFwd
+
+struct TransferScratch {
+  RbKdBuild kd;
+  RbBuf     pos2, off, flags, sums, moved, part, partDist, partCnt, refined1, candCnt, candOff, candKey, small;
+};
+std::map<rb200_ctx*, TransferScratch*> g_transfer;
+
+TransferScratch* scratch_of( rb200_ctx* c ) {
+  auto it = g_transfer.find( c );
+  if ( it != g_transfer.end() ) { return it->second; }
+  auto* s       = new TransferScratch;
+  g_transfer[c] = s;
+  return s;
+}
+
+__device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
+  int lo = 0, hi = F - 1;
+  while ( lo < hi ) {
+    const int mid = ( lo + hi + 1 ) >> 1;
+    if ( off[mid] <= i ) {
+      lo = mid;
+    } else {
+      hi = mid - 1;
+    }
+  }
+  return lo;
+}
+
+__global__ void k_flag_moved( const short4* __restrict__ pos, int64_t n, uint32_t* __restrict__ flags ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i > n ) { return; }
+  flags[i] = ( i < n && pos[i].w == 3 ) ? 1u : 0u;
+}
+__global__ void k_list_moved( const uint32_t* __restrict__ scan, int64_t n, uint32_t* __restrict__ moved ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  if ( scan[i + 1] != scan[i] ) { moved[scan[i]] = (uint32_t)i; }
+}
+
+struct TArgs {
+  KdForest        forest;
+  int             F;
+  const int64_t*  frame_off;  // [F + 1]
+  const short4*   posS;       // pre-smoothing positions
+  const short4*   posT;       // smoothed positions (w = boundary type)
+  ushort4*        col;        // colours16 (source == target before the transfer)
+  const uint32_t* moved;      // global indices of the type-3 points, ascending
+  const uint32_t* rank;       // scan of the moved flags: rank[g] = position of g in `moved`
+  uint32_t        nMoved;
+  uint32_t*       part;       // [nMoved][KF] source index inside the frame
+  uint32_t*       partDist;   // [nMoved][KF]
+  uint8_t*        partCnt;    // [nMoved]
+  ushort4*        refined1;   // [nMoved]
+  uint32_t*       candCnt;    // [nMoved + 1]
+  const uint32_t* candOff;
+  uint64_t*       candKey;    // dist << 32 | partSource index
+  int             lossless;
+  uint32_t*       err;
+};
+
+// forward direction (:1165-1265)
+__global__ void __launch_bounds__( 128 ) k_transfer_fwd( const TArgs a ) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( m >= a.nMoved ) { return; }
+  const int64_t g    = a.moved[m];
+  const int     f    = frame_of( a.frame_off, a.F, g );
+  const int64_t base = a.frame_off[f];
+  const short4  p    = a.posT[g];
+  const int     q[3] = {p.x - a.forest.ox, p.y - a.forest.oy, p.z - a.forest.oz};
+  KdResult<KF>  res;
+  kd_search<KF>( a.forest, (uint32_t)f + 1u, q, res );  // kdtreeSource.search( target[index], 8 )
+  a.partCnt[m] = (uint8_t)res.count;
+  for ( int j = 0; j < res.count; j++ ) {
+    a.part[(size_t)m * KF + j]     = res.idx[j];
+    a.partDist[(size_t)m * KF + j] = res.dist[j];
+  }
+  ushort4 out;
+  if ( res.dist[0] == 0 || res.count == 1 ) {  // identical source point present (:1186-1191) or a single neighbour (:1195-1198)
+    out = a.col[base + res.idx[0]];
+  } else {
+    // maxColorDist2 <= DBL_MAX always holds: distance-weighted mean of all neighbours (:1212-1222, :1252-1256)
+    double rc[3] = {0.0, 0.0, 0.0}, sw = 0.0;
+    for ( int j = 0; j < res.count; j++ ) {
+      const double  w = 1.0 / ( (double)res.dist[j] + 4.0 );
+      const ushort4 c = a.col[base + res.idx[j]];
+      rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
+      rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
+      rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
+      sw              = __dadd_rn( sw, w );
+    }
+    out.x = (unsigned short)fmin( fmax( round( rc[0] / sw ), 0.0 ), 65535.0 );
+    out.y = (unsigned short)fmin( fmax( round( rc[1] / sw ), 0.0 ), 65535.0 );
+    out.z = (unsigned short)fmin( fmax( round( rc[2] / sw ), 0.0 ), 65535.0 );
+  }
+  out.w         = 0;
+  a.refined1[m] = out;
+}
+
+// backward direction (:1275-1293): pass 0 counts the accepted candidates per moved target, pass 1 stores them
+__global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a, int pass ) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( p >= a.nMoved * KF ) { return; }
+  const uint32_t m = p / KF, j = p % KF;
+  if ( j >= a.partCnt[m] ) { return; }
+  const int64_t  g    = a.moved[m];
+  const int      f    = frame_of( a.frame_off, a.F, g );
+  const int64_t  base = a.frame_off[f];
+  const uint32_t s    = a.part[p];
+  const short4   ps   = a.posS[base + s];
+  const int      q[3] = {ps.x - a.forest.ox, ps.y - a.forest.oy, ps.z - a.forest.oz};
+  KdResult<1>    res;
+  kd_search<1>( a.forest, (uint32_t)( a.F + f ) + 1u, q, res );  // kdtreeTarget.search( partSource[index], 1 )
+  if ( res.count == 0 ) { return; }
+  const int64_t r = base + res.idx[0];
+  if ( a.posT[r].w != 3 ) { return; }  // only type-3 targets are recomputed (:1319)
+  const ushort4 cs = a.col[base + s], ct = a.col[r];
+  if ( abs( (int)cs.x - (int)ct.x ) < 40 && abs( (int)cs.y - (int)ct.y ) < 40 && abs( (int)cs.z - (int)ct.z ) < 40 ) {
+    const uint32_t mr = a.rank[r];
+    if ( pass == 0 ) {
+      atomicAdd( &a.candCnt[mr], 1u );
+    } else {
+      const uint32_t slot = a.candOff[mr] + atomicAdd( &a.candCnt[mr], 1u );
+      a.candKey[slot]     = ( (uint64_t)res.dist[0] << 32 ) | p;
+    }
+  }
+}
+
+// ---- libstdc++ std::sort( first, last, dist < dist ) on an array of keys whose high 32 bits are the distance ----
+__device__ __forceinline__ bool k_less( uint64_t x, uint64_t y ) { return ( x >> 32 ) < ( y >> 32 ); }
+__device__ __forceinline__ void k_swap( uint64_t& x, uint64_t& y ) {
+  const uint64_t t = x;
+  x                = y;
+  y                = t;
+}
+__device__ void std_unguarded_linear_insert( uint64_t* v, int last ) {
+  const uint64_t val  = v[last];
+  int            next = last - 1;
+  while ( k_less( val, v[next] ) ) {
+    v[last] = v[next];
+    last    = next;
+    --next;
+  }
+  v[last] = val;
+}
+__device__ void std_insertion_sort( uint64_t* v, int first, int last ) {
+  if ( first == last ) { return; }
+  for ( int i = first + 1; i != last; ++i ) {
+    if ( k_less( v[i], v[first] ) ) {
+      const uint64_t val = v[i];
+      for ( int k = i; k > first; --k ) { v[k] = v[k - 1]; }
+      v[first] = val;
+    } else {
+      std_unguarded_linear_insert( v, i );
+    }
+  }
+}
+// returns false when the depth limit would send libstdc++ into its heapsort fallback (not reproduced: fail loudly)
+__device__ bool std_sort_emulated( uint64_t* v, int n ) {
+  if ( n <= 1 ) { return true; }
+  // __introsort_loop( first, last, 2 * lg(n) ) with an explicit stack for the recursive call on [cut, last)
+  int stF[64], stL[64], stD[64];
+  int sp = 0;
+  stF[sp] = 0, stL[sp] = n, stD[sp] = 2 * ( 31 - __clz( n ) );
+  sp++;
+  while ( sp > 0 ) {
+    --sp;
+    int first = stF[sp], last = stL[sp], depth = stD[sp];
+    while ( last - first > 16 ) {
+      if ( depth == 0 ) { return false; }
+      --depth;
+      // __unguarded_partition_pivot
+      const int mid = first + ( last - first ) / 2;
+      {  // __move_median_to_first( first, first + 1, mid, last - 1 )
+        const int a = first + 1, b = mid, c = last - 1;
+        if ( k_less( v[a], v[b] ) ) {
+          if ( k_less( v[b], v[c] ) ) {
+            k_swap( v[first], v[b] );
+          } else if ( k_less( v[a], v[c] ) ) {
+            k_swap( v[first], v[c] );
+          } else {
+            k_swap( v[first], v[a] );
+          }
+        } else if ( k_less( v[a], v[c] ) ) {
+          k_swap( v[first], v[a] );
+        } else if ( k_less( v[b], v[c] ) ) {
+          k_swap( v[first], v[c] );
+        } else {
+          k_swap( v[first], v[b] );
+        }
+      }
+      int lo = first + 1, hi = last;  // __unguarded_partition( first + 1, last, first )
+      for ( ;; ) {
+        while ( k_less( v[lo], v[first] ) ) { ++lo; }
+        --hi;
+        while ( k_less( v[first], v[hi] ) ) { --hi; }
+        if ( !( lo < hi ) ) { break; }
+        k_swap( v[lo], v[hi] );
+        ++lo;
+      }
+      const int cut = lo;
+      if ( sp >= 64 ) { return false; }
+      stF[sp] = cut, stL[sp] = last, stD[sp] = depth;  // __introsort_loop( cut, last, depth_limit )
+      sp++;
+      last = cut;
+    }
+  }
+  // __final_insertion_sort
+  if ( n > 16 ) {
+    std_insertion_sort( v, 0, 16 );
+    for ( int i = 16; i != n; ++i ) { std_unguarded_linear_insert( v, i ); }
+  } else {
+    std_insertion_sort( v, 0, n );
+  }
+  return true;
+}
+
+// the pending recursive calls of __introsort_loop run AFTER the current loop finishes in the real recursion order
+// "loop body: recurse on [cut,last) first, then continue with [first,cut)".  Since the two ranges are disjoint and
+// the algorithm only touches elements of its own range, the order in which disjoint ranges are processed does not
+// change the result.
+
+// final colours of the moved targets (:1319-1483)
+__global__ void __launch_bounds__( 128 ) k_transfer_final( const TArgs a ) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( m >= a.nMoved ) { return; }
+  const int64_t  g    = a.moved[m];
+  const int      f    = frame_of( a.frame_off, a.F, g );
+  const uint32_t beg = a.candOff[m], end = a.candOff[m + 1];
+  const int      n   = (int)( end - beg );
+  ushort4        out = a.refined1[m];
+  out.w              = a.col[g].w;  // the layer index travels in .w
+  if ( n > 0 && !a.lossless ) {
+    uint64_t* v = a.candKey + beg;
+    // the candidates were appended in partSource order (:1280-1292) before std::sort: restore that order first
+    for ( int i = 1; i < n; i++ ) {  // insertion sort on the partSource index (low 32 bits)
+      const uint64_t val = v[i];
+      int            k   = i - 1;
+      while ( k >= 0 && (uint32_t)v[k] > (uint32_t)val ) {
+        v[k + 1] = v[k];
+        k--;
+      }
+      v[k + 1] = val;
+    }
+    if ( !std_sort_emulated( v, n ) ) { atomicOr( a.err, 1u ); }
+    double c2[3] = {0.0, 0.0, 0.0};
+    if ( n == 1 ) {  // :1342-1348
+      const uint32_t p    = (uint32_t)v[0];
+      const int64_t  base = a.frame_off[frame_of( a.frame_off, a.F, a.moved[p / KF] )];
+      const ushort4  c    = a.col[base + a.part[p]];
+      c2[0] = c.x, c2[1] = c.y, c2[2] = c.z;
+    } else {  // maxColorDist2 <= DBL_MAX: weighted mean with 1 / (sqrt(d2) + 4) (:1364-1372)
+      double sw = 0.0;
+      for ( int i = 0; i < n; i++ ) {
+        const uint32_t p    = (uint32_t)v[i];
+        const int64_t  base = a.frame_off[frame_of( a.frame_off, a.F, a.moved[p / KF] )];
+        const ushort4  c    = a.col[base + a.part[p]];
+        const double   w    = 1.0 / ( sqrt( (double)( v[i] >> 32 ) ) + 4.0 );
+        c2[0]               = __dadd_rn( c2[0], __dmul_rn( (double)c.x, w ) );
+        c2[1]               = __dadd_rn( c2[1], __dmul_rn( (double)c.y, w ) );
+        c2[2]               = __dadd_rn( c2[2], __dmul_rn( (double)c.z, w ) );
+        sw                  = __dadd_rn( sw, w );
+      }
+      c2[0] /= sw, c2[1] /= sw, c2[2] /= sw;
+    }
+    // fixWeight: w = 0 -> color0 = clip( round( 0 * centroid1 + 1 * centroid2 ) ); searchRange 0 keeps color0 (:1413-1466)
+    const ushort4 c1 = a.refined1[m];
+    out.x = (unsigned short)fmin( fmax( round( __dadd_rn( __dmul_rn( 0.0, (double)c1.x ), __dmul_rn( 1.0, c2[0] ) ) ), 0.0 ), 65535.0 );
+    out.y = (unsigned short)fmin( fmax( round( __dadd_rn( __dmul_rn( 0.0, (double)c1.y ), __dmul_rn( 1.0, c2[1] ) ) ), 0.0 ), 65535.0 );
+    out.z = (unsigned short)fmin( fmax( round( __dadd_rn( __dmul_rn( 0.0, (double)c1.z ), __dmul_rn( 1.0, c2[2] ) ) ), 0.0 ), 65535.0 );
+  }
+  (void)f;
+  a.refined1[m] = out;  // written to the cloud by k_transfer_store once every target has read the old colours
+}
+
+__global__ void k_transfer_store( const TArgs a ) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( m >= a.nMoved ) { return; }
+  a.col[a.moved[m]] = a.refined1[m];
+}
+
+// PCCKdTree::search for a batch of queries (test / integration entry: pins the emulation against the reference)
+template <int K>
+__global__ void k_knn_queries( const KdForest f, const int16_t* __restrict__ q, int64_t nq, int64_t* __restrict__ outIdx,
+                               double* __restrict__ outDist ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= nq ) { return; }
+  const int   qq[3] = {q[3 * i] - f.ox, q[3 * i + 1] - f.oy, q[3 * i + 2] - f.oz};
+  KdResult<K> res;
+  kd_search<K>( f, 1u, qq, res );
+  for ( int j = 0; j < K; j++ ) {
+    outIdx[i * K + j]  = j < res.count ? (int64_t)res.idx[j] : -1;
+    outDist[i * K + j] = j < res.count ? (double)res.dist[j] : -1.0;
+  }
+}
+
+__global__ void k_unpack_positions( const int16_t* __restrict__ in, int64_t n, short4* __restrict__ out ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n ) { return; }
+  out[i] = make_short4( in[3 * i], in[3 * i + 1], in[3 * i + 2], 0 );
+}
+
+template <int K>
+int launch_knn( rb200_ctx* c, const KdForest& f, const int16_t* q, int64_t nq, int64_t* oi, double* od ) {
+  RB_LAUNCH( "kd_knn", k_knn_queries<K>, rb_div_up( nq, 128 ), 128, 0, f, q, nq, oi, od );
+  return RB200_OK;
+}
+
+}  // namespace
+
+void rb_transfer_release( rb200_ctx* c ) {
+  auto it = g_transfer.find( c );
+  if ( it == g_transfer.end() ) { return; }
+  TransferScratch* s = it->second;
+  s->kd.release();
+  RbBuf* b[] = {&s->pos2, &s->off, &s->flags, &s->sums, &s->moved, &s->part, &s->partDist, &s->partCnt, &s->refined1,
+                &s->candCnt, &s->candOff, &s->candKey, &s->small};
+  for ( auto* x : b ) { x->release(); }
+  delete s;
+  g_transfer.erase( it );
+}
+
+int rb_transfer_colors_impl( rb200_ctx* c ) {
+  const rb200_params& P = c->P;
+  const int           F = c->F;
+  const int64_t       N = c->h_frame_off[F];
+  if ( N == 0 || P.attribute_count == 0 ) { return RB200_OK; }
+  if ( !c->d_pos_pre.p || c->d_pos_pre.cap < (size_t)N * 8 ) {
+    return rb_fail( c, RB200_ERR_STATE, "transfer_colors: the pre-smoothing cloud was not kept (attr_transfer_filter_type != 1?)" );
+  }
+  if ( P.geometry_bitdepth_3d > 12 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "transfer_colors: geometry bit depth above 12 is not supported by the kd-tree emulation" );
+  }
+  for ( int f = 0; f < F; f++ ) {
+    const int64_t n = c->h_frame_off[f + 1] - c->h_frame_off[f];
+    if ( n > 0 && n < KF ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "transfer_colors: frame %d has fewer than %d points", f, KF );
+    }
+  }
+  TransferScratch* S = scratch_of( c );
+  // ---- moved (type 3) points ----
+  RB_CUDA( S->flags.ensure( (size_t)( N + 8 ) * 4 ) );
+  RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( N + 1 ) ) );
+  uint32_t* flags = S->flags.as<uint32_t>();
+  RB_LAUNCH( "tr_flag_moved", k_flag_moved, rb_div_up( N + 1, TPB ), TPB, 0, c->d_pos.as<short4>(), N, flags );
+  int r = rb_scan_u32( c, flags, flags, N + 1, S->sums.as<uint32_t>() );
+  if ( r ) { return r; }
+  uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( h, flags + N, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  const uint32_t M = h[0];
+  if ( M == 0 ) { return RB200_OK; }  // nothing moved: every colour stays (:1163-1164 with type != 3)
+  // ---- forest: trees 1..F over the pre-smoothing frames, F+1..2F over the smoothed frames ----
+  std::vector<int64_t> hOff;
+  std::vector<int>     treeOfS( F, -1 ), treeOfT( F, -1 );
+  hOff.push_back( 0 );
+  // empty frames own no tree; the roots of the others are numbered consecutively, so keep a frame -> root map
+  for ( int pass = 0; pass < 2; pass++ ) {
+    for ( int f = 0; f < F; f++ ) {
+      const int64_t n = c->h_frame_off[f + 1] - c->h_frame_off[f];
+      if ( n == 0 ) { continue; }
+      ( pass == 0 ? treeOfS : treeOfT )[f] = (int)hOff.size() - 1;
+      hOff.push_back( hOff.back() + n );
+    }
+  }
+  bool dense = true;  // no empty frame: tree ids are f and F + f (the kernels assume this layout)
+  for ( int f = 0; f < F; f++ ) { dense &= ( treeOfS[f] == f && treeOfT[f] == F + f ); }
+  if ( !dense ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "transfer_colors: a GOF with an empty frame next to smoothed frames is not supported" );
+  }
+  RB_CUDA( S->pos2.ensure( (size_t)2 * N * 8 ) );
+  RB_CUDA( cudaMemcpyAsync( S->pos2.p, c->d_pos_pre.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( S->pos2.as<char>() + (size_t)N * 8, c->d_pos.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+  RB_CUDA( S->off.ensure( hOff.size() * 8 ) );
+  {
+    int64_t* hp = (int64_t*)rb_pinned( c, hOff.size() * 8 );
+    if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    memcpy( hp, hOff.data(), hOff.size() * 8 );
+    RB_CUDA( cudaMemcpyAsync( S->off.p, hp, hOff.size() * 8, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  r = rb_kd_build( c, S->kd, S->pos2.as<short4>(), S->off.as<int64_t>(), hOff, 0, 0, 0 );
+  if ( r ) { return r; }
+  // ---- transfer ----
+  RB_CUDA( S->moved.ensure( (size_t)M * 4 ) );
+  RB_CUDA( S->part.ensure( (size_t)M * KF * 4 ) );
+  RB_CUDA( S->partDist.ensure( (size_t)M * KF * 4 ) );
+  RB_CUDA( S->partCnt.ensure( (size_t)M ) );
+  RB_CUDA( S->refined1.ensure( (size_t)M * 8 ) );
+  RB_CUDA( S->candCnt.ensure( (size_t)( M + 8 ) * 4 ) );
+  RB_CUDA( S->candOff.ensure( (size_t)( M + 8 ) * 4 ) );
+  RB_CUDA( S->candKey.ensure( (size_t)M * KF * 8 ) );
+  RB_CUDA( S->small.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( S->small.p, 0, 64, c->stream ) );
+  RB_LAUNCH( "tr_list_moved", k_list_moved, rb_div_up( N, TPB ), TPB, 0, flags, N, S->moved.as<uint32_t>() );
+  TArgs a{};
+  a.forest    = S->kd.forest;
+  a.F         = F;
+  a.frame_off = c->d_frame_off.as<int64_t>();
+  a.posS      = c->d_pos_pre.as<short4>();
+  a.posT      = c->d_pos.as<short4>();
+  a.col       = c->d_col.as<ushort4>();
+  a.moved     = S->moved.as<uint32_t>();
+  a.rank      = flags;
+  a.nMoved    = M;
+  a.part      = S->part.as<uint32_t>();
+  a.partDist  = S->partDist.as<uint32_t>();
+  a.partCnt   = S->partCnt.as<uint8_t>();
+  a.refined1  = S->refined1.as<ushort4>();
+  a.candCnt   = S->candCnt.as<uint32_t>();
+  a.candOff   = S->candOff.as<uint32_t>();
+  a.candKey   = S->candKey.as<uint64_t>();
+  a.lossless  = P.attribute_rgb444;
+  a.err       = S->small.as<uint32_t>();
+  RB_LAUNCH( "tr_forward", k_transfer_fwd, rb_div_up( M, 128 ), 128, 0, a );
+  RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );
+  RB_LAUNCH( "tr_backward_count", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a, 0 );
+  r = rb_scan_u32( c, a.candCnt, S->candOff.as<uint32_t>(), M + 1, S->sums.as<uint32_t>() );
+  if ( r ) { return r; }
+  RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );
+  RB_LAUNCH( "tr_backward_store", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a, 1 );
+  RB_LAUNCH( "tr_final", k_transfer_final, rb_div_up( M, 128 ), 128, 0, a );
+  RB_LAUNCH( "tr_store", k_transfer_store, rb_div_up( M, 128 ), 128, 0, a );
+  RB_CUDA( cudaMemcpyAsync( h, a.err, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  if ( h[0] ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "transfer_colors: a candidate list drove std::sort into its heapsort fallback "
+                                              "(not reproduced)" );
+  }
+  return RB200_OK;
+}
+
+extern "C" int rb200_kdtree_search( rb200_ctx* c, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, int k,
+                                    int64_t* outIdx, double* outDist ) {
+  if ( !c || !cloud || !queries || !outIdx || !outDist || n <= 0 || nq < 0 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "kdtree_search: bad arguments" );
+  }
+  if ( k < 1 || k > 8 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kdtree_search: k must be 1..8" ); }
+  cudaSetDevice( c->device );
+  if ( nq == 0 ) { return RB200_OK; }
+  TransferScratch* S = scratch_of( c );
+  // origin = per-axis minimum over cloud and queries (host side: the arrays are the caller's host or device memory)
+  RB_CUDA( S->pos2.ensure( (size_t)n * 8 + (size_t)( n + nq ) * 6 + (size_t)nq * k * 16 + 256 ) );
+  char*    base = S->pos2.as<char>();
+  short4*  dPos = (short4*)base;
+  int16_t* dRaw = (int16_t*)( base + (size_t)n * 8 );
+  int16_t* dQ   = dRaw + 3 * n;
+  char*    dOut = (char*)( ( (uintptr_t)( dQ + 3 * nq ) + 15 ) & ~(uintptr_t)15 );
+  int64_t* dIdx = (int64_t*)dOut;
+  double*  dDst = (double*)( dOut + (size_t)nq * k * 8 );
+  RB_CUDA( cudaMemcpyAsync( dRaw, cloud, (size_t)n * 6, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( dQ, queries, (size_t)nq * 6, cudaMemcpyDefault, c->stream ) );
+  RB_LAUNCH( "kd_unpack", k_unpack_positions, rb_div_up( n, TPB ), TPB, 0, dRaw, n, dPos );
+  // the origin must make every coordinate of the cloud non-negative: take it from a host-side pass when the cloud
+  // is host memory, else assume 0 (decoded clouds are non-negative)
+  int ox = 0, oy = 0, oz = 0;
+  cudaPointerAttributes attr{};
+  if ( cudaPointerGetAttributes( &attr, cloud ) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered ||
+       attr.type == cudaMemoryTypeHost ) {
+    cudaGetLastError();
+    ox = oy = oz = 32767;
+    for ( int64_t i = 0; i < n; i++ ) {
+      ox = std::min<int>( ox, cloud[3 * i] );
+      oy = std::min<int>( oy, cloud[3 * i + 1] );
+      oz = std::min<int>( oz, cloud[3 * i + 2] );
+    }
+  }
+  std::vector<int64_t> hOff{0, n};
+  RB_CUDA( S->off.ensure( 16 ) );
+  {
+    int64_t* hp = (int64_t*)rb_pinned( c, 16 );
+    if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    hp[0] = 0, hp[1] = n;
+    RB_CUDA( cudaMemcpyAsync( S->off.p, hp, 16, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  int r = rb_kd_build( c, S->kd, dPos, S->off.as<int64_t>(), hOff, ox, oy, oz );
+  if ( r ) { return r; }
+  switch ( k ) {
+    case 1: r = launch_knn<1>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 2: r = launch_knn<2>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 3: r = launch_knn<3>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 4: r = launch_knn<4>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 5: r = launch_knn<5>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 6: r = launch_knn<6>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    case 7: r = launch_knn<7>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+    default: r = launch_knn<8>( c, S->kd.forest, dQ, nq, dIdx, dDst ); break;
+  }
+  if ( r ) { return r; }
+  RB_CUDA( cudaMemcpyAsync( outIdx, dIdx, (size_t)nq * k * 8, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( outDist, dDst, (size_t)nq * k * 8, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  return RB200_OK;
+}

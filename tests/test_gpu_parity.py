@@ -133,3 +133,40 @@ def test_error_paths(rb, codec):
     with pytest.raises(rb.codec.RabbitError) as e:
         codec.uploadGof(g)
     assert e.value.status == rb.abi.RB200_ERR_UNSUPPORTED
+
+
+# ---- attribute re-transfer (PCCPointSet3::transferColors16bitBP): the decoder's default Rec-1 flow ----
+ALL_STAGES = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
+
+
+def test_transfer_colors_default(rb, codec, checker_backend):
+    g = small(rb, transfer_filter=1, seed=51)
+    ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="transfer")
+    assert ref.counts(0).smoothed > 50
+
+
+def test_transfer_colors_orientations_reverse(rb, codec, checker_backend):
+    g = small(rb, transfer_filter=1, seed=52, orientations=tuple(range(9)), occupancy_precision=2, precedence_reverse=True,
+              n_frames=3)
+    run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="transfer-orient")
+
+
+def test_transfer_colors_heavy_noise(rb, codec, checker_backend):
+    """more coding noise -> more moved points, longer candidate lists (std::sort beyond 16 elements)"""
+    g = small(rb, transfer_filter=1, seed=53, noise_fraction=0.45, bitdepth=9, width=512, scale=0.8, n_frames=1)
+    g.params.threshold_smoothing = 8.0
+    ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="transfer-noise")
+    assert ref.counts(0).smoothed > 2000
+
+
+def test_transfer_colors_rgb444_lossless_attribute(rb, codec, checker_backend):
+    g = small(rb, transfer_filter=1, seed=54)
+    g.params.attribute_rgb444 = 1
+    run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="transfer-rgb444")
+
+
+def test_vox10_full_size_frame_with_transfer(rb, codec, checker_backend):
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=10, width=1280, scale=0.68, seed=55, transfer_filter=1,
+                                  height_blocks=80)
+    ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="vox10-transfer")
+    assert ref.counts(0).smoothed > 5000
