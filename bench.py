@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-metrics", action="store_true", help="skip the D1/D2 metrics leg")
+    ap.add_argument("--no-full", action="store_true", help="skip the full Rec-1 decoder leg (attribute re-transfer)")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = auto)")
     return ap.parse_args()
 
@@ -58,7 +59,9 @@ WORKLOADS = {
 
 def make_gof(rb, args, rank, world, frames=None):
     kw = dict(WORKLOADS[args.workload])
-    kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=1 if rb.abi.HAVE_TRANSFER else 0)
+    # BASELINE.json configs[1] = "reconstruction + geometry/colour smoothing": the attribute re-transfer of the decoder's
+    # Rec-1 profile (PCCPointSet3::transferColors16bitBP) is measured as its own leg ("full_decoder")
+    kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=0)
     ncpu = os.cpu_count() or 1
     workers = max(1, min(frames or args.frames, ncpu // max(1, world)))
     return rb.synthetic.generate_gof_parallel(frames or args.frames, workers=workers, **kw)
@@ -252,6 +255,35 @@ def run_b200(args):
                "h2d_bytes_per_step": st.h2d_bytes // args.steps, "d2h_bytes_per_step": st.d2h_bytes // args.steps,
                "ms_per_step": ms_e2e / args.steps}
 
+    # ---------------- leg 2a: the decoder's full Rec-1 sequence (adds transferColors16bitBP after geometry smoothing) ----
+    full = None
+    if rb.abi.HAVE_TRANSFER and not args.no_full:
+        gof.params.attr_transfer_filter_type = 1
+        codec.uploadGof(gof)
+        for _ in range(2):
+            codec.decodeGof()
+        fsteps = max(1, min(args.steps, 3))
+        codec.stats(reset=True)
+        barrier()
+        torch.cuda.synchronize()
+        clocks.on()
+        e0.record(stream)
+        for _ in range(fsteps):
+            codec.decodeGof()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        clocks.off()
+        barrier()
+        ms_full = max_over_ranks(e0.elapsed_time(e1))
+        full = {"value": round(all_points * fsteps / (ms_full * 1e-3) / 1e6, 2), "unit": UNIT,
+                "ms_per_step": round(ms_full / fsteps, 3), "gpu_launches_per_step": codec.stats(reset=True).kernel_launches // fsteps,
+                "what": "reconstruction + geometry smoothing + transferColors16bitBP (two nanoflann-order kd-trees per "
+                        "frame rebuilt on the GPU) + colour smoothing + RGB8, planes resident in HBM"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            sub = rb.synthetic.slice_gof(gof, 0, min(8, gof.n_frames))
+            full["cpu_reference"] = cpu_reference(rb, sub, threads=1, max_frames=sub.n_frames)
+        gof.params.attr_transfer_filter_type = 0
+
     # ---------------- leg 2b: D1 / D2 / colour metrics of every frame against its source cloud ----------------
     metrics_leg = None
     if not args.no_metrics and rb.abi.HAVE_METRICS:
@@ -280,13 +312,17 @@ def run_b200(args):
         barrier()
         ms_met = max_over_ranks(e0.elapsed_time(e1))
         st = codec.stats(reset=True)
+        codec.enableTiming(True)
+        met.compute(srcs, resident, srcs)
+        mk = {k: round(v[0], 3) for k, v in sorted(codec.timings().items(), key=lambda kv: -kv[1][0])[:12]}
+        codec.enableTiming(False)
         d1 = [r.qf.c2c_psnr for r in res]
         d2 = [r.qf.c2p_psnr for r in res]
         metrics_leg = {"value": round(world * gof.n_frames * msteps / (ms_met * 1e-3), 2), "unit": "frames/s",
                        "ms_per_gof": round(ms_met / msteps, 3), "what": "D1 + D2 + colour, both directions, duplicate "
                        "removal included; reconstruction resident in HBM, source clouds (positions, RGB, normals) "
                        "copied from pinned host memory inside the timed region",
-                       "h2d_bytes_per_step": st.h2d_bytes // msteps, "gpu_launches_per_step": st.kernel_launches // msteps,
+                       "h2d_bytes_per_step": st.h2d_bytes // msteps, "gpu_launches_per_step": st.kernel_launches // msteps, "kernel_ms": mk,
                        "d1_psnr_mean_db": round(float(np.mean(d1)), 4), "d2_psnr_mean_db": round(float(np.mean(d2)), 4)}
 
     # ---------------- leg 3: per-kernel events -> roofline of the dominant kernel ----------------
@@ -347,7 +383,7 @@ def run_b200(args):
                        "l2_policy": f"inputs larger than L2 ({gof.input_bytes() >> 20} MiB of planes per GPU per step)",
                        "sharding": "one GOF per GPU, no data-path collective"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "metrics": metrics_leg, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
+            "cpu_baseline": cpu, "metrics": metrics_leg, "full_decoder": full, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
             "generate_s": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)

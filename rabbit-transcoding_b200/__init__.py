@@ -5,4 +5,4 @@ Only what the path needs: `csrc/` (hand-written sm_100a kernels + the C ABI of i
 entry points for this path), `synthetic.py` (seeded decoded-GOF generator), `dist.py` (frame sharding).
 The directory name carries a hyphen; import it as `rabbit_transcoding_b200` (see the loader at the repo root).
 """
-from . import abi, codec, metrics, synthetic  # noqa: F401
+from . import abi, codec, dist, metrics, synthetic  # noqa: F401

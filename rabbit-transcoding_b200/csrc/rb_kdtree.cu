@@ -18,26 +18,17 @@
 
 namespace {
 
-constexpr int TPB = 256;
+constexpr int TPB      = 256;
+constexpr int KD_CHUNK = 32;
 
-__device__ __forceinline__ void atomic_minmax16( KdNode* n, int axis, int mn, int mx ) {
-  // int16 pairs are updated through their containing 32-bit words
-  auto upd = [&]( int16_t* base, int v, bool isMin ) {
-    int16_t*  p    = base + axis;
-    uint32_t* w    = (uint32_t*)( (uintptr_t)p & ~(uintptr_t)3 );
-    const int sh   = ( (uintptr_t)p & 2 ) ? 16 : 0;
-    uint32_t  old  = *w;
-    for ( ;; ) {
-      const int cur = (int16_t)( ( old >> sh ) & 0xFFFFu );
-      if ( isMin ? ( v >= cur ) : ( v <= cur ) ) { break; }
-      const uint32_t neu = ( old & ~( 0xFFFFu << sh ) ) | ( ( (uint32_t)(uint16_t)v ) << sh );
-      const uint32_t got = atomicCAS( w, old, neu );
-      if ( got == old ) { break; }
-      old = got;
-    }
-  };
-  upd( n->tmin, mn, true );
-  upd( n->tmax, mx, false );
+// per-node {min[3], max[3]} of the level-parallel phase: plain int32 so the updates are single RED instructions
+__device__ __forceinline__ void stat_update( int32_t* __restrict__ st, uint32_t node, const int mn[3], const int mx[3] ) {
+  int32_t* p = st + (size_t)node * 6;
+#pragma unroll
+  for ( int k = 0; k < 3; k++ ) {
+    atomicMin( p + k, mn[k] );
+    atomicMax( p + 3 + k, mx[k] );
+  }
 }
 
 // records from positions (all clouds of the forest are concatenated; tree t owns [off[t], off[t+1]))
@@ -62,9 +53,13 @@ __global__ void k_kd_init( const short4* __restrict__ pos, const int64_t* __rest
   nid[e] = (uint32_t)lo + 1u;
 }
 
-__global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restrict__ off, int nTrees ) {
+__global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restrict__ off, int nTrees, int32_t* __restrict__ st ) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ( t >= nTrees ) { return; }
+  for ( int k = 0; k < 3; k++ ) {
+    st[(size_t)( t + 1 ) * 6 + k]     = 0x7FFFFFFF;
+    st[(size_t)( t + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
+  }
   KdNode n{};
   n.left  = (uint32_t)off[t];
   n.right = (uint32_t)off[t + 1];
@@ -80,10 +75,14 @@ __global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restric
   }
 }
 
-// per-node tight bounding box of the nodes of this level (computeMinMax for all three axes at once)
-__global__ void k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, KdNode* __restrict__ nodes,
-                            int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
+// per-node tight bounding box of the nodes of this level (computeMinMax for all three axes at once):
+// warp shuffle reduction -> CTA combine in shared memory -> one RED per CTA and node in the common case
+__global__ void __launch_bounds__( TPB ) k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid,
+                                                     int32_t* __restrict__ st, int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
+  __shared__ uint32_t wNode[TPB / 32];
+  __shared__ int      wMin[TPB / 32][3], wMax[TPB / 32][3];
   const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t      node = 0;
   int           c[3] = {0, 0, 0};
   bool          on   = false;
@@ -95,12 +94,12 @@ __global__ void k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __
       c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
     }
   }
-  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
-  if ( !on ) { return; }
-  const uint32_t peers = __match_any_sync( act, node );
-  const int      lane = threadIdx.x & 31, leader = __ffs( peers ) - 1;
+  const uint32_t act     = __ballot_sync( 0xFFFFFFFFu, on );
+  const uint32_t peers   = on ? __match_any_sync( act, node ) : 0u;
+  const bool     uniform = on && peers == act && act == 0xFFFFFFFFu;  // warp-uniform predicate (all lanes agree)
+  const bool     wuni    = __all_sync( 0xFFFFFFFFu, uniform );
   int            mn[3] = {c[0], c[1], c[2]}, mx[3] = {c[0], c[1], c[2]};
-  if ( peers == act && act == 0xFFFFFFFFu ) {  // whole warp in one node: shuffle reduction
+  if ( wuni ) {
 #pragma unroll
     for ( int k = 0; k < 3; k++ ) {
 #pragma unroll
@@ -110,22 +109,39 @@ __global__ void k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __
       }
     }
     if ( lane == 0 ) {
-      for ( int k = 0; k < 3; k++ ) { atomic_minmax16( &nodes[node], k, mn[k], mx[k] ); }
+      wNode[w] = node;
+      for ( int k = 0; k < 3; k++ ) { wMin[w][k] = mn[k], wMax[w][k] = mx[k]; }
     }
-    return;
-  }
-  // mixed warp: reduce inside every peer group through the leader
-  for ( uint32_t m = peers & ~( 1u << leader ); m; m &= m - 1 ) {
-    const int src = __ffs( m ) - 1;
+  } else {
+    if ( lane == 0 ) { wNode[w] = 0xFFFFFFFFu; }
+    if ( on ) {  // mixed warp: reduce inside every peer group through its leader
+      const int leader = __ffs( peers ) - 1;
+      for ( uint32_t m = peers & ~( 1u << leader ); m; m &= m - 1 ) {
+        const int src = __ffs( m ) - 1;
 #pragma unroll
-    for ( int k = 0; k < 3; k++ ) {
-      const int v = __shfl_sync( peers, c[k], src );
-      mn[k] = min( mn[k], v );
-      mx[k] = max( mx[k], v );
+        for ( int k = 0; k < 3; k++ ) {
+          const int v = __shfl_sync( peers, c[k], src );
+          mn[k] = min( mn[k], v );
+          mx[k] = max( mx[k], v );
+        }
+      }
+      if ( lane == leader ) { stat_update( st, node, mn, mx ); }
     }
   }
-  if ( lane == leader ) {
-    for ( int k = 0; k < 3; k++ ) { atomic_minmax16( &nodes[node], k, mn[k], mx[k] ); }
+  __syncthreads();
+  if ( threadIdx.x < TPB / 32 ) {  // combine the uniform warps of this CTA: a run of equal nodes is flushed by its first warp
+    const int      i  = threadIdx.x;
+    const uint32_t nd = wNode[i];
+    if ( nd != 0xFFFFFFFFu && ( i == 0 || wNode[i - 1] != nd ) ) {
+      int a[3] = {wMin[i][0], wMin[i][1], wMin[i][2]}, b[3] = {wMax[i][0], wMax[i][1], wMax[i][2]};
+      for ( int j = i + 1; j < TPB / 32 && wNode[j] == nd; j++ ) {
+        for ( int k = 0; k < 3; k++ ) {
+          a[k] = min( a[k], wMin[j][k] );
+          b[k] = max( b[k], wMax[j][k] );
+        }
+      }
+      stat_update( st, nd, a, b );
+    }
   }
 }
 
@@ -160,10 +176,15 @@ __device__ __forceinline__ void kd_choose_split( KdNode& n, int o[3] ) {
 
 // the nodes of this level: leaf / small root / split decision
 __global__ void k_kd_split( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, int small, int ox, int oy, int oz,
-                            uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters, int isRoot ) {
+                            uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters, int isRoot,
+                            const int32_t* __restrict__ st ) {
   const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
   if ( i >= lvlEnd ) { return; }
   KdNode& n = nodes[i];
+  for ( int k = 0; k < 3; k++ ) {
+    n.tmin[k] = (int16_t)st[(size_t)i * 6 + k];
+    n.tmax[k] = (int16_t)st[(size_t)i * 6 + 3 + k];
+  }
   if ( isRoot ) {  // a root: divideTree( 0, N, root_bbox ) starts from the tight box
     for ( int k = 0; k < 3; k++ ) {
       n.lo[k] = n.tmin[k];
@@ -281,7 +302,7 @@ __global__ void k_kd_swap( uint64_t* __restrict__ rec, const uint32_t* __restric
 
 // children of the split nodes of this level (divideTree :1070-1078)
 __global__ void k_kd_children( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, uint32_t* __restrict__ counters,
-                               uint32_t nodeCap ) {
+                               uint32_t nodeCap, int32_t* __restrict__ st ) {
   const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
   if ( i >= lvlEnd ) { return; }
   KdNode& n = nodes[i];
@@ -318,6 +339,10 @@ __global__ void k_kd_children( KdNode* __restrict__ nodes, uint32_t lvlBegin, ui
   b.lo[n.cutfeat] = n.cutval;  // right_bbox[cutfeat].low = cutval
   nodes[c1]       = a;
   nodes[c1 + 1]   = b;
+  for ( int k = 0; k < 3; k++ ) {
+    st[(size_t)c1 * 6 + k] = st[(size_t)( c1 + 1 ) * 6 + k] = 0x7FFFFFFF;
+    st[(size_t)c1 * 6 + 3 + k] = st[(size_t)( c1 + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
+  }
 }
 
 __global__ void k_kd_assign( uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E, uint32_t lvlBegin,
@@ -349,6 +374,9 @@ __global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec,
   for ( uint32_t i = 0; i < total; i++ ) { EL( i ) = rec[base + i]; }
   uint32_t stack[SMALL + 2];
   uint8_t  dstack[SMALL + 2];
+  uint32_t inner[SMALL + 2];      // split nodes of this subtree (divlow / divhigh are filled in at the end)
+  int      nInner = 0;
+  uint32_t poolNext = 0, poolEnd = 0;  // node ids are taken from the global pool in chunks of KD_CHUNK
   int      sp  = 0;
   stack[sp]    = rootId;
   dstack[sp++] = 0;
@@ -411,7 +439,12 @@ __global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec,
     } else {
       idx = count / 2;
     }
-    const uint32_t c1 = atomicAdd( &counters[0], 2u );
+    if ( poolNext + 2 > poolEnd ) {
+      poolNext = atomicAdd( &counters[0], (uint32_t)KD_CHUNK );
+      poolEnd  = poolNext + KD_CHUNK;
+    }
+    const uint32_t c1 = poolNext;
+    poolNext += 2;
     if ( c1 + 2 > nodeCap ) {
       counters[3] = 1;
       n.child1    = 0;
@@ -424,6 +457,7 @@ __global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec,
     n.lt     = lim1;
     n.le     = lim2;
     nodes[id] = n;
+    inner[nInner++] = id;
     KdNode a{}, b{};
     a.left  = n.left;
     a.right = n.left + idx;
@@ -443,6 +477,11 @@ __global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec,
     dstack[sp++]  = (uint8_t)( depth + 1 );
   }
   for ( uint32_t i = 0; i < total; i++ ) { rec[base + i] = EL( i ); }
+  for ( int i = 0; i < nInner; i++ ) {  // divideTree :1080-1081
+    KdNode& n = nodes[inner[i]];
+    n.divlow  = nodes[n.child1].tmax[n.cutfeat];
+    n.divhigh = nodes[n.child1 + 1].tmin[n.cutfeat];
+  }
   atomicMax( &counters[4], (uint32_t)maxDepth );
 #undef EL
 }
@@ -479,6 +518,9 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( B.sums.ensure( rb_scan_scratch_bytes( E + 1 ) ) );
   RB_CUDA( B.smallRoots.ensure( (size_t)( E + nTrees ) * 4 ) );
   RB_CUDA( B.counters.ensure( 64 ) );
+  const uint32_t statCap = (uint32_t)std::min<int64_t>( nodeCap, E / 16 + 64ll * nTrees + 4096 );
+  RB_CUDA( B.stats.ensure( (size_t)statCap * 24 ) );
+  int32_t* st = B.stats.as<int32_t>();
   uint64_t* rec      = B.rec.as<uint64_t>();
   uint32_t* nid      = B.nid.as<uint32_t>();
   KdNode*   nodes    = B.nodes.as<KdNode>();
@@ -492,17 +534,17 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( cudaMemcpyAsync( counters, h, 32, cudaMemcpyHostToDevice, c->stream ) );
   const int G = rb_div_up( E, TPB );
   RB_LAUNCH( "kd_init", k_kd_init, G, TPB, 0, pos, dOff, nTrees, E, ox, oy, oz, rec, nid, counters + 5 );
-  RB_LAUNCH( "kd_roots", k_kd_roots, rb_div_up( nTrees, 128 ), 128, 0, nodes, dOff, nTrees );
+  RB_LAUNCH( "kd_roots", k_kd_roots, rb_div_up( nTrees, 128 ), 128, 0, nodes, dOff, nTrees, st );
   uint32_t lvlBegin = 1, lvlEnd = (uint32_t)nTrees + 1;
   int      level = 0;
   bool     roots = true;
   for ( ;; level++ ) {
     if ( level > 200 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree deeper than 200 levels" ); }
     const uint32_t nLvl = lvlEnd - lvlBegin;
-    RB_LAUNCH( "kd_stats", k_kd_stats, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd );
+    RB_LAUNCH( "kd_stats", k_kd_stats, G, TPB, 0, rec, nid, st, E, lvlBegin, lvlEnd );
     RB_CUDA( cudaMemsetAsync( counters + 2, 0, 4, c->stream ) );
     RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KD_SMALL, ox, oy, oz,
-               B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0 );
+               B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0, st );
     roots = false;
     RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
@@ -519,13 +561,14 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
                  B.pairR.as<uint32_t>() );
     }
     const uint32_t before = h[0];
-    RB_LAUNCH( "kd_children", k_kd_children, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, counters, nodeCap );
+    RB_LAUNCH( "kd_children", k_kd_children, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, counters,
+               std::min( nodeCap, statCap ), st );
     RB_LAUNCH( "kd_assign", k_kd_assign, G, TPB, 0, nid, nodes, E, lvlBegin, lvlEnd );
     lvlBegin = before;
     lvlEnd   = before + 2 * h[2];
-    if ( lvlEnd > nodeCap ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
+    if ( lvlEnd > std::min( nodeCap, statCap ) ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
   }
-  const uint32_t nRoots = h[1];
+  const uint32_t nRoots = h[1], nLevelNodes = h[0];  // nodes [1, nLevelNodes) were created by the level-parallel phase
   if ( nRoots ) {
     constexpr int BS = 64;
     const size_t  smem = (size_t)KD_SMALL * BS * 8;
@@ -541,7 +584,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   if ( h[3] ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
   const uint32_t nNodes = h[0];
-  RB_LAUNCH( "kd_finalize", k_kd_finalize, rb_div_up( nNodes, TPB ), TPB, 0, nodes, nNodes );
+  RB_LAUNCH( "kd_finalize", k_kd_finalize, rb_div_up( nLevelNodes, TPB ), TPB, 0, nodes, nLevelNodes );
   if ( level + (int)h[4] + 2 >= KD_STACK ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree depth %d exceeds the traversal stack", level + (int)h[4] );
   }

@@ -8,13 +8,13 @@
 constexpr int KD_SMALL = 128;  // subtrees of at most this many points are built by one thread in shared memory
 
 struct RbKdBuild {
-  RbBuf    rec, nid, nodes, flags, pairL, pairR, sums, smallRoots, counters;
+  RbBuf    rec, nid, nodes, flags, pairL, pairR, sums, smallRoots, counters, stats;
   KdForest forest{};
   uint32_t nNodes = 0;
   int      nTrees = 0;
   int      levels = 0;
   void     release() {
-    RbBuf* b[] = {&rec, &nid, &nodes, &flags, &pairL, &pairR, &sums, &smallRoots, &counters};
+    RbBuf* b[] = {&rec, &nid, &nodes, &flags, &pairL, &pairR, &sums, &smallRoots, &counters, &stats};
     for ( auto* x : b ) { x->release(); }
   }
 };

@@ -335,7 +335,10 @@ __device__ __forceinline__ void rgb_to_yuv709( int r, int g, int b, float yuv[3]
 }
 
 struct Contribution {
-  double c2p, col[3];
+  double             c2p, col[3];
+  unsigned long long d2;        // squared distance to the nearest neighbour (exact)
+  double             c2p_max;   // same as c2p (kept separately so the reduction can take a maximum)
+  unsigned int       overflow;  // tie set larger than 30
 };
 
 template <int MODE>
@@ -364,10 +367,8 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     return;
   }
   // QualityMetrics::compute body for one point of A, PCCMetrics.cpp:92-191
-  Acc* acc = a.acc + d.acc;
-  atomicAdd( &acc->sse_c2c, (unsigned long long)t.best );
-  atomicMax( &acc->max_c2c, (unsigned long long)t.best );
-  if ( t.overflow ) { atomicAdd( &acc->tie_overflow, 1u ); }
+  out.d2       = t.best;
+  out.overflow = t.overflow ? 1u : 0u;
   sort_ties( t );
   const short4 pA = b.u_pos[uA];
   if ( a.compute_c2p && d.nrmA >= 0 && d.nrmB >= 0 ) {  // :113-124
@@ -382,7 +383,7 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     }
     const double v = sum / (double)t.n;
     out.c2p        = v;
-    atomicMax( &acc->max_c2p_bits, (unsigned long long)__double_as_longlong( v ) );
+    out.c2p_max    = v;
   }
   if ( a.compute_color ) {  // :126-178
     const uchar4 cA = b.u_col[uA];
@@ -474,6 +475,24 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
   if ( MODE == MODE_METRIC ) {  // fixed-order CTA reduction of the double contributions
     double    v[4] = {ct.c2p, ct.col[0], ct.col[1], ct.col[2]};
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    {  // exact integer sums / maxima: one atomic per warp instead of one per query
+      unsigned long long s2 = ct.d2, m2 = ct.d2, mp = (unsigned long long)__double_as_longlong( ct.c2p_max );
+      unsigned int       ov = ct.overflow;
+#pragma unroll
+      for ( int s = 16; s > 0; s >>= 1 ) {
+        s2 += __shfl_down_sync( 0xFFFFFFFFu, s2, s );
+        m2 = max( m2, __shfl_down_sync( 0xFFFFFFFFu, m2, s ) );
+        mp = max( mp, __shfl_down_sync( 0xFFFFFFFFu, mp, s ) );
+        ov += __shfl_down_sync( 0xFFFFFFFFu, ov, s );
+      }
+      if ( lane == 0 ) {
+        Acc* acc = a.acc + d.acc;
+        if ( s2 ) { atomicAdd( &acc->sse_c2c, s2 ); }
+        if ( m2 ) { atomicMax( &acc->max_c2c, m2 ); }
+        if ( mp ) { atomicMax( &acc->max_c2p_bits, mp ); }
+        if ( ov ) { atomicAdd( &acc->tie_overflow, ov ); }
+      }
+    }
 #pragma unroll
     for ( int k = 0; k < 4; k++ ) {
 #pragma unroll
@@ -571,6 +590,10 @@ __global__ void __launch_bounds__( TPB ) k_nn_far( const NNArgs a ) {
       consume<MODE>( a, d, uA, t, ct );
       if ( MODE == MODE_METRIC ) {
         Acc* acc = a.acc + d.acc;
+        atomicAdd( &acc->sse_c2c, ct.d2 );
+        atomicMax( &acc->max_c2c, ct.d2 );
+        atomicMax( &acc->max_c2p_bits, (unsigned long long)__double_as_longlong( ct.c2p_max ) );
+        if ( ct.overflow ) { atomicAdd( &acc->tie_overflow, 1u ); }
         atomicAdd( &acc->far_c2p, ct.c2p );
         atomicAdd( &acc->far_col[0], ct.col[0] );
         atomicAdd( &acc->far_col[1], ct.col[1] );

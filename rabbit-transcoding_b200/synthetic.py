@@ -314,7 +314,9 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
             top = 0
             while not placed and top < rows_cap - ch:
                 bot = min(rows_cap, top + ch + 64)
-                hit = _correlate_valid(grid[top:bot], cm)
+                # the decoder gives a block to the LAST patch whose bounding box covers it (PCCCodec.cpp:1725-1763), so
+                # a patch may sit in the holes of earlier bounding boxes but its own box must not cover occupied blocks
+                hit = _correlate_valid(grid[top:bot], np.ones_like(cm))
                 ys, xs = np.nonzero(hit == 0)
                 if len(ys):
                     y, x = int(ys[0]) + top, int(xs[0])
