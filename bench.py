@@ -140,12 +140,12 @@ def algorithmic_bytes(name, g, n_points, n_type1, n_moved):
         "reproject_emit": geo + occ + N * 6 + N * (6 + 6 + 2 + 4 + 8),
         "occupancy_bitmap": occ + F * H * ((W + 31) // 32) * 4,
         # B_geo split over its passes (pos+type 8 B, partition 4 B)
-        "mark_cells": N * 8,
+        # B_geo / B_col split over their passes (pos + type 8 B, partition 4 B, colour16 6 B, boundary index 4 B)
         "geo_accumulate": N * 12,
-        "geo_filter": N * 8 + n_moved * 8,
+        "geo_filter": n_type1 * (4 + 8) + n_moved * 8,
         "col_accumulate": N * (8 + 6 + 4),
         "col_scatter_lum": N * (8 + 2) + N * 2,
-        "col_filter": N * (8 + 6) + n_type1 * 6,
+        "col_filter": n_type1 * (4 + 8 + 6) + n_type1 * 6,
         "to_rgb8": N * (6 + 3),
     }
     return table.get(name)

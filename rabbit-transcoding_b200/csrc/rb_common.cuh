@@ -94,6 +94,8 @@ struct rb200_ctx {
   RbBuf d_rgb;   // uchar4  {r, g, b, 0}
   RbBuf d_pos_pre;  // copy of d_pos before geometry smoothing (tempFrameBuffer, PCCDecoder.cpp:435)
   RbBuf d_pack;     // staging for packed downloads
+  RbBuf d_blist, d_blist_n;  // indices of the boundary (type 1) points of the GOF + their count (device)
+  int64_t blist_cap = 0;     // that count on the host
   std::vector<int64_t>            h_frame_off;  // [F+1]
   std::vector<rb200_frame_counts> h_counts;
   RbBuf                           d_frame_off;  // [F+1] int64 on device

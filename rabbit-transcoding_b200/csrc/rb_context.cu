@@ -148,7 +148,7 @@ void rb200_destroy( rb200_ctx* c ) {
                    &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
                    &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
-                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off};
+                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n};
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }
   rb_metrics_release( c );

@@ -46,6 +46,8 @@ struct ReprojArgs {
   uint32_t*       part;
   RbFrameInfo*    finfo;
   short4*         eom_stage;
+  uint32_t*       blist;    // indices of the points classified as boundary (type 1)
+  uint32_t*       blist_n;
 };
 
 // PCCPatch::patch2Canvas restricted to one 16x16 block (PCCPatch.cpp:192-251)
@@ -197,13 +199,14 @@ __global__ void k_size_quantization( const RbPatch* __restrict__ patches, const 
 // K2 / K4: the per-pixel reprojection, as a counting pass (EMIT=false) and an emitting pass (EMIT=true).
 // 8 warps per CTA, one 16x16 patch block per warp.
 // ---------------------------------------------------------------------------------------------------
-constexpr int WARPS = 8;
+constexpr int WARPS = 4;
 
 struct TileSmem {
   uint16_t g[2][256];     // geometry D0 / D1 tile
   uint16_t a[2][3][256];  // attribute tiles
   uint32_t rows[20];      // occupancy bits of canvas rows Y0-2..Y0+17, bit k <-> x = X0-2+k
   uint32_t pad[4];
+  uint16_t desc[512];     // emission-ordered point descriptors: u1 | v1 << 4 | layer << 8 | boundary << 15
 };
 
 template <bool EMIT, bool EOM>
@@ -351,10 +354,96 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject( const ReprojArgs a 
 
   // ---- pass B: emit ----
   const int64_t base  = a.frame_off[f] + ( a.wi_base[wi] - a.wi_base[a.frame_wi_off[f]] ) + ( incl - myCount );
-  int64_t       ebase = 0;
-  if ( EOM ) { ebase = a.wi_eom_base[wi] + ( inclE - myEom ); }
-  int     k = 0, ke = 0;
   int     maxc = 0;
+  if ( !EOM ) {
+    // every lane lists its points (emission order = lane order) as descriptors in shared memory; then the warp walks
+    // the list 32 points at a time, so consecutive lanes compute and store consecutive points: full-line stores
+    {
+      int o = incl - myCount;
+#pragma unroll
+      for ( int j = 0; j < 8; j++ ) {
+        const int c = ( cnt4 >> ( 4 * j ) ) & 15;
+        if ( c > 0 ) { S.desc[o++] = (uint16_t)( ( ubase + j ) | ( v1 << 4 ) ); }
+        if ( c > 1 ) { S.desc[o++] = (uint16_t)( ( ubase + j ) | ( v1 << 4 ) | 0x100 ); }
+      }
+    }
+    const int     total = __shfl_sync( 0xFFFFFFFFu, incl, 31 );
+    const int64_t wbase = a.frame_off[f] + ( a.wi_base[wi] - a.wi_base[a.frame_wi_off[f]] );
+    __syncwarp();
+    int nb = 0;
+    for ( int k0 = 0; k0 < total; k0 += 32 ) {
+      const int k     = k0 + lane;
+      int       btype = 0;
+      if ( k < total ) {
+        const int d  = S.desc[k];
+        const int u1 = d & 15, vv1 = ( d >> 4 ) & 15, layer = ( d >> 8 ) & 1;
+        int       tx, ty;
+        tile_coord( p.orient, u1, vv1, tx, ty );
+        const int x = X0 + tx, y = Y0 + ty;
+        const int u = ub * 16 + u1, v = vb * 16 + vv1;
+        const int d0 = S.g[0][ty * 16 + tx];
+        // PCCPatch::generatePoint (PCCPatch.h:201-207)
+        int16_t Q[3] = {0, 0, 0};
+        set_axis( Q, p.tangent_axis, u * p.lodx + p.u1 );
+        set_axis( Q, p.bitangent_axis, v * p.lody + p.v1 );
+        if ( layer == 0 ) {
+          set_axis( Q, p.normal_axis, normal_coord( p, d0 ) );
+        } else {
+          const int g1 = S.g[1][ty * 16 + tx];
+          if ( a.absolute_d1 ) {
+            set_axis( Q, p.normal_axis, normal_coord( p, g1 ) );  // generatePoint( u, v, frame1 ), :503
+          } else {
+            const int n0 = (int16_t)normal_coord( p, d0 );
+            set_axis( Q, p.normal_axis, p.mode == 0 ? n0 + g1 : n0 - g1 );  // :505-509
+          }
+        }
+        if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
+        // boundary classification (identifyBoundaryPoints, :266-325) on the staged row masks
+        if ( a.classify ) {
+          const int      r  = ty + 2, kx = tx + 2;
+          const uint32_t m3 = 7u << ( kx - 1 ), m5 = 31u << ( kx - 2 );
+          if ( x == 0 || y == 0 || x == a.W - 1 || y == a.H - 1 ) {
+            btype = 1;
+          } else if ( ( S.rows[r - 1] & m3 ) != m3 || ( S.rows[r] & m3 ) != m3 || ( S.rows[r + 1] & m3 ) != m3 ) {
+            btype = 1;
+          } else if ( ( S.rows[r - 2] & m5 ) != m5 || ( S.rows[r - 1] & m5 ) != m5 || ( S.rows[r] & m5 ) != m5 ||
+                      ( S.rows[r + 1] & m5 ) != m5 || ( S.rows[r + 2] & m5 ) != m5 ) {
+            btype = 1;
+          } else if ( x == 1 || y == 1 || x == a.W - 2 || y == a.H - 2 ) {
+            btype = 1;
+          }
+        }
+        const int64_t o = wbase + k;
+        a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
+        ushort4 cv      = make_ushort4( 0, 0, 0, (unsigned short)layer );
+        if ( a.attr_count > 0 ) {
+          cv = make_ushort4( S.a[layer][0][ty * 16 + tx], S.a[layer][1][ty * 16 + tx], S.a[layer][2][ty * 16 + tx],
+                             (unsigned short)layer );
+        }
+        a.col[o]  = cv;
+        a.pix[o]  = (uint32_t)x | ( (uint32_t)y << 16 );
+        a.part[o] = (uint32_t)p.frame_patch;
+        maxc      = max( maxc, max( (int)Q[0], max( (int)Q[1], (int)Q[2] ) ) );
+        if ( btype ) { S.desc[k] = (uint16_t)( d | 0x8000 ); }
+      }
+      nb += __popc( __ballot_sync( 0xFFFFFFFFu, btype != 0 ) );
+    }
+    if ( nb > 0 ) {  // boundary list: one atomic per patch block, entries written 32 at a time
+      uint32_t lb = 0;
+      if ( lane == 0 ) { lb = atomicAdd( a.blist_n, (uint32_t)nb ); }
+      lb = __shfl_sync( 0xFFFFFFFFu, lb, 0 );
+      __syncwarp();
+      for ( int k0 = 0; k0 < total; k0 += 32 ) {
+        const int      k    = k0 + lane;
+        const bool     isb  = k < total && ( S.desc[k] & 0x8000 );
+        const uint32_t bal  = __ballot_sync( 0xFFFFFFFFu, isb );
+        if ( isb ) { a.blist[lb + __popc( bal & ( ( 1u << lane ) - 1u ) )] = (uint32_t)( wbase + k ); }
+        lb += __popc( bal );
+      }
+    }
+  } else {
+  int64_t ebase = a.wi_eom_base[wi] + ( inclE - myEom );
+  int     k = 0, ke = 0;
 #pragma unroll
   for ( int j = 0; j < 8; j++ ) {
     const int c = ( cnt4 >> ( 4 * j ) ) & 15;
@@ -486,6 +575,7 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject( const ReprojArgs a 
         }
       }
     }
+  }
   }
   // per-frame max coordinate, feeds the geometry-smoothing grid width (:68-79)
 #pragma unroll
@@ -665,7 +755,8 @@ __global__ void k_raw_points( const RawDesc* __restrict__ descs, const FrameLayo
 // boundary classification as a separate pass (:953-973) — needed when EOM marks changed the occupancy map
 // after the regular points were emitted.  Covers regular + EOM points (not raw points).
 __global__ void k_classify_points( const FrameLayout* __restrict__ layout, int F, const uint32_t* __restrict__ bitmap,
-                                   int W, int H, int words, const uint32_t* __restrict__ pix, short4* __restrict__ pos ) {
+                                   int W, int H, int words, const uint32_t* __restrict__ pix, short4* __restrict__ pos,
+                                   uint32_t* __restrict__ blist, uint32_t* __restrict__ blist_n ) {
   const int          f = blockIdx.y;
   const FrameLayout  L = layout[f];
   const int64_t      n = L.regular + L.eom;
@@ -696,7 +787,10 @@ __global__ void k_classify_points( const FrameLayout* __restrict__ layout, int F
       }
       if ( !t && ( x == 1 || y == 1 || x == W - 2 || y == H - 2 ) ) { t = 1; }
     }
-    if ( t ) { pos[L.off + i].w = 1; }
+    if ( t ) {
+      pos[L.off + i].w                = 1;
+      blist[atomicAdd( blist_n, 1u )] = (uint32_t)( L.off + i );
+    }
   }
 }
 
@@ -912,6 +1006,11 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.col  = c->d_col.as<ushort4>();
   a.pix  = c->d_pix.as<uint32_t>();
   a.part = c->d_part.as<uint32_t>();
+  RB_CUDA( c->d_blist.ensure( cap * 4 ) );
+  RB_CUDA( c->d_blist_n.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( c->d_blist_n.p, 0, 4, c->stream ) );
+  a.blist   = c->d_blist.as<uint32_t>();
+  a.blist_n = c->d_blist_n.as<uint32_t>();
   if ( eom ) {
     // staged EOM extras (per patch, emission order)
     int64_t* hb = (int64_t*)rb_pinned( c, 64 );
@@ -959,7 +1058,13 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   }
   if ( classify && eom ) {
     RB_LAUNCH( "classify_points", k_classify_points, dim3( 256, F ), 256, 0, (const FrameLayout*)( dS + oLayout ), F,
-               c->d_bitmap.as<uint32_t>(), c->W, c->H, c->bmWords, a.pix, a.pos );
+               c->d_bitmap.as<uint32_t>(), c->W, c->H, c->bmWords, a.pix, a.pos, a.blist, a.blist_n );
+  }
+  {  // length of the boundary list (launch size of the smoothing filters)
+    uint32_t* hb = (uint32_t*)rb_pinned( c, 64 );
+    RB_CUDA( cudaMemcpyAsync( hb, a.blist_n, 4, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    c->blist_cap = hb[0];
   }
   return RB200_OK;
 }

@@ -23,30 +23,47 @@
 
 namespace {
 
-struct Cell {  // compact accumulator of one marked cell; all-zero == empty
-  uint32_t cnt;
-  uint32_t s0, s1, s2;   // coordinate sums (geometry) / colour sums (colour)
-  uint32_t pmax, pinv;   // max(partition+1), max(0xFFFFFFFF - (partition+1))
+struct Cell {  // accumulator of one occupied cell; all-zero == empty.  32 bytes, 8-byte aligned pairs
+  uint32_t cnt, s0;      // {cnt, s0} and {s1, s2} are each updated with ONE 64-bit atomic add
+  uint32_t s1, s2;       // coordinate sums (geometry) / colour sums (colour)
+  uint32_t pfirst;       // partition + 1 of the first point that reached the cell (0: none yet)
+  uint32_t multi;        // 1 once a second, different partition was seen: the reference's doSmooth (:989-995)
   uint32_t lum_off;      // colour: start of the cell's luma list;   geometry: unused
   uint32_t aux;          // colour: scatter cursor, then the mean/median gate flag
 };
+__device__ __forceinline__ bool cell_do_smooth( const Cell& c ) { return c.cnt != 0 && c.multi != 0; }
+__device__ __forceinline__ Cell cell_load( const Cell* p ) {  // read-only path (filters): two 16-byte non-coherent loads
+  const uint4 lo = __ldg( reinterpret_cast<const uint4*>( p ) ), hi = __ldg( reinterpret_cast<const uint4*>( p ) + 1 );
+  Cell        c;
+  c.cnt = lo.x, c.s0 = lo.y, c.s1 = lo.z, c.s2 = lo.w, c.pfirst = hi.x, c.multi = hi.y, c.lum_off = hi.z, c.aux = hi.w;
+  return c;
+}
 
+// The reference walks a dense int grid (w^3 ints per frame, memset every frame).  Here every frame owns an
+// open-addressing hash table keyed by the cell coordinates: 4x4x4 neighbourhoods of cells share 64 consecutive slots,
+// so the 2x2x2 cells a boundary point reads sit in one or two cache lines and the whole table of a frame (a few MB)
+// stays in L2 while that frame is being processed.  Every occupied cell is accumulated (the reference only
+// accumulates cells marked by a boundary point, but its filter never reads any other cell, so the result is the
+// same and the marking pass disappears).  Claimed slots are recorded and reset by the cleanup pass.
 struct GridArgs {
   int            F;
   int            g;          // cell size
-  int            wmax;       // dense grid stride (cells per axis)
+  int            wmax;       // cells per axis
   int            by_bbox;    // geometry: th = g * ceil(maxCoord / g); colour: th = 2^bitdepth
   int            pcmax;      // 2^geometryBitDepth3D
-  int32_t*       grid;       // [F][wmax^3]
-  Cell*          cells;
-  uint64_t*      cell_addr;  // grid address of every claimed cell (for cleanup)
-  int64_t        cell_cap;
-  int32_t*       counters;   // [0] cells claimed, [1] overflow flag, [2] luma cursor
+  uint32_t*      keys;       // [F][slots] 0 = empty, else (cx | cy << 10 | cz << 20) + 1
+  Cell*          cells;      // [F][slots]
+  uint32_t       slots;      // per frame, power of two
+  uint32_t*      used;       // global slot index of every claimed slot (cleanup list)
+  uint32_t       used_cap;
+  int32_t*       counters;   // [0] claimed slots, [1] overflow flag, [2] luma cursor
   const int64_t* frame_off;
   RbFrameInfo*   finfo;
   short4*        pos;
   ushort4*       col;
   const uint32_t* part;
+  const uint32_t* blist;     // indices of the points classified as boundary (type 1) by the reconstruction
+  const uint32_t* blist_n;
 };
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -72,102 +89,150 @@ __device__ __forceinline__ bool inside( int x, int y, int z, int disth, int th )
   return !( x < disth || y < disth || z < disth || th <= x + disth || th <= y + disth || th <= z + disth );
 }
 
-// ---- pass 1: type-1 points inside the margin claim their 2x2x2 cell neighbourhood (:89-112, :171-195) ----
-__global__ void k_mark_cells( const GridArgs a, int64_t n ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4 p = a.pos[i];
-  if ( p.w != 1 ) { return; }
-  const int f     = frame_of( a.frame_off, a.F, i );
-  const int disth = max( a.g / 2, 1 ), th = grid_th( a, f );
-  if ( !inside( p.x, p.y, p.z, disth, th ) ) { return; }
-  const int     g  = a.g, hg = g / 2;
-  const int     qx = p.x / g + ( ( p.x % g < hg ) ? -1 : 0 );
-  const int     qy = p.y / g + ( ( p.y % g < hg ) ? -1 : 0 );
-  const int     qz = p.z / g + ( ( p.z % g < hg ) ? -1 : 0 );
-  const int64_t w  = a.wmax;
-  int32_t*      G  = a.grid + (size_t)f * w * w * w;
-  for ( int k = 0; k < 8; k++ ) {
-    const int64_t cid = ( qx + ( k & 1 ) ) + ( qy + ( ( k >> 1 ) & 1 ) ) * w + ( qz + ( k >> 2 ) ) * w * w;
-    if ( G[cid] != -1 ) { continue; }
-    if ( atomicCAS( &G[cid], -1, -2 ) == -1 ) {
-      const int idx = atomicAdd( &a.counters[0], 1 );
-      if ( idx < a.cell_cap ) {
-        a.cell_addr[idx] = (uint64_t)( (size_t)f * w * w * w + cid );
-        atomicExch( &G[cid], idx );
-      } else {
-        a.counters[1] = 1;          // overflow: host grows the tables and repeats the pass
-        atomicExch( &G[cid], -1 );  // leave the grid clean
+__device__ __forceinline__ uint32_t cell_key( int cx, int cy, int cz ) {
+  return ( (uint32_t)cx | ( (uint32_t)cy << 10 ) | ( (uint32_t)cz << 20 ) ) + 1u;
+}
+__device__ __forceinline__ uint32_t cell_home( int cx, int cy, int cz, uint32_t mask ) {
+  const uint32_t h = ( (uint32_t)( cx >> 2 ) * 73856093u ) ^ ( (uint32_t)( cy >> 2 ) * 19349663u ) ^ ( (uint32_t)( cz >> 2 ) * 83492791u );
+  return ( ( h << 6 ) | (uint32_t)( ( cx & 3 ) | ( ( cy & 3 ) << 2 ) | ( ( cz & 3 ) << 4 ) ) ) & mask;
+}
+constexpr int MAX_PROBES = 64;
+
+// slot of the cell (global index), or 0xFFFFFFFF when the cell holds no point
+__device__ __forceinline__ uint32_t cell_find( const GridArgs& a, int f, int cx, int cy, int cz ) {
+  const uint32_t mask = a.slots - 1, key = cell_key( cx, cy, cz );
+  uint32_t       s    = cell_home( cx, cy, cz, mask );
+  const uint32_t base = (uint32_t)f * a.slots;
+  for ( int k = 0; k < MAX_PROBES; k++ ) {
+    const uint32_t v = __ldg( a.keys + base + s );  // the keys are final once the accumulate kernel has finished
+    if ( v == key ) { return base + s; }
+    if ( v == 0 ) { return 0xFFFFFFFFu; }
+    s = ( s + 64 ) & mask;
+  }
+  return 0xFFFFFFFFu;
+}
+// find or claim; 0xFFFFFFFF on table overflow (flagged)
+__device__ __forceinline__ uint32_t cell_claim( const GridArgs& a, int f, int cx, int cy, int cz ) {
+  const uint32_t mask = a.slots - 1, key = cell_key( cx, cy, cz );
+  uint32_t       s    = cell_home( cx, cy, cz, mask );
+  const uint32_t base = (uint32_t)f * a.slots;
+  for ( int k = 0; k < MAX_PROBES; k++ ) {
+    uint32_t v = a.keys[base + s];
+    if ( v == 0 ) {
+      v = atomicCAS( &a.keys[base + s], 0u, key );
+      if ( v == 0 ) {
+        const int i = atomicAdd( &a.counters[0], 1 );
+        if ( (uint32_t)i < a.used_cap ) {
+          a.used[i] = base + s;
+        } else {
+          a.counters[1] = 1;
+        }
+        return base + s;
       }
+    }
+    if ( v == key ) { return base + s; }
+    s = ( s + 64 ) & mask;
+  }
+  a.counters[1] = 1;
+  return 0xFFFFFFFFu;
+}
+
+// warp-aggregated accumulation: lanes that hit the same cell are reduced with one hardware warp reduction per field
+// and their leader issues the atomics (points arrive in patch-block order, so a warp touches one to four cells)
+__device__ __forceinline__ void cell_accumulate( const GridArgs& a, bool valid, uint32_t slot, uint32_t v0, uint32_t v1,
+                                                 uint32_t v2, uint32_t pp ) {
+  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, valid );
+  if ( !valid ) { return; }
+  const uint32_t peers = __match_any_sync( act, slot );
+  const uint32_t n     = __popc( peers );
+  const uint32_t t0 = __reduce_add_sync( peers, v0 ), t1 = __reduce_add_sync( peers, v1 ), t2 = __reduce_add_sync( peers, v2 );
+  const uint32_t mx = __reduce_max_sync( peers, pp ), mn = __reduce_min_sync( peers, pp );
+  if ( ( threadIdx.x & 31 ) == __ffs( peers ) - 1 ) {
+    Cell* c = a.cells + slot;
+    atomicAdd( (unsigned long long*)&c->cnt, (unsigned long long)n | ( (unsigned long long)t0 << 32 ) );
+    atomicAdd( (unsigned long long*)&c->s1, (unsigned long long)t1 | ( (unsigned long long)t2 << 32 ) );
+    if ( mx != mn ) {
+      c->multi = 1;  // two partitions inside this very group
+      atomicCAS( &c->pfirst, 0u, mx );
+    } else {
+      const uint32_t old = atomicCAS( &c->pfirst, 0u, mx );
+      if ( old != 0 && old != mx ) { c->multi = 1; }
     }
   }
 }
 
-// ---- pass 2 (geometry): every inside point whose own cell is claimed accumulates (:120-134, :980-998) ----
-__global__ void k_accumulate_geo( const GridArgs a, int64_t n ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4 p     = a.pos[i];
-  const int    f     = frame_of( a.frame_off, a.F, i );
-  const int    disth = max( a.g / 2, 1 ), th = grid_th( a, f );
-  if ( !inside( p.x, p.y, p.z, disth, th ) ) { return; }
-  const int64_t w   = a.wmax;
-  const int64_t cid = ( p.x / a.g ) + ( p.y / a.g ) * w + ( p.z / a.g ) * w * w;
-  const int     idx = a.grid[(size_t)f * w * w * w + cid];
-  if ( idx < 0 ) { return; }
-  Cell*          c  = a.cells + idx;
-  const uint32_t pp = a.part[i] + 1u;
-  atomicAdd( &c->cnt, 1u );
-  atomicAdd( &c->s0, (uint32_t)p.x );
-  atomicAdd( &c->s1, (uint32_t)p.y );
-  atomicAdd( &c->s2, (uint32_t)p.z );
-  atomicMax( &c->pmax, pp );
-  atomicMax( &c->pinv, 0xFFFFFFFFu - pp );
-}
-
-// ---- pass 2 (colour): every point (no margin test, :208-224) whose own cell is claimed accumulates ----
-__global__ void k_accumulate_col( const GridArgs a, int64_t n ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4  p = a.pos[i];
-  const int     f = frame_of( a.frame_off, a.F, i );
-  const int64_t w = a.wmax;
-  if ( p.x < 0 || p.y < 0 || p.z < 0 ) { return; }
-  const int64_t cid = ( p.x / a.g ) + ( p.y / a.g ) * w + ( p.z / a.g ) * w * w;
-  if ( cid >= w * w * w || p.x / a.g >= w || p.y / a.g >= w ) { return; }  // :212 guard
-  const int idx = a.grid[(size_t)f * w * w * w + cid];
-  if ( idx < 0 ) { return; }
-  Cell*          c  = a.cells + idx;
-  const ushort4  cv = a.col[i];
-  const uint32_t pp = a.part[i] + 1u;
-  atomicAdd( &c->cnt, 1u );
-  atomicAdd( &c->s0, (uint32_t)cv.x );
-  atomicAdd( &c->s1, (uint32_t)cv.y );
-  atomicAdd( &c->s2, (uint32_t)cv.z );
-  atomicMax( &c->pmax, pp );
-  atomicMax( &c->pinv, 0xFFFFFFFFu - pp );
-}
-
-// exactness guard of App. A.3 + luma list allocation (colour)
-__global__ void k_finalize_cells( const GridArgs a, int nCells, int colour, int64_t wcube ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nCells ) { return; }
-  Cell* c = a.cells + i;
-  if ( c->s0 >= ( 1u << 24 ) || c->s1 >= ( 1u << 24 ) || c->s2 >= ( 1u << 24 ) || c->cnt > 65535u ) {
-    const int f = (int)( a.cell_addr[i] / (uint64_t)wcube );
-    a.finfo[f].sum_overflow = 1;
+// ---- geometry: every inside point accumulates into its own cell (:120-134, :980-998) ----
+__global__ void __launch_bounds__( 256 ) k_accumulate_geo( const GridArgs a, int64_t n ) {
+  const int64_t i     = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool          valid = false;
+  uint32_t      slot = 0, pp = 0;
+  short4        p = make_short4( 0, 0, 0, 0 );
+  if ( i < n ) {
+    p               = a.pos[i];
+    const int f     = frame_of( a.frame_off, a.F, i );
+    const int disth = max( a.g / 2, 1 ), th = grid_th( a, f );
+    if ( inside( p.x, p.y, p.z, disth, th ) ) {
+      slot  = cell_claim( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
+      valid = slot != 0xFFFFFFFFu;
+      pp    = a.part[i] + 1u;
+    }
   }
-  if ( colour ) {
-    c->lum_off = (uint32_t)atomicAdd( &a.counters[2], (int)c->cnt );
+  cell_accumulate( a, valid, slot, (uint32_t)p.x, (uint32_t)p.y, (uint32_t)p.z, pp );
+}
+
+// ---- colour: every point (no margin test, :208-224) accumulates its colour ----
+__global__ void __launch_bounds__( 256 ) k_accumulate_col( const GridArgs a, int64_t n ) {
+  const int64_t i     = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool          valid = false;
+  uint32_t      slot = 0, pp = 0;
+  ushort4       cv = make_ushort4( 0, 0, 0, 0 );
+  if ( i < n ) {
+    const short4 p = a.pos[i];
+    const int    f = frame_of( a.frame_off, a.F, i );
+    if ( p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x / a.g < a.wmax && p.y / a.g < a.wmax && p.z / a.g < a.wmax ) {  // :212 guard
+      slot  = cell_claim( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
+      valid = slot != 0xFFFFFFFFu;
+      cv    = a.col[i];
+      pp    = a.part[i] + 1u;
+    }
+  }
+  cell_accumulate( a, valid, slot, cv.x, cv.y, cv.z, pp );
+}
+
+// exactness guard of App. A.3 + luma list allocation (colour), over the claimed slots
+__global__ void k_finalize_cells( const GridArgs a, int nUsed, int colour ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= nUsed ) { return; }
+  const uint32_t slot = a.used[i];
+  Cell*          c    = a.cells + slot;
+  if ( c->s0 >= ( 1u << 24 ) || c->s1 >= ( 1u << 24 ) || c->s2 >= ( 1u << 24 ) || c->cnt > 65535u ) {
+    a.finfo[slot / a.slots].sum_overflow = 1;
+  }
+  if ( colour ) {  // luma list offsets: one atomic per warp, shuffle prefix inside
+    const uint32_t want = c->cnt > 1 ? c->cnt : 0u;
+    const uint32_t act  = __activemask();
+    const int      lane = threadIdx.x & 31;
+    uint32_t       incl = want;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+      const uint32_t t = __shfl_up_sync( act, incl, d );
+      if ( lane >= d && ( act >> ( lane - d ) & 1u ) ) { incl += t; }
+    }
+    const int last = 31 - __clz( act );
+    uint32_t  base = 0;
+    if ( lane == last ) { base = (uint32_t)atomicAdd( &a.counters[2], (int)incl ); }
+    base       = __shfl_sync( act, base, last );
+    c->lum_off = base + incl - want;
     c->aux     = 0;
   }
 }
 
 // ---- geometry filter: smoothPointCloudGrid + gridFiltering (:1000-1104) ----
-__global__ void k_filter_geo( const GridArgs a, int64_t n, double threshold ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4 p = a.pos[i];
+__global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double threshold ) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( li >= *a.blist_n ) { return; }
+  const int64_t i = a.blist[li];
+  const short4  p = a.pos[i];
   if ( p.w != 1 ) { return; }  // :1087
   const int f     = frame_of( a.frame_off, a.F, i );
   const int g     = a.g, hg = g / 2;
@@ -176,17 +241,18 @@ __global__ void k_filter_geo( const GridArgs a, int64_t n, double threshold ) {
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
-  const int64_t  w = a.wmax;
-  const int32_t* G = a.grid + (size_t)f * w * w * w;
-  int            idx[8];
-  bool           other = false;
-  uint32_t       cnt[8];
+  Cell     cl[8];
+  bool     other = false;
+  uint32_t cnt[8];
   for ( int k = 0; k < 8; k++ ) {  // k = dz*4 + dy*2 + dx, the reference's loop order (:1019-1027)
-    const int dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
-    idx[k]       = G[( S[0] + dx ) + ( S[1] + dy ) * w + ( S[2] + dz ) * w * w];
-    const Cell* c = a.cells + idx[k];
-    cnt[k]        = c->cnt;
-    if ( cnt[k] != 0 && c->pmax != 0xFFFFFFFFu - c->pinv ) { other = true; }  // doSmooth && count (:1024)
+    const int      dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
+    const uint32_t ix = cell_find( a, f, S[0] + dx, S[1] + dy, S[2] + dz );
+    cnt[k]            = 0;
+    if ( ix != 0xFFFFFFFFu ) {
+      cl[k]  = cell_load( a.cells + ix );
+      cnt[k] = cl[k].cnt;
+      if ( cell_do_smooth( cl[k] ) ) { other = true; }  // doSmooth && count (:1024)
+    }
   }
   if ( !other ) { return; }  // :1028
   const int    g2 = 2 * g;
@@ -202,7 +268,7 @@ __global__ void k_filter_geo( const GridArgs a, int64_t n, double threshold ) {
     const int    wgt = ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] );
     double       v[3];
     if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
-      const Cell* c = a.cells + idx[k];
+      const Cell* c = &cl[k];
       const float fc = (float)cnt[k];
       v[0]           = (double)__fdiv_rn( (float)c->s0, fc );
       v[1]           = (double)__fdiv_rn( (float)c->s1, fc );
@@ -246,21 +312,18 @@ __global__ void k_filter_geo( const GridArgs a, int64_t n, double threshold ) {
 }
 
 // ---- colour: scatter lumas into the per-cell lists (colorSmoothingLum_, :1179) ----
-__global__ void k_scatter_lum( const GridArgs a, int64_t n, uint16_t* __restrict__ lum ) {
+__global__ void __launch_bounds__( 256 ) k_scatter_lum( const GridArgs a, int64_t n, uint16_t* __restrict__ lum ) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( i >= n ) { return; }
-  const short4  p = a.pos[i];
-  const int     f = frame_of( a.frame_off, a.F, i );
-  const int64_t w = a.wmax;
-  if ( p.x < 0 || p.y < 0 || p.z < 0 ) { return; }
-  const int64_t cid = ( p.x / a.g ) + ( p.y / a.g ) * w + ( p.z / a.g ) * w * w;
-  if ( cid >= w * w * w || p.x / a.g >= w || p.y / a.g >= w ) { return; }
-  const int idx = a.grid[(size_t)f * w * w * w + cid];
-  if ( idx < 0 ) { return; }
-  Cell* c = a.cells + idx;
+  const short4 p = a.pos[i];
+  const int    f = frame_of( a.frame_off, a.F, i );
+  if ( p.x < 0 || p.y < 0 || p.z < 0 || p.x / a.g >= a.wmax || p.y / a.g >= a.wmax || p.z / a.g >= a.wmax ) { return; }
+  const uint32_t slot = cell_find( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
+  if ( slot == 0xFFFFFFFFu ) { return; }
+  Cell* c = a.cells + slot;
   if ( c->cnt < 2 ) { return; }  // the median is only consulted for count > 1 (:1228, :1239)
-  const uint32_t slot       = atomicAdd( &c->aux, 1u );
-  lum[c->lum_off + slot]    = a.col[i].x;
+  const uint32_t k       = atomicAdd( &c->aux, 1u );
+  lum[c->lum_off + k]    = a.col[i].x;
 }
 
 // ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243); one warp per cell, rank selection ----
@@ -268,7 +331,7 @@ __global__ void k_cell_median_gate( const GridArgs a, int nCells, const uint16_t
   const int cell = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
   const int lane = threadIdx.x & 31;
   if ( cell >= nCells ) { return; }
-  Cell*     c = a.cells + cell;
+  Cell*     c = a.cells + a.used[cell];
   const int n = (int)c->cnt;
   if ( n < 2 ) {
     if ( lane == 0 ) { c->aux = 0; }
@@ -302,10 +365,11 @@ __global__ void k_cell_median_gate( const GridArgs a, int nCells, const uint16_t
 }
 
 // ---- colour filter: smoothPointCloudColorLC + gridFilteringColor (:1182-1306) ----
-__global__ void k_filter_col( const GridArgs a, int64_t n, double thrSmoothing, double yThresh ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4 p = a.pos[i];
+__global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( li >= *a.blist_n ) { return; }
+  const int64_t i = a.blist[li];
+  const short4  p = a.pos[i];
   if ( p.w != 1 ) { return; }  // :1288
   const int g = a.g, hg = g / 2, disth = max( hg, 1 );
   if ( !inside( p.x, p.y, p.z, disth, a.pcmax ) ) { return; }  // :1280-1283
@@ -313,15 +377,16 @@ __global__ void k_filter_col( const GridArgs a, int64_t n, double thrSmoothing, 
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
-  const int64_t  w = a.wmax;
-  const int32_t* G = a.grid + (size_t)f * w * w * w;
-  int            idx[8];
-  bool           other = false;
+  Cell cl[8];
+  bool other = false;
   for ( int k = 0; k < 8; k++ ) {
-    const int dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
-    idx[k]       = G[( S[0] + dx ) + ( S[1] + dy ) * w + ( S[2] + dz ) * w * w];
-    const Cell* c = a.cells + idx[k];
-    if ( c->cnt != 0 && c->pmax != 0xFFFFFFFFu - c->pinv ) { other = true; }  // :1204
+    const int      dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
+    const uint32_t ix = cell_find( a, f, S[0] + dx, S[1] + dy, S[2] + dz );
+    cl[k].cnt         = 0;
+    if ( ix != 0xFFFFFFFFu ) {
+      cl[k] = cell_load( a.cells + ix );
+      if ( cell_do_smooth( cl[k] ) ) { other = true; }  // :1204
+    }
   }
   if ( !other ) { return; }  // :1210
   const ushort4 cv     = a.col[i];
@@ -336,7 +401,7 @@ __global__ void k_filter_col( const GridArgs a, int64_t n, double thrSmoothing, 
   double Y0       = 0.0;
   bool   keep_own = false;
   for ( int k = 0; k < 8; k++ ) {  // :1218-1251, loop order dz, dy, dx
-    const Cell* c = a.cells + idx[k];
+    const Cell* c = &cl[k];
     double*     d = c3[k];
     if ( c->cnt > 0 ) {
       const double dn = (double)c->cnt;
@@ -392,13 +457,14 @@ __global__ void k_filter_col( const GridArgs a, int64_t n, double thrSmoothing, 
   }
 }
 
-// ---- cleanup: reset exactly the claimed grid cells and accumulators ----
-__global__ void k_cleanup_cells( const GridArgs a, int nCells ) {
+// ---- cleanup: reset exactly the claimed slots ----
+__global__ void k_cleanup_cells( const GridArgs a, int nUsed ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nCells ) { return; }
-  a.grid[a.cell_addr[i]] = -1;
+  if ( i >= nUsed ) { return; }
+  const uint32_t slot = a.used[i];
+  a.keys[slot]        = 0;
   Cell z{};
-  a.cells[i] = z;
+  a.cells[slot] = z;
 }
 
 // ---- convertYUV16ToRGB8 (PCCPointSet.h:133-166) / copyRGB16ToRGB8 (:121-127) ----
@@ -431,54 +497,47 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
   rgb[i]   = make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
 }
 
-__global__ void k_fill_i32( int32_t* p, int64_t n, int32_t v ) {
-  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) { p[i] = v; }
+// table geometry + (re)allocation; the tables are all-zero between calls (cleanup resets exactly what was claimed)
+int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& used, RbBuf& counters, int g, int wmax ) {
+  if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
+  int64_t maxFrame = 1;
+  for ( int f = 0; f < c->F; f++ ) { maxFrame = std::max<int64_t>( maxFrame, c->h_frame_off[f + 1] - c->h_frame_off[f] ); }
+  int64_t want = std::min<int64_t>( 2 * maxFrame, std::max<int64_t>( 4096, 4 * maxFrame / ( (int64_t)g * g ) ) );
+  uint32_t slots = 4096;
+  while ( (int64_t)slots < want ) { slots <<= 1; }
+  const size_t nSlots = (size_t)c->F * slots;
+  if ( nSlots >= ( 1ull << 32 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing hash table too large" ); }
+  const size_t usedCap = (size_t)c->h_frame_off[c->F] + 1024;  // a cell holds at least one point
+  if ( keys.cap < nSlots * 4 || cells.cap < nSlots * sizeof( Cell ) ) {
+    RB_CUDA( keys.ensure( nSlots * 4 ) );
+    RB_CUDA( cells.ensure( nSlots * sizeof( Cell ) ) );
+    RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
+  }
+  RB_CUDA( used.ensure( usedCap * 4 ) );
+  RB_CUDA( counters.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( counters.p, 0, 16, c->stream ) );
+  a.keys     = keys.as<uint32_t>();
+  a.cells    = cells.as<Cell>();
+  a.slots    = slots;
+  a.used     = used.as<uint32_t>();
+  a.used_cap = (uint32_t)usedCap;
+  a.counters = counters.as<int32_t>();
+  return RB200_OK;
 }
 
-// shared driver of the mark pass (with table growth)
-int run_mark( rb200_ctx* c, GridArgs& a, RbBuf& cellsBuf, RbBuf& addrBuf, int64_t& cellCap, int64_t n, int* nCellsOut,
-              const char* name ) {
-  for ( int attempt = 0; attempt < 3; attempt++ ) {
-    a.cells     = cellsBuf.as<Cell>();
-    a.cell_addr = addrBuf.as<uint64_t>();
-    a.cell_cap  = cellCap;
-    RB_CUDA( cudaMemsetAsync( a.counters, 0, 16, c->stream ) );
-    RB_LAUNCH( "mark_cells", k_mark_cells, rb_div_up( n, 256 ), 256, 0, a, n );
-    int32_t* h = (int32_t*)rb_pinned( c, 64 );
-    if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-    RB_CUDA( cudaMemcpyAsync( h, a.counters, 16, cudaMemcpyDeviceToHost, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
-    c->stats.d2h_bytes += 16;
-    const int claimed = h[0], overflow = h[1];
-    if ( !overflow ) {
-      *nCellsOut = claimed;
-      return RB200_OK;
-    }
-    // undo the cells that were claimed, grow, repeat
-    const int kept = (int)std::min<int64_t>( claimed, cellCap );
-    if ( kept > 0 ) { RB_LAUNCH( "cleanup_cells", k_cleanup_cells, rb_div_up( kept, 256 ), 256, 0, a, kept ); }
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
-    const int64_t want = (int64_t)claimed + claimed / 4 + 1024;
-    RB_CUDA( cellsBuf.ensure( (size_t)want * sizeof( Cell ) ) );
-    RB_CUDA( addrBuf.ensure( (size_t)want * 8 ) );
-    RB_CUDA( cudaMemsetAsync( cellsBuf.p, 0, (size_t)want * sizeof( Cell ), c->stream ) );
-    cellCap = want;
-    (void)name;
+// claimed-slot count + overflow flag (one small read-back; the launch sizes of the per-cell kernels need it)
+int read_counters( rb200_ctx* c, const GridArgs& a, int* nUsed ) {
+  int32_t* h = (int32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( h, a.counters, 16, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.d2h_bytes += 16;
+  *nUsed = std::min<int64_t>( h[0], a.used_cap );
+  if ( h[1] ) {
+    // leave the tables clean before failing
+    return -1;
   }
-  return rb_fail( c, RB200_ERR_NOMEM, "cell table did not converge" );
-}
-
-int ensure_grid( rb200_ctx* c, RbBuf& gridBuf, int& curW, int& curF, int w, int F ) {
-  const size_t cells = (size_t)F * w * w * w;
-  if ( gridBuf.p && curW == w && curF >= F ) { return RB200_OK; }
-  cudaError_t e = gridBuf.ensure( cells * 4 );
-  if ( e != cudaSuccess ) {
-    cudaGetLastError();
-    return rb_fail( c, RB200_ERR_NOMEM, "cannot allocate the %d^3 x %d-frame cell grid (%zu MB)", w, F, cells * 4 >> 20 );
-  }
-  RB_LAUNCH( "grid_init", k_fill_i32, 148 * 8, 256, 0, gridBuf.as<int32_t>(), (int64_t)( gridBuf.cap / 4 ), -1 );
-  curW = w;
-  curF = F;
   return RB200_OK;
 }
 
@@ -497,37 +556,34 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     RB_CUDA( c->d_pos_pre.ensure( (size_t)n * 8 ) );
     RB_CUDA( cudaMemcpyAsync( c->d_pos_pre.p, c->d_pos.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream ) );
   }
-  int r = ensure_grid( c, c->d_geo_grid, c->geo_grid_w, c->geo_grid_frames, wmax, c->F );
-  if ( r ) { return r; }
-  RB_CUDA( c->d_scratch[2].ensure( 64 ) );
-  if ( c->geo_cell_cap == 0 ) {
-    c->geo_cell_cap = 1 << 16;
-    RB_CUDA( c->d_geo_cells.ensure( (size_t)c->geo_cell_cap * sizeof( Cell ) ) );
-    RB_CUDA( c->d_geo_cell_ids.ensure( (size_t)c->geo_cell_cap * 8 ) );
-    RB_CUDA( cudaMemsetAsync( c->d_geo_cells.p, 0, (size_t)c->geo_cell_cap * sizeof( Cell ), c->stream ) );
-  }
   GridArgs a{};
   a.F         = c->F;
   a.g         = g;
   a.wmax      = wmax;
   a.by_bbox   = 1;
   a.pcmax     = pcmax;
-  a.grid      = c->d_geo_grid.as<int32_t>();
-  a.counters  = c->d_scratch[2].as<int32_t>();
   a.frame_off = c->d_frame_off.as<int64_t>();
   a.finfo     = c->d_frame_info.as<RbFrameInfo>();
   a.pos       = c->d_pos.as<short4>();
   a.col       = c->d_col.as<ushort4>();
   a.part      = c->d_part.as<uint32_t>();
-  int nCells  = 0;
-  r           = run_mark( c, a, c->d_geo_cells, c->d_geo_cell_ids, c->geo_cell_cap, n, &nCells, "geo" );
+  a.blist     = c->d_blist.as<uint32_t>();
+  a.blist_n   = c->d_blist_n.as<uint32_t>();
+  int r       = setup_grid( c, a, c->d_geo_grid, c->d_geo_cells, c->d_geo_cell_ids, c->d_scratch[2], g, wmax );
   if ( r ) { return r; }
-  if ( nCells == 0 ) { return RB200_OK; }
-  const int G = rb_div_up( n, 256 );
-  RB_LAUNCH( "geo_accumulate", k_accumulate_geo, G, 256, 0, a, n );
-  RB_LAUNCH( "geo_finalize", k_finalize_cells, rb_div_up( nCells, 256 ), 256, 0, a, nCells, 0, (int64_t)wmax * wmax * wmax );
-  RB_LAUNCH( "geo_filter", k_filter_geo, G, 256, 0, a, n, P.threshold_smoothing );
-  RB_LAUNCH( "geo_cleanup", k_cleanup_cells, rb_div_up( nCells, 256 ), 256, 0, a, nCells );
+  RB_LAUNCH( "geo_accumulate", k_accumulate_geo, rb_div_up( n, 256 ), 256, 0, a, n );
+  if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
+  int nUsed = 0;
+  r         = read_counters( c, a, &nUsed );
+  if ( nUsed > 0 ) {
+    RB_LAUNCH( "geo_finalize", k_finalize_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed, 0 );
+    RB_LAUNCH( "geo_cleanup", k_cleanup_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed );
+  }
+  if ( r ) {
+    RB_CUDA( cudaMemsetAsync( c->d_geo_grid.p, 0, c->d_geo_grid.cap, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( c->d_geo_cells.p, 0, c->d_geo_cells.cap, c->stream ) );
+    return rb_fail( c, RB200_ERR_NOMEM, "geometry smoothing: cell table overflow" );
+  }
   return RB200_OK;
 }
 
@@ -539,41 +595,42 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   const int pcmax = 1 << P.geometry_bitdepth_3d;
   const int wmax  = pcmax / g;  // :154
   if ( wmax < 2 ) { return rb_fail( c, RB200_ERR_INVALID, "colour grid degenerate" ); }
-  int r = ensure_grid( c, c->d_col_grid, c->col_grid_w, c->col_grid_frames, wmax, c->F );
-  if ( r ) { return r; }
-  RB_CUDA( c->d_scratch[3].ensure( 64 ) );
-  if ( c->col_cell_cap == 0 ) {
-    c->col_cell_cap = 1 << 16;
-    RB_CUDA( c->d_col_cells.ensure( (size_t)c->col_cell_cap * sizeof( Cell ) ) );
-    RB_CUDA( c->d_col_cell_ids.ensure( (size_t)c->col_cell_cap * 8 ) );
-    RB_CUDA( cudaMemsetAsync( c->d_col_cells.p, 0, (size_t)c->col_cell_cap * sizeof( Cell ), c->stream ) );
-  }
   GridArgs a{};
   a.F         = c->F;
   a.g         = g;
   a.wmax      = wmax;
   a.by_bbox   = 0;
   a.pcmax     = pcmax;
-  a.grid      = c->d_col_grid.as<int32_t>();
-  a.counters  = c->d_scratch[3].as<int32_t>();
   a.frame_off = c->d_frame_off.as<int64_t>();
   a.finfo     = c->d_frame_info.as<RbFrameInfo>();
   a.pos       = c->d_pos.as<short4>();
   a.col       = c->d_col.as<ushort4>();
   a.part      = c->d_part.as<uint32_t>();
-  int nCells  = 0;
-  r           = run_mark( c, a, c->d_col_cells, c->d_col_cell_ids, c->col_cell_cap, n, &nCells, "col" );
+  a.blist     = c->d_blist.as<uint32_t>();
+  a.blist_n   = c->d_blist_n.as<uint32_t>();
+  int r       = setup_grid( c, a, c->d_col_grid, c->d_col_cells, c->d_col_cell_ids, c->d_scratch[3], g, wmax );
   if ( r ) { return r; }
-  if ( nCells == 0 ) { return RB200_OK; }
   const int G = rb_div_up( n, 256 );
   RB_CUDA( c->d_col_lum.ensure( (size_t)n * 2 + 64 ) );
   RB_LAUNCH( "col_accumulate", k_accumulate_col, G, 256, 0, a, n );
-  RB_LAUNCH( "col_finalize", k_finalize_cells, rb_div_up( nCells, 256 ), 256, 0, a, nCells, 1, (int64_t)wmax * wmax * wmax );
-  RB_LAUNCH( "col_scatter_lum", k_scatter_lum, G, 256, 0, a, n, c->d_col_lum.as<uint16_t>() );
-  RB_LAUNCH( "col_median_gate", k_cell_median_gate, rb_div_up( (int64_t)nCells * 32, 256 ), 256, 0, a, nCells,
-             c->d_col_lum.as<uint16_t>(), P.threshold_color_variation * 256.0 );
-  RB_LAUNCH( "col_filter", k_filter_col, G, 256, 0, a, n, P.threshold_color_smoothing, P.threshold_color_difference * 256.0 );
-  RB_LAUNCH( "col_cleanup", k_cleanup_cells, rb_div_up( nCells, 256 ), 256, 0, a, nCells );
+  int nUsed = 0;
+  r         = read_counters( c, a, &nUsed );
+  if ( !r && nUsed > 0 ) {
+    RB_LAUNCH( "col_finalize", k_finalize_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed, 1 );
+    RB_LAUNCH( "col_scatter_lum", k_scatter_lum, G, 256, 0, a, n, c->d_col_lum.as<uint16_t>() );
+    RB_LAUNCH( "col_median_gate", k_cell_median_gate, rb_div_up( (int64_t)nUsed * 32, 256 ), 256, 0, a, nUsed,
+               c->d_col_lum.as<uint16_t>(), P.threshold_color_variation * 256.0 );
+    if ( c->blist_cap > 0 ) {
+      RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
+                 P.threshold_color_difference * 256.0 );
+    }
+  }
+  if ( nUsed > 0 ) { RB_LAUNCH( "col_cleanup", k_cleanup_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed ); }
+  if ( r ) {
+    RB_CUDA( cudaMemsetAsync( c->d_col_grid.p, 0, c->d_col_grid.cap, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( c->d_col_cells.p, 0, c->d_col_cells.cap, c->stream ) );
+    return rb_fail( c, RB200_ERR_NOMEM, "colour smoothing: cell table overflow" );
+  }
   return RB200_OK;
 }
 

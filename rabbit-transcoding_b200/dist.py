@@ -37,11 +37,27 @@ def pack_result(frame, r):
     return out
 
 
+_libm = None
+
+
+def _log10f(x):
+    """glibc's log10f — the call the reference makes (numpy's float32 log10 is a different implementation)"""
+    global _libm
+    if _libm is None:
+        import ctypes
+        import ctypes.util
+        _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _libm.log10f.restype = ctypes.c_float
+        _libm.log10f.argtypes = [ctypes.c_float]
+    return np.float32(_libm.log10f(float(x)))
+
+
 def psnr(dist, peak, factor=1.0):
-    """getPSNR (PCCMetrics.cpp:44-48) in float32, log10f"""
+    """getPSNR (PCCMetrics.cpp:44-48): float max_energy = p * p; 10 * log10f( factor * max_energy / dist )"""
     dist, peak, factor = np.float32(dist), np.float32(peak), np.float32(factor)
     with np.errstate(divide="ignore"):
-        return np.float32(10) * np.log10((factor * peak * peak) / dist, dtype=np.float32)
+        ratio = np.float32(factor * np.float32(peak * peak)) / dist
+    return np.float32(10) * _log10f(ratio)
 
 
 def quality_from_sums(sse_c2c, sse_c2p, sse_col, num, resolution):
