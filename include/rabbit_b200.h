@@ -190,6 +190,11 @@ int rb200_decode_gof(rb200_ctx* ctx);
 /* ---- results ---------------------------------------------------------------------------------- */
 int rb200_frame_counts_get(rb200_ctx* ctx, rb200_frame_counts* out /* [n_frames] */);
 int rb200_download_frame(rb200_ctx* ctx, int frame, const rb200_cloud_host* dst);
+/* A frame-by-frame caller (the reference's decoder loop) sees the state every stage left although each stage runs for
+ * the whole GOF at once: enable before rb200_reconstruct, then ask for the state after stage 0 reconstruction + colour
+ * fetch, 1 geometry smoothing, 2 attribute re-transfer, 3 colour smoothing, >= 4 current. */
+int rb200_enable_stage_snapshots(rb200_ctx* ctx, int enable);
+int rb200_download_frame_stage(rb200_ctx* ctx, int frame, int stage, const rb200_cloud_host* dst);
 /* all frames of the GOF back to back in frame order (frame f = counts[f].total points): one packed copy per field */
 int rb200_download_gof(rb200_ctx* ctx, const rb200_cloud_host* dst);
 /* block-to-patch map (tile.getBlockToPatch(), value = patch index + 1, 0 = none), [H/R][W/R] uint32 */

@@ -22,11 +22,16 @@ import rabbit_transcoding_b200 as rb  # noqa: E402
 abi = rb.abi
 REF_LIB = os.path.join(_HERE, "_ref", "librabbit_ref.so")
 PORT_LIB = os.path.join(_HERE, "liboracle.so")
+DROPIN_LIB = os.path.join(_HERE, "_ref", "librabbit_dropin.so")
 STAGES = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
 
 
 def have_reference():
     return os.path.exists(REF_LIB)
+
+
+def have_dropin():
+    return os.path.exists(DROPIN_LIB)
 
 
 def have_port():
@@ -184,6 +189,15 @@ class Reference(_Backend):
 
     def __init__(self):
         super().__init__(REF_LIB)
+
+
+class DropIn(_Backend):
+    """the reference's harness and objects with the hot member functions replaced by the C++ shim
+    (rabbit-transcoding_b200/host/PCCCodecB200.cpp -> librabbit_b200.so): the drop-in boundary under test."""
+    prefix = "ref_"
+
+    def __init__(self):
+        super().__init__(DROPIN_LIB)
 
 
 class Port(_Backend):

@@ -94,6 +94,12 @@ struct rb200_ctx {
   RbBuf d_rgb;   // uchar4  {r, g, b, 0}
   RbBuf d_pos_pre;  // copy of d_pos before geometry smoothing (tempFrameBuffer, PCCDecoder.cpp:435)
   RbBuf d_pack;     // staging for packed downloads
+  // optional per-stage copies (rb200_enable_stage_snapshots): positions after reconstruction / geometry smoothing,
+  // colours16 after reconstruction / transfer / colour smoothing — lets a frame-by-frame caller see the state each
+  // stage left although every stage runs for the whole GOF at once
+  bool  snapshots = false;
+  RbBuf d_snap_pos[2], d_snap_col[3];
+  bool  have_snap_pos[2] = {false, false}, have_snap_col[3] = {false, false, false};
   RbBuf d_blist, d_blist_n;  // indices of the boundary (type 1) points of the GOF + their count (device)
   int64_t blist_cap = 0;     // that count on the host
   std::vector<int64_t>            h_frame_off;  // [F+1]

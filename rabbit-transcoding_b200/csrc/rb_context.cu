@@ -148,7 +148,8 @@ void rb200_destroy( rb200_ctx* c ) {
                    &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
                    &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
-                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n};
+                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n,
+                   &c->d_snap_pos[0], &c->d_snap_pos[1], &c->d_snap_col[0], &c->d_snap_col[1], &c->d_snap_col[2]};
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }
   rb_metrics_release( c );
@@ -393,6 +394,15 @@ int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* a
   return RB200_OK;
 }
 
+static int take_snapshot( rb200_ctx* c, RbBuf& dst, bool& have, const RbBuf& src ) {
+  const size_t bytes = (size_t)c->h_frame_off[c->F] * 8;
+  if ( !c->snapshots || bytes == 0 ) { return RB200_OK; }
+  RB_CUDA( dst.ensure( bytes ) );
+  RB_CUDA( cudaMemcpyAsync( dst.p, src.p, bytes, cudaMemcpyDeviceToDevice, c->stream ) );
+  have = true;
+  return RB200_OK;
+}
+
 int rb200_reconstruct( rb200_ctx* c ) {
   if ( !c ) { return RB200_ERR_INVALID; }
   if ( !c->uploaded ) { return rb_fail( c, RB200_ERR_STATE, "reconstruct before gof_upload" ); }
@@ -401,6 +411,9 @@ int rb200_reconstruct( rb200_ctx* c ) {
   if ( r == RB200_OK ) {
     c->reconstructed = true;
     c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+    c->have_snap_pos[0] = c->have_snap_pos[1] = c->have_snap_col[0] = c->have_snap_col[1] = c->have_snap_col[2] = false;
+    r = take_snapshot( c, c->d_snap_pos[0], c->have_snap_pos[0], c->d_pos );
+    if ( r == RB200_OK ) { r = take_snapshot( c, c->d_snap_col[0], c->have_snap_col[0], c->d_col ); }
   }
   return r;
 }
@@ -410,7 +423,10 @@ int rb200_smooth_geometry( rb200_ctx* c ) {
   if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "smooth_geometry before reconstruct" ); }
   cudaSetDevice( c->device );
   int r = rb_smooth_geometry_impl( c );
-  if ( r == RB200_OK ) { c->geo_smoothed = true; }
+  if ( r == RB200_OK ) {
+    c->geo_smoothed = true;
+    r               = take_snapshot( c, c->d_snap_pos[1], c->have_snap_pos[1], c->d_pos );
+  }
   return r;
 }
 
@@ -419,7 +435,10 @@ int rb200_transfer_colors( rb200_ctx* c ) {
   if ( !c->geo_smoothed ) { return rb_fail( c, RB200_ERR_STATE, "transfer_colors before smooth_geometry" ); }
   cudaSetDevice( c->device );
   int r = rb_transfer_colors_impl( c );
-  if ( r == RB200_OK ) { c->colors_transferred = true; }
+  if ( r == RB200_OK ) {
+    c->colors_transferred = true;
+    r                     = take_snapshot( c, c->d_snap_col[1], c->have_snap_col[1], c->d_col );
+  }
   return r;
 }
 
@@ -428,7 +447,10 @@ int rb200_smooth_color( rb200_ctx* c ) {
   if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "smooth_color before reconstruct" ); }
   cudaSetDevice( c->device );
   int r = rb_smooth_color_impl( c );
-  if ( r == RB200_OK ) { c->color_smoothed = true; }
+  if ( r == RB200_OK ) {
+    c->color_smoothed = true;
+    r                 = take_snapshot( c, c->d_snap_col[2], c->have_snap_col[2], c->d_col );
+  }
   return r;
 }
 
@@ -492,8 +514,11 @@ int rb200_frame_counts_get( rb200_ctx* c, rb200_frame_counts* out ) {
 
 // packs the points [b, b+n) of the GOF arena into the reference's std::vector layouts and copies them out;
 // every requested field gets its own slice of the staging buffer so one synchronisation covers them all
-static int download_range( rb200_ctx* c, int64_t b, int64_t n, const rb200_cloud_host* dst ) {
+static int download_range( rb200_ctx* c, int64_t b, int64_t n, const rb200_cloud_host* dst, const short4* srcPos = nullptr,
+                           const ushort4* srcCol = nullptr ) {
   if ( n == 0 ) { return RB200_OK; }
+  if ( !srcPos ) { srcPos = c->d_pos.as<short4>(); }
+  if ( !srcCol ) { srcCol = c->d_col.as<ushort4>(); }
   auto         al = []( size_t x ) { return ( x + 255 ) & ~size_t( 255 ); };
   const size_t oPos = 0, oTyp = oPos + ( dst->positions ? al( n * 6 ) : 0 ), oC16 = oTyp + ( dst->boundary_types ? al( n * 2 ) : 0 ),
                oRgb = oC16 + ( dst->colors16 ? al( n * 6 ) : 0 ), oPix = oRgb + ( dst->colors && c->rgb_done ? al( n * 3 ) : 0 ),
@@ -502,17 +527,17 @@ static int download_range( rb200_ctx* c, int64_t b, int64_t n, const rb200_cloud
   char*     pk = c->d_pack.as<char>();
   const int T = 256, G = rb_div_up( n, T );
   if ( dst->positions ) {
-    RB_LAUNCH( "pack_positions", k_pack_positions, G, T, 0, c->d_pos.as<short4>() + b, n, (int16_t*)( pk + oPos ) );
+    RB_LAUNCH( "pack_positions", k_pack_positions, G, T, 0, srcPos + b, n, (int16_t*)( pk + oPos ) );
     RB_CUDA( cudaMemcpyAsync( dst->positions, pk + oPos, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 6;
   }
   if ( dst->boundary_types ) {
-    RB_LAUNCH( "pack_types", k_pack_types, G, T, 0, c->d_pos.as<short4>() + b, n, (uint16_t*)( pk + oTyp ) );
+    RB_LAUNCH( "pack_types", k_pack_types, G, T, 0, srcPos + b, n, (uint16_t*)( pk + oTyp ) );
     RB_CUDA( cudaMemcpyAsync( dst->boundary_types, pk + oTyp, n * 2, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 2;
   }
   if ( dst->colors16 ) {
-    RB_LAUNCH( "pack_colors16", k_pack_colors16, G, T, 0, c->d_col.as<ushort4>() + b, n, (uint16_t*)( pk + oC16 ) );
+    RB_LAUNCH( "pack_colors16", k_pack_colors16, G, T, 0, srcCol + b, n, (uint16_t*)( pk + oC16 ) );
     RB_CUDA( cudaMemcpyAsync( dst->colors16, pk + oC16, n * 6, cudaMemcpyDeviceToHost, c->stream ) );
     c->stats.d2h_bytes += n * 6;
   }
@@ -545,6 +570,40 @@ int rb200_download_frame( rb200_ctx* c, int f, const rb200_cloud_host* dst ) {
   if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
   cudaSetDevice( c->device );
   return download_range( c, c->h_frame_off[f], c->h_frame_off[f + 1] - c->h_frame_off[f], dst );
+}
+
+int rb200_enable_stage_snapshots( rb200_ctx* c, int enable ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  c->snapshots = enable != 0;
+  return RB200_OK;
+}
+
+// stage: 0 after reconstruction (+ colour fetch), 1 after geometry smoothing, 2 after the attribute re-transfer,
+// 3 after colour smoothing, 4 (or more) current state.  Needs rb200_enable_stage_snapshots before the GOF is decoded.
+int rb200_download_frame_stage( rb200_ctx* c, int f, int stage, const rb200_cloud_host* dst ) {
+  if ( !c || !dst ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed ) { return rb_fail( c, RB200_ERR_STATE, "download before reconstruct" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  if ( stage < 4 && !c->snapshots ) { return rb_fail( c, RB200_ERR_STATE, "stage snapshots are not enabled" ); }
+  cudaSetDevice( c->device );
+  const short4*  sp = nullptr;
+  const ushort4* sc = nullptr;
+  if ( stage < 4 ) {
+    // the state after `stage` is the LATEST snapshot taken at or before it (a stage that did not run changes nothing)
+    if ( stage >= 1 && c->have_snap_pos[1] ) {
+      sp = c->d_snap_pos[1].as<short4>();
+    } else if ( c->have_snap_pos[0] ) {
+      sp = c->d_snap_pos[0].as<short4>();
+    }
+    if ( stage >= 3 && c->have_snap_col[2] ) {
+      sc = c->d_snap_col[2].as<ushort4>();
+    } else if ( stage >= 2 && c->have_snap_col[1] ) {
+      sc = c->d_snap_col[1].as<ushort4>();
+    } else if ( c->have_snap_col[0] ) {
+      sc = c->d_snap_col[0].as<ushort4>();
+    }
+  }
+  return download_range( c, c->h_frame_off[f], c->h_frame_off[f + 1] - c->h_frame_off[f], dst, sp, sc );
 }
 
 int rb200_download_gof( rb200_ctx* c, const rb200_cloud_host* dst ) {

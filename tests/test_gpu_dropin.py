@@ -1,0 +1,86 @@
+"""The drop-in boundary: the reference's own classes and decoder sequence (oracle/ref_harness.cpp, unmodified reference
+objects) with the hot member functions replaced by rabbit-transcoding_b200/host/PCCCodecB200.cpp, which calls the CUDA
+library.  Everything the callers see — PCCPointSet3 contents after every stage, partition, pointToPixel, block-to-patch,
+point counts, ordered MD5, PCCMetrics results — must equal the unmodified reference's."""
+import numpy as np
+import pytest
+
+from util import FIELDS, assert_cloud_equal
+
+pytestmark = pytest.mark.gpu
+STAGES = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
+
+
+@pytest.fixture(scope="module")
+def backends():
+    from oracle import checker
+    if not (checker.have_reference() and checker.have_dropin()):
+        pytest.skip("oracle/_ref/librabbit_ref.so / librabbit_dropin.so not built (make -C oracle ref dropin)")
+    return checker.Reference(), checker.DropIn()
+
+
+def compare(rb, backends, what, **kw):
+    ref_b, drop_b = backends
+    args = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=71, transfer_filter=1)
+    args.update(kw)
+    g = rb.synthetic.generate_gof(**args)
+    want = ref_b.run_gof(g, keep=STAGES)
+    got = drop_b.run_gof(rb.synthetic.generate_gof(**args), keep=STAGES)  # fresh arrays: the original binarises in place
+    for f in range(g.n_frames):
+        cw, cg = want.counts(f), got.counts(f)
+        assert (cw.total, cw.regular, cw.eom, cw.raw, cw.smoothed, cw.recolored) == \
+            (cg.total, cg.regular, cg.eom, cg.raw, cg.smoothed, cg.recolored), f"{what} frame {f} counts"
+        for st in STAGES:
+            try:
+                w = want.cloud(f, st)
+            except KeyError:
+                continue
+            assert_cloud_equal(got.cloud(f, st), w, f"{what} frame {f} stage {st}", FIELDS)
+        assert got.md5(f) == want.md5(f)
+        assert np.array_equal(got.block_to_patch(f, g.params), want.block_to_patch(f, g.params))
+        assert np.array_equal(got.occupancy(f, g.params) != 0, want.occupancy(f, g.params) != 0)
+    return g, want
+
+
+def test_dropin_default_decoder_sequence(rb, backends):
+    g, want = compare(rb, backends, "default")
+    assert want.counts(0).smoothed > 0
+
+
+def test_dropin_orientations_reverse_precision2(rb, backends):
+    compare(rb, backends, "orient", orientations=tuple(range(9)), occupancy_precision=2, precedence_reverse=True, seed=72)
+
+
+def test_dropin_eom_and_raw(rb, backends):
+    compare(rb, backends, "eom", eom=True, geometry_smoothing=False, color_smoothing=False, transfer_filter=0, seed=73)
+    compare(rb, backends, "raw", raw_points=700, transfer_filter=0, seed=74)
+
+
+def test_dropin_unsupported_mode_falls_back_to_the_reference_body(rb, backends):
+    """pixel interleaving is not implemented on the GPU: the shim must hand the frame to the original body"""
+    ref_b, drop_b = backends
+    args = dict(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=75, transfer_filter=1, map_count=1)
+    g = rb.synthetic.generate_gof(**args)
+    g.params.single_map_pixel_interleaving = 1
+    want = ref_b.run_gof(g, keep=("rgb8",))
+    g2 = rb.synthetic.generate_gof(**args)
+    g2.params.single_map_pixel_interleaving = 1
+    got = drop_b.run_gof(g2, keep=("rgb8",))
+    assert got.md5(0) == want.md5(0)
+
+
+def test_dropin_metrics(rb, backends):
+    from oracle import checker
+    ref_b, drop_b = backends
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=76, transfer_filter=0)
+    rec = ref_b.run_gof(g, keep=("rgb8",)).cloud(0, "rgb8")
+    mp = checker.default_metrics_params(resolution=255.0)
+    want, _ = ref_b.metrics(mp, g.sources[0], rec, g.sources[0])
+    got, _ = drop_b.metrics(mp, g.sources[0], rec, g.sources[0])
+    for tag in ("q1", "q2", "qf"):
+        a, b = getattr(got, tag), getattr(want, tag)
+        assert a.c2c_mse == b.c2c_mse
+        assert abs(a.c2c_psnr - b.c2c_psnr) <= 1e-6 and abs(a.c2p_psnr - b.c2p_psnr) <= 1e-6
+        for k in range(3):
+            assert abs(a.color_psnr[k] - b.color_psnr[k]) <= 1e-6
+    assert (got.source_after_dedup, got.rec_after_dedup) == (want.source_after_dedup, want.rec_after_dedup)
