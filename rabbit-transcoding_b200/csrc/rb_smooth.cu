@@ -54,9 +54,7 @@ struct GridArgs {
   uint32_t*      keys;       // [F][slots] 0 = empty, else (cx | cy << 10 | cz << 20) + 1
   Cell*          cells;      // [F][slots]
   uint32_t       slots;      // per frame, power of two
-  uint32_t*      used;       // global slot index of every claimed slot (cleanup list)
-  uint32_t       used_cap;
-  int32_t*       counters;   // [0] claimed slots, [1] overflow flag, [2] luma cursor
+  int32_t*       counters;   // [1] overflow flag, [2] luma cursor
   const int64_t* frame_off;
   RbFrameInfo*   finfo;
   short4*        pos;
@@ -64,6 +62,7 @@ struct GridArgs {
   const uint32_t* part;
   const uint32_t* blist;     // indices of the points classified as boundary (type 1) by the reconstruction
   const uint32_t* blist_n;
+  double*         means;     // [F][slots][3] per-cell centre / mean colour, computed once per cell by k_finalize_cells
 };
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -111,6 +110,49 @@ __device__ __forceinline__ uint32_t cell_find( const GridArgs& a, int f, int cx,
   }
   return 0xFFFFFFFFu;
 }
+// the 2x2x2 cells a boundary point blends: all eight first probes are issued before any of them is examined, and the
+// eight accumulators are then fetched together (memory-level parallelism instead of eight dependent round trips)
+__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], Cell cl[8], uint32_t ix[8] ) {
+  const uint32_t mask = a.slots - 1, base = (uint32_t)f * a.slots;
+  uint32_t       s[8], key[8], v[8];
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {  // k = dz*4 + dy*2 + dx, the reference's loop order (:1019-1027)
+    const int cx = S[0] + ( k & 1 ), cy = S[1] + ( ( k >> 1 ) & 1 ), cz = S[2] + ( k >> 2 );
+    key[k]       = cell_key( cx, cy, cz );
+    s[k]         = cell_home( cx, cy, cz, mask );
+  }
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) { v[k] = __ldg( a.keys + base + s[k] ); }
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {
+    if ( v[k] == key[k] ) {
+      ix[k] = base + s[k];
+    } else if ( v[k] == 0 ) {
+      ix[k] = 0xFFFFFFFFu;
+    } else {  // collision: continue the probe sequence
+      ix[k]      = 0xFFFFFFFFu;
+      uint32_t t = s[k];
+      for ( int j = 1; j < MAX_PROBES; j++ ) {
+        t                = ( t + 64 ) & mask;
+        const uint32_t w = __ldg( a.keys + base + t );
+        if ( w == key[k] ) {
+          ix[k] = base + t;
+          break;
+        }
+        if ( w == 0 ) { break; }
+      }
+    }
+  }
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {
+    if ( ix[k] != 0xFFFFFFFFu ) {
+      cl[k] = cell_load( a.cells + ix[k] );
+    } else {
+      cl[k] = Cell{};
+    }
+  }
+}
+
 // find or claim; 0xFFFFFFFF on table overflow (flagged)
 __device__ __forceinline__ uint32_t cell_claim( const GridArgs& a, int f, int cx, int cy, int cz ) {
   const uint32_t mask = a.slots - 1, key = cell_key( cx, cy, cz );
@@ -120,15 +162,7 @@ __device__ __forceinline__ uint32_t cell_claim( const GridArgs& a, int f, int cx
     uint32_t v = a.keys[base + s];
     if ( v == 0 ) {
       v = atomicCAS( &a.keys[base + s], 0u, key );
-      if ( v == 0 ) {
-        const int i = atomicAdd( &a.counters[0], 1 );
-        if ( (uint32_t)i < a.used_cap ) {
-          a.used[i] = base + s;
-        } else {
-          a.counters[1] = 1;
-        }
-        return base + s;
-      }
+      if ( v == 0 ) { return base + s; }  // claimed (no global list: the per-cell passes walk the slot array)
     }
     if ( v == key ) { return base + s; }
     s = ( s + 64 ) & mask;
@@ -161,69 +195,153 @@ __device__ __forceinline__ void cell_accumulate( const GridArgs& a, bool valid, 
   }
 }
 
-// ---- geometry: every inside point accumulates into its own cell (:120-134, :980-998) ----
-__global__ void __launch_bounds__( 256 ) k_accumulate_geo( const GridArgs a, int64_t n ) {
-  const int64_t i     = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  bool          valid = false;
-  uint32_t      slot = 0, pp = 0;
-  short4        p = make_short4( 0, 0, 0, 0 );
-  if ( i < n ) {
-    p               = a.pos[i];
-    const int f     = frame_of( a.frame_off, a.F, i );
-    const int disth = max( a.g / 2, 1 ), th = grid_th( a, f );
-    if ( inside( p.x, p.y, p.z, disth, th ) ) {
-      slot  = cell_claim( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
-      valid = slot != 0xFFFFFFFFu;
-      pp    = a.part[i] + 1u;
-    }
+constexpr int ACC_RUN = 8;  // consecutive points per thread
+
+// Points arrive in emission order (patch -> 16x16 block -> pixel row -> layer), so the 8 consecutive points of a
+// thread — 4 neighbouring pixels x 2 layers — fall into one or two cells: the thread merges them in registers and
+// issues one hash probe and three atomics per distinct cell instead of per point.
+struct RunAcc {
+  uint32_t slot, n, t0, t1, t2, mx, mn;
+};
+__device__ __forceinline__ void run_flush( const GridArgs& a, RunAcc& r ) {
+  if ( r.n == 0 || r.slot == 0xFFFFFFFFu ) {
+    r.n = 0;
+    return;
   }
-  cell_accumulate( a, valid, slot, (uint32_t)p.x, (uint32_t)p.y, (uint32_t)p.z, pp );
+  Cell* c = a.cells + r.slot;
+  atomicAdd( (unsigned long long*)&c->cnt, (unsigned long long)r.n | ( (unsigned long long)r.t0 << 32 ) );
+  atomicAdd( (unsigned long long*)&c->s1, (unsigned long long)r.t1 | ( (unsigned long long)r.t2 << 32 ) );
+  if ( r.mx != r.mn ) {
+    c->multi = 1;  // two partitions inside this very run
+    atomicCAS( &c->pfirst, 0u, r.mx );
+  } else {
+    const uint32_t old = atomicCAS( &c->pfirst, 0u, r.mx );
+    if ( old != 0 && old != r.mx ) { c->multi = 1; }
+  }
+  r.n = 0;
 }
 
-// ---- colour: every point (no margin test, :208-224) accumulates its colour ----
-__global__ void __launch_bounds__( 256 ) k_accumulate_col( const GridArgs a, int64_t n ) {
-  const int64_t i     = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  bool          valid = false;
-  uint32_t      slot = 0, pp = 0;
-  ushort4       cv = make_ushort4( 0, 0, 0, 0 );
-  if ( i < n ) {
-    const short4 p = a.pos[i];
-    const int    f = frame_of( a.frame_off, a.F, i );
-    if ( p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x / a.g < a.wmax && p.y / a.g < a.wmax && p.z / a.g < a.wmax ) {  // :212 guard
-      slot  = cell_claim( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
-      valid = slot != 0xFFFFFFFFu;
-      cv    = a.col[i];
-      pp    = a.part[i] + 1u;
+template <bool COLOUR>
+__global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t n ) {
+  const int64_t i0 = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
+  if ( i0 >= n ) { return; }
+  short4   p[ACC_RUN];
+  ushort4  cv[ACC_RUN];
+  uint32_t pp[ACC_RUN];
+  if ( i0 + ACC_RUN <= n ) {  // 16-byte loads: the arena is 16-byte aligned and i0 is a multiple of 8
+    const uint4* vp = reinterpret_cast<const uint4*>( a.pos + i0 );
+    const uint4* vq = reinterpret_cast<const uint4*>( a.part + i0 );
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN / 2; k++ ) {
+      const uint4 v = vp[k];
+      p[2 * k]      = make_short4( (short)( v.x & 0xFFFF ), (short)( v.x >> 16 ), (short)( v.y & 0xFFFF ), (short)( v.y >> 16 ) );
+      p[2 * k + 1]  = make_short4( (short)( v.z & 0xFFFF ), (short)( v.z >> 16 ), (short)( v.w & 0xFFFF ), (short)( v.w >> 16 ) );
+    }
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN / 4; k++ ) {
+      const uint4 v = vq[k];
+      pp[4 * k] = v.x + 1u, pp[4 * k + 1] = v.y + 1u, pp[4 * k + 2] = v.z + 1u, pp[4 * k + 3] = v.w + 1u;
+    }
+    if ( COLOUR ) {
+      const uint4* vc = reinterpret_cast<const uint4*>( a.col + i0 );
+#pragma unroll
+      for ( int k = 0; k < ACC_RUN / 2; k++ ) {
+        const uint4 v = vc[k];
+        cv[2 * k]     = make_ushort4( v.x & 0xFFFF, v.x >> 16, v.y & 0xFFFF, v.y >> 16 );
+        cv[2 * k + 1] = make_ushort4( v.z & 0xFFFF, v.z >> 16, v.w & 0xFFFF, v.w >> 16 );
+      }
+    }
+  } else {
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      const bool ok = i0 + k < n;
+      p[k]          = ok ? a.pos[i0 + k] : make_short4( -1, -1, -1, 0 );
+      pp[k]         = ok ? a.part[i0 + k] + 1u : 0u;
+      if ( COLOUR ) { cv[k] = ok ? a.col[i0 + k] : make_ushort4( 0, 0, 0, 0 ); }
     }
   }
-  cell_accumulate( a, valid, slot, cv.x, cv.y, cv.z, pp );
+  int       f      = frame_of( a.frame_off, a.F, i0 );
+  int64_t   fend   = a.frame_off[f + 1];
+  const int disth  = max( a.g / 2, 1 );
+  int       th     = COLOUR ? 0 : grid_th( a, f );
+  int       lx = -1, ly = -1, lz = -1, lf = -1;
+  RunAcc    r{0xFFFFFFFFu, 0, 0, 0, 0, 0, 0xFFFFFFFFu};
+#pragma unroll
+  for ( int k = 0; k < ACC_RUN; k++ ) {
+    const int64_t i = i0 + k;
+    if ( i >= n ) { break; }
+    while ( i >= fend ) {  // the run crosses into the next frame (empty frames are skipped)
+      f++;
+      fend = a.frame_off[f + 1];
+      if ( !COLOUR ) { th = grid_th( a, f ); }
+    }
+    const short4 q = p[k];
+    bool         in;
+    if ( COLOUR ) {  // no margin test, :208-224 with the :212 guard
+      in = q.x >= 0 && q.y >= 0 && q.z >= 0 && q.x / a.g < a.wmax && q.y / a.g < a.wmax && q.z / a.g < a.wmax;
+    } else {  // :120-134
+      in = inside( q.x, q.y, q.z, disth, th );
+    }
+    if ( !in ) { continue; }
+    const int cx = q.x / a.g, cy = q.y / a.g, cz = q.z / a.g;
+    if ( cx != lx || cy != ly || cz != lz || f != lf ) {
+      run_flush( a, r );
+      r.slot = cell_claim( a, f, cx, cy, cz );
+      r.t0 = r.t1 = r.t2 = r.mx = 0;
+      r.mn               = 0xFFFFFFFFu;
+      lx = cx, ly = cy, lz = cz, lf = f;
+    }
+    r.n++;
+    if ( COLOUR ) {
+      r.t0 += cv[k].x, r.t1 += cv[k].y, r.t2 += cv[k].z;
+    } else {
+      r.t0 += (uint32_t)q.x, r.t1 += (uint32_t)q.y, r.t2 += (uint32_t)q.z;
+    }
+    r.mx = max( r.mx, pp[k] );
+    r.mn = min( r.mn, pp[k] );
+  }
+  run_flush( a, r );
 }
 
 // exactness guard of App. A.3 + luma list allocation (colour), over the claimed slots
-__global__ void k_finalize_cells( const GridArgs a, int nUsed, int colour ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nUsed ) { return; }
-  const uint32_t slot = a.used[i];
-  Cell*          c    = a.cells + slot;
-  if ( c->s0 >= ( 1u << 24 ) || c->s1 >= ( 1u << 24 ) || c->s2 >= ( 1u << 24 ) || c->cnt > 65535u ) {
-    a.finfo[slot / a.slots].sum_overflow = 1;
+__global__ void k_finalize_cells( const GridArgs a, uint32_t nSlots, int colour ) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool     live = slot < nSlots && a.keys[slot] != 0;
+  if ( !__any_sync( 0xFFFFFFFFu, live ) ) { return; }
+  uint32_t cnt = 0, s0 = 0, s1 = 0, s2 = 0;
+  if ( live ) {
+    const Cell* c = a.cells + slot;
+    cnt = c->cnt, s0 = c->s0, s1 = c->s1, s2 = c->s2;
+    if ( s0 >= ( 1u << 24 ) || s1 >= ( 1u << 24 ) || s2 >= ( 1u << 24 ) || cnt > 65535u ) {
+      a.finfo[slot / a.slots].sum_overflow = 1;
+    }
+    if ( cnt > 0 ) {  // the per-cell centre, once per cell instead of once per boundary point and neighbour
+      double* m = a.means + (size_t)slot * 3;
+      if ( colour ) {  // :1225: float accumulator read back as double, divided by the count in double
+        const double dn = (double)cnt;
+        m[0] = (double)(float)s0 / dn, m[1] = (double)(float)s1 / dn, m[2] = (double)(float)s2 / dn;
+      } else {  // :135-137: centre = float sum / float count (one IEEE float division)
+        const float fc = (float)cnt;
+        m[0] = (double)__fdiv_rn( (float)s0, fc ), m[1] = (double)__fdiv_rn( (float)s1, fc ), m[2] = (double)__fdiv_rn( (float)s2, fc );
+      }
+    }
   }
   if ( colour ) {  // luma list offsets: one atomic per warp, shuffle prefix inside
-    const uint32_t want = c->cnt > 1 ? c->cnt : 0u;
-    const uint32_t act  = __activemask();
+    const uint32_t want = ( live && cnt > 1 ) ? cnt : 0u;
     const int      lane = threadIdx.x & 31;
     uint32_t       incl = want;
 #pragma unroll
     for ( int d = 1; d < 32; d <<= 1 ) {
-      const uint32_t t = __shfl_up_sync( act, incl, d );
-      if ( lane >= d && ( act >> ( lane - d ) & 1u ) ) { incl += t; }
+      const uint32_t t = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+      if ( lane >= d ) { incl += t; }
     }
-    const int last = 31 - __clz( act );
-    uint32_t  base = 0;
-    if ( lane == last ) { base = (uint32_t)atomicAdd( &a.counters[2], (int)incl ); }
-    base       = __shfl_sync( act, base, last );
-    c->lum_off = base + incl - want;
-    c->aux     = 0;
+    uint32_t base = 0;
+    if ( lane == 31 && incl ) { base = (uint32_t)atomicAdd( &a.counters[2], (int)incl ); }
+    base = __shfl_sync( 0xFFFFFFFFu, base, 31 );
+    if ( live ) {
+      a.cells[slot].lum_off = base + incl - want;
+      a.cells[slot].aux     = 0;
+    }
   }
 }
 
@@ -243,16 +361,11 @@ __global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double 
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
   Cell     cl[8];
   bool     other = false;
-  uint32_t cnt[8];
-  for ( int k = 0; k < 8; k++ ) {  // k = dz*4 + dy*2 + dx, the reference's loop order (:1019-1027)
-    const int      dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
-    const uint32_t ix = cell_find( a, f, S[0] + dx, S[1] + dy, S[2] + dz );
-    cnt[k]            = 0;
-    if ( ix != 0xFFFFFFFFu ) {
-      cl[k]  = cell_load( a.cells + ix );
-      cnt[k] = cl[k].cnt;
-      if ( cell_do_smooth( cl[k] ) ) { other = true; }  // doSmooth && count (:1024)
-    }
+  uint32_t cnt[8], ix[8];
+  cell_find8( a, f, S, cl, ix );
+  for ( int k = 0; k < 8; k++ ) {
+    cnt[k] = cl[k].cnt;
+    if ( cell_do_smooth( cl[k] ) ) { other = true; }  // doSmooth && count (:1024)
   }
   if ( !other ) { return; }  // :1028
   const int    g2 = 2 * g;
@@ -267,12 +380,9 @@ __global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double 
     const int    dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
     const int    wgt = ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] );
     double       v[3];
-    if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
-      const Cell* c = &cl[k];
-      const float fc = (float)cnt[k];
-      v[0]           = (double)__fdiv_rn( (float)c->s0, fc );
-      v[1]           = (double)__fdiv_rn( (float)c->s1, fc );
-      v[2]           = (double)__fdiv_rn( (float)c->s2, fc );
+    if ( cnt[k] > 0 ) {  // :1040: the cell centre (float sum / float count, k_finalize_cells)
+      const double* m = a.means + (size_t)ix[k] * 3;
+      v[0] = __ldg( m ), v[1] = __ldg( m + 1 ), v[2] = __ldg( m + 2 );
     } else {
       v[0] = (double)P[0];
       v[1] = (double)P[1];
@@ -326,17 +436,8 @@ __global__ void __launch_bounds__( 256 ) k_scatter_lum( const GridArgs a, int64_
   lum[c->lum_off + k]    = a.col[i].x;
 }
 
-// ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243); one warp per cell, rank selection ----
-__global__ void k_cell_median_gate( const GridArgs a, int nCells, const uint16_t* __restrict__ lum, double mmThresh ) {
-  const int cell = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
-  const int lane = threadIdx.x & 31;
-  if ( cell >= nCells ) { return; }
-  Cell*     c = a.cells + a.used[cell];
+__device__ __forceinline__ void k_median_one( const GridArgs& a, Cell* c, int lane, const uint16_t* __restrict__ lum, double mmThresh ) {
   const int n = (int)c->cnt;
-  if ( n < 2 ) {
-    if ( lane == 0 ) { c->aux = 0; }
-    return;
-  }
   const uint16_t* L  = lum + c->lum_off;
   const int       hi = n / 2, lo = n / 2 - 1;
   int             vhi = -1, vlo = -1;
@@ -364,6 +465,17 @@ __global__ void k_cell_median_gate( const GridArgs a, int nCells, const uint16_t
   }
 }
 
+// ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243); one warp per cell, rank selection ----
+__global__ void k_cell_median_gate( const GridArgs a, uint32_t nSlots, const uint16_t* __restrict__ lum, double mmThresh ) {
+  const uint32_t s0   = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31u;  // this warp owns slots s0 .. s0+31
+  const int      lane = threadIdx.x & 31;
+  const bool     want = s0 + lane < nSlots && a.keys[s0 + lane] != 0 && a.cells[s0 + lane].cnt > 1;
+  uint32_t       todo = __ballot_sync( 0xFFFFFFFFu, want );
+  if ( s0 + lane < nSlots && a.keys[s0 + lane] != 0 && !want ) { a.cells[s0 + lane].aux = 0; }
+  for ( ; todo; todo &= todo - 1 ) {
+    k_median_one( a, a.cells + s0 + ( __ffs( todo ) - 1 ), lane, lum, mmThresh );
+  }
+}
 // ---- colour filter: smoothPointCloudColorLC + gridFilteringColor (:1182-1306) ----
 __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
   const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,16 +489,12 @@ __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double 
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
-  Cell cl[8];
-  bool other = false;
+  Cell     cl[8];
+  uint32_t ix[8];
+  bool     other = false;
+  cell_find8( a, f, S, cl, ix );
   for ( int k = 0; k < 8; k++ ) {
-    const int      dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
-    const uint32_t ix = cell_find( a, f, S[0] + dx, S[1] + dy, S[2] + dz );
-    cl[k].cnt         = 0;
-    if ( ix != 0xFFFFFFFFu ) {
-      cl[k] = cell_load( a.cells + ix );
-      if ( cell_do_smooth( cl[k] ) ) { other = true; }  // :1204
-    }
+    if ( cell_do_smooth( cl[k] ) ) { other = true; }  // :1204
   }
   if ( !other ) { return; }  // :1210
   const ushort4 cv     = a.col[i];
@@ -404,10 +512,8 @@ __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double 
     const Cell* c = &cl[k];
     double*     d = c3[k];
     if ( c->cnt > 0 ) {
-      const double dn = (double)c->cnt;
-      d[0]            = (double)(float)c->s0 / dn;  // :1225 (float accumulator read back as double)
-      d[1]            = (double)(float)c->s1 / dn;
-      d[2]            = (double)(float)c->s2 / dn;
+      const double* m = a.means + (size_t)ix[k] * 3;  // :1225, computed once per cell by k_finalize_cells
+      d[0] = __ldg( m ), d[1] = __ldg( m + 1 ), d[2] = __ldg( m + 2 );
       if ( k == 0 ) {
         if ( c->cnt > 1 && c->aux ) {  // :1228-1235: result = own colour
           keep_own = true;
@@ -458,13 +564,12 @@ __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double 
 }
 
 // ---- cleanup: reset exactly the claimed slots ----
-__global__ void k_cleanup_cells( const GridArgs a, int nUsed ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nUsed ) { return; }
-  const uint32_t slot = a.used[i];
-  a.keys[slot]        = 0;
-  Cell z{};
-  a.cells[slot] = z;
+__global__ void k_cleanup_cells( const GridArgs a, uint32_t nSlots ) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( slot >= nSlots || a.keys[slot] == 0 ) { return; }
+  a.keys[slot] = 0;
+  uint4* c     = reinterpret_cast<uint4*>( a.cells + slot );
+  c[0] = c[1] = make_uint4( 0, 0, 0, 0 );
 }
 
 // ---- convertYUV16ToRGB8 (PCCPointSet.h:133-166) / copyRGB16ToRGB8 (:121-127) ----
@@ -497,8 +602,9 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
   rgb[i]   = make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
 }
 
-// table geometry + (re)allocation; the tables are all-zero between calls (cleanup resets exactly what was claimed)
-int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& used, RbBuf& counters, int g, int wmax ) {
+// table geometry + (re)allocation; the tables are all-zero between calls (the cleanup pass resets what was claimed)
+int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& counters, RbBuf& means, int g, int wmax,
+                uint32_t* nSlotsOut ) {
   if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
   int64_t maxFrame = 1;
   for ( int f = 0; f < c->F; f++ ) { maxFrame = std::max<int64_t>( maxFrame, c->h_frame_off[f + 1] - c->h_frame_off[f] ); }
@@ -507,36 +613,35 @@ int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& use
   while ( (int64_t)slots < want ) { slots <<= 1; }
   const size_t nSlots = (size_t)c->F * slots;
   if ( nSlots >= ( 1ull << 32 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing hash table too large" ); }
-  const size_t usedCap = (size_t)c->h_frame_off[c->F] + 1024;  // a cell holds at least one point
   if ( keys.cap < nSlots * 4 || cells.cap < nSlots * sizeof( Cell ) ) {
     RB_CUDA( keys.ensure( nSlots * 4 ) );
     RB_CUDA( cells.ensure( nSlots * sizeof( Cell ) ) );
     RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
     RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
   }
-  RB_CUDA( used.ensure( usedCap * 4 ) );
+  RB_CUDA( means.ensure( nSlots * 24 ) );
   RB_CUDA( counters.ensure( 64 ) );
-  RB_CUDA( cudaMemsetAsync( counters.p, 0, 16, c->stream ) );
+  RB_CUDA( cudaMemsetAsync( counters.p, 0, 64, c->stream ) );
   a.keys     = keys.as<uint32_t>();
   a.cells    = cells.as<Cell>();
   a.slots    = slots;
-  a.used     = used.as<uint32_t>();
-  a.used_cap = (uint32_t)usedCap;
+  a.means    = means.as<double>();
   a.counters = counters.as<int32_t>();
+  *nSlotsOut = (uint32_t)nSlots;
   return RB200_OK;
 }
 
-// claimed-slot count + overflow flag (one small read-back; the launch sizes of the per-cell kernels need it)
-int read_counters( rb200_ctx* c, const GridArgs& a, int* nUsed ) {
+// the table-overflow flag, read after the stage has been enqueued (one small read-back, also the stage's error check)
+int check_overflow( rb200_ctx* c, const GridArgs& a, RbBuf& keys, RbBuf& cells, const char* what ) {
   int32_t* h = (int32_t*)rb_pinned( c, 64 );
   if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
   RB_CUDA( cudaMemcpyAsync( h, a.counters, 16, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   c->stats.d2h_bytes += 16;
-  *nUsed = std::min<int64_t>( h[0], a.used_cap );
   if ( h[1] ) {
-    // leave the tables clean before failing
-    return -1;
+    RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
+    return rb_fail( c, RB200_ERR_NOMEM, "%s: cell table overflow", what );
   }
   return RB200_OK;
 }
@@ -569,22 +674,14 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  int r       = setup_grid( c, a, c->d_geo_grid, c->d_geo_cells, c->d_geo_cell_ids, c->d_scratch[2], g, wmax );
+  uint32_t nSlots = 0;
+  int      r      = setup_grid( c, a, c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_scratch[5], g, wmax, &nSlots );
   if ( r ) { return r; }
-  RB_LAUNCH( "geo_accumulate", k_accumulate_geo, rb_div_up( n, 256 ), 256, 0, a, n );
+  RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+  RB_LAUNCH( "geo_finalize", k_finalize_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, 0 );
   if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
-  int nUsed = 0;
-  r         = read_counters( c, a, &nUsed );
-  if ( nUsed > 0 ) {
-    RB_LAUNCH( "geo_finalize", k_finalize_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed, 0 );
-    RB_LAUNCH( "geo_cleanup", k_cleanup_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed );
-  }
-  if ( r ) {
-    RB_CUDA( cudaMemsetAsync( c->d_geo_grid.p, 0, c->d_geo_grid.cap, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( c->d_geo_cells.p, 0, c->d_geo_cells.cap, c->stream ) );
-    return rb_fail( c, RB200_ERR_NOMEM, "geometry smoothing: cell table overflow" );
-  }
-  return RB200_OK;
+  RB_LAUNCH( "geo_cleanup", k_cleanup_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots );
+  return check_overflow( c, a, c->d_geo_grid, c->d_geo_cells, "geometry smoothing" );
 }
 
 int rb_smooth_color_impl( rb200_ctx* c ) {
@@ -608,30 +705,21 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  int r       = setup_grid( c, a, c->d_col_grid, c->d_col_cells, c->d_col_cell_ids, c->d_scratch[3], g, wmax );
+  uint32_t nSlots = 0;
+  int      r      = setup_grid( c, a, c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_scratch[6], g, wmax, &nSlots );
   if ( r ) { return r; }
-  const int G = rb_div_up( n, 256 );
   RB_CUDA( c->d_col_lum.ensure( (size_t)n * 2 + 64 ) );
-  RB_LAUNCH( "col_accumulate", k_accumulate_col, G, 256, 0, a, n );
-  int nUsed = 0;
-  r         = read_counters( c, a, &nUsed );
-  if ( !r && nUsed > 0 ) {
-    RB_LAUNCH( "col_finalize", k_finalize_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed, 1 );
-    RB_LAUNCH( "col_scatter_lum", k_scatter_lum, G, 256, 0, a, n, c->d_col_lum.as<uint16_t>() );
-    RB_LAUNCH( "col_median_gate", k_cell_median_gate, rb_div_up( (int64_t)nUsed * 32, 256 ), 256, 0, a, nUsed,
-               c->d_col_lum.as<uint16_t>(), P.threshold_color_variation * 256.0 );
-    if ( c->blist_cap > 0 ) {
-      RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
-                 P.threshold_color_difference * 256.0 );
-    }
+  RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+  RB_LAUNCH( "col_finalize", k_finalize_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, 1 );
+  RB_LAUNCH( "col_scatter_lum", k_scatter_lum, rb_div_up( n, 256 ), 256, 0, a, n, c->d_col_lum.as<uint16_t>() );
+  RB_LAUNCH( "col_median_gate", k_cell_median_gate, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, c->d_col_lum.as<uint16_t>(),
+             P.threshold_color_variation * 256.0 );
+  if ( c->blist_cap > 0 ) {
+    RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
+               P.threshold_color_difference * 256.0 );
   }
-  if ( nUsed > 0 ) { RB_LAUNCH( "col_cleanup", k_cleanup_cells, rb_div_up( nUsed, 256 ), 256, 0, a, nUsed ); }
-  if ( r ) {
-    RB_CUDA( cudaMemsetAsync( c->d_col_grid.p, 0, c->d_col_grid.cap, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( c->d_col_cells.p, 0, c->d_col_cells.cap, c->stream ) );
-    return rb_fail( c, RB200_ERR_NOMEM, "colour smoothing: cell table overflow" );
-  }
-  return RB200_OK;
+  RB_LAUNCH( "col_cleanup", k_cleanup_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots );
+  return check_overflow( c, a, c->d_col_grid, c->d_col_cells, "colour smoothing" );
 }
 
 int rb_convert_rgb8_impl( rb200_ctx* c ) {
