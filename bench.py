@@ -279,6 +279,10 @@ def run_b200(args):
                 "ms_per_step": round(ms_full / fsteps, 3), "gpu_launches_per_step": codec.stats(reset=True).kernel_launches // fsteps,
                 "what": "reconstruction + geometry smoothing + transferColors16bitBP (two nanoflann-order kd-trees per "
                         "frame rebuilt on the GPU) + colour smoothing + RGB8, planes resident in HBM"}
+        codec.enableTiming(True)
+        codec.decodeGof()
+        full["kernel_ms"] = {k: [round(v[0], 3), v[1]] for k, v in sorted(codec.timings().items(), key=lambda kv: -kv[1][0])[:14]}
+        codec.enableTiming(False)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             sub = rb.synthetic.slice_gof(gof, 0, min(8, gof.n_frames))
             full["cpu_reference"] = cpu_reference(rb, sub, threads=1, max_frames=sub.n_frames)

@@ -3,13 +3,13 @@
 // Restates KDTreeSingleIndexAdaptor::buildIndex / computeBoundingBox / divideTree / middleSplit_ / planeSplit /
 // computeMinMax (dependencies/nanoflann/nanoflann.hpp:858-866, 1009-1181) for a FOREST of trees (one per cloud of a
 // GOF) in two phases:
-//  * level-parallel phase for nodes with more than KD_SMALL points: every level is a handful of passes over the
+//  * level-parallel phase for nodes with more than KB_CAP (2048) points: every level is a handful of passes over the
 //    element records of all trees (per-node min/max and counts with warp-aggregated atomics, then the two Hoare
 //    passes of planeSplit as "rank the misplaced elements with one prefix sum, swap the i-th misplaced element from
 //    the left with the i-th misplaced element from the right");
-//  * serial phase for subtrees of at most KD_SMALL points: one thread per subtree runs the sequential algorithm on a
-//    bank-conflict-free shared-memory copy of its records.
-// A final pass fills divlow / divhigh from the children's tight boxes (divideTree :1080-1081).
+//  * block phase for subtrees of at most KB_CAP points: one CTA per subtree runs the same level-synchronous
+//    formulation entirely in shared memory, down to the leaves.
+// divlow / divhigh come from the children's tight boxes (divideTree :1080-1081).
 #include <algorithm>
 
 #include "rb_common.cuh"
@@ -19,7 +19,6 @@
 namespace {
 
 constexpr int TPB      = 256;
-constexpr int KD_CHUNK = 32;
 
 // per-node {min[3], max[3]} of the level-parallel phase: plain int32 so the updates are single RED instructions
 __device__ __forceinline__ void stat_update( int32_t* __restrict__ st, uint32_t node, const int mn[3], const int mx[3] ) {
@@ -357,133 +356,320 @@ __global__ void k_kd_assign( uint32_t* __restrict__ nid, const KdNode* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// serial phase: one thread per subtree of <= SMALL elements, records staged in shared memory.
-// element i of thread t sits at sm[i * BS + t] (consecutive threads -> consecutive banks)
+// block phase: one CTA builds a whole subtree of at most KB_CAP elements, level by level, in shared memory.
+// Same formulation as the level-parallel phase (tight boxes with atomics, counts, the two Hoare passes as
+// rank-the-misplaced + pairwise swap), but every pass is a few hundred cycles on 2048 shared-memory records.
 // ---------------------------------------------------------------------------------------------------
-template <int SMALL, int BS>
-__global__ void __launch_bounds__( BS ) k_kd_serial( uint64_t* __restrict__ rec, KdNode* __restrict__ nodes,
-                                                     const uint32_t* __restrict__ smallRoots, uint32_t nRoots,
-                                                     uint32_t* __restrict__ counters, uint32_t nodeCap, int ox, int oy, int oz ) {
-  extern __shared__ uint64_t sm[];
-  const uint32_t t = blockIdx.x * BS + threadIdx.x;
-  if ( t >= nRoots ) { return; }
-  const uint32_t rootId = smallRoots[t];
+constexpr int KB_CAP   = 2048;  // elements per CTA subtree
+constexpr int KB_LEVEL = 512;   // nodes per level: children only come from nodes with > 10 elements, so <= 2 * 2048 / 11
+constexpr int KB_TPB   = 256;
+constexpr int KB_EPT   = KB_CAP / KB_TPB;
+
+struct KbNode {  // a node of the level being processed
+  int32_t  tmin[3], tmax[3];
+  uint32_t gid, pgid, lt, le;
+  uint16_t left, right, child;  // element range inside the CTA subtree; child: index of child1 in the next level
+  int16_t  lo[3], hi[3], cutval;
+  uint8_t  cutfeat, pfeat, state, side;  // side: 0 left child, 1 right child of pgid (pgid == 0: subtree root)
+};
+struct KbNext {  // a node of the next level, as created by its parent
+  uint32_t gid, pgid;
+  uint16_t left, right;
+  int16_t  lo[3], hi[3];
+  uint8_t  pfeat, side;
+};
+
+struct KbShared {
+  uint64_t rec[KB_CAP];
+  KbNode   cur[KB_LEVEL];
+  KbNext   nxt[KB_LEVEL];
+  uint16_t nid[KB_CAP];
+  uint16_t scan[KB_CAP + 2];
+  uint16_t pairL[KB_CAP], pairR[KB_CAP];
+  uint32_t warpSum[KB_TPB / 32];
+  uint32_t nNext, gBase, big;
+};
+
+__global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ grec, KdNode* __restrict__ nodes,
+                                                        const uint32_t* __restrict__ smallRoots, uint32_t nRoots,
+                                                        uint32_t* __restrict__ counters, uint32_t nodeCap, int ox, int oy, int oz ) {
+  extern __shared__ __align__( 16 ) unsigned char kb_smem[];
+  KbShared&  S     = *reinterpret_cast<KbShared*>( kb_smem );
+  uint64_t*  rec   = S.rec;
+  uint16_t*  nid   = S.nid;
+  uint16_t*  scan  = S.scan;
+  uint16_t*  pairL = S.pairL;
+  uint16_t*  pairR = S.pairR;
+  KbNode*    cur   = S.cur;
+  KbNext*    nxt   = S.nxt;
+  uint32_t*  warpSum = S.warpSum;
+  uint32_t&  sNNext = S.nNext;
+  uint32_t&  sGBase = S.gBase;
+  uint32_t&  sBig   = S.big;
+  const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t rootId = smallRoots[blockIdx.x];
   const uint32_t base = nodes[rootId].left, total = nodes[rootId].right - base;
-  uint64_t*      S = sm + threadIdx.x;
-#define EL( i ) S[( i ) * BS]
-  for ( uint32_t i = 0; i < total; i++ ) { EL( i ) = rec[base + i]; }
-  uint32_t stack[SMALL + 2];
-  uint8_t  dstack[SMALL + 2];
-  uint32_t inner[SMALL + 2];      // split nodes of this subtree (divlow / divhigh are filled in at the end)
-  int      nInner = 0;
-  uint32_t poolNext = 0, poolEnd = 0;  // node ids are taken from the global pool in chunks of KD_CHUNK
-  int      sp  = 0;
-  stack[sp]    = rootId;
-  dstack[sp++] = 0;
-  int o[3]     = {ox, oy, oz};
-  int maxDepth = 0;
-  while ( sp > 0 ) {
-    const uint32_t id    = stack[--sp];
-    const int      depth = dstack[sp];
-    maxDepth             = max( maxDepth, depth );
-    KdNode         n  = nodes[id];
-    const uint32_t l = n.left - base, r = n.right - base, count = r - l;
-    // tight box (computeMinMax on every axis; also what the node hands back up)
-    for ( int k = 0; k < 3; k++ ) {
-      int mn = 32767, mx = -32768;
-      for ( uint32_t i = l; i < r; i++ ) {
-        const int v = kd_coord( EL( i ), k );
-        mn = min( mn, v ), mx = max( mx, v );
+  int            o[3] = {ox, oy, oz};
+  for ( uint32_t i = t; i < total; i += KB_TPB ) {
+    rec[i] = grec[base + i];
+    nid[i] = 0;
+  }
+  if ( t == 0 ) {
+    const KdNode r = nodes[rootId];
+    KbNext       n{};
+    n.gid = rootId, n.pgid = 0, n.left = 0, n.right = (uint16_t)total, n.pfeat = 0, n.side = 0;
+    for ( int k = 0; k < 3; k++ ) { n.lo[k] = r.lo[k], n.hi[k] = r.hi[k]; }
+    nxt[0] = n;
+    sNNext = 1;
+  }
+  __syncthreads();
+  int level = 0;
+  for ( ;; level++ ) {
+    // ---- this level's nodes ----
+    const uint32_t nl = sNNext;
+    __syncthreads();
+    if ( nl == 0 ) { break; }
+    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
+      const KbNext x = nxt[j];
+      KbNode       n{};
+      n.gid = x.gid, n.pgid = x.pgid, n.left = x.left, n.right = x.right, n.pfeat = x.pfeat, n.side = x.side;
+      for ( int k = 0; k < 3; k++ ) {
+        n.lo[k] = x.lo[k], n.hi[k] = x.hi[k];
+        n.tmin[k] = 0x7FFFFFFF, n.tmax[k] = (int32_t)0x80000000;
       }
-      n.tmin[k] = (int16_t)mn;
-      n.tmax[k] = (int16_t)mx;
+      cur[j] = n;
     }
-    if ( count <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
-      n.child1  = 0;
-      n.state   = 3;
-      nodes[id] = n;
-      continue;
+    if ( t == 0 ) { sNNext = 0, sBig = 0; }
+    __syncthreads();
+    // ---- tight boxes ----
+#pragma unroll
+    for ( int q = 0; q < KB_EPT; q++ ) {
+      const uint32_t e = q * KB_TPB + t;
+      const uint32_t j = e < total ? nid[e] : 0xFFFFu;
+      const bool     on = j != 0xFFFFu;
+      int            c[3] = {0, 0, 0};
+      if ( on ) {
+        const uint64_t r = rec[e];
+        c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
+      }
+      const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
+      int allSame = 0;
+      if ( act == 0xFFFFFFFFu ) { __match_all_sync( 0xFFFFFFFFu, j, &allSame ); }
+      if ( allSame ) {
+        int mn[3], mx[3];
+#pragma unroll
+        for ( int k = 0; k < 3; k++ ) {
+          mn[k] = __reduce_min_sync( 0xFFFFFFFFu, c[k] );
+          mx[k] = __reduce_max_sync( 0xFFFFFFFFu, c[k] );
+        }
+        if ( lane == 0 ) {
+          for ( int k = 0; k < 3; k++ ) {
+            atomicMin( &cur[j].tmin[k], mn[k] );
+            atomicMax( &cur[j].tmax[k], mx[k] );
+          }
+        }
+      } else if ( on ) {
+        for ( int k = 0; k < 3; k++ ) {
+          atomicMin( &cur[j].tmin[k], c[k] );
+          atomicMax( &cur[j].tmax[k], c[k] );
+        }
+      }
     }
-    kd_choose_split( n, o );
-    const int axis = n.cutfeat, cut = n.cutval;
-    // planeSplit (:1154-1181), indices relative to the node
-    uint32_t left = 0, right = count - 1;
-    for ( ;; ) {
-      while ( left <= right && kd_coord( EL( l + left ), axis ) < cut ) { ++left; }
-      while ( right && left <= right && kd_coord( EL( l + right ), axis ) >= cut ) { --right; }
-      if ( left > right || !right ) { break; }
-      const uint64_t x = EL( l + left );
-      EL( l + left )   = EL( l + right );
-      EL( l + right )  = x;
-      ++left;
-      --right;
+    __syncthreads();
+    // ---- leaf / split decision; the node reports its tight bound to its parent (divideTree :1080-1081) ----
+    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
+      KbNode&        n     = cur[j];
+      const uint32_t count = n.right - n.left;
+      if ( n.pgid ) {
+        if ( n.side == 0 ) {
+          nodes[n.pgid].divlow = (int16_t)n.tmax[n.pfeat];
+        } else {
+          nodes[n.pgid].divhigh = (int16_t)n.tmin[n.pfeat];
+        }
+      }
+      if ( count <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
+        KdNode g{};
+        g.left = base + n.left, g.right = base + n.right, g.child1 = 0, g.state = 3;
+        for ( int k = 0; k < 3; k++ ) {
+          g.lo[k] = n.lo[k], g.hi[k] = n.hi[k];
+          g.tmin[k] = (int16_t)n.tmin[k], g.tmax[k] = (int16_t)n.tmax[k];
+        }
+        nodes[n.gid] = g;
+        n.state      = 3;
+      } else {
+        KdNode tmp{};
+        for ( int k = 0; k < 3; k++ ) {
+          tmp.lo[k] = n.lo[k], tmp.hi[k] = n.hi[k];
+          tmp.tmin[k] = (int16_t)n.tmin[k], tmp.tmax[k] = (int16_t)n.tmax[k];
+        }
+        kd_choose_split( tmp, o );
+        n.cutfeat = (uint8_t)tmp.cutfeat, n.cutval = tmp.cutval;
+        n.lt = n.le = 0;
+        n.state     = 1;
+        atomicAdd( &sBig, 1u );
+      }
     }
-    const uint32_t lim1 = left;
-    right               = count - 1;
-    for ( ;; ) {
-      while ( left <= right && kd_coord( EL( l + left ), axis ) <= cut ) { ++left; }
-      while ( right && left <= right && kd_coord( EL( l + right ), axis ) > cut ) { --right; }
-      if ( left > right || !right ) { break; }
-      const uint64_t x = EL( l + left );
-      EL( l + left )   = EL( l + right );
-      EL( l + right )  = x;
-      ++left;
-      --right;
+    __syncthreads();
+    if ( sBig == 0 ) { break; }
+    // ---- lim1 / lim2 ----
+#pragma unroll
+    for ( int q = 0; q < KB_EPT; q++ ) {
+      const uint32_t e = q * KB_TPB + t;
+      const uint32_t j = e < total ? nid[e] : 0xFFFFu;
+      if ( j != 0xFFFFu && cur[j].state == 1 ) {
+        const int v = kd_coord( rec[e], cur[j].cutfeat ), cut = cur[j].cutval;
+        if ( v < cut ) { atomicAdd( &cur[j].lt, 1u ); }
+        if ( v <= cut ) { atomicAdd( &cur[j].le, 1u ); }
+      }
     }
-    const uint32_t lim2 = left;
-    uint32_t       idx;
-    if ( lim1 > count / 2 ) {
-      idx = lim1;
-    } else if ( lim2 < count / 2 ) {
-      idx = lim2;
-    } else {
-      idx = count / 2;
+    __syncthreads();
+    // ---- the two Hoare passes of planeSplit (:1154-1181) ----
+    for ( int pass = 0; pass < 2; pass++ ) {
+      // flags of this thread's 8 CONSECUTIVE elements + block exclusive scan
+      uint32_t f[KB_EPT], loc = 0;
+#pragma unroll
+      for ( int q = 0; q < KB_EPT; q++ ) {
+        const uint32_t e = t * KB_EPT + q;
+        uint32_t       m = 0;
+        const uint32_t j = e < total ? nid[e] : 0xFFFFu;
+        if ( j != 0xFFFFu && cur[j].state == 1 ) {
+          const KbNode&  n = cur[j];
+          const uint32_t p = e - n.left;
+          const int      v = kd_coord( rec[e], n.cutfeat );
+          if ( pass == 0 ) {
+            const bool in = v < n.cutval;
+            m             = ( p < n.lt ) ? !in : in;
+          } else if ( p >= n.lt ) {
+            const bool in = v <= n.cutval;
+            m             = ( p < n.le ) ? !in : in;
+          }
+        }
+        f[q] = m;
+        loc += m;
+      }
+      uint32_t incl = loc;
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 ) {
+        const uint32_t x = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+        if ( lane >= d ) { incl += x; }
+      }
+      if ( lane == 31 ) { warpSum[w] = incl; }
+      __syncthreads();
+      uint32_t wbase = 0;
+      for ( int k = 0; k < w; k++ ) { wbase += warpSum[k]; }
+      uint32_t run = wbase + incl - loc;
+#pragma unroll
+      for ( int q = 0; q < KB_EPT; q++ ) {
+        scan[t * KB_EPT + q] = (uint16_t)run;
+        run += f[q];
+      }
+      if ( t == KB_TPB - 1 ) { scan[KB_CAP] = (uint16_t)run; }
+      __syncthreads();
+      // pair lists
+#pragma unroll
+      for ( int q = 0; q < KB_EPT; q++ ) {
+        const uint32_t e = t * KB_EPT + q;
+        if ( f[q] ) {
+          const KbNode&  n     = cur[nid[e]];
+          const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
+          const uint32_t lim   = pass == 0 ? n.left + n.lt : n.left + n.le;
+          const uint32_t m     = ( (uint32_t)scan[n.right] - scan[begin] ) >> 1;
+          const uint32_t r     = (uint32_t)scan[e] - scan[begin];
+          if ( e < lim ) {
+            pairL[begin + r] = (uint16_t)e;
+          } else {
+            pairR[begin + ( m - 1 - ( r - m ) )] = (uint16_t)e;
+          }
+        }
+      }
+      __syncthreads();
+      // swaps
+#pragma unroll
+      for ( int q = 0; q < KB_EPT; q++ ) {
+        const uint32_t e = q * KB_TPB + t;
+        const uint32_t j = e < total ? nid[e] : 0xFFFFu;
+        if ( j != 0xFFFFu && cur[j].state == 1 ) {
+          const KbNode&  n     = cur[j];
+          const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
+          if ( e >= begin ) {
+            const uint32_t m = ( (uint32_t)scan[n.right] - scan[begin] ) >> 1, k = e - begin;
+            if ( k < m ) {
+              const uint32_t a = pairL[begin + k], b = pairR[begin + k];
+              const uint64_t ra = rec[a], rb = rec[b];
+              rec[a] = rb;
+              rec[b] = ra;
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
-    if ( poolNext + 2 > poolEnd ) {
-      poolNext = atomicAdd( &counters[0], (uint32_t)KD_CHUNK );
-      poolEnd  = poolNext + KD_CHUNK;
+    // ---- children (divideTree :1070-1078) ----
+    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
+      KbNode& n = cur[j];
+      if ( n.state == 1 ) { n.child = (uint16_t)atomicAdd( &sNNext, 2u ); }
     }
-    const uint32_t c1 = poolNext;
-    poolNext += 2;
-    if ( c1 + 2 > nodeCap ) {
-      counters[3] = 1;
-      n.child1    = 0;
-      n.state     = 3;
-      nodes[id]   = n;
-      continue;
+    __syncthreads();
+    if ( t == 0 ) { sGBase = atomicAdd( &counters[0], sNNext ); }
+    __syncthreads();
+    const uint32_t gbase = sGBase;
+    if ( gbase + sNNext > nodeCap ) {  // node pool exhausted: flag it, leave the subtree as a (wrong) leaf — the host fails
+      if ( t == 0 ) { counters[3] = 1; }
+      break;
     }
-    n.child1 = c1;
-    n.state  = 1;
-    n.lt     = lim1;
-    n.le     = lim2;
-    nodes[id] = n;
-    inner[nInner++] = id;
-    KdNode a{}, b{};
-    a.left  = n.left;
-    a.right = n.left + idx;
-    b.left  = n.left + idx;
-    b.right = n.right;
-    for ( int k = 0; k < 3; k++ ) {
-      a.lo[k] = b.lo[k] = n.lo[k];
-      a.hi[k] = b.hi[k] = n.hi[k];
+    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
+      KbNode& n = cur[j];
+      if ( n.state != 1 ) { continue; }
+      const uint32_t count = n.right - n.left;
+      uint32_t       idx;  // :1137-1139
+      if ( n.lt > count / 2 ) {
+        idx = n.lt;
+      } else if ( n.le < count / 2 ) {
+        idx = n.le;
+      } else {
+        idx = count / 2;
+      }
+      KbNext a{}, b{};
+      a.gid = gbase + n.child, b.gid = gbase + n.child + 1;
+      a.pgid = b.pgid = n.gid;
+      a.pfeat = b.pfeat = n.cutfeat;
+      a.side = 0, b.side = 1;
+      a.left = n.left, a.right = (uint16_t)( n.left + idx ), b.left = (uint16_t)( n.left + idx ), b.right = n.right;
+      for ( int k = 0; k < 3; k++ ) {
+        a.lo[k] = b.lo[k] = n.lo[k];
+        a.hi[k] = b.hi[k] = n.hi[k];
+      }
+      a.hi[n.cutfeat] = n.cutval;  // left_bbox[cutfeat].high = cutval
+      b.lo[n.cutfeat] = n.cutval;  // right_bbox[cutfeat].low = cutval
+      nxt[n.child]     = a;
+      nxt[n.child + 1] = b;
+      KdNode g{};
+      g.left = base + n.left, g.right = base + n.right, g.child1 = a.gid, g.lt = n.lt, g.le = n.le;
+      g.cutfeat = (int8_t)n.cutfeat, g.cutval = n.cutval, g.state = 1;
+      for ( int k = 0; k < 3; k++ ) {
+        g.lo[k] = n.lo[k], g.hi[k] = n.hi[k];
+        g.tmin[k] = (int16_t)n.tmin[k], g.tmax[k] = (int16_t)n.tmax[k];
+      }
+      nodes[n.gid] = g;  // divlow / divhigh are written by the children at the next level
     }
-    a.hi[axis]    = (int16_t)cut;
-    b.lo[axis]    = (int16_t)cut;
-    nodes[c1]     = a;
-    nodes[c1 + 1] = b;
-    stack[sp]     = c1 + 1;
-    dstack[sp++]  = (uint8_t)( depth + 1 );
-    stack[sp]     = c1;
-    dstack[sp++]  = (uint8_t)( depth + 1 );
+    __syncthreads();
+    // ---- elements move to their child; elements of finished leaves drop out ----
+#pragma unroll
+    for ( int q = 0; q < KB_EPT; q++ ) {
+      const uint32_t e = q * KB_TPB + t;
+      if ( e < total ) {
+        const uint32_t j = nid[e];
+        if ( j != 0xFFFFu ) {
+          const KbNode& n = cur[j];
+          nid[e]          = n.state == 1 ? (uint16_t)( e < nxt[n.child].right ? n.child : n.child + 1 ) : (uint16_t)0xFFFFu;
+        }
+      }
+    }
+    __syncthreads();
   }
-  for ( uint32_t i = 0; i < total; i++ ) { rec[base + i] = EL( i ); }
-  for ( int i = 0; i < nInner; i++ ) {  // divideTree :1080-1081
-    KdNode& n = nodes[inner[i]];
-    n.divlow  = nodes[n.child1].tmax[n.cutfeat];
-    n.divhigh = nodes[n.child1 + 1].tmin[n.cutfeat];
-  }
-  atomicMax( &counters[4], (uint32_t)maxDepth );
-#undef EL
+  __syncthreads();
+  for ( uint32_t i = t; i < total; i += KB_TPB ) { grec[base + i] = rec[i]; }
+  if ( t == 0 ) { atomicMax( &counters[4], (uint32_t)level + 1u ); }
 }
 
 // divlow / divhigh from the children's tight boxes (divideTree :1080-1081); depth bookkeeping
@@ -543,7 +729,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     const uint32_t nLvl = lvlEnd - lvlBegin;
     RB_LAUNCH( "kd_stats", k_kd_stats, G, TPB, 0, rec, nid, st, E, lvlBegin, lvlEnd );
     RB_CUDA( cudaMemsetAsync( counters + 2, 0, 4, c->stream ) );
-    RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KD_SMALL, ox, oy, oz,
+    RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KB_CAP, ox, oy, oz,
                B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0, st );
     roots = false;
     RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
@@ -570,15 +756,14 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   }
   const uint32_t nRoots = h[1], nLevelNodes = h[0];  // nodes [1, nLevelNodes) were created by the level-parallel phase
   if ( nRoots ) {
-    constexpr int BS = 64;
-    const size_t  smem = (size_t)KD_SMALL * BS * 8;
-    static bool   attr = false;
+    const size_t smem = sizeof( KbShared );
+    static bool  attr = false;
     if ( !attr ) {
-      RB_CUDA( cudaFuncSetAttribute( k_kd_serial<KD_SMALL, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+      RB_CUDA( cudaFuncSetAttribute( k_kd_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
       attr = true;
     }
-    RB_LAUNCH( "kd_serial", ( k_kd_serial<KD_SMALL, BS> ), rb_div_up( nRoots, BS ), BS, smem, rec, nodes,
-               B.smallRoots.as<uint32_t>(), nRoots, counters, nodeCap, ox, oy, oz );
+    RB_LAUNCH( "kd_block", k_kd_block, nRoots, KB_TPB, smem, rec, nodes, B.smallRoots.as<uint32_t>(), nRoots, counters, nodeCap,
+               ox, oy, oz );
   }
   RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );

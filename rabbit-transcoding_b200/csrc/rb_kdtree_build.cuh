@@ -5,7 +5,6 @@
 #include "rb_common.cuh"
 #include "rb_kdtree.cuh"
 
-constexpr int KD_SMALL = 128;  // subtrees of at most this many points are built by one thread in shared memory
 
 struct RbKdBuild {
   RbBuf    rec, nid, nodes, flags, pairL, pairR, sums, smallRoots, counters, stats;
