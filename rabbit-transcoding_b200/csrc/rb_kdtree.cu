@@ -361,7 +361,7 @@ __global__ void k_kd_assign( uint32_t* __restrict__ nid, const KdNode* __restric
 // rank-the-misplaced + pairwise swap), but every pass is a few hundred cycles on 2048 shared-memory records.
 // ---------------------------------------------------------------------------------------------------
 constexpr int KB_CAP   = 2048;  // elements per CTA subtree
-constexpr int KB_LEVEL = 512;   // nodes per level: children only come from nodes with > 10 elements, so <= 2 * 2048 / 11
+constexpr int KB_LEVEL = 384;   // nodes per level: children only come from nodes with > 10 elements, so <= 2 * 2048 / 11 = 372
 constexpr int KB_TPB   = 256;
 constexpr int KB_EPT   = KB_CAP / KB_TPB;
 
@@ -388,6 +388,7 @@ struct KbShared {
   uint16_t pairL[KB_CAP], pairR[KB_CAP];
   uint32_t warpSum[KB_TPB / 32];
   uint32_t nNext, gBase, big;
+  uint8_t  active[KB_CAP / 32];  // chunk of 32 consecutive elements still has an element in an unfinished node
 };
 
 __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ grec, KdNode* __restrict__ nodes,
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
   uint32_t&  sNNext = S.nNext;
   uint32_t&  sGBase = S.gBase;
   uint32_t&  sBig   = S.big;
+  uint8_t*   active = S.active;
   const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
   const uint32_t rootId = smallRoots[blockIdx.x];
   const uint32_t base = nodes[rootId].left, total = nodes[rootId].right - base;
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
     rec[i] = grec[base + i];
     nid[i] = 0;
   }
+  if ( t < KB_CAP / 32 ) { active[t] = (uint32_t)t * 32 < total; }
   if ( t == 0 ) {
     const KdNode r = nodes[rootId];
     KbNext       n{};
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
 #pragma unroll
     for ( int q = 0; q < KB_EPT; q++ ) {
       const uint32_t e = q * KB_TPB + t;
+      if ( !active[e >> 5] ) { continue; }  // warp-uniform
       const uint32_t j = e < total ? nid[e] : 0xFFFFu;
       const bool     on = j != 0xFFFFu;
       int            c[3] = {0, 0, 0};
@@ -511,27 +515,43 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
     }
     __syncthreads();
     if ( sBig == 0 ) { break; }
-    // ---- lim1 / lim2 ----
+    // ---- lim1 / lim2 (one shared-memory atomic per warp when the warp sits inside one node) ----
 #pragma unroll
     for ( int q = 0; q < KB_EPT; q++ ) {
-      const uint32_t e = q * KB_TPB + t;
-      const uint32_t j = e < total ? nid[e] : 0xFFFFu;
-      if ( j != 0xFFFFu && cur[j].state == 1 ) {
+      const uint32_t e  = q * KB_TPB + t;
+      if ( !active[e >> 5] ) { continue; }
+      const uint32_t j  = e < total ? nid[e] : 0xFFFFu;
+      const bool     on = j != 0xFFFFu && cur[j].state == 1;
+      bool           lt = false, le = false;
+      if ( on ) {
         const int v = kd_coord( rec[e], cur[j].cutfeat ), cut = cur[j].cutval;
-        if ( v < cut ) { atomicAdd( &cur[j].lt, 1u ); }
-        if ( v <= cut ) { atomicAdd( &cur[j].le, 1u ); }
+        lt = v < cut, le = v <= cut;
+      }
+      int allSame = 0;
+      __match_all_sync( 0xFFFFFFFFu, on ? j : 0xFFFFu, &allSame );
+      if ( allSame ) {
+        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, lt ), be = __ballot_sync( 0xFFFFFFFFu, le );
+        if ( on && lane == 0 ) {
+          if ( bl ) { atomicAdd( &cur[j].lt, (uint32_t)__popc( bl ) ); }
+          if ( be ) { atomicAdd( &cur[j].le, (uint32_t)__popc( be ) ); }
+        }
+      } else if ( on ) {
+        if ( lt ) { atomicAdd( &cur[j].lt, 1u ); }
+        if ( le ) { atomicAdd( &cur[j].le, 1u ); }
       }
     }
     __syncthreads();
     // ---- the two Hoare passes of planeSplit (:1154-1181) ----
     for ( int pass = 0; pass < 2; pass++ ) {
-      // flags of this thread's 8 CONSECUTIVE elements + block exclusive scan
-      uint32_t f[KB_EPT], loc = 0;
+      // flags + block exclusive scan.  Warp w owns the 256 consecutive elements [256 w, 256 w + 256) and walks them 32
+      // at a time (consecutive lanes = consecutive elements: conflict-free), carrying its running count in a register
+      uint32_t fbits = 0, run = 0;
+      uint16_t pre[KB_EPT];
 #pragma unroll
       for ( int q = 0; q < KB_EPT; q++ ) {
-        const uint32_t e = t * KB_EPT + q;
+        const uint32_t e = w * ( KB_EPT * 32 ) + q * 32 + lane;
         uint32_t       m = 0;
-        const uint32_t j = e < total ? nid[e] : 0xFFFFu;
+        const uint32_t j = ( active[e >> 5] && e < total ) ? nid[e] : 0xFFFFu;
         if ( j != 0xFFFFu && cur[j].state == 1 ) {
           const KbNode&  n = cur[j];
           const uint32_t p = e - n.left;
@@ -544,32 +564,24 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
             m             = ( p < n.le ) ? !in : in;
           }
         }
-        f[q] = m;
-        loc += m;
+        const uint32_t bal = __ballot_sync( 0xFFFFFFFFu, m != 0 );
+        pre[q]             = (uint16_t)( run + __popc( bal & ( ( 1u << lane ) - 1u ) ) );
+        run += __popc( bal );
+        fbits |= m << q;
       }
-      uint32_t incl = loc;
-#pragma unroll
-      for ( int d = 1; d < 32; d <<= 1 ) {
-        const uint32_t x = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
-        if ( lane >= d ) { incl += x; }
-      }
-      if ( lane == 31 ) { warpSum[w] = incl; }
+      if ( lane == 0 ) { warpSum[w] = run; }
       __syncthreads();
       uint32_t wbase = 0;
       for ( int k = 0; k < w; k++ ) { wbase += warpSum[k]; }
-      uint32_t run = wbase + incl - loc;
 #pragma unroll
-      for ( int q = 0; q < KB_EPT; q++ ) {
-        scan[t * KB_EPT + q] = (uint16_t)run;
-        run += f[q];
-      }
-      if ( t == KB_TPB - 1 ) { scan[KB_CAP] = (uint16_t)run; }
+      for ( int q = 0; q < KB_EPT; q++ ) { scan[w * ( KB_EPT * 32 ) + q * 32 + lane] = (uint16_t)( wbase + pre[q] ); }
+      if ( t == KB_TPB - 1 ) { scan[KB_CAP] = (uint16_t)( wbase + run ); }
       __syncthreads();
       // pair lists
 #pragma unroll
       for ( int q = 0; q < KB_EPT; q++ ) {
-        const uint32_t e = t * KB_EPT + q;
-        if ( f[q] ) {
+        const uint32_t e = w * ( KB_EPT * 32 ) + q * 32 + lane;
+        if ( ( fbits >> q ) & 1u ) {
           const KbNode&  n     = cur[nid[e]];
           const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
           const uint32_t lim   = pass == 0 ? n.left + n.lt : n.left + n.le;
@@ -587,6 +599,7 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
 #pragma unroll
       for ( int q = 0; q < KB_EPT; q++ ) {
         const uint32_t e = q * KB_TPB + t;
+        if ( !active[e >> 5] ) { continue; }
         const uint32_t j = e < total ? nid[e] : 0xFFFFu;
         if ( j != 0xFFFFu && cur[j].state == 1 ) {
           const KbNode&  n     = cur[j];
@@ -657,13 +670,18 @@ __global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ g
 #pragma unroll
     for ( int q = 0; q < KB_EPT; q++ ) {
       const uint32_t e = q * KB_TPB + t;
+      if ( !active[e >> 5] ) { continue; }
+      bool still = false;
       if ( e < total ) {
         const uint32_t j = nid[e];
         if ( j != 0xFFFFu ) {
           const KbNode& n = cur[j];
-          nid[e]          = n.state == 1 ? (uint16_t)( e < nxt[n.child].right ? n.child : n.child + 1 ) : (uint16_t)0xFFFFu;
+          still           = n.state == 1;
+          nid[e]          = still ? (uint16_t)( e < nxt[n.child].right ? n.child : n.child + 1 ) : (uint16_t)0xFFFFu;
         }
       }
+      const uint32_t any = __ballot_sync( 0xFFFFFFFFu, still );
+      if ( lane == 0 && any == 0 ) { active[e >> 5] = 0; }
     }
     __syncthreads();
   }
