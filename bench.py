@@ -163,6 +163,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; the driver wants one JSON line there
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -310,6 +312,9 @@ def run_b200(args):
         e0.record(stream)
         for _ in range(msteps):
             res = met.compute(srcs, resident, srcs)
+            if world > 1:  # the one exchange step of the path: all-gather of the per-frame accumulators (NCCL)
+                local = {rank + world * i: r for i, r in enumerate(res)}
+                table, seq_mean = rb.dist.gather_metrics(local, world * gof.n_frames, mp.resolution, device="cuda")
         e1.record(stream)
         torch.cuda.synchronize()
         clocks.off()
@@ -328,6 +333,9 @@ def run_b200(args):
                        "copied from pinned host memory inside the timed region",
                        "h2d_bytes_per_step": st.h2d_bytes // msteps, "gpu_launches_per_step": st.kernel_launches // msteps, "kernel_ms": mk,
                        "d1_psnr_mean_db": round(float(np.mean(d1)), 4), "d2_psnr_mean_db": round(float(np.mean(d2)), 4)}
+        if world > 1:
+            metrics_leg["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in seq_mean.items()}
+            metrics_leg["frames_gathered"] = len(table)
 
     # ---------------- leg 3: per-kernel events -> roofline of the dominant kernel ----------------
     codec.uploadGof(gof)
