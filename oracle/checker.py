@@ -3,8 +3,10 @@
 Two back-ends with the same interface:
   * `Reference`  : oracle/_ref/librabbit_ref.so — the UNMODIFIED reference sources compiled from
                    /root/reference by oracle/Makefile (`make ref`), driven by oracle/ref_harness.cpp.
-  * `Port`       : oracle/liboracle.so — the plain-C restatement (oracle/oracle_*.c), pinned against
-                   `Reference` by tests/test_oracle_vs_reference.py and against tests/golden/.
+  * `DropIn`     : oracle/_ref/librabbit_dropin.so — the same reference objects and harness with the hot member
+                   functions replaced by rabbit-transcoding_b200/host/PCCCodecB200.cpp (the drop-in boundary under test).
+  The CPU restatement of the algorithm lives in oracle/oracle_np.py (numpy), pinned against `Reference` by
+  tests/test_oracle_port_cpu.py and against tests/golden/.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 module.  The product package never does.

@@ -1,0 +1,427 @@
+"""oracle/oracle_np.py — CPU restatement (numpy) of the reference's algorithm for the hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this; the product never does.
+
+Every function restates one reference function (file:line relative to /root/reference/source/lib) on the CTC branch the
+BASELINE configs exercise: one or two maps in a single geometry stream, no EOM / raw patches / PLR / pixel
+interleaving / PBF (those raise NotImplementedError here — the compiled reference in oracle/_ref covers them).
+It is pinned against the unmodified reference (oracle/_ref/librabbit_ref.so) by tests/test_oracle_port_cpu.py, stage
+by stage and bit for bit, and against the golden fixtures in tests/golden/ — so it is a usable checker on a box that
+has neither /root/reference nor oracle/_ref.  Not restated here: PCCPointSet3::transferColors16bitBP (needs the
+nanoflann traversal order; covered by oracle/_ref and by the GPU kd-tree tests) and the D2 (point-to-plane) metric.
+"""
+import numpy as np
+
+SWITCHED = (1, 2, 4, 6, 8)  # orientations that exchange U and V on the canvas (PCCPatch.h:63-70)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCPatch::patch2Canvas (PccLibCommon/source/PCCPatch.cpp:192-251) / patchBlock2CanvasBlock (:253-308)
+# ---------------------------------------------------------------------------------------------------------------
+def patch2canvas(orient, u, v, su, sv, x0, y0):
+    """patch-local pixel (u, v) -> canvas pixel; su, sv = patch size in pixels, (x0, y0) = patch origin in pixels"""
+    if orient == 0:
+        x, y = u, v
+    elif orient in (1, 8):
+        x, y = v, u
+    elif orient == 2:
+        x, y = sv - 1 - v, u
+    elif orient == 3:
+        x, y = su - 1 - u, sv - 1 - v
+    elif orient == 4:
+        x, y = v, su - 1 - u
+    elif orient == 5:
+        x, y = su - 1 - u, v
+    elif orient == 6:
+        x, y = sv - 1 - v, su - 1 - u
+    elif orient == 7:
+        x, y = u, sv - 1 - v
+    else:
+        raise ValueError(orient)
+    return x + x0, y + y0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::generateOccupancyMap (PccLibCommon/source/PCCCodec.cpp:1584-1606) + the up-sampling of
+# generatePointCloud (:557-570)
+# ---------------------------------------------------------------------------------------------------------------
+def occupancy_map(video, precision, threshold):
+    """video: u8 [H/p][W/p].  The reference thresholds the video sample IN PLACE once per full-resolution pixel
+    (:1597-1600), i.e. p*p times: with threshold >= 1 and p > 1 the second visit sees the binarised 0/1 and clears it."""
+    v = video.astype(np.int64)
+    if precision == 1 or threshold == 0:
+        lo = (v > threshold)
+    else:
+        lo = np.zeros_like(v, bool)
+    return np.repeat(np.repeat(lo, precision, axis=0), precision, axis=1).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::generateBlockToPatchFromOccupancyMapVideo (:1725-1763)
+# ---------------------------------------------------------------------------------------------------------------
+def block_to_patch(occ, patches, R=16):
+    H, W = occ.shape
+    blocks = occ.reshape(H // R, R, W // R, R).any(axis=(1, 3))
+    b2p = np.zeros((H // R, W // R), np.uint32)
+    for i, p in enumerate(patches):
+        cw, ch = (p["size_v0"], p["size_u0"]) if p["orientation"] in SWITCHED else (p["size_u0"], p["size_v0"])
+        sub = blocks[p["v0"]:p["v0"] + ch, p["u0"]:p["u0"] + cw]
+        b2p[p["v0"]:p["v0"] + ch, p["u0"]:p["u0"] + cw][sub] = i + 1  # the last patch that covers an occupied block wins
+    return b2p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::identifyBoundaryPoints (:266-325), evaluated for every pixel of the frame at once
+# ---------------------------------------------------------------------------------------------------------------
+def boundary_map(occ):
+    H, W = occ.shape
+    o = np.pad(occ != 0, 2, constant_values=True)  # outside the image counts as occupied; borders are explicit
+
+    def all_occupied(r):
+        acc = np.ones((H, W), bool)
+        for dy in range(-r, r + 1):
+            for dx in range(-r, r + 1):
+                acc &= o[2 + dy:2 + dy + H, 2 + dx:2 + dx + W]
+        return acc
+    ys, xs = np.mgrid[0:H, 0:W]
+    border1 = (xs == 0) | (ys == 0) | (xs == W - 1) | (ys == H - 1)
+    border2 = (xs == 1) | (ys == 1) | (xs == W - 2) | (ys == H - 2)
+    return (border1 | ~all_occupied(1) | ~all_occupied(2) | border2).astype(np.uint16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::generatePointCloud (:517-978) + generatePoints (:327-515, default branch :497-513) +
+# PCCPatch::generatePoint (PCCPatch.h:177-207) + colorPointCloud (:1308-1449, single-stream branch :1418-1422)
+# ---------------------------------------------------------------------------------------------------------------
+def reconstruct_frame(params, occ_video, geometry, attribute, patches):
+    """returns a dict of arrays in PCCPointSet3 layouts, in the reference's emission order"""
+    P = params
+    if (P.enhanced_occupancy_map_code or P.use_additional_points_patch or P.single_map_pixel_interleaving or
+            P.point_local_reconstruction or P.pbf_enable or P.enable_size_quantization):
+        raise NotImplementedError("oracle_np restates the default CTC branch only (see the module docstring)")
+    R, M = P.occupancy_resolution, P.map_count_minus1 + 1
+    occ = occupancy_map(occ_video, P.occupancy_precision, P.threshold_lossy_om)
+    b2p = block_to_patch(occ, patches, R)
+    btype = boundary_map(occ) if P.flag_geometry_smoothing else np.zeros(occ.shape, np.uint16)
+    order = range(len(patches) - 1, -1, -1) if P.patch_precedence_reverse else range(len(patches))
+    pos, col, typ, part, p2p = [], [], [], [], []
+    for i in order:
+        p = patches[i]
+        su0, sv0 = int(p["size_u0"]), int(p["size_v0"])
+        if su0 == 0 or sv0 == 0:
+            continue
+        # emission order: v0, u0 (blocks), then v1, u1 (pixels), then the layers (:648-840)
+        v0, u0, v1, u1 = np.meshgrid(np.arange(sv0), np.arange(su0), np.arange(R), np.arange(R), indexing="ij")
+        u, v = (u0 * R + u1).ravel(), (v0 * R + v1).ravel()
+        x, y = patch2canvas(int(p["orientation"]), u, v, su0 * R, sv0 * R, int(p["u0"]) * R, int(p["v0"]) * R)
+        keep = (b2p[y // R, x // R] == i + 1) & (occ[y, x] != 0)  # :650, :668
+        u, v, x, y = u[keep], v[keep], x[keep], y[keep]
+        n = len(u)
+        d0 = geometry[0][y, x].astype(np.int64)
+
+        def normal(depth):  # PCCPatch::generateNormalCoordinate, PCCPatch.h:177-186
+            return depth + int(p["d1"]) if p["projection_mode"] == 0 else np.maximum(int(p["d1"]) - depth, 0)
+        P0 = np.zeros((n, 3), np.int64)
+        P0[:, p["normal_axis"]] = normal(d0)
+        P0[:, p["tangent_axis"]] = u * int(p["lod_x"]) + int(p["u1"])
+        P0[:, p["bitangent_axis"]] = v * int(p["lod_y"]) + int(p["v1"])
+        P0 = P0.astype(np.int16)  # double -> int16 (PCCMath.h:79-84)
+        layers = [P0]
+        if M > 1:
+            g1 = geometry[1][y, x].astype(np.int64)
+            P1 = P0.copy()
+            if P.absolute_d1:
+                P1[:, p["normal_axis"]] = normal(g1).astype(np.int16)  # generatePoint( u, v, frame1 ), :503
+            else:
+                n0 = P0[:, p["normal_axis"]].astype(np.int64)
+                P1[:, p["normal_axis"]] = (n0 + g1 if p["projection_mode"] == 0 else n0 - g1).astype(np.int16)  # :505-509
+            layers.append(P1)
+        # interleave the layers per pixel; D1 == D0 is dropped when removeDuplicatePoints (:794-795)
+        emit = np.ones((n, len(layers)), bool)
+        if M > 1 and P.remove_duplicate_points:
+            emit[:, 1] = (layers[1] != layers[0]).any(axis=1)
+        idx = np.nonzero(emit.ravel())[0]
+        pix, lay = idx // len(layers), idx % len(layers)
+        allp = np.stack(layers, axis=1).reshape(-1, 3)
+        pos.append(allp[idx])
+        typ.append(btype[y[pix], x[pix]])
+        part.append(np.full(len(idx), i, np.uint32))
+        p2p.append(np.stack([x[pix], y[pix], lay], axis=1).astype(np.uint32))
+        if P.attribute_count > 0:
+            col.append(np.stack([attribute[lay, c, y[pix], x[pix]] for c in range(3)], axis=1).astype(np.uint16))
+
+    def cat(parts, shape, dt):
+        return np.concatenate(parts) if parts else np.zeros(shape, dt)
+    n = sum(len(a) for a in pos)
+    out = dict(positions=cat(pos, (0, 3), np.int16), boundary_types=cat(typ, (0,), np.uint16).astype(np.uint16),
+               partition=cat(part, (0,), np.uint32), point_to_pixel=cat(p2p, (0, 3), np.uint32),
+               colors16=cat(col, (0, 3), np.uint16) if P.attribute_count > 0 else np.zeros((n, 3), np.uint16),
+               colors=np.zeros((n, 3), np.uint8))
+    return out, b2p, occ
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::smoothPointCloudPostprocess (:52-147) + addGridCentroid (:980-998) + smoothPointCloudGrid / gridFiltering
+# (:1000-1104)
+# ---------------------------------------------------------------------------------------------------------------
+def _cell_tables(cell_ids, values, partition):
+    """per occupied cell: count, float32 sums accumulated in emission order, doSmooth (>= 2 distinct partitions)"""
+    uniq, inv = np.unique(cell_ids, return_inverse=True)
+    cnt = np.bincount(inv, minlength=len(uniq))
+    sums = np.stack([np.bincount(inv, weights=values[:, k].astype(np.float64), minlength=len(uniq)) for k in range(3)], axis=1)
+    assert sums.max(initial=0) < 2 ** 24, "float accumulator would leave the exact range (SURVEY App. A.3)"
+    pmin = np.full(len(uniq), np.iinfo(np.int64).max)
+    pmax = np.full(len(uniq), -1)
+    np.minimum.at(pmin, inv, partition.astype(np.int64))
+    np.maximum.at(pmax, inv, partition.astype(np.int64))
+    return uniq, cnt, sums.astype(np.float32), pmin != pmax
+
+
+def smooth_geometry(params, cloud):
+    g = params.grid_size
+    pos = cloud["positions"].astype(np.int64)
+    typ = cloud["boundary_types"].copy()
+    n = len(pos)
+    if n == 0 or not params.flag_geometry_smoothing or not params.grid_smoothing:
+        return cloud
+    w = (int(pos.max()) + g - 1) // g  # :68-79
+    disth, th = max(g // 2, 1), g * w
+    inside = ~((pos < disth).any(axis=1) | (th <= pos + disth).any(axis=1))  # :92-95
+    W = w + 2
+    cid = (pos[:, 0] // g) + (pos[:, 1] // g) * W + (pos[:, 2] // g) * W * W
+    uniq, cnt, sums, multi = _cell_tables(cid[inside], pos[inside], cloud["partition"][inside])
+    centre = (sums / cnt[:, None].astype(np.float32)).astype(np.float64)  # :135-137, one float division per component
+    look = {int(c): k for k, c in enumerate(uniq)}
+    out = cloud["positions"].copy()
+    g2, hg = 2 * g, g // 2
+    thr = int(params.threshold_smoothing)
+    for i in np.nonzero(inside & (typ == 1))[0]:  # :1087
+        Pp = pos[i]
+        S = Pp // g - ((Pp % g) < hg)  # :1014-1017
+        cells = [look.get(int((S[0] + dx) + (S[1] + dy) * W + (S[2] + dz) * W * W), -1)
+                 for dz in (0, 1) for dy in (0, 1) for dx in (0, 1)]
+        if not any(k >= 0 and multi[k] for k in cells):  # doSmooth && count (:1024)
+            continue
+        Wt = (Pp - S * g - hg) * 2 + 1  # :1034
+        Q = g2 - Wt
+        c4 = np.zeros(3)
+        count = 0
+        kk = 0
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    wgt = int((Wt[0] if dx else Q[0]) * (Wt[1] if dy else Q[1]) * (Wt[2] if dz else Q[2]))
+                    k = cells[kk]
+                    kk += 1
+                    v = centre[k] if k >= 0 else Pp.astype(np.float64)
+                    c4 = c4 + v * float(wgt)  # :1050-1058
+                    count += wgt * (int(cnt[k]) if k >= 0 else 0)
+        c4 = c4 / float(g2 ** 3)
+        count //= g2 ** 3  # int division; 0 is common (App. A.4): 0/0 = NaN, NaN >= x is false
+        if count == 0:
+            continue
+        cen = c4 * float(count)
+        e = Pp.astype(np.float64) * float(count) - cen
+        dist2 = ((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]) / float(count) + 0.5  # :1093
+        if dist2 >= float(max(thr, count) * 2):  # :1094
+            out[i] = np.trunc(cen / float(count) + 0.5).astype(np.int64).astype(np.int16)  # :1095-1097
+            typ[i] = 3
+    res = dict(cloud)
+    res["positions"], res["boundary_types"] = out, typ
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::colorSmoothing (:149-236) + addGridColorCentroid (:1159-1180) + gridFilteringColor (:1182-1266) +
+# smoothPointCloudColorLC (:1268-1306); median / mean: PCCCodec.h:271-285
+# ---------------------------------------------------------------------------------------------------------------
+def smooth_color(params, cloud):
+    g = params.occupancy_precision  # the colour grid uses occupancyPrecision (:152)
+    pcmax = 1 << params.geometry_bitdepth_3d
+    w = pcmax // g
+    pos = cloud["positions"].astype(np.int64)
+    typ = cloud["boundary_types"]
+    col = cloud["colors16"].astype(np.int64)
+    n = len(pos)
+    if n == 0:
+        return cloud
+    disth, hg, g2 = max(g // 2, 1), g // 2, 2 * g
+    ok = (pos >= 0).all(axis=1) & ((pos // g) < w).all(axis=1)  # :212 guard
+    cid = (pos[:, 0] // g) + (pos[:, 1] // g) * w + (pos[:, 2] // g) * w * w
+    uniq, cnt, sums, multi = _cell_tables(cid[ok], col[ok], cloud["partition"][ok])
+    mean = sums.astype(np.float64) / cnt[:, None].astype(np.float64)  # :1225
+    look = {int(c): k for k, c in enumerate(uniq)}
+    # per-cell luma lists in emission order (colorSmoothingLum_, :1179)
+    order = np.argsort(cid[ok], kind="stable")
+    lum_sorted = col[ok][order, 0]
+    starts = np.concatenate([[0], np.cumsum(cnt)])
+    var_thr, diff_thr = params.threshold_color_variation * 256.0, params.threshold_color_difference * 256.0
+
+    def gate(k):  # |trunc(mean - median)| > variation * 256, int abs(int) on a truncated double (App. A.9)
+        if cnt[k] <= 1:
+            return False
+        lum = np.sort(lum_sorted[starts[k]:starts[k + 1]])
+        m = len(lum)
+        med = (lum[m // 2] + lum[m // 2 - 1]) / 2.0 if m % 2 == 0 else float(lum[m // 2])
+        mn = float(lum.sum()) / m
+        return abs(int(mn - med)) > var_thr
+    gates = {}
+    out = cloud["colors16"].copy()
+    inside = ~((pos < disth).any(axis=1) | (pcmax <= pos + disth).any(axis=1))  # :1280-1283
+    for i in np.nonzero(inside & (typ == 1))[0]:  # :1288
+        Pp = pos[i]
+        S = Pp // g - ((Pp % g) < hg)  # :1197-1199
+        cells = [look.get(int((S[0] + dx) + (S[1] + dy) * w + (S[2] + dz) * w * w), -1)
+                 if 0 <= S[0] + dx < w and 0 <= S[1] + dy < w and 0 <= S[2] + dz < w else -1
+                 for dz in (0, 1) for dy in (0, 1) for dx in (0, 1)]
+        if not any(k >= 0 and multi[k] for k in cells):  # :1204
+            continue
+        cur = col[i].astype(np.float64)
+        Wt = (Pp - S * g - hg) * 2 + 1
+        Q = g2 - Wt
+        c3 = []
+        keep_own = False
+        Y0 = 0.0
+        for kk, k in enumerate(cells):  # :1218-1251
+            if k >= 0:
+                if k not in gates:
+                    gates[k] = gate(k)
+                d = mean[k].copy()
+                if kk == 0:
+                    if gates[k]:
+                        keep_own = True
+                        break
+                else:
+                    own = abs(int(Y0 - d[0])) > diff_thr  # :1238
+                    if gates[k]:
+                        own = True
+                    if own:
+                        d = cur.copy()
+            else:
+                d = cur.copy()
+            if kk == 0:
+                Y0 = d[0]
+            c3.append(d)
+        if keep_own:
+            continue
+        c4 = np.zeros(3)
+        kk = 0
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    wgt = float(int((Wt[0] if dx else Q[0]) * (Wt[1] if dy else Q[1]) * (Wt[2] if dz else Q[2])))
+                    c4 = c4 + c3[kk] * wgt
+                    kk += 1
+        res = np.trunc(c4 / float(g2 ** 3) + 0.5)  # :1262, :1294-1295
+        dist = abs(int(res[0] - cur[0])) * 10.0 / 256.0  # :1299
+        if dist >= params.threshold_color_smoothing:
+            out[i] = res.astype(np.int64).astype(np.uint16)
+    r = dict(cloud)
+    r["colors16"] = out
+    return r
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCPointSet3::convertYUV16ToRGB8 / copyRGB16ToRGB8 (PccLibCommon/include/PCCPointSet.h:121-166)
+# ---------------------------------------------------------------------------------------------------------------
+def to_rgb8(params, cloud):
+    c = cloud["colors16"].astype(np.float64)
+    out = dict(cloud)
+    if params.attribute_count == 0:
+        out["colors"] = np.full((len(c), 3), 127, np.uint8)
+        return out
+    if params.attribute_rgb444:
+        out["colors"] = cloud["colors16"].astype(np.uint8)
+        return out
+    wgt = 1.0 / 65535.0
+    y1 = np.clip(wgt * c[:, 0], 0.0, 1.0)
+    u1 = np.clip(wgt * (c[:, 1] - 32768.0), -0.5, 0.5)
+    v1 = np.clip(wgt * (c[:, 2] - 32768.0), -0.5, 0.5)
+    r = y1 + 1.57480 * v1
+    g = (y1 - 0.18733 * u1) - 0.46813 * v1
+    b = y1 + 1.85563 * u1
+
+    def rnd(a):  # round() = half away from zero, then clip to [0, 255]
+        a = a * 255.0
+        return np.clip(np.where(a >= 0, np.floor(a + 0.5), np.ceil(a - 0.5)), 0, 255)
+    out["colors"] = np.stack([rnd(r), rnd(g), rnd(b)], axis=1).astype(np.uint8)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCPointSet3::removeDuplicate( out, dropDuplicates ) (PccLibCommon/source/PCCPointSet.cpp:169-218)
+# ---------------------------------------------------------------------------------------------------------------
+def remove_duplicates(positions, colors, drop=2):
+    p = positions.astype(np.int64)
+    key = ((p[:, 0] + 32768) << 32) | ((p[:, 1] + 32768) << 16) | (p[:, 2] + 32768)
+    order = np.argsort(key, kind="stable")  # nested std::map<float,...>: lexicographic (x, y, z); lists in index order
+    ks = key[order]
+    first = np.concatenate([[True], ks[1:] != ks[:-1]])
+    starts = np.nonzero(first)[0]
+    out_p = positions[order][starts]
+    if colors is None:
+        return out_p, None
+    c = colors[order].astype(np.int64)
+    if drop == 1:
+        return out_p, colors[order][starts]
+    counts = np.diff(np.concatenate([starts, [len(ks)]]))
+    sums = np.add.reduceat(c, starts, axis=0)
+    return out_p, (sums // counts[:, None]).astype(np.uint8)  # size_t division (:197-199)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# QualityMetrics::compute — D1 (point-to-point) and colour only (PccLibMetrics/source/PCCMetrics.cpp:75-231)
+# ---------------------------------------------------------------------------------------------------------------
+def _yuv709(rgb):  # convertRGBtoYUVBT709, :50-55 (double arithmetic, each channel narrowed to float)
+    r, g, b = (rgb[:, k].astype(np.float64) for k in range(3))
+    return np.stack([((0.2126 * r + 0.7152 * g) + 0.0722 * b) / 255.0,
+                     ((-0.1146 * r - 0.3854 * g) + 0.5000 * b) / 255.0 + 0.5000,
+                     ((0.5000 * r - 0.4542 * g) - 0.0458 * b) / 255.0 + 0.5000], axis=1).astype(np.float32)
+
+
+def quality_d1_colour(posA, colA, posB, colB):
+    """one direction A -> B; the tie set is every point of B at the nearest distance, colours averaged (neighborsProc 1)"""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(posB.astype(np.float64))
+    d, _ = tree.query(posA.astype(np.float64), k=1)
+    d2 = np.rint(d * d).astype(np.int64)
+    sse_c2c = float(d2.sum())
+    yA = _yuv709(colA)
+    sse_col = np.zeros(3)
+    ties = tree.query_ball_point(posA.astype(np.float64), np.sqrt(d2) + 1e-6)
+    for i, t in enumerate(ties):
+        pb = posB[t].astype(np.int64) - posA[i].astype(np.int64)
+        t = np.array(t)[(pb * pb).sum(axis=1) == d2[i]]
+        assert 0 < len(t) <= 30
+        s = colB[t].astype(np.int64).sum(axis=0)
+        rgb = np.floor(s / len(t) + 0.5).astype(np.uint8)[None, :]  # round() of a non-negative double
+        yB = _yuv709(rgb)[0]
+        diff = (yA[i] - yB).astype(np.float32)
+        sse_col += (diff * diff).astype(np.float32).astype(np.float64)  # powf( float, 2 ) then summed in double
+    return sse_c2c, sse_col, len(posA)
+
+
+class Port:
+    """same calling convention as oracle.checker backends for the stages it restates"""
+
+    def run_gof(self, gof, stages=("reconstruct", "smooth_geometry", "smooth_color", "rgb8")):
+        P = gof.params
+        out = []
+        for f in range(gof.n_frames):
+            patches = gof.patches[gof.patch_offset[f]:gof.patch_offset[f + 1]]
+            cloud, b2p, occ = reconstruct_frame(P, gof.occupancy[f], gof.geometry[f], gof.attribute[f], patches)
+            snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ}
+            if P.apply_geo_smoothing and P.flag_geometry_smoothing:
+                if P.grid_smoothing:
+                    cloud = smooth_geometry(P, cloud)
+                snaps["smooth_geometry"] = cloud
+                if P.attribute_count > 0 and P.attr_transfer_filter_type != 0:
+                    raise NotImplementedError("transferColors16bitBP is not restated in oracle_np (use oracle/_ref)")
+            if P.attribute_count > 0:
+                if P.apply_attr_smoothing and P.flag_color_smoothing:
+                    cloud = smooth_color(P, cloud)
+                snaps["smooth_color"] = cloud
+            cloud = to_rgb8(P, cloud)
+            snaps["rgb8"] = cloud
+            out.append(snaps)
+        return out

@@ -1,0 +1,97 @@
+"""Pins the numpy restatement (oracle/oracle_np.py) against the unmodified reference (oracle/_ref) stage by stage and
+bit for bit, on small seeded GOFs, and against the golden fixtures.  CPU only."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from util import FIELDS, assert_cloud_equal
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ref():
+    from oracle import checker
+    if not checker.have_reference():
+        pytest.skip("oracle/_ref not built")
+    return checker, checker.Reference()
+
+
+CASES = {
+    "default": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=201, transfer_filter=0),
+    "orient_reverse_p2": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=202, transfer_filter=0,
+                              orientations=tuple(range(9)), occupancy_precision=2, precedence_reverse=True),
+    "single_map_p1": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=203, transfer_filter=0, map_count=1,
+                          occupancy_precision=1),
+    "relative_d1": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=204, transfer_filter=0, absolute_d1=False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_port_equals_reference_every_stage(rb, name):
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+    g = rb.synthetic.generate_gof(**CASES[name])
+    if name == "relative_d1":
+        g.params.remove_duplicate_points = 0
+    stages = ("reconstruct", "smooth_geometry", "smooth_color", "rgb8")
+    want = ref_b.run_gof(g, keep=stages)
+    g2 = rb.synthetic.generate_gof(**CASES[name])  # fresh planes: the reference binarises the occupancy video in place
+    g2.params = g.params
+    got = oracle_np.Port().run_gof(g2, stages)
+    for f in range(g.n_frames):
+        assert np.array_equal(got[f]["block_to_patch"], want.block_to_patch(f, g.params))
+        assert np.array_equal(got[f]["occupancy"] != 0, want.occupancy(f, g.params) != 0)
+        for st in stages:
+            w = want.cloud(f, st)
+            c = dict(got[f][st])
+            if st != "rgb8":
+                c["colors"] = w["colors"]
+            assert_cloud_equal(c, w, f"{name} frame {f} stage {st}", FIELDS)
+        assert want.counts(f).smoothed > 0 and want.counts(f).recolored > 0
+
+
+def test_port_remove_duplicates_and_d1(rb):
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+    g = rb.synthetic.generate_gof(**CASES["default"])
+    rec = ref_b.run_gof(g, keep=("rgb8",)).cloud(0, "rgb8")
+    for drop in (1, 2):
+        wp, wc = ref_b.remove_duplicates(rec["positions"], rec["colors"], drop)
+        gp, gc = oracle_np.remove_duplicates(rec["positions"], rec["colors"], drop)
+        assert np.array_equal(gp, wp) and np.array_equal(gc, wc)
+    mp = checker.default_metrics_params(resolution=127.0, c2p=False)
+    want, _ = ref_b.metrics(mp, g.sources[0], rec, None)
+    sp, sc = oracle_np.remove_duplicates(g.sources[0]["positions"], g.sources[0]["colors"], 2)
+    rp, rc = oracle_np.remove_duplicates(rec["positions"], rec["colors"], 2)
+    for (pa, ca, pb, cb), q in (((sp, sc, rp, rc), want.q1), ((rp, rc, sp, sc), want.q2)):
+        sse, ssec, num = oracle_np.quality_d1_colour(pa, ca, pb, cb)
+        assert np.float32(sse / num) == np.float32(q.c2c_mse)
+        for k in range(3):
+            assert abs(np.float32(ssec[k] / num) - q.color_mse[k]) <= 1e-6 * max(q.color_mse[k], 1e-30)
+
+
+def test_port_matches_golden_fixture(rb):
+    """the restatement against the committed fixtures only (no reference needed): ordered MD5 of the final cloud"""
+    import hashlib
+    from oracle import oracle_np
+    gold = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+    name = "raw_single_map"  # no transfer stage; raw points are outside the restated branch -> use a restated case
+    kw = dict(gold["default"]["args"])
+    kw["transfer_filter"] = 0
+    # the golden "default" case runs the attribute re-transfer, which the port does not restate: compare the stages
+    # before it (reconstruction and geometry smoothing digests are transfer-independent)
+    g = rb.synthetic.generate_gof(**kw)
+    got = oracle_np.Port().run_gof(g, ("reconstruct", "smooth_geometry"))
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    for f, fr in enumerate(gold["default"]["frames"]):
+        c = dict(got[f]["reconstruct"])
+        assert make_golden.cloud_digest(c) == fr["stages"]["reconstruct"], f"frame {f}: reconstruct digest"
+        c = dict(got[f]["smooth_geometry"])
+        assert make_golden.cloud_digest(c) == fr["stages"]["smooth_geometry"], f"frame {f}: smooth_geometry digest"
+        assert int((c["boundary_types"] == 3).sum()) == fr["smoothed"]
+    assert name
