@@ -170,3 +170,18 @@ def test_vox10_full_size_frame_with_transfer(rb, codec, checker_backend):
                                   height_blocks=80)
     ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="vox10-transfer")
     assert ref.counts(0).smoothed > 5000
+
+
+# ---- BASELINE.json config 4 shapes: vox11 (11-bit, 2560-wide atlas), lossy two-layer and the lossless-style EOM variant ----
+def test_vox11_frame_lossy_full_decoder(rb, codec, checker_backend):
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=11, width=2560, scale=0.55, seed=61, transfer_filter=1)
+    assert g.params.geometry_bitdepth_3d == 11
+    ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="vox11")
+    assert ref.counts(0).total > 1500000
+
+
+def test_vox11_frame_eom_lossless_style(rb, codec, checker_backend):
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=11, width=2560, scale=0.45, seed=62, transfer_filter=0, eom=True,
+                                  geometry_smoothing=False, color_smoothing=False)
+    ref = run_stages(codec, g, checker_backend, stages=("reconstruct", "rgb8"), what="vox11-eom")
+    assert ref.counts(0).eom > 0
