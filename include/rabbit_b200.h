@@ -251,6 +251,15 @@ int rb200_remove_duplicates(rb200_ctx* ctx, const rb200_cloud_view* in, int drop
 int rb200_kdtree_search(rb200_ctx* ctx, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, int k,
                         int64_t* out_idx, double* out_dist);
 
+/* ---- PCCPointSet3::computeChecksum( false ) (PCCPointSet.cpp:222-245): MD5 of positions || RGB8 of a decoded frame ---- */
+int rb200_frame_md5(rb200_ctx* ctx, int frame, uint8_t* out16);
+/* ---- PCCPointSet3::write( file, asAscii = false ) (:359-457): binary little-endian PLY, float xyz + uchar rgb,
+ *      byte-identical to the reference's file for a decoded frame.  Records are packed on the device. ------------------- */
+int rb200_write_ply(rb200_ctx* ctx, int frame, const char* path);
+/* ---- PCCPointSet3::read (:459-757) for x, y, z (+ red, green, blue): ascii or binary little-endian.  out_pos NULL or
+ *      capacity too small: only *out_count (and *has_colors) are filled. ------------------------------------------------ */
+int rb200_read_ply(const char* path, int16_t* out_pos, uint8_t* out_col, int64_t capacity, int64_t* out_count, int* has_colors);
+
 /* ---- instrumentation --------------------------------------------------------------------------- */
 typedef struct rb200_launch_stats {
   int64_t kernel_launches;    /* number of this library's kernels launched since the last reset        */

@@ -177,6 +177,25 @@ class _Backend:
         m = self._lib_call("remove_duplicates", C.byref(v), drop, abi.ptr(op), abi.ptr(oc) if colors is not None else None)
         return op[:m].copy(), (oc[:m].copy() if colors is not None else None)
 
+    def write_ply(self, positions, colors, path):
+        """PCCPointSet3::write through oracle/_ref/ref_ply_tool (a separate process, see ref_ply_tool.cpp)"""
+        import subprocess
+        import tempfile
+        tool = os.path.join(_HERE, "_ref", "ref_ply_tool")
+        with tempfile.TemporaryDirectory() as d:
+            np.ascontiguousarray(positions, np.int16).tofile(os.path.join(d, "p"))
+            np.ascontiguousarray(colors, np.uint8).tofile(os.path.join(d, "c"))
+            return subprocess.call([tool, "write", str(len(positions)), os.path.join(d, "p"), os.path.join(d, "c"), path])
+
+    def read_ply(self, path, cap=None):
+        import subprocess
+        import tempfile
+        tool = os.path.join(_HERE, "_ref", "ref_ply_tool")
+        with tempfile.TemporaryDirectory() as d:
+            subprocess.check_call([tool, "read", path, os.path.join(d, "p"), os.path.join(d, "c")], stdout=subprocess.DEVNULL)
+            return (np.fromfile(os.path.join(d, "p"), np.int16).reshape(-1, 3),
+                    np.fromfile(os.path.join(d, "c"), np.uint8).reshape(-1, 3))
+
     def knn(self, cloud, queries, k):
         cloud = np.ascontiguousarray(cloud, np.int16)
         queries = np.ascontiguousarray(queries, np.int16)

@@ -589,6 +589,22 @@ int ref_knn( const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq
   return 0;
 }
 
+// PCCPointSet3::write / read (PCCPointSet.cpp:359-757) on a flat cloud: pins the PLY wire format
+int ref_write_ply( const rb200_cloud_view* in, const char* path ) {
+  PCCPointSet3 pc;
+  viewToCloud( *in, pc, false );
+  return pc.write( path, false ) ? 0 : 1;
+}
+int64_t ref_read_ply( const char* path, int16_t* outPos, uint8_t* outCol, int64_t cap ) {
+  PCCPointSet3 pc;
+  if ( !pc.read( path ) ) { return -1; }
+  const int64_t n = (int64_t)pc.getPointCount();
+  if ( n > cap ) { return n; }
+  if ( outPos && n ) { std::memcpy( outPos, pc.positions_.data(), n * 6 ); }
+  if ( outCol && n && pc.colors_.size() == (size_t)n ) { std::memcpy( outCol, pc.colors_.data(), n * 3 ); }
+  return n;
+}
+
 int ref_abi_version( void ) { return RB200_ABI_VERSION; }
 
 }  // extern "C"

@@ -152,6 +152,29 @@ class PCCCodecB200:
         self._check(self._lib.rb200_download_occupancy(self._h, f, abi.ptr(a)))
         return a
 
+    def computeChecksum(self, f):
+        """PCCPointSet3::computeChecksum( false ): MD5 of positions || RGB8 of frame f, as a hex string"""
+        d = (C.c_uint8 * 16)()
+        self._check(self._lib.rb200_frame_md5(self._h, f, d))
+        return bytes(d).hex()
+
+    def write(self, f, file_name):
+        """PCCPointSet3::write( fileName, asAscii=false ) for decoded frame f"""
+        self._check(self._lib.rb200_write_ply(self._h, f, file_name.encode()))
+
+    def read(self, file_name):
+        """PCCPointSet3::read: returns dict(positions, colors or None)"""
+        n, hc = abi.i64(0), C.c_int(0)
+        st = self._lib.rb200_read_ply(file_name.encode(), None, None, 0, C.byref(n), C.byref(hc))
+        if st != abi.RB200_OK:
+            raise RabbitError(st, f"cannot read {file_name}")
+        pos = np.zeros((n.value, 3), np.int16)
+        col = np.zeros((n.value, 3), np.uint8) if hc.value else None
+        st = self._lib.rb200_read_ply(file_name.encode(), abi.ptr(pos), abi.ptr(col), n.value, C.byref(n), C.byref(hc))
+        if st != abi.RB200_OK:
+            raise RabbitError(st, f"cannot read {file_name}")
+        return dict(positions=pos, colors=col)
+
     # ---- instrumentation ----
     def stats(self, reset=False):
         s = abi.LaunchStats()

@@ -185,3 +185,22 @@ def test_vox11_frame_eom_lossless_style(rb, codec, checker_backend):
                                   geometry_smoothing=False, color_smoothing=False)
     ref = run_stages(codec, g, checker_backend, stages=("reconstruct", "rgb8"), what="vox11-eom")
     assert ref.counts(0).eom > 0
+
+
+# ---- wire format and checksum (PCCPointSet3::write / read / computeChecksum) ----
+def test_ply_and_md5_match_reference(rb, codec, checker_backend, tmp_path):
+    g = small(rb, seed=65, transfer_filter=1)
+    ref = checker_backend.run_gof(small(rb, seed=65, transfer_filter=1), keep=("rgb8",))
+    codec.uploadGof(g)
+    codec.decodeGof()
+    for f in range(g.n_frames):
+        want = ref.cloud(f, "rgb8")
+        assert codec.computeChecksum(f) == ref.md5(f)
+        mine, theirs = str(tmp_path / f"b200_{f}.ply"), str(tmp_path / f"ref_{f}.ply")
+        codec.write(f, mine)
+        assert checker_backend.write_ply(want["positions"], want["colors"], theirs) == 0
+        assert open(mine, "rb").read() == open(theirs, "rb").read(), "PLY file differs from PCCPointSet3::write"
+        back = codec.read(theirs)
+        assert np.array_equal(back["positions"], want["positions"]) and np.array_equal(back["colors"], want["colors"])
+        rp, rc = checker_backend.read_ply(mine)
+        assert np.array_equal(rp, want["positions"]) and np.array_equal(rc, want["colors"])
