@@ -62,7 +62,7 @@ struct GridArgs {
   const uint32_t* part;
   const uint32_t* blist;     // indices of the points classified as boundary (type 1) by the reconstruction
   const uint32_t* blist_n;
-  double*         means;     // [F][slots][3] per-cell centre / mean colour, computed once per cell by k_finalize_cells
+  uint4*          fcell;     // [F][slots] what the filters read: {float sum0, sum1, sum2, cnt | multi << 30 | gate << 31}
 };
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -110,9 +110,13 @@ __device__ __forceinline__ uint32_t cell_find( const GridArgs& a, int f, int cx,
   }
   return 0xFFFFFFFFu;
 }
-// the 2x2x2 cells a boundary point blends: all eight first probes are issued before any of them is examined, and the
-// eight accumulators are then fetched together (memory-level parallelism instead of eight dependent round trips)
-__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], Cell cl[8], uint32_t ix[8] ) {
+// What the filters need of a cell, in ONE 16-byte record written by k_finalize_cells / k_cell_median_gate: the three
+// sums as floats (exact: < 2^24, App. A.3), the count, doSmooth and the mean/median gate.
+constexpr uint32_t FC_MULTI = 1u << 30, FC_GATE = 1u << 31, FC_CNT = 0xFFFFFu;
+
+// the 2x2x2 cells a boundary point blends: all eight first probes are issued before any of them is examined, then the
+// eight 16-byte records are fetched together — two dependent memory round trips instead of dozens
+__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], uint4 fc[8] ) {
   const uint32_t mask = a.slots - 1, base = (uint32_t)f * a.slots;
   uint32_t       s[8], key[8], v[8];
 #pragma unroll
@@ -123,20 +127,23 @@ __device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int 
   }
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) { v[k] = __ldg( a.keys + base + s[k] ); }
+  uint32_t miss = 0;  // cells whose first probe hit another key: continue their probe sequence (rare)
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( v[k] == key[k] ) {
-      ix[k] = base + s[k];
-    } else if ( v[k] == 0 ) {
-      ix[k] = 0xFFFFFFFFu;
-    } else {  // collision: continue the probe sequence
-      ix[k]      = 0xFFFFFFFFu;
+    if ( v[k] != key[k] && v[k] != 0 ) { miss |= 1u << k; }
+  }
+  if ( miss ) {
+#pragma unroll
+    for ( int k = 0; k < 8; k++ ) {
+      if ( !( miss >> k & 1u ) ) { continue; }
       uint32_t t = s[k];
+      v[k]       = 0;
       for ( int j = 1; j < MAX_PROBES; j++ ) {
         t                = ( t + 64 ) & mask;
         const uint32_t w = __ldg( a.keys + base + t );
         if ( w == key[k] ) {
-          ix[k] = base + t;
+          s[k] = t;
+          v[k] = w;
           break;
         }
         if ( w == 0 ) { break; }
@@ -144,12 +151,10 @@ __device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int 
     }
   }
 #pragma unroll
+  for ( int k = 0; k < 8; k++ ) { fc[k] = __ldg( a.fcell + base + s[k] ); }  // always a valid address
+#pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( ix[k] != 0xFFFFFFFFu ) {
-      cl[k] = cell_load( a.cells + ix[k] );
-    } else {
-      cl[k] = Cell{};
-    }
+    if ( v[k] != key[k] ) { fc[k] = make_uint4( 0, 0, 0, 0 ); }  // the cell holds no point
   }
 }
 
@@ -315,16 +320,9 @@ __global__ void k_finalize_cells( const GridArgs a, uint32_t nSlots, int colour 
     if ( s0 >= ( 1u << 24 ) || s1 >= ( 1u << 24 ) || s2 >= ( 1u << 24 ) || cnt > 65535u ) {
       a.finfo[slot / a.slots].sum_overflow = 1;
     }
-    if ( cnt > 0 ) {  // the per-cell centre, once per cell instead of once per boundary point and neighbour
-      double* m = a.means + (size_t)slot * 3;
-      if ( colour ) {  // :1225: float accumulator read back as double, divided by the count in double
-        const double dn = (double)cnt;
-        m[0] = (double)(float)s0 / dn, m[1] = (double)(float)s1 / dn, m[2] = (double)(float)s2 / dn;
-      } else {  // :135-137: centre = float sum / float count (one IEEE float division)
-        const float fc = (float)cnt;
-        m[0] = (double)__fdiv_rn( (float)s0, fc ), m[1] = (double)__fdiv_rn( (float)s1, fc ), m[2] = (double)__fdiv_rn( (float)s2, fc );
-      }
-    }
+    const Cell* cc = a.cells + slot;
+    a.fcell[slot]  = make_uint4( __float_as_uint( (float)s0 ), __float_as_uint( (float)s1 ), __float_as_uint( (float)s2 ),
+                                 min( cnt, FC_CNT ) | ( cc->multi ? FC_MULTI : 0u ) );
   }
   if ( colour ) {  // luma list offsets: one atomic per warp, shuffle prefix inside
     const uint32_t want = ( live && cnt > 1 ) ? cnt : 0u;
@@ -346,7 +344,7 @@ __global__ void k_finalize_cells( const GridArgs a, uint32_t nSlots, int colour 
 }
 
 // ---- geometry filter: smoothPointCloudGrid + gridFiltering (:1000-1104) ----
-__global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double threshold ) {
+__global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, double threshold ) {
   const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
   if ( li >= *a.blist_n ) { return; }
   const int64_t i = a.blist[li];
@@ -359,13 +357,14 @@ __global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double 
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
-  Cell     cl[8];
+  uint4    fc[8];
   bool     other = false;
-  uint32_t cnt[8], ix[8];
-  cell_find8( a, f, S, cl, ix );
+  uint32_t cnt[8];
+  cell_find8( a, f, S, fc );
+#pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    cnt[k] = cl[k].cnt;
-    if ( cell_do_smooth( cl[k] ) ) { other = true; }  // doSmooth && count (:1024)
+    cnt[k] = fc[k].w & FC_CNT;
+    if ( cnt[k] != 0 && ( fc[k].w & FC_MULTI ) ) { other = true; }  // doSmooth && count (:1024)
   }
   if ( !other ) { return; }  // :1028
   const int    g2 = 2 * g;
@@ -380,9 +379,11 @@ __global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double 
     const int    dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
     const int    wgt = ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] );
     double       v[3];
-    if ( cnt[k] > 0 ) {  // :1040: the cell centre (float sum / float count, k_finalize_cells)
-      const double* m = a.means + (size_t)ix[k] * 3;
-      v[0] = __ldg( m ), v[1] = __ldg( m + 1 ), v[2] = __ldg( m + 2 );
+    if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
+      const float fcn = (float)cnt[k];
+      v[0]            = (double)__fdiv_rn( __uint_as_float( fc[k].x ), fcn );
+      v[1]            = (double)__fdiv_rn( __uint_as_float( fc[k].y ), fcn );
+      v[2]            = (double)__fdiv_rn( __uint_as_float( fc[k].z ), fcn );
     } else {
       v[0] = (double)P[0];
       v[1] = (double)P[1];
@@ -461,7 +462,9 @@ __device__ __forceinline__ void k_median_one( const GridArgs& a, Cell* c, int la
     const double med  = ( n % 2 == 0 ) ? ( (double)vhi + (double)vlo ) / 2.0 : (double)vhi;
     const double mean = (double)c->s0 / (double)n;
     const int    diff = (int)( mean - med );
-    c->aux            = ( (double)( diff < 0 ? -diff : diff ) > mmThresh ) ? 1u : 0u;
+    const bool gate = (double)( diff < 0 ? -diff : diff ) > mmThresh;
+    c->aux          = gate ? 1u : 0u;
+    if ( gate ) { a.fcell[c - a.cells].w |= FC_GATE; }
   }
 }
 
@@ -477,7 +480,7 @@ __global__ void k_cell_median_gate( const GridArgs a, uint32_t nSlots, const uin
   }
 }
 // ---- colour filter: smoothPointCloudColorLC + gridFilteringColor (:1182-1306) ----
-__global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
+__global__ void __launch_bounds__( 128, 10 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
   const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
   if ( li >= *a.blist_n ) { return; }
   const int64_t i = a.blist[li];
@@ -489,15 +492,15 @@ __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double 
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
-  Cell     cl[8];
-  uint32_t ix[8];
-  bool     other = false;
-  cell_find8( a, f, S, cl, ix );
+  const ushort4 cv = a.col[i];  // issued with the probes: independent of them
+  uint4         fc[8];
+  bool          other = false;
+  cell_find8( a, f, S, fc );
+#pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( cell_do_smooth( cl[k] ) ) { other = true; }  // :1204
+    if ( ( fc[k].w & FC_CNT ) != 0 && ( fc[k].w & FC_MULTI ) ) { other = true; }  // :1204
   }
   if ( !other ) { return; }  // :1210
-  const ushort4 cv     = a.col[i];
   const double  cur[3] = {(double)cv.x, (double)cv.y, (double)cv.z};
   int           Wt[3], Q[3];
   const int     g2 = 2 * g;
@@ -509,20 +512,23 @@ __global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double 
   double Y0       = 0.0;
   bool   keep_own = false;
   for ( int k = 0; k < 8; k++ ) {  // :1218-1251, loop order dz, dy, dx
-    const Cell* c = &cl[k];
-    double*     d = c3[k];
-    if ( c->cnt > 0 ) {
-      const double* m = a.means + (size_t)ix[k] * 3;  // :1225, computed once per cell by k_finalize_cells
-      d[0] = __ldg( m ), d[1] = __ldg( m + 1 ), d[2] = __ldg( m + 2 );
+    const uint32_t cn   = fc[k].w & FC_CNT;
+    const bool     gate = cn > 1 && ( fc[k].w & FC_GATE );
+    double*        d    = c3[k];
+    if ( cn > 0 ) {
+      const double dn = (double)cn;  // :1225: float accumulator read back as double, divided by the count in double
+      d[0]            = (double)__uint_as_float( fc[k].x ) / dn;
+      d[1]            = (double)__uint_as_float( fc[k].y ) / dn;
+      d[2]            = (double)__uint_as_float( fc[k].z ) / dn;
       if ( k == 0 ) {
-        if ( c->cnt > 1 && c->aux ) {  // :1228-1235: result = own colour
+        if ( gate ) {  // :1228-1235: result = own colour
           keep_own = true;
           break;
         }
       } else {
         const int dy0 = (int)( Y0 - d[0] );  // abs() truncates (App. A.9), :1238
         bool      own = (double)( dy0 < 0 ? -dy0 : dy0 ) > yThresh;
-        if ( c->cnt > 1 && c->aux ) { own = true; }  // :1239-1243
+        if ( gate ) { own = true; }  // :1239-1243
         if ( own ) {
           d[0] = cur[0];
           d[1] = cur[1];
@@ -603,7 +609,7 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
 }
 
 // table geometry + (re)allocation; the tables are all-zero between calls (the cleanup pass resets what was claimed)
-int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& counters, RbBuf& means, int g, int wmax,
+int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& counters, RbBuf& fcell, int g, int wmax,
                 uint32_t* nSlotsOut ) {
   if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
   int64_t maxFrame = 1;
@@ -619,13 +625,13 @@ int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& cou
     RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
     RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
   }
-  RB_CUDA( means.ensure( nSlots * 24 ) );
+  RB_CUDA( fcell.ensure( nSlots * 16 ) );
   RB_CUDA( counters.ensure( 64 ) );
   RB_CUDA( cudaMemsetAsync( counters.p, 0, 64, c->stream ) );
   a.keys     = keys.as<uint32_t>();
   a.cells    = cells.as<Cell>();
   a.slots    = slots;
-  a.means    = means.as<double>();
+  a.fcell    = fcell.as<uint4>();
   a.counters = counters.as<int32_t>();
   *nSlotsOut = (uint32_t)nSlots;
   return RB200_OK;
