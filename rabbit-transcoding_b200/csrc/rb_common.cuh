@@ -111,6 +111,8 @@ struct rb200_ctx {
   RbBuf d_col_grid, d_col_cells, d_col_cell_ids, d_col_lum, d_col_lum_off;
   RbBuf d_scratch[8];
   int   geo_grid_w = 0, col_grid_w = 0;
+  int   geo_grow = 0, col_grow = 0;  // smoothing tables: times the block pool was quadrupled after an overflow
+  int64_t col_lum_want = 0;          // colour smoothing: luma list length asked for by a truncated cell
   int64_t geo_cell_cap = 0, col_cell_cap = 0;
   bool  geo_grid_clean = false, col_grid_clean = false;
   int   geo_grid_frames = 0, col_grid_frames = 0;

@@ -8,13 +8,19 @@
 //   PCCPointSet3::convertYUV16ToRGB8 / copyRGB16ToRGB8           PccLibCommon/include/PCCPointSet.h:121-166
 //
 // The reference walks a dense int grid (w^3 ints, memset per frame) and appends to std::vectors.  Here:
-//  * a dense int32 index grid per frame stays resident and *clean* between GOFs: the mark pass records every
-//    cell it claims, and a cleanup pass resets exactly those cells and their accumulators, so no per-GOF memset
-//    of w^3 cells (8 MB .. 537 MB per frame) is ever paid;
+//  * the grid is sparse and two-level: a small per-frame hash table maps a 4x4x4 *block* of cells to a block of 64
+//    accumulators taken from a pool (one 8-byte table entry per occupied block, a few thousand per frame), so every
+//    cell lookup is "one table entry + one 32-byte accumulator", collisions are rare (table load < 25 %) and resolved
+//    for all eight neighbours of a point together; the table and the touched accumulators of a frame stay in L2;
+//  * every occupied cell is accumulated (the reference only accumulates cells marked by a boundary point, but its
+//    filter never reads any other cell, so the result is the same and the marking pass disappears);
 //  * accumulators are integer atomics.  The reference sums small integers in float in emission order; below 2^24
 //    every partial sum is exact, so the order-free integer sum converts to the identical float;
 //    a per-frame flag reports any cell that leaves that range;
-//  * "doSmooth" (a cell holds two different partitions) is kept order-free as max(p+1) and max(~(p+1));
+//  * "doSmooth" (a cell holds two different partitions) is order-free: first partition by CAS, flag on mismatch;
+//  * the per-cell luma lists of the colour gate are filled by the accumulation itself (the atomic add on the count
+//    hands out list positions), and the median is only computed for cells whose luma range can exceed the gate
+//    (|mean - median| <= max - min);
 //  * the filter passes repeat the reference's double arithmetic operation by operation (compiled with
 //    -fmad=false), including the integer-truncating abs() of the colour gates.
 #include <algorithm>
@@ -23,38 +29,37 @@
 
 namespace {
 
-struct Cell {  // accumulator of one occupied cell; all-zero == empty.  32 bytes, 8-byte aligned pairs
-  uint32_t cnt, s0;      // {cnt, s0} and {s1, s2} are each updated with ONE 64-bit atomic add
-  uint32_t s1, s2;       // coordinate sums (geometry) / colour sums (colour)
-  uint32_t pfirst;       // partition + 1 of the first point that reached the cell (0: none yet)
-  uint32_t multi;        // 1 once a second, different partition was seen: the reference's doSmooth (:989-995)
-  uint32_t lum_off;      // colour: start of the cell's luma list;   geometry: unused
-  uint32_t aux;          // colour: scatter cursor, then the mean/median gate flag
+// accumulator of one cell; all-zero == empty.  32 bytes = one L2 sector; the filters read the first 16 bytes.
+struct Cell {
+  uint32_t s0, s1;    // {s0, s1} and {cw, s2} are each updated with ONE 64-bit atomic add
+  uint32_t cw, s2;    // cw = point count | FC_MULTI | FC_GATE;  s* = coordinate sums (geometry) / colour sums (colour)
+  uint32_t pfirst;    // partition + 1 of the first point that reached the cell (0: none yet)
+  uint32_t pad;
+  uint32_t lmax;      // colour: max luma
+  uint32_t lmin_inv;  // colour: max of (65535 - luma)
 };
-__device__ __forceinline__ bool cell_do_smooth( const Cell& c ) { return c.cnt != 0 && c.multi != 0; }
-__device__ __forceinline__ Cell cell_load( const Cell* p ) {  // read-only path (filters): two 16-byte non-coherent loads
-  const uint4 lo = __ldg( reinterpret_cast<const uint4*>( p ) ), hi = __ldg( reinterpret_cast<const uint4*>( p ) + 1 );
-  Cell        c;
-  c.cnt = lo.x, c.s0 = lo.y, c.s1 = lo.z, c.s2 = lo.w, c.pfirst = hi.x, c.multi = hi.y, c.lum_off = hi.z, c.aux = hi.w;
-  return c;
-}
+// cw: the count can never carry into the flags (a frame has < 2^28 points); FC_MULTI is the reference's doSmooth
+// (:989-995), FC_GATE the mean/median gate of gridFilteringColor (:1228-1243)
+constexpr uint32_t FC_MULTI = 1u << 30, FC_GATE = 1u << 31, FC_CNT = 0x0FFFFFFFu;
+constexpr int      MAX_PROBES = 256;
+constexpr uint32_t NO_BLOCK   = 0xFFFFFFFFu;
+enum { CTR_CURSOR = 0, CTR_FLAGS = 1, CTR_MAXCNT = 2 };  // counters[]
+enum { OVF_BLOCKS = 1, OVF_LUM = 2, OVF_SPIN = 4 };     // CTR_FLAGS bits
 
-// The reference walks a dense int grid (w^3 ints per frame, memset every frame).  Here every frame owns an
-// open-addressing hash table keyed by the cell coordinates: 4x4x4 neighbourhoods of cells share 64 consecutive slots,
-// so the 2x2x2 cells a boundary point reads sit in one or two cache lines and the whole table of a frame (a few MB)
-// stays in L2 while that frame is being processed.  Every occupied cell is accumulated (the reference only
-// accumulates cells marked by a boundary point, but its filter never reads any other cell, so the result is the
-// same and the marking pass disappears).  Claimed slots are recorded and reset by the cleanup pass.
 struct GridArgs {
   int            F;
   int            g;          // cell size
   int            wmax;       // cells per axis
   int            by_bbox;    // geometry: th = g * ceil(maxCoord / g); colour: th = 2^bitdepth
   int            pcmax;      // 2^geometryBitDepth3D
-  uint32_t*      keys;       // [F][slots] 0 = empty, else (cx | cy << 10 | cz << 20) + 1
-  Cell*          cells;      // [F][slots]
-  uint32_t       slots;      // per frame, power of two
-  int32_t*       counters;   // [1] overflow flag, [2] luma cursor
+  unsigned long long* table; // [F][tslots] 0 = empty, else (bx | by << 8 | bz << 16) + 1  |  (block id + 1) << 32
+  uint32_t       tslots;     // per frame, power of two
+  int            tshift;     // 32 - log2( tslots )
+  Cell*          cells;      // [cap_blocks][64] pool; block-local cell index = cx&3 | (cy&3) << 2 | (cz&3) << 4
+  uint32_t       cap_blocks;
+  uint16_t*      lum;        // colour: [cap_blocks][64][lum_cap] luma lists
+  uint32_t       lum_cap;
+  int32_t*       counters;
   const int64_t* frame_off;
   RbFrameInfo*   finfo;
   short4*        pos;
@@ -62,7 +67,6 @@ struct GridArgs {
   const uint32_t* part;
   const uint32_t* blist;     // indices of the points classified as boundary (type 1) by the reconstruction
   const uint32_t* blist_n;
-  uint4*          fcell;     // [F][slots] what the filters read: {float sum0, sum1, sum2, cnt | multi << 30 | gate << 31}
 };
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -88,140 +92,129 @@ __device__ __forceinline__ bool inside( int x, int y, int z, int disth, int th )
   return !( x < disth || y < disth || z < disth || th <= x + disth || th <= y + disth || th <= z + disth );
 }
 
-__device__ __forceinline__ uint32_t cell_key( int cx, int cy, int cz ) {
-  return ( (uint32_t)cx | ( (uint32_t)cy << 10 ) | ( (uint32_t)cz << 20 ) ) + 1u;
+__device__ __forceinline__ uint32_t block_key( int cx, int cy, int cz ) {
+  return ( (uint32_t)( cx >> 2 ) | ( (uint32_t)( cy >> 2 ) << 8 ) | ( (uint32_t)( cz >> 2 ) << 16 ) ) + 1u;
 }
-__device__ __forceinline__ uint32_t cell_home( int cx, int cy, int cz, uint32_t mask ) {
-  const uint32_t h = ( (uint32_t)( cx >> 2 ) * 73856093u ) ^ ( (uint32_t)( cy >> 2 ) * 19349663u ) ^ ( (uint32_t)( cz >> 2 ) * 83492791u );
-  return ( ( h << 6 ) | (uint32_t)( ( cx & 3 ) | ( ( cy & 3 ) << 2 ) | ( ( cz & 3 ) << 4 ) ) ) & mask;
+__device__ __forceinline__ uint32_t cell_local( int cx, int cy, int cz ) {
+  return (uint32_t)( ( cx & 3 ) | ( ( cy & 3 ) << 2 ) | ( ( cz & 3 ) << 4 ) );
 }
-constexpr int MAX_PROBES = 64;
+__device__ __forceinline__ uint32_t block_home( const GridArgs& a, uint32_t key ) { return ( key * 0x9E3779B1u ) >> a.tshift; }
 
-// slot of the cell (global index), or 0xFFFFFFFF when the cell holds no point
-__device__ __forceinline__ uint32_t cell_find( const GridArgs& a, int f, int cx, int cy, int cz ) {
-  const uint32_t mask = a.slots - 1, key = cell_key( cx, cy, cz );
-  uint32_t       s    = cell_home( cx, cy, cz, mask );
-  const uint32_t base = (uint32_t)f * a.slots;
-  for ( int k = 0; k < MAX_PROBES; k++ ) {
-    const uint32_t v = __ldg( a.keys + base + s );  // the keys are final once the accumulate kernel has finished
-    if ( v == key ) { return base + s; }
-    if ( v == 0 ) { return 0xFFFFFFFFu; }
-    s = ( s + 64 ) & mask;
-  }
-  return 0xFFFFFFFFu;
-}
-// What the filters need of a cell, in ONE 16-byte record written by k_finalize_cells / k_cell_median_gate: the three
-// sums as floats (exact: < 2^24, App. A.3), the count, doSmooth and the mean/median gate.
-constexpr uint32_t FC_MULTI = 1u << 30, FC_GATE = 1u << 31, FC_CNT = 0xFFFFFu;
-
-// the 2x2x2 cells a boundary point blends: all eight first probes are issued before any of them is examined, then the
-// eight 16-byte records are fetched together — two dependent memory round trips instead of dozens
+// the 2x2x2 cells a boundary point blends.  All eight table probes are issued before any is examined, unresolved
+// probes (another block's key in the slot) advance together, then the eight 16-byte records are fetched together:
+// two dependent memory round trips in the common case.
 __device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], uint4 fc[8] ) {
-  const uint32_t mask = a.slots - 1, base = (uint32_t)f * a.slots;
-  uint32_t       s[8], key[8], v[8];
+  const uint32_t            mask = a.tslots - 1;
+  const unsigned long long* T    = a.table + (size_t)f * a.tslots;
+  uint32_t                  h[8], key[8], id[8];
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {  // k = dz*4 + dy*2 + dx, the reference's loop order (:1019-1027)
     const int cx = S[0] + ( k & 1 ), cy = S[1] + ( ( k >> 1 ) & 1 ), cz = S[2] + ( k >> 2 );
-    key[k]       = cell_key( cx, cy, cz );
-    s[k]         = cell_home( cx, cy, cz, mask );
+    key[k]       = block_key( cx, cy, cz );
+    h[k]         = block_home( a, key[k] );
+    id[k]        = NO_BLOCK;
   }
-#pragma unroll
-  for ( int k = 0; k < 8; k++ ) { v[k] = __ldg( a.keys + base + s[k] ); }
-  uint32_t miss = 0;  // cells whose first probe hit another key: continue their probe sequence (rare)
-#pragma unroll
-  for ( int k = 0; k < 8; k++ ) {
-    if ( v[k] != key[k] && v[k] != 0 ) { miss |= 1u << k; }
-  }
-  if ( miss ) {
+  uint32_t open = 0xFFu;
+  for ( int probe = 0; probe < MAX_PROBES && open; probe++ ) {
+    unsigned long long e[8];
 #pragma unroll
     for ( int k = 0; k < 8; k++ ) {
-      if ( !( miss >> k & 1u ) ) { continue; }
-      uint32_t t = s[k];
-      v[k]       = 0;
-      for ( int j = 1; j < MAX_PROBES; j++ ) {
-        t                = ( t + 64 ) & mask;
-        const uint32_t w = __ldg( a.keys + base + t );
-        if ( w == key[k] ) {
-          s[k] = t;
-          v[k] = w;
-          break;
-        }
-        if ( w == 0 ) { break; }
+      if ( open >> k & 1u ) { e[k] = __ldg( T + h[k] ); }
+    }
+#pragma unroll
+    for ( int k = 0; k < 8; k++ ) {
+      if ( !( open >> k & 1u ) ) { continue; }
+      const uint32_t v = (uint32_t)e[k];
+      if ( v == key[k] ) {
+        id[k] = (uint32_t)( e[k] >> 32 ) - 1u;
+        open &= ~( 1u << k );
+      } else if ( v == 0 ) {
+        open &= ~( 1u << k );
+      } else {
+        h[k] = ( h[k] + 1 ) & mask;
       }
     }
   }
 #pragma unroll
-  for ( int k = 0; k < 8; k++ ) { fc[k] = __ldg( a.fcell + base + s[k] ); }  // always a valid address
-#pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( v[k] != key[k] ) { fc[k] = make_uint4( 0, 0, 0, 0 ); }  // the cell holds no point
-  }
-}
-
-// find or claim; 0xFFFFFFFF on table overflow (flagged)
-__device__ __forceinline__ uint32_t cell_claim( const GridArgs& a, int f, int cx, int cy, int cz ) {
-  const uint32_t mask = a.slots - 1, key = cell_key( cx, cy, cz );
-  uint32_t       s    = cell_home( cx, cy, cz, mask );
-  const uint32_t base = (uint32_t)f * a.slots;
-  for ( int k = 0; k < MAX_PROBES; k++ ) {
-    uint32_t v = a.keys[base + s];
-    if ( v == 0 ) {
-      v = atomicCAS( &a.keys[base + s], 0u, key );
-      if ( v == 0 ) { return base + s; }  // claimed (no global list: the per-cell passes walk the slot array)
-    }
-    if ( v == key ) { return base + s; }
-    s = ( s + 64 ) & mask;
-  }
-  a.counters[1] = 1;
-  return 0xFFFFFFFFu;
-}
-
-// warp-aggregated accumulation: lanes that hit the same cell are reduced with one hardware warp reduction per field
-// and their leader issues the atomics (points arrive in patch-block order, so a warp touches one to four cells)
-__device__ __forceinline__ void cell_accumulate( const GridArgs& a, bool valid, uint32_t slot, uint32_t v0, uint32_t v1,
-                                                 uint32_t v2, uint32_t pp ) {
-  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, valid );
-  if ( !valid ) { return; }
-  const uint32_t peers = __match_any_sync( act, slot );
-  const uint32_t n     = __popc( peers );
-  const uint32_t t0 = __reduce_add_sync( peers, v0 ), t1 = __reduce_add_sync( peers, v1 ), t2 = __reduce_add_sync( peers, v2 );
-  const uint32_t mx = __reduce_max_sync( peers, pp ), mn = __reduce_min_sync( peers, pp );
-  if ( ( threadIdx.x & 31 ) == __ffs( peers ) - 1 ) {
-    Cell* c = a.cells + slot;
-    atomicAdd( (unsigned long long*)&c->cnt, (unsigned long long)n | ( (unsigned long long)t0 << 32 ) );
-    atomicAdd( (unsigned long long*)&c->s1, (unsigned long long)t1 | ( (unsigned long long)t2 << 32 ) );
-    if ( mx != mn ) {
-      c->multi = 1;  // two partitions inside this very group
-      atomicCAS( &c->pfirst, 0u, mx );
+    const int cx = S[0] + ( k & 1 ), cy = S[1] + ( ( k >> 1 ) & 1 ), cz = S[2] + ( k >> 2 );
+    if ( id[k] < a.cap_blocks ) {
+      fc[k] = __ldg( reinterpret_cast<const uint4*>( a.cells + (size_t)id[k] * 64 + cell_local( cx, cy, cz ) ) );
     } else {
-      const uint32_t old = atomicCAS( &c->pfirst, 0u, mx );
-      if ( old != 0 && old != mx ) { c->multi = 1; }
+      fc[k] = make_uint4( 0, 0, 0, 0 );  // the cell holds no point
     }
   }
+}
+
+// find or create the block of a cell; NO_BLOCK on overflow (flagged; the stage is then repeated with larger tables)
+__device__ __forceinline__ uint32_t block_claim( const GridArgs& a, int f, uint32_t key ) {
+  const uint32_t      mask = a.tslots - 1;
+  unsigned long long* T    = a.table + (size_t)f * a.tslots;
+  uint32_t            h    = block_home( a, key );
+  for ( int probe = 0; probe < MAX_PROBES; probe++ ) {
+    unsigned long long e = T[h];  // may be a stale L1 line: only a complete entry with the right key is trusted
+    if ( (uint32_t)e != key || ( e >> 32 ) == 0 ) { e = *reinterpret_cast<volatile unsigned long long*>( T + h ); }
+    if ( e == 0 ) {
+      e = atomicCAS( T + h, 0ull, (unsigned long long)key );
+      if ( e == 0 ) {  // this thread created the block: take accumulators from the pool and publish their id
+        uint32_t id = (uint32_t)atomicAdd( &a.counters[CTR_CURSOR], 1 );
+        if ( id >= a.cap_blocks ) {
+          atomicOr( &a.counters[CTR_FLAGS], OVF_BLOCKS );
+          id = NO_BLOCK - 1u;
+        }
+        atomicExch( T + h, (unsigned long long)key | ( (unsigned long long)( id + 1u ) << 32 ) );
+        return id < a.cap_blocks ? id : NO_BLOCK;
+      }
+    }
+    if ( (uint32_t)e == key ) {
+      for ( int spin = 0; ( e >> 32 ) == 0; spin++ ) {  // created by another thread a moment ago: wait for the id
+        if ( spin > ( 1 << 20 ) ) {
+          atomicOr( &a.counters[CTR_FLAGS], OVF_SPIN );
+          return NO_BLOCK;
+        }
+        e = *reinterpret_cast<volatile unsigned long long*>( T + h );
+      }
+      const uint32_t id = (uint32_t)( e >> 32 ) - 1u;
+      return id < a.cap_blocks ? id : NO_BLOCK;
+    }
+    h = ( h + 1 ) & mask;
+  }
+  atomicOr( &a.counters[CTR_FLAGS], OVF_BLOCKS );
+  return NO_BLOCK;
 }
 
 constexpr int ACC_RUN = 8;  // consecutive points per thread
 
 // Points arrive in emission order (patch -> 16x16 block -> pixel row -> layer), so the 8 consecutive points of a
 // thread — 4 neighbouring pixels x 2 layers — fall into one or two cells: the thread merges them in registers and
-// issues one hash probe and three atomics per distinct cell instead of per point.
+// issues one table probe and three or four atomics per distinct cell instead of per point.
 struct RunAcc {
-  uint32_t slot, n, t0, t1, t2, mx, mn;
+  uint32_t cell, n, t0, t1, t2, mx, mn, lmx, lmn, members;
 };
-__device__ __forceinline__ void run_flush( const GridArgs& a, RunAcc& r ) {
-  if ( r.n == 0 || r.slot == 0xFFFFFFFFu ) {
-    r.n = 0;
-    return;
-  }
-  Cell* c = a.cells + r.slot;
-  atomicAdd( (unsigned long long*)&c->cnt, (unsigned long long)r.n | ( (unsigned long long)r.t0 << 32 ) );
-  atomicAdd( (unsigned long long*)&c->s1, (unsigned long long)r.t1 | ( (unsigned long long)r.t2 << 32 ) );
-  if ( r.mx != r.mn ) {
-    c->multi = 1;  // two partitions inside this very run
-    atomicCAS( &c->pfirst, 0u, r.mx );
-  } else {
-    const uint32_t old = atomicCAS( &c->pfirst, 0u, r.mx );
-    if ( old != 0 && old != r.mx ) { c->multi = 1; }
+template <bool COLOUR>
+__device__ __forceinline__ void run_flush( const GridArgs& a, RunAcc& r, const ushort4 ( &cv )[ACC_RUN] ) {
+  if ( r.n != 0 && r.cell != NO_BLOCK ) {
+    Cell*                    c   = a.cells + r.cell;
+    const unsigned long long old = atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)r.n | ( (unsigned long long)r.t2 << 32 ) );
+    atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)r.t0 | ( (unsigned long long)r.t1 << 32 ) );
+    if ( !( (uint32_t)old & FC_MULTI ) ) {
+      bool           multi = r.mx != r.mn;  // two partitions inside this very run
+      const uint32_t first = atomicCAS( &c->pfirst, 0u, r.mx );
+      multi |= first != 0 && first != r.mx;
+      if ( multi ) { atomicOr( &c->cw, FC_MULTI ); }
+    }
+    if ( COLOUR ) {
+      atomicMax( &c->lmax, r.lmx );
+      atomicMax( &c->lmin_inv, 65535u - r.lmn );
+      uint32_t rank = (uint32_t)old & FC_CNT;  // list positions rank .. rank + n - 1 belong to this run
+      if ( rank + r.n <= a.lum_cap ) {
+        uint16_t* L = a.lum + (size_t)r.cell * a.lum_cap;
+#pragma unroll
+        for ( int k = 0; k < ACC_RUN; k++ ) {
+          if ( r.members >> k & 1u ) { L[rank++] = cv[k].x; }
+        }
+      }  // else: the gate kernel sees count > lum_cap and asks for a retry with longer lists
+    }
   }
   r.n = 0;
 }
@@ -270,7 +263,8 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
   const int disth  = max( a.g / 2, 1 );
   int       th     = COLOUR ? 0 : grid_th( a, f );
   int       lx = -1, ly = -1, lz = -1, lf = -1;
-  RunAcc    r{0xFFFFFFFFu, 0, 0, 0, 0, 0, 0xFFFFFFFFu};
+  uint32_t  lkey = 0, lblock = NO_BLOCK;
+  RunAcc    r{NO_BLOCK, 0, 0, 0, 0, 0, 0xFFFFFFFFu, 0, 0xFFFFu, 0};
 #pragma unroll
   for ( int k = 0; k < ACC_RUN; k++ ) {
     const int64_t i = i0 + k;
@@ -290,70 +284,128 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
     if ( !in ) { continue; }
     const int cx = q.x / a.g, cy = q.y / a.g, cz = q.z / a.g;
     if ( cx != lx || cy != ly || cz != lz || f != lf ) {
-      run_flush( a, r );
-      r.slot = cell_claim( a, f, cx, cy, cz );
-      r.t0 = r.t1 = r.t2 = r.mx = 0;
+      run_flush<COLOUR>( a, r, cv );
+      const uint32_t key = block_key( cx, cy, cz );
+      if ( key != lkey || f != lf ) {
+        lblock = block_claim( a, f, key );
+        lkey   = key;
+      }
+      r.cell = lblock == NO_BLOCK ? NO_BLOCK : lblock * 64u + cell_local( cx, cy, cz );
+      r.t0 = r.t1 = r.t2 = r.mx = r.lmx = r.members = 0;
       r.mn               = 0xFFFFFFFFu;
+      r.lmn              = 0xFFFFu;
       lx = cx, ly = cy, lz = cz, lf = f;
     }
     r.n++;
+    r.members |= 1u << k;
     if ( COLOUR ) {
       r.t0 += cv[k].x, r.t1 += cv[k].y, r.t2 += cv[k].z;
+      r.lmx = max( r.lmx, (uint32_t)cv[k].x );
+      r.lmn = min( r.lmn, (uint32_t)cv[k].x );
     } else {
       r.t0 += (uint32_t)q.x, r.t1 += (uint32_t)q.y, r.t2 += (uint32_t)q.z;
     }
     r.mx = max( r.mx, pp[k] );
     r.mn = min( r.mn, pp[k] );
   }
-  run_flush( a, r );
+  run_flush<COLOUR>( a, r, cv );
 }
 
-// exactness guard of App. A.3 + luma list allocation (colour), over the claimed slots
-__global__ void k_finalize_cells( const GridArgs a, uint32_t nSlots, int colour ) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool     live = slot < nSlots && a.keys[slot] != 0;
-  if ( !__any_sync( 0xFFFFFFFFu, live ) ) { return; }
-  uint32_t cnt = 0, s0 = 0, s1 = 0, s2 = 0;
-  if ( live ) {
-    const Cell* c = a.cells + slot;
-    cnt = c->cnt, s0 = c->s0, s1 = c->s1, s2 = c->s2;
-    if ( s0 >= ( 1u << 24 ) || s1 >= ( 1u << 24 ) || s2 >= ( 1u << 24 ) || cnt > 65535u ) {
-      a.finfo[slot / a.slots].sum_overflow = 1;
+// ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243) ----
+// One warp per 32 pool cells.  |mean - median| <= max - min, so only cells whose luma range exceeds the threshold
+// need the median; for those the warp ranks the list (held in registers up to 64 entries, shuffled around).
+__global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, double mmThresh ) {
+  const int      lane   = threadIdx.x & 31;
+  const uint32_t nCells = (uint32_t)min( (unsigned)a.counters[CTR_CURSOR], a.cap_blocks ) * 64u;
+  const uint32_t nWarps = ( gridDim.x * blockDim.x ) >> 5;
+  for ( uint32_t c0 = ( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 ) * 32u; c0 < nCells; c0 += nWarps * 32u ) {
+    Cell*          c   = a.cells + c0 + lane;
+    const uint4    lo  = *reinterpret_cast<const uint4*>( c );
+    const uint32_t n   = lo.z & FC_CNT;
+    bool           want = false;
+    if ( n > 1 ) {
+      const uint2 hi = *reinterpret_cast<const uint2*>( &c->lmax );  // {lmax, lmin_inv}
+      const int   range = (int)hi.x - ( 65535 - (int)hi.y );
+      want = (double)range > mmThresh;
+      if ( want && n > a.lum_cap ) {  // list truncated: repeat the stage with longer lists
+        atomicOr( &a.counters[CTR_FLAGS], OVF_LUM );
+        atomicMax( &a.counters[CTR_MAXCNT], (int)n );
+        want = false;
+      }
     }
-    const Cell* cc = a.cells + slot;
-    a.fcell[slot]  = make_uint4( __float_as_uint( (float)s0 ), __float_as_uint( (float)s1 ), __float_as_uint( (float)s2 ),
-                                 min( cnt, FC_CNT ) | ( cc->multi ? FC_MULTI : 0u ) );
-  }
-  if ( colour ) {  // luma list offsets: one atomic per warp, shuffle prefix inside
-    const uint32_t want = ( live && cnt > 1 ) ? cnt : 0u;
-    const int      lane = threadIdx.x & 31;
-    uint32_t       incl = want;
+    uint32_t todo = __ballot_sync( 0xFFFFFFFFu, want );
+    for ( ; todo; todo &= todo - 1 ) {
+      const int       src = __ffs( todo ) - 1;
+      const int       m   = (int)__shfl_sync( 0xFFFFFFFFu, n, src );
+      const uint32_t  s0  = __shfl_sync( 0xFFFFFFFFu, lo.x, src );
+      const uint16_t* L   = a.lum + (size_t)( c0 + src ) * a.lum_cap;
+      const int       hiR = m / 2, loR = m / 2 - 1;
+      int             vhi = -1, vlo = -1;
+      if ( m <= 64 ) {
+        const int v0 = lane < m ? (int)L[lane] : 0x10000, v1 = lane + 32 < m ? (int)L[lane + 32] : 0x10000;
+        int       r0 = 0, r1 = 0;
+        for ( int j = 0; j < m; j++ ) {
+          const int u = __shfl_sync( 0xFFFFFFFFu, j < 32 ? v0 : v1, j & 31 );
+          r0 += ( u < v0 ) || ( u == v0 && j < lane );
+          r1 += ( u < v1 ) || ( u == v1 && j < lane + 32 );
+        }
+        if ( lane < m ) {
+          if ( r0 == hiR ) { vhi = v0; }
+          if ( r0 == loR ) { vlo = v0; }
+        }
+        if ( lane + 32 < m ) {
+          if ( r1 == hiR ) { vhi = v1; }
+          if ( r1 == loR ) { vlo = v1; }
+        }
+      } else {
+        for ( int i = lane; i < m; i += 32 ) {
+          const int v    = L[i];
+          int       rank = 0;
+          for ( int j = 0; j < m; j++ ) {
+            const int u = L[j];
+            rank += ( u < v ) || ( u == v && j < i );
+          }
+          if ( rank == hiR ) { vhi = v; }
+          if ( rank == loR ) { vlo = v; }
+        }
+      }
 #pragma unroll
-    for ( int d = 1; d < 32; d <<= 1 ) {
-      const uint32_t t = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
-      if ( lane >= d ) { incl += t; }
-    }
-    uint32_t base = 0;
-    if ( lane == 31 && incl ) { base = (uint32_t)atomicAdd( &a.counters[2], (int)incl ); }
-    base = __shfl_sync( 0xFFFFFFFFu, base, 31 );
-    if ( live ) {
-      a.cells[slot].lum_off = base + incl - want;
-      a.cells[slot].aux     = 0;
+      for ( int d = 16; d > 0; d >>= 1 ) {
+        vhi = max( vhi, __shfl_xor_sync( 0xFFFFFFFFu, vhi, d ) );
+        vlo = max( vlo, __shfl_xor_sync( 0xFFFFFFFFu, vlo, d ) );
+      }
+      if ( lane == src ) {
+        // median (PCCCodec.h:271-278) and mean (:280-285); abs() on the double difference is int abs(int) (App. A.9)
+        const double med  = ( m % 2 == 0 ) ? ( (double)vhi + (double)vlo ) / 2.0 : (double)vhi;
+        const double mean = (double)s0 / (double)m;
+        const int    diff = (int)( mean - med );
+        if ( (double)( diff < 0 ? -diff : diff ) > mmThresh ) { c->cw = lo.z | FC_GATE; }
+      }
     }
   }
 }
 
 // ---- geometry filter: smoothPointCloudGrid + gridFiltering (:1000-1104) ----
-__global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, double threshold ) {
-  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( li >= *a.blist_n ) { return; }
+// per-frame statistics without same-address atomic storms: one atomic per warp and frame
+__device__ __forceinline__ void count_hits( int32_t* field0, int f, bool hit ) {  // field0 = &finfo[0].<field>
+  const uint32_t m = __ballot_sync( 0xFFFFFFFFu, hit );
+  if ( hit ) {
+    const uint32_t peers = __match_any_sync( m, f );
+    if ( ( threadIdx.x & 31 ) == __ffs( peers ) - 1 ) {
+      atomicAdd( field0 + (size_t)f * ( sizeof( RbFrameInfo ) / sizeof( int32_t ) ), __popc( peers ) );
+    }
+  }
+}
+
+__device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li, double threshold, int& f ) {
+  if ( li >= *a.blist_n || a.counters[CTR_FLAGS] ) { return false; }  // tables overflowed: the stage is repeated
   const int64_t i = a.blist[li];
   const short4  p = a.pos[i];
-  if ( p.w != 1 ) { return; }  // :1087
-  const int f     = frame_of( a.frame_off, a.F, i );
+  if ( p.w != 1 ) { return false; }  // :1087
+  f               = frame_of( a.frame_off, a.F, i );
   const int g     = a.g, hg = g / 2;
   const int disth = max( hg, 1 ), th = grid_th( a, f );
-  if ( !inside( p.x, p.y, p.z, disth, th ) ) { return; }  // :1078-1081
+  if ( !inside( p.x, p.y, p.z, disth, th ) ) { return false; }  // :1078-1081
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
@@ -363,10 +415,10 @@ __global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, dou
   cell_find8( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    cnt[k] = fc[k].w & FC_CNT;
-    if ( cnt[k] != 0 && ( fc[k].w & FC_MULTI ) ) { other = true; }  // doSmooth && count (:1024)
+    cnt[k] = fc[k].z & FC_CNT;
+    if ( cnt[k] != 0 && ( fc[k].z & FC_MULTI ) ) { other = true; }  // doSmooth && count (:1024)
   }
-  if ( !other ) { return; }  // :1028
+  if ( !other ) { return false; }  // :1028
   const int    g2 = 2 * g;
   int          Wt[3], Q[3];
   for ( int k = 0; k < 3; k++ ) {
@@ -375,15 +427,16 @@ __global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, dou
   }
   double c4[3] = {0.0, 0.0, 0.0};
   int    count = 0;
+#pragma unroll
   for ( int k = 0; k < 8; k++ ) {  // :1050-1058
     const int    dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
     const int    wgt = ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] );
     double       v[3];
     if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
       const float fcn = (float)cnt[k];
-      v[0]            = (double)__fdiv_rn( __uint_as_float( fc[k].x ), fcn );
-      v[1]            = (double)__fdiv_rn( __uint_as_float( fc[k].y ), fcn );
-      v[2]            = (double)__fdiv_rn( __uint_as_float( fc[k].z ), fcn );
+      v[0]            = (double)__fdiv_rn( (float)fc[k].x, fcn );
+      v[1]            = (double)__fdiv_rn( (float)fc[k].y, fcn );
+      v[2]            = (double)__fdiv_rn( (float)fc[k].w, fcn );
     } else {
       v[0] = (double)P[0];
       v[1] = (double)P[1];
@@ -400,7 +453,7 @@ __global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, dou
   c4[1]            = c4[1] / den;
   c4[2]            = c4[2] / den;
   count /= g2 * g2 * g2;  // :1060 integer division; 0 is common (App. A.4)
-  if ( count == 0 ) { return; }  // 0.0/0.0 = NaN, NaN >= x is false: the reference leaves the point alone
+  if ( count == 0 ) { return false; }  // 0.0/0.0 = NaN, NaN >= x is false: the reference leaves the point alone
   const double dc = (double)count;
   double       cen[3], d2 = 0.0;
   {
@@ -418,77 +471,25 @@ __global__ void __launch_bounds__( 128, 12 ) k_filter_geo( const GridArgs a, dou
     q.z      = (short)(long long)( __dadd_rn( cen[2] / dc, 0.5 ) );
     q.w      = 3;  // :1099
     a.pos[i] = q;
-    atomicAdd( &a.finfo[f].smoothed, 1 );
+    return true;
   }
+  return false;
+}
+__global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double threshold ) {
+  int        f   = 0;
+  const bool hit = filter_geo_point( a, blockIdx.x * blockDim.x + threadIdx.x, threshold, f );
+  count_hits( &a.finfo[0].smoothed, f, hit );
 }
 
-// ---- colour: scatter lumas into the per-cell lists (colorSmoothingLum_, :1179) ----
-__global__ void __launch_bounds__( 256 ) k_scatter_lum( const GridArgs a, int64_t n, uint16_t* __restrict__ lum ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const short4 p = a.pos[i];
-  const int    f = frame_of( a.frame_off, a.F, i );
-  if ( p.x < 0 || p.y < 0 || p.z < 0 || p.x / a.g >= a.wmax || p.y / a.g >= a.wmax || p.z / a.g >= a.wmax ) { return; }
-  const uint32_t slot = cell_find( a, f, p.x / a.g, p.y / a.g, p.z / a.g );
-  if ( slot == 0xFFFFFFFFu ) { return; }
-  Cell* c = a.cells + slot;
-  if ( c->cnt < 2 ) { return; }  // the median is only consulted for count > 1 (:1228, :1239)
-  const uint32_t k       = atomicAdd( &c->aux, 1u );
-  lum[c->lum_off + k]    = a.col[i].x;
-}
-
-__device__ __forceinline__ void k_median_one( const GridArgs& a, Cell* c, int lane, const uint16_t* __restrict__ lum, double mmThresh ) {
-  const int n = (int)c->cnt;
-  const uint16_t* L  = lum + c->lum_off;
-  const int       hi = n / 2, lo = n / 2 - 1;
-  int             vhi = -1, vlo = -1;
-  for ( int i = lane; i < n; i += 32 ) {
-    const int v    = L[i];
-    int       rank = 0;
-    for ( int j = 0; j < n; j++ ) {
-      const int u = L[j];
-      rank += ( u < v ) || ( u == v && j < i );
-    }
-    if ( rank == hi ) { vhi = v; }
-    if ( rank == lo ) { vlo = v; }
-  }
-#pragma unroll
-  for ( int d = 16; d > 0; d >>= 1 ) {
-    vhi = max( vhi, __shfl_xor_sync( 0xFFFFFFFFu, vhi, d ) );
-    vlo = max( vlo, __shfl_xor_sync( 0xFFFFFFFFu, vlo, d ) );
-  }
-  if ( lane == 0 ) {
-    // median (PCCCodec.h:271-278) and mean (:280-285); abs() on the double difference is int abs(int) (App. A.9)
-    const double med  = ( n % 2 == 0 ) ? ( (double)vhi + (double)vlo ) / 2.0 : (double)vhi;
-    const double mean = (double)c->s0 / (double)n;
-    const int    diff = (int)( mean - med );
-    const bool gate = (double)( diff < 0 ? -diff : diff ) > mmThresh;
-    c->aux          = gate ? 1u : 0u;
-    if ( gate ) { a.fcell[c - a.cells].w |= FC_GATE; }
-  }
-}
-
-// ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243); one warp per cell, rank selection ----
-__global__ void k_cell_median_gate( const GridArgs a, uint32_t nSlots, const uint16_t* __restrict__ lum, double mmThresh ) {
-  const uint32_t s0   = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31u;  // this warp owns slots s0 .. s0+31
-  const int      lane = threadIdx.x & 31;
-  const bool     want = s0 + lane < nSlots && a.keys[s0 + lane] != 0 && a.cells[s0 + lane].cnt > 1;
-  uint32_t       todo = __ballot_sync( 0xFFFFFFFFu, want );
-  if ( s0 + lane < nSlots && a.keys[s0 + lane] != 0 && !want ) { a.cells[s0 + lane].aux = 0; }
-  for ( ; todo; todo &= todo - 1 ) {
-    k_median_one( a, a.cells + s0 + ( __ffs( todo ) - 1 ), lane, lum, mmThresh );
-  }
-}
 // ---- colour filter: smoothPointCloudColorLC + gridFilteringColor (:1182-1306) ----
-__global__ void __launch_bounds__( 128, 10 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
-  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( li >= *a.blist_n ) { return; }
+__device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li, double thrSmoothing, double yThresh, int& f ) {
+  if ( li >= *a.blist_n || a.counters[CTR_FLAGS] ) { return false; }  // tables overflowed: the stage is repeated
   const int64_t i = a.blist[li];
   const short4  p = a.pos[i];
-  if ( p.w != 1 ) { return; }  // :1288
+  if ( p.w != 1 ) { return false; }  // :1288
   const int g = a.g, hg = g / 2, disth = max( hg, 1 );
-  if ( !inside( p.x, p.y, p.z, disth, a.pcmax ) ) { return; }  // :1280-1283
-  const int      f = frame_of( a.frame_off, a.F, i );
+  if ( !inside( p.x, p.y, p.z, disth, a.pcmax ) ) { return false; }  // :1280-1283
+  f = frame_of( a.frame_off, a.F, i );
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
@@ -498,9 +499,9 @@ __global__ void __launch_bounds__( 128, 10 ) k_filter_col( const GridArgs a, dou
   cell_find8( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( ( fc[k].w & FC_CNT ) != 0 && ( fc[k].w & FC_MULTI ) ) { other = true; }  // :1204
+    if ( ( fc[k].z & FC_CNT ) != 0 && ( fc[k].z & FC_MULTI ) ) { other = true; }  // :1204
   }
-  if ( !other ) { return; }  // :1210
+  if ( !other ) { return false; }  // :1210
   const double  cur[3] = {(double)cv.x, (double)cv.y, (double)cv.z};
   int           Wt[3], Q[3];
   const int     g2 = 2 * g;
@@ -508,48 +509,35 @@ __global__ void __launch_bounds__( 128, 10 ) k_filter_col( const GridArgs a, dou
     Wt[k] = ( P[k] - S[k] * g - hg ) * 2 + 1;  // :1212
     Q[k]  = g2 - Wt[k];                         // :1252
   }
-  double c3[8][3];
+  double c4[3]    = {0.0, 0.0, 0.0};
   double Y0       = 0.0;
-  bool   keep_own = false;
-  for ( int k = 0; k < 8; k++ ) {  // :1218-1251, loop order dz, dy, dx
-    const uint32_t cn   = fc[k].w & FC_CNT;
-    const bool     gate = cn > 1 && ( fc[k].w & FC_GATE );
-    double*        d    = c3[k];
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {  // :1218-1261, loop order dz, dy, dx; the blend is accumulated in the same order
+    const uint32_t cn   = fc[k].z & FC_CNT;
+    const bool     gate = cn > 1 && ( fc[k].z & FC_GATE );
+    double         d[3];
+    bool           own = cn == 0;
     if ( cn > 0 ) {
       const double dn = (double)cn;  // :1225: float accumulator read back as double, divided by the count in double
-      d[0]            = (double)__uint_as_float( fc[k].x ) / dn;
-      d[1]            = (double)__uint_as_float( fc[k].y ) / dn;
-      d[2]            = (double)__uint_as_float( fc[k].z ) / dn;
+      d[0]            = (double)(float)fc[k].x / dn;
       if ( k == 0 ) {
-        if ( gate ) {  // :1228-1235: result = own colour
-          keep_own = true;
-          break;
-        }
+        if ( gate ) { return false; }  // :1228-1235: centroid = own colour -> |dY| = 0 < threshold unless threshold <= 0
       } else {
         const int dy0 = (int)( Y0 - d[0] );  // abs() truncates (App. A.9), :1238
-        bool      own = (double)( dy0 < 0 ? -dy0 : dy0 ) > yThresh;
-        if ( gate ) { own = true; }  // :1239-1243
-        if ( own ) {
-          d[0] = cur[0];
-          d[1] = cur[1];
-          d[2] = cur[2];
-        }
+        own           = (double)( dy0 < 0 ? -dy0 : dy0 ) > yThresh || gate;  // :1238-1243
       }
-    } else {
-      d[0] = cur[0];
-      d[1] = cur[1];
-      d[2] = cur[2];
+      if ( !own ) {
+        d[1] = (double)(float)fc[k].y / dn;
+        d[2] = (double)(float)fc[k].w / dn;
+      }
     }
+    if ( own ) { d[0] = cur[0], d[1] = cur[1], d[2] = cur[2]; }
     if ( k == 0 ) { Y0 = d[0]; }  // :1248
-  }
-  if ( keep_own ) { return; }  // centroid = own colour -> |dY| = 0 < threshold unless threshold <= 0
-  double c4[3] = {0.0, 0.0, 0.0};
-  for ( int k = 0; k < 8; k++ ) {  // :1254-1261
     const int    dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
     const double dw = (double)( ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] ) );
-    c4[0]           = __dadd_rn( c4[0], __dmul_rn( c3[k][0], dw ) );
-    c4[1]           = __dadd_rn( c4[1], __dmul_rn( c3[k][1], dw ) );
-    c4[2]           = __dadd_rn( c4[2], __dmul_rn( c3[k][2], dw ) );
+    c4[0]           = __dadd_rn( c4[0], __dmul_rn( d[0], dw ) );
+    c4[1]           = __dadd_rn( c4[1], __dmul_rn( d[1], dw ) );
+    c4[2]           = __dadd_rn( c4[2], __dmul_rn( d[2], dw ) );
   }
   const double den = (double)( g2 * g2 * g2 );
   double       out[3];
@@ -564,18 +552,29 @@ __global__ void __launch_bounds__( 128, 10 ) k_filter_col( const GridArgs a, dou
     q.x       = (unsigned short)out[0];
     q.y       = (unsigned short)out[1];
     q.z       = (unsigned short)out[2];
-    if ( q.x != cv.x || q.y != cv.y || q.z != cv.z ) { atomicAdd( &a.finfo[f].recolored, 1 ); }
     a.col[i] = q;
+    return q.x != cv.x || q.y != cv.y || q.z != cv.z;
   }
+  return false;
+}
+__global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
+  int        f   = 0;
+  const bool hit = filter_col_point( a, blockIdx.x * blockDim.x + threadIdx.x, thrSmoothing, yThresh, f );
+  count_hits( &a.finfo[0].recolored, f, hit );
 }
 
-// ---- cleanup: reset exactly the claimed slots ----
-__global__ void k_cleanup_cells( const GridArgs a, uint32_t nSlots ) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( slot >= nSlots || a.keys[slot] == 0 ) { return; }
-  a.keys[slot] = 0;
-  uint4* c     = reinterpret_cast<uint4*>( a.cells + slot );
-  c[0] = c[1] = make_uint4( 0, 0, 0, 0 );
+// ---- cleanup: reset the used part of the pool (+ the exactness guard of App. A.3) and the block table ----
+__global__ void __launch_bounds__( 256 ) k_cleanup_cells( const GridArgs a ) {
+  const uint32_t nCells = (uint32_t)min( (unsigned)a.counters[CTR_CURSOR], a.cap_blocks ) * 64u;
+  for ( uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nCells; s += gridDim.x * blockDim.x ) {
+    uint4*      c  = reinterpret_cast<uint4*>( a.cells + s );
+    const uint4 lo = c[0];
+    if ( ( lo.x | lo.y | lo.z | lo.w ) == 0 ) { continue; }
+    if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || ( lo.z & FC_CNT ) > 65535u ) {
+      a.counters[3] = 1;  // a float accumulator of the reference would have left the exact range
+    }
+    c[0] = c[1] = make_uint4( 0, 0, 0, 0 );
+  }
 }
 
 // ---- convertYUV16ToRGB8 (PCCPointSet.h:133-166) / copyRGB16ToRGB8 (:121-127) ----
@@ -608,49 +607,71 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
   rgb[i]   = make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
 }
 
-// table geometry + (re)allocation; the tables are all-zero between calls (the cleanup pass resets what was claimed)
-int setup_grid( rb200_ctx* c, GridArgs& a, RbBuf& keys, RbBuf& cells, RbBuf& counters, RbBuf& fcell, int g, int wmax,
-                uint32_t* nSlotsOut ) {
+// table geometry + (re)allocation; table and pool are all-zero between calls (the cleanup pass resets what was used)
+struct GridBufs {
+  RbBuf &table, &cells, &counters, &lum;
+};
+int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool colour, int grow ) {
   if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
-  int64_t maxFrame = 1;
+  const int64_t n        = c->h_frame_off[c->F];
+  int64_t       maxFrame = 1;
   for ( int f = 0; f < c->F; f++ ) { maxFrame = std::max<int64_t>( maxFrame, c->h_frame_off[f + 1] - c->h_frame_off[f] ); }
-  int64_t want = std::min<int64_t>( 2 * maxFrame, std::max<int64_t>( 4096, 4 * maxFrame / ( (int64_t)g * g ) ) );
-  uint32_t slots = 4096;
-  while ( (int64_t)slots < want ) { slots <<= 1; }
-  const size_t nSlots = (size_t)c->F * slots;
-  if ( nSlots >= ( 1ull << 32 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing hash table too large" ); }
-  if ( keys.cap < nSlots * 4 || cells.cap < nSlots * sizeof( Cell ) ) {
-    RB_CUDA( keys.ensure( nSlots * 4 ) );
-    RB_CUDA( cells.ensure( nSlots * sizeof( Cell ) ) );
-    RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
+  // a 4x4x4 block of cells spans (4g)^3 voxels; a surface crossing it leaves ~ (4g)^2 .. 3 (4g)^2 points in it, so
+  // n / (6 g^2) blocks is about twice what a V-PCC cloud needs (`grow` quadruples it after an overflow)
+  const int64_t perBlock = std::max<int64_t>( 1, 6ll * g * g >> ( 2 * grow ) );
+  int64_t       cap      = std::min<int64_t>( n, n / perBlock + 1024ll * c->F ) + 64;
+  int64_t       wantT    = 4 * std::min<int64_t>( maxFrame, maxFrame / perBlock + 1024 );
+  uint32_t      tslots = 1024;
+  int           tlog   = 10;
+  while ( (int64_t)tslots < wantT ) { tslots <<= 1, tlog++; }
+  const size_t tBytes = (size_t)c->F * tslots * 8, cBytes = (size_t)cap * 64 * sizeof( Cell );
+  if ( cap >= ( 1ll << 25 ) ) { return rb_fail( c, RB200_ERR_NOMEM, "smoothing cell pool too large" ); }
+  if ( b.table.cap < tBytes ) {
+    RB_CUDA( b.table.ensure( tBytes ) );
+    RB_CUDA( cudaMemsetAsync( b.table.p, 0, b.table.cap, c->stream ) );
   }
-  RB_CUDA( fcell.ensure( nSlots * 16 ) );
-  RB_CUDA( counters.ensure( 64 ) );
-  RB_CUDA( cudaMemsetAsync( counters.p, 0, 64, c->stream ) );
-  a.keys     = keys.as<uint32_t>();
-  a.cells    = cells.as<Cell>();
-  a.slots    = slots;
-  a.fcell    = fcell.as<uint4>();
-  a.counters = counters.as<int32_t>();
-  *nSlotsOut = (uint32_t)nSlots;
+  if ( b.cells.cap < cBytes ) {
+    RB_CUDA( b.cells.ensure( cBytes ) );
+    RB_CUDA( cudaMemsetAsync( b.cells.p, 0, b.cells.cap, c->stream ) );
+  }
+  a.lum_cap = 0;
+  if ( colour ) {  // a cell of g^3 voxels seen by two layers (+ duplicates across patches)
+    const int64_t base = std::min<int64_t>( 64, std::max<int64_t>( 8, (int64_t)g * g * g ) );
+    a.lum_cap          = (uint32_t)std::max<int64_t>( base, c->col_lum_want );
+    RB_CUDA( b.lum.ensure( (size_t)cap * 64 * a.lum_cap * 2 + 64 ) );
+  }
+  RB_CUDA( b.counters.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( b.counters.p, 0, 64, c->stream ) );
+  a.table      = b.table.as<unsigned long long>();
+  a.tslots     = tslots;
+  a.tshift     = 32 - tlog;
+  a.cells      = b.cells.as<Cell>();
+  a.cap_blocks = (uint32_t)cap;
+  a.lum        = b.lum.as<uint16_t>();
+  a.counters   = b.counters.as<int32_t>();
   return RB200_OK;
 }
 
-// the table-overflow flag, read after the stage has been enqueued (one small read-back, also the stage's error check)
-int check_overflow( rb200_ctx* c, const GridArgs& a, RbBuf& keys, RbBuf& cells, const char* what ) {
+// the counters, read after the stage has been enqueued (one small read-back, also the stage's error check):
+// 0 = done, 1 = tables overflowed (nothing was modified: repeat with larger tables), < 0 = error
+int stage_result( rb200_ctx* c, const GridArgs& a, GridBufs b, const char* what ) {
   int32_t* h = (int32_t*)rb_pinned( c, 64 );
-  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  if ( !h ) { return -rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
   RB_CUDA( cudaMemcpyAsync( h, a.counters, 16, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   c->stats.d2h_bytes += 16;
-  if ( h[1] ) {
-    RB_CUDA( cudaMemsetAsync( keys.p, 0, keys.cap, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( cells.p, 0, cells.cap, c->stream ) );
-    return rb_fail( c, RB200_ERR_NOMEM, "%s: cell table overflow", what );
+  if ( h[CTR_FLAGS] & OVF_SPIN ) { return -rb_fail( c, RB200_ERR_CUDA, "%s: block table wait timed out", what ); }
+  if ( h[CTR_FLAGS] ) {
+    if ( h[CTR_FLAGS] & OVF_LUM ) { c->col_lum_want = std::max<int64_t>( c->col_lum_want, ( (int64_t)h[CTR_MAXCNT] + 15 ) & ~15ll ); }
+    return ( h[CTR_FLAGS] & OVF_BLOCKS ) ? 1 : 2;
   }
-  return RB200_OK;
+  if ( h[3] ) {
+    return -rb_fail( c, RB200_ERR_UNSUPPORTED, "%s: a cell accumulator left the exact float range (count > 65535 or sum >= 2^24)", what );
+  }
+  return 0;
 }
+
+constexpr int WALK_CTAS = 148 * 8;  // grid-stride passes over the used part of the pool
 
 }  // namespace
 
@@ -680,14 +701,19 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  uint32_t nSlots = 0;
-  int      r      = setup_grid( c, a, c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_scratch[5], g, wmax, &nSlots );
-  if ( r ) { return r; }
-  RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
-  RB_LAUNCH( "geo_finalize", k_finalize_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, 0 );
-  if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
-  RB_LAUNCH( "geo_cleanup", k_cleanup_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots );
-  return check_overflow( c, a, c->d_geo_grid, c->d_geo_cells, "geometry smoothing" );
+  GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum};
+  for ( ;; ) {
+    int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );
+    if ( r ) { return r; }
+    RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+    if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
+    RB_LAUNCH( "geo_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
+    RB_CUDA( cudaMemsetAsync( a.table, 0, (size_t)a.F * a.tslots * 8, c->stream ) );
+    r = stage_result( c, a, b, "geometry smoothing" );
+    if ( r < 0 ) { return -r; }
+    if ( r == 0 ) { return RB200_OK; }
+    if ( ++c->geo_grow > 6 ) { return rb_fail( c, RB200_ERR_NOMEM, "geometry smoothing: cell table overflow" ); }
+  }
 }
 
 int rb_smooth_color_impl( rb200_ctx* c ) {
@@ -711,21 +737,24 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  uint32_t nSlots = 0;
-  int      r      = setup_grid( c, a, c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_scratch[6], g, wmax, &nSlots );
-  if ( r ) { return r; }
-  RB_CUDA( c->d_col_lum.ensure( (size_t)n * 2 + 64 ) );
-  RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
-  RB_LAUNCH( "col_finalize", k_finalize_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, 1 );
-  RB_LAUNCH( "col_scatter_lum", k_scatter_lum, rb_div_up( n, 256 ), 256, 0, a, n, c->d_col_lum.as<uint16_t>() );
-  RB_LAUNCH( "col_median_gate", k_cell_median_gate, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots, c->d_col_lum.as<uint16_t>(),
-             P.threshold_color_variation * 256.0 );
-  if ( c->blist_cap > 0 ) {
-    RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
-               P.threshold_color_difference * 256.0 );
+  GridBufs b{c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_col_lum};
+  for ( int attempt = 0;; attempt++ ) {
+    int r = setup_grid( c, a, b, g, wmax, true, c->col_grow );
+    if ( r ) { return r; }
+    RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+    RB_LAUNCH( "col_median_gate", k_cell_median_gate, WALK_CTAS, 256, 0, a, P.threshold_color_variation * 256.0 );
+    if ( c->blist_cap > 0 ) {
+      RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
+                 P.threshold_color_difference * 256.0 );
+    }
+    RB_LAUNCH( "col_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
+    RB_CUDA( cudaMemsetAsync( a.table, 0, (size_t)a.F * a.tslots * 8, c->stream ) );
+    r = stage_result( c, a, b, "colour smoothing" );
+    if ( r < 0 ) { return -r; }
+    if ( r == 0 ) { return RB200_OK; }
+    if ( r == 1 && ++c->col_grow > 6 ) { return rb_fail( c, RB200_ERR_NOMEM, "colour smoothing: cell table overflow" ); }
+    if ( attempt > 8 ) { return rb_fail( c, RB200_ERR_NOMEM, "colour smoothing: luma lists do not fit" ); }
   }
-  RB_LAUNCH( "col_cleanup", k_cleanup_cells, rb_div_up( nSlots, 256 ), 256, 0, a, nSlots );
-  return check_overflow( c, a, c->d_col_grid, c->d_col_cells, "colour smoothing" );
 }
 
 int rb_convert_rgb8_impl( rb200_ctx* c ) {
