@@ -19,8 +19,8 @@
 //    a per-frame flag reports any cell that leaves that range;
 //  * "doSmooth" (a cell holds two different partitions) is order-free: first partition by CAS, flag on mismatch;
 //  * the per-cell luma lists of the colour gate are filled by the accumulation itself (the atomic add on the count
-//    hands out list positions), and the median is only computed for cells whose luma range can exceed the gate
-//    (|mean - median| <= max - min);
+//    hands out list positions), and the median is only computed for cells whose luma variance can exceed the gate
+//    (|mean - median| <= standard deviation);
 //  * the filter passes repeat the reference's double arithmetic operation by operation (compiled with
 //    -fmad=false), including the integer-truncating abs() of the colour gates.
 #include <algorithm>
@@ -35,8 +35,7 @@ struct Cell {
   uint32_t cw, s2;    // cw = point count | FC_MULTI | FC_GATE;  s* = coordinate sums (geometry) / colour sums (colour)
   uint32_t pfirst;    // partition + 1 of the first point that reached the cell (0: none yet)
   uint32_t pad;
-  uint32_t lmax;      // colour: max luma
-  uint32_t lmin_inv;  // colour: max of (65535 - luma)
+  unsigned long long q2;  // colour: sum of luma^2 (bounds |mean - median| by the standard deviation)
 };
 // cw: the count can never carry into the flags (a frame has < 2^28 points); FC_MULTI is the reference's doSmooth
 // (:989-995), FC_GATE the mean/median gate of gridFilteringColor (:1228-1243)
@@ -185,47 +184,19 @@ __device__ __forceinline__ uint32_t block_claim( const GridArgs& a, int f, uint3
 
 constexpr int ACC_RUN = 8;  // consecutive points per thread
 
-// Points arrive in emission order (patch -> 16x16 block -> pixel row -> layer), so the 8 consecutive points of a
-// thread — 4 neighbouring pixels x 2 layers — fall into one or two cells: the thread merges them in registers and
-// issues one table probe and three or four atomics per distinct cell instead of per point.
-struct RunAcc {
-  uint32_t cell, n, t0, t1, t2, mx, mn, lmx, lmn, members;
-};
-template <bool COLOUR>
-__device__ __forceinline__ void run_flush( const GridArgs& a, RunAcc& r, const ushort4 ( &cv )[ACC_RUN] ) {
-  if ( r.n != 0 && r.cell != NO_BLOCK ) {
-    Cell*                    c   = a.cells + r.cell;
-    const unsigned long long old = atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)r.n | ( (unsigned long long)r.t2 << 32 ) );
-    atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)r.t0 | ( (unsigned long long)r.t1 << 32 ) );
-    if ( !( (uint32_t)old & FC_MULTI ) ) {
-      bool           multi = r.mx != r.mn;  // two partitions inside this very run
-      const uint32_t first = atomicCAS( &c->pfirst, 0u, r.mx );
-      multi |= first != 0 && first != r.mx;
-      if ( multi ) { atomicOr( &c->cw, FC_MULTI ); }
-    }
-    if ( COLOUR ) {
-      atomicMax( &c->lmax, r.lmx );
-      atomicMax( &c->lmin_inv, 65535u - r.lmn );
-      uint32_t rank = (uint32_t)old & FC_CNT;  // list positions rank .. rank + n - 1 belong to this run
-      if ( rank + r.n <= a.lum_cap ) {
-        uint16_t* L = a.lum + (size_t)r.cell * a.lum_cap;
-#pragma unroll
-        for ( int k = 0; k < ACC_RUN; k++ ) {
-          if ( r.members >> k & 1u ) { L[rank++] = cv[k].x; }
-        }
-      }  // else: the gate kernel sees count > lum_cap and asks for a retry with longer lists
-    }
-  }
-  r.n = 0;
-}
-
+// Points arrive in emission order (patch -> 16x16 block -> pixel row -> layer): the 8 consecutive points of a thread
+// (4 neighbouring pixels x 2 layers) fall into one to four cells.  Every thread first merges its own points per cell
+// in registers (no memory traffic), then the warp flushes "the next cell of every lane" together: two to four rounds
+// of one table probe and three or four atomics per lane, instead of a flush at every point where some lane's cell
+// changes.  (Combining equal cells across lanes with per-group __reduce_*_sync masks was measured 4x slower: partial
+// masks are executed group by group.)
 template <bool COLOUR>
 __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t n ) {
-  const int64_t i0 = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
-  if ( i0 >= n ) { return; }
-  short4   p[ACC_RUN];
-  ushort4  cv[ACC_RUN];
-  uint32_t pp[ACC_RUN];
+  const int     lane = threadIdx.x & 31;
+  const int64_t i0   = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
+  short4        p[ACC_RUN];
+  ushort4       cv[ACC_RUN];
+  uint32_t      pp[ACC_RUN];
   if ( i0 + ACC_RUN <= n ) {  // 16-byte loads: the arena is 16-byte aligned and i0 is a multiple of 8
     const uint4* vp = reinterpret_cast<const uint4*>( a.pos + i0 );
     const uint4* vq = reinterpret_cast<const uint4*>( a.part + i0 );
@@ -258,129 +229,188 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
       if ( COLOUR ) { cv[k] = ok ? a.col[i0 + k] : make_ushort4( 0, 0, 0, 0 ); }
     }
   }
-  int       f      = frame_of( a.frame_off, a.F, i0 );
-  int64_t   fend   = a.frame_off[f + 1];
-  const int disth  = max( a.g / 2, 1 );
-  int       th     = COLOUR ? 0 : grid_th( a, f );
-  int       lx = -1, ly = -1, lz = -1, lf = -1;
-  uint32_t  lkey = 0, lblock = NO_BLOCK;
-  RunAcc    r{NO_BLOCK, 0, 0, 0, 0, 0, 0xFFFFFFFFu, 0, 0xFFFFu, 0};
+  // ---- per point: frame and cell key (cx | cy << 10 | cz << 20), `rem` = points that take part ----
+  uint32_t ck[ACC_RUN];
+  int      fr[ACC_RUN];
+  uint32_t rem = 0;
+  if ( i0 < n ) {
+    int       f     = frame_of( a.frame_off, a.F, i0 );
+    int64_t   fend  = a.frame_off[f + 1];
+    const int disth = max( a.g / 2, 1 );
+    int       th    = COLOUR ? 0 : grid_th( a, f );
 #pragma unroll
-  for ( int k = 0; k < ACC_RUN; k++ ) {
-    const int64_t i = i0 + k;
-    if ( i >= n ) { break; }
-    while ( i >= fend ) {  // the run crosses into the next frame (empty frames are skipped)
-      f++;
-      fend = a.frame_off[f + 1];
-      if ( !COLOUR ) { th = grid_th( a, f ); }
-    }
-    const short4 q = p[k];
-    bool         in;
-    if ( COLOUR ) {  // no margin test, :208-224 with the :212 guard
-      in = q.x >= 0 && q.y >= 0 && q.z >= 0 && q.x / a.g < a.wmax && q.y / a.g < a.wmax && q.z / a.g < a.wmax;
-    } else {  // :120-134
-      in = inside( q.x, q.y, q.z, disth, th );
-    }
-    if ( !in ) { continue; }
-    const int cx = q.x / a.g, cy = q.y / a.g, cz = q.z / a.g;
-    if ( cx != lx || cy != ly || cz != lz || f != lf ) {
-      run_flush<COLOUR>( a, r, cv );
-      const uint32_t key = block_key( cx, cy, cz );
-      if ( key != lkey || f != lf ) {
-        lblock = block_claim( a, f, key );
-        lkey   = key;
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      const int64_t i = i0 + k;
+      ck[k]           = 0;
+      fr[k]           = f;
+      if ( i >= n ) { continue; }
+      while ( i >= fend ) {  // the run crosses into the next frame (empty frames are skipped)
+        f++;
+        fend = a.frame_off[f + 1];
+        if ( !COLOUR ) { th = grid_th( a, f ); }
       }
-      r.cell = lblock == NO_BLOCK ? NO_BLOCK : lblock * 64u + cell_local( cx, cy, cz );
-      r.t0 = r.t1 = r.t2 = r.mx = r.lmx = r.members = 0;
-      r.mn               = 0xFFFFFFFFu;
-      r.lmn              = 0xFFFFu;
-      lx = cx, ly = cy, lz = cz, lf = f;
+      fr[k]          = f;
+      const short4 q = p[k];
+      bool         in;
+      if ( COLOUR ) {  // no margin test, :208-224 with the :212 guard
+        in = q.x >= 0 && q.y >= 0 && q.z >= 0 && q.x / a.g < a.wmax && q.y / a.g < a.wmax && q.z / a.g < a.wmax;
+      } else {  // :120-134
+        in = inside( q.x, q.y, q.z, disth, th );
+      }
+      if ( !in ) { continue; }
+      ck[k] = (uint32_t)( q.x / a.g ) | ( (uint32_t)( q.y / a.g ) << 10 ) | ( (uint32_t)( q.z / a.g ) << 20 );
+      rem |= 1u << k;
     }
-    r.n++;
-    r.members |= 1u << k;
-    if ( COLOUR ) {
-      r.t0 += cv[k].x, r.t1 += cv[k].y, r.t2 += cv[k].z;
-      r.lmx = max( r.lmx, (uint32_t)cv[k].x );
-      r.lmn = min( r.lmn, (uint32_t)cv[k].x );
-    } else {
-      r.t0 += (uint32_t)q.x, r.t1 += (uint32_t)q.y, r.t2 += (uint32_t)q.z;
-    }
-    r.mx = max( r.mx, pp[k] );
-    r.mn = min( r.mn, pp[k] );
+  } else {
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) { ck[k] = 0, fr[k] = 0; }
   }
-  run_flush<COLOUR>( a, r, cv );
+  // ---- one cell per lane and iteration, lanes with the same cell combined ----
+  while ( __any_sync( 0xFFFFFFFFu, rem != 0 ) ) {
+    const bool     act   = rem != 0;
+    const int      first = __ffs( rem ) - 1;
+    uint32_t       key = 0;
+    int            f   = 0;
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      if ( k == first ) { key = ck[k], f = fr[k]; }
+    }
+    uint32_t           mem = 0, cnt = 0, t0 = 0, t1 = 0, t2 = 0, mx = 0, mn = 0xFFFFFFFFu;
+    unsigned long long q2 = 0;
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      if ( ( rem >> k & 1u ) && ck[k] == key && fr[k] == f ) {
+        mem |= 1u << k;
+        cnt++;
+        if ( COLOUR ) {
+          t0 += cv[k].x, t1 += cv[k].y, t2 += cv[k].z;
+          q2 += (unsigned long long)( (uint32_t)cv[k].x * (uint32_t)cv[k].x );
+        } else {
+          t0 += (uint32_t)p[k].x, t1 += (uint32_t)p[k].y, t2 += (uint32_t)p[k].z;
+        }
+        mx = max( mx, pp[k] );
+        mn = min( mn, pp[k] );
+      }
+    }
+    rem &= ~mem;
+    const uint32_t mask = __ballot_sync( 0xFFFFFFFFu, act );
+    if ( !act ) { continue; }
+    // one lane per distinct block looks it up (or creates it): no lane ever waits for another lane of its own warp.
+    // (all warp primitives here use the same mask in every lane: per-group masks are executed group by group)
+    const int      cx = key & 1023, cy = ( key >> 10 ) & 1023, cz = key >> 20;
+    const uint32_t bk = block_key( cx, cy, cz );
+    const uint32_t bpeers  = __match_any_sync( mask, ( (unsigned long long)(uint32_t)f << 32 ) | bk );
+    const int      bleader = __ffs( bpeers ) - 1;
+    uint32_t       bl      = NO_BLOCK;
+    if ( lane == bleader ) { bl = block_claim( a, f, bk ); }
+    bl = __shfl_sync( mask, bl, bleader );
+    if ( bl == NO_BLOCK ) { continue; }
+    const uint32_t           cell = bl * 64u + cell_local( cx, cy, cz );
+    Cell*                    c    = a.cells + cell;
+    const unsigned long long old  = atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)cnt | ( (unsigned long long)t2 << 32 ) );
+    atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)t0 | ( (unsigned long long)t1 << 32 ) );
+    if ( !( (uint32_t)old & FC_MULTI ) ) {
+      bool           multi  = mx != mn;  // two partitions inside this very run
+      const uint32_t firstp = atomicCAS( &c->pfirst, 0u, mx );
+      multi |= firstp != 0 && firstp != mx;
+      if ( multi ) { atomicOr( &c->cw, FC_MULTI ); }
+    }
+    if ( COLOUR ) {  // the atomic add on the count hands out the list positions oldc .. oldc + cnt - 1
+      atomicAdd( &c->q2, q2 );
+      const uint32_t oldc = (uint32_t)old & FC_CNT;
+      if ( oldc + cnt <= a.lum_cap ) {
+        uint16_t* L = a.lum + (size_t)cell * a.lum_cap + oldc;
+#pragma unroll
+        for ( int k = 0; k < ACC_RUN; k++ ) {
+          if ( mem >> k & 1u ) { *L++ = cv[k].x; }
+        }
+      }  // else: the gate kernel sees count > lum_cap and asks for a retry with longer lists
+    }
+  }
 }
 
 // ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243) ----
-// One warp per 32 pool cells.  |mean - median| <= max - min, so only cells whose luma range exceeds the threshold
-// need the median; for those the warp ranks the list (held in registers up to 64 entries, shuffled around).
+// One warp per 32 pool cells.  |mean - median| <= standard deviation, so only cells whose luma variance can exceed the
+// threshold need the median; those are sorted four at a time with a 32-lane bitonic network in registers.
+__device__ __forceinline__ bool gate_of( int vhi, int vlo, int m, uint32_t s0, double mmThresh ) {
+  // median (PCCCodec.h:271-278) and mean (:280-285); abs() on the double difference is int abs(int) (App. A.9)
+  const double med  = ( m % 2 == 0 ) ? ( (double)vhi + (double)vlo ) / 2.0 : (double)vhi;
+  const double mean = (double)s0 / (double)m;
+  const int    diff = (int)( mean - med );
+  return (double)( diff < 0 ? -diff : diff ) > mmThresh;
+}
+
 __global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, double mmThresh ) {
   const int      lane   = threadIdx.x & 31;
   const uint32_t nCells = (uint32_t)min( (unsigned)a.counters[CTR_CURSOR], a.cap_blocks ) * 64u;
   const uint32_t nWarps = ( gridDim.x * blockDim.x ) >> 5;
+  const unsigned long long tf = mmThresh >= 1.0 ? (unsigned long long)mmThresh : 0ull;  // floor
   for ( uint32_t c0 = ( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 ) * 32u; c0 < nCells; c0 += nWarps * 32u ) {
-    Cell*          c   = a.cells + c0 + lane;
-    const uint4    lo  = *reinterpret_cast<const uint4*>( c );
-    const uint32_t n   = lo.z & FC_CNT;
+    Cell*          c    = a.cells + c0 + lane;
+    const uint4    lo   = *reinterpret_cast<const uint4*>( c );
+    const uint32_t n    = lo.z & FC_CNT;
     bool           want = false;
     if ( n > 1 ) {
-      const uint2 hi = *reinterpret_cast<const uint2*>( &c->lmax );  // {lmax, lmin_inv}
-      const int   range = (int)hi.x - ( 65535 - (int)hi.y );
-      want = (double)range > mmThresh;
+      // n * sum(x^2) - sum(x)^2 < floor(T)^2 n^2  =>  sigma < T  =>  |mean - median| < T: the gate is off
+      const unsigned __int128 var = (unsigned __int128)n * c->q2 - (unsigned __int128)lo.x * lo.x;
+      want                        = var >= (unsigned __int128)( tf * tf ) * ( (unsigned long long)n * n );
       if ( want && n > a.lum_cap ) {  // list truncated: repeat the stage with longer lists
         atomicOr( &a.counters[CTR_FLAGS], OVF_LUM );
         atomicMax( &a.counters[CTR_MAXCNT], (int)n );
         want = false;
       }
     }
-    uint32_t todo = __ballot_sync( 0xFFFFFFFFu, want );
-    for ( ; todo; todo &= todo - 1 ) {
-      const int       src = __ffs( todo ) - 1;
+    uint32_t small = __ballot_sync( 0xFFFFFFFFu, want && n <= 32 );
+    uint32_t large = __ballot_sync( 0xFFFFFFFFu, want && n > 32 );
+    while ( small ) {  // up to four cells per round: their loads and their sorting networks overlap
+      int src[4], m[4], v[4];
+#pragma unroll
+      for ( int q = 0; q < 4; q++ ) {
+        src[q] = small ? __ffs( small ) - 1 : -1;
+        small &= small - 1;
+        m[q] = src[q] >= 0 ? (int)__shfl_sync( 0xFFFFFFFFu, n, src[q] & 31 ) : 0;
+        v[q] = lane < m[q] ? (int)a.lum[(size_t)( c0 + src[q] ) * a.lum_cap + lane] : 0x10000;
+      }
+#pragma unroll
+      for ( int k = 2; k <= 32; k <<= 1 ) {
+#pragma unroll
+        for ( int j = k >> 1; j > 0; j >>= 1 ) {
+          const bool keep_min = ( ( lane & j ) == 0 ) == ( ( lane & k ) == 0 );
+#pragma unroll
+          for ( int q = 0; q < 4; q++ ) {
+            const int u = __shfl_xor_sync( 0xFFFFFFFFu, v[q], j );
+            v[q]        = keep_min ? min( v[q], u ) : max( v[q], u );
+          }
+        }
+      }
+#pragma unroll
+      for ( int q = 0; q < 4; q++ ) {
+        const int vhi = __shfl_sync( 0xFFFFFFFFu, v[q], ( m[q] / 2 ) & 31 ), vlo = __shfl_sync( 0xFFFFFFFFu, v[q], ( m[q] / 2 - 1 ) & 31 );
+        if ( lane == src[q] && gate_of( vhi, vlo, m[q], lo.x, mmThresh ) ) { c->cw = lo.z | FC_GATE; }
+      }
+    }
+    for ( ; large; large &= large - 1 ) {  // rare: more than 32 points in a cell, rank selection
+      const int       src = __ffs( large ) - 1;
       const int       m   = (int)__shfl_sync( 0xFFFFFFFFu, n, src );
-      const uint32_t  s0  = __shfl_sync( 0xFFFFFFFFu, lo.x, src );
       const uint16_t* L   = a.lum + (size_t)( c0 + src ) * a.lum_cap;
       const int       hiR = m / 2, loR = m / 2 - 1;
       int             vhi = -1, vlo = -1;
-      if ( m <= 64 ) {
-        const int v0 = lane < m ? (int)L[lane] : 0x10000, v1 = lane + 32 < m ? (int)L[lane + 32] : 0x10000;
-        int       r0 = 0, r1 = 0;
+      for ( int i = lane; i < m; i += 32 ) {
+        const int v    = L[i];
+        int       rank = 0;
         for ( int j = 0; j < m; j++ ) {
-          const int u = __shfl_sync( 0xFFFFFFFFu, j < 32 ? v0 : v1, j & 31 );
-          r0 += ( u < v0 ) || ( u == v0 && j < lane );
-          r1 += ( u < v1 ) || ( u == v1 && j < lane + 32 );
+          const int u = L[j];
+          rank += ( u < v ) || ( u == v && j < i );
         }
-        if ( lane < m ) {
-          if ( r0 == hiR ) { vhi = v0; }
-          if ( r0 == loR ) { vlo = v0; }
-        }
-        if ( lane + 32 < m ) {
-          if ( r1 == hiR ) { vhi = v1; }
-          if ( r1 == loR ) { vlo = v1; }
-        }
-      } else {
-        for ( int i = lane; i < m; i += 32 ) {
-          const int v    = L[i];
-          int       rank = 0;
-          for ( int j = 0; j < m; j++ ) {
-            const int u = L[j];
-            rank += ( u < v ) || ( u == v && j < i );
-          }
-          if ( rank == hiR ) { vhi = v; }
-          if ( rank == loR ) { vlo = v; }
-        }
+        if ( rank == hiR ) { vhi = v; }
+        if ( rank == loR ) { vlo = v; }
       }
 #pragma unroll
       for ( int d = 16; d > 0; d >>= 1 ) {
         vhi = max( vhi, __shfl_xor_sync( 0xFFFFFFFFu, vhi, d ) );
         vlo = max( vlo, __shfl_xor_sync( 0xFFFFFFFFu, vlo, d ) );
       }
-      if ( lane == src ) {
-        // median (PCCCodec.h:271-278) and mean (:280-285); abs() on the double difference is int abs(int) (App. A.9)
-        const double med  = ( m % 2 == 0 ) ? ( (double)vhi + (double)vlo ) / 2.0 : (double)vhi;
-        const double mean = (double)s0 / (double)m;
-        const int    diff = (int)( mean - med );
-        if ( (double)( diff < 0 ? -diff : diff ) > mmThresh ) { c->cw = lo.z | FC_GATE; }
-      }
+      if ( lane == src && gate_of( vhi, vlo, m, lo.x, mmThresh ) ) { c->cw = lo.z | FC_GATE; }
     }
   }
 }
