@@ -48,6 +48,7 @@ enum { OVF_BLOCKS = 1, OVF_LUM = 2, OVF_SPIN = 4 };     // CTR_FLAGS bits
 struct GridArgs {
   int            F;
   int            g;          // cell size
+  uint32_t       ginv;       // floor( 2^32 / g ) + 1: x / g == __umulhi( x, ginv ) for 0 <= x < 2^16, 2 <= g <= 64
   int            wmax;       // cells per axis
   int            by_bbox;    // geometry: th = g * ceil(maxCoord / g); colour: th = 2^bitdepth
   int            pcmax;      // 2^geometryBitDepth3D
@@ -59,6 +60,8 @@ struct GridArgs {
   uint16_t*      lum;        // colour: [cap_blocks][64][lum_cap] luma lists
   uint32_t       lum_cap;
   int32_t*       counters;
+  uint32_t*      marks;      // [F][wmax][wmax][mwords] one bit per cell: some boundary point blends it (or null: all)
+  int            mwords;
   const int64_t* frame_off;
   RbFrameInfo*   finfo;
   short4*        pos;
@@ -91,6 +94,9 @@ __device__ __forceinline__ bool inside( int x, int y, int z, int disth, int th )
   return !( x < disth || y < disth || z < disth || th <= x + disth || th <= y + disth || th <= z + disth );
 }
 
+__device__ __forceinline__ int cell_of( const GridArgs& a, int x ) {  // x / g for a non-negative coordinate
+  return a.g == 1 ? x : (int)__umulhi( (uint32_t)x, a.ginv );
+}
 __device__ __forceinline__ uint32_t block_key( int cx, int cy, int cz ) {
   return ( (uint32_t)( cx >> 2 ) | ( (uint32_t)( cy >> 2 ) << 8 ) | ( (uint32_t)( cz >> 2 ) << 16 ) ) + 1u;
 }
@@ -182,6 +188,33 @@ __device__ __forceinline__ uint32_t block_claim( const GridArgs& a, int f, uint3
   return NO_BLOCK;
 }
 
+// ---- marking (:89-112, :170-195): the 2x2x2 cells every in-margin boundary point blends.  The reference numbers the
+// marked cells; here they become one bit each in a dense bitmap, and the accumulation skips unmarked cells (the
+// filters never read those), which is most of the cloud. ----
+__global__ void __launch_bounds__( 256 ) k_mark_cells( const GridArgs a ) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( li >= *a.blist_n ) { return; }
+  const int64_t i = a.blist[li];
+  const short4  p = a.pos[i];
+  if ( p.w != 1 ) { return; }
+  const int f     = frame_of( a.frame_off, a.F, i );
+  const int g     = a.g, hg = g / 2;
+  const int disth = max( hg, 1 ), th = grid_th( a, f );
+  if ( !inside( p.x, p.y, p.z, disth, th ) ) { return; }
+  const int P[3] = {p.x, p.y, p.z};
+  int       S[3];
+  for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }
+  const uint64_t bits = 3ull << ( S[0] & 31 );  // cells S[0], S[0]+1: one word or two neighbouring words
+  const uint32_t b0 = (uint32_t)bits, b1 = (uint32_t)( bits >> 32 );
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) {
+    const int cy = S[1] + ( k & 1 ), cz = S[2] + ( k >> 1 );
+    uint32_t* w  = a.marks + ( ( (size_t)f * a.wmax + cz ) * a.wmax + cy ) * a.mwords + ( S[0] >> 5 );
+    if ( ( w[0] & b0 ) != b0 ) { atomicOr( w, b0 ); }  // a stale cached word only costs a redundant atomic
+    if ( b1 && ( w[1] & b1 ) != b1 ) { atomicOr( w + 1, b1 ); }
+  }
+}
+
 constexpr int ACC_RUN = 8;  // consecutive points per thread
 
 // Points arrive in emission order (patch -> 16x16 block -> pixel row -> layer): the 8 consecutive points of a thread
@@ -253,12 +286,14 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
       const short4 q = p[k];
       bool         in;
       if ( COLOUR ) {  // no margin test, :208-224 with the :212 guard
-        in = q.x >= 0 && q.y >= 0 && q.z >= 0 && q.x / a.g < a.wmax && q.y / a.g < a.wmax && q.z / a.g < a.wmax;
+        in = q.x >= 0 && q.y >= 0 && q.z >= 0;
       } else {  // :120-134
         in = inside( q.x, q.y, q.z, disth, th );
       }
       if ( !in ) { continue; }
-      ck[k] = (uint32_t)( q.x / a.g ) | ( (uint32_t)( q.y / a.g ) << 10 ) | ( (uint32_t)( q.z / a.g ) << 20 );
+      const int cx = cell_of( a, q.x ), cy = cell_of( a, q.y ), cz = cell_of( a, q.z );
+      if ( COLOUR && ( cx >= a.wmax || cy >= a.wmax || cz >= a.wmax ) ) { continue; }
+      ck[k] = (uint32_t)cx | ( (uint32_t)cy << 10 ) | ( (uint32_t)cz << 20 );
       rem |= 1u << k;
     }
   } else {
@@ -267,7 +302,7 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
   }
   // ---- one cell per lane and iteration, lanes with the same cell combined ----
   while ( __any_sync( 0xFFFFFFFFu, rem != 0 ) ) {
-    const bool     act   = rem != 0;
+    bool           act   = rem != 0;
     const int      first = __ffs( rem ) - 1;
     uint32_t       key = 0;
     int            f   = 0;
@@ -293,11 +328,14 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
       }
     }
     rem &= ~mem;
+    const int cx = key & 1023, cy = ( key >> 10 ) & 1023, cz = key >> 20;
+    if ( act && a.marks ) {  // cells no boundary point blends are never read
+      act = ( a.marks[( ( (size_t)f * a.wmax + cz ) * a.wmax + cy ) * a.mwords + ( cx >> 5 )] >> ( cx & 31 ) ) & 1u;
+    }
     const uint32_t mask = __ballot_sync( 0xFFFFFFFFu, act );
     if ( !act ) { continue; }
     // one lane per distinct block looks it up (or creates it): no lane ever waits for another lane of its own warp.
     // (all warp primitives here use the same mask in every lane: per-group masks are executed group by group)
-    const int      cx = key & 1023, cy = ( key >> 10 ) & 1023, cz = key >> 20;
     const uint32_t bk = block_key( cx, cy, cz );
     const uint32_t bpeers  = __match_any_sync( mask, ( (unsigned long long)(uint32_t)f << 32 ) | bk );
     const int      bleader = __ffs( bpeers ) - 1;
@@ -639,7 +677,7 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
 
 // table geometry + (re)allocation; table and pool are all-zero between calls (the cleanup pass resets what was used)
 struct GridBufs {
-  RbBuf &table, &cells, &counters, &lum;
+  RbBuf &table, &cells, &counters, &lum, &marks;
 };
 int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool colour, int grow ) {
   if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
@@ -672,6 +710,17 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
   }
   RB_CUDA( b.counters.ensure( 64 ) );
   RB_CUDA( cudaMemsetAsync( b.counters.p, 0, 64, c->stream ) );
+  // mark bitmap: dense, one bit per cell; beyond 1 GiB per GOF (cells of 1 or 2 voxels at 11+ bits) every cell is
+  // accumulated instead
+  a.ginv   = g > 1 ? (uint32_t)( ( 1ull << 32 ) / (unsigned)g ) + 1u : 0u;
+  a.mwords = ( wmax + 1 + 31 ) / 32 + 1;
+  a.marks  = nullptr;
+  const size_t mBytes = (size_t)c->F * wmax * wmax * a.mwords * 4;
+  if ( colour && c->blist_cap > 0 && mBytes <= ( 1ull << 30 ) ) {  // (geometry, 8-voxel cells: measured no gain)
+    RB_CUDA( b.marks.ensure( mBytes ) );
+    RB_CUDA( cudaMemsetAsync( b.marks.p, 0, mBytes, c->stream ) );
+    a.marks = b.marks.as<uint32_t>();
+  }
   a.table      = b.table.as<unsigned long long>();
   a.tslots     = tslots;
   a.tshift     = 32 - tlog;
@@ -731,10 +780,11 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum};
+  GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum, c->d_geo_cell_ids};
   for ( ;; ) {
     int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );
     if ( r ) { return r; }
+    if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
     RB_LAUNCH( "geo_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
@@ -753,7 +803,7 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   const int g     = P.occupancy_precision;  // the colour grid uses occupancyPrecision, not cgridSize (:152)
   const int pcmax = 1 << P.geometry_bitdepth_3d;
   const int wmax  = pcmax / g;  // :154
-  if ( wmax < 2 ) { return rb_fail( c, RB200_ERR_INVALID, "colour grid degenerate" ); }
+  if ( wmax < 2 || g < 1 || g > 64 ) { return rb_fail( c, RB200_ERR_INVALID, "colour grid degenerate (occupancy precision %d)", g ); }
   GridArgs a{};
   a.F         = c->F;
   a.g         = g;
@@ -767,10 +817,11 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  GridBufs b{c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_col_lum};
+  GridBufs b{c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_col_lum, c->d_col_cell_ids};
   for ( int attempt = 0;; attempt++ ) {
     int r = setup_grid( c, a, b, g, wmax, true, c->col_grow );
     if ( r ) { return r; }
+    if ( a.marks ) { RB_LAUNCH( "col_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     RB_LAUNCH( "col_median_gate", k_cell_median_gate, WALK_CTAS, 256, 0, a, P.threshold_color_variation * 256.0 );
     if ( c->blist_cap > 0 ) {
