@@ -17,7 +17,7 @@
 //  * accumulators are integer atomics.  The reference sums small integers in float in emission order; below 2^24
 //    every partial sum is exact, so the order-free integer sum converts to the identical float;
 //    a per-frame flag reports any cell that leaves that range;
-//  * "doSmooth" (a cell holds two different partitions) is order-free: first partition by CAS, flag on mismatch;
+//  * "doSmooth" (a cell holds two different partitions) is order-free: max and min partition, compared by the filter;
 //  * the per-cell luma lists of the colour gate are filled by the accumulation itself (the atomic add on the count
 //    hands out list positions), and the median is only computed for cells whose luma variance can exceed the gate
 //    (|mean - median| <= standard deviation);
@@ -32,14 +32,19 @@ namespace {
 // accumulator of one cell; all-zero == empty.  32 bytes = one L2 sector; the filters read the first 16 bytes.
 struct Cell {
   uint32_t s0, s1;    // {s0, s1} and {cw, s2} are each updated with ONE 64-bit atomic add
-  uint32_t cw, s2;    // cw = point count | FC_MULTI | FC_GATE;  s* = coordinate sums (geometry) / colour sums (colour)
-  uint32_t pfirst;    // partition + 1 of the first point that reached the cell (0: none yet)
-  uint32_t pad;
+  uint32_t cw, s2;    // cw = point count | FC_GATE;  s* = coordinate sums (geometry) / colour sums (colour)
+  uint32_t pmax;      // max of (partition + 1) over the points of the cell
+  uint32_t pmin_inv;  // max of ~(partition + 1): the cell holds two partitions (the reference's doSmooth, :989-995)
+                      // iff pmax != ~pmin_inv.  Order-free, and no atomic has to return a value
   unsigned long long q2;  // colour: sum of luma^2 (bounds |mean - median| by the standard deviation)
 };
-// cw: the count can never carry into the flags (a frame has < 2^28 points); FC_MULTI is the reference's doSmooth
-// (:989-995), FC_GATE the mean/median gate of gridFilteringColor (:1228-1243)
-constexpr uint32_t FC_MULTI = 1u << 30, FC_GATE = 1u << 31, FC_CNT = 0x0FFFFFFFu;
+// cw: the count can never carry into the flag (a frame has < 2^28 points); FC_GATE is the mean/median gate of
+// gridFilteringColor (:1228-1243)
+constexpr uint32_t FC_GATE = 1u << 31, FC_CNT = 0x0FFFFFFFu;
+struct CellView {  // what the filters read of a cell
+  uint32_t s0, s1, s2, cnt;
+  bool     multi, gate;
+};
 constexpr int      MAX_PROBES = 256;
 constexpr uint32_t NO_BLOCK   = 0xFFFFFFFFu;
 enum { CTR_CURSOR = 0, CTR_FLAGS = 1, CTR_MAXCNT = 2 };  // counters[]
@@ -108,7 +113,7 @@ __device__ __forceinline__ uint32_t block_home( const GridArgs& a, uint32_t key 
 // the 2x2x2 cells a boundary point blends.  All eight table probes are issued before any is examined, unresolved
 // probes (another block's key in the slot) advance together, then the eight 16-byte records are fetched together:
 // two dependent memory round trips in the common case.
-__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], uint4 fc[8] ) {
+__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], CellView fc[8] ) {
   const uint32_t            mask = a.tslots - 1;
   const unsigned long long* T    = a.table + (size_t)f * a.tslots;
   uint32_t                  h[8], key[8], id[8];
@@ -143,11 +148,16 @@ __device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int 
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
     const int cx = S[0] + ( k & 1 ), cy = S[1] + ( ( k >> 1 ) & 1 ), cz = S[2] + ( k >> 2 );
+    uint4 lo = make_uint4( 0, 0, 0, 0 );  // the cell holds no point
+    uint2 pm = make_uint2( 0, 0xFFFFFFFFu );
     if ( id[k] < a.cap_blocks ) {
-      fc[k] = __ldg( reinterpret_cast<const uint4*>( a.cells + (size_t)id[k] * 64 + cell_local( cx, cy, cz ) ) );
-    } else {
-      fc[k] = make_uint4( 0, 0, 0, 0 );  // the cell holds no point
+      const Cell* c = a.cells + (size_t)id[k] * 64 + cell_local( cx, cy, cz );
+      lo            = __ldg( reinterpret_cast<const uint4*>( c ) );
+      pm            = __ldg( reinterpret_cast<const uint2*>( &c->pmax ) );
     }
+    fc[k].s0 = lo.x, fc[k].s1 = lo.y, fc[k].s2 = lo.w, fc[k].cnt = lo.z & FC_CNT;
+    fc[k].gate  = ( lo.z & FC_GATE ) != 0;
+    fc[k].multi = fc[k].cnt != 0 && pm.x != ~pm.y;
   }
 }
 
@@ -345,14 +355,15 @@ __global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t
     if ( bl == NO_BLOCK ) { continue; }
     const uint32_t           cell = bl * 64u + cell_local( cx, cy, cz );
     Cell*                    c    = a.cells + cell;
-    const unsigned long long old  = atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)cnt | ( (unsigned long long)t2 << 32 ) );
-    atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)t0 | ( (unsigned long long)t1 << 32 ) );
-    if ( !( (uint32_t)old & FC_MULTI ) ) {
-      bool           multi  = mx != mn;  // two partitions inside this very run
-      const uint32_t firstp = atomicCAS( &c->pfirst, 0u, mx );
-      multi |= firstp != 0 && firstp != mx;
-      if ( multi ) { atomicOr( &c->cw, FC_MULTI ); }
+    unsigned long long old = 0;
+    if ( COLOUR ) {  // the returned count hands out the list positions; everything else is fire-and-forget
+      old = atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)cnt | ( (unsigned long long)t2 << 32 ) );
+    } else {
+      atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)cnt | ( (unsigned long long)t2 << 32 ) );
     }
+    atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)t0 | ( (unsigned long long)t1 << 32 ) );
+    atomicMax( &c->pmax, mx );
+    atomicMax( &c->pmin_inv, ~mn );
     if ( COLOUR ) {  // the atomic add on the count hands out the list positions oldc .. oldc + cnt - 1
       atomicAdd( &c->q2, q2 );
       const uint32_t oldc = (uint32_t)old & FC_CNT;
@@ -477,14 +488,14 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
-  uint4    fc[8];
+  CellView fc[8];
   bool     other = false;
   uint32_t cnt[8];
   cell_find8( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    cnt[k] = fc[k].z & FC_CNT;
-    if ( cnt[k] != 0 && ( fc[k].z & FC_MULTI ) ) { other = true; }  // doSmooth && count (:1024)
+    cnt[k] = fc[k].cnt;
+    if ( fc[k].multi ) { other = true; }  // doSmooth && count (:1024)
   }
   if ( !other ) { return false; }  // :1028
   const int    g2 = 2 * g;
@@ -502,9 +513,9 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
     double       v[3];
     if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
       const float fcn = (float)cnt[k];
-      v[0]            = (double)__fdiv_rn( (float)fc[k].x, fcn );
-      v[1]            = (double)__fdiv_rn( (float)fc[k].y, fcn );
-      v[2]            = (double)__fdiv_rn( (float)fc[k].w, fcn );
+      v[0]            = (double)__fdiv_rn( (float)fc[k].s0, fcn );
+      v[1]            = (double)__fdiv_rn( (float)fc[k].s1, fcn );
+      v[2]            = (double)__fdiv_rn( (float)fc[k].s2, fcn );
     } else {
       v[0] = (double)P[0];
       v[1] = (double)P[1];
@@ -562,12 +573,12 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
   const ushort4 cv = a.col[i];  // issued with the probes: independent of them
-  uint4         fc[8];
+  CellView      fc[8];
   bool          other = false;
   cell_find8( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
-    if ( ( fc[k].z & FC_CNT ) != 0 && ( fc[k].z & FC_MULTI ) ) { other = true; }  // :1204
+    if ( fc[k].multi ) { other = true; }  // :1204
   }
   if ( !other ) { return false; }  // :1210
   const double  cur[3] = {(double)cv.x, (double)cv.y, (double)cv.z};
@@ -581,13 +592,13 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   double Y0       = 0.0;
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {  // :1218-1261, loop order dz, dy, dx; the blend is accumulated in the same order
-    const uint32_t cn   = fc[k].z & FC_CNT;
-    const bool     gate = cn > 1 && ( fc[k].z & FC_GATE );
+    const uint32_t cn   = fc[k].cnt;
+    const bool     gate = cn > 1 && fc[k].gate;
     double         d[3];
     bool           own = cn == 0;
     if ( cn > 0 ) {
       const double dn = (double)cn;  // :1225: float accumulator read back as double, divided by the count in double
-      d[0]            = (double)(float)fc[k].x / dn;
+      d[0]            = (double)(float)fc[k].s0 / dn;
       if ( k == 0 ) {
         if ( gate ) { return false; }  // :1228-1235: centroid = own colour -> |dY| = 0 < threshold unless threshold <= 0
       } else {
@@ -595,8 +606,8 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
         own           = (double)( dy0 < 0 ? -dy0 : dy0 ) > yThresh || gate;  // :1238-1243
       }
       if ( !own ) {
-        d[1] = (double)(float)fc[k].y / dn;
-        d[2] = (double)(float)fc[k].w / dn;
+        d[1] = (double)(float)fc[k].s1 / dn;
+        d[2] = (double)(float)fc[k].s2 / dn;
       }
     }
     if ( own ) { d[0] = cur[0], d[1] = cur[1], d[2] = cur[2]; }
