@@ -18,6 +18,8 @@
 //  * occupancy lives as a 1-bit-per-pixel bitmap (L2-resident, 1/16 of a byte map); the 3x3 / 5x5 boundary
 //    stencils are bit tests on 20 staged row masks per tile;
 //  * count -> exclusive scan -> emit keeps the point order of the reference exactly (ordered MD5 parity).
+#include <algorithm>
+
 #include "rb_common.cuh"
 
 namespace {
@@ -580,43 +582,81 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject( const ReprojArgs a 
   // per-frame max coordinate, feeds the geometry-smoothing grid width (:68-79)
 #pragma unroll
   for ( int d = 16; d > 0; d >>= 1 ) { maxc = max( maxc, __shfl_xor_sync( 0xFFFFFFFFu, maxc, d ) ); }
-  if ( lane == 0 && maxc > 0 ) { atomicMax( &a.finfo[f].max_coord, maxc ); }
+  // (a stale cached value only costs a redundant atomic; without the test every warp hits the same address)
+  if ( lane == 0 && maxc > 0 && maxc > a.finfo[f].max_coord ) { atomicMax( &a.finfo[f].max_coord, maxc ); }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exclusive scan of int32 counts into int64 bases (n+1 outputs); single CTA, n is O(1e5)
+// exclusive scan of int32 counts into int64 bases (n+1 outputs), n is O(1e5..1e6): two launches.
+//   k_scan_tiles : every CTA scans one tile of 2048 counts (16-byte loads, shuffle scans) and publishes the tile sum
+//   k_scan_apply : every CTA reduces the sums of the tiles before it (at most a few hundred) and adds the offset
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__( 1024 ) k_scan_counts( const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out ) {
-  __shared__ int64_t warpSum[32];
-  const int          t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int64_t      chunk = ( n + 1023 ) / 1024;
-  const int64_t      b = min( n, (int64_t)t * chunk ), e = min( n, b + chunk );
-  int64_t            s = 0;
-  for ( int64_t i = b; i < e; i++ ) { s += in[i]; }
-  int64_t incl = s;
+constexpr int SCAN_TILE = 2048;  // 256 threads x 8
+
+__device__ __forceinline__ int64_t block_exclusive_256( int64_t v, int64_t* warpSum, int64_t& total ) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t   incl = v;
 #pragma unroll
   for ( int d = 1; d < 32; d <<= 1 ) {
-    const int64_t v = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
-    if ( lane >= d ) { incl += v; }
+    const int64_t t = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+    if ( lane >= d ) { incl += t; }
   }
   if ( lane == 31 ) { warpSum[w] = incl; }
   __syncthreads();
-  if ( w == 0 ) {
-    int64_t x = warpSum[lane], y = x;
+  int64_t off = 0, tot = 0;
 #pragma unroll
-    for ( int d = 1; d < 32; d <<= 1 ) {
-      const int64_t v = __shfl_up_sync( 0xFFFFFFFFu, y, d );
-      if ( lane >= d ) { y += v; }
-    }
-    warpSum[lane] = y - x;
+  for ( int k = 0; k < 8; k++ ) {
+    const int64_t x = warpSum[k];
+    if ( k < w ) { off += x; }
+    tot += x;
   }
+  total = tot;
   __syncthreads();
-  int64_t run = warpSum[w] + ( incl - s );
-  for ( int64_t i = b; i < e; i++ ) {
-    out[i] = run;
-    run += in[i];
+  return off + incl - v;
+}
+
+__global__ void __launch_bounds__( 256 ) k_scan_tiles( const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out,
+                                                       int64_t* __restrict__ tileSum ) {
+  __shared__ int64_t warpSum[8];
+  const int64_t      i0 = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  int32_t            v[8];
+  if ( i0 + 8 <= n ) {
+    const int4 a = *reinterpret_cast<const int4*>( in + i0 ), b = *reinterpret_cast<const int4*>( in + i0 + 4 );
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else {
+#pragma unroll
+    for ( int k = 0; k < 8; k++ ) { v[k] = i0 + k < n ? in[i0 + k] : 0; }
   }
-  if ( t == 1023 ) { out[n] = run; }
+  int64_t s = 0;
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) { s += v[k]; }
+  int64_t total;
+  int64_t run = block_exclusive_256( s, warpSum, total );
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {
+    if ( i0 + k < n ) { out[i0 + k] = run; }
+    run += v[k];
+  }
+  if ( threadIdx.x == 0 ) { tileSum[blockIdx.x] = total; }
+}
+
+__global__ void __launch_bounds__( 256 ) k_scan_apply( int64_t n, int64_t* __restrict__ out, const int64_t* __restrict__ tileSum,
+                                                       int nTiles ) {
+  __shared__ int64_t warpSum[8];
+  int64_t            s = 0;  // sum of the tiles before this one (the extra last CTA sums all: out[n])
+  for ( int t = threadIdx.x; t < min( (int)blockIdx.x, nTiles ); t += 256 ) { s += tileSum[t]; }
+  int64_t total;
+  block_exclusive_256( s, warpSum, total );
+  if ( (int)blockIdx.x == nTiles ) {
+    if ( threadIdx.x == 0 ) { out[n] = total; }
+    return;
+  }
+  if ( total == 0 ) { return; }
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+#pragma unroll
+  for ( int k = 0; k < 8; k++ ) {
+    if ( i0 + k < n ) { out[i0 + k] += total; }
+  }
 }
 
 struct FrameLayout {
@@ -860,10 +900,16 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     auto kCount = eom ? k_reproject<false, true> : k_reproject<false, false>;
     RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
   }
-  RB_LAUNCH( "scan_counts", k_scan_counts, 1, 1024, 0, c->d_wi_count.as<int32_t>(), nWI, c->d_wi_base.as<int64_t>() );
-  if ( eom ) {
-    RB_LAUNCH( "scan_counts", k_scan_counts, 1, 1024, 0, c->d_wi_eom_count.as<int32_t>(), nWI,
-               c->d_wi_eom_base.as<int64_t>() );
+  {
+    const int nTiles = rb_div_up( nWI, SCAN_TILE );
+    RB_CUDA( c->d_scratch[7].ensure( (size_t)( nTiles + 1 ) * 8 ) );
+    int64_t* tileSum = c->d_scratch[7].as<int64_t>();
+    RB_LAUNCH( "scan_counts", k_scan_tiles, std::max( nTiles, 1 ), 256, 0, c->d_wi_count.as<int32_t>(), nWI, c->d_wi_base.as<int64_t>(), tileSum );
+    RB_LAUNCH( "scan_counts", k_scan_apply, nTiles + 1, 256, 0, nWI, c->d_wi_base.as<int64_t>(), tileSum, nTiles );
+    if ( eom ) {
+      RB_LAUNCH( "scan_counts", k_scan_tiles, std::max( nTiles, 1 ), 256, 0, c->d_wi_eom_count.as<int32_t>(), nWI, c->d_wi_eom_base.as<int64_t>(), tileSum );
+      RB_LAUNCH( "scan_counts", k_scan_apply, nTiles + 1, 256, 0, nWI, c->d_wi_eom_base.as<int64_t>(), tileSum, nTiles );
+    }
   }
   a.wi_base     = c->d_wi_base.as<int64_t>();
   a.wi_eom_base = c->d_wi_eom_base.as<int64_t>();

@@ -636,7 +636,7 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   }
   return false;
 }
-__global__ void __launch_bounds__( 128 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
+__global__ void __launch_bounds__( 128, 6 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
   int        f   = 0;
   const bool hit = filter_col_point( a, blockIdx.x * blockDim.x + threadIdx.x, thrSmoothing, yThresh, f );
   count_hits( &a.finfo[0].recolored, f, hit );
