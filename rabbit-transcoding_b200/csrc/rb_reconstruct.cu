@@ -212,7 +212,7 @@ struct TileSmem {
 };
 
 template <bool EMIT, bool EOM>
-__global__ void __launch_bounds__( WARPS * 32 ) k_reproject( const ReprojArgs a ) {
+__global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs a ) {
   __shared__ __align__( 16 ) TileSmem sm[WARPS];
   const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int64_t wi   = (int64_t)blockIdx.x * WARPS + wq;

@@ -24,6 +24,7 @@
 //  * the filter passes repeat the reference's double arithmetic operation by operation (compiled with
 //    -fmad=false), including the integer-truncating abs() of the colour gates.
 #include <algorithm>
+#include <type_traits>
 
 #include "rb_common.cuh"
 
@@ -40,9 +41,16 @@ struct Cell {
 };
 // cw: the count can never carry into the flag (a frame has < 2^28 points); FC_GATE is the mean/median gate of
 // gridFilteringColor (:1228-1243)
-constexpr uint32_t FC_GATE = 1u << 31, FC_CNT = 0x0FFFFFFFu;
-struct CellView {  // what the filters read of a cell
-  uint32_t s0, s1, s2, cnt;
+constexpr uint32_t FC_GATE = 1u << 31, FC_MULTI = 1u << 30, FC_CNT = 0x0FFFFFFFu;
+// Once a grid is complete a per-cell pass turns the accumulators, in place, into what the filters read — so the
+// centre of a cell is divided once per cell instead of once per boundary point and neighbour:
+//   geometry: {float centre x, y, cw', centre z}            centre = float sum / float count (:135-137)
+//   colour  : {double mean c0, c1, c2, cw', -}              mean = (double)(float)sum / (double)count (:1225)
+// with cw' = count | FC_MULTI | FC_GATE.
+template <bool COLOUR>
+struct CellView {
+  typename std::conditional<COLOUR, double, float>::type m0, m1, m2;
+  uint32_t cnt;
   bool     multi, gate;
 };
 constexpr int      MAX_PROBES = 256;
@@ -113,7 +121,8 @@ __device__ __forceinline__ uint32_t block_home( const GridArgs& a, uint32_t key 
 // the 2x2x2 cells a boundary point blends.  All eight table probes are issued before any is examined, unresolved
 // probes (another block's key in the slot) advance together, then the eight 16-byte records are fetched together:
 // two dependent memory round trips in the common case.
-__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], CellView fc[8] ) {
+template <bool COLOUR>
+__device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int S[3], CellView<COLOUR> fc[8] ) {
   const uint32_t            mask = a.tslots - 1;
   const unsigned long long* T    = a.table + (size_t)f * a.tslots;
   uint32_t                  h[8], key[8], id[8];
@@ -148,16 +157,23 @@ __device__ __forceinline__ void cell_find8( const GridArgs& a, int f, const int 
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
     const int cx = S[0] + ( k & 1 ), cy = S[1] + ( ( k >> 1 ) & 1 ), cz = S[2] + ( k >> 2 );
-    uint4 lo = make_uint4( 0, 0, 0, 0 );  // the cell holds no point
-    uint2 pm = make_uint2( 0, 0xFFFFFFFFu );
+    uint32_t cw = 0;  // the cell holds no point
     if ( id[k] < a.cap_blocks ) {
       const Cell* c = a.cells + (size_t)id[k] * 64 + cell_local( cx, cy, cz );
-      lo            = __ldg( reinterpret_cast<const uint4*>( c ) );
-      pm            = __ldg( reinterpret_cast<const uint2*>( &c->pmax ) );
+      if ( COLOUR ) {
+        const double2 m01 = __ldg( reinterpret_cast<const double2*>( c ) );
+        const double2 m2w = __ldg( reinterpret_cast<const double2*>( c ) + 1 );
+        fc[k].m0 = m01.x, fc[k].m1 = m01.y, fc[k].m2 = m2w.x;
+        cw = (uint32_t)__double_as_longlong( m2w.y );
+      } else {
+        const uint4 lo = __ldg( reinterpret_cast<const uint4*>( c ) );
+        fc[k].m0 = __uint_as_float( lo.x ), fc[k].m1 = __uint_as_float( lo.y ), fc[k].m2 = __uint_as_float( lo.w );
+        cw = lo.z;
+      }
     }
-    fc[k].s0 = lo.x, fc[k].s1 = lo.y, fc[k].s2 = lo.w, fc[k].cnt = lo.z & FC_CNT;
-    fc[k].gate  = ( lo.z & FC_GATE ) != 0;
-    fc[k].multi = fc[k].cnt != 0 && pm.x != ~pm.y;
+    fc[k].cnt   = cw & FC_CNT;
+    fc[k].gate  = ( cw & FC_GATE ) != 0;
+    fc[k].multi = fc[k].cnt != 0 && ( cw & FC_MULTI );
   }
 }
 
@@ -234,7 +250,7 @@ constexpr int ACC_RUN = 8;  // consecutive points per thread
 // changes.  (Combining equal cells across lanes with per-group __reduce_*_sync masks was measured 4x slower: partial
 // masks are executed group by group.)
 template <bool COLOUR>
-__global__ void __launch_bounds__( 256 ) k_accumulate( const GridArgs a, int64_t n ) {
+__global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int64_t n ) {
   const int     lane = threadIdx.x & 31;
   const int64_t i0   = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
   short4        p[ACC_RUN];
@@ -409,6 +425,7 @@ __global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, d
         want = false;
       }
     }
+    bool     gate  = false;
     uint32_t small = __ballot_sync( 0xFFFFFFFFu, want && n <= 32 );
     uint32_t large = __ballot_sync( 0xFFFFFFFFu, want && n > 32 );
     while ( small ) {  // up to four cells per round: their loads and their sorting networks overlap
@@ -435,7 +452,7 @@ __global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, d
 #pragma unroll
       for ( int q = 0; q < 4; q++ ) {
         const int vhi = __shfl_sync( 0xFFFFFFFFu, v[q], ( m[q] / 2 ) & 31 ), vlo = __shfl_sync( 0xFFFFFFFFu, v[q], ( m[q] / 2 - 1 ) & 31 );
-        if ( lane == src[q] && gate_of( vhi, vlo, m[q], lo.x, mmThresh ) ) { c->cw = lo.z | FC_GATE; }
+        if ( lane == src[q] ) { gate = gate_of( vhi, vlo, m[q], lo.x, mmThresh ); }
       }
     }
     for ( ; large; large &= large - 1 ) {  // rare: more than 32 points in a cell, rank selection
@@ -459,8 +476,36 @@ __global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, d
         vhi = max( vhi, __shfl_xor_sync( 0xFFFFFFFFu, vhi, d ) );
         vlo = max( vlo, __shfl_xor_sync( 0xFFFFFFFFu, vlo, d ) );
       }
-      if ( lane == src && gate_of( vhi, vlo, m, lo.x, mmThresh ) ) { c->cw = lo.z | FC_GATE; }
+      if ( lane == src ) { gate = gate_of( vhi, vlo, m, lo.x, mmThresh ); }
     }
+    if ( n > 0 ) {  // finalise in place: mean colour (:1225: float accumulator read back as double / count), flags
+      if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || n > 65535u ) {
+        a.counters[3] = 1;  // a float accumulator of the reference would have left the exact range
+      }
+      const uint2    pm = *reinterpret_cast<const uint2*>( &c->pmax );
+      const uint32_t cw = n | ( pm.x != ~pm.y ? FC_MULTI : 0u ) | ( gate ? FC_GATE : 0u );
+      const double   dn = (double)n;
+      double2*       o  = reinterpret_cast<double2*>( c );
+      o[0]              = make_double2( (double)(float)lo.x / dn, (double)(float)lo.y / dn );
+      o[1]              = make_double2( (double)(float)lo.w / dn, __longlong_as_double( (long long)cw ) );
+    }
+  }
+}
+
+// geometry: finalise the cells in place (centre = float sum / float count, :135-137; doSmooth flag)
+__global__ void __launch_bounds__( 256 ) k_finalize_geo( const GridArgs a ) {
+  const uint32_t nCells = (uint32_t)min( (unsigned)a.counters[CTR_CURSOR], a.cap_blocks ) * 64u;
+  for ( uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nCells; s += gridDim.x * blockDim.x ) {
+    Cell*          c  = a.cells + s;
+    const uint4    lo = *reinterpret_cast<const uint4*>( c );
+    const uint32_t n  = lo.z & FC_CNT;
+    if ( n == 0 ) { continue; }
+    if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || n > 65535u ) { a.counters[3] = 1; }
+    const uint2 pm  = *reinterpret_cast<const uint2*>( &c->pmax );
+    const float fcn = (float)n;
+    *reinterpret_cast<uint4*>( c ) =
+        make_uint4( __float_as_uint( __fdiv_rn( (float)lo.x, fcn ) ), __float_as_uint( __fdiv_rn( (float)lo.y, fcn ) ),
+                    n | ( pm.x != ~pm.y ? FC_MULTI : 0u ), __float_as_uint( __fdiv_rn( (float)lo.w, fcn ) ) );
   }
 }
 
@@ -488,10 +533,10 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
   const int      P[3] = {p.x, p.y, p.z};
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( P[k] - ( P[k] / g ) * g < hg ) ? -1 : 0 ); }  // :1014-1017
-  CellView fc[8];
+  CellView<false> fc[8];
   bool     other = false;
   uint32_t cnt[8];
-  cell_find8( a, f, S, fc );
+  cell_find8<false>( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
     cnt[k] = fc[k].cnt;
@@ -511,11 +556,8 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
     const int    dx = k & 1, dy = ( k >> 1 ) & 1, dz = k >> 2;
     const int    wgt = ( dx ? Wt[0] : Q[0] ) * ( dy ? Wt[1] : Q[1] ) * ( dz ? Wt[2] : Q[2] );
     double       v[3];
-    if ( cnt[k] > 0 ) {  // :1040: centre = float sum / float count (one IEEE float division, :135-137)
-      const float fcn = (float)cnt[k];
-      v[0]            = (double)__fdiv_rn( (float)fc[k].s0, fcn );
-      v[1]            = (double)__fdiv_rn( (float)fc[k].s1, fcn );
-      v[2]            = (double)__fdiv_rn( (float)fc[k].s2, fcn );
+    if ( cnt[k] > 0 ) {  // :1040: the cell centre (k_finalize_geo)
+      v[0] = (double)fc[k].m0, v[1] = (double)fc[k].m1, v[2] = (double)fc[k].m2;
     } else {
       v[0] = (double)P[0];
       v[1] = (double)P[1];
@@ -554,7 +596,7 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
   }
   return false;
 }
-__global__ void __launch_bounds__( 128 ) k_filter_geo( const GridArgs a, double threshold ) {
+__global__ void __launch_bounds__( 128, 8 ) k_filter_geo( const GridArgs a, double threshold ) {
   int        f   = 0;
   const bool hit = filter_geo_point( a, blockIdx.x * blockDim.x + threadIdx.x, threshold, f );
   count_hits( &a.finfo[0].smoothed, f, hit );
@@ -573,9 +615,9 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   int            S[3];
   for ( int k = 0; k < 3; k++ ) { S[k] = P[k] / g + ( ( ( P[k] % g ) < hg ) ? -1 : 0 ); }  // :1197-1199
   const ushort4 cv = a.col[i];  // issued with the probes: independent of them
-  CellView      fc[8];
+  CellView<true> fc[8];
   bool          other = false;
-  cell_find8( a, f, S, fc );
+  cell_find8<true>( a, f, S, fc );
 #pragma unroll
   for ( int k = 0; k < 8; k++ ) {
     if ( fc[k].multi ) { other = true; }  // :1204
@@ -597,17 +639,12 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
     double         d[3];
     bool           own = cn == 0;
     if ( cn > 0 ) {
-      const double dn = (double)cn;  // :1225: float accumulator read back as double, divided by the count in double
-      d[0]            = (double)(float)fc[k].s0 / dn;
+      d[0] = fc[k].m0, d[1] = fc[k].m1, d[2] = fc[k].m2;  // :1225, divided once per cell by k_cell_median_gate
       if ( k == 0 ) {
         if ( gate ) { return false; }  // :1228-1235: centroid = own colour -> |dY| = 0 < threshold unless threshold <= 0
       } else {
         const int dy0 = (int)( Y0 - d[0] );  // abs() truncates (App. A.9), :1238
         own           = (double)( dy0 < 0 ? -dy0 : dy0 ) > yThresh || gate;  // :1238-1243
-      }
-      if ( !own ) {
-        d[1] = (double)(float)fc[k].s1 / dn;
-        d[2] = (double)(float)fc[k].s2 / dn;
       }
     }
     if ( own ) { d[0] = cur[0], d[1] = cur[1], d[2] = cur[2]; }
@@ -636,22 +673,19 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   }
   return false;
 }
-__global__ void __launch_bounds__( 128, 6 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
+__global__ void __launch_bounds__( 128, 8 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
   int        f   = 0;
   const bool hit = filter_col_point( a, blockIdx.x * blockDim.x + threadIdx.x, thrSmoothing, yThresh, f );
   count_hits( &a.finfo[0].recolored, f, hit );
 }
 
-// ---- cleanup: reset the used part of the pool (+ the exactness guard of App. A.3) and the block table ----
+// ---- cleanup: reset the used part of the pool ----
 __global__ void __launch_bounds__( 256 ) k_cleanup_cells( const GridArgs a ) {
   const uint32_t nCells = (uint32_t)min( (unsigned)a.counters[CTR_CURSOR], a.cap_blocks ) * 64u;
   for ( uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nCells; s += gridDim.x * blockDim.x ) {
     uint4*      c  = reinterpret_cast<uint4*>( a.cells + s );
-    const uint4 lo = c[0];
-    if ( ( lo.x | lo.y | lo.z | lo.w ) == 0 ) { continue; }
-    if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || ( lo.z & FC_CNT ) > 65535u ) {
-      a.counters[3] = 1;  // a float accumulator of the reference would have left the exact range
-    }
+    const uint4 lo = c[0], hi = c[1];
+    if ( ( lo.x | lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w ) == 0 ) { continue; }
     c[0] = c[1] = make_uint4( 0, 0, 0, 0 );
   }
 }
@@ -797,6 +831,7 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     if ( r ) { return r; }
     if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+    RB_LAUNCH( "geo_finalize", k_finalize_geo, WALK_CTAS, 256, 0, a );
     if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
     RB_LAUNCH( "geo_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
     RB_CUDA( cudaMemsetAsync( a.table, 0, (size_t)a.F * a.tslots * 8, c->stream ) );
