@@ -183,6 +183,10 @@ int rb200_smooth_color(rb200_ctx* ctx);
 
 /* ---- PCCPointSet3::convertYUV16ToRGB8 / copyRGB16ToRGB8 (PCCPointSet.h:121-166) ------------------ */
 int rb200_convert_rgb8(rb200_ctx* ctx);
+/* test hook: n host colour triples [n][3] through the conversion kernel of rb200_convert_rgb8 (a short
+ * evaluation of convertYUV16ToRGB8 that falls back to the reference's sequence of double operations near rounding ties), or,
+ * force_f64 != 0, through the double arithmetic alone; rgb [n][3] on the host */
+int rb200_debug_yuv16_to_rgb8(rb200_ctx* ctx, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64);
 
 /* ---- the decoder's whole per-frame sequence (PCCDecoder.cpp:330-508) governed by params ---------- */
 int rb200_decode_gof(rb200_ctx* ctx);

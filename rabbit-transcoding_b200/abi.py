@@ -120,7 +120,7 @@ class LaunchStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
     "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_reconstruct", "rb200_smooth_geometry",
-    "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_decode_gof",
+    "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
     "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
@@ -157,6 +157,7 @@ def load_library(path=None):
     for n in ("rb200_reconstruct", "rb200_smooth_geometry", "rb200_transfer_colors", "rb200_smooth_color",
               "rb200_convert_rgb8", "rb200_decode_gof"):
         getattr(lib, n).argtypes = [C.c_void_p]
+    lib.rb200_debug_yuv16_to_rgb8.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_int]
     lib.rb200_frame_counts_get.argtypes = [C.c_void_p, C.POINTER(FrameCounts)]
     lib.rb200_download_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(CloudHost)]
     lib.rb200_enable_stage_snapshots.argtypes = [C.c_void_p, C.c_int]

@@ -172,6 +172,7 @@ int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
+int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 );
 void rb_metrics_release( rb200_ctx* c );
 void rb_transfer_release( rb200_ctx* c );
 // exclusive scan of n uint32 (in == out allowed); `sums` needs rb_scan_scratch_bytes( n ) bytes

@@ -463,6 +463,13 @@ int rb200_convert_rgb8( rb200_ctx* c ) {
   return r;
 }
 
+int rb200_debug_yuv16_to_rgb8( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 ) {
+  if ( !c || !yuv || !rgb || n < 0 ) { return RB200_ERR_INVALID; }
+  if ( n == 0 ) { return RB200_OK; }
+  cudaSetDevice( c->device );
+  return rb_debug_rgb8_impl( c, yuv, n, rgb, force_f64 );
+}
+
 // The decoder's per-frame sequence, PCCDecoder.cpp:330-508, for the whole GOF.
 int rb200_decode_gof( rb200_ctx* c ) {
   if ( !c ) { return RB200_ERR_INVALID; }

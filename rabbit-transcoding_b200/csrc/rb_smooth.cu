@@ -691,19 +691,8 @@ __global__ void __launch_bounds__( 256 ) k_cleanup_cells( const GridArgs a ) {
 }
 
 // ---- convertYUV16ToRGB8 (PCCPointSet.h:133-166) / copyRGB16ToRGB8 (:121-127) ----
-__global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__ rgb, int64_t n, int rgb444,
-                           int attr_count ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  if ( attr_count == 0 ) {
-    rgb[i] = make_uchar4( 127, 127, 127, 0 );  // PCCCodec.cpp:1327-1330
-    return;
-  }
-  const ushort4 c = col[i];
-  if ( rgb444 ) {
-    rgb[i] = make_uchar4( (unsigned char)c.x, (unsigned char)c.y, (unsigned char)c.z, 0 );
-    return;
-  }
+// The reference's double arithmetic, operation by operation (the fallback of the short path below).
+__device__ __forceinline__ uchar4 yuv16_to_rgb8_f64( ushort4 c ) {
   const double offset = 32768.0, scale = 65535.0, weight = 1.0 / scale;
   double       y1 = __dmul_rn( weight, (double)c.x );
   double       u1 = __dmul_rn( weight, __dsub_rn( (double)c.y, offset ) );
@@ -717,7 +706,63 @@ __global__ void k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__
   r        = fmin( fmax( round( __dmul_rn( r, 255.0 ) ), 0.0 ), 255.0 );
   g        = fmin( fmax( round( __dmul_rn( g, 255.0 ) ), 0.0 ), 255.0 );
   b        = fmin( fmax( round( __dmul_rn( b, 255.0 ) ), 0.0 ), 255.0 );
-  rgb[i]   = make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
+  return make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
+}
+
+// The same function with a third of the double operations.  In exact arithmetic (with the clamps: only chroma 0 is
+// clamped, to -0.5, i.e. 2 (c - 32768) = -65535) a channel is  255 (Y + k_u U2 / 2 + k_v V2 / 2) / 65535
+// = (Y + k_u/2 U2 + k_v/2 V2) / 257 = num / 257000000 with integer num, so two different values are >= 3.9e-9
+// apart and a value that is not EXACTLY a tie k + 1/2 is at least that far from one.  Both the reference's sequence
+// of operations and the short sequence below are within 1e-12 of the exact value; hence wherever the short result
+// is further than 1e-9 from a tie, round-half-away of the reference sequence is the nearest integer of the short
+// result.  Only exact ties (a few colours per million million) take the reference sequence.
+__device__ __forceinline__ int round_channel( double x, bool& near_tie ) {
+  const double M  = 4503599627370496.0;                 // 2^52: adding it rounds to the nearest integer
+  const double xc = fmin( fmax( x, 0.0 ), 255.25 );     // PCCClip after round; ties 0.5 .. 254.5 are kept
+  const double z  = __dadd_rn( xc, M );
+  const double e  = __dsub_rn( xc, __dsub_rn( z, M ) );  // exact: distance to the nearest integer
+  near_tie |= fabs( e ) > 0.499999999;
+  return __double2loint( z );
+}
+__device__ __forceinline__ uchar4 yuv16_to_rgb8( ushort4 c ) {
+  const double M   = 4503599627370496.0;
+  const int    u2i = max( 2 * ( (int)c.y - 32768 ), -65535 ), v2i = max( 2 * ( (int)c.z - 32768 ), -65535 );
+  const double Y   = __dsub_rn( __hiloint2double( 0x43300000, (int)c.x ), M );  // exact int -> double without I2F
+  const double U2  = __dsub_rn( __hiloint2double( 0x43300000, u2i + 65536 ), M + 65536.0 );
+  const double V2  = __dsub_rn( __hiloint2double( 0x43300000, v2i + 65536 ), M + 65536.0 );
+  const double inv = 1.0 / 257.0;
+  bool         near_tie = false;
+  const int    r = round_channel( __dmul_rn( __fma_rn( 1.57480 * 0.5, V2, Y ), inv ), near_tie );
+  const int    g = round_channel( __dmul_rn( __fma_rn( -0.46813 * 0.5, V2, __fma_rn( -0.18733 * 0.5, U2, Y ) ), inv ), near_tie );
+  const int    b = round_channel( __dmul_rn( __fma_rn( 1.85563 * 0.5, U2, Y ), inv ), near_tie );
+  if ( near_tie ) { return yuv16_to_rgb8_f64( c ); }
+  return make_uchar4( (unsigned char)r, (unsigned char)g, (unsigned char)b, 0 );
+}
+
+__device__ __forceinline__ uchar4 to_rgb8_one( ushort4 c, int rgb444, int attr_count, int force_f64 ) {
+  if ( attr_count == 0 ) { return make_uchar4( 127, 127, 127, 0 ); }  // PCCCodec.cpp:1327-1330
+  if ( rgb444 ) { return make_uchar4( (unsigned char)c.x, (unsigned char)c.y, (unsigned char)c.z, 0 ); }
+  return force_f64 ? yuv16_to_rgb8_f64( c ) : yuv16_to_rgb8( c );
+}
+// four points per thread: two 16-byte loads, one 16-byte store
+__global__ void __launch_bounds__( 256 ) k_to_rgb8( const ushort4* __restrict__ col, uchar4* __restrict__ rgb, int64_t n,
+                                                     int rgb444, int attr_count, int force_f64 ) {
+  const int64_t i0 = ( blockIdx.x * (int64_t)blockDim.x + threadIdx.x ) * 4;
+  if ( i0 >= n ) { return; }
+  if ( i0 + 4 <= n ) {
+    const uint4 a = *reinterpret_cast<const uint4*>( col + i0 ), b = *reinterpret_cast<const uint4*>( col + i0 + 2 );
+    const ushort4 c[4] = {make_ushort4( a.x & 0xFFFF, a.x >> 16, a.y & 0xFFFF, a.y >> 16 ), make_ushort4( a.z & 0xFFFF, a.z >> 16, a.w & 0xFFFF, a.w >> 16 ),
+                          make_ushort4( b.x & 0xFFFF, b.x >> 16, b.y & 0xFFFF, b.y >> 16 ), make_ushort4( b.z & 0xFFFF, b.z >> 16, b.w & 0xFFFF, b.w >> 16 )};
+    uint32_t      o[4];
+#pragma unroll
+    for ( int k = 0; k < 4; k++ ) {
+      const uchar4 q = to_rgb8_one( c[k], rgb444, attr_count, force_f64 );
+      o[k]           = (uint32_t)q.x | ( (uint32_t)q.y << 8 ) | ( (uint32_t)q.z << 16 );
+    }
+    *reinterpret_cast<uint4*>( rgb + i0 ) = make_uint4( o[0], o[1], o[2], o[3] );
+  } else {
+    for ( int64_t i = i0; i < n; i++ ) { rgb[i] = to_rgb8_one( col[i], rgb444, attr_count, force_f64 ); }
+  }
 }
 
 // table geometry + (re)allocation; table and pool are all-zero between calls (the cleanup pass resets what was used)
@@ -887,7 +932,26 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
 int rb_convert_rgb8_impl( rb200_ctx* c ) {
   const int64_t n = c->h_frame_off[c->F];
   if ( n == 0 ) { return RB200_OK; }
-  RB_LAUNCH( "to_rgb8", k_to_rgb8, rb_div_up( n, 256 ), 256, 0, c->d_col.as<ushort4>(), c->d_rgb.as<uchar4>(), n,
-             c->P.attribute_rgb444, c->P.attribute_count );
+  RB_LAUNCH( "to_rgb8", k_to_rgb8, rb_div_up( n, 1024 ), 256, 0, c->d_col.as<ushort4>(), c->d_rgb.as<uchar4>(), n,
+             c->P.attribute_rgb444, c->P.attribute_count, 0 );
+  return RB200_OK;
+}
+
+// test hook (rb200_debug_yuv16_to_rgb8): n colour triples through the production conversion kernel (integer path with
+// double fallback) or, force_f64 != 0, through the double path alone
+int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 ) {
+  RbBuf in, out;
+  RB_CUDA( in.ensure( (size_t)n * 8 + 16 ) );
+  RB_CUDA( out.ensure( (size_t)n * 4 + 16 ) );
+  std::vector<uint16_t> h4( (size_t)n * 4 );
+  for ( int64_t i = 0; i < n; i++ ) { h4[4 * i] = yuv[3 * i], h4[4 * i + 1] = yuv[3 * i + 1], h4[4 * i + 2] = yuv[3 * i + 2], h4[4 * i + 3] = 0; }
+  RB_CUDA( cudaMemcpyAsync( in.p, h4.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream ) );
+  RB_LAUNCH( "to_rgb8", k_to_rgb8, rb_div_up( n, 1024 ), 256, 0, in.as<ushort4>(), out.as<uchar4>(), n, 0, 1, force_f64 );
+  std::vector<uint8_t> o4( (size_t)n * 4 );
+  RB_CUDA( cudaMemcpyAsync( o4.data(), out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  for ( int64_t i = 0; i < n; i++ ) { rgb[3 * i] = o4[4 * i], rgb[3 * i + 1] = o4[4 * i + 1], rgb[3 * i + 2] = o4[4 * i + 2]; }
+  in.release();
+  out.release();
   return RB200_OK;
 }
