@@ -143,8 +143,9 @@ def algorithmic_bytes(name, g, n_points, n_type1, n_moved):
         # B_geo / B_col split over their passes (pos + type 8 B, partition 4 B, colour16 6 B, boundary index 4 B)
         "geo_accumulate": N * 12,
         "geo_filter": n_type1 * (4 + 8) + n_moved * 8,
-        "col_accumulate": N * (8 + 6 + 4),
-        "col_scatter_lum": N * (8 + 2) + N * 2,
+        "col_mark": n_type1 * (4 + 8),
+        # the luma lists are written by the accumulation itself (2 B per point)
+        "col_accumulate": N * (8 + 6 + 4) + N * 2,
         "col_filter": n_type1 * (4 + 8 + 6) + n_type1 * 6,
         "to_rgb8": N * (6 + 3),
     }
@@ -253,9 +254,66 @@ def run_b200(args):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         st = codec.stats(reset=True)
         assert n_got == n_points
-        e2e = {"value": all_points * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": st.h2d_bytes // args.steps, "d2h_bytes_per_step": st.d2h_bytes // args.steps,
-               "ms_per_step": ms_e2e / args.steps}
+        serial = {"value": round(all_points * args.steps / (ms_e2e * 1e-3) / 1e6, 2), "ms_per_step": round(ms_e2e / args.steps, 3)}
+
+        # the same call sequence with two GOFs in flight: a second context on its own stream, driven by a second host
+        # thread, so the upload of one GOF overlaps the kernels and the download of the other (PCIe is full duplex)
+        codec2 = rb.codec.PCCCodecB200(device=local)
+        stream2 = torch.cuda.Stream()
+        codec2.setStream(stream2.cuda_stream)
+        out2 = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
+                    colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
+        lanes = [(codec, out), (codec2, out2)]
+        got = [0, 0]
+        errs = []
+        h2d_turn = threading.Lock()  # one upload at a time: the other GOF is then in its kernels / its download
+
+        def worker(k, nsteps):
+            try:
+                torch.cuda.set_device(local)
+                c_, o_ = lanes[k]
+                for _ in range(nsteps):
+                    with h2d_turn:
+                        c_.uploadGof(gof)
+                        c_.synchronize()
+                    c_.decodeGof()
+                    got[k] = c_.getGof(fields=("positions", "colors"), out=o_)[1]
+            except Exception as ex:  # surfaced after the join
+                errs.append(ex)
+
+        def run_pipelined(nsteps):
+            ts = [threading.Thread(target=worker, args=(k, (nsteps + 1 - k) // 2)) for k in range(2)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                raise errs[0]
+        run_pipelined(2)
+        psteps = max(2, args.steps)
+        codec.stats(reset=True)
+        codec2.stats(reset=True)
+        barrier()
+        torch.cuda.synchronize()
+        clocks.on()
+        e0.record(stream)
+        run_pipelined(psteps)
+        torch.cuda.synchronize()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        clocks.off()
+        barrier()
+        ms_pipe = max_over_ranks(e0.elapsed_time(e1))
+        st1, st2 = codec.stats(reset=True), codec2.stats(reset=True)
+        assert got[0] == n_points and got[1] == n_points
+        assert np.array_equal(out["positions"][:n_points], out2["positions"][:n_points])
+        codec2.close()
+        e2e = {"value": round(all_points * psteps / (ms_pipe * 1e-3) / 1e6, 2), "unit": UNIT,
+               "h2d_bytes_per_step": (st1.h2d_bytes + st2.h2d_bytes) // psteps,
+               "d2h_bytes_per_step": (st1.d2h_bytes + st2.d2h_bytes) // psteps,
+               "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps,
+               "mode": "uploadGof -> decodeGof -> getGof from pinned host buffers, two GOFs in flight (two contexts, two "
+                       "streams, two host threads)", "one_gof_in_flight": serial}
 
     # ---------------- leg 2a: the decoder's full Rec-1 sequence (adds transferColors16bitBP after geometry smoothing) ----
     full = None
