@@ -144,6 +144,9 @@ def algorithmic_bytes(name, g, n_points, n_type1, n_moved):
         "geo_accumulate": N * 12,
         "geo_filter": n_type1 * (4 + 8) + n_moved * 8,
         "col_mark": n_type1 * (4 + 8),
+        # decoder-native ingest: 8-bit 4:2:0 in (1.5 B / pixel), 16-bit 4:4:4 out (6 B / pixel) per attribute frame
+        "attribute_420_to_444": F * M * W * H // 2 + F * M * W * H * 4,
+        "attribute_luma_to_16": F * M * W * H * 3,
         # the luma lists are written by the accumulation itself (2 B per point)
         "col_accumulate": N * (8 + 6 + 4) + N * 2,
         "col_filter": n_type1 * (4 + 8 + 6) + n_type1 * 6,
@@ -268,52 +271,67 @@ def run_b200(args):
         errs = []
         h2d_turn = threading.Lock()  # one upload at a time: the other GOF is then in its kernels / its download
 
-        def worker(k, nsteps):
+        def worker(k, nsteps, upload):
             try:
                 torch.cuda.set_device(local)
                 c_, o_ = lanes[k]
                 for _ in range(nsteps):
                     with h2d_turn:
-                        c_.uploadGof(gof)
+                        upload(c_)
                         c_.synchronize()
                     c_.decodeGof()
                     got[k] = c_.getGof(fields=("positions", "colors"), out=o_)[1]
             except Exception as ex:  # surfaced after the join
                 errs.append(ex)
 
-        def run_pipelined(nsteps):
-            ts = [threading.Thread(target=worker, args=(k, (nsteps + 1 - k) // 2)) for k in range(2)]
+        def run_pipelined(nsteps, upload):
+            ts = [threading.Thread(target=worker, args=(k, (nsteps + 1 - k) // 2, upload)) for k in range(2)]
             for t in ts:
                 t.start()
             for t in ts:
                 t.join()
             if errs:
                 raise errs[0]
-        run_pipelined(2)
-        psteps = max(2, args.steps)
-        codec.stats(reset=True)
-        codec2.stats(reset=True)
-        barrier()
-        torch.cuda.synchronize()
-        clocks.on()
-        e0.record(stream)
-        run_pipelined(psteps)
-        torch.cuda.synchronize()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        clocks.off()
-        barrier()
-        ms_pipe = max_over_ranks(e0.elapsed_time(e1))
-        st1, st2 = codec.stats(reset=True), codec2.stats(reset=True)
-        assert got[0] == n_points and got[1] == n_points
-        assert np.array_equal(out["positions"][:n_points], out2["positions"][:n_points])
+
+        def time_pipelined(upload):
+            run_pipelined(2, upload)
+            psteps = max(2, args.steps)
+            codec.stats(reset=True)
+            codec2.stats(reset=True)
+            barrier()
+            torch.cuda.synchronize()
+            clocks.on()
+            e0.record(stream)
+            run_pipelined(psteps, upload)
+            torch.cuda.synchronize()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            clocks.off()
+            barrier()
+            ms_pipe = max_over_ranks(e0.elapsed_time(e1))
+            st1, st2 = codec.stats(reset=True), codec2.stats(reset=True)
+            assert got[0] == n_points and got[1] == n_points
+            assert np.array_equal(out["positions"][:n_points], out2["positions"][:n_points])
+            return {"value": round(all_points * psteps / (ms_pipe * 1e-3) / 1e6, 2), "unit": UNIT,
+                    "h2d_bytes_per_step": (st1.h2d_bytes + st2.h2d_bytes) // psteps,
+                    "d2h_bytes_per_step": (st1.d2h_bytes + st2.d2h_bytes) // psteps,
+                    "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps}
+
+        from_444 = time_pipelined(lambda c_: c_.uploadGof(gof))
+        from_444["mode"] = "uploadGof (16-bit 4:4:4 frames, the reference's PCCVideo boundary) -> decodeGof -> getGof, two GOFs in flight"
+        from_444["one_gof_in_flight"] = serial
+        # the decoder-native boundary: 8-bit 4:2:0 attribute frames + 8-bit geometry luma as libav / NVDEC / HM leave
+        # them; PCCVideoDecoder's inverse colour conversion (YUV420ToYUV444_8_0) runs on the device inside the step
+        native = rb.synthetic.to_decoder_planes(gof, bitdepth=8, filt=0)
+        native["geometry"] = pin(native["geometry"]).numpy()
+        native["attribute"] = pin(native["attribute"]).numpy()
+        e2e = time_pipelined(lambda c_: c_.uploadGofYuv420(gof, native))
+        e2e["mode"] = ("uploadGofYuv420 (decoder-native planes: 8-bit 4:2:0 attribute frames + 8-bit geometry luma from pinned "
+                       "host memory; the decoder's 4:2:0 -> 4:4:4 16-bit conversion runs on the GPU inside the step) -> decodeGof "
+                       "-> getGof (positions + RGB8 to pinned host memory); two GOFs in flight (two contexts, two streams, two "
+                       "host threads)")
+        e2e["from_444_16bit_frames"] = from_444
         codec2.close()
-        e2e = {"value": round(all_points * psteps / (ms_pipe * 1e-3) / 1e6, 2), "unit": UNIT,
-               "h2d_bytes_per_step": (st1.h2d_bytes + st2.h2d_bytes) // psteps,
-               "d2h_bytes_per_step": (st1.d2h_bytes + st2.d2h_bytes) // psteps,
-               "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps,
-               "mode": "uploadGof -> decodeGof -> getGof from pinned host buffers, two GOFs in flight (two contexts, two "
-                       "streams, two host threads)", "one_gof_in_flight": serial}
 
     # ---------------- leg 2a: the decoder's full Rec-1 sequence (adds transferColors16bitBP after geometry smoothing) ----
     full = None

@@ -123,6 +123,20 @@ typedef struct rb200_frames {
   const uint16_t* attribute; /* [F][M][3][H][W]    4:4:4 16-bit attribute frame f*M+m; NULL if none       */
 } rb200_frames;
 
+/* Decoder-native planes of one GOF: the planar 4:2:0 frames a video decoder (HM, libav, NVDEC) leaves behind, BEFORE
+ * PCCVideoDecoder's inverse colour conversion (PccLibDecoder/source/PCCVideoDecoder.cpp:125-146, :365 ->
+ * PCCInternalColorConverter<T>::convertYUV420ToYUV444, PccLibColorConverter/source/PCCInternalColorConverter.cpp:
+ * 456-486), which then runs on the device.  host or device pointers. */
+typedef struct rb200_frames_yuv420 {
+  const uint8_t* occupancy;       /* [F][H/p][W/p]  as rb200_frames                                                    */
+  const void*    geometry;        /* [F][M][H][W]   luma samples of geometry_sample_bytes each                        */
+  const void*    attribute;       /* [F][M] frames { Y [H][W], U [H/2][W/2], V [H/2][W/2] } of attribute_sample_bytes */
+  int32_t geometry_sample_bytes;  /* 1 or 2                                                                            */
+  int32_t attribute_sample_bytes; /* 1 or 2                                                                            */
+  int32_t attribute_bitdepth;     /* 8 or 10: the "<bits>" of "YUV420ToYUV444_<bits>_<filter>" (nbyte = 1 for 8)       */
+  int32_t upsampling_filter;      /* "<filter>": index into g_filter420to444 (0..7), decoder parameter upsamplingFilter */
+} rb200_frames_yuv420;
+
 /* Patch tables of one GOF.  host pointers.  *_offset arrays have F+1 entries. */
 typedef struct rb200_atlas {
   const rb200_patch*     patches;
@@ -165,6 +179,12 @@ int         rb200_synchronize(rb200_ctx* ctx);
 /* ---- frame ingest: replaces PCCImage::set / PCCVideo containers on the path (PCCImage.h:97-138) --- */
 int rb200_gof_begin(rb200_ctx* ctx, const rb200_params* params, int n_frames);
 int rb200_gof_upload(rb200_ctx* ctx, const rb200_frames* frames, const rb200_atlas* atlas);
+/* the same with decoder-native planes: replaces PCCImage::set (PCCImage.h:97-138) + the inverse colour conversion of
+ * PCCVideoDecoder (PCCVideoDecoder.cpp:125-146, :365; PCCInternalColorConverter.cpp:456-486, :596-611, :669-695, :582-594) */
+int rb200_gof_upload_yuv420(rb200_ctx* ctx, const rb200_frames_yuv420* frames, const rb200_atlas* atlas);
+/* the planes the reconstruction reads as they sit in HBM after an upload: geometry [H][W], attribute [3][H][W] uint16 of
+ * frame `frame`, map `map` (either pointer may be NULL); used to check the ingest conversion */
+int rb200_download_planes(rb200_ctx* ctx, int frame, int map, uint16_t* geometry, uint16_t* attribute);
 
 /* ---- reconstruction: PCCCodec::generateOccupancyMap (PCCCodec.cpp:1584-1606) +
  *      generateBlockToPatchFromOccupancyMapVideo (:1725-1763) + generatePointCloud (:517-978, incl.

@@ -211,6 +211,18 @@ class Reference(_Backend):
     def __init__(self):
         super().__init__(REF_LIB)
 
+    def yuv420_to_yuv444(self, y, u, v, bitdepth, filt):
+        """the reference's own PCCInternalColorConverter<uint16_t>::convert("YUV420ToYUV444_<bits>_<filter>")"""
+        f = getattr(self.lib, "ref_yuv420_to_yuv444", None)
+        if f is None:
+            raise RuntimeError("oracle/_ref/librabbit_ref.so predates the colour converter: cd oracle && make ref")
+        f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+        y, u, v = (np.ascontiguousarray(a, np.uint16) for a in (y, u, v))
+        out = np.zeros((3,) + y.shape, np.uint16)
+        if f(abi.ptr(y), abi.ptr(u), abi.ptr(v), y.shape[1], y.shape[0], bitdepth, filt, abi.ptr(out)) != 0:
+            raise RuntimeError("ref_yuv420_to_yuv444 failed")
+        return out
+
 
 class DropIn(_Backend):
     """the reference's harness and objects with the hot member functions replaced by the C++ shim

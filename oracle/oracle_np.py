@@ -425,3 +425,75 @@ class Port:
             snaps["rgb8"] = cloud
             out.append(snaps)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCInternalColorConverter<T>::convertYUV420ToYUV444 (PccLibColorConverter/source/PCCInternalColorConverter.cpp:
+# 456-486) as PCCVideoDecoder runs it after the attribute video is decoded (PccLibDecoder/source/PCCVideoDecoder.cpp:
+# 125-146, :365): YUVtoFloatYUV (:596-611), upsampling (:669-695) with upsamplingVertical0/1 and
+# upsamplingHorizontal0/1 (include/PCCInternalColorConverter.h:187-249), floatYUVToYUV (:582-594).
+# All filter arithmetic is sequential single-precision (np.float32), the sample scaling goes through double.
+# ---------------------------------------------------------------------------------------------------------------
+# g_filter420to444 (PCCInternalColorConverter.cpp:297-337): (horizontal0, vertical0, horizontal1, vertical1), shift 8
+UPSAMPLING_FILTERS = [
+    ((0, 256), (-8, 64, 216, -16), (-16, 144, 144, -16), (-16, 216, 64, -8)),                                    # UF_F0
+    ((0, 256), (0, -16, 56, 240, -32, 8), (-16, 144, 144, -16), (8, -32, 240, 56, -16, 0)),                      # UF_FV
+    ((0, 256), (-6, 58, 222, -18), (-16, 144, 144, -16), (-18, 222, 58, -6)),                                    # UF_GS
+    ((0, 256), (2, -18, 70, 228, -34, 8), (6, -34, 156, 156, -34, 6), (8, -34, 228, 70, -18, 2)),                # UF_LS3
+    ((0, 256), (-1, 8, -23, 72, 229, -39, 14, -4), (-3, 15, -43, 159, 159, -43, 15, -3),
+     (-4, 14, -39, 229, 72, -23, 8, -1)),                                                                        # UF_LS4
+    ((0, 256), (3, -16, 67, 227, -32, 7), (21, -52, 159, 159, -52, 21), (7, -32, 227, 67, -16, 3)),              # UF_TM
+    ((0, 256), (1, -5, 12, -27, 74, 230, -41, 18, -8, 2), (2, -8, 21, -47, 160, 160, -47, 21, -8, 2),
+     (2, -8, 18, -41, 230, 74, -27, 12, -5, 1)),                                                                 # UF_LS5
+    ((0, 256), (0, 3, -7, 14, -29, 75, 230, -43, 20, -10, 5, -2), (-1, 5, -12, 24, -49, 161, 161, -49, 24, -12, 5, -1),
+     (-2, 5, -10, 20, -43, 230, 75, -29, 14, -7, 3, 0)),                                                         # UF_LS6
+]
+
+
+def _yuv_to_float(src, chroma, nbyte):  # YUVtoFloatYUV :596-611
+    offset = (128 if nbyte == 1 else 512) if chroma else 0
+    weight = 1.0 / (255.0 if nbyte == 1 else 1023.0)
+    f = (weight * (src.astype(np.int32) - offset).astype(np.float64)).astype(np.float32)
+    return np.clip(f, np.float32(-0.5 if chroma else 0.0), np.float32(0.5 if chroma else 1.0))
+
+
+def _float_to_yuv16(f, chroma):  # floatYUVToYUV :582-594 with nbyte = 2
+    x = (65535.0 * f.astype(np.float64) + (32768.0 if chroma else 0.0)).astype(np.float32)
+    t = np.trunc(x)  # std::round(float): half away from zero, without forming x + 0.5f
+    r = (t + np.where(np.abs(x - t) >= np.float32(0.5), np.sign(x), np.float32(0))).astype(np.float32)
+    return np.clip(r, np.float32(0), np.float32(65535)).astype(np.uint16)
+
+
+def _fir(im, taps, axis, shift_index):
+    """value = sum_t taps[t] * im[clamp(i0 + t - position)] accumulated in float32 in tap order, * 1/256;
+    i0 = index + shift_index (0 for the phase-0 filters, 1 for the phase-1 filters)"""
+    n = im.shape[axis]
+    position = (len(taps) + 1) >> 1
+    idx = np.arange(n)
+    value = np.zeros(im.shape, np.float32)
+    for t, c in enumerate(taps):
+        src = np.clip(idx + shift_index + t - position, 0, n - 1)
+        value = (value + np.float32(c) * np.take(im, src, axis=axis)).astype(np.float32)
+    return ((value + np.float32(0.0)) * np.float32(1.0 / 256.0)).astype(np.float32)
+
+
+def _upsample(ch, filt):  # upsampling :669-695
+    h0, v0, h1, v1 = UPSAMPLING_FILTERS[filt]
+    hh, ww = ch.shape
+    temp = np.empty((2 * hh, ww), np.float32)
+    temp[0::2] = _fir(ch, v0, 0, 0)
+    temp[1::2] = _fir(ch, v1, 0, 1)
+    out = np.empty((2 * hh, 2 * ww), np.float32)
+    out[:, 0::2] = _fir(temp, h0, 1, 0)
+    out[:, 1::2] = _fir(temp, h1, 1, 1)
+    return out
+
+
+def yuv420_to_yuv444(y, u, v, bitdepth, filt):
+    """y [H][W], u / v [H/2][W/2] decoded samples (8 or 10 bit) -> [3][H][W] uint16 (16-bit 4:4:4)"""
+    nbyte = 1 if bitdepth == 8 else 2
+    out = np.empty((3,) + y.shape, np.uint16)
+    out[0] = _float_to_yuv16(_yuv_to_float(y, False, nbyte), False)
+    out[1] = _float_to_yuv16(_upsample(_yuv_to_float(u, True, nbyte), filt), True)
+    out[2] = _float_to_yuv16(_upsample(_yuv_to_float(v, True, nbyte), filt), True)
+    return out

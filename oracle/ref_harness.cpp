@@ -58,6 +58,7 @@
 #include "PCCPatch.h"
 #include "PCCContext.h"
 #include "PCCFrameContext.h"
+#include "PCCInternalColorConverter.h"
 #include "PCCGroupOfFrames.h"
 #include "PCCCodec.h"
 #include "PCCKdTree.h"
@@ -603,6 +604,24 @@ int64_t ref_read_ply( const char* path, int16_t* outPos, uint8_t* outCol, int64_
   if ( outPos && n ) { std::memcpy( outPos, pc.positions_.data(), n * 6 ); }
   if ( outCol && n && pc.colors_.size() == (size_t)n ) { std::memcpy( outCol, pc.colors_.data(), n * 3 ); }
   return n;
+}
+
+// PCCVideoDecoder's inverse colour conversion (PccLibDecoder/source/PCCVideoDecoder.cpp:125-146, :365): the decoded
+// 4:2:0 frame through the reference's own PCCInternalColorConverter<uint16_t>::convert( "YUV420ToYUV444_<bits>_<filter>" ).
+// y [H][W], u / v [H/2][W/2] samples as uint16; out [3][H][W] uint16 (16-bit 4:4:4)
+int ref_yuv420_to_yuv444( const uint16_t* y, const uint16_t* u, const uint16_t* v, int W, int H, int bitdepth, int filter,
+                          uint16_t* out ) {
+  PCCVideo<uint16_t, 3> src, dst;
+  src.resize( 1 );
+  src[0].resize( W, H, PCCCOLORFORMAT::YUV420 );
+  std::copy( y, y + (size_t)W * H, src[0].getChannel( 0 ).begin() );
+  std::copy( u, u + (size_t)( W / 2 ) * ( H / 2 ), src[0].getChannel( 1 ).begin() );
+  std::copy( v, v + (size_t)( W / 2 ) * ( H / 2 ), src[0].getChannel( 2 ).begin() );
+  PCCInternalColorConverter<uint16_t> conv;
+  conv.convert( "YUV420ToYUV444_" + std::to_string( bitdepth ) + "_" + std::to_string( filter ), src, dst, "", "" );
+  if ( dst.getFrameCount() != 1 || (int)dst[0].getWidth() != W || (int)dst[0].getHeight() != H ) { return -1; }
+  for ( int c = 0; c < 3; c++ ) { std::copy( dst[0].getChannel( c ).begin(), dst[0].getChannel( c ).end(), out + (size_t)c * W * H ); }
+  return 0;
 }
 
 int ref_abi_version( void ) { return RB200_ABI_VERSION; }

@@ -73,6 +73,12 @@ class Frames(C.Structure):
     _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p)]
 
 
+class FramesYuv420(C.Structure):
+    _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p),
+                ("geometry_sample_bytes", i32), ("attribute_sample_bytes", i32), ("attribute_bitdepth", i32),
+                ("upsampling_filter", i32)]
+
+
 class Atlas(C.Structure):
     _fields_ = [("patches", C.c_void_p), ("patch_offset", C.c_void_p),
                 ("eom_patches", C.c_void_p), ("eom_offset", C.c_void_p), ("eom_members", C.c_void_p),
@@ -119,7 +125,7 @@ class LaunchStats(C.Structure):
 # every symbol include/rabbit_b200.h declares; tests check the .so exports all of them
 EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
-    "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_reconstruct", "rb200_smooth_geometry",
+    "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
@@ -154,6 +160,8 @@ def load_library(path=None):
     lib.rb200_synchronize.argtypes = [C.c_void_p]
     lib.rb200_gof_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int]
     lib.rb200_gof_upload.argtypes = [C.c_void_p, C.POINTER(Frames), C.POINTER(Atlas)]
+    lib.rb200_gof_upload_yuv420.argtypes = [C.c_void_p, C.POINTER(FramesYuv420), C.POINTER(Atlas)]
+    lib.rb200_download_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     for n in ("rb200_reconstruct", "rb200_smooth_geometry", "rb200_transfer_colors", "rb200_smooth_color",
               "rb200_convert_rgb8", "rb200_decode_gof"):
         getattr(lib, n).argtypes = [C.c_void_p]

@@ -83,6 +83,29 @@ class PCCCodecB200:
         self.beginGof(gof.params, gof.n_frames)
         self.uploadFrames(gof.frames_struct(), gof.atlas_struct(), keep=gof)
 
+    def uploadGofYuv420(self, gof, native):
+        """decoder-native planes (synthetic.to_decoder_planes): 4:2:0 attribute frames of 8/10-bit samples and geometry
+        luma; PCCVideoDecoder's inverse colour conversion (PCCVideoDecoder.cpp:125-146) runs on the device"""
+        self.beginGof(gof.params, gof.n_frames)
+        f = abi.FramesYuv420()
+        f.occupancy = abi.ptr(gof.occupancy)
+        f.geometry = abi.ptr(native["geometry"])
+        f.attribute = abi.ptr(native["attribute"]) if native.get("attribute") is not None else None
+        f.geometry_sample_bytes = native["geometry"].dtype.itemsize
+        f.attribute_sample_bytes = native["attribute"].dtype.itemsize if native.get("attribute") is not None else 1
+        f.attribute_bitdepth = native["bitdepth"]
+        f.upsampling_filter = native["filter"]
+        self._keep = (gof, native)
+        self._check(self._lib.rb200_gof_upload_yuv420(self._h, C.byref(f), C.byref(gof.atlas_struct())))
+
+    def getPlanes(self, frame, m):
+        """geometry [H][W] and attribute [3][H][W] uint16 as they sit in HBM after the upload"""
+        p = self.params
+        geo = np.zeros((p.height, p.width), np.uint16)
+        att = np.zeros((3, p.height, p.width), np.uint16) if p.attribute_count > 0 else None
+        self._check(self._lib.rb200_download_planes(self._h, frame, m, abi.ptr(geo), abi.ptr(att)))
+        return geo, att
+
     # ---- the reference's entry points ----
     def generatePointCloud(self):
         self._check(self._lib.rb200_reconstruct(self._h))

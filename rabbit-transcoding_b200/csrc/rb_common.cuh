@@ -79,6 +79,7 @@ struct rb200_ctx {
 
   // ---- device inputs ----
   RbBuf d_occ_video, d_geometry, d_attribute, d_patches;
+  RbBuf d_raw_geo, d_raw_attr;  // decoder-native planes of rb200_gof_upload_yuv420 before the conversion kernels
   RbBuf d_wi_patch, d_wi_local, d_wi_count, d_wi_base, d_wi_eom_count, d_wi_eom_base, d_eom_order, d_wi_eom_slot;
   RbBuf d_frame_wi_off;  // [F+1] first work item of each frame
   RbBuf d_bitmap;        // [F][H][bmWords] uint32 full-resolution occupancy bits
@@ -172,6 +173,7 @@ int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
+int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter );
 int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 );
 void rb_metrics_release( rb200_ctx* c );
 void rb_transfer_release( rb200_ctx* c );

@@ -143,7 +143,7 @@ void rb200_destroy( rb200_ctx* c ) {
   if ( !c ) { return; }
   cudaSetDevice( c->device );
   cudaStreamSynchronize( c->stream );
-  RbBuf* bufs[] = {&c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
+  RbBuf* bufs[] = {&c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_raw_geo, &c->d_raw_attr, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
                    &c->d_wi_count, &c->d_wi_base, &c->d_wi_eom_count, &c->d_wi_eom_base, &c->d_eom_order,
                    &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
@@ -252,13 +252,26 @@ static bool patch_inside( const rb200_patch& p, int Wb, int Hb ) {
   return p.u0 >= 0 && p.v0 >= 0 && p.size_u0 >= 0 && p.size_v0 >= 0 && p.u0 + cw <= Wb && p.v0 + ch <= Hb;
 }
 
-int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* at ) {
-  if ( !c || !fr || !at ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: null argument" ); }
+// planes either as the reconstruction reads them (fr) or decoder-native (fy): see rb200_gof_upload_yuv420
+static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_frames_yuv420* fy, const rb200_atlas* at ) {
+  if ( !c || ( !fr && !fy ) || !at ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: null argument" ); }
   if ( !c->have_gof ) { return rb_fail( c, RB200_ERR_STATE, "gof_upload before gof_begin" ); }
   cudaSetDevice( c->device );
   const size_t F = c->F;
-  if ( !fr->occupancy || !fr->geometry || ( c->P.attribute_count > 0 && !fr->attribute ) || !at->patch_offset ) {
+  if ( fr && ( !fr->occupancy || !fr->geometry || ( c->P.attribute_count > 0 && !fr->attribute ) || !at->patch_offset ) ) {
     return rb_fail( c, RB200_ERR_INVALID, "gof_upload: missing plane or patch table" );
+  }
+  if ( fy ) {
+    if ( !fy->occupancy || !fy->geometry || ( c->P.attribute_count > 0 && !fy->attribute ) || !at->patch_offset ) {
+      return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: missing plane or patch table" );
+    }
+    if ( ( fy->geometry_sample_bytes != 1 && fy->geometry_sample_bytes != 2 ) ||
+         ( fy->attribute_sample_bytes != 1 && fy->attribute_sample_bytes != 2 ) ||
+         ( fy->attribute_bitdepth != 8 && fy->attribute_bitdepth != 10 ) || fy->upsampling_filter < 0 || fy->upsampling_filter > 7 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: sample bytes must be 1 or 2, bit depth 8 or 10, filter 0..7" );
+    }
+    if ( c->P.attribute_rgb444 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: RGB444 attributes are not 4:2:0 video" ); }
+    if ( ( c->W & 15 ) || ( c->H & 1 ) ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: width must be a multiple of 16, height even" ); }
   }
   // ---- patch tables (host) ----
   const int nPatches = at->patch_offset[F];
@@ -359,10 +372,30 @@ int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* a
   const size_t occBytes = F * (size_t)c->oW * c->oH;
   const size_t geoBytes = F * c->M * (size_t)c->W * c->H * 2;
   const size_t attBytes = c->P.attribute_count > 0 ? F * c->M * 3 * (size_t)c->W * c->H * 2 : 0;
-  RB_CUDA( cudaMemcpyAsync( c->d_occ_video.p, fr->occupancy, occBytes, cudaMemcpyDefault, c->stream ) );
-  RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fr->geometry, geoBytes, cudaMemcpyDefault, c->stream ) );
-  if ( attBytes ) { RB_CUDA( cudaMemcpyAsync( c->d_attribute.p, fr->attribute, attBytes, cudaMemcpyDefault, c->stream ) ); }
-  c->stats.h2d_bytes += (int64_t)( occBytes + geoBytes + attBytes );
+  if ( fr ) {
+    RB_CUDA( cudaMemcpyAsync( c->d_occ_video.p, fr->occupancy, occBytes, cudaMemcpyDefault, c->stream ) );
+    RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fr->geometry, geoBytes, cudaMemcpyDefault, c->stream ) );
+    if ( attBytes ) { RB_CUDA( cudaMemcpyAsync( c->d_attribute.p, fr->attribute, attBytes, cudaMemcpyDefault, c->stream ) ); }
+    c->stats.h2d_bytes += (int64_t)( occBytes + geoBytes + attBytes );
+  } else {  // decoder-native planes: a quarter of the bytes cross PCIe, the conversion runs on the device
+    const size_t plane  = (size_t)c->W * c->H;
+    const size_t rawGeo = F * c->M * plane * fy->geometry_sample_bytes;
+    const size_t rawAtt = attBytes ? F * c->M * ( plane + plane / 2 ) * fy->attribute_sample_bytes : 0;
+    RB_CUDA( cudaMemcpyAsync( c->d_occ_video.p, fy->occupancy, occBytes, cudaMemcpyDefault, c->stream ) );
+    if ( fy->geometry_sample_bytes == 2 ) {
+      RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fy->geometry, rawGeo, cudaMemcpyDefault, c->stream ) );
+    } else {
+      RB_CUDA( c->d_raw_geo.ensure( rawGeo + 64 ) );
+      RB_CUDA( cudaMemcpyAsync( c->d_raw_geo.p, fy->geometry, rawGeo, cudaMemcpyDefault, c->stream ) );
+    }
+    if ( rawAtt ) {
+      RB_CUDA( c->d_raw_attr.ensure( rawAtt + 64 ) );
+      RB_CUDA( cudaMemcpyAsync( c->d_raw_attr.p, fy->attribute, rawAtt, cudaMemcpyDefault, c->stream ) );
+    }
+    c->stats.h2d_bytes += (int64_t)( occBytes + rawGeo + rawAtt );
+    int r = rb_ingest_yuv420_impl( c, fy->geometry_sample_bytes, fy->attribute_sample_bytes, fy->attribute_bitdepth, fy->upsampling_filter );
+    if ( r ) { return r; }
+  }
   RB_CUDA( c->d_patches.ensure( std::max<size_t>( 1, nPatches ) * sizeof( RbPatch ) ) );
   RB_CUDA( c->d_wi_patch.ensure( std::max<int64_t>( 1, c->nWI ) * 4 ) );
   RB_CUDA( c->d_wi_local.ensure( std::max<int64_t>( 1, c->nWI ) * 4 ) );
@@ -391,6 +424,27 @@ int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* a
   c->stats.h2d_bytes += (int64_t)tb;
   c->uploaded      = true;
   c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+  return RB200_OK;
+}
+
+int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* at ) {
+  if ( !fr ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: null argument" ); }
+  return gof_upload_common( c, fr, nullptr, at );
+}
+int rb200_gof_upload_yuv420( rb200_ctx* c, const rb200_frames_yuv420* fy, const rb200_atlas* at ) {
+  if ( !fy ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: null argument" ); }
+  return gof_upload_common( c, nullptr, fy, at );
+}
+// the planes the reconstruction reads, as they are in HBM after an upload (tests of the ingest conversion)
+int rb200_download_planes( rb200_ctx* c, int frame, int map, uint16_t* geometry, uint16_t* attribute ) {
+  if ( !c || !c->uploaded || frame < 0 || frame >= c->F || map < 0 || map >= c->M ) { return rb_fail( c, RB200_ERR_INVALID, "download_planes: bad frame / map or nothing uploaded" ); }
+  cudaSetDevice( c->device );
+  const size_t plane = (size_t)c->W * c->H, fm = (size_t)frame * c->M + map;
+  if ( geometry ) { RB_CUDA( cudaMemcpyAsync( geometry, c->d_geometry.as<uint16_t>() + fm * plane, plane * 2, cudaMemcpyDeviceToHost, c->stream ) ); }
+  if ( attribute && c->P.attribute_count > 0 ) {
+    RB_CUDA( cudaMemcpyAsync( attribute, c->d_attribute.as<uint16_t>() + fm * 3 * plane, plane * 6, cudaMemcpyDeviceToHost, c->stream ) );
+  }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
   return RB200_OK;
 }
 

@@ -1,0 +1,185 @@
+// rb_ingest.cu — decoder-native planes -> the planes the reconstruction reads (sm_100a).
+//
+// Restates what PCCVideoDecoder does to the attribute video after the codec returns:
+//   PCCInternalColorConverter<T>::convertYUV420ToYUV444   PccLibColorConverter/source/PCCInternalColorConverter.cpp:456-486
+//     YUVtoFloatYUV (:596-611), upsampling (:669-695) with upsamplingVertical0/1 + upsamplingHorizontal0/1
+//     (include/PCCInternalColorConverter.h:187-249), floatYUVToYUV (:582-594), filters g_filter420to444 (:297-337)
+//   as invoked by PccLibDecoder/source/PCCVideoDecoder.cpp:125-146, :365 ("YUV420ToYUV444_<bits>_<filter>").
+// so that the 8/10-bit 4:2:0 planes a video decoder leaves behind go straight to HBM (a quarter of the bytes of the
+// 16-bit 4:4:4 frames) and the conversion — a dense separable single-precision filter — runs on the GPU.
+//
+// Arithmetic: every sample goes through the reference's float / double steps (compiled with -fmad=false), the filter
+// sums are accumulated in single precision in tap order.  The per-sample scalings are pure functions of an 8/10-bit
+// value and are tabulated per CTA.  One CTA converts one 64x32 tile of one chroma plane: the chroma tile and its
+// 6-sample halo are staged as floats in shared memory, filtered vertically into shared memory, then horizontally
+// into 16-bit output rows (16-byte stores); there is no intermediate plane in HBM.
+#include "rb_common.cuh"
+
+namespace {
+
+constexpr int MAX_TAPS = 12;
+struct UpFilter {
+  float h0[MAX_TAPS], v0[MAX_TAPS], h1[MAX_TAPS], v1[MAX_TAPS];
+  int   nh0, nv0, nh1, nv1;
+};
+#define TAPS( ... ) { __VA_ARGS__ }
+// g_filter420to444 (PCCInternalColorConverter.cpp:297-337), field order horizontal0, vertical0, horizontal1, vertical1
+// (include/PCCInternalColorConverter.h:50-55); every filter has shift 8, the offsets are not used by upsampling
+__constant__ UpFilter c_up[8] = {
+    {TAPS( 0, 256 ), TAPS( -8, 64, 216, -16 ), TAPS( -16, 144, 144, -16 ), TAPS( -16, 216, 64, -8 ), 2, 4, 4, 4},
+    {TAPS( 0, 256 ), TAPS( 0, -16, 56, 240, -32, 8 ), TAPS( -16, 144, 144, -16 ), TAPS( 8, -32, 240, 56, -16, 0 ), 2, 6, 4, 6},
+    {TAPS( 0, 256 ), TAPS( -6, 58, 222, -18 ), TAPS( -16, 144, 144, -16 ), TAPS( -18, 222, 58, -6 ), 2, 4, 4, 4},
+    {TAPS( 0, 256 ), TAPS( 2, -18, 70, 228, -34, 8 ), TAPS( 6, -34, 156, 156, -34, 6 ), TAPS( 8, -34, 228, 70, -18, 2 ), 2, 6, 6, 6},
+    {TAPS( 0, 256 ), TAPS( -1, 8, -23, 72, 229, -39, 14, -4 ), TAPS( -3, 15, -43, 159, 159, -43, 15, -3 ),
+     TAPS( -4, 14, -39, 229, 72, -23, 8, -1 ), 2, 8, 8, 8},
+    {TAPS( 0, 256 ), TAPS( 3, -16, 67, 227, -32, 7 ), TAPS( 21, -52, 159, 159, -52, 21 ), TAPS( 7, -32, 227, 67, -16, 3 ), 2, 6, 6, 6},
+    {TAPS( 0, 256 ), TAPS( 1, -5, 12, -27, 74, 230, -41, 18, -8, 2 ), TAPS( 2, -8, 21, -47, 160, 160, -47, 21, -8, 2 ),
+     TAPS( 2, -8, 18, -41, 230, 74, -27, 12, -5, 1 ), 2, 10, 10, 10},
+    {TAPS( 0, 256 ), TAPS( 0, 3, -7, 14, -29, 75, 230, -43, 20, -10, 5, -2 ), TAPS( -1, 5, -12, 24, -49, 161, 161, -49, 24, -12, 5, -1 ),
+     TAPS( -2, 5, -10, 20, -43, 230, 75, -29, 14, -7, 3, 0 ), 2, 12, 12, 12},
+};
+
+// YUVtoFloatYUV (:596-611): clamp( (float)( weight * (double)( sample - offset ) ), min, max )
+__device__ __forceinline__ float sample_to_float( int s, bool chroma, int nbyte ) {
+  const int    offset = chroma ? ( nbyte == 1 ? 128 : 512 ) : 0;
+  const double weight = 1.0 / ( nbyte == 1 ? 255. : 1023. );
+  const float  f      = (float)__dmul_rn( weight, (double)( s - offset ) );
+  return fminf( fmaxf( f, chroma ? -0.5f : 0.f ), chroma ? 0.5f : 1.f );
+}
+// floatYUVToYUV (:582-594) with nbyte = 2: (T) fClip( round( (float)( 65535. * (double)f + offset ) ), 0, 65535 )
+__device__ __forceinline__ uint16_t float_to_u16( float f, bool chroma ) {
+  const float x = (float)__dadd_rn( __dmul_rn( 65535.0, (double)f ), chroma ? 32768.0 : 0.0 );
+  return (uint16_t)fminf( fmaxf( roundf( x ), 0.f ), 65535.f );
+}
+
+// ---- luma: a pure function of the sample, tabulated per CTA ----
+template <typename T>
+__global__ void __launch_bounds__( 256 ) k_luma_to_16( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
+                                                        int nbyte, size_t srcFrameStride, size_t dstFrameStride ) {
+  __shared__ uint16_t lut[1024];
+  const int           levels = nbyte == 1 ? 256 : 1024;
+  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = float_to_u16( sample_to_float( s, false, nbyte ), false ); }
+  __syncthreads();
+  const T*      in  = src + (size_t)blockIdx.y * srcFrameStride;
+  uint16_t*     out = dst + (size_t)blockIdx.y * dstFrameStride;
+  const int64_t n   = (int64_t)W * H;
+  for ( int64_t i = ( (int64_t)blockIdx.x * blockDim.x + threadIdx.x ) * 8; i < n; i += (int64_t)gridDim.x * blockDim.x * 8 ) {
+    if ( i + 8 <= n ) {  // W is a multiple of 16 and the planes are 16-byte aligned
+      uint16_t o[8];
+#pragma unroll
+      for ( int k = 0; k < 8; k++ ) {
+        const int s = (int)in[i + k];
+        o[k]        = s < levels ? lut[s] : float_to_u16( sample_to_float( s, false, nbyte ), false );
+      }
+      *reinterpret_cast<uint4*>( out + i ) = *reinterpret_cast<const uint4*>( o );
+    } else {
+      for ( int64_t j = i; j < n; j++ ) { out[j] = float_to_u16( sample_to_float( (int)in[j], false, nbyte ), false ); }
+    }
+  }
+}
+
+// ---- chroma: 64 x 32 output tile per CTA ----
+constexpr int TW = 64, TH = 32, HALO = 6;
+constexpr int IW = TW / 2 + 2 * HALO, IH = TH / 2 + 2 * HALO;  // 44 x 28 staged chroma samples
+
+template <typename T>
+__global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
+                                                               int nbyte, int filter, size_t srcFrameStride,
+                                                               size_t dstFrameStride ) {
+  __shared__ float lut[1024];
+  __shared__ float in[IH][IW];
+  __shared__ float tmp[TH][IW + 1];
+  const int        levels = nbyte == 1 ? 256 : 1024;
+  const int        cw = W / 2, ch = H / 2;
+  const int        frame = blockIdx.z >> 1, plane = 1 + ( blockIdx.z & 1 );
+  // frame layout of the source: Y [H][W], U [H/2][W/2], V [H/2][W/2]
+  const T*  cin  = src + (size_t)frame * srcFrameStride + (size_t)W * H + (size_t)( plane - 1 ) * cw * ch;
+  uint16_t* cout = dst + (size_t)frame * dstFrameStride + (size_t)plane * W * H;
+  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = sample_to_float( s, true, nbyte ); }
+  __syncthreads();
+  const UpFilter& F  = c_up[filter];
+  const int       ox = blockIdx.x * TW, oy = blockIdx.y * TH;  // output tile origin
+  const int       jx = ox / 2 - HALO, iy = oy / 2 - HALO;      // staged chroma origin
+  for ( int k = threadIdx.x; k < IW * IH; k += blockDim.x ) {
+    const int r = k / IW, c = k - r * IW;
+    const int gy = min( max( iy + r, 0 ), ch - 1 ), gx = min( max( jx + c, 0 ), cw - 1 );  // clamp( ., 0, size - 1 ) of every tap
+    const int s  = (int)cin[(size_t)gy * cw + gx];
+    in[r][c]     = s < levels ? lut[s] : sample_to_float( s, true, nbyte );
+  }
+  __syncthreads();
+  // vertical: row 2i from vertical0 at i0 = i, row 2i+1 from vertical1 at i0 = i + 1 (:678-686)
+  const float scale = 1.0f / 256.0f;
+  for ( int k = threadIdx.x; k < TH * IW; k += blockDim.x ) {
+    const int    y = k / IW, c = k - y * IW;
+    const int    odd = y & 1, li = ( y >> 1 ) + HALO + odd;
+    const float* taps = odd ? F.v1 : F.v0;
+    const int    n = odd ? F.nv1 : F.nv0, position = ( n + 1 ) >> 1;
+    float        value = 0.f;
+    for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], in[li + t - position][c] ) ); }
+    tmp[y][c] = __fmul_rn( __fadd_rn( value, 0.f ), scale );
+  }
+  __syncthreads();
+  // horizontal: column 2j from horizontal0 at j0 = j, column 2j+1 from horizontal1 at j0 = j + 1 (:687-694);
+  // every thread produces 8 consecutive outputs of one row
+  {
+    const int y = threadIdx.x >> 3, x0 = ( threadIdx.x & 7 ) * 8;
+    if ( oy + y < H && ox + x0 < W ) {
+      uint16_t o[8];
+#pragma unroll
+      for ( int k = 0; k < 8; k++ ) {
+        const int    x = x0 + k, odd = x & 1, lj = ( x >> 1 ) + HALO + odd;
+        const float* taps = odd ? F.h1 : F.h0;
+        const int    n = odd ? F.nh1 : F.nh0, position = ( n + 1 ) >> 1;
+        float        value = 0.f;
+        for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], tmp[y][lj + t - position] ) ); }
+        o[k] = float_to_u16( __fmul_rn( __fadd_rn( value, 0.f ), scale ), true );
+      }
+      *reinterpret_cast<uint4*>( cout + (size_t)( oy + y ) * W + ox + x0 ) = *reinterpret_cast<const uint4*>( o );
+    }
+  }
+}
+
+// geometry luma samples of one byte -> the uint16 plane the reprojection reads
+__global__ void __launch_bounds__( 256 ) k_widen_u8( const uint8_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t n ) {
+  const int64_t i = ( (int64_t)blockIdx.x * blockDim.x + threadIdx.x ) * 16;
+  if ( i + 16 <= n ) {
+    const uint4 v = *reinterpret_cast<const uint4*>( src + i );
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t       o[8];
+#pragma unroll
+    for ( int k = 0; k < 4; k++ ) {
+      o[2 * k]     = ( w[k] & 0xFFu ) | ( ( w[k] & 0xFF00u ) << 8 );
+      o[2 * k + 1] = ( ( w[k] >> 16 ) & 0xFFu ) | ( ( w[k] >> 8 ) & 0xFF0000u );
+    }
+    uint4* d = reinterpret_cast<uint4*>( dst + i );
+    d[0]     = make_uint4( o[0], o[1], o[2], o[3] );
+    d[1]     = make_uint4( o[4], o[5], o[6], o[7] );
+  } else {
+    for ( int64_t j = i; j < n; j++ ) { dst[j] = src[j]; }
+  }
+}
+
+}  // namespace
+
+// raw decoder planes (already in c->d_raw_geo / c->d_raw_attr) -> c->d_geometry / c->d_attribute
+int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter ) {
+  const size_t  plane = (size_t)c->W * c->H;
+  const int64_t nGeo  = (int64_t)c->F * c->M * plane;
+  if ( geo_bytes == 1 ) {
+    RB_LAUNCH( "geometry_widen", k_widen_u8, rb_div_up( nGeo, 256 * 16 ), 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo );
+  }
+  if ( c->P.attribute_count > 0 ) {
+    const int    nbyte  = attr_bitdepth == 8 ? 1 : 2;
+    const int    frames = c->F * c->M;
+    const size_t sfs = plane + plane / 2, dfs = 3 * plane;
+    const dim3   gl( 64, frames ), gc( rb_div_up( c->W, TW ), rb_div_up( c->H, TH ), frames * 2 );
+    if ( attr_bytes == 1 ) {
+      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint8_t>, gl, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, sfs, dfs );
+      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint8_t>, gc, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, filter, sfs, dfs );
+    } else {
+      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint16_t>, gl, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, sfs, dfs );
+      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint16_t>, gc, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, filter, sfs, dfs );
+    }
+  }
+  return RB200_OK;
+}

@@ -608,3 +608,26 @@ def generate_gof_parallel(n_frames, workers=None, **kw):
         with mp.get_context("fork").Pool(workers) as pool:
             parts = pool.map(_gen_one, jobs)
     return concat_gofs(parts)
+
+
+def to_decoder_planes(gof, bitdepth=8, filt=0, sample_dtype=np.uint8):
+    """The GOF as a video decoder would hand it over (before PCCVideoDecoder's inverse colour conversion): geometry luma
+    and 4:2:0 attribute frames { Y [H][W], U [H/2][W/2], V [H/2][W/2] } of `bitdepth`-bit samples, made from the GOF's
+    16-bit 4:4:4 attribute frames by dropping the low bits and every second chroma row / column.  Returns the native
+    planes for PCCCodecB200.uploadGofYuv420; the GOF's own 4:4:4 frames must then be REPLACED by the conversion of these
+    planes (oracle / reference) before it is used as the expected input."""
+    F, M = gof.n_frames, gof.params.map_count_minus1 + 1
+    H, W = gof.params.height, gof.params.width
+    out = {"bitdepth": bitdepth, "filter": filt, "geometry": None, "attribute": None}
+    g = gof.geometry.reshape(F, M, H, W)
+    out["geometry"] = np.ascontiguousarray(g.astype(sample_dtype)) if g.max() < (1 << (8 * np.dtype(sample_dtype).itemsize)) else np.ascontiguousarray(g)
+    if gof.attribute is not None:
+        a = gof.attribute.reshape(F, M, 3, H, W)
+        sh = 16 - bitdepth
+        frames = np.empty((F, M, H * W + 2 * (H // 2) * (W // 2)), sample_dtype)
+        frames[:, :, :H * W] = (a[:, :, 0] >> sh).reshape(F, M, -1)
+        q = (H // 2) * (W // 2)
+        frames[:, :, H * W:H * W + q] = (a[:, :, 1, ::2, ::2] >> sh).reshape(F, M, -1)
+        frames[:, :, H * W + q:] = (a[:, :, 2, ::2, ::2] >> sh).reshape(F, M, -1)
+        out["attribute"] = np.ascontiguousarray(frames)
+    return out

@@ -1,0 +1,107 @@
+"""GPU parity of the decoder-native ingest (rb200_gof_upload_yuv420): the inverse colour conversion of PCCVideoDecoder
+(PccLibDecoder/source/PCCVideoDecoder.cpp:125-146 -> PCCInternalColorConverter::convertYUV420ToYUV444) on the device,
+bit-exact against the committed golden digests of the reference converter, against the numpy restatement, and — through
+the whole decoder sequence — against the reference run on the converted frames."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from util import assert_cloud_equal
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden_yuv420 as mg  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "yuv420.json")))
+
+
+def _params(rb, W, H):
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=1)
+    p = g.params
+    p.width, p.height, p.map_count_minus1 = W, H, 0
+    return g, p
+
+
+def _convert_on_gpu(rb, codec, y, u, v, bd, f, dtype):
+    """one 4:2:0 frame through rb200_gof_upload_yuv420, planes read back from HBM"""
+    H, W = y.shape
+    g, p = _params(rb, W, H)
+    g.occupancy = np.zeros((1, H // p.occupancy_precision, W // p.occupancy_precision), np.uint8)
+    g.patches = g.patches[:0]
+    g.patch_offset = np.zeros(2, np.int32)
+    native = {"bitdepth": bd, "filter": f,
+              "geometry": np.ascontiguousarray(y.astype(dtype) if dtype == np.uint16 else (y & 0xFF).astype(np.uint8)).reshape(1, 1, H, W),
+              "attribute": np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)]).astype(dtype).reshape(1, 1, -1)}
+    codec.uploadGofYuv420(g, native)
+    geo, att = codec.getPlanes(0, 0)
+    assert np.array_equal(geo, native["geometry"].reshape(H, W)), "geometry samples changed by the ingest"
+    return att
+
+
+@pytest.mark.parametrize("case", mg.CASES, ids=lambda c: f"{c[1]}x{c[2]}_{c[3]}bit_f{c[4]}")
+def test_conversion_matches_reference_golden(rb, codec, case):
+    seed, W, H, bd, f = case
+    y, u, v = mg.frame(seed, W, H, bd)
+    dtypes = (np.uint8, np.uint16) if bd == 8 else (np.uint16,)
+    for dt in dtypes:
+        att = _convert_on_gpu(rb, codec, y, u, v, bd, f, dt)
+        assert mg.digest(att) == GOLD[f"{seed}_{W}x{H}_{bd}bit_filter{f}"], f"4:2:0 -> 4:4:4 differs from the reference ({dt.__name__} samples)"
+
+
+def test_conversion_full_size_frame_matches_restatement(rb, codec):
+    """a vox10-sized frame (tiles, halos and image borders of the CUDA tiling) against the numpy restatement"""
+    from oracle import oracle_np
+    rng = np.random.default_rng(9)
+    W, H = 1280, 1296
+    yy, xx = np.mgrid[0:H, 0:W]
+    y = ((np.sin(xx * 0.02) * np.cos(yy * 0.015) * 100 + 128) + rng.normal(0, 6, (H, W))).clip(0, 255).astype(np.uint16)
+    u = rng.integers(0, 256, (H // 2, W // 2)).astype(np.uint16)
+    v = ((np.sin(xx[::2, ::2] * 0.05) * 120 + 128)).clip(0, 255).astype(np.uint16)
+    for f in (0, 4, 7):
+        att = _convert_on_gpu(rb, codec, y, u, v, 8, f, np.uint8)
+        assert np.array_equal(att, oracle_np.yuv420_to_yuv444(y, u, v, 8, f)), f"filter {f}"
+
+
+@pytest.mark.parametrize("bd,filt,dt", [(8, 0, np.uint8), (8, 4, np.uint8), (10, 2, np.uint16)])
+def test_decode_gof_from_decoder_planes(rb, codec, checker_backend, bd, filt, dt):
+    """the whole decoder sequence fed with decoder-native planes == the reference fed with the frames its own converter
+    (restated in numpy, pinned above) makes of those planes"""
+    from oracle import oracle_np
+    kw = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=21, transfer_filter=0)
+    gof = rb.synthetic.generate_gof(**kw)
+    native = rb.synthetic.to_decoder_planes(gof, bitdepth=bd, filt=filt, sample_dtype=dt)
+    p = gof.params
+    F, M, H, W = gof.n_frames, p.map_count_minus1 + 1, p.height, p.width
+    conv = np.empty((F, M, 3, H, W), np.uint16)
+    fr = native["attribute"].reshape(F, M, -1).astype(np.uint16)
+    q = (H // 2) * (W // 2)
+    for f in range(F):
+        for m in range(M):
+            conv[f, m] = oracle_np.yuv420_to_yuv444(fr[f, m, :H * W].reshape(H, W), fr[f, m, H * W:H * W + q].reshape(H // 2, W // 2),
+                                                    fr[f, m, H * W + q:].reshape(H // 2, W // 2), bd, filt)
+    gof.attribute = np.ascontiguousarray(conv.reshape(gof.attribute.shape))
+    ref = checker_backend.run_gof(gof, keep=("rgb8",))
+    codec.uploadGofYuv420(gof, native)
+    codec.decodeGof()
+    counts = codec.frameCounts()
+    for f in range(F):
+        assert_cloud_equal(codec.getPointCloud(f, counts), ref.cloud(f, "rgb8"), f"frame {f}")
+    _, att = codec.getPlanes(1, M - 1)
+    assert np.array_equal(att, conv[1, M - 1])
+
+
+def test_upload_yuv420_error_paths(rb, codec):
+    g, p = _params(rb, 64, 32)
+    g.occupancy = np.zeros((1, 32 // p.occupancy_precision, 64 // p.occupancy_precision), np.uint8)
+    g.patches = g.patches[:0]
+    g.patch_offset = np.zeros(2, np.int32)
+    nat = {"bitdepth": 9, "filter": 0, "geometry": np.zeros((1, 1, 32, 64), np.uint8), "attribute": np.zeros((1, 1, 64 * 32 * 3 // 2), np.uint8)}
+    with pytest.raises(rb.codec.RabbitError):
+        codec.uploadGofYuv420(g, nat)
+    nat["bitdepth"], nat["filter"] = 8, 8
+    with pytest.raises(rb.codec.RabbitError):
+        codec.uploadGofYuv420(g, nat)

@@ -1,0 +1,49 @@
+"""CPU suite for the decoder-native ingest: the numpy restatement of PCCVideoDecoder's inverse colour
+conversion (oracle/oracle_np.yuv420_to_yuv444) against the unmodified reference converter and against the committed
+golden digests, for every upsampling filter and both bit depths."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden_yuv420 as mg  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "yuv420.json")))
+
+
+@pytest.mark.parametrize("case", mg.CASES, ids=lambda c: f"{c[1]}x{c[2]}_{c[3]}bit_f{c[4]}")
+def test_restatement_matches_golden(case):
+    from oracle import oracle_np
+    seed, W, H, bd, f = case
+    y, u, v = mg.frame(seed, W, H, bd)
+    assert mg.digest(oracle_np.yuv420_to_yuv444(y, u, v, bd, f)) == GOLD[f"{seed}_{W}x{H}_{bd}bit_filter{f}"]
+
+
+def test_reference_matches_golden_and_restatement():
+    from oracle import checker, oracle_np
+    if not checker.have_reference():
+        pytest.skip("oracle/_ref not built")
+    ref = checker.Reference()
+    for seed, W, H, bd, f in mg.CASES[::3]:
+        y, u, v = mg.frame(seed, W, H, bd)
+        want = ref.yuv420_to_yuv444(y, u, v, bd, f)
+        assert mg.digest(want) == GOLD[f"{seed}_{W}x{H}_{bd}bit_filter{f}"]
+        assert np.array_equal(oracle_np.yuv420_to_yuv444(y, u, v, bd, f), want)
+
+
+def test_decoder_planes_round_trip(rb):
+    """synthetic.to_decoder_planes keeps the top bits of the 4:4:4 frames and the layout { Y, U, V } per frame"""
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=3)
+    nat = rb.synthetic.to_decoder_planes(g, bitdepth=8, filt=0)
+    p = g.params
+    H, W, M = p.height, p.width, p.map_count_minus1 + 1
+    a = g.attribute.reshape(1, M, 3, H, W)
+    fr = nat["attribute"].reshape(1, M, -1)
+    assert fr.dtype == np.uint8 and fr.shape[2] == H * W * 3 // 2
+    assert np.array_equal(fr[0, 0, :H * W].reshape(H, W), a[0, 0, 0] >> 8)
+    assert np.array_equal(fr[0, 1, H * W:H * W + (H // 2) * (W // 2)].reshape(H // 2, W // 2), a[0, 1, 1, ::2, ::2] >> 8)
+    assert nat["geometry"].dtype == np.uint8 and np.array_equal(nat["geometry"].reshape(-1), g.geometry.reshape(-1))
