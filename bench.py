@@ -167,8 +167,11 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; the driver wants one JSON line there
+    # the driver wants ONE JSON line on stdout: NCCL's version banner (and anything else a library prints there) is sent
+    # to stderr by pointing fd 1 at fd 2 for the whole run; the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -474,7 +477,9 @@ def run_b200(args):
             "cpu_baseline": cpu, "metrics": metrics_leg, "full_decoder": full, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
             "generate_s": round(t_gen, 1),
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     codec.close()
     if world > 1:
         dist.destroy_process_group()
