@@ -95,7 +95,8 @@ typedef struct rb200_params {
   int32_t single_map_pixel_interleaving; /* UNSUPPORTED (status 2) when non-zero                        */
   int32_t point_local_reconstruction;    /* UNSUPPORTED when non-zero                                   */
   int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
-  int32_t multiple_streams;         /* layout only: caller still hands geometry as [F][M][H][W]         */
+  int32_t multiple_streams;         /* sps.getMultipleMapStreamsPresentFlag: the caller still hands planes
+                                     * as [F][M][..][H][W] (map m of frame f = frame f of stream m)       */
   int32_t attribute_count;          /* 0: colours become 127 (PCCCodec.cpp:1327-1330)                   */
   int32_t attribute_rgb444;         /* 1: copyRGB16ToRGB8 instead of convertYUV16ToRGB8                 */
   int32_t geometry_bitdepth_3d;     /* geometryBitDepth3D_ (10 / 11)                                    */
@@ -108,7 +109,8 @@ typedef struct rb200_params {
   /* attribute smoothing SEI (PCCDecoder.cpp:754-775) + decoder switch applyAttrSmoothingType           */
   int32_t flag_color_smoothing;
   int32_t apply_attr_smoothing;
-  int32_t reserved0;
+  int32_t relative_t1;              /* multiple_streams only: map 1 of the attribute is a delta on map 0
+                                     * (!absoluteT1List[1], PCCCodec.cpp:1387-1416; CTC condition T1-from-rec-T0) */
   double  threshold_smoothing;
   double  threshold_color_smoothing;
   double  threshold_color_difference;

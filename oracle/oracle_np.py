@@ -148,7 +148,15 @@ def reconstruct_frame(params, occ_video, geometry, attribute, patches):
         part.append(np.full(len(idx), i, np.uint32))
         p2p.append(np.stack([x[pix], y[pix], lay], axis=1).astype(np.uint32))
         if P.attribute_count > 0:
-            col.append(np.stack([attribute[lay, c, y[pix], x[pix]] for c in range(3)], axis=1).astype(np.uint16))
+            c16 = np.stack([attribute[lay, c, y[pix], x[pix]] for c in range(3)], axis=1).astype(np.uint16)
+            if P.multiple_streams and P.relative_t1 and M > 1:
+                # colorPointCloud, multiple streams with !absoluteT1List[1] (:1387-1416): T1 = T0 + clamped delta
+                bits = 8 if P.attribute_rgb444 else 16
+                offset, maxv = 1 << (bits - 1), (1 << bits) - 1
+                v0 = np.stack([attribute[0, c, y[pix], x[pix]] for c in range(3)], axis=1).astype(np.int64)
+                nv = np.clip(c16.astype(np.int64) - offset, -offset, offset - 1) + v0
+                c16 = np.where((lay == 1)[:, None], np.clip(nv, 0, maxv), c16).astype(np.uint16)
+            col.append(c16)
 
     def cat(parts, shape, dt):
         return np.concatenate(parts) if parts else np.zeros(shape, dt)

@@ -139,7 +139,7 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
   g.thresholdSmoothing_            = p.threshold_smoothing;
   g.rawPointColorFormat_           = 0;
   g.nbThread_                      = 1;
-  g.multipleStreams_               = false;  // the harness always lays geometry out as one stream f*M+m
+  g.multipleStreams_               = p.multiple_streams != 0;  // streams: video m holds map m of every frame
   g.absoluteD1_                    = p.absolute_d1 != 0;
   g.surfaceThickness_              = 4;
   g.thresholdColorSmoothing_       = p.threshold_color_smoothing;
@@ -218,25 +218,28 @@ ref_gof* ref_gof_run( const rb200_params* pp,
   auto& occVideo = context.getVideoOccupancyMap();
   occVideo.resize( nFrames );
   auto& geoVideos = context.getVideoGeometryMultiple();
-  geoVideos.resize( 1 );
-  geoVideos[0].resize( nFrames * M );
+  const bool streams = p.multiple_streams != 0;  // PCCCodec.cpp:609-618: video m, frame f instead of video 0, frame f*M+m
+  geoVideos.resize( streams ? M : 1 );
+  for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { geoVideos[m].resize( streams ? nFrames : nFrames * M ); }
   for ( int f = 0; f < nFrames; f++ ) {
     auto& o = occVideo.getFrame( f );
     o.resize( oW, oH, PCCCOLORFORMAT::YUV444 );
     std::memcpy( o.getChannel( 0 ).data(), fr->occupancy + (size_t)f * oW * oH, oW * oH );
     for ( size_t m = 0; m < M; m++ ) {
-      auto& g = geoVideos[0].getFrame( f * M + m );
+      auto& g = streams ? geoVideos[m].getFrame( f ) : geoVideos[0].getFrame( f * M + m );
       g.resize( W, H, PCCCOLORFORMAT::YUV444 );
       std::memcpy( g.getChannel( 0 ).data(), fr->geometry + ( (size_t)f * M + m ) * W * H, W * H * 2 );
     }
   }
   if ( p.attribute_count > 0 ) {
     auto& attrVideos = context.getVideoAttributesMultiple();
-    attrVideos[0].resize( nFrames * M );
+    if ( streams && attrVideos.size() < M ) { attrVideos.resize( M ); }
+    for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { attrVideos[m].resize( streams ? nFrames : nFrames * M ); }
     for ( int f = 0; f < nFrames; f++ ) {
       for ( size_t m = 0; m < M; m++ ) {
-        auto& a = attrVideos[0].getFrame( f * M + m );
+        auto& a = streams ? attrVideos[m].getFrame( f ) : attrVideos[0].getFrame( f * M + m );
         a.resize( W, H, p.attribute_rgb444 ? PCCCOLORFORMAT::RGB444 : PCCCOLORFORMAT::YUV444 );
+        a.setDeprecatedColorFormat( p.attribute_rgb444 ? 0 : 1 );  // PCCVideoDecoder.cpp:130-136
         for ( int c = 0; c < 3; c++ ) {
           std::memcpy( a.getChannel( c ).data(), fr->attribute + ( ( (size_t)f * M + m ) * 3 + c ) * W * H, W * H * 2 );
         }
@@ -353,7 +356,8 @@ ref_gof* ref_gof_run( const rb200_params* pp,
         reconstruct.addColors();
         reconstruct.addColors16bit();
         std::vector<bool> absoluteT1List( M, true );
-        codec.colorPointCloud( reconstruct, context, tile, absoluteT1List, 0, 1, 0, gpc );
+        if ( M > 1 && p.relative_t1 ) { absoluteT1List[1] = false; }  // sps.getMapAbsoluteCodingEnableFlag, PCCDecoder.cpp:321
+        codec.colorPointCloud( reconstruct, context, tile, absoluteT1List, p.multiple_streams != 0 ? 1 : 0, 1, 0, gpc );
       }
       auto t1          = std::chrono::steady_clock::now();
       fo.msReconstruct = std::chrono::duration<double, std::milli>( t1 - t0 ).count();

@@ -209,6 +209,12 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   if ( p->map_count_minus1 < 0 || p->map_count_minus1 > 1 ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "map_count_minus1 must be 0 or 1" );
   }
+  if ( p->relative_t1 && ( !p->multiple_streams || p->map_count_minus1 != 1 ) ) {
+    return rb_fail( c, RB200_ERR_INVALID, "relative_t1 needs multiple_streams and two maps (PCCCodec.cpp:1387-1416)" );
+  }
+  if ( p->relative_t1 && ( p->enhanced_occupancy_map_code || p->use_additional_points_patch ) ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "relative_t1 together with EOM or raw patches is not implemented" );
+  }
   if ( p->flag_geometry_smoothing && p->apply_geo_smoothing && !p->grid_smoothing ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothPointCloud (PCCCodec.cpp:1106-1157) is not implemented" );
   }

@@ -36,6 +36,7 @@ struct ReprojArgs {
   const uint32_t* b2p;
   int             W, H, oW, oH, Wb, Hb, M, prec, bmWords;
   int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
+  int             t1_bits;  // multi-stream attribute: 0 = map 1 is absolute, 8 / 16 = map 1 is a delta on map 0
   int32_t*        wi_count;
   int32_t*        wi_eom_count;
   const int64_t*  wi_base;
@@ -274,6 +275,22 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     }
   }
   __syncwarp();
+  if ( EMIT && a.t1_bits && a.attr_count > 0 && a.M > 1 ) {
+    // multiple streams with a delta-coded second map (colorPointCloud, PCCCodec.cpp:1387-1416): the tile of map 1
+    // is reconstructed in shared memory once, T1 = clip( T0 + clamp( T1 - offset, -offset, offset - 1 ), 0, max )
+    const int offset = 1 << ( a.t1_bits - 1 ), maxv = ( 1 << a.t1_bits ) - 1;
+#pragma unroll
+    for ( int ch = 0; ch < 3; ch++ ) {
+#pragma unroll
+      for ( int j = 0; j < 8; j++ ) {
+        const int i  = lane * 8 + j;
+        int       nv = (int)S.a[1][ch][i] - offset;
+        nv           = min( max( nv, -offset ), offset - 1 ) + (int)S.a[0][ch][i];
+        S.a[1][ch][i] = (uint16_t)min( max( nv, 0 ), maxv );
+      }
+    }
+    __syncwarp();
+  }
 
   const int v1 = lane >> 1, ubase = 8 * ( lane & 1 );
   // ---- pass A: per-pixel point counts (4 bits per pixel: regular; EOM extras separately) ----
@@ -885,6 +902,8 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.eom_fix_bits = P.eom_fix_bit_count;
   a.classify     = ( classify && !eom ) ? 1 : 0;  // with EOM the marks (:880) come first, classification after
   a.attr_count   = P.attribute_count;
+  // image0.getDeprecatedColorFormat() == 0 ? 8 : 16 (:1388): format 0 is the 4:4:4 (RGB) video, PCCVideoDecoder.cpp:132
+  a.t1_bits      = ( P.multiple_streams && P.relative_t1 ) ? ( P.attribute_rgb444 ? 8 : 16 ) : 0;
   a.bitdepth3d   = P.geometry_bitdepth_3d;
   a.wi_count     = c->d_wi_count.as<int32_t>();
   a.frame_wi_off = c->d_frame_wi_off.as<int32_t>();

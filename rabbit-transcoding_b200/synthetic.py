@@ -631,3 +631,23 @@ def to_decoder_planes(gof, bitdepth=8, filt=0, sample_dtype=np.uint8):
         frames[:, :, H * W + q:] = (a[:, :, 2, ::2, ::2] >> sh).reshape(F, M, -1)
         out["attribute"] = np.ascontiguousarray(frames)
     return out
+
+
+def make_relative_t1(gof, seed=0):
+    """Turns the GOF into the multiple-streams layout with a delta-coded second attribute map (CTC condition
+    T1-from-rec-T0; colorPointCloud, PCCCodec.cpp:1387-1416): map 1 becomes clip(T1 - T0 + 32768), with a sprinkling of
+    extreme codes so that both clamps of the reconstruction are exercised."""
+    p = gof.params
+    F, M, H, W = gof.n_frames, p.map_count_minus1 + 1, p.height, p.width
+    assert M == 2 and gof.attribute is not None
+    a = gof.attribute.reshape(F, M, 3, H, W)
+    rng = np.random.default_rng([seed, 991])
+    delta = a[:, 1].astype(np.int64) - a[:, 0].astype(np.int64) + 32768
+    code = np.clip(delta, 0, 65535)
+    r = rng.random(code.shape)
+    code = np.where(r < 0.003, 0, np.where(r > 0.997, 65535, code))
+    a[:, 1] = code.astype(np.uint16)
+    gof.attribute = np.ascontiguousarray(a.reshape(gof.attribute.shape))
+    p.multiple_streams = 1
+    p.relative_t1 = 1
+    return gof

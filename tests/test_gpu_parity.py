@@ -37,6 +37,15 @@ def test_relative_d1_keep_duplicates(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, what="reld1")
 
 
+def test_multiple_streams_relative_t1(rb, codec, checker_backend):
+    """CTC condition T1-from-rec-T0: the second attribute map is a delta on the first (PCCCodec.cpp:1387-1416)"""
+    g = rb.synthetic.make_relative_t1(small(rb, seed=18), seed=2)
+    run_stages(codec, g, checker_backend, what="relt1")
+    g = rb.synthetic.make_relative_t1(small(rb, seed=19, orientations=tuple(range(9)), occupancy_precision=2), seed=4)
+    g.params.relative_t1 = 0  # multiple streams with an absolute second map: the planes are used as they are
+    run_stages(codec, g, checker_backend, what="streams_abs_t1")
+
+
 def _lossy(rb, precision):
     g = small(rb, seed=16, occupancy_precision=precision)
     rng = np.random.default_rng(5)

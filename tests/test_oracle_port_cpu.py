@@ -26,6 +26,7 @@ CASES = {
     "single_map_p1": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=203, transfer_filter=0, map_count=1,
                           occupancy_precision=1),
     "relative_d1": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=204, transfer_filter=0, absolute_d1=False),
+    "relative_t1": dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=205, transfer_filter=0),
 }
 
 
@@ -36,9 +37,13 @@ def test_port_equals_reference_every_stage(rb, name):
     g = rb.synthetic.generate_gof(**CASES[name])
     if name == "relative_d1":
         g.params.remove_duplicate_points = 0
+    if name == "relative_t1":
+        rb.synthetic.make_relative_t1(g, seed=3)
     stages = ("reconstruct", "smooth_geometry", "smooth_color", "rgb8")
     want = ref_b.run_gof(g, keep=stages)
     g2 = rb.synthetic.generate_gof(**CASES[name])  # fresh planes: the reference binarises the occupancy video in place
+    if name == "relative_t1":
+        rb.synthetic.make_relative_t1(g2, seed=3)
     g2.params = g.params
     got = oracle_np.Port().run_gof(g2, stages)
     for f in range(g.n_frames):
