@@ -249,10 +249,9 @@ constexpr int ACC_RUN = 8;  // consecutive points per thread
 // of one table probe and three or four atomics per lane, instead of a flush at every point where some lane's cell
 // changes.  (Combining equal cells across lanes with per-group __reduce_*_sync masks was measured 4x slower: partial
 // masks are executed group by group.)
-template <bool COLOUR>
-__global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int64_t n ) {
-  const int     lane = threadIdx.x & 31;
-  const int64_t i0   = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
+// ONEFRAME: all 256 points of the warp lie in frame `fw` (all but a handful of warps): no per-point frame bookkeeping
+template <bool COLOUR, bool ONEFRAME>
+__device__ __forceinline__ void accumulate_warp( const GridArgs& a, int64_t n, int64_t i0, int lane, int fw ) {
   short4        p[ACC_RUN];
   ushort4       cv[ACC_RUN];
   uint32_t      pp[ACC_RUN];
@@ -293,8 +292,8 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
   int      fr[ACC_RUN];
   uint32_t rem = 0;
   if ( i0 < n ) {
-    int       f     = frame_of( a.frame_off, a.F, i0 );
-    int64_t   fend  = a.frame_off[f + 1];
+    int       f     = ONEFRAME ? fw : frame_of( a.frame_off, a.F, i0 );
+    int64_t   fend  = ONEFRAME ? 0 : a.frame_off[f + 1];
     const int disth = max( a.g / 2, 1 );
     int       th    = COLOUR ? 0 : grid_th( a, f );
 #pragma unroll
@@ -303,12 +302,14 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
       ck[k]           = 0;
       fr[k]           = f;
       if ( i >= n ) { continue; }
-      while ( i >= fend ) {  // the run crosses into the next frame (empty frames are skipped)
-        f++;
-        fend = a.frame_off[f + 1];
-        if ( !COLOUR ) { th = grid_th( a, f ); }
+      if ( !ONEFRAME ) {
+        while ( i >= fend ) {  // the run crosses into the next frame (empty frames are skipped)
+          f++;
+          fend = a.frame_off[f + 1];
+          if ( !COLOUR ) { th = grid_th( a, f ); }
+        }
+        fr[k] = f;
       }
-      fr[k]          = f;
       const short4 q = p[k];
       bool         in;
       if ( COLOUR ) {  // no margin test, :208-224 with the :212 guard
@@ -331,16 +332,19 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
     bool           act   = rem != 0;
     const int      first = __ffs( rem ) - 1;
     uint32_t       key = 0;
-    int            f   = 0;
+    int            f   = fw;
 #pragma unroll
     for ( int k = 0; k < ACC_RUN; k++ ) {
-      if ( k == first ) { key = ck[k], f = fr[k]; }
+      if ( k == first ) {
+        key = ck[k];
+        if ( !ONEFRAME ) { f = fr[k]; }
+      }
     }
     uint32_t           mem = 0, cnt = 0, t0 = 0, t1 = 0, t2 = 0, mx = 0, mn = 0xFFFFFFFFu;
     unsigned long long q2 = 0;
 #pragma unroll
     for ( int k = 0; k < ACC_RUN; k++ ) {
-      if ( ( rem >> k & 1u ) && ck[k] == key && fr[k] == f ) {
+      if ( ( rem >> k & 1u ) && ck[k] == key && ( ONEFRAME || fr[k] == f ) ) {
         mem |= 1u << k;
         cnt++;
         if ( COLOUR ) {
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
     // one lane per distinct block looks it up (or creates it): no lane ever waits for another lane of its own warp.
     // (all warp primitives here use the same mask in every lane: per-group masks are executed group by group)
     const uint32_t bk = block_key( cx, cy, cz );
-    const uint32_t bpeers  = __match_any_sync( mask, ( (unsigned long long)(uint32_t)f << 32 ) | bk );
+    const uint32_t bpeers  = ONEFRAME ? __match_any_sync( mask, bk ) : __match_any_sync( mask, ( (unsigned long long)(uint32_t)f << 32 ) | bk );
     const int      bleader = __ffs( bpeers ) - 1;
     uint32_t       bl      = NO_BLOCK;
     if ( lane == bleader ) { bl = block_claim( a, f, bk ); }
@@ -391,6 +395,21 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
         }
       }  // else: the gate kernel sees count > lum_cap and asks for a retry with longer lists
     }
+  }
+}
+
+template <bool COLOUR>
+__global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int64_t n ) {
+  const int     lane = threadIdx.x & 31;
+  const int64_t i0   = ( (int64_t)blockIdx.x * 256 + threadIdx.x ) * ACC_RUN;
+  const int64_t w0   = i0 - (int64_t)lane * ACC_RUN;  // first point of the warp
+  if ( w0 >= n ) { return; }
+  const int  fw  = frame_of( a.frame_off, a.F, w0 );
+  const bool one = min( w0 + 32 * ACC_RUN, n ) <= a.frame_off[fw + 1];
+  if ( one ) {
+    accumulate_warp<COLOUR, true>( a, n, i0, lane, fw );
+  } else {
+    accumulate_warp<COLOUR, false>( a, n, i0, lane, fw );
   }
 }
 
