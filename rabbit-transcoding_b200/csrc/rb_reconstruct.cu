@@ -69,6 +69,30 @@ __device__ __forceinline__ void tile_coord( int orient, int u1, int v1, int& tx,
   }
 }
 
+// the same map as two affine forms, set up once per patch block: tx = au u1 + av v1 + a0, ty = bu u1 + bv v1 + b0
+struct TileMap {
+  int au, av, a0, bu, bv, b0;
+};
+__device__ __forceinline__ TileMap tile_map( int orient ) {
+  switch ( orient ) {
+    default:
+    case 0: return {1, 0, 0, 0, 1, 0};
+    case 1: return {0, 1, 0, 1, 0, 0};
+    case 2: return {0, -1, 15, 1, 0, 0};
+    case 3: return {-1, 0, 15, 0, -1, 15};
+    case 4: return {0, 1, 0, -1, 0, 15};
+    case 5: return {-1, 0, 15, 0, 1, 0};
+    case 6: return {0, -1, 15, -1, 0, 15};
+    case 7: return {1, 0, 0, 0, -1, 15};
+    case 8: return {0, 1, 0, 1, 0, 0};
+  }
+}
+#define TILE_XY( tm, u1, v1, tx, ty )                        \
+  do {                                                        \
+    tx = ( tm ).au * ( u1 ) + ( tm ).av * ( v1 ) + ( tm ).a0; \
+    ty = ( tm ).bu * ( u1 ) + ( tm ).bv * ( v1 ) + ( tm ).b0; \
+  } while ( 0 )
+
 // PCCPatch::patchBlock2CanvasBlock (PCCPatch.cpp:253-308); patches are validated inside the canvas at upload
 __device__ __forceinline__ void canvas_block( const RbPatch& p, int ub, int vb, int& bx, int& by ) {
   switch ( p.orient ) {
@@ -208,7 +232,7 @@ struct TileSmem {
   uint16_t g[2][256];     // geometry D0 / D1 tile
   uint16_t a[2][3][256];  // attribute tiles
   uint32_t rows[20];      // occupancy bits of canvas rows Y0-2..Y0+17, bit k <-> x = X0-2+k
-  uint32_t pad[4];
+  uint16_t bnd[16];       // per tile row: bit tx = the pixel is a boundary pixel (identifyBoundaryPoints)
   uint16_t desc[512];     // emission-ordered point descriptors: u1 | v1 << 4 | layer << 8 | boundary << 15
 };
 
@@ -233,7 +257,8 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     }
     return;
   }
-  const int X0 = bx * 16, Y0 = by * 16;
+  const int     X0 = bx * 16, Y0 = by * 16;
+  const TileMap tm = tile_map( p.orient );
   // ---- stage occupancy row masks ----
   if ( lane < 20 ) {
     const int y    = Y0 - 2 + lane;
@@ -292,13 +317,29 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     __syncwarp();
   }
 
+  if ( EMIT && a.classify ) {
+    // identifyBoundaryPoints (:266-325) for the whole tile at once, 16 rows in 16 lanes: a pixel is type 1 when it is
+    // on / next to the image border or any pixel of its 5x5 neighbourhood is unoccupied (the 3x3 test of :274-305 is
+    // implied: a full 5x5 contains a full 3x3).  Pixels outside the image read as occupied (staging above).
+    if ( lane < 16 ) {
+      const int      r  = lane + 2, y = Y0 + lane;
+      const uint32_t v5 = S.rows[r - 2] & S.rows[r - 1] & S.rows[r] & S.rows[r + 1] & S.rows[r + 2];
+      const uint32_t h5 = v5 & ( v5 >> 1 ) & ( v5 << 1 ) & ( v5 >> 2 ) & ( v5 << 2 );  // bit kx: columns kx-2..kx+2 full
+      uint32_t       b  = ( ~h5 >> 2 ) & 0xFFFFu;                                        // bit tx <-> kx = tx + 2
+      if ( y <= 1 || y >= a.H - 2 ) { b = 0xFFFFu; }
+      if ( X0 == 0 ) { b |= 0x3u; }
+      if ( X0 + 16 >= a.W ) { b |= ( X0 + 16 == a.W ) ? 0xC000u : 0xFFFFu; }
+      S.bnd[lane] = (uint16_t)b;
+    }
+    __syncwarp();
+  }
   const int v1 = lane >> 1, ubase = 8 * ( lane & 1 );
   // ---- pass A: per-pixel point counts (4 bits per pixel: regular; EOM extras separately) ----
   uint32_t cnt4 = 0, eom4 = 0;
 #pragma unroll
   for ( int j = 0; j < 8; j++ ) {
     int tx, ty;
-    tile_coord( p.orient, ubase + j, v1, tx, ty );
+    TILE_XY( tm, ubase + j, v1, tx, ty );
     const uint32_t occ = ( S.rows[ty + 2] >> ( tx + 2 ) ) & 1u;
     if ( !occ ) { continue; }
     const int d0 = S.g[0][ty * 16 + tx];
@@ -397,7 +438,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
         const int d  = S.desc[k];
         const int u1 = d & 15, vv1 = ( d >> 4 ) & 15, layer = ( d >> 8 ) & 1;
         int       tx, ty;
-        tile_coord( p.orient, u1, vv1, tx, ty );
+        TILE_XY( tm, u1, vv1, tx, ty );
         const int x = X0 + tx, y = Y0 + ty;
         const int u = ub * 16 + u1, v = vb * 16 + vv1;
         const int d0 = S.g[0][ty * 16 + tx];
@@ -417,21 +458,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
           }
         }
         if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
-        // boundary classification (identifyBoundaryPoints, :266-325) on the staged row masks
-        if ( a.classify ) {
-          const int      r  = ty + 2, kx = tx + 2;
-          const uint32_t m3 = 7u << ( kx - 1 ), m5 = 31u << ( kx - 2 );
-          if ( x == 0 || y == 0 || x == a.W - 1 || y == a.H - 1 ) {
-            btype = 1;
-          } else if ( ( S.rows[r - 1] & m3 ) != m3 || ( S.rows[r] & m3 ) != m3 || ( S.rows[r + 1] & m3 ) != m3 ) {
-            btype = 1;
-          } else if ( ( S.rows[r - 2] & m5 ) != m5 || ( S.rows[r - 1] & m5 ) != m5 || ( S.rows[r] & m5 ) != m5 ||
-                      ( S.rows[r + 1] & m5 ) != m5 || ( S.rows[r + 2] & m5 ) != m5 ) {
-            btype = 1;
-          } else if ( x == 1 || y == 1 || x == a.W - 2 || y == a.H - 2 ) {
-            btype = 1;
-          }
-        }
+        if ( a.classify ) { btype = ( S.bnd[ty] >> tx ) & 1; }  // identifyBoundaryPoints, per-tile masks above
         const int64_t o = wbase + k;
         a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
         ushort4 cv      = make_ushort4( 0, 0, 0, (unsigned short)layer );
@@ -469,7 +496,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     if ( c == 0 ) { continue; }
     int       tx, ty;
     const int u1 = ubase + j;
-    tile_coord( p.orient, u1, v1, tx, ty );
+    TILE_XY( tm, u1, v1, tx, ty );
     const int x = X0 + tx, y = Y0 + ty;
     const int u = ub * 16 + u1, v = vb * 16 + v1;
     const int d0 = S.g[0][ty * 16 + tx];
