@@ -733,26 +733,38 @@ __global__ void k_frame_layout( int F, const int32_t* __restrict__ frame_wi_off,
                                 const EomSeg* __restrict__ segs, const int32_t* __restrict__ seg_size, int nSeg,
                                 const int32_t* __restrict__ raw_per_frame, FrameLayout* __restrict__ out,
                                 int64_t* __restrict__ frame_off, RbFrameInfo* __restrict__ finfo ) {
-  if ( blockIdx.x != 0 || threadIdx.x != 0 ) { return; }
-  int64_t run = 0;
-  int     s   = 0;
-  for ( int f = 0; f < F; f++ ) {
-    FrameLayout L;
-    L.off     = run;
-    L.regular = wi_base[frame_wi_off[f + 1]] - wi_base[frame_wi_off[f]];
-    L.eom     = 0;
-    while ( s < nSeg && segs[s].frame == f ) {
-      L.eom += seg_size[s];
-      s++;
+  // every frame's counts are fetched by its own thread (the loads are dependent chains), then one thread forms the
+  // running offsets from shared memory
+  __shared__ int64_t tot[256];
+  if ( blockIdx.x != 0 ) { return; }
+  for ( int f0 = 0; f0 < F; f0 += 256 ) {  // 256 frames per pass (blockDim.x), the offset is carried
+    const int f = f0 + threadIdx.x;
+    if ( f < F ) {
+      FrameLayout L;
+      L.off     = 0;
+      L.regular = wi_base[frame_wi_off[f + 1]] - wi_base[frame_wi_off[f]];
+      L.eom     = 0;
+      for ( int s = 0; s < nSeg; s++ ) {
+        if ( segs[s].frame == f ) { L.eom += seg_size[s]; }
+      }
+      L.raw  = raw_per_frame ? raw_per_frame[f] : 0;
+      out[f] = L;
+      tot[threadIdx.x] = L.regular + L.eom + L.raw;
+      RbFrameInfo z{};
+      finfo[f] = z;
     }
-    L.raw        = raw_per_frame ? raw_per_frame[f] : 0;
-    out[f]       = L;
-    frame_off[f] = run;
-    run += L.regular + L.eom + L.raw;
-    RbFrameInfo z{};
-    finfo[f] = z;
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+      int64_t run = f0 == 0 ? 0 : frame_off[f0];
+      for ( int k = 0; k < min( 256, F - f0 ); k++ ) {
+        frame_off[f0 + k] = run;
+        out[f0 + k].off   = run;
+        run += tot[k];
+      }
+      frame_off[min( F, f0 + 256 )] = run;
+    }
+    __syncthreads();
   }
-  frame_off[F] = run;
 }
 
 // EOM append (:846-891): one CTA per segment; synthetic pixel addresses, occupancy marks, colours from
@@ -1057,7 +1069,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
                (const int32_t*)( dS + oPfw ), (const int32_t*)( dS + oPnb ), c->d_wi_eom_base.as<int64_t>(),
                (int32_t*)( dS + oSegSize ) );
   }
-  RB_LAUNCH( "frame_layout", k_frame_layout, 1, 32, 0, F, c->d_frame_wi_off.as<int32_t>(), c->d_wi_base.as<int64_t>(),
+  RB_LAUNCH( "frame_layout", k_frame_layout, 1, 256, 0, F, c->d_frame_wi_off.as<int32_t>(), c->d_wi_base.as<int64_t>(),
              (const EomSeg*)( dS + oSegs ), (const int32_t*)( dS + oSegSize ), nSeg, (const int32_t*)( dS + oRpf ),
              (FrameLayout*)( dS + oLayout ), c->d_frame_off.as<int64_t>(), c->d_frame_info.as<RbFrameInfo>() );
 
