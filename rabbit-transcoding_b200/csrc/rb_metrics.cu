@@ -685,6 +685,10 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
       nrm_raw, partial, far_list;
+  // the normals of the sources are uploaded on their own stream, underneath the column build of the same call
+  cudaStream_t         copy_stream = nullptr;
+  cudaEvent_t          ev_ready = nullptr, ev_copied = nullptr;
+  std::vector<int64_t> raw_off;  // per cloud: offset of its raw positions inside `raw` (-1: resident frame)
 };
 std::map<rb200_ctx*, MetricsScratch*> g_scratch;
 
@@ -696,6 +700,9 @@ void rb_metrics_release( rb200_ctx* c ) {
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
   for ( auto* b : bufs ) { b->release(); }
+  if ( s->copy_stream ) { cudaStreamDestroy( s->copy_stream ); }
+  if ( s->ev_ready ) { cudaEventDestroy( s->ev_ready ); }
+  if ( s->ev_copied ) { cudaEventDestroy( s->ev_copied ); }
   delete s;
   g_scratch.erase( it );
 }
@@ -803,10 +810,12 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   uchar4* inCol = S->in_col.as<uchar4>();
   if ( maxRaw > 0 ) { RB_CUDA( S->raw.ensure( (size_t)N * 9 + (size_t)nC * 32 + 64 ) ); }
   int64_t rawOff = 0;
+  S->raw_off.assign( nC, -1 );
   for ( int i = 0; i < nC; i++ ) {
     const CloudIn& cl = clouds[i];
     if ( cl.n == 0 ) { continue; }
     if ( cl.view ) {
+      S->raw_off[i] = rawOff;
       char*   rp = S->raw.as<char>() + rawOff;
       char*   rc = rp + ( ( cl.n * 6 + 15 ) & ~15ll );
       RB_CUDA( cudaMemcpyAsync( rp, cl.view->positions, cl.n * 6, cudaMemcpyDefault, c->stream ) );
@@ -941,6 +950,30 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
     if ( clouds[2 * i + 1].n <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty reconstruction %d", i ); }
     if ( sources[i].normals ) { anyNormals = true; }
   }
+  // ---- normals of the sources: their upload starts now, on its own stream, and overlaps the column build ----
+  std::vector<int64_t> nrmOff( nPairs, -1 );
+  if ( mp->compute_c2p != 0 && anyNormals ) {
+    int64_t tot = 0;
+    for ( int i = 0; i < nPairs; i++ ) {
+      if ( !sources[i].normals ) { continue; }
+      nrmOff[i] = tot;
+      tot += ( sources[i].count * 12 + 255 ) & ~255ll;
+    }
+    RB_CUDA( S->nrm_raw.ensure( (size_t)tot + 64 ) );
+    if ( !S->copy_stream ) {
+      RB_CUDA( cudaStreamCreateWithFlags( &S->copy_stream, cudaStreamNonBlocking ) );
+      RB_CUDA( cudaEventCreateWithFlags( &S->ev_ready, cudaEventDisableTiming ) );
+      RB_CUDA( cudaEventCreateWithFlags( &S->ev_copied, cudaEventDisableTiming ) );
+    }
+    RB_CUDA( cudaEventRecord( S->ev_ready, c->stream ) );  // earlier work on the compute stream may still read nrm_raw
+    RB_CUDA( cudaStreamWaitEvent( S->copy_stream, S->ev_ready, 0 ) );
+    for ( int i = 0; i < nPairs; i++ ) {
+      if ( nrmOff[i] < 0 ) { continue; }
+      RB_CUDA( cudaMemcpyAsync( S->nrm_raw.as<char>() + nrmOff[i], sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
+      c->stats.h2d_bytes += sources[i].count * 12;
+    }
+    RB_CUDA( cudaEventRecord( S->ev_copied, S->copy_stream ) );
+  }
   Batch                B{};
   std::vector<int64_t> hOff;
   int                  r = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff );
@@ -1039,18 +1072,14 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
     RB_CUDA( cudaMemsetAsync( S->last_idx.p, 0, (size_t)N * 4, c->stream ) );
     a.nrm     = S->nrm.as<double>();
     a.nrm_cnt = S->nrm_cnt.as<uint32_t>();
-    int64_t maxN = 0;
-    for ( int i = 0; i < nPairs; i++ ) { maxN = std::max<int64_t>( maxN, sources[i].normals ? sources[i].count : 0 ); }
-    RB_CUDA( S->nrm_raw.ensure( (size_t)maxN * 18 + 64 ) );
+    RB_CUDA( cudaStreamWaitEvent( c->stream, S->ev_copied, 0 ) );
     for ( int i = 0; i < nPairs; i++ ) {
       if ( !sources[i].normals ) { continue; }
-      // the normal cloud of pair i is the source view itself (positions + normals in file order)
-      const int64_t n  = sources[i].count;
-      int16_t*      rp = S->nrm_raw.as<int16_t>();
-      float*        rn = (float*)( S->nrm_raw.as<char>() + ( ( n * 6 + 15 ) & ~15ll ) );
-      RB_CUDA( cudaMemcpyAsync( rp, sources[i].positions, n * 6, cudaMemcpyDefault, c->stream ) );
-      RB_CUDA( cudaMemcpyAsync( rn, sources[i].normals, n * 12, cudaMemcpyDefault, c->stream ) );
-      c->stats.h2d_bytes += n * 18;
+      // the normal cloud of pair i is the source view itself (positions + normals in file order): its positions are
+      // still in the import buffer of build_batch, its normals came in on the copy stream
+      const int64_t  n  = sources[i].count;
+      const int16_t* rp = (const int16_t*)( S->raw.as<char>() + S->raw_off[2 * i] );
+      const float*   rn = (const float*)( S->nrm_raw.as<char>() + nrmOff[i] );
       RB_LAUNCH( "met_normal_lookup", k_normal_lookup, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rp, n, S->last_idx.as<uint32_t>(), dErr );
       RB_LAUNCH( "met_normal_gather", k_normal_gather, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rn, n,
                  S->last_idx.as<uint32_t>(), a.nrm, dErr );

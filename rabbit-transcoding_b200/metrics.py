@@ -83,7 +83,9 @@ class PCCMetricsB200:
                 # the normal cloud carries the same points as the source (PCCPointSet3::copyNormals looks them up
                 # by position); the ABI takes positions + normals of that cloud through the source view
                 nc = normals[i]
-                if nc["positions"].shape[0] != src["positions"].shape[0] or not np.array_equal(nc["positions"], src["positions"]):
+                same = nc["positions"] is src["positions"] or (
+                    nc["positions"].shape[0] == src["positions"].shape[0] and np.array_equal(nc["positions"], src["positions"]))
+                if not same:
                     src = self._attach_normals(src, nc)
                 else:
                     src["normals"] = nc["normals"]
