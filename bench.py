@@ -264,13 +264,17 @@ def run_b200(args):
 
         # the same call sequence with two GOFs in flight: a second context on its own stream, driven by a second host
         # thread, so the upload of one GOF overlaps the kernels and the download of the other (PCIe is full duplex)
-        codec2 = rb.codec.PCCCodecB200(device=local)
-        stream2 = torch.cuda.Stream()
-        codec2.setStream(stream2.cuda_stream)
-        out2 = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
-                    colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
-        lanes = [(codec, out), (codec2, out2)]
-        got = [0, 0]
+        NL = int(os.environ.get("RB200_BENCH_LANES", "2"))
+        lanes = [(codec, out)]
+        extra_streams = []
+        for _ in range(NL - 1):
+            cx = rb.codec.PCCCodecB200(device=local)
+            sx = torch.cuda.Stream()
+            extra_streams.append(sx)
+            cx.setStream(sx.cuda_stream)
+            lanes.append((cx, dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
+                                   colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())))
+        got = [0] * NL
         errs = []
         h2d_turn = threading.Lock()  # one upload at a time: the other GOF is then in its kernels / its download
 
@@ -288,7 +292,7 @@ def run_b200(args):
                 errs.append(ex)
 
         def run_pipelined(nsteps, upload):
-            ts = [threading.Thread(target=worker, args=(k, (nsteps + 1 - k) // 2, upload)) for k in range(2)]
+            ts = [threading.Thread(target=worker, args=(k, (nsteps + NL - 1 - k) // NL, upload)) for k in range(NL)]
             for t in ts:
                 t.start()
             for t in ts:
@@ -297,10 +301,10 @@ def run_b200(args):
                 raise errs[0]
 
         def time_pipelined(upload):
-            run_pipelined(2, upload)
-            psteps = max(2, args.steps)
-            codec.stats(reset=True)
-            codec2.stats(reset=True)
+            run_pipelined(NL, upload)
+            psteps = max(int(os.environ.get("RB200_BENCH_E2E_STEPS", "0")), args.steps, NL)
+            for c_, _ in lanes:
+                c_.stats(reset=True)
             barrier()
             torch.cuda.synchronize()
             clocks.on()
@@ -312,12 +316,12 @@ def run_b200(args):
             clocks.off()
             barrier()
             ms_pipe = max_over_ranks(e0.elapsed_time(e1))
-            st1, st2 = codec.stats(reset=True), codec2.stats(reset=True)
-            assert got[0] == n_points and got[1] == n_points
-            assert np.array_equal(out["positions"][:n_points], out2["positions"][:n_points])
+            sts = [c_.stats(reset=True) for c_, _ in lanes]
+            assert all(g_ == n_points for g_ in got)
+            assert all(np.array_equal(out["positions"][:n_points], o_["positions"][:n_points]) for _, o_ in lanes[1:])
             return {"value": round(all_points * psteps / (ms_pipe * 1e-3) / 1e6, 2), "unit": UNIT,
-                    "h2d_bytes_per_step": (st1.h2d_bytes + st2.h2d_bytes) // psteps,
-                    "d2h_bytes_per_step": (st1.d2h_bytes + st2.d2h_bytes) // psteps,
+                    "h2d_bytes_per_step": sum(s_.h2d_bytes for s_ in sts) // psteps,
+                    "d2h_bytes_per_step": sum(s_.d2h_bytes for s_ in sts) // psteps,
                     "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps}
 
         from_444 = time_pipelined(lambda c_: c_.uploadGof(gof))
@@ -334,7 +338,8 @@ def run_b200(args):
                        "-> getGof (positions + RGB8 to pinned host memory); two GOFs in flight (two contexts, two streams, two "
                        "host threads)")
         e2e["from_444_16bit_frames"] = from_444
-        codec2.close()
+        for c_, _ in lanes[1:]:
+            c_.close()
 
     # ---------------- leg 2a: the decoder's full Rec-1 sequence (adds transferColors16bitBP after geometry smoothing) ----
     full = None
