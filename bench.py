@@ -229,7 +229,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     clocks.off()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_local)
+    print(f"[bench rank {rank}] resident leg {ms_local / args.steps:.4f} ms per step, {n_points} points", file=sys.stderr, flush=True)
     launches = codec.stats(reset=True).kernel_launches
     all_points = sum_over_ranks(n_points)
     value = all_points * args.steps / (ms_total * 1e-3) / 1e6
