@@ -431,6 +431,14 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     const int64_t wbase = a.frame_off[f] + ( a.wi_base[wi] - a.wi_base[a.frame_wi_off[f]] );
     __syncwarp();
     int nb = 0;
+    // generateNormalCoordinate (PCCPatch.h:177-186) as max( d1 + nsgn * depth, nlo )
+    const int nsgn = p.mode == 0 ? 1 : -1, nlo = p.mode == 0 ? -( 1 << 30 ) : 0;
+    // bit c of each nibble: output coordinate c takes the tangent (bits 0-2) / bitangent (4-6) / normal (8-10) value
+    uint32_t axw = 0;
+    {
+      const uint32_t wn = 1u << p.normal_axis, wb = ( 1u << p.bitangent_axis ) & ~wn, wt = ( 1u << p.tangent_axis ) & ~wn & ~wb;
+      axw               = wt | ( wb << 4 ) | ( wn << 8 );
+    }
     for ( int k0 = 0; k0 < total; k0 += 32 ) {
       const int k     = k0 + lane;
       int       btype = 0;
@@ -442,20 +450,19 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
         const int x = X0 + tx, y = Y0 + ty;
         const int u = ub * 16 + u1, v = vb * 16 + vv1;
         const int d0 = S.g[0][ty * 16 + tx];
-        // PCCPatch::generatePoint (PCCPatch.h:201-207)
-        int16_t Q[3] = {0, 0, 0};
-        set_axis( Q, p.tangent_axis, u * p.lodx + p.u1 );
-        set_axis( Q, p.bitangent_axis, v * p.lody + p.v1 );
-        if ( layer == 0 ) {
-          set_axis( Q, p.normal_axis, normal_coord( p, d0 ) );
-        } else {
-          const int g1 = S.g[1][ty * 16 + tx];
-          if ( a.absolute_d1 ) {
-            set_axis( Q, p.normal_axis, normal_coord( p, g1 ) );  // generatePoint( u, v, frame1 ), :503
-          } else {
-            const int n0 = (int16_t)normal_coord( p, d0 );
-            set_axis( Q, p.normal_axis, p.mode == 0 ? n0 + g1 : n0 - g1 );  // :505-509
-          }
+        // PCCPatch::generatePoint (PCCPatch.h:201-207), branch-free: the axis permutation is three 0/1 weights per
+        // output coordinate set up once per block (later writes win: tangent, bitangent, normal); the normal
+        // coordinate of both layers is formed and selected
+        const int g1 = a.M > 1 ? (int)S.g[1][ty * 16 + tx] : 0;
+        const int n0 = (int16_t)max( p.d1 + nsgn * d0, nlo );   // generateNormalCoordinate( D0 )
+        int       n1 = max( p.d1 + nsgn * g1, nlo );            // generatePoint( u, v, frame1 ), :503
+        if ( !a.absolute_d1 ) { n1 = n0 + nsgn * g1; }          // :505-509
+        const int nn = layer ? n1 : n0;
+        const int tt = u * p.lodx + p.u1, bb = v * p.lody + p.v1;
+        int16_t   Q[3];
+#pragma unroll
+        for ( int cdx = 0; cdx < 3; cdx++ ) {
+          Q[cdx] = (int16_t)( ( ( axw >> cdx ) & 1 ) * tt + ( ( axw >> ( 4 + cdx ) ) & 1 ) * bb + ( ( axw >> ( 8 + cdx ) ) & 1 ) * nn );
         }
         if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
         if ( a.classify ) { btype = ( S.bnd[ty] >> tx ) & 1; }  // identifyBoundaryPoints, per-tile masks above
