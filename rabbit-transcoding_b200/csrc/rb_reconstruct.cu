@@ -335,7 +335,8 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
   }
   const int v1 = lane >> 1, ubase = 8 * ( lane & 1 );
   // ---- pass A: per-pixel point counts (4 bits per pixel: regular; EOM extras separately) ----
-  uint32_t cnt4 = 0, eom4 = 0;
+  const int nsgnA = p.mode == 0 ? 1 : -1, nloA = p.mode == 0 ? -( 1 << 30 ) : 0;  // generateNormalCoordinate, see pass B
+  uint32_t  cnt4 = 0, eom4 = 0;
 #pragma unroll
   for ( int j = 0; j < 8; j++ ) {
     int tx, ty;
@@ -375,14 +376,9 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
       }
     } else if ( a.M > 1 ) {
       // :497-512 far layer; :794-795 duplicate removal compares the int16 points
-      const int16_t n0 = (int16_t)normal_coord( p, d0 );
-      int16_t       n1;
-      if ( a.absolute_d1 ) {
-        n1 = (int16_t)normal_coord( p, g1 );
-      } else {
-        n1 = (int16_t)( p.mode == 0 ? (int)n0 + g1 : (int)n0 - g1 );
-      }
-      c = ( a.remove_dup && n1 == n0 ) ? 1 : 2;
+      const int16_t n0 = (int16_t)max( p.d1 + nsgnA * d0, nloA );
+      const int16_t n1 = (int16_t)( a.absolute_d1 ? max( p.d1 + nsgnA * g1, nloA ) : (int)n0 + nsgnA * g1 );
+      c                = ( a.remove_dup && n1 == n0 ) ? 1 : 2;
     }
     cnt4 |= (uint32_t)c << ( 4 * j );
     eom4 |= (uint32_t)e << ( 4 * j );
