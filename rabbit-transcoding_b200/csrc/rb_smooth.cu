@@ -327,6 +327,23 @@ __device__ __forceinline__ void accumulate_warp( const GridArgs& a, int64_t n, i
 #pragma unroll
     for ( int k = 0; k < ACC_RUN; k++ ) { ck[k] = 0, fr[k] = 0; }
   }
+  if ( COLOUR && a.marks ) {
+    // cells no boundary point blends are never read: the mark words of the thread's 8 points are fetched together
+    // and unmarked points leave before the flush rounds (half of the rounds disappear)
+    uint32_t w[ACC_RUN];
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      w[k] = 0;
+      if ( rem >> k & 1u ) {
+        const int cx = ck[k] & 1023, cy = ( ck[k] >> 10 ) & 1023, cz = ck[k] >> 20;
+        w[k]         = a.marks[( ( (size_t)( ONEFRAME ? fw : fr[k] ) * a.wmax + cz ) * a.wmax + cy ) * a.mwords + ( cx >> 5 )];
+      }
+    }
+#pragma unroll
+    for ( int k = 0; k < ACC_RUN; k++ ) {
+      if ( !( ( w[k] >> ( ck[k] & 31 ) ) & 1u ) ) { rem &= ~( 1u << k ); }
+    }
+  }
   // ---- one cell per lane and iteration, lanes with the same cell combined ----
   while ( __any_sync( 0xFFFFFFFFu, rem != 0 ) ) {
     bool           act   = rem != 0;
@@ -359,9 +376,6 @@ __device__ __forceinline__ void accumulate_warp( const GridArgs& a, int64_t n, i
     }
     rem &= ~mem;
     const int cx = key & 1023, cy = ( key >> 10 ) & 1023, cz = key >> 20;
-    if ( act && a.marks ) {  // cells no boundary point blends are never read
-      act = ( a.marks[( ( (size_t)f * a.wmax + cz ) * a.wmax + cy ) * a.mwords + ( cx >> 5 )] >> ( cx & 31 ) ) & 1u;
-    }
     const uint32_t mask = __ballot_sync( 0xFFFFFFFFu, act );
     if ( !act ) { continue; }
     // one lane per distinct block looks it up (or creates it): no lane ever waits for another lane of its own warp.
