@@ -812,8 +812,16 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
   const int64_t perBlock = std::max<int64_t>( 1, 6ll * g * g >> ( 2 * grow ) );
   int64_t       cap      = std::min<int64_t>( n, n / perBlock + 1024ll * c->F ) + 64;
   int64_t       wantT    = 4 * std::min<int64_t>( maxFrame, maxFrame / perBlock + 1024 );
-  uint32_t      tslots = 1024;
-  int           tlog   = 10;
+  // test hook: RB200_TEST_GRID_SHRINK=k starts with 2^k times smaller tables and 4-entry luma lists, so that the
+  // overflow -> regrow -> repeat path runs on small inputs (tests/test_gpu_parity.py)
+  const char* shrinkEnv = getenv( "RB200_TEST_GRID_SHRINK" );
+  const int   shrink    = shrinkEnv ? std::max( 0, std::min( 16, atoi( shrinkEnv ) ) ) : 0;
+  if ( shrink ) {
+    cap   = std::max<int64_t>( 8, ( cap >> shrink ) << ( 2 * grow ) );
+    wantT = std::max<int64_t>( 16, ( wantT >> shrink ) << ( 2 * grow ) );
+  }
+  uint32_t tslots = shrink ? 16 : 1024;
+  int      tlog   = shrink ? 4 : 10;
   while ( (int64_t)tslots < wantT ) { tslots <<= 1, tlog++; }
   const size_t tBytes = (size_t)c->F * tslots * 8, cBytes = (size_t)cap * 64 * sizeof( Cell );
   if ( cap >= ( 1ll << 25 ) ) { return rb_fail( c, RB200_ERR_NOMEM, "smoothing cell pool too large" ); }
@@ -827,7 +835,7 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
   }
   a.lum_cap = 0;
   if ( colour ) {  // a cell of g^3 voxels seen by two layers (+ duplicates across patches)
-    const int64_t base = std::min<int64_t>( 64, std::max<int64_t>( 8, (int64_t)g * g * g ) );
+    const int64_t base = shrink ? 4 : std::min<int64_t>( 64, std::max<int64_t>( 8, (int64_t)g * g * g ) );
     a.lum_cap          = (uint32_t)std::max<int64_t>( base, c->col_lum_want );
     RB_CUDA( b.lum.ensure( (size_t)cap * 64 * a.lum_cap * 2 + 64 ) );
   }
