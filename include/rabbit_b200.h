@@ -137,6 +137,11 @@ typedef struct rb200_frames_yuv420 {
   int32_t attribute_sample_bytes; /* 1 or 2                                                                            */
   int32_t attribute_bitdepth;     /* 8 or 10: the "<bits>" of "YUV420ToYUV444_<bits>_<filter>" (nbyte = 1 for 8)       */
   int32_t upsampling_filter;      /* "<filter>": index into g_filter420to444 (0..7), decoder parameter upsamplingFilter */
+  /* PCCImage::set (PCCImage.h:97-138) as the decoder wrappers call it (PCCHMLibVideoDecoderImpl.cpp:360-363) with
+   * shiftbits = internal bit depth - output bit depth: every sample becomes
+   * clamp( (sample + (1 << (shift-1))) >> shift, 0, (1 << (10 - shift)) - 1 ); 0 = samples are copied as they are */
+  int32_t geometry_shift;
+  int32_t attribute_shift;
 } rb200_frames_yuv420;
 
 /* Patch tables of one GOF.  host pointers.  *_offset arrays have F+1 entries. */

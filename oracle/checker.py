@@ -211,6 +211,17 @@ class Reference(_Backend):
     def __init__(self):
         super().__init__(REF_LIB)
 
+    def image_set_yuv420(self, y, u, v, shift):
+        """PCCImage<uint16_t,3>::set on int16 decoder planes (dense strides): returns (Y, U, V) uint16"""
+        f = self.lib.ref_image_set_yuv420
+        f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p]
+        y, u, v = (np.ascontiguousarray(a, np.int16) for a in (y, u, v))
+        H, W = y.shape
+        out = np.zeros(H * W + 2 * (H // 2) * (W // 2), np.uint16)
+        f(abi.ptr(y), abi.ptr(u), abi.ptr(v), W, H, shift, abi.ptr(out))
+        q = (H // 2) * (W // 2)
+        return out[:H * W].reshape(H, W), out[H * W:H * W + q].reshape(H // 2, W // 2), out[H * W + q:].reshape(H // 2, W // 2)
+
     def yuv420_to_yuv444(self, y, u, v, bitdepth, filt):
         """the reference's own PCCInternalColorConverter<uint16_t>::convert("YUV420ToYUV444_<bits>_<filter>")"""
         f = getattr(self.lib, "ref_yuv420_to_yuv444", None)

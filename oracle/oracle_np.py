@@ -458,6 +458,14 @@ UPSAMPLING_FILTERS = [
 ]
 
 
+def image_set(src, shift):
+    """PCCImage<T,3>::set (PccLibCommon/include/PCCImage.h:97-138): decoder samples -> stored uint16 samples"""
+    if shift <= 0:
+        return src.astype(np.uint16)
+    v = ((src.astype(np.int32) + (1 << (shift - 1))) >> shift) & 0xFFFF
+    return np.clip(v, 0, (1 << (10 - shift)) - 1).astype(np.uint16)
+
+
 def _yuv_to_float(src, chroma, nbyte):  # YUVtoFloatYUV :596-611
     offset = (128 if nbyte == 1 else 512) if chroma else 0
     weight = 1.0 / (255.0 if nbyte == 1 else 1023.0)

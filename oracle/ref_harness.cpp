@@ -628,6 +628,18 @@ int ref_yuv420_to_yuv444( const uint16_t* y, const uint16_t* u, const uint16_t* 
   return 0;
 }
 
+// PCCImage<uint16_t,3>::set (PCCImage.h:97-138) as the HM wrapper calls it (PCCHMLibVideoDecoderImpl.cpp:360-363): decoder
+// picture planes (Pel = int16, dense strides here) -> stored samples with the rounding shift and clamp.
+// out: Y [H][W] then U, V [H/2][W/2] uint16
+int ref_image_set_yuv420( const int16_t* y, const int16_t* u, const int16_t* v, int W, int H, int shift, uint16_t* out ) {
+  PCCImage<uint16_t, 3> img;
+  img.set( y, u, v, (size_t)W, (size_t)H, (size_t)W, (size_t)( W / 2 ), (size_t)( H / 2 ), (size_t)( W / 2 ), (int16_t)shift,
+           PCCCOLORFORMAT::YUV420, false );
+  uint16_t* o = out;
+  for ( int c = 0; c < 3; c++ ) { o = std::copy( img.getChannel( c ).begin(), img.getChannel( c ).end(), o ); }
+  return 0;
+}
+
 int ref_abi_version( void ) { return RB200_ABI_VERSION; }
 
 }  // extern "C"

@@ -76,7 +76,7 @@ class Frames(C.Structure):
 class FramesYuv420(C.Structure):
     _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p),
                 ("geometry_sample_bytes", i32), ("attribute_sample_bytes", i32), ("attribute_bitdepth", i32),
-                ("upsampling_filter", i32)]
+                ("upsampling_filter", i32), ("geometry_shift", i32), ("attribute_shift", i32)]
 
 
 class Atlas(C.Structure):

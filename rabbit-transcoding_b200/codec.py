@@ -95,6 +95,8 @@ class PCCCodecB200:
         f.attribute_sample_bytes = native["attribute"].dtype.itemsize if native.get("attribute") is not None else 1
         f.attribute_bitdepth = native["bitdepth"]
         f.upsampling_filter = native["filter"]
+        f.geometry_shift = native.get("geometry_shift", 0)
+        f.attribute_shift = native.get("attribute_shift", 0)
         self._keep = (gof, native)
         self._check(self._lib.rb200_gof_upload_yuv420(self._h, C.byref(f), C.byref(gof.atlas_struct())))
 

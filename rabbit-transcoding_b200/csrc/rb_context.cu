@@ -276,6 +276,9 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
          ( fy->attribute_bitdepth != 8 && fy->attribute_bitdepth != 10 ) || fy->upsampling_filter < 0 || fy->upsampling_filter > 7 ) {
       return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: sample bytes must be 1 or 2, bit depth 8 or 10, filter 0..7" );
     }
+    if ( fy->geometry_shift < 0 || fy->geometry_shift > 9 || fy->attribute_shift < 0 || fy->attribute_shift > 9 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: shift must be 0..9 (PCCImage.h:118-119)" );
+    }
     if ( c->P.attribute_rgb444 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: RGB444 attributes are not 4:2:0 video" ); }
     if ( ( c->W & 15 ) || ( c->H & 1 ) ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: width must be a multiple of 16, height even" ); }
   }
@@ -399,7 +402,8 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
       RB_CUDA( cudaMemcpyAsync( c->d_raw_attr.p, fy->attribute, rawAtt, cudaMemcpyDefault, c->stream ) );
     }
     c->stats.h2d_bytes += (int64_t)( occBytes + rawGeo + rawAtt );
-    int r = rb_ingest_yuv420_impl( c, fy->geometry_sample_bytes, fy->attribute_sample_bytes, fy->attribute_bitdepth, fy->upsampling_filter );
+    int r = rb_ingest_yuv420_impl( c, fy->geometry_sample_bytes, fy->attribute_sample_bytes, fy->attribute_bitdepth, fy->upsampling_filter,
+                                   fy->geometry_shift, fy->attribute_shift );
     if ( r ) { return r; }
   }
   RB_CUDA( c->d_patches.ensure( std::max<size_t>( 1, nPatches ) * sizeof( RbPatch ) ) );

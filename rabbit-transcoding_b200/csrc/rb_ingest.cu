@@ -39,6 +39,13 @@ __constant__ UpFilter c_up[8] = {
      TAPS( -2, 5, -10, 20, -43, 230, 75, -29, 14, -7, 3, 0 ), 2, 12, 12, 12},
 };
 
+// PCCImage::set (PccLibCommon/include/PCCImage.h:97-138): the decoder's sample -> the stored sample
+__device__ __forceinline__ int image_set( int s, int shift ) {
+  if ( shift <= 0 ) { return s; }
+  const int v = ( s + ( 1 << ( shift - 1 ) ) ) >> shift;  // (T)( ( src + rounding ) >> shiftbits )
+  return min( max( v & 0xFFFF, 0 ), ( 1 << ( 10 - shift ) ) - 1 );
+}
+
 // YUVtoFloatYUV (:596-611): clamp( (float)( weight * (double)( sample - offset ) ), min, max )
 __device__ __forceinline__ float sample_to_float( int s, bool chroma, int nbyte ) {
   const int    offset = chroma ? ( nbyte == 1 ? 128 : 512 ) : 0;
@@ -55,10 +62,10 @@ __device__ __forceinline__ uint16_t float_to_u16( float f, bool chroma ) {
 // ---- luma: a pure function of the sample, tabulated per CTA ----
 template <typename T>
 __global__ void __launch_bounds__( 256 ) k_luma_to_16( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
-                                                        int nbyte, size_t srcFrameStride, size_t dstFrameStride ) {
+                                                        int nbyte, int shift, size_t srcFrameStride, size_t dstFrameStride ) {
   __shared__ uint16_t lut[1024];
-  const int           levels = nbyte == 1 ? 256 : 1024;
-  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = float_to_u16( sample_to_float( s, false, nbyte ), false ); }
+  const int           levels = 1024;  // decoder samples below 1024 go through the table, anything else is computed
+  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = float_to_u16( sample_to_float( image_set( s, shift ), false, nbyte ), false ); }
   __syncthreads();
   const T*      in  = src + (size_t)blockIdx.y * srcFrameStride;
   uint16_t*     out = dst + (size_t)blockIdx.y * dstFrameStride;
@@ -69,11 +76,11 @@ __global__ void __launch_bounds__( 256 ) k_luma_to_16( const T* __restrict__ src
 #pragma unroll
       for ( int k = 0; k < 8; k++ ) {
         const int s = (int)in[i + k];
-        o[k]        = s < levels ? lut[s] : float_to_u16( sample_to_float( s, false, nbyte ), false );
+        o[k]        = s < levels ? lut[s] : float_to_u16( sample_to_float( image_set( s, shift ), false, nbyte ), false );
       }
       *reinterpret_cast<uint4*>( out + i ) = *reinterpret_cast<const uint4*>( o );
     } else {
-      for ( int64_t j = i; j < n; j++ ) { out[j] = float_to_u16( sample_to_float( (int)in[j], false, nbyte ), false ); }
+      for ( int64_t j = i; j < n; j++ ) { out[j] = float_to_u16( sample_to_float( image_set( (int)in[j], shift ), false, nbyte ), false ); }
     }
   }
 }
@@ -84,18 +91,18 @@ constexpr int IW = TW / 2 + 2 * HALO, IH = TH / 2 + 2 * HALO;  // 44 x 28 staged
 
 template <typename T>
 __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
-                                                               int nbyte, int filter, size_t srcFrameStride,
+                                                               int nbyte, int shift, int filter, size_t srcFrameStride,
                                                                size_t dstFrameStride ) {
   __shared__ float lut[1024];
   __shared__ float in[IH][IW];
   __shared__ float tmp[TH][IW + 1];
-  const int        levels = nbyte == 1 ? 256 : 1024;
+  const int        levels = 1024;
   const int        cw = W / 2, ch = H / 2;
   const int        frame = blockIdx.z >> 1, plane = 1 + ( blockIdx.z & 1 );
   // frame layout of the source: Y [H][W], U [H/2][W/2], V [H/2][W/2]
   const T*  cin  = src + (size_t)frame * srcFrameStride + (size_t)W * H + (size_t)( plane - 1 ) * cw * ch;
   uint16_t* cout = dst + (size_t)frame * dstFrameStride + (size_t)plane * W * H;
-  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = sample_to_float( s, true, nbyte ); }
+  for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = sample_to_float( image_set( s, shift ), true, nbyte ); }
   __syncthreads();
   const UpFilter& F  = c_up[filter];
   const int       ox = blockIdx.x * TW, oy = blockIdx.y * TH;  // output tile origin
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restric
     const int r = k / IW, c = k - r * IW;
     const int gy = min( max( iy + r, 0 ), ch - 1 ), gx = min( max( jx + c, 0 ), cw - 1 );  // clamp( ., 0, size - 1 ) of every tap
     const int s  = (int)cin[(size_t)gy * cw + gx];
-    in[r][c]     = s < levels ? lut[s] : sample_to_float( s, true, nbyte );
+    in[r][c]     = s < levels ? lut[s] : sample_to_float( image_set( s, shift ), true, nbyte );
   }
   __syncthreads();
   // vertical: row 2i from vertical0 at i0 = i, row 2i+1 from vertical1 at i0 = i + 1 (:678-686)
@@ -159,14 +166,26 @@ __global__ void __launch_bounds__( 256 ) k_widen_u8( const uint8_t* __restrict__
   }
 }
 
+// geometry luma samples with PCCImage::set's shift -> the uint16 plane (in == out allowed for 2-byte samples)
+template <typename T>
+__global__ void __launch_bounds__( 256 ) k_geometry_set( const T* src, uint16_t* dst, int64_t n, int shift ) {
+  for ( int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) {
+    dst[i] = (uint16_t)image_set( (int)src[i], shift );
+  }
+}
+
 }  // namespace
 
 // raw decoder planes (already in c->d_raw_geo / c->d_raw_attr) -> c->d_geometry / c->d_attribute
-int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter ) {
+int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter, int geo_shift, int attr_shift ) {
   const size_t  plane = (size_t)c->W * c->H;
   const int64_t nGeo  = (int64_t)c->F * c->M * plane;
-  if ( geo_bytes == 1 ) {
+  if ( geo_bytes == 1 && geo_shift == 0 ) {
     RB_LAUNCH( "geometry_widen", k_widen_u8, rb_div_up( nGeo, 256 * 16 ), 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo );
+  } else if ( geo_bytes == 1 ) {
+    RB_LAUNCH( "geometry_set", k_geometry_set<uint8_t>, 148 * 8, 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift );
+  } else if ( geo_shift > 0 ) {  // 2-byte samples were copied straight into d_geometry
+    RB_LAUNCH( "geometry_set", k_geometry_set<uint16_t>, 148 * 8, 256, 0, c->d_geometry.as<uint16_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift );
   }
   if ( c->P.attribute_count > 0 ) {
     const int    nbyte  = attr_bitdepth == 8 ? 1 : 2;
@@ -174,11 +193,11 @@ int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr
     const size_t sfs = plane + plane / 2, dfs = 3 * plane;
     const dim3   gl( 64, frames ), gc( rb_div_up( c->W, TW ), rb_div_up( c->H, TH ), frames * 2 );
     if ( attr_bytes == 1 ) {
-      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint8_t>, gl, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, sfs, dfs );
-      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint8_t>, gc, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, filter, sfs, dfs );
+      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint8_t>, gl, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, sfs, dfs );
+      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint8_t>, gc, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, filter, sfs, dfs );
     } else {
-      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint16_t>, gl, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, sfs, dfs );
-      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint16_t>, gc, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, filter, sfs, dfs );
+      RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint16_t>, gl, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, sfs, dfs );
+      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint16_t>, gc, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, filter, sfs, dfs );
     }
   }
   return RB200_OK;

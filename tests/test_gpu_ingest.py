@@ -105,3 +105,28 @@ def test_upload_yuv420_error_paths(rb, codec):
     nat["bitdepth"], nat["filter"] = 8, 8
     with pytest.raises(rb.codec.RabbitError):
         codec.uploadGofYuv420(g, nat)
+
+
+@pytest.mark.parametrize("shift", [1, 2])
+def test_ingest_applies_image_set_shift(rb, codec, shift):
+    """decoder planes at the codec's internal bit depth: PCCImage::set's rounding shift + clamp, then the conversion"""
+    from oracle import oracle_np
+    rng = np.random.default_rng(17 + shift)
+    W, H = 96, 64
+    y = rng.integers(0, 1024, (H, W)).astype(np.uint16)
+    u = rng.integers(0, 1024, (H // 2, W // 2)).astype(np.uint16)
+    v = rng.integers(0, 1024, (H // 2, W // 2)).astype(np.uint16)
+    y[0, :4] = [0, 1, 1022, 1023]
+    bd = 10 - shift if 10 - shift in (8, 10) else 8  # stored samples have 10 - shift bits; the converter is told 8 or 10
+    g, p = _params(rb, W, H)
+    g.occupancy = np.zeros((1, H // p.occupancy_precision, W // p.occupancy_precision), np.uint8)
+    g.patches = g.patches[:0]
+    g.patch_offset = np.zeros(2, np.int32)
+    native = {"bitdepth": bd, "filter": 3, "geometry_shift": shift, "attribute_shift": shift,
+              "geometry": np.ascontiguousarray(y).reshape(1, 1, H, W),
+              "attribute": np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)]).reshape(1, 1, -1)}
+    codec.uploadGofYuv420(g, native)
+    geo, att = codec.getPlanes(0, 0)
+    ys, us, vs = (oracle_np.image_set(a, shift) for a in (y, u, v))
+    assert np.array_equal(geo, ys)
+    assert np.array_equal(att, oracle_np.yuv420_to_yuv444(ys, us, vs, bd, 3))

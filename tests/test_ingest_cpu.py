@@ -47,3 +47,20 @@ def test_decoder_planes_round_trip(rb):
     assert np.array_equal(fr[0, 0, :H * W].reshape(H, W), a[0, 0, 0] >> 8)
     assert np.array_equal(fr[0, 1, H * W:H * W + (H // 2) * (W // 2)].reshape(H // 2, W // 2), a[0, 1, 1, ::2, ::2] >> 8)
     assert nat["geometry"].dtype == np.uint8 and np.array_equal(nat["geometry"].reshape(-1), g.geometry.reshape(-1))
+
+
+def test_image_set_restatement_matches_reference():
+    """PCCImage::set's rounding shift + clamp (decoder internal bit depth -> output bit depth)"""
+    from oracle import checker, oracle_np
+    if not checker.have_reference():
+        pytest.skip("oracle/_ref not built")
+    ref = checker.Reference()
+    rng = np.random.default_rng(4)
+    for shift in (0, 1, 2, 4):
+        y = rng.integers(0, 1024, (16, 32)).astype(np.int16)
+        u = rng.integers(0, 1024, (8, 16)).astype(np.int16)
+        v = rng.integers(0, 1024, (8, 16)).astype(np.int16)
+        y[0, :4] = [0, 1, 1022, 1023]
+        got = ref.image_set_yuv420(y, u, v, shift)
+        for a, b in zip(got, (y, u, v)):
+            assert np.array_equal(a, oracle_np.image_set(b, shift)), f"shift {shift}"
