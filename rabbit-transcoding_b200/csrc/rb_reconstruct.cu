@@ -280,21 +280,36 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     }
     S.rows[lane] = bits;
   }
-  // ---- stage geometry (and attribute) tiles: 16-byte loads, two lanes per 32-byte sector ----
+  // ---- stage geometry (and attribute) tiles: 16-byte loads, two lanes per 32-byte sector; all loads of the block
+  // are in flight before the first one is stored to shared memory ----
   {
     const int    r = lane >> 1, h = lane & 1;
     const size_t o = (size_t)( Y0 + r ) * a.W + X0 + 8 * h;
     const size_t plane = (size_t)a.W * a.H;
-    for ( int m = 0; m < a.M; m++ ) {
-      const uint4 v = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * a.M + m ) * plane + o );
-      *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = v;
+    uint4        vg[2], va[2][3];
+#pragma unroll
+    for ( int m = 0; m < 2; m++ ) {
+      if ( m < a.M ) { vg[m] = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * a.M + m ) * plane + o ); }
     }
     if ( EMIT && a.attr_count > 0 ) {
-      for ( int m = 0; m < a.M; m++ ) {
+#pragma unroll
+      for ( int m = 0; m < 2; m++ ) {
 #pragma unroll
         for ( int ch = 0; ch < 3; ch++ ) {
-          const uint4 v = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * a.M + m ) * 3 + ch ) * plane + o );
-          *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = v;
+          if ( m < a.M ) { va[m][ch] = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * a.M + m ) * 3 + ch ) * plane + o ); }
+        }
+      }
+    }
+#pragma unroll
+    for ( int m = 0; m < 2; m++ ) {
+      if ( m < a.M ) { *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = vg[m]; }
+    }
+    if ( EMIT && a.attr_count > 0 ) {
+#pragma unroll
+      for ( int m = 0; m < 2; m++ ) {
+#pragma unroll
+        for ( int ch = 0; ch < 3; ch++ ) {
+          if ( m < a.M ) { *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = va[m][ch]; }
         }
       }
     }
