@@ -685,10 +685,14 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
       nrm_raw, partial, far_list;
-  // the normals of the sources are uploaded on their own stream, underneath the column build of the same call
+  // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
+  // sets of import buffers, `cur` = the set the running chunk reads.
+  RbBuf                rawSet[2], nrmSet[2];
+  int                  cur = 0;
+  bool                 prefetched = false;  // the running chunk's clouds are already in rawSet[cur] / nrmSet[cur]
   cudaStream_t         copy_stream = nullptr;
-  cudaEvent_t          ev_ready = nullptr, ev_copied = nullptr;
-  std::vector<int64_t> raw_off;  // per cloud: offset of its raw positions inside `raw` (-1: resident frame)
+  cudaEvent_t          ev_free[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  std::vector<int64_t> raw_off;  // per cloud: offset of its raw positions inside the import buffer (-1: resident frame)
 };
 std::map<rb200_ctx*, MetricsScratch*> g_scratch;
 
@@ -700,9 +704,13 @@ void rb_metrics_release( rb200_ctx* c ) {
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
   for ( auto* b : bufs ) { b->release(); }
+  for ( int k = 0; k < 2; k++ ) {
+    s->rawSet[k].release();
+    s->nrmSet[k].release();
+    if ( s->ev_free[k] ) { cudaEventDestroy( s->ev_free[k] ); }
+    if ( s->ev_copied[k] ) { cudaEventDestroy( s->ev_copied[k] ); }
+  }
   if ( s->copy_stream ) { cudaStreamDestroy( s->copy_stream ); }
-  if ( s->ev_ready ) { cudaEventDestroy( s->ev_ready ); }
-  if ( s->ev_copied ) { cudaEventDestroy( s->ev_copied ); }
   delete s;
   g_scratch.erase( it );
 }
@@ -808,7 +816,9 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   // ---- import ----
   short4* inPos = S->in_pos.as<short4>();
   uchar4* inCol = S->in_col.as<uchar4>();
-  if ( maxRaw > 0 ) { RB_CUDA( S->raw.ensure( (size_t)N * 9 + (size_t)nC * 32 + 64 ) ); }
+  RbBuf& rawBuf = S->rawSet[S->cur];
+  if ( maxRaw > 0 && !S->prefetched ) { RB_CUDA( rawBuf.ensure( (size_t)N * 9 + (size_t)nC * 32 + 64 ) ); }
+  if ( S->prefetched ) { RB_CUDA( cudaStreamWaitEvent( c->stream, S->ev_copied[S->cur], 0 ) ); }
   int64_t rawOff = 0;
   S->raw_off.assign( nC, -1 );
   for ( int i = 0; i < nC; i++ ) {
@@ -816,11 +826,13 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
     if ( cl.n == 0 ) { continue; }
     if ( cl.view ) {
       S->raw_off[i] = rawOff;
-      char*   rp = S->raw.as<char>() + rawOff;
+      char*   rp = rawBuf.as<char>() + rawOff;
       char*   rc = rp + ( ( cl.n * 6 + 15 ) & ~15ll );
-      RB_CUDA( cudaMemcpyAsync( rp, cl.view->positions, cl.n * 6, cudaMemcpyDefault, c->stream ) );
-      if ( cl.view->colors ) { RB_CUDA( cudaMemcpyAsync( rc, cl.view->colors, cl.n * 3, cudaMemcpyDefault, c->stream ) ); }
-      c->stats.h2d_bytes += cl.n * ( cl.view->colors ? 9 : 6 );
+      if ( !S->prefetched ) {
+        RB_CUDA( cudaMemcpyAsync( rp, cl.view->positions, cl.n * 6, cudaMemcpyDefault, c->stream ) );
+        if ( cl.view->colors ) { RB_CUDA( cudaMemcpyAsync( rc, cl.view->colors, cl.n * 3, cudaMemcpyDefault, c->stream ) ); }
+        c->stats.h2d_bytes += cl.n * ( cl.view->colors ? 9 : 6 );
+      }
       RB_LAUNCH( "met_unpack", k_unpack_cloud, rb_div_up( cl.n, TPB ), TPB, 0, (const int16_t*)rp,
                  cl.view->colors ? (const uint8_t*)rc : nullptr, cl.n, inPos + hOff[i], inCol + hOff[i] );
       rawOff += ( ( cl.n * 6 + 15 ) & ~15ll ) + ( ( cl.n * 3 + 15 ) & ~15ll );
@@ -919,19 +931,10 @@ int run_nn( rb200_ctx* c, MetricsScratch* S, NNArgs& a, const std::vector<Direct
 
 extern "C" {
 
-int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, const rb200_cloud_view* sources,
-                   const rb200_cloud_view* recs, rb200_metrics_result* results ) {
-  if ( !c || !mp || nPairs <= 0 || !sources || !recs || !results ) {
-    return rb_fail( c, RB200_ERR_INVALID, "metrics: bad arguments" );
-  }
-  if ( mp->drop_duplicates < 0 || mp->drop_duplicates > 2 ) {
-    return rb_fail( c, RB200_ERR_INVALID, "metrics: drop_duplicates must be 0, 1 or 2" );
-  }
-  if ( mp->compute_color && ( mp->neighbors_proc < 1 || mp->neighbors_proc > 4 ) ) {
-    // neighborsProc 0 takes result.indices(0), the first tie in nanoflann's traversal order (PCCMetrics.cpp:126,177)
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "metrics: neighbors_proc %d is not implemented (1..4 are)", mp->neighbors_proc );
-  }
-  cudaSetDevice( c->device );
+// pairs [first, first + nPairs) of one rb200_metrics call; their host clouds are already in the import buffers of
+// set S->cur (prefetch_pairs)
+static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int first, int nPairs, const rb200_cloud_view* sources,
+                          const rb200_cloud_view* recs, rb200_metrics_result* results ) {
   MetricsScratch* S = scratch_of( c );
   // clouds: 2 per pair (source, reconstruction)
   std::vector<CloudIn> clouds( 2 * nPairs );
@@ -942,15 +945,16 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
     if ( recs[i].positions ) {
       clouds[2 * i + 1] = CloudIn{&recs[i], -1, recs[i].count};
     } else {
-      if ( !c->reconstructed || !c->rgb_done || i >= c->F ) {
-        return rb_fail( c, RB200_ERR_STATE, "metrics: pair %d asks for the resident frame but no decoded GOF is resident", i );
+      const int fr = first + i;
+      if ( !c->reconstructed || !c->rgb_done || fr >= c->F ) {
+        return rb_fail( c, RB200_ERR_STATE, "metrics: pair %d asks for the resident frame but no decoded GOF is resident", fr );
       }
-      clouds[2 * i + 1] = CloudIn{nullptr, i, c->h_frame_off[i + 1] - c->h_frame_off[i]};
+      clouds[2 * i + 1] = CloudIn{nullptr, fr, c->h_frame_off[fr + 1] - c->h_frame_off[fr]};
     }
     if ( clouds[2 * i + 1].n <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty reconstruction %d", i ); }
     if ( sources[i].normals ) { anyNormals = true; }
   }
-  // ---- normals of the sources: their upload starts now, on its own stream, and overlaps the column build ----
+  // ---- normals of the sources: uploaded by prefetch_pairs at these offsets of nrmSet[cur] ----
   std::vector<int64_t> nrmOff( nPairs, -1 );
   if ( mp->compute_c2p != 0 && anyNormals ) {
     int64_t tot = 0;
@@ -959,20 +963,6 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
       nrmOff[i] = tot;
       tot += ( sources[i].count * 12 + 255 ) & ~255ll;
     }
-    RB_CUDA( S->nrm_raw.ensure( (size_t)tot + 64 ) );
-    if ( !S->copy_stream ) {
-      RB_CUDA( cudaStreamCreateWithFlags( &S->copy_stream, cudaStreamNonBlocking ) );
-      RB_CUDA( cudaEventCreateWithFlags( &S->ev_ready, cudaEventDisableTiming ) );
-      RB_CUDA( cudaEventCreateWithFlags( &S->ev_copied, cudaEventDisableTiming ) );
-    }
-    RB_CUDA( cudaEventRecord( S->ev_ready, c->stream ) );  // earlier work on the compute stream may still read nrm_raw
-    RB_CUDA( cudaStreamWaitEvent( S->copy_stream, S->ev_ready, 0 ) );
-    for ( int i = 0; i < nPairs; i++ ) {
-      if ( nrmOff[i] < 0 ) { continue; }
-      RB_CUDA( cudaMemcpyAsync( S->nrm_raw.as<char>() + nrmOff[i], sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
-      c->stats.h2d_bytes += sources[i].count * 12;
-    }
-    RB_CUDA( cudaEventRecord( S->ev_copied, S->copy_stream ) );
   }
   Batch                B{};
   std::vector<int64_t> hOff;
@@ -1072,14 +1062,13 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
     RB_CUDA( cudaMemsetAsync( S->last_idx.p, 0, (size_t)N * 4, c->stream ) );
     a.nrm     = S->nrm.as<double>();
     a.nrm_cnt = S->nrm_cnt.as<uint32_t>();
-    RB_CUDA( cudaStreamWaitEvent( c->stream, S->ev_copied, 0 ) );
     for ( int i = 0; i < nPairs; i++ ) {
       if ( !sources[i].normals ) { continue; }
       // the normal cloud of pair i is the source view itself (positions + normals in file order): its positions are
       // still in the import buffer of build_batch, its normals came in on the copy stream
       const int64_t  n  = sources[i].count;
-      const int16_t* rp = (const int16_t*)( S->raw.as<char>() + S->raw_off[2 * i] );
-      const float*   rn = (const float*)( S->nrm_raw.as<char>() + nrmOff[i] );
+      const int16_t* rp = (const int16_t*)( S->rawSet[S->cur].as<char>() + S->raw_off[2 * i] );
+      const float*   rn = (const float*)( S->nrmSet[S->cur].as<char>() + nrmOff[i] );
       RB_LAUNCH( "met_normal_lookup", k_normal_lookup, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rp, n, S->last_idx.as<uint32_t>(), dErr );
       RB_LAUNCH( "met_normal_gather", k_normal_gather, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rn, n,
                  S->last_idx.as<uint32_t>(), a.nrm, dErr );
@@ -1135,6 +1124,96 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
   if ( status == RB200_ERR_TIE_OVERFLOW ) {
     rb_fail( c, status, "metrics: a nearest-distance shell holds more than 30 points; the reference's result depends on its "
                         "kd-tree traversal order there (results are filled in with the first 30 by index)" );
+  }
+  return status;
+}
+
+// host clouds of pairs [first, first + nPairs) -> import buffers of `set`, on the copy stream (same offsets as
+// build_batch / metrics_range compute)
+static int prefetch_pairs( rb200_ctx* c, MetricsScratch* S, const rb200_metrics_params* mp, int nPairs, const rb200_cloud_view* sources,
+                           const rb200_cloud_view* recs, int set ) {
+  if ( !S->copy_stream ) {
+    RB_CUDA( cudaStreamCreateWithFlags( &S->copy_stream, cudaStreamNonBlocking ) );
+    for ( int k = 0; k < 2; k++ ) {
+      RB_CUDA( cudaEventCreateWithFlags( &S->ev_free[k], cudaEventDisableTiming ) );
+      RB_CUDA( cudaEventCreateWithFlags( &S->ev_copied[k], cudaEventDisableTiming ) );
+      RB_CUDA( cudaEventRecord( S->ev_free[k], c->stream ) );
+    }
+  }
+  int64_t rawBytes = 0, nrmBytes = 0;
+  for ( int i = 0; i < nPairs; i++ ) {
+    const rb200_cloud_view* v[2] = {&sources[i], recs[i].positions ? &recs[i] : nullptr};
+    for ( int k = 0; k < 2; k++ ) {
+      if ( v[k] && v[k]->count > 0 ) { rawBytes += ( ( v[k]->count * 6 + 15 ) & ~15ll ) + ( ( v[k]->count * 3 + 15 ) & ~15ll ); }
+    }
+    if ( mp->compute_c2p && sources[i].normals ) { nrmBytes += ( sources[i].count * 12 + 255 ) & ~255ll; }
+  }
+  RB_CUDA( S->rawSet[set].ensure( (size_t)rawBytes + (size_t)nPairs * 64 + 64 ) );
+  RB_CUDA( S->nrmSet[set].ensure( (size_t)nrmBytes + 64 ) );
+  RB_CUDA( cudaStreamWaitEvent( S->copy_stream, S->ev_free[set], 0 ) );  // the chunk that read this set has finished
+  int64_t rawOff = 0, nOff = 0;
+  for ( int i = 0; i < nPairs; i++ ) {
+    const rb200_cloud_view* v[2] = {&sources[i], recs[i].positions ? &recs[i] : nullptr};
+    for ( int k = 0; k < 2; k++ ) {
+      if ( !v[k] || v[k]->count <= 0 ) { continue; }
+      const int64_t n  = v[k]->count;
+      char*         rp = S->rawSet[set].as<char>() + rawOff;
+      char*         rc = rp + ( ( n * 6 + 15 ) & ~15ll );
+      RB_CUDA( cudaMemcpyAsync( rp, v[k]->positions, n * 6, cudaMemcpyDefault, S->copy_stream ) );
+      if ( v[k]->colors ) { RB_CUDA( cudaMemcpyAsync( rc, v[k]->colors, n * 3, cudaMemcpyDefault, S->copy_stream ) ); }
+      c->stats.h2d_bytes += n * ( v[k]->colors ? 9 : 6 );
+      rawOff += ( ( n * 6 + 15 ) & ~15ll ) + ( ( n * 3 + 15 ) & ~15ll );
+    }
+    if ( mp->compute_c2p && sources[i].normals ) {
+      RB_CUDA( cudaMemcpyAsync( S->nrmSet[set].as<char>() + nOff, sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
+      c->stats.h2d_bytes += sources[i].count * 12;
+      nOff += ( sources[i].count * 12 + 255 ) & ~255ll;
+    }
+  }
+  RB_CUDA( cudaEventRecord( S->ev_copied[set], S->copy_stream ) );
+  return RB200_OK;
+}
+
+int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, const rb200_cloud_view* sources,
+                   const rb200_cloud_view* recs, rb200_metrics_result* results ) {
+  if ( !c || !mp || nPairs <= 0 || !sources || !recs || !results ) {
+    return rb_fail( c, RB200_ERR_INVALID, "metrics: bad arguments" );
+  }
+  if ( mp->drop_duplicates < 0 || mp->drop_duplicates > 2 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "metrics: drop_duplicates must be 0, 1 or 2" );
+  }
+  if ( mp->compute_color && ( mp->neighbors_proc < 1 || mp->neighbors_proc > 4 ) ) {
+    // neighborsProc 0 takes result.indices(0), the first tie in nanoflann's traversal order (PCCMetrics.cpp:126,177)
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "metrics: neighbors_proc %d is not implemented (1..4 are)", mp->neighbors_proc );
+  }
+  for ( int i = 0; i < nPairs; i++ ) {
+    if ( !sources[i].positions || sources[i].count <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty source cloud %d", i ); }
+  }
+  cudaSetDevice( c->device );
+  MetricsScratch* S = scratch_of( c );
+  // The pairs are independent (PCCMetrics::compute loops over the frames, PCCMetrics.cpp:348-384).  They are processed
+  // in chunks so that the host clouds of chunk k+1 cross PCIe on the copy stream while the kernels of chunk k run.
+  const int nChunks = nPairs >= 8 ? 4 : 1, per = ( nPairs + nChunks - 1 ) / nChunks;
+  int       status = RB200_OK;
+  int       r = prefetch_pairs( c, S, mp, std::min( per, nPairs ), sources, recs, 0 );
+  if ( r ) { return r; }
+  for ( int k = 0, b = 0; b < nPairs; k++, b += per ) {
+    const int e = std::min( nPairs, b + per ), set = k & 1;
+    if ( e < nPairs ) {
+      r = prefetch_pairs( c, S, mp, std::min( per, nPairs - e ), sources + e, recs + e, set ^ 1 );
+      if ( r ) { return r; }
+    }
+    S->cur        = set;
+    S->prefetched = true;
+    r             = metrics_range( c, mp, b, e - b, sources + b, recs + b, results + b );
+    S->prefetched = false;
+    cudaEventRecord( S->ev_free[set], c->stream );
+    if ( r == RB200_ERR_TIE_OVERFLOW ) {
+      status = r;
+    } else if ( r ) {
+      cudaStreamSynchronize( S->copy_stream );  // nothing may still be reading the caller's buffers
+      return r;
+    }
   }
   return status;
 }
