@@ -442,7 +442,6 @@ __device__ __forceinline__ const Direction& direction_of_block( const NNArgs& a,
 
 template <int MODE>
 __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
-  __shared__ double red[TPB / 32][4];
   const Direction&  d  = direction_of_block( a, blockIdx.x );
   const Batch&      b  = a.b;
   const int64_t     iu = (int64_t)( blockIdx.x - d.block_begin ) * TPB + threadIdx.x;
@@ -497,13 +496,9 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
     for ( int k = 0; k < 4; k++ ) {
 #pragma unroll
       for ( int s = 16; s > 0; s >>= 1 ) { v[k] += __shfl_down_sync( 0xFFFFFFFFu, v[k], s ); }
-      if ( lane == 0 ) { red[w][k] = v[k]; }
-    }
-    __syncthreads();
-    if ( threadIdx.x < 4 ) {
-      double s = 0.0;
-      for ( int i = 0; i < TPB / 32; i++ ) { s += red[i][threadIdx.x]; }
-      a.partial[(int64_t)blockIdx.x * 4 + threadIdx.x] = s;
+      // per-warp partials go to global memory: no barrier (a CTA's warps finish at very different times), and
+      // k_reduce_partials adds them in the same fixed order (warp 0 .. 7 of CTA 0, then CTA 1, ...)
+      if ( lane == 0 ) { a.partial[( (int64_t)blockIdx.x * ( TPB / 32 ) + w ) * 4 + k] = v[k]; }
     }
   }
 }
@@ -612,7 +607,11 @@ __global__ void __launch_bounds__( TPB ) k_reduce_partials( const NNArgs a, cons
   double            s[4] = {0, 0, 0, 0};
   for ( int blk = d.block_begin + threadIdx.x; blk < block_end[blockIdx.x]; blk += TPB ) {
 #pragma unroll
-    for ( int k = 0; k < 4; k++ ) { s[k] += a.partial[(int64_t)blk * 4 + k]; }
+    for ( int k = 0; k < 4; k++ ) {
+      double bs = 0.0;  // the CTA's sum, warp by warp
+      for ( int w = 0; w < TPB / 32; w++ ) { bs += a.partial[( (int64_t)blk * ( TPB / 32 ) + w ) * 4 + k]; }
+      s[k] += bs;
+    }
   }
 #pragma unroll
   for ( int k = 0; k < 4; k++ ) { red[threadIdx.x][k] = s[k]; }
@@ -1040,7 +1039,7 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
     c->stats.h2d_bytes += (int64_t)( szDirs + szEnds );
   }
-  RB_CUDA( S->partial.ensure( (size_t)std::max( maxBlocks, 1 ) * 32 ) );
+  RB_CUDA( S->partial.ensure( (size_t)std::max( maxBlocks, 1 ) * 32 * ( TPB / 32 ) ) );
   RB_CUDA( S->far_list.ensure( (size_t)( N + 1 ) * 8 ) );
   NNArgs a{};
   a.b              = B;
