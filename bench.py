@@ -62,8 +62,8 @@ def make_gof(rb, args, rank, world, frames=None):
     # BASELINE.json configs[1] = "reconstruction + geometry/colour smoothing": the attribute re-transfer of the decoder's
     # Rec-1 profile (PCCPointSet3::transferColors16bitBP) is measured as its own leg ("full_decoder")
     kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=0)
-    ncpu = os.cpu_count() or 1
-    workers = max(1, min(frames or args.frames, ncpu // max(1, world)))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(frames or args.frames, min(ncpu, (os.cpu_count() or 1) // max(1, world))))
     return rb.synthetic.generate_gof_parallel(frames or args.frames, workers=workers, **kw)
 
 
@@ -167,6 +167,19 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    # host threads and pinned buffers of a rank stay on the NUMA node of its GPU (8 ranks otherwise share one node's
+    # memory controllers for 600 MB of PCIe traffic per GOF each)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h_ = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h_, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        if cpus and not os.environ.get("RB200_BENCH_NO_AFFINITY"):
+            os.sched_setaffinity(0, cpus)
+            print(f"[bench rank {rank}] bound to {len(cpus)} cpus of GPU {local}'s NUMA node", file=sys.stderr, flush=True)
+    except Exception as ex:
+        print(f"[bench rank {rank}] no cpu affinity: {ex}", file=sys.stderr, flush=True)
     # the driver wants ONE JSON line on stdout: NCCL's version banner (and anything else a library prints there) is sent
     # to stderr by pointing fd 1 at fd 2 for the whole run; the JSON line goes to the saved descriptor
     sys.stdout.flush()
