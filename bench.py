@@ -51,8 +51,9 @@ def parse():
 
 WORKLOADS = {
     # name: generator arguments (synthetic.generate_gof) — vox10: ~0.84 M points / frame, atlas 1280x1280
-    "vox10": dict(bitdepth=10, width=1280, scale=0.68, height_blocks=80),
-    "vox11": dict(bitdepth=11, width=2560, scale=0.62, height_blocks=176),
+    # max_depth: patches stay inside the range of the 8-bit geometry video (geometryNominal2dBitdepth 8, maxAllowedDepth)
+    "vox10": dict(bitdepth=10, width=1280, scale=0.68, height_blocks=80, max_depth=249),
+    "vox11": dict(bitdepth=11, width=2560, scale=0.62, height_blocks=176, max_depth=249),
     "tiny": dict(bitdepth=8, width=256, scale=0.9, height_blocks=32),
 }
 

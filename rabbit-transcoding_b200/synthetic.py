@@ -231,7 +231,7 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
                  noise_fraction=0.10, color_noise=6.0, max_patch_blocks=12, orientations=(0, 1),
                  eom=False, raw_points=0, map_count=2, precedence_reverse=False, min_height_blocks=0,
                  with_sources=True, color_smoothing=True, geometry_smoothing=True, transfer_filter=1,
-                 height_blocks=None, absolute_d1=True, frame_offset=0):
+                 height_blocks=None, absolute_d1=True, frame_offset=0, max_depth=None):
     """Generate one GOF.  `scale` sizes the body relative to the cube (1.0 ~ vox10-like point counts at
     bitdepth 10: ~0.4 M occupied pixels, ~0.8 M points).  `height_blocks` forces the atlas height (all
     frames of a GOF share W x H as the video does); otherwise H = tallest packing over the GOF."""
@@ -360,6 +360,11 @@ def generate_gof(n_frames=1, bitdepth=10, width=1280, occupancy_precision=4, sca
             else:
                 d1 = int(dep.max())
                 d0 = d1 - dep
+            if max_depth is not None:
+                # the encoder keeps a patch inside the range of the 8-bit geometry video (maxAllowedDepth): deeper
+                # pixels are not part of the patch
+                ok = d0 <= max_depth
+                xx, yy, gu, gv, d0 = xx[ok], yy[ok], gu[ok], gv[ok], d0[ok]
             recs[i] = (pt["u0"], pt["v0"], pt["su0"], pt["sv0"], pt["u1"], pt["v1"], d1, vw["nrm"], vw["tan"],
                        vw["bit"], vw["mode"], pt["orient"], 1, 1, 0, su, sv)
             pix.append(dict(u=xx, v=yy, d0=d0.astype(np.int64), nrm=vw["normal"][gv, gu]))
