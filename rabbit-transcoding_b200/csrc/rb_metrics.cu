@@ -54,10 +54,17 @@ struct Batch {
   short4*         u_pos;   // unique points, cloud c at [off[c], off[c] + ucount[c])
   int16_t*        u_z;
   uchar4*         u_col;
+  float4*         u_yuv;   // convertRGBtoYUVBT709 of u_col (PCCMetrics.cpp:50-55), once per unique point
   uint32_t*       u_orig;  // index (inside the cloud) of the first original point at that position
   uint32_t*       ucount;  // [nClouds]
   int             drop;    // dropDuplicates_: 0 keep every point, 1 first colour, 2 mean colour
 };
+
+__device__ __forceinline__ void rgb_to_yuv709( int r, int g, int b, float yuv[3] ) {  // PCCMetrics.cpp:50-55
+  yuv[0] = (float)( ( 0.2126 * r + 0.7152 * g + 0.0722 * b ) / 255.0 );
+  yuv[1] = (float)( ( -0.1146 * r - 0.3854 * g + 0.5000 * b ) / 255.0 + 0.5000 );
+  yuv[2] = (float)( ( 0.5000 * r - 0.4542 * g - 0.0458 * b ) / 255.0 + 0.5000 );
+}
 
 __device__ __forceinline__ int cloud_of( const int64_t* __restrict__ off, int n, int64_t i ) {
   int lo = 0, hi = n - 1;
@@ -178,6 +185,11 @@ __global__ void k_column_compact( const Batch b, int64_t n ) {
   b.u_pos[U]  = p;
   b.u_z[U]    = p.z;
   b.u_col[U]  = cv;
+  {
+    float y[3];
+    rgb_to_yuv709( cv.x, cv.y, cv.z, y );
+    b.u_yuv[U] = make_float4( y[0], y[1], y[2], 0.f );
+  }
   b.u_orig[U] = (uint32_t)key;
 }
 // the CSR of the sorted slots becomes the CSR of the unique points; per-cloud unique counts
@@ -328,11 +340,6 @@ struct NNArgs {
   int              compute_c2p, compute_color, neighbors_proc;
 };
 
-__device__ __forceinline__ void rgb_to_yuv709( int r, int g, int b, float yuv[3] ) {  // PCCMetrics.cpp:50-55
-  yuv[0] = (float)( ( 0.2126 * r + 0.7152 * g + 0.0722 * b ) / 255.0 );
-  yuv[1] = (float)( ( -0.1146 * r - 0.3854 * g + 0.5000 * b ) / 255.0 + 0.5000 );
-  yuv[2] = (float)( ( 0.5000 * r - 0.4542 * g - 0.0458 * b ) / 255.0 + 0.5000 );
-}
 
 struct Contribution {
   double             c2p, col[3];
@@ -386,11 +393,15 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     out.c2p_max    = v;
   }
   if ( a.compute_color ) {  // :126-178
-    const uchar4 cA = b.u_col[uA];
-    float        yA[3], yB[3];
-    rgb_to_yuv709( cA.x, cA.y, cA.z, yA );
-    int rB, gB, bB;
-    if ( a.neighbors_proc == 1 || a.neighbors_proc == 2 ) {  // mean colour of the tie set, :137-156
+    const float4 fA = b.u_yuv[uA];  // the conversion of the point's own colour, done once when the cloud was built
+    float        yA[3] = {fA.x, fA.y, fA.z}, yB[3];
+    int          rB = 0, gB = 0, bB = 0;
+    bool         haveB = false;
+    if ( ( a.neighbors_proc == 1 || a.neighbors_proc == 2 ) && t.n == 1 ) {  // mean of one colour = that colour
+      const float4 fB = b.u_yuv[t.idx[0]];
+      yB[0] = fB.x, yB[1] = fB.y, yB[2] = fB.z;
+      haveB = true;
+    } else if ( a.neighbors_proc == 1 || a.neighbors_proc == 2 ) {  // mean colour of the tie set, :137-156
       unsigned int r = 0, g = 0, bl = 0;
       for ( int j = 0; j < t.n; j++ ) {
         const uchar4 q = b.u_col[t.idx[j]];
@@ -418,7 +429,7 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
       const uchar4 q = b.u_col[b.off[d.cloudB]];
       rB = q.x, gB = q.y, bB = q.z;
     }
-    rgb_to_yuv709( rB, gB, bB, yB );
+    if ( !haveB ) { rgb_to_yuv709( rB, gB, bB, yB ); }
 #pragma unroll
     for ( int k = 0; k < 3; k++ ) {
       const float df = __fsub_rn( yA[k], yB[k] );
@@ -682,6 +693,7 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 // host side
 // ------------------------------------------------------------------------------------------------
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
+  RbBuf u_yuv;
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
       nrm_raw, partial, far_list;
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
@@ -703,6 +715,7 @@ void rb_metrics_release( rb200_ctx* c ) {
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
   for ( auto* b : bufs ) { b->release(); }
+  s->u_yuv.release();
   for ( int k = 0; k < 2; k++ ) {
     s->rawSet[k].release();
     s->nrmSet[k].release();
@@ -871,6 +884,7 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   RB_CUDA( S->u_pos.ensure( (size_t)( N + 1 ) * 8 ) );
   RB_CUDA( S->u_z.ensure( (size_t)( N + 1 ) * 2 ) );
   RB_CUDA( S->u_col.ensure( (size_t)( N + 1 ) * 4 ) );
+  RB_CUDA( S->u_yuv.ensure( (size_t)( N + 1 ) * 16 ) );
   RB_CUDA( S->u_orig.ensure( (size_t)( N + 1 ) * 4 ) );
   // offsets + unique counts live in the small block: [64 B bbox][off: (nC+1) x 8][ucount: nC x 4]
   int64_t*  dOff    = (int64_t*)( S->small.as<char>() + 64 );
@@ -892,6 +906,7 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   B.u_pos  = S->u_pos.as<short4>();
   B.u_z    = S->u_z.as<int16_t>();
   B.u_col  = S->u_col.as<uchar4>();
+  B.u_yuv  = S->u_yuv.as<float4>();
   B.u_orig = S->u_orig.as<uint32_t>();
   B.ucount = dUcount;
   RB_CUDA( cudaMemsetAsync( B.tab, 0, (size_t)tabN * 4, c->stream ) );
