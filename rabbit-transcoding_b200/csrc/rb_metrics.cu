@@ -79,21 +79,56 @@ __device__ __forceinline__ int cloud_of( const int64_t* __restrict__ off, int n,
   return lo;
 }
 
-__global__ void k_unpack_cloud( const int16_t* __restrict__ pos, const uint8_t* __restrict__ col, int64_t n,
-                                short4* __restrict__ out_pos, uchar4* __restrict__ out_col ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  out_pos[i] = make_short4( pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2], 0 );
-  out_col[i] = col ? make_uchar4( col[i * 3], col[i * 3 + 1], col[i * 3 + 2], 0 ) : make_uchar4( 0, 0, 0, 0 );
-}
-__global__ void k_copy_resident( const short4* __restrict__ pos, const uchar4* __restrict__ rgb, int64_t n,
-                                 short4* __restrict__ out_pos, uchar4* __restrict__ out_col ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  short4 p   = pos[i];
-  p.w        = 0;
-  out_pos[i] = p;
-  out_col[i] = rgb[i];
+// import of all clouds of a batch in one launch (grid.y = cloud): host clouds arrive as packed int16 x 3 / uint8 x 3
+// rows, resident reconstructions as the context's short4 / uchar4 arrays
+struct ImportDesc {
+  const void* pos;  // int16 [n][3]  or  short4 [n] (resident)
+  const void* col;  // uint8 [n][3]  or  uchar4 [n] (resident); may be null for a host cloud
+  int64_t     n, dst;
+  int32_t     resident, pad;
+};
+__global__ void __launch_bounds__( 256 ) k_import_clouds( const ImportDesc* __restrict__ descs, short4* __restrict__ out_pos,
+                                                          uchar4* __restrict__ out_col ) {
+  const ImportDesc d = descs[blockIdx.y];
+  short4*          op = out_pos + d.dst;
+  uchar4*          oc = out_col + d.dst;
+  if ( d.resident ) {
+    const short4* pos = (const short4*)d.pos;
+    const uchar4* rgb = (const uchar4*)d.col;
+    for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x ) {
+      short4 p = pos[i];
+      p.w      = 0;
+      op[i]    = p;
+      oc[i]    = rgb[i];
+    }
+    return;
+  }
+  // four points per thread: 24 bytes of positions as three 8-byte loads, 12 bytes of colours as three 4-byte loads
+  const int64_t  groups = d.n / 4;
+  const uint2*   p8     = (const uint2*)d.pos;
+  const uint32_t* c4    = (const uint32_t*)d.col;
+  for ( int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x ) {
+    const uint2 a = p8[3 * g], b = p8[3 * g + 1], c = p8[3 * g + 2];  // x0 y0 | z0 x1 ; y1 z1 | x2 y2 ; z2 x3 | y3 z3
+    uint2*      o = reinterpret_cast<uint2*>( op + 4 * g );  // (the clouds start at arbitrary points: 8-byte stores)
+    o[0] = make_uint2( a.x, a.y & 0xFFFFu );
+    o[1] = make_uint2( ( a.y >> 16 ) | ( b.x << 16 ), b.x >> 16 );
+    o[2] = make_uint2( b.y, c.x & 0xFFFFu );
+    o[3] = make_uint2( ( c.x >> 16 ) | ( c.y << 16 ), c.y >> 16 );
+    uint4 q = make_uint4( 0, 0, 0, 0 );
+    if ( c4 ) {
+      const uint32_t u = c4[3 * g], v = c4[3 * g + 1], w = c4[3 * g + 2];  // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+      q = make_uint4( u & 0xFFFFFFu, ( u >> 24 ) | ( ( v & 0xFFFFu ) << 8 ), ( v >> 16 ) | ( ( w & 0xFFu ) << 16 ), w >> 8 );
+    }
+    uint32_t* oq = reinterpret_cast<uint32_t*>( oc + 4 * g );
+    oq[0] = q.x, oq[1] = q.y, oq[2] = q.z, oq[3] = q.w;
+  }
+  if ( blockIdx.x == 0 && threadIdx.x < d.n - 4 * groups ) {  // up to three trailing points
+    const int64_t  i   = 4 * groups + threadIdx.x;
+    const int16_t* pos = (const int16_t*)d.pos;
+    const uint8_t* col = (const uint8_t*)d.col;
+    op[i] = make_short4( pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2], 0 );
+    oc[i] = col ? make_uchar4( col[i * 3], col[i * 3 + 1], col[i * 3 + 2], 0 ) : make_uchar4( 0, 0, 0, 0 );
+  }
 }
 
 // bounding box of every coordinate of every cloud: bb = { minx, miny, minz, maxx, maxy, maxz }
@@ -693,7 +728,7 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 // host side
 // ------------------------------------------------------------------------------------------------
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
-  RbBuf u_yuv;
+  RbBuf u_yuv, descs;
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
       nrm_raw, partial, far_list;
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
@@ -716,6 +751,7 @@ void rb_metrics_release( rb200_ctx* c ) {
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
   for ( auto* b : bufs ) { b->release(); }
   s->u_yuv.release();
+  s->descs.release();
   for ( int k = 0; k < 2; k++ ) {
     s->rawSet[k].release();
     s->nrmSet[k].release();
@@ -833,8 +869,13 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   if ( S->prefetched ) { RB_CUDA( cudaStreamWaitEvent( c->stream, S->ev_copied[S->cur], 0 ) ); }
   int64_t rawOff = 0;
   S->raw_off.assign( nC, -1 );
+  std::vector<ImportDesc> hd( nC );
+  int64_t                 maxN = 0;
   for ( int i = 0; i < nC; i++ ) {
     const CloudIn& cl = clouds[i];
+    ImportDesc&    d  = hd[i];
+    d                 = ImportDesc{nullptr, nullptr, cl.n, hOff[i], 0, 0};
+    maxN              = std::max( maxN, cl.n );
     if ( cl.n == 0 ) { continue; }
     if ( cl.view ) {
       S->raw_off[i] = rawOff;
@@ -845,14 +886,25 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
         if ( cl.view->colors ) { RB_CUDA( cudaMemcpyAsync( rc, cl.view->colors, cl.n * 3, cudaMemcpyDefault, c->stream ) ); }
         c->stats.h2d_bytes += cl.n * ( cl.view->colors ? 9 : 6 );
       }
-      RB_LAUNCH( "met_unpack", k_unpack_cloud, rb_div_up( cl.n, TPB ), TPB, 0, (const int16_t*)rp,
-                 cl.view->colors ? (const uint8_t*)rc : nullptr, cl.n, inPos + hOff[i], inCol + hOff[i] );
+      d.pos = rp;
+      d.col = cl.view->colors ? rc : nullptr;
       rawOff += ( ( cl.n * 6 + 15 ) & ~15ll ) + ( ( cl.n * 3 + 15 ) & ~15ll );
     } else {
       const int64_t b = c->h_frame_off[cl.resident];
-      RB_LAUNCH( "met_copy_resident", k_copy_resident, rb_div_up( cl.n, TPB ), TPB, 0, c->d_pos.as<short4>() + b,
-                 c->d_rgb.as<uchar4>() + b, cl.n, inPos + hOff[i], inCol + hOff[i] );
+      d.pos      = c->d_pos.as<short4>() + b;
+      d.col      = c->d_rgb.as<uchar4>() + b;
+      d.resident = 1;
     }
+  }
+  if ( maxN > 0 ) {
+    ImportDesc* hp = (ImportDesc*)rb_pinned( c, nC * sizeof( ImportDesc ) + 64 );
+    if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the staging block may still be in flight
+    memcpy( hp, hd.data(), nC * sizeof( ImportDesc ) );
+    RB_CUDA( S->descs.ensure( nC * sizeof( ImportDesc ) + 64 ) );
+    RB_CUDA( cudaMemcpyAsync( S->descs.p, hp, nC * sizeof( ImportDesc ), cudaMemcpyHostToDevice, c->stream ) );
+    const dim3 grid( (unsigned)std::min<int64_t>( rb_div_up( maxN, 4 * 256 ), 2048 ), (unsigned)nC );
+    RB_LAUNCH( "met_import", k_import_clouds, grid, 256, 0, S->descs.as<ImportDesc>(), inPos, inCol );
   }
   // ---- bounding box -> table geometry (one small read-back) ----
   int* dSmall = S->small.as<int>();
