@@ -678,38 +678,50 @@ __global__ void __launch_bounds__( TPB ) k_reduce_partials( const NNArgs a, cons
 
 // copyNormals (PCCPointSet.cpp:2282-2320): exact position lookup of every point of the normal cloud in the source
 // cloud's CSR; the LAST normal-cloud index at a position wins (map[x][y][z] = i)
-__global__ void k_normal_lookup( const Batch b, int cloudS, const int16_t* __restrict__ npos, int64_t n,
-                                 uint32_t* __restrict__ last_idx, uint32_t* __restrict__ err ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  const int x = npos[3 * i], y = npos[3 * i + 1], z = npos[3 * i + 2];
-  if ( (unsigned)( x - b.ox ) < (unsigned)b.dim && (unsigned)( y - b.oy ) < (unsigned)b.dim ) {
-    const int64_t  col = column_of( b, cloudS, x, y );
-    const uint32_t beg = b.tab[col - 1], end = b.tab[col];
-    for ( uint32_t k = beg; k < end; k++ ) {
-      if ( (int)b.u_z[k] == z ) {
-        atomicMax( &last_idx[k], (uint32_t)i + 1u );
-        return;
+struct NormalDesc {  // one source cloud with normals: its cloud index in the batch, its normals, its point count
+  const float* nrm_in;
+  int64_t      n;
+  int32_t      cloudS, pad;
+};
+// all source clouds in one launch (grid.y = cloud); the normal cloud's positions are the imported positions of the
+// source cloud itself (in_pos, file order)
+__global__ void __launch_bounds__( 256 ) k_normal_lookup( const Batch b, const NormalDesc* __restrict__ descs,
+                                                          uint32_t* __restrict__ last_idx ) {
+  const NormalDesc d   = descs[blockIdx.y];
+  const short4*    pos = b.in_pos + b.off[d.cloudS];
+  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x ) {
+    const short4 p = pos[i];
+    const int    x = p.x, y = p.y, z = p.z;
+    if ( (unsigned)( x - b.ox ) < (unsigned)b.dim && (unsigned)( y - b.oy ) < (unsigned)b.dim ) {
+      const int64_t  col = column_of( b, d.cloudS, x, y );
+      const uint32_t beg = b.tab[col - 1], end = b.tab[col];
+      for ( uint32_t k = beg; k < end; k++ ) {
+        if ( (int)b.u_z[k] == z ) {
+          atomicMax( &last_idx[k], (uint32_t)i + 1u );
+          break;
+        }
       }
     }
+    // a normal-cloud point that is not in the source is harmless to the reference unless a source point stays uncovered
   }
-  // a normal-cloud point that is not in the source is harmless to the reference unless a source point stays uncovered
 }
-__global__ void k_normal_gather( const Batch b, int cloudS, const float* __restrict__ nrm_in, int64_t nNormal,
-                                 const uint32_t* __restrict__ last_idx, double* __restrict__ nrm, uint32_t* __restrict__ err ) {
-  const int64_t iu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nU = b.ucount[cloudS];
-  if ( iu == 0 && nU != nNormal ) { atomicOr( err, 1u ); }  // "must have the same number of points", :2287-2293
-  if ( iu >= nU ) { return; }
-  const int64_t  U  = b.off[cloudS] + iu;
-  const uint32_t li = last_idx[U];
-  if ( li == 0 ) {
-    atomicOr( err, 2u );  // "point i of the current points cloud is not present in the normal point cloud", :2311-2318
-    return;
+__global__ void __launch_bounds__( 256 ) k_normal_gather( const Batch b, const NormalDesc* __restrict__ descs,
+                                                          const uint32_t* __restrict__ last_idx, double* __restrict__ nrm,
+                                                          uint32_t* __restrict__ err ) {
+  const NormalDesc d  = descs[blockIdx.y];
+  const int64_t    nU = b.ucount[d.cloudS];
+  if ( blockIdx.x == 0 && threadIdx.x == 0 && nU != d.n ) { atomicOr( err, 1u ); }  // "must have the same number of points", :2287-2293
+  for ( int64_t iu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; iu < nU; iu += (int64_t)gridDim.x * blockDim.x ) {
+    const int64_t  U  = b.off[d.cloudS] + iu;
+    const uint32_t li = last_idx[U];
+    if ( li == 0 ) {
+      atomicOr( err, 2u );  // "point i of the current points cloud is not present in the normal point cloud", :2311-2318
+      continue;
+    }
+    nrm[3 * U + 0] = (double)d.nrm_in[3 * (int64_t)( li - 1 ) + 0];
+    nrm[3 * U + 1] = (double)d.nrm_in[3 * (int64_t)( li - 1 ) + 1];
+    nrm[3 * U + 2] = (double)d.nrm_in[3 * (int64_t)( li - 1 ) + 2];
   }
-  nrm[3 * U + 0] = (double)nrm_in[3 * (int64_t)( li - 1 ) + 0];
-  nrm[3 * U + 1] = (double)nrm_in[3 * (int64_t)( li - 1 ) + 1];
-  nrm[3 * U + 2] = (double)nrm_in[3 * (int64_t)( li - 1 ) + 2];
 }
 
 __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ pos, uint8_t* __restrict__ col ) {
@@ -728,7 +740,7 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 // host side
 // ------------------------------------------------------------------------------------------------
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
-  RbBuf u_yuv, descs;
+  RbBuf u_yuv, descs, ndescs;
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
       nrm_raw, partial, far_list;
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
@@ -752,6 +764,7 @@ void rb_metrics_release( rb200_ctx* c ) {
   for ( auto* b : bufs ) { b->release(); }
   s->u_yuv.release();
   s->descs.release();
+  s->ndescs.release();
   for ( int k = 0; k < 2; k++ ) {
     s->rawSet[k].release();
     s->nrmSet[k].release();
@@ -1128,16 +1141,25 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
     RB_CUDA( cudaMemsetAsync( S->last_idx.p, 0, (size_t)N * 4, c->stream ) );
     a.nrm     = S->nrm.as<double>();
     a.nrm_cnt = S->nrm_cnt.as<uint32_t>();
+    std::vector<NormalDesc> hn;
+    int64_t                 maxN = 0;
     for ( int i = 0; i < nPairs; i++ ) {
       if ( !sources[i].normals ) { continue; }
-      // the normal cloud of pair i is the source view itself (positions + normals in file order): its positions are
-      // still in the import buffer of build_batch, its normals came in on the copy stream
-      const int64_t  n  = sources[i].count;
-      const int16_t* rp = (const int16_t*)( S->rawSet[S->cur].as<char>() + S->raw_off[2 * i] );
-      const float*   rn = (const float*)( S->nrmSet[S->cur].as<char>() + nrmOff[i] );
-      RB_LAUNCH( "met_normal_lookup", k_normal_lookup, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rp, n, S->last_idx.as<uint32_t>(), dErr );
-      RB_LAUNCH( "met_normal_gather", k_normal_gather, rb_div_up( n, TPB ), TPB, 0, B, 2 * i, rn, n,
-                 S->last_idx.as<uint32_t>(), a.nrm, dErr );
+      // the normal cloud of pair i is the source view itself (positions + normals in file order): its positions were
+      // imported by build_batch, its normals came in on the copy stream
+      hn.push_back( NormalDesc{(const float*)( S->nrmSet[S->cur].as<char>() + nrmOff[i] ), sources[i].count, 2 * i, 0} );
+      maxN = std::max<int64_t>( maxN, sources[i].count );
+    }
+    if ( !hn.empty() ) {
+      NormalDesc* hp = (NormalDesc*)rb_pinned( c, hn.size() * sizeof( NormalDesc ) + 64 );
+      if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+      RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the staging block may still be in flight
+      memcpy( hp, hn.data(), hn.size() * sizeof( NormalDesc ) );
+      RB_CUDA( S->ndescs.ensure( hn.size() * sizeof( NormalDesc ) + 64 ) );
+      RB_CUDA( cudaMemcpyAsync( S->ndescs.p, hp, hn.size() * sizeof( NormalDesc ), cudaMemcpyHostToDevice, c->stream ) );
+      const dim3 grid( (unsigned)std::min<int64_t>( rb_div_up( maxN, 256 ), 1024 ), (unsigned)hn.size() );
+      RB_LAUNCH( "met_normal_lookup", k_normal_lookup, grid, 256, 0, B, S->ndescs.as<NormalDesc>(), S->last_idx.as<uint32_t>() );
+      RB_LAUNCH( "met_normal_gather", k_normal_gather, grid, 256, 0, B, S->ndescs.as<NormalDesc>(), S->last_idx.as<uint32_t>(), a.nrm, dErr );
     }
     a.dirs  = dDirs + dMetric.size();
     a.nDirs = (int)dScale.size();
