@@ -38,6 +38,28 @@ def test_struct_sizes_match_header(rb):
     assert C.sizeof(rb.abi.CloudView) == 4 * 8
 
 
+def test_header_is_plain_c_and_struct_sizes_agree(rb, tmp_path):
+    """include/rabbit_b200.h compiles as C99 (the drop-in boundary is a C ABI: plain pointers and sizes) and the
+    ctypes mirror has the sizes the C compiler sees"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    names = ["rb200_patch", "rb200_params", "rb200_frames", "rb200_frames_yuv420", "rb200_atlas", "rb200_cloud_host",
+             "rb200_frame_counts", "rb200_metrics_params", "rb200_cloud_view", "rb200_metrics_result"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "rabbit_b200.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    mirror = [rb.abi.Patch, rb.abi.Params, rb.abi.Frames, rb.abi.FramesYuv420, rb.abi.Atlas, rb.abi.CloudHost,
+              rb.abi.FrameCounts, rb.abi.MetricsParams, rb.abi.CloudView, rb.abi.MetricsResult]
+    for n, sz, m in zip(names, sizes, mirror):
+        assert C.sizeof(m) == sz, f"{n}: header {sz} bytes, ctypes mirror {C.sizeof(m)}"
+
+
 def test_no_cpu_fallback_without_gpu(rb, lib):
     import torch
     if torch.cuda.is_available():
