@@ -93,10 +93,10 @@ template <typename T>
 __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
                                                                int nbyte, int shift, int filter, size_t srcFrameStride,
                                                                size_t dstFrameStride ) {
-  __shared__ float lut[1024];
+  constexpr int    levels = sizeof( T ) == 1 ? 256 : 1024;  // samples below go through the table, others are computed
+  __shared__ float lut[levels];
   __shared__ float in[IH][IW];
   __shared__ float tmp[TH][IW + 1];
-  const int        levels = 1024;
   const int        cw = W / 2, ch = H / 2;
   const int        frame = blockIdx.z >> 1, plane = 1 + ( blockIdx.z & 1 );
   // frame layout of the source: Y [H][W], U [H/2][W/2], V [H/2][W/2]
@@ -134,12 +134,20 @@ __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restric
       uint16_t o[8];
 #pragma unroll
       for ( int k = 0; k < 8; k++ ) {
-        const int    x = x0 + k, odd = x & 1, lj = ( x >> 1 ) + HALO + odd;
-        const float* taps = odd ? F.h1 : F.h0;
-        const int    n = odd ? F.nh1 : F.nh0, position = ( n + 1 ) >> 1;
-        float        value = 0.f;
-        for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], tmp[y][lj + t - position] ) ); }
-        o[k] = float_to_u16( __fmul_rn( __fadd_rn( value, 0.f ), scale ), true );
+        const int x = x0 + k, odd = x & 1, lj = ( x >> 1 ) + HALO + odd;
+        float     r;
+        if ( !odd && F.nh0 == 2 && F.h0[0] == 0.f && F.h0[1] == 256.f ) {
+          // horizontal0 = {0, 256} >> 8 in every filter of the table: ( 0 * a + 256 * b ) / 256 is b exactly (the sign
+          // of a zero is lost in the reference too: 0 + -0 = +0, and the final scaling maps both zeros to 32768)
+          r = __fadd_rn( tmp[y][lj], 0.f );
+        } else {
+          const float* taps = odd ? F.h1 : F.h0;
+          const int    n = odd ? F.nh1 : F.nh0, position = ( n + 1 ) >> 1;
+          float        value = 0.f;
+          for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], tmp[y][lj + t - position] ) ); }
+          r = __fmul_rn( __fadd_rn( value, 0.f ), scale );
+        }
+        o[k] = float_to_u16( r, true );
       }
       *reinterpret_cast<uint4*>( cout + (size_t)( oy + y ) * W + ox + x0 ) = *reinterpret_cast<const uint4*>( o );
     }
