@@ -89,7 +89,9 @@ __global__ void __launch_bounds__( 256 ) k_luma_to_16( const T* __restrict__ src
 constexpr int TW = 64, TH = 32, HALO = 6;
 constexpr int IW = TW / 2 + 2 * HALO, IH = TH / 2 + 2 * HALO;  // 44 x 28 staged chroma samples
 
-template <typename T>
+// NV / NH: taps of the two vertical filters / of horizontal1 (4 .. 12; horizontal0 is {0, 256} in every entry of the
+// table): the tap loops unroll and the coefficients sit in registers
+template <typename T, int NV, int NH>
 __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
                                                                int nbyte, int shift, int filter, size_t srcFrameStride,
                                                                size_t dstFrameStride ) {
@@ -103,10 +105,15 @@ __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restric
   const T*  cin  = src + (size_t)frame * srcFrameStride + (size_t)W * H + (size_t)( plane - 1 ) * cw * ch;
   uint16_t* cout = dst + (size_t)frame * dstFrameStride + (size_t)plane * W * H;
   for ( int s = threadIdx.x; s < levels; s += blockDim.x ) { lut[s] = sample_to_float( image_set( s, shift ), true, nbyte ); }
+  const UpFilter& F = c_up[filter];
+  float           v0[NV], v1[NV], h1[NH];
+#pragma unroll
+  for ( int t = 0; t < NV; t++ ) { v0[t] = F.v0[t], v1[t] = F.v1[t]; }
+#pragma unroll
+  for ( int t = 0; t < NH; t++ ) { h1[t] = F.h1[t]; }
   __syncthreads();
-  const UpFilter& F  = c_up[filter];
-  const int       ox = blockIdx.x * TW, oy = blockIdx.y * TH;  // output tile origin
-  const int       jx = ox / 2 - HALO, iy = oy / 2 - HALO;      // staged chroma origin
+  const int ox = blockIdx.x * TW, oy = blockIdx.y * TH;  // output tile origin
+  const int jx = ox / 2 - HALO, iy = oy / 2 - HALO;      // staged chroma origin
   for ( int k = threadIdx.x; k < IW * IH; k += blockDim.x ) {
     const int r = k / IW, c = k - r * IW;
     const int gy = min( max( iy + r, 0 ), ch - 1 ), gx = min( max( jx + c, 0 ), cw - 1 );  // clamp( ., 0, size - 1 ) of every tap
@@ -115,39 +122,32 @@ __global__ void __launch_bounds__( 256 ) k_chroma_420_to_444( const T* __restric
   }
   __syncthreads();
   // vertical: row 2i from vertical0 at i0 = i, row 2i+1 from vertical1 at i0 = i + 1 (:678-686)
-  const float scale = 1.0f / 256.0f;
+  const float   scale = 1.0f / 256.0f;
+  constexpr int pv = ( NV + 1 ) >> 1, ph = ( NH + 1 ) >> 1;  // `position` of the reference
   for ( int k = threadIdx.x; k < TH * IW; k += blockDim.x ) {
-    const int    y = k / IW, c = k - y * IW;
-    const int    odd = y & 1, li = ( y >> 1 ) + HALO + odd;
-    const float* taps = odd ? F.v1 : F.v0;
-    const int    n = odd ? F.nv1 : F.nv0, position = ( n + 1 ) >> 1;
-    float        value = 0.f;
-    for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], in[li + t - position][c] ) ); }
+    const int y = k / IW, c = k - y * IW;
+    const int odd = y & 1, li = ( y >> 1 ) + HALO + odd - pv;
+    float     value = 0.f;
+#pragma unroll
+    for ( int t = 0; t < NV; t++ ) { value = __fadd_rn( value, __fmul_rn( odd ? v1[t] : v0[t], in[li + t][c] ) ); }
     tmp[y][c] = __fmul_rn( __fadd_rn( value, 0.f ), scale );
   }
   __syncthreads();
   // horizontal: column 2j from horizontal0 at j0 = j, column 2j+1 from horizontal1 at j0 = j + 1 (:687-694);
-  // every thread produces 8 consecutive outputs of one row
+  // every thread produces 8 consecutive outputs of one row.  horizontal0 = {0, 256} >> 8 in every filter of the table:
+  // ( 0 * a + 256 * b ) / 256 is b exactly (the sign of a zero is lost in the reference too: 0 + -0 = +0)
   {
     const int y = threadIdx.x >> 3, x0 = ( threadIdx.x & 7 ) * 8;
     if ( oy + y < H && ox + x0 < W ) {
       uint16_t o[8];
 #pragma unroll
-      for ( int k = 0; k < 8; k++ ) {
-        const int x = x0 + k, odd = x & 1, lj = ( x >> 1 ) + HALO + odd;
-        float     r;
-        if ( !odd && F.nh0 == 2 && F.h0[0] == 0.f && F.h0[1] == 256.f ) {
-          // horizontal0 = {0, 256} >> 8 in every filter of the table: ( 0 * a + 256 * b ) / 256 is b exactly (the sign
-          // of a zero is lost in the reference too: 0 + -0 = +0, and the final scaling maps both zeros to 32768)
-          r = __fadd_rn( tmp[y][lj], 0.f );
-        } else {
-          const float* taps = odd ? F.h1 : F.h0;
-          const int    n = odd ? F.nh1 : F.nh0, position = ( n + 1 ) >> 1;
-          float        value = 0.f;
-          for ( int t = 0; t < n; t++ ) { value = __fadd_rn( value, __fmul_rn( taps[t], tmp[y][lj + t - position] ) ); }
-          r = __fmul_rn( __fadd_rn( value, 0.f ), scale );
-        }
-        o[k] = float_to_u16( r, true );
+      for ( int k = 0; k < 8; k += 2 ) {
+        const int j = ( ( x0 + k ) >> 1 ) + HALO;
+        o[k]        = float_to_u16( __fadd_rn( tmp[y][j], 0.f ), true );
+        float value = 0.f;
+#pragma unroll
+        for ( int t = 0; t < NH; t++ ) { value = __fadd_rn( value, __fmul_rn( h1[t], tmp[y][j + 1 + t - ph] ) ); }
+        o[k + 1] = float_to_u16( __fmul_rn( __fadd_rn( value, 0.f ), scale ), true );
       }
       *reinterpret_cast<uint4*>( cout + (size_t)( oy + y ) * W + ox + x0 ) = *reinterpret_cast<const uint4*>( o );
     }
@@ -200,12 +200,27 @@ int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr
     const int    frames = c->F * c->M;
     const size_t sfs = plane + plane / 2, dfs = 3 * plane;
     const dim3   gl( 64, frames ), gc( rb_div_up( c->W, TW ), rb_div_up( c->H, TH ), frames * 2 );
+    // tap counts of g_filter420to444[filter]: vertical0/1, horizontal1 (the table above)
+    static const int NVt[8] = {4, 6, 4, 6, 8, 6, 10, 12}, NHt[8] = {4, 4, 4, 6, 8, 6, 10, 12};
+    const int        nv = NVt[filter], nh = NHt[filter];
+#define RB_CHROMA_CASE( TYPE, NV, NH )                                                                                     \
+  if ( nv == NV && nh == NH ) {                                                                                            \
+    RB_LAUNCH( "attribute_420_to_444", ( k_chroma_420_to_444<TYPE, NV, NH> ), gc, 256, 0, c->d_raw_attr.as<TYPE>(),        \
+               c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, filter, sfs, dfs );                           \
+  }
+#define RB_CHROMA( TYPE )          \
+  RB_CHROMA_CASE( TYPE, 4, 4 )     \
+  RB_CHROMA_CASE( TYPE, 6, 4 )     \
+  RB_CHROMA_CASE( TYPE, 6, 6 )     \
+  RB_CHROMA_CASE( TYPE, 8, 8 )     \
+  RB_CHROMA_CASE( TYPE, 10, 10 )   \
+  RB_CHROMA_CASE( TYPE, 12, 12 )
     if ( attr_bytes == 1 ) {
       RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint8_t>, gl, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, sfs, dfs );
-      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint8_t>, gc, 256, 0, c->d_raw_attr.as<uint8_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, filter, sfs, dfs );
+      RB_CHROMA( uint8_t );
     } else {
       RB_LAUNCH( "attribute_luma_to_16", k_luma_to_16<uint16_t>, gl, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, sfs, dfs );
-      RB_LAUNCH( "attribute_420_to_444", k_chroma_420_to_444<uint16_t>, gc, 256, 0, c->d_raw_attr.as<uint16_t>(), c->d_attribute.as<uint16_t>(), c->W, c->H, nbyte, attr_shift, filter, sfs, dfs );
+      RB_CHROMA( uint16_t );
     }
   }
   return RB200_OK;
