@@ -10,11 +10,17 @@ boundary types -> attribute fetch), grid geometry smoothing, attribute re-transf
 colour smoothing, YUV16 -> RGB8, and (when --metrics) the D1/D2/colour metrics against the source clouds.
 
 `value`  : whole-job Mpts/s with the decoded frames already resident in HBM (rb200_decode_gof only).
-`e2e`    : the same metric through the reference-facing call sequence with HOST buffers: pinned H2D upload of
-           the decoded planes + patch tables, decode, D2H of positions + RGB8 of every frame, inside the timer.
+`e2e`    : the same metric through the reference-facing call sequence with HOST buffers, inside the timer every step:
+           pinned H2D of the decoder-native planes (8-bit 4:2:0 attribute frames + 8-bit geometry luma + occupancy) and
+           the patch tables, the decoder's 4:2:0 -> 4:4:4 16-bit conversion on the GPU, decode, D2H of positions + RGB8
+           of every frame; two GOFs in flight (two contexts / streams / host threads).  `e2e.from_444_16bit_frames` is
+           the same from the 16-bit 4:4:4 frames of the reference's PCCVideo boundary, `one_gof_in_flight` unpipelined.
 `roofline`: the dominant kernel of the step (per-kernel CUDA events on the launching stream), algorithmic
-           bytes per launch / its average duration, against MEASURED_PEAKS.json.
+           bytes per launch / its average duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes
+           of that kernel from the committed ncu capture (profiles/ncu_traffic.json).
 `cpu_baseline`: the unmodified reference (oracle/_ref/librabbit_ref.so) on this box's host cores, same GOF.
+`metrics` : D1 + D2 + colour of every frame against its source cloud (frames/s), sources from pinned host memory.
+`full_decoder`: the decoder's whole Rec-1 sequence including transferColors16bitBP.
 
 Nothing here reads /root/reference.
 """
