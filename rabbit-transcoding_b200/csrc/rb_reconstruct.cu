@@ -38,6 +38,7 @@ struct ReprojArgs {
   int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
   int             t1_bits;  // multi-stream attribute: 0 = map 1 is absolute, 8 / 16 = map 1 is a delta on map 0
   int32_t*        wi_count;
+  uint32_t*       wi_cnt4;  // [nWI][32] per-lane packed pixel counts of the counting pass, reused by the emitting pass
   int32_t*        wi_eom_count;
   const int64_t*  wi_base;
   const int64_t*  wi_eom_base;
@@ -352,8 +353,11 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
   // ---- pass A: per-pixel point counts (4 bits per pixel: regular; EOM extras separately) ----
   const int nsgnA = p.mode == 0 ? 1 : -1, nloA = p.mode == 0 ? -( 1 << 30 ) : 0;  // generateNormalCoordinate, see pass B
   uint32_t  cnt4 = 0, eom4 = 0;
+  const bool reuse = EMIT && !EOM && a.wi_cnt4 != nullptr;  // the counting pass left this lane's counts behind
+  if ( reuse ) { cnt4 = a.wi_cnt4[wi * 32 + lane]; }
 #pragma unroll
   for ( int j = 0; j < 8; j++ ) {
+    if ( reuse ) { break; }
     int tx, ty;
     TILE_XY( tm, ubase + j, v1, tx, ty );
     const uint32_t occ = ( S.rows[ty + 2] >> ( tx + 2 ) ) & 1u;
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
       a.wi_count[wi] = incl;
       if ( EOM ) { a.wi_eom_count[wi] = inclE; }
     }
+    if ( !EOM && a.wi_cnt4 ) { a.wi_cnt4[wi * 32 + lane] = cnt4; }
     return;
   }
 
@@ -963,6 +968,11 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.t1_bits      = ( P.multiple_streams && P.relative_t1 ) ? ( P.attribute_rgb444 ? 8 : 16 ) : 0;
   a.bitdepth3d   = P.geometry_bitdepth_3d;
   a.wi_count     = c->d_wi_count.as<int32_t>();
+  a.wi_cnt4      = nullptr;
+  if ( !eom && nWI > 0 ) {  // 128 bytes per patch block: the emitting pass skips its own counting of the pixels
+    RB_CUDA( c->d_wi_eom_slot.ensure( (size_t)nWI * 128 ) );
+    a.wi_cnt4 = c->d_wi_eom_slot.as<uint32_t>();
+  }
   a.frame_wi_off = c->d_frame_wi_off.as<int32_t>();
   a.frame_off    = c->d_frame_off.as<int64_t>();
   a.finfo        = c->d_frame_info.as<RbFrameInfo>();
