@@ -237,10 +237,14 @@ struct TileSmem {
   uint16_t desc[512];     // emission-ordered point descriptors: u1 | v1 << 4 | layer << 8 | boundary << 15
 };
 
-template <bool EMIT, bool EOM>
+// STD: the CTC configuration (two maps, absolute D1, attributes, boundary classification, no delta-coded T1) with
+// its switches resolved at compile time
+template <bool EMIT, bool EOM, bool STD>
 __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs a ) {
   __shared__ __align__( 16 ) TileSmem sm[WARPS];
   const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int     kM   = STD ? 2 : a.M;
+  const bool    kAbs = STD ? true : a.absolute_d1 != 0, kAttr = STD ? true : a.attr_count > 0, kCls = STD ? true : a.classify != 0;
   const int64_t wi   = (int64_t)blockIdx.x * WARPS + wq;
   if ( wi >= a.nWI ) { return; }
   TileSmem&     S  = sm[wq];
@@ -290,33 +294,33 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     uint4        vg[2], va[2][3];
 #pragma unroll
     for ( int m = 0; m < 2; m++ ) {
-      if ( m < a.M ) { vg[m] = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * a.M + m ) * plane + o ); }
+      if ( m < kM ) { vg[m] = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * kM + m ) * plane + o ); }
     }
-    if ( EMIT && a.attr_count > 0 ) {
+    if ( EMIT && kAttr ) {
 #pragma unroll
       for ( int m = 0; m < 2; m++ ) {
 #pragma unroll
         for ( int ch = 0; ch < 3; ch++ ) {
-          if ( m < a.M ) { va[m][ch] = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * a.M + m ) * 3 + ch ) * plane + o ); }
+          if ( m < kM ) { va[m][ch] = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * kM + m ) * 3 + ch ) * plane + o ); }
         }
       }
     }
 #pragma unroll
     for ( int m = 0; m < 2; m++ ) {
-      if ( m < a.M ) { *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = vg[m]; }
+      if ( m < kM ) { *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = vg[m]; }
     }
-    if ( EMIT && a.attr_count > 0 ) {
+    if ( EMIT && kAttr ) {
 #pragma unroll
       for ( int m = 0; m < 2; m++ ) {
 #pragma unroll
         for ( int ch = 0; ch < 3; ch++ ) {
-          if ( m < a.M ) { *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = va[m][ch]; }
+          if ( m < kM ) { *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = va[m][ch]; }
         }
       }
     }
   }
   __syncwarp();
-  if ( EMIT && a.t1_bits && a.attr_count > 0 && a.M > 1 ) {
+  if ( EMIT && !STD && a.t1_bits && kAttr && kM > 1 ) {
     // multiple streams with a delta-coded second map (colorPointCloud, PCCCodec.cpp:1387-1416): the tile of map 1
     // is reconstructed in shared memory once, T1 = clip( T0 + clamp( T1 - offset, -offset, offset - 1 ), 0, max )
     const int offset = 1 << ( a.t1_bits - 1 ), maxv = ( 1 << a.t1_bits ) - 1;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     __syncwarp();
   }
 
-  if ( EMIT && a.classify ) {
+  if ( EMIT && kCls ) {
     // identifyBoundaryPoints (:266-325) for the whole tile at once, 16 rows in 16 lanes: a pixel is type 1 when it is
     // on / next to the image border or any pixel of its 5x5 neighbourhood is unoccupied (the 3x3 test of :274-305 is
     // implied: a full 5x5 contains a full 3x3).  Pixels outside the image read as occupied (staging above).
@@ -363,14 +367,14 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     const uint32_t occ = ( S.rows[ty + 2] >> ( tx + 2 ) ) & 1u;
     if ( !occ ) { continue; }
     const int d0 = S.g[0][ty * 16 + tx];
-    const int g1 = ( a.M > 1 ) ? S.g[1][ty * 16 + tx] : 0;
+    const int g1 = ( kM > 1 ) ? S.g[1][ty * 16 + tx] : 0;
     int       c  = 1, e = 0;
     if ( EOM ) {
       // :686-714 eomCode from the D1-D0 difference and the occupancy symbol
       const int sym = a.occ_video[( (size_t)f * a.oH + ( Y0 + ty ) / a.prec ) * a.oW + ( X0 + tx ) / a.prec];
       uint32_t  code;
-      if ( a.M > 1 ) {
-        const int diff = a.absolute_d1 ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
+      if ( kM > 1 ) {
+        const int diff = kAbs ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
         if ( diff == 1 ) {
           code = 1;
         } else if ( diff > 1 ) {
@@ -386,17 +390,17 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
         if ( !a.remove_dup ) { c = 2; }
       } else {
         const int nb = __popc( code & 0x3FFu );
-        if ( a.M > 1 && nb > 0 ) {
+        if ( kM > 1 && nb > 0 ) {
           c = 2;
           e = nb - 1;
         } else {
           e = nb;
         }
       }
-    } else if ( a.M > 1 ) {
+    } else if ( kM > 1 ) {
       // :497-512 far layer; :794-795 duplicate removal compares the int16 points
       const int16_t n0 = (int16_t)max( p.d1 + nsgnA * d0, nloA );
-      const int16_t n1 = (int16_t)( a.absolute_d1 ? max( p.d1 + nsgnA * g1, nloA ) : (int)n0 + nsgnA * g1 );
+      const int16_t n1 = (int16_t)( kAbs ? max( p.d1 + nsgnA * g1, nloA ) : (int)n0 + nsgnA * g1 );
       c                = ( a.remove_dup && n1 == n0 ) ? 1 : 2;
     }
     cnt4 |= (uint32_t)c << ( 4 * j );
@@ -469,10 +473,10 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
         // PCCPatch::generatePoint (PCCPatch.h:201-207), branch-free: the axis permutation is three 0/1 weights per
         // output coordinate set up once per block (later writes win: tangent, bitangent, normal); the normal
         // coordinate of both layers is formed and selected
-        const int g1 = a.M > 1 ? (int)S.g[1][ty * 16 + tx] : 0;
+        const int g1 = kM > 1 ? (int)S.g[1][ty * 16 + tx] : 0;
         const int n0 = (int16_t)max( p.d1 + nsgn * d0, nlo );   // generateNormalCoordinate( D0 )
         int       n1 = max( p.d1 + nsgn * g1, nlo );            // generatePoint( u, v, frame1 ), :503
-        if ( !a.absolute_d1 ) { n1 = n0 + nsgn * g1; }          // :505-509
+        if ( !kAbs ) { n1 = n0 + nsgn * g1; }          // :505-509
         const int nn = layer ? n1 : n0;
         const int tt = u * p.lodx + p.u1, bb = v * p.lody + p.v1;
         int16_t   Q[3];
@@ -481,11 +485,11 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
           Q[cdx] = (int16_t)( ( ( axw >> cdx ) & 1 ) * tt + ( ( axw >> ( 4 + cdx ) ) & 1 ) * bb + ( ( axw >> ( 8 + cdx ) ) & 1 ) * nn );
         }
         if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
-        if ( a.classify ) { btype = ( S.bnd[ty] >> tx ) & 1; }  // identifyBoundaryPoints, per-tile masks above
+        if ( kCls ) { btype = ( S.bnd[ty] >> tx ) & 1; }  // identifyBoundaryPoints, per-tile masks above
         const int64_t o = wbase + k;
         a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
         ushort4 cv      = make_ushort4( 0, 0, 0, (unsigned short)layer );
-        if ( a.attr_count > 0 ) {
+        if ( kAttr ) {
           cv = make_ushort4( S.a[layer][0][ty * 16 + tx], S.a[layer][1][ty * 16 + tx], S.a[layer][2][ty * 16 + tx],
                              (unsigned short)layer );
         }
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     const int x = X0 + tx, y = Y0 + ty;
     const int u = ub * 16 + u1, v = vb * 16 + v1;
     const int d0 = S.g[0][ty * 16 + tx];
-    const int g1 = ( a.M > 1 ) ? S.g[1][ty * 16 + tx] : 0;
+    const int g1 = ( kM > 1 ) ? S.g[1][ty * 16 + tx] : 0;
     // PCCPatch::generatePoint (PCCPatch.h:201-207)
     int16_t P0[3] = {0, 0, 0};
     set_axis( P0, p.normal_axis, normal_coord( p, d0 ) );
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     set_axis( P0, p.bitangent_axis, v * p.lody + p.v1 );
     // boundary classification (identifyBoundaryPoints, :266-325) on the staged row masks
     int btype = 0;
-    if ( a.classify ) {
+    if ( kCls ) {
       const int      r  = ty + 2, kx = tx + 2;
       const uint32_t m3 = 7u << ( kx - 1 ), m5 = 31u << ( kx - 2 );
       if ( x == 0 || y == 0 || x == a.W - 1 || y == a.H - 1 ) {
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
       const int64_t o = base + k;
       a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
       ushort4 cv      = make_ushort4( 0, 0, 0, 0 );
-      if ( a.attr_count > 0 ) { cv = make_ushort4( S.a[0][0][ty * 16 + tx], S.a[0][1][ty * 16 + tx], S.a[0][2][ty * 16 + tx], 0 ); }
+      if ( kAttr ) { cv = make_ushort4( S.a[0][0][ty * 16 + tx], S.a[0][1][ty * 16 + tx], S.a[0][2][ty * 16 + tx], 0 ); }
       a.col[o]  = cv;
       a.pix[o]  = pixv;
       a.part[o] = (uint32_t)p.frame_patch;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     if ( !EOM ) {
       if ( c > 1 ) {
         int16_t P1[3] = {P0[0], P0[1], P0[2]};
-        if ( a.absolute_d1 ) {
+        if ( kAbs ) {
           set_axis( P1, p.normal_axis, normal_coord( p, g1 ) );  // generatePoint( u, v, frame1 ), :503
         } else {
           const int n0 = get_axis( P0, p.normal_axis );
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
         const int64_t o = base + k;
         a.pos[o]        = make_short4( P1[0], P1[1], P1[2], (short)btype );
         ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
-        if ( a.attr_count > 0 ) {
+        if ( kAttr ) {
           cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
         }
         a.col[o]  = cv;
@@ -586,8 +590,8 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
       // EOM branch (:669-779): recompute the code, emit the in-place D1 and stage the extra points
       const int sym = a.occ_video[( (size_t)f * a.oH + y / a.prec ) * a.oW + x / a.prec];
       uint32_t  code;
-      if ( a.M > 1 ) {
-        const int diff = a.absolute_d1 ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
+      if ( kM > 1 ) {
+        const int diff = kAbs ? (int)(int16_t)g1 - (int)(int16_t)d0 : (int)(int16_t)g1;
         if ( diff == 1 ) {
           code = 1;
         } else if ( diff > 1 ) {
@@ -607,9 +611,9 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
           const int64_t o = base + k;
           a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
           ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
-          if ( a.attr_count > 0 && a.M > 1 ) {
+          if ( kAttr && kM > 1 ) {
             cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
-          } else if ( a.attr_count > 0 ) {
+          } else if ( kAttr ) {
             cv = make_ushort4( 0, 0, 0, 1 );
           }
           a.col[o]  = cv;
@@ -625,11 +629,11 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
           int16_t Q[3] = {P0[0], P0[1], P0[2]};
           set_axis( Q, p.normal_axis, p.mode == 0 ? n0 + ( i + 1 ) : n0 - ( i + 1 ) );  // :741-748
           if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
-          if ( ( code == 1 || i == d1pos ) && a.M > 1 ) {  // in-place D1 (:749-762)
+          if ( ( code == 1 || i == d1pos ) && kM > 1 ) {  // in-place D1 (:749-762)
             const int64_t o = base + k;
             a.pos[o]        = make_short4( Q[0], Q[1], Q[2], (short)btype );
             ushort4 cv      = make_ushort4( 0, 0, 0, 1 );
-            if ( a.attr_count > 0 ) {
+            if ( kAttr ) {
               cv = make_ushort4( S.a[1][0][ty * 16 + tx], S.a[1][1][ty * 16 + tx], S.a[1][2][ty * 16 + tx], 1 );
             }
             a.col[o]  = cv;
@@ -983,7 +987,8 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   }
   const int G = rb_div_up( nWI, WARPS );
   if ( nWI > 0 ) {
-    auto kCount = eom ? k_reproject<false, true> : k_reproject<false, false>;
+    const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
+    auto kCount = eom ? k_reproject<false, true, false> : ( std_cfg ? k_reproject<false, false, true> : k_reproject<false, false, false> );
     RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
   }
   {
@@ -1157,7 +1162,8 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
   }
   if ( nWI > 0 ) {
-    auto kEmit = eom ? k_reproject<true, true> : k_reproject<true, false>;
+    const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
+    auto kEmit = eom ? k_reproject<true, true, false> : ( std_cfg ? k_reproject<true, false, true> : k_reproject<true, false, false> );
     RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
   }
   if ( eom && nSeg ) {
