@@ -554,13 +554,15 @@ __device__ __forceinline__ void count_hits( int32_t* field0, int f, bool hit ) {
   }
 }
 
+// G: the cell size when it is known at compile time (8: CTC gridSize), 0: a.g
+template <int G>
 __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li, double threshold, int& f ) {
   if ( li >= *a.blist_n || a.counters[CTR_FLAGS] ) { return false; }  // tables overflowed: the stage is repeated
   const int64_t i = a.blist[li];
   const short4  p = a.pos[i];
   if ( p.w != 1 ) { return false; }  // :1087
   f               = frame_of( a.frame_off, a.F, i );
-  const int g     = a.g, hg = g / 2;
+  const int g     = G ? G : a.g, hg = g / 2;
   const int disth = max( hg, 1 ), th = grid_th( a, f );
   if ( !inside( p.x, p.y, p.z, disth, th ) ) { return false; }  // :1078-1081
   const int      P[3] = {p.x, p.y, p.z};
@@ -629,19 +631,21 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
   }
   return false;
 }
+template <int G>
 __global__ void __launch_bounds__( 128, 8 ) k_filter_geo( const GridArgs a, double threshold ) {
   int        f   = 0;
-  const bool hit = filter_geo_point( a, blockIdx.x * blockDim.x + threadIdx.x, threshold, f );
+  const bool hit = filter_geo_point<G>( a, blockIdx.x * blockDim.x + threadIdx.x, threshold, f );
   count_hits( &a.finfo[0].smoothed, f, hit );
 }
 
 // ---- colour filter: smoothPointCloudColorLC + gridFilteringColor (:1182-1306) ----
+template <int G>
 __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li, double thrSmoothing, double yThresh, int& f ) {
   if ( li >= *a.blist_n || a.counters[CTR_FLAGS] ) { return false; }  // tables overflowed: the stage is repeated
   const int64_t i = a.blist[li];
   const short4  p = a.pos[i];
   if ( p.w != 1 ) { return false; }  // :1288
-  const int g = a.g, hg = g / 2, disth = max( hg, 1 );
+  const int g = G ? G : a.g, hg = g / 2, disth = max( hg, 1 );
   if ( !inside( p.x, p.y, p.z, disth, a.pcmax ) ) { return false; }  // :1280-1283
   f = frame_of( a.frame_off, a.F, i );
   const int      P[3] = {p.x, p.y, p.z};
@@ -706,9 +710,10 @@ __device__ __forceinline__ bool filter_col_point( const GridArgs& a, uint32_t li
   }
   return false;
 }
+template <int G>
 __global__ void __launch_bounds__( 128, 8 ) k_filter_col( const GridArgs a, double thrSmoothing, double yThresh ) {
   int        f   = 0;
-  const bool hit = filter_col_point( a, blockIdx.x * blockDim.x + threadIdx.x, thrSmoothing, yThresh, f );
+  const bool hit = filter_col_point<G>( a, blockIdx.x * blockDim.x + threadIdx.x, thrSmoothing, yThresh, f );
   count_hits( &a.finfo[0].recolored, f, hit );
 }
 
@@ -918,7 +923,10 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     RB_LAUNCH( "geo_finalize", k_finalize_geo, WALK_CTAS, 256, 0, a );
-    if ( c->blist_cap > 0 ) { RB_LAUNCH( "geo_filter", k_filter_geo, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing ); }
+    if ( c->blist_cap > 0 ) {
+      auto kf = g == 8 ? k_filter_geo<8> : k_filter_geo<0>;
+      RB_LAUNCH( "geo_filter", kf, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing );
+    }
     RB_LAUNCH( "geo_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
     RB_CUDA( cudaMemsetAsync( a.table, 0, (size_t)a.F * a.tslots * 8, c->stream ) );
     r = stage_result( c, a, b, "geometry smoothing" );
@@ -957,7 +965,8 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
     RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     RB_LAUNCH( "col_median_gate", k_cell_median_gate, WALK_CTAS, 256, 0, a, P.threshold_color_variation * 256.0 );
     if ( c->blist_cap > 0 ) {
-      RB_LAUNCH( "col_filter", k_filter_col, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
+      auto kf = g == 4 ? k_filter_col<4> : ( g == 2 ? k_filter_col<2> : k_filter_col<0> );
+      RB_LAUNCH( "col_filter", kf, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,
                  P.threshold_color_difference * 256.0 );
     }
     RB_LAUNCH( "col_cleanup", k_cleanup_cells, WALK_CTAS, 256, 0, a );
