@@ -76,8 +76,12 @@ __global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restric
 
 // per-node tight bounding box of the nodes of this level (computeMinMax for all three axes at once):
 // warp shuffle reduction -> CTA combine in shared memory -> one RED per CTA and node in the common case
-__global__ void __launch_bounds__( TPB ) k_kd_stats( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid,
-                                                     int32_t* __restrict__ st, int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
+// ASSIGN: the elements of the split nodes of level [lvlBegin, lvlEnd) first move to their child (what k_kd_assign
+// does), and the boxes are those of the children — the statistics pass of the next level rides on the assignment pass
+template <bool ASSIGN>
+__global__ void __launch_bounds__( TPB ) k_kd_stats( const uint64_t* __restrict__ rec, uint32_t* __restrict__ nid,
+                                                     const KdNode* __restrict__ nodes, int32_t* __restrict__ st, int64_t E,
+                                                     uint32_t lvlBegin, uint32_t lvlEnd ) {
   __shared__ uint32_t wNode[TPB / 32];
   __shared__ int      wMin[TPB / 32][3], wMax[TPB / 32][3];
   const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -88,6 +92,14 @@ __global__ void __launch_bounds__( TPB ) k_kd_stats( const uint64_t* __restrict_
   if ( e < E ) {
     node = nid[e];
     on   = node >= lvlBegin && node < lvlEnd;
+    if ( ASSIGN && on ) {
+      const KdNode& n = nodes[node];
+      on              = n.state == 1 && n.child1 != 0;
+      if ( on ) {
+        node   = ( (uint32_t)e < nodes[n.child1].right ) ? n.child1 : n.child1 + 1;
+        nid[e] = node;
+      }
+    }
     if ( on ) {
       const uint64_t r = rec[e];
       c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
@@ -342,17 +354,6 @@ __global__ void k_kd_children( KdNode* __restrict__ nodes, uint32_t lvlBegin, ui
     st[(size_t)c1 * 6 + k] = st[(size_t)( c1 + 1 ) * 6 + k] = 0x7FFFFFFF;
     st[(size_t)c1 * 6 + 3 + k] = st[(size_t)( c1 + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
   }
-}
-
-__global__ void k_kd_assign( uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E, uint32_t lvlBegin,
-                             uint32_t lvlEnd ) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( e >= E ) { return; }
-  const uint32_t node = nid[e];
-  if ( node < lvlBegin || node >= lvlEnd ) { return; }
-  const KdNode& n = nodes[node];
-  if ( n.state != 1 || n.child1 == 0 ) { return; }
-  nid[e] = ( (uint32_t)e < nodes[n.child1].right ) ? n.child1 : n.child1 + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -745,7 +746,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   for ( ;; level++ ) {
     if ( level > 200 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree deeper than 200 levels" ); }
     const uint32_t nLvl = lvlEnd - lvlBegin;
-    RB_LAUNCH( "kd_stats", k_kd_stats, G, TPB, 0, rec, nid, st, E, lvlBegin, lvlEnd );
+    if ( level == 0 ) { RB_LAUNCH( "kd_stats", k_kd_stats<false>, G, TPB, 0, rec, nid, nodes, st, E, lvlBegin, lvlEnd ); }
     RB_CUDA( cudaMemsetAsync( counters + 2, 0, 4, c->stream ) );
     RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KB_CAP, ox, oy, oz,
                B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0, st );
@@ -767,7 +768,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     const uint32_t before = h[0];
     RB_LAUNCH( "kd_children", k_kd_children, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, counters,
                std::min( nodeCap, statCap ), st );
-    RB_LAUNCH( "kd_assign", k_kd_assign, G, TPB, 0, nid, nodes, E, lvlBegin, lvlEnd );
+    // assignment to the children + the children's tight boxes (the next level's statistics) in one pass
+    RB_LAUNCH( "kd_assign", k_kd_stats<true>, G, TPB, 0, rec, nid, nodes, st, E, lvlBegin, lvlEnd );
     lvlBegin = before;
     lvlEnd   = before + 2 * h[2];
     if ( lvlEnd > std::min( nodeCap, statCap ) ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
