@@ -3,8 +3,10 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this; the product never does.
 
 Every function restates one reference function (file:line relative to /root/reference/source/lib) on the CTC branch the
-BASELINE configs exercise: one or two maps in a single geometry stream, no EOM / raw patches / PLR / pixel
-interleaving / PBF (those raise NotImplementedError here — the compiled reference in oracle/_ref covers them).
+BASELINE configs exercise: one or two maps (single stream, or multiple streams with an absolute or delta-coded second
+attribute map), no EOM / raw patches / PLR / pixel interleaving / PBF (those raise NotImplementedError here — the
+compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
+16-bit conversion of PCCInternalColorConverter (all eight upsampling filters).
 It is pinned against the unmodified reference (oracle/_ref/librabbit_ref.so) by tests/test_oracle_port_cpu.py, stage
 by stage and bit for bit, and against the golden fixtures in tests/golden/ — so it is a usable checker on a box that
 has neither /root/reference nor oracle/_ref.  Not restated here: PCCPointSet3::transferColors16bitBP (needs the
