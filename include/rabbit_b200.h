@@ -92,7 +92,8 @@ typedef struct rb200_params {
   int32_t patch_precedence_reverse; /* bDecoder && asps.patchPrecedenceOrderFlag, PCCCodec.cpp:627-629  */
   int32_t use_additional_points_patch; /* raw patches in the geometry video                             */
   int32_t total_raw_points_known;   /* tile.getTotalNumberOfRawPoints() is set by the caller's syntax layer */
-  int32_t single_map_pixel_interleaving; /* UNSUPPORTED (status 2) when non-zero                        */
+  int32_t single_map_pixel_interleaving; /* generatePoints :350-471: one map, layers on a checkerboard; needs
+                                          * map_count_minus1 == 0, surface_thickness >= 1, no EOM / raw patches */
   int32_t point_local_reconstruction;    /* UNSUPPORTED when non-zero                                   */
   int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
   int32_t multiple_streams;         /* sps.getMultipleMapStreamsPresentFlag: the caller still hands planes
@@ -111,6 +112,7 @@ typedef struct rb200_params {
   int32_t apply_attr_smoothing;
   int32_t relative_t1;              /* multiple_streams only: map 1 of the attribute is a delta on map 0
                                      * (!absoluteT1List[1], PCCCodec.cpp:1387-1416; CTC condition T1-from-rec-T0) */
+  int32_t surface_thickness;        /* surfaceThickness_ (ctc-common.cfg:25: 4); read by pixel interleaving only */
   double  threshold_smoothing;
   double  threshold_color_smoothing;
   double  threshold_color_difference;

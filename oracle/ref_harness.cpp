@@ -141,7 +141,7 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
   g.nbThread_                      = 1;
   g.multipleStreams_               = p.multiple_streams != 0;  // streams: video m holds map m of every frame
   g.absoluteD1_                    = p.absolute_d1 != 0;
-  g.surfaceThickness_              = 4;
+  g.surfaceThickness_              = p.surface_thickness > 0 ? p.surface_thickness : 4;
   g.thresholdColorSmoothing_       = p.threshold_color_smoothing;
   g.cgridSize_                     = 0;
   g.thresholdColorDifference_      = p.threshold_color_difference;

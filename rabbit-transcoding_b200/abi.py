@@ -63,7 +63,8 @@ class Params(C.Structure):
         "single_map_pixel_interleaving", "point_local_reconstruction", "pbf_enable", "multiple_streams",
         "attribute_count", "attribute_rgb444", "geometry_bitdepth_3d",
         "flag_geometry_smoothing", "grid_smoothing", "grid_size", "apply_geo_smoothing",
-        "attr_transfer_filter_type", "flag_color_smoothing", "apply_attr_smoothing", "relative_t1")] + [
+        "attr_transfer_filter_type", "flag_color_smoothing", "apply_attr_smoothing", "relative_t1",
+        "surface_thickness")] + [
         (n, C.c_double) for n in (
             "threshold_smoothing", "threshold_color_smoothing", "threshold_color_difference",
             "threshold_color_variation")]

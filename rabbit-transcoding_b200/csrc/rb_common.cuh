@@ -171,6 +171,7 @@ static inline int rb_div_up( int64_t a, int64_t b ) { return (int)( ( a + b - 1 
 int rb_reconstruct_impl( rb200_ctx* c );
 int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
+int rb_interleave_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
 int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter, int geo_shift, int attr_shift );

@@ -201,10 +201,17 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   if ( p->width % R || p->height % R || p->width > 65535 || p->height > 65535 ) {
     return rb_fail( c, RB200_ERR_INVALID, "atlas %dx%d must be a multiple of %d and < 65536", p->width, p->height, R );
   }
-  if ( p->single_map_pixel_interleaving || p->point_local_reconstruction || p->pbf_enable ) {
+  if ( p->point_local_reconstruction || p->pbf_enable ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED,
-                    "singleMapPixelInterleaving / pointLocalReconstruction / PBF (PCCCodec.cpp:350-496,541-554) "
-                    "are not implemented in this build" );
+                    "pointLocalReconstruction / PBF (PCCCodec.cpp:472-496,541-554) are not implemented in this build" );
+  }
+  if ( p->single_map_pixel_interleaving ) {  // generatePoints :350-471 + transferColorWeight (colorPointCloud :1367-1434)
+    if ( p->map_count_minus1 != 0 || p->surface_thickness < 1 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "single_map_pixel_interleaving needs one map and surface_thickness >= 1" );
+    }
+    if ( p->enhanced_occupancy_map_code || p->use_additional_points_patch || p->multiple_streams ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving together with EOM, raw patches or multiple streams is not implemented" );
+    }
   }
   if ( p->map_count_minus1 < 0 || p->map_count_minus1 > 1 ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "map_count_minus1 must be 0 or 1" );

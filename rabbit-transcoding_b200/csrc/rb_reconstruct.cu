@@ -36,6 +36,7 @@ struct ReprojArgs {
   const uint32_t* b2p;
   int             W, H, oW, oH, Wb, Hb, M, prec, bmWords;
   int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
+  int             surface_thickness;
   int             t1_bits;  // multi-stream attribute: 0 = map 1 is absolute, 8 / 16 = map 1 is a delta on map 0
   int32_t*        wi_count;
   uint32_t*       wi_cnt4;  // [nWI][32] per-lane packed pixel counts of the counting pass, reused by the emitting pass
@@ -658,6 +659,140 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
 }
 
 // ---------------------------------------------------------------------------------------------------
+// singleMapPixelInterleaving (generatePoints, PCCCodec.cpp:350-471): one map whose pixels alternate between the near
+// and the far layer on a checkerboard.  Every occupied pixel yields its coded point, the other layer interpolated
+// from the 4-neighbours of the same patch, and the fill points strictly between the two (:463-468).  Same work
+// items, counting / emitting passes and point order as k_reproject; the pixels are independent, so every lane walks
+// its 8 pixels on its own (this is not the CTC path: plain global loads, no staging).
+// ---------------------------------------------------------------------------------------------------
+struct IlvPixel {
+  int n0, n1;  // normal coordinate of the coded point / of the interpolated one
+  int two;     // the interpolated point exists (count != 0, :434)
+  int xmin, nfill;
+};
+
+__device__ __forceinline__ IlvPixel interleave_pixel( const ReprojArgs& a, const RbPatch& p, int f, int x, int y ) {
+  const size_t    plane = (size_t)a.W * a.H;
+  const uint16_t* g     = a.geo + (size_t)f * a.M * plane;
+  const uint32_t* bm    = a.bitmap + (size_t)f * a.H * a.bmWords;
+  const uint32_t* b2p   = a.b2p + (size_t)f * a.Hb * a.Wb;
+  IlvPixel        r{};
+  r.n0 = (int16_t)normal_coord( p, g[(size_t)y * a.W + x] );
+  // neighbours in the reference's order: left, right, top, bottom (:380-433)
+  const int nx[4] = {x - 1, x + 1, x, x}, ny[4] = {y, y, y - 1, y + 1};
+  double    dn[4] = {0.0, 0.0, 0.0, 0.0}, mn = (double)r.n0, mx = (double)r.n0;
+  int       count = 0;
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) {
+    if ( nx[k] < 0 || ny[k] < 0 || nx[k] >= a.W || ny[k] >= a.H ) { continue; }           // :362-365
+    if ( !( ( bm[(size_t)ny[k] * a.bmWords + ( nx[k] >> 5 ) ] >> ( nx[k] & 31 ) ) & 1u ) ) { continue; }
+    if ( b2p[( ny[k] >> 4 ) * a.Wb + ( nx[k] >> 4 )] != (uint32_t)p.frame_patch + 1u ) { continue; }
+    const long long v = g[(size_t)ny[k] * a.W + nx[k]];
+    // size_t arithmetic: d1 - value wraps for value > d1 and becomes a huge double (:385-389)
+    dn[k] = p.mode == 0 ? (double)( v + p.d1 ) : (double)(unsigned long long)( (long long)p.d1 - v );
+    count++;
+    mn = fmin( mn, dn[k] );
+    mx = fmax( mx, dn[k] );
+  }
+  if ( count == 0 ) { return r; }
+  const double st = (double)a.surface_thickness, own = (double)r.n0;
+  double       other;
+  if ( ( x + y ) & 1 ) {  // the coded point is D1, D0 is interpolated (:435-446)
+    other = p.mode == 0 ? round( fmin( fmax( mn, own - st ), own ) ) : round( fmax( fmin( mx, own + st ), own ) );
+  } else {                // the coded point is D0, D1 is the clamped neighbour mean (:447-462)
+    const double avg = ( ( ( dn[0] + dn[1] ) + dn[2] ) + dn[3] ) / (double)count;
+    other = p.mode == 0 ? round( fmax( fmin( avg, own + st ), own ) ) : round( fmin( fmax( avg, own - st ), own ) );
+  }
+  r.two  = 1;
+  r.n1   = (int16_t)(int)other;
+  const int lo = min( r.n0, r.n1 ), hi = max( r.n0, r.n1 );
+  r.xmin  = lo;
+  r.nfill = max( hi - lo - 1, 0 );  // for ( step = 1; step < xmax - xmin; ++step ), :463-468
+  return r;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const ReprojArgs a ) {
+  const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t wi   = (int64_t)blockIdx.x * WARPS + wq;
+  if ( wi >= a.nWI ) { return; }
+  const RbPatch p  = a.patches[a.wi_patch[wi]];
+  const int     lb = a.wi_local[wi];
+  const int     ub = lb % p.su0, vb = lb / p.su0;
+  int           bx, by;
+  canvas_block( p, ub, vb, bx, by );
+  const int  f     = p.frame;
+  const bool owned = a.b2p[( (size_t)f * a.Hb + by ) * a.Wb + bx] == (uint32_t)p.frame_patch + 1u;  // :650
+  if ( !owned ) {
+    if ( !EMIT && lane == 0 ) { a.wi_count[wi] = 0; }
+    return;
+  }
+  const int       X0 = bx * 16, Y0 = by * 16;
+  const TileMap   tm = tile_map( p.orient );
+  const int       v1 = lane >> 1, ubase = 8 * ( lane & 1 );
+  const uint32_t* bm = a.bitmap + (size_t)f * a.H * a.bmWords;
+  const size_t    plane = (size_t)a.W * a.H;
+  // ---- per-lane counts, ordered scan (lane order == emission order v1, u1) ----
+  int myCount = 0;
+  for ( int j = 0; j < 8; j++ ) {
+    int tx, ty;
+    TILE_XY( tm, ubase + j, v1, tx, ty );
+    const int x = X0 + tx, y = Y0 + ty;
+    if ( !( ( bm[(size_t)y * a.bmWords + ( x >> 5 )] >> ( x & 31 ) ) & 1u ) ) { continue; }
+    const IlvPixel q = interleave_pixel( a, p, f, x, y );
+    myCount += 1 + ( q.two && !( a.remove_dup && q.n1 == q.n0 ) ? 1 : 0 ) + ( q.two ? q.nfill : 0 );
+  }
+  int incl = myCount;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const int t = __shfl_up_sync( 0xFFFFFFFFu, incl, d );
+    if ( lane >= d ) { incl += t; }
+  }
+  if ( !EMIT ) {
+    if ( lane == 31 ) { a.wi_count[wi] = incl; }
+    return;
+  }
+  int64_t o    = a.frame_off[f] + ( a.wi_base[wi] - a.wi_base[a.frame_wi_off[f]] ) + ( incl - myCount );
+  int     maxc = 0;
+  for ( int j = 0; j < 8; j++ ) {
+    int       tx, ty;
+    const int u1 = ubase + j;
+    TILE_XY( tm, u1, v1, tx, ty );
+    const int x = X0 + tx, y = Y0 + ty;
+    if ( !( ( bm[(size_t)y * a.bmWords + ( x >> 5 )] >> ( x & 31 ) ) & 1u ) ) { continue; }
+    const IlvPixel q  = interleave_pixel( a, p, f, x, y );
+    const int      u  = ub * 16 + u1, v = vb * 16 + v1;
+    const int      np = 1 + ( q.two ? 1 + q.nfill : 0 );
+    for ( int i = 0; i < np; i++ ) {  // createdPoints: coded, interpolated, fills (:781-835)
+      if ( i == 1 && a.remove_dup && q.n1 == q.n0 ) { continue; }  // :794-795 (a fill never equals the coded point)
+      const int nn = i == 0 ? q.n0 : ( i == 1 ? q.n1 : q.xmin + ( i - 1 ) );
+      int16_t   Q[3] = {0, 0, 0};
+      set_axis( Q, p.normal_axis, nn );
+      set_axis( Q, p.tangent_axis, u * p.lodx + p.u1 );
+      set_axis( Q, p.bitangent_axis, v * p.lody + p.v1 );
+      if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
+      // pointToPixel layer (:821-825): the coded point sits on its own checkerboard layer, the interpolated one on
+      // the other, fills on g_intermediateLayerIndex (PCCCommon.h:126)
+      const int layer = i == 0 ? ( ( x + y ) & 1 ) : ( i == 1 ? ( ( x + y + 1 ) & 1 ) : 100 );
+      a.pos[o]        = make_short4( Q[0], Q[1], Q[2], 0 );
+      ushort4 cv      = make_ushort4( 0, 0, 0, (unsigned short)layer );
+      if ( i == 0 && a.attr_count > 0 ) {  // colorPointCloud :1367-1374: only the coded point reads the attribute frame
+        const uint16_t* at = a.attr + (size_t)f * a.M * 3 * plane + (size_t)y * a.W + x;
+        cv                 = make_ushort4( at[0], at[plane], at[2 * plane], (unsigned short)layer );
+      }
+      a.col[o]  = cv;
+      a.pix[o]  = (uint32_t)x | ( (uint32_t)y << 16 );
+      a.part[o] = (uint32_t)p.frame_patch;
+      maxc      = max( maxc, max( (int)Q[0], max( (int)Q[1], (int)Q[2] ) ) );
+      o++;
+    }
+  }
+#pragma unroll
+  for ( int d = 16; d > 0; d >>= 1 ) { maxc = max( maxc, __shfl_xor_sync( 0xFFFFFFFFu, maxc, d ) ); }
+  if ( lane == 0 && maxc > 0 ) { atomicMax( &a.finfo[f].max_coord, maxc ); }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // exclusive scan of int32 counts into int64 bases (n+1 outputs), n is O(1e5..1e6): two launches.
 //   k_scan_tiles : every CTA scans one tile of 2048 counts (16-byte loads, shuffle scans) and publishes the tile sum
 //   k_scan_apply : every CTA reduces the sums of the tiles before it (at most a few hundred) and adds the offset
@@ -923,6 +1058,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   const rb200_params& P = c->P;
   const int           F = c->F;
   const bool          eom = P.enhanced_occupancy_map_code != 0;
+  const bool          ilv = P.single_map_pixel_interleaving != 0;
   const int64_t       nWI = c->nWI;
   RB_CUDA( cudaMemsetAsync( c->d_b2p.p, 0, (size_t)F * c->Wb * c->Hb * 4, c->stream ) );
   {
@@ -966,14 +1102,15 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.absolute_d1  = P.absolute_d1;
   a.remove_dup   = P.remove_duplicate_points;
   a.eom_fix_bits = P.eom_fix_bit_count;
-  a.classify     = ( classify && !eom ) ? 1 : 0;  // with EOM the marks (:880) come first, classification after
+  a.classify     = ( classify && !eom && !ilv ) ? 1 : 0;  // with EOM the marks (:880) come first, classification after
+  a.surface_thickness = P.surface_thickness;
   a.attr_count   = P.attribute_count;
   // image0.getDeprecatedColorFormat() == 0 ? 8 : 16 (:1388): format 0 is the 4:4:4 (RGB) video, PCCVideoDecoder.cpp:132
   a.t1_bits      = ( P.multiple_streams && P.relative_t1 ) ? ( P.attribute_rgb444 ? 8 : 16 ) : 0;
   a.bitdepth3d   = P.geometry_bitdepth_3d;
   a.wi_count     = c->d_wi_count.as<int32_t>();
   a.wi_cnt4      = nullptr;
-  if ( !eom && nWI > 0 ) {  // 128 bytes per patch block: the emitting pass skips its own counting of the pixels
+  if ( !eom && !ilv && nWI > 0 ) {  // 128 bytes per patch block: the emitting pass skips its own counting of the pixels
     RB_CUDA( c->d_wi_eom_slot.ensure( (size_t)nWI * 128 ) );
     a.wi_cnt4 = c->d_wi_eom_slot.as<uint32_t>();
   }
@@ -989,6 +1126,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     auto kCount = eom ? k_reproject<false, true, false> : ( std_cfg ? k_reproject<false, false, true> : k_reproject<false, false, false> );
+    if ( ilv ) { kCount = k_reproject_interleaved<false>; }
     RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
   }
   {
@@ -1164,6 +1302,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     auto kEmit = eom ? k_reproject<true, true, false> : ( std_cfg ? k_reproject<true, false, true> : k_reproject<true, false, false> );
+    if ( ilv ) { kEmit = k_reproject_interleaved<true>; }
     RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
   }
   if ( eom && nSeg ) {
@@ -1194,7 +1333,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
                c->d_attribute.as<uint16_t>(), c->W, c->H, c->M, P.attribute_count, a.pos, a.col, a.pix, a.part,
                c->d_frame_info.as<RbFrameInfo>() );
   }
-  if ( classify && eom ) {
+  if ( classify && ( eom || ilv ) ) {
     RB_LAUNCH( "classify_points", k_classify_points, dim3( 256, F ), 256, 0, (const FrameLayout*)( dS + oLayout ), F,
                c->d_bitmap.as<uint32_t>(), c->W, c->H, c->bmWords, a.pix, a.pos, a.blist, a.blist_n );
   }
@@ -1204,5 +1343,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
     c->blist_cap = hb[0];
   }
+  // pixel interleaving: the interpolated and the fill points take their colour from the coded ones (:1367-1434)
+  if ( ilv && P.attribute_count > 0 ) { return rb_interleave_colors_impl( c ); }
   return RB200_OK;
 }

@@ -331,7 +331,127 @@ int launch_knn( rb200_ctx* c, const KdForest& f, const int16_t* q, int64_t nq, i
   return RB200_OK;
 }
 
+// ---- singleMapPixelInterleaving: colours of the interpolated and fill points ----
+// colorPointCloud (PCCCodec.cpp:1367-1374, :1429-1434): the coded point of every pixel (layer == checkerboard parity)
+// reads the attribute frame and joins `source`; every other point joins `target` and gets
+// PCCPointSet3::transferColorWeight (PCCPointSet.cpp:2250-2280): 5-NN in a kd-tree over `source`, the colour of an
+// identical / single neighbour, else the 1/(d^2)^2-weighted mean in double, truncated to uint16.
+constexpr int KW = 5;
+
+__global__ void k_ilv_flag( const ushort4* __restrict__ col, const uint32_t* __restrict__ pix, int64_t n, uint32_t* __restrict__ flags ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i > n ) { return; }
+  uint32_t s = 0;
+  if ( i < n ) {
+    const uint32_t pv = pix[i];
+    s                 = col[i].w == ( ( ( pv & 0xFFFFu ) + ( pv >> 16 ) ) & 1u ) ? 1u : 0u;
+  }
+  flags[i] = s;
+}
+__global__ void k_ilv_compact( const uint32_t* __restrict__ scan, int64_t n, const short4* __restrict__ pos,
+                               short4* __restrict__ srcPos, uint32_t* __restrict__ srcIdx ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n || scan[i + 1] == scan[i] ) { return; }
+  short4 p        = pos[i];
+  p.w             = 0;
+  srcPos[scan[i]] = p;
+  srcIdx[scan[i]] = (uint32_t)i;
+}
+__global__ void __launch_bounds__( 128 ) k_ilv_transfer( const KdForest forest, int F, const int64_t* __restrict__ frame_off,
+                                                         const uint32_t* __restrict__ scan, const int32_t* __restrict__ rootOf,
+                                                         const uint32_t* __restrict__ srcIdx, const short4* __restrict__ pos,
+                                                         ushort4* __restrict__ col, int64_t n ) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= n || scan[i + 1] != scan[i] ) { return; }  // source points keep their colour
+  const int f    = frame_of( frame_off, F, i );
+  const int root = rootOf[f];
+  if ( root < 0 ) { return; }  // no source: transferColorWeight returns early, the colour stays 0 (:2253)
+  const uint32_t  sb   = scan[frame_off[f]];  // first compacted source point of the frame
+  const short4    p    = pos[i];
+  const int       q[3] = {p.x - forest.ox, p.y - forest.oy, p.z - forest.oz};
+  KdResult<KW>    res;
+  kd_search<KW>( forest, (uint32_t)root, q, res );
+  ushort4 out = col[srcIdx[sb + res.idx[0]]];
+  if ( res.count > 1 && res.dist[0] != 0 ) {  // result.size() > 1 && result.dist( 0 ) > 0.0001 (:2262)
+    double rc[3] = {0.0, 0.0, 0.0}, sw = 0.0;
+    for ( int j = 0; j < res.count; j++ ) {
+      const double  d = (double)res.dist[j];
+      const double  w = __ddiv_rn( 1.0, __dmul_rn( d, d ) );  // 1.0 / pow( dist, 2.0 ), dist = squared distance
+      const ushort4 c = col[srcIdx[sb + res.idx[j]]];
+      rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
+      rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
+      rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
+      sw              = __dadd_rn( sw, w );
+    }
+    out.x = (unsigned short)(int)__ddiv_rn( rc[0], sw );  // PCCVector3D -> PCCColor16bit: (uint16_t) truncation
+    out.y = (unsigned short)(int)__ddiv_rn( rc[1], sw );
+    out.z = (unsigned short)(int)__ddiv_rn( rc[2], sw );
+  }
+  out.w  = col[i].w;  // the pointToPixel layer travels in .w
+  col[i] = out;
+}
+
 }  // namespace
+
+int rb_interleave_colors_impl( rb200_ctx* c ) {
+  const rb200_params& P = c->P;
+  const int           F = c->F;
+  const int64_t       N = c->h_frame_off[F];
+  if ( N == 0 || P.attribute_count == 0 ) { return RB200_OK; }
+  if ( P.geometry_bitdepth_3d > 12 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving: geometry bit depth above 12 is not supported by the kd-tree emulation" );
+  }
+  TransferScratch* S = scratch_of( c );
+  RB_CUDA( S->flags.ensure( (size_t)( N + 8 ) * 4 ) );
+  RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( N + 1 ) ) );
+  uint32_t* flags = S->flags.as<uint32_t>();
+  RB_LAUNCH( "ilv_flag", k_ilv_flag, rb_div_up( N + 1, TPB ), TPB, 0, c->d_col.as<ushort4>(), c->d_pix.as<uint32_t>(), N, flags );
+  int r = rb_scan_u32( c, flags, flags, N + 1, S->sums.as<uint32_t>() );
+  if ( r ) { return r; }
+  // compacted index of the first source point of every frame (and the total)
+  uint32_t* h = (uint32_t*)rb_pinned( c, (size_t)( F + 1 ) * 4 + (size_t)F * 4 + ( F + 2 ) * 8 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  for ( int f = 0; f <= F; f++ ) {
+    RB_CUDA( cudaMemcpyAsync( h + f, flags + c->h_frame_off[f], 4, cudaMemcpyDeviceToHost, c->stream ) );
+  }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  const uint32_t nSrc = h[F];
+  if ( nSrc == 0 || (int64_t)nSrc == N ) { return RB200_OK; }
+  std::vector<int64_t> hOff{0};
+  int32_t*             hRoot = (int32_t*)( h + F + 1 );
+  for ( int f = 0; f < F; f++ ) {
+    const int64_t ns = (int64_t)h[f + 1] - h[f], nt = ( c->h_frame_off[f + 1] - c->h_frame_off[f] ) - ns;
+    hRoot[f]         = -1;
+    if ( ns == 0 || nt == 0 ) { continue; }
+    if ( ns < KW ) {  // PCCKdTree::search leaves result.size() at 5 whatever nanoflann found (PCCKdTree.cpp:62-67)
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving: frame %d has fewer than %d coded points", f, KW );
+    }
+    hRoot[f] = (int32_t)hOff.size();  // tree t has root t + 1
+    hOff.push_back( h[f + 1] );
+    if ( hOff[hOff.size() - 2] != h[f] ) {  // a frame without targets in between: its source points own no tree
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving: a frame without interpolated points inside the GOF is not supported" );
+    }
+  }
+  if ( hOff.size() == 1 ) { return RB200_OK; }
+  RB_CUDA( S->pos2.ensure( (size_t)nSrc * 8 ) );
+  RB_CUDA( S->moved.ensure( (size_t)nSrc * 4 ) );
+  RB_CUDA( S->off.ensure( hOff.size() * 8 ) );
+  RB_CUDA( S->small.ensure( std::max<size_t>( 64, (size_t)F * 4 ) ) );
+  {
+    int64_t* hp = (int64_t*)( h + 2 * F + 2 );  // 8-byte aligned behind h[F + 1] and hRoot[F]
+    memcpy( hp, hOff.data(), hOff.size() * 8 );
+    RB_CUDA( cudaMemcpyAsync( S->off.p, hp, hOff.size() * 8, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaMemcpyAsync( S->small.p, hRoot, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  RB_LAUNCH( "ilv_compact", k_ilv_compact, rb_div_up( N, TPB ), TPB, 0, flags, N, c->d_pos.as<short4>(), S->pos2.as<short4>(),
+             S->moved.as<uint32_t>() );
+  r = rb_kd_build( c, S->kd, S->pos2.as<short4>(), S->off.as<int64_t>(), hOff, 0, 0, 0 );
+  if ( r ) { return r; }
+  RB_LAUNCH( "ilv_transfer", k_ilv_transfer, rb_div_up( N, 128 ), 128, 0, S->kd.forest, F, c->d_frame_off.as<int64_t>(), flags,
+             S->small.as<int32_t>(), S->moved.as<uint32_t>(), c->d_pos.as<short4>(), c->d_col.as<ushort4>(), N );
+  return RB200_OK;
+}
 
 void rb_transfer_release( rb200_ctx* c ) {
   auto it = g_transfer.find( c );

@@ -47,6 +47,7 @@ def default_params(width, height, bitdepth=10, occupancy_precision=4):
     p.threshold_color_smoothing = 10.0
     p.threshold_color_difference = 10.0
     p.threshold_color_variation = 6.0
+    p.surface_thickness = 4
     return p
 
 
@@ -655,4 +656,22 @@ def make_relative_t1(gof, seed=0):
     gof.attribute = np.ascontiguousarray(a.reshape(gof.attribute.shape))
     p.multiple_streams = 1
     p.relative_t1 = 1
+    return gof
+
+
+def make_pixel_interleaved(gof, surface_thickness=4):
+    """Turns a two-map GOF into the singleMapPixelInterleaving layout (generatePoints, PCCCodec.cpp:350-471): one map
+    whose pixels carry the near layer where (x + y) is even and the far layer where it is odd."""
+    p = gof.params
+    F, M, H, W = gof.n_frames, p.map_count_minus1 + 1, p.height, p.width
+    assert M == 2
+    odd = ((np.arange(H)[:, None] + np.arange(W)[None, :]) & 1).astype(bool)
+    g = gof.geometry.reshape(F, M, H, W)
+    gof.geometry = np.ascontiguousarray(np.where(odd, g[:, 1], g[:, 0]).reshape(F, 1, H, W))
+    if gof.attribute is not None:
+        a = gof.attribute.reshape(F, M, 3, H, W)
+        gof.attribute = np.ascontiguousarray(np.where(odd, a[:, 1], a[:, 0]).reshape(F, 1, 3, H, W))
+    p.map_count_minus1 = 0
+    p.single_map_pixel_interleaving = 1
+    p.surface_thickness = surface_thickness
     return gof

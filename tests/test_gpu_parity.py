@@ -225,3 +225,44 @@ def test_ply_and_md5_match_reference(rb, codec, checker_backend, tmp_path):
         assert np.array_equal(back["positions"], want["positions"]) and np.array_equal(back["colors"], want["colors"])
         rp, rc = checker_backend.read_ply(mine)
         assert np.array_equal(rp, want["positions"]) and np.array_equal(rc, want["colors"])
+
+
+def _need_reference(chk):
+    from oracle import checker
+    if not isinstance(chk, checker.Reference):
+        pytest.skip("pixel interleaving is checked against the unmodified reference (oracle/_ref) only")
+
+
+def test_single_map_pixel_interleaving(rb, codec, checker_backend):
+    """singleMapPixelInterleaving (generatePoints, PCCCodec.cpp:350-471): checkerboard layers, the other layer
+    interpolated from the 4-neighbours, fill points; their colours by transferColorWeight (5-NN in nanoflann order)"""
+    _need_reference(checker_backend)
+    g = rb.synthetic.make_pixel_interleaved(small(rb, seed=21))
+    ref = run_stages(codec, g, checker_backend, what="ilv")
+    layers = ref.cloud(0, "reconstruct")["point_to_pixel"][:, 2]
+    assert (layers == 100).sum() > 1000 and (layers == 0).sum() > 1000 and (layers == 1).sum() > 1000
+    # every orientation, p = 2, thinner surface, duplicates kept
+    g = rb.synthetic.make_pixel_interleaved(small(rb, seed=22, orientations=tuple(range(9)), occupancy_precision=2),
+                                            surface_thickness=2)
+    g.params.remove_duplicate_points = 0
+    run_stages(codec, g, checker_backend, what="ilv_orient")
+
+
+def test_pixel_interleaving_noisy_depth_and_full_decoder(rb, codec, checker_backend):
+    """random depth codes drive both clamps of the interpolation and the size_t wrap of d1 - depth (:385-389); then the
+    whole Rec-1 sequence including the attribute re-transfer runs on the interleaved cloud"""
+    _need_reference(checker_backend)
+    g = rb.synthetic.make_pixel_interleaved(small(rb, seed=23, transfer_filter=1), surface_thickness=6)
+    rng = np.random.default_rng(77)
+    noisy = rng.random(g.geometry.shape) < 0.02
+    g.geometry[noisy] = rng.integers(0, 256, int(noisy.sum())).astype(np.uint16)
+    g.params.geometry_bitdepth_3d = 9  # the noise pushes coordinates past 255; 2^bitdepth must still bound them
+    run_stages(codec, g, checker_backend,
+               stages=("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8"), what="ilv_full")
+
+
+def test_pixel_interleaving_argument_checks(rb, codec):
+    g = rb.synthetic.make_pixel_interleaved(small(rb, seed=24))
+    g.params.surface_thickness = 0
+    with pytest.raises(Exception):
+        codec.uploadGof(g)
