@@ -4,8 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 
 Every function restates one reference function (file:line relative to /root/reference/source/lib) on the CTC branch the
 BASELINE configs exercise: one or two maps (single stream, or multiple streams with an absolute or delta-coded second
-attribute map), no EOM / raw patches / PLR / pixel interleaving / PBF (those raise NotImplementedError here — the
-compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
+attribute map) and singleMapPixelInterleaving (its transferColorWeight colours are flagged exact only where they do not
+hinge on nanoflann's order of equidistant neighbours), no EOM / raw patches / PLR / PBF (those raise
+NotImplementedError here — the compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
 16-bit conversion of PCCInternalColorConverter (all eight upsampling filters).
 It is pinned against the unmodified reference (oracle/_ref/librabbit_ref.so) by tests/test_oracle_port_cpu.py, stage
 by stage and bit for bit, and against the golden fixtures in tests/golden/ — so it is a usable checker on a box that
@@ -98,9 +99,11 @@ def boundary_map(occ):
 def reconstruct_frame(params, occ_video, geometry, attribute, patches):
     """returns a dict of arrays in PCCPointSet3 layouts, in the reference's emission order"""
     P = params
-    if (P.enhanced_occupancy_map_code or P.use_additional_points_patch or P.single_map_pixel_interleaving or
+    if (P.enhanced_occupancy_map_code or P.use_additional_points_patch or
             P.point_local_reconstruction or P.pbf_enable or P.enable_size_quantization):
         raise NotImplementedError("oracle_np restates the default CTC branch only (see the module docstring)")
+    if P.single_map_pixel_interleaving:
+        return reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches)
     R, M = P.occupancy_resolution, P.map_count_minus1 + 1
     occ = occupancy_map(occ_video, P.occupancy_precision, P.threshold_lossy_om)
     b2p = block_to_patch(occ, patches, R)
@@ -167,6 +170,128 @@ def reconstruct_frame(params, occ_video, geometry, attribute, patches):
                partition=cat(part, (0,), np.uint32), point_to_pixel=cat(p2p, (0, 3), np.uint32),
                colors16=cat(col, (0, 3), np.uint16) if P.attribute_count > 0 else np.zeros((n, 3), np.uint16),
                colors=np.zeros((n, 3), np.uint8))
+    return out, b2p, occ
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# singleMapPixelInterleaving: generatePoints (:350-471), the caller's bookkeeping (:781-835) and the colours
+# (colorPointCloud :1367-1374, :1429-1434 -> PCCPointSet3::transferColorWeight, PCCPointSet.cpp:2250-2280)
+# ---------------------------------------------------------------------------------------------------------------
+def _round_half_away(x):
+    return np.where(x >= 0, np.floor(x + 0.5), -np.floor(-x + 0.5))
+
+
+def reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches):
+    """as reconstruct_frame; additionally returns, under "colors16_exact", which colours do not depend on nanoflann's
+    traversal order (the 5 nearest coded points are strictly ordered by distance and separated from the 6th)"""
+    from scipy.spatial import cKDTree
+    P = params
+    assert P.map_count_minus1 == 0
+    R, st = P.occupancy_resolution, float(P.surface_thickness)
+    occ = occupancy_map(occ_video, P.occupancy_precision, P.threshold_lossy_om)
+    H, W = occ.shape
+    b2p = block_to_patch(occ, patches, R)
+    btype = boundary_map(occ) if P.flag_geometry_smoothing else np.zeros(occ.shape, np.uint16)
+    order = range(len(patches) - 1, -1, -1) if P.patch_precedence_reverse else range(len(patches))
+    geo = geometry[0].astype(np.int64)
+    pos, col, typ, part, p2p, src = [], [], [], [], [], []
+    for i in order:
+        p = patches[i]
+        su0, sv0 = int(p["size_u0"]), int(p["size_v0"])
+        if su0 == 0 or sv0 == 0:
+            continue
+        v0, u0, v1, u1 = np.meshgrid(np.arange(sv0), np.arange(su0), np.arange(R), np.arange(R), indexing="ij")
+        u, v = (u0 * R + u1).ravel(), (v0 * R + v1).ravel()
+        x, y = patch2canvas(int(p["orientation"]), u, v, su0 * R, sv0 * R, int(p["u0"]) * R, int(p["v0"]) * R)
+        keep = (b2p[y // R, x // R] == i + 1) & (occ[y, x] != 0)
+        u, v, x, y = u[keep], v[keep], x[keep], y[keep]
+        n, d1, mode = len(u), int(p["d1"]), int(p["projection_mode"])
+        own = (geo[y, x] + d1 if mode == 0 else np.maximum(d1 - geo[y, x], 0)).astype(np.int16).astype(np.float64)
+        # the four neighbours in the reference's order: left, right, top, bottom (:380-433)
+        dn = np.zeros((4, n))
+        cnt = np.zeros(n, np.int64)
+        mn, mx = own.copy(), own.copy()
+        for k, (dx, dy) in enumerate(((-1, 0), (1, 0), (0, -1), (0, 1))):
+            nx, ny = x + dx, y + dy
+            ok = (nx >= 0) & (ny >= 0) & (nx < W) & (ny < H)
+            cx, cy = np.clip(nx, 0, W - 1), np.clip(ny, 0, H - 1)
+            ok &= (occ[cy, cx] != 0) & (b2p[cy // R, cx // R] == i + 1)
+            val = geo[cy, cx]
+            # size_t arithmetic: d1 - value wraps to a huge value for value > d1 (:385-389)
+            if mode == 0:
+                dk = (val + d1).astype(np.float64)
+            else:
+                diff = d1 - val
+                dk = np.where(diff >= 0, diff.astype(np.float64), diff.astype(np.float64) + 18446744073709551616.0)
+            dn[k] = np.where(ok, dk, 0.0)
+            cnt += ok
+            mn = np.where(ok, np.minimum(mn, dk), mn)
+            mx = np.where(ok, np.maximum(mx, dk), mx)
+        two = cnt > 0  # :434
+        odd = ((x + y) & 1) == 1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            avg = (((dn[0] + dn[1]) + dn[2]) + dn[3]) / cnt
+        if mode == 0:
+            other = np.where(odd, np.minimum(np.maximum(mn, own - st), own), np.maximum(np.minimum(avg, own + st), own))
+        else:
+            other = np.where(odd, np.maximum(np.minimum(mx, own + st), own), np.minimum(np.maximum(avg, own - st), own))
+        other = np.where(two, _round_half_away(np.where(two, other, 0.0)), 0.0).astype(np.int64).astype(np.int16).astype(np.int64)
+        ownI = own.astype(np.int64)
+        lo, hi = np.minimum(ownI, other), np.maximum(ownI, other)
+        nfill = np.where(two, np.maximum(hi - lo - 1, 0), 0)
+        emit1 = two & ~((other == ownI) & bool(P.remove_duplicate_points))  # :794-795
+        per = 1 + emit1 + nfill
+        tot = int(per.sum())
+        pixi = np.repeat(np.arange(n), per)
+        k = np.arange(tot) - np.repeat(np.cumsum(per) - per, per)  # position inside the pixel's run
+        is0 = k == 0
+        is1 = (k == 1) & emit1[pixi]
+        fillk = k - 1 - emit1[pixi] + 1  # 1-based step of a fill point
+        nn = np.where(is0, ownI[pixi], np.where(is1, other[pixi], lo[pixi] + fillk))
+        Pn = np.zeros((tot, 3), np.int64)
+        Pn[:, p["normal_axis"]] = nn
+        Pn[:, p["tangent_axis"]] = u[pixi] * int(p["lod_x"]) + int(p["u1"])
+        Pn[:, p["bitangent_axis"]] = v[pixi] * int(p["lod_y"]) + int(p["v1"])
+        par = (x[pixi] + y[pixi]) & 1
+        lay = np.where(is0, par, np.where(is1, par ^ 1, 100))  # :821-825, g_intermediateLayerIndex
+        pos.append(Pn.astype(np.int16))
+        typ.append(btype[y[pixi], x[pixi]])
+        part.append(np.full(tot, i, np.uint32))
+        p2p.append(np.stack([x[pixi], y[pixi], lay], axis=1).astype(np.uint32))
+        src.append(is0)
+        if P.attribute_count > 0:
+            c16 = np.stack([attribute[0, c, y[pixi], x[pixi]] for c in range(3)], axis=1).astype(np.uint16)
+            col.append(np.where(is0[:, None], c16, 0).astype(np.uint16))
+
+    def cat(parts, shape, dt):
+        return np.concatenate(parts) if parts else np.zeros(shape, dt)
+    n = sum(len(a) for a in pos)
+    out = dict(positions=cat(pos, (0, 3), np.int16), boundary_types=cat(typ, (0,), np.uint16).astype(np.uint16),
+               partition=cat(part, (0,), np.uint32), point_to_pixel=cat(p2p, (0, 3), np.uint32),
+               colors16=cat(col, (0, 3), np.uint16) if P.attribute_count > 0 else np.zeros((n, 3), np.uint16),
+               colors=np.zeros((n, 3), np.uint8))
+    exact = np.ones(n, bool)
+    is_src = cat(src, (0,), bool)
+    if P.attribute_count > 0 and is_src.any() and (~is_src).any() and is_src.sum() >= 6:
+        # transferColorWeight: 5-NN among the coded points, w = 1 / (d^2)^2, double sums in result order, truncation
+        S, T = np.nonzero(is_src)[0], np.nonzero(~is_src)[0]
+        sp, tp = out["positions"][S].astype(np.int64), out["positions"][T].astype(np.int64)
+        _, nb = cKDTree(sp).query(tp, k=6)
+        d2 = ((sp[nb] - tp[:, None, :]) ** 2).sum(axis=2)
+        o = np.argsort(d2, axis=1, kind="stable")
+        nb, d2 = np.take_along_axis(nb, o, 1), np.take_along_axis(d2, o, 1)
+        strict = (np.diff(d2, axis=1) > 0).all(axis=1)  # no tie anywhere among the six nearest
+        c = out["colors16"][S][nb[:, :5]].astype(np.float64)
+        same = d2[:, 0] == 0  # result.dist( 0 ) <= 0.0001: the colour of that coded point (:2262, :2274-2276)
+        w = 1.0 / (np.where(same[:, None], 1, d2[:, :5]).astype(np.float64) ** 2)
+        acc, sw = np.zeros((len(T), 3)), np.zeros(len(T))
+        for j in range(5):
+            acc = acc + c[:, j] * w[:, j][:, None]
+            sw = sw + w[:, j]
+        res = (acc / sw[:, None]).astype(np.int64).astype(np.uint16)
+        out["colors16"][T] = np.where(same[:, None], out["colors16"][S][nb[:, 0]], res)
+        exact[T] = np.where(same, d2[:, 1] > 0, strict)
+    out["colors16_exact"] = exact
     return out, b2p, occ
 
 
@@ -420,7 +545,8 @@ class Port:
         for f in range(gof.n_frames):
             patches = gof.patches[gof.patch_offset[f]:gof.patch_offset[f + 1]]
             cloud, b2p, occ = reconstruct_frame(P, gof.occupancy[f], gof.geometry[f], gof.attribute[f], patches)
-            snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ}
+            exact = cloud.pop("colors16_exact", None)  # pixel interleaving: colours that do not hinge on kd-tree tie order
+            snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ, "colors16_exact": exact}
             if P.apply_geo_smoothing and P.flag_geometry_smoothing:
                 if P.grid_smoothing:
                     cloud = smooth_geometry(P, cloud)

@@ -100,3 +100,34 @@ def test_port_matches_golden_fixture(rb):
         assert make_golden.cloud_digest(c) == fr["stages"]["smooth_geometry"], f"frame {f}: smooth_geometry digest"
         assert int((c["boundary_types"] == 3).sum()) == fr["smoothed"]
     assert name
+
+
+@pytest.mark.parametrize("noisy", [False, True])
+def test_port_pixel_interleaving(rb, noisy):
+    """singleMapPixelInterleaving (PCCCodec.cpp:350-471): points, layers, boundary types and partition bit-exact; the
+    transferColorWeight colours wherever they do not hinge on nanoflann's order of equidistant neighbours"""
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+
+    def make():
+        g = rb.synthetic.generate_gof(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=206, transfer_filter=0,
+                                      orientations=tuple(range(9)))
+        rb.synthetic.make_pixel_interleaved(g, surface_thickness=4)
+        if noisy:  # both clamps of the interpolation and the size_t wrap of d1 - depth (:385-389)
+            rng = np.random.default_rng(7)
+            m = rng.random(g.geometry.shape) < 0.03
+            g.geometry[m] = rng.integers(0, 128, int(m.sum())).astype(np.uint16)
+            g.params.geometry_bitdepth_3d = 8
+        return g
+    g = make()
+    want = ref_b.run_gof(g, keep=("reconstruct",)).cloud(0, "reconstruct")
+    got = oracle_np.Port().run_gof(make(), ("reconstruct",))[0]
+    c = got["reconstruct"]
+    assert_cloud_equal(c, want, "interleaved", ("positions", "boundary_types", "partition", "point_to_pixel"))
+    p2p = want["point_to_pixel"]
+    coded = p2p[:, 2] == ((p2p[:, 0] + p2p[:, 1]) & 1)
+    assert (p2p[:, 2] == 100).sum() > 1000 and (~coded).sum() > 10000
+    assert np.array_equal(c["colors16"][coded], want["colors16"][coded])
+    exact = got["colors16_exact"] & ~coded
+    assert exact.sum() > 2000
+    assert np.array_equal(c["colors16"][exact], want["colors16"][exact])
