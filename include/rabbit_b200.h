@@ -94,7 +94,7 @@ typedef struct rb200_params {
   int32_t total_raw_points_known;   /* tile.getTotalNumberOfRawPoints() is set by the caller's syntax layer */
   int32_t single_map_pixel_interleaving; /* generatePoints :350-471: one map, layers on a checkerboard; needs
                                           * map_count_minus1 == 0, surface_thickness >= 1, no EOM / raw patches */
-  int32_t point_local_reconstruction;    /* UNSUPPORTED when non-zero                                   */
+  int32_t point_local_reconstruction;    /* generatePoints :472-496; needs one map and rb200_gof_set_plr */
   int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
   int32_t multiple_streams;         /* sps.getMultipleMapStreamsPresentFlag: the caller still hands planes
                                      * as [F][M][..][H][W] (map m of frame f = frame f of stream m)       */
@@ -188,6 +188,22 @@ int         rb200_synchronize(rb200_ctx* ctx);
 /* ---- frame ingest: replaces PCCImage::set / PCCVideo containers on the path (PCCImage.h:97-138) --- */
 int rb200_gof_begin(rb200_ctx* ctx, const rb200_params* params, int n_frames);
 int rb200_gof_upload(rb200_ctx* ctx, const rb200_frames* frames, const rb200_atlas* atlas);
+
+/* Point local reconstruction (params.point_local_reconstruction): the mode table the decoder builds in
+ * PCCDecoder::setPointLocalReconstruction (PccLibDecoder/source/PCCDecoder.cpp:528-550; entry 0 is {0,0,0,1}) and, for
+ * every block of every patch, the mode PCCPatch::getPointLocalReconstructionMode(u0, v0) resolves to
+ * (PCCPatch.h:283-289, filled by PCCDecoder::setPLRData :552-591).  Call after rb200_gof_upload, before
+ * rb200_reconstruct.  Host pointers; copied. */
+typedef struct rb200_plr_mode {
+  uint8_t interpolate, filling, min_d1, neighbor; /* PointLocalReconstructionMode, PCCPLRInformation.h:40-45 */
+} rb200_plr_mode;
+typedef struct rb200_plr {
+  int32_t               n_modes;
+  const rb200_plr_mode* modes;        /* [n_modes]                                                              */
+  const uint8_t*        block_mode;   /* patch i (atlas order) owns block_mode[block_offset[i] + v0 * size_u0 + u0] */
+  const int64_t*        block_offset; /* [total patches + 1]                                                    */
+} rb200_plr;
+int rb200_gof_set_plr(rb200_ctx* ctx, const rb200_plr* plr);
 /* the same with decoder-native planes: replaces PCCImage::set (PCCImage.h:97-138) + the inverse colour conversion of
  * PCCVideoDecoder (PCCVideoDecoder.cpp:125-146, :365; PCCInternalColorConverter.cpp:456-486, :596-611, :669-695, :582-594) */
 int rb200_gof_upload_yuv420(rb200_ctx* ctx, const rb200_frames_yuv420* frames, const rb200_atlas* atlas);

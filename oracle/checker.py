@@ -134,6 +134,13 @@ class _Backend:
             mask |= 1 << STAGES.index(k)
         p = params if params is not None else gof.params
         fr, at = gof.frames_struct(), gof.atlas_struct()
+        set_plr = getattr(self.lib, self.prefix + "gof_set_plr", None)
+        plr = abi.plr_struct(gof.plr) if getattr(gof, "plr", None) is not None else None
+        if set_plr is not None:
+            set_plr.argtypes, set_plr.restype = [C.c_void_p], None
+            set_plr(C.byref(plr) if plr is not None else None)
+        elif plr is not None:
+            raise NotImplementedError("this checker backend has no point local reconstruction")
         h = self._lib_call("gof_run", C.byref(p), gof.n_frames, C.byref(fr), C.byref(at), mask, threads,
                            1 if canonical_md5 else 0, 1 if quiet else 0)
         if not h:

@@ -173,7 +173,12 @@ struct ref_gof {
   std::vector<FrameOut> frames;
 };
 
+// point local reconstruction tables for the next ref_gof_run (same layout as rb200_gof_set_plr); consumed by that run
+static const rb200_plr* g_pending_plr = nullptr;
+
 extern "C" {
+
+void ref_gof_set_plr( const rb200_plr* plr ) { g_pending_plr = plr; }
 
 // Runs the reference on a whole GOF.  keep_mask bit s keeps the snapshot after stage s
 // (0 reconstruct+colour, 1 geometry smoothing, 2 colour transfer, 3 colour smoothing, 4 RGB8).
@@ -247,6 +252,13 @@ ref_gof* ref_gof_run( const rb200_params* pp,
     }
   }
 
+  if ( p.point_local_reconstruction && g_pending_plr ) {  // PCCDecoder::setPointLocalReconstruction (PCCDecoder.cpp:528-541)
+    for ( int i = 0; i < g_pending_plr->n_modes; i++ ) {
+      const rb200_plr_mode&        m = g_pending_plr->modes[i];
+      PointLocalReconstructionMode mode = {m.interpolate != 0, m.filling != 0, m.min_d1, m.neighbor};
+      context.addPointLocalReconstructionMode( mode );
+    }
+  }
   // ---- patch tables ----
   for ( int f = 0; f < nFrames; f++ ) {
     auto& afc = context[f];
@@ -282,6 +294,15 @@ ref_gof* ref_gof_run( const rb200_params* pp,
       d.setLodScaleYIdc( s.lod_y );
       d.setPatchSize2DXInPixel( s.size2d_x_px );
       d.setPatchSize2DYInPixel( s.size2d_y_px );
+      if ( p.point_local_reconstruction && g_pending_plr ) {  // PCCDecoder::setPLRData (PCCDecoder.cpp:552-578), block level
+        d.allocOneLayerData();
+        d.getPointLocalReconstructionLevel() = 0;
+        for ( int v0 = 0; v0 < s.size_v0; v0++ ) {
+          for ( int u0 = 0; u0 < s.size_u0; u0++ ) {
+            d.setPointLocalReconstructionMode( u0, v0, g_pending_plr->block_mode[g_pending_plr->block_offset[i] + v0 * s.size_u0 + u0] );
+          }
+        }
+      }
       patches.push_back( d );
     }
     if ( at->eom_patches && at->eom_offset ) {

@@ -70,6 +70,15 @@ class Params(C.Structure):
             "threshold_color_variation")]
 
 
+class PlrMode(C.Structure):
+    """rb200_plr_mode (PointLocalReconstructionMode, PCCPLRInformation.h:40-45)"""
+    _fields_ = [("interpolate", C.c_uint8), ("filling", C.c_uint8), ("min_d1", C.c_uint8), ("neighbor", C.c_uint8)]
+
+
+class Plr(C.Structure):
+    _fields_ = [("n_modes", i32), ("modes", C.c_void_p), ("block_mode", C.c_void_p), ("block_offset", C.c_void_p)]
+
+
 class Frames(C.Structure):
     _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p)]
 
@@ -126,7 +135,7 @@ class LaunchStats(C.Structure):
 # every symbol include/rabbit_b200.h declares; tests check the .so exports all of them
 EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
-    "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
+    "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_set_plr", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
@@ -161,6 +170,7 @@ def load_library(path=None):
     lib.rb200_synchronize.argtypes = [C.c_void_p]
     lib.rb200_gof_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int]
     lib.rb200_gof_upload.argtypes = [C.c_void_p, C.POINTER(Frames), C.POINTER(Atlas)]
+    lib.rb200_gof_set_plr.argtypes = [C.c_void_p, C.POINTER(Plr)]
     lib.rb200_gof_upload_yuv420.argtypes = [C.c_void_p, C.POINTER(FramesYuv420), C.POINTER(Atlas)]
     lib.rb200_download_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     for n in ("rb200_reconstruct", "rb200_smooth_geometry", "rb200_transfer_colors", "rb200_smooth_color",
@@ -200,3 +210,14 @@ def ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
     return int(a)
+
+
+def plr_struct(plr):
+    """rb200_plr over the arrays of a dict(modes=uint8[n, 4], block_mode=uint8[], block_offset=int64[])"""
+    import numpy as np
+    assert plr["modes"].dtype == np.uint8 and plr["modes"].ndim == 2 and plr["modes"].shape[1] == 4
+    assert plr["block_mode"].dtype == np.uint8 and plr["block_offset"].dtype == np.int64
+    s = Plr()
+    s.n_modes = plr["modes"].shape[0]
+    s.modes, s.block_mode, s.block_offset = ptr(plr["modes"]), ptr(plr["block_mode"]), ptr(plr["block_offset"])
+    return s

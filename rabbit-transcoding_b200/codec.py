@@ -82,6 +82,14 @@ class PCCCodecB200:
     def uploadGof(self, gof):
         self.beginGof(gof.params, gof.n_frames)
         self.uploadFrames(gof.frames_struct(), gof.atlas_struct(), keep=gof)
+        if getattr(gof, "plr", None) is not None:
+            self.setPointLocalReconstruction(gof.plr)
+
+    def setPointLocalReconstruction(self, plr):
+        """PCCDecoder::setPointLocalReconstruction / setPLRData (PCCDecoder.cpp:528-591): the mode table and the mode of
+        every patch block; plr = dict(modes=uint8[n, 4] (interpolate, filling, minD1, neighbor), block_mode=uint8[],
+        block_offset=int64[patches + 1])"""
+        self._check(self._lib.rb200_gof_set_plr(self._h, C.byref(abi.plr_struct(plr))))
 
     def uploadGofYuv420(self, gof, native):
         """decoder-native planes (synthetic.to_decoder_planes): 4:2:0 attribute frames of 8/10-bit samples and geometry

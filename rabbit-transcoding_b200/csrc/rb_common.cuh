@@ -86,6 +86,8 @@ struct rb200_ctx {
   RbBuf d_b2p;           // [F][Hb][Wb] uint32
   RbBuf d_frame_info;    // per-frame device scalars (RbFrameInfo)
   RbBuf d_raw_desc;
+  RbBuf d_plr_modes, d_plr_block_mode, d_plr_block_off;  // rb200_gof_set_plr
+  bool  have_plr = false;
 
   // ---- device outputs: SoA cloud of the whole GOF, frame f = [h_frame_off[f], h_frame_off[f+1]) ----
   RbBuf d_pos;   // short4  {x, y, z, boundaryType}

@@ -146,6 +146,7 @@ void rb200_destroy( rb200_ctx* c ) {
   RbBuf* bufs[] = {&c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_raw_geo, &c->d_raw_attr, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
                    &c->d_wi_count, &c->d_wi_base, &c->d_wi_eom_count, &c->d_wi_eom_base, &c->d_eom_order,
                    &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
+                   &c->d_plr_modes, &c->d_plr_block_mode, &c->d_plr_block_off,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
                    &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
                    &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n,
@@ -201,16 +202,20 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   if ( p->width % R || p->height % R || p->width > 65535 || p->height > 65535 ) {
     return rb_fail( c, RB200_ERR_INVALID, "atlas %dx%d must be a multiple of %d and < 65536", p->width, p->height, R );
   }
-  if ( p->point_local_reconstruction || p->pbf_enable ) {
-    return rb_fail( c, RB200_ERR_UNSUPPORTED,
-                    "pointLocalReconstruction / PBF (PCCCodec.cpp:472-496,541-554) are not implemented in this build" );
+  if ( p->pbf_enable ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "PBF (PCCCodec.cpp:541-554) is not implemented in this build" );
   }
-  if ( p->single_map_pixel_interleaving ) {  // generatePoints :350-471 + transferColorWeight (colorPointCloud :1367-1434)
-    if ( p->map_count_minus1 != 0 || p->surface_thickness < 1 ) {
-      return rb_fail( c, RB200_ERR_INVALID, "single_map_pixel_interleaving needs one map and surface_thickness >= 1" );
+  if ( p->single_map_pixel_interleaving || p->point_local_reconstruction ) {
+    // generatePoints :350-471 / :472-496 + transferColorWeight (colorPointCloud :1367-1434)
+    if ( p->map_count_minus1 != 0 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "pixel interleaving / point local reconstruction need a single map" );
+    }
+    if ( p->single_map_pixel_interleaving && p->surface_thickness < 1 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "single_map_pixel_interleaving needs surface_thickness >= 1" );
     }
     if ( p->enhanced_occupancy_map_code || p->use_additional_points_patch || p->multiple_streams ) {
-      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving together with EOM, raw patches or multiple streams is not implemented" );
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving / point local reconstruction together with EOM, raw "
+                                                "patches or multiple streams is not implemented" );
     }
   }
   if ( p->map_count_minus1 < 0 || p->map_count_minus1 > 1 ) {
@@ -241,6 +246,7 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   c->M       = p->map_count_minus1 + 1;
   c->bmWords = ( c->W + 31 ) / 32;
   c->have_gof = true;
+  c->have_plr = false;
   c->uploaded = c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
   const size_t F = nFrames;
   RB_CUDA( c->d_occ_video.ensure( F * c->oW * c->oH ) );
@@ -440,7 +446,38 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   RB_CUDA( cudaMemcpyAsync( c->d_frame_wi_off.p, st + o, ( F + 1 ) * 4, cudaMemcpyHostToDevice, c->stream ) );
   c->stats.h2d_bytes += (int64_t)tb;
   c->uploaded      = true;
+  c->have_plr      = false;  // rb200_gof_set_plr follows the upload
   c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
+  return RB200_OK;
+}
+
+int rb200_gof_set_plr( rb200_ctx* c, const rb200_plr* plr ) {
+  if ( !c || !plr || !plr->modes || !plr->block_mode || !plr->block_offset || plr->n_modes < 1 || plr->n_modes > 256 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "gof_set_plr: bad arguments" );
+  }
+  if ( !c->uploaded ) { return rb_fail( c, RB200_ERR_STATE, "gof_set_plr: call rb200_gof_upload first" ); }
+  cudaSetDevice( c->device );
+  const size_t np = c->h_patches.size();
+  for ( size_t i = 0; i < np; i++ ) {
+    const int64_t nb = (int64_t)c->h_patches[i].size_u0 * c->h_patches[i].size_v0;
+    if ( plr->block_offset[i] < 0 || plr->block_offset[i + 1] - plr->block_offset[i] < nb ) {
+      return rb_fail( c, RB200_ERR_INVALID, "gof_set_plr: patch %zu has %lld blocks but %lld modes", i, (long long)nb,
+                      (long long)( plr->block_offset[i + 1] - plr->block_offset[i] ) );
+    }
+  }
+  const int64_t total = plr->block_offset[np];
+  for ( int64_t i = 0; i < total; i++ ) {
+    if ( plr->block_mode[i] >= plr->n_modes ) { return rb_fail( c, RB200_ERR_INVALID, "gof_set_plr: block mode %d out of range", plr->block_mode[i] ); }
+  }
+  RB_CUDA( c->d_plr_modes.ensure( 256 * sizeof( rb200_plr_mode ) ) );
+  RB_CUDA( c->d_plr_block_mode.ensure( (size_t)std::max<int64_t>( total, 1 ) ) );
+  RB_CUDA( c->d_plr_block_off.ensure( ( np + 1 ) * 8 ) );
+  RB_CUDA( cudaMemcpyAsync( c->d_plr_modes.p, plr->modes, plr->n_modes * sizeof( rb200_plr_mode ), cudaMemcpyHostToDevice, c->stream ) );
+  if ( total > 0 ) { RB_CUDA( cudaMemcpyAsync( c->d_plr_block_mode.p, plr->block_mode, (size_t)total, cudaMemcpyHostToDevice, c->stream ) ); }
+  RB_CUDA( cudaMemcpyAsync( c->d_plr_block_off.p, plr->block_offset, ( np + 1 ) * 8, cudaMemcpyHostToDevice, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the caller's arrays are pageable and may go away
+  c->stats.h2d_bytes += (int64_t)( total + ( np + 1 ) * 8 + plr->n_modes * sizeof( rb200_plr_mode ) );
+  c->have_plr = true;
   return RB200_OK;
 }
 

@@ -37,6 +37,9 @@ struct ReprojArgs {
   int             W, H, oW, oH, Wb, Hb, M, prec, bmWords;
   int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
   int             surface_thickness;
+  const rb200_plr_mode* plr_modes;  // point local reconstruction (rb200_gof_set_plr)
+  const uint8_t*  plr_block_mode;
+  const int64_t*  plr_block_off;
   int             t1_bits;  // multi-stream attribute: 0 = map 1 is absolute, 8 / 16 = map 1 is a delta on map 0
   int32_t*        wi_count;
   uint32_t*       wi_cnt4;  // [nWI][32] per-lane packed pixel counts of the counting pass, reused by the emitting pass
@@ -711,7 +714,51 @@ __device__ __forceinline__ IlvPixel interleave_pixel( const ReprojArgs& a, const
   return r;
 }
 
-template <bool EMIT>
+// pointLocalReconstruction (generatePoints :472-496, getDeltaNeighbors :238-264): the coded point, a second point
+// deltaDepth along the normal (the largest depth step within the threshold inside a (2n+1)^2 window of the geometry
+// frame, occupied or not, never less than minD1), and optionally the points in between.
+__device__ __forceinline__ IlvPixel plr_pixel( const ReprojArgs& a, const RbPatch& p, int f, int x, int y, const rb200_plr_mode m ) {
+  const size_t    plane = (size_t)a.W * a.H;
+  const uint16_t* g     = a.geo + (size_t)f * a.M * plane;
+  IlvPixel        r{};
+  const int dOrg = normal_coord( p, g[(size_t)y * a.W + x] );  // generateNormalCoordinate: a double holding an integer
+  r.n0           = (int16_t)dOrg;
+  int delta = 0;
+  if ( m.interpolate ) {
+    const int nb = m.neighbor, thr = 4;  // g_neighborThreshold, PCCCommon.h:127
+    const int x0 = max( 0, x - nb ), x1 = min( x + nb, a.W ), y0 = max( 0, y - nb ), y1 = min( y + nb, a.H );
+    for ( int xx = x0; xx <= x1; xx++ ) {    // both bounds are inclusive in the reference (:249-252): x == W reads
+      for ( int yy = y0; yy <= y1; yy++ ) {  // the first sample of the next row; past the last row it reads beyond
+        const size_t idx = (size_t)yy * a.W + xx;  // the plane, which has no defined value: skipped here
+        if ( idx >= plane ) { continue; }
+        const int d = normal_coord( p, g[idx] ) - dOrg;
+        if ( p.mode == 0 ) {
+          if ( d <= thr && d > delta ) { delta = d; }
+        } else {
+          if ( d >= -thr && d < delta ) { delta = d; }
+        }
+      }
+    }
+    if ( delta != 0 ) { delta += p.mode == 0 ? -1 : 1; }  // :261
+  }
+  delta = p.mode == 0 ? max( delta, (int)m.min_d1 ) : min( delta, -(int)m.min_d1 );  // :478-482
+  if ( delta == 0 ) { return r; }
+  r.two = 1;
+  r.n1  = (int16_t)( r.n0 + delta );
+  if ( m.filling ) {  // size_t xmin / xmax (:487-488): a negative minimum wraps, and -1 + 1 wraps back to 0
+    const int lo = min( r.n0, r.n1 ), hi = max( r.n0, r.n1 );
+    if ( lo >= 0 ) {
+      r.xmin  = lo;
+      r.nfill = max( hi - lo - 1, 0 );
+    } else if ( lo == -1 && hi >= 0 ) {
+      r.xmin  = -1;
+      r.nfill = hi;
+    }
+  }
+  return r;
+}
+
+template <bool EMIT, bool PLR>
 __global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const ReprojArgs a ) {
   const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int64_t wi   = (int64_t)blockIdx.x * WARPS + wq;
@@ -732,6 +779,8 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const R
   const int       v1 = lane >> 1, ubase = 8 * ( lane & 1 );
   const uint32_t* bm = a.bitmap + (size_t)f * a.H * a.bmWords;
   const size_t    plane = (size_t)a.W * a.H;
+  rb200_plr_mode  pm{};  // context.getPointLocalReconstructionMode( patch.getPointLocalReconstructionMode( u0, v0 ) ), :783-784
+  if ( PLR ) { pm = a.plr_modes[a.plr_block_mode[a.plr_block_off[a.wi_patch[wi]] + lb]]; }
   // ---- per-lane counts, ordered scan (lane order == emission order v1, u1) ----
   int myCount = 0;
   for ( int j = 0; j < 8; j++ ) {
@@ -739,7 +788,7 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const R
     TILE_XY( tm, ubase + j, v1, tx, ty );
     const int x = X0 + tx, y = Y0 + ty;
     if ( !( ( bm[(size_t)y * a.bmWords + ( x >> 5 )] >> ( x & 31 ) ) & 1u ) ) { continue; }
-    const IlvPixel q = interleave_pixel( a, p, f, x, y );
+    const IlvPixel q = PLR ? plr_pixel( a, p, f, x, y, pm ) : interleave_pixel( a, p, f, x, y );
     myCount += 1 + ( q.two && !( a.remove_dup && q.n1 == q.n0 ) ? 1 : 0 ) + ( q.two ? q.nfill : 0 );
   }
   int incl = myCount;
@@ -760,7 +809,7 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const R
     TILE_XY( tm, u1, v1, tx, ty );
     const int x = X0 + tx, y = Y0 + ty;
     if ( !( ( bm[(size_t)y * a.bmWords + ( x >> 5 )] >> ( x & 31 ) ) & 1u ) ) { continue; }
-    const IlvPixel q  = interleave_pixel( a, p, f, x, y );
+    const IlvPixel q  = PLR ? plr_pixel( a, p, f, x, y, pm ) : interleave_pixel( a, p, f, x, y );
     const int      u  = ub * 16 + u1, v = vb * 16 + v1;
     const int      np = 1 + ( q.two ? 1 + q.nfill : 0 );
     for ( int i = 0; i < np; i++ ) {  // createdPoints: coded, interpolated, fills (:781-835)
@@ -773,7 +822,9 @@ __global__ void __launch_bounds__( WARPS * 32 ) k_reproject_interleaved( const R
       if ( p.addplane ) { inverse_rotate45( p.addplane, a.bitdepth3d, Q ); }
       // pointToPixel layer (:821-825): the coded point sits on its own checkerboard layer, the interpolated one on
       // the other, fills on g_intermediateLayerIndex (PCCCommon.h:126)
-      const int layer = i == 0 ? ( ( x + y ) & 1 ) : ( i == 1 ? ( ( x + y + 1 ) & 1 ) : 100 );
+      // (:826-828) point local reconstruction: 0, g_intermediateLayerIndex, g_intermediateLayerIndex + 1
+      const int layer = PLR ? ( i == 0 ? 0 : ( i == 1 ? 100 : 101 ) )
+                            : ( i == 0 ? ( ( x + y ) & 1 ) : ( i == 1 ? ( ( x + y + 1 ) & 1 ) : 100 ) );
       a.pos[o]        = make_short4( Q[0], Q[1], Q[2], 0 );
       ushort4 cv      = make_ushort4( 0, 0, 0, (unsigned short)layer );
       if ( i == 0 && a.attr_count > 0 ) {  // colorPointCloud :1367-1374: only the coded point reads the attribute frame
@@ -1058,7 +1109,10 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   const rb200_params& P = c->P;
   const int           F = c->F;
   const bool          eom = P.enhanced_occupancy_map_code != 0;
-  const bool          ilv = P.single_map_pixel_interleaving != 0;
+  // pixel interleaving wins when both are set (generatePoints tests it first, :350 / :472)
+  const bool          plr = P.point_local_reconstruction != 0 && !P.single_map_pixel_interleaving;
+  const bool          ilv = P.single_map_pixel_interleaving != 0 || plr;  // the per-pixel variable-count path
+  if ( plr && !c->have_plr ) { return rb_fail( c, RB200_ERR_STATE, "point_local_reconstruction: rb200_gof_set_plr was not called for this GOF" ); }
   const int64_t       nWI = c->nWI;
   RB_CUDA( cudaMemsetAsync( c->d_b2p.p, 0, (size_t)F * c->Wb * c->Hb * 4, c->stream ) );
   {
@@ -1104,6 +1158,9 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.eom_fix_bits = P.eom_fix_bit_count;
   a.classify     = ( classify && !eom && !ilv ) ? 1 : 0;  // with EOM the marks (:880) come first, classification after
   a.surface_thickness = P.surface_thickness;
+  a.plr_modes         = c->d_plr_modes.as<rb200_plr_mode>();
+  a.plr_block_mode    = c->d_plr_block_mode.as<uint8_t>();
+  a.plr_block_off     = c->d_plr_block_off.as<int64_t>();
   a.attr_count   = P.attribute_count;
   // image0.getDeprecatedColorFormat() == 0 ? 8 : 16 (:1388): format 0 is the 4:4:4 (RGB) video, PCCVideoDecoder.cpp:132
   a.t1_bits      = ( P.multiple_streams && P.relative_t1 ) ? ( P.attribute_rgb444 ? 8 : 16 ) : 0;
@@ -1126,7 +1183,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     auto kCount = eom ? k_reproject<false, true, false> : ( std_cfg ? k_reproject<false, false, true> : k_reproject<false, false, false> );
-    if ( ilv ) { kCount = k_reproject_interleaved<false>; }
+    if ( ilv ) { kCount = plr ? k_reproject_interleaved<false, true> : k_reproject_interleaved<false, false>; }
     RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
   }
   {
@@ -1302,7 +1359,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     auto kEmit = eom ? k_reproject<true, true, false> : ( std_cfg ? k_reproject<true, false, true> : k_reproject<true, false, false> );
-    if ( ilv ) { kEmit = k_reproject_interleaved<true>; }
+    if ( ilv ) { kEmit = plr ? k_reproject_interleaved<true, true> : k_reproject_interleaved<true, false>; }
     RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
   }
   if ( eom && nSeg ) {

@@ -331,20 +331,22 @@ int launch_knn( rb200_ctx* c, const KdForest& f, const int16_t* q, int64_t nq, i
   return RB200_OK;
 }
 
-// ---- singleMapPixelInterleaving: colours of the interpolated and fill points ----
+// ---- singleMapPixelInterleaving / pointLocalReconstruction: colours of the interpolated and fill points ----
 // colorPointCloud (PCCCodec.cpp:1367-1374, :1429-1434): the coded point of every pixel (layer == checkerboard parity)
 // reads the attribute frame and joins `source`; every other point joins `target` and gets
 // PCCPointSet3::transferColorWeight (PCCPointSet.cpp:2250-2280): 5-NN in a kd-tree over `source`, the colour of an
 // identical / single neighbour, else the 1/(d^2)^2-weighted mean in double, truncated to uint16.
 constexpr int KW = 5;
 
-__global__ void k_ilv_flag( const ushort4* __restrict__ col, const uint32_t* __restrict__ pix, int64_t n, uint32_t* __restrict__ flags ) {
+__global__ void k_ilv_flag( const ushort4* __restrict__ col, const uint32_t* __restrict__ pix, int64_t n, int plr,
+                            uint32_t* __restrict__ flags ) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( i > n ) { return; }
   uint32_t s = 0;
   if ( i < n ) {
     const uint32_t pv = pix[i];
-    s                 = col[i].w == ( ( ( pv & 0xFFFFu ) + ( pv >> 16 ) ) & 1u ) ? 1u : 0u;
+    // interleaving: the layer equals the checkerboard parity (:1367-1369); PLR: f < mapCount, i.e. layer 0 (:1418)
+    s = col[i].w == ( plr ? 0u : ( ( ( pv & 0xFFFFu ) + ( pv >> 16 ) ) & 1u ) ) ? 1u : 0u;
   }
   flags[i] = s;
 }
@@ -405,7 +407,8 @@ int rb_interleave_colors_impl( rb200_ctx* c ) {
   RB_CUDA( S->flags.ensure( (size_t)( N + 8 ) * 4 ) );
   RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( N + 1 ) ) );
   uint32_t* flags = S->flags.as<uint32_t>();
-  RB_LAUNCH( "ilv_flag", k_ilv_flag, rb_div_up( N + 1, TPB ), TPB, 0, c->d_col.as<ushort4>(), c->d_pix.as<uint32_t>(), N, flags );
+  RB_LAUNCH( "ilv_flag", k_ilv_flag, rb_div_up( N + 1, TPB ), TPB, 0, c->d_col.as<ushort4>(), c->d_pix.as<uint32_t>(), N,
+             ( P.point_local_reconstruction && !P.single_map_pixel_interleaving ) ? 1 : 0, flags );
   int r = rb_scan_u32( c, flags, flags, N + 1, S->sums.as<uint32_t>() );
   if ( r ) { return r; }
   // compacted index of the first source point of every frame (and the total)

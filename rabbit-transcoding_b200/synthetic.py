@@ -67,6 +67,7 @@ class SyntheticGOF:
         self.eom_members = None
         self.raw_patches = None
         self.raw_offset = None
+        self.plr = None         # point local reconstruction tables (make_plr)
         self.sources = []       # per frame: dict(positions i16[n,3], colors u8[n,3], normals f32[n,3])
 
     def frames_struct(self):
@@ -674,4 +675,31 @@ def make_pixel_interleaved(gof, surface_thickness=4):
     p.map_count_minus1 = 0
     p.single_map_pixel_interleaving = 1
     p.surface_thickness = surface_thickness
+    return gof
+
+
+def make_plr(gof, seed=0):
+    """Turns a single-map GOF into a point-local-reconstruction one (generatePoints, PCCCodec.cpp:472-496): the mode
+    table of PCCDecoder::setPointLocalReconstruction (entry 0 = no second point) and a random mode per patch block."""
+    p = gof.params
+    assert p.map_count_minus1 == 0
+    rng = np.random.default_rng([seed, 4471])
+    # (interpolate, filling, minD1, neighbor)
+    gof_modes = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [1, 1, 0, 1], [1, 1, 1, 2], [0, 1, 2, 1], [1, 0, 3, 2], [0, 0, 1, 1]], np.uint8)
+    nblk = gof.patches["size_u0"].astype(np.int64) * gof.patches["size_v0"].astype(np.int64)
+    off = np.zeros(len(nblk) + 1, np.int64)
+    off[1:] = np.cumsum(nblk)
+    bm = rng.integers(0, len(gof_modes), int(off[-1])).astype(np.uint8)
+    for i in np.nonzero(rng.random(len(nblk)) < 0.3)[0]:  # patch-level mode (level flag 1): every block the same
+        bm[off[i]:off[i + 1]] = rng.integers(0, len(gof_modes))
+    # getDeltaNeighbors (:249-252) reads one row past the frame for pixels within `neighbor` of the bottom edge (its
+    # bounds are inclusive): undefined in the reference, so patches that reach the last block row do not interpolate
+    Hb = p.height // p.occupancy_resolution
+    swapped = np.isin(gof.patches["orientation"], (1, 2, 4, 6, 8))
+    rows = np.where(swapped, gof.patches["size_u0"], gof.patches["size_v0"])
+    for i in np.nonzero(gof.patches["v0"] + rows >= Hb)[0]:
+        blk = bm[off[i]:off[i + 1]]
+        blk[gof_modes[blk, 0] != 0] = 4
+    gof.plr = dict(modes=gof_modes, block_mode=bm, block_offset=off)
+    p.point_local_reconstruction = 1
     return gof

@@ -150,10 +150,15 @@ def test_error_paths(rb, codec):
         codec.uploadGof(g)
     assert e.value.status == rb.abi.RB200_ERR_PATCH_OUT_OF_CANVAS
     g = small(rb, seed=24)
-    g.params.point_local_reconstruction = 1
+    g.params.pbf_enable = 1  # Rec-2 occupancy synthesis is not implemented: refused, never approximated
     with pytest.raises(rb.codec.RabbitError) as e:
         codec.uploadGof(g)
     assert e.value.status == rb.abi.RB200_ERR_UNSUPPORTED
+    g = small(rb, seed=24)
+    g.params.point_local_reconstruction = 1  # needs a single map (and its mode tables)
+    with pytest.raises(rb.codec.RabbitError) as e:
+        codec.uploadGof(g)
+    assert e.value.status == rb.abi.RB200_ERR_INVALID
 
 
 # ---- attribute re-transfer (PCCPointSet3::transferColors16bitBP): the decoder's default Rec-1 flow ----
@@ -266,3 +271,25 @@ def test_pixel_interleaving_argument_checks(rb, codec):
     g.params.surface_thickness = 0
     with pytest.raises(Exception):
         codec.uploadGof(g)
+
+
+def test_point_local_reconstruction(rb, codec, checker_backend):
+    """pointLocalReconstruction (generatePoints :472-496, getDeltaNeighbors :238-264): per-block modes (interpolate,
+    filling, minD1, neighbour window), second point and fills on layers 100 / 101, coloured by transferColorWeight"""
+    _need_reference(checker_backend)
+    g = rb.synthetic.make_plr(small(rb, seed=41, map_count=1), seed=1)
+    ref = run_stages(codec, g, checker_backend, what="plr")
+    layers = ref.cloud(0, "reconstruct")["point_to_pixel"][:, 2]
+    assert (layers == 100).sum() > 1000 and (layers == 101).sum() > 1000
+    g = rb.synthetic.make_plr(small(rb, seed=42, map_count=1, orientations=tuple(range(9)), occupancy_precision=2,
+                                    transfer_filter=1), seed=2)
+    run_stages(codec, g, checker_backend,
+               stages=("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8"), what="plr_full")
+
+
+def test_point_local_reconstruction_needs_its_tables(rb, codec):
+    g = rb.synthetic.make_plr(small(rb, seed=43, map_count=1), seed=3)
+    g.plr = None
+    codec.uploadGof(g)
+    with pytest.raises(Exception):
+        codec.generatePointCloud()
