@@ -13,7 +13,7 @@
 //   PCCMetrics::compute( sources, reconstructs, normals )  PccLibMetrics/source/PCCMetrics.cpp:334-385
 // The originals stay linked under the names rb200_orig_* (oracle/Makefile renames the symbols with objcopy), and every
 // replaced body falls back to its original whenever the request is outside what the CUDA path implements (multiple
-// tiles, auxiliary video, point local reconstruction, pixel interleaving, PBF, other transfer-filter arguments ...):
+// tiles, auxiliary video, multiple streams, PBF, other transfer-filter arguments ...):
 // an unsupported mode therefore gives the reference's result, never a different one.
 //
 // Per-frame calls, per-GOF execution: the reference calls these functions frame by frame; the CUDA path processes the
@@ -114,9 +114,12 @@ Gof g;  // the decoder's frame loop is single-threaded (PCCDecoder.cpp:330) and 
   } while ( 0 )
 
 bool supported( PCCContext& context, const GeneratePointCloudParameters& p ) {
-  if ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ || p.pbfEnableFlag_ || p.useAuxSeperateVideo_ ||
-       p.multipleStreams_ || p.mapCountMinus1_ > 1 || p.occupancyResolution_ != 16 ) {
+  if ( p.pbfEnableFlag_ || p.useAuxSeperateVideo_ || p.multipleStreams_ || p.mapCountMinus1_ > 1 || p.occupancyResolution_ != 16 ) {
     return false;
+  }
+  if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
+       ( p.mapCountMinus1_ != 0 || p.enhancedOccupancyMapCode_ || p.useAdditionalPointsPatch_ || p.surfaceThickness_ < 1 ) ) {
+    return false;  // combinations the C ABI refuses (rb200_gof_begin)
   }
   for ( size_t f = 0; f < context.size(); f++ ) {
     if ( context[f].getNumTilesInAtlasFrame() != 1 ) { return false; }
@@ -152,6 +155,9 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   auto& asps                    = context.getAtlasSequenceParameterSet( 0 );
   p.patch_precedence_reverse    = bDecoder && asps.getPatchPrecedenceOrderFlag();
   p.use_additional_points_patch = gp.useAdditionalPointsPatch_;
+  p.single_map_pixel_interleaving = gp.singleMapPixelInterleaving_;
+  p.point_local_reconstruction    = gp.pointLocalReconstruction_;
+  p.surface_thickness             = (int)gp.surfaceThickness_;
   p.attribute_count             = hasAttr ? 1 : 0;
   p.attribute_rgb444 = hasAttr && context.getVideoAttributesMultiple()[0].getFrameCount() > 0 &&
                        context.getVideoAttributesMultiple()[0].getColorFormat() == PCCCOLORFORMAT::RGB444;
@@ -228,6 +234,27 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   RB( rb200_enable_stage_snapshots( g.ctx, 1 ) );  // the caller walks the stages frame by frame
   RB( rb200_gof_begin( g.ctx, &p, (int)F ) );
   RB( rb200_gof_upload( g.ctx, &fr, &at ) );
+  if ( gp.pointLocalReconstruction_ && !gp.singleMapPixelInterleaving_ ) {
+    // what PCCDecoder::setPointLocalReconstruction / setPLRData (PCCDecoder.cpp:528-591) left in the context and patches
+    std::vector<rb200_plr_mode> modes;
+    for ( size_t i = 0; i < context.getPointLocalReconstructionModeNumber(); i++ ) {
+      const auto& m = context.getPointLocalReconstructionMode( i );
+      modes.push_back( rb200_plr_mode{(uint8_t)m.interpolate_, (uint8_t)m.filling_, m.minD1_, m.neighbor_} );
+    }
+    std::vector<uint8_t> blockMode;
+    std::vector<int64_t> blockOff{0};
+    for ( size_t f = 0; f < F; f++ ) {
+      for ( auto& s : context[f].getTile( 0 ).getPatches() ) {
+        for ( size_t v0 = 0; v0 < s.getSizeV0(); v0++ ) {
+          for ( size_t u0 = 0; u0 < s.getSizeU0(); u0++ ) { blockMode.push_back( s.getPointLocalReconstructionMode( u0, v0 ) ); }
+        }
+        blockOff.push_back( (int64_t)blockMode.size() );
+      }
+    }
+    if ( blockMode.empty() ) { blockMode.push_back( 0 ); }
+    rb200_plr plr{(int32_t)modes.size(), modes.data(), blockMode.data(), blockOff.data()};
+    RB( rb200_gof_set_plr( g.ctx, &plr ) );
+  }
   RB( rb200_reconstruct( g.ctx ) );
   g.counts.resize( F );
   RB( rb200_frame_counts_get( g.ctx, g.counts.data() ) );

@@ -57,16 +57,31 @@ def test_dropin_eom_and_raw(rb, backends):
 
 
 def test_dropin_unsupported_mode_falls_back_to_the_reference_body(rb, backends):
-    """pixel interleaving is not implemented on the GPU: the shim must hand the frame to the original body"""
+    """multiple map streams are not wired through the shim: it must hand the frame to the original body"""
     ref_b, drop_b = backends
-    args = dict(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=75, transfer_filter=1, map_count=1)
-    g = rb.synthetic.generate_gof(**args)
-    g.params.single_map_pixel_interleaving = 1
+    args = dict(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=75, transfer_filter=1)
+    g = rb.synthetic.make_relative_t1(rb.synthetic.generate_gof(**args), seed=5)
     want = ref_b.run_gof(g, keep=("rgb8",))
-    g2 = rb.synthetic.generate_gof(**args)
-    g2.params.single_map_pixel_interleaving = 1
+    g2 = rb.synthetic.make_relative_t1(rb.synthetic.generate_gof(**args), seed=5)
     got = drop_b.run_gof(g2, keep=("rgb8",))
     assert got.md5(0) == want.md5(0)
+
+
+def test_dropin_pixel_interleaving_and_plr(rb, backends):
+    """singleMapPixelInterleaving and pointLocalReconstruction run on the GPU behind the reference's member functions"""
+    ref_b, drop_b = backends
+    stages = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
+    for tag, make in (("ilv", lambda: rb.synthetic.make_pixel_interleaved(
+                           rb.synthetic.generate_gof(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=77, transfer_filter=1))),
+                      ("plr", lambda: rb.synthetic.make_plr(
+                           rb.synthetic.generate_gof(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=78, transfer_filter=1,
+                                                     map_count=1), seed=6))):
+        want = ref_b.run_gof(make(), keep=stages)
+        got = drop_b.run_gof(make(), keep=stages)
+        for f in range(2):
+            assert got.md5(f) == want.md5(f), tag
+            for st in stages:
+                assert_cloud_equal(got.cloud(f, st), want.cloud(f, st), f"dropin {tag} frame {f} {st}")
 
 
 def test_dropin_metrics(rb, backends):
