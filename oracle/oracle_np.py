@@ -4,9 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 
 Every function restates one reference function (file:line relative to /root/reference/source/lib) on the CTC branch the
 BASELINE configs exercise: one or two maps (single stream, or multiple streams with an absolute or delta-coded second
-attribute map) and singleMapPixelInterleaving (its transferColorWeight colours are flagged exact only where they do not
-hinge on nanoflann's order of equidistant neighbours), no EOM / raw patches / PLR / PBF (those raise
-NotImplementedError here — the compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
+attribute map), singleMapPixelInterleaving and pointLocalReconstruction (their transferColorWeight colours are flagged
+exact only where they do not hinge on nanoflann's order of equidistant neighbours), no EOM / raw patches / PBF (those
+raise NotImplementedError here — the compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
 16-bit conversion of PCCInternalColorConverter (all eight upsampling filters).
 It is pinned against the unmodified reference (oracle/_ref/librabbit_ref.so) by tests/test_oracle_port_cpu.py, stage
 by stage and bit for bit, and against the golden fixtures in tests/golden/ — so it is a usable checker on a box that
@@ -96,14 +96,14 @@ def boundary_map(occ):
 # PCCCodec::generatePointCloud (:517-978) + generatePoints (:327-515, default branch :497-513) +
 # PCCPatch::generatePoint (PCCPatch.h:177-207) + colorPointCloud (:1308-1449, single-stream branch :1418-1422)
 # ---------------------------------------------------------------------------------------------------------------
-def reconstruct_frame(params, occ_video, geometry, attribute, patches):
-    """returns a dict of arrays in PCCPointSet3 layouts, in the reference's emission order"""
+def reconstruct_frame(params, occ_video, geometry, attribute, patches, plr=None, patch_base=0):
+    """returns a dict of arrays in PCCPointSet3 layouts, in the reference's emission order; plr / patch_base: the point
+    local reconstruction tables of the GOF (rb200_plr layout) and the GOF index of this frame's first patch"""
     P = params
-    if (P.enhanced_occupancy_map_code or P.use_additional_points_patch or
-            P.point_local_reconstruction or P.pbf_enable or P.enable_size_quantization):
+    if P.enhanced_occupancy_map_code or P.use_additional_points_patch or P.pbf_enable or P.enable_size_quantization:
         raise NotImplementedError("oracle_np restates the default CTC branch only (see the module docstring)")
-    if P.single_map_pixel_interleaving:
-        return reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches)
+    if P.single_map_pixel_interleaving or P.point_local_reconstruction:
+        return reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches, plr, patch_base)
     R, M = P.occupancy_resolution, P.map_count_minus1 + 1
     occ = occupancy_map(occ_video, P.occupancy_precision, P.threshold_lossy_om)
     b2p = block_to_patch(occ, patches, R)
@@ -174,19 +174,98 @@ def reconstruct_frame(params, occ_video, geometry, attribute, patches):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# singleMapPixelInterleaving: generatePoints (:350-471), the caller's bookkeeping (:781-835) and the colours
+# singleMapPixelInterleaving: generatePoints (:350-471); pointLocalReconstruction: generatePoints (:472-496) with
+# getDeltaNeighbors (:238-264); the caller's bookkeeping (:781-835) and the colours
 # (colorPointCloud :1367-1374, :1429-1434 -> PCCPointSet3::transferColorWeight, PCCPointSet.cpp:2250-2280)
 # ---------------------------------------------------------------------------------------------------------------
 def _round_half_away(x):
     return np.where(x >= 0, np.floor(x + 0.5), -np.floor(-x + 0.5))
 
 
-def reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches):
+def _interleaved_pixels(p, i, geo, occ, b2p, x, y, R, st):
+    """generatePoints :350-471 for the occupied pixels (x, y) of patch i: normal coordinate of the coded point, of the
+    interpolated one, whether it exists, and the fill run (start - 1, length)"""
+    H, W = occ.shape
+    n, d1, mode = len(x), int(p["d1"]), int(p["projection_mode"])
+    own = (geo[y, x] + d1 if mode == 0 else np.maximum(d1 - geo[y, x], 0)).astype(np.int16).astype(np.float64)
+    # the four neighbours in the reference's order: left, right, top, bottom (:380-433)
+    dn = np.zeros((4, n))
+    cnt = np.zeros(n, np.int64)
+    mn, mx = own.copy(), own.copy()
+    for k, (dx, dy) in enumerate(((-1, 0), (1, 0), (0, -1), (0, 1))):
+        nx, ny = x + dx, y + dy
+        ok = (nx >= 0) & (ny >= 0) & (nx < W) & (ny < H)
+        cx, cy = np.clip(nx, 0, W - 1), np.clip(ny, 0, H - 1)
+        ok &= (occ[cy, cx] != 0) & (b2p[cy // R, cx // R] == i + 1)
+        val = geo[cy, cx]
+        # size_t arithmetic: d1 - value wraps to a huge value for value > d1 (:385-389)
+        if mode == 0:
+            dk = (val + d1).astype(np.float64)
+        else:
+            diff = d1 - val
+            dk = np.where(diff >= 0, diff.astype(np.float64), diff.astype(np.float64) + 18446744073709551616.0)
+        dn[k] = np.where(ok, dk, 0.0)
+        cnt += ok
+        mn = np.where(ok, np.minimum(mn, dk), mn)
+        mx = np.where(ok, np.maximum(mx, dk), mx)
+    two = cnt > 0  # :434
+    odd = ((x + y) & 1) == 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        avg = (((dn[0] + dn[1]) + dn[2]) + dn[3]) / cnt
+    if mode == 0:
+        other = np.where(odd, np.minimum(np.maximum(mn, own - st), own), np.maximum(np.minimum(avg, own + st), own))
+    else:
+        other = np.where(odd, np.maximum(np.minimum(mx, own + st), own), np.minimum(np.maximum(avg, own - st), own))
+    other = np.where(two, _round_half_away(np.where(two, other, 0.0)), 0.0).astype(np.int64).astype(np.int16).astype(np.int64)
+    ownI = own.astype(np.int64)
+    lo, hi = np.minimum(ownI, other), np.maximum(ownI, other)
+    nfill = np.where(two, np.maximum(hi - lo - 1, 0), 0)
+    return ownI, other, two, lo, nfill
+
+
+def _plr_pixels(p, plr, gi, geo, u, v, x, y, R):
+    """generatePoints :472-496 + getDeltaNeighbors :238-264 for the occupied pixels of GOF patch gi"""
+    H, W = geo.shape
+    d1, mode, su0 = int(p["d1"]), int(p["projection_mode"]), int(p["size_u0"])
+    m = plr["modes"][plr["block_mode"][plr["block_offset"][gi] + (v // R) * su0 + (u // R)]].astype(np.int64)
+    interp, filling, min_d1, nb = m[:, 0] != 0, m[:, 1] != 0, m[:, 2], m[:, 3]
+
+    def normal(depth):
+        return depth + d1 if mode == 0 else np.maximum(d1 - depth, 0)
+    flat = geo.ravel()
+    d_org = normal(geo[y, x])
+    delta = np.zeros(len(x), np.int64)
+    r = int(nb.max(initial=0))
+    for dx in range(-r, r + 1):
+        for dy in range(-r, r + 1):
+            xx, yy = x + dx, y + dy
+            # inclusive upper bounds (:249-252): x == W is the first sample of the next row; past the plane: skipped
+            idx = yy * W + xx
+            ok = interp & (abs(dx) <= nb) & (abs(dy) <= nb) & (xx >= 0) & (yy >= 0) & (xx <= W) & (yy <= H) & (idx < H * W)
+            d = normal(flat[np.clip(idx, 0, H * W - 1)]) - d_org
+            if mode == 0:
+                delta = np.where(ok & (d <= 4) & (d > delta), d, delta)  # g_neighborThreshold
+            else:
+                delta = np.where(ok & (d >= -4) & (d < delta), d, delta)
+    delta = np.where(delta != 0, delta + (-1 if mode == 0 else 1), 0)  # :261
+    delta = np.maximum(delta, min_d1) if mode == 0 else np.minimum(delta, -min_d1)  # :478-482
+    ownI = d_org.astype(np.int16).astype(np.int64)
+    two = delta != 0
+    other = (ownI + delta).astype(np.int16).astype(np.int64)
+    lo, hi = np.minimum(ownI, other), np.maximum(ownI, other)
+    # size_t xmin / xmax (:487-488): a negative minimum wraps to a huge start, except -1, whose successor is 0
+    nfill = np.where(two & filling & (lo >= -1), np.maximum(hi - lo - 1, 0), 0)
+    return ownI, other, two, lo, nfill
+
+
+def reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches, plr=None, patch_base=0):
     """as reconstruct_frame; additionally returns, under "colors16_exact", which colours do not depend on nanoflann's
     traversal order (the 5 nearest coded points are strictly ordered by distance and separated from the 6th)"""
     from scipy.spatial import cKDTree
     P = params
     assert P.map_count_minus1 == 0
+    use_plr = bool(P.point_local_reconstruction) and not P.single_map_pixel_interleaving  # :350 is tested before :472
+    assert not use_plr or plr is not None
     R, st = P.occupancy_resolution, float(P.surface_thickness)
     occ = occupancy_map(occ_video, P.occupancy_precision, P.threshold_lossy_om)
     H, W = occ.shape
@@ -206,39 +285,12 @@ def reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patche
         keep = (b2p[y // R, x // R] == i + 1) & (occ[y, x] != 0)
         u, v, x, y = u[keep], v[keep], x[keep], y[keep]
         n, d1, mode = len(u), int(p["d1"]), int(p["projection_mode"])
-        own = (geo[y, x] + d1 if mode == 0 else np.maximum(d1 - geo[y, x], 0)).astype(np.int16).astype(np.float64)
-        # the four neighbours in the reference's order: left, right, top, bottom (:380-433)
-        dn = np.zeros((4, n))
-        cnt = np.zeros(n, np.int64)
-        mn, mx = own.copy(), own.copy()
-        for k, (dx, dy) in enumerate(((-1, 0), (1, 0), (0, -1), (0, 1))):
-            nx, ny = x + dx, y + dy
-            ok = (nx >= 0) & (ny >= 0) & (nx < W) & (ny < H)
-            cx, cy = np.clip(nx, 0, W - 1), np.clip(ny, 0, H - 1)
-            ok &= (occ[cy, cx] != 0) & (b2p[cy // R, cx // R] == i + 1)
-            val = geo[cy, cx]
-            # size_t arithmetic: d1 - value wraps to a huge value for value > d1 (:385-389)
-            if mode == 0:
-                dk = (val + d1).astype(np.float64)
-            else:
-                diff = d1 - val
-                dk = np.where(diff >= 0, diff.astype(np.float64), diff.astype(np.float64) + 18446744073709551616.0)
-            dn[k] = np.where(ok, dk, 0.0)
-            cnt += ok
-            mn = np.where(ok, np.minimum(mn, dk), mn)
-            mx = np.where(ok, np.maximum(mx, dk), mx)
-        two = cnt > 0  # :434
-        odd = ((x + y) & 1) == 1
-        with np.errstate(divide="ignore", invalid="ignore"):
-            avg = (((dn[0] + dn[1]) + dn[2]) + dn[3]) / cnt
-        if mode == 0:
-            other = np.where(odd, np.minimum(np.maximum(mn, own - st), own), np.maximum(np.minimum(avg, own + st), own))
+        if use_plr:
+            ownI, other, two, lo, nfill = _plr_pixels(p, plr, patch_base + i, geo, u, v, x, y, R)
+            lay_of = (0, 100, 101)  # :826-828: 0, g_intermediateLayerIndex, g_intermediateLayerIndex + 1
         else:
-            other = np.where(odd, np.maximum(np.minimum(mx, own + st), own), np.minimum(np.maximum(avg, own - st), own))
-        other = np.where(two, _round_half_away(np.where(two, other, 0.0)), 0.0).astype(np.int64).astype(np.int16).astype(np.int64)
-        ownI = own.astype(np.int64)
-        lo, hi = np.minimum(ownI, other), np.maximum(ownI, other)
-        nfill = np.where(two, np.maximum(hi - lo - 1, 0), 0)
+            ownI, other, two, lo, nfill = _interleaved_pixels(p, i, geo, occ, b2p, x, y, R, st)
+            lay_of = None
         emit1 = two & ~((other == ownI) & bool(P.remove_duplicate_points))  # :794-795
         per = 1 + emit1 + nfill
         tot = int(per.sum())
@@ -253,7 +305,10 @@ def reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patche
         Pn[:, p["tangent_axis"]] = u[pixi] * int(p["lod_x"]) + int(p["u1"])
         Pn[:, p["bitangent_axis"]] = v[pixi] * int(p["lod_y"]) + int(p["v1"])
         par = (x[pixi] + y[pixi]) & 1
-        lay = np.where(is0, par, np.where(is1, par ^ 1, 100))  # :821-825, g_intermediateLayerIndex
+        if lay_of is None:
+            lay = np.where(is0, par, np.where(is1, par ^ 1, 100))  # :821-825, g_intermediateLayerIndex
+        else:
+            lay = np.where(is0, lay_of[0], np.where(is1, lay_of[1], lay_of[2]))
         pos.append(Pn.astype(np.int16))
         typ.append(btype[y[pixi], x[pixi]])
         part.append(np.full(tot, i, np.uint32))
@@ -544,7 +599,8 @@ class Port:
         out = []
         for f in range(gof.n_frames):
             patches = gof.patches[gof.patch_offset[f]:gof.patch_offset[f + 1]]
-            cloud, b2p, occ = reconstruct_frame(P, gof.occupancy[f], gof.geometry[f], gof.attribute[f], patches)
+            cloud, b2p, occ = reconstruct_frame(P, gof.occupancy[f], gof.geometry[f], gof.attribute[f], patches,
+                                                getattr(gof, "plr", None), int(gof.patch_offset[f]))
             exact = cloud.pop("colors16_exact", None)  # pixel interleaving: colours that do not hinge on kd-tree tie order
             snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ, "colors16_exact": exact}
             if P.apply_geo_smoothing and P.flag_geometry_smoothing:

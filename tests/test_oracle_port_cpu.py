@@ -131,3 +131,30 @@ def test_port_pixel_interleaving(rb, noisy):
     exact = got["colors16_exact"] & ~coded
     assert exact.sum() > 2000
     assert np.array_equal(c["colors16"][exact], want["colors16"][exact])
+
+
+def test_port_point_local_reconstruction(rb):
+    """pointLocalReconstruction (PCCCodec.cpp:472-496, getDeltaNeighbors :238-264): points, layers 0 / 100 / 101, types and
+    partition bit-exact; colours wherever nanoflann's tie order cannot matter"""
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+
+    def make():
+        g = rb.synthetic.generate_gof(n_frames=2, bitdepth=7, width=128, scale=0.9, seed=207, transfer_filter=0, map_count=1,
+                                      orientations=tuple(range(9)))
+        rng = np.random.default_rng(9)  # depth steps beyond the neighbour threshold, and below d1 for projection mode 1
+        m = rng.random(g.geometry.shape) < 0.03
+        g.geometry[m] = rng.integers(0, 128, int(m.sum())).astype(np.uint16)
+        g.params.geometry_bitdepth_3d = 8
+        return rb.synthetic.make_plr(g, seed=5)
+    g = make()
+    want = ref_b.run_gof(g, keep=("reconstruct",))
+    got = oracle_np.Port().run_gof(make(), ("reconstruct",))
+    for f in range(2):
+        w, c = want.cloud(f, "reconstruct"), got[f]["reconstruct"]
+        assert_cloud_equal(c, w, f"plr frame {f}", ("positions", "boundary_types", "partition", "point_to_pixel"))
+        lay = w["point_to_pixel"][:, 2]
+        assert (lay == 100).sum() > 1000 and (lay == 101).sum() > 500
+        exact = got[f]["colors16_exact"]
+        assert (exact & (lay != 0)).sum() > 500
+        assert np.array_equal(c["colors16"][exact], w["colors16"][exact])
