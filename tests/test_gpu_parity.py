@@ -293,3 +293,26 @@ def test_point_local_reconstruction_needs_its_tables(rb, codec):
     codec.uploadGof(g)
     with pytest.raises(Exception):
         codec.generatePointCloud()
+
+
+def test_interleaving_and_plr_with_lossy_occupancy_reverse_order(rb, codec, checker_backend):
+    """both variable-count modes on top of the other switches of the reprojection: lossy occupancy threshold, patch
+    size quantisation (the neighbour tests read the quantised map), reversed patch precedence, precision 1"""
+    _need_reference(checker_backend)
+    for tag in ("ilv", "plr"):
+        g = _lossy(rb, 1)
+        g.params.enable_size_quantization = 1
+        g.params.log2_quantizer_x = 2
+        g.params.log2_quantizer_y = 3
+        g.patches["size2d_x_px"] -= 5
+        g.patches["size2d_y_px"] -= 3
+        g.params.patch_precedence_reverse = 1
+        if tag == "ilv":
+            rb.synthetic.make_pixel_interleaved(g, surface_thickness=3)
+        else:
+            h, w = g.params.height, g.params.width
+            g.geometry = np.ascontiguousarray(g.geometry.reshape(g.n_frames, 2, h, w)[:, :1])
+            g.attribute = np.ascontiguousarray(g.attribute.reshape(g.n_frames, 2, 3, h, w)[:, :1])
+            g.params.map_count_minus1 = 0
+            rb.synthetic.make_plr(g, seed=8)
+        run_stages(codec, g, checker_backend, what="lossy_" + tag)
