@@ -13,7 +13,7 @@ colour smoothing, YUV16 -> RGB8, and (when --metrics) the D1/D2/colour metrics a
 `e2e`    : the same metric through the reference-facing call sequence with HOST buffers, inside the timer every step:
            pinned H2D of the decoder-native planes (8-bit 4:2:0 attribute frames + 8-bit geometry luma + occupancy) and
            the patch tables, the decoder's 4:2:0 -> 4:4:4 16-bit conversion on the GPU, decode, D2H of positions + RGB8
-           of every frame; two GOFs in flight (two contexts / streams / host threads).  `e2e.from_444_16bit_frames` is
+           of every frame; three GOFs in flight (contexts / streams / host threads; RB200_BENCH_LANES).  `e2e.from_444_16bit_frames` is
            the same from the 16-bit 4:4:4 frames of the reference's PCCVideo boundary, `one_gof_in_flight` unpipelined.
 `roofline`: the dominant kernel of the step (per-kernel CUDA events on the launching stream), algorithmic
            bytes per launch / its average duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes
@@ -284,9 +284,10 @@ def run_b200(args):
         assert n_got == n_points
         serial = {"value": round(all_points * args.steps / (ms_e2e * 1e-3) / 1e6, 2), "ms_per_step": round(ms_e2e / args.steps, 3)}
 
-        # the same call sequence with two GOFs in flight: a second context on its own stream, driven by a second host
-        # thread, so the upload of one GOF overlaps the kernels and the download of the other (PCIe is full duplex)
-        NL = int(os.environ.get("RB200_BENCH_LANES", "2"))
+        # the same call sequence with several GOFs in flight (3 by default; measured 2: 3.62, 3: 3.83, 4: 3.86 Gpts/s): every
+        # extra lane is a context on its own stream driven by its own host thread, so the upload of one GOF overlaps the
+        # kernels and the download of the others (PCIe is full duplex)
+        NL = int(os.environ.get("RB200_BENCH_LANES", "3"))
         lanes = [(codec, out)]
         extra_streams = []
         for _ in range(NL - 1):
@@ -347,7 +348,7 @@ def run_b200(args):
                     "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps}
 
         from_444 = time_pipelined(lambda c_: c_.uploadGof(gof))
-        from_444["mode"] = "uploadGof (16-bit 4:4:4 frames, the reference's PCCVideo boundary) -> decodeGof -> getGof, two GOFs in flight"
+        from_444["mode"] = f"uploadGof (16-bit 4:4:4 frames, the reference's PCCVideo boundary) -> decodeGof -> getGof, {NL} GOFs in flight"
         from_444["one_gof_in_flight"] = serial
         # the decoder-native boundary: 8-bit 4:2:0 attribute frames + 8-bit geometry luma as libav / NVDEC / HM leave
         # them; PCCVideoDecoder's inverse colour conversion (YUV420ToYUV444_8_0) runs on the device inside the step
@@ -357,7 +358,7 @@ def run_b200(args):
         e2e = time_pipelined(lambda c_: c_.uploadGofYuv420(gof, native))
         e2e["mode"] = ("uploadGofYuv420 (decoder-native planes: 8-bit 4:2:0 attribute frames + 8-bit geometry luma from pinned "
                        "host memory; the decoder's 4:2:0 -> 4:4:4 16-bit conversion runs on the GPU inside the step) -> decodeGof "
-                       "-> getGof (positions + RGB8 to pinned host memory); two GOFs in flight (two contexts, two streams, two "
+                       f"-> getGof (positions + RGB8 to pinned host memory); {NL} GOFs in flight ({NL} contexts, {NL} streams, {NL} "
                        "host threads)")
         e2e["from_444_16bit_frames"] = from_444
         for c_, _ in lanes[1:]:
