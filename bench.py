@@ -13,7 +13,7 @@ colour smoothing, YUV16 -> RGB8, and (when --metrics) the D1/D2/colour metrics a
 `e2e`    : the same metric through the reference-facing call sequence with HOST buffers, inside the timer every step:
            pinned H2D of the decoder-native planes (8-bit 4:2:0 attribute frames + 8-bit geometry luma + occupancy) and
            the patch tables, the decoder's 4:2:0 -> 4:4:4 16-bit conversion on the GPU, decode, D2H of positions + RGB8
-           of every frame; three GOFs in flight (contexts / streams / host threads; RB200_BENCH_LANES).  `e2e.from_444_16bit_frames` is
+           of every frame; three GOFs in flight at N = 1, two per GPU at N > 1 (contexts / streams / host threads; RB200_BENCH_LANES).  `e2e.from_444_16bit_frames` is
            the same from the 16-bit 4:4:4 frames of the reference's PCCVideo boundary, `one_gof_in_flight` unpipelined.
 `roofline`: the dominant kernel of the step (per-kernel CUDA events on the launching stream), algorithmic
            bytes per launch / its average duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes
@@ -287,7 +287,7 @@ def run_b200(args):
         # the same call sequence with several GOFs in flight (3 by default; measured 2: 3.62, 3: 3.83, 4: 3.86 Gpts/s): every
         # extra lane is a context on its own stream driven by its own host thread, so the upload of one GOF overlaps the
         # kernels and the download of the others (PCIe is full duplex)
-        NL = int(os.environ.get("RB200_BENCH_LANES", "3"))
+        NL = int(os.environ.get("RB200_BENCH_LANES", "3" if world == 1 else "2"))  # N > 1: the host side is the limit, 2 measured best
         lanes = [(codec, out)]
         extra_streams = []
         for _ in range(NL - 1):
