@@ -93,7 +93,7 @@ typedef struct rb200_params {
   int32_t use_additional_points_patch; /* raw patches in the geometry video                             */
   int32_t total_raw_points_known;   /* tile.getTotalNumberOfRawPoints() is set by the caller's syntax layer */
   int32_t single_map_pixel_interleaving; /* generatePoints :350-471: one map, layers on a checkerboard; needs
-                                          * map_count_minus1 == 0, surface_thickness >= 1, no EOM / raw patches */
+                                          * map_count_minus1 == 0, surface_thickness >= 1, no EOM / multiple streams */
   int32_t point_local_reconstruction;    /* generatePoints :472-496; needs one map and rb200_gof_set_plr */
   int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
   int32_t multiple_streams;         /* sps.getMultipleMapStreamsPresentFlag: the caller still hands planes

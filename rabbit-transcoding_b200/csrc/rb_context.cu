@@ -213,9 +213,9 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
     if ( p->single_map_pixel_interleaving && p->surface_thickness < 1 ) {
       return rb_fail( c, RB200_ERR_INVALID, "single_map_pixel_interleaving needs surface_thickness >= 1" );
     }
-    if ( p->enhanced_occupancy_map_code || p->use_additional_points_patch || p->multiple_streams ) {
-      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving / point local reconstruction together with EOM, raw "
-                                                "patches or multiple streams is not implemented" );
+    if ( p->enhanced_occupancy_map_code || p->multiple_streams ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "pixel interleaving / point local reconstruction together with EOM or "
+                                                "multiple streams is not implemented" );
     }
   }
   if ( p->map_count_minus1 < 0 || p->map_count_minus1 > 1 ) {

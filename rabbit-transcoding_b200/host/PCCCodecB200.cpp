@@ -118,7 +118,7 @@ bool supported( PCCContext& context, const GeneratePointCloudParameters& p ) {
     return false;
   }
   if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
-       ( p.mapCountMinus1_ != 0 || p.enhancedOccupancyMapCode_ || p.useAdditionalPointsPatch_ || p.surfaceThickness_ < 1 ) ) {
+       ( p.mapCountMinus1_ != 0 || p.enhancedOccupancyMapCode_ || p.surfaceThickness_ < 1 ) ) {
     return false;  // combinations the C ABI refuses (rb200_gof_begin)
   }
   for ( size_t f = 0; f < context.size(); f++ ) {

@@ -316,3 +316,16 @@ def test_interleaving_and_plr_with_lossy_occupancy_reverse_order(rb, codec, chec
             g.params.map_count_minus1 = 0
             rb.synthetic.make_plr(g, seed=8)
         run_stages(codec, g, checker_backend, what="lossy_" + tag)
+
+
+def test_interleaving_and_plr_with_raw_patches(rb, codec, checker_backend):
+    """raw (missed-point) patches next to the variable-count modes: with pixel interleaving colorPointCloud applies the
+    checkerboard rule to the raw points as well (:1367-1374: those on odd pixels are coloured by transferColorWeight),
+    with point local reconstruction they sit on layer 0 and read the attribute frame"""
+    _need_reference(checker_backend)
+    g = rb.synthetic.make_pixel_interleaved(small(rb, seed=61, raw_points=700))
+    ref = run_stages(codec, g, checker_backend, what="ilv_raw")
+    assert ref.counts(0).raw == 700
+    g = rb.synthetic.make_plr(small(rb, seed=62, raw_points=500, map_count=1), seed=9)
+    ref = run_stages(codec, g, checker_backend, what="plr_raw")
+    assert ref.counts(0).raw == 500
