@@ -325,7 +325,9 @@ def run_b200(args):
 
         def time_pipelined(upload):
             run_pipelined(NL, upload)
-            psteps = max(int(os.environ.get("RB200_BENCH_E2E_STEPS", "0")), args.steps, NL)
+            # at least six GOFs per lane, every lane the same number: with fewer the fill / drain of the pipeline is what is timed
+            psteps = max(int(os.environ.get("RB200_BENCH_E2E_STEPS", "0")), args.steps, 6 * NL)
+            psteps = -(-psteps // NL) * NL
             for c_, _ in lanes:
                 c_.stats(reset=True)
             barrier()
