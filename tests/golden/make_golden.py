@@ -6,7 +6,7 @@ generator, (b) the reference build itself (compiler / flags), and give the GPU t
 box where oracle/_ref is absent.  Per case and frame: point counts, the MD5 of positions||RGB8 in emission order
 (PCCPointSet3::computeChecksum, PCCPointSet.cpp:222-245) after every stage, and the metric floats.
 
-    python tests/golden/make_golden.py            # rewrites golden.json
+    python tests/golden/make_golden.py            # adds the missing cases to golden.json (--all: regenerates every case)
 """
 import hashlib
 import json
@@ -28,6 +28,11 @@ CASES = {
                          geometry_smoothing=False, color_smoothing=False),
     "raw_single_map": dict(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=104, transfer_filter=0, raw_points=500,
                            map_count=1, occupancy_precision=1),
+    # "transform": a synthetic.* step applied to the generated GOF (not a generate_gof argument)
+    "pixel_interleaved": dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=106, transfer_filter=1,
+                              orientations=tuple(range(9)), transform="pixel_interleaved"),
+    "point_local_reconstruction": dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=107, transfer_filter=1, map_count=1,
+                                       transform="plr"),
 }
 STAGES = ("reconstruct", "smooth_geometry", "transfer_colors", "smooth_color", "rgb8")
 
@@ -50,8 +55,22 @@ def f32hex(x):
     return struct.pack("<f", float(x)).hex()
 
 
-def run_case(rb, chk, checker, name, kw):
+def make_gof(rb, kw):
+    """the GOF of a case: generate_gof( args ) followed by the case's transform"""
+    kw = dict(kw)
+    if "orientations" in kw:
+        kw["orientations"] = tuple(kw["orientations"])
+    transform = kw.pop("transform", None)
     g = rb.synthetic.generate_gof(**kw)
+    if transform == "pixel_interleaved":
+        rb.synthetic.make_pixel_interleaved(g, surface_thickness=4)
+    elif transform == "plr":
+        rb.synthetic.make_plr(g, seed=11)
+    return g
+
+
+def run_case(rb, chk, checker, name, kw):
+    g = make_gof(rb, kw)
     run = chk.run_gof(g, keep=STAGES)
     out = dict(args={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
                input_md5=hashlib.md5(g.occupancy.tobytes() + g.geometry.tobytes() + g.attribute.tobytes() +
@@ -76,7 +95,11 @@ def main():
     import rabbit_transcoding_b200 as rb
     from oracle import checker
     chk = checker.Reference()
-    gold = {name: run_case(rb, chk, checker, name, kw) for name, kw in CASES.items()}
+    path = os.path.join(HERE, "golden.json")
+    gold = json.load(open(path)) if os.path.exists(path) and "--all" not in sys.argv else {}
+    for name, kw in CASES.items():  # existing cases are kept as they are unless --all is given
+        if name not in gold:
+            gold[name] = run_case(rb, chk, checker, name, kw)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "golden.json"))

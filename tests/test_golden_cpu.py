@@ -24,7 +24,7 @@ def _kw(name):
 
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_generator_is_pinned(rb, name):
-    g = rb.synthetic.generate_gof(**_kw(name))
+    g = make_golden.make_gof(rb, _kw(name))
     md5 = hashlib.md5(g.occupancy.tobytes() + g.geometry.tobytes() + g.attribute.tobytes() + g.patches.tobytes()).hexdigest()
     assert md5 == GOLD[name]["input_md5"], "the synthetic generator changed: regenerate tests/golden (make_golden.py)"
 

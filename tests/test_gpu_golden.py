@@ -24,9 +24,7 @@ def f32(hexstr):
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_decode_and_metrics_match_golden(rb, codec, name):
     kw = dict(GOLD[name]["args"])
-    if "orientations" in kw:
-        kw["orientations"] = tuple(kw["orientations"])
-    g = rb.synthetic.generate_gof(**kw)
+    g = make_golden.make_gof(rb, kw)
     codec.uploadGof(g)
     codec.decodeGof()
     counts = codec.frameCounts()
