@@ -185,6 +185,17 @@ const char* rb200_error_string(const rb200_ctx* ctx); /* last error text of this
 int         rb200_set_stream(rb200_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = own stream */);
 int         rb200_synchronize(rb200_ctx* ctx);
 
+/* pinned (page-locked) host memory for staging planes and results: copies to / from it are true DMA transfers */
+void*       rb200_host_alloc(size_t bytes);
+void        rb200_host_free(void* p);
+
+/* ---- PCCCodec::generateOccupancyMap (PccLibCommon/source/PCCCodec.cpp:1584-1606) for ONE frame, as the decoder calls it
+ *      before it knows the GOF (PCCDecoder.cpp:361-365): `video` [oH][oW] (host) is thresholded IN PLACE exactly as the
+ *      reference does it (once per full-resolution pixel, i.e. precision^2 times per sample, :1597-1600), `map_out`
+ *      [oH * precision][oW * precision] uint32 (host) is tile.getOccupancyMap(). ----------------------------------------- */
+int rb200_occupancy_map(rb200_ctx* ctx, uint8_t* video, int o_width, int o_height, int precision, int threshold_lossy_om,
+                        int enhanced_occupancy_map, uint32_t* map_out);
+
 /* ---- frame ingest: replaces PCCImage::set / PCCVideo containers on the path (PCCImage.h:97-138) --- */
 int rb200_gof_begin(rb200_ctx* ctx, const rb200_params* params, int n_frames);
 int rb200_gof_upload(rb200_ctx* ctx, const rb200_frames* frames, const rb200_atlas* atlas);
@@ -232,6 +243,10 @@ int rb200_convert_rgb8(rb200_ctx* ctx);
  * evaluation of convertYUV16ToRGB8 that falls back to the reference's sequence of double operations near rounding ties), or,
  * force_f64 != 0, through the double arithmetic alone; rgb [n][3] on the host */
 int rb200_debug_yuv16_to_rgb8(rb200_ctx* ctx, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64);
+
+/* test hook: the sparse smoothing tables of this context start 2^shrink times smaller (and the luma lists at 4 entries),
+ * so that the overflow -> regrow -> repeat path runs on small inputs; 0 restores the production sizes */
+int rb200_debug_set_grid_shrink(rb200_ctx* ctx, int shrink);
 
 /* ---- the decoder's whole per-frame sequence (PCCDecoder.cpp:330-508) governed by params ---------- */
 int rb200_decode_gof(rb200_ctx* ctx);

@@ -249,6 +249,13 @@ class DropIn(_Backend):
 
     def __init__(self):
         super().__init__(DROPIN_LIB)
+        self.lib.rb200_shim_stats.argtypes = [C.POINTER(abi.LaunchStats), C.c_int]
+
+    def stats(self, reset=True):
+        """kernel launches / bytes moved by the shim's CUDA context since the last reset"""
+        s = abi.LaunchStats()
+        assert self.lib.rb200_shim_stats(C.byref(s), 1 if reset else 0) == 0
+        return s
 
 
 class Port(_Backend):

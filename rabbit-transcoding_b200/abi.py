@@ -135,8 +135,8 @@ class LaunchStats(C.Structure):
 # every symbol include/rabbit_b200.h declares; tests check the .so exports all of them
 EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
-    "rb200_synchronize", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_set_plr", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
-    "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_decode_gof",
+    "rb200_synchronize", "rb200_host_alloc", "rb200_host_free", "rb200_occupancy_map", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_set_plr", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
+    "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_debug_set_grid_shrink", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
     "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
@@ -168,6 +168,11 @@ def load_library(path=None):
     lib.rb200_destroy.restype = None
     lib.rb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb200_synchronize.argtypes = [C.c_void_p]
+    lib.rb200_host_alloc.argtypes = [C.c_size_t]
+    lib.rb200_host_alloc.restype = C.c_void_p
+    lib.rb200_host_free.argtypes = [C.c_void_p]
+    lib.rb200_host_free.restype = None
+    lib.rb200_occupancy_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.rb200_gof_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int]
     lib.rb200_gof_upload.argtypes = [C.c_void_p, C.POINTER(Frames), C.POINTER(Atlas)]
     lib.rb200_gof_set_plr.argtypes = [C.c_void_p, C.POINTER(Plr)]
@@ -177,6 +182,7 @@ def load_library(path=None):
               "rb200_convert_rgb8", "rb200_decode_gof"):
         getattr(lib, n).argtypes = [C.c_void_p]
     lib.rb200_debug_yuv16_to_rgb8.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_int]
+    lib.rb200_debug_set_grid_shrink.argtypes = [C.c_void_p, C.c_int]
     lib.rb200_frame_counts_get.argtypes = [C.c_void_p, C.POINTER(FrameCounts)]
     lib.rb200_download_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(CloudHost)]
     lib.rb200_enable_stage_snapshots.argtypes = [C.c_void_p, C.c_int]

@@ -120,6 +120,12 @@ struct rb200_ctx {
   bool  geo_grid_clean = false, col_grid_clean = false;
   int   geo_grid_frames = 0, col_grid_frames = 0;
 
+  // scratch of the transfer / metrics translation units: created lazily by them, freed by rb200_destroy (opaque here)
+  void* transfer_scratch = nullptr;
+  void* metrics_scratch  = nullptr;
+  bool  pos_pre_valid    = false;  // d_pos_pre holds the pre-smoothing cloud of THIS GOF
+  int   test_grid_shrink = 0;      // rb200_debug_set_grid_shrink
+
   // pinned host staging for small read-backs
   void*  h_pinned     = nullptr;
   size_t h_pinned_cap = 0;

@@ -117,9 +117,61 @@ __global__ void k_expand_bitmap( const uint32_t* __restrict__ bm, int W, int H, 
   out[i] = ( bm[(size_t)y * words + ( x >> 5 )] >> ( x & 31 ) ) & 1u;
 }
 
+// generateOccupancyMap (:1584-1606) for one frame: thread (v, u) of the full-resolution map.  The reference visits the
+// pixels in row-major order and writes the 0/1 result back into the video sample (:1599-1600), so the FIRST visit of a
+// sample (its top-left pixel) sees the decoded value and every later visit sees the 0/1 left by the first one.
+__global__ void k_occupancy_frame( const uint8_t* __restrict__ video, int oW, int oH, int prec, int threshold, int eom,
+                                   uint32_t* __restrict__ map, uint8_t* __restrict__ video_out ) {
+  const int     W = oW * prec, H = oH * prec;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( i >= (int64_t)W * H ) { return; }
+  const int u = (int)( i % W ), v = (int)( i / W );
+  const int s = video[( v / prec ) * oW + u / prec];
+  if ( eom ) {
+    map[i] = (uint32_t)s;
+    return;
+  }
+  const int  first = s > threshold;
+  const bool top   = ( u % prec == 0 ) && ( v % prec == 0 );
+  const int  val   = top ? first : ( first > threshold );
+  map[i]           = (uint32_t)val;
+  // the value the sample holds after its last visit (bottom-right pixel)
+  if ( ( u % prec == prec - 1 ) && ( v % prec == prec - 1 ) ) { video_out[( v / prec ) * oW + u / prec] = (uint8_t)( prec == 1 ? first : val ); }
+}
+
 extern "C" {
 
 int rb200_abi_version( void ) { return RB200_ABI_VERSION; }
+
+void* rb200_host_alloc( size_t bytes ) {
+  void* p = nullptr;
+  if ( cudaMallocHost( &p, bytes ? bytes : 1 ) != cudaSuccess ) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void rb200_host_free( void* p ) {
+  if ( p ) { cudaFreeHost( p ); }
+}
+
+int rb200_occupancy_map( rb200_ctx* c, uint8_t* video, int oW, int oH, int prec, int threshold, int eom, uint32_t* map_out ) {
+  if ( !c || !video || !map_out || oW <= 0 || oH <= 0 || prec < 1 ) { return rb_fail( c, RB200_ERR_INVALID, "occupancy_map: bad arguments" ); }
+  cudaSetDevice( c->device );
+  const size_t nv = (size_t)oW * oH, nm = nv * prec * prec;
+  RB_CUDA( c->d_pack.ensure( nm * 4 + 2 * nv + 512 ) );
+  uint32_t* dMap = c->d_pack.as<uint32_t>();
+  uint8_t*  dIn  = c->d_pack.as<uint8_t>() + nm * 4, *dOut = dIn + ( ( nv + 255 ) & ~size_t( 255 ) );
+  RB_CUDA( cudaMemcpyAsync( dIn, video, nv, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( dOut, dIn, nv, cudaMemcpyDeviceToDevice, c->stream ) );
+  RB_LAUNCH( "occupancy_frame", k_occupancy_frame, rb_div_up( nm, 256 ), 256, 0, dIn, oW, oH, prec, threshold, eom, dMap, dOut );
+  RB_CUDA( cudaMemcpyAsync( map_out, dMap, nm * 4, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( video, dOut, nv, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  c->stats.h2d_bytes += (int64_t)nv;
+  c->stats.d2h_bytes += (int64_t)( nm * 4 + nv );
+  return RB200_OK;
+}
 
 int rb200_create( int device, rb200_ctx** out ) {
   if ( !out ) { return RB200_ERR_INVALID; }
@@ -226,9 +278,6 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   }
   if ( p->relative_t1 && ( p->enhanced_occupancy_map_code || p->use_additional_points_patch ) ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "relative_t1 together with EOM or raw patches is not implemented" );
-  }
-  if ( p->flag_geometry_smoothing && p->apply_geo_smoothing && !p->grid_smoothing ) {
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothPointCloud (PCCCodec.cpp:1106-1157) is not implemented" );
   }
   if ( p->geometry_bitdepth_3d < 1 || p->geometry_bitdepth_3d > 14 ) {
     return rb_fail( c, RB200_ERR_INVALID, "geometry_bitdepth_3d out of range" );
@@ -367,10 +416,19 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   c->h_eom_members.clear();
   if ( c->P.enhanced_occupancy_map_code && at->eom_patches && at->eom_offset ) {
     const int n = at->eom_offset[F];
+    if ( at->eom_offset[0] != 0 || n < 0 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: bad EOM patch offsets" ); }
+    for ( size_t f = 0; f < F; f++ ) {
+      if ( at->eom_offset[f + 1] < at->eom_offset[f] ) { return rb_fail( c, RB200_ERR_INVALID, "EOM patch offsets not monotone" ); }
+    }
     c->h_eom.assign( at->eom_patches, at->eom_patches + n );
     c->h_eom_off.assign( at->eom_offset, at->eom_offset + F + 1 );
     int nm = 0;
-    for ( auto& e : c->h_eom ) { nm = std::max( nm, e.member_begin + e.member_count ); }
+    for ( auto& e : c->h_eom ) {
+      if ( e.member_begin < 0 || e.member_count < 0 || e.member_begin > ( 1 << 30 ) - e.member_count ) {
+        return rb_fail( c, RB200_ERR_INVALID, "EOM patch member range is negative" );
+      }
+      nm = std::max( nm, e.member_begin + e.member_count );
+    }
     if ( nm > 0 ) {
       if ( !at->eom_members ) { return rb_fail( c, RB200_ERR_INVALID, "eom_members missing" ); }
       c->h_eom_members.assign( at->eom_members, at->eom_members + nm );
@@ -380,12 +438,18 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   c->h_raw_off.assign( F + 1, 0 );
   if ( c->P.use_additional_points_patch && at->raw_patches && at->raw_offset ) {
     const int n = at->raw_offset[F];
+    if ( at->raw_offset[0] != 0 || n < 0 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: bad raw patch offsets" ); }
+    for ( size_t f = 0; f < F; f++ ) {
+      if ( at->raw_offset[f + 1] < at->raw_offset[f] ) { return rb_fail( c, RB200_ERR_INVALID, "raw patch offsets not monotone" ); }
+    }
     c->h_raw.assign( at->raw_patches, at->raw_patches + n );
     c->h_raw_off.assign( at->raw_offset, at->raw_offset + F + 1 );
     for ( auto& r : c->h_raw ) {
-      if ( r.u0 < 0 || r.v0 < 0 || r.u0 + r.size_u0 > c->Wb || r.v0 + r.size_v0 > c->Hb ||
-           (int64_t)r.num_points > (int64_t)r.size_u0 * r.size_v0 * c->R * c->R ) {
-        return rb_fail( c, RB200_ERR_INVALID, "raw patch outside the canvas or too small for its points" );
+      // the patch stores X, then Y, then Z: 3 * numberOfRawPoints samples must fit its rectangle (the reference's fill
+      // loop is bounded by sizeU * sizeV, PCCCodec.cpp:913-928, and never leaves the patch)
+      if ( r.u0 < 0 || r.v0 < 0 || r.size_u0 < 0 || r.size_v0 < 0 || r.num_points < 0 || r.u0 + r.size_u0 > c->Wb ||
+           r.v0 + r.size_v0 > c->Hb || 3 * (int64_t)r.num_points > (int64_t)r.size_u0 * r.size_v0 * c->R * c->R ) {
+        return rb_fail( c, RB200_ERR_INVALID, "raw patch outside the canvas or too small for its 3 x %d samples", r.num_points );
       }
     }
   }
@@ -446,6 +510,7 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   RB_CUDA( cudaMemcpyAsync( c->d_frame_wi_off.p, st + o, ( F + 1 ) * 4, cudaMemcpyHostToDevice, c->stream ) );
   c->stats.h2d_bytes += (int64_t)tb;
   c->uploaded      = true;
+  c->pos_pre_valid = false;
   c->have_plr      = false;  // rb200_gof_set_plr follows the upload
   c->reconstructed = c->geo_smoothed = c->colors_transferred = c->color_smoothed = c->rgb_done = false;
   return RB200_OK;
@@ -515,6 +580,7 @@ int rb200_reconstruct( rb200_ctx* c ) {
   if ( !c ) { return RB200_ERR_INVALID; }
   if ( !c->uploaded ) { return rb_fail( c, RB200_ERR_STATE, "reconstruct before gof_upload" ); }
   cudaSetDevice( c->device );
+  c->pos_pre_valid = false;
   int r = rb_reconstruct_impl( c );
   if ( r == RB200_OK ) {
     c->reconstructed = true;
@@ -594,9 +660,12 @@ int rb200_decode_gof( rb200_ctx* c ) {
         return rb_fail( c, RB200_ERR_UNSUPPORTED, "attrTransferFilterType %d not implemented (only 0 and 1)",
                         p.attr_transfer_filter_type );
       }
-      if ( !c->geo_smoothed ) { c->geo_smoothed = true; }
-      r = rb200_transfer_colors( c );
-      if ( r ) { return r; }
+      // gridSmoothing_ == 0: tempFrameBuffer == reconstruct and no point is of type 3, so transferColors16bitBP
+      // changes nothing (PCCPointSet.cpp:1163-1164) and is skipped
+      if ( p.grid_smoothing && !p.pbf_enable ) {  // :446
+        r = rb200_transfer_colors( c );
+        if ( r ) { return r; }
+      }
     }
   }
   if ( p.attribute_count > 0 ) {
@@ -752,6 +821,12 @@ int rb200_download_occupancy( rb200_ctx* c, int f, uint8_t* dst ) {
   RB_CUDA( cudaMemcpyAsync( dst, c->d_pack.p, n, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   c->stats.d2h_bytes += n;
+  return RB200_OK;
+}
+
+int rb200_debug_set_grid_shrink( rb200_ctx* c, int shrink ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  c->test_grid_shrink = std::max( 0, std::min( 16, shrink ) );
   return RB200_OK;
 }
 

@@ -2,13 +2,21 @@
 //
 // Restates KDTreeSingleIndexAdaptor::buildIndex / computeBoundingBox / divideTree / middleSplit_ / planeSplit /
 // computeMinMax (dependencies/nanoflann/nanoflann.hpp:858-866, 1009-1181) for a FOREST of trees (one per cloud of a
-// GOF) in two phases:
-//  * level-parallel phase for nodes with more than KB_CAP (2048) points: every level is a handful of passes over the
-//    element records of all trees (per-node min/max and counts with warp-aggregated atomics, then the two Hoare
-//    passes of planeSplit as "rank the misplaced elements with one prefix sum, swap the i-th misplaced element from
-//    the left with the i-th misplaced element from the right");
-//  * block phase for subtrees of at most KB_CAP points: one CTA per subtree runs the same level-synchronous
-//    formulation entirely in shared memory, down to the leaves.
+// GOF).  The element order inside every leaf is part of the result (ties of a kNN query come back in traversal
+// order), so planeSplit's two Hoare passes are reproduced as the permutation they are: with lim1 = #(v < cut),
+//   pass 1 swaps the i-th element >= cut of [0, lim1) (ascending) with the i-th element < cut of [lim1, n) (descending),
+//   pass 2 does the same on [lim1, n) with "<= cut" and lim2 = #(v <= cut).
+// Two phases:
+//  * level phase, nodes of more than KS_CAP elements: every node is cut into chunks of GT consecutive elements, one CTA
+//    per chunk, so no pass has to look up "which node does this element belong to".  The predicates of a level are
+//    written ONCE as bit masks (2 bits per element); all ranks (prefix counts inside a node) come from the masks and a
+//    per-chunk prefix — 1/32 of the element traffic.  A Hoare pass is "misplaced elements to a staging array at their
+//    rank" + "every misplaced position reads its partner by rank": coalesced on both sides, no pair lists, no scans over
+//    the elements.  The last pass of a level also reduces the tight boxes of the two children (the next level's
+//    computeMinMax).  ~44 bytes per element and level.
+//  * subtree phase, nodes of at most KS_CAP elements: one CTA loads the subtree into shared memory; its warps take nodes
+//    from a shared stack (a warp splits a node, keeps the left child and pushes the right one), every pass is a
+//    lane-strided loop with ballots — no CTA barrier, no atomics on the elements.
 // divlow / divhigh come from the children's tight boxes (divideTree :1080-1081).
 #include <algorithm>
 
@@ -18,687 +26,877 @@
 
 namespace {
 
-constexpr int TPB      = 256;
+constexpr int TPB    = 256;
+constexpr int GT     = 2048;          // elements per chunk of the level phase
+constexpr int GWORDS = GT / 32;       // mask words per chunk
+constexpr int GEPT   = GT / TPB;      // elements per thread
+constexpr int KS_CAP = 2048;          // largest node of the subtree phase
+constexpr int KS_WARPS = 8;
+constexpr int KS_STACK = 448;         // pending nodes of a subtree: <= warps x depth (depth <= 36 + 11, see below)
 
-// per-node {min[3], max[3]} of the level-parallel phase: plain int32 so the updates are single RED instructions
-__device__ __forceinline__ void stat_update( int32_t* __restrict__ st, uint32_t node, const int mn[3], const int mx[3] ) {
-  int32_t* p = st + (size_t)node * 6;
-#pragma unroll
-  for ( int k = 0; k < 3; k++ ) {
-    atomicMin( p + k, mn[k] );
-    atomicMax( p + 3 + k, mx[k] );
-  }
+// counters[]: [0] next free level-phase node, [1] small roots, [2] split nodes of the level, [3] pool exhausted,
+//             [4] depth of the deepest subtree, [5] coordinate range error, [6] chunks of the level, [7] subtree stack overflow
+enum { C_NEXT = 0, C_SMALL = 1, C_BIG = 2, C_POOL = 3, C_DEPTH = 4, C_RANGE = 5, C_CHUNKS = 6, C_STACK = 7 };
+
+// build-time node of the level phase
+struct GNode {
+  uint32_t left, right;   // element range [left, right) in rec
+  uint32_t child1;        // 0: not split here
+  uint32_t lim1, lim2;    // elements < cutval, <= cutval
+  uint32_t m1, m2;        // misplaced pairs of the two Hoare passes
+  uint32_t idx;           // the left child takes [left, left + idx)
+  uint32_t firstChunk;
+  int16_t  lo[3], hi[3];      // the (loose) box handed down by the parent (divideTree's bbox argument)
+  int16_t  tmin[3], tmax[3];  // tight box of the node's points (what divideTree hands back up)
+  int16_t  cutval;
+  int8_t   cutfeat;
+  int8_t   state;             // 0 new, 1 split by the level phase, 2 root of a shared-memory subtree
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm( "mov.u32 %0, %%lanemask_lt;" : "=r"( m ) );
+  return m;
 }
 
-// records from positions (all clouds of the forest are concatenated; tree t owns [off[t], off[t+1]))
-__global__ void k_kd_init( const short4* __restrict__ pos, const int64_t* __restrict__ off, int nTrees, int64_t E, int ox, int oy,
-                           int oz, uint64_t* __restrict__ rec, uint32_t* __restrict__ nid, uint32_t* __restrict__ err ) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( e >= E ) { return; }
-  int lo = 0, hi = nTrees - 1;
-  while ( lo < hi ) {
-    const int mid = ( lo + hi + 1 ) >> 1;
-    if ( off[mid] <= e ) {
-      lo = mid;
-    } else {
-      hi = mid - 1;
+// middleSplit_ (nanoflann.hpp:1103-1142): cut axis and cut value from the loose box lo/hi and the tight box tmin/tmax
+__device__ __forceinline__ void kd_choose_split( const int lo[3], const int hi[3], const int tmin[3], const int tmax[3], const int o[3],
+                                                 int& cutfeat, int& cutval ) {
+  int max_span = hi[0] - lo[0];
+  for ( int i = 1; i < 3; i++ ) { max_span = max( max_span, hi[i] - lo[i] ); }
+  int cf = 0, max_spread = -1;
+  for ( int i = 0; i < 3; i++ ) {
+    const int span = hi[i] - lo[i];
+    if ( (double)span > ( 1.0 - 0.00001 ) * (double)max_span ) {  // span > (1 - EPS) * max_span in double
+      const int spread = tmax[i] - tmin[i];
+      if ( spread > max_spread ) {
+        cf         = i;
+        max_spread = spread;
+      }
     }
   }
-  const short4 p = pos[e];
-  const int    x = p.x - ox, y = p.y - oy, z = p.z - oz;
-  if ( (unsigned)x > 4095u || (unsigned)y > 4095u || (unsigned)z > 4095u ) { atomicOr( err, 1u ); }
-  rec[e] = (uint64_t)( x & 0xFFF ) | ( (uint64_t)( y & 0xFFF ) << 12 ) | ( (uint64_t)( z & 0xFFF ) << 24 ) |
-           ( (uint64_t)( e - off[lo] ) << 36 );
-  nid[e] = (uint32_t)lo + 1u;
+  const int loc = cf == 0 ? lo[0] : ( cf == 1 ? lo[1] : lo[2] ), hic = cf == 0 ? hi[0] : ( cf == 1 ? hi[1] : hi[2] );
+  const int tmn = cf == 0 ? tmin[0] : ( cf == 1 ? tmin[1] : tmin[2] ), tmx = cf == 0 ? tmax[0] : ( cf == 1 ? tmax[1] : tmax[2] );
+  const int oc  = cf == 0 ? o[0] : ( cf == 1 ? o[1] : o[2] );
+  // split_val = (bbox.low + bbox.high) / 2 is an int division of the ABSOLUTE coordinates (truncation toward zero)
+  const int split = ( ( loc + oc ) + ( hic + oc ) ) / 2 - oc;
+  cutfeat         = cf;
+  cutval          = split < tmn ? tmn : ( split > tmx ? tmx : split );
 }
 
-__global__ void k_kd_roots( KdNode* __restrict__ nodes, const int64_t* __restrict__ off, int nTrees, int32_t* __restrict__ st ) {
+// :1137-1139
+__device__ __forceinline__ uint32_t kd_split_index( uint32_t count, uint32_t lim1, uint32_t lim2 ) {
+  if ( lim1 > count / 2 ) { return lim1; }
+  if ( lim2 < count / 2 ) { return lim2; }
+  return count / 2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// level phase
+// ---------------------------------------------------------------------------------------------------
+
+// element records from positions (all clouds of the forest are concatenated; tree t owns [off[t], off[t+1])) and the
+// tight boxes of the roots (computeBoundingBox, :1009-1024): one RED per CTA and box side in the common case
+__global__ void __launch_bounds__( TPB ) k_g_init( const short4* __restrict__ pos, const int64_t* __restrict__ off, int nTrees, int64_t E,
+                                                   int ox, int oy, int oz, uint64_t* __restrict__ rec, int32_t* __restrict__ st,
+                                                   uint32_t* __restrict__ counters ) {
+  __shared__ int sTree[TPB / 32];
+  __shared__ int sBox[TPB / 32][6];
+  const int64_t e0   = (int64_t)blockIdx.x * ( TPB * GEPT );
+  const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // the tree of the first element of the CTA; a CTA rarely crosses into the next tree
+  int t0;
+  {
+    int lo = 0, hi = nTrees - 1;
+    while ( lo < hi ) {
+      const int mid = ( lo + hi + 1 ) >> 1;
+      if ( off[mid] <= e0 ) {
+        lo = mid;
+      } else {
+        hi = mid - 1;
+      }
+    }
+    t0 = lo;
+  }
+  int  mn[3] = {1 << 20, 1 << 20, 1 << 20}, mx[3] = {-( 1 << 20 ), -( 1 << 20 ), -( 1 << 20 )};
+  int  cur   = t0;         // tree the running box belongs to
+  bool bad   = false;
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const int64_t e = e0 + q * TPB + threadIdx.x;
+    if ( e >= E ) { break; }
+    int t = cur;
+    while ( e >= off[t + 1] ) { t++; }  // empty clouds are rejected by the host
+    if ( t != cur ) {  // this thread walked into the next tree: flush what it has
+      if ( mn[0] <= mx[0] ) {
+        for ( int k = 0; k < 3; k++ ) {
+          atomicMin( &st[(size_t)( cur + 1 ) * 6 + k], mn[k] );
+          atomicMax( &st[(size_t)( cur + 1 ) * 6 + 3 + k], mx[k] );
+        }
+      }
+      for ( int k = 0; k < 3; k++ ) { mn[k] = 1 << 20, mx[k] = -( 1 << 20 ); }
+      cur = t;
+    }
+    const short4 p = pos[e];
+    const int    x = p.x - ox, y = p.y - oy, z = p.z - oz;
+    bad |= (unsigned)x > 4095u || (unsigned)y > 4095u || (unsigned)z > 4095u;
+    rec[e] = (uint64_t)( x & 0xFFF ) | ( (uint64_t)( y & 0xFFF ) << 12 ) | ( (uint64_t)( z & 0xFFF ) << 24 ) |
+             ( (uint64_t)( e - off[t] ) << 36 );
+    mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
+    mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
+  }
+  if ( bad ) { atomicOr( &counters[C_RANGE], 1u ); }
+  // combine: warps whose lanes all ended in the same tree reduce with shuffles; the others flush per lane
+  const bool     have = mn[0] <= mx[0];
+  const uint32_t act  = __ballot_sync( 0xFFFFFFFFu, have );
+  int            same = 0;
+  if ( act == 0xFFFFFFFFu ) { __match_all_sync( 0xFFFFFFFFu, cur, &same ); }
+  if ( same ) {
+#pragma unroll
+    for ( int k = 0; k < 3; k++ ) {
+      mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
+      mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
+    }
+    if ( lane == 0 ) {
+      sTree[w] = cur;
+      for ( int k = 0; k < 3; k++ ) { sBox[w][k] = mn[k], sBox[w][3 + k] = mx[k]; }
+    }
+  } else {
+    if ( lane == 0 ) { sTree[w] = -1; }
+    if ( have ) {
+      for ( int k = 0; k < 3; k++ ) {
+        atomicMin( &st[(size_t)( cur + 1 ) * 6 + k], mn[k] );
+        atomicMax( &st[(size_t)( cur + 1 ) * 6 + 3 + k], mx[k] );
+      }
+    }
+  }
+  __syncthreads();
+  if ( threadIdx.x < TPB / 32 ) {  // a run of warps with the same tree is flushed by its first warp
+    const int i = threadIdx.x, t = sTree[i];
+    if ( t >= 0 && ( i == 0 || sTree[i - 1] != t ) ) {
+      int b[6];
+      for ( int k = 0; k < 6; k++ ) { b[k] = sBox[i][k]; }
+      for ( int j = i + 1; j < TPB / 32 && sTree[j] == t; j++ ) {
+        for ( int k = 0; k < 3; k++ ) { b[k] = min( b[k], sBox[j][k] ), b[3 + k] = max( b[3 + k], sBox[j][3 + k] ); }
+      }
+      for ( int k = 0; k < 3; k++ ) {
+        atomicMin( &st[(size_t)( t + 1 ) * 6 + k], b[k] );
+        atomicMax( &st[(size_t)( t + 1 ) * 6 + 3 + k], b[3 + k] );
+      }
+    }
+  }
+}
+
+__global__ void k_g_roots( GNode* __restrict__ nodes, const int64_t* __restrict__ off, int nTrees, int32_t* __restrict__ st ) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ( t >= nTrees ) { return; }
   for ( int k = 0; k < 3; k++ ) {
     st[(size_t)( t + 1 ) * 6 + k]     = 0x7FFFFFFF;
     st[(size_t)( t + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
   }
-  KdNode n{};
-  n.left  = (uint32_t)off[t];
-  n.right = (uint32_t)off[t + 1];
-  for ( int k = 0; k < 3; k++ ) {
-    n.tmin[k] = 32767;
-    n.tmax[k] = -32768;
-  }
-  n.state      = 0;
+  GNode n{};
+  n.left       = (uint32_t)off[t];
+  n.right      = (uint32_t)off[t + 1];
   nodes[t + 1] = n;
   if ( t == 0 ) {
-    KdNode z{};
+    GNode z{};
     nodes[0] = z;
   }
 }
 
-// per-node tight bounding box of the nodes of this level (computeMinMax for all three axes at once):
-// warp shuffle reduction -> CTA combine in shared memory -> one RED per CTA and node in the common case
-// ASSIGN: the elements of the split nodes of level [lvlBegin, lvlEnd) first move to their child (what k_kd_assign
-// does), and the boxes are those of the children — the statistics pass of the next level rides on the assignment pass
-template <bool ASSIGN>
-__global__ void __launch_bounds__( TPB ) k_kd_stats( const uint64_t* __restrict__ rec, uint32_t* __restrict__ nid,
-                                                     const KdNode* __restrict__ nodes, int32_t* __restrict__ st, int64_t E,
-                                                     uint32_t lvlBegin, uint32_t lvlEnd ) {
-  __shared__ uint32_t wNode[TPB / 32];
-  __shared__ int      wMin[TPB / 32][3], wMax[TPB / 32][3];
-  const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t      node = 0;
-  int           c[3] = {0, 0, 0};
-  bool          on   = false;
-  if ( e < E ) {
-    node = nid[e];
-    on   = node >= lvlBegin && node < lvlEnd;
-    if ( ASSIGN && on ) {
-      const KdNode& n = nodes[node];
-      on              = n.state == 1 && n.child1 != 0;
-      if ( on ) {
-        node   = ( (uint32_t)e < nodes[n.child1].right ) ? n.child1 : n.child1 + 1;
-        nid[e] = node;
-      }
-    }
-    if ( on ) {
-      const uint64_t r = rec[e];
-      c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
-    }
-  }
-  const uint32_t act     = __ballot_sync( 0xFFFFFFFFu, on );
-  const uint32_t peers   = on ? __match_any_sync( act, node ) : 0u;
-  const bool     uniform = on && peers == act && act == 0xFFFFFFFFu;  // warp-uniform predicate (all lanes agree)
-  const bool     wuni    = __all_sync( 0xFFFFFFFFu, uniform );
-  int            mn[3] = {c[0], c[1], c[2]}, mx[3] = {c[0], c[1], c[2]};
-  if ( wuni ) {
-#pragma unroll
-    for ( int k = 0; k < 3; k++ ) {
-#pragma unroll
-      for ( int d = 16; d > 0; d >>= 1 ) {
-        mn[k] = min( mn[k], __shfl_xor_sync( 0xFFFFFFFFu, mn[k], d ) );
-        mx[k] = max( mx[k], __shfl_xor_sync( 0xFFFFFFFFu, mx[k], d ) );
-      }
-    }
-    if ( lane == 0 ) {
-      wNode[w] = node;
-      for ( int k = 0; k < 3; k++ ) { wMin[w][k] = mn[k], wMax[w][k] = mx[k]; }
-    }
-  } else {
-    if ( lane == 0 ) { wNode[w] = 0xFFFFFFFFu; }
-    if ( on ) {  // mixed warp: reduce inside every peer group through its leader
-      const int leader = __ffs( peers ) - 1;
-      for ( uint32_t m = peers & ~( 1u << leader ); m; m &= m - 1 ) {
-        const int src = __ffs( m ) - 1;
-#pragma unroll
-        for ( int k = 0; k < 3; k++ ) {
-          const int v = __shfl_sync( peers, c[k], src );
-          mn[k] = min( mn[k], v );
-          mx[k] = max( mx[k], v );
-        }
-      }
-      if ( lane == leader ) { stat_update( st, node, mn, mx ); }
-    }
-  }
+// the nodes of this level: tight box from the statistics, small root / split decision (middleSplit_), chunk table and
+// the ids of the children.  One CTA: a level has at most a few ten thousand nodes.
+constexpr int SETUP_TPB = 1024;
+__global__ void __launch_bounds__( SETUP_TPB ) k_g_setup( GNode* __restrict__ nodes, const int32_t* __restrict__ st, uint32_t lvlBegin,
+                                                          uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
+                                                          uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
+                                                          uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap ) {
+  __shared__ uint32_t wsA[32], wsB[32];
+  __shared__ uint32_t carryC, carryB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if ( threadIdx.x == 0 ) { carryC = 0, carryB = 0; }
   __syncthreads();
-  if ( threadIdx.x < TPB / 32 ) {  // combine the uniform warps of this CTA: a run of equal nodes is flushed by its first warp
-    const int      i  = threadIdx.x;
-    const uint32_t nd = wNode[i];
-    if ( nd != 0xFFFFFFFFu && ( i == 0 || wNode[i - 1] != nd ) ) {
-      int a[3] = {wMin[i][0], wMin[i][1], wMin[i][2]}, b[3] = {wMax[i][0], wMax[i][1], wMax[i][2]};
-      for ( int j = i + 1; j < TPB / 32 && wNode[j] == nd; j++ ) {
-        for ( int k = 0; k < 3; k++ ) {
-          a[k] = min( a[k], wMin[j][k] );
-          b[k] = max( b[k], wMax[j][k] );
-        }
-      }
-      stat_update( st, nd, a, b );
-    }
-  }
-}
-
-// middleSplit_ (nanoflann.hpp:1103-1142) for one node: cut axis and cut value
-__device__ __forceinline__ void kd_choose_split( KdNode& n, int o[3] ) {
-  int max_span = n.hi[0] - n.lo[0];
-  for ( int i = 1; i < 3; i++ ) { max_span = max( max_span, n.hi[i] - n.lo[i] ); }
-  int cutfeat = 0, max_spread = -1;
-  for ( int i = 0; i < 3; i++ ) {
-    const int span = n.hi[i] - n.lo[i];
-    if ( (double)span > ( 1.0 - 0.00001 ) * (double)max_span ) {  // span > (1 - EPS) * max_span in double
-      const int spread = n.tmax[i] - n.tmin[i];
-      if ( spread > max_spread ) {
-        cutfeat    = i;
-        max_spread = spread;
-      }
-    }
-  }
-  // split_val = (bbox.low + bbox.high) / 2 is an int division of the ABSOLUTE coordinates (truncation toward zero)
-  const int split = ( ( n.lo[cutfeat] + o[cutfeat] ) + ( n.hi[cutfeat] + o[cutfeat] ) ) / 2 - o[cutfeat];
-  int       cut;
-  if ( split < n.tmin[cutfeat] ) {
-    cut = n.tmin[cutfeat];
-  } else if ( split > n.tmax[cutfeat] ) {
-    cut = n.tmax[cutfeat];
-  } else {
-    cut = split;
-  }
-  n.cutfeat = (int8_t)cutfeat;
-  n.cutval  = (int16_t)cut;
-}
-
-// the nodes of this level: leaf / small root / split decision
-__global__ void k_kd_split( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, int small, int ox, int oy, int oz,
-                            uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters, int isRoot,
-                            const int32_t* __restrict__ st ) {
-  const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= lvlEnd ) { return; }
-  KdNode& n = nodes[i];
-  for ( int k = 0; k < 3; k++ ) {
-    n.tmin[k] = (int16_t)st[(size_t)i * 6 + k];
-    n.tmax[k] = (int16_t)st[(size_t)i * 6 + 3 + k];
-  }
-  if ( isRoot ) {  // a root: divideTree( 0, N, root_bbox ) starts from the tight box
-    for ( int k = 0; k < 3; k++ ) {
-      n.lo[k] = n.tmin[k];
-      n.hi[k] = n.tmax[k];
-    }
-  }
-  const uint32_t count = n.right - n.left;
-  if ( count <= (uint32_t)small ) {
-    n.state                                = 2;
-    smallRoots[atomicAdd( &counters[1], 1u )] = i;
-    return;
-  }
-  int o[3] = {ox, oy, oz};
-  kd_choose_split( n, o );
-  n.lt = n.le = 0;
-  n.state     = 1;
-  atomicAdd( &counters[2], 1u );  // big nodes of this level
-}
-
-// lim1 / lim2 of planeSplit: elements < cutval and <= cutval
-__global__ void k_kd_count( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, KdNode* __restrict__ nodes,
-                            int64_t E, uint32_t lvlBegin, uint32_t lvlEnd ) {
-  const int64_t e    = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  uint32_t      node = 0;
-  bool          on = false, lt = false, le = false;
-  if ( e < E ) {
-    node = nid[e];
-    if ( node >= lvlBegin && node < lvlEnd ) {
-      const KdNode& n = nodes[node];
-      if ( n.state == 1 ) {
-        on          = true;
-        const int v = kd_coord( rec[e], n.cutfeat );
-        lt          = v < n.cutval;
-        le          = v <= n.cutval;
-      }
-    }
-  }
-  const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
-  if ( !on ) { return; }
-  const uint32_t peers = __match_any_sync( act, node );
-  const uint32_t bl = __ballot_sync( act, lt ), be = __ballot_sync( act, le );
-  if ( ( threadIdx.x & 31 ) == __ffs( peers ) - 1 ) {
-    const uint32_t a = __popc( bl & peers ), b = __popc( be & peers );
-    if ( a ) { atomicAdd( &nodes[node].lt, a ); }
-    if ( b ) { atomicAdd( &nodes[node].le, b ); }
-  }
-}
-
-// misplaced-element flags of one Hoare pass.  pass 0: [0, count) split at lim1 by (v < cutval);
-// pass 1: [lim1, count) split at lim2 by (v <= cutval)
-__global__ void k_kd_flag( const uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes,
-                           int64_t E, uint32_t lvlBegin, uint32_t lvlEnd, int pass, uint32_t* __restrict__ flags ) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( e > E ) { return; }
-  uint32_t f = 0;
-  if ( e < E ) {
-    const uint32_t node = nid[e];
-    if ( node >= lvlBegin && node < lvlEnd ) {
-      const KdNode& n = nodes[node];
-      if ( n.state == 1 ) {
-        const uint32_t p = (uint32_t)e - n.left;
-        const int      v = kd_coord( rec[e], n.cutfeat );
-        if ( pass == 0 ) {
-          const bool in = v < n.cutval;
-          f             = ( p < n.lt ) ? !in : in;
-        } else if ( p >= n.lt ) {
-          const bool in = v <= n.cutval;
-          f             = ( p < n.le ) ? !in : in;
-        }
-      }
-    }
-  }
-  flags[e] = f;
-}
-
-// pair lists: the i-th misplaced element from the left (ascending position) meets the i-th misplaced element
-// from the right (descending position) — exactly the swaps of the two-pointer loop (:1154-1181)
-__global__ void k_kd_pairs( const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E, uint32_t lvlBegin,
-                            uint32_t lvlEnd, int pass, const uint32_t* __restrict__ scan, const uint32_t* __restrict__ flags_unused,
-                            uint32_t* __restrict__ pairL, uint32_t* __restrict__ pairR ) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( e >= E ) { return; }
-  if ( scan[e + 1] == scan[e] ) { return; }
-  const KdNode&  n     = nodes[nid[e]];
-  const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
-  const uint32_t lim   = pass == 0 ? n.left + n.lt : n.left + n.le;
-  const uint32_t m     = ( scan[n.right] - scan[begin] ) >> 1;  // misplaced on each side
-  const uint32_t r     = scan[e] - scan[begin];
-  if ( (uint32_t)e < lim ) {
-    pairL[begin + r] = (uint32_t)e;
-  } else {
-    pairR[begin + ( m - 1 - ( r - m ) )] = (uint32_t)e;
-  }
-}
-
-__global__ void k_kd_swap( uint64_t* __restrict__ rec, const uint32_t* __restrict__ nid, const KdNode* __restrict__ nodes, int64_t E,
-                           uint32_t lvlBegin, uint32_t lvlEnd, int pass, const uint32_t* __restrict__ scan,
-                           const uint32_t* __restrict__ pairL, const uint32_t* __restrict__ pairR ) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( e >= E ) { return; }
-  const uint32_t node = nid[e];
-  if ( node < lvlBegin || node >= lvlEnd ) { return; }
-  const KdNode& n = nodes[node];
-  if ( n.state != 1 ) { return; }
-  const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
-  if ( (uint32_t)e < begin ) { return; }
-  const uint32_t m = ( scan[n.right] - scan[begin] ) >> 1;
-  const uint32_t k = (uint32_t)e - begin;
-  if ( k >= m ) { return; }
-  const uint32_t a = pairL[begin + k], b = pairR[begin + k];
-  const uint64_t ra = rec[a], rb = rec[b];
-  rec[a] = rb;
-  rec[b] = ra;
-}
-
-// children of the split nodes of this level (divideTree :1070-1078)
-__global__ void k_kd_children( KdNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd, uint32_t* __restrict__ counters,
-                               uint32_t nodeCap, int32_t* __restrict__ st ) {
-  const uint32_t i = lvlBegin + blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= lvlEnd ) { return; }
-  KdNode& n = nodes[i];
-  if ( n.state != 1 ) { return; }
-  const uint32_t count = n.right - n.left;
-  uint32_t       idx;  // :1137-1139
-  if ( n.lt > count / 2 ) {
-    idx = n.lt;
-  } else if ( n.le < count / 2 ) {
-    idx = n.le;
-  } else {
-    idx = count / 2;
-  }
-  const uint32_t c1 = atomicAdd( &counters[0], 2u );
-  if ( c1 + 2 > nodeCap ) {
-    counters[3] = 1;  // node pool exhausted
-    n.state     = 3;
-    n.child1    = 0;
-    return;
-  }
-  n.child1 = c1;
-  KdNode a{}, b{};
-  a.left  = n.left;
-  a.right = n.left + idx;
-  b.left  = n.left + idx;
-  b.right = n.right;
-  for ( int k = 0; k < 3; k++ ) {
-    a.lo[k] = b.lo[k] = n.lo[k];
-    a.hi[k] = b.hi[k] = n.hi[k];
-    a.tmin[k] = b.tmin[k] = 32767;
-    a.tmax[k] = b.tmax[k] = -32768;
-  }
-  a.hi[n.cutfeat] = n.cutval;  // left_bbox[cutfeat].high = cutval
-  b.lo[n.cutfeat] = n.cutval;  // right_bbox[cutfeat].low = cutval
-  nodes[c1]       = a;
-  nodes[c1 + 1]   = b;
-  for ( int k = 0; k < 3; k++ ) {
-    st[(size_t)c1 * 6 + k] = st[(size_t)( c1 + 1 ) * 6 + k] = 0x7FFFFFFF;
-    st[(size_t)c1 * 6 + 3 + k] = st[(size_t)( c1 + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// block phase: one CTA builds a whole subtree of at most KB_CAP elements, level by level, in shared memory.
-// Same formulation as the level-parallel phase (tight boxes with atomics, counts, the two Hoare passes as
-// rank-the-misplaced + pairwise swap), but every pass is a few hundred cycles on 2048 shared-memory records.
-// ---------------------------------------------------------------------------------------------------
-constexpr int KB_CAP   = 2048;  // elements per CTA subtree
-constexpr int KB_LEVEL = 384;   // nodes per level: children only come from nodes with > 10 elements, so <= 2 * 2048 / 11 = 372
-constexpr int KB_TPB   = 256;
-constexpr int KB_EPT   = KB_CAP / KB_TPB;
-
-struct KbNode {  // a node of the level being processed
-  int32_t  tmin[3], tmax[3];
-  uint32_t gid, pgid, lt, le;
-  uint16_t left, right, child;  // element range inside the CTA subtree; child: index of child1 in the next level
-  int16_t  lo[3], hi[3], cutval;
-  uint8_t  cutfeat, pfeat, state, side;  // side: 0 left child, 1 right child of pgid (pgid == 0: subtree root)
-};
-struct KbNext {  // a node of the next level, as created by its parent
-  uint32_t gid, pgid;
-  uint16_t left, right;
-  int16_t  lo[3], hi[3];
-  uint8_t  pfeat, side;
-};
-
-struct KbShared {
-  uint64_t rec[KB_CAP];
-  KbNode   cur[KB_LEVEL];
-  KbNext   nxt[KB_LEVEL];
-  uint16_t nid[KB_CAP];
-  uint16_t scan[KB_CAP + 2];
-  uint16_t pairL[KB_CAP], pairR[KB_CAP];
-  uint32_t warpSum[KB_TPB / 32];
-  uint32_t nNext, gBase, big;
-  uint8_t  active[KB_CAP / 32];  // chunk of 32 consecutive elements still has an element in an unfinished node
-};
-
-__global__ void __launch_bounds__( KB_TPB ) k_kd_block( uint64_t* __restrict__ grec, KdNode* __restrict__ nodes,
-                                                        const uint32_t* __restrict__ smallRoots, uint32_t nRoots,
-                                                        uint32_t* __restrict__ counters, uint32_t nodeCap, int ox, int oy, int oz ) {
-  extern __shared__ __align__( 16 ) unsigned char kb_smem[];
-  KbShared&  S     = *reinterpret_cast<KbShared*>( kb_smem );
-  uint64_t*  rec   = S.rec;
-  uint16_t*  nid   = S.nid;
-  uint16_t*  scan  = S.scan;
-  uint16_t*  pairL = S.pairL;
-  uint16_t*  pairR = S.pairR;
-  KbNode*    cur   = S.cur;
-  KbNext*    nxt   = S.nxt;
-  uint32_t*  warpSum = S.warpSum;
-  uint32_t&  sNNext = S.nNext;
-  uint32_t&  sGBase = S.gBase;
-  uint32_t&  sBig   = S.big;
-  uint8_t*   active = S.active;
-  const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const uint32_t rootId = smallRoots[blockIdx.x];
-  const uint32_t base = nodes[rootId].left, total = nodes[rootId].right - base;
-  int            o[3] = {ox, oy, oz};
-  for ( uint32_t i = t; i < total; i += KB_TPB ) {
-    rec[i] = grec[base + i];
-    nid[i] = 0;
-  }
-  if ( t < KB_CAP / 32 ) { active[t] = (uint32_t)t * 32 < total; }
-  if ( t == 0 ) {
-    const KdNode r = nodes[rootId];
-    KbNext       n{};
-    n.gid = rootId, n.pgid = 0, n.left = 0, n.right = (uint16_t)total, n.pfeat = 0, n.side = 0;
-    for ( int k = 0; k < 3; k++ ) { n.lo[k] = r.lo[k], n.hi[k] = r.hi[k]; }
-    nxt[0] = n;
-    sNNext = 1;
-  }
-  __syncthreads();
-  int level = 0;
-  for ( ;; level++ ) {
-    // ---- this level's nodes ----
-    const uint32_t nl = sNNext;
-    __syncthreads();
-    if ( nl == 0 ) { break; }
-    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
-      const KbNext x = nxt[j];
-      KbNode       n{};
-      n.gid = x.gid, n.pgid = x.pgid, n.left = x.left, n.right = x.right, n.pfeat = x.pfeat, n.side = x.side;
+  const uint32_t childBase = counters[C_NEXT];
+  const int      o[3]      = {ox, oy, oz};
+  for ( uint32_t base = lvlBegin; base < lvlEnd; base += SETUP_TPB ) {
+    const uint32_t i   = base + threadIdx.x;
+    uint32_t       nch = 0, big = 0;
+    if ( i < lvlEnd ) {
+      GNode& n = nodes[i];
+      int    lo[3], hi[3], tmin[3], tmax[3];
       for ( int k = 0; k < 3; k++ ) {
-        n.lo[k] = x.lo[k], n.hi[k] = x.hi[k];
-        n.tmin[k] = 0x7FFFFFFF, n.tmax[k] = (int32_t)0x80000000;
-      }
-      cur[j] = n;
-    }
-    if ( t == 0 ) { sNNext = 0, sBig = 0; }
-    __syncthreads();
-    // ---- tight boxes ----
-#pragma unroll
-    for ( int q = 0; q < KB_EPT; q++ ) {
-      const uint32_t e = q * KB_TPB + t;
-      if ( !active[e >> 5] ) { continue; }  // warp-uniform
-      const uint32_t j = e < total ? nid[e] : 0xFFFFu;
-      const bool     on = j != 0xFFFFu;
-      int            c[3] = {0, 0, 0};
-      if ( on ) {
-        const uint64_t r = rec[e];
-        c[0] = kd_coord( r, 0 ), c[1] = kd_coord( r, 1 ), c[2] = kd_coord( r, 2 );
-      }
-      const uint32_t act = __ballot_sync( 0xFFFFFFFFu, on );
-      int allSame = 0;
-      if ( act == 0xFFFFFFFFu ) { __match_all_sync( 0xFFFFFFFFu, j, &allSame ); }
-      if ( allSame ) {
-        int mn[3], mx[3];
-#pragma unroll
-        for ( int k = 0; k < 3; k++ ) {
-          mn[k] = __reduce_min_sync( 0xFFFFFFFFu, c[k] );
-          mx[k] = __reduce_max_sync( 0xFFFFFFFFu, c[k] );
+        tmin[k]   = st[(size_t)i * 6 + k];
+        tmax[k]   = st[(size_t)i * 6 + 3 + k];
+        n.tmin[k] = (int16_t)tmin[k];
+        n.tmax[k] = (int16_t)tmax[k];
+        if ( isRoot ) {  // divideTree( 0, N, root_bbox ) starts from the tight box
+          n.lo[k] = (int16_t)tmin[k];
+          n.hi[k] = (int16_t)tmax[k];
         }
-        if ( lane == 0 ) {
-          for ( int k = 0; k < 3; k++ ) {
-            atomicMin( &cur[j].tmin[k], mn[k] );
-            atomicMax( &cur[j].tmax[k], mx[k] );
-          }
-        }
-      } else if ( on ) {
-        for ( int k = 0; k < 3; k++ ) {
-          atomicMin( &cur[j].tmin[k], c[k] );
-          atomicMax( &cur[j].tmax[k], c[k] );
-        }
+        lo[k] = n.lo[k], hi[k] = n.hi[k];
       }
-    }
-    __syncthreads();
-    // ---- leaf / split decision; the node reports its tight bound to its parent (divideTree :1080-1081) ----
-    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
-      KbNode&        n     = cur[j];
       const uint32_t count = n.right - n.left;
-      if ( n.pgid ) {
-        if ( n.side == 0 ) {
-          nodes[n.pgid].divlow = (int16_t)n.tmax[n.pfeat];
-        } else {
-          nodes[n.pgid].divhigh = (int16_t)n.tmin[n.pfeat];
-        }
-      }
-      if ( count <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
-        KdNode g{};
-        g.left = base + n.left, g.right = base + n.right, g.child1 = 0, g.state = 3;
-        for ( int k = 0; k < 3; k++ ) {
-          g.lo[k] = n.lo[k], g.hi[k] = n.hi[k];
-          g.tmin[k] = (int16_t)n.tmin[k], g.tmax[k] = (int16_t)n.tmax[k];
-        }
-        nodes[n.gid] = g;
-        n.state      = 3;
+      if ( count <= (uint32_t)KS_CAP ) {
+        n.state                                     = 2;
+        smallRoots[atomicAdd( &counters[C_SMALL], 1u )] = i;
       } else {
-        KdNode tmp{};
-        for ( int k = 0; k < 3; k++ ) {
-          tmp.lo[k] = n.lo[k], tmp.hi[k] = n.hi[k];
-          tmp.tmin[k] = (int16_t)n.tmin[k], tmp.tmax[k] = (int16_t)n.tmax[k];
-        }
-        kd_choose_split( tmp, o );
-        n.cutfeat = (uint8_t)tmp.cutfeat, n.cutval = tmp.cutval;
-        n.lt = n.le = 0;
-        n.state     = 1;
-        atomicAdd( &sBig, 1u );
+        int cf, cv;
+        kd_choose_split( lo, hi, tmin, tmax, o, cf, cv );
+        n.cutfeat = (int8_t)cf;
+        n.cutval  = (int16_t)cv;
+        n.state   = 1;
+        nch       = ( count + GT - 1 ) / GT;
+        big       = 1;
       }
+    }
+    // CTA-wide exclusive scans of the chunk counts and of the split flags
+    uint32_t ia = nch, ib = big;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+      const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ia, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, ib, d );
+      if ( lane >= d ) { ia += ta, ib += tb; }
+    }
+    if ( lane == 31 ) { wsA[w] = ia, wsB[w] = ib; }
+    __syncthreads();
+    if ( w == 0 ) {
+      const uint32_t xa = wsA[lane], xb = wsB[lane];
+      uint32_t       ya = xa, yb = xb;
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 ) {
+        const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ya, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, yb, d );
+        if ( lane >= d ) { ya += ta, yb += tb; }
+      }
+      wsA[lane] = ya - xa, wsB[lane] = yb - xb;
+      if ( lane == 31 ) { wsA[31] = ya - xa, wsB[31] = yb - xb; }
     }
     __syncthreads();
-    if ( sBig == 0 ) { break; }
-    // ---- lim1 / lim2 (one shared-memory atomic per warp when the warp sits inside one node) ----
-#pragma unroll
-    for ( int q = 0; q < KB_EPT; q++ ) {
-      const uint32_t e  = q * KB_TPB + t;
-      if ( !active[e >> 5] ) { continue; }
-      const uint32_t j  = e < total ? nid[e] : 0xFFFFu;
-      const bool     on = j != 0xFFFFu && cur[j].state == 1;
-      bool           lt = false, le = false;
-      if ( on ) {
-        const int v = kd_coord( rec[e], cur[j].cutfeat ), cut = cur[j].cutval;
-        lt = v < cut, le = v <= cut;
-      }
-      int allSame = 0;
-      __match_all_sync( 0xFFFFFFFFu, on ? j : 0xFFFFu, &allSame );
-      if ( allSame ) {
-        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, lt ), be = __ballot_sync( 0xFFFFFFFFu, le );
-        if ( on && lane == 0 ) {
-          if ( bl ) { atomicAdd( &cur[j].lt, (uint32_t)__popc( bl ) ); }
-          if ( be ) { atomicAdd( &cur[j].le, (uint32_t)__popc( be ) ); }
-        }
-      } else if ( on ) {
-        if ( lt ) { atomicAdd( &cur[j].lt, 1u ); }
-        if ( le ) { atomicAdd( &cur[j].le, 1u ); }
-      }
-    }
-    __syncthreads();
-    // ---- the two Hoare passes of planeSplit (:1154-1181) ----
-    for ( int pass = 0; pass < 2; pass++ ) {
-      // flags + block exclusive scan.  Warp w owns the 256 consecutive elements [256 w, 256 w + 256) and walks them 32
-      // at a time (consecutive lanes = consecutive elements: conflict-free), carrying its running count in a register
-      uint32_t fbits = 0, run = 0;
-      uint16_t pre[KB_EPT];
-#pragma unroll
-      for ( int q = 0; q < KB_EPT; q++ ) {
-        const uint32_t e = w * ( KB_EPT * 32 ) + q * 32 + lane;
-        uint32_t       m = 0;
-        const uint32_t j = ( active[e >> 5] && e < total ) ? nid[e] : 0xFFFFu;
-        if ( j != 0xFFFFu && cur[j].state == 1 ) {
-          const KbNode&  n = cur[j];
-          const uint32_t p = e - n.left;
-          const int      v = kd_coord( rec[e], n.cutfeat );
-          if ( pass == 0 ) {
-            const bool in = v < n.cutval;
-            m             = ( p < n.lt ) ? !in : in;
-          } else if ( p >= n.lt ) {
-            const bool in = v <= n.cutval;
-            m             = ( p < n.le ) ? !in : in;
-          }
-        }
-        const uint32_t bal = __ballot_sync( 0xFFFFFFFFu, m != 0 );
-        pre[q]             = (uint16_t)( run + __popc( bal & ( ( 1u << lane ) - 1u ) ) );
-        run += __popc( bal );
-        fbits |= m << q;
-      }
-      if ( lane == 0 ) { warpSum[w] = run; }
-      __syncthreads();
-      uint32_t wbase = 0;
-      for ( int k = 0; k < w; k++ ) { wbase += warpSum[k]; }
-#pragma unroll
-      for ( int q = 0; q < KB_EPT; q++ ) { scan[w * ( KB_EPT * 32 ) + q * 32 + lane] = (uint16_t)( wbase + pre[q] ); }
-      if ( t == KB_TPB - 1 ) { scan[KB_CAP] = (uint16_t)( wbase + run ); }
-      __syncthreads();
-      // pair lists
-#pragma unroll
-      for ( int q = 0; q < KB_EPT; q++ ) {
-        const uint32_t e = w * ( KB_EPT * 32 ) + q * 32 + lane;
-        if ( ( fbits >> q ) & 1u ) {
-          const KbNode&  n     = cur[nid[e]];
-          const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
-          const uint32_t lim   = pass == 0 ? n.left + n.lt : n.left + n.le;
-          const uint32_t m     = ( (uint32_t)scan[n.right] - scan[begin] ) >> 1;
-          const uint32_t r     = (uint32_t)scan[e] - scan[begin];
-          if ( e < lim ) {
-            pairL[begin + r] = (uint16_t)e;
-          } else {
-            pairR[begin + ( m - 1 - ( r - m ) )] = (uint16_t)e;
-          }
-        }
-      }
-      __syncthreads();
-      // swaps
-#pragma unroll
-      for ( int q = 0; q < KB_EPT; q++ ) {
-        const uint32_t e = q * KB_TPB + t;
-        if ( !active[e >> 5] ) { continue; }
-        const uint32_t j = e < total ? nid[e] : 0xFFFFu;
-        if ( j != 0xFFFFu && cur[j].state == 1 ) {
-          const KbNode&  n     = cur[j];
-          const uint32_t begin = pass == 0 ? n.left : n.left + n.lt;
-          if ( e >= begin ) {
-            const uint32_t m = ( (uint32_t)scan[n.right] - scan[begin] ) >> 1, k = e - begin;
-            if ( k < m ) {
-              const uint32_t a = pairL[begin + k], b = pairR[begin + k];
-              const uint64_t ra = rec[a], rb = rec[b];
-              rec[a] = rb;
-              rec[b] = ra;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- children (divideTree :1070-1078) ----
-    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
-      KbNode& n = cur[j];
-      if ( n.state == 1 ) { n.child = (uint16_t)atomicAdd( &sNNext, 2u ); }
-    }
-    __syncthreads();
-    if ( t == 0 ) { sGBase = atomicAdd( &counters[0], sNNext ); }
-    __syncthreads();
-    const uint32_t gbase = sGBase;
-    if ( gbase + sNNext > nodeCap ) {  // node pool exhausted: flag it, leave the subtree as a (wrong) leaf — the host fails
-      if ( t == 0 ) { counters[3] = 1; }
-      break;
-    }
-    for ( uint32_t j = t; j < nl; j += KB_TPB ) {
-      KbNode& n = cur[j];
-      if ( n.state != 1 ) { continue; }
-      const uint32_t count = n.right - n.left;
-      uint32_t       idx;  // :1137-1139
-      if ( n.lt > count / 2 ) {
-        idx = n.lt;
-      } else if ( n.le < count / 2 ) {
-        idx = n.le;
+    const uint32_t offC = carryC + wsA[w] + ia - nch, offB = carryB + wsB[w] + ib - big;
+    if ( big ) {
+      GNode&         n  = nodes[i];
+      const uint32_t c1 = childBase + 2u * offB;
+      if ( c1 + 2u > nodeCap || offC + nch > chunkCap ) {
+        counters[C_POOL] = 1;
+        n.child1         = 0;
+        n.firstChunk     = 0;
       } else {
-        idx = count / 2;
+        n.child1     = c1;
+        n.firstChunk = offC;
+        for ( uint32_t k = 0; k < nch; k++ ) { chunkNode[offC + k] = i; }
       }
-      KbNext a{}, b{};
-      a.gid = gbase + n.child, b.gid = gbase + n.child + 1;
-      a.pgid = b.pgid = n.gid;
-      a.pfeat = b.pfeat = n.cutfeat;
-      a.side = 0, b.side = 1;
-      a.left = n.left, a.right = (uint16_t)( n.left + idx ), b.left = (uint16_t)( n.left + idx ), b.right = n.right;
+    }
+    __syncthreads();
+    if ( threadIdx.x == SETUP_TPB - 1 ) { carryC = offC + nch, carryB = offB + big; }
+    __syncthreads();
+  }
+  if ( threadIdx.x == 0 ) {
+    counters[C_NEXT]   = childBase + 2u * carryB;
+    counters[C_BIG]    = carryB;
+    counters[C_CHUNKS] = carryC;
+  }
+}
+
+struct ChunkCtx {
+  uint32_t node, left, e0, cnt, p0;  // p0 = position of the chunk's first element inside the node
+};
+__device__ __forceinline__ ChunkCtx chunk_ctx( const GNode& n, uint32_t node, uint32_t c ) {
+  ChunkCtx x;
+  x.node = node;
+  x.left = n.left;
+  x.p0   = ( c - n.firstChunk ) * (uint32_t)GT;
+  x.e0   = n.left + x.p0;
+  x.cnt  = min( (uint32_t)GT, n.right - x.e0 );
+  return x;
+}
+
+// pass A: the predicates of planeSplit for every element of the level, as bit masks, and their per-chunk counts
+__global__ void __launch_bounds__( TPB ) k_g_count( const uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
+                                                    const uint32_t* __restrict__ chunkNode, uint32_t* __restrict__ wA,
+                                                    uint32_t* __restrict__ wB, uint32_t* __restrict__ cA, uint32_t* __restrict__ cB ) {
+  __shared__ uint32_t sA[TPB / 32], sB[TPB / 32];
+  const uint32_t c    = blockIdx.x, node = chunkNode[c];
+  const GNode&   n    = nodes[node];
+  const ChunkCtx x    = chunk_ctx( n, node, c );
+  const int      cf   = n.cutfeat, cut = n.cutval;
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint64_t       r[GEPT];
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i = q * TPB + threadIdx.x;
+    r[q]             = i < x.cnt ? rec[x.e0 + i] : ~0ull;  // all-ones: coordinate 4095 in a slot that does not exist
+  }
+  uint32_t ca = 0, cb = 0;
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i  = q * TPB + threadIdx.x;
+    const int      v  = kd_coord( r[q], cf );
+    const bool     ok = i < x.cnt;
+    const uint32_t ma = __ballot_sync( 0xFFFFFFFFu, ok && v < cut ), mb = __ballot_sync( 0xFFFFFFFFu, ok && v <= cut );
+    if ( lane == 0 ) {
+      wA[(size_t)c * GWORDS + q * ( TPB / 32 ) + w] = ma;
+      wB[(size_t)c * GWORDS + q * ( TPB / 32 ) + w] = mb;
+    }
+    ca += __popc( ma ), cb += __popc( mb );
+  }
+  if ( lane == 0 ) { sA[w] = ca, sB[w] = cb; }
+  __syncthreads();
+  if ( threadIdx.x == 0 ) {
+    uint32_t ta = 0, tb = 0;
+    for ( int k = 0; k < TPB / 32; k++ ) { ta += sA[k], tb += sB[k]; }
+    cA[c] = ta, cB[c] = tb;
+  }
+}
+
+// number of set bits of the node's mask `words` in positions [0, pos): chunk prefix + whole words + partial word
+__device__ __forceinline__ uint32_t mask_prefix_at( const uint32_t* __restrict__ words, uint32_t firstChunk, uint32_t chunkExcl,
+                                                    uint32_t pos, int lane ) {
+  const uint32_t  ch = pos / GT, wi = ( pos % GT ) >> 5, bit = pos & 31u;
+  const uint32_t* W  = words + (size_t)( firstChunk + ch ) * GWORDS;
+  uint32_t        s  = 0;
+  for ( uint32_t j = lane; j <= wi; j += 32 ) {
+    const uint32_t v = W[j];
+    s += j < wi ? __popc( v ) : __popc( v & ( ( 1u << bit ) - 1u ) );
+  }
+  return chunkExcl + __reduce_add_sync( 0xFFFFFFFFu, s );
+}
+
+// pass B / E: one warp per node of the level.  Exclusive prefix of the chunk counts, lim1 / lim2, the number of
+// misplaced pairs, and (SECOND == false) the children (divideTree :1070-1078)
+template <bool SECOND>
+__global__ void __launch_bounds__( TPB ) k_g_nodescan( GNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd,
+                                                       uint32_t* __restrict__ cA, uint32_t* __restrict__ cB,
+                                                       const uint32_t* __restrict__ wA, const uint32_t* __restrict__ wB,
+                                                       int32_t* __restrict__ st ) {
+  const uint32_t i    = lvlBegin + ( blockIdx.x * TPB + threadIdx.x ) / 32;
+  const int      lane = threadIdx.x & 31;
+  if ( i >= lvlEnd ) { return; }
+  GNode& n = nodes[i];
+  if ( n.state != 1 || n.child1 == 0 ) { return; }
+  const uint32_t count = n.right - n.left, nch = ( count + GT - 1 ) / GT, first = n.firstChunk;
+  if ( !SECOND ) {
+    uint32_t runA = 0, runB = 0;
+    for ( uint32_t k0 = 0; k0 < nch; k0 += 32 ) {
+      const uint32_t k = k0 + lane;
+      const uint32_t a = k < nch ? cA[first + k] : 0u, b = k < nch ? cB[first + k] : 0u;
+      uint32_t       ia = a, ib = b;
+#pragma unroll
+      for ( int d = 1; d < 32; d <<= 1 ) {
+        const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ia, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, ib, d );
+        if ( lane >= d ) { ia += ta, ib += tb; }
+      }
+      if ( k < nch ) { cA[first + k] = runA + ia - a, cB[first + k] = runB + ib - b; }
+      runA += __shfl_sync( 0xFFFFFFFFu, ia, 31 );
+      runB += __shfl_sync( 0xFFFFFFFFu, ib, 31 );
+    }
+    __syncwarp();
+    const uint32_t lim1 = runA, lim2 = runB;
+    // misplaced on the left of pass 1 = elements >= cut among the first lim1 = lim1 - #(v < cut in [0, lim1))
+    uint32_t m1 = 0;
+    if ( lim1 > 0 && lim1 < count ) { m1 = lim1 - mask_prefix_at( wA, first, cA[first + lim1 / GT], lim1, lane ); }
+    const uint32_t idx = kd_split_index( count, lim1, lim2 );
+    if ( lane == 0 ) {
+      n.lim1 = lim1, n.lim2 = lim2, n.m1 = m1, n.idx = idx;
+      GNode a{}, b{};
+      a.left = n.left, a.right = n.left + idx, b.left = n.left + idx, b.right = n.right;
       for ( int k = 0; k < 3; k++ ) {
         a.lo[k] = b.lo[k] = n.lo[k];
         a.hi[k] = b.hi[k] = n.hi[k];
       }
-      a.hi[n.cutfeat] = n.cutval;  // left_bbox[cutfeat].high = cutval
-      b.lo[n.cutfeat] = n.cutval;  // right_bbox[cutfeat].low = cutval
-      nxt[n.child]     = a;
-      nxt[n.child + 1] = b;
-      KdNode g{};
-      g.left = base + n.left, g.right = base + n.right, g.child1 = a.gid, g.lt = n.lt, g.le = n.le;
-      g.cutfeat = (int8_t)n.cutfeat, g.cutval = n.cutval, g.state = 1;
+      a.hi[n.cutfeat]     = n.cutval;  // left_bbox[cutfeat].high = cutval
+      b.lo[n.cutfeat]     = n.cutval;  // right_bbox[cutfeat].low = cutval
+      nodes[n.child1]     = a;
+      nodes[n.child1 + 1] = b;
       for ( int k = 0; k < 3; k++ ) {
-        g.lo[k] = n.lo[k], g.hi[k] = n.hi[k];
-        g.tmin[k] = (int16_t)n.tmin[k], g.tmax[k] = (int16_t)n.tmax[k];
+        st[(size_t)n.child1 * 6 + k] = st[(size_t)( n.child1 + 1 ) * 6 + k] = 0x7FFFFFFF;
+        st[(size_t)n.child1 * 6 + 3 + k] = st[(size_t)( n.child1 + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
       }
-      nodes[n.gid] = g;  // divlow / divhigh are written by the children at the next level
     }
-    __syncthreads();
-    // ---- elements move to their child; elements of finished leaves drop out ----
+  } else {
+    // cB now holds the per-chunk counts of "<= cut" among the positions >= lim1 AFTER pass 1
+    uint32_t run = 0;
+    for ( uint32_t k0 = 0; k0 < nch; k0 += 32 ) {
+      const uint32_t k = k0 + lane;
+      const uint32_t b = k < nch ? cB[first + k] : 0u;
+      uint32_t       ib = b;
 #pragma unroll
-    for ( int q = 0; q < KB_EPT; q++ ) {
-      const uint32_t e = q * KB_TPB + t;
-      if ( !active[e >> 5] ) { continue; }
-      bool still = false;
-      if ( e < total ) {
-        const uint32_t j = nid[e];
-        if ( j != 0xFFFFu ) {
-          const KbNode& n = cur[j];
-          still           = n.state == 1;
-          nid[e]          = still ? (uint16_t)( e < nxt[n.child].right ? n.child : n.child + 1 ) : (uint16_t)0xFFFFu;
-        }
+      for ( int d = 1; d < 32; d <<= 1 ) {
+        const uint32_t tb = __shfl_up_sync( 0xFFFFFFFFu, ib, d );
+        if ( lane >= d ) { ib += tb; }
       }
-      const uint32_t any = __ballot_sync( 0xFFFFFFFFu, still );
-      if ( lane == 0 && any == 0 ) { active[e >> 5] = 0; }
+      if ( k < nch ) { cB[first + k] = run + ib - b; }
+      run += __shfl_sync( 0xFFFFFFFFu, ib, 31 );
     }
-    __syncthreads();
+    __syncwarp();
+    const uint32_t lim1 = n.lim1, lim2 = n.lim2;
+    uint32_t       m2 = 0;
+    if ( lim2 > lim1 && lim2 < count ) { m2 = ( lim2 - lim1 ) - mask_prefix_at( wB, first, cB[first + lim2 / GT], lim2, lane ); }
+    if ( lane == 0 ) { n.m2 = m2; }
   }
-  __syncthreads();
-  for ( uint32_t i = t; i < total; i += KB_TPB ) { grec[base + i] = rec[i]; }
-  if ( t == 0 ) { atomicMax( &counters[4], (uint32_t)level + 1u ); }
 }
 
-// divlow / divhigh from the children's tight boxes (divideTree :1080-1081); depth bookkeeping
-__global__ void k_kd_finalize( KdNode* __restrict__ nodes, uint32_t nNodes ) {
+// per-chunk prefix of the mask words in shared memory: pre[w] = set bits in words [0, w) of the chunk
+__device__ __forceinline__ void chunk_word_prefix( const uint32_t* __restrict__ words, uint32_t* sWord, uint32_t* sPre ) {
+  if ( threadIdx.x < GWORDS ) { sWord[threadIdx.x] = words[threadIdx.x]; }
+  __syncthreads();
+  if ( threadIdx.x < 32 ) {  // GWORDS == 64: two words per lane
+    const int      l = threadIdx.x;
+    const uint32_t a = __popc( sWord[2 * l] ), b = __popc( sWord[2 * l + 1] );
+    uint32_t       in = a + b;
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+      const uint32_t t = __shfl_up_sync( 0xFFFFFFFFu, in, d );
+      if ( l >= d ) { in += t; }
+    }
+    sPre[2 * l]     = in - a - b;
+    sPre[2 * l + 1] = in - b;
+  }
+  __syncthreads();
+}
+static_assert( GWORDS == 64, "chunk_word_prefix handles two words per lane" );
+
+// pass C / F: the misplaced elements of a Hoare pass go to the staging array at their rank.
+//   pass 1 (SECOND == false): left = positions < lim1 with v >= cut -> tmp[left + i]; right = positions >= lim1 with
+//                             v < cut -> tmp[left + lim1 + r] (r = rank from the left)
+//   pass 2 (SECOND == true) : left = positions in [lim1, lim2) with v > cut -> tmp[left + lim1 + i]; right = positions >= lim2
+//                             with v <= cut -> tmp[left + lim2 + r]
+template <bool SECOND>
+__global__ void __launch_bounds__( TPB ) k_g_stage( const uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
+                                                    const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ words,
+                                                    const uint32_t* __restrict__ cPre, uint64_t* __restrict__ tmp ) {
+  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
+  const uint32_t c = blockIdx.x, node = chunkNode[c];
+  const GNode&   n = nodes[node];
+  const uint32_t m = SECOND ? n.m2 : n.m1;
+  if ( m == 0 ) { return; }
+  const ChunkCtx x    = chunk_ctx( n, node, c );
+  const uint32_t lim1 = n.lim1, lim2 = n.lim2;
+  // nothing of this chunk takes part in pass 2 when it lies below lim1
+  if ( SECOND && x.p0 + x.cnt <= lim1 ) { return; }
+  chunk_word_prefix( words + (size_t)c * GWORDS, sWord, sPre );
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t base = cPre[c];
+  const uint32_t lt   = lanemask_lt();
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i = q * TPB + threadIdx.x;
+    if ( i >= x.cnt ) { continue; }
+    const int      wi  = q * ( TPB / 32 ) + w;
+    const uint32_t wd  = sWord[wi];
+    const bool     bit = ( wd >> lane ) & 1u;
+    const uint32_t pre = base + sPre[wi] + __popc( wd & lt );  // set bits of the node's mask before this position
+    const uint32_t p   = x.p0 + i;
+    if ( !SECOND ) {
+      if ( p < lim1 ) {
+        if ( !bit ) { tmp[x.left + ( p - pre )] = rec[x.e0 + i]; }
+      } else if ( bit ) {
+        tmp[x.left + lim1 + ( pre - ( lim1 - m ) )] = rec[x.e0 + i];
+      }
+    } else if ( p >= lim1 ) {
+      if ( p < lim2 ) {
+        if ( !bit ) { tmp[x.left + lim1 + ( ( p - lim1 ) - pre )] = rec[x.e0 + i]; }
+      } else if ( bit ) {
+        tmp[x.left + lim2 + ( pre - ( ( lim2 - lim1 ) - m ) )] = rec[x.e0 + i];
+      }
+    }
+  }
+}
+
+// pass D: every misplaced position of pass 1 takes its partner; the "<= cut" mask of the positions >= lim1 is
+// rewritten for the new arrangement (pass 2 works on it) together with its per-chunk counts
+__global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
+                                                     const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ wA,
+                                                     uint32_t* __restrict__ wB, const uint32_t* __restrict__ cA,
+                                                     uint32_t* __restrict__ cB, const uint64_t* __restrict__ tmp ) {
+  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
+  __shared__ uint32_t sCnt[TPB / 32];
+  const uint32_t c = blockIdx.x, node = chunkNode[c];
+  const GNode&   n = nodes[node];
+  const ChunkCtx x    = chunk_ctx( n, node, c );
+  const uint32_t lim1 = n.lim1, m = n.m1;
+  const int      cf = n.cutfeat, cut = n.cutval;
+  chunk_word_prefix( wA + (size_t)c * GWORDS, sWord, sPre );
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t base = cA[c];
+  const uint32_t lt   = lanemask_lt();
+  uint32_t       cnt  = 0;
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i   = q * TPB + threadIdx.x;
+    const int      wi  = q * ( TPB / 32 ) + w;
+    const uint32_t wd  = sWord[wi];
+    const bool     bit = ( wd >> lane ) & 1u;
+    const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
+    const uint32_t p   = x.p0 + i;
+    const bool     ok  = i < x.cnt;
+    bool           b2  = ok && p >= lim1 && ( ( wB[(size_t)c * GWORDS + wi] >> lane ) & 1u );
+    if ( ok && m ) {
+      if ( p < lim1 ) {
+        if ( !bit ) { rec[x.e0 + i] = tmp[x.left + lim1 + ( m - 1u - ( p - pre ) )]; }
+      } else if ( bit ) {
+        const uint64_t v = tmp[x.left + ( m - 1u - ( pre - ( lim1 - m ) ) )];
+        rec[x.e0 + i]    = v;
+        b2               = kd_coord( v, cf ) <= cut;
+      }
+    }
+    const uint32_t mb = __ballot_sync( 0xFFFFFFFFu, b2 );
+    __syncwarp();  // every lane has read the old word before lane 0 replaces it
+    if ( lane == 0 ) { wB[(size_t)c * GWORDS + wi] = mb; }
+    cnt += __popc( mb );
+  }
+  if ( lane == 0 ) { sCnt[w] = cnt; }
+  __syncthreads();
+  if ( threadIdx.x == 0 ) {
+    uint32_t t = 0;
+    for ( int k = 0; k < TPB / 32; k++ ) { t += sCnt[k]; }
+    cB[c] = t;
+  }
+}
+
+// pass G: the partners of pass 2, and the tight boxes of the two children (computeMinMax of the next level)
+__global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
+                                                     const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ wB,
+                                                     const uint32_t* __restrict__ cB, const uint64_t* __restrict__ tmp,
+                                                     int32_t* __restrict__ st ) {
+  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
+  __shared__ int      sBox[TPB / 32][12];
+  const uint32_t c = blockIdx.x, node = chunkNode[c];
+  const GNode&   n = nodes[node];
+  const ChunkCtx x    = chunk_ctx( n, node, c );
+  const uint32_t lim1 = n.lim1, lim2 = n.lim2, m = n.m2, idx = n.idx, child1 = n.child1;
+  chunk_word_prefix( wB + (size_t)c * GWORDS, sWord, sPre );
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t base = cB[c];
+  const uint32_t lt   = lanemask_lt();
+  int            bx[12];  // {min[3], max[3]} of the left child, then of the right child
+#pragma unroll
+  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = 1 << 20, bx[3 + k] = bx[9 + k] = -( 1 << 20 ); }
+  uint64_t r[GEPT];
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i = q * TPB + threadIdx.x;
+    r[q]             = i < x.cnt ? rec[x.e0 + i] : 0ull;
+  }
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i = q * TPB + threadIdx.x;
+    if ( i >= x.cnt ) { continue; }
+    const int      wi  = q * ( TPB / 32 ) + w;
+    const uint32_t wd  = sWord[wi];
+    const bool     bit = ( wd >> lane ) & 1u;
+    const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
+    const uint32_t p   = x.p0 + i;
+    uint64_t       v   = r[q];
+    if ( m && p >= lim1 ) {
+      if ( p < lim2 ) {
+        if ( !bit ) {
+          v             = tmp[x.left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )];
+          rec[x.e0 + i] = v;
+        }
+      } else if ( bit ) {
+        v             = tmp[x.left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )];
+        rec[x.e0 + i] = v;
+      }
+    }
+    const int  cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
+    const bool rt = p >= idx;
+    // (selects, not branches: both boxes live in registers)
+    bx[0] = min( bx[0], rt ? ( 1 << 20 ) : cx ), bx[1] = min( bx[1], rt ? ( 1 << 20 ) : cy ), bx[2] = min( bx[2], rt ? ( 1 << 20 ) : cz );
+    bx[3] = max( bx[3], rt ? -( 1 << 20 ) : cx ), bx[4] = max( bx[4], rt ? -( 1 << 20 ) : cy ), bx[5] = max( bx[5], rt ? -( 1 << 20 ) : cz );
+    bx[6] = min( bx[6], rt ? cx : ( 1 << 20 ) ), bx[7] = min( bx[7], rt ? cy : ( 1 << 20 ) ), bx[8] = min( bx[8], rt ? cz : ( 1 << 20 ) );
+    bx[9] = max( bx[9], rt ? cx : -( 1 << 20 ) ), bx[10] = max( bx[10], rt ? cy : -( 1 << 20 ) ), bx[11] = max( bx[11], rt ? cz : -( 1 << 20 ) );
+  }
+#pragma unroll
+  for ( int k = 0; k < 12; k++ ) {
+    const bool isMin = ( k % 6 ) < 3;
+    bx[k]            = isMin ? __reduce_min_sync( 0xFFFFFFFFu, bx[k] ) : __reduce_max_sync( 0xFFFFFFFFu, bx[k] );
+  }
+  if ( lane == 0 ) {
+#pragma unroll
+    for ( int k = 0; k < 12; k++ ) { sBox[w][k] = bx[k]; }
+  }
+  __syncthreads();
+  if ( threadIdx.x < 12 ) {
+    const int  k     = threadIdx.x;
+    const bool isMin = ( k % 6 ) < 3;
+    int        v     = sBox[0][k];
+    for ( int j = 1; j < TPB / 32; j++ ) { v = isMin ? min( v, sBox[j][k] ) : max( v, sBox[j][k] ); }
+    int32_t* dst = st + (size_t)( child1 + ( k >= 6 ? 1 : 0 ) ) * 6 + ( k % 6 );
+    if ( isMin ) {
+      if ( v < ( 1 << 20 ) ) { atomicMin( dst, v ); }
+    } else {
+      if ( v > -( 1 << 20 ) ) { atomicMax( dst, v ); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// subtree phase: one CTA builds a whole subtree of at most KS_CAP elements in shared memory.
+// Depth of such a subtree: every split halves the loose box along its longest side, 36 splits reduce a 4096^3 box to
+// a single lattice point, and from there on cutval == tmin == tmax gives lim1 = 0, lim2 = n, idx = n / 2 — so at most
+// 36 + log2( KS_CAP ) levels; each warp's path owns at most one pending sibling per level.
+// ---------------------------------------------------------------------------------------------------
+struct KsItem {
+  uint32_t gid;          // node id
+  uint32_t pgid;         // parent's node id in KdNode numbering, 0 for the subtree root
+  uint16_t left, right;  // element range inside the subtree
+  int16_t  lo[3], hi[3];
+  uint8_t  side, depth;  // side: 0 left / 1 right child of pgid
+  uint8_t  pfeat, pad;   // cut axis of the parent
+};
+
+struct KsShared {
+  uint64_t rec[KS_CAP];
+  uint64_t tmp[KS_CAP];
+  KsItem   stack[KS_STACK];
+  KsItem   slot[KS_WARPS];  // the item a warp popped (copied under the lock)
+  int      top, lock, pending, nextId, maxDepth, abort;
+};
+
+__global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __restrict__ grec, GNode* __restrict__ gnodes,
+                                                                 KdNode* __restrict__ nodes, const uint32_t* __restrict__ smallRoots,
+                                                                 uint32_t* __restrict__ counters, uint32_t subBase, int ox, int oy,
+                                                                 int oz ) {
+  extern __shared__ __align__( 16 ) unsigned char ks_smem[];
+  KsShared&      S      = *reinterpret_cast<KsShared*>( ks_smem );
+  const int      lane   = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t rootId = smallRoots[blockIdx.x];
+  const uint32_t base   = gnodes[rootId].left, total = gnodes[rootId].right - base;
+  const int      o[3]   = {ox, oy, oz};
+  const uint32_t lt     = lanemask_lt();
+  // node ids of this subtree: a contiguous block behind the level-phase nodes, 2 ids per element is the worst case
+  const uint32_t idBase = subBase + 2u * base;
+  for ( uint32_t i = threadIdx.x; i < total; i += KS_WARPS * 32 ) { S.rec[i] = grec[base + i]; }
+  if ( threadIdx.x == 0 ) { S.top = 0, S.lock = 0, S.pending = 1, S.nextId = 0, S.maxDepth = 0, S.abort = 0; }
+  __syncthreads();
+  KsItem cur{};
+  bool   have = false;
+  if ( w == 0 ) {
+    const GNode& r = gnodes[rootId];
+    cur.gid = rootId, cur.pgid = 0, cur.left = 0, cur.right = (uint16_t)total, cur.side = 0, cur.depth = 0;
+    for ( int k = 0; k < 3; k++ ) { cur.lo[k] = r.lo[k], cur.hi[k] = r.hi[k]; }
+    have = true;
+  }
+  int maxDepth = 0;
+  for ( ;; ) {
+    if ( !have ) {  // take a node from the shared stack, or leave when the subtree is complete
+      int got = 0;
+      if ( lane == 0 ) {
+        for ( int spin = 0;; spin++ ) {
+          if ( *( (volatile int*)&S.abort ) ) { break; }
+          if ( *( (volatile int*)&S.top ) > 0 ) {
+            if ( atomicCAS( &S.lock, 0, 1 ) == 0 ) {
+              __threadfence_block();
+              const int t = *( (volatile int*)&S.top );
+              if ( t > 0 ) {
+                S.slot[w] = S.stack[t - 1];
+                S.top     = t - 1;
+                got       = 1;
+              }
+              __threadfence_block();
+              atomicExch( &S.lock, 0 );
+              if ( got ) { break; }
+            }
+          } else if ( *( (volatile int*)&S.pending ) <= 0 ) {
+            break;
+          } else {
+            __nanosleep( 100 );
+            if ( spin > ( 1 << 22 ) ) {  // never seen; a stuck subtree must not hang the device
+              atomicOr( &counters[C_STACK], 2u );
+              atomicExch( &S.abort, 1 );
+              break;
+            }
+          }
+        }
+      }
+      got = __shfl_sync( 0xFFFFFFFFu, got, 0 );
+      if ( !got ) { break; }
+      cur  = S.slot[w];
+      have = true;
+      __syncwarp();
+    }
+    const uint32_t left = cur.left, right = cur.right, n = right - left;
+    maxDepth = max( maxDepth, (int)cur.depth );
+    // ---- tight box (computeMinMax) ----
+    int mn[3] = {4096, 4096, 4096}, mx[3] = {-1, -1, -1};
+    for ( uint32_t p = left + lane; p < right; p += 32 ) {
+      const uint64_t r = S.rec[p];
+      const int      x = kd_coord( r, 0 ), y = kd_coord( r, 1 ), z = kd_coord( r, 2 );
+      mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
+      mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
+    }
+#pragma unroll
+    for ( int k = 0; k < 3; k++ ) {
+      mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
+      mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
+    }
+    // the node reports its tight bound to its parent (divideTree :1080-1081)
+    if ( lane == 0 ) {
+      if ( cur.pgid ) {
+        const int pf = cur.pfeat;
+        if ( cur.side == 0 ) {
+          nodes[cur.pgid].divlow = (int16_t)( pf == 0 ? mx[0] : ( pf == 1 ? mx[1] : mx[2] ) );
+        } else {
+          nodes[cur.pgid].divhigh = (int16_t)( pf == 0 ? mn[0] : ( pf == 1 ? mn[1] : mn[2] ) );
+        }
+      } else {  // the parent is a level-phase node: k_g_finalize reads the box from the build node
+        GNode& g = gnodes[cur.gid];
+        for ( int k = 0; k < 3; k++ ) { g.tmin[k] = (int16_t)mn[k], g.tmax[k] = (int16_t)mx[k]; }
+      }
+    }
+    if ( n <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
+      if ( lane == 0 ) {
+        nodes[cur.gid].a = base + left;
+        nodes[cur.gid].b = KD_LEAF | n;
+        atomicSub( &S.pending, 1 );
+      }
+      have = false;
+      continue;
+    }
+    int cf, cut;
+    {
+      const int lo[3] = {cur.lo[0], cur.lo[1], cur.lo[2]}, hi[3] = {cur.hi[0], cur.hi[1], cur.hi[2]};
+      kd_choose_split( lo, hi, mn, mx, o, cf, cut );
+    }
+    // ---- lim1 / lim2 ----
+    uint32_t lim1 = 0, lim2 = 0;
+    for ( uint32_t p = left + lane; p < right; p += 32 ) {
+      const int v = kd_coord( S.rec[p], cf );
+      lim1 += v < cut, lim2 += v <= cut;
+    }
+    lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
+    lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
+    // ---- the two Hoare passes of planeSplit (:1154-1181) ----
+    if ( lim1 > 0 && lim1 < n ) {
+      uint32_t ml = 0, mr = 0;
+      for ( uint32_t p0 = left; p0 < right; p0 += 32 ) {
+        const uint32_t p   = p0 + lane;
+        const bool     ok  = p < right;
+        const uint64_t r   = ok ? S.rec[p] : 0ull;
+        const bool     in  = kd_coord( r, cf ) < cut;
+        const bool     isL = ok && p - left < lim1 && !in, isR = ok && p - left >= lim1 && in;
+        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+        if ( isL ) { S.tmp[left + ml + __popc( bl & lt )] = r; }
+        if ( isR ) { S.tmp[left + lim1 + mr + __popc( br & lt )] = r; }
+        ml += __popc( bl ), mr += __popc( br );
+      }
+      const uint32_t m = ml;
+      __syncwarp();
+      if ( m ) {
+        ml = mr = 0;
+        for ( uint32_t p0 = left; p0 < right; p0 += 32 ) {
+          const uint32_t p   = p0 + lane;
+          const bool     ok  = p < right;
+          const bool     in  = ok && kd_coord( S.rec[p], cf ) < cut;
+          const bool     isL = ok && p - left < lim1 && !in, isR = ok && p - left >= lim1 && in;
+          const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+          if ( isL ) { S.rec[p] = S.tmp[left + lim1 + ( m - 1u - ( ml + __popc( bl & lt ) ) )]; }
+          if ( isR ) { S.rec[p] = S.tmp[left + ( m - 1u - ( mr + __popc( br & lt ) ) )]; }
+          ml += __popc( bl ), mr += __popc( br );
+        }
+        __syncwarp();
+      }
+    }
+    if ( lim2 > lim1 && lim2 < n ) {
+      uint32_t ml = 0, mr = 0;
+      for ( uint32_t p0 = left + lim1; p0 < right; p0 += 32 ) {
+        const uint32_t p   = p0 + lane;
+        const bool     ok  = p < right;
+        const uint64_t r   = ok ? S.rec[p] : 0ull;
+        const bool     in  = kd_coord( r, cf ) <= cut;
+        const bool     isL = ok && p - left < lim2 && !in, isR = ok && p - left >= lim2 && in;
+        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+        if ( isL ) { S.tmp[left + lim1 + ml + __popc( bl & lt )] = r; }
+        if ( isR ) { S.tmp[left + lim2 + mr + __popc( br & lt )] = r; }
+        ml += __popc( bl ), mr += __popc( br );
+      }
+      const uint32_t m = ml;
+      __syncwarp();
+      if ( m ) {
+        ml = mr = 0;
+        for ( uint32_t p0 = left + lim1; p0 < right; p0 += 32 ) {
+          const uint32_t p   = p0 + lane;
+          const bool     ok  = p < right;
+          const bool     in  = ok && kd_coord( S.rec[p], cf ) <= cut;
+          const bool     isL = ok && p - left < lim2 && !in, isR = ok && p - left >= lim2 && in;
+          const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+          if ( isL ) { S.rec[p] = S.tmp[left + lim2 + ( m - 1u - ( ml + __popc( bl & lt ) ) )]; }
+          if ( isR ) { S.rec[p] = S.tmp[left + lim1 + ( m - 1u - ( mr + __popc( br & lt ) ) )]; }
+          ml += __popc( bl ), mr += __popc( br );
+        }
+        __syncwarp();
+      }
+    }
+    // ---- children (divideTree :1070-1078): keep the left one, push the right one ----
+    const uint32_t idx = kd_split_index( n, lim1, lim2 );
+    uint32_t       c1  = 0;
+    int            ovf = 0;
+    if ( lane == 0 ) {
+      c1               = idBase + (uint32_t)atomicAdd( &S.nextId, 2 );
+      nodes[cur.gid].a = c1;
+      nodes[cur.gid].b = (uint32_t)cf;
+      KsItem rgt{};
+      rgt.gid = c1 + 1, rgt.pgid = cur.gid, rgt.left = (uint16_t)( left + idx ), rgt.right = (uint16_t)right, rgt.side = 1;
+      rgt.depth = (uint8_t)( cur.depth + 1 ), rgt.pfeat = (uint8_t)cf;
+      for ( int k = 0; k < 3; k++ ) { rgt.hi[k] = cur.hi[k]; }
+      rgt.lo[0] = cf == 0 ? (int16_t)cut : cur.lo[0];  // right_bbox[cutfeat].low = cutval
+      rgt.lo[1] = cf == 1 ? (int16_t)cut : cur.lo[1];
+      rgt.lo[2] = cf == 2 ? (int16_t)cut : cur.lo[2];
+      __threadfence_block();      // the parent's words are written before a child can report its bound
+      while ( atomicCAS( &S.lock, 0, 1 ) != 0 ) {}
+      __threadfence_block();
+      const int t = *( (volatile int*)&S.top );
+      if ( t < KS_STACK ) {
+        S.stack[t] = rgt;
+        __threadfence_block();
+        S.top = t + 1;
+        atomicAdd( &S.pending, 1 );
+      } else {
+        ovf = 1;
+      }
+      __threadfence_block();
+      atomicExch( &S.lock, 0 );
+    }
+    ovf = __shfl_sync( 0xFFFFFFFFu, ovf, 0 );
+    if ( ovf ) {  // cannot happen for 12-bit coordinates (see above); fail loudly instead of looping
+      if ( lane == 0 ) {
+        atomicOr( &counters[C_STACK], 1u );
+        atomicExch( &S.abort, 1 );
+      }
+      break;
+    }
+    c1 = __shfl_sync( 0xFFFFFFFFu, c1, 0 );
+    cur.pgid = cur.gid, cur.gid = c1, cur.right = (uint16_t)( left + idx ), cur.side = 0;
+    cur.depth = (uint8_t)( cur.depth + 1 ), cur.pfeat = (uint8_t)cf;
+    if ( cf == 0 ) {
+      cur.hi[0] = (int16_t)cut;  // left_bbox[cutfeat].high = cutval
+    } else if ( cf == 1 ) {
+      cur.hi[1] = (int16_t)cut;
+    } else {
+      cur.hi[2] = (int16_t)cut;
+    }
+  }
+  if ( lane == 0 ) { atomicMax( &S.maxDepth, maxDepth ); }
+  __syncthreads();
+  for ( uint32_t i = threadIdx.x; i < total; i += KS_WARPS * 32 ) { grec[base + i] = S.rec[i]; }
+  if ( threadIdx.x == 0 ) { atomicMax( &counters[C_DEPTH], (uint32_t)S.maxDepth + 1u ); }
+}
+
+// level-phase nodes -> search nodes: divlow / divhigh from the children's tight boxes (divideTree :1080-1081), and the
+// root boxes for computeInitialDistances
+__global__ void k_g_finalize( const GNode* __restrict__ gnodes, uint32_t nLevelNodes, int nTrees, KdNode* __restrict__ nodes,
+                              int16_t* __restrict__ rootBox ) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nNodes || i == 0 ) { return; }
-  KdNode& n = nodes[i];
-  if ( n.child1 == 0 ) { return; }
-  n.divlow  = nodes[n.child1].tmax[n.cutfeat];
-  n.divhigh = nodes[n.child1 + 1].tmin[n.cutfeat];
+  if ( i >= nLevelNodes || i == 0 ) { return; }
+  const GNode& n = gnodes[i];
+  if ( i <= (uint32_t)nTrees ) {
+    for ( int k = 0; k < 3; k++ ) { rootBox[(size_t)i * 6 + k] = n.tmin[k], rootBox[(size_t)i * 6 + 3 + k] = n.tmax[k]; }
+  }
+  if ( n.state != 1 ) { return; }  // roots of shared-memory subtrees wrote their own search node
+  KdNode s{};
+  s.a       = n.child1;
+  s.b       = (uint32_t)n.cutfeat;
+  s.divlow  = gnodes[n.child1].tmax[n.cutfeat];
+  s.divhigh = gnodes[n.child1 + 1].tmin[n.cutfeat];
+  nodes[i]  = s;
 }
 
 }  // namespace
@@ -708,98 +906,94 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   const int     nTrees = (int)hOff.size() - 1;
   const int64_t E      = hOff[nTrees];
   if ( E <= 0 || nTrees <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "kd build: empty forest" ); }
-  if ( E >= ( 1ll << 31 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: more than 2^31 points" ); }
+  if ( E >= ( 1ll << 30 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: more than 2^30 points" ); }
   for ( int t = 0; t < nTrees; t++ ) {
     if ( hOff[t + 1] - hOff[t] <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "kd build: empty cloud %d", t ); }
     if ( hOff[t + 1] - hOff[t] >= ( 1ll << 28 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: cloud too large" ); }
   }
-  const uint32_t nodeCap = (uint32_t)std::min<int64_t>( 2 * E + nTrees + 16, ( E * 3 ) / 4 + 64ll * nTrees + 4096 );
+  // level-phase nodes: every split node holds more than KS_CAP elements, so a level has at most E / KS_CAP of them
+  const uint32_t gCap     = (uint32_t)( E / 16 + 64ll * nTrees + 4096 );
+  const uint32_t chunkCap = (uint32_t)( 2 * ( E / GT ) + 2ll * nTrees + 64 );
+  const size_t   nodeCap  = (size_t)gCap + 2 * (size_t)E + 2;  // + the id blocks of the subtrees (2 ids per element)
   RB_CUDA( B.rec.ensure( (size_t)E * 8 ) );
-  RB_CUDA( B.nid.ensure( (size_t)E * 4 ) );
-  RB_CUDA( B.nodes.ensure( (size_t)nodeCap * sizeof( KdNode ) ) );
-  RB_CUDA( B.flags.ensure( (size_t)( E + 8 ) * 4 ) );
-  RB_CUDA( B.pairL.ensure( (size_t)E * 4 ) );
-  RB_CUDA( B.pairR.ensure( (size_t)E * 4 ) );
-  RB_CUDA( B.sums.ensure( rb_scan_scratch_bytes( E + 1 ) ) );
-  RB_CUDA( B.smallRoots.ensure( (size_t)( E + nTrees ) * 4 ) );
+  RB_CUDA( B.tmp.ensure( (size_t)E * 8 ) );
+  RB_CUDA( B.gnodes.ensure( (size_t)gCap * sizeof( GNode ) ) );
+  RB_CUDA( B.nodes.ensure( nodeCap * sizeof( KdNode ) ) );
+  RB_CUDA( B.rootBox.ensure( (size_t)( nTrees + 1 ) * 12 ) );
+  RB_CUDA( B.chunkNode.ensure( (size_t)chunkCap * 4 ) );
+  RB_CUDA( B.wA.ensure( (size_t)chunkCap * GWORDS * 4 ) );
+  RB_CUDA( B.wB.ensure( (size_t)chunkCap * GWORDS * 4 ) );
+  RB_CUDA( B.cA.ensure( (size_t)chunkCap * 4 ) );
+  RB_CUDA( B.cB.ensure( (size_t)chunkCap * 4 ) );
+  RB_CUDA( B.smallRoots.ensure( (size_t)gCap * 4 ) );
   RB_CUDA( B.counters.ensure( 64 ) );
-  const uint32_t statCap = (uint32_t)std::min<int64_t>( nodeCap, E / 16 + 64ll * nTrees + 4096 );
-  RB_CUDA( B.stats.ensure( (size_t)statCap * 24 ) );
-  int32_t* st = B.stats.as<int32_t>();
-  uint64_t* rec      = B.rec.as<uint64_t>();
-  uint32_t* nid      = B.nid.as<uint32_t>();
-  KdNode*   nodes    = B.nodes.as<KdNode>();
-  uint32_t* flags    = B.flags.as<uint32_t>();
-  uint32_t* counters = B.counters.as<uint32_t>();
-  uint32_t* h        = (uint32_t*)rb_pinned( c, 64 );
+  RB_CUDA( B.stats.ensure( (size_t)gCap * 24 ) );
+  int32_t*  st        = B.stats.as<int32_t>();
+  uint64_t* rec       = B.rec.as<uint64_t>();
+  uint64_t* tmp       = B.tmp.as<uint64_t>();
+  GNode*    gnodes    = B.gnodes.as<GNode>();
+  KdNode*   nodes     = B.nodes.as<KdNode>();
+  uint32_t* counters  = B.counters.as<uint32_t>();
+  uint32_t* chunkNode = B.chunkNode.as<uint32_t>();
+  uint32_t *wA = B.wA.as<uint32_t>(), *wB = B.wB.as<uint32_t>(), *cA = B.cA.as<uint32_t>(), *cB = B.cB.as<uint32_t>();
+  uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
   if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-  // counters: [0] next free node, [1] small roots, [2] big nodes of the level, [3] pool exhausted, [4] depth, [5] range error
-  h[0] = (uint32_t)nTrees + 1;
-  h[1] = h[2] = h[3] = h[4] = h[5] = 0;
+  for ( int k = 0; k < 8; k++ ) { h[k] = 0; }
+  h[C_NEXT] = (uint32_t)nTrees + 1;
   RB_CUDA( cudaMemcpyAsync( counters, h, 32, cudaMemcpyHostToDevice, c->stream ) );
-  const int G = rb_div_up( E, TPB );
-  RB_LAUNCH( "kd_init", k_kd_init, G, TPB, 0, pos, dOff, nTrees, E, ox, oy, oz, rec, nid, counters + 5 );
-  RB_LAUNCH( "kd_roots", k_kd_roots, rb_div_up( nTrees, 128 ), 128, 0, nodes, dOff, nTrees, st );
+  RB_LAUNCH( "kd_roots", k_g_roots, rb_div_up( nTrees, 128 ), 128, 0, gnodes, dOff, nTrees, st );
+  RB_LAUNCH( "kd_init", k_g_init, rb_div_up( E, TPB * GEPT ), TPB, 0, pos, dOff, nTrees, E, ox, oy, oz, rec, st, counters );
   uint32_t lvlBegin = 1, lvlEnd = (uint32_t)nTrees + 1;
   int      level = 0;
-  bool     roots = true;
   for ( ;; level++ ) {
     if ( level > 200 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree deeper than 200 levels" ); }
     const uint32_t nLvl = lvlEnd - lvlBegin;
-    if ( level == 0 ) { RB_LAUNCH( "kd_stats", k_kd_stats<false>, G, TPB, 0, rec, nid, nodes, st, E, lvlBegin, lvlEnd ); }
-    RB_CUDA( cudaMemsetAsync( counters + 2, 0, 4, c->stream ) );
-    RB_LAUNCH( "kd_split", k_kd_split, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, KB_CAP, ox, oy, oz,
-               B.smallRoots.as<uint32_t>(), counters, roots ? 1 : 0, st );
-    roots = false;
+    RB_LAUNCH( "kd_setup", k_g_setup, 1, SETUP_TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
+               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap );
     RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
-    if ( h[5] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: coordinate range of the clouds exceeds 4096" ); }
-    if ( h[2] == 0 ) { break; }  // no node of this level is large enough for the level-parallel phase
-    RB_LAUNCH( "kd_count", k_kd_count, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd );
-    for ( int pass = 0; pass < 2; pass++ ) {
-      RB_LAUNCH( "kd_flag", k_kd_flag, rb_div_up( E + 1, TPB ), TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd, pass, flags );
-      int r = rb_scan_u32( c, flags, flags, E + 1, B.sums.as<uint32_t>() );
-      if ( r ) { return r; }
-      RB_LAUNCH( "kd_pairs", k_kd_pairs, G, TPB, 0, nid, nodes, E, lvlBegin, lvlEnd, pass, flags, nullptr, B.pairL.as<uint32_t>(),
-                 B.pairR.as<uint32_t>() );
-      RB_LAUNCH( "kd_swap", k_kd_swap, G, TPB, 0, rec, nid, nodes, E, lvlBegin, lvlEnd, pass, flags, B.pairL.as<uint32_t>(),
-                 B.pairR.as<uint32_t>() );
-    }
-    const uint32_t before = h[0];
-    RB_LAUNCH( "kd_children", k_kd_children, rb_div_up( nLvl, 128 ), 128, 0, nodes, lvlBegin, lvlEnd, counters,
-               std::min( nodeCap, statCap ), st );
-    // assignment to the children + the children's tight boxes (the next level's statistics) in one pass
-    RB_LAUNCH( "kd_assign", k_kd_stats<true>, G, TPB, 0, rec, nid, nodes, st, E, lvlBegin, lvlEnd );
-    lvlBegin = before;
-    lvlEnd   = before + 2 * h[2];
-    if ( lvlEnd > std::min( nodeCap, statCap ) ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
+    if ( h[C_RANGE] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: coordinate range of the clouds exceeds 4096" ); }
+    if ( h[C_POOL] ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
+    const uint32_t nBig = h[C_BIG], nChunks = h[C_CHUNKS];
+    if ( nBig == 0 ) { break; }  // no node of this level is large enough for the level phase
+    const int GW = rb_div_up( (int64_t)nLvl * 32, TPB );
+    RB_LAUNCH( "kd_count", k_g_count, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, cA, cB );
+    RB_LAUNCH( "kd_nodescan", k_g_nodescan<false>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wB, st );
+    RB_LAUNCH( "kd_stage1", k_g_stage<false>, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, cA, tmp );
+    RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, cA, cB, tmp );
+    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wB, st );
+    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, gnodes, chunkNode, wB, cB, tmp );
+    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, gnodes, chunkNode, wB, cB, tmp, st );
+    lvlBegin = lvlEnd;  // the children were numbered consecutively behind the nodes that existed
+    lvlEnd   = h[C_NEXT];
   }
-  const uint32_t nRoots = h[1], nLevelNodes = h[0];  // nodes [1, nLevelNodes) were created by the level-parallel phase
+  const uint32_t nRoots = h[C_SMALL], nLevelNodes = h[C_NEXT];  // nodes [1, nLevelNodes) were created by the level phase
   if ( nRoots ) {
-    const size_t smem = sizeof( KbShared );
+    const size_t smem = sizeof( KsShared );
     static bool  attr = false;
     if ( !attr ) {
-      RB_CUDA( cudaFuncSetAttribute( k_kd_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+      RB_CUDA( cudaFuncSetAttribute( k_kd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
       attr = true;
     }
-    RB_LAUNCH( "kd_block", k_kd_block, nRoots, KB_TPB, smem, rec, nodes, B.smallRoots.as<uint32_t>(), nRoots, counters, nodeCap,
-               ox, oy, oz );
+    RB_LAUNCH( "kd_subtree", k_kd_subtree, nRoots, KS_WARPS * 32, smem, rec, gnodes, nodes, B.smallRoots.as<uint32_t>(), counters,
+               gCap, ox, oy, oz );
   }
+  RB_LAUNCH( "kd_finalize", k_g_finalize, rb_div_up( nLevelNodes, TPB ), TPB, 0, gnodes, nLevelNodes, nTrees, nodes,
+             B.rootBox.as<int16_t>() );
   RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
-  if ( h[3] ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
-  const uint32_t nNodes = h[0];
-  RB_LAUNCH( "kd_finalize", k_kd_finalize, rb_div_up( nLevelNodes, TPB ), TPB, 0, nodes, nLevelNodes );
-  if ( level + (int)h[4] + 2 >= KD_STACK ) {
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree depth %d exceeds the traversal stack", level + (int)h[4] );
+  if ( h[C_STACK] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: a subtree is deeper than its work stack" ); }
+  if ( level + (int)h[C_DEPTH] + 2 >= KD_STACK ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree depth %d exceeds the traversal stack", level + (int)h[C_DEPTH] );
   }
-  B.forest.rec   = rec;
-  B.forest.nodes = nodes;
-  B.forest.ox    = ox;
-  B.forest.oy    = oy;
-  B.forest.oz    = oz;
-  B.nNodes       = nNodes;
-  B.nTrees       = nTrees;
-  B.levels       = level + (int)h[4];
+  B.forest.rec     = rec;
+  B.forest.nodes   = nodes;
+  B.forest.rootBox = B.rootBox.as<int16_t>();
+  B.forest.ox      = ox;
+  B.forest.oy      = oy;
+  B.forest.oz      = oz;
+  B.nNodes         = nLevelNodes;
+  B.nTrees         = nTrees;
+  B.levels         = level + (int)h[C_DEPTH];
   return RB200_OK;
 }

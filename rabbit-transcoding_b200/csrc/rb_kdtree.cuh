@@ -10,16 +10,16 @@
 #pragma once
 #include <stdint.h>
 
+// search node, 16 bytes = one vector load per visit.  The build-time state of a node (boxes, counts) lives in the
+// builder's own scratch (rb_kdtree.cu); what nanoflann's searchLevel reads is all that is kept:
+//   leaf     : a = first element in KdForest::rec, b = KD_LEAF | count            (node.lr.left / right)
+//   interior : a = child1 (children are a and a + 1), b = cut axis, divlow / divhigh (node.sub)
 struct KdNode {
-  uint32_t left, right;        // element range [left, right) in KdForest::rec (nanoflann's vind[left..right))
-  uint32_t child1;             // 0: leaf; otherwise children are child1 and child1 + 1
-  uint32_t lt, le;             // build scratch: elements < cutval, <= cutval
-  int16_t  lo[3], hi[3];       // the (loose) bounding box handed down by the parent (divideTree's bbox argument)
-  int16_t  tmin[3], tmax[3];   // tight bounding box of the node's points (what divideTree hands back up)
-  int16_t  cutval, divlow, divhigh;
-  int8_t   cutfeat;
-  int8_t   state;              // 0 new, 1 split by the level-parallel phase, 2 small root (serial phase), 3 leaf
+  uint32_t a, b;
+  int16_t  divlow, divhigh;
+  uint32_t pad;
 };
+constexpr uint32_t KD_LEAF = 0x80000000u;
 
 // element record: x | y << 12 | z << 24 | index << 36 (coordinates relative to the forest origin, < 4096;
 // index = position of the point inside its cloud, < 2^28)
@@ -27,8 +27,9 @@ __host__ __device__ __forceinline__ int      kd_coord( uint64_t r, int axis ) { 
 __host__ __device__ __forceinline__ uint32_t kd_index( uint64_t r ) { return (uint32_t)( r >> 36 ); }
 
 struct KdForest {
-  const uint64_t* rec;    // [E] permuted element records of all trees
-  const KdNode*   nodes;  // node 0 is unused (child1 == 0 means leaf); tree t has root `t + 1`
+  const uint64_t* rec;      // [E] permuted element records of all trees
+  const KdNode*   nodes;    // node 0 is unused; tree t has root `t + 1`
+  const int16_t*  rootBox;  // [nTrees + 1][6] tight box {min[3], max[3]} of every root (root_bbox, nanoflann.hpp:1009-1024)
   int             ox, oy, oz;  // origin subtracted from every coordinate
 };
 
@@ -75,16 +76,17 @@ __device__ __forceinline__ void kd_search( const KdForest& f, uint32_t root, con
   uint32_t dists[3] = {0, 0, 0};
   uint32_t mind     = 0;
   {
-    const KdNode& r = f.nodes[root];  // computeInitialDistances against root_bbox (:1183-1201)
+    const int16_t* rb = f.rootBox + (size_t)root * 6;  // computeInitialDistances against root_bbox (:1183-1201)
 #pragma unroll
     for ( int i = 0; i < 3; i++ ) {
-      if ( q[i] < r.tmin[i] ) {
-        const int d = q[i] - r.tmin[i];
+      const int tmin = rb[i], tmax = rb[3 + i];
+      if ( q[i] < tmin ) {
+        const int d = q[i] - tmin;
         dists[i]    = (uint32_t)( d * d );
         mind += dists[i];
       }
-      if ( q[i] > r.tmax[i] ) {
-        const int d = q[i] - r.tmax[i];
+      if ( q[i] > tmax ) {
+        const int d = q[i] - tmax;
         dists[i]    = (uint32_t)( d * d );
         mind += dists[i];
       }
@@ -102,10 +104,11 @@ __device__ __forceinline__ void kd_search( const KdForest& f, uint32_t root, con
   for ( ;; ) {
     // ---- descend to a leaf ----
     for ( ;; ) {
-      const KdNode& n = f.nodes[node];
-      if ( n.child1 == 0 ) {
+      const uint4 nv = __ldg( reinterpret_cast<const uint4*>( f.nodes + node ) );
+      if ( nv.y & KD_LEAF ) {
         const uint32_t worst = res.worst();  // read once per leaf (:1213)
-        for ( uint32_t i = n.left; i < n.right; i++ ) {
+        const uint32_t lend  = nv.x + ( nv.y & 0xFFFFu );
+        for ( uint32_t i = nv.x; i < lend; i++ ) {
           const uint64_t r  = f.rec[i];
           const int      dx = q[0] - kd_coord( r, 0 ), dy = q[1] - kd_coord( r, 1 ), dz = q[2] - kd_coord( r, 2 );
           const uint32_t d  = (uint32_t)( dx * dx ) + (uint32_t)( dy * dy ) + (uint32_t)( dz * dz );
@@ -113,19 +116,20 @@ __device__ __forceinline__ void kd_search( const KdForest& f, uint32_t root, con
         }
         break;
       }
-      const int axis  = n.cutfeat;
-      const int val   = q[axis];
-      const int diff1 = val - n.divlow, diff2 = val - n.divhigh;
+      const int axis   = (int)( nv.y & 3u );
+      const int val    = axis == 0 ? q[0] : ( axis == 1 ? q[1] : q[2] );
+      const int divlow = (int16_t)( nv.z & 0xFFFFu ), divhigh = (int16_t)( nv.z >> 16 );
+      const int diff1  = val - divlow, diff2 = val - divhigh;
       uint32_t  best, other;
       int       cd;
       if ( diff1 + diff2 < 0 ) {
-        best  = n.child1;
-        other = n.child1 + 1;
-        cd    = val - n.divhigh;
+        best  = nv.x;
+        other = nv.x + 1;
+        cd    = val - divhigh;
       } else {
-        best  = n.child1 + 1;
-        other = n.child1;
-        cd    = val - n.divlow;
+        best  = nv.x + 1;
+        other = nv.x;
+        cd    = val - divlow;
       }
       stNode[sp] = other;
       stA[sp]    = (uint32_t)( cd * cd );

@@ -752,13 +752,11 @@ struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   cudaEvent_t          ev_free[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   std::vector<int64_t> raw_off;  // per cloud: offset of its raw positions inside the import buffer (-1: resident frame)
 };
-std::map<rb200_ctx*, MetricsScratch*> g_scratch;
 
 }  // namespace
 void rb_metrics_release( rb200_ctx* c ) {
-  auto it = g_scratch.find( c );
-  if ( it == g_scratch.end() ) { return; }
-  MetricsScratch* s = it->second;
+  MetricsScratch* s = static_cast<MetricsScratch*>( c->metrics_scratch );
+  if ( !s ) { return; }
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
   for ( auto* b : bufs ) { b->release(); }
@@ -773,15 +771,12 @@ void rb_metrics_release( rb200_ctx* c ) {
   }
   if ( s->copy_stream ) { cudaStreamDestroy( s->copy_stream ); }
   delete s;
-  g_scratch.erase( it );
+  c->metrics_scratch = nullptr;
 }
 namespace {
-MetricsScratch* scratch_of( rb200_ctx* c ) {
-  auto it = g_scratch.find( c );
-  if ( it != g_scratch.end() ) { return it->second; }
-  auto* s      = new MetricsScratch;
-  g_scratch[c] = s;
-  return s;
+MetricsScratch* scratch_of( rb200_ctx* c ) {  // one context is driven by one host thread at a time
+  if ( !c->metrics_scratch ) { c->metrics_scratch = new MetricsScratch; }
+  return static_cast<MetricsScratch*>( c->metrics_scratch );
 }
 
 float get_psnr( float dist, float p, float factor = 1.0 ) {  // PCCMetrics.cpp:44-48 (log10 on a float is log10f)

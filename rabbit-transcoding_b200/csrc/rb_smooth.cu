@@ -817,10 +817,9 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
   const int64_t perBlock = std::max<int64_t>( 1, 6ll * g * g >> ( 2 * grow ) );
   int64_t       cap      = std::min<int64_t>( n, n / perBlock + 1024ll * c->F ) + 64;
   int64_t       wantT    = 4 * std::min<int64_t>( maxFrame, maxFrame / perBlock + 1024 );
-  // test hook: RB200_TEST_GRID_SHRINK=k starts with 2^k times smaller tables and 4-entry luma lists, so that the
+  // test hook (rb200_debug_set_grid_shrink): start with 2^k times smaller tables and 4-entry luma lists, so that the
   // overflow -> regrow -> repeat path runs on small inputs (tests/test_gpu_parity.py)
-  const char* shrinkEnv = getenv( "RB200_TEST_GRID_SHRINK" );
-  const int   shrink    = shrinkEnv ? std::max( 0, std::min( 16, atoi( shrinkEnv ) ) ) : 0;
+  const int shrink = c->test_grid_shrink;
   if ( shrink ) {
     cap   = std::max<int64_t>( 8, ( cap >> shrink ) << ( 2 * grow ) );
     wantT = std::max<int64_t>( 16, ( wantT >> shrink ) << ( 2 * grow ) );
@@ -893,7 +892,10 @@ constexpr int WALK_CTAS = 148 * 8;  // grid-stride passes over the used part of 
 int rb_smooth_geometry_impl( rb200_ctx* c ) {
   const rb200_params& P = c->P;
   const int64_t       n = c->h_frame_off[c->F];
-  if ( n == 0 || !P.flag_geometry_smoothing || !P.grid_smoothing ) { return RB200_OK; }  // :64-66
+  if ( n == 0 || !P.flag_geometry_smoothing ) { return RB200_OK; }  // :64-65
+  if ( !P.grid_smoothing ) {  // :141 (never reached from the decoder, PCCDecoder.cpp:436)
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothPointCloud (PCCCodec.cpp:1106-1157) is not implemented" );
+  }
   const int g = P.grid_size;
   if ( g < 1 || g > 64 ) { return rb_fail( c, RB200_ERR_INVALID, "grid_size %d out of range", g ); }
   const int pcmax = 1 << P.geometry_bitdepth_3d;
@@ -902,6 +904,7 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     // tempFrameBuffer = reconstruct (PCCDecoder.cpp:435): the colour transfer needs the pre-smoothing cloud
     RB_CUDA( c->d_pos_pre.ensure( (size_t)n * 8 ) );
     RB_CUDA( cudaMemcpyAsync( c->d_pos_pre.p, c->d_pos.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+    c->pos_pre_valid = true;
   }
   GridArgs a{};
   a.F         = c->F;
@@ -989,8 +992,7 @@ int rb_convert_rgb8_impl( rb200_ctx* c ) {
 
 // test hook (rb200_debug_yuv16_to_rgb8): n colour triples through the production conversion kernel (integer path with
 // double fallback) or, force_f64 != 0, through the double path alone
-int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 ) {
-  RbBuf in, out;
+static int debug_rgb8_run( rb200_ctx* c, RbBuf& in, RbBuf& out, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 ) {
   RB_CUDA( in.ensure( (size_t)n * 8 + 16 ) );
   RB_CUDA( out.ensure( (size_t)n * 4 + 16 ) );
   std::vector<uint16_t> h4( (size_t)n * 4 );
@@ -1001,7 +1003,12 @@ int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* r
   RB_CUDA( cudaMemcpyAsync( o4.data(), out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   for ( int64_t i = 0; i < n; i++ ) { rgb[3 * i] = o4[4 * i], rgb[3 * i + 1] = o4[4 * i + 1], rgb[3 * i + 2] = o4[4 * i + 2]; }
-  in.release();
-  out.release();
   return RB200_OK;
+}
+int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 ) {
+  RbBuf     in, out;
+  const int r = debug_rgb8_run( c, in, out, yuv, n, rgb, force_f64 );
+  in.release();  // on every path
+  out.release();
+  return r;
 }

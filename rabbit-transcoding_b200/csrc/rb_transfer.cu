@@ -27,16 +27,12 @@ constexpr int KF  = 8;  // numNeighborsColorTransferFwd
 
 struct TransferScratch {
   RbKdBuild kd;
-  RbBuf     pos2, off, flags, sums, moved, part, partDist, partCnt, refined1, candCnt, candOff, candKey, small;
+  RbBuf     pos2, off, flags, sums, moved, part, partDist, bwdT, partCnt, refined1, candCnt, candOff, candKey, small;
 };
-std::map<rb200_ctx*, TransferScratch*> g_transfer;
 
-TransferScratch* scratch_of( rb200_ctx* c ) {
-  auto it = g_transfer.find( c );
-  if ( it != g_transfer.end() ) { return it->second; }
-  auto* s       = new TransferScratch;
-  g_transfer[c] = s;
-  return s;
+TransferScratch* scratch_of( rb200_ctx* c ) {  // one context is driven by one host thread at a time
+  if ( !c->transfer_scratch ) { c->transfer_scratch = new TransferScratch; }
+  return static_cast<TransferScratch*>( c->transfer_scratch );
 }
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -75,6 +71,7 @@ struct TArgs {
   uint32_t        nMoved;
   uint32_t*       part;       // [nMoved][KF] source index inside the frame
   uint32_t*       partDist;   // [nMoved][KF]
+  uint32_t*       bwdT;       // [nMoved][KF] rank of the accepted nearest target among the moved points, or ~0
   uint8_t*        partCnt;    // [nMoved]
   ushort4*        refined1;   // [nMoved]
   uint32_t*       candCnt;    // [nMoved + 1]
@@ -122,11 +119,13 @@ __global__ void __launch_bounds__( 128 ) k_transfer_fwd( const TArgs a ) {
   a.refined1[m] = out;
 }
 
-// backward direction (:1275-1293): pass 0 counts the accepted candidates per moved target, pass 1 stores them
-__global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a, int pass ) {
+// backward direction (:1275-1293): every partSource point looks up its nearest target ONCE; the accepted ones are
+// counted per moved target and remembered (target rank, distance), then k_transfer_bwd_store files them
+__global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a ) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if ( p >= a.nMoved * KF ) { return; }
   const uint32_t m = p / KF, j = p % KF;
+  a.bwdT[p]        = 0xFFFFFFFFu;
   if ( j >= a.partCnt[m] ) { return; }
   const int64_t  g    = a.moved[m];
   const int      f    = frame_of( a.frame_off, a.F, g );
@@ -142,13 +141,18 @@ __global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a, int pass
   const ushort4 cs = a.col[base + s], ct = a.col[r];
   if ( abs( (int)cs.x - (int)ct.x ) < 40 && abs( (int)cs.y - (int)ct.y ) < 40 && abs( (int)cs.z - (int)ct.z ) < 40 ) {
     const uint32_t mr = a.rank[r];
-    if ( pass == 0 ) {
-      atomicAdd( &a.candCnt[mr], 1u );
-    } else {
-      const uint32_t slot = a.candOff[mr] + atomicAdd( &a.candCnt[mr], 1u );
-      a.candKey[slot]     = ( (uint64_t)res.dist[0] << 32 ) | p;
-    }
+    atomicAdd( &a.candCnt[mr], 1u );
+    a.bwdT[p]     = mr;
+    a.partDist[p] = res.dist[0];  // (the forward distances are not needed any more)
   }
+}
+__global__ void __launch_bounds__( 256 ) k_transfer_bwd_store( const TArgs a ) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( p >= a.nMoved * KF ) { return; }
+  const uint32_t mr = a.bwdT[p];
+  if ( mr == 0xFFFFFFFFu ) { return; }
+  const uint32_t slot = a.candOff[mr] + atomicAdd( &a.candCnt[mr], 1u );
+  a.candKey[slot]     = ( (uint64_t)a.partDist[p] << 32 ) | p;
 }
 
 // ---- libstdc++ std::sort( first, last, dist < dist ) on an array of keys whose high 32 bits are the distance ----
@@ -457,15 +461,14 @@ int rb_interleave_colors_impl( rb200_ctx* c ) {
 }
 
 void rb_transfer_release( rb200_ctx* c ) {
-  auto it = g_transfer.find( c );
-  if ( it == g_transfer.end() ) { return; }
-  TransferScratch* s = it->second;
+  TransferScratch* s = static_cast<TransferScratch*>( c->transfer_scratch );
+  if ( !s ) { return; }
   s->kd.release();
-  RbBuf* b[] = {&s->pos2, &s->off, &s->flags, &s->sums, &s->moved, &s->part, &s->partDist, &s->partCnt, &s->refined1,
+  RbBuf* b[] = {&s->pos2, &s->off, &s->flags, &s->sums, &s->moved, &s->part, &s->partDist, &s->bwdT, &s->partCnt, &s->refined1,
                 &s->candCnt, &s->candOff, &s->candKey, &s->small};
   for ( auto* x : b ) { x->release(); }
   delete s;
-  g_transfer.erase( it );
+  c->transfer_scratch = nullptr;
 }
 
 int rb_transfer_colors_impl( rb200_ctx* c ) {
@@ -473,7 +476,7 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   const int           F = c->F;
   const int64_t       N = c->h_frame_off[F];
   if ( N == 0 || P.attribute_count == 0 ) { return RB200_OK; }
-  if ( !c->d_pos_pre.p || c->d_pos_pre.cap < (size_t)N * 8 ) {
+  if ( !c->pos_pre_valid || !c->d_pos_pre.p || c->d_pos_pre.cap < (size_t)N * 8 ) {
     return rb_fail( c, RB200_ERR_STATE, "transfer_colors: the pre-smoothing cloud was not kept (attr_transfer_filter_type != 1?)" );
   }
   if ( P.geometry_bitdepth_3d > 12 ) {
@@ -534,6 +537,7 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   RB_CUDA( S->moved.ensure( (size_t)M * 4 ) );
   RB_CUDA( S->part.ensure( (size_t)M * KF * 4 ) );
   RB_CUDA( S->partDist.ensure( (size_t)M * KF * 4 ) );
+  RB_CUDA( S->bwdT.ensure( (size_t)M * KF * 4 ) );
   RB_CUDA( S->partCnt.ensure( (size_t)M ) );
   RB_CUDA( S->refined1.ensure( (size_t)M * 8 ) );
   RB_CUDA( S->candCnt.ensure( (size_t)( M + 8 ) * 4 ) );
@@ -554,6 +558,7 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   a.nMoved    = M;
   a.part      = S->part.as<uint32_t>();
   a.partDist  = S->partDist.as<uint32_t>();
+  a.bwdT      = S->bwdT.as<uint32_t>();
   a.partCnt   = S->partCnt.as<uint8_t>();
   a.refined1  = S->refined1.as<ushort4>();
   a.candCnt   = S->candCnt.as<uint32_t>();
@@ -563,11 +568,11 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   a.err       = S->small.as<uint32_t>();
   RB_LAUNCH( "tr_forward", k_transfer_fwd, rb_div_up( M, 128 ), 128, 0, a );
   RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );
-  RB_LAUNCH( "tr_backward_count", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a, 0 );
+  RB_LAUNCH( "tr_backward", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a );
   r = rb_scan_u32( c, a.candCnt, S->candOff.as<uint32_t>(), M + 1, S->sums.as<uint32_t>() );
   if ( r ) { return r; }
   RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );
-  RB_LAUNCH( "tr_backward_store", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a, 1 );
+  RB_LAUNCH( "tr_backward_store", k_transfer_bwd_store, rb_div_up( (int64_t)M * KF, 256 ), 256, 0, a );
   RB_LAUNCH( "tr_final", k_transfer_final, rb_div_up( M, 128 ), 128, 0, a );
   RB_LAUNCH( "tr_store", k_transfer_store, rb_div_up( M, 128 ), 128, 0, a );
   RB_CUDA( cudaMemcpyAsync( h, a.err, 4, cudaMemcpyDeviceToHost, c->stream ) );

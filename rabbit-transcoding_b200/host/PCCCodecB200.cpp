@@ -10,15 +10,17 @@
 //   PCCCodec::smoothPointCloudPostprocess                  :52-147
 //   PCCCodec::colorSmoothing                               :149-236
 //   PCCPointSet3::transferColors16bitBP                    PccLibCommon/source/PCCPointSet.cpp:1126-1485
-//   PCCMetrics::compute( sources, reconstructs, normals )  PccLibMetrics/source/PCCMetrics.cpp:334-385
-// The originals stay linked under the names rb200_orig_* (oracle/Makefile renames the symbols with objcopy), and every
-// replaced body falls back to its original whenever the request is outside what the CUDA path implements (multiple
-// tiles, auxiliary video, multiple streams, PBF, other transfer-filter arguments ...):
-// an unsupported mode therefore gives the reference's result, never a different one.
+//   PCCMetrics::compute( sources, reconstructs, normals )  PccLibMetrics/source/PCCMetrics.cpp:334-369
+//   PCCMetrics::compute( source, reconstruct, normals )    :371-385
+// There is NO fallback into the reference's bodies: the originals are not linked (oracle/Makefile drops them from the
+// objects), every result comes from the CUDA library, and a mode the CUDA path does not implement (multiple tiles,
+// auxiliary video, PBF, other transfer-filter arguments ...) ends the way the reference ends on an error: a message and
+// exit( -1 ) (PCCMetrics.cpp:342-346, PCCPatch.cpp:237-245).
 //
 // Per-frame calls, per-GOF execution: the reference calls these functions frame by frame; the CUDA path processes the
 // whole GOF in one batched launch sequence.  The first call of a stage for a GOF runs that stage for every frame on
-// the GPU, every call then copies the frame it was asked for into the caller's containers.
+// the GPU and brings the stage's result of the whole GOF back with ONE packed copy per field into pinned staging;
+// every call then fills the caller's containers for the frame it was asked for from that staging.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -69,36 +71,45 @@
 
 using namespace pcc;
 
-// the reference's own bodies (renamed by objcopy; Itanium ABI: `this` is the first argument)
-extern "C" {
-void   rb200_orig_generateOccupancyMap( PCCCodec*, PCCFrameContext&, PCCImageOccupancyMap&, size_t, size_t, bool );
-void   rb200_orig_generateBlockToPatch( PCCCodec*, PCCContext&, PCCFrameContext&, size_t, PCCImageOccupancyMap&, size_t, size_t );
-void   rb200_orig_generatePointCloud( PCCCodec*, PCCPointSet3&, PCCContext&, size_t, size_t, const GeneratePointCloudParameters&,
-                                      std::vector<uint32_t>&, bool );
-size_t rb200_orig_colorPointCloud( PCCCodec*, PCCPointSet3&, PCCContext&, PCCFrameContext&, const std::vector<bool>&, size_t,
-                                   uint8_t, size_t, const GeneratePointCloudParameters& );
-void   rb200_orig_smoothPointCloudPostprocess( PCCCodec*, PCCPointSet3&, PCCColorTransform, const GeneratePointCloudParameters&,
-                                               std::vector<uint32_t>& );
-void   rb200_orig_colorSmoothing( PCCCodec*, PCCPointSet3&, PCCColorTransform, const GeneratePointCloudParameters& );
-bool   rb200_orig_transferColors16bitBP( const PCCPointSet3*, PCCPointSet3&, int, int32_t, bool, int, int, bool, bool, bool, bool,
-                                         double, double, double, double, double, double, bool, double );
-void   rb200_orig_metricsCompute( PCCMetrics*, const PCCGroupOfFrames&, const PCCGroupOfFrames&, const PCCGroupOfFrames& );
-}
-
 namespace {
+
+struct Pinned {  // grow-only pinned staging (rb200_host_alloc): transfers to / from it are DMA, and it is reused GOF after GOF
+  void*  p   = nullptr;
+  size_t cap = 0;
+  template <typename T>
+  T* get( size_t count ) {
+    const size_t bytes = count * sizeof( T );
+    if ( bytes > cap ) {
+      rb200_host_free( p );
+      cap = bytes + bytes / 8 + 4096;
+      p   = rb200_host_alloc( cap );
+      if ( !p ) {
+        std::fprintf( stderr, "rabbit_b200: pinned host allocation of %zu bytes failed\n", cap );
+        std::exit( -1 );
+      }
+    }
+    return static_cast<T*>( p );
+  }
+};
 
 struct Gof {  // the GOF currently resident on the GPU
   rb200_ctx*                      ctx     = nullptr;
-  const PCCContext*               context = nullptr;
+  PCCContext*                     context = nullptr;
   size_t                          frames  = 0;
   rb200_params                    P{};
+  GeneratePointCloudParameters    gp;
+  bool                            bDecoder      = false;
   bool                            reconstructed = false, geo = false, transfer = false, color = false;
   std::vector<rb200_frame_counts> counts;
+  std::vector<size_t>             off;  // [frames + 1] first point of every frame in the staging arrays
   std::map<size_t, std::vector<uint8_t>> occOriginal;  // occupancy video of the frames seen by generateOccupancyMap
   size_t                          thresholdLossyOM = 0;
-  bool                            eom              = false;
   size_t                          currentFrame     = 0;
-  bool                            active           = false;  // false: the CUDA path declined this GOF (fallback)
+  // pinned staging: the planes going up, and per stage the fields coming down (whole GOF, frame after frame)
+  Pinned inOcc, inGeo, inAtt;
+  Pinned pos[2], typ[2];  // after reconstruction / after geometry smoothing
+  Pinned col[3];          // colours16 after reconstruction / attribute re-transfer / colour smoothing
+  Pinned part, p2p;
 };
 Gof g;  // the decoder's frame loop is single-threaded (PCCDecoder.cpp:330) and PCCCodec is not re-entrant per instance
 
@@ -107,37 +118,56 @@ Gof g;  // the decoder's frame loop is single-threaded (PCCDecoder.cpp:330) and 
   std::fprintf( stderr, "rabbit_b200: %s\n", rb200_error_string( g.ctx ) );
   std::exit( status == RB200_ERR_PATCH_OUT_OF_CANVAS ? 180 : -1 );
 }
+[[noreturn]] void unsupported( const char* what ) {
+  std::fprintf( stderr, "rabbit_b200: %s is not implemented on the CUDA path (there is no CPU fallback)\n", what );
+  std::exit( -1 );
+}
 #define RB( call )                             \
   do {                                         \
     int st__ = ( call );                       \
     if ( st__ != RB200_OK ) { die( st__ ); }   \
   } while ( 0 )
 
-bool supported( PCCContext& context, const GeneratePointCloudParameters& p ) {
-  if ( p.pbfEnableFlag_ || p.useAuxSeperateVideo_ || p.multipleStreams_ || p.mapCountMinus1_ > 1 || p.occupancyResolution_ != 16 ) {
-    return false;
+void ensureContext() {
+  if ( g.ctx ) { return; }
+  const char* dev = std::getenv( "RB200_DEVICE" );  // the GPU of this process (one process per GPU)
+  const int   st  = rb200_create( dev ? std::atoi( dev ) : 0, &g.ctx );
+  if ( st != RB200_OK ) {
+    std::fprintf( stderr, "rabbit_b200: no usable CUDA device %s (status %d); there is no CPU fallback\n", dev ? dev : "0", st );
+    std::exit( -1 );
   }
-  if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
-       ( p.mapCountMinus1_ != 0 || p.enhancedOccupancyMapCode_ || p.surfaceThickness_ < 1 ) ) {
-    return false;  // combinations the C ABI refuses (rb200_gof_begin)
-  }
-  for ( size_t f = 0; f < context.size(); f++ ) {
-    if ( context[f].getNumTilesInAtlasFrame() != 1 ) { return false; }
-    auto& tile = context[f].getTile( 0 );
-    if ( tile.getLeftTopXInFrame() != 0 || tile.getLeftTopYInFrame() != 0 || tile.getUseRawPointsSeparateVideo() ) { return false; }
-  }
-  return true;
 }
 
-// PCCContext -> flat structs of the C ABI, upload, reconstruction of every frame
-void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp, bool bDecoder ) {
+void checkSupported( PCCContext& context, const GeneratePointCloudParameters& p, size_t tileIndex ) {
+  if ( p.pbfEnableFlag_ ) { unsupported( "occupancy synthesis / PBF (PCCCodec.cpp:541-554)" ); }
+  if ( p.useAuxSeperateVideo_ ) { unsupported( "raw / EOM points in an auxiliary video (PCCCodec.cpp:1451-1582)" ); }
+  if ( p.mapCountMinus1_ > 1 ) { unsupported( "more than two maps" ); }
+  if ( p.occupancyResolution_ != 16 ) { unsupported( "an occupancy resolution other than 16" ); }
+  if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
+       ( p.mapCountMinus1_ != 0 || p.enhancedOccupancyMapCode_ || p.multipleStreams_ ) ) {
+    unsupported( "pixel interleaving / point local reconstruction together with two maps, EOM or multiple streams" );
+  }
+  if ( tileIndex != 0 ) { unsupported( "an atlas frame with several tiles (PCCDecoder.cpp:356-381)" ); }
+  for ( size_t f = 0; f < context.size(); f++ ) {
+    if ( context[f].getNumTilesInAtlasFrame() != 1 ) { unsupported( "an atlas frame with several tiles (PCCDecoder.cpp:356-381)" ); }
+    auto& tile = context[f].getTile( 0 );
+    if ( tile.getLeftTopXInFrame() != 0 || tile.getLeftTopYInFrame() != 0 ) { unsupported( "a tile that does not start at (0, 0)" ); }
+    if ( tile.getUseRawPointsSeparateVideo() ) { unsupported( "raw points in a separate video" ); }
+  }
+}
+
+// PCCContext -> flat structs of the C ABI (planes through pinned staging), upload, reconstruction of every frame,
+// one packed download of everything generatePointCloud / colorPointCloud hand back
+void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp, bool bDecoder, bool relativeT1 ) {
   const size_t F = context.size();
   const size_t W = context[0].getAtlasFrameWidth(), H = context[0].getAtlasFrameHeight();
   const size_t M = gp.mapCountMinus1_ + 1, P = gp.occupancyPrecision_;
   const size_t oW = W / P, oH = H / P;
   auto&        ai       = context.getVps().getAttributeInformation( 0 );
   const bool   hasAttr  = ai.getAttributeCount() > 0;
-  auto&        geoVideo = context.getVideoGeometryMultiple()[0];
+  const bool   streams  = gp.multipleStreams_;  // map m of frame f = frame f of video m (PCCCodec.cpp:609-618)
+  auto&        geoVideos = context.getVideoGeometryMultiple();
+  auto&        attVideos = context.getVideoAttributesMultiple();
   rb200_params& p = g.P;
   std::memset( &p, 0, sizeof( p ) );
   p.width = (int)W, p.height = (int)H;
@@ -158,9 +188,10 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   p.single_map_pixel_interleaving = gp.singleMapPixelInterleaving_;
   p.point_local_reconstruction    = gp.pointLocalReconstruction_;
   p.surface_thickness             = (int)gp.surfaceThickness_;
+  p.multiple_streams              = streams ? 1 : 0;
+  p.relative_t1                   = ( streams && M > 1 && relativeT1 ) ? 1 : 0;
   p.attribute_count             = hasAttr ? 1 : 0;
-  p.attribute_rgb444 = hasAttr && context.getVideoAttributesMultiple()[0].getFrameCount() > 0 &&
-                       context.getVideoAttributesMultiple()[0].getColorFormat() == PCCCOLORFORMAT::RGB444;
+  p.attribute_rgb444 = hasAttr && attVideos[0].getFrameCount() > 0 && attVideos[0].getColorFormat() == PCCCOLORFORMAT::RGB444;
   p.geometry_bitdepth_3d       = (int)gp.geometryBitDepth3D_;
   p.flag_geometry_smoothing    = gp.flagGeometrySmoothing_;
   p.grid_smoothing             = gp.gridSmoothing_;
@@ -174,9 +205,10 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   p.threshold_color_difference = gp.thresholdColorDifference_;
   p.threshold_color_variation  = gp.thresholdColorVariation_;
 
-  std::vector<uint8_t>  occ( F * oW * oH );
-  std::vector<uint16_t> geo( F * M * W * H ), att( hasAttr ? F * M * 3 * W * H : 0 );
-  auto&                 occVideo = context.getVideoOccupancyMap();
+  uint8_t*  occ = g.inOcc.get<uint8_t>( F * oW * oH );
+  uint16_t* geo = g.inGeo.get<uint16_t>( F * M * W * H );
+  uint16_t* att = hasAttr ? g.inAtt.get<uint16_t>( F * M * 3 * W * H ) : nullptr;
+  auto&     occVideo = context.getVideoOccupancyMap();
   for ( size_t f = 0; f < F; f++ ) {
     auto it = g.occOriginal.find( f );  // a frame generateOccupancyMap already binarised in place: use the saved copy
     if ( it != g.occOriginal.end() ) {
@@ -185,9 +217,10 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
       std::memcpy( &occ[f * oW * oH], occVideo.getFrame( f ).getChannel( 0 ).data(), oW * oH );
     }
     for ( size_t m = 0; m < M; m++ ) {
-      std::memcpy( &geo[( f * M + m ) * W * H], geoVideo.getFrame( f * M + m ).getChannel( 0 ).data(), W * H * 2 );
+      auto& gf = streams ? geoVideos[m].getFrame( f ) : geoVideos[0].getFrame( f * M + m );
+      std::memcpy( &geo[( f * M + m ) * W * H], gf.getChannel( 0 ).data(), W * H * 2 );
       if ( hasAttr ) {
-        auto& a = context.getVideoAttributesMultiple()[0].getFrame( f * M + m );
+        auto& a = streams ? attVideos[m].getFrame( f ) : attVideos[0].getFrame( f * M + m );
         for ( int c = 0; c < 3; c++ ) { std::memcpy( &att[( ( f * M + m ) * 3 + c ) * W * H], a.getChannel( c ).data(), W * H * 2 ); }
       }
     }
@@ -227,11 +260,10 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
     rOff.push_back( (int32_t)raws.size() );
   }
   if ( members.empty() ) { members.push_back( 0 ); }
-  rb200_frames fr{occ.data(), geo.data(), hasAttr ? att.data() : nullptr};
+  rb200_frames fr{occ, geo, att};
   rb200_atlas  at{patches.data(), pOff.data(), eoms.empty() ? nullptr : eoms.data(), eOff.data(), members.data(),
                   raws.empty() ? nullptr : raws.data(), rOff.data()};
-  if ( !g.ctx ) { RB( rb200_create( 0, &g.ctx ) ); }
-  RB( rb200_enable_stage_snapshots( g.ctx, 1 ) );  // the caller walks the stages frame by frame
+  ensureContext();
   RB( rb200_gof_begin( g.ctx, &p, (int)F ) );
   RB( rb200_gof_upload( g.ctx, &fr, &at ) );
   if ( gp.pointLocalReconstruction_ && !gp.singleMapPixelInterleaving_ ) {
@@ -258,13 +290,44 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   RB( rb200_reconstruct( g.ctx ) );
   g.counts.resize( F );
   RB( rb200_frame_counts_get( g.ctx, g.counts.data() ) );
+  g.off.assign( F + 1, 0 );
+  for ( size_t f = 0; f < F; f++ ) { g.off[f + 1] = g.off[f] + (size_t)g.counts[f].total; }
+  const size_t N = g.off[F];
+  if ( N ) {
+    rb200_cloud_host h{};
+    h.positions      = g.pos[0].get<int16_t>( N * 3 );
+    h.boundary_types = g.typ[0].get<uint16_t>( N );
+    h.colors16       = hasAttr ? g.col[0].get<uint16_t>( N * 3 ) : nullptr;
+    h.partition      = g.part.get<uint32_t>( N );
+    h.point_to_pixel = g.p2p.get<uint32_t>( N * 3 );
+    RB( rb200_download_gof( g.ctx, &h ) );
+  }
   g.context       = &context;
   g.frames        = F;
+  g.gp            = gp;
+  g.bDecoder      = bDecoder;
   g.reconstructed = true;
   g.geo = g.transfer = g.color = false;
 }
 
+void checkFrame( const char* who, size_t f, size_t points ) {
+  if ( !g.reconstructed || f >= g.frames || points != (size_t)g.counts[f].total ) {
+    std::fprintf( stderr, "rabbit_b200: %s called for a cloud that generatePointCloud did not produce (frame %zu, %zu points)\n", who,
+                  f, points );
+    std::exit( -1 );
+  }
+}
+
 }  // namespace
+
+// instrumentation for the tests: the launch / transfer counters of the shim's context (tests assert the GPU ran)
+extern "C" int rb200_shim_stats( rb200_launch_stats* out, int reset ) {
+  if ( !g.ctx ) {
+    *out = rb200_launch_stats{};
+    return RB200_OK;
+  }
+  return rb200_stats_get( g.ctx, out, reset );
+}
 
 namespace pcc {
 
@@ -274,14 +337,24 @@ void PCCCodec::generateOccupancyMap( PCCFrameContext& tile, PCCImageOccupancyMap
   if ( f == 0 || g.occOriginal.count( f ) ) {  // a new GOF starts
     g.occOriginal.clear();
     g.reconstructed = g.geo = g.transfer = g.color = false;
-    g.active                                       = false;
   }
-  g.occOriginal[f]   = videoFrame.getChannel( 0 );  // the original body thresholds the video sample in place (:1597-1600)
+  if ( tile.getLeftTopXInFrame() != 0 || tile.getLeftTopYInFrame() != 0 ) { unsupported( "a tile that does not start at (0, 0)" ); }
+  g.occOriginal[f]   = videoFrame.getChannel( 0 );  // the reconstruction of the GOF starts from the decoded samples
   g.thresholdLossyOM = thresholdLossyOM;
-  g.eom              = enhancedOccupancyMapForDepthFlag;
-  // keep the caller-visible side effects of the original (binarised video frame, tile.getOccupancyMap()) by running it;
-  // the map used for the reconstruction is recomputed on the GPU from the saved samples
-  rb200_orig_generateOccupancyMap( this, tile, videoFrame, occupancyPrecision, thresholdLossyOM, enhancedOccupancyMapForDepthFlag );
+  // the caller-visible results of the original — tile.getOccupancyMap() and the video frame thresholded in place
+  // (:1597-1600) — computed on the GPU for this frame
+  ensureContext();
+  const size_t width = tile.getWidth(), height = tile.getHeight();
+  auto&        occupancyMap = tile.getOccupancyMap();
+  occupancyMap.resize( width * height, 0 );
+  if ( width * height == 0 ) { return; }
+  if ( width % occupancyPrecision || height % occupancyPrecision || videoFrame.getWidth() != width / occupancyPrecision ||
+       videoFrame.getHeight() != height / occupancyPrecision ) {
+    unsupported( "an occupancy video that is not exactly tile size / occupancy precision" );
+  }
+  RB( rb200_occupancy_map( g.ctx, videoFrame.getChannel( 0 ).data(), (int)( width / occupancyPrecision ),
+                           (int)( height / occupancyPrecision ), (int)occupancyPrecision, (int)thresholdLossyOM,
+                           enhancedOccupancyMapForDepthFlag ? 1 : 0, occupancyMap.data() ) );
 }
 
 void PCCCodec::generateBlockToPatchFromOccupancyMapVideo( PCCContext& context, PCCFrameContext& tile, size_t frameIdx,
@@ -298,32 +371,38 @@ void PCCCodec::generateBlockToPatchFromOccupancyMapVideo( PCCContext& context, P
 
 void PCCCodec::generatePointCloud( PCCPointSet3& reconstruct, PCCContext& context, size_t frameIndex, size_t tileIndex,
                                    const GeneratePointCloudParameters& params, std::vector<uint32_t>& partition, bool bDecoder ) {
-  if ( !g.reconstructed ) { g.active = supported( context, params ) && tileIndex == 0; }
   auto& tile = context[frameIndex].getTile( tileIndex );
-  if ( !g.active ) {
-    rb200_orig_generateBlockToPatch( this, context, tile, frameIndex, context.getVideoOccupancyMap().getFrame( frameIndex ),
-                                     params.occupancyResolution_, params.occupancyPrecision_ );
-    rb200_orig_generatePointCloud( this, reconstruct, context, frameIndex, tileIndex, params, partition, bDecoder );
-    return;
+  if ( !g.reconstructed ) {
+    checkSupported( context, params, tileIndex );
+    // the second attribute map is a delta on the first when the stream says so (PCCDecoder.cpp:309-323); colorPointCloud
+    // receives the list itself and repeats the reconstruction should it disagree
+    bool relT1 = false;
+    if ( params.multipleStreams_ && params.mapCountMinus1_ >= 1 ) {
+      auto& sps = context.getVps();
+      auto& ai  = sps.getAttributeInformation( 0 );
+      if ( ai.getAttributeCount() > 0 && ai.getAttributeMapAbsoluteCodingPersistenceFlag( 0 ) == 0u ) {
+        relT1 = !sps.getMapAbsoluteCodingEnableFlag( context.getAtlasIndex(), 1 );
+      }
+    }
+    reconstructGof( context, params, bDecoder, relT1 );
   }
-  if ( !g.reconstructed ) { reconstructGof( context, params, bDecoder ); }
+  if ( tileIndex != 0 || frameIndex >= g.frames ) { unsupported( "an atlas frame with several tiles (PCCDecoder.cpp:356-381)" ); }
   g.currentFrame                = frameIndex;
   const rb200_frame_counts& cnt = g.counts[frameIndex];
-  const size_t              n   = (size_t)cnt.total;
+  const size_t              n = (size_t)cnt.total, o = g.off[frameIndex];
   reconstruct.resize( n );
   partition.resize( n );
-  std::vector<uint32_t> p2p( n * 3 );
-  rb200_cloud_host      h{};
-  h.positions      = n ? reinterpret_cast<int16_t*>( reconstruct.getPositions().data() ) : nullptr;
-  h.boundary_types = n ? reconstruct.getBoundaryPointTypes().data() : nullptr;
-  h.partition      = n ? partition.data() : nullptr;
-  h.point_to_pixel = n ? p2p.data() : nullptr;
-  RB( rb200_download_frame_stage( g.ctx, (int)frameIndex, 0, &h ) );
   auto& pointToPixel = tile.getPointToPixel();
   pointToPixel.resize( n );
-  for ( size_t i = 0; i < n; i++ ) {
-    pointToPixel[i] = PCCVector3<size_t>( p2p[3 * i], p2p[3 * i + 1], p2p[3 * i + 2] );
-    reconstruct.setPointPatchIndex( i, (uint32_t)tileIndex, partition[i] );
+  if ( n ) {
+    std::memcpy( reconstruct.getPositions().data(), static_cast<int16_t*>( g.pos[0].p ) + 3 * o, n * 6 );
+    std::memcpy( reconstruct.getBoundaryPointTypes().data(), static_cast<uint16_t*>( g.typ[0].p ) + o, n * 2 );
+    std::memcpy( partition.data(), static_cast<uint32_t*>( g.part.p ) + o, n * 4 );
+    const uint32_t* p2p = static_cast<uint32_t*>( g.p2p.p ) + 3 * o;
+    for ( size_t i = 0; i < n; i++ ) {
+      pointToPixel[i] = PCCVector3<size_t>( p2p[3 * i], p2p[3 * i + 1], p2p[3 * i + 2] );
+      reconstruct.setPointPatchIndex( i, (uint32_t)tileIndex, partition[i] );
+    }
   }
   tile.setTotalNumberOfRegularPoints( (size_t)cnt.regular );
   tile.setTotalNumberOfEOMPoints( (size_t)cnt.eom );
@@ -341,21 +420,27 @@ size_t PCCCodec::colorPointCloud( PCCPointSet3& reconstruct, PCCContext& context
                                   const std::vector<bool>& absoluteT1List, const size_t multipleStreams, const uint8_t attributeCount,
                                   size_t accTilePointCount, const GeneratePointCloudParameters& params ) {
   const size_t f = tile.getFrameIndex();
-  if ( !g.active || !g.reconstructed || multipleStreams || accTilePointCount != 0 ||
-       reconstruct.getPointCount() != (size_t)g.counts[f].total ) {
-    return rb200_orig_colorPointCloud( this, reconstruct, context, tile, absoluteT1List, multipleStreams, attributeCount,
-                                       accTilePointCount, params );
-  }
+  if ( accTilePointCount != 0 ) { unsupported( "an atlas frame with several tiles (PCCDecoder.cpp:356-381)" ); }
+  checkFrame( "colorPointCloud", f, reconstruct.getPointCount() );
+  if ( ( multipleStreams != 0 ) != ( g.P.multiple_streams != 0 ) ) { unsupported( "colorPointCloud with a stream layout other than generatePointCloud's" ); }
   const size_t n = reconstruct.getPointCount();
   if ( n == 0 ) { return accTilePointCount; }
   reconstruct.fillColor();  // :1319
   if ( attributeCount == 0 ) {
     for ( auto& color : reconstruct.getColors() ) { color[0] = color[1] = color[2] = 127; }  // :1327-1330
   } else {
-    rb200_cloud_host h{};
-    h.colors16 = reinterpret_cast<uint16_t*>( reconstruct.getColors16bit().data() );  // gathered by the reprojection kernel
-    RB( rb200_download_frame_stage( g.ctx, (int)f, 0, &h ) );
+    // the colours were gathered by the reprojection kernel; a delta-coded second map (:1387-1416) is part of that kernel,
+    // so the reconstruction is repeated when the caller's list differs from what the stream announced
+    const bool relT1 = multipleStreams && g.P.map_count_minus1 >= 1 && absoluteT1List.size() > 1 && !absoluteT1List[1];
+    if ( relT1 != ( g.P.relative_t1 != 0 ) ) {
+      if ( g.geo || g.transfer || g.color ) { unsupported( "a change of absoluteT1List after post-processing has started" ); }
+      reconstructGof( *g.context, g.gp, g.bDecoder, relT1 );
+      checkFrame( "colorPointCloud", f, n );
+    }
+    std::memcpy( reconstruct.getColors16bit().data(), static_cast<uint16_t*>( g.col[0].p ) + 3 * g.off[f], n * 6 );
   }
+  (void)context;
+  (void)params;
   return accTilePointCount + tile.getTotalNumberOfRegularPoints() + tile.getTotalNumberOfEOMPoints() +
          tile.getTotalNumberOfRawPoints();
 }
@@ -363,19 +448,26 @@ size_t PCCCodec::colorPointCloud( PCCPointSet3& reconstruct, PCCContext& context
 void PCCCodec::smoothPointCloudPostprocess( PCCPointSet3& reconstruct, const PCCColorTransform colorTransform,
                                             const GeneratePointCloudParameters& params, std::vector<uint32_t>& partition ) {
   const size_t f = g.currentFrame;
-  if ( !g.active || !g.reconstructed || reconstruct.getPointCount() != (size_t)g.counts[f].total ) {
-    rb200_orig_smoothPointCloudPostprocess( this, reconstruct, colorTransform, params, partition );
-    return;
+  if ( reconstruct.getPointCount() == 0 ) { return; }  // :64
+  checkFrame( "smoothPointCloudPostprocess", f, reconstruct.getPointCount() );
+  if ( params.flagGeometrySmoothing_ && !params.gridSmoothing_ && !params.pbfEnableFlag_ ) {
+    unsupported( "the non-grid smoothPointCloud (PCCCodec.cpp:1106-1157)" );
   }
   if ( !g.geo ) {
     RB( rb200_smooth_geometry( g.ctx ) );
+    const size_t N = g.off[g.frames];
+    rb200_cloud_host h{};
+    h.positions      = g.pos[1].get<int16_t>( N * 3 );
+    h.boundary_types = g.typ[1].get<uint16_t>( N );
+    RB( rb200_download_gof( g.ctx, &h ) );
+    RB( rb200_frame_counts_get( g.ctx, g.counts.data() ) );
     g.geo = true;
   }
-  if ( reconstruct.getPointCount() == 0 ) { return; }
-  rb200_cloud_host h{};
-  h.positions      = reinterpret_cast<int16_t*>( reconstruct.getPositions().data() );
-  h.boundary_types = reconstruct.getBoundaryPointTypes().data();
-  RB( rb200_download_frame_stage( g.ctx, (int)f, 1, &h ) );
+  const size_t n = reconstruct.getPointCount(), o = g.off[f];
+  std::memcpy( reconstruct.getPositions().data(), static_cast<int16_t*>( g.pos[1].p ) + 3 * o, n * 6 );
+  std::memcpy( reconstruct.getBoundaryPointTypes().data(), static_cast<uint16_t*>( g.typ[1].p ) + o, n * 2 );
+  (void)colorTransform;
+  (void)partition;
 }
 
 bool PCCPointSet3::transferColors16bitBP( PCCPointSet3& target, const int filterType, const int32_t searchRange,
@@ -387,108 +479,151 @@ bool PCCPointSet3::transferColors16bitBP( PCCPointSet3& target, const int filter
                                           double maxColorDist2Fwd, double maxColorDist2Bwd, const bool excludeColorOutlier,
                                           const double thresholdColorOutlierDist ) const {
   const size_t f = g.currentFrame;
-  // exactly the decoder's call (PCCDecoder.cpp:447-465); anything else runs the original body
+  // exactly the decoder's call (PCCDecoder.cpp:447-465); the encoder's other argument sets are not on this path
   const bool decoderCall = filterType == 1 && searchRange == 0 && numNeighborsColorTransferFwd == 8 &&
                            numNeighborsColorTransferBwd == 1 && useDistWeightedAverageFwd && useDistWeightedAverageBwd &&
                            skipAvgIfIdenticalSourcePointPresentFwd && !skipAvgIfIdenticalSourcePointPresentBwd &&
                            distOffsetFwd == 4 && distOffsetBwd == 4 && maxGeometryDist2Fwd >= 512 && maxGeometryDist2Bwd >= 512 &&
                            maxColorDist2Fwd >= 131072 && maxColorDist2Bwd >= 131072 && !excludeColorOutlier;
-  if ( !decoderCall || !g.active || !g.geo || target.getPointCount() != (size_t)g.counts[f].total ||
-       getPointCount() != target.getPointCount() || losslessAttribute != ( g.P.attribute_rgb444 != 0 ) ) {
-    return rb200_orig_transferColors16bitBP( this, target, filterType, searchRange, losslessAttribute, numNeighborsColorTransferFwd,
-                                             numNeighborsColorTransferBwd, useDistWeightedAverageFwd, useDistWeightedAverageBwd,
-                                             skipAvgIfIdenticalSourcePointPresentFwd, skipAvgIfIdenticalSourcePointPresentBwd,
-                                             distOffsetFwd, distOffsetBwd, maxGeometryDist2Fwd, maxGeometryDist2Bwd,
-                                             maxColorDist2Fwd, maxColorDist2Bwd, excludeColorOutlier, thresholdColorOutlierDist );
-  }
+  if ( !decoderCall ) { unsupported( "transferColors16bitBP with arguments other than the decoder's (PCCDecoder.cpp:447-465)" ); }
   if ( getPointCount() == 0 || !hasColors() ) { return false; }  // :1147
+  checkFrame( "transferColors16bitBP", f, target.getPointCount() );
+  if ( getPointCount() != target.getPointCount() || losslessAttribute != ( g.P.attribute_rgb444 != 0 ) ) {
+    unsupported( "transferColors16bitBP between clouds other than a decoded frame and its smoothed copy" );
+  }
+  (void)thresholdColorOutlierDist;
+  target.addColors16bit();
+  const size_t n = target.getPointCount(), o = g.off[f];
+  if ( !g.geo ) {  // gridSmoothing_ == 0: both clouds are the reconstruction, no point is of type 3, nothing changes (:1163-1164)
+    std::memcpy( target.getColors16bit().data(), static_cast<uint16_t*>( g.col[0].p ) + 3 * o, n * 6 );
+    return true;
+  }
   if ( !g.transfer ) {
     RB( rb200_transfer_colors( g.ctx ) );
+    rb200_cloud_host h{};
+    h.colors16 = g.col[1].get<uint16_t>( g.off[g.frames] * 3 );
+    RB( rb200_download_gof( g.ctx, &h ) );
     g.transfer = true;
   }
-  target.addColors16bit();
-  rb200_cloud_host h{};
-  h.colors16 = reinterpret_cast<uint16_t*>( target.getColors16bit().data() );
-  RB( rb200_download_frame_stage( g.ctx, (int)f, 2, &h ) );
+  std::memcpy( target.getColors16bit().data(), static_cast<uint16_t*>( g.col[1].p ) + 3 * o, n * 6 );
   return true;
 }
 
 void PCCCodec::colorSmoothing( PCCPointSet3& reconstruct, const PCCColorTransform colorTransform,
                                const GeneratePointCloudParameters& params ) {
   const size_t f = g.currentFrame;
-  if ( !g.active || !g.reconstructed || reconstruct.getPointCount() != (size_t)g.counts[f].total ) {
-    rb200_orig_colorSmoothing( this, reconstruct, colorTransform, params );
-    return;
-  }
+  if ( reconstruct.getPointCount() == 0 ) { return; }
+  checkFrame( "colorSmoothing", f, reconstruct.getPointCount() );
   if ( !g.color ) {
     RB( rb200_smooth_color( g.ctx ) );
+    rb200_cloud_host h{};
+    h.colors16 = g.col[2].get<uint16_t>( g.off[g.frames] * 3 );
+    RB( rb200_download_gof( g.ctx, &h ) );
+    RB( rb200_frame_counts_get( g.ctx, g.counts.data() ) );
     g.color = true;
   }
-  if ( reconstruct.getPointCount() == 0 ) { return; }
-  rb200_cloud_host h{};
-  h.colors16 = reinterpret_cast<uint16_t*>( reconstruct.getColors16bit().data() );
-  RB( rb200_download_frame_stage( g.ctx, (int)f, 3, &h ) );
+  std::memcpy( reconstruct.getColors16bit().data(), static_cast<uint16_t*>( g.col[2].p ) + 3 * g.off[f], reconstruct.getPointCount() * 6 );
+  (void)colorTransform;
+  (void)params;
 }
 
-void PCCMetrics::compute( const PCCGroupOfFrames& sources, const PCCGroupOfFrames& reconstructs, const PCCGroupOfFrames& normals ) {
-  const size_t n = sources.getFrameCount();
-  bool         ok = n > 0 && n == reconstructs.getFrameCount() && params_.neighborsProc_ >= 1 && params_.neighborsProc_ <= 4 &&
-            !params_.computeLidar_ && !params_.computeReflectance_ && ( normals.getFrameCount() == 0 || normals.getFrameCount() == n );
-  for ( size_t i = 0; ok && i < n; i++ ) {
-    ok = sources[i].getPointCount() > 0 && reconstructs[i].getPointCount() > 0 && sources[i].hasColors() == reconstructs[i].hasColors();
-    if ( ok && normals.getFrameCount() ) {
-      // the C ABI takes the normal cloud through the source view: same points in the same order
-      ok = normals[i].getPointCount() == sources[i].getPointCount() &&
-           std::memcmp( normals[i].positions_.data(), sources[i].positions_.data(), sources[i].getPointCount() * 6 ) == 0;
-    }
-  }
-  if ( !ok ) {  // includes the error paths of the original (:337-347), which prints and exits itself
-    rb200_orig_metricsCompute( this, sources, reconstructs, normals );
-    return;
-  }
+namespace {
+rb200_metrics_params metricsParams( const PCCMetricsParameters& p ) {
+  if ( p.computeLidar_ || p.computeReflectance_ ) { unsupported( "lidar / reflectance metrics" ); }
+  if ( p.neighborsProc_ < 1 || p.neighborsProc_ > 4 ) { unsupported( "metrics with neighborsProc = 0 (PCCMetrics.cpp:134-136)" ); }
   rb200_metrics_params mp{};
-  mp.compute_c2c = params_.computeC2c_, mp.compute_c2p = params_.computeC2p_, mp.compute_color = params_.computeColor_;
-  mp.compute_hausdorff = params_.computeHausdorff_, mp.drop_duplicates = (int)params_.dropDuplicates_;
-  mp.neighbors_proc = (int)params_.neighborsProc_, mp.resolution = (float)params_.resolution_;
+  mp.compute_c2c = p.computeC2c_, mp.compute_c2p = p.computeC2p_, mp.compute_color = p.computeColor_;
+  mp.compute_hausdorff = p.computeHausdorff_, mp.drop_duplicates = (int)p.dropDuplicates_;
+  mp.neighbors_proc = (int)p.neighborsProc_, mp.resolution = (float)p.resolution_;
+  return mp;
+}
+QualityMetrics fillQuality( const PCCMetricsParameters& params, const rb200_quality& s ) {
+  QualityMetrics q;
+  q.setParameters( params );
+  q.psnr_    = params.resolution_;
+  q.c2cMse_  = s.c2c_mse, q.c2cPsnr_ = s.c2c_psnr, q.c2cHausdorff_ = s.c2c_hausdorff, q.c2cHausdorffPsnr_ = s.c2c_hausdorff_psnr;
+  q.c2pMse_  = s.c2p_mse, q.c2pPsnr_ = s.c2p_psnr, q.c2pHausdorff_ = s.c2p_hausdorff, q.c2pHausdorffPsnr_ = s.c2p_hausdorff_psnr;
+  for ( int k = 0; k < 3; k++ ) { q.colorMse_[k] = s.color_mse[k], q.colorPsnr_[k] = s.color_psnr[k]; }
+  return q;
+}
+// the C ABI takes the normals through the source view: the normal cloud must hold the source's points in the source's order
+bool sameOrder( const PCCPointSet3& normals, const PCCPointSet3& source ) {
+  return normals.getPointCount() == source.getPointCount() &&
+         std::memcmp( normals.positions_.data(), source.positions_.data(), source.getPointCount() * 6 ) == 0;
+}
+std::vector<float> floatNormals( const PCCPointSet3& normals ) {
+  std::vector<float> out( normals.getPointCount() * 3 );
+  for ( size_t k = 0; k < normals.getPointCount(); k++ ) {
+    for ( int c = 0; c < 3; c++ ) { out[3 * k + c] = (float)normals.normals_[k][c]; }
+  }
+  return out;
+}
+rb200_cloud_view viewOf( const PCCPointSet3& pc ) {
+  return rb200_cloud_view{reinterpret_cast<const int16_t*>( pc.positions_.data() ),
+                          pc.hasColors() ? reinterpret_cast<const uint8_t*>( pc.colors_.data() ) : nullptr, nullptr,
+                          (int64_t)pc.getPointCount()};
+}
+}  // namespace
+
+void PCCMetrics::compute( const PCCGroupOfFrames& sources, const PCCGroupOfFrames& reconstructs, const PCCGroupOfFrames& normals ) {
+  if ( normals.getFrameCount() != 0 && sources.getFrameCount() != normals.getFrameCount() ) { params_.computeC2p_ = false; }  // :338-340
+  if ( sources.getFrameCount() != reconstructs.getFrameCount() ) {  // :341-347
+    printf( "Error: group of frames must have same numbers of frames. ( src = %zu rec = %zu norm = %zu ) \n", sources.getFrameCount(),
+            reconstructs.getFrameCount(), normals.getFrameCount() );
+    exit( -1 );
+  }
+  const size_t n = sources.getFrameCount();
+  if ( n == 0 ) { return; }
+  const bool                      useNormals = normals.getFrameCount() == n;
+  rb200_metrics_params            mp         = metricsParams( params_ );
   std::vector<rb200_cloud_view>   vs( n ), vr( n );
   std::vector<std::vector<float>> nrm( n );
   for ( size_t i = 0; i < n; i++ ) {
-    vs[i] = rb200_cloud_view{reinterpret_cast<const int16_t*>( sources[i].positions_.data() ),
-                             sources[i].hasColors() ? reinterpret_cast<const uint8_t*>( sources[i].colors_.data() ) : nullptr, nullptr,
-                             (int64_t)sources[i].getPointCount()};
-    vr[i] = rb200_cloud_view{reinterpret_cast<const int16_t*>( reconstructs[i].positions_.data() ),
-                             reconstructs[i].hasColors() ? reinterpret_cast<const uint8_t*>( reconstructs[i].colors_.data() ) : nullptr,
-                             nullptr, (int64_t)reconstructs[i].getPointCount()};
-    if ( normals.getFrameCount() ) {
-      nrm[i].resize( normals[i].getPointCount() * 3 );
-      for ( size_t k = 0; k < normals[i].getPointCount(); k++ ) {
-        for ( int c = 0; c < 3; c++ ) { nrm[i][3 * k + c] = (float)normals[i].normals_[k][c]; }
-      }
+    if ( sources[i].getPointCount() == 0 || reconstructs[i].getPointCount() == 0 ) { unsupported( "metrics of an empty cloud" ); }
+    vs[i] = viewOf( sources[i] );
+    vr[i] = viewOf( reconstructs[i] );
+    if ( useNormals && normals[i].getPointCount() > 0 ) {
+      if ( !sameOrder( normals[i], sources[i] ) ) { unsupported( "a normal cloud that is not the source cloud point for point" ); }
+      nrm[i]        = floatNormals( normals[i] );
       vs[i].normals = nrm[i].data();
     }
   }
-  if ( !g.ctx ) { RB( rb200_create( 0, &g.ctx ) ); }
+  ensureContext();
   std::vector<rb200_metrics_result> res( n );
   const int                         st = rb200_metrics( g.ctx, &mp, (int)n, vs.data(), vr.data(), res.data() );
   if ( st != RB200_OK && st != RB200_ERR_TIE_OVERFLOW ) { die( st ); }
-  auto fill = [&]( const rb200_quality& s ) {
-    QualityMetrics q;
-    q.setParameters( params_ );
-    q.psnr_    = params_.resolution_;
-    q.c2cMse_  = s.c2c_mse, q.c2cPsnr_ = s.c2c_psnr, q.c2cHausdorff_ = s.c2c_hausdorff, q.c2cHausdorffPsnr_ = s.c2c_hausdorff_psnr;
-    q.c2pMse_  = s.c2p_mse, q.c2pPsnr_ = s.c2p_psnr, q.c2pHausdorff_ = s.c2p_hausdorff, q.c2pHausdorffPsnr_ = s.c2p_hausdorff_psnr;
-    for ( int k = 0; k < 3; k++ ) { q.colorMse_[k] = s.color_mse[k], q.colorPsnr_[k] = s.color_psnr[k]; }
-    return q;
-  };
   for ( size_t i = 0; i < n; i++ ) {
     sourcePoints_.push_back( (size_t)res[i].source_points );
     reconstructPoints_.push_back( (size_t)res[i].rec_points );
     sourceDuplicates_.push_back( (size_t)res[i].source_after_dedup );
     reconstructDuplicates_.push_back( (size_t)res[i].rec_after_dedup );
-    quality1_.push_back( fill( res[i].q1 ) );
-    quality2_.push_back( fill( res[i].q2 ) );
-    qualityF_.push_back( fill( res[i].qf ) );
+    quality1_.push_back( fillQuality( params_, res[i].q1 ) );
+    quality2_.push_back( fillQuality( params_, res[i].q2 ) );
+    qualityF_.push_back( fillQuality( params_, res[i].qf ) );
   }
+}
+
+// the per-pair overload (:371-385): the clouds are compared as they are (the caller removed the duplicates, :358-361).
+// The reference also leaves the transferred normals in `source` / `reconstruct` (copyNormals / scaleNormals); no caller
+// of the path reads them afterwards, and they are not produced here.
+void PCCMetrics::compute( PCCPointSet3& source, PCCPointSet3& reconstruct, const PCCPointSet3& normalSource ) {
+  rb200_metrics_params mp = metricsParams( params_ );
+  mp.drop_duplicates      = 0;
+  if ( source.getPointCount() == 0 || reconstruct.getPointCount() == 0 ) { unsupported( "metrics of an empty cloud" ); }
+  rb200_cloud_view   vs = viewOf( source ), vr = viewOf( reconstruct );
+  std::vector<float> nrm;
+  if ( normalSource.getPointCount() > 0 ) {
+    if ( !sameOrder( normalSource, source ) ) { unsupported( "a normal cloud that is not the source cloud point for point" ); }
+    nrm        = floatNormals( normalSource );
+    vs.normals = nrm.data();
+  }
+  ensureContext();
+  rb200_metrics_result res{};
+  const int            st = rb200_metrics( g.ctx, &mp, 1, &vs, &vr, &res );
+  if ( st != RB200_OK && st != RB200_ERR_TIE_OVERFLOW ) { die( st ); }
+  quality1_.push_back( fillQuality( params_, res.q1 ) );
+  quality2_.push_back( fillQuality( params_, res.q2 ) );
+  qualityF_.push_back( fillQuality( params_, res.qf ) );
 }
 
 }  // namespace pcc

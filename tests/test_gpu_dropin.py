@@ -2,6 +2,10 @@
 objects) with the hot member functions replaced by rabbit-transcoding_b200/host/PCCCodecB200.cpp, which calls the CUDA
 library.  Everything the callers see — PCCPointSet3 contents after every stage, partition, pointToPixel, block-to-patch,
 point counts, ordered MD5, PCCMetrics results — must equal the unmodified reference's."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -19,13 +23,18 @@ def backends():
     return checker.Reference(), checker.DropIn()
 
 
-def compare(rb, backends, what, **kw):
+def compare(rb, backends, what, make=None, **kw):
     ref_b, drop_b = backends
     args = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=71, transfer_filter=1)
     args.update(kw)
-    g = rb.synthetic.generate_gof(**args)
+    g = make(rb.synthetic.generate_gof(**args)) if make else rb.synthetic.generate_gof(**args)
     want = ref_b.run_gof(g, keep=STAGES)
-    got = drop_b.run_gof(rb.synthetic.generate_gof(**args), keep=STAGES)  # fresh arrays: the original binarises in place
+    drop_b.stats(reset=True)
+    g2 = make(rb.synthetic.generate_gof(**args)) if make else rb.synthetic.generate_gof(**args)
+    got = drop_b.run_gof(g2, keep=STAGES)  # fresh arrays: the original binarises in place
+    st = drop_b.stats()
+    # the results below were computed by the CUDA library: its kernels ran and the clouds came back over PCIe
+    assert st.kernel_launches >= 5 * g.n_frames and st.d2h_bytes > 0 and st.h2d_bytes > 0, (st.kernel_launches, st.d2h_bytes)
     for f in range(g.n_frames):
         cw, cg = want.counts(f), got.counts(f)
         assert (cw.total, cw.regular, cw.eom, cw.raw, cw.smoothed, cw.recolored) == \
@@ -56,15 +65,39 @@ def test_dropin_eom_and_raw(rb, backends):
     compare(rb, backends, "raw", raw_points=700, transfer_filter=0, seed=74)
 
 
-def test_dropin_unsupported_mode_falls_back_to_the_reference_body(rb, backends):
-    """multiple map streams are not wired through the shim: it must hand the frame to the original body"""
-    ref_b, drop_b = backends
-    args = dict(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=75, transfer_filter=1)
-    g = rb.synthetic.make_relative_t1(rb.synthetic.generate_gof(**args), seed=5)
-    want = ref_b.run_gof(g, keep=("rgb8",))
-    g2 = rb.synthetic.make_relative_t1(rb.synthetic.generate_gof(**args), seed=5)
-    got = drop_b.run_gof(g2, keep=("rgb8",))
-    assert got.md5(0) == want.md5(0)
+def test_dropin_links_no_reference_body():
+    """the shim has no way back into the reference's own bodies: no rb200_orig_* symbol, and every replaced member is
+    defined exactly once (the shim's strong definition)"""
+    from oracle import checker
+    if not checker.have_dropin():
+        pytest.skip("librabbit_dropin.so not built")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", checker.DROPIN_LIB], text=True)
+    assert "rb200_orig" not in out
+    for member in ("PCCCodec18generatePointCloud", "PCCCodec15colorPointCloud", "PCCCodec27smoothPointCloudPostprocess",
+                   "PCCCodec14colorSmoothing", "PCCCodec20generateOccupancyMap", "PCCPointSet321transferColors16bitBP",
+                   "PCCMetrics7computeERKNS_16PCCGroupOfFrames"):
+        assert sum(1 for line in out.splitlines() if member in line and ".cold" not in line) == 1, member
+
+
+def test_dropin_multiple_streams_relative_t1(rb, backends):
+    """multiple map streams with a delta-coded second attribute map run on the GPU behind the member functions"""
+    compare(rb, backends, "relt1", make=lambda g: rb.synthetic.make_relative_t1(g, seed=5), n_frames=2, seed=75)
+
+
+def test_dropin_unsupported_mode_exits_like_the_reference(rb, backends):
+    """a mode the CUDA path does not implement ends with a message and a non-zero exit status (the reference's error
+    convention, PCCMetrics.cpp:342-346) — never with a result computed somewhere else"""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import rabbit_transcoding_b200 as rb\n"
+        "from oracle import checker\n"
+        "g = rb.synthetic.generate_gof(n_frames=1, bitdepth=8, width=256, scale=0.9, seed=79, transfer_filter=1)\n"
+        "g.params.occupancy_resolution = 8\n"
+        "checker.DropIn().run_gof(g, keep=('rgb8',), quiet=False)\n"
+        "print('SURVIVED')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "SURVIVED" not in r.stdout
+    assert "not implemented on the CUDA path" in r.stderr, r.stderr[-2000:]
 
 
 def test_dropin_pixel_interleaving_and_plr(rb, backends):
@@ -77,7 +110,9 @@ def test_dropin_pixel_interleaving_and_plr(rb, backends):
                            rb.synthetic.generate_gof(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=78, transfer_filter=1,
                                                      map_count=1), seed=6))):
         want = ref_b.run_gof(make(), keep=stages)
+        drop_b.stats(reset=True)
         got = drop_b.run_gof(make(), keep=stages)
+        assert drop_b.stats().kernel_launches > 10
         for f in range(2):
             assert got.md5(f) == want.md5(f), tag
             for st in stages:
@@ -91,7 +126,9 @@ def test_dropin_metrics(rb, backends):
     rec = ref_b.run_gof(g, keep=("rgb8",)).cloud(0, "rgb8")
     mp = checker.default_metrics_params(resolution=255.0)
     want, _ = ref_b.metrics(mp, g.sources[0], rec, g.sources[0])
+    drop_b.stats(reset=True)
     got, _ = drop_b.metrics(mp, g.sources[0], rec, g.sources[0])
+    assert drop_b.stats().kernel_launches > 5
     for tag in ("q1", "q2", "qf"):
         a, b = getattr(got, tag), getattr(want, tag)
         assert a.c2c_mse == b.c2c_mse

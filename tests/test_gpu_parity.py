@@ -46,11 +46,11 @@ def test_multiple_streams_relative_t1(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, what="streams_abs_t1")
 
 
-def test_smoothing_tables_overflow_and_regrow(rb, checker_backend, monkeypatch):
+def test_smoothing_tables_overflow_and_regrow(rb, checker_backend):
     """the sparse smoothing grids start far too small (test hook): block pool, block table and luma lists overflow, the
     filters do nothing, the stage is repeated with larger tables — and the result is still the reference's"""
-    monkeypatch.setenv("RB200_TEST_GRID_SHRINK", "9")
     c = rb.codec.PCCCodecB200(device=0)  # a fresh context: the growth state lives in the context
+    assert c._lib.rb200_debug_set_grid_shrink(c._h, 9) == 0
     try:
         run_stages(c, small(rb, seed=31), checker_backend, what="regrow")
         run_stages(c, small(rb, seed=32, occupancy_precision=2, orientations=tuple(range(9))), checker_backend, what="regrow2")
