@@ -14,9 +14,10 @@
 //    rank" + "every misplaced position reads its partner by rank": coalesced on both sides, no pair lists, no scans over
 //    the elements.  The last pass of a level also reduces the tight boxes of the two children (the next level's
 //    computeMinMax).  ~44 bytes per element and level.
-//  * subtree phase, nodes of at most KS_CAP elements: one CTA loads the subtree into shared memory; its warps take nodes
-//    from a shared stack (a warp splits a node, keeps the left child and pushes the right one), every pass is a
-//    lane-strided loop with ballots — no CTA barrier, no atomics on the elements.
+//  * subtree phase, nodes of at most KS_CAP elements: one WARP owns a subtree in its slice of shared memory and builds it
+//    depth first (it splits a node, keeps the left child and pushes the right one on its own stack); every pass is a
+//    lane-strided loop with ballots — no CTA barrier, no lock, no atomics on the elements.  Warps are persistent and
+//    take subtrees from a global counter, so an SM always holds ~20 independent instruction streams.
 // divlow / divhigh come from the children's tight boxes (divideTree :1080-1081).
 #include <algorithm>
 
@@ -30,13 +31,14 @@ constexpr int TPB    = 256;
 constexpr int GT     = 2048;          // elements per chunk of the level phase
 constexpr int GWORDS = GT / 32;       // mask words per chunk
 constexpr int GEPT   = GT / TPB;      // elements per thread
-constexpr int KS_CAP = 2048;          // largest node of the subtree phase
-constexpr int KS_WARPS = 8;
-constexpr int KS_STACK = 448;         // pending nodes of a subtree: <= warps x depth (depth <= 36 + 11, see below)
+constexpr int KS_CAP   = 512;         // largest node of the subtree phase
+constexpr int KS_WARPS = 4;           // warps (= independent subtrees) per CTA
+constexpr int KS_STACK = 56;          // pending right children of one subtree: <= its depth (<= 36 + 9, see below)
 
 // counters[]: [0] next free level-phase node, [1] small roots, [2] split nodes of the level, [3] pool exhausted,
-//             [4] depth of the deepest subtree, [5] coordinate range error, [6] chunks of the level, [7] subtree stack overflow
-enum { C_NEXT = 0, C_SMALL = 1, C_BIG = 2, C_POOL = 3, C_DEPTH = 4, C_RANGE = 5, C_CHUNKS = 6, C_STACK = 7 };
+//             [4] depth of the deepest subtree, [5] coordinate range error, [6] chunks of the level, [7] subtree stack
+//             overflow, [8] next subtree to build (work counter of the persistent warps)
+enum { C_NEXT = 0, C_SMALL = 1, C_BIG = 2, C_POOL = 3, C_DEPTH = 4, C_RANGE = 5, C_CHUNKS = 6, C_STACK = 7, C_WORK = 8 };
 
 // build-time node of the level phase
 struct GNode {
@@ -67,7 +69,9 @@ __device__ __forceinline__ void kd_choose_split( const int lo[3], const int hi[3
   int cf = 0, max_spread = -1;
   for ( int i = 0; i < 3; i++ ) {
     const int span = hi[i] - lo[i];
-    if ( (double)span > ( 1.0 - 0.00001 ) * (double)max_span ) {  // span > (1 - EPS) * max_span in double
+    // span > (1 - EPS) * max_span in double (:1112): for integer spans below 100000 the right side lies strictly between
+    // max_span - 1 and max_span, so the test is span == max_span — and false for every axis when max_span == 0
+    if ( span == max_span && max_span > 0 ) {
       const int spread = tmax[i] - tmin[i];
       if ( spread > max_spread ) {
         cf         = i;
@@ -205,93 +209,78 @@ __global__ void k_g_roots( GNode* __restrict__ nodes, const int64_t* __restrict_
 }
 
 // the nodes of this level: tight box from the statistics, small root / split decision (middleSplit_), chunk table and
-// the ids of the children.  One CTA: a level has at most a few ten thousand nodes.
-constexpr int SETUP_TPB = 1024;
-__global__ void __launch_bounds__( SETUP_TPB ) k_g_setup( GNode* __restrict__ nodes, const int32_t* __restrict__ st, uint32_t lvlBegin,
-                                                          uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
-                                                          uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
-                                                          uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap ) {
-  __shared__ uint32_t wsA[32], wsB[32];
-  __shared__ uint32_t carryC, carryB;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if ( threadIdx.x == 0 ) { carryC = 0, carryB = 0; }
-  __syncthreads();
-  const uint32_t childBase = counters[C_NEXT];
-  const int      o[3]      = {ox, oy, oz};
-  for ( uint32_t base = lvlBegin; base < lvlEnd; base += SETUP_TPB ) {
-    const uint32_t i   = base + threadIdx.x;
-    uint32_t       nch = 0, big = 0;
-    if ( i < lvlEnd ) {
-      GNode& n = nodes[i];
-      int    lo[3], hi[3], tmin[3], tmax[3];
-      for ( int k = 0; k < 3; k++ ) {
-        tmin[k]   = st[(size_t)i * 6 + k];
-        tmax[k]   = st[(size_t)i * 6 + 3 + k];
-        n.tmin[k] = (int16_t)tmin[k];
-        n.tmax[k] = (int16_t)tmax[k];
-        if ( isRoot ) {  // divideTree( 0, N, root_bbox ) starts from the tight box
-          n.lo[k] = (int16_t)tmin[k];
-          n.hi[k] = (int16_t)tmax[k];
-        }
-        lo[k] = n.lo[k], hi[k] = n.hi[k];
+// the ids of the children.  One thread per node; chunks and child ids are handed out with one atomic per warp (the
+// numbering of nodes and chunks is free: only the tree they describe is the result).  C_BIG / C_CHUNKS are zeroed by
+// the host before the launch; nothing else allocates from C_NEXT while this kernel runs.
+__global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, const int32_t* __restrict__ st, uint32_t lvlBegin,
+                                                    uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
+                                                    uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap ) {
+  const int      lane = threadIdx.x & 31;
+  const uint32_t i    = lvlBegin + blockIdx.x * TPB + threadIdx.x;
+  const int      o[3] = {ox, oy, oz};
+  uint32_t       nch = 0, big = 0, small = 0;
+  if ( i < lvlEnd ) {
+    GNode& n = nodes[i];
+    int    lo[3], hi[3], tmin[3], tmax[3];
+    for ( int k = 0; k < 3; k++ ) {
+      tmin[k]   = st[(size_t)i * 6 + k];
+      tmax[k]   = st[(size_t)i * 6 + 3 + k];
+      n.tmin[k] = (int16_t)tmin[k];
+      n.tmax[k] = (int16_t)tmax[k];
+      if ( isRoot ) {  // divideTree( 0, N, root_bbox ) starts from the tight box
+        n.lo[k] = (int16_t)tmin[k];
+        n.hi[k] = (int16_t)tmax[k];
       }
-      const uint32_t count = n.right - n.left;
-      if ( count <= (uint32_t)KS_CAP ) {
-        n.state                                     = 2;
-        smallRoots[atomicAdd( &counters[C_SMALL], 1u )] = i;
-      } else {
-        int cf, cv;
-        kd_choose_split( lo, hi, tmin, tmax, o, cf, cv );
-        n.cutfeat = (int8_t)cf;
-        n.cutval  = (int16_t)cv;
-        n.state   = 1;
-        nch       = ( count + GT - 1 ) / GT;
-        big       = 1;
-      }
+      lo[k] = n.lo[k], hi[k] = n.hi[k];
     }
-    // CTA-wide exclusive scans of the chunk counts and of the split flags
-    uint32_t ia = nch, ib = big;
-#pragma unroll
-    for ( int d = 1; d < 32; d <<= 1 ) {
-      const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ia, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, ib, d );
-      if ( lane >= d ) { ia += ta, ib += tb; }
+    const uint32_t count = n.right - n.left;
+    if ( count <= (uint32_t)KS_CAP ) {
+      n.state = 2;
+      small   = 1;
+    } else {
+      int cf, cv;
+      kd_choose_split( lo, hi, tmin, tmax, o, cf, cv );
+      n.cutfeat = (int8_t)cf;
+      n.cutval  = (int16_t)cv;
+      n.state   = 1;
+      nch       = ( count + GT - 1 ) / GT;
+      big       = 1;
     }
-    if ( lane == 31 ) { wsA[w] = ia, wsB[w] = ib; }
-    __syncthreads();
-    if ( w == 0 ) {
-      const uint32_t xa = wsA[lane], xb = wsB[lane];
-      uint32_t       ya = xa, yb = xb;
-#pragma unroll
-      for ( int d = 1; d < 32; d <<= 1 ) {
-        const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ya, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, yb, d );
-        if ( lane >= d ) { ya += ta, yb += tb; }
-      }
-      wsA[lane] = ya - xa, wsB[lane] = yb - xb;
-      if ( lane == 31 ) { wsA[31] = ya - xa, wsB[31] = yb - xb; }
-    }
-    __syncthreads();
-    const uint32_t offC = carryC + wsA[w] + ia - nch, offB = carryB + wsB[w] + ib - big;
-    if ( big ) {
-      GNode&         n  = nodes[i];
-      const uint32_t c1 = childBase + 2u * offB;
-      if ( c1 + 2u > nodeCap || offC + nch > chunkCap ) {
-        counters[C_POOL] = 1;
-        n.child1         = 0;
-        n.firstChunk     = 0;
-      } else {
-        n.child1     = c1;
-        n.firstChunk = offC;
-        for ( uint32_t k = 0; k < nch; k++ ) { chunkNode[offC + k] = i; }
-      }
-    }
-    __syncthreads();
-    if ( threadIdx.x == SETUP_TPB - 1 ) { carryC = offC + nch, carryB = offB + big; }
-    __syncthreads();
   }
-  if ( threadIdx.x == 0 ) {
-    counters[C_NEXT]   = childBase + 2u * carryB;
-    counters[C_BIG]    = carryB;
-    counters[C_CHUNKS] = carryC;
+  // warp-wide exclusive scans, one allocation per warp
+  uint32_t ia = nch, ib = big, is = small;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const uint32_t ta = __shfl_up_sync( 0xFFFFFFFFu, ia, d ), tb = __shfl_up_sync( 0xFFFFFFFFu, ib, d ),
+                   ts = __shfl_up_sync( 0xFFFFFFFFu, is, d );
+    if ( lane >= d ) { ia += ta, ib += tb, is += ts; }
+  }
+  uint32_t baseC = 0, baseB = 0, baseS = 0;
+  if ( lane == 31 ) {
+    if ( ia ) { baseC = atomicAdd( &counters[C_CHUNKS], ia ); }
+    if ( ib ) {
+      baseB = atomicAdd( &counters[C_NEXT], 2u * ib );
+      atomicAdd( &counters[C_BIG], ib );
+    }
+    if ( is ) { baseS = atomicAdd( &counters[C_SMALL], is ); }
+  }
+  baseC = __shfl_sync( 0xFFFFFFFFu, baseC, 31 );
+  baseB = __shfl_sync( 0xFFFFFFFFu, baseB, 31 );
+  baseS = __shfl_sync( 0xFFFFFFFFu, baseS, 31 );
+  if ( small ) { smallRoots[baseS + is - 1u] = i; }
+  if ( big ) {
+    GNode&         n    = nodes[i];
+    const uint32_t offC = baseC + ia - nch, c1 = baseB + 2u * ( ib - 1u );
+    if ( c1 + 2u > nodeCap || offC + nch > chunkCap ) {
+      counters[C_POOL] = 1;
+      n.child1         = 0;
+      n.firstChunk     = 0;
+    } else {
+      n.child1     = c1;
+      n.firstChunk = offC;
+      for ( uint32_t k = 0; k < nch; k++ ) { chunkNode[offC + k] = i; }
+    }
   }
 }
 
@@ -500,24 +489,28 @@ __global__ void __launch_bounds__( TPB ) k_g_stage( const uint64_t* __restrict__
   }
 }
 
-// pass D: every misplaced position of pass 1 takes its partner; the "<= cut" mask of the positions >= lim1 is
-// rewritten for the new arrangement (pass 2 works on it) together with its per-chunk counts
+// pass D: every misplaced position of pass 1 takes its partner; the "<= cut" mask of the positions >= lim1 is written
+// for the new arrangement (pass 2 works on it: wC) together with its per-chunk counts.  All loads of the chunk are
+// issued before the first ballot, so a CTA pays one memory round trip, not one per 256 elements.
 __global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
                                                      const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ wA,
-                                                     uint32_t* __restrict__ wB, const uint32_t* __restrict__ cA,
-                                                     uint32_t* __restrict__ cB, const uint64_t* __restrict__ tmp ) {
-  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
+                                                     const uint32_t* __restrict__ wB, uint32_t* __restrict__ wC,
+                                                     const uint32_t* __restrict__ cA, uint32_t* __restrict__ cB,
+                                                     const uint64_t* __restrict__ tmp ) {
+  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS], sWordB[GWORDS];
   __shared__ uint32_t sCnt[TPB / 32];
   const uint32_t c = blockIdx.x, node = chunkNode[c];
   const GNode&   n = nodes[node];
   const ChunkCtx x    = chunk_ctx( n, node, c );
   const uint32_t lim1 = n.lim1, m = n.m1;
   const int      cf = n.cutfeat, cut = n.cutval;
+  if ( threadIdx.x < GWORDS ) { sWordB[threadIdx.x] = wB[(size_t)c * GWORDS + threadIdx.x]; }
   chunk_word_prefix( wA + (size_t)c * GWORDS, sWord, sPre );
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t base = cA[c];
   const uint32_t lt   = lanemask_lt();
-  uint32_t       cnt  = 0;
+  uint64_t       nv[GEPT];   // the partner of a misplaced position
+  uint32_t       kind = 0;   // bit q: position q of this thread is misplaced
 #pragma unroll
   for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i   = q * TPB + threadIdx.x;
@@ -526,20 +519,28 @@ __global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec,
     const bool     bit = ( wd >> lane ) & 1u;
     const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
     const uint32_t p   = x.p0 + i;
-    const bool     ok  = i < x.cnt;
-    bool           b2  = ok && p >= lim1 && ( ( wB[(size_t)c * GWORDS + wi] >> lane ) & 1u );
-    if ( ok && m ) {
+    nv[q]              = 0;
+    if ( i < x.cnt && m ) {
       if ( p < lim1 ) {
-        if ( !bit ) { rec[x.e0 + i] = tmp[x.left + lim1 + ( m - 1u - ( p - pre ) )]; }
+        if ( !bit ) { nv[q] = tmp[x.left + lim1 + ( m - 1u - ( p - pre ) )], kind |= 1u << q; }
       } else if ( bit ) {
-        const uint64_t v = tmp[x.left + ( m - 1u - ( pre - ( lim1 - m ) ) )];
-        rec[x.e0 + i]    = v;
-        b2               = kd_coord( v, cf ) <= cut;
+        nv[q] = tmp[x.left + ( m - 1u - ( pre - ( lim1 - m ) ) )], kind |= 1u << q;
       }
     }
+  }
+  uint32_t cnt = 0;
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i  = q * TPB + threadIdx.x;
+    const int      wi = q * ( TPB / 32 ) + w;
+    const uint32_t p  = x.p0 + i;
+    bool           b2 = i < x.cnt && p >= lim1 && ( ( sWordB[wi] >> lane ) & 1u );
+    if ( kind >> q & 1u ) {
+      rec[x.e0 + i] = nv[q];
+      if ( p >= lim1 ) { b2 = kd_coord( nv[q], cf ) <= cut; }
+    }
     const uint32_t mb = __ballot_sync( 0xFFFFFFFFu, b2 );
-    __syncwarp();  // every lane has read the old word before lane 0 replaces it
-    if ( lane == 0 ) { wB[(size_t)c * GWORDS + wi] = mb; }
+    if ( lane == 0 ) { wC[(size_t)c * GWORDS + wi] = mb; }
     cnt += __popc( mb );
   }
   if ( lane == 0 ) { sCnt[w] = cnt; }
@@ -570,32 +571,32 @@ __global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec,
 #pragma unroll
   for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = 1 << 20, bx[3 + k] = bx[9 + k] = -( 1 << 20 ); }
   uint64_t r[GEPT];
+  uint32_t moved = 0;
 #pragma unroll
-  for ( int q = 0; q < GEPT; q++ ) {
+  for ( int q = 0; q < GEPT; q++ ) {  // every load of the chunk is in flight before the first use
     const uint32_t i = q * TPB + threadIdx.x;
-    r[q]             = i < x.cnt ? rec[x.e0 + i] : 0ull;
-  }
-#pragma unroll
-  for ( int q = 0; q < GEPT; q++ ) {
-    const uint32_t i = q * TPB + threadIdx.x;
+    r[q]             = 0ull;
     if ( i >= x.cnt ) { continue; }
     const int      wi  = q * ( TPB / 32 ) + w;
     const uint32_t wd  = sWord[wi];
     const bool     bit = ( wd >> lane ) & 1u;
     const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
     const uint32_t p   = x.p0 + i;
-    uint64_t       v   = r[q];
-    if ( m && p >= lim1 ) {
-      if ( p < lim2 ) {
-        if ( !bit ) {
-          v             = tmp[x.left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )];
-          rec[x.e0 + i] = v;
-        }
-      } else if ( bit ) {
-        v             = tmp[x.left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )];
-        rec[x.e0 + i] = v;
-      }
+    if ( m && p >= lim1 && p < lim2 && !bit ) {
+      r[q] = tmp[x.left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )], moved |= 1u << q;
+    } else if ( m && p >= lim2 && bit ) {
+      r[q] = tmp[x.left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )], moved |= 1u << q;
+    } else {
+      r[q] = rec[x.e0 + i];
     }
+  }
+#pragma unroll
+  for ( int q = 0; q < GEPT; q++ ) {
+    const uint32_t i = q * TPB + threadIdx.x;
+    if ( i >= x.cnt ) { continue; }
+    const uint32_t p = x.p0 + i;
+    const uint64_t v = r[q];
+    if ( moved >> q & 1u ) { rec[x.e0 + i] = v; }
     const int  cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
     const bool rt = p >= idx;
     // (selects, not branches: both boxes live in registers)
@@ -629,10 +630,10 @@ __global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// subtree phase: one CTA builds a whole subtree of at most KS_CAP elements in shared memory.
+// subtree phase: one WARP builds a whole subtree of at most KS_CAP elements in its slice of shared memory.
 // Depth of such a subtree: every split halves the loose box along its longest side, 36 splits reduce a 4096^3 box to
 // a single lattice point, and from there on cutval == tmin == tmax gives lim1 = 0, lim2 = n, idx = n / 2 — so at most
-// 36 + log2( KS_CAP ) levels; each warp's path owns at most one pending sibling per level.
+// 36 + log2( KS_CAP ) levels, and the stack of pending right children is never deeper than that.
 // ---------------------------------------------------------------------------------------------------
 struct KsItem {
   uint32_t gid;          // node id
@@ -643,241 +644,266 @@ struct KsItem {
   uint8_t  pfeat, pad;   // cut axis of the parent
 };
 
-struct KsShared {
+struct KsWarp {
   uint64_t rec[KS_CAP];
   uint64_t tmp[KS_CAP];
   KsItem   stack[KS_STACK];
-  KsItem   slot[KS_WARPS];  // the item a warp popped (copied under the lock)
-  int      top, lock, pending, nextId, maxDepth, abort;
 };
+
+// one Hoare pass of planeSplit (:1154-1181) on positions [begin, right) of the warp's subtree: the positions before
+// `lim` (node-relative) must hold the elements with kd_coord < bound (INCL: <= bound)
+template <bool INCL>
+__device__ __forceinline__ void ks_hoare( KsWarp& S, uint32_t left, uint32_t begin, uint32_t right, uint32_t lim, int cf, int bound,
+                                          int lane, uint32_t lt ) {
+  // misplaced elements to the staging array at their rank: left ones at [begin, ...), right ones at [left + lim, ...)
+  uint32_t ml = 0, mr = 0;
+  for ( uint32_t p0 = begin; p0 < right; p0 += 32 ) {
+    const uint32_t p   = p0 + lane;
+    const bool     ok  = p < right;
+    const uint64_t r   = ok ? S.rec[p] : 0ull;
+    const int      v   = kd_coord( r, cf );
+    const bool     in  = INCL ? v <= bound : v < bound;
+    const bool     isL = ok && p - left < lim && !in, isR = ok && p - left >= lim && in;
+    const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+    if ( isL ) { S.tmp[begin + ml + __popc( bl & lt )] = r; }
+    if ( isR ) { S.tmp[left + lim + mr + __popc( br & lt )] = r; }
+    ml += __popc( bl ), mr += __popc( br );
+  }
+  const uint32_t m = ml;
+  __syncwarp();
+  if ( m == 0 ) { return; }
+  // the i-th misplaced element from the left meets the i-th misplaced element from the right
+  ml = mr = 0;
+  for ( uint32_t p0 = begin; p0 < right; p0 += 32 ) {
+    const uint32_t p   = p0 + lane;
+    const bool     ok  = p < right;
+    const int      v   = kd_coord( ok ? S.rec[p] : 0ull, cf );
+    const bool     in  = INCL ? v <= bound : v < bound;
+    const bool     isL = ok && p - left < lim && !in, isR = ok && p - left >= lim && in;
+    const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+    if ( isL ) { S.rec[p] = S.tmp[left + lim + ( m - 1u - ( ml + __popc( bl & lt ) ) )]; }
+    if ( isR ) { S.rec[p] = S.tmp[begin + ( m - 1u - ( mr + __popc( br & lt ) ) )]; }
+    ml += __popc( bl ), mr += __popc( br );
+  }
+  __syncwarp();
+}
+
+constexpr uint32_t KS_NOREPORT = 0xFFFFFFFFu;  // KsItem::pgid: the parent computed this node's bound itself
+
+// a child of at most leaf_max_size (10, PCCKdTree.cpp:58) elements is finished by its parent: the leaf record, and the
+// bound it hands up (divideTree :1080-1081) unless the parent has it already
+__device__ __forceinline__ void ks_leaf_child( KsWarp& S, KdNode* __restrict__ nodes, uint32_t base, uint32_t parent, uint32_t gid,
+                                               uint32_t first, uint32_t cnt, int side, int cf, bool report, int lane ) {
+  if ( report ) {
+    const int v = lane < (int)cnt ? kd_coord( S.rec[first + lane], cf ) : ( side ? 4096 : -1 );
+    const int e = side ? __reduce_min_sync( 0xFFFFFFFFu, v ) : __reduce_max_sync( 0xFFFFFFFFu, v );
+    if ( lane == 0 ) {
+      if ( side ) {
+        nodes[parent].divhigh = (int16_t)e;
+      } else {
+        nodes[parent].divlow = (int16_t)e;
+      }
+    }
+  }
+  if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[gid] ) = make_uint2( base + first, KD_LEAF | cnt ); }
+}
 
 __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __restrict__ grec, GNode* __restrict__ gnodes,
                                                                  KdNode* __restrict__ nodes, const uint32_t* __restrict__ smallRoots,
-                                                                 uint32_t* __restrict__ counters, uint32_t subBase, int ox, int oy,
-                                                                 int oz ) {
+                                                                 uint32_t nRoots, uint32_t* __restrict__ counters, uint32_t subBase,
+                                                                 int ox, int oy, int oz ) {
   extern __shared__ __align__( 16 ) unsigned char ks_smem[];
-  KsShared&      S      = *reinterpret_cast<KsShared*>( ks_smem );
-  const int      lane   = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t rootId = smallRoots[blockIdx.x];
-  const uint32_t base   = gnodes[rootId].left, total = gnodes[rootId].right - base;
-  const int      o[3]   = {ox, oy, oz};
-  const uint32_t lt     = lanemask_lt();
-  // node ids of this subtree: a contiguous block behind the level-phase nodes, 2 ids per element is the worst case
-  const uint32_t idBase = subBase + 2u * base;
-  for ( uint32_t i = threadIdx.x; i < total; i += KS_WARPS * 32 ) { S.rec[i] = grec[base + i]; }
-  if ( threadIdx.x == 0 ) { S.top = 0, S.lock = 0, S.pending = 1, S.nextId = 0, S.maxDepth = 0, S.abort = 0; }
-  __syncthreads();
-  KsItem cur{};
-  bool   have = false;
-  if ( w == 0 ) {
-    const GNode& r = gnodes[rootId];
-    cur.gid = rootId, cur.pgid = 0, cur.left = 0, cur.right = (uint16_t)total, cur.side = 0, cur.depth = 0;
-    for ( int k = 0; k < 3; k++ ) { cur.lo[k] = r.lo[k], cur.hi[k] = r.hi[k]; }
-    have = true;
-  }
-  int maxDepth = 0;
-  for ( ;; ) {
-    if ( !have ) {  // take a node from the shared stack, or leave when the subtree is complete
-      int got = 0;
-      if ( lane == 0 ) {
-        for ( int spin = 0;; spin++ ) {
-          if ( *( (volatile int*)&S.abort ) ) { break; }
-          if ( *( (volatile int*)&S.top ) > 0 ) {
-            if ( atomicCAS( &S.lock, 0, 1 ) == 0 ) {
-              __threadfence_block();
-              const int t = *( (volatile int*)&S.top );
-              if ( t > 0 ) {
-                S.slot[w] = S.stack[t - 1];
-                S.top     = t - 1;
-                got       = 1;
-              }
-              __threadfence_block();
-              atomicExch( &S.lock, 0 );
-              if ( got ) { break; }
-            }
-          } else if ( *( (volatile int*)&S.pending ) <= 0 ) {
-            break;
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  KsWarp&        S    = reinterpret_cast<KsWarp*>( ks_smem )[w];
+  const int      o[3] = {ox, oy, oz};
+  const uint32_t lt   = lanemask_lt();
+  int            maxDepth = 0;
+  bool           overflow = false;
+  for ( ;; ) {  // persistent warp: next subtree from the global counter
+    uint32_t job = 0;
+    if ( lane == 0 ) { job = atomicAdd( &counters[C_WORK], 1u ); }
+    job = __shfl_sync( 0xFFFFFFFFu, job, 0 );
+    if ( job >= nRoots ) { break; }
+    const uint32_t rootId = smallRoots[job];
+    const uint32_t base   = gnodes[rootId].left, total = gnodes[rootId].right - base;
+    // node ids of this subtree: a contiguous block behind the level-phase nodes, 2 ids per element is the worst case
+    const uint32_t idBase = subBase + 2u * base;
+    uint32_t       nextId = 0;
+    for ( uint32_t i = lane; i < total; i += 32 ) { S.rec[i] = grec[base + i]; }
+    KsItem cur{};
+    {
+      const GNode& r = gnodes[rootId];
+      cur.gid = rootId, cur.pgid = 0, cur.left = 0, cur.right = (uint16_t)total, cur.side = 0, cur.depth = 0;
+      for ( int k = 0; k < 3; k++ ) { cur.lo[k] = r.lo[k], cur.hi[k] = r.hi[k]; }
+    }
+    int sp = 0;
+    __syncwarp();
+    for ( ;; ) {
+      const uint32_t left = cur.left, right = cur.right, n = right - left;
+      maxDepth = max( maxDepth, (int)cur.depth );
+      const bool small = n <= 32;  // the whole node lives in one register per lane
+      uint64_t   r     = 0;
+      // ---- tight box (computeMinMax) ----
+      int mn[3] = {4096, 4096, 4096}, mx[3] = {-1, -1, -1};
+      if ( small ) {
+        if ( lane < (int)n ) {
+          r = S.rec[left + lane];
+          mn[0] = mx[0] = kd_coord( r, 0 ), mn[1] = mx[1] = kd_coord( r, 1 ), mn[2] = mx[2] = kd_coord( r, 2 );
+        }
+      } else {
+        for ( uint32_t p = left + lane; p < right; p += 32 ) {
+          const uint64_t q = S.rec[p];
+          const int      x = kd_coord( q, 0 ), y = kd_coord( q, 1 ), z = kd_coord( q, 2 );
+          mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
+          mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
+        }
+      }
+#pragma unroll
+      for ( int k = 0; k < 3; k++ ) {
+        mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
+        mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
+      }
+      // the node reports its tight bound to its parent (divideTree :1080-1081)
+      if ( lane == 0 && cur.pgid != KS_NOREPORT ) {
+        if ( cur.pgid ) {
+          const int pf = cur.pfeat;
+          if ( cur.side == 0 ) {
+            nodes[cur.pgid].divlow = (int16_t)( pf == 0 ? mx[0] : ( pf == 1 ? mx[1] : mx[2] ) );
           } else {
-            __nanosleep( 100 );
-            if ( spin > ( 1 << 22 ) ) {  // never seen; a stuck subtree must not hang the device
-              atomicOr( &counters[C_STACK], 2u );
-              atomicExch( &S.abort, 1 );
-              break;
+            nodes[cur.pgid].divhigh = (int16_t)( pf == 0 ? mn[0] : ( pf == 1 ? mn[1] : mn[2] ) );
+          }
+        } else {  // the parent is a level-phase node: k_g_finalize reads the box from the build node
+          GNode& g = gnodes[cur.gid];
+          for ( int k = 0; k < 3; k++ ) { g.tmin[k] = (int16_t)mn[k], g.tmax[k] = (int16_t)mx[k]; }
+        }
+      }
+      bool haveNext = false;  // `cur` holds the next node to split
+      if ( n <= 10 ) {        // only the root of a subtree can arrive here as a leaf
+        if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[cur.gid] ) = make_uint2( base + left, KD_LEAF | n ); }
+      } else {
+        int cf, cut;
+        {
+          const int lo[3] = {cur.lo[0], cur.lo[1], cur.lo[2]}, hi[3] = {cur.hi[0], cur.hi[1], cur.hi[2]};
+          kd_choose_split( lo, hi, mn, mx, o, cf, cut );
+        }
+        uint32_t lim1, lim2, idx;
+        bool     divKnown = false;  // the parent wrote divlow / divhigh itself
+        const uint32_t c1 = idBase + nextId;
+        nextId += 2;
+        if ( small ) {
+          // ---- planeSplit on registers: one element per lane, ranks from ballots, partners through the staging slots ----
+          const bool act = lane < (int)n;
+          int        v   = kd_coord( r, cf );
+          lim1           = __popc( __ballot_sync( 0xFFFFFFFFu, act && v < cut ) );
+          lim2           = __popc( __ballot_sync( 0xFFFFFFFFu, act && v <= cut ) );
+          if ( lim1 > 0 && lim1 < n ) {
+            const bool     isL = act && lane < (int)lim1 && v >= cut, isR = act && lane >= (int)lim1 && v < cut;
+            const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+            const uint32_t m = __popc( bl );
+            if ( m ) {
+              if ( isL ) { S.tmp[left + __popc( bl & lt )] = r; }
+              if ( isR ) { S.tmp[left + lim1 + __popc( br & lt )] = r; }
+              __syncwarp();
+              if ( isL ) { r = S.tmp[left + lim1 + ( m - 1u - __popc( bl & lt ) )]; }
+              if ( isR ) { r = S.tmp[left + ( m - 1u - __popc( br & lt ) )]; }
+              __syncwarp();
+              v = kd_coord( r, cf );
             }
           }
-        }
-      }
-      got = __shfl_sync( 0xFFFFFFFFu, got, 0 );
-      if ( !got ) { break; }
-      cur  = S.slot[w];
-      have = true;
-      __syncwarp();
-    }
-    const uint32_t left = cur.left, right = cur.right, n = right - left;
-    maxDepth = max( maxDepth, (int)cur.depth );
-    // ---- tight box (computeMinMax) ----
-    int mn[3] = {4096, 4096, 4096}, mx[3] = {-1, -1, -1};
-    for ( uint32_t p = left + lane; p < right; p += 32 ) {
-      const uint64_t r = S.rec[p];
-      const int      x = kd_coord( r, 0 ), y = kd_coord( r, 1 ), z = kd_coord( r, 2 );
-      mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
-      mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
-    }
-#pragma unroll
-    for ( int k = 0; k < 3; k++ ) {
-      mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
-      mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
-    }
-    // the node reports its tight bound to its parent (divideTree :1080-1081)
-    if ( lane == 0 ) {
-      if ( cur.pgid ) {
-        const int pf = cur.pfeat;
-        if ( cur.side == 0 ) {
-          nodes[cur.pgid].divlow = (int16_t)( pf == 0 ? mx[0] : ( pf == 1 ? mx[1] : mx[2] ) );
+          if ( lim2 > lim1 && lim2 < n ) {
+            const bool     isL = act && lane >= (int)lim1 && lane < (int)lim2 && v > cut, isR = act && lane >= (int)lim2 && v <= cut;
+            const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
+            const uint32_t m = __popc( bl );
+            if ( m ) {
+              if ( isL ) { S.tmp[left + lim1 + __popc( bl & lt )] = r; }
+              if ( isR ) { S.tmp[left + lim2 + __popc( br & lt )] = r; }
+              __syncwarp();
+              if ( isL ) { r = S.tmp[left + lim2 + ( m - 1u - __popc( bl & lt ) )]; }
+              if ( isR ) { r = S.tmp[left + lim1 + ( m - 1u - __popc( br & lt ) )]; }
+              __syncwarp();
+              v = kd_coord( r, cf );
+            }
+          }
+          idx = kd_split_index( n, lim1, lim2 );
+          if ( act ) { S.rec[left + lane] = r; }
+          // both children's bounds along the cut axis are at hand: the node is written complete
+          const int divlow  = __reduce_max_sync( 0xFFFFFFFFu, lane < (int)idx ? v : -1 );
+          const int divhigh = __reduce_min_sync( 0xFFFFFFFFu, act && lane >= (int)idx ? v : 4096 );
+          if ( lane == 0 ) {
+            *reinterpret_cast<uint4*>( &nodes[cur.gid] ) =
+                make_uint4( c1, (uint32_t)cf, ( (uint32_t)divlow & 0xFFFFu ) | ( (uint32_t)divhigh << 16 ), 0u );
+          }
+          divKnown = true;
+          __syncwarp();
         } else {
-          nodes[cur.pgid].divhigh = (int16_t)( pf == 0 ? mn[0] : ( pf == 1 ? mn[1] : mn[2] ) );
+          // ---- lim1 / lim2 ----
+          lim1 = lim2 = 0;
+          for ( uint32_t p = left + lane; p < right; p += 32 ) {
+            const int v = kd_coord( S.rec[p], cf );
+            lim1 += v < cut, lim2 += v <= cut;
+          }
+          lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
+          lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
+          // ---- the two Hoare passes of planeSplit ----
+          if ( lim1 > 0 && lim1 < n ) { ks_hoare<false>( S, left, left, right, lim1, cf, cut, lane, lt ); }
+          if ( lim2 > lim1 && lim2 < n ) { ks_hoare<true>( S, left, left + lim1, right, lim2, cf, cut, lane, lt ); }
+          idx = kd_split_index( n, lim1, lim2 );
+          if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[cur.gid] ) = make_uint2( c1, (uint32_t)cf ); }
         }
-      } else {  // the parent is a level-phase node: k_g_finalize reads the box from the build node
-        GNode& g = gnodes[cur.gid];
-        for ( int k = 0; k < 3; k++ ) { g.tmin[k] = (int16_t)mn[k], g.tmax[k] = (int16_t)mx[k]; }
-      }
-    }
-    if ( n <= 10 ) {  // leaf_max_size, PCCKdTree.cpp:58
-      if ( lane == 0 ) {
-        nodes[cur.gid].a = base + left;
-        nodes[cur.gid].b = KD_LEAF | n;
-        atomicSub( &S.pending, 1 );
-      }
-      have = false;
-      continue;
-    }
-    int cf, cut;
-    {
-      const int lo[3] = {cur.lo[0], cur.lo[1], cur.lo[2]}, hi[3] = {cur.hi[0], cur.hi[1], cur.hi[2]};
-      kd_choose_split( lo, hi, mn, mx, o, cf, cut );
-    }
-    // ---- lim1 / lim2 ----
-    uint32_t lim1 = 0, lim2 = 0;
-    for ( uint32_t p = left + lane; p < right; p += 32 ) {
-      const int v = kd_coord( S.rec[p], cf );
-      lim1 += v < cut, lim2 += v <= cut;
-    }
-    lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
-    lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
-    // ---- the two Hoare passes of planeSplit (:1154-1181) ----
-    if ( lim1 > 0 && lim1 < n ) {
-      uint32_t ml = 0, mr = 0;
-      for ( uint32_t p0 = left; p0 < right; p0 += 32 ) {
-        const uint32_t p   = p0 + lane;
-        const bool     ok  = p < right;
-        const uint64_t r   = ok ? S.rec[p] : 0ull;
-        const bool     in  = kd_coord( r, cf ) < cut;
-        const bool     isL = ok && p - left < lim1 && !in, isR = ok && p - left >= lim1 && in;
-        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-        if ( isL ) { S.tmp[left + ml + __popc( bl & lt )] = r; }
-        if ( isR ) { S.tmp[left + lim1 + mr + __popc( br & lt )] = r; }
-        ml += __popc( bl ), mr += __popc( br );
-      }
-      const uint32_t m = ml;
-      __syncwarp();
-      if ( m ) {
-        ml = mr = 0;
-        for ( uint32_t p0 = left; p0 < right; p0 += 32 ) {
-          const uint32_t p   = p0 + lane;
-          const bool     ok  = p < right;
-          const bool     in  = ok && kd_coord( S.rec[p], cf ) < cut;
-          const bool     isL = ok && p - left < lim1 && !in, isR = ok && p - left >= lim1 && in;
-          const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-          if ( isL ) { S.rec[p] = S.tmp[left + lim1 + ( m - 1u - ( ml + __popc( bl & lt ) ) )]; }
-          if ( isR ) { S.rec[p] = S.tmp[left + ( m - 1u - ( mr + __popc( br & lt ) ) )]; }
-          ml += __popc( bl ), mr += __popc( br );
+        // ---- children (divideTree :1070-1078): leaves are finished here, the left child is kept, the right one pushed ----
+        const uint32_t nl = idx, nr = n - idx;
+        if ( nl <= 10 ) { ks_leaf_child( S, nodes, base, cur.gid, c1, left, nl, 0, cf, !divKnown, lane ); }
+        if ( nr <= 10 ) { ks_leaf_child( S, nodes, base, cur.gid, c1 + 1, left + idx, nr, 1, cf, !divKnown, lane ); }
+        KsItem rgt = cur;  // (only built when needed below)
+        if ( nr > 10 ) {
+          rgt.gid = c1 + 1, rgt.pgid = divKnown ? KS_NOREPORT : cur.gid, rgt.left = (uint16_t)( left + idx ), rgt.side = 1;
+          rgt.depth = (uint8_t)( cur.depth + 1 ), rgt.pfeat = (uint8_t)cf;
+          rgt.lo[0] = cf == 0 ? (int16_t)cut : cur.lo[0];  // right_bbox[cutfeat].low = cutval
+          rgt.lo[1] = cf == 1 ? (int16_t)cut : cur.lo[1];
+          rgt.lo[2] = cf == 2 ? (int16_t)cut : cur.lo[2];
         }
+        if ( nl > 10 ) {
+          if ( nr > 10 ) {
+            if ( sp >= KS_STACK ) {  // cannot happen for 12-bit coordinates (see above); fail loudly
+              overflow = true;
+              sp       = 0;
+            } else {
+              if ( lane == 0 ) { S.stack[sp] = rgt; }
+              sp++;
+            }
+          }
+          if ( !overflow ) {
+            cur.pgid = divKnown ? KS_NOREPORT : cur.gid;
+            cur.gid = c1, cur.right = (uint16_t)( left + idx ), cur.side = 0;
+            cur.depth = (uint8_t)( cur.depth + 1 ), cur.pfeat = (uint8_t)cf;
+            if ( cf == 0 ) {
+              cur.hi[0] = (int16_t)cut;  // left_bbox[cutfeat].high = cutval
+            } else if ( cf == 1 ) {
+              cur.hi[1] = (int16_t)cut;
+            } else {
+              cur.hi[2] = (int16_t)cut;
+            }
+            haveNext = true;
+          }
+        } else if ( nr > 10 ) {
+          cur      = rgt;
+          haveNext = true;
+        }
+      }
+      if ( !haveNext ) {
+        if ( sp == 0 ) { break; }
         __syncwarp();
+        cur = S.stack[--sp];
       }
     }
-    if ( lim2 > lim1 && lim2 < n ) {
-      uint32_t ml = 0, mr = 0;
-      for ( uint32_t p0 = left + lim1; p0 < right; p0 += 32 ) {
-        const uint32_t p   = p0 + lane;
-        const bool     ok  = p < right;
-        const uint64_t r   = ok ? S.rec[p] : 0ull;
-        const bool     in  = kd_coord( r, cf ) <= cut;
-        const bool     isL = ok && p - left < lim2 && !in, isR = ok && p - left >= lim2 && in;
-        const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-        if ( isL ) { S.tmp[left + lim1 + ml + __popc( bl & lt )] = r; }
-        if ( isR ) { S.tmp[left + lim2 + mr + __popc( br & lt )] = r; }
-        ml += __popc( bl ), mr += __popc( br );
-      }
-      const uint32_t m = ml;
-      __syncwarp();
-      if ( m ) {
-        ml = mr = 0;
-        for ( uint32_t p0 = left + lim1; p0 < right; p0 += 32 ) {
-          const uint32_t p   = p0 + lane;
-          const bool     ok  = p < right;
-          const bool     in  = ok && kd_coord( S.rec[p], cf ) <= cut;
-          const bool     isL = ok && p - left < lim2 && !in, isR = ok && p - left >= lim2 && in;
-          const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-          if ( isL ) { S.rec[p] = S.tmp[left + lim2 + ( m - 1u - ( ml + __popc( bl & lt ) ) )]; }
-          if ( isR ) { S.rec[p] = S.tmp[left + lim1 + ( m - 1u - ( mr + __popc( br & lt ) ) )]; }
-          ml += __popc( bl ), mr += __popc( br );
-        }
-        __syncwarp();
-      }
-    }
-    // ---- children (divideTree :1070-1078): keep the left one, push the right one ----
-    const uint32_t idx = kd_split_index( n, lim1, lim2 );
-    uint32_t       c1  = 0;
-    int            ovf = 0;
-    if ( lane == 0 ) {
-      c1               = idBase + (uint32_t)atomicAdd( &S.nextId, 2 );
-      nodes[cur.gid].a = c1;
-      nodes[cur.gid].b = (uint32_t)cf;
-      KsItem rgt{};
-      rgt.gid = c1 + 1, rgt.pgid = cur.gid, rgt.left = (uint16_t)( left + idx ), rgt.right = (uint16_t)right, rgt.side = 1;
-      rgt.depth = (uint8_t)( cur.depth + 1 ), rgt.pfeat = (uint8_t)cf;
-      for ( int k = 0; k < 3; k++ ) { rgt.hi[k] = cur.hi[k]; }
-      rgt.lo[0] = cf == 0 ? (int16_t)cut : cur.lo[0];  // right_bbox[cutfeat].low = cutval
-      rgt.lo[1] = cf == 1 ? (int16_t)cut : cur.lo[1];
-      rgt.lo[2] = cf == 2 ? (int16_t)cut : cur.lo[2];
-      __threadfence_block();      // the parent's words are written before a child can report its bound
-      while ( atomicCAS( &S.lock, 0, 1 ) != 0 ) {}
-      __threadfence_block();
-      const int t = *( (volatile int*)&S.top );
-      if ( t < KS_STACK ) {
-        S.stack[t] = rgt;
-        __threadfence_block();
-        S.top = t + 1;
-        atomicAdd( &S.pending, 1 );
-      } else {
-        ovf = 1;
-      }
-      __threadfence_block();
-      atomicExch( &S.lock, 0 );
-    }
-    ovf = __shfl_sync( 0xFFFFFFFFu, ovf, 0 );
-    if ( ovf ) {  // cannot happen for 12-bit coordinates (see above); fail loudly instead of looping
-      if ( lane == 0 ) {
-        atomicOr( &counters[C_STACK], 1u );
-        atomicExch( &S.abort, 1 );
-      }
-      break;
-    }
-    c1 = __shfl_sync( 0xFFFFFFFFu, c1, 0 );
-    cur.pgid = cur.gid, cur.gid = c1, cur.right = (uint16_t)( left + idx ), cur.side = 0;
-    cur.depth = (uint8_t)( cur.depth + 1 ), cur.pfeat = (uint8_t)cf;
-    if ( cf == 0 ) {
-      cur.hi[0] = (int16_t)cut;  // left_bbox[cutfeat].high = cutval
-    } else if ( cf == 1 ) {
-      cur.hi[1] = (int16_t)cut;
-    } else {
-      cur.hi[2] = (int16_t)cut;
-    }
+    __syncwarp();
+    for ( uint32_t i = lane; i < total; i += 32 ) { grec[base + i] = S.rec[i]; }
+    __syncwarp();
   }
-  if ( lane == 0 ) { atomicMax( &S.maxDepth, maxDepth ); }
-  __syncthreads();
-  for ( uint32_t i = threadIdx.x; i < total; i += KS_WARPS * 32 ) { grec[base + i] = S.rec[i]; }
-  if ( threadIdx.x == 0 ) { atomicMax( &counters[C_DEPTH], (uint32_t)S.maxDepth + 1u ); }
+  if ( lane == 0 ) {
+    atomicMax( &counters[C_DEPTH], (uint32_t)maxDepth + 1u );
+    if ( overflow ) { atomicOr( &counters[C_STACK], 1u ); }
+  }
 }
 
 // level-phase nodes -> search nodes: divlow / divhigh from the children's tight boxes (divideTree :1080-1081), and the
@@ -923,6 +949,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( B.chunkNode.ensure( (size_t)chunkCap * 4 ) );
   RB_CUDA( B.wA.ensure( (size_t)chunkCap * GWORDS * 4 ) );
   RB_CUDA( B.wB.ensure( (size_t)chunkCap * GWORDS * 4 ) );
+  RB_CUDA( B.wC.ensure( (size_t)chunkCap * GWORDS * 4 ) );
   RB_CUDA( B.cA.ensure( (size_t)chunkCap * 4 ) );
   RB_CUDA( B.cB.ensure( (size_t)chunkCap * 4 ) );
   RB_CUDA( B.smallRoots.ensure( (size_t)gCap * 4 ) );
@@ -935,12 +962,13 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   KdNode*   nodes     = B.nodes.as<KdNode>();
   uint32_t* counters  = B.counters.as<uint32_t>();
   uint32_t* chunkNode = B.chunkNode.as<uint32_t>();
-  uint32_t *wA = B.wA.as<uint32_t>(), *wB = B.wB.as<uint32_t>(), *cA = B.cA.as<uint32_t>(), *cB = B.cB.as<uint32_t>();
+  uint32_t *wA = B.wA.as<uint32_t>(), *wB = B.wB.as<uint32_t>(), *wC = B.wC.as<uint32_t>(), *cA = B.cA.as<uint32_t>(),
+           *cB = B.cB.as<uint32_t>();
   uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
   if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-  for ( int k = 0; k < 8; k++ ) { h[k] = 0; }
+  for ( int k = 0; k < 16; k++ ) { h[k] = 0; }
   h[C_NEXT] = (uint32_t)nTrees + 1;
-  RB_CUDA( cudaMemcpyAsync( counters, h, 32, cudaMemcpyHostToDevice, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( counters, h, 64, cudaMemcpyHostToDevice, c->stream ) );
   RB_LAUNCH( "kd_roots", k_g_roots, rb_div_up( nTrees, 128 ), 128, 0, gnodes, dOff, nTrees, st );
   RB_LAUNCH( "kd_init", k_g_init, rb_div_up( E, TPB * GEPT ), TPB, 0, pos, dOff, nTrees, E, ox, oy, oz, rec, st, counters );
   uint32_t lvlBegin = 1, lvlEnd = (uint32_t)nTrees + 1;
@@ -948,7 +976,9 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   for ( ;; level++ ) {
     if ( level > 200 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: tree deeper than 200 levels" ); }
     const uint32_t nLvl = lvlEnd - lvlBegin;
-    RB_LAUNCH( "kd_setup", k_g_setup, 1, SETUP_TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
+    RB_CUDA( cudaMemsetAsync( counters + C_BIG, 0, 4, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( counters + C_CHUNKS, 0, 4, c->stream ) );
+    RB_LAUNCH( "kd_setup", k_g_setup, rb_div_up( nLvl, TPB ), TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
                B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap );
     RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
@@ -960,27 +990,27 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     RB_LAUNCH( "kd_count", k_g_count, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, cA, cB );
     RB_LAUNCH( "kd_nodescan", k_g_nodescan<false>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wB, st );
     RB_LAUNCH( "kd_stage1", k_g_stage<false>, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, cA, tmp );
-    RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, cA, cB, tmp );
-    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wB, st );
-    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, gnodes, chunkNode, wB, cB, tmp );
-    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, gnodes, chunkNode, wB, cB, tmp, st );
+    RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, wC, cA, cB, tmp );
+    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wC, st );
+    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, gnodes, chunkNode, wC, cB, tmp );
+    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, gnodes, chunkNode, wC, cB, tmp, st );
     lvlBegin = lvlEnd;  // the children were numbered consecutively behind the nodes that existed
     lvlEnd   = h[C_NEXT];
   }
   const uint32_t nRoots = h[C_SMALL], nLevelNodes = h[C_NEXT];  // nodes [1, nLevelNodes) were created by the level phase
   if ( nRoots ) {
-    const size_t smem = sizeof( KsShared );
-    static bool  attr = false;
-    if ( !attr ) {
-      RB_CUDA( cudaFuncSetAttribute( k_kd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
-      attr = true;
-    }
-    RB_LAUNCH( "kd_subtree", k_kd_subtree, nRoots, KS_WARPS * 32, smem, rec, gnodes, nodes, B.smallRoots.as<uint32_t>(), counters,
-               gCap, ox, oy, oz );
+    const size_t smem = sizeof( KsWarp ) * KS_WARPS;
+    int          perSM = 1, nSM = 148;
+    RB_CUDA( cudaFuncSetAttribute( k_kd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+    RB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSM, k_kd_subtree, KS_WARPS * 32, smem ) );
+    RB_CUDA( cudaDeviceGetAttribute( &nSM, cudaDevAttrMultiProcessorCount, c->device ) );
+    const uint32_t grid = (uint32_t)std::min<int64_t>( (int64_t)std::max( perSM, 1 ) * nSM, ( (int64_t)nRoots + KS_WARPS - 1 ) / KS_WARPS );
+    RB_LAUNCH( "kd_subtree", k_kd_subtree, grid, KS_WARPS * 32, smem, rec, gnodes, nodes, B.smallRoots.as<uint32_t>(), nRoots,
+               counters, gCap, ox, oy, oz );
   }
   RB_LAUNCH( "kd_finalize", k_g_finalize, rb_div_up( nLevelNodes, TPB ), TPB, 0, gnodes, nLevelNodes, nTrees, nodes,
              B.rootBox.as<int16_t>() );
-  RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( h, counters, 64, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   if ( h[C_STACK] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: a subtree is deeper than its work stack" ); }
   if ( level + (int)h[C_DEPTH] + 2 >= KD_STACK ) {

@@ -31,9 +31,30 @@ def default_parameters(resolution=1023.0, compute_c2p=True):
     return m
 
 
+def _is_device(a):
+    return hasattr(a, "data_ptr")  # a torch tensor (host or CUDA): the ABI resolves the pointer itself (UVA)
+
+
 def _view(cloud, keep, with_normals=False):
     v = abi.CloudView()
     if cloud is None:
+        return v
+    if _is_device(cloud["positions"]):
+        # clouds cached on the device (or in pinned memory) as torch tensors: int16 [n,3], uint8 [n,3], float32 [n,3]
+        pos = cloud["positions"]
+        assert pos.is_contiguous() and pos.element_size() == 2 and pos.shape[1] == 3
+        keep.append(pos)
+        v.positions, v.count = pos.data_ptr(), pos.shape[0]
+        col = cloud.get("colors")
+        if col is not None:
+            assert col.is_contiguous() and col.element_size() == 1
+            keep.append(col)
+            v.colors = col.data_ptr()
+        nrm = cloud.get("normals") if with_normals else None
+        if nrm is not None:
+            assert nrm.is_contiguous() and nrm.element_size() == 4
+            keep.append(nrm)
+            v.normals = nrm.data_ptr()
         return v
     pos = np.ascontiguousarray(cloud["positions"], np.int16)
     keep.append(pos)
@@ -83,8 +104,10 @@ class PCCMetricsB200:
                 # the normal cloud carries the same points as the source (PCCPointSet3::copyNormals looks them up
                 # by position); the ABI takes positions + normals of that cloud through the source view
                 nc = normals[i]
-                same = nc["positions"] is src["positions"] or (
-                    nc["positions"].shape[0] == src["positions"].shape[0] and np.array_equal(nc["positions"], src["positions"]))
+                same = nc["positions"] is src["positions"] or (not _is_device(nc["positions"]) and (
+                    nc["positions"].shape[0] == src["positions"].shape[0] and np.array_equal(nc["positions"], src["positions"])))
+                if not same and _is_device(nc["positions"]):
+                    raise RabbitError(abi.RB200_ERR_INVALID, "device-resident normal clouds must be the source cloud itself")
                 if not same:
                     src = self._attach_normals(src, nc)
                 else:
