@@ -9,12 +9,17 @@ A *step* is one pass of the post-video-decode path over one synthetic 32-frame v
 boundary types -> attribute fetch), grid geometry smoothing, attribute re-transfer for the moved points,
 colour smoothing, YUV16 -> RGB8, and (when --metrics) the D1/D2/colour metrics against the source clouds.
 
-`value`  : whole-job Mpts/s with the decoded frames already resident in HBM (rb200_decode_gof only).
-`e2e`    : the same metric through the reference-facing call sequence with HOST buffers, inside the timer every step:
-           pinned H2D of the decoder-native planes (8-bit 4:2:0 attribute frames + 8-bit geometry luma + occupancy) and
-           the patch tables, the decoder's 4:2:0 -> 4:4:4 16-bit conversion on the GPU, decode, D2H of positions + RGB8
-           of every frame; three GOFs in flight at N = 1, two per GPU at N > 1 (contexts / streams / host threads; RB200_BENCH_LANES).  `e2e.from_444_16bit_frames` is
-           the same from the 16-bit 4:4:4 frames of the reference's PCCVideo boundary, `one_gof_in_flight` unpipelined.
+`value`  : whole-job Mpts/s of the decoder's Rec-1 sequence (PCCDecoder.cpp:330-508: reconstruction, grid geometry
+           smoothing, transferColors16bitBP, colour smoothing, RGB8) with the decoded frames already resident in HBM
+           (rb200_decode_gof only).  Every frame's ordered MD5 is compared with the unmodified reference's before the line is
+           printed (`parity_checked_frames`); a mismatch ends the run without a value.
+`e2e`    : the transcode loop of BASELINE.json configs[2] through the reference-facing calls with HOST buffers, inside the
+           timer every step: pinned H2D of the decoder-native planes (8-bit 4:2:0 attribute frames + 8-bit geometry luma +
+           occupancy) and the patch tables, the decoder's 4:2:0 -> 4:4:4 16-bit conversion on the GPU, the Rec-1 decode,
+           D1 + D2 + colour metrics of every frame against its source cloud ON THE RESIDENT RECONSTRUCTION, D2H of the
+           metric records (and their all-gather at N > 1).  Source clouds are cached in HBM (the same source is measured
+           against every rate point of a transcode); `e2e.with_source_upload` moves them from pinned host memory every
+           step, `e2e.decode_and_download` is the decoder alone with positions + RGB8 of every frame copied back.
 `roofline`: the dominant kernel of the step (per-kernel CUDA events on the launching stream), algorithmic
            bytes per launch / its average duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes
            of that kernel from the committed ncu capture (profiles/ncu_traffic.json).
@@ -50,7 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-metrics", action="store_true", help="skip the D1/D2 metrics leg")
-    ap.add_argument("--no-full", action="store_true", help="skip the full Rec-1 decoder leg (attribute re-transfer)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the MD5 check against the reference (debugging only)")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = auto)")
     return ap.parse_args()
 
@@ -66,9 +71,9 @@ WORKLOADS = {
 
 def make_gof(rb, args, rank, world, frames=None):
     kw = dict(WORKLOADS[args.workload])
-    # BASELINE.json configs[1] = "reconstruction + geometry/colour smoothing": the attribute re-transfer of the decoder's
-    # Rec-1 profile (PCCPointSet3::transferColors16bitBP) is measured as its own leg ("full_decoder")
-    kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=0)
+    # the decoder-faithful Rec-1 sequence: every profile that smooths the geometry also re-transfers the attributes
+    # (PCCDecoder.cpp:434-465); BASELINE.json configs[1] without the re-transfer is reported as config.without_retransfer
+    kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=1)  # Rec-1: attrTransferFilterType_ = 1 (PCCDecoderParameters.cpp:125-134)
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workers = max(1, min(frames or args.frames, min(ncpu, (os.cpu_count() or 1) // max(1, world))))
     return rb.synthetic.generate_gof_parallel(frames or args.frames, workers=workers, **kw)
@@ -158,8 +163,23 @@ def algorithmic_bytes(name, g, n_points, n_type1, n_moved):
         "col_accumulate": N * (8 + 6 + 4) + N * 2,
         "col_filter": n_type1 * (4 + 8 + 6) + n_type1 * 6,
         "to_rgb8": N * (6 + 3),
+        # kd forest of transferColors16bitBP: 2 trees per frame, E = 2 N element records of 8 bytes; per level launch
+        "kd_init": 2 * N * (8 + 8),
+        "kd_count": 2 * N * 8,
+        "kd_stage1": 2 * N * (8 + 4),
+        "kd_apply1": 2 * N * (4 + 4),
+        "kd_stage2": 2 * N * 2,
+        "kd_apply2": 2 * N * (8 + 2),
+        "kd_subtree": 2 * N * (8 + 8),
     }
     return table.get(name)
+
+
+def workload_string(args, p, n_frames):
+    return (f"synthetic {args.workload} {n_frames}-frame GOF per GPU, C2RA r3 shape: atlas {p.width}x{p.height}, 2 maps, "
+            f"p={p.occupancy_precision}; value = Rec-1 decode (reconstruction + grid geometry smoothing + "
+            "transferColors16bitBP + colour smoothing + RGB8); e2e = transcode loop (decoder-native planes in, Rec-1 decode, "
+            "D1 + D2 + colour metrics of every frame out)")
 
 
 def run_b200(args):
@@ -174,8 +194,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
-    # host threads and pinned buffers of a rank stay on the NUMA node of its GPU (8 ranks otherwise share one node's
-    # memory controllers for 600 MB of PCIe traffic per GOF each)
+    ncpu_all = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # host threads and pinned buffers of a rank stay on the NUMA node of its GPU
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -217,10 +237,8 @@ def run_b200(args):
     gof = make_gof(rb, args, rank, world)
     t_gen = time.time() - t0
 
-    # pinned host copies of the decoded planes (what the video decoders hand over)
     def pin(a):
-        t = torch.from_numpy(a).pin_memory()
-        return t
+        return torch.from_numpy(a).pin_memory()
     pinned = dict(occupancy=pin(gof.occupancy), geometry=pin(gof.geometry), attribute=pin(gof.attribute))
     gof.occupancy, gof.geometry, gof.attribute = (pinned[k].numpy() for k in ("occupancy", "geometry", "attribute"))
 
@@ -229,230 +247,250 @@ def run_b200(args):
     codec.setStream(stream.cuda_stream)
     clocks = ClockSampler(local)
     clocks.start()
-
-    # ---------------- leg 1: inputs resident in HBM ----------------
-    codec.uploadGof(gof)
-    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 0):
-        codec.decodeGof()
-    counts = codec.frameCounts()
-    n_points = sum(c.total for c in counts)
-    n_moved = sum(c.smoothed for c in counts)
-    codec.stats(reset=True)
-    barrier()
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.on()
-    e0.record(stream)
-    for _ in range(args.steps):
-        codec.decodeGof()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    clocks.off()
-    barrier()
-    ms_local = e0.elapsed_time(e1)
-    ms_total = max_over_ranks(ms_local)
-    print(f"[bench rank {rank}] resident leg {ms_local / args.steps:.4f} ms per step, {n_points} points", file=sys.stderr, flush=True)
-    launches = codec.stats(reset=True).kernel_launches
-    all_points = sum_over_ranks(n_points)
-    value = all_points * args.steps / (ms_total * 1e-3) / 1e6
+    W = max(args.warmup, 3)
 
-    # ---------------- leg 2: end to end from host buffers ----------------
-    e2e = None
-    if not args.no_e2e:
-        out = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
-                   colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
-
-        def e2e_step():
-            codec.uploadGof(gof)
+    def timed_resident(steps):
+        for _ in range(W):
             codec.decodeGof()
-            return codec.getGof(fields=("positions", "colors"), out=out)
-        for _ in range(2):
-            e2e_step()
         codec.stats(reset=True)
         barrier()
         torch.cuda.synchronize()
         clocks.on()
         e0.record(stream)
-        for _ in range(args.steps):
-            _, n_got = e2e_step()
+        for _ in range(steps):
+            codec.decodeGof()
         e1.record(stream)
         torch.cuda.synchronize()
         clocks.off()
         barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-        st = codec.stats(reset=True)
-        assert n_got == n_points
-        serial = {"value": round(all_points * args.steps / (ms_e2e * 1e-3) / 1e6, 2), "ms_per_step": round(ms_e2e / args.steps, 3)}
+        return max_over_ranks(e0.elapsed_time(e1)), codec.stats(reset=True).kernel_launches
 
-        # the same call sequence with several GOFs in flight (3 by default; measured 2: 3.62, 3: 3.83, 4: 3.86 Gpts/s): every
-        # extra lane is a context on its own stream driven by its own host thread, so the upload of one GOF overlaps the
-        # kernels and the download of the others (PCIe is full duplex)
-        NL = int(os.environ.get("RB200_BENCH_LANES", "3" if world == 1 else "2"))  # N > 1: the host side is the limit, 2 measured best
-        lanes = [(codec, out)]
-        extra_streams = []
-        for _ in range(NL - 1):
-            cx = rb.codec.PCCCodecB200(device=local)
-            sx = torch.cuda.Stream()
-            extra_streams.append(sx)
-            cx.setStream(sx.cuda_stream)
-            lanes.append((cx, dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
-                                   colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())))
-        got = [0] * NL
+    # ---------------- leg 1: inputs resident in HBM, the decoder's Rec-1 sequence ----------------
+    codec.uploadGof(gof)
+    ms_total, launches = timed_resident(args.steps)
+    counts = codec.frameCounts()
+    n_points = sum(c.total for c in counts)
+    n_moved = sum(c.smoothed for c in counts)
+    all_points = sum_over_ranks(n_points)
+    value = all_points * args.steps / (ms_total * 1e-3) / 1e6
+    print(f"[bench rank {rank}] resident Rec-1 leg {ms_total / args.steps:.4f} ms per step, {n_points} points", file=sys.stderr, flush=True)
+    gpu_md5 = [codec.computeChecksum(f) for f in range(gof.n_frames)]  # PCCPointSet3::computeChecksum of every decoded frame
+
+    # BASELINE.json configs[1] as worded ("reconstruction + geometry/colour smoothing"): the same without the re-transfer
+    gof.params.attr_transfer_filter_type = 0
+    codec.uploadGof(gof)
+    ms_nt, _ = timed_resident(max(3, min(args.steps, 10)))
+    without_retransfer = {"value": round(all_points * max(3, min(args.steps, 10)) / (ms_nt * 1e-3) / 1e6, 2), "unit": UNIT,
+                          "ms_per_step": round(ms_nt / max(3, min(args.steps, 10)), 4),
+                          "what": "attr_transfer_filter_type = 0 (round-1 headline configuration)"}
+    gof.params.attr_transfer_filter_type = 1
+
+    # ---------------- parity of the benchmarked workload (outside every timed region) ----------------
+    # N = 1: the reference run below is also the cpu_baseline (1 thread, the reference's real behaviour);
+    # N > 1: every rank checks its own GOF frame-parallel on its share of the host cores
+    cpu = None
+    parity_frames = 0
+    if not args.no_parity:
+        from oracle import checker
+        if not checker.have_reference():
+            raise SystemExit("bench.py: oracle/_ref/librabbit_ref.so is missing: the benchmarked workload cannot be checked")
+        chk = checker.Reference()
+        threads = 1 if (world == 1 and not args.no_cpu_baseline) else max(1, ncpu_all // world)
+        t0 = time.time()
+        run = chk.run_gof(gof, keep=(), threads=threads)
+        wall = time.time() - t0
+        bad = [f for f in range(gof.n_frames) if run.md5(f) != gpu_md5[f]]
+        if bad:
+            raise SystemExit(f"bench.py: rank {rank}: frames {bad} differ from the reference (ordered MD5); no value is reported")
+        parity_frames = gof.n_frames
+        if world == 1 and not args.no_cpu_baseline:
+            rec_ms = sum(run.time_ms(f, 0) for f in range(gof.n_frames))
+            post_ms = sum(run.time_ms(f, 1) for f in range(gof.n_frames))
+            cpu = {"value": round(n_points / wall / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"all {gof.n_frames} frames of the same GOF, Rec-1 decode, {n_points} points, {wall:.1f} s wall "
+                             f"(reconstruction {rec_ms / 1e3:.1f} s + post-processing {post_ms / 1e3:.1f} s of CPU time); the "
+                             "ordered MD5 of every frame equals the CUDA path's",
+                   "wall_s": round(wall, 2)}
+        del run
+    parity_frames = int(sum_over_ranks(parity_frames))
+
+    # ---------------- leg 2: the transcode loop, end to end from host buffers ----------------
+    e2e = None
+    metrics_leg = None
+    mp = rb.metrics.default_parameters(resolution=float((1 << gof.params.geometry_bitdepth_3d) - 1))
+    if not args.no_e2e:
+        native = rb.synthetic.to_decoder_planes(gof, bitdepth=8, filt=0)
+        native["geometry"] = pin(native["geometry"]).numpy()
+        native["attribute"] = pin(native["attribute"]).numpy()
+        # source clouds: pinned host copies (uploaded every step in the `with_source_upload` variant) and copies cached in HBM
+        src_host = [dict(positions=pin(s["positions"]), colors=pin(s["colors"]), normals=pin(s["normals"])) for s in gof.sources]
+        src_dev = [{k: v.cuda(non_blocking=True) for k, v in s.items()} for s in src_host]
+        torch.cuda.synchronize()
+        src_bytes = sum(v.numel() * v.element_size() for s in src_host for v in s.values())
+        NL = int(os.environ.get("RB200_BENCH_LANES", "2"))
+        lanes = []
+        for k in range(NL):
+            cx = codec if k == 0 else rb.codec.PCCCodecB200(device=local)
+            if k:
+                sx = torch.cuda.Stream()
+                cx.setStream(sx.cuda_stream)
+                cx._stream_keep = sx
+            mx = rb.metrics.PCCMetricsB200(cx)
+            mx.setParameters(mp)
+            lanes.append(dict(codec=cx, met=mx, res=None, out=None))
+        resident = [None] * gof.n_frames
         errs = []
-        h2d_turn = threading.Lock()  # one upload at a time: the other GOF is then in its kernels / its download
+        gathered = {}
 
-        def worker(k, nsteps, upload):
+        def loop_step(L, sources, download, step):
+            c_ = L["codec"]
+            c_.uploadGofYuv420(gof, native)
+            c_.decodeGof()
+            if download:
+                L["n_got"] = c_.getGof(fields=("positions", "colors"), out=L["out"])[1]
+                return
+            L["met"].results_.clear()
+            res = L["met"].compute(sources, resident, sources)
+            if world > 1:
+                # the one exchange step of the path: all-gather of the per-frame accumulators (NCCL).  Lanes take turns
+                # in step order, so every rank issues the collectives in the same sequence.
+                with turn:
+                    turn.wait_for(lambda: order[0] >= step)
+                    table, seq_mean = rb.dist.gather_metrics({rank + world * i: r for i, r in enumerate(res)},
+                                                             world * gof.n_frames, mp.resolution, device="cuda")
+                    gathered["frames"], gathered["mean"] = len(table), seq_mean
+                    order[0] += 1
+                    turn.notify_all()
+            L["res"] = res
+
+        turn = threading.Condition()
+        order = [0]
+
+        def worker(k, nsteps, sources, download, nl):
             try:
                 torch.cuda.set_device(local)
-                c_, o_ = lanes[k]
-                for _ in range(nsteps):
-                    with h2d_turn:
-                        upload(c_)
-                        c_.synchronize()
-                    c_.decodeGof()
-                    got[k] = c_.getGof(fields=("positions", "colors"), out=o_)[1]
+                for i in range(nsteps):
+                    loop_step(lanes[k], sources, download, k + i * nl)
             except Exception as ex:  # surfaced after the join
                 errs.append(ex)
+                with turn:
+                    order[0] = 1 << 60
+                    turn.notify_all()
 
-        def run_pipelined(nsteps, upload):
-            ts = [threading.Thread(target=worker, args=(k, (nsteps + NL - 1 - k) // NL, upload)) for k in range(NL)]
+        def run_lanes(nsteps, sources, download, nl):
+            order[0] = 0
+            ts = [threading.Thread(target=worker, args=(k, (nsteps + nl - 1 - k) // nl, sources, download, nl)) for k in range(nl)]
             for t in ts:
                 t.start()
             for t in ts:
                 t.join()
             if errs:
                 raise errs[0]
+            return nl
 
-        def time_pipelined(upload):
-            run_pipelined(NL, upload)
-            # at least six GOFs per lane, every lane the same number: with fewer the fill / drain of the pipeline is what is timed
-            psteps = max(int(os.environ.get("RB200_BENCH_E2E_STEPS", "0")), args.steps, 6 * NL)
+        def time_loop(sources, download=False):
+            run_lanes(2 * NL, sources, download, NL)  # warm-up: tables, scratch, pinned staging of every lane
+            psteps = max(int(os.environ.get("RB200_BENCH_E2E_STEPS", "0")), args.steps, 4 * NL)
             psteps = -(-psteps // NL) * NL
-            for c_, _ in lanes:
-                c_.stats(reset=True)
+            for L in lanes:
+                L["codec"].stats(reset=True)
             barrier()
             torch.cuda.synchronize()
             clocks.on()
             e0.record(stream)
-            run_pipelined(psteps, upload)
+            nl = run_lanes(psteps, sources, download, NL)
             torch.cuda.synchronize()
             e1.record(stream)
             torch.cuda.synchronize()
             clocks.off()
             barrier()
-            ms_pipe = max_over_ranks(e0.elapsed_time(e1))
-            sts = [c_.stats(reset=True) for c_, _ in lanes]
-            assert all(g_ == n_points for g_ in got)
-            assert all(np.array_equal(out["positions"][:n_points], o_["positions"][:n_points]) for _, o_ in lanes[1:])
-            return {"value": round(all_points * psteps / (ms_pipe * 1e-3) / 1e6, 2), "unit": UNIT,
-                    "h2d_bytes_per_step": sum(s_.h2d_bytes for s_ in sts) // psteps,
-                    "d2h_bytes_per_step": sum(s_.d2h_bytes for s_ in sts) // psteps,
-                    "ms_per_step": round(ms_pipe / psteps, 3), "steps": psteps}
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            sts = [L["codec"].stats(reset=True) for L in lanes]
+            return ms, psteps, sts, nl
 
-        from_444 = time_pipelined(lambda c_: c_.uploadGof(gof))
-        from_444["mode"] = f"uploadGof (16-bit 4:4:4 frames, the reference's PCCVideo boundary) -> decodeGof -> getGof, {NL} GOFs in flight"
-        from_444["one_gof_in_flight"] = serial
-        # the decoder-native boundary: 8-bit 4:2:0 attribute frames + 8-bit geometry luma as libav / NVDEC / HM leave
-        # them; PCCVideoDecoder's inverse colour conversion (YUV420ToYUV444_8_0) runs on the device inside the step
-        native = rb.synthetic.to_decoder_planes(gof, bitdepth=8, filt=0)
-        native["geometry"] = pin(native["geometry"]).numpy()
-        native["attribute"] = pin(native["attribute"]).numpy()
-        e2e = time_pipelined(lambda c_: c_.uploadGofYuv420(gof, native))
-        e2e["mode"] = ("uploadGofYuv420 (decoder-native planes: 8-bit 4:2:0 attribute frames + 8-bit geometry luma from pinned "
-                       "host memory; the decoder's 4:2:0 -> 4:4:4 16-bit conversion runs on the GPU inside the step) -> decodeGof "
-                       f"-> getGof (positions + RGB8 to pinned host memory); {NL} GOFs in flight ({NL} contexts, {NL} streams, {NL} "
-                       "host threads)")
-        e2e["from_444_16bit_frames"] = from_444
-        for c_, _ in lanes[1:]:
-            c_.close()
-
-    # ---------------- leg 2a: the decoder's full Rec-1 sequence (adds transferColors16bitBP after geometry smoothing) ----
-    full = None
-    if rb.abi.HAVE_TRANSFER and not args.no_full:
-        gof.params.attr_transfer_filter_type = 1
-        codec.uploadGof(gof)
-        for _ in range(2):
-            codec.decodeGof()
-        fsteps = max(1, min(args.steps, 3))
-        codec.stats(reset=True)
-        barrier()
-        torch.cuda.synchronize()
-        clocks.on()
-        e0.record(stream)
-        for _ in range(fsteps):
-            codec.decodeGof()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        clocks.off()
-        barrier()
-        ms_full = max_over_ranks(e0.elapsed_time(e1))
-        full = {"value": round(all_points * fsteps / (ms_full * 1e-3) / 1e6, 2), "unit": UNIT,
-                "ms_per_step": round(ms_full / fsteps, 3), "gpu_launches_per_step": codec.stats(reset=True).kernel_launches // fsteps,
-                "what": "reconstruction + geometry smoothing + transferColors16bitBP (two nanoflann-order kd-trees per "
-                        "frame rebuilt on the GPU) + colour smoothing + RGB8, planes resident in HBM"}
-        codec.enableTiming(True)
-        codec.decodeGof()
-        full["kernel_ms"] = {k: [round(v[0], 3), v[1]] for k, v in sorted(codec.timings().items(), key=lambda kv: -kv[1][0])[:14]}
-        codec.enableTiming(False)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            sub = rb.synthetic.slice_gof(gof, 0, min(8, gof.n_frames))
-            full["cpu_reference"] = cpu_reference(rb, sub, threads=1, max_frames=sub.n_frames)
-        gof.params.attr_transfer_filter_type = 0
-
-    # ---------------- leg 2b: D1 / D2 / colour metrics of every frame against its source cloud ----------------
-    metrics_leg = None
-    if not args.no_metrics and rb.abi.HAVE_METRICS:
-        mp = rb.metrics.default_parameters(resolution=float((1 << gof.params.geometry_bitdepth_3d) - 1))
-        met = rb.metrics.PCCMetricsB200(codec)
-        met.setParameters(mp)
-        srcs = [dict(positions=torch.from_numpy(s["positions"]).pin_memory().numpy(),
-                     colors=torch.from_numpy(s["colors"]).pin_memory().numpy(),
-                     normals=torch.from_numpy(s["normals"]).pin_memory().numpy()) for s in gof.sources]
-        codec.uploadGof(gof)
-        codec.decodeGof()
-        resident = [None] * gof.n_frames
-        for _ in range(2):
-            res = met.compute(srcs, resident, srcs)
-        codec.stats(reset=True)
-        barrier()
-        torch.cuda.synchronize()
-        msteps = max(1, min(args.steps, 5))
-        clocks.on()
-        e0.record(stream)
-        for _ in range(msteps):
-            res = met.compute(srcs, resident, srcs)
-            if world > 1:  # the one exchange step of the path: all-gather of the per-frame accumulators (NCCL)
-                local = {rank + world * i: r for i, r in enumerate(res)}
-                table, seq_mean = rb.dist.gather_metrics(local, world * gof.n_frames, mp.resolution, device="cuda")
-        e1.record(stream)
-        torch.cuda.synchronize()
-        clocks.off()
-        barrier()
-        ms_met = max_over_ranks(e0.elapsed_time(e1))
-        st = codec.stats(reset=True)
-        codec.enableTiming(True)
-        met.compute(srcs, resident, srcs)
-        mk = {k: round(v[0], 3) for k, v in sorted(codec.timings().items(), key=lambda kv: -kv[1][0])[:12]}
-        codec.enableTiming(False)
-        d1 = [r.qf.c2c_psnr for r in res]
-        d2 = [r.qf.c2p_psnr for r in res]
-        metrics_leg = {"value": round(world * gof.n_frames * msteps / (ms_met * 1e-3), 2), "unit": "frames/s",
-                       "ms_per_gof": round(ms_met / msteps, 3), "what": "D1 + D2 + colour, both directions, duplicate "
-                       "removal included; reconstruction resident in HBM, source clouds (positions, RGB, normals) "
-                       "copied from pinned host memory inside the timed region",
-                       "h2d_bytes_per_step": st.h2d_bytes // msteps, "gpu_launches_per_step": st.kernel_launches // msteps, "kernel_ms": mk,
-                       "d1_psnr_mean_db": round(float(np.mean(d1)), 4), "d2_psnr_mean_db": round(float(np.mean(d2)), 4)}
+        # (a) the headline: sources cached in HBM.  rb200_metrics counts the device-to-device import of a cached cloud as
+        # "h2d": what crosses PCIe is the planes and the tables, counted from the upload alone.
+        lanes[0]["codec"].stats(reset=True)
+        lanes[0]["codec"].uploadGofYuv420(gof, native)
+        plane_bytes = lanes[0]["codec"].stats(reset=True).h2d_bytes
+        ms, psteps, sts, nl = time_loop(src_dev)
+        res = lanes[0]["res"]
+        result_bytes = len(res) * C_sizeof_result(rb)
+        e2e = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+               "h2d_bytes_per_step": int(plane_bytes), "d2h_bytes_per_step": int(result_bytes),
+               "ms_per_step": round(ms / psteps, 3), "steps": psteps,
+               "metric_frames_per_s": round(world * gof.n_frames * psteps / (ms * 1e-3), 1),
+               "mode": ("transcode loop: uploadGofYuv420 (8-bit 4:2:0 attribute frames + 8-bit geometry luma + occupancy from "
+                        "pinned host memory; 4:2:0 -> 4:4:4 16-bit conversion on the GPU) -> decodeGof (Rec-1) -> "
+                        "PCCMetrics::compute (D1 + D2 + colour, both directions, duplicate removal) on the resident "
+                        f"reconstruction against source clouds cached in HBM -> metric records to the host; {nl} GOF(s) in "
+                        "flight per GPU" + ("; all-gather of the records over NCCL every step" if world > 1 else "")),
+               "d1_psnr_mean_db": round(float(np.mean([r.qf.c2c_psnr for r in res])), 4),
+               "d2_psnr_mean_db": round(float(np.mean([r.qf.c2p_psnr for r in res])), 4)}
         if world > 1:
-            metrics_leg["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in seq_mean.items()}
-            metrics_leg["frames_gathered"] = len(table)
+            e2e["frames_gathered"] = gathered.get("frames")
+            e2e["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in gathered.get("mean", {}).items()}
+        # (b) the same with the source clouds (positions, RGB, normals) crossing PCIe every step
+        ms, psteps, sts, nl = time_loop([{k: v for k, v in s.items()} for s in src_host])
+        e2e["with_source_upload"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+                                     "h2d_bytes_per_step": int(plane_bytes + src_bytes), "ms_per_step": round(ms / psteps, 3),
+                                     "metric_frames_per_s": round(world * gof.n_frames * psteps / (ms * 1e-3), 1)}
+        # (c) the decoder alone with the clouds copied back (what PccAppDecoder hands to its PLY writer)
+        for L in lanes:
+            L["out"] = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
+                            colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
+        ms, psteps, sts, nl = time_loop(None, download=True)
+        assert all(L["n_got"] == n_points for L in lanes)
+        assert all(np.array_equal(lanes[0]["out"]["positions"][:n_points], L["out"]["positions"][:n_points]) for L in lanes[1:])
+        e2e["decode_and_download"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+                                      "h2d_bytes_per_step": int(plane_bytes), "d2h_bytes_per_step": int(n_points * 9),
+                                      "ms_per_step": round(ms / psteps, 3), "gofs_in_flight": nl}
+        for L in lanes[1:]:
+            L["codec"].close()
+
+        # ---------------- leg 2b: the metrics alone, reconstruction and sources resident ----------------
+        if not args.no_metrics:
+            met = lanes[0]["met"]
+            codec.uploadGof(gof)
+            codec.decodeGof()
+            for _ in range(2):
+                met.compute(src_dev, resident, src_dev)
+            codec.stats(reset=True)
+            barrier()
+            torch.cuda.synchronize()
+            msteps = max(1, min(args.steps, 5))
+            clocks.on()
+            e0.record(stream)
+            for _ in range(msteps):
+                res = met.compute(src_dev, resident, src_dev)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            clocks.off()
+            barrier()
+            ms_met = max_over_ranks(e0.elapsed_time(e1))
+            st = codec.stats(reset=True)
+            codec.enableTiming(True)
+            met.compute(src_dev, resident, src_dev)
+            mk = {k: round(v[0], 3) for k, v in sorted(codec.timings().items(), key=lambda kv: -kv[1][0])[:12]}
+            codec.enableTiming(False)
+            metrics_leg = {"value": round(world * gof.n_frames * msteps / (ms_met * 1e-3), 2), "unit": "frames/s",
+                           "ms_per_gof": round(ms_met / msteps, 3),
+                           "what": "D1 + D2 + colour, both directions, duplicate removal included; reconstruction and source "
+                                   "clouds resident in HBM", "gpu_launches_per_step": st.kernel_launches // msteps, "kernel_ms": mk,
+                           "d1_psnr_mean_db": round(float(np.mean([r.qf.c2c_psnr for r in res])), 4),
+                           "d2_psnr_mean_db": round(float(np.mean([r.qf.c2p_psnr for r in res])), 4)}
+            if world == 1 and not args.no_cpu_baseline and not args.no_parity:
+                metrics_leg["cpu_reference"] = cpu_metrics_reference(rb, gof, mp, max_frames=2)
 
     # ---------------- leg 3: per-kernel events -> roofline of the dominant kernel ----------------
     codec.uploadGof(gof)
     codec.decodeGof()
     cloud = codec.getGof(fields=("boundary_types",))[0]
     n_type1 = int((cloud["boundary_types"] == 1).sum()) + n_moved
+    ksteps = max(2, min(args.steps, 5))
     codec.enableTiming(True)
-    for _ in range(max(2, min(args.steps, 5))):
+    for _ in range(ksteps):
         codec.decodeGof()
     timings = codec.timings()
     codec.enableTiming(False)
@@ -466,9 +504,9 @@ def run_b200(args):
     for name, (ms, n) in timings.items():
         b = algorithmic_bytes(name, gof, n_points, n_type1, n_moved)
         avg = ms / max(n, 1)
-        kernels[name] = {"ms_per_launch": round(avg, 4), "launches_per_step": n / max(2, min(args.steps, 5)),
+        kernels[name] = {"ms_per_launch": round(avg, 4), "launches_per_step": n / ksteps, "ms_per_step": round(ms / ksteps, 4),
                          "algorithmic_bytes": b, "gbs": (round(b / (avg * 1e-3) / 1e9, 1) if b and avg > 0 else None)}
-    step_kernel_ms = sum(ms for ms, _ in timings.values()) / max(2, min(args.steps, 5))
+    step_kernel_ms = sum(ms for ms, _ in timings.values()) / ksteps
     dom = max(timings.items(), key=lambda kv: kv[1][0])[0] if timings else None
     roofline = None
     if dom:
@@ -481,30 +519,26 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peak, "peak_source": peak_src,
                     "unit": "GB/s", "frac": (round(k["gbs"] / peak, 4) if k["gbs"] else None), "traffic": traffic,
                     "algorithmic_bytes": k["algorithmic_bytes"], "ms_per_launch": k["ms_per_launch"],
+                    "launches_per_step": k["launches_per_step"],
                     "share_of_step_kernel_time": round(timings[dom][0] / max(1e-9, sum(ms for ms, _ in timings.values())), 3)}
     clocks.stop()
-
-    # ---------------- leg 4 (rank 0, N=1): the reference's CPU path on the same GOF ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(rb, gof, threads=1, max_frames=min(gof.n_frames, 32))
 
     if rank == 0:
         p = gof.params
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+            "warmup": W, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i16/u16 (+f64 filters)", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.workload} {gof.n_frames}-frame GOF per GPU, C2RA r3 shape: "
-                                   f"atlas {p.width}x{p.height}, 2 maps, p={p.occupancy_precision}, "
-                                   "reconstruction + grid geometry smoothing + colour smoothing + RGB8",
+            "config": {"workload": workload_string(args, p, gof.n_frames),
                        "frames_per_gpu": gof.n_frames, "points_per_frame": n_points // gof.n_frames,
                        "points_moved_per_frame": n_moved // gof.n_frames,
                        "attr_transfer_filter_type": int(p.attr_transfer_filter_type),
+                       "without_retransfer": without_retransfer,
                        "l2_policy": f"inputs larger than L2 ({gof.input_bytes() >> 20} MiB of planes per GPU per step)",
-                       "sharding": "one GOF per GPU, no data-path collective"},
+                       "sharding": "one GOF per GPU, no data-path collective; the per-frame metric records are all-gathered"},
+            "parity_checked_frames": parity_frames,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "metrics": metrics_leg, "full_decoder": full, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
+            "cpu_baseline": cpu, "metrics": metrics_leg, "kernels": kernels, "step_kernel_ms": round(step_kernel_ms, 3),
             "generate_s": round(t_gen, 1),
         }
         sys.stdout.flush()
@@ -515,60 +549,74 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def cpu_reference(rb, gof, threads, max_frames):
-    """times the unmodified reference (oracle/_ref) on the first `max_frames` frames of `gof` (bounded sample)."""
+def C_sizeof_result(rb):
+    import ctypes
+    return ctypes.sizeof(rb.abi.MetricsResult)
+
+
+def cpu_metrics_reference(rb, gof, mp, max_frames):
+    """PCCMetrics::compute of the unmodified reference on the first frames of the GOF, 1 thread (bounded sample)"""
     from oracle import checker
-    if not checker.have_reference():
-        return {"unavailable": "oracle/_ref/librabbit_ref.so not built"}
     chk = checker.Reference()
     sub = rb.synthetic.slice_gof(gof, 0, max_frames)
+    run = chk.run_gof(sub, keep=("rgb8",), threads=max_frames)
     t0 = time.time()
-    run = chk.run_gof(sub, keep=(), threads=threads)
+    for f in range(sub.n_frames):
+        rec = run.cloud(f, "rgb8")
+        chk.metrics(mp, sub.sources[f], rec, sub.sources[f])
     wall = time.time() - t0
-    pts = sum(run.counts(f).total for f in range(sub.n_frames))
-    rec_ms = sum(run.time_ms(f, 0) for f in range(sub.n_frames))
-    post_ms = sum(run.time_ms(f, 1) for f in range(sub.n_frames))
-    return {"value": round(pts / wall / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": f"{sub.n_frames} frames of the same GOF, {pts} points, {wall:.1f} s wall "
-                      f"(reconstruction {rec_ms / 1e3:.1f} s + post-processing {post_ms / 1e3:.1f} s of CPU time)",
-            "wall_s": round(wall, 2)}
+    return {"value": round(sub.n_frames / wall, 4), "unit": "frames/s", "cores": 1, "kind": "reference",
+            "sample": f"{sub.n_frames} frames, D1 + D2 + colour, {wall:.1f} s wall"}
 
 
 def run_reference(args):
+    """the reference's own CPU implementation of the same two things, on this box's host cores: `value` = its Rec-1 decode
+    (frame-parallel over every host thread), `e2e` = its transcode loop (the same decode + PCCMetrics::compute of every
+    frame, frame-parallel).  Each step is a bounded sample: one frame per host thread, capped at the GOF size."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import concurrent.futures as cf
     import rabbit_transcoding_b200 as rb
     from oracle import checker
     if not checker.have_reference():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librabbit_ref.so not built"}))
         return
     threads = os.cpu_count() or 1
-    # bounded sample per step: one frame per host thread, capped at the GOF size
     nf = args.ref_frames or max(1, min(args.frames, threads))
     gof = make_gof(rb, args, 0, 1, frames=nf)
     chk = checker.Reference()
-    for _ in range(max(0, min(args.warmup, 1))):
+    mp = rb.metrics.default_parameters(resolution=float((1 << gof.params.geometry_bitdepth_3d) - 1))
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
         chk.run_gof(gof, keep=(), threads=threads)
-    steps = max(1, min(args.steps, 3))
-    pts = 0
-    t0 = time.time()
+    steps = max(1, min(args.steps, 2))
+    pts, t_dec, t_met = 0, 0.0, 0.0
     for _ in range(steps):
-        run = chk.run_gof(gof, keep=(), threads=threads)
+        t0 = time.time()
+        run = chk.run_gof(gof, keep=("rgb8",), threads=threads)
+        t_dec += time.time() - t0
         pts += sum(run.counts(f).total for f in range(gof.n_frames))
-    wall = time.time() - t0
-    v = round(pts / wall / 1e6, 4)
+        recs = [run.cloud(f, "rgb8") for f in range(gof.n_frames)]  # (not timed: the reference holds these clouds already)
+        t0 = time.time()
+        with cf.ThreadPoolExecutor(max_workers=threads) as pool:  # ctypes releases the GIL: one PCCMetrics per frame and thread
+            list(pool.map(lambda f: chk.metrics(mp, gof.sources[f], recs[f], gof.sources[f]), range(gof.n_frames)))
+        t_met += time.time() - t0
+        del run, recs
+    v = round(pts / t_dec / 1e6, 4)
+    v_loop = round(pts / (t_dec + t_met) / 1e6, 4)
     p = gof.params
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(0, min(args.warmup, 1)), "ms_per_step": round(wall * 1e3 / steps, 2), "higher_is_better": True,
+            "warmup": warm, "ms_per_step": round((t_dec + t_met) * 1e3 / steps, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i16/u16 (+f64 filters)", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.workload} GOF, C2RA r3 shape: atlas {p.width}x{p.height}, 2 maps, "
-                                   f"p={p.occupancy_precision}, reconstruction + grid geometry smoothing + colour "
-                                   "smoothing + RGB8", "frames_per_step": gof.n_frames,
-                       "attr_transfer_filter_type": int(p.attr_transfer_filter_type)},
+            "config": {"workload": workload_string(args, p, args.frames), "frames_per_step": gof.n_frames,
+                       "attr_transfer_filter_type": int(p.attr_transfer_filter_type),
+                       "value_is": "Rec-1 decode alone", "e2e_is": "transcode loop: Rec-1 decode + D1 + D2 + colour metrics"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{gof.n_frames} frames per step, frame-parallel over {threads} host threads"},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                             "sample": f"{gof.n_frames} frames per step, frame-parallel over {threads} host threads: decode "
+                                       f"{t_dec / steps:.1f} s + metrics {t_met / steps:.1f} s per step"},
+            "e2e": {"value": v_loop, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "metric_frames_per_s": round(gof.n_frames * steps / (t_dec + t_met), 3)},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

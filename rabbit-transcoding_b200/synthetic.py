@@ -703,3 +703,23 @@ def make_plr(gof, seed=0):
     gof.plr = dict(modes=gof_modes, block_mode=bm, block_offset=off)
     p.point_local_reconstruction = 1
     return gof
+
+
+def make_lod_and_oblique(gof, seed=0, lod=True, planes=True):
+    """Turns some patches of a generated GOF into level-of-detail-2 patches (PCCPatch::generatePoint, PCCPatch.h:201-207:
+    u * lodX + u1, v * lodY + v1) and / or patches of the 45-degree projection planes (axisOfAdditionalPlane 1..3:
+    PCCCodec::inverseRotatePosition45DegreeOnAxis, PCCCodec.cpp:2503-2524, with its wrap of negative intermediates).
+    The planes stay as they are: the patches simply decode to other positions — what matters is that the CUDA path and
+    the reference decode the same thing.  A patch only gets lod 2 when its points stay inside the cube."""
+    rng = np.random.default_rng([seed, 0x10D])
+    cube = 1 << gof.params.geometry_bitdepth_3d
+    R = gof.params.occupancy_resolution
+    for p in gof.patches:
+        if lod:
+            if p["u1"] + 2 * p["size_u0"] * R < cube and rng.random() < 0.5:
+                p["lod_x"] = 2
+            if p["v1"] + 2 * p["size_v0"] * R < cube and rng.random() < 0.5:
+                p["lod_y"] = 2
+        if planes and rng.random() < 0.6:
+            p["axis_of_additional_plane"] = int(rng.integers(1, 4))
+    return gof
