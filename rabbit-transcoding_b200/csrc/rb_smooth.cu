@@ -55,7 +55,8 @@ struct CellView {
 };
 constexpr int      MAX_PROBES = 256;
 constexpr uint32_t NO_BLOCK   = 0xFFFFFFFFu;
-enum { CTR_CURSOR = 0, CTR_FLAGS = 1, CTR_MAXCNT = 2 };  // counters[]
+enum { CTR_CURSOR = 0, CTR_FLAGS = 1, CTR_MAXCNT = 2, CTR_RANGE = 3, CTR_ORDERED = 4 };  // counters[]
+constexpr uint32_t ORDERED_CAP = 4096;  // cells per stage whose float sums are re-done in emission order (see k_ordered_cells)
 enum { OVF_BLOCKS = 1, OVF_LUM = 2, OVF_SPIN = 4 };     // CTR_FLAGS bits
 
 struct GridArgs {
@@ -72,6 +73,8 @@ struct GridArgs {
   uint32_t       cap_blocks;
   uint16_t*      lum;        // colour: [cap_blocks][64][lum_cap] luma lists
   uint32_t       lum_cap;
+  uint2*         binfo;      // [cap_blocks] {frame, block key} of every pool block (written by the thread that created it)
+  uint32_t*      ordered;    // [ORDERED_CAP] pool cells whose sums left the exact float range
   int32_t*       counters;
   uint32_t*      marks;      // [F][wmax][wmax][mwords] one bit per cell: some boundary point blends it (or null: all)
   int            mwords;
@@ -193,6 +196,7 @@ __device__ __forceinline__ uint32_t block_claim( const GridArgs& a, int f, uint3
           atomicOr( &a.counters[CTR_FLAGS], OVF_BLOCKS );
           id = NO_BLOCK - 1u;
         }
+        if ( id < a.cap_blocks ) { a.binfo[id] = make_uint2( (uint32_t)f, key ); }
         atomicExch( T + h, (unsigned long long)key | ( (unsigned long long)( id + 1u ) << 32 ) );
         return id < a.cap_blocks ? id : NO_BLOCK;
       }
@@ -427,6 +431,22 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
   }
 }
 
+// The reference sums the cell members in float, in emission order (:996, :1177).  Integer sums convert to the same float
+// while every partial sum stays below 2^24; a cell beyond that is listed and k_ordered_cells repeats
+// its float accumulation in emission order.  More than 65535 members wrap the reference's uint16 counter (not reproduced).
+__device__ __forceinline__ void note_inexact_cell( const GridArgs& a, uint32_t cell, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t n ) {
+  if ( n > 65535u ) {
+    a.counters[CTR_RANGE] = 1;
+  } else if ( s0 >= ( 1u << 24 ) || s1 >= ( 1u << 24 ) || s2 >= ( 1u << 24 ) ) {
+    const uint32_t k = (uint32_t)atomicAdd( &a.counters[CTR_ORDERED], 1 );
+    if ( k < ORDERED_CAP ) {
+      a.ordered[k] = cell;
+    } else {
+      a.counters[CTR_RANGE] = 2;
+    }
+  }
+}
+
 // ---- colour: per-cell mean/median gate (:1228-1236, :1239-1243) ----
 // One warp per 32 pool cells.  |mean - median| <= standard deviation, so only cells whose luma variance can exceed the
 // threshold need the median; those are sorted four at a time with a 32-lane bitonic network in registers.
@@ -512,9 +532,7 @@ __global__ void __launch_bounds__( 256 ) k_cell_median_gate( const GridArgs a, d
       if ( lane == src ) { gate = gate_of( vhi, vlo, m, lo.x, mmThresh ); }
     }
     if ( n > 0 ) {  // finalise in place: mean colour (:1225: float accumulator read back as double / count), flags
-      if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || n > 65535u ) {
-        a.counters[3] = 1;  // a float accumulator of the reference would have left the exact range
-      }
+      note_inexact_cell( a, c0 + lane, lo.x, lo.y, lo.w, n );
       const uint2    pm = *reinterpret_cast<const uint2*>( &c->pmax );
       const uint32_t cw = n | ( pm.x != ~pm.y ? FC_MULTI : 0u ) | ( gate ? FC_GATE : 0u );
       const double   dn = (double)n;
@@ -533,12 +551,69 @@ __global__ void __launch_bounds__( 256 ) k_finalize_geo( const GridArgs a ) {
     const uint4    lo = *reinterpret_cast<const uint4*>( c );
     const uint32_t n  = lo.z & FC_CNT;
     if ( n == 0 ) { continue; }
-    if ( lo.x >= ( 1u << 24 ) || lo.y >= ( 1u << 24 ) || lo.w >= ( 1u << 24 ) || n > 65535u ) { a.counters[3] = 1; }
+    note_inexact_cell( a, s, lo.x, lo.y, lo.w, n );
     const uint2 pm  = *reinterpret_cast<const uint2*>( &c->pmax );
     const float fcn = (float)n;
     *reinterpret_cast<uint4*>( c ) =
         make_uint4( __float_as_uint( __fdiv_rn( (float)lo.x, fcn ) ), __float_as_uint( __fdiv_rn( (float)lo.y, fcn ) ),
                     n | ( pm.x != ~pm.y ? FC_MULTI : 0u ), __float_as_uint( __fdiv_rn( (float)lo.w, fcn ) ) );
+  }
+}
+
+// ordered float accumulation of the listed cells (one warp per cell): the frame's points are walked in emission order,
+// 32 at a time; the members of the cell are added one after the other in float, exactly as addGridCentroid /
+// addGridColorCentroid do (:996, :1177), and the cell's finalised record is rewritten from those sums
+template <bool COLOUR>
+__global__ void __launch_bounds__( 256 ) k_ordered_cells( const GridArgs a ) {
+  const int      lane = threadIdx.x & 31;
+  const uint32_t k    = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+  if ( k >= min( (uint32_t)a.counters[CTR_ORDERED], ORDERED_CAP ) ) { return; }
+  const uint32_t cell = a.ordered[k], bl = cell >> 6, loc = cell & 63u;
+  const uint2    bi   = a.binfo[bl];
+  const int      f    = (int)bi.x;
+  const uint32_t bk   = bi.y - 1u;
+  const int      cx = (int)( ( bk & 0xFFu ) << 2 | ( loc & 3u ) ), cy = (int)( ( ( bk >> 8 ) & 0xFFu ) << 2 | ( ( loc >> 2 ) & 3u ) ),
+                 cz = (int)( ( ( bk >> 16 ) & 0xFFu ) << 2 | ( loc >> 4 ) );
+  const int      disth = max( a.g / 2, 1 ), th = COLOUR ? 0 : grid_th( a, f );
+  float          s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  uint32_t       n  = 0;
+  for ( int64_t i0 = a.frame_off[f]; i0 < a.frame_off[f + 1]; i0 += 32 ) {
+    const int64_t i = i0 + lane;
+    bool          in = false;
+    float         v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if ( i < a.frame_off[f + 1] ) {
+      const short4 q = a.pos[i];
+      in = COLOUR ? ( q.x >= 0 && q.y >= 0 && q.z >= 0 ) : inside( q.x, q.y, q.z, disth, th );
+      in = in && cell_of( a, q.x ) == cx && cell_of( a, q.y ) == cy && cell_of( a, q.z ) == cz;
+      if ( in ) {
+        if ( COLOUR ) {
+          const ushort4 cv = a.col[i];
+          v0 = (float)cv.x, v1 = (float)cv.y, v2 = (float)cv.z;
+        } else {
+          v0 = (float)q.x, v1 = (float)q.y, v2 = (float)q.z;
+        }
+      }
+    }
+    for ( uint32_t m = __ballot_sync( 0xFFFFFFFFu, in ); m; m &= m - 1 ) {  // members of this chunk, in order
+      const int src = __ffs( m ) - 1;
+      s0 = __fadd_rn( s0, __shfl_sync( 0xFFFFFFFFu, v0, src ) );
+      s1 = __fadd_rn( s1, __shfl_sync( 0xFFFFFFFFu, v1, src ) );
+      s2 = __fadd_rn( s2, __shfl_sync( 0xFFFFFFFFu, v2, src ) );
+      n++;
+    }
+  }
+  if ( lane != 0 ) { return; }
+  Cell* c = a.cells + cell;
+  if ( COLOUR ) {  // {double mean c0, c1, c2, cw'}: the flags of k_cell_median_gate stay
+    double2*     o  = reinterpret_cast<double2*>( c );
+    const double dn = (double)n;
+    const double cw = o[1].y;
+    o[0]            = make_double2( (double)s0 / dn, (double)s1 / dn );
+    o[1]            = make_double2( (double)s2 / dn, cw );
+  } else {  // {float centre x, y, cw', centre z}
+    uint4*      o   = reinterpret_cast<uint4*>( c );
+    const float fcn = (float)n;
+    o->x = __float_as_uint( __fdiv_rn( s0, fcn ) ), o->y = __float_as_uint( __fdiv_rn( s1, fcn ) ), o->w = __float_as_uint( __fdiv_rn( s2, fcn ) );
   }
 }
 
@@ -805,7 +880,7 @@ __global__ void __launch_bounds__( 256 ) k_to_rgb8( const ushort4* __restrict__ 
 
 // table geometry + (re)allocation; table and pool are all-zero between calls (the cleanup pass resets what was used)
 struct GridBufs {
-  RbBuf &table, &cells, &counters, &lum, &marks;
+  RbBuf &table, &cells, &counters, &lum, &marks, &binfo;
 };
 int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool colour, int grow ) {
   if ( wmax > 1024 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "smoothing grid wider than 1024 cells per axis" ); }
@@ -843,8 +918,9 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
     a.lum_cap          = (uint32_t)std::max<int64_t>( base, c->col_lum_want );
     RB_CUDA( b.lum.ensure( (size_t)cap * 64 * a.lum_cap * 2 + 64 ) );
   }
-  RB_CUDA( b.counters.ensure( 64 ) );
+  RB_CUDA( b.counters.ensure( 64 + ORDERED_CAP * 4 ) );
   RB_CUDA( cudaMemsetAsync( b.counters.p, 0, 64, c->stream ) );
+  RB_CUDA( b.binfo.ensure( (size_t)cap * 8 ) );
   // mark bitmap: dense, one bit per cell; beyond 1 GiB per GOF (cells of 1 or 2 voxels at 11+ bits) every cell is
   // accumulated instead
   a.ginv   = g > 1 ? (uint32_t)( ( 1ull << 32 ) / (unsigned)g ) + 1u : 0u;
@@ -863,6 +939,8 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
   a.cap_blocks = (uint32_t)cap;
   a.lum        = b.lum.as<uint16_t>();
   a.counters   = b.counters.as<int32_t>();
+  a.ordered    = b.counters.as<uint32_t>() + 16;
+  a.binfo      = b.binfo.as<uint2>();
   return RB200_OK;
 }
 
@@ -871,16 +949,17 @@ int setup_grid( rb200_ctx* c, GridArgs& a, GridBufs b, int g, int wmax, bool col
 int stage_result( rb200_ctx* c, const GridArgs& a, GridBufs b, const char* what ) {
   int32_t* h = (int32_t*)rb_pinned( c, 64 );
   if ( !h ) { return -rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-  RB_CUDA( cudaMemcpyAsync( h, a.counters, 16, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( h, a.counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
-  c->stats.d2h_bytes += 16;
+  c->stats.d2h_bytes += 32;
   if ( h[CTR_FLAGS] & OVF_SPIN ) { return -rb_fail( c, RB200_ERR_CUDA, "%s: block table wait timed out", what ); }
   if ( h[CTR_FLAGS] ) {
     if ( h[CTR_FLAGS] & OVF_LUM ) { c->col_lum_want = std::max<int64_t>( c->col_lum_want, ( (int64_t)h[CTR_MAXCNT] + 15 ) & ~15ll ); }
     return ( h[CTR_FLAGS] & OVF_BLOCKS ) ? 1 : 2;
   }
-  if ( h[3] ) {
-    return -rb_fail( c, RB200_ERR_UNSUPPORTED, "%s: a cell accumulator left the exact float range (count > 65535 or sum >= 2^24)", what );
+  if ( h[CTR_RANGE] ) {
+    return -rb_fail( c, RB200_ERR_UNSUPPORTED, h[CTR_RANGE] == 1 ? "%s: a cell holds more than 65535 points (the reference's uint16 counter wraps)"
+                                                                  : "%s: too many cells whose float sums need ordered accumulation", what );
   }
   return 0;
 }
@@ -919,13 +998,14 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum, c->d_geo_cell_ids};
+  GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum, c->d_geo_cell_ids, c->d_scratch[5]};
   for ( ;; ) {
     int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );
     if ( r ) { return r; }
     if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     RB_LAUNCH( "geo_finalize", k_finalize_geo, WALK_CTAS, 256, 0, a );
+    RB_LAUNCH( "geo_ordered", k_ordered_cells<false>, ORDERED_CAP / 8, 256, 0, a );
     if ( c->blist_cap > 0 ) {
       auto kf = g == 8 ? k_filter_geo<8> : k_filter_geo<0>;
       RB_LAUNCH( "geo_filter", kf, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_smoothing );
@@ -960,13 +1040,14 @@ int rb_smooth_color_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
-  GridBufs b{c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_col_lum, c->d_col_cell_ids};
+  GridBufs b{c->d_col_grid, c->d_col_cells, c->d_scratch[3], c->d_col_lum, c->d_col_cell_ids, c->d_scratch[6]};
   for ( int attempt = 0;; attempt++ ) {
     int r = setup_grid( c, a, b, g, wmax, true, c->col_grow );
     if ( r ) { return r; }
     if ( a.marks ) { RB_LAUNCH( "col_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
     RB_LAUNCH( "col_accumulate", k_accumulate<true>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
     RB_LAUNCH( "col_median_gate", k_cell_median_gate, WALK_CTAS, 256, 0, a, P.threshold_color_variation * 256.0 );
+    RB_LAUNCH( "col_ordered", k_ordered_cells<true>, ORDERED_CAP / 8, 256, 0, a );
     if ( c->blist_cap > 0 ) {
       auto kf = g == 4 ? k_filter_col<4> : ( g == 2 ? k_filter_col<2> : k_filter_col<0> );
       RB_LAUNCH( "col_filter", kf, rb_div_up( c->blist_cap, 128 ), 128, 0, a, P.threshold_color_smoothing,

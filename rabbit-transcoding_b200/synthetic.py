@@ -723,3 +723,40 @@ def make_lod_and_oblique(gof, seed=0, lod=True, planes=True):
         if planes and rng.random() < 0.6:
             p["axis_of_additional_plane"] = int(rng.integers(1, 4))
     return gof
+
+
+def generate_stacked_gof(n_patches=12, n_frames=1, seed=0, luma=65535, transfer_filter=0):
+    """A pathological GOF: `n_patches` patches of 32x32 pixels that all decode to (nearly) the same 3-D slab, with a
+    saturated luma.  Every 4^3 colour cell then holds a few hundred points whose float luma sum exceeds 2^24, the range
+    in which the reference's float accumulators (PCCCodec.cpp:996, :1177) are exact — the case in which the order of the
+    additions shows in the result."""
+    R, W, H, bitdepth = 16, 256, 256, 8
+    p = default_params(W, H, bitdepth, 4)
+    p.attr_transfer_filter_type = transfer_filter
+    M = 2
+    g = SyntheticGOF()
+    g.params, g.n_frames = p, n_frames
+    g.occupancy = np.zeros((n_frames, H // 4, W // 4), np.uint8)
+    g.geometry = np.zeros((n_frames, M, H, W), np.uint16)
+    g.attribute = np.zeros((n_frames, M, 3, H, W), np.uint16)
+    recs = np.zeros(n_frames * n_patches, abi.PATCH_DTYPE)
+    rng = np.random.default_rng([seed, 0x57AC])
+    for f in range(n_frames):
+        for k in range(n_patches):
+            bx, by = (k % 8) * 2, (k // 8) * 2
+            nrm, tan, bit, mode = VIEW_AXES[0]
+            # (u0, v0, sizeU0, sizeV0, u1, v1, d1, axes, mode, orientation, lod, lod, plane, size2d)
+            recs[f * n_patches + k] = (bx, by, 2, 2, 64 + (k % 3), 64, 40 + (k % 2), nrm, tan, bit, mode, 0, 1, 1, 0, 32, 32)
+            ys, xs = slice(by * R, by * R + 32), slice(bx * R, bx * R + 32)
+            g.occupancy[f, by * 4:by * 4 + 8, bx * 4:bx * 4 + 8] = 1
+            d0 = (4 + rng.integers(0, 3, size=(32, 32))).astype(np.uint16)
+            g.geometry[f, 0, ys, xs] = d0
+            g.geometry[f, 1, ys, xs] = d0 + rng.integers(0, 3, size=(32, 32)).astype(np.uint16)
+            for m in range(M):
+                g.attribute[f, m, 0, ys, xs] = np.clip(luma - 257 * k - rng.integers(0, 600, size=(32, 32)), 0, 65535)
+                g.attribute[f, m, 1, ys, xs] = 30000 + rng.integers(0, 2000, size=(32, 32))
+                g.attribute[f, m, 2, ys, xs] = 34000 + rng.integers(0, 2000, size=(32, 32))
+    g.patches = recs
+    g.patch_offset = np.arange(0, (n_frames + 1) * n_patches, n_patches, dtype=np.int32)
+    g.sources = []
+    return g

@@ -53,6 +53,21 @@ def test_level_of_detail_and_45_degree_planes(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="lod/oblique rec-1")
 
 
+def test_cell_sums_beyond_the_exact_float_range(rb, codec, checker_backend):
+    """twelve patches decode to the same slab with a saturated luma: the colour cells hold a few hundred points and their
+    float sums pass 2^24, where the reference's result depends on the ORDER of its float additions.
+    Those cells are re-accumulated in emission order on the device (k_ordered_cells) and must still match bit for bit."""
+    g = rb.synthetic.generate_stacked_gof(n_patches=12, n_frames=2, seed=5)
+    ref = run_stages(codec, g, checker_backend, what="stacked")
+    assert ref.counts(0).recolored > 0 and ref.counts(0).total > 12 * 32 * 32
+    # the construction really leaves the exact range: one 4^3 cell holds far more than 2^24 / 65535 = 256 points
+    pos = ref.cloud(0, "smooth_geometry")["positions"].astype(np.int64) // 4
+    key = (pos[:, 0] << 32) | (pos[:, 1] << 16) | pos[:, 2]
+    assert np.unique(key, return_counts=True)[1].max() > 300
+    g = rb.synthetic.generate_stacked_gof(n_patches=12, n_frames=1, seed=6, transfer_filter=1)
+    run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="stacked rec-1")
+
+
 def test_multiple_streams_relative_t1(rb, codec, checker_backend):
     """CTC condition T1-from-rec-T0: the second attribute map is a delta on the first (PCCCodec.cpp:1387-1416)"""
     g = rb.synthetic.make_relative_t1(small(rb, seed=18), seed=2)
@@ -215,6 +230,15 @@ def test_vox10_full_size_frame_with_transfer(rb, codec, checker_backend):
 
 
 # ---- BASELINE.json config 4 shapes: vox11 (11-bit, 2560-wide atlas), lossy two-layer and the lossless-style EOM variant ----
+def test_vox10_r5_full_size_frame_precision2(rb, codec, checker_backend):
+    """the r5 rate point (cfg/rate/ctc-r5.cfg: occupancyPrecision 2, colour cells of 2^3 voxels) at full vox10 size through
+    the whole Rec-1 sequence"""
+    g = rb.synthetic.generate_gof(n_frames=1, bitdepth=10, width=1280, scale=0.68, seed=0x0AB817 + 5, transfer_filter=1,
+                                  occupancy_precision=2, max_depth=249)
+    ref = run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="vox10 r5")
+    assert ref.counts(0).total > 600000 and ref.counts(0).recolored > 0
+
+
 def test_vox11_frame_lossy_full_decoder(rb, codec, checker_backend):
     g = rb.synthetic.generate_gof(n_frames=1, bitdepth=11, width=2560, scale=0.55, seed=61, transfer_filter=1)
     assert g.params.geometry_bitdepth_3d == 11
