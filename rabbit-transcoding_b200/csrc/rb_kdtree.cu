@@ -208,18 +208,34 @@ __global__ void k_g_roots( GNode* __restrict__ nodes, const int64_t* __restrict_
   }
 }
 
-// the nodes of this level: tight box from the statistics, small root / split decision (middleSplit_), chunk table and
+// One chunk of GT consecutive elements of a node of the current level: everything an element pass needs, in one
+// 48-byte record (written by the CTA of k_g_count, completed by the node scans), so the CTAs of the other passes start
+// with ONE metadata round trip.
+struct GChunk {
+  uint32_t e0, left, cnt;  // first element (global), first element of the node, elements in the chunk
+  uint32_t node;
+  uint32_t cutcf;          // (uint16) cutval | cutfeat << 16
+  uint32_t lim1, lim2;     // node-wide: elements < cutval, <= cutval               (k_g_nodescan<false>)
+  uint32_t m, pre;         // misplaced pairs of the running Hoare pass and the exclusive prefix of its mask in the node
+  uint32_t idx, child1;    // the left child takes positions [0, idx); children are child1, child1 + 1
+  uint32_t pad;
+};
+constexpr int BIG = 1 << 20;
+
+// the nodes of this level: tight box from the statistics, small root / split decision (middleSplit_), chunk records and
 // the ids of the children.  One thread per node; chunks and child ids are handed out with one atomic per warp (the
 // numbering of nodes and chunks is free: only the tree they describe is the result).  C_BIG / C_CHUNKS are zeroed by
 // the host before the launch; nothing else allocates from C_NEXT while this kernel runs.
 __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, const int32_t* __restrict__ st, uint32_t lvlBegin,
                                                     uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
                                                     uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
-                                                    uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap ) {
+                                                    uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap,
+                                                    int32_t* __restrict__ cls ) {
   const int      lane = threadIdx.x & 31;
   const uint32_t i    = lvlBegin + blockIdx.x * TPB + threadIdx.x;
   const int      o[3] = {ox, oy, oz};
   uint32_t       nch = 0, big = 0, small = 0;
+  int            cf = 0, cv = 0;
   if ( i < lvlEnd ) {
     GNode& n = nodes[i];
     int    lo[3], hi[3], tmin[3], tmax[3];
@@ -239,7 +255,6 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
       n.state = 2;
       small   = 1;
     } else {
-      int cf, cv;
       kd_choose_split( lo, hi, tmin, tmax, o, cf, cv );
       n.cutfeat = (int8_t)cf;
       n.cutval  = (int16_t)cv;
@@ -280,58 +295,89 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
       n.child1     = c1;
       n.firstChunk = offC;
       for ( uint32_t k = 0; k < nch; k++ ) { chunkNode[offC + k] = i; }
+      // boxes of the classes "< cut" and "> cut" of planeSplit, filled by k_g_count
+      for ( int j = 0; j < 12; j++ ) { cls[(size_t)i * 12 + j] = ( j % 6 ) < 3 ? BIG : -BIG; }
     }
   }
 }
 
-struct ChunkCtx {
-  uint32_t node, left, e0, cnt, p0;  // p0 = position of the chunk's first element inside the node
-};
-__device__ __forceinline__ ChunkCtx chunk_ctx( const GNode& n, uint32_t node, uint32_t c ) {
-  ChunkCtx x;
-  x.node = node;
-  x.left = n.left;
-  x.p0   = ( c - n.firstChunk ) * (uint32_t)GT;
-  x.e0   = n.left + x.p0;
-  x.cnt  = min( (uint32_t)GT, n.right - x.e0 );
-  return x;
-}
-
-// pass A: the predicates of planeSplit for every element of the level, as bit masks, and their per-chunk counts
+// pass A: the predicates of planeSplit for every element of the level as bit masks, their per-chunk counts, and the
+// boxes of the classes "< cut" and "> cut": the children's tight boxes follow from those (the few elements == cut are
+// added by k_g_apply2 once their final positions are known) without another pass over the elements.  The CTA also
+// writes the chunk record the later passes start from.
 __global__ void __launch_bounds__( TPB ) k_g_count( const uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
-                                                    const uint32_t* __restrict__ chunkNode, uint32_t* __restrict__ wA,
-                                                    uint32_t* __restrict__ wB, uint32_t* __restrict__ cA, uint32_t* __restrict__ cB ) {
+                                                    const uint32_t* __restrict__ chunkNode, GChunk* __restrict__ chunks,
+                                                    uint32_t* __restrict__ wA, uint32_t* __restrict__ wB,
+                                                    uint32_t* __restrict__ cA, uint32_t* __restrict__ cB, int32_t* __restrict__ cls ) {
   __shared__ uint32_t sA[TPB / 32], sB[TPB / 32];
-  const uint32_t c    = blockIdx.x, node = chunkNode[c];
-  const GNode&   n    = nodes[node];
-  const ChunkCtx x    = chunk_ctx( n, node, c );
-  const int      cf   = n.cutfeat, cut = n.cutval;
+  __shared__ int      sBox[TPB / 32][12];
+  const uint32_t c = blockIdx.x, node = chunkNode[c];
+  const GNode&   n = nodes[node];
+  const uint32_t e0 = n.left + ( c - n.firstChunk ) * (uint32_t)GT, cnt = min( (uint32_t)GT, n.right - e0 );
+  const int      cf = n.cutfeat, cut = n.cutval;
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint64_t       r[GEPT];
+  if ( threadIdx.x == 0 ) {
+    GChunk d{};
+    d.e0 = e0, d.left = n.left, d.cnt = cnt, d.node = node, d.cutcf = ( (uint32_t)cut & 0xFFFFu ) | ( (uint32_t)cf << 16 );
+    d.child1  = n.child1;
+    chunks[c] = d;
+  }
+  uint64_t r[GEPT];
 #pragma unroll
   for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i = q * TPB + threadIdx.x;
-    r[q]             = i < x.cnt ? rec[x.e0 + i] : ~0ull;  // all-ones: coordinate 4095 in a slot that does not exist
+    r[q]             = i < cnt ? rec[e0 + i] : ~0ull;
   }
+  int bx[12];  // {min[3], max[3]} of "< cut", then of "> cut"
+#pragma unroll
+  for ( int j = 0; j < 12; j++ ) { bx[j] = ( j % 6 ) < 3 ? BIG : -BIG; }
   uint32_t ca = 0, cb = 0;
 #pragma unroll
   for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i  = q * TPB + threadIdx.x;
-    const int      v  = kd_coord( r[q], cf );
-    const bool     ok = i < x.cnt;
-    const uint32_t ma = __ballot_sync( 0xFFFFFFFFu, ok && v < cut ), mb = __ballot_sync( 0xFFFFFFFFu, ok && v <= cut );
+    const bool     ok = i < cnt;
+    const int      x = kd_coord( r[q], 0 ), y = kd_coord( r[q], 1 ), z = kd_coord( r[q], 2 );
+    const int      v  = cf == 0 ? x : ( cf == 1 ? y : z );
+    const bool     lt = ok && v < cut, le = ok && v <= cut;
+    const uint32_t ma = __ballot_sync( 0xFFFFFFFFu, lt ), mb = __ballot_sync( 0xFFFFFFFFu, le );
     if ( lane == 0 ) {
       wA[(size_t)c * GWORDS + q * ( TPB / 32 ) + w] = ma;
       wB[(size_t)c * GWORDS + q * ( TPB / 32 ) + w] = mb;
     }
     ca += __popc( ma ), cb += __popc( mb );
+    if ( lt ) {
+      bx[0] = min( bx[0], x ), bx[1] = min( bx[1], y ), bx[2] = min( bx[2], z );
+      bx[3] = max( bx[3], x ), bx[4] = max( bx[4], y ), bx[5] = max( bx[5], z );
+    } else if ( ok && !le ) {
+      bx[6] = min( bx[6], x ), bx[7] = min( bx[7], y ), bx[8] = min( bx[8], z );
+      bx[9] = max( bx[9], x ), bx[10] = max( bx[10], y ), bx[11] = max( bx[11], z );
+    }
   }
-  if ( lane == 0 ) { sA[w] = ca, sB[w] = cb; }
+#pragma unroll
+  for ( int j = 0; j < 12; j++ ) {
+    bx[j] = ( j % 6 ) < 3 ? __reduce_min_sync( 0xFFFFFFFFu, bx[j] ) : __reduce_max_sync( 0xFFFFFFFFu, bx[j] );
+  }
+  if ( lane == 0 ) {
+    sA[w] = ca, sB[w] = cb;
+#pragma unroll
+    for ( int j = 0; j < 12; j++ ) { sBox[w][j] = bx[j]; }
+  }
   __syncthreads();
   if ( threadIdx.x == 0 ) {
     uint32_t ta = 0, tb = 0;
     for ( int k = 0; k < TPB / 32; k++ ) { ta += sA[k], tb += sB[k]; }
     cA[c] = ta, cB[c] = tb;
+  }
+  if ( threadIdx.x >= 32 && threadIdx.x < 32 + 12 ) {
+    const int  j     = threadIdx.x - 32;
+    const bool isMin = ( j % 6 ) < 3;
+    int        v     = sBox[0][j];
+    for ( int k = 1; k < TPB / 32; k++ ) { v = isMin ? min( v, sBox[k][j] ) : max( v, sBox[k][j] ); }
+    if ( isMin ) {
+      if ( v < BIG ) { atomicMin( &cls[(size_t)node * 12 + j], v ); }
+    } else {
+      if ( v > -BIG ) { atomicMax( &cls[(size_t)node * 12 + j], v ); }
+    }
   }
 }
 
@@ -349,12 +395,14 @@ __device__ __forceinline__ uint32_t mask_prefix_at( const uint32_t* __restrict__
 }
 
 // pass B / E: one warp per node of the level.  Exclusive prefix of the chunk counts, lim1 / lim2, the number of
-// misplaced pairs, and (SECOND == false) the children (divideTree :1070-1078)
+// misplaced pairs — completed into the chunk records — and (SECOND == false) the children (divideTree :1070-1078) with
+// their tight boxes from the class boxes of k_g_count
 template <bool SECOND>
 __global__ void __launch_bounds__( TPB ) k_g_nodescan( GNode* __restrict__ nodes, uint32_t lvlBegin, uint32_t lvlEnd,
-                                                       uint32_t* __restrict__ cA, uint32_t* __restrict__ cB,
-                                                       const uint32_t* __restrict__ wA, const uint32_t* __restrict__ wB,
-                                                       int32_t* __restrict__ st ) {
+                                                       GChunk* __restrict__ chunks, uint32_t* __restrict__ cA,
+                                                       uint32_t* __restrict__ cB, const uint32_t* __restrict__ wA,
+                                                       const uint32_t* __restrict__ wB, int32_t* __restrict__ st,
+                                                       const int32_t* __restrict__ cls ) {
   const uint32_t i    = lvlBegin + ( blockIdx.x * TPB + threadIdx.x ) / 32;
   const int      lane = threadIdx.x & 31;
   if ( i >= lvlEnd ) { return; }
@@ -382,6 +430,10 @@ __global__ void __launch_bounds__( TPB ) k_g_nodescan( GNode* __restrict__ nodes
     uint32_t m1 = 0;
     if ( lim1 > 0 && lim1 < count ) { m1 = lim1 - mask_prefix_at( wA, first, cA[first + lim1 / GT], lim1, lane ); }
     const uint32_t idx = kd_split_index( count, lim1, lim2 );
+    for ( uint32_t k = lane; k < nch; k += 32 ) {
+      GChunk& d = chunks[first + k];
+      d.lim1 = lim1, d.lim2 = lim2, d.m = m1, d.pre = cA[first + k], d.idx = idx;
+    }
     if ( lane == 0 ) {
       n.lim1 = lim1, n.lim2 = lim2, n.m1 = m1, n.idx = idx;
       GNode a{}, b{};
@@ -394,9 +446,14 @@ __global__ void __launch_bounds__( TPB ) k_g_nodescan( GNode* __restrict__ nodes
       b.lo[n.cutfeat]     = n.cutval;  // right_bbox[cutfeat].low = cutval
       nodes[n.child1]     = a;
       nodes[n.child1 + 1] = b;
+      // tight boxes of the children so far: the left child holds the class "< cut", the right child the class "> cut";
+      // k_g_apply2 adds the elements == cut (positions [lim1, lim2) after pass 2) to the side they end up on
+      const int32_t* C = cls + (size_t)i * 12;
       for ( int k = 0; k < 3; k++ ) {
-        st[(size_t)n.child1 * 6 + k] = st[(size_t)( n.child1 + 1 ) * 6 + k] = 0x7FFFFFFF;
-        st[(size_t)n.child1 * 6 + 3 + k] = st[(size_t)( n.child1 + 1 ) * 6 + 3 + k] = (int32_t)0x80000000;
+        st[(size_t)n.child1 * 6 + k]             = C[k] >= BIG ? 0x7FFFFFFF : C[k];
+        st[(size_t)n.child1 * 6 + 3 + k]         = C[3 + k] <= -BIG ? (int32_t)0x80000000 : C[3 + k];
+        st[(size_t)( n.child1 + 1 ) * 6 + k]     = C[6 + k] >= BIG ? 0x7FFFFFFF : C[6 + k];
+        st[(size_t)( n.child1 + 1 ) * 6 + 3 + k] = C[9 + k] <= -BIG ? (int32_t)0x80000000 : C[9 + k];
       }
     }
   } else {
@@ -418,6 +475,10 @@ __global__ void __launch_bounds__( TPB ) k_g_nodescan( GNode* __restrict__ nodes
     const uint32_t lim1 = n.lim1, lim2 = n.lim2;
     uint32_t       m2 = 0;
     if ( lim2 > lim1 && lim2 < count ) { m2 = ( lim2 - lim1 ) - mask_prefix_at( wB, first, cB[first + lim2 / GT], lim2, lane ); }
+    for ( uint32_t k = lane; k < nch; k += 32 ) {
+      GChunk& d = chunks[first + k];
+      d.m = m2, d.pre = cB[first + k];
+    }
     if ( lane == 0 ) { n.m2 = m2; }
   }
 }
@@ -448,42 +509,39 @@ static_assert( GWORDS == 64, "chunk_word_prefix handles two words per lane" );
 //   pass 2 (SECOND == true) : left = positions in [lim1, lim2) with v > cut -> tmp[left + lim1 + i]; right = positions >= lim2
 //                             with v <= cut -> tmp[left + lim2 + r]
 template <bool SECOND>
-__global__ void __launch_bounds__( TPB ) k_g_stage( const uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
-                                                    const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ words,
-                                                    const uint32_t* __restrict__ cPre, uint64_t* __restrict__ tmp ) {
+__global__ void __launch_bounds__( TPB ) k_g_stage( const uint64_t* __restrict__ rec, const GChunk* __restrict__ chunks,
+                                                    const uint32_t* __restrict__ words, uint64_t* __restrict__ tmp ) {
   __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
-  const uint32_t c = blockIdx.x, node = chunkNode[c];
-  const GNode&   n = nodes[node];
-  const uint32_t m = SECOND ? n.m2 : n.m1;
+  const uint32_t c = blockIdx.x;
+  const GChunk&  D = chunks[c];
+  const uint32_t m = D.m;
   if ( m == 0 ) { return; }
-  const ChunkCtx x    = chunk_ctx( n, node, c );
-  const uint32_t lim1 = n.lim1, lim2 = n.lim2;
+  const uint32_t e0 = D.e0, left = D.left, cnt = D.cnt, p0 = e0 - left, lim1 = D.lim1, lim2 = D.lim2, base = D.pre;
   // nothing of this chunk takes part in pass 2 when it lies below lim1
-  if ( SECOND && x.p0 + x.cnt <= lim1 ) { return; }
+  if ( SECOND && p0 + cnt <= lim1 ) { return; }
   chunk_word_prefix( words + (size_t)c * GWORDS, sWord, sPre );
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t base = cPre[c];
   const uint32_t lt   = lanemask_lt();
 #pragma unroll
   for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i = q * TPB + threadIdx.x;
-    if ( i >= x.cnt ) { continue; }
+    if ( i >= cnt ) { continue; }
     const int      wi  = q * ( TPB / 32 ) + w;
     const uint32_t wd  = sWord[wi];
     const bool     bit = ( wd >> lane ) & 1u;
     const uint32_t pre = base + sPre[wi] + __popc( wd & lt );  // set bits of the node's mask before this position
-    const uint32_t p   = x.p0 + i;
+    const uint32_t p   = p0 + i;
     if ( !SECOND ) {
       if ( p < lim1 ) {
-        if ( !bit ) { tmp[x.left + ( p - pre )] = rec[x.e0 + i]; }
+        if ( !bit ) { tmp[left + ( p - pre )] = rec[e0 + i]; }
       } else if ( bit ) {
-        tmp[x.left + lim1 + ( pre - ( lim1 - m ) )] = rec[x.e0 + i];
+        tmp[left + lim1 + ( pre - ( lim1 - m ) )] = rec[e0 + i];
       }
     } else if ( p >= lim1 ) {
       if ( p < lim2 ) {
-        if ( !bit ) { tmp[x.left + lim1 + ( ( p - lim1 ) - pre )] = rec[x.e0 + i]; }
+        if ( !bit ) { tmp[left + lim1 + ( ( p - lim1 ) - pre )] = rec[e0 + i]; }
       } else if ( bit ) {
-        tmp[x.left + lim2 + ( pre - ( ( lim2 - lim1 ) - m ) )] = rec[x.e0 + i];
+        tmp[left + lim2 + ( pre - ( ( lim2 - lim1 ) - m ) )] = rec[e0 + i];
       }
     }
   }
@@ -492,22 +550,19 @@ __global__ void __launch_bounds__( TPB ) k_g_stage( const uint64_t* __restrict__
 // pass D: every misplaced position of pass 1 takes its partner; the "<= cut" mask of the positions >= lim1 is written
 // for the new arrangement (pass 2 works on it: wC) together with its per-chunk counts.  All loads of the chunk are
 // issued before the first ballot, so a CTA pays one memory round trip, not one per 256 elements.
-__global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
-                                                     const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ wA,
-                                                     const uint32_t* __restrict__ wB, uint32_t* __restrict__ wC,
-                                                     const uint32_t* __restrict__ cA, uint32_t* __restrict__ cB,
+__global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec, const GChunk* __restrict__ chunks,
+                                                     const uint32_t* __restrict__ wA, const uint32_t* __restrict__ wB,
+                                                     uint32_t* __restrict__ wC, uint32_t* __restrict__ cB,
                                                      const uint64_t* __restrict__ tmp ) {
   __shared__ uint32_t sWord[GWORDS], sPre[GWORDS], sWordB[GWORDS];
   __shared__ uint32_t sCnt[TPB / 32];
-  const uint32_t c = blockIdx.x, node = chunkNode[c];
-  const GNode&   n = nodes[node];
-  const ChunkCtx x    = chunk_ctx( n, node, c );
-  const uint32_t lim1 = n.lim1, m = n.m1;
-  const int      cf = n.cutfeat, cut = n.cutval;
+  const uint32_t c = blockIdx.x;
+  const GChunk&  D = chunks[c];
+  const uint32_t e0 = D.e0, left = D.left, cnt = D.cnt, p0 = e0 - left, lim1 = D.lim1, m = D.m, base = D.pre;
+  const int      cf = ( D.cutcf >> 16 ) & 3, cut = (int16_t)( D.cutcf & 0xFFFFu );
   if ( threadIdx.x < GWORDS ) { sWordB[threadIdx.x] = wB[(size_t)c * GWORDS + threadIdx.x]; }
   chunk_word_prefix( wA + (size_t)c * GWORDS, sWord, sPre );
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t base = cA[c];
   const uint32_t lt   = lanemask_lt();
   uint64_t       nv[GEPT];   // the partner of a misplaced position
   uint32_t       kind = 0;   // bit q: position q of this thread is misplaced
@@ -518,32 +573,32 @@ __global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec,
     const uint32_t wd  = sWord[wi];
     const bool     bit = ( wd >> lane ) & 1u;
     const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
-    const uint32_t p   = x.p0 + i;
+    const uint32_t p   = p0 + i;
     nv[q]              = 0;
-    if ( i < x.cnt && m ) {
+    if ( i < cnt && m ) {
       if ( p < lim1 ) {
-        if ( !bit ) { nv[q] = tmp[x.left + lim1 + ( m - 1u - ( p - pre ) )], kind |= 1u << q; }
+        if ( !bit ) { nv[q] = tmp[left + lim1 + ( m - 1u - ( p - pre ) )], kind |= 1u << q; }
       } else if ( bit ) {
-        nv[q] = tmp[x.left + ( m - 1u - ( pre - ( lim1 - m ) ) )], kind |= 1u << q;
+        nv[q] = tmp[left + ( m - 1u - ( pre - ( lim1 - m ) ) )], kind |= 1u << q;
       }
     }
   }
-  uint32_t cnt = 0;
+  uint32_t cntB = 0;
 #pragma unroll
   for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i  = q * TPB + threadIdx.x;
     const int      wi = q * ( TPB / 32 ) + w;
-    const uint32_t p  = x.p0 + i;
-    bool           b2 = i < x.cnt && p >= lim1 && ( ( sWordB[wi] >> lane ) & 1u );
+    const uint32_t p  = p0 + i;
+    bool           b2 = i < cnt && p >= lim1 && ( ( sWordB[wi] >> lane ) & 1u );
     if ( kind >> q & 1u ) {
-      rec[x.e0 + i] = nv[q];
+      rec[e0 + i] = nv[q];
       if ( p >= lim1 ) { b2 = kd_coord( nv[q], cf ) <= cut; }
     }
     const uint32_t mb = __ballot_sync( 0xFFFFFFFFu, b2 );
     if ( lane == 0 ) { wC[(size_t)c * GWORDS + wi] = mb; }
-    cnt += __popc( mb );
+    cntB += __popc( mb );
   }
-  if ( lane == 0 ) { sCnt[w] = cnt; }
+  if ( lane == 0 ) { sCnt[w] = cntB; }
   __syncthreads();
   if ( threadIdx.x == 0 ) {
     uint32_t t = 0;
@@ -552,59 +607,56 @@ __global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec,
   }
 }
 
-// pass G: the partners of pass 2, and the tight boxes of the two children (computeMinMax of the next level)
-__global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec, const GNode* __restrict__ nodes,
-                                                     const uint32_t* __restrict__ chunkNode, const uint32_t* __restrict__ wB,
-                                                     const uint32_t* __restrict__ cB, const uint64_t* __restrict__ tmp,
+// pass G: the partners of pass 2, and the children's boxes of the elements == cut.  After pass 2 those elements sit at
+// positions [lim1, lim2) and belong to the child their position falls in, which is only known now; everything else of
+// the boxes came from the count pass.  Only chunks that reach into [lim1, n) with work to do run past the first lines.
+__global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec, const GChunk* __restrict__ chunks,
+                                                     const uint32_t* __restrict__ wC, const uint64_t* __restrict__ tmp,
                                                      int32_t* __restrict__ st ) {
   __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
   __shared__ int      sBox[TPB / 32][12];
-  const uint32_t c = blockIdx.x, node = chunkNode[c];
-  const GNode&   n = nodes[node];
-  const ChunkCtx x    = chunk_ctx( n, node, c );
-  const uint32_t lim1 = n.lim1, lim2 = n.lim2, m = n.m2, idx = n.idx, child1 = n.child1;
-  chunk_word_prefix( wB + (size_t)c * GWORDS, sWord, sPre );
+  const uint32_t c = blockIdx.x;
+  const GChunk&  D = chunks[c];
+  const uint32_t e0 = D.e0, left = D.left, cnt = D.cnt, p0 = e0 - left, lim1 = D.lim1, lim2 = D.lim2, m = D.m, base = D.pre;
+  const bool     slab = p0 < lim2 && p0 + cnt > lim1;  // the chunk holds positions of [lim1, lim2)
+  if ( ( m == 0 || p0 + cnt <= lim1 ) && !slab ) { return; }
+  const uint32_t idx = D.idx, child1 = D.child1;
+  chunk_word_prefix( wC + (size_t)c * GWORDS, sWord, sPre );
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t base = cB[c];
   const uint32_t lt   = lanemask_lt();
-  int            bx[12];  // {min[3], max[3]} of the left child, then of the right child
+  int            bx[12];  // {min[3], max[3]} of the left child, then of the right child ("== cut" elements only)
 #pragma unroll
-  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = 1 << 20, bx[3 + k] = bx[9 + k] = -( 1 << 20 ); }
-  uint64_t r[GEPT];
-  uint32_t moved = 0;
+  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = BIG, bx[3 + k] = bx[9 + k] = -BIG; }
 #pragma unroll
-  for ( int q = 0; q < GEPT; q++ ) {  // every load of the chunk is in flight before the first use
+  for ( int q = 0; q < GEPT; q++ ) {
     const uint32_t i = q * TPB + threadIdx.x;
-    r[q]             = 0ull;
-    if ( i >= x.cnt ) { continue; }
+    if ( i >= cnt ) { continue; }
+    const uint32_t p = p0 + i;
+    if ( p < lim1 ) { continue; }
     const int      wi  = q * ( TPB / 32 ) + w;
     const uint32_t wd  = sWord[wi];
     const bool     bit = ( wd >> lane ) & 1u;
     const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
-    const uint32_t p   = x.p0 + i;
-    if ( m && p >= lim1 && p < lim2 && !bit ) {
-      r[q] = tmp[x.left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )], moved |= 1u << q;
+    uint64_t       v   = 0;
+    bool           have = false;
+    if ( m && p < lim2 && !bit ) {
+      v           = tmp[left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )];
+      rec[e0 + i] = v, have = true;
     } else if ( m && p >= lim2 && bit ) {
-      r[q] = tmp[x.left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )], moved |= 1u << q;
-    } else {
-      r[q] = rec[x.e0 + i];
+      v           = tmp[left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )];
+      rec[e0 + i] = v, have = true;
+    }
+    if ( slab && p < lim2 ) {  // after pass 2 this position holds an element == cut
+      if ( !have ) { v = rec[e0 + i]; }
+      const int  cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
+      const bool rt = p >= idx;
+      bx[0] = min( bx[0], rt ? BIG : cx ), bx[1] = min( bx[1], rt ? BIG : cy ), bx[2] = min( bx[2], rt ? BIG : cz );
+      bx[3] = max( bx[3], rt ? -BIG : cx ), bx[4] = max( bx[4], rt ? -BIG : cy ), bx[5] = max( bx[5], rt ? -BIG : cz );
+      bx[6] = min( bx[6], rt ? cx : BIG ), bx[7] = min( bx[7], rt ? cy : BIG ), bx[8] = min( bx[8], rt ? cz : BIG );
+      bx[9] = max( bx[9], rt ? cx : -BIG ), bx[10] = max( bx[10], rt ? cy : -BIG ), bx[11] = max( bx[11], rt ? cz : -BIG );
     }
   }
-#pragma unroll
-  for ( int q = 0; q < GEPT; q++ ) {
-    const uint32_t i = q * TPB + threadIdx.x;
-    if ( i >= x.cnt ) { continue; }
-    const uint32_t p = x.p0 + i;
-    const uint64_t v = r[q];
-    if ( moved >> q & 1u ) { rec[x.e0 + i] = v; }
-    const int  cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
-    const bool rt = p >= idx;
-    // (selects, not branches: both boxes live in registers)
-    bx[0] = min( bx[0], rt ? ( 1 << 20 ) : cx ), bx[1] = min( bx[1], rt ? ( 1 << 20 ) : cy ), bx[2] = min( bx[2], rt ? ( 1 << 20 ) : cz );
-    bx[3] = max( bx[3], rt ? -( 1 << 20 ) : cx ), bx[4] = max( bx[4], rt ? -( 1 << 20 ) : cy ), bx[5] = max( bx[5], rt ? -( 1 << 20 ) : cz );
-    bx[6] = min( bx[6], rt ? cx : ( 1 << 20 ) ), bx[7] = min( bx[7], rt ? cy : ( 1 << 20 ) ), bx[8] = min( bx[8], rt ? cz : ( 1 << 20 ) );
-    bx[9] = max( bx[9], rt ? cx : -( 1 << 20 ) ), bx[10] = max( bx[10], rt ? cy : -( 1 << 20 ) ), bx[11] = max( bx[11], rt ? cz : -( 1 << 20 ) );
-  }
+  if ( !slab ) { return; }
 #pragma unroll
   for ( int k = 0; k < 12; k++ ) {
     const bool isMin = ( k % 6 ) < 3;
@@ -622,9 +674,9 @@ __global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec,
     for ( int j = 1; j < TPB / 32; j++ ) { v = isMin ? min( v, sBox[j][k] ) : max( v, sBox[j][k] ); }
     int32_t* dst = st + (size_t)( child1 + ( k >= 6 ? 1 : 0 ) ) * 6 + ( k % 6 );
     if ( isMin ) {
-      if ( v < ( 1 << 20 ) ) { atomicMin( dst, v ); }
+      if ( v < BIG ) { atomicMin( dst, v ); }
     } else {
-      if ( v > -( 1 << 20 ) ) { atomicMax( dst, v ); }
+      if ( v > -BIG ) { atomicMax( dst, v ); }
     }
   }
 }
@@ -947,6 +999,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( B.nodes.ensure( nodeCap * sizeof( KdNode ) ) );
   RB_CUDA( B.rootBox.ensure( (size_t)( nTrees + 1 ) * 12 ) );
   RB_CUDA( B.chunkNode.ensure( (size_t)chunkCap * 4 ) );
+  RB_CUDA( B.chunks.ensure( (size_t)chunkCap * sizeof( GChunk ) ) );
+  RB_CUDA( B.cls.ensure( (size_t)gCap * 12 * 4 ) );
   RB_CUDA( B.wA.ensure( (size_t)chunkCap * GWORDS * 4 ) );
   RB_CUDA( B.wB.ensure( (size_t)chunkCap * GWORDS * 4 ) );
   RB_CUDA( B.wC.ensure( (size_t)chunkCap * GWORDS * 4 ) );
@@ -962,6 +1016,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   KdNode*   nodes     = B.nodes.as<KdNode>();
   uint32_t* counters  = B.counters.as<uint32_t>();
   uint32_t* chunkNode = B.chunkNode.as<uint32_t>();
+  GChunk*   chunks    = B.chunks.as<GChunk>();
+  int32_t*  cls       = B.cls.as<int32_t>();
   uint32_t *wA = B.wA.as<uint32_t>(), *wB = B.wB.as<uint32_t>(), *wC = B.wC.as<uint32_t>(), *cA = B.cA.as<uint32_t>(),
            *cB = B.cB.as<uint32_t>();
   uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
@@ -979,7 +1035,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     RB_CUDA( cudaMemsetAsync( counters + C_BIG, 0, 4, c->stream ) );
     RB_CUDA( cudaMemsetAsync( counters + C_CHUNKS, 0, 4, c->stream ) );
     RB_LAUNCH( "kd_setup", k_g_setup, rb_div_up( nLvl, TPB ), TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
-               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap );
+               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap, cls );
     RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
     if ( h[C_RANGE] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: coordinate range of the clouds exceeds 4096" ); }
@@ -987,13 +1043,13 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     const uint32_t nBig = h[C_BIG], nChunks = h[C_CHUNKS];
     if ( nBig == 0 ) { break; }  // no node of this level is large enough for the level phase
     const int GW = rb_div_up( (int64_t)nLvl * 32, TPB );
-    RB_LAUNCH( "kd_count", k_g_count, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, cA, cB );
-    RB_LAUNCH( "kd_nodescan", k_g_nodescan<false>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wB, st );
-    RB_LAUNCH( "kd_stage1", k_g_stage<false>, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, cA, tmp );
-    RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, gnodes, chunkNode, wA, wB, wC, cA, cB, tmp );
-    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, cA, cB, wA, wC, st );
-    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, gnodes, chunkNode, wC, cB, tmp );
-    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, gnodes, chunkNode, wC, cB, tmp, st );
+    RB_LAUNCH( "kd_count", k_g_count, nChunks, TPB, 0, rec, gnodes, chunkNode, chunks, wA, wB, cA, cB, cls );
+    RB_LAUNCH( "kd_nodescan", k_g_nodescan<false>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, chunks, cA, cB, wA, wB, st, cls );
+    RB_LAUNCH( "kd_stage1", k_g_stage<false>, nChunks, TPB, 0, rec, chunks, wA, tmp );
+    RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, chunks, wA, wB, wC, cB, tmp );
+    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, chunks, cA, cB, wA, wC, st, cls );
+    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, chunks, wC, tmp );
+    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, chunks, wC, tmp, st );
     lvlBegin = lvlEnd;  // the children were numbered consecutively behind the nodes that existed
     lvlEnd   = h[C_NEXT];
   }
