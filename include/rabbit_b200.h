@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RB200_ABI_VERSION 1
+#define RB200_ABI_VERSION 2
 
 typedef enum rb200_status {
   RB200_OK                   = 0,
@@ -144,6 +144,13 @@ typedef struct rb200_frames_yuv420 {
    * clamp( (sample + (1 << (shift-1))) >> shift, 0, (1 << (10 - shift)) - 1 ); 0 = samples are copied as they are */
   int32_t geometry_shift;
   int32_t attribute_shift;
+  /* PCCImage::convertBitdepth (PccLibCommon/source/PCCImage.cpp:258-299) as the decoder runs it on every decoded geometry
+   * video (PCCDecoder.cpp:148-149, :173: decoder output bit depth -> gi.getGeometry2dBitdepthMinus1() + 1) and on the
+   * occupancy video (PCCDecoder.cpp:119: 8 -> oi.getOccupancy2DBitdepthMinus1() + 1), fused into the ingest kernels:
+   * diff = in - out >= 0: msb_align ? sample >> diff : min( sample, 2^out - 1 );  diff < 0: msb_align ? sample << -diff : sample.
+   * bitdepth_out == 0: no conversion. */
+  int32_t geometry_bitdepth_in, geometry_bitdepth_out, geometry_msb_align;
+  int32_t occupancy_bitdepth_out, occupancy_msb_align; /* occupancy input depth is 8 */
 } rb200_frames_yuv420;
 
 /* Patch tables of one GOF.  host pointers.  *_offset arrays have F+1 entries. */
@@ -303,6 +310,16 @@ typedef struct rb200_metrics_result {
 int rb200_metrics(rb200_ctx* ctx, const rb200_metrics_params* params, int n_pairs,
                   const rb200_cloud_view* sources, const rb200_cloud_view* reconstructs,
                   rb200_metrics_result* results /* [n_pairs] */);
+
+/* ---- multi-GPU: the one exchange step of the path.  Frames / GOFs / streams are sharded over one context
+ *      per GPU with no data-path collective; what ranks exchange is one fixed-size record of accumulators per frame.
+ *      A C / C++ host packs its results, all-gathers the records with its own communicator (ncclAllGather / MPI_Allgather
+ *      on RB200_METRICS_RECORD doubles per frame) and unpacks: the float results are derived again from the sums exactly as
+ *      QualityMetrics::compute (PCCMetrics.cpp:204-226) and operator+ (:299-332) do, so they equal the owning rank's.
+ *      (rabbit_transcoding_b200.dist.gather_metrics is the torch.distributed form of the same.) -------------------------- */
+#define RB200_METRICS_RECORD 24
+int rb200_metrics_pack(int frame, const rb200_metrics_result* result, double* record /* [RB200_METRICS_RECORD] */);
+int rb200_metrics_unpack(const double* record, const rb200_metrics_params* params, int* frame, rb200_metrics_result* out);
 
 /* PCCPointSet3::removeDuplicate(out, dropDuplicates) (PCCPointSet.cpp:169-218): lexicographic sort +
  * merge.  Returns the number of output points; out_* may be NULL to only count. */

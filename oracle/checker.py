@@ -229,6 +229,15 @@ class Reference(_Backend):
         q = (H // 2) * (W // 2)
         return out[:H * W].reshape(H, W), out[H * W:H * W + q].reshape(H // 2, W // 2), out[H * W + q:].reshape(H // 2, W // 2)
 
+    def convert_bitdepth(self, plane, bits_in, bits_out, msb_align):
+        """PCCImage<T,3>::convertBitdepth on a copy of `plane` (uint8 or uint16, 2-D)"""
+        a = np.ascontiguousarray(plane).copy()
+        f = self.lib.ref_convert_bitdepth_u16 if a.dtype == np.uint16 else self.lib.ref_convert_bitdepth_u8
+        f.argtypes = [C.c_void_p] + [C.c_int] * 5
+        H, W = a.shape
+        f(abi.ptr(a), W, H, bits_in, bits_out, 1 if msb_align else 0)
+        return a
+
     def yuv420_to_yuv444(self, y, u, v, bitdepth, filt):
         """the reference's own PCCInternalColorConverter<uint16_t>::convert("YUV420ToYUV444_<bits>_<filter>")"""
         f = getattr(self.lib, "ref_yuv420_to_yuv444", None)

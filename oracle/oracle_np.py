@@ -697,3 +697,16 @@ def yuv420_to_yuv444(y, u, v, bitdepth, filt):
     out[1] = _float_to_yuv16(_upsample(_yuv_to_float(u, True, nbyte), filt), True)
     out[2] = _float_to_yuv16(_upsample(_yuv_to_float(v, True, nbyte), filt), True)
     return out
+
+
+def convert_bitdepth(plane, bits_in, bits_out, msb_align):
+    """PCCImage<T, N>::convertBitdepth (PccLibCommon/source/PCCImage.cpp:258-299): the result is stored back into the
+    sample type T of `plane` (uint8 / uint16), i.e. truncated to it."""
+    a = np.asarray(plane)
+    diff = int(bits_in) - int(bits_out)
+    v = a.astype(np.int64)
+    if diff >= 0:
+        v = (v >> diff) if msb_align else np.minimum(v, (1 << bits_out) - 1)
+    elif msb_align:
+        v = v << (-diff)
+    return v.astype(a.dtype)  # C conversion to T: modulo 2^bits

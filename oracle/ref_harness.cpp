@@ -68,6 +68,7 @@
 #undef protected
 
 #include "rabbit_b200.h"
+#include "../rabbit-transcoding_b200/host/rb200_atlas_export.h"
 
 using namespace pcc;
 
@@ -168,98 +169,22 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
 
 }  // namespace
 
+// point local reconstruction tables for the next ref_gof_run (same layout as rb200_gof_set_plr); consumed by that run
+static const rb200_plr* g_pending_plr = nullptr;
+
 struct ref_gof {
   int                   nFrames = 0;
   std::vector<FrameOut> frames;
 };
 
-// point local reconstruction tables for the next ref_gof_run (same layout as rb200_gof_set_plr); consumed by that run
-static const rb200_plr* g_pending_plr = nullptr;
-
 extern "C" {
 
 void ref_gof_set_plr( const rb200_plr* plr ) { g_pending_plr = plr; }
 
-// Runs the reference on a whole GOF.  keep_mask bit s keeps the snapshot after stage s
-// (0 reconstruct+colour, 1 geometry smoothing, 2 colour transfer, 3 colour smoothing, 4 RGB8).
-// n_threads > 1 = frame-parallel (one PCCCodec instance per worker; frames are independent).
-// want_canonical_md5: also compute computeChecksum(true) (slow: nested std::map).
-ref_gof* ref_gof_run( const rb200_params* pp,
-                      int                 nFrames,
-                      const rb200_frames* fr,
-                      const rb200_atlas*  at,
-                      uint32_t            keep_mask,
-                      int                 n_threads,
-                      int                 want_canonical_md5,
-                      int                 quiet ) {
-  const rb200_params& p = *pp;
-  const size_t        W = p.width, H = p.height, P = p.occupancy_precision, M = p.map_count_minus1 + 1;
-  const size_t        oW = W / P, oH = H / P;
-  std::unique_ptr<QuietStdout> q;
-  if ( quiet ) { q.reset( new QuietStdout ); }
-
-  PCCContext context;
-  context.resizeAtlas( 1 );
-  context.setAtlasIndex( 0 );
-  context.allocateAtlasHLS( 1 );
-  auto& asps = context.addAtlasSequenceParameterSet();
-  asps.setPatchPrecedenceOrderFlag( p.patch_precedence_reverse != 0 );
-  auto& vps = context.addV3CParameterSet();
-  vps.init( 0, 0, (uint16_t)W, (uint16_t)H, 30, (uint32_t)( M - 1 ), false, false, true, true, p.attribute_count > 0 );
-  vps.allocateMap( 0 );
-  auto& ai = vps.getAttributeInformation( 0 );
-  ai.setAttributeCount( p.attribute_count > 0 ? 1 : 0 );
-  ai.allocate();
-  if ( p.attribute_count > 0 ) {
-    ai.setAttributeDimensionMinus1( 0, 2 );
-    ai.setAttributeDimensionPartitionsMinus1( 0, 0 );
-    ai.setAttribute2dBitdepthMinus1( 0, 7 );
-  }
-  context.setActiveVpsId( 0 );
-  context.getAtlas( 0 ).allocateVideoFrames( context, 0 );
-  context.resize( nFrames );
-
-  // ---- frame ingest (PCCImage layout: planar channels_, PCCImage.h:205-212) ----
-  auto& occVideo = context.getVideoOccupancyMap();
-  occVideo.resize( nFrames );
-  auto& geoVideos = context.getVideoGeometryMultiple();
-  const bool streams = p.multiple_streams != 0;  // PCCCodec.cpp:609-618: video m, frame f instead of video 0, frame f*M+m
-  geoVideos.resize( streams ? M : 1 );
-  for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { geoVideos[m].resize( streams ? nFrames : nFrames * M ); }
-  for ( int f = 0; f < nFrames; f++ ) {
-    auto& o = occVideo.getFrame( f );
-    o.resize( oW, oH, PCCCOLORFORMAT::YUV444 );
-    std::memcpy( o.getChannel( 0 ).data(), fr->occupancy + (size_t)f * oW * oH, oW * oH );
-    for ( size_t m = 0; m < M; m++ ) {
-      auto& g = streams ? geoVideos[m].getFrame( f ) : geoVideos[0].getFrame( f * M + m );
-      g.resize( W, H, PCCCOLORFORMAT::YUV444 );
-      std::memcpy( g.getChannel( 0 ).data(), fr->geometry + ( (size_t)f * M + m ) * W * H, W * H * 2 );
-    }
-  }
-  if ( p.attribute_count > 0 ) {
-    auto& attrVideos = context.getVideoAttributesMultiple();
-    if ( streams && attrVideos.size() < M ) { attrVideos.resize( M ); }
-    for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { attrVideos[m].resize( streams ? nFrames : nFrames * M ); }
-    for ( int f = 0; f < nFrames; f++ ) {
-      for ( size_t m = 0; m < M; m++ ) {
-        auto& a = streams ? attrVideos[m].getFrame( f ) : attrVideos[0].getFrame( f * M + m );
-        a.resize( W, H, p.attribute_rgb444 ? PCCCOLORFORMAT::RGB444 : PCCCOLORFORMAT::YUV444 );
-        a.setDeprecatedColorFormat( p.attribute_rgb444 ? 0 : 1 );  // PCCVideoDecoder.cpp:130-136
-        for ( int c = 0; c < 3; c++ ) {
-          std::memcpy( a.getChannel( c ).data(), fr->attribute + ( ( (size_t)f * M + m ) * 3 + c ) * W * H, W * H * 2 );
-        }
-      }
-    }
-  }
-
-  if ( p.point_local_reconstruction && g_pending_plr ) {  // PCCDecoder::setPointLocalReconstruction (PCCDecoder.cpp:528-541)
-    for ( int i = 0; i < g_pending_plr->n_modes; i++ ) {
-      const rb200_plr_mode&        m = g_pending_plr->modes[i];
-      PointLocalReconstructionMode mode = {m.interpolate != 0, m.filling != 0, m.min_d1, m.neighbor};
-      context.addPointLocalReconstructionMode( mode );
-    }
-  }
-  // ---- patch tables ----
+// the patch tables of every frame as PCCDecoder::createPatchFrameDataStructure leaves them in the tiles
+// (PCCDecoder.cpp:869-1238), built from the flat rows
+static void fillPatchTables( PCCContext& context, const rb200_params& p, int nFrames, const rb200_atlas* at ) {
+  const size_t W = p.width, H = p.height;
   for ( int f = 0; f < nFrames; f++ ) {
     auto& afc = context[f];
     afc.setAtlasFrameWidth( W );
@@ -346,6 +271,89 @@ ref_gof* ref_gof_run( const rb200_params* pp,
     // PCCDecoder::createPatchFrameDataStructure sets this from the syntax (PCCDecoder.cpp:1150-1238)
     tile.setTotalNumberOfRawPoints( p.use_additional_points_patch ? totalRaw : 0 );
   }
+
+}
+
+// Runs the reference on a whole GOF.  keep_mask bit s keeps the snapshot after stage s
+// (0 reconstruct+colour, 1 geometry smoothing, 2 colour transfer, 3 colour smoothing, 4 RGB8).
+// n_threads > 1 = frame-parallel (one PCCCodec instance per worker; frames are independent).
+// want_canonical_md5: also compute computeChecksum(true) (slow: nested std::map).
+ref_gof* ref_gof_run( const rb200_params* pp,
+                      int                 nFrames,
+                      const rb200_frames* fr,
+                      const rb200_atlas*  at,
+                      uint32_t            keep_mask,
+                      int                 n_threads,
+                      int                 want_canonical_md5,
+                      int                 quiet ) {
+  const rb200_params& p = *pp;
+  const size_t        W = p.width, H = p.height, P = p.occupancy_precision, M = p.map_count_minus1 + 1;
+  const size_t        oW = W / P, oH = H / P;
+  std::unique_ptr<QuietStdout> q;
+  if ( quiet ) { q.reset( new QuietStdout ); }
+
+  PCCContext context;
+  context.resizeAtlas( 1 );
+  context.setAtlasIndex( 0 );
+  context.allocateAtlasHLS( 1 );
+  auto& asps = context.addAtlasSequenceParameterSet();
+  asps.setPatchPrecedenceOrderFlag( p.patch_precedence_reverse != 0 );
+  auto& vps = context.addV3CParameterSet();
+  vps.init( 0, 0, (uint16_t)W, (uint16_t)H, 30, (uint32_t)( M - 1 ), false, false, true, true, p.attribute_count > 0 );
+  vps.allocateMap( 0 );
+  auto& ai = vps.getAttributeInformation( 0 );
+  ai.setAttributeCount( p.attribute_count > 0 ? 1 : 0 );
+  ai.allocate();
+  if ( p.attribute_count > 0 ) {
+    ai.setAttributeDimensionMinus1( 0, 2 );
+    ai.setAttributeDimensionPartitionsMinus1( 0, 0 );
+    ai.setAttribute2dBitdepthMinus1( 0, 7 );
+  }
+  context.setActiveVpsId( 0 );
+  context.getAtlas( 0 ).allocateVideoFrames( context, 0 );
+  context.resize( nFrames );
+
+  // ---- frame ingest (PCCImage layout: planar channels_, PCCImage.h:205-212) ----
+  auto& occVideo = context.getVideoOccupancyMap();
+  occVideo.resize( nFrames );
+  auto& geoVideos = context.getVideoGeometryMultiple();
+  const bool streams = p.multiple_streams != 0;  // PCCCodec.cpp:609-618: video m, frame f instead of video 0, frame f*M+m
+  geoVideos.resize( streams ? M : 1 );
+  for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { geoVideos[m].resize( streams ? nFrames : nFrames * M ); }
+  for ( int f = 0; f < nFrames; f++ ) {
+    auto& o = occVideo.getFrame( f );
+    o.resize( oW, oH, PCCCOLORFORMAT::YUV444 );
+    std::memcpy( o.getChannel( 0 ).data(), fr->occupancy + (size_t)f * oW * oH, oW * oH );
+    for ( size_t m = 0; m < M; m++ ) {
+      auto& g = streams ? geoVideos[m].getFrame( f ) : geoVideos[0].getFrame( f * M + m );
+      g.resize( W, H, PCCCOLORFORMAT::YUV444 );
+      std::memcpy( g.getChannel( 0 ).data(), fr->geometry + ( (size_t)f * M + m ) * W * H, W * H * 2 );
+    }
+  }
+  if ( p.attribute_count > 0 ) {
+    auto& attrVideos = context.getVideoAttributesMultiple();
+    if ( streams && attrVideos.size() < M ) { attrVideos.resize( M ); }
+    for ( size_t m = 0; m < ( streams ? M : 1 ); m++ ) { attrVideos[m].resize( streams ? nFrames : nFrames * M ); }
+    for ( int f = 0; f < nFrames; f++ ) {
+      for ( size_t m = 0; m < M; m++ ) {
+        auto& a = streams ? attrVideos[m].getFrame( f ) : attrVideos[0].getFrame( f * M + m );
+        a.resize( W, H, p.attribute_rgb444 ? PCCCOLORFORMAT::RGB444 : PCCCOLORFORMAT::YUV444 );
+        a.setDeprecatedColorFormat( p.attribute_rgb444 ? 0 : 1 );  // PCCVideoDecoder.cpp:130-136
+        for ( int c = 0; c < 3; c++ ) {
+          std::memcpy( a.getChannel( c ).data(), fr->attribute + ( ( (size_t)f * M + m ) * 3 + c ) * W * H, W * H * 2 );
+        }
+      }
+    }
+  }
+
+  if ( p.point_local_reconstruction && g_pending_plr ) {  // PCCDecoder::setPointLocalReconstruction (PCCDecoder.cpp:528-541)
+    for ( int i = 0; i < g_pending_plr->n_modes; i++ ) {
+      const rb200_plr_mode&        m = g_pending_plr->modes[i];
+      PointLocalReconstructionMode mode = {m.interpolate != 0, m.filling != 0, m.min_d1, m.neighbor};
+      context.addPointLocalReconstructionMode( mode );
+    }
+  }
+  fillPatchTables( context, p, nFrames, at );
 
   GeneratePointCloudParameters gpc;
   fillGpc( gpc, p );
@@ -659,6 +667,54 @@ int ref_image_set_yuv420( const int16_t* y, const int16_t* u, const int16_t* v, 
   uint16_t* o = out;
   for ( int c = 0; c < 3; c++ ) { o = std::copy( img.getChannel( c ).begin(), img.getChannel( c ).end(), o ); }
   return 0;
+}
+
+// PCCImage<T, 3>::convertBitdepth (PCCImage.cpp:258-299) on one plane, in place: T = uint16_t (geometry video,
+// PCCDecoder.cpp:148-149) or uint8_t (occupancy video, :119)
+int ref_convert_bitdepth_u16( uint16_t* plane, int W, int H, int in, int out, int msb ) {
+  PCCImage<uint16_t, 3> img;
+  img.resize( (size_t)W, (size_t)H, PCCCOLORFORMAT::YUV444 );
+  std::copy( plane, plane + (size_t)W * H, img.getChannel( 0 ).begin() );
+  img.convertBitdepth( (uint8_t)in, (uint8_t)out, msb != 0 );
+  std::copy( img.getChannel( 0 ).begin(), img.getChannel( 0 ).end(), plane );
+  return 0;
+}
+int ref_convert_bitdepth_u8( uint8_t* plane, int W, int H, int in, int out, int msb ) {
+  PCCImage<uint8_t, 3> img;
+  img.resize( (size_t)W, (size_t)H, PCCCOLORFORMAT::YUV444 );
+  std::copy( plane, plane + (size_t)W * H, img.getChannel( 0 ).begin() );
+  img.convertBitdepth( (uint8_t)in, (uint8_t)out, msb != 0 );
+  std::copy( img.getChannel( 0 ).begin(), img.getChannel( 0 ).end(), plane );
+  return 0;
+}
+
+// patch-table export (rabbit-transcoding_b200/host/rb200_atlas_export.h): the rows are turned into the reference's tile
+// containers exactly as for a GOF run, exported again, and handed back — they must come back unchanged.
+// out_* arrays are sized like the inputs; returns the number of patches, or -1 when a table does not fit.
+int ref_atlas_export_roundtrip( const rb200_params* pp, int nFrames, const rb200_atlas* at, rb200_patch* outPatches,
+                                int32_t* outPatchOffset, rb200_eom_patch* outEoms, int32_t* outEomOffset, int32_t* outMembers,
+                                rb200_raw_patch* outRaws, int32_t* outRawOffset ) {
+  PCCContext context;
+  context.resizeAtlas( 1 );
+  context.setAtlasIndex( 0 );
+  context.allocateAtlasHLS( 1 );
+  context.addAtlasSequenceParameterSet();
+  auto& vps = context.addV3CParameterSet();
+  vps.init( 0, 0, (uint16_t)pp->width, (uint16_t)pp->height, 30, (uint32_t)pp->map_count_minus1, false, false, true, true, true );
+  vps.allocateMap( 0 );
+  context.setActiveVpsId( 0 );
+  context.resize( nFrames );
+  fillPatchTables( context, *pp, nFrames, at );
+  rb200::AtlasTables t;
+  rb200::exportAtlas( context, t );
+  std::copy( t.patches.begin(), t.patches.end(), outPatches );
+  std::copy( t.patchOffset.begin(), t.patchOffset.end(), outPatchOffset );
+  if ( outEoms ) { std::copy( t.eoms.begin(), t.eoms.end(), outEoms ); }
+  if ( outEomOffset ) { std::copy( t.eomOffset.begin(), t.eomOffset.end(), outEomOffset ); }
+  if ( outMembers ) { std::copy( t.members.begin(), t.members.end(), outMembers ); }
+  if ( outRaws ) { std::copy( t.raws.begin(), t.raws.end(), outRaws ); }
+  if ( outRawOffset ) { std::copy( t.rawOffset.begin(), t.rawOffset.end(), outRawOffset ); }
+  return (int)t.patches.size();
 }
 
 int ref_abi_version( void ) { return RB200_ABI_VERSION; }

@@ -86,7 +86,9 @@ class Frames(C.Structure):
 class FramesYuv420(C.Structure):
     _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p),
                 ("geometry_sample_bytes", i32), ("attribute_sample_bytes", i32), ("attribute_bitdepth", i32),
-                ("upsampling_filter", i32), ("geometry_shift", i32), ("attribute_shift", i32)]
+                ("upsampling_filter", i32), ("geometry_shift", i32), ("attribute_shift", i32),
+                ("geometry_bitdepth_in", i32), ("geometry_bitdepth_out", i32), ("geometry_msb_align", i32),
+                ("occupancy_bitdepth_out", i32), ("occupancy_msb_align", i32)]
 
 
 class Atlas(C.Structure):
@@ -139,7 +141,7 @@ EXPORTED_SYMBOLS = [
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_debug_set_grid_shrink", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
-    "rb200_download_occupancy", "rb200_metrics", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
+    "rb200_download_occupancy", "rb200_metrics", "rb200_metrics_pack", "rb200_metrics_unpack", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
     "rb200_timing_enable", "rb200_timing_get",
 ]
 
@@ -192,6 +194,8 @@ def load_library(path=None):
     lib.rb200_download_occupancy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.rb200_metrics.argtypes = [C.c_void_p, C.POINTER(MetricsParams), C.c_int, C.POINTER(CloudView),
                                   C.POINTER(CloudView), C.POINTER(MetricsResult)]
+    lib.rb200_metrics_pack.argtypes = [C.c_int, C.POINTER(MetricsResult), C.POINTER(C.c_double)]
+    lib.rb200_metrics_unpack.argtypes = [C.POINTER(C.c_double), C.POINTER(MetricsParams), C.POINTER(C.c_int), C.POINTER(MetricsResult)]
     lib.rb200_remove_duplicates.argtypes = [C.c_void_p, C.POINTER(CloudView), C.c_int, C.c_void_p, C.c_void_p,
                                             C.POINTER(i64)]
     lib.rb200_kdtree_search.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_int, C.c_void_p, C.c_void_p]

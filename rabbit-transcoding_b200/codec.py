@@ -34,7 +34,7 @@ class RabbitError(RuntimeError):
 class PCCCodecB200:
     def __init__(self, device=0, stream=None):
         self._lib = abi.load_library()
-        if self._lib.rb200_abi_version() != 1:
+        if self._lib.rb200_abi_version() != 2:
             raise RuntimeError("rabbit_b200 ABI version mismatch")
         h = C.c_void_p()
         st = self._lib.rb200_create(device, C.byref(h))
@@ -105,6 +105,12 @@ class PCCCodecB200:
         f.upsampling_filter = native["filter"]
         f.geometry_shift = native.get("geometry_shift", 0)
         f.attribute_shift = native.get("attribute_shift", 0)
+        # PCCImage::convertBitdepth of the geometry / occupancy video (PCCDecoder.cpp:119, :148-149): (in, out, msbAlign)
+        gb, ob = native.get("geometry_bitdepth"), native.get("occupancy_bitdepth")
+        if gb is not None:
+            f.geometry_bitdepth_in, f.geometry_bitdepth_out, f.geometry_msb_align = gb
+        if ob is not None:
+            f.occupancy_bitdepth_out, f.occupancy_msb_align = ob
         self._keep = (gof, native)
         self._check(self._lib.rb200_gof_upload_yuv420(self._h, C.byref(f), C.byref(gof.atlas_struct())))
 

@@ -338,6 +338,11 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
          ( fy->attribute_bitdepth != 8 && fy->attribute_bitdepth != 10 ) || fy->upsampling_filter < 0 || fy->upsampling_filter > 7 ) {
       return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: sample bytes must be 1 or 2, bit depth 8 or 10, filter 0..7" );
     }
+    if ( fy->geometry_bitdepth_out < 0 || fy->geometry_bitdepth_out > 16 || fy->occupancy_bitdepth_out < 0 || fy->occupancy_bitdepth_out > 8 ||
+         ( fy->geometry_bitdepth_out > 0 && ( fy->geometry_bitdepth_in < 1 || fy->geometry_bitdepth_in > 16 ) ) ) {
+      // PCCImage.cpp:262-269: a bit depth beyond the sample type prints and exits
+      return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: wrong bitdepth parameter (geometry in/out 1..16, occupancy out 1..8)" );
+    }
     if ( fy->geometry_shift < 0 || fy->geometry_shift > 9 || fy->attribute_shift < 0 || fy->attribute_shift > 9 ) {
       return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: shift must be 0..9 (PCCImage.h:118-119)" );
     }
@@ -479,8 +484,10 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
       RB_CUDA( cudaMemcpyAsync( c->d_raw_attr.p, fy->attribute, rawAtt, cudaMemcpyDefault, c->stream ) );
     }
     c->stats.h2d_bytes += (int64_t)( occBytes + rawGeo + rawAtt );
+    const int gbd[3] = {fy->geometry_bitdepth_in, fy->geometry_bitdepth_out, fy->geometry_msb_align};
+    const int obd[2] = {fy->occupancy_bitdepth_out, fy->occupancy_msb_align};
     int r = rb_ingest_yuv420_impl( c, fy->geometry_sample_bytes, fy->attribute_sample_bytes, fy->attribute_bitdepth, fy->upsampling_filter,
-                                   fy->geometry_shift, fy->attribute_shift );
+                                   fy->geometry_shift, fy->attribute_shift, gbd, obd );
     if ( r ) { return r; }
   }
   RB_CUDA( c->d_patches.ensure( std::max<size_t>( 1, nPatches ) * sizeof( RbPatch ) ) );

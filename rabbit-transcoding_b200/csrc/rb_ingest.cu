@@ -174,26 +174,68 @@ __global__ void __launch_bounds__( 256 ) k_widen_u8( const uint8_t* __restrict__
   }
 }
 
-// geometry luma samples with PCCImage::set's shift -> the uint16 plane (in == out allowed for 2-byte samples)
+// PCCImage<T, N>::convertBitdepth (PccLibCommon/source/PCCImage.cpp:258-299) of one sample held in a TOut:
+// mode 0 none, 1: >> amount (msb aligned, input wider), 2: min( v, amount ) (input wider), 3: << amount (msb aligned,
+// input narrower; the result is stored back into the sample type, i.e. truncated to it)
+template <typename TOut>
+__device__ __forceinline__ TOut convert_bitdepth( int v, int mode, int amount ) {
+  if ( mode == 1 ) { return (TOut)( v >> amount ); }
+  if ( mode == 2 ) { return (TOut)min( v, amount ); }
+  if ( mode == 3 ) { return (TOut)( v << amount ); }
+  return (TOut)v;
+}
+
+// geometry luma samples with PCCImage::set's shift, then convertBitdepth -> the uint16 plane (in == out allowed for
+// 2-byte samples)
 template <typename T>
-__global__ void __launch_bounds__( 256 ) k_geometry_set( const T* src, uint16_t* dst, int64_t n, int shift ) {
+__global__ void __launch_bounds__( 256 ) k_geometry_set( const T* src, uint16_t* dst, int64_t n, int shift, int mode, int amount ) {
   for ( int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) {
-    dst[i] = (uint16_t)image_set( (int)src[i], shift );
+    dst[i] = convert_bitdepth<uint16_t>( (uint16_t)image_set( (int)src[i], shift ), mode, amount );
+  }
+}
+// the occupancy video in place (PCCDecoder.cpp:119)
+__global__ void __launch_bounds__( 256 ) k_occupancy_convert( uint8_t* v, int64_t n, int mode, int amount ) {
+  for ( int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) {
+    v[i] = convert_bitdepth<uint8_t>( v[i], mode, amount );
   }
 }
 
 }  // namespace
 
 // raw decoder planes (already in c->d_raw_geo / c->d_raw_attr) -> c->d_geometry / c->d_attribute
-int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter, int geo_shift, int attr_shift ) {
+// (mode, amount) of convert_bitdepth for convertBitdepth( in, out, msbAlign ) on samples of `bits` bits
+static void bitdepth_mode( int in, int out, int msb, int& mode, int& amount ) {
+  mode = amount = 0;
+  if ( out <= 0 ) { return; }
+  const int diff = in - out;
+  if ( diff >= 0 ) {
+    mode   = msb ? 1 : 2;
+    amount = msb ? diff : ( 1 << out ) - 1;
+  } else if ( msb ) {
+    mode   = 3;
+    amount = -diff;
+  }
+  if ( mode == 1 && amount == 0 ) { mode = 0; }
+}
+
+int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter, int geo_shift, int attr_shift,
+                           const int* geo_bd, const int* occ_bd ) {
   const size_t  plane = (size_t)c->W * c->H;
   const int64_t nGeo  = (int64_t)c->F * c->M * plane;
-  if ( geo_bytes == 1 && geo_shift == 0 ) {
+  int           gm, ga, om, oa;
+  bitdepth_mode( geo_bd[0], geo_bd[1], geo_bd[2], gm, ga );
+  bitdepth_mode( 8, occ_bd[0], occ_bd[1], om, oa );
+  if ( gm == 2 && ga >= 65535 ) { gm = 0; }  // min( v, 2^16 - 1 ) on 16-bit samples
+  if ( om == 2 && oa >= 255 ) { om = 0; }
+  if ( om ) {
+    RB_LAUNCH( "occupancy_convert", k_occupancy_convert, 148 * 4, 256, 0, c->d_occ_video.as<uint8_t>(), (int64_t)c->F * c->oW * c->oH, om, oa );
+  }
+  if ( geo_bytes == 1 && geo_shift == 0 && gm == 0 ) {
     RB_LAUNCH( "geometry_widen", k_widen_u8, rb_div_up( nGeo, 256 * 16 ), 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo );
   } else if ( geo_bytes == 1 ) {
-    RB_LAUNCH( "geometry_set", k_geometry_set<uint8_t>, 148 * 8, 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift );
-  } else if ( geo_shift > 0 ) {  // 2-byte samples were copied straight into d_geometry
-    RB_LAUNCH( "geometry_set", k_geometry_set<uint16_t>, 148 * 8, 256, 0, c->d_geometry.as<uint16_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift );
+    RB_LAUNCH( "geometry_set", k_geometry_set<uint8_t>, 148 * 8, 256, 0, c->d_raw_geo.as<uint8_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift, gm, ga );
+  } else if ( geo_shift > 0 || gm ) {  // 2-byte samples were copied straight into d_geometry
+    RB_LAUNCH( "geometry_set", k_geometry_set<uint16_t>, 148 * 8, 256, 0, c->d_geometry.as<uint16_t>(), c->d_geometry.as<uint16_t>(), nGeo, geo_shift, gm, ga );
   }
   if ( c->P.attribute_count > 0 ) {
     const int    nbyte  = attr_bitdepth == 8 ? 1 : 2;

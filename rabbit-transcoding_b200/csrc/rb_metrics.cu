@@ -1334,4 +1334,55 @@ int rb200_remove_duplicates( rb200_ctx* c, const rb200_cloud_view* in, int drop,
   return RB200_OK;
 }
 
+// ---- the one exchange step of the path: fixed-size records of the per-frame accumulators ----
+// record layout (RB200_METRICS_RECORD doubles): [0] frame, then per direction (q1, q2) {sse_c2c, sse_c2p, sse_color[3],
+// max_c2c, max_c2p, num}, then source_points, source_after_dedup, rec_points, rec_after_dedup, tie_overflow, 0, 0
+int rb200_metrics_pack( int frame, const rb200_metrics_result* r, double* record ) {
+  if ( !r || !record ) { return RB200_ERR_INVALID; }
+  int k       = 0;
+  record[k++] = (double)frame;
+  for ( const rb200_quality* q : {&r->q1, &r->q2} ) {
+    record[k++] = q->sse_c2c, record[k++] = q->sse_c2p;
+    for ( int c = 0; c < 3; c++ ) { record[k++] = q->sse_color[c]; }
+    record[k++] = q->max_c2c, record[k++] = q->max_c2p, record[k++] = (double)q->num;
+  }
+  record[k++] = (double)r->source_points, record[k++] = (double)r->source_after_dedup;
+  record[k++] = (double)r->rec_points, record[k++] = (double)r->rec_after_dedup, record[k++] = (double)r->tie_overflow;
+  while ( k < RB200_METRICS_RECORD ) { record[k++] = 0.0; }
+  return RB200_OK;
+}
+
+// the float results are derived again from the accumulators exactly as QualityMetrics::compute (PCCMetrics.cpp:204-226)
+// and QualityMetrics::operator+ (:299-332) do, so every rank ends with the numbers the owning rank computed
+int rb200_metrics_unpack( const double* record, const rb200_metrics_params* mp, int* frame, rb200_metrics_result* out ) {
+  if ( !record || !mp || !out ) { return RB200_ERR_INVALID; }
+  memset( out, 0, sizeof( *out ) );
+  int k = 0;
+  if ( frame ) { *frame = (int)record[0]; }
+  k = 1;
+  rb200_quality* qs[2] = {&out->q1, &out->q2};
+  for ( int d = 0; d < 2; d++ ) {
+    Acc a{};
+    a.sse_c2c = (unsigned long long)record[k], a.sum_c2p = record[k + 1];
+    for ( int c = 0; c < 3; c++ ) { a.sum_col[c] = record[k + 2 + c]; }
+    const double maxC2c = record[k + 5], maxC2p = record[k + 6];
+    const int64_t num   = (int64_t)record[k + 7];
+    a.max_c2c           = (unsigned long long)maxC2c;
+    memcpy( &a.max_c2p_bits, &maxC2p, 8 );
+    // sse_c2p travels as the finished sum: keep it whatever the normals were
+    rb200_metrics_params m2 = *mp;
+    finish_quality( *qs[d], a, num, m2, true );
+    qs[d]->max_c2c = maxC2c;
+    if ( mp->compute_hausdorff && mp->compute_c2c ) {
+      qs[d]->c2c_hausdorff      = float( maxC2c );
+      qs[d]->c2c_hausdorff_psnr = get_psnr( qs[d]->c2c_hausdorff, mp->resolution, 3 );
+    }
+    k += 8;
+  }
+  combine_quality( out->qf, out->q1, out->q2, *mp );
+  out->source_points = (int64_t)record[k], out->source_after_dedup = (int64_t)record[k + 1];
+  out->rec_points = (int64_t)record[k + 2], out->rec_after_dedup = (int64_t)record[k + 3], out->tie_overflow = (int32_t)record[k + 4];
+  return RB200_OK;
+}
+
 }  // extern "C"

@@ -68,6 +68,7 @@
 #undef protected
 
 #include "rabbit_b200.h"
+#include "rb200_atlas_export.h"
 
 using namespace pcc;
 
@@ -225,44 +226,10 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
       }
     }
   }
-  std::vector<rb200_patch>     patches;
-  std::vector<rb200_eom_patch> eoms;
-  std::vector<rb200_raw_patch> raws;
-  std::vector<int32_t>         pOff{0}, eOff{0}, rOff{0}, members;
-  for ( size_t f = 0; f < F; f++ ) {
-    auto& tile = context[f].getTile( 0 );
-    for ( auto& s : tile.getPatches() ) {
-      rb200_patch d{};
-      d.u0 = (int)s.getU0(), d.v0 = (int)s.getV0(), d.size_u0 = (int)s.getSizeU0(), d.size_v0 = (int)s.getSizeV0();
-      d.u1 = (int)s.getU1(), d.v1 = (int)s.getV1(), d.d1 = (int)s.getD1();
-      d.normal_axis = (int)s.getNormalAxis(), d.tangent_axis = (int)s.getTangentAxis(), d.bitangent_axis = (int)s.getBitangentAxis();
-      d.projection_mode = (int)s.getProjectionMode(), d.orientation = (int)s.getPatchOrientation();
-      d.lod_x = (int)s.getLodScaleX(), d.lod_y = (int)s.getLodScaleY();
-      d.axis_of_additional_plane = (int)s.getAxisOfAdditionalPlane();
-      d.size2d_x_px = (int)s.getPatchSize2DXInPixel(), d.size2d_y_px = (int)s.getPatchSize2DYInPixel();
-      patches.push_back( d );
-    }
-    pOff.push_back( (int32_t)patches.size() );
-    for ( auto& s : tile.getEomPatches() ) {
-      rb200_eom_patch e{};
-      e.u0 = (int)s.u0_, e.v0 = (int)s.v0_, e.member_begin = (int)members.size(), e.member_count = (int)s.memberPatches_.size();
-      e.eom_count = (int)s.eomCount_;
-      for ( auto m : s.memberPatches_ ) { members.push_back( (int32_t)m ); }
-      eoms.push_back( e );
-    }
-    eOff.push_back( (int32_t)eoms.size() );
-    for ( auto& s : tile.getRawPointsPatches() ) {
-      rb200_raw_patch r{};
-      r.u0 = (int)s.u0_, r.v0 = (int)s.v0_, r.size_u0 = (int)s.sizeU0_, r.size_v0 = (int)s.sizeV0_;
-      r.u1 = (int)s.u1_, r.v1 = (int)s.v1_, r.d1 = (int)s.d1_, r.num_points = (int)s.getNumberOfRawPoints();
-      raws.push_back( r );
-    }
-    rOff.push_back( (int32_t)raws.size() );
-  }
-  if ( members.empty() ) { members.push_back( 0 ); }
+  rb200::AtlasTables tables;  // the atlas layer's patches as flat rows (rb200_atlas_export.h)
+  rb200::exportAtlas( context, tables );
   rb200_frames fr{occ, geo, att};
-  rb200_atlas  at{patches.data(), pOff.data(), eoms.empty() ? nullptr : eoms.data(), eOff.data(), members.data(),
-                  raws.empty() ? nullptr : raws.data(), rOff.data()};
+  rb200_atlas  at = tables.view();
   ensureContext();
   RB( rb200_gof_begin( g.ctx, &p, (int)F ) );
   RB( rb200_gof_upload( g.ctx, &fr, &at ) );

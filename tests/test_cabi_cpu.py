@@ -23,7 +23,7 @@ def test_header_symbols_exported(rb, lib):
     assert declared == set(rb.abi.EXPORTED_SYMBOLS), declared ^ set(rb.abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by librabbit_b200.so"
-    assert lib.rb200_abi_version() == 1
+    assert lib.rb200_abi_version() == 2
 
 
 def test_struct_sizes_match_header(rb):

@@ -78,3 +78,29 @@ def test_psnr_matches_reference_formula(rb):
     v = rb.dist.psnr(np.float32(0.163), 1023.0, 3)
     assert abs(float(v) - 10 * np.log10(3 * 1023.0 ** 2 / 0.163)) < 1e-4
     assert np.isinf(rb.dist.psnr(0.0, 1023.0, 3))
+
+
+def test_c_abi_pack_unpack_equals_python_gather(rb):
+    """rb200_metrics_pack / rb200_metrics_unpack (the C form of the exchange record, for a C++ host with its own
+    communicator) derive the same floats from the accumulators as rabbit_transcoding_b200.dist does"""
+    import ctypes as C
+    lib = rb.abi.load_library()
+    mp = rb.metrics.default_parameters(resolution=1023.0)
+    for frame in (0, 3, 17):
+        r = _fake_result(rb, frame)
+        rec = (C.c_double * 24)()
+        assert lib.rb200_metrics_pack(frame, C.byref(r), rec) == 0
+        assert list(rec)[:len(rb.dist.pack_result(frame, r))] == rb.dist.pack_result(frame, r)  # the same record layout
+        out, fr = rb.abi.MetricsResult(), C.c_int(-1)
+        assert lib.rb200_metrics_unpack(rec, C.byref(mp), C.byref(fr), C.byref(out)) == 0
+        assert fr.value == frame and out.q1.num == r.q1.num and out.rec_after_dedup == r.rec_after_dedup
+        for q_c, q_in in ((out.q1, r.q1), (out.q2, r.q2)):
+            want = rb.dist.quality_from_sums(q_in.sse_c2c, q_in.sse_c2p, list(q_in.sse_color), q_in.num, 1023.0)
+            assert np.float32(q_c.c2c_mse) == want["c2c_mse"] and np.float32(q_c.c2c_psnr) == want["c2c_psnr"]
+            assert np.float32(q_c.c2p_mse) == want["c2p_mse"] and np.float32(q_c.c2p_psnr) == want["c2p_psnr"]
+            for k in range(3):
+                assert np.float32(q_c.color_psnr[k]) == want["color_psnr"][k]
+        a = rb.dist.quality_from_sums(r.q1.sse_c2c, r.q1.sse_c2p, list(r.q1.sse_color), r.q1.num, 1023.0)
+        b = rb.dist.quality_from_sums(r.q2.sse_c2c, r.q2.sse_c2p, list(r.q2.sse_color), r.q2.num, 1023.0)
+        sym = rb.dist.symmetric(a, b)
+        assert np.float32(out.qf.c2c_psnr) == sym["c2c_psnr"] and np.float32(out.qf.c2p_psnr) == sym["c2p_psnr"]

@@ -130,3 +130,55 @@ def test_ingest_applies_image_set_shift(rb, codec, shift):
     ys, us, vs = (oracle_np.image_set(a, shift) for a in (y, u, v))
     assert np.array_equal(geo, ys)
     assert np.array_equal(att, oracle_np.yuv420_to_yuv444(ys, us, vs, bd, 3))
+
+
+@pytest.mark.parametrize("case", [(10, 8, True), (10, 8, False), (8, 10, True), (12, 10, False), (10, 16, True)],
+                         ids=lambda c: f"{c[0]}to{c[1]}_{'msb' if c[2] else 'lsb'}")
+def test_ingest_applies_convert_bitdepth_to_geometry(rb, codec, checker_backend, case):
+    """PCCImage::convertBitdepth runs on every decoded geometry video (PCCDecoder.cpp:148-149); here it is fused into the
+    geometry ingest kernel and must equal the reference's own function on the same plane"""
+    bi, bo, msb = case
+    rng = np.random.default_rng(31 + bi + bo)
+    W, H = 96, 64
+    y = rng.integers(0, 1 << bi, (H, W)).astype(np.uint16)
+    y[0, :3] = [0, (1 << bi) - 1, 1 << (bi - 1)]
+    g, p = _params(rb, W, H)
+    g.occupancy = np.zeros((1, H // p.occupancy_precision, W // p.occupancy_precision), np.uint8)
+    g.patches = g.patches[:0]
+    g.patch_offset = np.zeros(2, np.int32)
+    native = {"bitdepth": 8, "filter": 0, "geometry": np.ascontiguousarray(y).reshape(1, 1, H, W),
+              "attribute": np.zeros((1, 1, H * W * 3 // 2), np.uint8), "geometry_bitdepth": (bi, bo, 1 if msb else 0)}
+    codec.uploadGofYuv420(g, native)
+    geo, _ = codec.getPlanes(0, 0)
+    assert np.array_equal(geo, checker_backend.convert_bitdepth(y, bi, bo, msb))
+
+
+def test_ingest_convert_bitdepth_of_the_occupancy_video(rb, codec, checker_backend):
+    """the occupancy video goes through convertBitdepth( 8, occupancy2DBitdepth, msbAlign ) (PCCDecoder.cpp:119) before
+    generateOccupancyMap: a decoder handing over 8-bit msb-aligned samples of a 1-bit map decodes to the same clouds as the
+    reference fed with the plane its own convertBitdepth produces"""
+    kw = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=55, transfer_filter=0)
+    g = rb.synthetic.generate_gof(**kw)
+    native = rb.synthetic.to_decoder_planes(g, bitdepth=8, filt=0)
+    raw_occ = (g.occupancy.astype(np.uint8) << 7) | np.random.default_rng(3).integers(0, 64, g.occupancy.shape).astype(np.uint8)
+    want_occ = np.stack([checker_backend.convert_bitdepth(o, 8, 1, True) for o in raw_occ])
+    assert np.array_equal(want_occ, g.occupancy)
+    # expected attribute planes: the reference's own conversion of the native frames
+    F, M, H, W = g.n_frames, g.params.map_count_minus1 + 1, g.params.height, g.params.width
+    fr = native["attribute"].reshape(F, M, -1)
+    q = (H // 2) * (W // 2)
+    conv = np.zeros((F, M, 3, H, W), np.uint16)
+    for f in range(F):
+        for m in range(M):
+            conv[f, m] = checker_backend.yuv420_to_yuv444(fr[f, m, :H * W].reshape(H, W), fr[f, m, H * W:H * W + q].reshape(H // 2, W // 2),
+                                                          fr[f, m, H * W + q:].reshape(H // 2, W // 2), 8, 0)
+    g.attribute = np.ascontiguousarray(conv.reshape(g.attribute.shape))
+    ref = checker_backend.run_gof(g, keep=("rgb8",))
+    g2 = rb.synthetic.generate_gof(**kw)
+    g2.occupancy = np.ascontiguousarray(raw_occ)
+    native["occupancy_bitdepth"] = (1, 1)
+    codec.uploadGofYuv420(g2, native)
+    codec.decodeGof()
+    counts = codec.frameCounts()
+    for f in range(F):
+        assert_cloud_equal(codec.getPointCloud(f, counts), ref.cloud(f, "rgb8"), f"frame {f}")

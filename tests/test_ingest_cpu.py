@@ -64,3 +64,24 @@ def test_image_set_restatement_matches_reference():
         got = ref.image_set_yuv420(y, u, v, shift)
         for a, b in zip(got, (y, u, v)):
             assert np.array_equal(a, oracle_np.image_set(b, shift)), f"shift {shift}"
+
+
+BITDEPTH_CASES = [(10, 8, True), (10, 8, False), (8, 10, True), (8, 10, False), (8, 8, True), (16, 10, False), (10, 16, True),
+                  (12, 10, True)]
+
+
+def test_convert_bitdepth_restatement_matches_reference():
+    """PCCImage::convertBitdepth (PCCImage.cpp:258-299) as run on every geometry video (PCCDecoder.cpp:148-149) and on
+    the occupancy video (:119): shift / clamp / left shift with truncation to the sample type"""
+    from oracle import checker, oracle_np
+    if not checker.have_reference():
+        pytest.skip("oracle/_ref not built")
+    ref = checker.Reference()
+    rng = np.random.default_rng(9)
+    for bi, bo, msb in BITDEPTH_CASES:
+        g = rng.integers(0, 1 << min(bi, 16), (8, 24)).astype(np.uint16)
+        g[0, :3] = [0, (1 << min(bi, 16)) - 1, 1 << (min(bi, 16) - 1)]
+        assert np.array_equal(ref.convert_bitdepth(g, bi, bo, msb), oracle_np.convert_bitdepth(g, bi, bo, msb)), (bi, bo, msb)
+    for bo, msb in ((1, False), (1, True), (4, True), (8, False), (8, True)):
+        o = rng.integers(0, 256, (8, 8)).astype(np.uint8)
+        assert np.array_equal(ref.convert_bitdepth(o, 8, bo, msb), oracle_np.convert_bitdepth(o, 8, bo, msb)), (bo, msb)
