@@ -51,7 +51,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--frames", type=int, default=32, help="frames per GOF per GPU")
-    ap.add_argument("--workload", default="vox10", choices=("vox10", "vox11", "tiny"))
+    ap.add_argument("--workload", default="vox10", choices=("vox10", "vox11", "vox11_eom", "streams", "tiny"),
+                    help="vox10: BASELINE configs[1]/[2] (default); vox11 / vox11_eom: configs[3] (use --frames 38 on 8 GPUs "
+                         "for the 300-frame sequence); streams: configs[4], 8 vox10 streams at rates r1-r5")
+    ap.add_argument("--distinct-frames", type=int, default=0,
+                    help="generate only this many distinct frames and repeat them up to --frames (0 = all distinct)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-metrics", action="store_true", help="skip the D1/D2 metrics leg")
@@ -65,18 +69,30 @@ WORKLOADS = {
     # max_depth: patches stay inside the range of the 8-bit geometry video (geometryNominal2dBitdepth 8, maxAllowedDepth)
     "vox10": dict(bitdepth=10, width=1280, scale=0.68, height_blocks=80, max_depth=249),
     "vox11": dict(bitdepth=11, width=2560, scale=0.62, height_blocks=176, max_depth=249),
+    # the lossless-style variant of configs[3]: occupancy precision 1, enhanced occupancy map code, one EOM patch per
+    # frame, geometry / colour smoothing off as in cfg/common/ctc-common-lossless-geometry-attribute.cfg
+    "vox11_eom": dict(bitdepth=11, width=2560, scale=0.62, height_blocks=208, max_depth=249, eom=True,
+                      geometry_smoothing=False, color_smoothing=False),
     "tiny": dict(bitdepth=8, width=256, scale=0.9, height_blocks=32),
 }
 
 
-def make_gof(rb, args, rank, world, frames=None):
+def make_gof(rb, args, rank, world, frames=None, extra=None):
     kw = dict(WORKLOADS[args.workload])
     # the decoder-faithful Rec-1 sequence: every profile that smooths the geometry also re-transfers the attributes
     # (PCCDecoder.cpp:434-465); BASELINE.json configs[1] without the re-transfer is reported as config.without_retransfer
     kw.update(seed=0x0AB817 + 1000 * rank, transfer_filter=1)  # Rec-1: attrTransferFilterType_ = 1 (PCCDecoderParameters.cpp:125-134)
+    if kw.get("eom"):
+        kw["transfer_filter"] = 0
+    kw.update(extra or {})
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    workers = max(1, min(frames or args.frames, min(ncpu, (os.cpu_count() or 1) // max(1, world))))
-    return rb.synthetic.generate_gof_parallel(frames or args.frames, workers=workers, **kw)
+    n = frames or args.frames
+    distinct = min(n, args.distinct_frames) if getattr(args, "distinct_frames", 0) else n
+    workers = max(1, min(distinct, min(ncpu, (os.cpu_count() or 1) // max(1, world))))
+    g = rb.synthetic.generate_gof_parallel(distinct, workers=workers, **kw)
+    if distinct < n:  # the distinct frames repeated cyclically (throughput runs of long sequences)
+        g = rb.synthetic.concat_gofs([rb.synthetic.slice_gof(g, f % distinct, f % distinct + 1) for f in range(n)])
+    return g
 
 
 class ClockSampler:
@@ -549,6 +565,107 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# BASELINE.json configs[4]: 8 concurrent vox10 streams at the CTC rate points r1..r5 (cfg/rate/ctc-r1.cfg .. ctc-r5.cfg):
+# r1-r4 code the occupancy map at precision 4, r5 at precision 2; lower rates carry more coding noise
+STREAM_RATES = [dict(name="r1", occupancy_precision=4, noise_fraction=0.22, color_noise=14.0),
+                dict(name="r2", occupancy_precision=4, noise_fraction=0.16, color_noise=10.0),
+                dict(name="r3", occupancy_precision=4, noise_fraction=0.10, color_noise=6.0),
+                dict(name="r4", occupancy_precision=4, noise_fraction=0.06, color_noise=4.0),
+                dict(name="r5", occupancy_precision=2, noise_fraction=0.03, color_noise=2.0)]
+
+
+def run_streams(args):
+    """8 streams sharded whole over the ranks (rabbit_transcoding_b200.dist.shard_streams); every rank runs the transcode
+    loop (planes in, Rec-1 decode, D1 + D2 + colour out) on the GOFs of its streams, interleaved GOF by GOF"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rabbit_transcoding_b200 as rb
+    rank, world, local = (int(os.environ.get(k, "0")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    world = max(world, 1)
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_streams = 8
+    mine = rb.dist.shard_streams(n_streams, world, rank)
+    args.workload = "vox10"
+    lanes = []
+    for s_ in mine:
+        rate = STREAM_RATES[s_ % len(STREAM_RATES)]
+        extra = {k: v for k, v in rate.items() if k != "name"}
+        extra["seed"] = 0x0AB817 + 77 * s_
+        g = make_gof(rb, args, rank, world, extra=extra)
+        native = rb.synthetic.to_decoder_planes(g, bitdepth=8, filt=0)
+        for k in ("geometry", "attribute"):
+            native[k] = torch.from_numpy(native[k]).pin_memory().numpy()
+        g.occupancy = torch.from_numpy(g.occupancy).pin_memory().numpy()
+        cx = rb.codec.PCCCodecB200(device=local)
+        mx = rb.metrics.PCCMetricsB200(cx)
+        mp = rb.metrics.default_parameters(resolution=float((1 << g.params.geometry_bitdepth_3d) - 1))
+        mx.setParameters(mp)
+        src = [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in g.sources]
+        lanes.append(dict(stream=s_, rate=rate["name"], gof=g, native=native, codec=cx, met=mx, src=src, ms=0.0, pts=0))
+    stream = torch.cuda.current_stream()
+    for L in lanes:
+        L["codec"].setStream(stream.cuda_stream)
+
+    def step(L):
+        L["codec"].uploadGofYuv420(L["gof"], L["native"])
+        L["codec"].decodeGof()
+        L["met"].results_.clear()
+        return L["met"].compute(L["src"], [None] * L["gof"].n_frames, L["src"])
+    for L in lanes:  # warm-up
+        for _ in range(2):
+            L["res"] = step(L)
+        L["pts"] = sum(c.total for c in L["codec"].frameCounts())
+    steps = max(2, min(args.steps, 6))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        for L in lanes:  # GOFs of the rank's streams interleaved
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            L["res"] = step(L)
+            b.record(stream)
+            L.setdefault("ev", []).append((a, b))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_rank = e0.elapsed_time(e1)
+    per = [dict(stream=L["stream"], rate=L["rate"], rank=rank, occupancy_precision=int(L["gof"].params.occupancy_precision),
+                points_per_gof=int(L["pts"]), ms_per_gof=round(sum(a.elapsed_time(b) for a, b in L["ev"]) / steps, 3),
+                mpts_s=round(L["pts"] * steps / (sum(a.elapsed_time(b) for a, b in L["ev"]) * 1e-3) / 1e6, 2),
+                d1_psnr_mean_db=round(float(np.mean([r.qf.c2c_psnr for r in L["res"]])), 4)) for L in lanes]
+    allper = [per]
+    ms_all = [ms_rank]
+    if world > 1:
+        allper = [None] * world
+        dist.all_gather_object(allper, per)
+        ms_all = [None] * world
+        dist.all_gather_object(ms_all, ms_rank)
+    if rank == 0:
+        flat = sorted((x for p_ in allper for x in p_), key=lambda x: x["stream"])
+        pts = sum(x["points_per_gof"] for x in flat) * steps
+        line = {"metric": METRIC, "value": round(pts / (max(ms_all) * 1e-3) / 1e6, 2), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": 2, "ms_per_step": round(max(ms_all) / steps, 3), "higher_is_better": True, "scaling": "strong",
+                "data": "synthetic", "dtype": "i16/u16 (+f64 filters)",
+                "config": {"workload": f"8 concurrent synthetic vox10 streams at rates r1-r5 ({args.frames}-frame GOFs), whole "
+                                       "streams sharded over the GPUs; per GOF: decoder-native planes in, Rec-1 decode, "
+                                       "D1 + D2 + colour metrics out", "streams": n_streams},
+                "per_stream": flat}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
+    for L in lanes:
+        L["codec"].close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def C_sizeof_result(rb):
     import ctypes
     return ctypes.sizeof(rb.abi.MetricsResult)
@@ -625,5 +742,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "streams":
+        run_streams(a)
     else:
         run_b200(a)

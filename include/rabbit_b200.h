@@ -153,6 +153,26 @@ typedef struct rb200_frames_yuv420 {
   int32_t occupancy_bitdepth_out, occupancy_msb_align; /* occupancy input depth is 8 */
 } rb200_frames_yuv420;
 
+/* Decoder surfaces of one GOF as a hardware decoder leaves them (libav AV_PIX_FMT_CUDA frames of NVDEC in RABBIT's
+ * --useCuda path, PccLibTranscoder/source/PCCTranscoder.cpp:693-704, :791-817: data[0] = luma, data[1] = interleaved
+ * chroma, linesize[] = pitch): one surface per video frame, pitched, NV12 (1-byte samples) or P010 / P016 (2-byte samples,
+ * value in the high bits).  Pointers must be device memory or device-accessible (pinned) host memory: the planes are
+ * gathered by a kernel, so a device-resident decode has NO host-to-device traffic for the planes. */
+typedef struct rb200_surface {
+  const void* luma;     /* rows of `pitch_luma` bytes                                                              */
+  const void* chroma;   /* interleaved U, V rows (H/2 rows of W samples) of `pitch_chroma` bytes; NULL: luma only   */
+  int32_t     pitch_luma, pitch_chroma;
+} rb200_surface;
+typedef struct rb200_frames_nv12 {
+  const rb200_surface* occupancy; /* [F]     luma = occupancy video frame f, (W/p) x (H/p), always 1-byte samples    */
+  const rb200_surface* geometry;  /* [F][M]  luma = geometry frame                                                   */
+  const rb200_surface* attribute; /* [F][M]  luma + chroma of the 4:2:0 attribute frame; NULL if none                */
+  int32_t sample_bytes;           /* geometry and attribute samples: 1 (NV12) or 2 (P010 / P016)                     */
+  int32_t sample_lsb_shift;       /* 2-byte samples are shifted right by this on read (P010: 6)                      */
+  /* the conversion parameters of rb200_frames_yuv420; its pointers and sample-byte fields are ignored */
+  rb200_frames_yuv420 conversion;
+} rb200_frames_nv12;
+
 /* Patch tables of one GOF.  host pointers.  *_offset arrays have F+1 entries. */
 typedef struct rb200_atlas {
   const rb200_patch*     patches;
@@ -225,6 +245,9 @@ int rb200_gof_set_plr(rb200_ctx* ctx, const rb200_plr* plr);
 /* the same with decoder-native planes: replaces PCCImage::set (PCCImage.h:97-138) + the inverse colour conversion of
  * PCCVideoDecoder (PCCVideoDecoder.cpp:125-146, :365; PCCInternalColorConverter.cpp:456-486, :596-611, :669-695, :582-594) */
 int rb200_gof_upload_yuv420(rb200_ctx* ctx, const rb200_frames_yuv420* frames, const rb200_atlas* atlas);
+/* the same from pitched NV12 / P010 decoder surfaces (host arrays of rb200_surface; the surfaces themselves in device or
+ * pinned memory) */
+int rb200_gof_upload_nv12(rb200_ctx* ctx, const rb200_frames_nv12* frames, const rb200_atlas* atlas);
 /* the planes the reconstruction reads as they sit in HBM after an upload: geometry [H][W], attribute [3][H][W] uint16 of
  * frame `frame`, map `map` (either pointer may be NULL); used to check the ingest conversion */
 int rb200_download_planes(rb200_ctx* ctx, int frame, int map, uint16_t* geometry, uint16_t* attribute);

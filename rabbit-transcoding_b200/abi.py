@@ -91,6 +91,16 @@ class FramesYuv420(C.Structure):
                 ("occupancy_bitdepth_out", i32), ("occupancy_msb_align", i32)]
 
 
+class Surface(C.Structure):
+    """rb200_surface: one pitched decoder surface (luma + interleaved chroma)"""
+    _fields_ = [("luma", C.c_void_p), ("chroma", C.c_void_p), ("pitch_luma", i32), ("pitch_chroma", i32)]
+
+
+class FramesNv12(C.Structure):
+    _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p),
+                ("sample_bytes", i32), ("sample_lsb_shift", i32), ("conversion", FramesYuv420)]
+
+
 class Atlas(C.Structure):
     _fields_ = [("patches", C.c_void_p), ("patch_offset", C.c_void_p),
                 ("eom_patches", C.c_void_p), ("eom_offset", C.c_void_p), ("eom_members", C.c_void_p),
@@ -137,7 +147,7 @@ class LaunchStats(C.Structure):
 # every symbol include/rabbit_b200.h declares; tests check the .so exports all of them
 EXPORTED_SYMBOLS = [
     "rb200_abi_version", "rb200_create", "rb200_destroy", "rb200_error_string", "rb200_set_stream",
-    "rb200_synchronize", "rb200_host_alloc", "rb200_host_free", "rb200_occupancy_map", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_set_plr", "rb200_gof_upload_yuv420", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
+    "rb200_synchronize", "rb200_host_alloc", "rb200_host_free", "rb200_occupancy_map", "rb200_gof_begin", "rb200_gof_upload", "rb200_gof_set_plr", "rb200_gof_upload_yuv420", "rb200_gof_upload_nv12", "rb200_download_planes", "rb200_reconstruct", "rb200_smooth_geometry",
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_debug_set_grid_shrink", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
@@ -179,6 +189,7 @@ def load_library(path=None):
     lib.rb200_gof_upload.argtypes = [C.c_void_p, C.POINTER(Frames), C.POINTER(Atlas)]
     lib.rb200_gof_set_plr.argtypes = [C.c_void_p, C.POINTER(Plr)]
     lib.rb200_gof_upload_yuv420.argtypes = [C.c_void_p, C.POINTER(FramesYuv420), C.POINTER(Atlas)]
+    lib.rb200_gof_upload_nv12.argtypes = [C.c_void_p, C.POINTER(FramesNv12), C.POINTER(Atlas)]
     lib.rb200_download_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     for n in ("rb200_reconstruct", "rb200_smooth_geometry", "rb200_transfer_colors", "rb200_smooth_color",
               "rb200_convert_rgb8", "rb200_decode_gof"):

@@ -114,6 +114,33 @@ class PCCCodecB200:
         self._keep = (gof, native)
         self._check(self._lib.rb200_gof_upload_yuv420(self._h, C.byref(f), C.byref(gof.atlas_struct())))
 
+    def uploadGofNv12(self, gof, surfaces):
+        """pitched NV12 / P010 decoder surfaces in device (or pinned) memory — what NVDEC leaves behind in RABBIT's --useCuda
+        path: surfaces = dict(occupancy=[F x (luma_ptr, pitch)], geometry=[F*M x (luma_ptr, pitch)],
+        attribute=[F*M x (luma_ptr, pitch, chroma_ptr, pitch)], sample_bytes, sample_lsb_shift, bitdepth, filter, ...)"""
+        self.beginGof(gof.params, gof.n_frames)
+
+        def table(rows):
+            arr = (abi.Surface * len(rows))()
+            for i, r in enumerate(rows):
+                arr[i].luma, arr[i].pitch_luma = r[0], r[1]
+                if len(r) > 2:
+                    arr[i].chroma, arr[i].pitch_chroma = r[2], r[3]
+            return arr
+        occ, geo = table(surfaces["occupancy"]), table(surfaces["geometry"])
+        att = table(surfaces["attribute"]) if surfaces.get("attribute") else None
+        f = abi.FramesNv12()
+        f.occupancy, f.geometry = C.cast(occ, C.c_void_p), C.cast(geo, C.c_void_p)
+        f.attribute = C.cast(att, C.c_void_p) if att is not None else None
+        f.sample_bytes = surfaces.get("sample_bytes", 1)
+        f.sample_lsb_shift = surfaces.get("sample_lsb_shift", 0)
+        f.conversion.attribute_bitdepth = surfaces.get("bitdepth", 8)
+        f.conversion.upsampling_filter = surfaces.get("filter", 0)
+        f.conversion.geometry_shift = surfaces.get("geometry_shift", 0)
+        f.conversion.attribute_shift = surfaces.get("attribute_shift", 0)
+        self._keep = (gof, surfaces, occ, geo, att)
+        self._check(self._lib.rb200_gof_upload_nv12(self._h, C.byref(f), C.byref(gof.atlas_struct())))
+
     def getPlanes(self, frame, m):
         """geometry [H][W] and attribute [3][H][W] uint16 as they sit in HBM after the upload"""
         p = self.params

@@ -184,6 +184,7 @@ int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );
 int rb_ingest_yuv420_impl( rb200_ctx* c, int geo_bytes, int attr_bytes, int attr_bitdepth, int filter, int geo_shift, int attr_shift,
                            const int* geo_bitdepth /* in, out, msb */, const int* occ_bitdepth /* out, msb */ );
+int rb_gather_nv12_impl( rb200_ctx* c, const rb200_frames_nv12* fr );
 int rb_debug_rgb8_impl( rb200_ctx* c, const uint16_t* yuv, int64_t n, uint8_t* rgb, int force_f64 );
 void rb_metrics_release( rb200_ctx* c );
 void rb_transfer_release( rb200_ctx* c );

@@ -321,7 +321,8 @@ static bool patch_inside( const rb200_patch& p, int Wb, int Hb ) {
 }
 
 // planes either as the reconstruction reads them (fr) or decoder-native (fy): see rb200_gof_upload_yuv420
-static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_frames_yuv420* fy, const rb200_atlas* at ) {
+static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_frames_yuv420* fy, const rb200_atlas* at,
+                              const rb200_frames_nv12* fn = nullptr ) {
   if ( !c || ( !fr && !fy ) || !at ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload: null argument" ); }
   if ( !c->have_gof ) { return rb_fail( c, RB200_ERR_STATE, "gof_upload before gof_begin" ); }
   cudaSetDevice( c->device );
@@ -330,9 +331,10 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
     return rb_fail( c, RB200_ERR_INVALID, "gof_upload: missing plane or patch table" );
   }
   if ( fy ) {
-    if ( !fy->occupancy || !fy->geometry || ( c->P.attribute_count > 0 && !fy->attribute ) || !at->patch_offset ) {
+    if ( !fn && ( !fy->occupancy || !fy->geometry || ( c->P.attribute_count > 0 && !fy->attribute ) ) ) {
       return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: missing plane or patch table" );
     }
+    if ( !at->patch_offset ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: missing plane or patch table" ); }
     if ( ( fy->geometry_sample_bytes != 1 && fy->geometry_sample_bytes != 2 ) ||
          ( fy->attribute_sample_bytes != 1 && fy->attribute_sample_bytes != 2 ) ||
          ( fy->attribute_bitdepth != 8 && fy->attribute_bitdepth != 10 ) || fy->upsampling_filter < 0 || fy->upsampling_filter > 7 ) {
@@ -468,6 +470,14 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
     RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fr->geometry, geoBytes, cudaMemcpyDefault, c->stream ) );
     if ( attBytes ) { RB_CUDA( cudaMemcpyAsync( c->d_attribute.p, fr->attribute, attBytes, cudaMemcpyDefault, c->stream ) ); }
     c->stats.h2d_bytes += (int64_t)( occBytes + geoBytes + attBytes );
+  } else if ( fn ) {  // pitched decoder surfaces in device / pinned memory: gathered by a kernel, then the same conversion
+    int r = rb_gather_nv12_impl( c, fn );
+    if ( r ) { return r; }
+    const int gbd[3] = {fy->geometry_bitdepth_in, fy->geometry_bitdepth_out, fy->geometry_msb_align};
+    const int obd[2] = {fy->occupancy_bitdepth_out, fy->occupancy_msb_align};
+    r = rb_ingest_yuv420_impl( c, fy->geometry_sample_bytes, fy->attribute_sample_bytes, fy->attribute_bitdepth, fy->upsampling_filter,
+                               fy->geometry_shift, fy->attribute_shift, gbd, obd );
+    if ( r ) { return r; }
   } else {  // decoder-native planes: a quarter of the bytes cross PCIe, the conversion runs on the device
     const size_t plane  = (size_t)c->W * c->H;
     const size_t rawGeo = F * c->M * plane * fy->geometry_sample_bytes;
@@ -560,6 +570,30 @@ int rb200_gof_upload( rb200_ctx* c, const rb200_frames* fr, const rb200_atlas* a
 int rb200_gof_upload_yuv420( rb200_ctx* c, const rb200_frames_yuv420* fy, const rb200_atlas* at ) {
   if ( !fy ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_yuv420: null argument" ); }
   return gof_upload_common( c, nullptr, fy, at );
+}
+int rb200_gof_upload_nv12( rb200_ctx* c, const rb200_frames_nv12* fn, const rb200_atlas* at ) {
+  if ( !c || !fn || !fn->occupancy || !fn->geometry ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: null argument" ); }
+  if ( !c->have_gof ) { return rb_fail( c, RB200_ERR_STATE, "gof_upload before gof_begin" ); }
+  if ( fn->sample_bytes != 1 && fn->sample_bytes != 2 ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: sample_bytes must be 1 or 2" ); }
+  if ( fn->sample_lsb_shift < 0 || fn->sample_lsb_shift > 15 || ( fn->sample_bytes == 1 && fn->sample_lsb_shift ) ) {
+    return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: sample_lsb_shift out of range" );
+  }
+  if ( c->P.attribute_count > 0 && !fn->attribute ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: missing attribute surfaces" ); }
+  const int nGA = c->F * c->M;
+  for ( int i = 0; i < c->F; i++ ) {
+    if ( !fn->occupancy[i].luma || fn->occupancy[i].pitch_luma < c->oW ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: bad occupancy surface %d", i ); }
+  }
+  for ( int i = 0; i < nGA; i++ ) {
+    if ( !fn->geometry[i].luma || fn->geometry[i].pitch_luma < c->W * fn->sample_bytes ) { return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: bad geometry surface %d", i ); }
+    if ( c->P.attribute_count > 0 && ( !fn->attribute[i].luma || !fn->attribute[i].chroma || fn->attribute[i].pitch_luma < c->W * fn->sample_bytes ||
+                                       fn->attribute[i].pitch_chroma < c->W * fn->sample_bytes ) ) {
+      return rb_fail( c, RB200_ERR_INVALID, "gof_upload_nv12: bad attribute surface %d", i );
+    }
+  }
+  rb200_frames_yuv420 fy    = fn->conversion;
+  fy.geometry_sample_bytes  = fn->sample_bytes;
+  fy.attribute_sample_bytes = fn->sample_bytes;
+  return gof_upload_common( c, nullptr, &fy, at, fn );
 }
 // the planes the reconstruction reads, as they are in HBM after an upload (tests of the ingest conversion)
 int rb200_download_planes( rb200_ctx* c, int frame, int map, uint16_t* geometry, uint16_t* attribute ) {

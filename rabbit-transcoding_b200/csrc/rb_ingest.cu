@@ -200,7 +200,72 @@ __global__ void __launch_bounds__( 256 ) k_occupancy_convert( uint8_t* v, int64_
   }
 }
 
+// pitched decoder surfaces -> the dense planar layout of rb200_frames_yuv420 (luma rows packed; interleaved chroma
+// split into a U and a V plane).  grid (x tiles, rows, surfaces); T = sample type, `shift` = right shift of 2-byte samples
+struct SurfDev {
+  const uint8_t* luma;
+  const uint8_t* chroma;
+  int32_t        pitch_luma, pitch_chroma;
+};
+template <typename T>
+__global__ void __launch_bounds__( 256 ) k_gather_surfaces( const SurfDev* __restrict__ surf, T* __restrict__ dst, int W, int H,
+                                                            size_t frameStride /* samples */, int withChroma, int shift ) {
+  const SurfDev s = surf[blockIdx.z];
+  const int     x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if ( x >= W ) { return; }
+  T* out = dst + (size_t)blockIdx.z * frameStride;
+  out[(size_t)y * W + x] = (T)( reinterpret_cast<const T*>( s.luma + (size_t)y * s.pitch_luma )[x] >> shift );
+  if ( withChroma && y < H / 2 ) {  // row y of the interleaved chroma plane holds W samples: U0 V0 U1 V1 ...
+    const T v = (T)( reinterpret_cast<const T*>( s.chroma + (size_t)y * s.pitch_chroma )[x] >> shift );
+    T*      c = out + (size_t)W * H + ( ( x & 1 ) ? (size_t)( W / 2 ) * ( H / 2 ) : 0 );
+    c[(size_t)y * ( W / 2 ) + ( x >> 1 )] = v;
+  }
+}
+
 }  // namespace
+
+// pitched NV12 / P010 surfaces (device or pinned memory) -> c->d_occ_video, c->d_raw_geo (or c->d_geometry for 2-byte
+// samples) and c->d_raw_attr in the planar layout rb_ingest_yuv420_impl reads
+int rb_gather_nv12_impl( rb200_ctx* c, const rb200_frames_nv12* fr ) {
+  const int    F = c->F, M = c->M, nGA = F * M, bytes = fr->sample_bytes;
+  const bool   attr = c->P.attribute_count > 0;
+  const size_t plane = (size_t)c->W * c->H;
+  const int    nSurf = F + nGA + ( attr ? nGA : 0 );
+  SurfDev*     h = (SurfDev*)rb_pinned( c, (size_t)nSurf * sizeof( SurfDev ) );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the pinned block may still be read by an earlier copy
+  auto put = [&]( int i, const rb200_surface& s ) {
+    h[i] = SurfDev{(const uint8_t*)s.luma, (const uint8_t*)s.chroma, s.pitch_luma, s.pitch_chroma};
+  };
+  for ( int f = 0; f < F; f++ ) { put( f, fr->occupancy[f] ); }
+  for ( int i = 0; i < nGA; i++ ) { put( F + i, fr->geometry[i] ); }
+  for ( int i = 0; attr && i < nGA; i++ ) { put( F + nGA + i, fr->attribute[i] ); }
+  RB_CUDA( c->d_scratch[0].ensure( (size_t)nSurf * sizeof( SurfDev ) + 256 ) );
+  SurfDev* d = c->d_scratch[0].as<SurfDev>();
+  RB_CUDA( cudaMemcpyAsync( d, h, (size_t)nSurf * sizeof( SurfDev ), cudaMemcpyHostToDevice, c->stream ) );
+  c->stats.h2d_bytes += (int64_t)nSurf * sizeof( SurfDev );
+  RB_LAUNCH( "gather_occupancy", k_gather_surfaces<uint8_t>, dim3( rb_div_up( c->oW, 256 ), c->oH, F ), 256, 0, d,
+             c->d_occ_video.as<uint8_t>(), c->oW, c->oH, (size_t)c->oW * c->oH, 0, 0 );
+  if ( bytes == 1 ) {
+    RB_CUDA( c->d_raw_geo.ensure( (size_t)nGA * plane + 64 ) );
+    RB_LAUNCH( "gather_geometry", k_gather_surfaces<uint8_t>, dim3( rb_div_up( c->W, 256 ), c->H, nGA ), 256, 0, d + F,
+               c->d_raw_geo.as<uint8_t>(), c->W, c->H, plane, 0, 0 );
+  } else {
+    RB_LAUNCH( "gather_geometry", k_gather_surfaces<uint16_t>, dim3( rb_div_up( c->W, 256 ), c->H, nGA ), 256, 0, d + F,
+               c->d_geometry.as<uint16_t>(), c->W, c->H, plane, 0, fr->sample_lsb_shift );
+  }
+  if ( attr ) {
+    RB_CUDA( c->d_raw_attr.ensure( (size_t)nGA * ( plane + plane / 2 ) * bytes + 64 ) );
+    if ( bytes == 1 ) {
+      RB_LAUNCH( "gather_attribute", k_gather_surfaces<uint8_t>, dim3( rb_div_up( c->W, 256 ), c->H, nGA ), 256, 0, d + F + nGA,
+                 c->d_raw_attr.as<uint8_t>(), c->W, c->H, plane + plane / 2, 1, 0 );
+    } else {
+      RB_LAUNCH( "gather_attribute", k_gather_surfaces<uint16_t>, dim3( rb_div_up( c->W, 256 ), c->H, nGA ), 256, 0, d + F + nGA,
+                 c->d_raw_attr.as<uint16_t>(), c->W, c->H, plane + plane / 2, 1, fr->sample_lsb_shift );
+    }
+  }
+  return RB200_OK;
+}
 
 // raw decoder planes (already in c->d_raw_geo / c->d_raw_attr) -> c->d_geometry / c->d_attribute
 // (mode, amount) of convert_bitdepth for convertBitdepth( in, out, msbAlign ) on samples of `bits` bits

@@ -182,3 +182,69 @@ def test_ingest_convert_bitdepth_of_the_occupancy_video(rb, codec, checker_backe
     counts = codec.frameCounts()
     for f in range(F):
         assert_cloud_equal(codec.getPointCloud(f, counts), ref.cloud(f, "rgb8"), f"frame {f}")
+
+
+def _nv12_surfaces(torch, gof, native, pad=96, p010=False):
+    """the native planar frames as pitched NV12 (or P010: 10-bit samples in the high bits of 16-bit words) surfaces in
+    device memory, one allocation per surface with `pad` extra bytes per row — what NVDEC hands to libav"""
+    F, M = gof.n_frames, gof.params.map_count_minus1 + 1
+    H, W, pr = gof.params.height, gof.params.width, gof.params.occupancy_precision
+    keep, out = [], dict(occupancy=[], geometry=[], attribute=[], sample_bytes=2 if p010 else 1,
+                         sample_lsb_shift=6 if p010 else 0, bitdepth=native["bitdepth"], filter=native["filter"])
+    dt = torch.int16 if p010 else torch.uint8
+    bpe = 2 if p010 else 1
+
+    def surface(plane2d, dtype, elem):
+        h, w = plane2d.shape
+        pitch = w * elem + pad
+        buf = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+        src = torch.from_numpy(np.ascontiguousarray(plane2d)).cuda()
+        buf[:, :w * elem] = src.view(torch.uint8).reshape(h, w * elem)
+        keep.append(buf)
+        return buf.data_ptr(), pitch
+    for f in range(F):
+        out["occupancy"].append(surface(gof.occupancy[f], torch.uint8, 1))
+    geo = native["geometry"].reshape(F * M, H, W)
+    att = native["attribute"].reshape(F * M, -1)
+    q = (H // 2) * (W // 2)
+    for i in range(F * M):
+        g = geo[i].astype(np.uint16) << 6 if p010 else geo[i]
+        out["geometry"].append(surface(g, dt, bpe))
+        y = att[i, :H * W].reshape(H, W)
+        u = att[i, H * W:H * W + q].reshape(H // 2, W // 2)
+        v = att[i, H * W + q:].reshape(H // 2, W // 2)
+        uv = np.empty((H // 2, W), att.dtype)
+        uv[:, 0::2], uv[:, 1::2] = u, v
+        if p010:
+            y, uv = y.astype(np.uint16) << 6, uv.astype(np.uint16) << 6
+        out["attribute"].append(surface(y, dt, bpe) + surface(uv, dt, bpe))
+    out["_keep"] = keep
+    return out
+
+
+@pytest.mark.parametrize("p010", [False, True], ids=["nv12", "p010"])
+def test_upload_nv12_device_surfaces_equals_planar_upload(rb, codec, p010):
+    """pitched NV12 / P010 surfaces resident in device memory (RABBIT's --useCuda decode, PCCTranscoder.cpp:693-704) are
+    gathered on the device and decode to exactly what the planar 4:2:0 upload of the same samples decodes to"""
+    import torch
+    kw = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=57, transfer_filter=1)
+    g = rb.synthetic.generate_gof(**kw)
+    bd = 10 if p010 else 8
+    native = rb.synthetic.to_decoder_planes(g, bitdepth=bd, filt=2, sample_dtype=np.uint16 if p010 else np.uint8)
+    codec.uploadGofYuv420(g, native)
+    codec.decodeGof()
+    counts = codec.frameCounts()
+    want = [codec.getPointCloud(f, counts) for f in range(g.n_frames)]
+    want_planes = codec.getPlanes(1, 1)
+    surf = _nv12_surfaces(torch, g, native, p010=p010)
+    torch.cuda.synchronize()
+    st0 = codec.stats(reset=True)
+    codec.uploadGofNv12(g, surf)
+    up = codec.stats(reset=True)
+    assert up.h2d_bytes < 200000, up.h2d_bytes  # only the surface table and the patch tables cross PCIe
+    codec.decodeGof()
+    counts = codec.frameCounts()
+    got_planes = codec.getPlanes(1, 1)
+    assert np.array_equal(got_planes[0], want_planes[0]) and np.array_equal(got_planes[1], want_planes[1])
+    for f in range(g.n_frames):
+        assert_cloud_equal(codec.getPointCloud(f, counts), want[f], f"nv12 frame {f}")
