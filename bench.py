@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-metrics", action="store_true", help="skip the D1/D2 metrics leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the MD5 check against the reference (debugging only)")
+    ap.add_argument("--quick", action="store_true", help="only value, parity, e2e (transcode loop) and the roofline legs")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = auto)")
     return ap.parse_args()
 
@@ -294,13 +295,15 @@ def run_b200(args):
     gpu_md5 = [codec.computeChecksum(f) for f in range(gof.n_frames)]  # PCCPointSet3::computeChecksum of every decoded frame
 
     # BASELINE.json configs[1] as worded ("reconstruction + geometry/colour smoothing"): the same without the re-transfer
-    gof.params.attr_transfer_filter_type = 0
-    codec.uploadGof(gof)
-    ms_nt, _ = timed_resident(max(3, min(args.steps, 10)))
-    without_retransfer = {"value": round(all_points * max(3, min(args.steps, 10)) / (ms_nt * 1e-3) / 1e6, 2), "unit": UNIT,
-                          "ms_per_step": round(ms_nt / max(3, min(args.steps, 10)), 4),
-                          "what": "attr_transfer_filter_type = 0 (round-1 headline configuration)"}
-    gof.params.attr_transfer_filter_type = 1
+    without_retransfer = None
+    if not args.quick and gof.params.attr_transfer_filter_type == 1:
+        gof.params.attr_transfer_filter_type = 0
+        codec.uploadGof(gof)
+        ms_nt, _ = timed_resident(max(3, min(args.steps, 10)))
+        without_retransfer = {"value": round(all_points * max(3, min(args.steps, 10)) / (ms_nt * 1e-3) / 1e6, 2), "unit": UNIT,
+                              "ms_per_step": round(ms_nt / max(3, min(args.steps, 10)), 4),
+                              "what": "attr_transfer_filter_type = 0 (round-1 headline configuration)"}
+        gof.params.attr_transfer_filter_type = 1
 
     # ---------------- parity of the benchmarked workload (outside every timed region) ----------------
     # N = 1: the reference run below is also the cpu_baseline (1 thread, the reference's real behaviour);
@@ -448,25 +451,31 @@ def run_b200(args):
             e2e["frames_gathered"] = gathered.get("frames")
             e2e["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in gathered.get("mean", {}).items()}
         # (b) the same with the source clouds (positions, RGB, normals) crossing PCIe every step
-        ms, psteps, sts, nl = time_loop([{k: v for k, v in s.items()} for s in src_host])
-        e2e["with_source_upload"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
-                                     "h2d_bytes_per_step": int(plane_bytes + src_bytes), "ms_per_step": round(ms / psteps, 3),
-                                     "metric_frames_per_s": round(world * gof.n_frames * psteps / (ms * 1e-3), 1)}
+        if args.quick:
+            for L in lanes[1:]:
+                L["codec"].close()
+            lanes = lanes[:1]
+        ms, psteps, sts, nl = (None,) * 4 if args.quick else time_loop([{k: v for k, v in s.items()} for s in src_host])
+        if not args.quick:
+            e2e["with_source_upload"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+                                         "h2d_bytes_per_step": int(plane_bytes + src_bytes), "ms_per_step": round(ms / psteps, 3),
+                                         "metric_frames_per_s": round(world * gof.n_frames * psteps / (ms * 1e-3), 1)}
         # (c) the decoder alone with the clouds copied back (what PccAppDecoder hands to its PLY writer)
-        for L in lanes:
+        for L in ([] if args.quick else lanes):
             L["out"] = dict(positions=torch.empty((n_points + 1024, 3), dtype=torch.int16).pin_memory().numpy(),
                             colors=torch.empty((n_points + 1024, 3), dtype=torch.uint8).pin_memory().numpy())
-        ms, psteps, sts, nl = time_loop(None, download=True)
-        assert all(L["n_got"] == n_points for L in lanes)
-        assert all(np.array_equal(lanes[0]["out"]["positions"][:n_points], L["out"]["positions"][:n_points]) for L in lanes[1:])
-        e2e["decode_and_download"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
-                                      "h2d_bytes_per_step": int(plane_bytes), "d2h_bytes_per_step": int(n_points * 9),
-                                      "ms_per_step": round(ms / psteps, 3), "gofs_in_flight": nl}
-        for L in lanes[1:]:
-            L["codec"].close()
+        if not args.quick:
+            ms, psteps, sts, nl = time_loop(None, download=True)
+            assert all(L["n_got"] == n_points for L in lanes)
+            assert all(np.array_equal(lanes[0]["out"]["positions"][:n_points], L["out"]["positions"][:n_points]) for L in lanes[1:])
+            e2e["decode_and_download"] = {"value": round(all_points * psteps / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+                                          "h2d_bytes_per_step": int(plane_bytes), "d2h_bytes_per_step": int(n_points * 9),
+                                          "ms_per_step": round(ms / psteps, 3), "gofs_in_flight": nl}
+            for L in lanes[1:]:
+                L["codec"].close()
 
         # ---------------- leg 2b: the metrics alone, reconstruction and sources resident ----------------
-        if not args.no_metrics:
+        if not args.no_metrics and not args.quick:
             met = lanes[0]["met"]
             codec.uploadGof(gof)
             codec.decodeGof()
