@@ -330,6 +330,15 @@ __device__ __forceinline__ bool search_near( const Batch& b, int cB, int x, int 
   return false;
 }
 
+// ring 0 alone (the query's own column): complete exactly when the point itself is in B (distance 0 < 1)
+__device__ __forceinline__ bool search_ring0( const Batch& b, int cB, int x, int y, int z, TieSet& t ) {
+  t.best     = 0xFFFFFFFFu;
+  t.n        = 0;
+  t.overflow = false;
+  probe_column( b, cB, x, y, z, 0u, t );
+  return t.best == 0u;
+}
+
 __device__ __forceinline__ void sort_ties( TieSet& t ) {  // ascending index = the reference's std::sort, PCCMetrics.cpp:110
   for ( int i = 1; i < t.n; i++ ) {
     const uint32_t v = t.idx[i];
@@ -372,6 +381,12 @@ struct NNArgs {
   double*          partial;   // [blocks][4]
   uint32_t*        far_list;  // [capacity][2] (direction, unique index)
   uint32_t*        far_count;
+  // queries the ring-0 pass could not finish, compacted IN ORDER (so the double sums do not depend on scheduling):
+  uint32_t*        pend_mask;  // [warps of the ring-0 grid] ballot of the unfinished lanes
+  uint32_t*        pend_off;   // [warps + 1] their counts, then the exclusive prefix
+  uint32_t*        pend_list;  // [pending] global thread id of the query in the ring-0 grid
+  double*          contrib;    // [pending][4] MODE_METRIC: the query's c2p / colour terms (added by k_reduce_partials)
+  uint32_t         nPending;
   int              compute_c2p, compute_color, neighbors_proc;
 };
 
@@ -486,13 +501,48 @@ __device__ __forceinline__ const Direction& direction_of_block( const NNArgs& a,
   return a.dirs[lo];
 }
 
+// the fixed-order reduction of one warp's METRIC contributions: exact integer sums / maxima through one atomic per warp,
+// the double terms as per-warp partials (k_reduce_partials adds them in warp order)
+__device__ __forceinline__ void warp_reduce_metric( const NNArgs& a, const Direction& d, const Contribution& ct, int64_t partialSlot ) {
+  double    v[4] = {ct.c2p, ct.col[0], ct.col[1], ct.col[2]};
+  const int lane = threadIdx.x & 31;
+  unsigned long long s2 = ct.d2, m2 = ct.d2, mp = (unsigned long long)__double_as_longlong( ct.c2p_max );
+  unsigned int       ov = ct.overflow;
+#pragma unroll
+  for ( int s = 16; s > 0; s >>= 1 ) {
+    s2 += __shfl_down_sync( 0xFFFFFFFFu, s2, s );
+    m2 = max( m2, __shfl_down_sync( 0xFFFFFFFFu, m2, s ) );
+    mp = max( mp, __shfl_down_sync( 0xFFFFFFFFu, mp, s ) );
+    ov += __shfl_down_sync( 0xFFFFFFFFu, ov, s );
+  }
+  if ( lane == 0 ) {
+    Acc* acc = a.acc + d.acc;
+    if ( s2 ) { atomicAdd( &acc->sse_c2c, s2 ); }
+    if ( m2 ) { atomicMax( &acc->max_c2c, m2 ); }
+    if ( mp ) { atomicMax( &acc->max_c2p_bits, mp ); }
+    if ( ov ) { atomicAdd( &acc->tie_overflow, ov ); }
+  }
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) {
+#pragma unroll
+    for ( int s = 16; s > 0; s >>= 1 ) { v[k] += __shfl_down_sync( 0xFFFFFFFFu, v[k], s ); }
+    // per-warp partials go to global memory: no barrier (a CTA's warps finish at very different times), and
+    // k_reduce_partials adds them in the same fixed order (warp 0 .. 7 of CTA 0, then CTA 1, ...)
+    if ( lane == 0 ) { a.partial[partialSlot * 4 + k] = v[k]; }
+  }
+}
+
+// pass 1, one thread per unique point of A: the query's own column.  Most points of a decoded cloud ARE in the other
+// cloud (distance 0) and are finished here; the others are only marked — walking the 8 + 16 columns of rings 1 and 2
+// for a few lanes of every warp is what kept two thirds of the lanes idle.
 template <int MODE>
 __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
   const Direction&  d  = direction_of_block( a, blockIdx.x );
   const Batch&      b  = a.b;
   const int64_t     iu = (int64_t)( blockIdx.x - d.block_begin ) * TPB + threadIdx.x;
   Contribution      ct{};
-  const bool        active = iu < (int64_t)b.ucount[d.cloudA];
+  const bool        active  = iu < (int64_t)b.ucount[d.cloudA];
+  bool              pending = false;
   if ( active ) {
     const int64_t uA   = b.off[d.cloudA] + iu;
     bool          need = true;
@@ -508,43 +558,82 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
     if ( need ) {
       const short4 p = b.u_pos[uA];
       TieSet       t;
-      if ( search_near( b, d.cloudB, p.x, p.y, p.z, t ) ) {
+      if ( search_ring0( b, d.cloudB, p.x, p.y, p.z, t ) ) {
         consume<MODE>( a, d, uA, t, ct );
       } else {
-        const uint32_t slot      = atomicAdd( a.far_count, 1u );
-        a.far_list[2 * slot]     = (uint32_t)( &d - a.dirs );
-        a.far_list[2 * slot + 1] = (uint32_t)iu;
+        pending = true;
       }
     }
   }
-  if ( MODE == MODE_METRIC ) {  // fixed-order CTA reduction of the double contributions
-    double    v[4] = {ct.c2p, ct.col[0], ct.col[1], ct.col[2]};
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {  // exact integer sums / maxima: one atomic per warp instead of one per query
-      unsigned long long s2 = ct.d2, m2 = ct.d2, mp = (unsigned long long)__double_as_longlong( ct.c2p_max );
-      unsigned int       ov = ct.overflow;
-#pragma unroll
-      for ( int s = 16; s > 0; s >>= 1 ) {
-        s2 += __shfl_down_sync( 0xFFFFFFFFu, s2, s );
-        m2 = max( m2, __shfl_down_sync( 0xFFFFFFFFu, m2, s ) );
-        mp = max( mp, __shfl_down_sync( 0xFFFFFFFFu, mp, s ) );
-        ov += __shfl_down_sync( 0xFFFFFFFFu, ov, s );
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t pm   = __ballot_sync( 0xFFFFFFFFu, pending );
+  if ( lane == 0 ) {
+    const int64_t gw = (int64_t)blockIdx.x * ( TPB / 32 ) + w;
+    a.pend_mask[gw]  = pm;
+    a.pend_off[gw]   = __popc( pm );
+  }
+  if ( MODE == MODE_METRIC ) { warp_reduce_metric( a, d, ct, (int64_t)blockIdx.x * ( TPB / 32 ) + w ); }
+}
+
+// the unfinished queries as an ordered list (pend_off is the exclusive prefix of the per-warp counts by now)
+__global__ void __launch_bounds__( TPB ) k_nn_list_pending( const NNArgs a ) {
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t  gw   = (int64_t)blockIdx.x * ( TPB / 32 ) + w;
+  const uint32_t pm   = a.pend_mask[gw];
+  if ( ( pm >> lane ) & 1u ) {
+    a.pend_list[a.pend_off[gw] + __popc( pm & ( ( 1u << lane ) - 1u ) )] = (uint32_t)( (int64_t)blockIdx.x * TPB + threadIdx.x );
+  }
+}
+
+// pass 2, one thread per unfinished query: rings 0..2 with every lane busy; what is still open goes to the warp-per-query
+// kernel.  The double terms of a METRIC query are stored per list slot and added in slot order by k_reduce_partials.
+template <int MODE>
+__global__ void __launch_bounds__( TPB ) k_nn_pending( const NNArgs a ) {
+  const Batch&   b = a.b;
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  Contribution   ct{};
+  int            accIdx = -1;
+  if ( s < a.nPending ) {
+    const uint32_t   gt  = a.pend_list[s];
+    const int        blk = (int)( gt / TPB );
+    const Direction& d   = direction_of_block( a, blk );
+    const int64_t    iu  = (int64_t)( blk - d.block_begin ) * TPB + ( gt % TPB );
+    const int64_t    uA  = b.off[d.cloudA] + iu;
+    const short4     p   = b.u_pos[uA];
+    TieSet           t;
+    if ( search_near( b, d.cloudB, p.x, p.y, p.z, t ) ) {
+      consume<MODE>( a, d, uA, t, ct );
+      accIdx = d.acc;
+    } else {
+      const uint32_t slot      = atomicAdd( a.far_count, 1u );
+      a.far_list[2 * slot]     = (uint32_t)( &d - a.dirs );
+      a.far_list[2 * slot + 1] = (uint32_t)iu;
+    }
+    if ( MODE == MODE_METRIC ) {
+      double* o = a.contrib + (size_t)s * 4;
+      o[0] = ct.c2p, o[1] = ct.col[0], o[2] = ct.col[1], o[3] = ct.col[2];
+    }
+  }
+  if ( MODE == MODE_METRIC ) {  // exact integer parts: one atomic per group of lanes with the same accumulator
+    const uint32_t live = __ballot_sync( 0xFFFFFFFFu, accIdx >= 0 );
+    if ( accIdx >= 0 ) {
+      const uint32_t peers  = __match_any_sync( live, accIdx );
+      const int      leader = __ffs( peers ) - 1;
+      unsigned long long s2 = 0, m2 = 0, mp = 0;
+      unsigned int       ov = 0;
+      for ( uint32_t m = peers; m; m &= m - 1 ) {
+        const int src = __ffs( m ) - 1;
+        const unsigned long long q2 = __shfl_sync( peers, ct.d2, src );
+        const unsigned long long qp = __shfl_sync( peers, (unsigned long long)__double_as_longlong( ct.c2p_max ), src );
+        s2 += q2, m2 = max( m2, q2 ), mp = max( mp, qp ), ov += __shfl_sync( peers, ct.overflow, src );
       }
-      if ( lane == 0 ) {
-        Acc* acc = a.acc + d.acc;
+      if ( ( threadIdx.x & 31 ) == leader ) {
+        Acc* acc = a.acc + accIdx;
         if ( s2 ) { atomicAdd( &acc->sse_c2c, s2 ); }
         if ( m2 ) { atomicMax( &acc->max_c2c, m2 ); }
         if ( mp ) { atomicMax( &acc->max_c2p_bits, mp ); }
         if ( ov ) { atomicAdd( &acc->tie_overflow, ov ); }
       }
-    }
-#pragma unroll
-    for ( int k = 0; k < 4; k++ ) {
-#pragma unroll
-      for ( int s = 16; s > 0; s >>= 1 ) { v[k] += __shfl_down_sync( 0xFFFFFFFFu, v[k], s ); }
-      // per-warp partials go to global memory: no barrier (a CTA's warps finish at very different times), and
-      // k_reduce_partials adds them in the same fixed order (warp 0 .. 7 of CTA 0, then CTA 1, ...)
-      if ( lane == 0 ) { a.partial[( (int64_t)blockIdx.x * ( TPB / 32 ) + w ) * 4 + k] = v[k]; }
     }
   }
 }
@@ -646,11 +735,18 @@ __global__ void __launch_bounds__( TPB ) k_nn_far( const NNArgs a ) {
   }
 }
 
-// one CTA per direction sums that direction's CTA partials in a fixed order
+// one CTA per direction sums that direction's CTA partials, then the terms of its pass-2 queries, in a fixed order
 __global__ void __launch_bounds__( TPB ) k_reduce_partials( const NNArgs a, const int32_t* __restrict__ block_end ) {
   __shared__ double red[TPB][4];
   const Direction&  d = a.dirs[blockIdx.x];
   double            s[4] = {0, 0, 0, 0};
+  {
+    const uint32_t pb = a.pend_off[(int64_t)d.block_begin * ( TPB / 32 )], pe = a.pend_off[(int64_t)block_end[blockIdx.x] * ( TPB / 32 )];
+    for ( uint32_t q = pb + threadIdx.x; q < pe; q += TPB ) {
+#pragma unroll
+      for ( int k = 0; k < 4; k++ ) { s[k] += a.contrib[(size_t)q * 4 + k]; }
+    }
+  }
   for ( int blk = d.block_begin + threadIdx.x; blk < block_end[blockIdx.x]; blk += TPB ) {
 #pragma unroll
     for ( int k = 0; k < 4; k++ ) {
@@ -742,7 +838,7 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   RbBuf u_yuv, descs, ndescs;
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
-      nrm_raw, partial, far_list;
+      nrm_raw, partial, far_list, pend_mask, pend_off, pend_list, contrib;
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
   // sets of import buffers, `cur` = the set the running chunk reads.
   RbBuf                rawSet[2], nrmSet[2];
@@ -758,7 +854,8 @@ void rb_metrics_release( rb200_ctx* c ) {
   MetricsScratch* s = static_cast<MetricsScratch*>( c->metrics_scratch );
   if ( !s ) { return; }
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
-                   &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list};
+                   &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list,
+                   &s->pend_mask, &s->pend_off, &s->pend_list, &s->contrib};
   for ( auto* b : bufs ) { b->release(); }
   s->u_yuv.release();
   s->descs.release();
@@ -993,10 +1090,29 @@ int run_nn( rb200_ctx* c, MetricsScratch* S, NNArgs& a, const std::vector<Direct
   if ( dirs.empty() || totalBlocks == 0 ) { return RB200_OK; }
   RB_CUDA( cudaMemsetAsync( a.far_count, 0, 4, c->stream ) );
   const char* nNear = MODE == MODE_SCALE ? "met_nn_scale" : ( MODE == MODE_FILL ? "met_nn_fill" : "met_nn_metric" );
+  const char* nPend = MODE == MODE_SCALE ? "met_nn_scale_rings" : ( MODE == MODE_FILL ? "met_nn_fill_rings" : "met_nn_metric_rings" );
   const char* nFar  = MODE == MODE_SCALE ? "met_nn_scale_far" : ( MODE == MODE_FILL ? "met_nn_fill_far" : "met_nn_metric_far" );
+  const int64_t nWarps = (int64_t)totalBlocks * ( TPB / 32 );
+  RB_CUDA( cudaMemsetAsync( a.pend_off + nWarps, 0, 4, c->stream ) );
   RB_LAUNCH( nNear, k_nn_near<MODE>, totalBlocks, TPB, 0, a );
+  int r = rb_scan_u32( c, a.pend_off, a.pend_off, nWarps + 1, S->sums.as<uint32_t>() );
+  if ( r ) { return r; }
+  uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( h, a.pend_off + nWarps, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  a.nPending = h[0];
+  if ( a.nPending ) {
+    RB_CUDA( S->pend_list.ensure( (size_t)a.nPending * 4 ) );
+    a.pend_list = S->pend_list.as<uint32_t>();
+    if ( MODE == MODE_METRIC ) {
+      RB_CUDA( S->contrib.ensure( (size_t)a.nPending * 32 ) );
+      a.contrib = S->contrib.as<double>();
+    }
+    RB_LAUNCH( "met_nn_list", k_nn_list_pending, totalBlocks, TPB, 0, a );
+    RB_LAUNCH( nPend, k_nn_pending<MODE>, rb_div_up( a.nPending, TPB ), TPB, 0, a );
+  }
   RB_LAUNCH( nFar, k_nn_far<MODE>, 148 * 2, TPB, 0, a );
-  (void)S;
   (void)farCap;
   return RB200_OK;
 }
@@ -1116,12 +1232,17 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   }
   RB_CUDA( S->partial.ensure( (size_t)std::max( maxBlocks, 1 ) * 32 * ( TPB / 32 ) ) );
   RB_CUDA( S->far_list.ensure( (size_t)( N + 1 ) * 8 ) );
+  RB_CUDA( S->pend_mask.ensure( (size_t)( std::max( maxBlocks, 1 ) * ( TPB / 32 ) + 8 ) * 4 ) );
+  RB_CUDA( S->pend_off.ensure( (size_t)( std::max( maxBlocks, 1 ) * ( TPB / 32 ) + 8 ) * 4 ) );
+  RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( (int64_t)std::max( maxBlocks, 1 ) * ( TPB / 32 ) + 8 ) ) );
   NNArgs a{};
   a.b              = B;
   a.acc            = dAcc;
   a.partial        = S->partial.as<double>();
   a.far_list       = S->far_list.as<uint32_t>();
   a.far_count      = dFarCount;
+  a.pend_mask      = S->pend_mask.as<uint32_t>();
+  a.pend_off       = S->pend_off.as<uint32_t>();
   a.compute_c2p    = wantC2p ? 1 : 0;
   a.compute_color  = mp->compute_color;
   a.neighbors_proc = mp->neighbors_proc;
