@@ -575,14 +575,13 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
   if ( MODE == MODE_METRIC ) { warp_reduce_metric( a, d, ct, (int64_t)blockIdx.x * ( TPB / 32 ) + w ); }
 }
 
-// the unfinished queries as an ordered list (pend_off is the exclusive prefix of the per-warp counts by now)
-__global__ void __launch_bounds__( TPB ) k_nn_list_pending( const NNArgs a ) {
-  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t  gw   = (int64_t)blockIdx.x * ( TPB / 32 ) + w;
-  const uint32_t pm   = a.pend_mask[gw];
-  if ( ( pm >> lane ) & 1u ) {
-    a.pend_list[a.pend_off[gw] + __popc( pm & ( ( 1u << lane ) - 1u ) )] = (uint32_t)( (int64_t)blockIdx.x * TPB + threadIdx.x );
-  }
+// the unfinished queries as an ordered list (pend_off is the exclusive prefix of the per-warp counts by now): one thread
+// per warp of the ring-0 grid
+__global__ void __launch_bounds__( TPB ) k_nn_list_pending( const NNArgs a, int64_t nWarps ) {
+  const int64_t gw = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if ( gw >= nWarps ) { return; }
+  uint32_t o = a.pend_off[gw];
+  for ( uint32_t pm = a.pend_mask[gw]; pm; pm &= pm - 1 ) { a.pend_list[o++] = (uint32_t)( gw * 32 + ( __ffs( pm ) - 1 ) ); }
 }
 
 // pass 2, one thread per unfinished query: rings 0..2 with every lane busy; what is still open goes to the warp-per-query
@@ -735,26 +734,10 @@ __global__ void __launch_bounds__( TPB ) k_nn_far( const NNArgs a ) {
   }
 }
 
-// one CTA per direction sums that direction's CTA partials, then the terms of its pass-2 queries, in a fixed order
-__global__ void __launch_bounds__( TPB ) k_reduce_partials( const NNArgs a, const int32_t* __restrict__ block_end ) {
-  __shared__ double red[TPB][4];
-  const Direction&  d = a.dirs[blockIdx.x];
-  double            s[4] = {0, 0, 0, 0};
-  {
-    const uint32_t pb = a.pend_off[(int64_t)d.block_begin * ( TPB / 32 )], pe = a.pend_off[(int64_t)block_end[blockIdx.x] * ( TPB / 32 )];
-    for ( uint32_t q = pb + threadIdx.x; q < pe; q += TPB ) {
-#pragma unroll
-      for ( int k = 0; k < 4; k++ ) { s[k] += a.contrib[(size_t)q * 4 + k]; }
-    }
-  }
-  for ( int blk = d.block_begin + threadIdx.x; blk < block_end[blockIdx.x]; blk += TPB ) {
-#pragma unroll
-    for ( int k = 0; k < 4; k++ ) {
-      double bs = 0.0;  // the CTA's sum, warp by warp
-      for ( int w = 0; w < TPB / 32; w++ ) { bs += a.partial[( (int64_t)blk * ( TPB / 32 ) + w ) * 4 + k]; }
-      s[k] += bs;
-    }
-  }
+// the double terms of a direction are added in a fixed order: RED_SEG CTAs per direction each sum a fixed slice of the
+// direction's warp partials and pass-2 terms (k_reduce_segments), one CTA per direction adds the slices in slice order
+constexpr int RED_SEG = 16;
+__device__ __forceinline__ void cta_sum4( double s[4], double ( *red )[4] ) {
 #pragma unroll
   for ( int k = 0; k < 4; k++ ) { red[threadIdx.x][k] = s[k]; }
   __syncthreads();
@@ -765,11 +748,43 @@ __global__ void __launch_bounds__( TPB ) k_reduce_partials( const NNArgs a, cons
     }
     __syncthreads();
   }
-  if ( threadIdx.x == 0 ) {
-    Acc* acc     = a.acc + d.acc;
-    acc->sum_c2p = red[0][0] + acc->far_c2p;
-    for ( int k = 0; k < 3; k++ ) { acc->sum_col[k] = red[0][1 + k] + acc->far_col[k]; }
+}
+__global__ void __launch_bounds__( TPB ) k_reduce_segments( const NNArgs a, const int32_t* __restrict__ block_end, double* __restrict__ seg ) {
+  __shared__ double red[TPB][4];
+  const int         dir = blockIdx.x / RED_SEG, sg = blockIdx.x % RED_SEG;
+  const Direction&  d   = a.dirs[dir];
+  double            s[4] = {0, 0, 0, 0};
+  {
+    const int64_t nb = block_end[dir] - d.block_begin, per = ( nb + RED_SEG - 1 ) / RED_SEG;
+    const int64_t b0 = d.block_begin + sg * per, b1 = min( (int64_t)block_end[dir], b0 + per );
+    for ( int64_t blk = b0 + threadIdx.x; blk < b1; blk += TPB ) {
+#pragma unroll
+      for ( int k = 0; k < 4; k++ ) {
+        double bs = 0.0;  // the CTA's sum, warp by warp
+        for ( int w = 0; w < TPB / 32; w++ ) { bs += a.partial[( blk * ( TPB / 32 ) + w ) * 4 + k]; }
+        s[k] += bs;
+      }
+    }
+    const int64_t pb = a.pend_off[(int64_t)d.block_begin * ( TPB / 32 )], pe = a.pend_off[(int64_t)block_end[dir] * ( TPB / 32 )];
+    const int64_t pper = ( pe - pb + RED_SEG - 1 ) / RED_SEG, q0 = pb + sg * pper, q1 = min( pe, q0 + pper );
+    for ( int64_t q = q0 + threadIdx.x; q < q1; q += TPB ) {
+      const double2 u = *reinterpret_cast<const double2*>( a.contrib + (size_t)q * 4 ), v = *reinterpret_cast<const double2*>( a.contrib + (size_t)q * 4 + 2 );
+      s[0] += u.x, s[1] += u.y, s[2] += v.x, s[3] += v.y;
+    }
   }
+  cta_sum4( s, red );
+  if ( threadIdx.x < 4 ) { seg[(size_t)blockIdx.x * 4 + threadIdx.x] = red[0][threadIdx.x]; }
+}
+__global__ void k_reduce_partials( const NNArgs a, const double* __restrict__ seg ) {
+  const int dir = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( dir >= a.nDirs ) { return; }
+  double s[4] = {0, 0, 0, 0};
+  for ( int g = 0; g < RED_SEG; g++ ) {
+    for ( int k = 0; k < 4; k++ ) { s[k] += seg[( (size_t)dir * RED_SEG + g ) * 4 + k]; }
+  }
+  Acc* acc     = a.acc + a.dirs[dir].acc;
+  acc->sum_c2p = s[0] + acc->far_c2p;
+  for ( int k = 0; k < 3; k++ ) { acc->sum_col[k] = s[1 + k] + acc->far_col[k]; }
 }
 
 // copyNormals (PCCPointSet.cpp:2282-2320): exact position lookup of every point of the normal cloud in the source
@@ -838,7 +853,7 @@ __global__ void k_pack_unique( const Batch b, int cloud, int16_t* __restrict__ p
 struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   RbBuf u_yuv, descs, ndescs;
   RbBuf in_pos, in_col, raw, key_a, key_b, first, u_pos, u_z, u_col, u_orig, tab, sums, small, nrm, nrm_cnt, last_idx,
-      nrm_raw, partial, far_list, pend_mask, pend_off, pend_list, contrib;
+      nrm_raw, partial, far_list, pend_mask, pend_off, pend_list, contrib, seg;
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
   // sets of import buffers, `cur` = the set the running chunk reads.
   RbBuf                rawSet[2], nrmSet[2];
@@ -855,7 +870,7 @@ void rb_metrics_release( rb200_ctx* c ) {
   if ( !s ) { return; }
   RbBuf* bufs[] = {&s->in_pos, &s->in_col, &s->raw, &s->key_a, &s->key_b, &s->first, &s->u_pos, &s->u_z, &s->u_col, &s->u_orig,
                    &s->tab, &s->sums, &s->small, &s->nrm, &s->nrm_cnt, &s->last_idx, &s->nrm_raw, &s->partial, &s->far_list,
-                   &s->pend_mask, &s->pend_off, &s->pend_list, &s->contrib};
+                   &s->pend_mask, &s->pend_off, &s->pend_list, &s->contrib, &s->seg};
   for ( auto* b : bufs ) { b->release(); }
   s->u_yuv.release();
   s->descs.release();
@@ -1109,7 +1124,7 @@ int run_nn( rb200_ctx* c, MetricsScratch* S, NNArgs& a, const std::vector<Direct
       RB_CUDA( S->contrib.ensure( (size_t)a.nPending * 32 ) );
       a.contrib = S->contrib.as<double>();
     }
-    RB_LAUNCH( "met_nn_list", k_nn_list_pending, totalBlocks, TPB, 0, a );
+    RB_LAUNCH( "met_nn_list", k_nn_list_pending, rb_div_up( nWarps, TPB ), TPB, 0, a, nWarps );
     RB_LAUNCH( nPend, k_nn_pending<MODE>, rb_div_up( a.nPending, TPB ), TPB, 0, a );
   }
   RB_LAUNCH( nFar, k_nn_far<MODE>, 148 * 2, TPB, 0, a );
@@ -1291,7 +1306,9 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   a.nDirs = (int)dMetric.size();
   r       = run_nn<MODE_METRIC>( c, S, a, dMetric, bMetric, N );
   if ( r ) { return r; }
-  RB_LAUNCH( "met_reduce", k_reduce_partials, (unsigned)dMetric.size(), TPB, 0, a, dEnds );
+  RB_CUDA( S->seg.ensure( dMetric.size() * RED_SEG * 32 + 64 ) );
+  RB_LAUNCH( "met_reduce", k_reduce_segments, (unsigned)dMetric.size() * RED_SEG, TPB, 0, a, dEnds, S->seg.as<double>() );
+  RB_LAUNCH( "met_reduce", k_reduce_partials, rb_div_up( (int64_t)dMetric.size(), 64 ), 64, 0, a, S->seg.as<double>() );
 
   // ---- read back ----
   const size_t rbBytes = szAcc + nC * 4 + 64;
