@@ -18,11 +18,46 @@
 //  * occupancy lives as a 1-bit-per-pixel bitmap (L2-resident, 1/16 of a byte map); the 3x3 / 5x5 boundary
 //    stencils are bit tests on 20 staged row masks per tile;
 //  * count -> exclusive scan -> emit keeps the point order of the reference exactly (ordered MD5 parity).
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link against libcuda)
+
 #include <algorithm>
 
 #include "rb_common.cuh"
 
 namespace {
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the canvas tiles of a patch block go global -> shared memory as two bulk
+// tensor copies issued by one lane, instead of sixteen 16-byte loads and stores per lane ----
+__device__ __forceinline__ uint32_t smem_u32( const void* p ) { return (uint32_t)__cvta_generic_to_shared( p ); }
+__device__ __forceinline__ void mbar_init( uint64_t* bar, uint32_t count ) {
+  asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( smem_u32( bar ) ), "r"( count ) : "memory" );
+  // visible to the async proxy (the TMA unit) before the copy is issued; CTA scope: a cluster-scope fence would compile to
+  // CCTL.IVALL and drop the SM's L1
+  asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );
+}
+__device__ __forceinline__ void mbar_expect_tx( uint64_t* bar, uint32_t bytes ) {
+  asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( smem_u32( bar ) ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ void mbar_wait( uint64_t* bar, uint32_t parity ) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"( smem_u32( bar ) ),
+      "r"( parity )
+      : "memory" );
+}
+// box of the tensor map at (x, y, plane) -> dst; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d( void* dst, const CUtensorMap* map, int x, int y, int plane, uint64_t* bar ) {
+  asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    smem_u32( dst ) ),
+                "l"( map ), "r"( x ), "r"( y ), "r"( plane ), "r"( smem_u32( bar ) )
+                : "memory" );
+}
 
 struct ReprojArgs {
   const RbPatch*  patches;
@@ -233,19 +268,21 @@ __global__ void k_size_quantization( const RbPatch* __restrict__ patches, const 
 // ---------------------------------------------------------------------------------------------------
 constexpr int WARPS = 4;
 
-struct TileSmem {
+struct __align__( 128 ) TileSmem {  // g and a are the destinations of the bulk tensor copies (128-byte aligned)
   uint16_t g[2][256];     // geometry D0 / D1 tile
   uint16_t a[2][3][256];  // attribute tiles
   uint32_t rows[20];      // occupancy bits of canvas rows Y0-2..Y0+17, bit k <-> x = X0-2+k
   uint16_t bnd[16];       // per tile row: bit tx = the pixel is a boundary pixel (identifyBoundaryPoints)
   uint16_t desc[512];     // emission-ordered point descriptors: u1 | v1 << 4 | layer << 8 | boundary << 15
+  uint64_t bar;           // mbarrier the tile copies complete on
 };
 
 // STD: the CTC configuration (two maps, absolute D1, attributes, boundary classification, no delta-coded T1) with
 // its switches resolved at compile time
 template <bool EMIT, bool EOM, bool STD>
-__global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs a ) {
-  __shared__ __align__( 16 ) TileSmem sm[WARPS];
+__global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs a, const __grid_constant__ CUtensorMap tmGeo,
+                                                                const __grid_constant__ CUtensorMap tmAttr ) {
+  __shared__ TileSmem sm[WARPS];
   const int     lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int     kM   = STD ? 2 : a.M;
   const bool    kAbs = STD ? true : a.absolute_d1 != 0, kAttr = STD ? true : a.attr_count > 0, kCls = STD ? true : a.classify != 0;
@@ -268,6 +305,16 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
   }
   const int     X0 = bx * 16, Y0 = by * 16;
   const TileMap tm = tile_map( p.orient );
+  // ---- the geometry (and attribute) tiles of the block: one bulk tensor copy each (box 16 x 16 x planes of the frame),
+  // issued by lane 0 and landing on the warp's mbarrier while the other lanes stage the occupancy rows ----
+  if ( lane == 0 ) { mbar_init( &S.bar, 1 ); }
+  __syncwarp();
+  if ( lane == 0 ) {
+    const bool attrTiles = EMIT && kAttr;
+    mbar_expect_tx( &S.bar, (uint32_t)( kM * 512 + ( attrTiles ? kM * 3 * 512 : 0 ) ) );
+    tma_load_3d( &S.g[0][0], &tmGeo, X0, Y0, f * kM, &S.bar );
+    if ( attrTiles ) { tma_load_3d( &S.a[0][0][0], &tmAttr, X0, Y0, f * kM * 3, &S.bar ); }
+  }
   // ---- stage occupancy row masks ----
   if ( lane < 20 ) {
     const int y    = Y0 - 2 + lane;
@@ -289,40 +336,7 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     }
     S.rows[lane] = bits;
   }
-  // ---- stage geometry (and attribute) tiles: 16-byte loads, two lanes per 32-byte sector; all loads of the block
-  // are in flight before the first one is stored to shared memory ----
-  {
-    const int    r = lane >> 1, h = lane & 1;
-    const size_t o = (size_t)( Y0 + r ) * a.W + X0 + 8 * h;
-    const size_t plane = (size_t)a.W * a.H;
-    uint4        vg[2], va[2][3];
-#pragma unroll
-    for ( int m = 0; m < 2; m++ ) {
-      if ( m < kM ) { vg[m] = *reinterpret_cast<const uint4*>( a.geo + ( (size_t)f * kM + m ) * plane + o ); }
-    }
-    if ( EMIT && kAttr ) {
-#pragma unroll
-      for ( int m = 0; m < 2; m++ ) {
-#pragma unroll
-        for ( int ch = 0; ch < 3; ch++ ) {
-          if ( m < kM ) { va[m][ch] = *reinterpret_cast<const uint4*>( a.attr + ( ( (size_t)f * kM + m ) * 3 + ch ) * plane + o ); }
-        }
-      }
-    }
-#pragma unroll
-    for ( int m = 0; m < 2; m++ ) {
-      if ( m < kM ) { *reinterpret_cast<uint4*>( &S.g[m][r * 16 + 8 * h] ) = vg[m]; }
-    }
-    if ( EMIT && kAttr ) {
-#pragma unroll
-      for ( int m = 0; m < 2; m++ ) {
-#pragma unroll
-        for ( int ch = 0; ch < 3; ch++ ) {
-          if ( m < kM ) { *reinterpret_cast<uint4*>( &S.a[m][ch][r * 16 + 8 * h] ) = va[m][ch]; }
-        }
-      }
-    }
-  }
+  mbar_wait( &S.bar, 0 );  // the tiles have landed (the wait also orders the async writes before the reads below)
   __syncwarp();
   if ( EMIT && !STD && a.t1_bits && kAttr && kM > 1 ) {
     // multiple streams with a delta-coded second map (colorPointCloud, PCCCodec.cpp:1387-1416): the tile of map 1
@@ -1105,6 +1119,30 @@ __global__ void k_classify_points( const FrameLayout* __restrict__ layout, int F
 
 }  // namespace
 
+// tensor map of a stack of u16 planes [planes][H][W], box 16 x 16 x boxPlanes (the tiles of one patch block)
+static int encode_plane_map( rb200_ctx* c, CUtensorMap* map, void* base, int W, int H, int64_t planes, int boxPlanes ) {
+  typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+  static EncodeFn encode = nullptr;
+  if ( !encode ) {
+    void*                           fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if ( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q ) != cudaSuccess || !fn ) {
+      return rb_fail( c, RB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver" );
+    }
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[3]    = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)std::max<int64_t>( planes, 1 )};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)W * H * 2};
+  const cuuint32_t box[3]     = {16, 16, (cuuint32_t)boxPlanes};
+  const cuuint32_t estr[3]    = {1, 1, 1};
+  const CUresult   r = encode( map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+  if ( r != CUDA_SUCCESS ) { return rb_fail( c, RB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%d x %lld planes", (int)r, W, H, (long long)planes ); }
+  return RB200_OK;
+}
+
 int rb_reconstruct_impl( rb200_ctx* c ) {
   const rb200_params& P = c->P;
   const int           F = c->F;
@@ -1180,11 +1218,27 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     a.wi_eom_count = c->d_wi_eom_count.as<int32_t>();
   }
   const int G = rb_div_up( nWI, WARPS );
+  // the planes as TMA tensors: geometry [F * M][H][W], attribute [F * M * 3][H][W]; a box is the tile stack of one block
+  alignas( 64 ) CUtensorMap tmGeo{}, tmAttr{};
+  if ( nWI > 0 && !ilv ) {
+    int r = encode_plane_map( c, &tmGeo, c->d_geometry.p, c->W, c->H, (int64_t)F * c->M, c->M );
+    if ( r ) { return r; }
+    if ( P.attribute_count > 0 ) {
+      r = encode_plane_map( c, &tmAttr, c->d_attribute.p, c->W, c->H, (int64_t)F * c->M * 3, c->M * 3 );
+      if ( r ) { return r; }
+    } else {
+      tmAttr = tmGeo;
+    }
+  }
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
-    auto kCount = eom ? k_reproject<false, true, false> : ( std_cfg ? k_reproject<false, false, true> : k_reproject<false, false, false> );
-    if ( ilv ) { kCount = plr ? k_reproject_interleaved<false, true> : k_reproject_interleaved<false, false>; }
-    RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
+    if ( ilv ) {
+      auto kCount = plr ? k_reproject_interleaved<false, true> : k_reproject_interleaved<false, false>;
+      RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
+    } else {
+      auto kCount = eom ? k_reproject<false, true, false> : ( std_cfg ? k_reproject<false, false, true> : k_reproject<false, false, false> );
+      RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a, tmGeo, tmAttr );
+    }
   }
   {
     const int nTiles = rb_div_up( nWI, SCAN_TILE );
@@ -1358,9 +1412,13 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   }
   if ( nWI > 0 ) {
     const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
-    auto kEmit = eom ? k_reproject<true, true, false> : ( std_cfg ? k_reproject<true, false, true> : k_reproject<true, false, false> );
-    if ( ilv ) { kEmit = plr ? k_reproject_interleaved<true, true> : k_reproject_interleaved<true, false>; }
-    RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
+    if ( ilv ) {
+      auto kEmit = plr ? k_reproject_interleaved<true, true> : k_reproject_interleaved<true, false>;
+      RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );
+    } else {
+      auto kEmit = eom ? k_reproject<true, true, false> : ( std_cfg ? k_reproject<true, false, true> : k_reproject<true, false, false> );
+      RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a, tmGeo, tmAttr );
+    }
   }
   if ( eom && nSeg ) {
     // per-segment destination offset inside the frame's EOM range and synthetic pixel counter (resets per EOM patch)
