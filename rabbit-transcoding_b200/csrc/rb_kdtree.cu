@@ -38,7 +38,8 @@ constexpr int KS_STACK = 56;          // pending right children of one subtree: 
 // counters[]: [0] next free level-phase node, [1] small roots, [2] split nodes of the level, [3] pool exhausted,
 //             [4] depth of the deepest subtree, [5] coordinate range error, [6] chunks of the level, [7] subtree stack
 //             overflow, [8] next subtree to build (work counter of the persistent warps)
-enum { C_NEXT = 0, C_SMALL = 1, C_BIG = 2, C_POOL = 3, C_DEPTH = 4, C_RANGE = 5, C_CHUNKS = 6, C_STACK = 7, C_WORK = 8 };
+enum { C_NEXT = 0, C_SMALL = 1, C_BIG = 2, C_POOL = 3, C_DEPTH = 4, C_RANGE = 5, C_CHUNKS = 6, C_STACK = 7, C_WORK = 8, C_LARGE = 9 };
+constexpr uint32_t P2_WARP_MAX = 16384;  // nodes up to this size get a warp for their second Hoare pass, larger ones a CTA
 
 // build-time node of the level phase
 struct GNode {
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
                                                     uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
                                                     uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
                                                     uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap,
-                                                    int32_t* __restrict__ cls ) {
+                                                    int32_t* __restrict__ cls, uint32_t* __restrict__ largeList ) {
   const int      lane = threadIdx.x & 31;
   const uint32_t i    = lvlBegin + blockIdx.x * TPB + threadIdx.x;
   const int      o[3] = {ox, oy, oz};
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
       n.child1     = c1;
       n.firstChunk = offC;
       for ( uint32_t k = 0; k < nch; k++ ) { chunkNode[offC + k] = i; }
+      if ( n.right - n.left > P2_WARP_MAX ) { largeList[atomicAdd( &counters[C_LARGE], 1u )] = i; }
       // boxes of the classes "< cut" and "> cut" of planeSplit, filled by k_g_count
       for ( int j = 0; j < 12; j++ ) { cls[(size_t)i * 12 + j] = ( j % 6 ) < 3 ? BIG : -BIG; }
     }
@@ -681,6 +683,214 @@ __global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec,
   }
 }
 
+// pass E-G for one node (one CTA per node of the level): the second Hoare pass of planeSplit only concerns the elements
+// == cut, a thin slab of the node.  After pass 1 they sit somewhere in [lim1, n); "<= cut" of that range is the mask wC.
+// The CTA lists the positions of [lim1, lim2) that hold an element > cut (ascending) and the positions of [lim2, n) that
+// hold an element == cut (ascending), swaps the i-th of the first list with the i-th from the END of the second —
+// exactly the two-pointer loop (:1169-1181) — and then adds the slab [lim1, lim2), which now holds all elements == cut,
+// to the tight box of the child each position belongs to.  Lists longer than P2_CAP are handled in rounds.
+constexpr int P2_CAP = 2048;
+__device__ __forceinline__ uint32_t node_word( const uint32_t* __restrict__ W, uint32_t wi, uint32_t lo, uint32_t hi, bool invert ) {
+  // word wi of the node's mask restricted to positions [lo, hi), optionally inverted
+  uint32_t       v    = invert ? ~W[wi] : W[wi];
+  const uint32_t base = wi << 5;
+  if ( base < lo ) { v &= lo - base >= 32 ? 0u : ( 0xFFFFFFFFu << ( lo - base ) ); }
+  if ( base + 32 > hi ) { v &= hi <= base ? 0u : ( 0xFFFFFFFFu >> ( base + 32 - hi ) ); }
+  return v;
+}
+// ordered positions of the set bits of the (restricted) mask with ranks in [r0, r0 + P2_CAP) -> out[rank - r0]; returns the
+// total number of set bits.  Every thread owns a contiguous slice of the words.
+__device__ __forceinline__ uint32_t node_list( const uint32_t* __restrict__ W, uint32_t lo, uint32_t hi, bool invert, uint32_t r0,
+                                               uint32_t* out, uint32_t* sScan ) {
+  const uint32_t w0 = lo >> 5, w1 = ( hi + 31 ) >> 5, nw = w1 > w0 ? w1 - w0 : 0, per = ( nw + TPB - 1 ) / TPB;
+  const uint32_t a = w0 + threadIdx.x * per, b = min( w1, a + per );
+  uint32_t       cnt = 0;
+  for ( uint32_t wi = a; wi < b; wi++ ) { cnt += __popc( node_word( W, wi, lo, hi, invert ) ); }
+  // CTA exclusive scan of the 256 slice counts
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t  inc  = cnt;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const uint32_t t = __shfl_up_sync( 0xFFFFFFFFu, inc, d );
+    if ( lane >= d ) { inc += t; }
+  }
+  __syncthreads();  // sScan may still be read from the previous call
+  if ( lane == 31 ) { sScan[w] = inc; }
+  __syncthreads();
+  uint32_t off = inc - cnt, total = 0;
+  for ( int k = 0; k < TPB / 32; k++ ) {
+    const uint32_t x = sScan[k];
+    if ( k < w ) { off += x; }
+    total += x;
+  }
+  for ( uint32_t wi = a; wi < b; wi++ ) {
+    for ( uint32_t v = node_word( W, wi, lo, hi, invert ); v; v &= v - 1 ) {
+      if ( off >= r0 && off - r0 < (uint32_t)P2_CAP ) { out[off - r0] = ( wi << 5 ) + ( __ffs( v ) - 1 ); }
+      off++;
+    }
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__( TPB ) k_g_pass2_node( uint64_t* __restrict__ rec, GNode* __restrict__ nodes,
+                                                         const uint32_t* __restrict__ largeList, const uint32_t* __restrict__ wC,
+                                                         int32_t* __restrict__ st ) {
+  __shared__ uint32_t sL[P2_CAP], sR[P2_CAP], sScan[TPB / 32];
+  __shared__ int      sBox[TPB / 32][12];
+  const uint32_t i = largeList[blockIdx.x];
+  GNode&         n = nodes[i];
+  if ( n.state != 1 || n.child1 == 0 ) { return; }
+  const uint32_t  left = n.left, count = n.right - n.left, lim1 = n.lim1, lim2 = n.lim2, idx = n.idx, child1 = n.child1;
+  const uint32_t* W = wC + (size_t)n.firstChunk * GWORDS;  // chunks are node-aligned: position p is bit p & 31 of word p >> 5
+  uint32_t        m = 0;
+  if ( lim2 > lim1 && lim2 < count ) {
+    for ( uint32_t r0 = 0;; r0 += P2_CAP ) {
+      // misplaced on the left: zeros of [lim1, lim2), ranks r0.. ascending; on the right: ones of [lim2, n), ranks from the END
+      m = node_list( W, lim1, lim2, true, r0, sL, sScan );
+      if ( m == 0 || r0 >= m ) { break; }
+      const uint32_t take = min( (uint32_t)P2_CAP, m - r0 );
+      // the partners of ranks [r0, r0 + take) are the right ranks m - 1 - r0 down to m - r0 - take
+      node_list( W, lim2, count, false, m - r0 - take, sR, sScan );
+      __syncthreads();
+      for ( uint32_t k = threadIdx.x; k < take; k += TPB ) {
+        const uint32_t pl = left + sL[k], pr = left + sR[take - 1 - k];
+        const uint64_t a = rec[pl], b = rec[pr];
+        rec[pl] = b, rec[pr] = a;
+      }
+      __syncthreads();
+      if ( r0 + take >= m ) { break; }
+    }
+  }
+  if ( threadIdx.x == 0 ) { n.m2 = m; }
+  if ( lim2 == lim1 ) { return; }
+  // the slab [lim1, lim2): every position holds an element == cut now
+  __threadfence_block();
+  __syncthreads();
+  int bx[12];
+#pragma unroll
+  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = BIG, bx[3 + k] = bx[9 + k] = -BIG; }
+  for ( uint32_t p = lim1 + threadIdx.x; p < lim2; p += TPB ) {
+    const uint64_t v  = rec[left + p];
+    const int      cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
+    if ( p < idx ) {
+      bx[0] = min( bx[0], cx ), bx[1] = min( bx[1], cy ), bx[2] = min( bx[2], cz );
+      bx[3] = max( bx[3], cx ), bx[4] = max( bx[4], cy ), bx[5] = max( bx[5], cz );
+    } else {
+      bx[6] = min( bx[6], cx ), bx[7] = min( bx[7], cy ), bx[8] = min( bx[8], cz );
+      bx[9] = max( bx[9], cx ), bx[10] = max( bx[10], cy ), bx[11] = max( bx[11], cz );
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for ( int k = 0; k < 12; k++ ) {
+    bx[k] = ( k % 6 ) < 3 ? __reduce_min_sync( 0xFFFFFFFFu, bx[k] ) : __reduce_max_sync( 0xFFFFFFFFu, bx[k] );
+  }
+  if ( lane == 0 ) {
+#pragma unroll
+    for ( int k = 0; k < 12; k++ ) { sBox[w][k] = bx[k]; }
+  }
+  __syncthreads();
+  if ( threadIdx.x < 12 ) {
+    const int  k     = threadIdx.x;
+    const bool isMin = ( k % 6 ) < 3;
+    int        v     = sBox[0][k];
+    for ( int j = 1; j < TPB / 32; j++ ) { v = isMin ? min( v, sBox[j][k] ) : max( v, sBox[j][k] ); }
+    int32_t* dst = st + (size_t)( child1 + ( k >= 6 ? 1 : 0 ) ) * 6 + ( k % 6 );
+    if ( isMin ) {
+      if ( v < BIG ) { atomicMin( dst, v ); }
+    } else {
+      if ( v > -BIG ) { atomicMax( dst, v ); }
+    }
+  }
+}
+
+// the same for the many nodes of at most P2_WARP_MAX elements: one warp per node (its mask is at most 512 words)
+constexpr int P2_WCAP = 256;
+__device__ __forceinline__ uint32_t node_list_warp( const uint32_t* __restrict__ W, uint32_t lo, uint32_t hi, bool invert, uint32_t r0,
+                                                    uint32_t* out, int lane ) {
+  const uint32_t w0 = lo >> 5, w1 = ( hi + 31 ) >> 5, nw = w1 > w0 ? w1 - w0 : 0, per = ( nw + 31 ) / 32;
+  const uint32_t a = w0 + lane * per, b = min( w1, a + per );
+  uint32_t       cnt = 0;
+  for ( uint32_t wi = a; wi < b; wi++ ) { cnt += __popc( node_word( W, wi, lo, hi, invert ) ); }
+  uint32_t inc = cnt;
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const uint32_t t = __shfl_up_sync( 0xFFFFFFFFu, inc, d );
+    if ( lane >= d ) { inc += t; }
+  }
+  const uint32_t total = __shfl_sync( 0xFFFFFFFFu, inc, 31 );
+  uint32_t       off   = inc - cnt;
+  if ( total == 0 ) { return 0; }
+  for ( uint32_t wi = a; wi < b; wi++ ) {
+    for ( uint32_t v = node_word( W, wi, lo, hi, invert ); v; v &= v - 1 ) {
+      if ( off >= r0 && off - r0 < (uint32_t)P2_WCAP ) { out[off - r0] = ( wi << 5 ) + ( __ffs( v ) - 1 ); }
+      off++;
+    }
+  }
+  return total;
+}
+__global__ void __launch_bounds__( TPB ) k_g_pass2_warp( uint64_t* __restrict__ rec, GNode* __restrict__ nodes, uint32_t lvlBegin,
+                                                         uint32_t lvlEnd, const uint32_t* __restrict__ wC, int32_t* __restrict__ st ) {
+  __shared__ uint32_t sL[TPB / 32][P2_WCAP], sR[TPB / 32][P2_WCAP];
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t i    = lvlBegin + blockIdx.x * ( TPB / 32 ) + w;
+  if ( i >= lvlEnd ) { return; }
+  GNode& n = nodes[i];
+  if ( n.state != 1 || n.child1 == 0 ) { return; }
+  const uint32_t left = n.left, count = n.right - n.left, lim1 = n.lim1, lim2 = n.lim2, idx = n.idx, child1 = n.child1;
+  if ( count > P2_WARP_MAX || lim2 == lim1 ) { return; }
+  const uint32_t* W = wC + (size_t)n.firstChunk * GWORDS;
+  if ( lim2 < count ) {
+    for ( uint32_t r0 = 0;; r0 += P2_WCAP ) {
+      const uint32_t m = node_list_warp( W, lim1, lim2, true, r0, sL[w], lane );
+      if ( m == 0 || r0 >= m ) { break; }
+      const uint32_t take = min( (uint32_t)P2_WCAP, m - r0 );
+      node_list_warp( W, lim2, count, false, m - r0 - take, sR[w], lane );
+      __syncwarp();
+      for ( uint32_t k = lane; k < take; k += 32 ) {
+        const uint32_t pl = left + sL[w][k], pr = left + sR[w][take - 1 - k];
+        const uint64_t a = rec[pl], b = rec[pr];
+        rec[pl] = b, rec[pr] = a;
+      }
+      __syncwarp();
+      if ( r0 + take >= m ) { break; }
+    }
+  }
+  __threadfence_block();
+  __syncwarp();
+  int bx[12];
+#pragma unroll
+  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = BIG, bx[3 + k] = bx[9 + k] = -BIG; }
+  for ( uint32_t p = lim1 + lane; p < lim2; p += 32 ) {
+    const uint64_t v  = rec[left + p];
+    const int      cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
+    if ( p < idx ) {
+      bx[0] = min( bx[0], cx ), bx[1] = min( bx[1], cy ), bx[2] = min( bx[2], cz );
+      bx[3] = max( bx[3], cx ), bx[4] = max( bx[4], cy ), bx[5] = max( bx[5], cz );
+    } else {
+      bx[6] = min( bx[6], cx ), bx[7] = min( bx[7], cy ), bx[8] = min( bx[8], cz );
+      bx[9] = max( bx[9], cx ), bx[10] = max( bx[10], cy ), bx[11] = max( bx[11], cz );
+    }
+  }
+#pragma unroll
+  for ( int k = 0; k < 12; k++ ) {
+    bx[k] = ( k % 6 ) < 3 ? __reduce_min_sync( 0xFFFFFFFFu, bx[k] ) : __reduce_max_sync( 0xFFFFFFFFu, bx[k] );
+  }
+  if ( lane < 12 ) {
+    int v = 0;
+#pragma unroll
+    for ( int k = 0; k < 12; k++ ) {
+      if ( lane == k ) { v = bx[k]; }
+    }
+    int32_t* dst = st + (size_t)( child1 + ( lane >= 6 ? 1 : 0 ) ) * 6 + ( lane % 6 );
+    if ( ( lane % 6 ) < 3 ) {
+      if ( v < BIG ) { atomicMin( dst, v ); }
+    } else {
+      if ( v > -BIG ) { atomicMax( dst, v ); }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // subtree phase: one WARP builds a whole subtree of at most KS_CAP elements in its slice of shared memory.
 // Depth of such a subtree: every split halves the loose box along its longest side, 36 splits reduce a 4096^3 box to
@@ -1007,6 +1217,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   RB_CUDA( B.cA.ensure( (size_t)chunkCap * 4 ) );
   RB_CUDA( B.cB.ensure( (size_t)chunkCap * 4 ) );
   RB_CUDA( B.smallRoots.ensure( (size_t)gCap * 4 ) );
+  RB_CUDA( B.largeList.ensure( (size_t)( E / P2_WARP_MAX + nTrees + 64 ) * 4 ) );
   RB_CUDA( B.counters.ensure( 64 ) );
   RB_CUDA( B.stats.ensure( (size_t)gCap * 24 ) );
   int32_t*  st        = B.stats.as<int32_t>();
@@ -1034,10 +1245,12 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     const uint32_t nLvl = lvlEnd - lvlBegin;
     RB_CUDA( cudaMemsetAsync( counters + C_BIG, 0, 4, c->stream ) );
     RB_CUDA( cudaMemsetAsync( counters + C_CHUNKS, 0, 4, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( counters + C_LARGE, 0, 4, c->stream ) );
     RB_LAUNCH( "kd_setup", k_g_setup, rb_div_up( nLvl, TPB ), TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
-               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap, cls );
-    RB_CUDA( cudaMemcpyAsync( h, counters, 32, cudaMemcpyDeviceToHost, c->stream ) );
+               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap, cls, B.largeList.as<uint32_t>() );
+    RB_CUDA( cudaMemcpyAsync( h, counters, 64, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    const uint32_t nLarge = h[C_LARGE];
     if ( h[C_RANGE] ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: coordinate range of the clouds exceeds 4096" ); }
     if ( h[C_POOL] ) { return rb_fail( c, RB200_ERR_NOMEM, "kd build: node pool exhausted" ); }
     const uint32_t nBig = h[C_BIG], nChunks = h[C_CHUNKS];
@@ -1047,9 +1260,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     RB_LAUNCH( "kd_nodescan", k_g_nodescan<false>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, chunks, cA, cB, wA, wB, st, cls );
     RB_LAUNCH( "kd_stage1", k_g_stage<false>, nChunks, TPB, 0, rec, chunks, wA, tmp );
     RB_LAUNCH( "kd_apply1", k_g_apply1, nChunks, TPB, 0, rec, chunks, wA, wB, wC, cB, tmp );
-    RB_LAUNCH( "kd_nodescan", k_g_nodescan<true>, GW, TPB, 0, gnodes, lvlBegin, lvlEnd, chunks, cA, cB, wA, wC, st, cls );
-    RB_LAUNCH( "kd_stage2", k_g_stage<true>, nChunks, TPB, 0, rec, chunks, wC, tmp );
-    RB_LAUNCH( "kd_apply2", k_g_apply2, nChunks, TPB, 0, rec, chunks, wC, tmp, st );
+    if ( nLarge ) { RB_LAUNCH( "kd_pass2", k_g_pass2_node, nLarge, TPB, 0, rec, gnodes, B.largeList.as<uint32_t>(), wC, st ); }
+    RB_LAUNCH( "kd_pass2", k_g_pass2_warp, rb_div_up( nLvl, TPB / 32 ), TPB, 0, rec, gnodes, lvlBegin, lvlEnd, wC, st );
     lvlBegin = lvlEnd;  // the children were numbered consecutively behind the nodes that existed
     lvlEnd   = h[C_NEXT];
   }

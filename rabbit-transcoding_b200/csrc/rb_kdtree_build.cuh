@@ -7,13 +7,13 @@
 
 
 struct RbKdBuild {
-  RbBuf    rec, tmp, gnodes, nodes, rootBox, chunkNode, chunks, cls, wA, wB, wC, cA, cB, smallRoots, counters, stats;
+  RbBuf    rec, tmp, gnodes, nodes, rootBox, chunkNode, chunks, cls, wA, wB, wC, cA, cB, smallRoots, largeList, counters, stats;
   KdForest forest{};
   uint32_t nNodes = 0;
   int      nTrees = 0;
   int      levels = 0;
   void     release() {
-    RbBuf* b[] = {&rec, &tmp, &gnodes, &nodes, &rootBox, &chunkNode, &chunks, &cls, &wA, &wB, &wC, &cA, &cB, &smallRoots, &counters, &stats};
+    RbBuf* b[] = {&rec, &tmp, &gnodes, &nodes, &rootBox, &chunkNode, &chunks, &cls, &wA, &wB, &wC, &cA, &cB, &smallRoots, &largeList, &counters, &stats};
     for ( auto* x : b ) { x->release(); }
   }
 };
