@@ -12,8 +12,10 @@
 //   PCCPointSet3::transferColors16bitBP                    PccLibCommon/source/PCCPointSet.cpp:1126-1485
 //   PCCMetrics::compute( sources, reconstructs, normals )  PccLibMetrics/source/PCCMetrics.cpp:334-369
 //   PCCMetrics::compute( source, reconstruct, normals )    :371-385
-// There is NO fallback into the reference's bodies: the originals are not linked (oracle/Makefile drops them from the
-// objects), every result comes from the CUDA library, and a mode the CUDA path does not implement (multiple tiles,
+// There is NO fallback into the reference's bodies: the shim never calls them (in the test build their definitions are
+// weakened in the copied objects, oracle/Makefile, so the strong definitions below are the ones every caller binds to;
+// nothing named rb200_orig_* exists), every result comes from the CUDA library, and a mode the CUDA path does not
+// implement (multiple tiles,
 // auxiliary video, PBF, other transfer-filter arguments ...) ends the way the reference ends on an error: a message and
 // exit( -1 ) (PCCMetrics.cpp:342-346, PCCPatch.cpp:237-245).
 //
