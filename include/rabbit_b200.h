@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RB200_ABI_VERSION 2
+#define RB200_ABI_VERSION 3
 
 typedef enum rb200_status {
   RB200_OK                   = 0,
@@ -95,7 +95,10 @@ typedef struct rb200_params {
   int32_t single_map_pixel_interleaving; /* generatePoints :350-471: one map, layers on a checkerboard; needs
                                           * map_count_minus1 == 0, surface_thickness >= 1, no EOM / multiple streams */
   int32_t point_local_reconstruction;    /* generatePoints :472-496; needs one map and rb200_gof_set_plr */
-  int32_t pbf_enable;                    /* UNSUPPORTED when non-zero (Rec-2 occupancy synthesis)       */
+  int32_t pbf_enable;                    /* Rec-2 occupancy synthesis (patch border filtering, PCCCodec.cpp:541-554):
+                                          * one or two maps, no EOM / pixel interleaving / PLR / size quantisation,
+                                          * every patch at level of detail 1 without an additional plane; the
+                                          * pbf_* fields at the end of this struct hold the SEI's parameters   */
   int32_t multiple_streams;         /* sps.getMultipleMapStreamsPresentFlag: the caller still hands planes
                                      * as [F][M][..][H][W] (map m of frame f = frame f of stream m)       */
   int32_t attribute_count;          /* 0: colours become 127 (PCCCodec.cpp:1327-1330)                   */
@@ -117,6 +120,11 @@ typedef struct rb200_params {
   double  threshold_color_smoothing;
   double  threshold_color_difference;
   double  threshold_color_variation;
+  /* occupancy synthesis SEI (PCCDecoder.cpp:627-640): pbfPassesCount_, pbfFilterSize_, pbfLog2Threshold_ */
+  int32_t pbf_passes_count;
+  int32_t pbf_filter_size;
+  int32_t pbf_log2_threshold;
+  int32_t reserved0;
 } rb200_params;
 
 /* Decoded video planes of one GOF (what PCCVideoDecoder leaves in PCCContext, PCCContext.h:48-50).

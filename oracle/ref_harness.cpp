@@ -161,10 +161,10 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
   g.plrlNumberOfModes_             = 0;
   g.geometryBitDepth3D_            = p.geometry_bitdepth_3d;
   g.geometry3dCoordinatesBitdepth_ = p.geometry_bitdepth_3d;
-  g.pbfEnableFlag_                 = false;
-  g.pbfPassesCount_                = 0;
-  g.pbfFilterSize_                 = 0;
-  g.pbfLog2Threshold_              = 0;
+  g.pbfEnableFlag_                 = p.pbf_enable != 0;  // setPostProcessingSeiParameters, PCCDecoder.cpp:627-640
+  g.pbfPassesCount_                = p.pbf_passes_count;
+  g.pbfFilterSize_                 = p.pbf_filter_size;
+  g.pbfLog2Threshold_              = p.pbf_log2_threshold;
 }
 
 }  // namespace
@@ -374,8 +374,10 @@ ref_gof* ref_gof_run( const rb200_params* pp,
       PCCPointSet3          reconstruct;
       std::vector<uint32_t> partition;
       auto                  t0 = std::chrono::steady_clock::now();
-      codec.generateOccupancyMap( tile, occVideo.getFrame( f ), P, p.threshold_lossy_om,
-                                  p.enhanced_occupancy_map_code != 0 );
+      if ( !p.pbf_enable ) {  // PCCDecoder.cpp:362-366
+        codec.generateOccupancyMap( tile, occVideo.getFrame( f ), P, p.threshold_lossy_om,
+                                    p.enhanced_occupancy_map_code != 0 );
+      }
       codec.generateBlockToPatchFromOccupancyMapVideo( context, tile, f, occVideo.getFrame( f ),
                                                        p.occupancy_resolution, P );
       PCCPointSet3 tileRec;
@@ -419,7 +421,7 @@ ref_gof* ref_gof_run( const rb200_params* pp,
         auto t3       = std::chrono::steady_clock::now();
         fo.msStage[1] = std::chrono::duration<double, std::milli>( t3 - t2 ).count();
         if ( keep_mask & 2u ) { snap( fo.stage[1], reconstruct ); }
-        if ( p.attribute_count > 0 && p.attr_transfer_filter_type == 1 ) {
+        if ( p.attribute_count > 0 && p.attr_transfer_filter_type == 1 && !p.pbf_enable ) {  // :445
           tempFrameBuffer.transferColors16bitBP( reconstruct, 1, int32_t( 0 ), p.attribute_rgb444 != 0, 8, 1, true, true,
                                                  true, false, 4, 4, 1000, 1000, 1000 * 256, 1000 * 256 );
         }

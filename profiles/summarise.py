@@ -22,7 +22,10 @@ BENCH_NAME = [("k_reproject<1", "reproject_emit"), ("k_reproject<(bool)1", "repr
               ("k_reproject<(bool)0", "reproject_count"), ("k_accumulate<0", "geo_accumulate"), ("k_accumulate<(bool)0", "geo_accumulate"),
               ("k_accumulate<1", "col_accumulate"), ("k_accumulate<(bool)1", "col_accumulate"), ("k_filter_geo", "geo_filter"),
               ("k_filter_col", "col_filter"), ("k_cell_median_gate", "col_median_gate"), ("k_to_rgb8", "to_rgb8"),
-              ("k_mark_cells", "col_mark"), ("k_occupancy_bitmap", "occupancy_bitmap"), ("k_yuv420", "attribute_420_to_444")]
+              ("k_mark_cells", "col_mark"), ("k_occupancy_bitmap", "occupancy_bitmap"), ("k_yuv420", "attribute_420_to_444"),
+              ("k_kd_subtree", "kd_subtree"), ("k_g_count", "kd_count"), ("k_g_stage", "kd_stage1"), ("k_g_apply1", "kd_apply1"),
+              ("k_transfer_fwd", "tr_forward"), ("k_transfer_bwd(", "tr_backward"), ("k_transfer_final", "tr_final"),
+              ("k_nn_near", "met_nn_near"), ("k_nn_pending", "met_nn_rings")]
 
 
 def short(name):
@@ -91,13 +94,14 @@ def full(tag, rep, cmd):
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
             for pat, bn in BENCH_NAME:
                 if pat in name:
-                    traffic[bn] = int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+                    traffic.setdefault(bn, []).append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
     tj = os.path.join(HERE, "ncu_traffic.json")
     old = {}
     if os.path.exists(tj):
         old = json.load(open(tj))
-    old.update(traffic)
-    old["_source"] = f"{tag}: dram__bytes_read.sum + dram__bytes_write.sum per launch, `{cmd}`"
+    old.update({k: int(sum(v) / len(v)) for k, v in traffic.items()})  # mean over the captured launches of a kernel
+    old["_source"] = (old.get("_source", "") + " | " if old.get("_source") else "") + \
+        f"{tag} ({', '.join(sorted(traffic))}): dram__bytes_read.sum + dram__bytes_write.sum per launch, `{cmd}`"
     json.dump(old, open(tj, "w"), indent=1, sort_keys=True)
     return out
 

@@ -67,7 +67,8 @@ class Params(C.Structure):
         "surface_thickness")] + [
         (n, C.c_double) for n in (
             "threshold_smoothing", "threshold_color_smoothing", "threshold_color_difference",
-            "threshold_color_variation")]
+            "threshold_color_variation")] + [
+        (n, i32) for n in ("pbf_passes_count", "pbf_filter_size", "pbf_log2_threshold", "reserved0")]
 
 
 class PlrMode(C.Structure):

@@ -34,7 +34,7 @@ class RabbitError(RuntimeError):
 class PCCCodecB200:
     def __init__(self, device=0, stream=None):
         self._lib = abi.load_library()
-        if self._lib.rb200_abi_version() != 2:
+        if self._lib.rb200_abi_version() != 3:
             raise RuntimeError("rabbit_b200 ABI version mismatch")
         h = C.c_void_p()
         st = self._lib.rb200_create(device, C.byref(h))

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -104,6 +105,8 @@ struct rb200_ctx {
   RbBuf d_snap_pos[2], d_snap_col[3];
   bool  have_snap_pos[2] = {false, false}, have_snap_col[3] = {false, false, false};
   RbBuf d_blist, d_blist_n;  // indices of the boundary (type 1) points of the GOF + their count (device)
+  RbBuf d_pbf;               // occupancy synthesis: the patch-local maps of the GOF (rb_pbf.cu)
+  RbBuf d_bnd_bitmap;        // occupancy synthesis: [F][H][bmWords] PCCPatch::isBorder of every occupied pixel
   int64_t blist_cap = 0;     // that count on the host
   std::vector<int64_t>            h_frame_off;  // [F+1]
   std::vector<rb200_frame_counts> h_counts;
@@ -129,6 +132,8 @@ struct rb200_ctx {
   // pinned host staging for small read-backs
   void*  h_pinned     = nullptr;
   size_t h_pinned_cap = 0;
+  char*  h_ring       = nullptr;  // pinned ring for small host -> device tables (rb_pinned_ring)
+  size_t h_ring_off   = 0;
 
   // ---- instrumentation ----
   rb200_launch_stats          stats{};
@@ -155,6 +160,9 @@ int  rb_cuda( rb200_ctx* c, cudaError_t e, const char* what );
 void rb_timing_begin( rb200_ctx* c, const char* name );
 void rb_timing_end( rb200_ctx* c );
 void* rb_pinned( rb200_ctx* c, size_t bytes );
+// a fresh slice of a pinned ring for a small table that is copied to the device asynchronously and never read back:
+// no wait before the host writes it (the stream is only synchronised when the ring wraps)
+void* rb_pinned_ring( rb200_ctx* c, size_t bytes );
 
 #define RB_CUDA( call )                                                \
   do {                                                                 \
@@ -177,6 +185,7 @@ static inline int rb_div_up( int64_t a, int64_t b ) { return (int)( ( a + b - 1 
 
 // stage entry points implemented in the other translation units
 int rb_reconstruct_impl( rb200_ctx* c );
+int rb_pbf_impl( rb200_ctx* c );
 int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
 int rb_interleave_colors_impl( rb200_ctx* c );

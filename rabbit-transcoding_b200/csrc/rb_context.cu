@@ -44,6 +44,23 @@ void* rb_pinned( rb200_ctx* c, size_t bytes ) {
   return c->h_pinned;
 }
 
+void* rb_pinned_ring( rb200_ctx* c, size_t bytes ) {
+  constexpr size_t RING = 4u << 20;
+  bytes = ( bytes + 255 ) & ~size_t( 255 );
+  if ( bytes > RING ) { return nullptr; }
+  if ( !c->h_ring ) {
+    if ( cudaMallocHost( (void**)&c->h_ring, RING ) != cudaSuccess ) { return nullptr; }
+    c->h_ring_off = 0;
+  }
+  if ( c->h_ring_off + bytes > RING ) {  // every earlier slice was handed to a copy on c->stream
+    cudaStreamSynchronize( c->stream );
+    c->h_ring_off = 0;
+  }
+  void* p = c->h_ring + c->h_ring_off;
+  c->h_ring_off += bytes;
+  return p;
+}
+
 static void rb_timing_resolve( rb200_ctx* c ) {
   if ( c->timing_events.empty() ) { return; }
   cudaStreamSynchronize( c->stream );
@@ -201,13 +218,14 @@ void rb200_destroy( rb200_ctx* c ) {
                    &c->d_plr_modes, &c->d_plr_block_mode, &c->d_plr_block_off,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
                    &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
-                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n,
+                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n, &c->d_pbf, &c->d_bnd_bitmap,
                    &c->d_snap_pos[0], &c->d_snap_pos[1], &c->d_snap_col[0], &c->d_snap_col[1], &c->d_snap_col[2]};
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }
   rb_metrics_release( c );
   rb_transfer_release( c );
   if ( c->h_pinned ) { cudaFreeHost( c->h_pinned ); }
+  if ( c->h_ring ) { cudaFreeHost( c->h_ring ); }
   for ( auto& t : c->timing_events ) {
     cudaEventDestroy( t.a );
     cudaEventDestroy( t.b );
@@ -254,8 +272,17 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   if ( p->width % R || p->height % R || p->width > 65535 || p->height > 65535 ) {
     return rb_fail( c, RB200_ERR_INVALID, "atlas %dx%d must be a multiple of %d and < 65536", p->width, p->height, R );
   }
-  if ( p->pbf_enable ) {
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "PBF (PCCCodec.cpp:541-554) is not implemented in this build" );
+  if ( p->pbf_enable ) {  // occupancy synthesis (PCCCodec.cpp:541-554, PCCPatch.cpp:797-977)
+    if ( p->enhanced_occupancy_map_code || p->single_map_pixel_interleaving || p->point_local_reconstruction ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "occupancy synthesis together with EOM, pixel interleaving or point local "
+                                                "reconstruction is not implemented" );
+    }
+    if ( p->enable_size_quantization ) {  // the reference clears pixels of a map it never allocated there (:571-597)
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "occupancy synthesis together with patch size quantisation is undefined in the reference" );
+    }
+    if ( p->pbf_passes_count < 1 || p->pbf_filter_size < 1 || p->pbf_log2_threshold < 1 ) {
+      return rb_fail( c, RB200_ERR_INVALID, "pbf_enable needs pbf_passes_count, pbf_filter_size and pbf_log2_threshold >= 1" );
+    }
   }
   if ( p->single_map_pixel_interleaving || p->point_local_reconstruction ) {
     // generatePoints :350-471 / :472-496 + transferColorWeight (colorPointCloud :1367-1434)

@@ -609,80 +609,6 @@ __global__ void __launch_bounds__( TPB ) k_g_apply1( uint64_t* __restrict__ rec,
   }
 }
 
-// pass G: the partners of pass 2, and the children's boxes of the elements == cut.  After pass 2 those elements sit at
-// positions [lim1, lim2) and belong to the child their position falls in, which is only known now; everything else of
-// the boxes came from the count pass.  Only chunks that reach into [lim1, n) with work to do run past the first lines.
-__global__ void __launch_bounds__( TPB ) k_g_apply2( uint64_t* __restrict__ rec, const GChunk* __restrict__ chunks,
-                                                     const uint32_t* __restrict__ wC, const uint64_t* __restrict__ tmp,
-                                                     int32_t* __restrict__ st ) {
-  __shared__ uint32_t sWord[GWORDS], sPre[GWORDS];
-  __shared__ int      sBox[TPB / 32][12];
-  const uint32_t c = blockIdx.x;
-  const GChunk&  D = chunks[c];
-  const uint32_t e0 = D.e0, left = D.left, cnt = D.cnt, p0 = e0 - left, lim1 = D.lim1, lim2 = D.lim2, m = D.m, base = D.pre;
-  const bool     slab = p0 < lim2 && p0 + cnt > lim1;  // the chunk holds positions of [lim1, lim2)
-  if ( ( m == 0 || p0 + cnt <= lim1 ) && !slab ) { return; }
-  const uint32_t idx = D.idx, child1 = D.child1;
-  chunk_word_prefix( wC + (size_t)c * GWORDS, sWord, sPre );
-  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t lt   = lanemask_lt();
-  int            bx[12];  // {min[3], max[3]} of the left child, then of the right child ("== cut" elements only)
-#pragma unroll
-  for ( int k = 0; k < 3; k++ ) { bx[k] = bx[6 + k] = BIG, bx[3 + k] = bx[9 + k] = -BIG; }
-#pragma unroll
-  for ( int q = 0; q < GEPT; q++ ) {
-    const uint32_t i = q * TPB + threadIdx.x;
-    if ( i >= cnt ) { continue; }
-    const uint32_t p = p0 + i;
-    if ( p < lim1 ) { continue; }
-    const int      wi  = q * ( TPB / 32 ) + w;
-    const uint32_t wd  = sWord[wi];
-    const bool     bit = ( wd >> lane ) & 1u;
-    const uint32_t pre = base + sPre[wi] + __popc( wd & lt );
-    uint64_t       v   = 0;
-    bool           have = false;
-    if ( m && p < lim2 && !bit ) {
-      v           = tmp[left + lim2 + ( m - 1u - ( ( p - lim1 ) - pre ) )];
-      rec[e0 + i] = v, have = true;
-    } else if ( m && p >= lim2 && bit ) {
-      v           = tmp[left + lim1 + ( m - 1u - ( pre - ( ( lim2 - lim1 ) - m ) ) )];
-      rec[e0 + i] = v, have = true;
-    }
-    if ( slab && p < lim2 ) {  // after pass 2 this position holds an element == cut
-      if ( !have ) { v = rec[e0 + i]; }
-      const int  cx = kd_coord( v, 0 ), cy = kd_coord( v, 1 ), cz = kd_coord( v, 2 );
-      const bool rt = p >= idx;
-      bx[0] = min( bx[0], rt ? BIG : cx ), bx[1] = min( bx[1], rt ? BIG : cy ), bx[2] = min( bx[2], rt ? BIG : cz );
-      bx[3] = max( bx[3], rt ? -BIG : cx ), bx[4] = max( bx[4], rt ? -BIG : cy ), bx[5] = max( bx[5], rt ? -BIG : cz );
-      bx[6] = min( bx[6], rt ? cx : BIG ), bx[7] = min( bx[7], rt ? cy : BIG ), bx[8] = min( bx[8], rt ? cz : BIG );
-      bx[9] = max( bx[9], rt ? cx : -BIG ), bx[10] = max( bx[10], rt ? cy : -BIG ), bx[11] = max( bx[11], rt ? cz : -BIG );
-    }
-  }
-  if ( !slab ) { return; }
-#pragma unroll
-  for ( int k = 0; k < 12; k++ ) {
-    const bool isMin = ( k % 6 ) < 3;
-    bx[k]            = isMin ? __reduce_min_sync( 0xFFFFFFFFu, bx[k] ) : __reduce_max_sync( 0xFFFFFFFFu, bx[k] );
-  }
-  if ( lane == 0 ) {
-#pragma unroll
-    for ( int k = 0; k < 12; k++ ) { sBox[w][k] = bx[k]; }
-  }
-  __syncthreads();
-  if ( threadIdx.x < 12 ) {
-    const int  k     = threadIdx.x;
-    const bool isMin = ( k % 6 ) < 3;
-    int        v     = sBox[0][k];
-    for ( int j = 1; j < TPB / 32; j++ ) { v = isMin ? min( v, sBox[j][k] ) : max( v, sBox[j][k] ); }
-    int32_t* dst = st + (size_t)( child1 + ( k >= 6 ? 1 : 0 ) ) * 6 + ( k % 6 );
-    if ( isMin ) {
-      if ( v < BIG ) { atomicMin( dst, v ); }
-    } else {
-      if ( v > -BIG ) { atomicMax( dst, v ); }
-    }
-  }
-}
-
 // pass E-G for one node (one CTA per node of the level): the second Hoare pass of planeSplit only concerns the elements
 // == cut, a thin slab of the node.  After pass 1 they sit somewhere in [lim1, n); "<= cut" of that range is the mask wC.
 // The CTA lists the positions of [lim1, lim2) that hold an element > cut (ascending) and the positions of [lim2, n) that
@@ -893,24 +819,39 @@ __global__ void __launch_bounds__( TPB ) k_g_pass2_warp( uint64_t* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------------
 // subtree phase: one WARP builds a whole subtree of at most KS_CAP elements in its slice of shared memory.
+//  * nodes of more than KS_SMALL elements are split by the whole warp, depth first (lane-strided passes, ballots);
+//  * nodes of at most KS_SMALL elements are only LISTED by that phase and then finished one per LANE: every lane runs
+//    nanoflann's own sequential algorithm (computeMinMax, middleSplit_, the two-pointer loops of planeSplit) on its
+//    node's slice of the shared records.  A warp-wide pass over <= 32 elements is one instruction of data work under
+//    ~400 instructions of warp-uniform bookkeeping; per lane the bookkeeping runs for 32 nodes at once.
+// A node is written complete by whoever splits it: with lim1 <= idx <= lim2 the left child holds an element == cut
+// exactly when idx > lim1 (else its largest coordinate is the largest one < cut), and the same on the right, so
+// divlow / divhigh (divideTree :1080-1081) need no report from the children.  The ids of a node's children follow from
+// the split position ( every position between two elements of the subtree is cut exactly once ): no id counter.
 // Depth of such a subtree: every split halves the loose box along its longest side, 36 splits reduce a 4096^3 box to
 // a single lattice point, and from there on cutval == tmin == tmax gives lim1 = 0, lim2 = n, idx = n / 2 — so at most
 // 36 + log2( KS_CAP ) levels, and the stack of pending right children is never deeper than that.
 // ---------------------------------------------------------------------------------------------------
+constexpr int KS_SMALL      = 32;                   // largest node finished by a single lane
+constexpr int KS_LEAF       = 10;                   // leaf_max_size (PCCKdTree.cpp:58)
+constexpr int KS_SMALL_LIST = KS_CAP / ( KS_LEAF + 1 ) + 2;  // such nodes hold more than KS_LEAF elements each
+constexpr int KS_LSTACK     = 6;                    // pending nodes of one lane: disjoint, > KS_LEAF elements, <= KS_SMALL in total
+
 struct KsItem {
   uint32_t gid;          // node id
-  uint32_t pgid;         // parent's node id in KdNode numbering, 0 for the subtree root
   uint16_t left, right;  // element range inside the subtree
-  int16_t  lo[3], hi[3];
-  uint8_t  side, depth;  // side: 0 left / 1 right child of pgid
-  uint8_t  pfeat, pad;   // cut axis of the parent
+  int16_t  lo[3], hi[3]; // loose box (divideTree's bbox argument)
+  uint16_t depth, pad;
 };
+static_assert( sizeof( KsItem ) == 24, "KsItem is copied as 6 words" );
 
 struct KsWarp {
   uint64_t rec[KS_CAP];
-  uint64_t tmp[KS_CAP];
+  uint64_t tmp[KS_CAP];  // warp phase: staging of the Hoare passes; lane phase: the lanes' stacks (word-interleaved)
   KsItem   stack[KS_STACK];
+  KsItem   small[KS_SMALL_LIST];
 };
+static_assert( KS_LSTACK * 5 * 32 * 4 <= KS_CAP * 8 && KS_CAP <= 1024, "lane stacks live in the staging array" );
 
 // one Hoare pass of planeSplit (:1154-1181) on positions [begin, right) of the warp's subtree: the positions before
 // `lim` (node-relative) must hold the elements with kd_coord < bound (INCL: <= bound)
@@ -950,27 +891,101 @@ __device__ __forceinline__ void ks_hoare( KsWarp& S, uint32_t left, uint32_t beg
   __syncwarp();
 }
 
-constexpr uint32_t KS_NOREPORT = 0xFFFFFFFFu;  // KsItem::pgid: the parent computed this node's bound itself
-
-// a child of at most leaf_max_size (10, PCCKdTree.cpp:58) elements is finished by its parent: the leaf record, and the
-// bound it hands up (divideTree :1080-1081) unless the parent has it already
-__device__ __forceinline__ void ks_leaf_child( KsWarp& S, KdNode* __restrict__ nodes, uint32_t base, uint32_t parent, uint32_t gid,
-                                               uint32_t first, uint32_t cnt, int side, int cf, bool report, int lane ) {
-  if ( report ) {
-    const int v = lane < (int)cnt ? kd_coord( S.rec[first + lane], cf ) : ( side ? 4096 : -1 );
-    const int e = side ? __reduce_min_sync( 0xFFFFFFFFu, v ) : __reduce_max_sync( 0xFFFFFFFFu, v );
-    if ( lane == 0 ) {
-      if ( side ) {
-        nodes[parent].divhigh = (int16_t)e;
+// lane phase: this lane finishes the node `it` (more than KS_LEAF, at most KS_SMALL elements) and everything below it.
+// `stk` is the lane's stack: word w of entry d at stk[( d * 5 + w ) * 32].  Returns the depth of the deepest node.
+__device__ __forceinline__ int ks_lane_subtree( KsWarp& S, KdNode* __restrict__ nodes, uint32_t base, uint32_t idBase, KsItem it,
+                                                bool have, uint32_t* __restrict__ stk, const int o[3] ) {
+  uint32_t gid = it.gid;
+  int      l = it.left, r = it.right, depth = it.depth, deepest = 0, sp = 0;
+  int      lo0 = it.lo[0], lo1 = it.lo[1], lo2 = it.lo[2], hi0 = it.hi[0], hi1 = it.hi[1], hi2 = it.hi[2];
+  while ( have ) {
+    const int n = r - l;
+    deepest     = max( deepest, depth );
+    // computeMinMax (:1092-1101)
+    int mn[3] = {4096, 4096, 4096}, mx[3] = {-1, -1, -1};
+    for ( int p = l; p < r; p++ ) {
+      const uint64_t q = S.rec[p];
+      const int      x = kd_coord( q, 0 ), y = kd_coord( q, 1 ), z = kd_coord( q, 2 );
+      mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
+      mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
+    }
+    int cf, cut;
+    {
+      const int lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+      kd_choose_split( lo, hi, mn, mx, o, cf, cut );
+    }
+    const int sh = 12 * cf;
+    // planeSplit (:1154-1181), both pointers stepped together: a pointer that may move does, two blocked pointers swap.
+    // (`right &&` of the original only keeps an unsigned index from wrapping; the indices are signed here.)
+    int a = l, z = r - 1, maxLT = -1, minGT = 4096;
+    while ( a <= z ) {
+      const uint64_t ra = S.rec[a], rz = S.rec[z];
+      const int      va = (int)( ra >> sh ) & 0xFFF, vz = (int)( rz >> sh ) & 0xFFF;
+      const bool     okA = va < cut, okZ = vz >= cut;
+      if ( okA ) { maxLT = max( maxLT, va ); }
+      if ( !okZ ) { maxLT = max( maxLT, vz ); }
+      if ( !okA && !okZ ) {
+        S.rec[a] = rz, S.rec[z] = ra;
+        a++, z--;
       } else {
-        nodes[parent].divlow = (int16_t)e;
+        a += okA, z -= okZ;
       }
     }
+    const int lim1 = a - l;
+    z              = r - 1;
+    while ( a <= z ) {
+      const uint64_t ra = S.rec[a], rz = S.rec[z];
+      const int      va = (int)( ra >> sh ) & 0xFFF, vz = (int)( rz >> sh ) & 0xFFF;
+      const bool     okA = va <= cut, okZ = vz > cut;
+      if ( !okA ) { minGT = min( minGT, va ); }
+      if ( okZ ) { minGT = min( minGT, vz ); }
+      if ( !okA && !okZ ) {
+        S.rec[a] = rz, S.rec[z] = ra;
+        a++, z--;
+      } else {
+        a += okA, z -= okZ;
+      }
+    }
+    const int lim2 = a - l;
+    const int idx  = (int)kd_split_index( (uint32_t)n, (uint32_t)lim1, (uint32_t)lim2 );
+    const int s    = l + idx;  // split position inside the subtree, 1 <= s < total
+    const uint32_t c1     = idBase + 2u * (uint32_t)( s - 1 );
+    const int      divlow = idx > lim1 ? cut : maxLT, divhigh = idx < lim2 ? cut : minGT;
+    *reinterpret_cast<uint4*>( &nodes[gid] ) = make_uint4( c1, (uint32_t)cf, ( (uint32_t)divlow & 0xFFFFu ) | ( (uint32_t)divhigh << 16 ), 0u );
+    const int nl = idx, nr = n - idx;
+    if ( nl <= KS_LEAF ) { *reinterpret_cast<uint2*>( &nodes[c1] ) = make_uint2( base + (uint32_t)l, KD_LEAF | (uint32_t)nl ); }
+    if ( nr <= KS_LEAF ) { *reinterpret_cast<uint2*>( &nodes[c1 + 1] ) = make_uint2( base + (uint32_t)s, KD_LEAF | (uint32_t)nr ); }
+    depth++;
+    if ( nl > KS_LEAF ) {
+      if ( nr > KS_LEAF && sp < KS_LSTACK ) {  // right child: [s, r), box with low[cf] = cut (sp < KS_LSTACK always holds, see above)
+        uint32_t* e = stk + sp * 5 * 32;
+        e[0]        = c1 + 1;
+        e[32]       = (uint32_t)s | ( (uint32_t)r << 10 ) | ( (uint32_t)depth << 20 );
+        e[64]       = (uint32_t)( cf == 0 ? cut : lo0 ) | ( (uint32_t)( cf == 1 ? cut : lo1 ) << 16 );
+        e[96]       = (uint32_t)( cf == 2 ? cut : lo2 ) | ( (uint32_t)hi0 << 16 );
+        e[128]      = (uint32_t)hi1 | ( (uint32_t)hi2 << 16 );
+        sp++;
+      }
+      gid = c1, r = s;  // left child: [l, s), box with high[cf] = cut
+      hi0 = cf == 0 ? cut : hi0, hi1 = cf == 1 ? cut : hi1, hi2 = cf == 2 ? cut : hi2;
+    } else if ( nr > KS_LEAF ) {
+      gid = c1 + 1, l = s;
+      lo0 = cf == 0 ? cut : lo0, lo1 = cf == 1 ? cut : lo1, lo2 = cf == 2 ? cut : lo2;
+    } else if ( sp > 0 ) {
+      sp--;
+      const uint32_t* e = stk + sp * 5 * 32;
+      gid               = e[0];
+      l = (int)( e[32] & 0x3FFu ), r = (int)( ( e[32] >> 10 ) & 0x3FFu ), depth = (int)( e[32] >> 20 );
+      lo0 = (int)( e[64] & 0xFFFFu ), lo1 = (int)( e[64] >> 16 ), lo2 = (int)( e[96] & 0xFFFFu );
+      hi0 = (int)( e[96] >> 16 ), hi1 = (int)( e[128] & 0xFFFFu ), hi2 = (int)( e[128] >> 16 );
+    } else {
+      have = false;
+    }
   }
-  if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[gid] ) = make_uint2( base + first, KD_LEAF | cnt ); }
+  return deepest;
 }
 
-__global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __restrict__ grec, GNode* __restrict__ gnodes,
+__global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __restrict__ grec, const GNode* __restrict__ gnodes,
                                                                  KdNode* __restrict__ nodes, const uint32_t* __restrict__ smallRoots,
                                                                  uint32_t nRoots, uint32_t* __restrict__ counters, uint32_t subBase,
                                                                  int ox, int oy, int oz ) {
@@ -987,181 +1002,136 @@ __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __res
     job = __shfl_sync( 0xFFFFFFFFu, job, 0 );
     if ( job >= nRoots ) { break; }
     const uint32_t rootId = smallRoots[job];
-    const uint32_t base   = gnodes[rootId].left, total = gnodes[rootId].right - base;
-    // node ids of this subtree: a contiguous block behind the level-phase nodes, 2 ids per element is the worst case
+    const GNode&   root   = gnodes[rootId];
+    const uint32_t base = root.left, total = root.right - base;
+    // node ids of this subtree: a contiguous block behind the level-phase nodes, the children of the node that cuts
+    // between elements s - 1 and s are idBase + 2 ( s - 1 ) and the id after it
     const uint32_t idBase = subBase + 2u * base;
-    uint32_t       nextId = 0;
     for ( uint32_t i = lane; i < total; i += 32 ) { S.rec[i] = grec[base + i]; }
     KsItem cur{};
-    {
-      const GNode& r = gnodes[rootId];
-      cur.gid = rootId, cur.pgid = 0, cur.left = 0, cur.right = (uint16_t)total, cur.side = 0, cur.depth = 0;
-      for ( int k = 0; k < 3; k++ ) { cur.lo[k] = r.lo[k], cur.hi[k] = r.hi[k]; }
-    }
-    int sp = 0;
+    cur.gid = rootId, cur.left = 0, cur.right = (uint16_t)total, cur.depth = 0;
+    for ( int k = 0; k < 3; k++ ) { cur.lo[k] = root.lo[k], cur.hi[k] = root.hi[k]; }
+    // the root's tight box is the level phase's (k_g_setup)
+    int mn[3] = {root.tmin[0], root.tmin[1], root.tmin[2]}, mx[3] = {root.tmax[0], root.tmax[1], root.tmax[2]};
+    int sp = 0, nSmall = 0;
+    bool haveBox = true;
     __syncwarp();
-    for ( ;; ) {
-      const uint32_t left = cur.left, right = cur.right, n = right - left;
-      maxDepth = max( maxDepth, (int)cur.depth );
-      const bool small = n <= 32;  // the whole node lives in one register per lane
-      uint64_t   r     = 0;
-      // ---- tight box (computeMinMax) ----
-      int mn[3] = {4096, 4096, 4096}, mx[3] = {-1, -1, -1};
-      if ( small ) {
-        if ( lane < (int)n ) {
-          r = S.rec[left + lane];
-          mn[0] = mx[0] = kd_coord( r, 0 ), mn[1] = mx[1] = kd_coord( r, 1 ), mn[2] = mx[2] = kd_coord( r, 2 );
-        }
-      } else {
-        for ( uint32_t p = left + lane; p < right; p += 32 ) {
-          const uint64_t q = S.rec[p];
-          const int      x = kd_coord( q, 0 ), y = kd_coord( q, 1 ), z = kd_coord( q, 2 );
-          mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
-          mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
-        }
-      }
-#pragma unroll
-      for ( int k = 0; k < 3; k++ ) {
-        mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
-        mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
-      }
-      // the node reports its tight bound to its parent (divideTree :1080-1081)
-      if ( lane == 0 && cur.pgid != KS_NOREPORT ) {
-        if ( cur.pgid ) {
-          const int pf = cur.pfeat;
-          if ( cur.side == 0 ) {
-            nodes[cur.pgid].divlow = (int16_t)( pf == 0 ? mx[0] : ( pf == 1 ? mx[1] : mx[2] ) );
-          } else {
-            nodes[cur.pgid].divhigh = (int16_t)( pf == 0 ? mn[0] : ( pf == 1 ? mn[1] : mn[2] ) );
+    if ( total <= (uint32_t)KS_LEAF ) {  // only the root of a subtree can arrive here as a leaf
+      if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[rootId] ) = make_uint2( base, KD_LEAF | total ); }
+    } else if ( total <= (uint32_t)KS_SMALL ) {
+      if ( lane == 0 ) { S.small[0] = cur; }
+      nSmall = 1;
+    } else {
+      // ---- warp phase: nodes of more than KS_SMALL elements ----
+      for ( ;; ) {
+        const uint32_t left = cur.left, right = cur.right, n = right - left;
+        // ---- tight box (computeMinMax) ----
+        if ( !haveBox ) {
+          mn[0] = mn[1] = mn[2] = 4096, mx[0] = mx[1] = mx[2] = -1;
+          for ( uint32_t p = left + lane; p < right; p += 32 ) {
+            const uint64_t q = S.rec[p];
+            const int      x = kd_coord( q, 0 ), y = kd_coord( q, 1 ), z = kd_coord( q, 2 );
+            mn[0] = min( mn[0], x ), mn[1] = min( mn[1], y ), mn[2] = min( mn[2], z );
+            mx[0] = max( mx[0], x ), mx[1] = max( mx[1], y ), mx[2] = max( mx[2], z );
           }
-        } else {  // the parent is a level-phase node: k_g_finalize reads the box from the build node
-          GNode& g = gnodes[cur.gid];
-          for ( int k = 0; k < 3; k++ ) { g.tmin[k] = (int16_t)mn[k], g.tmax[k] = (int16_t)mx[k]; }
+#pragma unroll
+          for ( int k = 0; k < 3; k++ ) {
+            mn[k] = __reduce_min_sync( 0xFFFFFFFFu, mn[k] );
+            mx[k] = __reduce_max_sync( 0xFFFFFFFFu, mx[k] );
+          }
         }
-      }
-      bool haveNext = false;  // `cur` holds the next node to split
-      if ( n <= 10 ) {        // only the root of a subtree can arrive here as a leaf
-        if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[cur.gid] ) = make_uint2( base + left, KD_LEAF | n ); }
-      } else {
+        haveBox = false;
         int cf, cut;
         {
           const int lo[3] = {cur.lo[0], cur.lo[1], cur.lo[2]}, hi[3] = {cur.hi[0], cur.hi[1], cur.hi[2]};
           kd_choose_split( lo, hi, mn, mx, o, cf, cut );
         }
-        uint32_t lim1, lim2, idx;
-        bool     divKnown = false;  // the parent wrote divlow / divhigh itself
-        const uint32_t c1 = idBase + nextId;
-        nextId += 2;
-        if ( small ) {
-          // ---- planeSplit on registers: one element per lane, ranks from ballots, partners through the staging slots ----
-          const bool act = lane < (int)n;
-          int        v   = kd_coord( r, cf );
-          lim1           = __popc( __ballot_sync( 0xFFFFFFFFu, act && v < cut ) );
-          lim2           = __popc( __ballot_sync( 0xFFFFFFFFu, act && v <= cut ) );
-          if ( lim1 > 0 && lim1 < n ) {
-            const bool     isL = act && lane < (int)lim1 && v >= cut, isR = act && lane >= (int)lim1 && v < cut;
-            const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-            const uint32_t m = __popc( bl );
-            if ( m ) {
-              if ( isL ) { S.tmp[left + __popc( bl & lt )] = r; }
-              if ( isR ) { S.tmp[left + lim1 + __popc( br & lt )] = r; }
-              __syncwarp();
-              if ( isL ) { r = S.tmp[left + lim1 + ( m - 1u - __popc( bl & lt ) )]; }
-              if ( isR ) { r = S.tmp[left + ( m - 1u - __popc( br & lt ) )]; }
-              __syncwarp();
-              v = kd_coord( r, cf );
-            }
-          }
-          if ( lim2 > lim1 && lim2 < n ) {
-            const bool     isL = act && lane >= (int)lim1 && lane < (int)lim2 && v > cut, isR = act && lane >= (int)lim2 && v <= cut;
-            const uint32_t bl = __ballot_sync( 0xFFFFFFFFu, isL ), br = __ballot_sync( 0xFFFFFFFFu, isR );
-            const uint32_t m = __popc( bl );
-            if ( m ) {
-              if ( isL ) { S.tmp[left + lim1 + __popc( bl & lt )] = r; }
-              if ( isR ) { S.tmp[left + lim2 + __popc( br & lt )] = r; }
-              __syncwarp();
-              if ( isL ) { r = S.tmp[left + lim2 + ( m - 1u - __popc( bl & lt ) )]; }
-              if ( isR ) { r = S.tmp[left + lim1 + ( m - 1u - __popc( br & lt ) )]; }
-              __syncwarp();
-              v = kd_coord( r, cf );
-            }
-          }
-          idx = kd_split_index( n, lim1, lim2 );
-          if ( act ) { S.rec[left + lane] = r; }
-          // both children's bounds along the cut axis are at hand: the node is written complete
-          const int divlow  = __reduce_max_sync( 0xFFFFFFFFu, lane < (int)idx ? v : -1 );
-          const int divhigh = __reduce_min_sync( 0xFFFFFFFFu, act && lane >= (int)idx ? v : 4096 );
-          if ( lane == 0 ) {
-            *reinterpret_cast<uint4*>( &nodes[cur.gid] ) =
-                make_uint4( c1, (uint32_t)cf, ( (uint32_t)divlow & 0xFFFFu ) | ( (uint32_t)divhigh << 16 ), 0u );
-          }
-          divKnown = true;
-          __syncwarp();
-        } else {
-          // ---- lim1 / lim2 ----
-          lim1 = lim2 = 0;
-          for ( uint32_t p = left + lane; p < right; p += 32 ) {
-            const int v = kd_coord( S.rec[p], cf );
-            lim1 += v < cut, lim2 += v <= cut;
-          }
-          lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
-          lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
-          // ---- the two Hoare passes of planeSplit ----
-          if ( lim1 > 0 && lim1 < n ) { ks_hoare<false>( S, left, left, right, lim1, cf, cut, lane, lt ); }
-          if ( lim2 > lim1 && lim2 < n ) { ks_hoare<true>( S, left, left + lim1, right, lim2, cf, cut, lane, lt ); }
-          idx = kd_split_index( n, lim1, lim2 );
-          if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[cur.gid] ) = make_uint2( c1, (uint32_t)cf ); }
+        // ---- lim1 / lim2, and the coordinates next to the cut on both sides ----
+        uint32_t lim1 = 0, lim2 = 0;
+        int      maxLT = -1, minGT = 4096;
+        for ( uint32_t p = left + lane; p < right; p += 32 ) {
+          const int v = kd_coord( S.rec[p], cf );
+          lim1 += v < cut, lim2 += v <= cut;
+          if ( v < cut ) { maxLT = max( maxLT, v ); }
+          if ( v > cut ) { minGT = min( minGT, v ); }
         }
-        // ---- children (divideTree :1070-1078): leaves are finished here, the left child is kept, the right one pushed ----
+        lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
+        lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
+        // ---- the two Hoare passes of planeSplit ----
+        if ( lim1 > 0 && lim1 < n ) { ks_hoare<false>( S, left, left, right, lim1, cf, cut, lane, lt ); }
+        if ( lim2 > lim1 && lim2 < n ) { ks_hoare<true>( S, left, left + lim1, right, lim2, cf, cut, lane, lt ); }
+        const uint32_t idx = kd_split_index( n, lim1, lim2 );
+        const uint32_t s   = left + idx, c1 = idBase + 2u * ( s - 1u );
+        int divlow = cut, divhigh = cut;
+        if ( idx == lim1 ) { divlow = __reduce_max_sync( 0xFFFFFFFFu, maxLT ); }
+        if ( idx == lim2 ) { divhigh = __reduce_min_sync( 0xFFFFFFFFu, minGT ); }
+        if ( lane == 0 ) {
+          *reinterpret_cast<uint4*>( &nodes[cur.gid] ) =
+              make_uint4( c1, (uint32_t)cf, ( (uint32_t)divlow & 0xFFFFu ) | ( (uint32_t)divhigh << 16 ), 0u );
+        }
+        // ---- children (divideTree :1070-1078): leaves are written, small ones listed, the left large one is kept ----
         const uint32_t nl = idx, nr = n - idx;
-        if ( nl <= 10 ) { ks_leaf_child( S, nodes, base, cur.gid, c1, left, nl, 0, cf, !divKnown, lane ); }
-        if ( nr <= 10 ) { ks_leaf_child( S, nodes, base, cur.gid, c1 + 1, left + idx, nr, 1, cf, !divKnown, lane ); }
-        KsItem rgt = cur;  // (only built when needed below)
-        if ( nr > 10 ) {
-          rgt.gid = c1 + 1, rgt.pgid = divKnown ? KS_NOREPORT : cur.gid, rgt.left = (uint16_t)( left + idx ), rgt.side = 1;
-          rgt.depth = (uint8_t)( cur.depth + 1 ), rgt.pfeat = (uint8_t)cf;
-          rgt.lo[0] = cf == 0 ? (int16_t)cut : cur.lo[0];  // right_bbox[cutfeat].low = cutval
-          rgt.lo[1] = cf == 1 ? (int16_t)cut : cur.lo[1];
-          rgt.lo[2] = cf == 2 ? (int16_t)cut : cur.lo[2];
+        KsItem lft = cur, rgt = cur;
+        lft.gid = c1, lft.right = (uint16_t)s, lft.depth = rgt.depth = (uint16_t)( cur.depth + 1 );
+        rgt.gid = c1 + 1, rgt.left = (uint16_t)s;
+        if ( cf == 0 ) {  // left_bbox[cutfeat].high = right_bbox[cutfeat].low = cutval
+          lft.hi[0] = rgt.lo[0] = (int16_t)cut;
+        } else if ( cf == 1 ) {
+          lft.hi[1] = rgt.lo[1] = (int16_t)cut;
+        } else {
+          lft.hi[2] = rgt.lo[2] = (int16_t)cut;
         }
-        if ( nl > 10 ) {
-          if ( nr > 10 ) {
+        if ( lane == 0 ) {
+          if ( nl <= (uint32_t)KS_LEAF ) {
+            *reinterpret_cast<uint2*>( &nodes[c1] ) = make_uint2( base + left, KD_LEAF | nl );
+          } else if ( nl <= (uint32_t)KS_SMALL ) {
+            S.small[nSmall] = lft;
+          }
+        }
+        if ( nl > (uint32_t)KS_LEAF && nl <= (uint32_t)KS_SMALL ) { nSmall++; }
+        if ( lane == 0 ) {
+          if ( nr <= (uint32_t)KS_LEAF ) {
+            *reinterpret_cast<uint2*>( &nodes[c1 + 1] ) = make_uint2( base + s, KD_LEAF | nr );
+          } else if ( nr <= (uint32_t)KS_SMALL ) {
+            S.small[nSmall] = rgt;
+          }
+        }
+        if ( nr > (uint32_t)KS_LEAF && nr <= (uint32_t)KS_SMALL ) { nSmall++; }
+        maxDepth = max( maxDepth, (int)cur.depth );
+        const bool bigL = nl > (uint32_t)KS_SMALL, bigR = nr > (uint32_t)KS_SMALL;
+        if ( bigL ) {
+          if ( bigR ) {
             if ( sp >= KS_STACK ) {  // cannot happen for 12-bit coordinates (see above); fail loudly
               overflow = true;
-              sp       = 0;
-            } else {
-              if ( lane == 0 ) { S.stack[sp] = rgt; }
-              sp++;
+              break;
             }
+            if ( lane == 0 ) { S.stack[sp] = rgt; }
+            sp++;
           }
-          if ( !overflow ) {
-            cur.pgid = divKnown ? KS_NOREPORT : cur.gid;
-            cur.gid = c1, cur.right = (uint16_t)( left + idx ), cur.side = 0;
-            cur.depth = (uint8_t)( cur.depth + 1 ), cur.pfeat = (uint8_t)cf;
-            if ( cf == 0 ) {
-              cur.hi[0] = (int16_t)cut;  // left_bbox[cutfeat].high = cutval
-            } else if ( cf == 1 ) {
-              cur.hi[1] = (int16_t)cut;
-            } else {
-              cur.hi[2] = (int16_t)cut;
-            }
-            haveNext = true;
-          }
-        } else if ( nr > 10 ) {
-          cur      = rgt;
-          haveNext = true;
+          cur = lft;
+        } else if ( bigR ) {
+          cur = rgt;
+        } else {
+          if ( sp == 0 ) { break; }
+          __syncwarp();
+          cur = S.stack[--sp];
         }
       }
-      if ( !haveNext ) {
-        if ( sp == 0 ) { break; }
-        __syncwarp();
-        cur = S.stack[--sp];
-      }
+    }
+    __syncwarp();
+    // ---- lane phase: the listed nodes, one per lane ----
+    for ( int b = 0; b < nSmall; b += 32 ) {
+      const bool have = b + lane < nSmall;
+      KsItem     it{};
+      if ( have ) { it = S.small[b + lane]; }
+      const int d = ks_lane_subtree( S, nodes, base, idBase, it, have, reinterpret_cast<uint32_t*>( S.tmp ) + lane, o );
+      maxDepth    = max( maxDepth, d );
     }
     __syncwarp();
     for ( uint32_t i = lane; i < total; i += 32 ) { grec[base + i] = S.rec[i]; }
     __syncwarp();
   }
+  maxDepth = __reduce_max_sync( 0xFFFFFFFFu, maxDepth );
   if ( lane == 0 ) {
     atomicMax( &counters[C_DEPTH], (uint32_t)maxDepth + 1u );
     if ( overflow ) { atomicOr( &counters[C_STACK], 1u ); }
@@ -1203,6 +1173,9 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   const uint32_t gCap     = (uint32_t)( E / 16 + 64ll * nTrees + 4096 );
   const uint32_t chunkCap = (uint32_t)( 2 * ( E / GT ) + 2ll * nTrees + 64 );
   const size_t   nodeCap  = (size_t)gCap + 2 * (size_t)E + 2;  // + the id blocks of the subtrees (2 ids per element)
+  if ( nodeCap >= (size_t)KD_NODE_MAX ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: %lld elements need more node ids than a search stack entry holds", (long long)E );
+  }
   RB_CUDA( B.rec.ensure( (size_t)E * 8 ) );
   RB_CUDA( B.tmp.ensure( (size_t)E * 8 ) );
   RB_CUDA( B.gnodes.ensure( (size_t)gCap * sizeof( GNode ) ) );

@@ -33,77 +33,64 @@ struct KdForest {
   int             ox, oy, oz;  // origin subtracted from every coordinate
 };
 
-constexpr int      KD_STACK = 96;
-constexpr uint32_t KD_INF   = 0xFFFFFFFFu;
+constexpr int      KD_STACK    = 96;
+constexpr uint32_t KD_INF      = 0xFFFFFFFFu;
+constexpr uint32_t KD_NODE_MAX = 1u << 29;  // node ids share a stack word with the axis and the entry kind
 
 // KNNResultSet::addPoint (nanoflann.hpp:110-133): insertion from the back, only entries with a LARGER distance shift,
 // so ties keep first-seen order and a candidate equal to the current k-th distance is dropped when the set is full.
+// Unused slots hold KD_INF (no real distance reaches it), which makes the insertion a fixed sequence of K selects on
+// registers: slot i takes the candidate when dist[i] > d >= dist[i - 1], the old dist[i - 1] when that is larger too.
 template <int K>
 struct KdResult {
   uint32_t dist[K];
   uint32_t idx[K];
   int      count;
   __device__ __forceinline__ void init() {
-    count       = 0;
-    dist[K - 1] = KD_INF;  // (std::numeric_limits<DistanceType>::max)(), :96
+    count = 0;
+#pragma unroll
+    for ( int i = 0; i < K; i++ ) { dist[i] = KD_INF, idx[i] = 0; }  // worstDist() = (std::numeric_limits<DistanceType>::max)(), :96
   }
   __device__ __forceinline__ uint32_t worst() const { return dist[K - 1]; }
   __device__ __forceinline__ void     add( uint32_t d, uint32_t index ) {
-    int i;
-    for ( i = count; i > 0; --i ) {
-      if ( dist[i - 1] > d ) {
-        if ( i < K ) {
-          dist[i] = dist[i - 1];
-          idx[i]  = idx[i - 1];
-        }
-      } else {
-        break;
+#pragma unroll
+    for ( int i = K - 1; i >= 1; --i ) {
+      if ( dist[i] > d ) {
+        const bool sh = dist[i - 1] > d;
+        dist[i]       = sh ? dist[i - 1] : d;
+        idx[i]        = sh ? idx[i - 1] : index;
       }
     }
-    if ( i < K ) {
-      dist[i] = d;
-      idx[i]  = index;
-    }
+    if ( dist[0] > d ) { dist[0] = d, idx[0] = index; }
     if ( count < K ) { count++; }
   }
 };
 
 // findNeighbors + searchLevel (nanoflann.hpp:901-915, 1207-1253) for the tree rooted at `root`; the query is given in
 // forest-relative coordinates (may lie outside [0, 4096): it is an int).  All distances are exact integers.
+// One loop, one step per iteration — a node visit (interior: push the far child and go to the near one; leaf: scan) or
+// one entry off the stack — so the threads of a warp meet again after every step.  mindistsq is always the sum of
+// dists[] (:911, :1246-1251), so an entry is two words: far child | axis << 29 | kind << 31, and cut_dist (kind 0,
+// "the far child is pending") or the saved dists[axis] (kind 1, "restore it", :1251).
 template <int K>
 __device__ __forceinline__ void kd_search( const KdForest& f, uint32_t root, const int q[3], KdResult<K>& res ) {
   res.init();
-  uint32_t dists[3] = {0, 0, 0};
-  uint32_t mind     = 0;
+  uint32_t d0 = 0, d1 = 0, d2 = 0;
   {
     const int16_t* rb = f.rootBox + (size_t)root * 6;  // computeInitialDistances against root_bbox (:1183-1201)
-#pragma unroll
-    for ( int i = 0; i < 3; i++ ) {
-      const int tmin = rb[i], tmax = rb[3 + i];
-      if ( q[i] < tmin ) {
-        const int d = q[i] - tmin;
-        dists[i]    = (uint32_t)( d * d );
-        mind += dists[i];
-      }
-      if ( q[i] > tmax ) {
-        const int d = q[i] - tmax;
-        dists[i]    = (uint32_t)( d * d );
-        mind += dists[i];
-      }
-    }
+    int            t;
+    t  = q[0] < rb[0] ? q[0] - rb[0] : ( q[0] > rb[3] ? q[0] - rb[3] : 0 );
+    d0 = (uint32_t)( t * t );
+    t  = q[1] < rb[1] ? q[1] - rb[1] : ( q[1] > rb[4] ? q[1] - rb[4] : 0 );
+    d1 = (uint32_t)( t * t );
+    t  = q[2] < rb[2] ? q[2] - rb[2] : ( q[2] > rb[5] ? q[2] - rb[5] : 0 );
+    d2 = (uint32_t)( t * t );
   }
-  // explicit stack: kind 0 = "visit the other child" (pending check), kind 1 = "restore dists[axis]"
-  uint32_t stNode[KD_STACK];
-  uint32_t stA[KD_STACK];  // pending: cut_dist;        restore: saved dists[axis]
-  uint32_t stB[KD_STACK];  // pending: mindistsq at the parent | axis << 30 ... kept separately below
-  uint8_t  stAxis[KD_STACK];
-  uint8_t  stKind[KD_STACK];
+  uint32_t stN[KD_STACK], stV[KD_STACK];
   int      sp   = 0;
-  uint32_t node = root;
-  uint32_t cur  = mind;
+  uint32_t node = root;  // 0 (never a node) = nothing to visit, take the next entry off the stack
   for ( ;; ) {
-    // ---- descend to a leaf ----
-    for ( ;; ) {
+    if ( node ) {
       const uint4 nv = __ldg( reinterpret_cast<const uint4*>( f.nodes + node ) );
       if ( nv.y & KD_LEAF ) {
         const uint32_t worst = res.worst();  // read once per leaf (:1213)
@@ -114,54 +101,36 @@ __device__ __forceinline__ void kd_search( const KdForest& f, uint32_t root, con
           const uint32_t d  = (uint32_t)( dx * dx ) + (uint32_t)( dy * dy ) + (uint32_t)( dz * dz );
           if ( d < worst ) { res.add( d, kd_index( r ) ); }
         }
-        break;
-      }
-      const int axis   = (int)( nv.y & 3u );
-      const int val    = axis == 0 ? q[0] : ( axis == 1 ? q[1] : q[2] );
-      const int divlow = (int16_t)( nv.z & 0xFFFFu ), divhigh = (int16_t)( nv.z >> 16 );
-      const int diff1  = val - divlow, diff2 = val - divhigh;
-      uint32_t  best, other;
-      int       cd;
-      if ( diff1 + diff2 < 0 ) {
-        best  = nv.x;
-        other = nv.x + 1;
-        cd    = val - divhigh;
+        node = 0;
       } else {
-        best  = nv.x + 1;
-        other = nv.x;
-        cd    = val - divlow;
-      }
-      stNode[sp] = other;
-      stA[sp]    = (uint32_t)( cd * cd );
-      stB[sp]    = cur;
-      stAxis[sp] = (uint8_t)axis;
-      stKind[sp] = 0;
-      sp++;
-      node = best;
-    }
-    // ---- unwind ----
-    bool descend = false;
-    while ( sp > 0 ) {
-      sp--;
-      const int axis = stAxis[sp];
-      if ( stKind[sp] == 1 ) {
-        dists[axis] = stA[sp];
-        continue;
-      }
-      const uint32_t cut = stA[sp], dst = dists[axis];
-      const uint32_t m   = stB[sp] + cut - dst;  // mindistsq + cut_dist - dists[idx] (:1246)
-      if ( m <= res.worst() ) {                  // mindistsq * epsError <= worstDist(), epsError = 1 (:1248)
-        const uint32_t other = stNode[sp];
-        stKind[sp]           = 1;  // restore dists[axis] = dst once the other subtree is done (:1251)
-        stA[sp]              = dst;
+        const uint32_t axis   = nv.y & 3u;
+        const int      val    = axis == 0 ? q[0] : ( axis == 1 ? q[1] : q[2] );
+        const int      divlow = (int16_t)( nv.z & 0xFFFFu ), divhigh = (int16_t)( nv.z >> 16 );
+        const int      diff1 = val - divlow, diff2 = val - divhigh;
+        const bool     nearLeft = diff1 + diff2 < 0;
+        const int      cd       = nearLeft ? diff2 : diff1;
+        stN[sp]                 = ( nv.x + ( nearLeft ? 1u : 0u ) ) | ( axis << 29 );
+        stV[sp]                 = (uint32_t)( cd * cd );
         sp++;
-        dists[axis] = cut;
-        node        = other;
-        cur         = m;
-        descend     = true;
-        break;
+        node = nv.x + ( nearLeft ? 0u : 1u );
+      }
+    } else {
+      if ( sp == 0 ) { break; }
+      sp--;
+      const uint32_t e = stN[sp], v = stV[sp], axis = ( e >> 29 ) & 3u;
+      if ( e >> 31 ) {
+        d0 = axis == 0 ? v : d0, d1 = axis == 1 ? v : d1, d2 = axis == 2 ? v : d2;
+      } else {
+        const uint32_t dst = axis == 0 ? d0 : ( axis == 1 ? d1 : d2 );
+        const uint32_t m   = d0 + d1 + d2 + v - dst;  // mindistsq + cut_dist - dists[idx] (:1246)
+        if ( m <= res.worst() ) {                     // mindistsq * epsError <= worstDist(), epsError = 1 (:1248)
+          stN[sp] = e | 0x80000000u;                  // restore dists[axis] = dst once the far subtree is done (:1251)
+          stV[sp] = dst;
+          sp++;
+          d0 = axis == 0 ? v : d0, d1 = axis == 1 ? v : d1, d2 = axis == 2 ? v : d2;
+          node = e & ( KD_NODE_MAX - 1u );
+        }
       }
     }
-    if ( !descend ) { break; }
   }
 }

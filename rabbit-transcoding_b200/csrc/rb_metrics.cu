@@ -1017,9 +1017,8 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
     }
   }
   if ( maxN > 0 ) {
-    ImportDesc* hp = (ImportDesc*)rb_pinned( c, nC * sizeof( ImportDesc ) + 64 );
+    ImportDesc* hp = (ImportDesc*)rb_pinned_ring( c, nC * sizeof( ImportDesc ) + 64 );
     if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the staging block may still be in flight
     memcpy( hp, hd.data(), nC * sizeof( ImportDesc ) );
     RB_CUDA( S->descs.ensure( nC * sizeof( ImportDesc ) + 64 ) );
     RB_CUDA( cudaMemcpyAsync( S->descs.p, hp, nC * sizeof( ImportDesc ), cudaMemcpyHostToDevice, c->stream ) );
@@ -1029,11 +1028,12 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   // ---- bounding box -> table geometry (one small read-back) ----
   int* dSmall = S->small.as<int>();
   {
-    int* h = (int*)rb_pinned( c, 64 );
-    if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-    h[0] = h[1] = h[2] = 32767;
-    h[3] = h[4] = h[5] = -32768;
-    RB_CUDA( cudaMemcpyAsync( dSmall, h, 24, cudaMemcpyHostToDevice, c->stream ) );
+    int* h  = (int*)rb_pinned( c, 64 );
+    int* hi = (int*)rb_pinned_ring( c, 64 );
+    if ( !h || !hi ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    hi[0] = hi[1] = hi[2] = 32767;
+    hi[3] = hi[4] = hi[5] = -32768;
+    RB_CUDA( cudaMemcpyAsync( dSmall, hi, 24, cudaMemcpyHostToDevice, c->stream ) );
     if ( N > 0 ) { RB_LAUNCH( "met_bbox", k_bbox, 148 * 4, TPB, 0, inPos, N, dSmall ); }
     RB_CUDA( cudaMemcpyAsync( h, dSmall, 24, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
@@ -1062,11 +1062,10 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   int64_t*  dOff    = (int64_t*)( S->small.as<char>() + 64 );
   uint32_t* dUcount = (uint32_t*)( S->small.as<char>() + 64 + ( nC + 1 ) * 8 );
   {
-    int64_t* h = (int64_t*)rb_pinned( c, ( nC + 1 ) * 8 + 64 );
+    int64_t* h = (int64_t*)rb_pinned_ring( c, ( nC + 1 ) * 8 + 64 );
     if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
     memcpy( h, hOff.data(), ( nC + 1 ) * 8 );
     RB_CUDA( cudaMemcpyAsync( dOff, h, ( nC + 1 ) * 8, cudaMemcpyHostToDevice, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
   }
   B.off    = dOff;
   B.tab    = S->tab.as<uint32_t>();
@@ -1228,7 +1227,7 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   uint32_t*  dFarCount = (uint32_t*)( dS + al( szDirs ) + al( szEnds ) + al( szAcc ) );
   uint32_t*  dErr      = dFarCount + 16;
   {
-    char* h = (char*)rb_pinned( c, al( szDirs ) + al( szEnds ) + 64 );
+    char* h = (char*)rb_pinned_ring( c, al( szDirs ) + al( szEnds ) + 64 );
     if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
     Direction* hd = (Direction*)h;
     int32_t*   he = (int32_t*)( h + al( szDirs ) );
@@ -1242,7 +1241,6 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
     }
     RB_CUDA( cudaMemcpyAsync( dS, h, al( szDirs ) + al( szEnds ), cudaMemcpyHostToDevice, c->stream ) );
     RB_CUDA( cudaMemsetAsync( dAcc, 0, al( szAcc ) + 1024, c->stream ) );
-    RB_CUDA( cudaStreamSynchronize( c->stream ) );
     c->stats.h2d_bytes += (int64_t)( szDirs + szEnds );
   }
   RB_CUDA( S->partial.ensure( (size_t)std::max( maxBlocks, 1 ) * 32 * ( TPB / 32 ) ) );
@@ -1282,9 +1280,8 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
       maxN = std::max<int64_t>( maxN, sources[i].count );
     }
     if ( !hn.empty() ) {
-      NormalDesc* hp = (NormalDesc*)rb_pinned( c, hn.size() * sizeof( NormalDesc ) + 64 );
+      NormalDesc* hp = (NormalDesc*)rb_pinned_ring( c, hn.size() * sizeof( NormalDesc ) + 64 );
       if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-      RB_CUDA( cudaStreamSynchronize( c->stream ) );  // the staging block may still be in flight
       memcpy( hp, hn.data(), hn.size() * sizeof( NormalDesc ) );
       RB_CUDA( S->ndescs.ensure( hn.size() * sizeof( NormalDesc ) + 64 ) );
       RB_CUDA( cudaMemcpyAsync( S->ndescs.p, hp, hn.size() * sizeof( NormalDesc ), cudaMemcpyHostToDevice, c->stream ) );
@@ -1414,7 +1411,24 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
   MetricsScratch* S = scratch_of( c );
   // The pairs are independent (PCCMetrics::compute loops over the frames, PCCMetrics.cpp:348-384).  They are processed
   // in chunks so that the host clouds of chunk k+1 cross PCIe on the copy stream while the kernels of chunk k run.
-  const int nChunks = nPairs >= 8 ? 4 : 1, per = ( nPairs + nChunks - 1 ) / nChunks;
+  // Clouds that are already in device memory (sources cached across calls, resident reconstructions) have nothing to
+  // overlap: one chunk, a quarter of the launches and host round trips.
+  bool onDevice = true;
+  for ( int i = 0; i < nPairs && onDevice; i++ ) {
+    const void* ptrs[2] = {sources[i].positions, recs[i].positions};
+    for ( const void* q : ptrs ) {
+      if ( !q ) { continue; }
+      cudaPointerAttributes attr{};
+      if ( cudaPointerGetAttributes( &attr, q ) != cudaSuccess || attr.type != cudaMemoryTypeDevice ) {
+        cudaGetLastError();
+        onDevice = false;
+      }
+    }
+  }
+  int64_t total = 0;
+  for ( int i = 0; i < nPairs; i++ ) { total += 2 * sources[i].count; }
+  const int nDev    = (int)std::min<int64_t>( nPairs, ( total + ( 64ll << 20 ) - 1 ) / ( 64ll << 20 ) );  // scratch is ~100 B per point
+  const int nChunks = onDevice ? std::max( nDev, 1 ) : ( nPairs >= 8 ? 4 : 1 ), per = ( nPairs + nChunks - 1 ) / nChunks;
   int       status = RB200_OK;
   int       r = prefetch_pairs( c, S, mp, std::min( per, nPairs ), sources, recs, 0 );
   if ( r ) { return r; }

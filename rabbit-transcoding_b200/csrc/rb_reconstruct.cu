@@ -68,6 +68,7 @@ struct ReprojArgs {
   const uint16_t* geo;
   const uint16_t* attr;
   const uint32_t* bitmap;
+  const uint32_t* bnd_bitmap;  // occupancy synthesis: the boundary type of a pixel's points (PCCPatch::isBorder), else null
   const uint32_t* b2p;
   int             W, H, oW, oH, Wb, Hb, M, prec, bmWords;
   int             absolute_d1, remove_dup, eom_fix_bits, classify, attr_count, bitdepth3d;
@@ -359,7 +360,13 @@ __global__ void __launch_bounds__( WARPS * 32, 8 ) k_reproject( const ReprojArgs
     // identifyBoundaryPoints (:266-325) for the whole tile at once, 16 rows in 16 lanes: a pixel is type 1 when it is
     // on / next to the image border or any pixel of its 5x5 neighbourhood is unoccupied (the 3x3 test of :274-305 is
     // implied: a full 5x5 contains a full 3x3).  Pixels outside the image read as occupied (staging above).
-    if ( lane < 16 ) {
+    if ( !STD && a.bnd_bitmap ) {
+      // occupancy synthesis: reconstruct.setBoundaryPointType( isBoundary ) with patch.isBorder( u, v ) (:664, :809)
+      if ( lane < 16 ) {
+        const uint32_t wv = a.bnd_bitmap[( (size_t)f * a.H + Y0 + lane ) * a.bmWords + ( X0 >> 5 )];
+        S.bnd[lane]       = (uint16_t)( wv >> ( X0 & 31 ) );
+      }
+    } else if ( lane < 16 ) {
       const int      r  = lane + 2, y = Y0 + lane;
       const uint32_t v5 = S.rows[r - 2] & S.rows[r - 1] & S.rows[r] & S.rows[r + 1] & S.rows[r + 2];
       const uint32_t h5 = v5 & ( v5 >> 1 ) & ( v5 << 1 ) & ( v5 >> 2 ) & ( v5 << 2 );  // bit kx: columns kx-2..kx+2 full
@@ -1153,11 +1160,14 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   if ( plr && !c->have_plr ) { return rb_fail( c, RB200_ERR_STATE, "point_local_reconstruction: rb200_gof_set_plr was not called for this GOF" ); }
   const int64_t       nWI = c->nWI;
   RB_CUDA( cudaMemsetAsync( c->d_b2p.p, 0, (size_t)F * c->Wb * c->Hb * 4, c->stream ) );
+  const bool pbf = P.pbf_enable != 0;
   {
+    // occupancy synthesis: generateOccupancyMap is skipped (PCCDecoder.cpp:362-366), so block-to-patch sees the raw
+    // video samples != 0 (:1757) — the same test as the EOM symbol
     const int64_t total = (int64_t)F * c->H * c->bmWords;
     RB_LAUNCH( "occupancy_bitmap", k_occupancy_bitmap, rb_div_up( total, 256 ), 256, 0, c->d_occ_video.as<uint8_t>(),
                c->d_bitmap.as<uint32_t>(), F, c->W, c->H, c->oW, c->oH, c->prec, c->bmWords, P.threshold_lossy_om,
-               eom ? 1 : 0 );
+               ( eom || pbf ) ? 1 : 0 );
   }
   if ( nWI > 0 ) {
     RB_LAUNCH( "block_to_patch", k_block_to_patch, rb_div_up( nWI, 256 ), 256, 0, c->d_patches.as<RbPatch>(),
@@ -1169,8 +1179,12 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
                  c->d_b2p.as<uint32_t>(), c->H, c->Wb, c->Hb, c->bmWords, P.log2_quantizer_x, P.log2_quantizer_y );
     }
   }
-  // geometry smoothing is only signalled through flagGeometrySmoothing_ (:953)
-  const bool classify = P.flag_geometry_smoothing != 0;
+  if ( pbf ) {  // the synthesised occupancy replaces the bitmap; the points' boundary types come with it
+    int r = rb_pbf_impl( c );
+    if ( r ) { return r; }
+  }
+  // geometry smoothing is only signalled through flagGeometrySmoothing_ (:953); occupancy synthesis types every point (:809)
+  const bool classify = P.flag_geometry_smoothing != 0 || pbf;
 
   ReprojArgs a{};
   a.patches      = c->d_patches.as<RbPatch>();
@@ -1181,6 +1195,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   a.geo          = c->d_geometry.as<uint16_t>();
   a.attr         = c->d_attribute.as<uint16_t>();
   a.bitmap       = c->d_bitmap.as<uint32_t>();
+  a.bnd_bitmap   = pbf ? c->d_bnd_bitmap.as<uint32_t>() : nullptr;
   a.b2p          = c->d_b2p.as<uint32_t>();
   a.W            = c->W;
   a.H            = c->H;
@@ -1231,7 +1246,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     }
   }
   if ( nWI > 0 ) {
-    const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
+    const bool std_cfg = !eom && !pbf && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     if ( ilv ) {
       auto kCount = plr ? k_reproject_interleaved<false, true> : k_reproject_interleaved<false, false>;
       RB_LAUNCH( "reproject_count", kCount, G, WARPS * 32, 0, a );
@@ -1411,7 +1426,7 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
   }
   if ( nWI > 0 ) {
-    const bool std_cfg = !eom && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
+    const bool std_cfg = !eom && !pbf && c->M == 2 && P.absolute_d1 && P.attribute_count > 0 && classify && a.t1_bits == 0;
     if ( ilv ) {
       auto kEmit = plr ? k_reproject_interleaved<true, true> : k_reproject_interleaved<true, false>;
       RB_LAUNCH( "reproject_emit", kEmit, G, WARPS * 32, 0, a );

@@ -27,7 +27,7 @@ constexpr int KF  = 8;  // numNeighborsColorTransferFwd
 
 struct TransferScratch {
   RbKdBuild kd;
-  RbBuf     pos2, off, flags, sums, moved, part, partDist, bwdT, partCnt, refined1, candCnt, candOff, candKey, small;
+  RbBuf     pos2, off, flags, sums, moved, part, partDist, bwdT, partCnt, refined1, candCnt, candOff, candKey, small, claim, srcList, srcNN;
 };
 
 TransferScratch* scratch_of( rb200_ctx* c ) {  // one context is driven by one host thread at a time
@@ -70,7 +70,11 @@ struct TArgs {
   const uint32_t* rank;       // scan of the moved flags: rank[g] = position of g in `moved`
   uint32_t        nMoved;
   uint32_t*       part;       // [nMoved][KF] source index inside the frame
-  uint32_t*       partDist;   // [nMoved][KF]
+  uint32_t*       partDist;   // [nMoved][KF] distance of an accepted backward candidate
+  uint32_t*       claim;      // one bit per point of the GOF: listed in srcList
+  uint32_t*       srcList;    // the distinct partSource points (global indices), *nSrc of them
+  uint32_t*       nSrc;
+  uint2*          srcNN;      // [N] nearest smoothed point of a listed source point {index in frame, distance}
   uint32_t*       bwdT;       // [nMoved][KF] rank of the accepted nearest target among the moved points, or ~0
   uint8_t*        partCnt;    // [nMoved]
   ushort4*        refined1;   // [nMoved]
@@ -93,9 +97,9 @@ __global__ void __launch_bounds__( 128 ) k_transfer_fwd( const TArgs a ) {
   KdResult<KF>  res;
   kd_search<KF>( a.forest, (uint32_t)f + 1u, q, res );  // kdtreeSource.search( target[index], 8 )
   a.partCnt[m] = (uint8_t)res.count;
-  for ( int j = 0; j < res.count; j++ ) {
-    a.part[(size_t)m * KF + j]     = res.idx[j];
-    a.partDist[(size_t)m * KF + j] = res.dist[j];
+#pragma unroll
+  for ( int j = 0; j < KF; j++ ) {  // (the result set lives in registers: no dynamic indexing)
+    if ( j < res.count ) { a.part[(size_t)m * KF + j] = res.idx[j]; }
   }
   ushort4 out;
   if ( res.dist[0] == 0 || res.count == 1 ) {  // identical source point present (:1186-1191) or a single neighbour (:1195-1198)
@@ -103,13 +107,16 @@ __global__ void __launch_bounds__( 128 ) k_transfer_fwd( const TArgs a ) {
   } else {
     // maxColorDist2 <= DBL_MAX always holds: distance-weighted mean of all neighbours (:1212-1222, :1252-1256)
     double rc[3] = {0.0, 0.0, 0.0}, sw = 0.0;
-    for ( int j = 0; j < res.count; j++ ) {
-      const double  w = 1.0 / ( (double)res.dist[j] + 4.0 );
-      const ushort4 c = a.col[base + res.idx[j]];
-      rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
-      rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
-      rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
-      sw              = __dadd_rn( sw, w );
+#pragma unroll
+    for ( int j = 0; j < KF; j++ ) {
+      if ( j < res.count ) {
+        const double  w = 1.0 / ( (double)res.dist[j] + 4.0 );
+        const ushort4 c = a.col[base + res.idx[j]];
+        rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
+        rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
+        rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
+        sw              = __dadd_rn( sw, w );
+      }
     }
     out.x = (unsigned short)fmin( fmax( round( rc[0] / sw ), 0.0 ), 65535.0 );
     out.y = (unsigned short)fmin( fmax( round( rc[1] / sw ), 0.0 ), 65535.0 );
@@ -119,9 +126,44 @@ __global__ void __launch_bounds__( 128 ) k_transfer_fwd( const TArgs a ) {
   a.refined1[m] = out;
 }
 
-// backward direction (:1275-1293): every partSource point looks up its nearest target ONCE; the accepted ones are
-// counted per moved target and remembered (target rank, distance), then k_transfer_bwd_store files them
-__global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a ) {
+// backward direction (:1275-1293): every partSource point looks up its nearest target.  Neighbouring moved targets share
+// most of their 8 source points, so the DISTINCT source points are listed first (a claim bit per point, one append per
+// warp), searched once each by full warps, and the 8 x nMoved entries then read the answer of their point.  The accepted
+// ones are counted per moved target and remembered (target rank, distance); k_transfer_bwd_store files them.
+__global__ void __launch_bounds__( 256 ) k_transfer_bwd_claim( const TArgs a ) {
+  const uint32_t p    = blockIdx.x * blockDim.x + threadIdx.x;
+  const int      lane = threadIdx.x & 31;
+  bool           mine = false;
+  uint32_t       gs   = 0;
+  if ( p < a.nMoved * KF ) {
+    const uint32_t m = p / KF, j = p % KF;
+    if ( j < a.partCnt[m] ) {
+      const int64_t g = a.moved[m];
+      const int     f = frame_of( a.frame_off, a.F, g );
+      gs              = (uint32_t)( a.frame_off[f] + a.part[p] );
+      const uint32_t bit = 1u << ( gs & 31u );
+      mine               = ( atomicOr( &a.claim[gs >> 5], bit ) & bit ) == 0;
+    }
+  }
+  const uint32_t b = __ballot_sync( 0xFFFFFFFFu, mine );
+  if ( b == 0 ) { return; }
+  uint32_t at = 0;
+  if ( lane == __ffs( b ) - 1 ) { at = atomicAdd( a.nSrc, (uint32_t)__popc( b ) ); }
+  at = __shfl_sync( 0xFFFFFFFFu, at, __ffs( b ) - 1 );
+  if ( mine ) { a.srcList[at + __popc( b & ( ( 1u << lane ) - 1u ) )] = gs; }
+}
+__global__ void __launch_bounds__( 128 ) k_transfer_bwd_search( const TArgs a ) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= *a.nSrc ) { return; }
+  const uint32_t gs   = a.srcList[i];
+  const int      f    = frame_of( a.frame_off, a.F, gs );
+  const short4   ps   = a.posS[gs];
+  const int      q[3] = {ps.x - a.forest.ox, ps.y - a.forest.oy, ps.z - a.forest.oz};
+  KdResult<1>    res;
+  kd_search<1>( a.forest, (uint32_t)( a.F + f ) + 1u, q, res );  // kdtreeTarget.search( partSource[index], 1 )
+  a.srcNN[gs] = res.count ? make_uint2( res.idx[0], res.dist[0] ) : make_uint2( 0xFFFFFFFFu, 0u );
+}
+__global__ void __launch_bounds__( 256 ) k_transfer_bwd( const TArgs a ) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if ( p >= a.nMoved * KF ) { return; }
   const uint32_t m = p / KF, j = p % KF;
@@ -131,19 +173,16 @@ __global__ void __launch_bounds__( 128 ) k_transfer_bwd( const TArgs a ) {
   const int      f    = frame_of( a.frame_off, a.F, g );
   const int64_t  base = a.frame_off[f];
   const uint32_t s    = a.part[p];
-  const short4   ps   = a.posS[base + s];
-  const int      q[3] = {ps.x - a.forest.ox, ps.y - a.forest.oy, ps.z - a.forest.oz};
-  KdResult<1>    res;
-  kd_search<1>( a.forest, (uint32_t)( a.F + f ) + 1u, q, res );  // kdtreeTarget.search( partSource[index], 1 )
-  if ( res.count == 0 ) { return; }
-  const int64_t r = base + res.idx[0];
+  const uint2    nn   = a.srcNN[base + s];
+  if ( nn.x == 0xFFFFFFFFu ) { return; }
+  const int64_t r = base + nn.x;
   if ( a.posT[r].w != 3 ) { return; }  // only type-3 targets are recomputed (:1319)
   const ushort4 cs = a.col[base + s], ct = a.col[r];
   if ( abs( (int)cs.x - (int)ct.x ) < 40 && abs( (int)cs.y - (int)ct.y ) < 40 && abs( (int)cs.z - (int)ct.z ) < 40 ) {
     const uint32_t mr = a.rank[r];
     atomicAdd( &a.candCnt[mr], 1u );
     a.bwdT[p]     = mr;
-    a.partDist[p] = res.dist[0];  // (the forward distances are not needed any more)
+    a.partDist[p] = nn.y;
   }
 }
 __global__ void __launch_bounds__( 256 ) k_transfer_bwd_store( const TArgs a ) {
@@ -317,6 +356,7 @@ __global__ void k_knn_queries( const KdForest f, const int16_t* __restrict__ q, 
   const int   qq[3] = {q[3 * i] - f.ox, q[3 * i + 1] - f.oy, q[3 * i + 2] - f.oz};
   KdResult<K> res;
   kd_search<K>( f, 1u, qq, res );
+#pragma unroll
   for ( int j = 0; j < K; j++ ) {
     outIdx[i * K + j]  = j < res.count ? (int64_t)res.idx[j] : -1;
     outDist[i * K + j] = j < res.count ? (double)res.dist[j] : -1.0;
@@ -380,14 +420,17 @@ __global__ void __launch_bounds__( 128 ) k_ilv_transfer( const KdForest forest, 
   ushort4 out = col[srcIdx[sb + res.idx[0]]];
   if ( res.count > 1 && res.dist[0] != 0 ) {  // result.size() > 1 && result.dist( 0 ) > 0.0001 (:2262)
     double rc[3] = {0.0, 0.0, 0.0}, sw = 0.0;
-    for ( int j = 0; j < res.count; j++ ) {
-      const double  d = (double)res.dist[j];
-      const double  w = __ddiv_rn( 1.0, __dmul_rn( d, d ) );  // 1.0 / pow( dist, 2.0 ), dist = squared distance
-      const ushort4 c = col[srcIdx[sb + res.idx[j]]];
-      rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
-      rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
-      rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
-      sw              = __dadd_rn( sw, w );
+#pragma unroll
+    for ( int j = 0; j < KW; j++ ) {
+      if ( j < res.count ) {
+        const double  d = (double)res.dist[j];
+        const double  w = __ddiv_rn( 1.0, __dmul_rn( d, d ) );  // 1.0 / pow( dist, 2.0 ), dist = squared distance
+        const ushort4 c = col[srcIdx[sb + res.idx[j]]];
+        rc[0]           = __dadd_rn( rc[0], __dmul_rn( (double)c.x, w ) );
+        rc[1]           = __dadd_rn( rc[1], __dmul_rn( (double)c.y, w ) );
+        rc[2]           = __dadd_rn( rc[2], __dmul_rn( (double)c.z, w ) );
+        sw              = __dadd_rn( sw, w );
+      }
     }
     out.x = (unsigned short)(int)__ddiv_rn( rc[0], sw );  // PCCVector3D -> PCCColor16bit: (uint16_t) truncation
     out.y = (unsigned short)(int)__ddiv_rn( rc[1], sw );
@@ -465,7 +508,7 @@ void rb_transfer_release( rb200_ctx* c ) {
   if ( !s ) { return; }
   s->kd.release();
   RbBuf* b[] = {&s->pos2, &s->off, &s->flags, &s->sums, &s->moved, &s->part, &s->partDist, &s->bwdT, &s->partCnt, &s->refined1,
-                &s->candCnt, &s->candOff, &s->candKey, &s->small};
+                &s->candCnt, &s->candOff, &s->candKey, &s->small, &s->claim, &s->srcList, &s->srcNN};
   for ( auto* x : b ) { x->release(); }
   delete s;
   c->transfer_scratch = nullptr;
@@ -545,6 +588,10 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   RB_CUDA( S->candKey.ensure( (size_t)M * KF * 8 ) );
   RB_CUDA( S->small.ensure( 64 ) );
   RB_CUDA( cudaMemsetAsync( S->small.p, 0, 64, c->stream ) );
+  RB_CUDA( S->claim.ensure( (size_t)( N / 32 + 2 ) * 4 ) );
+  RB_CUDA( S->srcList.ensure( (size_t)M * KF * 4 ) );
+  RB_CUDA( S->srcNN.ensure( (size_t)N * 8 ) );
+  RB_CUDA( cudaMemsetAsync( S->claim.p, 0, (size_t)( N / 32 + 2 ) * 4, c->stream ) );
   RB_LAUNCH( "tr_list_moved", k_list_moved, rb_div_up( N, TPB ), TPB, 0, flags, N, S->moved.as<uint32_t>() );
   TArgs a{};
   a.forest    = S->kd.forest;
@@ -566,9 +613,16 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   a.candKey   = S->candKey.as<uint64_t>();
   a.lossless  = P.attribute_rgb444;
   a.err       = S->small.as<uint32_t>();
+  a.claim     = S->claim.as<uint32_t>();
+  a.srcList   = S->srcList.as<uint32_t>();
+  a.nSrc      = S->small.as<uint32_t>() + 4;
+  a.srcNN     = S->srcNN.as<uint2>();
   RB_LAUNCH( "tr_forward", k_transfer_fwd, rb_div_up( M, 128 ), 128, 0, a );
   RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );
-  RB_LAUNCH( "tr_backward", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a );
+  RB_LAUNCH( "tr_backward_claim", k_transfer_bwd_claim, rb_div_up( (int64_t)M * KF, 256 ), 256, 0, a );
+  // (the number of distinct source points stays on the device: the grid covers the worst case, surplus CTAs leave)
+  RB_LAUNCH( "tr_backward_search", k_transfer_bwd_search, rb_div_up( (int64_t)M * KF, 128 ), 128, 0, a );
+  RB_LAUNCH( "tr_backward", k_transfer_bwd, rb_div_up( (int64_t)M * KF, 256 ), 256, 0, a );
   r = rb_scan_u32( c, a.candCnt, S->candOff.as<uint32_t>(), M + 1, S->sums.as<uint32_t>() );
   if ( r ) { return r; }
   RB_CUDA( cudaMemsetAsync( a.candCnt, 0, (size_t)( M + 1 ) * 4, c->stream ) );

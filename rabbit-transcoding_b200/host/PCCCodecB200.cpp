@@ -106,6 +106,8 @@ struct Gof {  // the GOF currently resident on the GPU
   std::vector<rb200_frame_counts> counts;
   std::vector<size_t>             off;  // [frames + 1] first point of every frame in the staging arrays
   std::map<size_t, std::vector<uint8_t>> occOriginal;  // occupancy video of the frames seen by generateOccupancyMap
+  bool                            occFresh = false;    // generateOccupancyMap ran for the frame block-to-patch is called for
+  std::set<size_t>                rawSeen;             // frames of this GOF that skipped it (occupancy synthesis)
   size_t                          thresholdLossyOM = 0;
   size_t                          currentFrame     = 0;
   // pinned staging: the planes going up, and per stage the fields coming down (whole GOF, frame after frame)
@@ -142,7 +144,11 @@ void ensureContext() {
 }
 
 void checkSupported( PCCContext& context, const GeneratePointCloudParameters& p, size_t tileIndex ) {
-  if ( p.pbfEnableFlag_ ) { unsupported( "occupancy synthesis / PBF (PCCCodec.cpp:541-554)" ); }
+  if ( p.pbfEnableFlag_ && ( p.enhancedOccupancyMapCode_ || p.singleMapPixelInterleaving_ || p.pointLocalReconstruction_ ||
+                             p.enableSizeQuantization_ ) ) {
+    unsupported( "occupancy synthesis (PCCCodec.cpp:541-554) together with EOM, pixel interleaving, point local reconstruction or "
+                 "patch size quantisation" );
+  }
   if ( p.useAuxSeperateVideo_ ) { unsupported( "raw / EOM points in an auxiliary video (PCCCodec.cpp:1451-1582)" ); }
   if ( p.mapCountMinus1_ > 1 ) { unsupported( "more than two maps" ); }
   if ( p.occupancyResolution_ != 16 ) { unsupported( "an occupancy resolution other than 16" ); }
@@ -176,7 +182,13 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   p.width = (int)W, p.height = (int)H;
   p.occupancy_resolution        = (int)gp.occupancyResolution_;
   p.occupancy_precision         = (int)P;
-  p.threshold_lossy_om          = (int)g.thresholdLossyOM;
+  // with occupancy synthesis the decoder never calls generateOccupancyMap (PCCDecoder.cpp:362-366): the threshold
+  // travels in the parameters (PCCCodec.cpp:551)
+  p.threshold_lossy_om          = gp.pbfEnableFlag_ ? (int)gp.thresholdLossyOM_ : (int)g.thresholdLossyOM;
+  p.pbf_enable                  = gp.pbfEnableFlag_;
+  p.pbf_passes_count            = gp.pbfPassesCount_;
+  p.pbf_filter_size             = gp.pbfFilterSize_;
+  p.pbf_log2_threshold          = gp.pbfLog2Threshold_;
   p.map_count_minus1            = (int)gp.mapCountMinus1_;
   p.absolute_d1                 = gp.absoluteD1_;
   p.remove_duplicate_points     = gp.removeDuplicatePoints_;
@@ -305,8 +317,10 @@ void PCCCodec::generateOccupancyMap( PCCFrameContext& tile, PCCImageOccupancyMap
   const size_t f = tile.getFrameIndex();
   if ( f == 0 || g.occOriginal.count( f ) ) {  // a new GOF starts
     g.occOriginal.clear();
+    g.rawSeen.clear();
     g.reconstructed = g.geo = g.transfer = g.color = false;
   }
+  g.occFresh = true;
   if ( tile.getLeftTopXInFrame() != 0 || tile.getLeftTopYInFrame() != 0 ) { unsupported( "a tile that does not start at (0, 0)" ); }
   g.occOriginal[f]   = videoFrame.getChannel( 0 );  // the reconstruction of the GOF starts from the decoded samples
   g.thresholdLossyOM = thresholdLossyOM;
@@ -334,6 +348,15 @@ void PCCCodec::generateBlockToPatchFromOccupancyMapVideo( PCCContext& context, P
   const size_t bw = context[frameIdx].getAtlasFrameWidth() / occupancyResolution;
   const size_t bh = context[frameIdx].getAtlasFrameHeight() / occupancyResolution;
   tile.getBlockToPatch().assign( bw * bh, 0 );
+  if ( !g.occFresh ) {  // generateOccupancyMap was skipped for this frame (occupancy synthesis, PCCDecoder.cpp:362-366)
+    if ( frameIdx == 0 || g.rawSeen.count( frameIdx ) ) {  // a new GOF starts
+      g.occOriginal.clear();
+      g.rawSeen.clear();
+      g.reconstructed = g.geo = g.transfer = g.color = false;
+    }
+    g.rawSeen.insert( frameIdx );
+  }
+  g.occFresh = false;
   (void)occupancyMapImage;
   (void)occupancyPrecision;
 }
@@ -380,9 +403,11 @@ void PCCCodec::generatePointCloud( PCCPointSet3& reconstruct, PCCContext& contex
   std::vector<uint32_t> b2p( ( W / R ) * ( H / R ) );
   RB( rb200_download_block_to_patch( g.ctx, (int)frameIndex, b2p.data() ) );
   tile.getBlockToPatch().assign( b2p.begin(), b2p.end() );
-  std::vector<uint8_t> om( W * H );
-  RB( rb200_download_occupancy( g.ctx, (int)frameIndex, om.data() ) );
-  tile.getOccupancyMap().assign( om.begin(), om.end() );
+  if ( !params.pbfEnableFlag_ ) {  // (occupancy synthesis keeps its maps inside the patches; the tile's map stays as it was)
+    std::vector<uint8_t> om( W * H );
+    RB( rb200_download_occupancy( g.ctx, (int)frameIndex, om.data() ) );
+    tile.getOccupancyMap().assign( om.begin(), om.end() );
+  }
 }
 
 size_t PCCCodec::colorPointCloud( PCCPointSet3& reconstruct, PCCContext& context, PCCFrameContext& tile,

@@ -23,13 +23,13 @@ def test_header_symbols_exported(rb, lib):
     assert declared == set(rb.abi.EXPORTED_SYMBOLS), declared ^ set(rb.abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by librabbit_b200.so"
-    assert lib.rb200_abi_version() == 2
+    assert lib.rb200_abi_version() == 3
 
 
 def test_struct_sizes_match_header(rb):
     # sizes computed from the header layout (all int32 / double / pointer fields, natural alignment)
     assert C.sizeof(rb.abi.Patch) == 17 * 4
-    assert C.sizeof(rb.abi.Params) == 31 * 4 + 4 + 4 * 8
+    assert C.sizeof(rb.abi.Params) == 32 * 4 + 4 * 8 + 4 * 4
     assert C.sizeof(rb.abi.Frames) == 3 * 8
     assert C.sizeof(rb.abi.Atlas) == 7 * 8
     assert C.sizeof(rb.abi.CloudHost) == 6 * 8

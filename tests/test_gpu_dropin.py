@@ -65,6 +65,14 @@ def test_dropin_eom_and_raw(rb, backends):
     compare(rb, backends, "raw", raw_points=700, transfer_filter=0, seed=74)
 
 
+def test_dropin_occupancy_synthesis(rb, backends):
+    """Rec-2 through the shim: the decoder skips generateOccupancyMap and the re-transfer (PCCDecoder.cpp:362, :445), the
+    patch border filter and the points' boundary types run on the GPU"""
+    from test_gpu_parity import pbf
+    g, want = compare(rb, backends, "pbf", make=pbf, orientations=tuple(range(9)), seed=77)
+    assert (want.cloud(0, "reconstruct")["boundary_types"] == 1).any() and want.counts(0).smoothed > 0
+
+
 def test_dropin_links_no_reference_body():
     """the shim has no way back into the reference's own bodies: no rb200_orig_* symbol, and every replaced member is
     defined exactly once (the shim's strong definition)"""

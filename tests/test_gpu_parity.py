@@ -68,6 +68,43 @@ def test_cell_sums_beyond_the_exact_float_range(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="stacked rec-1")
 
 
+def pbf(g, passes=None, filter_size=None, log2_threshold=2, grid_smoothing=True):
+    """switch a GOF to Rec-2 occupancy synthesis with the encoder's defaults (PCCEncoderParameters.cpp:1132-1133)"""
+    p = g.params
+    prec = p.occupancy_precision
+    p.pbf_enable = 1
+    p.pbf_passes_count = passes or (1 if prec <= 2 else 2 if prec == 4 else 4)
+    p.pbf_filter_size = filter_size or prec
+    p.pbf_log2_threshold = log2_threshold
+    p.flag_geometry_smoothing = 1  # the occupancy synthesis SEI sets it (PCCDecoder.cpp:631)
+    p.grid_smoothing = 1 if grid_smoothing else 0
+    return g
+
+
+def test_occupancy_synthesis_pbf(rb, codec, checker_backend):
+    """Rec-2: PatchBlockFiltering::patchBorderFiltering (PCCPatch.cpp:797-977) trims the block-upsampled occupancy of
+    every patch against the border points of its 3-D neighbours; the points' boundary type is PCCPatch::isBorder"""
+    if not hasattr(checker_backend, "run_gof") or type(checker_backend).__name__ != "Reference":
+        pytest.skip("occupancy synthesis is pinned against the compiled reference only")
+    for seed, kw, pk in ((71, dict(), dict()),
+                         (72, dict(orientations=tuple(range(9)), occupancy_precision=2), dict()),
+                         (73, dict(orientations=tuple(range(9)), map_count=1), dict(passes=3, filter_size=3, log2_threshold=3)),
+                         (74, dict(occupancy_precision=8, bitdepth=9, width=512), dict()),
+                         (75, dict(orientations=tuple(range(9))), dict(grid_smoothing=False))):
+        g = pbf(small(rb, seed=seed, **kw), **pk)
+        ref = run_stages(codec, g, checker_backend, what=f"pbf {kw} {pk}")
+        plain = checker_backend.run_gof(small(rb, seed=seed, **kw), keep=("reconstruct",))
+        assert ref.counts(0).total < plain.counts(0).total  # the filter really removed border pixels
+        assert (ref.cloud(0, "reconstruct")["boundary_types"] == 1).any()
+    # the whole decoder sequence in one call: the attribute re-transfer is skipped (PCCDecoder.cpp:445)
+    g = pbf(small(rb, seed=76, transfer_filter=1, orientations=tuple(range(9))))
+    ref = checker_backend.run_gof(g, keep=("rgb8",))
+    codec.uploadGof(g)
+    codec.decodeGof()
+    for f in range(g.n_frames):
+        assert codec.computeChecksum(f) == ref.md5(f)
+
+
 def test_multiple_streams_relative_t1(rb, codec, checker_backend):
     """CTC condition T1-from-rec-T0: the second attribute map is a delta on the first (PCCCodec.cpp:1387-1416)"""
     g = rb.synthetic.make_relative_t1(small(rb, seed=18), seed=2)
@@ -180,8 +217,8 @@ def test_error_paths(rb, codec):
     with pytest.raises(rb.codec.RabbitError) as e:
         codec.uploadGof(g)
     assert e.value.status == rb.abi.RB200_ERR_PATCH_OUT_OF_CANVAS
-    g = small(rb, seed=24)
-    g.params.pbf_enable = 1  # Rec-2 occupancy synthesis is not implemented: refused, never approximated
+    g = pbf(small(rb, seed=24, map_count=1))
+    g.params.single_map_pixel_interleaving = 1  # occupancy synthesis with pixel interleaving: refused, never approximated
     with pytest.raises(rb.codec.RabbitError) as e:
         codec.uploadGof(g)
     assert e.value.status == rb.abi.RB200_ERR_UNSUPPORTED
