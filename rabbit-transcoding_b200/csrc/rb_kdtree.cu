@@ -231,7 +231,7 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
                                                     uint32_t lvlEnd, int isRoot, int ox, int oy, int oz,
                                                     uint32_t* __restrict__ smallRoots, uint32_t* __restrict__ counters,
                                                     uint32_t* __restrict__ chunkNode, uint32_t chunkCap, uint32_t nodeCap,
-                                                    int32_t* __restrict__ cls, uint32_t* __restrict__ largeList ) {
+                                                    int32_t* __restrict__ cls, uint32_t* __restrict__ largeList, uint32_t ksCap ) {
   const int      lane = threadIdx.x & 31;
   const uint32_t i    = lvlBegin + blockIdx.x * TPB + threadIdx.x;
   const int      o[3] = {ox, oy, oz};
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__( TPB ) k_g_setup( GNode* __restrict__ nodes, c
       lo[k] = n.lo[k], hi[k] = n.hi[k];
     }
     const uint32_t count = n.right - n.left;
-    if ( count <= (uint32_t)KS_CAP ) {
+    if ( count <= ksCap ) {
       n.state = 2;
       small   = 1;
     } else {
@@ -834,8 +834,7 @@ __global__ void __launch_bounds__( TPB ) k_g_pass2_warp( uint64_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------
 constexpr int KS_SMALL      = 32;                   // largest node finished by a single lane
 constexpr int KS_LEAF       = 10;                   // leaf_max_size (PCCKdTree.cpp:58)
-constexpr int KS_SMALL_LIST = KS_CAP / ( KS_LEAF + 1 ) + 2;  // such nodes hold more than KS_LEAF elements each
-constexpr int KS_LSTACK     = 6;                    // pending nodes of one lane: disjoint, > KS_LEAF elements, <= KS_SMALL in total
+constexpr int KS_LSTACK     = 3;                    // pending nodes of one lane: disjoint, > KS_LEAF elements each, the node is <= 43
 
 struct KsItem {
   uint32_t gid;          // node id
@@ -845,17 +844,18 @@ struct KsItem {
 };
 static_assert( sizeof( KsItem ) == 24, "KsItem is copied as 6 words" );
 
-struct KsWarp {
-  uint64_t rec[KS_CAP];
-  uint64_t tmp[KS_CAP];  // warp phase: staging of the Hoare passes; lane phase: the lanes' stacks (word-interleaved)
+template <int CAP>
+struct KsWarpT {
+  uint64_t rec[CAP];
+  uint64_t tmp[CAP];  // warp phase: staging of the Hoare passes; lane phase: the lanes' stacks (word-interleaved)
   KsItem   stack[KS_STACK];
-  KsItem   small[KS_SMALL_LIST];
+  KsItem   small[CAP / ( KS_LEAF + 1 ) + 2];  // listed nodes hold more than KS_LEAF elements each
 };
-static_assert( KS_LSTACK * 5 * 32 * 4 <= KS_CAP * 8 && KS_CAP <= 1024, "lane stacks live in the staging array" );
+static_assert( KS_LSTACK * 5 * 32 * 4 <= KS_CAP * 8 && KS_CAP <= 2047 && KS_SMALL < ( KS_LSTACK + 1 ) * ( KS_LEAF + 1 ), "lane stacks live in the staging array" );
 
 // one Hoare pass of planeSplit (:1154-1181) on positions [begin, right) of the warp's subtree: the positions before
 // `lim` (node-relative) must hold the elements with kd_coord < bound (INCL: <= bound)
-template <bool INCL>
+template <bool INCL, typename KsWarp>
 __device__ __forceinline__ void ks_hoare( KsWarp& S, uint32_t left, uint32_t begin, uint32_t right, uint32_t lim, int cf, int bound,
                                           int lane, uint32_t lt ) {
   // misplaced elements to the staging array at their rank: left ones at [begin, ...), right ones at [left + lim, ...)
@@ -893,6 +893,7 @@ __device__ __forceinline__ void ks_hoare( KsWarp& S, uint32_t left, uint32_t beg
 
 // lane phase: this lane finishes the node `it` (more than KS_LEAF, at most KS_SMALL elements) and everything below it.
 // `stk` is the lane's stack: word w of entry d at stk[( d * 5 + w ) * 32].  Returns the depth of the deepest node.
+template <typename KsWarp>
 __device__ __forceinline__ int ks_lane_subtree( KsWarp& S, KdNode* __restrict__ nodes, uint32_t base, uint32_t idBase, KsItem it,
                                                 bool have, uint32_t* __restrict__ stk, const int o[3] ) {
   uint32_t gid = it.gid;
@@ -960,7 +961,7 @@ __device__ __forceinline__ int ks_lane_subtree( KsWarp& S, KdNode* __restrict__ 
       if ( nr > KS_LEAF && sp < KS_LSTACK ) {  // right child: [s, r), box with low[cf] = cut (sp < KS_LSTACK always holds, see above)
         uint32_t* e = stk + sp * 5 * 32;
         e[0]        = c1 + 1;
-        e[32]       = (uint32_t)s | ( (uint32_t)r << 10 ) | ( (uint32_t)depth << 20 );
+        e[32]       = (uint32_t)s | ( (uint32_t)r << 11 ) | ( (uint32_t)depth << 22 );
         e[64]       = (uint32_t)( cf == 0 ? cut : lo0 ) | ( (uint32_t)( cf == 1 ? cut : lo1 ) << 16 );
         e[96]       = (uint32_t)( cf == 2 ? cut : lo2 ) | ( (uint32_t)hi0 << 16 );
         e[128]      = (uint32_t)hi1 | ( (uint32_t)hi2 << 16 );
@@ -975,7 +976,7 @@ __device__ __forceinline__ int ks_lane_subtree( KsWarp& S, KdNode* __restrict__ 
       sp--;
       const uint32_t* e = stk + sp * 5 * 32;
       gid               = e[0];
-      l = (int)( e[32] & 0x3FFu ), r = (int)( ( e[32] >> 10 ) & 0x3FFu ), depth = (int)( e[32] >> 20 );
+      l = (int)( e[32] & 0x7FFu ), r = (int)( ( e[32] >> 11 ) & 0x7FFu ), depth = (int)( e[32] >> 22 );
       lo0 = (int)( e[64] & 0xFFFFu ), lo1 = (int)( e[64] >> 16 ), lo2 = (int)( e[96] & 0xFFFFu );
       hi0 = (int)( e[96] >> 16 ), hi1 = (int)( e[128] & 0xFFFFu ), hi2 = (int)( e[128] >> 16 );
     } else {
@@ -985,12 +986,14 @@ __device__ __forceinline__ int ks_lane_subtree( KsWarp& S, KdNode* __restrict__ 
   return deepest;
 }
 
+template <int CAP>
 __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __restrict__ grec, const GNode* __restrict__ gnodes,
                                                                  KdNode* __restrict__ nodes, const uint32_t* __restrict__ smallRoots,
                                                                  uint32_t nRoots, uint32_t* __restrict__ counters, uint32_t subBase,
-                                                                 int ox, int oy, int oz ) {
+                                                                 int ox, int oy, int oz, uint32_t ksSmall ) {
   extern __shared__ __align__( 16 ) unsigned char ks_smem[];
   const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  using KsWarp        = KsWarpT<CAP>;
   KsWarp&        S    = reinterpret_cast<KsWarp*>( ks_smem )[w];
   const int      o[3] = {ox, oy, oz};
   const uint32_t lt   = lanemask_lt();
@@ -1018,7 +1021,7 @@ __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __res
     __syncwarp();
     if ( total <= (uint32_t)KS_LEAF ) {  // only the root of a subtree can arrive here as a leaf
       if ( lane == 0 ) { *reinterpret_cast<uint2*>( &nodes[rootId] ) = make_uint2( base, KD_LEAF | total ); }
-    } else if ( total <= (uint32_t)KS_SMALL ) {
+    } else if ( total <= ksSmall ) {
       if ( lane == 0 ) { S.small[0] = cur; }
       nSmall = 1;
     } else {
@@ -1058,8 +1061,8 @@ __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __res
         lim1 = __reduce_add_sync( 0xFFFFFFFFu, lim1 );
         lim2 = __reduce_add_sync( 0xFFFFFFFFu, lim2 );
         // ---- the two Hoare passes of planeSplit ----
-        if ( lim1 > 0 && lim1 < n ) { ks_hoare<false>( S, left, left, right, lim1, cf, cut, lane, lt ); }
-        if ( lim2 > lim1 && lim2 < n ) { ks_hoare<true>( S, left, left + lim1, right, lim2, cf, cut, lane, lt ); }
+        if ( lim1 > 0 && lim1 < n ) { ks_hoare<false, KsWarp>( S, left, left, right, lim1, cf, cut, lane, lt ); }
+        if ( lim2 > lim1 && lim2 < n ) { ks_hoare<true, KsWarp>( S, left, left + lim1, right, lim2, cf, cut, lane, lt ); }
         const uint32_t idx = kd_split_index( n, lim1, lim2 );
         const uint32_t s   = left + idx, c1 = idBase + 2u * ( s - 1u );
         int divlow = cut, divhigh = cut;
@@ -1084,21 +1087,21 @@ __global__ void __launch_bounds__( KS_WARPS * 32 ) k_kd_subtree( uint64_t* __res
         if ( lane == 0 ) {
           if ( nl <= (uint32_t)KS_LEAF ) {
             *reinterpret_cast<uint2*>( &nodes[c1] ) = make_uint2( base + left, KD_LEAF | nl );
-          } else if ( nl <= (uint32_t)KS_SMALL ) {
+          } else if ( nl <= ksSmall ) {
             S.small[nSmall] = lft;
           }
         }
-        if ( nl > (uint32_t)KS_LEAF && nl <= (uint32_t)KS_SMALL ) { nSmall++; }
+        if ( nl > (uint32_t)KS_LEAF && nl <= ksSmall ) { nSmall++; }
         if ( lane == 0 ) {
           if ( nr <= (uint32_t)KS_LEAF ) {
             *reinterpret_cast<uint2*>( &nodes[c1 + 1] ) = make_uint2( base + s, KD_LEAF | nr );
-          } else if ( nr <= (uint32_t)KS_SMALL ) {
+          } else if ( nr <= ksSmall ) {
             S.small[nSmall] = rgt;
           }
         }
-        if ( nr > (uint32_t)KS_LEAF && nr <= (uint32_t)KS_SMALL ) { nSmall++; }
+        if ( nr > (uint32_t)KS_LEAF && nr <= ksSmall ) { nSmall++; }
         maxDepth = max( maxDepth, (int)cur.depth );
-        const bool bigL = nl > (uint32_t)KS_SMALL, bigR = nr > (uint32_t)KS_SMALL;
+        const bool bigL = nl > ksSmall, bigR = nr > ksSmall;
         if ( bigL ) {
           if ( bigR ) {
             if ( sp >= KS_STACK ) {  // cannot happen for 12-bit coordinates (see above); fail loudly
@@ -1157,10 +1160,27 @@ __global__ void k_g_finalize( const GNode* __restrict__ gnodes, uint32_t nLevelN
   nodes[i]  = s;
 }
 
+template <int CAP>
+int launch_subtrees( rb200_ctx* c, uint64_t* rec, const GNode* gnodes, KdNode* nodes, const uint32_t* roots, uint32_t nRoots,
+                     uint32_t* counters, uint32_t subBase, int ox, int oy, int oz, uint32_t ksSmall ) {
+  const size_t smem = sizeof( KsWarpT<CAP> ) * KS_WARPS;
+  int          perSM = 1, nSM = 148;
+  RB_CUDA( cudaFuncSetAttribute( k_kd_subtree<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+  RB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSM, k_kd_subtree<CAP>, KS_WARPS * 32, smem ) );
+  RB_CUDA( cudaDeviceGetAttribute( &nSM, cudaDevAttrMultiProcessorCount, c->device ) );
+  const uint32_t grid = (uint32_t)std::min<int64_t>( (int64_t)std::max( perSM, 1 ) * nSM, ( (int64_t)nRoots + KS_WARPS - 1 ) / KS_WARPS );
+  RB_LAUNCH( "kd_subtree", k_kd_subtree<CAP>, grid, KS_WARPS * 32, smem, rec, gnodes, nodes, roots, nRoots, counters, subBase, ox, oy,
+             oz, ksSmall );
+  return RB200_OK;
+}
+
 }  // namespace
 
 int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* dOff, const std::vector<int64_t>& hOff, int ox,
                  int oy, int oz ) {
+  // measured alternatives on the 32-frame vox10 GOF (subtree kernel, ms): cap 512 / lane nodes <= 32: 3.78; lane nodes
+  // <= 16 / 24 / 48 / 64: 4.38 / 3.85 / 3.93 / 4.44; cap 1024 (one level less in the level phase, half the warps): 7.15
+  constexpr uint32_t ksCap = KS_CAP, ksSmall = KS_SMALL;
   const int     nTrees = (int)hOff.size() - 1;
   const int64_t E      = hOff[nTrees];
   if ( E <= 0 || nTrees <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "kd build: empty forest" ); }
@@ -1171,7 +1191,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   }
   // level-phase nodes: every split node holds more than KS_CAP elements, so a level has at most E / KS_CAP of them
   const uint32_t gCap     = (uint32_t)( E / 16 + 64ll * nTrees + 4096 );
-  const uint32_t chunkCap = (uint32_t)( 2 * ( E / GT ) + 2ll * nTrees + 64 );
+  // chunks of a level: every node of more than ksCap elements has at most one that is not full
+  const uint32_t chunkCap = (uint32_t)( E / GT + E / ksCap + 2ll * nTrees + 64 );
   const size_t   nodeCap  = (size_t)gCap + 2 * (size_t)E + 2;  // + the id blocks of the subtrees (2 ids per element)
   if ( nodeCap >= (size_t)KD_NODE_MAX ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "kd build: %lld elements need more node ids than a search stack entry holds", (long long)E );
@@ -1220,7 +1241,7 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
     RB_CUDA( cudaMemsetAsync( counters + C_CHUNKS, 0, 4, c->stream ) );
     RB_CUDA( cudaMemsetAsync( counters + C_LARGE, 0, 4, c->stream ) );
     RB_LAUNCH( "kd_setup", k_g_setup, rb_div_up( nLvl, TPB ), TPB, 0, gnodes, st, lvlBegin, lvlEnd, level == 0 ? 1 : 0, ox, oy, oz,
-               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap, cls, B.largeList.as<uint32_t>() );
+               B.smallRoots.as<uint32_t>(), counters, chunkNode, chunkCap, gCap, cls, B.largeList.as<uint32_t>(), ksCap );
     RB_CUDA( cudaMemcpyAsync( h, counters, 64, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
     const uint32_t nLarge = h[C_LARGE];
@@ -1240,14 +1261,8 @@ int rb_kd_build( rb200_ctx* c, RbKdBuild& B, const short4* pos, const int64_t* d
   }
   const uint32_t nRoots = h[C_SMALL], nLevelNodes = h[C_NEXT];  // nodes [1, nLevelNodes) were created by the level phase
   if ( nRoots ) {
-    const size_t smem = sizeof( KsWarp ) * KS_WARPS;
-    int          perSM = 1, nSM = 148;
-    RB_CUDA( cudaFuncSetAttribute( k_kd_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
-    RB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSM, k_kd_subtree, KS_WARPS * 32, smem ) );
-    RB_CUDA( cudaDeviceGetAttribute( &nSM, cudaDevAttrMultiProcessorCount, c->device ) );
-    const uint32_t grid = (uint32_t)std::min<int64_t>( (int64_t)std::max( perSM, 1 ) * nSM, ( (int64_t)nRoots + KS_WARPS - 1 ) / KS_WARPS );
-    RB_LAUNCH( "kd_subtree", k_kd_subtree, grid, KS_WARPS * 32, smem, rec, gnodes, nodes, B.smallRoots.as<uint32_t>(), nRoots,
-               counters, gCap, ox, oy, oz );
+    int r = launch_subtrees<KS_CAP>( c, rec, gnodes, nodes, B.smallRoots.as<uint32_t>(), nRoots, counters, gCap, ox, oy, oz, ksSmall );
+    if ( r ) { return r; }
   }
   RB_LAUNCH( "kd_finalize", k_g_finalize, rb_div_up( nLevelNodes, TPB ), TPB, 0, gnodes, nLevelNodes, nTrees, nodes,
              B.rootBox.as<int16_t>() );

@@ -29,6 +29,8 @@
 #include <algorithm>
 
 #include "rb_common.cuh"
+#include "rb_kdtree.cuh"
+#include "rb_kdtree_build.cuh"
 
 namespace {
 
@@ -44,6 +46,7 @@ struct Batch {
   const int64_t*  off;     // [nClouds + 1] first point of every cloud in the concatenated arrays
   int             dim;     // table is dim x dim columns per cloud (+1 lead entry): stride = dim * dim + 1
   int             ox, oy;  // coordinate origin of the table
+  int             oz;      // smallest z of the batch (origin of the kd forest of neighborsProc 0)
   int64_t         stride;
   uint32_t*       tab;     // [nClouds * stride] CSR starts (see build)
   const short4*   in_pos;  // [N] x, y, z
@@ -388,6 +391,7 @@ struct NNArgs {
   double*          contrib;    // [pending][4] MODE_METRIC: the query's c2p / colour terms (added by k_reduce_partials)
   uint32_t         nPending;
   int              compute_c2p, compute_color, neighbors_proc;
+  const uint32_t*  first_idx;  // neighborsProc 0: per unique point of A, the nearest point of B nanoflann returns first
 };
 
 
@@ -447,7 +451,11 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     float        yA[3] = {fA.x, fA.y, fA.z}, yB[3];
     int          rB = 0, gB = 0, bB = 0;
     bool         haveB = false;
-    if ( ( a.neighbors_proc == 1 || a.neighbors_proc == 2 ) && t.n == 1 ) {  // mean of one colour = that colour
+    if ( a.neighbors_proc == 0 ) {  // the colour of result.indices( 0 ), :126, :177: the first nearest point in traversal order
+      const float4 fB = b.u_yuv[t.n == 1 ? t.idx[0] : a.first_idx[uA]];
+      yB[0] = fB.x, yB[1] = fB.y, yB[2] = fB.z;
+      haveB = true;
+    } else if ( ( a.neighbors_proc == 1 || a.neighbors_proc == 2 ) && t.n == 1 ) {  // mean of one colour = that colour
       const float4 fB = b.u_yuv[t.idx[0]];
       yB[0] = fB.x, yB[1] = fB.y, yB[2] = fB.z;
       haveB = true;
@@ -573,6 +581,34 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
     a.pend_off[gw]   = __popc( pm );
   }
   if ( MODE == MODE_METRIC ) { warp_reduce_metric( a, d, ct, (int64_t)blockIdx.x * ( TPB / 32 ) + w ); }
+}
+
+// neighborsProc 0 (PCCMetrics.cpp:126, :177): the colour comes from result.indices( 0 ), the nearest point nanoflann's
+// traversal meets first.  The unique points of every cloud are in the order removeDuplicate leaves them (x, y, z
+// ascending), i.e. the order PCCKdTree indexes them in: the emulated trees of rb_kdtree.cu are built over them and a
+// 1-NN search (the first point at the smallest distance is the same for every k) gives that index.
+__global__ void k_gather_unique( const Batch b, const int64_t* __restrict__ coff, short4* __restrict__ out ) {
+  const int     cloud = blockIdx.y;
+  const int64_t n     = b.ucount[cloud];
+  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x ) {
+    short4 p = b.u_pos[b.off[cloud] + i];
+    p.w      = 0;
+    out[coff[cloud] + i] = p;
+  }
+}
+__global__ void __launch_bounds__( 128 ) k_nn_first( const NNArgs a, const KdForest forest, uint32_t* __restrict__ first_idx ) {
+  // (CTAs of 128 threads, two per CTA of the ring-0 grid the directions are laid out for)
+  const int        blk = blockIdx.x / ( TPB / 128 );
+  const Direction& d   = direction_of_block( a, blk );
+  const Batch&     b   = a.b;
+  const int64_t    iu  = (int64_t)( blk - d.block_begin ) * TPB + ( blockIdx.x % ( TPB / 128 ) ) * 128 + threadIdx.x;
+  if ( iu >= (int64_t)b.ucount[d.cloudA] ) { return; }
+  const int64_t uA   = b.off[d.cloudA] + iu;
+  const short4  p    = b.u_pos[uA];
+  const int     q[3] = {p.x - forest.ox, p.y - forest.oy, p.z - forest.oz};
+  KdResult<1>   res;
+  kd_search<1>( forest, (uint32_t)d.cloudB + 1u, q, res );
+  first_idx[uA] = (uint32_t)( b.off[d.cloudB] + res.idx[0] );
 }
 
 // the unfinished queries as an ordered list (pend_off is the exclusive prefix of the per-warp counts by now): one thread
@@ -857,6 +893,8 @@ struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
   // sets of import buffers, `cur` = the set the running chunk reads.
   RbBuf                rawSet[2], nrmSet[2];
+  RbKdBuild            kd;  // neighborsProc 0: the forest over the unique clouds
+  RbBuf                kd_pos, kd_off, first_idx;
   int                  cur = 0;
   bool                 prefetched = false;  // the running chunk's clouds are already in rawSet[cur] / nrmSet[cur]
   cudaStream_t         copy_stream = nullptr;
@@ -873,6 +911,10 @@ void rb_metrics_release( rb200_ctx* c ) {
                    &s->pend_mask, &s->pend_off, &s->pend_list, &s->contrib, &s->seg};
   for ( auto* b : bufs ) { b->release(); }
   s->u_yuv.release();
+  s->kd.release();
+  s->kd_pos.release();
+  s->kd_off.release();
+  s->first_idx.release();
   s->descs.release();
   s->ndescs.release();
   for ( int k = 0; k < 2; k++ ) {
@@ -1041,6 +1083,7 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
     if ( N == 0 ) { h[0] = h[1] = h[3] = h[4] = 0; }
     B.ox  = h[0];
     B.oy  = h[1];
+    B.oz  = N == 0 ? 0 : h[2];
     B.dim = std::max( h[3] - h[0], h[4] - h[1] ) + 1;
   }
   B.nClouds = nC;
@@ -1301,6 +1344,30 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   // ---- the two directions of every pair ----
   a.dirs  = dDirs;
   a.nDirs = (int)dMetric.size();
+  if ( mp->compute_color && mp->neighbors_proc == 0 && bMetric > 0 ) {
+    // the forest over the unique clouds (their sizes are only known on the device)
+    uint32_t* hu = (uint32_t*)rb_pinned( c, (size_t)nC * 4 + 64 );
+    if ( !hu ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    RB_CUDA( cudaMemcpyAsync( hu, B.ucount, (size_t)nC * 4, cudaMemcpyDeviceToHost, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+    std::vector<int64_t> coff( nC + 1, 0 );
+    for ( int i = 0; i < nC; i++ ) { coff[i + 1] = coff[i] + hu[i]; }
+    RB_CUDA( S->kd_pos.ensure( (size_t)( coff[nC] + 1 ) * 8 ) );
+    RB_CUDA( S->kd_off.ensure( (size_t)( nC + 1 ) * 8 ) );
+    RB_CUDA( S->first_idx.ensure( (size_t)( N + 1 ) * 4 ) );
+    int64_t* ho = (int64_t*)rb_pinned_ring( c, (size_t)( nC + 1 ) * 8 );
+    if ( !ho ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    memcpy( ho, coff.data(), (size_t)( nC + 1 ) * 8 );
+    RB_CUDA( cudaMemcpyAsync( S->kd_off.p, ho, (size_t)( nC + 1 ) * 8, cudaMemcpyHostToDevice, c->stream ) );
+    int64_t maxU = 1;
+    for ( int i = 0; i < nC; i++ ) { maxU = std::max<int64_t>( maxU, hu[i] ); }
+    RB_LAUNCH( "met_gather_unique", k_gather_unique, dim3( (unsigned)std::min<int64_t>( rb_div_up( maxU, 256 ), 1024 ), (unsigned)nC ), 256, 0,
+               B, S->kd_off.as<int64_t>(), S->kd_pos.as<short4>() );
+    r = rb_kd_build( c, S->kd, S->kd_pos.as<short4>(), S->kd_off.as<int64_t>(), coff, B.ox, B.oy, B.oz );
+    if ( r ) { return r; }
+    RB_LAUNCH( "met_nn_first", k_nn_first, bMetric * ( TPB / 128 ), 128, 0, a, S->kd.forest, S->first_idx.as<uint32_t>() );
+    a.first_idx = S->first_idx.as<uint32_t>();
+  }
   r       = run_nn<MODE_METRIC>( c, S, a, dMetric, bMetric, N );
   if ( r ) { return r; }
   RB_CUDA( S->seg.ensure( dMetric.size() * RED_SEG * 32 + 64 ) );
@@ -1400,9 +1467,8 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
   if ( mp->drop_duplicates < 0 || mp->drop_duplicates > 2 ) {
     return rb_fail( c, RB200_ERR_INVALID, "metrics: drop_duplicates must be 0, 1 or 2" );
   }
-  if ( mp->compute_color && ( mp->neighbors_proc < 1 || mp->neighbors_proc > 4 ) ) {
-    // neighborsProc 0 takes result.indices(0), the first tie in nanoflann's traversal order (PCCMetrics.cpp:126,177)
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "metrics: neighbors_proc %d is not implemented (1..4 are)", mp->neighbors_proc );
+  if ( mp->compute_color && ( mp->neighbors_proc < 0 || mp->neighbors_proc > 4 ) ) {
+    return rb_fail( c, RB200_ERR_INVALID, "metrics: neighbors_proc %d (0..4)", mp->neighbors_proc );
   }
   for ( int i = 0; i < nPairs; i++ ) {
     if ( !sources[i].positions || sources[i].count <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty source cloud %d", i ); }

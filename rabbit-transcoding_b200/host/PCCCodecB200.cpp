@@ -524,7 +524,6 @@ void PCCCodec::colorSmoothing( PCCPointSet3& reconstruct, const PCCColorTransfor
 namespace {
 rb200_metrics_params metricsParams( const PCCMetricsParameters& p ) {
   if ( p.computeLidar_ || p.computeReflectance_ ) { unsupported( "lidar / reflectance metrics" ); }
-  if ( p.neighborsProc_ < 1 || p.neighborsProc_ > 4 ) { unsupported( "metrics with neighborsProc = 0 (PCCMetrics.cpp:134-136)" ); }
   rb200_metrics_params mp{};
   mp.compute_c2c = p.computeC2c_, mp.compute_c2p = p.computeC2p_, mp.compute_color = p.computeColor_;
   mp.compute_hausdorff = p.computeHausdorff_, mp.drop_duplicates = (int)p.dropDuplicates_;

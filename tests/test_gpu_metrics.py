@@ -123,6 +123,37 @@ def test_hausdorff_dropdup_variants(rb, codec, checker_backend):
             _close(a.c2p_hausdorff_psnr, b.c2p_hausdorff_psnr, "c2p hausdorff psnr")
 
 
+def test_neighbors_proc_0_first_nearest_in_traversal_order(rb, codec, checker_backend):
+    """neighborsProc 0 (PCCMetrics.cpp:126, :177): the colour of result.indices( 0 ) — among equidistant nearest points the
+    one nanoflann's traversal meets first — through the emulated kd forest over the de-duplicated clouds"""
+    from oracle import checker
+    g, recs = _decoded_pair(rb, codec, seed=36, n_frames=2)
+    mp = checker.default_metrics_params(resolution=255.0)
+    mp.neighbors_proc = 0
+    m = rb.metrics.PCCMetricsB200(codec)
+    m.setParameters(mp)
+    res = m.compute(g.sources, recs, g.sources)
+    for f in range(g.n_frames):
+        want, _ = checker_backend.metrics(mp, g.sources[f], recs[f], g.sources[f])
+        _compare(res[f], want, f"nproc 0 frame {f}")
+    # a lattice with many equidistant neighbours and random colours: the choice among the ties decides the result
+    rng = np.random.default_rng(12)
+    a = np.unique(rng.integers(0, 24, size=(5000, 3)).astype(np.int16) * 2, axis=0)          # even coordinates
+    b = np.unique(rng.integers(0, 24, size=(5000, 3)).astype(np.int16) * 2 + 1, axis=0)      # odd: up to 8 ties at distance 3
+    src = dict(positions=a, colors=rng.integers(0, 256, size=(len(a), 3)).astype(np.uint8))
+    rec = dict(positions=b, colors=rng.integers(0, 256, size=(len(b), 3)).astype(np.uint8))
+    mp = checker.default_metrics_params(resolution=255.0, c2p=False)
+    mp.neighbors_proc = 0
+    m.setParameters(mp)
+    got = m.compute([src], [rec], None)[0]
+    want, _ = checker_backend.metrics(mp, src, rec, None)
+    _compare(got, want, "nproc 0 lattice", c2p=False)
+    mp.neighbors_proc = 1
+    m.setParameters(mp)
+    other = m.compute([src], [rec], None)[0]
+    assert other.q1.color_mse[0] != got.q1.color_mse[0]  # the tie rule matters on this input
+
+
 def test_far_queries_and_sparse_clouds(rb, codec, checker_backend):
     """clouds that are far apart / sparse exercise the warp-per-query ring search"""
     from oracle import checker
