@@ -425,6 +425,7 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     a.nrm[3 * uA + 0] = s[0] / (double)t.n;
     a.nrm[3 * uA + 1] = s[1] / (double)t.n;
     a.nrm[3 * uA + 2] = s[2] / (double)t.n;
+    a.nrm_cnt[uA]     = 1u;  // a finished normal: "sum / 1"
     return;
   }
   // QualityMetrics::compute body for one point of A, PCCMetrics.cpp:92-191
@@ -436,7 +437,12 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
     double sum = 0.0;
     for ( int j = 0; j < t.n; j++ ) {
       const short4  pB = b.u_pos[t.idx[j]];
-      const double* nB = a.nrm + 3 * (int64_t)t.idx[j];
+      const double* sB = a.nrm + 3 * (int64_t)t.idx[j];
+      double        nB[3] = {sB[0], sB[1], sB[2]};
+      if ( d.cloudB & 1 ) {  // B is a reconstruction: scaleNormals' sum / count (PCCPointSet.cpp:2357-2361)
+        const double cnt = (double)a.nrm_cnt[t.idx[j]];
+        nB[0] /= cnt, nB[1] /= cnt, nB[2] /= cnt;
+      }
       const double  e0 = (double)( (int)pA.x - (int)pB.x ), e1 = (double)( (int)pA.y - (int)pB.y ),
                    e2 = (double)( (int)pA.z - (int)pB.z );
       const double dot = __dadd_rn( __dadd_rn( __dmul_rn( e0, nB[0] ), __dmul_rn( e1, nB[1] ) ), __dmul_rn( e2, nB[2] ) );
@@ -554,16 +560,16 @@ __global__ void __launch_bounds__( TPB ) k_nn_near( const NNArgs a ) {
   if ( active ) {
     const int64_t uA   = b.off[d.cloudA] + iu;
     bool          need = true;
-    if ( MODE == MODE_FILL ) {  // points that received normals are only normalised, :2357-2361
-      const uint32_t cnt = a.nrm_cnt[uA];
-      if ( cnt > 0 ) {
-        a.nrm[3 * uA + 0] /= (double)cnt;
-        a.nrm[3 * uA + 1] /= (double)cnt;
-        a.nrm[3 * uA + 2] /= (double)cnt;
-        need = false;
-      }
+    if ( MODE == MODE_FILL ) {
+      // points that received normals are only normalised (:2357-2361): the sums stay as they are and the METRIC pass
+      // divides by the count where it reads them (the same double division, without a pass over 24 bytes per point)
+      if ( a.nrm_cnt[uA] > 0 ) { need = false; }
     }
-    if ( need ) {
+    if ( need && MODE == MODE_FILL ) {
+      // a point no source point chose has no source point at its own position (that one would have chosen it): its
+      // search starts in the dense pass, where every lane has one
+      pending = true;
+    } else if ( need ) {
       const short4 p = b.u_pos[uA];
       TieSet       t;
       if ( search_ring0( b, d.cloudB, p.x, p.y, p.z, t ) ) {
