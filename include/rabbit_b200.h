@@ -342,6 +342,14 @@ int rb200_metrics(rb200_ctx* ctx, const rb200_metrics_params* params, int n_pair
                   const rb200_cloud_view* sources, const rb200_cloud_view* reconstructs,
                   rb200_metrics_result* results /* [n_pairs] */);
 
+/* Source clouds that stay in DEVICE memory across calls (the transcode loop compares the same source frames with the
+ * reconstruction of every rate point, /root/reference transcode.sh:25-37 → PccAppMetrics per rate): with on != 0,
+ * a call whose sources are the same device pointers / counts, with the same drop_duplicates and normals, as the previous
+ * call keeps their de-duplicated points, column tables and gathered normals (removeDuplicate + copyNormals of the
+ * source, PCCMetrics.cpp:353-375) and only indexes the reconstructions.  The caller promises the buffers' contents did
+ * not change in between; calling this again (on or off) drops what is kept.  Results are bit-identical either way. */
+int rb200_metrics_cache_sources(rb200_ctx* ctx, int on);
+
 /* ---- multi-GPU: the one exchange step of the path.  Frames / GOFs / streams are sharded over one context
  *      per GPU with no data-path collective; what ranks exchange is one fixed-size record of accumulators per frame.
  *      A C / C++ host packs its results, all-gathers the records with its own communicator (ncclAllGather / MPI_Allgather

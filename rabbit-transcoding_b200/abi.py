@@ -152,7 +152,7 @@ EXPORTED_SYMBOLS = [
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_debug_set_grid_shrink", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
-    "rb200_download_occupancy", "rb200_metrics", "rb200_metrics_pack", "rb200_metrics_unpack", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
+    "rb200_download_occupancy", "rb200_metrics", "rb200_metrics_cache_sources", "rb200_metrics_pack", "rb200_metrics_unpack", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
     "rb200_timing_enable", "rb200_timing_get",
 ]
 
@@ -206,6 +206,7 @@ def load_library(path=None):
     lib.rb200_download_occupancy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.rb200_metrics.argtypes = [C.c_void_p, C.POINTER(MetricsParams), C.c_int, C.POINTER(CloudView),
                                   C.POINTER(CloudView), C.POINTER(MetricsResult)]
+    lib.rb200_metrics_cache_sources.argtypes = [C.c_void_p, C.c_int]
     lib.rb200_metrics_pack.argtypes = [C.c_int, C.POINTER(MetricsResult), C.POINTER(C.c_double)]
     lib.rb200_metrics_unpack.argtypes = [C.POINTER(C.c_double), C.POINTER(MetricsParams), C.POINTER(C.c_int), C.POINTER(MetricsResult)]
     lib.rb200_remove_duplicates.argtypes = [C.c_void_p, C.POINTER(CloudView), C.c_int, C.c_void_p, C.c_void_p,

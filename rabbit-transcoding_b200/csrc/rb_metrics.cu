@@ -161,8 +161,10 @@ __device__ __forceinline__ int64_t column_of( const Batch& b, int c, int x, int 
 }
 
 // CSR build 1/4: points per column
-__global__ void k_column_count( const Batch b, int64_t n ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// (the CSR kernels take the first point / slot they work on: with cached source clouds only the reconstructions'
+// part of the batch — the points, slots and tables behind the sources' — is rebuilt)
+__global__ void k_column_count( const Batch b, int64_t i0, int64_t n ) {
+  const int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( i >= n ) { return; }
   const int    c = cloud_of( b.off, b.nClouds, i );
   const short4 p = b.in_pos[i];
@@ -170,8 +172,8 @@ __global__ void k_column_count( const Batch b, int64_t n ) {
 }
 // CSR build 2/4 (after the exclusive scan): scatter (z, index) keys; tab[col] ends up as the END of the column, so
 // column col of cloud c is [tab[col - 1], tab[col]) with the per-cloud lead entry closing the first column
-__global__ void k_column_scatter( const Batch b, int64_t n ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_column_scatter( const Batch b, int64_t i0, int64_t n ) {
+  const int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( i >= n ) { return; }
   const int      c    = cloud_of( b.off, b.nClouds, i );
   const short4   p    = b.in_pos[i];
@@ -180,8 +182,8 @@ __global__ void k_column_scatter( const Batch b, int64_t n ) {
 }
 // CSR build 3/4: order every column by (z, original index) by rank counting (columns are short; a long column costs
 // O(L) per element but stays parallel over its elements) and flag the first point of every distinct position
-__global__ void k_column_rank( const Batch b, int64_t n ) {
-  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_column_rank( const Batch b, int64_t i0, int64_t n ) {
+  const int64_t s = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( s >= n ) { return; }
   const int      c   = cloud_of( b.off, b.nClouds, s );
   const uint64_t key = b.key_a[s];
@@ -199,8 +201,8 @@ __global__ void k_column_rank( const Batch b, int64_t n ) {
   b.first[beg + rank] = ( b.drop == 0 || !dup ) ? 1u : 0u;
 }
 // CSR build 4/4 (after the scan of `first`): write the unique points (position, merged colour, first original index)
-__global__ void k_column_compact( const Batch b, int64_t n ) {
-  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_column_compact( const Batch b, int64_t i0, int64_t n ) {
+  const int64_t s = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if ( s >= n ) { return; }
   const uint32_t u0 = b.first[s], u1 = b.first[s + 1];
   if ( u1 == u0 ) { return; }  // not the first of its position
@@ -231,9 +233,10 @@ __global__ void k_column_compact( const Batch b, int64_t n ) {
   b.u_orig[U] = (uint32_t)key;
 }
 // the CSR of the sorted slots becomes the CSR of the unique points; per-cloud unique counts
-__global__ void k_table_unique( const Batch b ) {
+__global__ void k_table_unique( const Batch b, int firstCloud ) {
   const int64_t total = (int64_t)b.nClouds * b.stride;
-  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x ) {
+  for ( int64_t i = (int64_t)firstCloud * b.stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+        i += (int64_t)gridDim.x * blockDim.x ) {
     const int     c    = (int)( i / b.stride );
     const int64_t base = b.off[c];
     b.tab[i]           = (uint32_t)( base + ( b.first[b.tab[i]] - b.first[base] ) );
@@ -392,6 +395,7 @@ struct NNArgs {
   uint32_t         nPending;
   int              compute_c2p, compute_color, neighbors_proc;
   const uint32_t*  first_idx;  // neighborsProc 0: per unique point of A, the nearest point of B nanoflann returns first
+  int              nPairs;     // clouds [0, nPairs) are the sources, [nPairs, 2 nPairs) the reconstructions
 };
 
 
@@ -439,7 +443,7 @@ __device__ __forceinline__ void consume( const NNArgs& a, const Direction& d, in
       const short4  pB = b.u_pos[t.idx[j]];
       const double* sB = a.nrm + 3 * (int64_t)t.idx[j];
       double        nB[3] = {sB[0], sB[1], sB[2]};
-      if ( d.cloudB & 1 ) {  // B is a reconstruction: scaleNormals' sum / count (PCCPointSet.cpp:2357-2361)
+      if ( d.cloudB >= a.nPairs ) {  // B is a reconstruction: scaleNormals' sum / count (PCCPointSet.cpp:2357-2361)
         const double cnt = (double)a.nrm_cnt[t.idx[j]];
         nB[0] /= cnt, nB[1] /= cnt, nB[2] /= cnt;
       }
@@ -899,6 +903,16 @@ struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
   // Host clouds (positions, colours, normals) come in on a copy stream, one chunk of pairs ahead of the kernels: two
   // sets of import buffers, `cur` = the set the running chunk reads.
   RbBuf                rawSet[2], nrmSet[2];
+  // source clouds kept across calls (rb200_metrics_cache_sources): their part of the batch — imported points, unique
+  // points, column tables, gathered normals — stays valid while the same device clouds come in with the same settings
+  struct SrcKey {
+    const void *pos, *col, *nrm;
+    int64_t     n;
+    bool        operator==( const SrcKey& o ) const { return pos == o.pos && col == o.col && nrm == o.nrm && n == o.n; }
+  };
+  bool                 cache_on = false, cache_valid = false;
+  std::vector<SrcKey>  cache_keys;
+  int                  cache_drop = 0, cache_c2p = 0, cache_ox = 0, cache_oy = 0, cache_oz = 0, cache_dim = 0;
   RbKdBuild            kd;  // neighborsProc 0: the forest over the unique clouds
   RbBuf                kd_pos, kd_off, first_idx;
   int                  cur = 0;
@@ -1014,14 +1028,25 @@ struct CloudIn {
   int64_t                 n;
 };
 
-// import the clouds and build the column CSR of every one of them.  `B` receives the device view.
+constexpr int RB_REBUILD = -1000;  // build_batch: the cached source part cannot be reused after all (caller retries)
+
+// import the clouds and build the column CSR of every one of them.  `B` receives the device view.  With `nKeep` > 0 the
+// first nKeep clouds (the cached sources) are already in place: only the clouds behind them are imported and indexed.
 int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& clouds, int drop, Batch& B,
-                 std::vector<int64_t>& hOff ) {
+                 std::vector<int64_t>& hOff, int nKeep = 0 ) {
   const int nC = (int)clouds.size();
   hOff.assign( nC + 1, 0 );
   for ( int i = 0; i < nC; i++ ) { hOff[i + 1] = hOff[i] + clouds[i].n; }
-  const int64_t N = hOff[nC];
+  const int64_t N = hOff[nC], N0 = hOff[nKeep];  // N0: first point that is (re)built
   if ( N >= ( 1ll << 31 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "metrics batch larger than 2^31 points" ); }
+  if ( nKeep > 0 ) {  // every array must still hold the kept part: growing one would lose it
+    const size_t need8 = (size_t)( N + 1 ) * 8, need4 = (size_t)( N + 8 ) * 4;
+    if ( S->in_pos.cap < need8 || S->in_col.cap < need4 || S->key_a.cap < need8 || S->key_b.cap < need8 || S->first.cap < need4 ||
+         S->u_pos.cap < need8 || S->u_z.cap < (size_t)( N + 1 ) * 2 || S->u_col.cap < need4 || S->u_yuv.cap < (size_t)( N + 1 ) * 16 ||
+         S->u_orig.cap < need4 ) {
+      return RB_REBUILD;
+    }
+  }
   RB_CUDA( S->in_pos.ensure( (size_t)( N + 1 ) * 8 ) );
   RB_CUDA( S->in_col.ensure( (size_t)( N + 1 ) * 4 ) );
   RB_CUDA( S->small.ensure( 4096 + (size_t)( nC + 1 ) * 16 ) );
@@ -1037,14 +1062,20 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   if ( S->prefetched ) { RB_CUDA( cudaStreamWaitEvent( c->stream, S->ev_copied[S->cur], 0 ) ); }
   int64_t rawOff = 0;
   S->raw_off.assign( nC, -1 );
-  std::vector<ImportDesc> hd( nC );
+  std::vector<ImportDesc> hd;
   int64_t                 maxN = 0;
   for ( int i = 0; i < nC; i++ ) {
     const CloudIn& cl = clouds[i];
-    ImportDesc&    d  = hd[i];
-    d                 = ImportDesc{nullptr, nullptr, cl.n, hOff[i], 0, 0};
+    if ( i < nKeep ) {  // already imported by an earlier call; its bytes still lead the prefetched set
+      if ( cl.view && cl.n > 0 ) { rawOff += ( ( cl.n * 6 + 15 ) & ~15ll ) + ( ( cl.n * 3 + 15 ) & ~15ll ); }
+      continue;
+    }
+    ImportDesc     d  = ImportDesc{nullptr, nullptr, cl.n, hOff[i], 0, 0};
     maxN              = std::max( maxN, cl.n );
-    if ( cl.n == 0 ) { continue; }
+    if ( cl.n == 0 ) {
+      hd.push_back( d );
+      continue;
+    }
     if ( cl.view ) {
       S->raw_off[i] = rawOff;
       char*   rp = rawBuf.as<char>() + rawOff;
@@ -1063,14 +1094,15 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
       d.col      = c->d_rgb.as<uchar4>() + b;
       d.resident = 1;
     }
+    hd.push_back( d );
   }
   if ( maxN > 0 ) {
-    ImportDesc* hp = (ImportDesc*)rb_pinned_ring( c, nC * sizeof( ImportDesc ) + 64 );
+    ImportDesc* hp = (ImportDesc*)rb_pinned_ring( c, hd.size() * sizeof( ImportDesc ) + 64 );
     if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-    memcpy( hp, hd.data(), nC * sizeof( ImportDesc ) );
-    RB_CUDA( S->descs.ensure( nC * sizeof( ImportDesc ) + 64 ) );
-    RB_CUDA( cudaMemcpyAsync( S->descs.p, hp, nC * sizeof( ImportDesc ), cudaMemcpyHostToDevice, c->stream ) );
-    const dim3 grid( (unsigned)std::min<int64_t>( rb_div_up( maxN, 4 * 256 ), 2048 ), (unsigned)nC );
+    memcpy( hp, hd.data(), hd.size() * sizeof( ImportDesc ) );
+    RB_CUDA( S->descs.ensure( hd.size() * sizeof( ImportDesc ) + 64 ) );
+    RB_CUDA( cudaMemcpyAsync( S->descs.p, hp, hd.size() * sizeof( ImportDesc ), cudaMemcpyHostToDevice, c->stream ) );
+    const dim3 grid( (unsigned)std::min<int64_t>( rb_div_up( maxN, 4 * 256 ), 2048 ), (unsigned)hd.size() );
     RB_LAUNCH( "met_import", k_import_clouds, grid, 256, 0, S->descs.as<ImportDesc>(), inPos, inCol );
   }
   // ---- bounding box -> table geometry (one small read-back) ----
@@ -1082,21 +1114,33 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
     hi[0] = hi[1] = hi[2] = 32767;
     hi[3] = hi[4] = hi[5] = -32768;
     RB_CUDA( cudaMemcpyAsync( dSmall, hi, 24, cudaMemcpyHostToDevice, c->stream ) );
-    if ( N > 0 ) { RB_LAUNCH( "met_bbox", k_bbox, 148 * 4, TPB, 0, inPos, N, dSmall ); }
+    if ( N > N0 ) { RB_LAUNCH( "met_bbox", k_bbox, 148 * 4, TPB, 0, inPos + N0, N - N0, dSmall ); }
     RB_CUDA( cudaMemcpyAsync( h, dSmall, 24, cudaMemcpyDeviceToHost, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
     c->stats.d2h_bytes += 24;
-    if ( N == 0 ) { h[0] = h[1] = h[3] = h[4] = 0; }
-    B.ox  = h[0];
-    B.oy  = h[1];
-    B.oz  = N == 0 ? 0 : h[2];
-    B.dim = std::max( h[3] - h[0], h[4] - h[1] ) + 1;
+    if ( N == N0 ) { h[0] = h[1] = h[2] = h[3] = h[4] = h[5] = 0; }
+    if ( nKeep > 0 ) {
+      // the tables of the kept clouds fix the geometry: the new clouds must fit into it
+      if ( N > N0 && ( h[0] < S->cache_ox || h[1] < S->cache_oy || h[3] >= S->cache_ox + S->cache_dim || h[4] >= S->cache_oy + S->cache_dim ) ) {
+        return RB_REBUILD;
+      }
+      B.ox = S->cache_ox, B.oy = S->cache_oy, B.dim = S->cache_dim;
+      B.oz = N > N0 ? std::min( S->cache_oz, h[2] ) : S->cache_oz;
+    } else {
+      // (with the source cache on, a margin lets the reconstructions of later calls fit the same tables)
+      const int m = S->cache_on ? 16 : 0;
+      B.ox  = h[0] - m;
+      B.oy  = h[1] - m;
+      B.oz  = N == 0 ? 0 : h[2];
+      B.dim = std::max( h[3] - h[0], h[4] - h[1] ) + 1 + 2 * m;
+    }
   }
   B.nClouds = nC;
   B.stride  = (int64_t)B.dim * B.dim + 1;
   B.drop    = drop;
-  const int64_t tabN = (int64_t)nC * B.stride;
+  const int64_t tabN = (int64_t)nC * B.stride, tab0 = (int64_t)nKeep * B.stride;
   if ( tabN >= ( 1ll << 32 ) ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "metrics column table too large" ); }
+  if ( nKeep > 0 && S->tab.cap < (size_t)( tabN + 4 ) * 4 ) { return RB_REBUILD; }
   RB_CUDA( S->tab.ensure( (size_t)( tabN + 4 ) * 4 ) );
   RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( std::max( tabN, N + 1 ) ) ) );
   RB_CUDA( S->key_a.ensure( (size_t)( N + 1 ) * 8 ) );
@@ -1110,10 +1154,13 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   // offsets + unique counts live in the small block: [64 B bbox][off: (nC+1) x 8][ucount: nC x 4]
   int64_t*  dOff    = (int64_t*)( S->small.as<char>() + 64 );
   uint32_t* dUcount = (uint32_t*)( S->small.as<char>() + 64 + ( nC + 1 ) * 8 );
+  const uint32_t* hSeed = nullptr;  // (pinned) the slot the first rebuilt column starts at
   {
     int64_t* h = (int64_t*)rb_pinned_ring( c, ( nC + 1 ) * 8 + 64 );
     if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
     memcpy( h, hOff.data(), ( nC + 1 ) * 8 );
+    *(uint32_t*)( h + nC + 1 ) = (uint32_t)N0;
+    hSeed                      = (const uint32_t*)( h + nC + 1 );
     RB_CUDA( cudaMemcpyAsync( dOff, h, ( nC + 1 ) * 8, cudaMemcpyHostToDevice, c->stream ) );
   }
   B.off    = dOff;
@@ -1129,22 +1176,26 @@ int build_batch( rb200_ctx* c, MetricsScratch* S, const std::vector<CloudIn>& cl
   B.u_yuv  = S->u_yuv.as<float4>();
   B.u_orig = S->u_orig.as<uint32_t>();
   B.ucount = dUcount;
-  RB_CUDA( cudaMemsetAsync( B.tab, 0, (size_t)tabN * 4, c->stream ) );
-  if ( N > 0 ) {
-    const int G = rb_div_up( N, TPB );
-    RB_LAUNCH( "met_column_count", k_column_count, G, TPB, 0, B, N );
-    int r = rb_scan_u32( c, B.tab, B.tab, tabN, S->sums.as<uint32_t>() );
+  RB_CUDA( cudaMemsetAsync( B.tab + tab0, 0, (size_t)( tabN - tab0 ) * 4, c->stream ) );
+  if ( N > N0 ) {
+    const int G = rb_div_up( N - N0, TPB );
+    RB_LAUNCH( "met_column_count", k_column_count, G, TPB, 0, B, N0, N );
+    // the rebuilt tables continue behind the kept slots: the (empty) lead entry of their first cloud carries N0 into the
+    // exclusive scan and is set to N0 itself afterwards
+    if ( N0 > 0 ) { RB_CUDA( cudaMemcpyAsync( B.tab + tab0, hSeed, 4, cudaMemcpyHostToDevice, c->stream ) ); }
+    int r = rb_scan_u32( c, B.tab + tab0, B.tab + tab0, tabN - tab0, S->sums.as<uint32_t>() );
     if ( r ) { return r; }
-    RB_LAUNCH( "met_column_scatter", k_column_scatter, G, TPB, 0, B, N );
-    RB_LAUNCH( "met_column_rank", k_column_rank, G, TPB, 0, B, N );
+    if ( N0 > 0 ) { RB_CUDA( cudaMemcpyAsync( B.tab + tab0, hSeed, 4, cudaMemcpyHostToDevice, c->stream ) ); }
+    RB_LAUNCH( "met_column_scatter", k_column_scatter, G, TPB, 0, B, N0, N );
+    RB_LAUNCH( "met_column_rank", k_column_rank, G, TPB, 0, B, N0, N );
     RB_CUDA( cudaMemsetAsync( B.first + N, 0, 4, c->stream ) );
-    r = rb_scan_u32( c, B.first, B.first, N + 1, S->sums.as<uint32_t>() );
+    r = rb_scan_u32( c, B.first + N0, B.first + N0, N - N0 + 1, S->sums.as<uint32_t>() );
     if ( r ) { return r; }
-    RB_LAUNCH( "met_column_compact", k_column_compact, G, TPB, 0, B, N );
-  } else {
+    RB_LAUNCH( "met_column_compact", k_column_compact, G, TPB, 0, B, N0, N );
+  } else if ( N0 == 0 ) {
     RB_CUDA( cudaMemsetAsync( B.first, 0, 8, c->stream ) );
   }
-  RB_LAUNCH( "met_table_unique", k_table_unique, 148 * 8, TPB, 0, B );
+  RB_LAUNCH( "met_table_unique", k_table_unique, 148 * 8, TPB, 0, B, nKeep );
   return RB200_OK;
 }
 
@@ -1187,24 +1238,24 @@ extern "C" {
 // pairs [first, first + nPairs) of one rb200_metrics call; their host clouds are already in the import buffers of
 // set S->cur (prefetch_pairs)
 static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int first, int nPairs, const rb200_cloud_view* sources,
-                          const rb200_cloud_view* recs, rb200_metrics_result* results ) {
+                          const rb200_cloud_view* recs, rb200_metrics_result* results, bool cacheable ) {
   MetricsScratch* S = scratch_of( c );
-  // clouds: 2 per pair (source, reconstruction)
+  // clouds: the sources first, then the reconstructions (pair i = clouds i and nPairs + i)
   std::vector<CloudIn> clouds( 2 * nPairs );
   bool                 anyNormals = false;
   for ( int i = 0; i < nPairs; i++ ) {
     if ( !sources[i].positions || sources[i].count <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty source cloud %d", i ); }
-    clouds[2 * i] = CloudIn{&sources[i], -1, sources[i].count};
+    clouds[i] = CloudIn{&sources[i], -1, sources[i].count};
     if ( recs[i].positions ) {
-      clouds[2 * i + 1] = CloudIn{&recs[i], -1, recs[i].count};
+      clouds[nPairs + i] = CloudIn{&recs[i], -1, recs[i].count};
     } else {
       const int fr = first + i;
       if ( !c->reconstructed || !c->rgb_done || fr >= c->F ) {
         return rb_fail( c, RB200_ERR_STATE, "metrics: pair %d asks for the resident frame but no decoded GOF is resident", fr );
       }
-      clouds[2 * i + 1] = CloudIn{nullptr, fr, c->h_frame_off[fr + 1] - c->h_frame_off[fr]};
+      clouds[nPairs + i] = CloudIn{nullptr, fr, c->h_frame_off[fr + 1] - c->h_frame_off[fr]};
     }
-    if ( clouds[2 * i + 1].n <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty reconstruction %d", i ); }
+    if ( clouds[nPairs + i].n <= 0 ) { return rb_fail( c, RB200_ERR_INVALID, "metrics: empty reconstruction %d", i ); }
     if ( sources[i].normals ) { anyNormals = true; }
   }
   // ---- normals of the sources: uploaded by prefetch_pairs at these offsets of nrmSet[cur] ----
@@ -1217,12 +1268,30 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
       tot += ( sources[i].count * 12 + 255 ) & ~255ll;
     }
   }
+  // ---- cached sources: the same device clouds with the same settings as the previous call keep their part ----
+  const bool wantC2p = mp->compute_c2p != 0 && anyNormals;
+  std::vector<MetricsScratch::SrcKey> keys;
+  if ( cacheable && S->cache_on ) {
+    for ( int i = 0; i < nPairs; i++ ) { keys.push_back( {sources[i].positions, sources[i].colors, sources[i].normals, sources[i].count} ); }
+  }
+  bool reuse = !keys.empty() && S->cache_valid && keys == S->cache_keys && S->cache_drop == mp->drop_duplicates &&
+               S->cache_c2p == ( wantC2p ? 1 : 0 );
+  if ( reuse && wantC2p ) {  // the gathered normals of the sources must survive as well
+    int64_t n = 0;
+    for ( auto& cl : clouds ) { n += cl.n; }
+    if ( S->nrm.cap < (size_t)( n + 1 ) * 24 || S->nrm_cnt.cap < (size_t)( n + 1 ) * 4 ) { reuse = false; }
+  }
+  S->cache_valid = false;
   Batch                B{};
   std::vector<int64_t> hOff;
-  int                  r = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff );
+  int                  r = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff, reuse ? nPairs : 0 );
+  if ( r == RB_REBUILD ) {
+    reuse = false;
+    r     = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff, 0 );
+  }
   if ( r ) { return r; }
   const int     nC = 2 * nPairs;
-  const int64_t N  = hOff[nC];
+  const int64_t N = hOff[nC], N0 = reuse ? hOff[nPairs] : 0;
 
   // ---- directions and CTA ranges ----
   auto makeDirs = [&]( std::vector<Direction>& dirs, std::vector<int32_t>& blockEnd, auto pick ) {
@@ -1239,13 +1308,12 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
     }
     return blocks;
   };
-  const bool wantC2p = mp->compute_c2p != 0 && anyNormals;
   std::vector<Direction> dMetric, dScale, dFill;
   std::vector<int32_t>   eMetric, eScale, eFill;
   const int bMetric = makeDirs( dMetric, eMetric, [&]( int i, int k, Direction& d ) {
     const bool hn = sources[i].normals != nullptr;
-    d.cloudA      = 2 * i + k;
-    d.cloudB      = 2 * i + 1 - k;
+    d.cloudA      = k == 0 ? i : nPairs + i;
+    d.cloudB      = k == 0 ? nPairs + i : i;
     d.nrmA = d.nrmB = hn ? 0 : -1;
     d.acc           = 2 * i + k;
     return true;
@@ -1254,12 +1322,12 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   if ( wantC2p ) {
     bScale = makeDirs( dScale, eScale, [&]( int i, int k, Direction& d ) {  // source (with normals) -> reconstruction
       if ( k != 0 || !sources[i].normals ) { return false; }
-      d.cloudA = 2 * i, d.cloudB = 2 * i + 1, d.nrmA = d.nrmB = 0, d.acc = 0;
+      d.cloudA = i, d.cloudB = nPairs + i, d.nrmA = d.nrmB = 0, d.acc = 0;
       return true;
     } );
     bFill = makeDirs( dFill, eFill, [&]( int i, int k, Direction& d ) {  // reconstruction -> source for count == 0
       if ( k != 1 || !sources[i].normals ) { return false; }
-      d.cloudA = 2 * i + 1, d.cloudB = 2 * i, d.nrmA = d.nrmB = 0, d.acc = 0;
+      d.cloudA = nPairs + i, d.cloudB = i, d.nrmA = d.nrmB = 0, d.acc = 0;
       return true;
     } );
   }
@@ -1308,24 +1376,26 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
   a.compute_c2p    = wantC2p ? 1 : 0;
   a.compute_color  = mp->compute_color;
   a.neighbors_proc = mp->neighbors_proc;
+  a.nPairs         = nPairs;
 
   // ---- normals: copyNormals on the sources, scaleNormals on the reconstructions (PCCMetrics.cpp:371-375) ----
   if ( wantC2p ) {
     RB_CUDA( S->nrm.ensure( (size_t)( N + 1 ) * 24 ) );
     RB_CUDA( S->nrm_cnt.ensure( (size_t)( N + 1 ) * 4 ) );
     RB_CUDA( S->last_idx.ensure( (size_t)( N + 1 ) * 4 ) );
-    RB_CUDA( cudaMemsetAsync( S->nrm.p, 0, (size_t)N * 24, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( S->nrm_cnt.p, 0, (size_t)N * 4, c->stream ) );
-    RB_CUDA( cudaMemsetAsync( S->last_idx.p, 0, (size_t)N * 4, c->stream ) );
+    // (the sources' gathered normals are final after k_normal_gather: a reused call only clears the reconstructions')
+    RB_CUDA( cudaMemsetAsync( S->nrm.as<char>() + (size_t)N0 * 24, 0, (size_t)( N - N0 ) * 24, c->stream ) );
+    RB_CUDA( cudaMemsetAsync( S->nrm_cnt.as<char>() + (size_t)N0 * 4, 0, (size_t)( N - N0 ) * 4, c->stream ) );
+    if ( !reuse ) { RB_CUDA( cudaMemsetAsync( S->last_idx.p, 0, (size_t)N * 4, c->stream ) ); }
     a.nrm     = S->nrm.as<double>();
     a.nrm_cnt = S->nrm_cnt.as<uint32_t>();
     std::vector<NormalDesc> hn;
     int64_t                 maxN = 0;
-    for ( int i = 0; i < nPairs; i++ ) {
+    for ( int i = 0; i < nPairs && !reuse; i++ ) {
       if ( !sources[i].normals ) { continue; }
       // the normal cloud of pair i is the source view itself (positions + normals in file order): its positions were
       // imported by build_batch, its normals came in on the copy stream
-      hn.push_back( NormalDesc{(const float*)( S->nrmSet[S->cur].as<char>() + nrmOff[i] ), sources[i].count, 2 * i, 0} );
+      hn.push_back( NormalDesc{(const float*)( S->nrmSet[S->cur].as<char>() + nrmOff[i] ), sources[i].count, i, 0} );
       maxN = std::max<int64_t>( maxN, sources[i].count );
     }
     if ( !hn.empty() ) {
@@ -1397,18 +1467,25 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
                     err & 1 ? "metrics: normal object and source must have the same number of points (PCCPointSet.cpp:2287)"
                             : "metrics: a source point is not present in the normal point cloud (PCCPointSet.cpp:2311)" );
   }
+  if ( !keys.empty() ) {  // what the next call may keep
+    S->cache_keys  = keys;
+    S->cache_drop  = mp->drop_duplicates;
+    S->cache_c2p   = wantC2p ? 1 : 0;
+    S->cache_ox = B.ox, S->cache_oy = B.oy, S->cache_oz = B.oz, S->cache_dim = B.dim;
+    S->cache_valid = true;
+  }
   int status = RB200_OK;
   for ( int i = 0; i < nPairs; i++ ) {
     rb200_metrics_result& R = results[i];
     memset( &R, 0, sizeof( R ) );
     const bool hn = sources[i].normals != nullptr && mp->compute_c2p;
-    finish_quality( R.q1, hAcc[2 * i], hUc[2 * i], *mp, hn );
-    finish_quality( R.q2, hAcc[2 * i + 1], hUc[2 * i + 1], *mp, hn );
+    finish_quality( R.q1, hAcc[2 * i], hUc[i], *mp, hn );
+    finish_quality( R.q2, hAcc[2 * i + 1], hUc[nPairs + i], *mp, hn );
     combine_quality( R.qf, R.q1, R.q2, *mp );
-    R.source_points      = clouds[2 * i].n;
-    R.rec_points         = clouds[2 * i + 1].n;
-    R.source_after_dedup = mp->drop_duplicates ? hUc[2 * i] : 0;  // sourceDuplicates_, PCCMetrics.cpp:356,363
-    R.rec_after_dedup    = mp->drop_duplicates ? hUc[2 * i + 1] : 0;
+    R.source_points      = clouds[i].n;
+    R.rec_points         = clouds[nPairs + i].n;
+    R.source_after_dedup = mp->drop_duplicates ? hUc[i] : 0;  // sourceDuplicates_, PCCMetrics.cpp:356,363
+    R.rec_after_dedup    = mp->drop_duplicates ? hUc[nPairs + i] : 0;
     R.tie_overflow       = (int32_t)( hAcc[2 * i].tie_overflow + hAcc[2 * i + 1].tie_overflow );
     if ( R.tie_overflow ) { status = RB200_ERR_TIE_OVERFLOW; }
   }
@@ -1443,18 +1520,22 @@ static int prefetch_pairs( rb200_ctx* c, MetricsScratch* S, const rb200_metrics_
   RB_CUDA( S->nrmSet[set].ensure( (size_t)nrmBytes + 64 ) );
   RB_CUDA( cudaStreamWaitEvent( S->copy_stream, S->ev_free[set], 0 ) );  // the chunk that read this set has finished
   int64_t rawOff = 0, nOff = 0;
-  for ( int i = 0; i < nPairs; i++ ) {
-    const rb200_cloud_view* v[2] = {&sources[i], recs[i].positions ? &recs[i] : nullptr};
-    for ( int k = 0; k < 2; k++ ) {
-      if ( !v[k] || v[k]->count <= 0 ) { continue; }
-      const int64_t n  = v[k]->count;
+  // the order of the batch: every source, then every reconstruction that is not the resident one (build_batch walks the
+  // clouds in the same order)
+  for ( int k = 0; k < 2; k++ ) {
+    for ( int i = 0; i < nPairs; i++ ) {
+      const rb200_cloud_view* v = k == 0 ? &sources[i] : ( recs[i].positions ? &recs[i] : nullptr );
+      if ( !v || v->count <= 0 ) { continue; }
+      const int64_t n  = v->count;
       char*         rp = S->rawSet[set].as<char>() + rawOff;
       char*         rc = rp + ( ( n * 6 + 15 ) & ~15ll );
-      RB_CUDA( cudaMemcpyAsync( rp, v[k]->positions, n * 6, cudaMemcpyDefault, S->copy_stream ) );
-      if ( v[k]->colors ) { RB_CUDA( cudaMemcpyAsync( rc, v[k]->colors, n * 3, cudaMemcpyDefault, S->copy_stream ) ); }
-      c->stats.h2d_bytes += n * ( v[k]->colors ? 9 : 6 );
+      RB_CUDA( cudaMemcpyAsync( rp, v->positions, n * 6, cudaMemcpyDefault, S->copy_stream ) );
+      if ( v->colors ) { RB_CUDA( cudaMemcpyAsync( rc, v->colors, n * 3, cudaMemcpyDefault, S->copy_stream ) ); }
+      c->stats.h2d_bytes += n * ( v->colors ? 9 : 6 );
       rawOff += ( ( n * 6 + 15 ) & ~15ll ) + ( ( n * 3 + 15 ) & ~15ll );
     }
+  }
+  for ( int i = 0; i < nPairs; i++ ) {
     if ( mp->compute_c2p && sources[i].normals ) {
       RB_CUDA( cudaMemcpyAsync( S->nrmSet[set].as<char>() + nOff, sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
       c->stats.h2d_bytes += sources[i].count * 12;
@@ -1512,7 +1593,7 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
     }
     S->cur        = set;
     S->prefetched = true;
-    r             = metrics_range( c, mp, b, e - b, sources + b, recs + b, results + b );
+    r             = metrics_range( c, mp, b, e - b, sources + b, recs + b, results + b, onDevice && nChunks == 1 );
     S->prefetched = false;
     cudaEventRecord( S->ev_free[set], c->stream );
     if ( r == RB200_ERR_TIE_OVERFLOW ) {
@@ -1525,6 +1606,15 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
   return status;
 }
 
+int rb200_metrics_cache_sources( rb200_ctx* c, int on ) {
+  if ( !c ) { return RB200_ERR_INVALID; }
+  MetricsScratch* S = scratch_of( c );
+  S->cache_on       = on != 0;
+  S->cache_valid    = false;
+  S->cache_keys.clear();
+  return RB200_OK;
+}
+
 int rb200_remove_duplicates( rb200_ctx* c, const rb200_cloud_view* in, int drop, int16_t* outPos, uint8_t* outCol,
                              int64_t* outCount ) {
   if ( !c || !in || !outCount ) { return rb_fail( c, RB200_ERR_INVALID, "remove_duplicates: bad arguments" ); }
@@ -1534,6 +1624,7 @@ int rb200_remove_duplicates( rb200_ctx* c, const rb200_cloud_view* in, int drop,
   if ( in->count == 0 ) { return RB200_OK; }
   if ( !in->positions ) { return rb_fail( c, RB200_ERR_INVALID, "remove_duplicates: null positions" ); }
   MetricsScratch*      S = scratch_of( c );
+  S->cache_valid         = false;
   std::vector<CloudIn> clouds{CloudIn{in, -1, in->count}};
   Batch                B{};
   std::vector<int64_t> hOff;

@@ -35,11 +35,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan( uint32_t v, uint32_t* 
   return smem[w] + incl - v;
 }
 
-__global__ void __launch_bounds__( TPB ) k_scan_sums( const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums ) {
+// `in` / `out` are the 16-byte aligned addresses at or below the caller's, `skip` (0..3) the elements in front of the
+// caller's first one: they read as 0 and are never written (n counts them)
+__global__ void __launch_bounds__( TPB ) k_scan_sums( const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums, int skip ) {
   __shared__ uint32_t sm[33];
   const int64_t       base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t            s    = 0;
-  if ( base + SCAN_ITEMS <= n ) {
+  if ( base + SCAN_ITEMS <= n && base >= skip ) {
     const uint4* p = reinterpret_cast<const uint4*>( in + base );
 #pragma unroll
     for ( int k = 0; k < SCAN_ITEMS / 4; k++ ) {
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__( TPB ) k_scan_sums( const uint32_t* __restrict
     }
   } else {
     for ( int k = 0; k < SCAN_ITEMS; k++ ) {
-      if ( base + k < n ) { s += in[base + k]; }
+      if ( base + k < n && base + k >= skip ) { s += in[base + k]; }
     }
   }
   uint32_t total;
@@ -93,12 +95,13 @@ __global__ void __launch_bounds__( 1024 ) k_scan_top( uint32_t* __restrict__ sum
 }
 
 __global__ void __launch_bounds__( TPB ) k_scan_apply( const uint32_t* __restrict__ in, int64_t n, const uint32_t* __restrict__ sums,
-                                                       uint32_t* __restrict__ out ) {
+                                                       uint32_t* __restrict__ out, int skip ) {
   __shared__ uint32_t sm[33];
   const int64_t       base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t            v[SCAN_ITEMS];
   uint32_t            s = 0;
-  if ( base + SCAN_ITEMS <= n ) {
+  const bool          whole = base + SCAN_ITEMS <= n && base >= skip;
+  if ( whole ) {
     const uint4* p = reinterpret_cast<const uint4*>( in + base );
 #pragma unroll
     for ( int k = 0; k < SCAN_ITEMS / 4; k++ ) {
@@ -107,13 +110,13 @@ __global__ void __launch_bounds__( TPB ) k_scan_apply( const uint32_t* __restric
     }
   } else {
 #pragma unroll
-    for ( int k = 0; k < SCAN_ITEMS; k++ ) { v[k] = ( base + k < n ) ? in[base + k] : 0u; }
+    for ( int k = 0; k < SCAN_ITEMS; k++ ) { v[k] = ( base + k < n && base + k >= skip ) ? in[base + k] : 0u; }
   }
 #pragma unroll
   for ( int k = 0; k < SCAN_ITEMS; k++ ) { s += v[k]; }
   uint32_t total;
   uint32_t run = block_exclusive_scan( s, sm, total ) + sums[blockIdx.x];
-  if ( base + SCAN_ITEMS <= n ) {
+  if ( whole ) {
     uint4* p = reinterpret_cast<uint4*>( out + base );
 #pragma unroll
     for ( int k = 0; k < SCAN_ITEMS / 4; k++ ) {
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__( TPB ) k_scan_apply( const uint32_t* __restric
   } else {
 #pragma unroll
     for ( int k = 0; k < SCAN_ITEMS; k++ ) {
-      if ( base + k < n ) { out[base + k] = run; }
+      if ( base + k < n && base + k >= skip ) { out[base + k] = run; }
       run += v[k];
     }
   }
@@ -140,10 +143,15 @@ size_t rb_scan_scratch_bytes( int64_t n ) { return (size_t)( n / SCAN_TILE + 2 )
 int rb_scan_u32( rb200_ctx* c, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums ) {
   uint32_t* total_out = nullptr;
   if ( n <= 0 ) { return RB200_OK; }
+  // a range that does not start on a 16-byte boundary (the rebuilt tail of a cached metrics batch) is scanned from the
+  // boundary below it, the elements in front masked out
+  const int skip = (int)( ( (uintptr_t)in >> 2 ) & 3 );
+  if ( skip != (int)( ( (uintptr_t)out >> 2 ) & 3 ) ) { return rb_fail( c, RB200_ERR_INVALID, "scan: in and out must be equally aligned" ); }
+  in -= skip, out -= skip, n += skip;
   const int64_t nb = ( n + SCAN_TILE - 1 ) / SCAN_TILE;
-  RB_LAUNCH( "scan_sums", k_scan_sums, (unsigned)nb, TPB, 0, in, n, sums );
+  RB_LAUNCH( "scan_sums", k_scan_sums, (unsigned)nb, TPB, 0, in, n, sums, skip );
   RB_LAUNCH( "scan_top", k_scan_top, 1, 1024, 0, sums, nb, total_out );
-  RB_LAUNCH( "scan_apply", k_scan_apply, (unsigned)nb, TPB, 0, in, n, sums, out );
+  RB_LAUNCH( "scan_apply", k_scan_apply, (unsigned)nb, TPB, 0, in, n, sums, out, skip );
   return RB200_OK;
 }
 

@@ -85,6 +85,12 @@ class PCCMetricsB200:
     def setParameters(self, params):
         self.params_ = params
 
+    def cacheSources(self, on=True):
+        """rb200_metrics_cache_sources: device-resident sources keep their index across compute() calls"""
+        st = self._lib.rb200_metrics_cache_sources(self._codec._h, 1 if on else 0)
+        if st != abi.RB200_OK:
+            raise RabbitError(st, "rb200_metrics_cache_sources")
+
     def compute(self, sources, reconstructs, normals=None):
         if len(sources) != len(reconstructs):
             # PCCMetrics.cpp:341-347 prints and exits(-1)

@@ -175,6 +175,53 @@ def test_far_queries_and_sparse_clouds(rb, codec, checker_backend):
     assert want.q1.c2c_hausdorff > 100
 
 
+def test_cached_device_sources_keep_their_index_across_calls(rb, codec, checker_backend):
+    """rb200_metrics_cache_sources: the transcode loop measures the same source frames against every rate point.  The
+    second and third call reuse the sources' part of the batch (different reconstructions, host views and the
+    resident GOF); a reconstruction outside the kept tables forces the rebuild path; all equal the reference."""
+    import torch
+    from oracle import checker
+    g, recs = _decoded_pair(rb, codec, seed=36, n_frames=3)
+    dev = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in s.items() if k in ("positions", "colors", "normals")}
+           for s in g.sources]
+    mp = checker.default_metrics_params(resolution=255.0)
+    m = rb.metrics.PCCMetricsB200(codec)
+    m.setParameters(mp)
+    m.cacheSources(True)
+    want = [checker_backend.metrics(mp, g.sources[f], recs[f], g.sources[f])[0] for f in range(g.n_frames)]
+    for rnd in range(2):  # first call builds, second reuses (resident reconstruction)
+        res = m.compute(dev, [None] * g.n_frames, dev)
+        for f in range(g.n_frames):
+            _compare(res[f], want[f], f"round {rnd} frame {f}")
+    # other reconstructions against the kept sources: frames rotated, as host views
+    rot = [recs[(f + 1) % g.n_frames] for f in range(g.n_frames)]
+    res = m.compute(dev, rot, dev)
+    for f in range(g.n_frames):
+        w, _ = checker_backend.metrics(mp, g.sources[f], rot[f], g.sources[f])
+        _compare(res[f], w, f"rotated frame {f}")
+    # a reconstruction far outside the kept column tables: rebuilt from scratch, same answer
+    far = [dict(positions=(r["positions"].astype(np.int32) + np.array([300, 0, 40])).astype(np.int16), colors=r["colors"]) for r in recs]
+    res = m.compute(dev, far, dev)
+    for f in range(g.n_frames):
+        w, _ = checker_backend.metrics(mp, g.sources[f], far[f], g.sources[f])
+        _compare(res[f], w, f"far frame {f}")
+    # and the settings are part of the key: drop_duplicates 1 after 2
+    mp1 = checker.default_metrics_params(resolution=255.0)
+    mp1.drop_duplicates = 1
+    m.setParameters(mp1)
+    res = m.compute(dev, recs, dev)
+    for f in range(g.n_frames):
+        w, _ = checker_backend.metrics(mp1, g.sources[f], recs[f], g.sources[f])
+        _compare(res[f], w, f"drop 1 frame {f}")
+    res = m.compute(dev, recs, None)  # without normals: D1 + colour only, cached index of the drop-1 call is not valid for c2p off
+    mpn = checker.default_metrics_params(resolution=255.0, c2p=False)
+    mpn.drop_duplicates = 1
+    for f in range(g.n_frames):
+        w, _ = checker_backend.metrics(mpn, g.sources[f], recs[f], None)
+        _compare(res[f], w, f"no normals frame {f}", c2p=False)
+    m.cacheSources(False)
+
+
 def test_vox10_frame_metrics(rb, codec, checker_backend):
     from oracle import checker
     g = rb.synthetic.generate_gof(n_frames=1, bitdepth=10, width=1280, scale=0.68, seed=35, transfer_filter=0,
