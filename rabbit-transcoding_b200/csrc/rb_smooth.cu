@@ -431,6 +431,189 @@ __global__ void __launch_bounds__( 256, 4 ) k_accumulate( const GridArgs a, int6
   }
 }
 
+// ---- warp-staged accumulation (geometry) ----
+// Points arrive in emission order: the 256 consecutive points of a warp are a few pixel rows of one 16x16 patch block
+// (two layers), i.e. a handful of cells, and consecutive points mostly share their cell.  Instead of sending every
+// thread's partial sums to L2 (one table probe + four atomics per thread and cell, ~80 groups per warp) the warp
+//   1. walks its points 64 at a time, two consecutive points per lane, merged in registers when they share the cell;
+//   2. adds the lanes of a run of equal cells with a segmented shuffle scan (full-mask shuffles, run boundaries from one
+//      ballot), so only the last lane of a run holds something to deliver (a second point that lies in another cell
+//      than the first is delivered by its lane; running those through a scan of their own measured slower);
+//   3. delivers into a 32-slot table of cell accumulators in the warp's slice of SHARED memory: a plain read finds the
+//      slot (a CAS only claims an empty one), two shared atomics add {count, sum dx} and {sum dy, sum dz} — sums of the
+//      offsets inside the cell (< g <= 64), so two words hold what four would — and the partition extrema are only
+//      tracked when the warp's points come from more than one patch;
+//   4. after its 256 points flushes every used slot once: one table probe and four atomics per distinct cell.
+// A warp whose points span two frames uses the per-thread path (k_accumulate_crossing); records that find the 32 slots
+// taken by other cells go to the grid directly.
+struct StageSlot {  // structure of arrays per warp: slot s of field f at f[s]
+  uint32_t key[32];       // cx | cy << 10 | cz << 20 | 1 << 30, 0 = free
+  uint32_t w1[32];        // count | sum dx << 9      (<= 256 points, dx < 64)
+  uint32_t w2[32];        // sum dy | sum dz << 16
+  uint32_t pmax[32], pmin_inv[32];
+};
+
+// one record per lane into the global grid (the tail of the per-thread path): `want` lanes take part
+__device__ __forceinline__ void flush_global( const GridArgs& a, int f, bool want, uint32_t key, uint32_t w1, uint32_t w2, uint32_t mx,
+                                              uint32_t mn_inv, int lane ) {
+  const uint32_t mask = __ballot_sync( 0xFFFFFFFFu, want );
+  if ( !want ) { return; }
+  const int      cx = key & 1023, cy = ( key >> 10 ) & 1023, cz = ( key >> 20 ) & 1023;
+  const uint32_t cnt = w1 & 511u;
+  const uint32_t t0 = cnt * (uint32_t)( cx * a.g ) + ( w1 >> 9 ), t1 = cnt * (uint32_t)( cy * a.g ) + ( w2 & 0xFFFFu ),
+                 t2 = cnt * (uint32_t)( cz * a.g ) + ( w2 >> 16 );
+  const uint32_t bk      = block_key( cx, cy, cz );
+  const uint32_t bpeers  = __match_any_sync( mask, bk );
+  const int      bleader = __ffs( bpeers ) - 1;
+  uint32_t       bl      = NO_BLOCK;
+  if ( lane == bleader ) { bl = block_claim( a, f, bk ); }
+  bl = __shfl_sync( mask, bl, bleader );
+  if ( bl == NO_BLOCK ) { return; }
+  Cell* c = a.cells + ( bl * 64u + cell_local( cx, cy, cz ) );
+  atomicAdd( (unsigned long long*)&c->cw, (unsigned long long)cnt | ( (unsigned long long)t2 << 32 ) );
+  atomicAdd( (unsigned long long*)&c->s0, (unsigned long long)t0 | ( (unsigned long long)t1 << 32 ) );
+  atomicMax( &c->pmax, mx );
+  atomicMax( &c->pmin_inv, mn_inv );
+}
+
+// one record per lane (`want`) into the warp's table
+__device__ __forceinline__ void stage_insert( const GridArgs& a, StageSlot& S, int f, int lane, bool onePart, bool want, uint32_t K, uint32_t W1,
+                                              uint32_t W2, uint32_t MX, uint32_t MN ) {
+  bool spill = false;
+  if ( want ) {
+    uint32_t h   = ( K * 0x9E3779B1u ) >> 27;
+    bool     hit = false;
+    for ( int probe = 0; probe < 32 && !hit; probe++ ) {
+      uint32_t cur = *reinterpret_cast<volatile uint32_t*>( &S.key[h] );
+      if ( cur == 0u ) {
+        cur = atomicCAS( &S.key[h], 0u, K );
+        if ( cur == 0u ) { cur = K; }
+      }
+      if ( cur == K ) {
+        hit = true;
+      } else {
+        h = ( h + 1 ) & 31u;
+      }
+    }
+    if ( hit ) {
+      atomicAdd( &S.w1[h], W1 );
+      atomicAdd( &S.w2[h], W2 );
+      if ( !onePart ) {
+        atomicMax( &S.pmax[h], MX );
+        atomicMax( &S.pmin_inv[h], MN );
+      }
+    } else {
+      spill = true;  // more than 32 distinct cells in this warp's points
+    }
+  }
+  if ( __any_sync( 0xFFFFFFFFu, spill ) ) { flush_global( a, f, spill, K, W1, W2, MX, MN, lane ); }
+}
+
+// runs of equal cells over the lanes (K = 0: the lane has nothing) -> their sums into the warp's table
+__device__ __forceinline__ void stage_runs( const GridArgs& a, StageSlot& S, int f, int lane, bool onePart, uint32_t K, uint32_t W1, uint32_t W2,
+                                            uint32_t MX, uint32_t MN ) {
+  const uint32_t prevK    = __shfl_up_sync( 0xFFFFFFFFu, K, 1 );
+  const bool     head     = lane == 0 || K != prevK;
+  const uint32_t heads    = __ballot_sync( 0xFFFFFFFFu, head );
+  const int      segstart = 31 - __clz( heads & ( 0xFFFFFFFFu >> ( 31 - lane ) ) );
+  const bool     tail     = lane == 31 || ( ( heads >> ( lane + 1 ) ) & 1u );
+#pragma unroll
+  for ( int d = 1; d < 32; d <<= 1 ) {
+    const uint32_t t1 = __shfl_up_sync( 0xFFFFFFFFu, W1, d ), t2 = __shfl_up_sync( 0xFFFFFFFFu, W2, d );
+    if ( lane - d >= segstart ) { W1 += t1, W2 += t2; }
+  }
+  if ( !onePart ) {
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+      const uint32_t tX = __shfl_up_sync( 0xFFFFFFFFu, MX, d ), tN = __shfl_up_sync( 0xFFFFFFFFu, MN, d );
+      if ( lane - d >= segstart ) { MX = max( MX, tX ), MN = max( MN, tN ); }
+    }
+  }
+  stage_insert( a, S, f, lane, onePart, tail && K != 0u, K, W1, W2, MX, MN );
+}
+
+// the (at most F - 1) warps of the staged kernel whose 256 points span two frames, on the per-thread path: warp j looks
+// at the window that holds the end of frame j
+template <bool COLOUR>
+__global__ void __launch_bounds__( 256 ) k_accumulate_crossing( const GridArgs a, int64_t n ) {
+  const int lane = threadIdx.x & 31, j = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+  if ( j >= a.F ) { return; }
+  const int64_t e = a.frame_off[j + 1];
+  if ( e >= n ) { return; }
+  const int64_t w0 = e & ~255ll;
+  if ( frame_of( a.frame_off, a.F, w0 ) != j ) { return; }  // the window starts in another frame (or exactly at e)
+  accumulate_warp<COLOUR, false>( a, n, w0 + (int64_t)lane * ACC_RUN, lane, j );
+}
+
+template <int MINB>
+__global__ void __launch_bounds__( 256, MINB ) k_accumulate_geo_staged( const GridArgs a, int64_t n ) {
+  __shared__ StageSlot stage[8];
+  const int     lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t w0   = ( (int64_t)blockIdx.x * 8 + wi ) * 256;  // first point of the warp
+  if ( w0 >= n ) { return; }
+  const int fw = frame_of( a.frame_off, a.F, w0 );
+  if ( min( w0 + 256, n ) > a.frame_off[fw + 1] ) { return; }  // spans two frames: k_accumulate_crossing
+  StageSlot& S = stage[wi];
+  S.key[lane] = 0, S.w1[lane] = 0, S.w2[lane] = 0, S.pmax[lane] = 0, S.pmin_inv[lane] = 0;
+  // ---- all loads first: iteration k covers points w0 + 64 k + 2 lane, + 1 ----
+  uint4 vp[4];
+  uint2 vq[4];
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) {
+    const int64_t i = w0 + 64 * k + 2 * lane;
+    if ( i + 1 < n ) {
+      vp[k] = *reinterpret_cast<const uint4*>( a.pos + i );
+      vq[k] = *reinterpret_cast<const uint2*>( a.part + i );
+    } else {
+      vp[k] = make_uint4( 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu );  // x = y = z = -1: outside
+      vq[k] = make_uint2( 0, 0 );
+      if ( i < n ) {
+        const short4 p = a.pos[i];
+        vp[k].x        = (uint32_t)(uint16_t)p.x | ( (uint32_t)(uint16_t)p.y << 16 );
+        vp[k].y        = (uint32_t)(uint16_t)p.z | ( (uint32_t)(uint16_t)p.w << 16 );
+        vq[k].x        = a.part[i];
+      }
+    }
+  }
+  // the points of a warp nearly always belong to one patch: then max / min partition need neither scans nor atomics
+  const uint32_t pFirst = __shfl_sync( 0xFFFFFFFFu, vq[0].x, 0 ) + 1u;
+  bool           uni    = true;
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) { uni = uni && vq[k].x + 1u == pFirst && vq[k].y + 1u == pFirst; }
+  const bool onePart = __all_sync( 0xFFFFFFFFu, uni );
+  __syncwarp();
+  const int g = a.g, disth = max( g / 2, 1 ), th = grid_th( a, fw );
+#pragma unroll
+  for ( int k = 0; k < 4; k++ ) {
+    // the lane's two points: cell and offsets inside the cell
+    const int x0 = (short)( vp[k].x & 0xFFFF ), y0 = (short)( vp[k].x >> 16 ), z0 = (short)( vp[k].y & 0xFFFF );
+    const int x1 = (short)( vp[k].z & 0xFFFF ), y1 = (short)( vp[k].z >> 16 ), z1 = (short)( vp[k].w & 0xFFFF );
+    const bool in0 = inside( x0, y0, z0, disth, th ), in1 = inside( x1, y1, z1, disth, th );
+    const int  cx0 = cell_of( a, x0 & 0xFFFF ), cy0 = cell_of( a, y0 & 0xFFFF ), cz0 = cell_of( a, z0 & 0xFFFF );
+    const int  cx1 = cell_of( a, x1 & 0xFFFF ), cy1 = cell_of( a, y1 & 0xFFFF ), cz1 = cell_of( a, z1 & 0xFFFF );
+    const uint32_t k0 = in0 ? ( (uint32_t)cx0 | ( (uint32_t)cy0 << 10 ) | ( (uint32_t)cz0 << 20 ) | 0x40000000u ) : 0u;
+    const uint32_t k1 = in1 ? ( (uint32_t)cx1 | ( (uint32_t)cy1 << 10 ) | ( (uint32_t)cz1 << 20 ) | 0x40000000u ) : 0u;
+    const uint32_t u1 = in0 ? ( 1u | ( (uint32_t)( x0 - cx0 * g ) << 9 ) ) : 0u;
+    const uint32_t u2 = in0 ? ( (uint32_t)( y0 - cy0 * g ) | ( (uint32_t)( z0 - cz0 * g ) << 16 ) ) : 0u;
+    const uint32_t v1 = in1 ? ( 1u | ( (uint32_t)( x1 - cx1 * g ) << 9 ) ) : 0u;
+    const uint32_t v2 = in1 ? ( (uint32_t)( y1 - cy1 * g ) | ( (uint32_t)( z1 - cz1 * g ) << 16 ) ) : 0u;
+    const uint32_t p0 = vq[k].x + 1u, p1 = vq[k].y + 1u;
+    // stream A: point 0 (with point 1 when it shares the cell), or point 1 alone; stream B: point 1 in another cell
+    const bool     same = k0 == k1;                 // (also when both are outside: nothing)
+    const bool     bB   = in0 && in1 && !same;
+    const bool     add1 = in1 && ( same || !in0 );
+    const uint32_t KA   = in0 ? k0 : k1;
+    uint32_t       W1 = u1, W2 = u2, MX = in0 ? p0 : 0u, MN = in0 ? ~p0 : 0u;
+    if ( add1 ) { W1 += v1, W2 += v2, MX = max( MX, p1 ), MN = max( MN, ~p1 ); }
+    stage_runs( a, S, fw, lane, onePart, KA, W1, W2, MX, MN );
+    if ( __any_sync( 0xFFFFFFFFu, bB ) ) { stage_insert( a, S, fw, lane, onePart, bB, k1, v1, v2, p1, ~p1 ); }
+  }
+  __syncwarp();
+  // ---- one flush per distinct cell ----
+  const uint32_t key = S.key[lane];
+  flush_global( a, fw, key != 0u, key, S.w1[lane], S.w2[lane], onePart ? pFirst : S.pmax[lane], onePart ? ~pFirst : S.pmin_inv[lane], lane );
+}
+
 // The reference sums the cell members in float, in emission order (:996, :1177).  Integer sums convert to the same float
 // while every partial sum stays below 2^24; a cell beyond that is listed and k_ordered_cells repeats
 // its float accumulation in emission order.  More than 65535 members wrap the reference's uint16 counter (not reproduced).
@@ -1003,7 +1186,15 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );
     if ( r ) { return r; }
     if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
-    RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+    // (RB200_GEO_ACC=thread selects the per-thread path for the whole GOF: the measured alternative, tools/full_prof.py)
+    static const bool perThread = getenv( "RB200_GEO_ACC" ) && !strcmp( getenv( "RB200_GEO_ACC" ), "thread" );
+    if ( perThread ) {
+      RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
+    } else {
+      // (5 CTAs per SM, 48 registers: 0.195 ms on the 32-frame vox10 GOF; 4 CTAs, 60 registers: 0.199; per-thread path: 0.235)
+      RB_LAUNCH( "geo_accumulate", k_accumulate_geo_staged<5>, rb_div_up( n, 2048 ), 256, 0, a, n );
+      if ( c->F > 1 ) { RB_LAUNCH( "geo_accumulate_x", k_accumulate_crossing<false>, rb_div_up( c->F, 8 ), 256, 0, a, n ); }
+    }
     RB_LAUNCH( "geo_finalize", k_finalize_geo, WALK_CTAS, 256, 0, a );
     RB_LAUNCH( "geo_ordered", k_ordered_cells<false>, ORDERED_CAP / 8, 256, 0, a );
     if ( c->blist_cap > 0 ) {

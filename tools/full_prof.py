@@ -14,5 +14,5 @@ for _ in range(3):
     codec.decodeGof()
 torch.cuda.synchronize(); print("ms per GOF", (time.time() - t0) / 3 * 1e3)
 codec.enableTiming(True); codec.decodeGof(); t = codec.timings()
-for k, v in sorted(t.items(), key=lambda kv: -kv[1][0])[:24]:
+for k, v in sorted(t.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[1]) if len(sys.argv) > 1 else 24]:
     print(k, round(v[0], 3), v[1])
