@@ -124,7 +124,12 @@ typedef struct rb200_params {
   int32_t pbf_passes_count;
   int32_t pbf_filter_size;
   int32_t pbf_log2_threshold;
-  int32_t reserved0;
+  /* the non-grid smoothPointCloud (PCCCodec.cpp:1106-1157), reached through smoothPointCloudPostprocess (:141) when
+   * grid_smoothing == 0 — the encoder's reconstruction (PCCEncoder.cpp:7905-7907); the decoder skips geometry smoothing
+   * in that case (PCCDecoder.cpp:436) and leaves neighbor_count_smoothing at 0, which rb200_decode_gof takes as "skip" */
+  int32_t neighbor_count_smoothing;   /* neighborCountSmoothing_ (4 * 16)                                 */
+  double  radius2_smoothing;          /* radius2Smoothing_ (64)                                           */
+  double  radius2_boundary_detection; /* radius2BoundaryDetection_ (64)                                   */
 } rb200_params;
 
 /* Decoded video planes of one GOF (what PCCVideoDecoder leaves in PCCContext, PCCContext.h:48-50).
@@ -370,6 +375,13 @@ int rb200_remove_duplicates(rb200_ctx* ctx, const rb200_cloud_view* in, int drop
  *      out_idx / out_dist are [nq][k]; missing entries (cloud smaller than k) are -1. ------------------------------- */
 int rb200_kdtree_search(rb200_ctx* ctx, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, int k,
                         int64_t* out_idx, double* out_dist);
+/* PCCKdTree::searchRadius (PCCKdTree.cpp:69-79): nanoflann radiusSearch (dist < radius2), std::sort by distance and, for
+ * equal distances, by index (the vendored IndexDist_Sorter, nanoflann.hpp:193-200), cut to max_results — what the non-grid smoothPointCloud asks per point (PCCCodec.cpp:1120).  sorted == 0 returns the unsorted
+ * traversal order instead (nanoflann SearchParams::sorted = false).  out_idx / out_dist are [nq][max_results] (missing
+ * entries -1), out_count [nq] is the number of points inside the radius before the cut. */
+int rb200_kdtree_search_radius(rb200_ctx* ctx, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq,
+                               double radius2, int max_results, int sorted, int64_t* out_idx, double* out_dist,
+                               int32_t* out_count);
 
 /* ---- PCCPointSet3::computeChecksum( false ) (PCCPointSet.cpp:222-245): MD5 of positions || RGB8 of a decoded frame ---- */
 int rb200_frame_md5(rb200_ctx* ctx, int frame, uint8_t* out16);

@@ -215,6 +215,19 @@ class _Backend:
 class Reference(_Backend):
     prefix = "ref_"
 
+    def knn_radius(self, cloud, queries, radius2, max_results, sorted_=True):
+        """PCCKdTree::searchRadius; sorted_ = False: nanoflann's traversal order (no std::sort)"""
+        f = self.lib.ref_knn_radius
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        cloud = np.ascontiguousarray(cloud, np.int16)
+        queries = np.ascontiguousarray(queries, np.int16)
+        idx = np.zeros((len(queries), max_results), np.int64)
+        dist = np.zeros((len(queries), max_results), np.float64)
+        cnt = np.zeros(len(queries), np.int32)
+        f(abi.ptr(cloud), len(cloud), abi.ptr(queries), len(queries), radius2, max_results, 1 if sorted_ else 0, abi.ptr(idx),
+          abi.ptr(dist), abi.ptr(cnt))
+        return idx, dist, cnt
+
     def __init__(self):
         super().__init__(REF_LIB)
 

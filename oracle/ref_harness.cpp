@@ -62,6 +62,7 @@
 #include "PCCGroupOfFrames.h"
 #include "PCCCodec.h"
 #include "PCCKdTree.h"
+#include "KDTreeVectorOfVectorsAdaptor.h"
 #include "PCCMetricsParameters.h"
 #include "PCCMetrics.h"
 #undef private
@@ -134,9 +135,9 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
   g.enableSizeQuantization_        = p.enable_size_quantization != 0;
   g.gridSmoothing_                 = p.grid_smoothing != 0;
   g.gridSize_                      = p.grid_size;
-  g.neighborCountSmoothing_        = 0;
-  g.radius2Smoothing_              = 0;
-  g.radius2BoundaryDetection_      = 0;
+  g.neighborCountSmoothing_        = p.neighbor_count_smoothing;
+  g.radius2Smoothing_              = p.radius2_smoothing;
+  g.radius2BoundaryDetection_      = p.radius2_boundary_detection;
   g.thresholdSmoothing_            = p.threshold_smoothing;
   g.rawPointColorFormat_           = 0;
   g.nbThread_                      = 1;
@@ -417,7 +418,10 @@ ref_gof* ref_gof_run( const rb200_params* pp,
       auto t2 = std::chrono::steady_clock::now();
       if ( p.apply_geo_smoothing && p.flag_geometry_smoothing ) {
         PCCPointSet3 tempFrameBuffer = reconstruct;
-        if ( p.grid_smoothing ) { codec.smoothPointCloudPostprocess( reconstruct, COLOR_TRANSFORM_NONE, gpc, partition ); }
+        // (neighbor_count_smoothing > 0 without grid smoothing: the encoder-side call with the non-grid filter, PCCCodec.cpp:141)
+        if ( p.grid_smoothing || p.neighbor_count_smoothing > 0 ) {
+          codec.smoothPointCloudPostprocess( reconstruct, COLOR_TRANSFORM_NONE, gpc, partition );
+        }
         auto t3       = std::chrono::steady_clock::now();
         fo.msStage[1] = std::chrono::duration<double, std::milli>( t3 - t2 ).count();
         if ( keep_mask & 2u ) { snap( fo.stage[1], reconstruct ); }
@@ -620,6 +624,42 @@ int ref_knn( const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq
     for ( int j = 0; j < k; j++ ) {
       outIdx[i * k + j]  = j < (int)res.size() ? (int64_t)res.indices( j ) : -1;
       outDist[i * k + j] = j < (int)res.size() ? res.dist( j ) : -1.0;
+    }
+  }
+  return 0;
+}
+
+// PCCKdTree::searchRadius (PCCKdTree.cpp:69-79); sorted == 0: the same index queried with SearchParams::sorted = false
+// (nanoflann's traversal order, before std::sort)
+int ref_knn_radius( const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, double radius2, int maxResults, int sorted,
+                    int64_t* outIdx, double* outDist, int32_t* outCount ) {
+  PCCPointSet3 pc;
+  pc.resize( n );
+  std::memcpy( pc.positions_.data(), cloud, n * 6 );
+  PCCKdTree tree( pc );
+  typedef KDTreeVectorOfVectorsAdaptor<PCCPointSet3, PCCType, float, 3, metric_L2_Simple_2, size_t> Adaptor;  // PCCKdTree.cpp:42
+  Adaptor raw( 3, pc, 10 );
+  for ( int64_t i = 0; i < nq; i++ ) {
+    PCCPoint3D qp( queries[i * 3], queries[i * 3 + 1], queries[i * 3 + 2] );
+    std::vector<std::pair<size_t, double> > ret;
+    {
+      nanoflann::SearchParams sp;
+      sp.sorted = false;
+      raw.index->radiusSearch( &qp[0], radius2, ret, sp );
+    }
+    outCount[i] = (int32_t)ret.size();
+    if ( sorted ) {
+      PCCNNResult res;
+      tree.searchRadius( qp, (size_t)maxResults, radius2, res );
+      for ( int j = 0; j < maxResults; j++ ) {
+        outIdx[i * maxResults + j]  = j < (int)res.count() ? (int64_t)res.indices( j ) : -1;
+        outDist[i * maxResults + j] = j < (int)res.count() ? res.dist( j ) : -1.0;
+      }
+    } else {
+      for ( int j = 0; j < maxResults; j++ ) {
+        outIdx[i * maxResults + j]  = j < (int)ret.size() ? (int64_t)ret[j].first : -1;
+        outDist[i * maxResults + j] = j < (int)ret.size() ? ret[j].second : -1.0;
+      }
     }
   }
   return 0;

@@ -188,6 +188,7 @@ int rb_reconstruct_impl( rb200_ctx* c );
 int rb_pbf_impl( rb200_ctx* c );
 int rb_smooth_geometry_impl( rb200_ctx* c );
 int rb_transfer_colors_impl( rb200_ctx* c );
+int rb_smooth_radius_impl( rb200_ctx* c );  // the non-grid smoothPointCloud (rb_transfer.cu: it needs the kd forest)
 int rb_interleave_colors_impl( rb200_ctx* c );
 int rb_smooth_color_impl( rb200_ctx* c );
 int rb_convert_rgb8_impl( rb200_ctx* c );

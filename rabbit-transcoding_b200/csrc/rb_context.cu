@@ -719,7 +719,7 @@ int rb200_decode_gof( rb200_ctx* c ) {
   if ( r ) { return r; }
   const rb200_params& p = c->P;
   if ( p.apply_geo_smoothing && p.flag_geometry_smoothing ) {  // :434
-    if ( p.grid_smoothing ) {
+    if ( p.grid_smoothing || p.neighbor_count_smoothing > 0 ) {  // (> 0 without the grid: the encoder-side call, rabbit_b200.h)
       r = rb200_smooth_geometry( c );  // :437
       if ( r ) { return r; }
     }

@@ -1155,8 +1155,8 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   const rb200_params& P = c->P;
   const int64_t       n = c->h_frame_off[c->F];
   if ( n == 0 || !P.flag_geometry_smoothing ) { return RB200_OK; }  // :64-65
-  if ( !P.grid_smoothing ) {  // :141 (never reached from the decoder, PCCDecoder.cpp:436)
-    return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothPointCloud (PCCCodec.cpp:1106-1157) is not implemented" );
+  if ( !P.grid_smoothing ) {  // :140-142 (never reached from the decoder, PCCDecoder.cpp:436: the encoder's reconstruction)
+    return P.pbf_enable ? RB200_OK : rb_smooth_radius_impl( c );
   }
   const int g = P.grid_size;
   if ( g < 1 || g > 64 ) { return rb_fail( c, RB200_ERR_INVALID, "grid_size %d out of range", g ); }

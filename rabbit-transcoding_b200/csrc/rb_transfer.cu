@@ -440,6 +440,191 @@ __global__ void __launch_bounds__( 128 ) k_ilv_transfer( const KdForest forest, 
   col[i] = out;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// PCCCodec::smoothPointCloud (PCCCodec.cpp:1106-1157), the non-grid geometry filter.  Per point: PCCKdTree::searchRadius
+// (PCCKdTree.cpp:69-79) = nanoflann radiusSearch — every point with dist < radius2Smoothing in TRAVERSAL order
+// (RadiusResultSet::addPoint, worstDist() == radius, nanoflann.hpp:945-952, 1207-1253), std::sort with the vendored
+// IndexDist_Sorter (by distance, EQUAL DISTANCES BY INDEX, :193-200 — a total order, unlike upstream nanoflann's) and
+// a cut to neighborCountSmoothing entries.  On the integer lattice the cut nearly always falls inside a shell of equal
+// distances: the lower indices of the shell survive.
+// ---------------------------------------------------------------------------------------------------
+struct RadiusArgs {
+  KdForest        forest;
+  int             F;
+  const int64_t*  frame_off;
+  const short4*   posIn;   // the reconstruction (kept copy)
+  short4*         posOut;  // smoothed positions, boundary type 1 -> 2 (:1132-1134)
+  const uint32_t* part;
+  int64_t         N;
+  uint32_t        dLim;    // dist < radius2Smoothing        <=>  d < dLim   (d is an integer)
+  uint32_t        visit;   // mindistsq <= radius2Smoothing  <=>  m <= visit
+  uint32_t        bLim;    // dist2 <= radius2BoundaryDetection <=> d <= bLim
+  int             maxCount;
+  double          threshold;
+  uint64_t*       lists;   // [threads][cap] dist << 32 | index in frame
+  int             cap;
+  uint32_t*       err;     // 1: list overflow
+};
+
+// ascending sort of dist << 32 | index keys: the reference's IndexDist_Sorter orders equal distances by index
+// (nanoflann.hpp:193-200 as vendored), a total order, so any sorting algorithm gives std::sort's result
+__device__ void sort_keys( uint64_t* v, int n ) {
+  for ( int start = n / 2 - 1; start >= 0; start-- ) {  // heapsort: in place, no recursion, O(n log n) on any input
+    int            root = start;
+    const uint64_t val  = v[root];
+    for ( int child = 2 * root + 1; child < n; child = 2 * root + 1 ) {
+      if ( child + 1 < n && v[child + 1] > v[child] ) { child++; }
+      if ( v[child] <= val ) { break; }
+      v[root] = v[child];
+      root    = child;
+    }
+    v[root] = val;
+  }
+  for ( int end = n - 1; end > 0; end-- ) {
+    const uint64_t val = v[end];
+    v[end]             = v[0];
+    int root           = 0;
+    for ( int child = 1; child < end; child = 2 * root + 1 ) {
+      if ( child + 1 < end && v[child + 1] > v[child] ) { child++; }
+      if ( v[child] <= val ) { break; }
+      v[root] = v[child];
+      root    = child;
+    }
+    v[root] = val;
+  }
+}
+
+// findNeighbors + searchLevel with a RadiusResultSet (the walk of kd_search; the bound is the constant radius): every
+// element with d < dLim, in traversal order, as dist << 32 | index into L[0, cap); returns how many there are
+__device__ __forceinline__ int kd_radius( const KdForest& f, uint32_t root, const int q[3], uint32_t dLim, uint32_t visit, uint64_t* L, int cap ) {
+  int      n  = 0;
+  uint32_t d0 = 0, d1 = 0, d2 = 0;
+  {
+    const int16_t* rb = f.rootBox + (size_t)root * 6;
+    int            t;
+    t  = q[0] < rb[0] ? q[0] - rb[0] : ( q[0] > rb[3] ? q[0] - rb[3] : 0 );
+    d0 = (uint32_t)( t * t );
+    t  = q[1] < rb[1] ? q[1] - rb[1] : ( q[1] > rb[4] ? q[1] - rb[4] : 0 );
+    d1 = (uint32_t)( t * t );
+    t  = q[2] < rb[2] ? q[2] - rb[2] : ( q[2] > rb[5] ? q[2] - rb[5] : 0 );
+    d2 = (uint32_t)( t * t );
+  }
+  uint32_t stN[KD_STACK], stV[KD_STACK];
+  int      sp   = 0;
+  uint32_t node = root;
+  for ( ;; ) {
+    if ( node ) {
+      const uint4 nv = __ldg( reinterpret_cast<const uint4*>( f.nodes + node ) );
+      if ( nv.y & KD_LEAF ) {
+        const uint32_t lend = nv.x + ( nv.y & 0xFFFFu );
+        for ( uint32_t e = nv.x; e < lend; e++ ) {
+          const uint64_t r  = f.rec[e];
+          const int      dx = q[0] - kd_coord( r, 0 ), dy = q[1] - kd_coord( r, 1 ), dz = q[2] - kd_coord( r, 2 );
+          const uint32_t d  = (uint32_t)( dx * dx ) + (uint32_t)( dy * dy ) + (uint32_t)( dz * dz );
+          if ( d < dLim ) {
+            if ( n < cap ) { L[n] = ( (uint64_t)d << 32 ) | kd_index( r ); }
+            n++;
+          }
+        }
+        node = 0;
+      } else {
+        const uint32_t axis   = nv.y & 3u;
+        const int      val    = axis == 0 ? q[0] : ( axis == 1 ? q[1] : q[2] );
+        const int      divlow = (int16_t)( nv.z & 0xFFFFu ), divhigh = (int16_t)( nv.z >> 16 );
+        const int      diff1 = val - divlow, diff2 = val - divhigh;
+        const bool     nearLeft = diff1 + diff2 < 0;
+        const int      cd       = nearLeft ? diff2 : diff1;
+        stN[sp]                 = ( nv.x + ( nearLeft ? 1u : 0u ) ) | ( axis << 29 );
+        stV[sp]                 = (uint32_t)( cd * cd );
+        sp++;
+        node = nv.x + ( nearLeft ? 0u : 1u );
+      }
+    } else {
+      if ( sp == 0 ) { break; }
+      sp--;
+      const uint32_t e = stN[sp], v = stV[sp], axis = ( e >> 29 ) & 3u;
+      if ( e >> 31 ) {
+        d0 = axis == 0 ? v : d0, d1 = axis == 1 ? v : d1, d2 = axis == 2 ? v : d2;
+      } else {
+        const uint32_t dst = axis == 0 ? d0 : ( axis == 1 ? d1 : d2 );
+        const uint32_t m   = d0 + d1 + d2 + v - dst;
+        if ( m <= visit ) {
+          stN[sp] = e | 0x80000000u;
+          stV[sp] = dst;
+          sp++;
+          d0 = axis == 0 ? v : d0, d1 = axis == 1 ? v : d1, d2 = axis == 2 ? v : d2;
+          node = e & ( KD_NODE_MAX - 1u );
+        }
+      }
+    }
+  }
+  return n;
+}
+
+// PCCKdTree::searchRadius for explicit queries (rb200_kdtree_search_radius): sorted == 0 leaves the traversal order
+__global__ void __launch_bounds__( 128 ) k_radius_query( const KdForest forest, const int16_t* __restrict__ queries, int64_t nq, uint32_t dLim,
+                                                         uint32_t visit, int maxResults, int sorted, uint64_t* lists, int cap,
+                                                         int64_t* __restrict__ outIdx, double* __restrict__ outDist, int32_t* __restrict__ outCount,
+                                                         uint32_t* err ) {
+  uint64_t* const L = lists + (size_t)( blockIdx.x * blockDim.x + threadIdx.x ) * cap;
+  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x ) {
+    const int q[3] = {queries[3 * i] - forest.ox, queries[3 * i + 1] - forest.oy, queries[3 * i + 2] - forest.oz};
+    const int n    = kd_radius( forest, 1u, q, dLim, visit, L, cap );
+    outCount[i]    = n;
+    if ( n > cap ) {
+      atomicOr( err, 1u );
+      continue;
+    }
+    if ( sorted ) { sort_keys( L, n ); }
+    for ( int r = 0; r < maxResults; r++ ) {
+      outIdx[i * maxResults + r]  = r < n ? (int64_t)(uint32_t)L[r] : -1;
+      outDist[i * maxResults + r] = r < n ? (double)(uint32_t)( L[r] >> 32 ) : -1.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__( 128 ) k_smooth_radius( const RadiusArgs a ) {
+  uint64_t* const L = a.lists + (size_t)( blockIdx.x * blockDim.x + threadIdx.x ) * a.cap;
+  for ( int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.N; i += (int64_t)gridDim.x * blockDim.x ) {
+    const int      f    = frame_of( a.frame_off, a.F, i );
+    const int64_t  base = a.frame_off[f];
+    const short4   p    = a.posIn[i];
+    const int      q[3] = {p.x - a.forest.ox, p.y - a.forest.oy, p.z - a.forest.oz};
+    const int      n    = kd_radius( a.forest, (uint32_t)f + 1u, q, a.dLim, a.visit, L, a.cap );
+    if ( n > a.cap ) { atomicOr( a.err, 1u ); }
+    short4 out = p;
+    if ( n <= a.cap ) {
+      sort_keys( L, n );  // searchParams.sorted (:949-950): by distance, equal distances by index
+      const int      cnt  = min( n, a.maxCount );                   // ret.resize( retSize ), PCCKdTree.cpp:75-76
+      const uint32_t mine = a.part[i];
+      long long      sx = 0, sy = 0, sz = 0;
+      bool           other = false;
+      for ( int r = 0; r < cnt; r++ ) {  // :1122-1129 (sums of int16 coordinates in double: exact)
+        const uint32_t j  = (uint32_t)L[r], d = (uint32_t)( L[r] >> 32 );
+        const short4   pj = a.posIn[base + j];
+        sx += pj.x, sy += pj.y, sz += pj.z;
+        other |= d <= a.bLim && a.part[base + j] != mine;
+      }
+      if ( other ) {
+        if ( p.w == 1 ) { out.w = 2; }  // :1131-1133
+        const double dn = (double)cnt;
+        const double ex = __dsub_rn( (double)sx, __dmul_rn( dn, (double)p.x ) ), ey = __dsub_rn( (double)sy, __dmul_rn( dn, (double)p.y ) ),
+                     ez = __dsub_rn( (double)sz, __dmul_rn( dn, (double)p.z ) );
+        const double norm2 = __dadd_rn( __dadd_rn( __dmul_rn( ex, ex ), __dmul_rn( ey, ey ) ), __dmul_rn( ez, ez ) );
+        const double dist  = (double)(long long)( __dadd_rn( norm2, dn / 2.0 ) ) / dn;  // :1136-1137
+        if ( dist >= a.threshold ) {                                                   // :1141
+          const double half = (double)( cnt / 2 );                                     // ( neighborCount / 2 ): size_t division
+          out.x = (short)(double)(long long)( __dadd_rn( (double)sx, half ) / dn );   // :1138-1140, then PCCPoint3D( centroid )
+          out.y = (short)(double)(long long)( __dadd_rn( (double)sy, half ) / dn );
+          out.z = (short)(double)(long long)( __dadd_rn( (double)sz, half ) / dn );
+        }
+      }
+    }
+    a.posOut[i] = out;
+  }
+}
+
 }  // namespace
 
 int rb_interleave_colors_impl( rb200_ctx* c ) {
@@ -500,6 +685,77 @@ int rb_interleave_colors_impl( rb200_ctx* c ) {
   if ( r ) { return r; }
   RB_LAUNCH( "ilv_transfer", k_ilv_transfer, rb_div_up( N, 128 ), 128, 0, S->kd.forest, F, c->d_frame_off.as<int64_t>(), flags,
              S->small.as<int32_t>(), S->moved.as<uint32_t>(), c->d_pos.as<short4>(), c->d_col.as<ushort4>(), N );
+  return RB200_OK;
+}
+
+// smoothPointCloud for every frame of the GOF: d_pos_pre keeps the reconstruction, d_pos receives the result
+int rb_smooth_radius_impl( rb200_ctx* c ) {
+  const rb200_params& P = c->P;
+  const int           F = c->F;
+  const int64_t       N = c->h_frame_off[F];
+  if ( N == 0 ) { return RB200_OK; }
+  if ( P.neighbor_count_smoothing < 1 || !( P.radius2_smoothing > 0.0 ) || !( P.radius2_boundary_detection >= 0.0 ) ) {
+    return rb_fail( c, RB200_ERR_INVALID, "non-grid smoothing needs neighbor_count_smoothing >= 1 and radius2_smoothing > 0" );
+  }
+  if ( P.radius2_smoothing > 4096.0 ) { return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothing: radius2_smoothing above 4096" ); }
+  if ( P.geometry_bitdepth_3d > 12 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothing: geometry bit depth above 12 is not supported by the kd-tree emulation" );
+  }
+  for ( int f = 0; f < F; f++ ) {
+    if ( c->h_frame_off[f + 1] == c->h_frame_off[f] ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "non-grid smoothing: a GOF with an empty frame is not supported" );
+    }
+  }
+  TransferScratch* S = scratch_of( c );
+  RB_CUDA( c->d_pos_pre.ensure( (size_t)N * 8 ) );
+  RB_CUDA( cudaMemcpyAsync( c->d_pos_pre.p, c->d_pos.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+  c->pos_pre_valid = true;
+  std::vector<int64_t> hOff( c->h_frame_off.begin(), c->h_frame_off.begin() + F + 1 );
+  RB_CUDA( S->off.ensure( hOff.size() * 8 ) );
+  {
+    int64_t* hp = (int64_t*)rb_pinned( c, hOff.size() * 8 );
+    if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    memcpy( hp, hOff.data(), hOff.size() * 8 );
+    RB_CUDA( cudaMemcpyAsync( S->off.p, hp, hOff.size() * 8, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  int r = rb_kd_build( c, S->kd, c->d_pos_pre.as<short4>(), S->off.as<int64_t>(), hOff, 0, 0, 0 );
+  if ( r ) { return r; }
+  // every lattice point of the ball twice over; a denser neighbourhood (heavy duplication) fails loudly
+  const double   r2      = P.radius2_smoothing;
+  const double   rad     = sqrt( r2 ) + 1.0;
+  const int      cap     = std::max( 256, 2 * (int)( 4.19 * rad * rad * rad ) );
+  const int      threads = (int)std::min<int64_t>( 148 * 4 * 128, ( ( N + 127 ) / 128 ) * 128 );
+  RB_CUDA( S->candKey.ensure( (size_t)threads * cap * 8 ) );
+  RB_CUDA( S->small.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( S->small.p, 0, 64, c->stream ) );
+  RadiusArgs a{};
+  a.forest    = S->kd.forest;
+  a.F         = F;
+  a.frame_off = c->d_frame_off.as<int64_t>();
+  a.posIn     = c->d_pos_pre.as<short4>();
+  a.posOut    = c->d_pos.as<short4>();
+  a.part      = c->d_part.as<uint32_t>();
+  a.N         = N;
+  a.dLim      = (uint32_t)ceil( r2 );   // integer d < r2  <=>  d < ceil( r2 )
+  a.visit     = (uint32_t)floor( r2 );  // integer m <= r2 <=>  m <= floor( r2 )
+  a.bLim      = (uint32_t)std::min( floor( P.radius2_boundary_detection ), 4.0e9 );
+  a.maxCount  = P.neighbor_count_smoothing;
+  a.threshold = P.threshold_smoothing;
+  a.lists     = S->candKey.as<uint64_t>();
+  a.cap       = cap;
+  a.err       = S->small.as<uint32_t>();
+  RB_LAUNCH( "geo_radius", k_smooth_radius, threads / 128, 128, 0, a );
+  uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( h, S->small.p, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  if ( h[0] ) {
+    // nothing usable was written for the failing points: put the reconstruction back
+    RB_CUDA( cudaMemcpyAsync( c->d_pos.p, c->d_pos_pre.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+    return rb_fail( c, RB200_ERR_UNSUPPORTED,
+                    "non-grid smoothing: more than %d points inside the smoothing radius of one point", cap );
+  }
   return RB200_OK;
 }
 
@@ -698,5 +954,73 @@ extern "C" int rb200_kdtree_search( rb200_ctx* c, const int16_t* cloud, int64_t 
   RB_CUDA( cudaMemcpyAsync( outIdx, dIdx, (size_t)nq * k * 8, cudaMemcpyDefault, c->stream ) );
   RB_CUDA( cudaMemcpyAsync( outDist, dDst, (size_t)nq * k * 8, cudaMemcpyDefault, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  return RB200_OK;
+}
+
+// PCCKdTree::searchRadius (PCCKdTree.cpp:69-79) for explicit queries; sorted == 0 returns nanoflann's traversal order
+// (radiusSearch with SearchParams::sorted == false) — the building block of the non-grid smoothPointCloud
+extern "C" int rb200_kdtree_search_radius( rb200_ctx* c, const int16_t* cloud, int64_t n, const int16_t* queries, int64_t nq, double radius2,
+                                           int maxResults, int sorted, int64_t* outIdx, double* outDist, int32_t* outCount ) {
+  if ( !c || !cloud || !queries || !outIdx || !outDist || !outCount || n <= 0 || nq < 0 || maxResults < 1 || !( radius2 > 0.0 ) ||
+       radius2 > 4096.0 ) {
+    return rb_fail( c, RB200_ERR_INVALID, "kdtree_search_radius: bad arguments" );
+  }
+  cudaSetDevice( c->device );
+  if ( nq == 0 ) { return RB200_OK; }
+  TransferScratch* S = scratch_of( c );
+  const size_t outB = (size_t)nq * maxResults * 16 + (size_t)nq * 4;
+  RB_CUDA( S->pos2.ensure( (size_t)n * 8 + (size_t)( n + nq ) * 6 + outB + 256 ) );
+  char*    base = S->pos2.as<char>();
+  short4*  dPos = (short4*)base;
+  int16_t* dRaw = (int16_t*)( base + (size_t)n * 8 );
+  int16_t* dQ   = dRaw + 3 * n;
+  char*    dOut = (char*)( ( (uintptr_t)( dQ + 3 * nq ) + 15 ) & ~(uintptr_t)15 );
+  int64_t* dIdx = (int64_t*)dOut;
+  double*  dDst = (double*)( dOut + (size_t)nq * maxResults * 8 );
+  int32_t* dCnt = (int32_t*)( dOut + (size_t)nq * maxResults * 16 );
+  RB_CUDA( cudaMemcpyAsync( dRaw, cloud, (size_t)n * 6, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( dQ, queries, (size_t)nq * 6, cudaMemcpyDefault, c->stream ) );
+  RB_LAUNCH( "kd_unpack", k_unpack_positions, rb_div_up( n, TPB ), TPB, 0, dRaw, n, dPos );
+  int ox = 0, oy = 0, oz = 0;
+  cudaPointerAttributes attr{};
+  if ( cudaPointerGetAttributes( &attr, cloud ) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered ||
+       attr.type == cudaMemoryTypeHost ) {
+    cudaGetLastError();
+    ox = oy = oz = 32767;
+    for ( int64_t i = 0; i < n; i++ ) {
+      ox = std::min<int>( ox, cloud[3 * i] );
+      oy = std::min<int>( oy, cloud[3 * i + 1] );
+      oz = std::min<int>( oz, cloud[3 * i + 2] );
+    }
+  }
+  std::vector<int64_t> hOff{0, n};
+  RB_CUDA( S->off.ensure( 16 ) );
+  {
+    int64_t* hp = (int64_t*)rb_pinned( c, 16 );
+    if ( !hp ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+    hp[0] = 0, hp[1] = n;
+    RB_CUDA( cudaMemcpyAsync( S->off.p, hp, 16, cudaMemcpyHostToDevice, c->stream ) );
+    RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  }
+  int r = rb_kd_build( c, S->kd, dPos, S->off.as<int64_t>(), hOff, ox, oy, oz );
+  if ( r ) { return r; }
+  const double rad     = sqrt( radius2 ) + 1.0;
+  const int    cap     = std::max( std::max( 256, maxResults ), 2 * (int)( 4.19 * rad * rad * rad ) );
+  const int    threads = (int)std::min<int64_t>( 148 * 4 * 128, ( ( nq + 127 ) / 128 ) * 128 );
+  RB_CUDA( S->candKey.ensure( (size_t)threads * cap * 8 ) );
+  RB_CUDA( S->small.ensure( 64 ) );
+  RB_CUDA( cudaMemsetAsync( S->small.p, 0, 64, c->stream ) );
+  RB_LAUNCH( "kd_radius", k_radius_query, threads / 128, 128, 0, S->kd.forest, dQ, nq, (uint32_t)ceil( radius2 ), (uint32_t)floor( radius2 ),
+             maxResults, sorted, S->candKey.as<uint64_t>(), cap, dIdx, dDst, dCnt, S->small.as<uint32_t>() );
+  uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
+  if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
+  RB_CUDA( cudaMemcpyAsync( h, S->small.p, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( outIdx, dIdx, (size_t)nq * maxResults * 8, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( outDist, dDst, (size_t)nq * maxResults * 8, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( outCount, dCnt, (size_t)nq * 4, cudaMemcpyDefault, c->stream ) );
+  RB_CUDA( cudaStreamSynchronize( c->stream ) );
+  if ( h[0] ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "kdtree_search_radius: more than %d points inside the radius of one query", cap );
+  }
   return RB200_OK;
 }

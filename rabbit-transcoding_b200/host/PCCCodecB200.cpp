@@ -216,6 +216,9 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   p.flag_color_smoothing       = gp.flagColorSmoothing_;
   p.apply_attr_smoothing       = 1;
   p.threshold_smoothing        = gp.thresholdSmoothing_;
+  p.neighbor_count_smoothing   = gp.gridSmoothing_ ? 0 : (int)gp.neighborCountSmoothing_;
+  p.radius2_smoothing          = gp.radius2Smoothing_;
+  p.radius2_boundary_detection = gp.radius2BoundaryDetection_;
   p.threshold_color_smoothing  = gp.thresholdColorSmoothing_;
   p.threshold_color_difference = gp.thresholdColorDifference_;
   p.threshold_color_variation  = gp.thresholdColorVariation_;
@@ -444,9 +447,8 @@ void PCCCodec::smoothPointCloudPostprocess( PCCPointSet3& reconstruct, const PCC
   const size_t f = g.currentFrame;
   if ( reconstruct.getPointCount() == 0 ) { return; }  // :64
   checkFrame( "smoothPointCloudPostprocess", f, reconstruct.getPointCount() );
-  if ( params.flagGeometrySmoothing_ && !params.gridSmoothing_ && !params.pbfEnableFlag_ ) {
-    unsupported( "the non-grid smoothPointCloud (PCCCodec.cpp:1106-1157)" );
-  }
+  // (gridSmoothing_ == 0: the non-grid smoothPointCloud, :1106-1157 — its debug colouring of the moved points, :1143, is not
+  // reproduced: every caller overwrites the 8-bit colours afterwards)
   if ( !g.geo ) {
     RB( rb200_smooth_geometry( g.ctx ) );
     const size_t N = g.off[g.frames];

@@ -73,6 +73,32 @@ def test_dropin_occupancy_synthesis(rb, backends):
     assert (want.cloud(0, "reconstruct")["boundary_types"] == 1).any() and want.counts(0).smoothed > 0
 
 
+def test_dropin_non_grid_smoothing(rb, backends):
+    """smoothPointCloudPostprocess with gridSmoothing_ == 0 through the shim (the encoder's reconstruction, PCCCodec.cpp:141):
+    the reference's 8-bit debug colouring of the moved points (:1143) is not reproduced — the callers overwrite the 8-bit
+    colours (convertYUV16ToRGB8), as the rgb8 stage compared here shows"""
+    def non_grid(g):
+        g.params.grid_smoothing = 0
+        g.params.neighbor_count_smoothing = 64
+        g.params.radius2_smoothing = 64.0
+        g.params.radius2_boundary_detection = 64.0
+        return g
+    ref_b, drop_b = backends
+    args = dict(n_frames=2, bitdepth=8, width=256, scale=0.9, seed=78, transfer_filter=1)
+    want = ref_b.run_gof(non_grid(rb.synthetic.generate_gof(**args)), keep=STAGES)
+    drop_b.stats(reset=True)
+    got = drop_b.run_gof(non_grid(rb.synthetic.generate_gof(**args)), keep=STAGES)
+    assert drop_b.stats().kernel_launches > 10
+    moved = 0
+    for f in range(2):
+        for st in STAGES:
+            fields = tuple(k for k in FIELDS if k != "colors" or st == "rgb8")
+            assert_cloud_equal(got.cloud(f, st), want.cloud(f, st), f"non-grid frame {f} stage {st}", fields)
+        assert got.md5(f) == want.md5(f)
+        moved += int((want.cloud(f, "reconstruct")["positions"] != want.cloud(f, "smooth_geometry")["positions"]).any(axis=1).sum())
+    assert moved > 100
+
+
 def test_dropin_links_no_reference_body():
     """the shim has no way back into the reference's own bodies: no rb200_orig_* symbol, and every replaced member is
     defined exactly once (the shim's strong definition)"""

@@ -72,3 +72,41 @@ def test_decoded_cloud_surface(rb, codec, checker_backend):
     sel = rng.integers(0, len(cloud), 20000)
     q = (cloud[sel].astype(np.int32) + rng.integers(-2, 3, size=(len(sel), 3))).astype(np.int16)
     check(rb, codec, checker_backend, cloud, q, ks=(1, 8))
+
+
+def gpu_radius(rb, codec, cloud, queries, radius2, max_results, sorted_):
+    cloud = np.ascontiguousarray(cloud, np.int16)
+    queries = np.ascontiguousarray(queries, np.int16)
+    idx = np.zeros((len(queries), max_results), np.int64)
+    dist = np.zeros((len(queries), max_results), np.float64)
+    cnt = np.zeros(len(queries), np.int32)
+    st = codec._lib.rb200_kdtree_search_radius(codec._h, rb.abi.ptr(cloud), len(cloud), rb.abi.ptr(queries), len(queries), radius2,
+                                               max_results, 1 if sorted_ else 0, rb.abi.ptr(idx), rb.abi.ptr(dist), rb.abi.ptr(cnt))
+    assert st == 0, codec._lib.rb200_error_string(codec._h).decode()
+    return idx, dist, cnt
+
+
+def test_radius_search_traversal_order_and_sorted_cut(rb, codec, checker_backend):
+    """PCCKdTree::searchRadius (the non-grid smoothPointCloud's query): first nanoflann's traversal order on its own
+    (SearchParams::sorted = false), then with std::sort (the vendored IndexDist_Sorter: distance, then index) and the cut to
+    64 results, which falls inside a shell of equal distances for nearly every query"""
+    rng = np.random.default_rng(7)
+    surf = rng.integers(0, 120, size=(40000, 3)).astype(np.int16)
+    surf[:, 2] = (20 + 10 * np.sin(surf[:, 0] / 9.0) + 8 * np.cos(surf[:, 1] / 7.0)).astype(np.int16) + rng.integers(0, 3, 40000)
+    dense = rng.integers(0, 24, size=(20000, 3)).astype(np.int16)  # ~1.4 points per lattice site: hundreds inside the ball
+    for cloud, r2 in ((surf, 64.0), (surf, 30.5), (dense, 17.0), (dense, 64.0)):
+        q = cloud[rng.integers(0, len(cloud), 600)]
+        wi, wd, wc = checker_backend.knn_radius(cloud, q, r2, 700, sorted_=False)
+        gi, gd, gc = gpu_radius(rb, codec, cloud, q, r2, 700, False)
+        assert np.array_equal(gc, wc), "number of points inside the radius"
+        bad = np.nonzero((gi != wi).any(axis=1))[0]
+        assert len(bad) == 0, f"traversal order differs for {len(bad)}/{len(q)} queries, first {bad[0]}: " \
+                              f"got {gi[bad[0]][:12].tolist()} want {wi[bad[0]][:12].tolist()}"
+        assert np.array_equal(gd, wd)
+        wi, wd, wc = checker_backend.knn_radius(cloud, q, r2, 64, sorted_=True)
+        gi, gd, gc = gpu_radius(rb, codec, cloud, q, r2, 64, True)
+        assert np.array_equal(gd, wd)
+        bad = np.nonzero((gi != wi).any(axis=1))[0]
+        assert len(bad) == 0, f"sorted order differs for {len(bad)}/{len(q)} queries, first {bad[0]}: " \
+                              f"got {gi[bad[0]].tolist()} want {wi[bad[0]].tolist()} dist {wd[bad[0]].tolist()}"
+        assert (wc > 64).mean() > 0.5

@@ -53,6 +53,38 @@ def test_level_of_detail_and_45_degree_planes(rb, codec, checker_backend):
     run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="lod/oblique rec-1")
 
 
+def test_non_grid_smoothing(rb, codec, checker_backend):
+    """smoothPointCloudPostprocess with gridSmoothing_ == 0 (PCCCodec.cpp:141 -> smoothPointCloud, :1106-1157; the encoder's
+    reconstruction): radius search, sorted by distance and index, the first 64; most neighbourhoods hold more than 64 points,
+    so the cut falls inside a shell of equal distances"""
+    for seed, kw in ((71, dict()), (72, dict(occupancy_precision=2, orientations=tuple(range(9)))), (73, dict(map_count=1))):
+        g = small(rb, seed=seed, **kw)
+        g.params.grid_smoothing = 0
+        g.params.neighbor_count_smoothing = 64  # PCCEncoderParameters.cpp:92-94
+        g.params.radius2_smoothing = 64.0
+        g.params.radius2_boundary_detection = 64.0
+        ref = run_stages(codec, g, checker_backend, what=f"non-grid {kw}")
+        a, b = ref.cloud(0, "reconstruct"), ref.cloud(0, "smooth_geometry")
+        assert (a["positions"] != b["positions"]).any(axis=1).sum() > 20     # points really move
+        assert (b["boundary_types"] == 2).sum() > 20                        # and boundary points are re-typed (:1131-1133)
+    # other radii / counts, and the whole decoder-style sequence behind it (no point is of type 3: the re-transfer is a no-op)
+    g = small(rb, seed=74, transfer_filter=1)
+    g.params.grid_smoothing = 0
+    g.params.neighbor_count_smoothing = 20
+    g.params.radius2_smoothing = 30.5
+    g.params.radius2_boundary_detection = 9.0
+    g.params.threshold_smoothing = 3.0
+    run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="non-grid r2 30.5")
+    # decodeGof takes the same branch
+    codec.uploadGof(g)
+    codec.decodeGof()
+    ref = checker_backend.run_gof(g, keep=("rgb8",))
+    for f in range(g.n_frames):
+        got = codec.getPointCloud(f, fields=("positions", "colors"))
+        want = ref.cloud(f, "rgb8")
+        assert np.array_equal(got["positions"], want["positions"]) and np.array_equal(got["colors"], want["colors"])
+
+
 def test_cell_sums_beyond_the_exact_float_range(rb, codec, checker_backend):
     """twelve patches decode to the same slab with a saturated luma: the colour cells hold a few hundred points and their
     float sums pass 2^24, where the reference's result depends on the ORDER of its float additions.

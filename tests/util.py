@@ -24,7 +24,7 @@ def run_stages(codec, gof, chk, stages=("reconstruct", "smooth_geometry", "smoot
         if st == "reconstruct":
             codec.generatePointCloud()
         elif st == "smooth_geometry":
-            if p.apply_geo_smoothing and p.flag_geometry_smoothing and p.grid_smoothing:
+            if p.apply_geo_smoothing and p.flag_geometry_smoothing and (p.grid_smoothing or p.neighbor_count_smoothing > 0):
                 codec.smoothPointCloudPostprocess()
         elif st == "transfer_colors":
             if p.apply_geo_smoothing and p.flag_geometry_smoothing and p.attr_transfer_filter_type == 1:
