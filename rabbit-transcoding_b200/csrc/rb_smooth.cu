@@ -1186,15 +1186,10 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
     int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );
     if ( r ) { return r; }
     if ( a.marks ) { RB_LAUNCH( "geo_mark", k_mark_cells, rb_div_up( c->blist_cap, 256 ), 256, 0, a ); }
-    // (RB200_GEO_ACC=thread selects the per-thread path for the whole GOF: the measured alternative, tools/full_prof.py)
-    static const bool perThread = getenv( "RB200_GEO_ACC" ) && !strcmp( getenv( "RB200_GEO_ACC" ), "thread" );
-    if ( perThread ) {
-      RB_LAUNCH( "geo_accumulate", k_accumulate<false>, rb_div_up( n, 256 * ACC_RUN ), 256, 0, a, n );
-    } else {
-      // (5 CTAs per SM, 48 registers: 0.195 ms on the 32-frame vox10 GOF; 4 CTAs, 60 registers: 0.199; per-thread path: 0.235)
-      RB_LAUNCH( "geo_accumulate", k_accumulate_geo_staged<5>, rb_div_up( n, 2048 ), 256, 0, a, n );
-      if ( c->F > 1 ) { RB_LAUNCH( "geo_accumulate_x", k_accumulate_crossing<false>, rb_div_up( c->F, 8 ), 256, 0, a, n ); }
-    }
+    // per-warp staging in shared memory; 5 CTAs per SM, 48 registers: 0.195 ms on the 32-frame vox10 GOF (4 CTAs, 60
+    // registers: 0.199; the per-thread path k_accumulate<false> for every point: 0.235)
+    RB_LAUNCH( "geo_accumulate", k_accumulate_geo_staged<5>, rb_div_up( n, 2048 ), 256, 0, a, n );
+    if ( c->F > 1 ) { RB_LAUNCH( "geo_accumulate_x", k_accumulate_crossing<false>, rb_div_up( c->F, 8 ), 256, 0, a, n ); }
     RB_LAUNCH( "geo_finalize", k_finalize_geo, WALK_CTAS, 256, 0, a );
     RB_LAUNCH( "geo_ordered", k_ordered_cells<false>, ORDERED_CAP / 8, 256, 0, a );
     if ( c->blist_cap > 0 ) {
