@@ -385,6 +385,10 @@ int rb200_kdtree_search_radius(rb200_ctx* ctx, const int16_t* cloud, int64_t n, 
 
 /* ---- PCCPointSet3::computeChecksum( false ) (PCCPointSet.cpp:222-245): MD5 of positions || RGB8 of a decoded frame ---- */
 int rb200_frame_md5(rb200_ctx* ctx, int frame, uint8_t* out16);
+/* PCCPointSet3::computeChecksum( true ) (:221-229, reorder :258-296): MD5 after the canonical reordering — points in
+ * lexicographic (x, y, z) order, one per position, colour = integer mean of its duplicates (the conformance checksum
+ * of PCCDecoder.cpp:420; north_star's "bit-exact after canonical sorting") */
+int rb200_frame_md5_canonical(rb200_ctx* ctx, int frame, uint8_t* out16);
 /* ---- PCCPointSet3::write( file, asAscii = false ) (:359-457): binary little-endian PLY, float xyz + uchar rgb,
  *      byte-identical to the reference's file for a decoded frame.  Records are packed on the device. ------------------- */
 int rb200_write_ply(rb200_ctx* ctx, int frame, const char* path);

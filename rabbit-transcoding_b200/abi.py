@@ -153,7 +153,7 @@ EXPORTED_SYMBOLS = [
     "rb200_transfer_colors", "rb200_smooth_color", "rb200_convert_rgb8", "rb200_debug_yuv16_to_rgb8", "rb200_debug_set_grid_shrink", "rb200_decode_gof",
     "rb200_frame_counts_get", "rb200_download_frame", "rb200_download_gof",
     "rb200_enable_stage_snapshots", "rb200_download_frame_stage", "rb200_download_block_to_patch",
-    "rb200_download_occupancy", "rb200_metrics", "rb200_metrics_cache_sources", "rb200_metrics_pack", "rb200_metrics_unpack", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_kdtree_search_radius", "rb200_frame_md5", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
+    "rb200_download_occupancy", "rb200_metrics", "rb200_metrics_cache_sources", "rb200_metrics_pack", "rb200_metrics_unpack", "rb200_remove_duplicates", "rb200_kdtree_search", "rb200_kdtree_search_radius", "rb200_frame_md5", "rb200_frame_md5_canonical", "rb200_write_ply", "rb200_read_ply", "rb200_stats_get",
     "rb200_timing_enable", "rb200_timing_get",
 ]
 
@@ -216,6 +216,7 @@ def load_library(path=None):
     lib.rb200_kdtree_search_radius.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_double, C.c_int, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p]
     lib.rb200_frame_md5.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.rb200_frame_md5_canonical.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.rb200_write_ply.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     lib.rb200_read_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, i64, C.POINTER(i64), C.POINTER(C.c_int)]
     lib.rb200_stats_get.argtypes = [C.c_void_p, C.POINTER(LaunchStats), C.c_int]

@@ -218,10 +218,11 @@ class PCCCodecB200:
         self._check(self._lib.rb200_download_occupancy(self._h, f, abi.ptr(a)))
         return a
 
-    def computeChecksum(self, f):
-        """PCCPointSet3::computeChecksum( false ): MD5 of positions || RGB8 of frame f, as a hex string"""
+    def computeChecksum(self, f, reorderPoints=False):
+        """PCCPointSet3::computeChecksum( reorderPoints ): MD5 of positions || RGB8 of frame f as a hex string; with
+        reorderPoints the canonical order (sorted, duplicates merged) is hashed"""
         d = (C.c_uint8 * 16)()
-        self._check(self._lib.rb200_frame_md5(self._h, f, d))
+        self._check((self._lib.rb200_frame_md5_canonical if reorderPoints else self._lib.rb200_frame_md5)(self._h, f, d))
         return bytes(d).hex()
 
     def write(self, f, file_name):

@@ -119,6 +119,41 @@ int rb200_frame_md5( rb200_ctx* c, int f, uint8_t* out16 ) {
   return RB200_OK;
 }
 
+// PCCPointSet3::computeChecksum( true ) (PCCPointSet.cpp:221-229): reorder( out, dropDuplicates = true ) (:258-296) — the
+// points in lexicographic (x, y, z) order, one per position, colour = integer mean of the duplicates — then computeMd5.
+// That is removeDuplicate( out, 2 )'s result (:169-218), so the device de-duplication of the metrics path produces it.
+int rb200_frame_md5_canonical( rb200_ctx* c, int f, uint8_t* out16 ) {
+  if ( !c || !out16 ) { return RB200_ERR_INVALID; }
+  if ( !c->reconstructed || !c->rgb_done ) { return rb_fail( c, RB200_ERR_STATE, "frame_md5_canonical needs a decoded GOF (RGB8 done)" ); }
+  if ( f < 0 || f >= c->F ) { return rb_fail( c, RB200_ERR_INVALID, "frame index out of range" ); }
+  if ( c->P.attribute_count == 0 ) {
+    return rb_fail( c, RB200_ERR_UNSUPPORTED, "frame_md5_canonical: clouds without colours keep their duplicates (PCCPointSet.cpp:287-295); not implemented" );
+  }
+  const int64_t        n = c->h_frame_off[f + 1] - c->h_frame_off[f];
+  std::vector<int16_t> pos( (size_t)n * 3 );
+  std::vector<uint8_t> col( (size_t)n * 3 );
+  int64_t              m = 0;
+  if ( n ) {
+    rb200_cloud_host h{};
+    h.positions = pos.data();
+    h.colors    = col.data();
+    int r       = rb200_download_frame( c, f, &h );
+    if ( r ) { return r; }
+    rb200_cloud_view v{pos.data(), col.data(), nullptr, n};
+    std::vector<int16_t> upos( (size_t)n * 3 );
+    std::vector<uint8_t> ucol( (size_t)n * 3 );
+    r = rb200_remove_duplicates( c, &v, 2, upos.data(), ucol.data(), &m );
+    if ( r ) { return r; }
+    pos.swap( upos );
+    col.swap( ucol );
+  }
+  Md5 md5;
+  md5.update( reinterpret_cast<const uint8_t*>( pos.data() ), (size_t)m * 6 );
+  md5.update( col.data(), (size_t)m * 3 );
+  md5.finalize( out16 );
+  return RB200_OK;
+}
+
 int rb200_write_ply( rb200_ctx* c, int f, const char* path ) {
   if ( !c || !path ) { return RB200_ERR_INVALID; }
   if ( !c->reconstructed || !c->rgb_done ) { return rb_fail( c, RB200_ERR_STATE, "write_ply needs a decoded GOF (RGB8 done)" ); }

@@ -911,6 +911,7 @@ struct MetricsScratch {  // lives in the context's scratch buffers (grow-only)
     bool        operator==( const SrcKey& o ) const { return pos == o.pos && col == o.col && nrm == o.nrm && n == o.n; }
   };
   bool                 cache_on = false, cache_valid = false;
+  bool                 skip_sources = false;  // this call's prefetch left the (cached) sources where they are
   std::vector<SrcKey>  cache_keys;
   int                  cache_drop = 0, cache_c2p = 0, cache_ox = 0, cache_oy = 0, cache_oz = 0, cache_dim = 0;
   RbKdBuild            kd;  // neighborsProc 0: the forest over the unique clouds
@@ -1282,10 +1283,12 @@ static int metrics_range( rb200_ctx* c, const rb200_metrics_params* mp, int firs
     if ( S->nrm.cap < (size_t)( n + 1 ) * 24 || S->nrm_cnt.cap < (size_t)( n + 1 ) * 4 ) { reuse = false; }
   }
   S->cache_valid = false;
+  if ( !reuse && S->skip_sources ) { return RB_REBUILD; }  // the sources were not copied in: the caller starts over
   Batch                B{};
   std::vector<int64_t> hOff;
   int                  r = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff, reuse ? nPairs : 0 );
   if ( r == RB_REBUILD ) {
+    if ( S->skip_sources ) { return RB_REBUILD; }
     reuse = false;
     r     = build_batch( c, S, clouds, mp->drop_duplicates, B, hOff, 0 );
   }
@@ -1529,16 +1532,20 @@ static int prefetch_pairs( rb200_ctx* c, MetricsScratch* S, const rb200_metrics_
       const int64_t n  = v->count;
       char*         rp = S->rawSet[set].as<char>() + rawOff;
       char*         rc = rp + ( ( n * 6 + 15 ) & ~15ll );
-      RB_CUDA( cudaMemcpyAsync( rp, v->positions, n * 6, cudaMemcpyDefault, S->copy_stream ) );
-      if ( v->colors ) { RB_CUDA( cudaMemcpyAsync( rc, v->colors, n * 3, cudaMemcpyDefault, S->copy_stream ) ); }
-      c->stats.h2d_bytes += n * ( v->colors ? 9 : 6 );
+      if ( !( k == 0 && S->skip_sources ) ) {  // (cached sources stay where the earlier call imported them)
+        RB_CUDA( cudaMemcpyAsync( rp, v->positions, n * 6, cudaMemcpyDefault, S->copy_stream ) );
+        if ( v->colors ) { RB_CUDA( cudaMemcpyAsync( rc, v->colors, n * 3, cudaMemcpyDefault, S->copy_stream ) ); }
+        c->stats.h2d_bytes += n * ( v->colors ? 9 : 6 );
+      }
       rawOff += ( ( n * 6 + 15 ) & ~15ll ) + ( ( n * 3 + 15 ) & ~15ll );
     }
   }
   for ( int i = 0; i < nPairs; i++ ) {
     if ( mp->compute_c2p && sources[i].normals ) {
-      RB_CUDA( cudaMemcpyAsync( S->nrmSet[set].as<char>() + nOff, sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
-      c->stats.h2d_bytes += sources[i].count * 12;
+      if ( !S->skip_sources ) {
+        RB_CUDA( cudaMemcpyAsync( S->nrmSet[set].as<char>() + nOff, sources[i].normals, sources[i].count * 12, cudaMemcpyDefault, S->copy_stream ) );
+        c->stats.h2d_bytes += sources[i].count * 12;
+      }
       nOff += ( sources[i].count * 12 + 255 ) & ~255ll;
     }
   }
@@ -1583,8 +1590,32 @@ int rb200_metrics( rb200_ctx* c, const rb200_metrics_params* mp, int nPairs, con
   const int nDev    = (int)std::min<int64_t>( nPairs, ( total + ( 64ll << 20 ) - 1 ) / ( 64ll << 20 ) );  // scratch is ~100 B per point
   const int nChunks = onDevice ? std::max( nDev, 1 ) : ( nPairs >= 8 ? 4 : 1 ), per = ( nPairs + nChunks - 1 ) / nChunks;
   int       status = RB200_OK;
+  // cached sources (rb200_metrics_cache_sources) are not even copied when the key of the previous call matches
+  S->skip_sources = false;
+  if ( onDevice && nChunks == 1 && S->cache_on && S->cache_valid && (int)S->cache_keys.size() == nPairs &&
+       S->cache_drop == mp->drop_duplicates ) {
+    S->skip_sources = true;
+    for ( int i = 0; i < nPairs && S->skip_sources; i++ ) {
+      S->skip_sources = S->cache_keys[i] == MetricsScratch::SrcKey{sources[i].positions, sources[i].colors, sources[i].normals, sources[i].count};
+    }
+  }
   int       r = prefetch_pairs( c, S, mp, std::min( per, nPairs ), sources, recs, 0 );
   if ( r ) { return r; }
+  if ( S->skip_sources ) {
+    S->cur = 0, S->prefetched = true;
+    r             = metrics_range( c, mp, 0, nPairs, sources, recs, results, true );
+    S->prefetched = false;
+    cudaEventRecord( S->ev_free[0], c->stream );
+    if ( r != RB_REBUILD ) {
+      if ( r && r != RB200_ERR_TIE_OVERFLOW ) { cudaStreamSynchronize( S->copy_stream ); }
+      S->skip_sources = false;
+      return r;
+    }
+    S->skip_sources = false;  // the kept part did not fit after all: everything again, sources included
+    S->cache_valid  = false;
+    r               = prefetch_pairs( c, S, mp, std::min( per, nPairs ), sources, recs, 0 );
+    if ( r ) { return r; }
+  }
   for ( int k = 0, b = 0; b < nPairs; k++, b += per ) {
     const int e = std::min( nPairs, b + per ), set = k & 1;
     if ( e < nPairs ) {

@@ -325,12 +325,14 @@ def test_vox11_frame_eom_lossless_style(rb, codec, checker_backend):
 # ---- wire format and checksum (PCCPointSet3::write / read / computeChecksum) ----
 def test_ply_and_md5_match_reference(rb, codec, checker_backend, tmp_path):
     g = small(rb, seed=65, transfer_filter=1)
-    ref = checker_backend.run_gof(small(rb, seed=65, transfer_filter=1), keep=("rgb8",))
+    ref = checker_backend.run_gof(small(rb, seed=65, transfer_filter=1), keep=("rgb8",), canonical_md5=True)
     codec.uploadGof(g)
     codec.decodeGof()
     for f in range(g.n_frames):
         want = ref.cloud(f, "rgb8")
         assert codec.computeChecksum(f) == ref.md5(f)
+        # computeChecksum( true ): the canonical order (PCCPointSet.cpp:258-296) — differs from the ordered one
+        assert codec.computeChecksum(f, True) == ref.md5(f, canonical=True) != ref.md5(f)
         mine, theirs = str(tmp_path / f"b200_{f}.ply"), str(tmp_path / f"ref_{f}.ply")
         codec.write(f, mine)
         assert checker_backend.write_ply(want["positions"], want["colors"], theirs) == 0
