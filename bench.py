@@ -374,13 +374,19 @@ def run_b200(args):
             if world > 1:
                 # the one exchange step of the path: all-gather of the per-frame accumulators (NCCL).  Lanes take turns
                 # in step order, so every rank issues the collectives in the same sequence.
+                # (the per-frame floats are derived from the gathered accumulators once, after the loop: the records are
+                # the step's result)
+                # the collective is issued here and finished one step later (or after the loop, still inside the timed
+                # region), so a rank never waits for the slowest one inside its frame loop
                 with turn:
                     turn.wait_for(lambda: order[0] >= step)
-                    table, seq_mean = rb.dist.gather_metrics({rank + world * i: r for i, r in enumerate(res)},
-                                                             world * gof.n_frames, mp.resolution, device="cuda")
-                    gathered["frames"], gathered["mean"] = len(table), seq_mean
+                    h = rb.dist.all_gather_records_begin({rank + world * i: r for i, r in enumerate(res)},
+                                                         world * gof.n_frames, device="cuda")
                     order[0] += 1
                     turn.notify_all()
+                prev, L["pending"] = L.get("pending"), h
+                if prev is not None:
+                    gathered["table"] = rb.dist.all_gather_records_end(prev)
             L["res"] = res
 
         turn = threading.Condition()
@@ -391,6 +397,8 @@ def run_b200(args):
                 torch.cuda.set_device(local)
                 for i in range(nsteps):
                     loop_step(lanes[k], sources, download, k + i * nl)
+                if lanes[k].get("pending") is not None:  # the last step's records
+                    gathered["table"] = rb.dist.all_gather_records_end(lanes[k].pop("pending"))
             except Exception as ex:  # surfaced after the join
                 errs.append(ex)
                 with turn:
@@ -453,8 +461,9 @@ def run_b200(args):
                "d1_psnr_mean_db": round(float(np.mean([r.qf.c2c_psnr for r in res])), 4),
                "d2_psnr_mean_db": round(float(np.mean([r.qf.c2p_psnr for r in res])), 4)}
         if world > 1:
-            e2e["frames_gathered"] = gathered.get("frames")
-            e2e["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in gathered.get("mean", {}).items()}
+            table, seq_mean = rb.dist.derive_table(gathered["table"], mp.resolution)
+            e2e["frames_gathered"] = len(table)
+            e2e["sequence_mean_over_all_ranks"] = {k: round(v, 4) for k, v in seq_mean.items()}
         # (b) the same with the source clouds (positions, RGB, normals) crossing PCIe every step
         if args.quick:
             for L in lanes[1:]:

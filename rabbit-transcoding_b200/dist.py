@@ -77,24 +77,44 @@ def symmetric(q1, q2):
                 color_psnr=[min(a, b) for a, b in zip(q1["color_psnr"], q2["color_psnr"])])
 
 
-def gather_metrics(local, n_frames, resolution, group=None, device=None):
-    """local: {frame: abi.MetricsResult} of the frames this rank owns.  Returns the per-frame table of the whole
-    sequence (same on every rank, frame order) and the sequence means — the only collective of the path."""
+def all_gather_records_begin(local, n_frames, group=None, device=None):
+    """Issues the collective and returns a handle for all_gather_records_end: {frame: abi.MetricsResult} of this rank ->
+    one host-to-device copy of its records and one (asynchronous) all-gather.  A caller that pipelines GOFs finishes the
+    handle one step later, so no rank ever waits for the slowest one inside its frame loop."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     per_rank = math.ceil(n_frames / world)
-    buf = torch.full((per_rank, RECORD), -1.0, dtype=torch.float64, device=device)
+    host = np.full((per_rank, RECORD), -1.0, np.float64)
     for i, (f, r) in enumerate(sorted(local.items())):
-        buf[i] = torch.tensor(pack_result(f, r), dtype=torch.float64)
-    if world > 1:
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf, group=group)
-        table = torch.cat(out).cpu().numpy()
+        host[i] = pack_result(f, r)
+    if world == 1:
+        return dict(table=host)
+    buf = torch.from_numpy(host).to(device) if device is not None else torch.from_numpy(host)
+    out = torch.empty((world * per_rank, RECORD), dtype=torch.float64, device=buf.device)
+    work = dist.all_gather_into_tensor(out, buf, group=group, async_op=True)
+    return dict(work=work, out=out, buf=buf)
+
+
+def all_gather_records_end(handle):
+    """-> the [n_frames, RECORD] table of the whole sequence in frame order, the same on every rank"""
+    if "table" in handle:
+        table = handle["table"]
     else:
-        table = buf.cpu().numpy()
+        handle["work"].wait()
+        table = handle["out"].cpu().numpy()
     table = table[table[:, 0] >= 0]
-    table = table[np.argsort(table[:, 0], kind="stable")]
+    return table[np.argsort(table[:, 0], kind="stable")]
+
+
+def all_gather_records(local, n_frames, group=None, device=None):
+    """The collective itself, blocking: one copy of this rank's records up, one all-gather, one copy back."""
+    return all_gather_records_end(all_gather_records_begin(local, n_frames, group=group, device=device))
+
+
+def derive_table(table, resolution):
+    """per-frame float results from the gathered accumulators, exactly as QualityMetrics::compute (:204-226) and
+    operator+ (:299-332) derive them, and the sequence means"""
     frames = []
     for row in table:
         q = []
@@ -107,3 +127,9 @@ def gather_metrics(local, n_frames, resolution, group=None, device=None):
                 d2_psnr=float(np.mean([f["qf"]["c2p_psnr"] for f in frames])) if frames else float("nan"),
                 y_psnr=float(np.mean([f["qf"]["color_psnr"][0] for f in frames])) if frames else float("nan"))
     return frames, mean
+
+
+def gather_metrics(local, n_frames, resolution, group=None, device=None):
+    """local: {frame: abi.MetricsResult} of the frames this rank owns.  Returns the per-frame table of the whole
+    sequence (same on every rank, frame order) and the sequence means — the only collective of the path."""
+    return derive_table(all_gather_records(local, n_frames, group=group, device=device), resolution)
