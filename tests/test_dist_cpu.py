@@ -48,6 +48,36 @@ def _worker(rank, world, port, n_frames, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_pipelined(rank, world, port, n_frames, out_dir):
+    """two steps in flight: the collective of step k is finished after the one of step k + 1 was issued (bench.py's loop)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import rabbit_transcoding_b200 as rb
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = rb.dist.shard_frames(n_frames, world, rank)
+    tables, pending = [], None
+    for step in range(3):
+        h = rb.dist.all_gather_records_begin({f: _fake_result(rb, f + 100 * step) for f in mine}, n_frames)
+        if pending is not None:
+            tables.append(rb.dist.all_gather_records_end(pending))
+        pending = h
+    tables.append(rb.dist.all_gather_records_end(pending))
+    np.save(os.path.join(out_dir, f"p{rank}.npy"), np.stack(tables))
+    dist.destroy_process_group()
+
+
+def test_pipelined_all_gather_world2_gloo(rb, tmp_path):
+    n_frames, world = 6, 2
+    mp.spawn(_worker_pipelined, args=(world, _free_port(), n_frames, str(tmp_path)), nprocs=world, join=True)
+    a, b = np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")
+    assert a.shape == (3, n_frames, rb.dist.RECORD) and np.array_equal(a, b)
+    for step in range(3):
+        assert a[step][:, 0].tolist() == list(range(n_frames))
+        for f in range(n_frames):
+            assert a[step][f].tolist() == rb.dist.pack_result(f, _fake_result(rb, f + 100 * step))
+
+
 def test_shard_frames_covers_every_frame_once(rb):
     for n in (1, 5, 32, 300):
         for world in (1, 2, 4, 8):
