@@ -130,6 +130,14 @@ typedef struct rb200_params {
   int32_t neighbor_count_smoothing;   /* neighborCountSmoothing_ (4 * 16)                                 */
   double  radius2_smoothing;          /* radius2Smoothing_ (64)                                           */
   double  radius2_boundary_detection; /* radius2BoundaryDetection_ (64)                                   */
+  /* raw (missed) points carried in the auxiliary video (asps.getAuxiliaryVideoEnabledFlag, PCCDecoder.cpp:783;
+   * tile.getUseRawPointsSeparateVideo, PCCCodec.cpp:606, :895-897, :1334, :1436-1439): the raw patches address the
+   * auxiliary frames (rb200_frames.aux_geometry / aux_attribute) instead of the atlas; their colours are the low 8
+   * bits of the auxiliary attribute samples (they pass through PCCColor3B, PCCCodec.cpp:1541-1543).  Not together
+   * with EOM (EOM attributes in the auxiliary video, :1551-1580, are not implemented). */
+  int32_t use_aux_separate_video;
+  int32_t aux_width, aux_height;      /* size of the auxiliary video frames                               */
+  int32_t reserved0;
 } rb200_params;
 
 /* Decoded video planes of one GOF (what PCCVideoDecoder leaves in PCCContext, PCCContext.h:48-50).
@@ -138,6 +146,9 @@ typedef struct rb200_frames {
   const uint8_t*  occupancy; /* [F][H/p][W/p]      channel 0 of PCCVideoOccupancyMap frame f             */
   const uint16_t* geometry;  /* [F][M][H][W]       channel 0 of geometry frame f*M+m (PCCCodec.cpp:613)   */
   const uint16_t* attribute; /* [F][M][3][H][W]    4:4:4 16-bit attribute frame f*M+m; NULL if none       */
+  /* params.use_aux_separate_video: context.getVideoRawPointsGeometry() / getVideoRawPointsAttribute()          */
+  const uint16_t* aux_geometry;  /* [F][aux_height][aux_width]     channel 0 of auxiliary geometry frame f       */
+  const uint16_t* aux_attribute; /* [F][3][aux_height][aux_width]  auxiliary attribute frame f; NULL if none     */
 } rb200_frames;
 
 /* Decoder-native planes of one GOF: the planar 4:2:0 frames a video decoder (HM, libav, NVDEC) leaves behind, BEFORE

@@ -158,7 +158,7 @@ void fillGpc( GeneratePointCloudParameters& g, const rb200_params& p ) {
   g.pointLocalReconstruction_      = p.point_local_reconstruction != 0;
   g.singleMapPixelInterleaving_    = p.single_map_pixel_interleaving != 0;
   g.useAdditionalPointsPatch_      = p.use_additional_points_patch != 0;
-  g.useAuxSeperateVideo_           = false;
+  g.useAuxSeperateVideo_           = p.use_aux_separate_video != 0;
   g.plrlNumberOfModes_             = 0;
   g.geometryBitDepth3D_            = p.geometry_bitdepth_3d;
   g.geometry3dCoordinatesBitdepth_ = p.geometry_bitdepth_3d;
@@ -196,7 +196,12 @@ static void fillPatchTables( PCCContext& context, const rb200_params& p, int nFr
     tile.setTileIndex( 0 );
     tile.setLeftTopXInFrame( 0 );
     tile.setLeftTopYInFrame( 0 );
-    tile.setUseRawPointsSeparateVideo( false );
+    tile.setUseRawPointsSeparateVideo( p.use_aux_separate_video != 0 );  // PCCDecoder.cpp: asps.getAuxiliaryVideoEnabledFlag
+    if ( p.use_aux_separate_video ) {  // setTilePartitionSizeAfti, PCCDecoder.cpp:1820-1824 (one tile)
+      context[f].setAuxVideoWidth( p.aux_width );
+      context[f].resizeAuxTileLeftTopY( 1, 0 );
+      context[f].resizeAuxTileHeight( 1, p.aux_height );
+    }
     tile.setLog2PatchQuantizerSizeX( p.log2_quantizer_x );
     tile.setLog2PatchQuantizerSizeY( p.log2_quantizer_y );
     auto& patches = tile.getPatches();
@@ -347,6 +352,28 @@ ref_gof* ref_gof_run( const rb200_params* pp,
     }
   }
 
+  if ( p.use_aux_separate_video ) {  // the auxiliary video's frames (PCCDecoder.cpp:187-230 decodes them into these)
+    const size_t Wa = p.aux_width, Ha = p.aux_height;
+    auto&        rawGeo = context.getVideoRawPointsGeometry();
+    rawGeo.resize( nFrames );
+    for ( int f = 0; f < nFrames; f++ ) {
+      auto& g = rawGeo.getFrame( f );
+      g.resize( Wa, Ha, PCCCOLORFORMAT::YUV444 );
+      std::memcpy( g.getChannel( 0 ).data(), fr->aux_geometry + (size_t)f * Wa * Ha, Wa * Ha * 2 );
+    }
+    if ( p.attribute_count > 0 ) {
+      auto& rawAtt = context.getVideoRawPointsAttribute();
+      rawAtt.resize( nFrames );
+      for ( int f = 0; f < nFrames; f++ ) {
+        auto& a = rawAtt.getFrame( f );
+        a.resize( Wa, Ha, PCCCOLORFORMAT::YUV444 );
+        for ( int c = 0; c < 3; c++ ) {
+          std::memcpy( a.getChannel( c ).data(), fr->aux_attribute + ( (size_t)f * 3 + c ) * Wa * Ha, Wa * Ha * 2 );
+        }
+      }
+    }
+  }
+
   if ( p.point_local_reconstruction && g_pending_plr ) {  // PCCDecoder::setPointLocalReconstruction (PCCDecoder.cpp:528-541)
     for ( int i = 0; i < g_pending_plr->n_modes; i++ ) {
       const rb200_plr_mode&        m = g_pending_plr->modes[i];
@@ -381,6 +408,10 @@ ref_gof* ref_gof_run( const rb200_params* pp,
       }
       codec.generateBlockToPatchFromOccupancyMapVideo( context, tile, f, occVideo.getFrame( f ),
                                                        p.occupancy_resolution, P );
+      if ( p.use_aux_separate_video ) {  // PCCDecoder.cpp:330-343 (the per-tile forms: the frame loop here runs frame-parallel)
+        codec.generateRawPointsGeometryfromVideo( context, tile, f );
+        if ( p.attribute_count > 0 ) { codec.generateRawPointsAttributefromVideo( context, tile, f ); }
+      }
       PCCPointSet3 tileRec;
       codec.generatePointCloud( tileRec, context, f, 0, gpc, partition, true );
       reconstruct.appendPointSet( tileRec );

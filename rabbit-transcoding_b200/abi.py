@@ -69,7 +69,8 @@ class Params(C.Structure):
             "threshold_smoothing", "threshold_color_smoothing", "threshold_color_difference",
             "threshold_color_variation")] + [
         (n, i32) for n in ("pbf_passes_count", "pbf_filter_size", "pbf_log2_threshold", "neighbor_count_smoothing")] + [
-        (n, C.c_double) for n in ("radius2_smoothing", "radius2_boundary_detection")]
+        (n, C.c_double) for n in ("radius2_smoothing", "radius2_boundary_detection")] + [
+        (n, i32) for n in ("use_aux_separate_video", "aux_width", "aux_height", "reserved0")]
 
 
 class PlrMode(C.Structure):
@@ -82,7 +83,8 @@ class Plr(C.Structure):
 
 
 class Frames(C.Structure):
-    _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p)]
+    _fields_ = [("occupancy", C.c_void_p), ("geometry", C.c_void_p), ("attribute", C.c_void_p),
+                ("aux_geometry", C.c_void_p), ("aux_attribute", C.c_void_p)]
 
 
 class FramesYuv420(C.Structure):

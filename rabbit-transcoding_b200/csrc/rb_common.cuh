@@ -80,6 +80,7 @@ struct rb200_ctx {
 
   // ---- device inputs ----
   RbBuf d_occ_video, d_geometry, d_attribute, d_patches;
+  RbBuf d_aux_geo, d_aux_attr;  // auxiliary video planes (raw points in a separate video)
   RbBuf d_raw_geo, d_raw_attr;  // decoder-native planes of rb200_gof_upload_yuv420 before the conversion kernels
   RbBuf d_wi_patch, d_wi_local, d_wi_count, d_wi_base, d_wi_eom_count, d_wi_eom_base, d_eom_order, d_wi_eom_slot;
   RbBuf d_frame_wi_off;  // [F+1] first work item of each frame

@@ -212,7 +212,7 @@ void rb200_destroy( rb200_ctx* c ) {
   if ( !c ) { return; }
   cudaSetDevice( c->device );
   cudaStreamSynchronize( c->stream );
-  RbBuf* bufs[] = {&c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_raw_geo, &c->d_raw_attr, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
+  RbBuf* bufs[] = {&c->d_aux_geo, &c->d_aux_attr, &c->d_occ_video, &c->d_geometry, &c->d_attribute, &c->d_raw_geo, &c->d_raw_attr, &c->d_patches, &c->d_wi_patch, &c->d_wi_local,
                    &c->d_wi_count, &c->d_wi_base, &c->d_wi_eom_count, &c->d_wi_eom_base, &c->d_eom_order,
                    &c->d_wi_eom_slot, &c->d_frame_wi_off, &c->d_bitmap, &c->d_b2p, &c->d_frame_info, &c->d_raw_desc,
                    &c->d_plr_modes, &c->d_plr_block_mode, &c->d_plr_block_off,
@@ -305,6 +305,16 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
   }
   if ( p->relative_t1 && ( p->enhanced_occupancy_map_code || p->use_additional_points_patch ) ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "relative_t1 together with EOM or raw patches is not implemented" );
+  }
+  if ( p->use_aux_separate_video ) {
+    if ( p->enhanced_occupancy_map_code ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "EOM attributes in the auxiliary video (PCCCodec.cpp:1551-1580) are not implemented" );
+    }
+    if ( p->use_additional_points_patch && ( p->aux_width < p->occupancy_resolution || p->aux_height < p->occupancy_resolution ||
+                                            p->aux_width % p->occupancy_resolution || p->aux_height % p->occupancy_resolution ||
+                                            p->aux_width > 16384 || p->aux_height > 16384 ) ) {
+      return rb_fail( c, RB200_ERR_INVALID, "use_aux_separate_video needs aux_width / aux_height (multiples of the occupancy resolution)" );
+    }
   }
   if ( p->geometry_bitdepth_3d < 1 || p->geometry_bitdepth_3d > 14 ) {
     return rb_fail( c, RB200_ERR_INVALID, "geometry_bitdepth_3d out of range" );
@@ -481,8 +491,10 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
     for ( auto& r : c->h_raw ) {
       // the patch stores X, then Y, then Z: 3 * numberOfRawPoints samples must fit its rectangle (the reference's fill
       // loop is bounded by sizeU * sizeV, PCCCodec.cpp:913-928, and never leaves the patch)
-      if ( r.u0 < 0 || r.v0 < 0 || r.size_u0 < 0 || r.size_v0 < 0 || r.num_points < 0 || r.u0 + r.size_u0 > c->Wb ||
-           r.v0 + r.size_v0 > c->Hb || 3 * (int64_t)r.num_points > (int64_t)r.size_u0 * r.size_v0 * c->R * c->R ) {
+      // (in the auxiliary video the rectangle lies in the auxiliary frame)
+      const int wb = c->P.use_aux_separate_video ? c->P.aux_width / c->R : c->Wb, hb = c->P.use_aux_separate_video ? c->P.aux_height / c->R : c->Hb;
+      if ( r.u0 < 0 || r.v0 < 0 || r.size_u0 < 0 || r.size_v0 < 0 || r.num_points < 0 || r.u0 + r.size_u0 > wb ||
+           r.v0 + r.size_v0 > hb || 3 * (int64_t)r.num_points > (int64_t)r.size_u0 * r.size_v0 * c->R * c->R ) {
         return rb_fail( c, RB200_ERR_INVALID, "raw patch outside the canvas or too small for its 3 x %d samples", r.num_points );
       }
     }
@@ -492,6 +504,20 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   const size_t occBytes = F * (size_t)c->oW * c->oH;
   const size_t geoBytes = F * c->M * (size_t)c->W * c->H * 2;
   const size_t attBytes = c->P.attribute_count > 0 ? F * c->M * 3 * (size_t)c->W * c->H * 2 : 0;
+  if ( c->P.use_aux_separate_video && c->P.use_additional_points_patch ) {
+    if ( !fr || !fr->aux_geometry || ( c->P.attribute_count > 0 && !fr->aux_attribute ) ) {
+      return rb_fail( c, RB200_ERR_UNSUPPORTED, "gof_upload: the auxiliary video planes are taken through rb200_gof_upload (aux_geometry / aux_attribute)" );
+    }
+    const size_t ap = (size_t)c->P.aux_width * c->P.aux_height;
+    RB_CUDA( c->d_aux_geo.ensure( F * ap * 2 ) );
+    RB_CUDA( cudaMemcpyAsync( c->d_aux_geo.p, fr->aux_geometry, F * ap * 2, cudaMemcpyDefault, c->stream ) );
+    c->stats.h2d_bytes += (int64_t)( F * ap * 2 );
+    if ( c->P.attribute_count > 0 ) {
+      RB_CUDA( c->d_aux_attr.ensure( F * ap * 6 ) );
+      RB_CUDA( cudaMemcpyAsync( c->d_aux_attr.p, fr->aux_attribute, F * ap * 6, cudaMemcpyDefault, c->stream ) );
+      c->stats.h2d_bytes += (int64_t)( F * ap * 6 );
+    }
+  }
   if ( fr ) {
     RB_CUDA( cudaMemcpyAsync( c->d_occ_video.p, fr->occupancy, occBytes, cudaMemcpyDefault, c->stream ) );
     RB_CUDA( cudaMemcpyAsync( c->d_geometry.p, fr->geometry, geoBytes, cudaMemcpyDefault, c->stream ) );

@@ -1048,14 +1048,16 @@ struct RawDesc {
   int32_t pad;
   int64_t dst;  // offset inside the frame's raw range
 };
+// gW x gH: the frames the raw patches address — the atlas (map 0 of frame f: gM frames per atlas frame), or the auxiliary
+// video (aux != 0, one frame per atlas frame; the colours pass through PCCColor3B there, PCCCodec.cpp:1541-1543, :1438)
 __global__ void k_raw_points( const RawDesc* __restrict__ descs, const FrameLayout* __restrict__ layout,
                               const int32_t* __restrict__ patch_count_of_frame, const uint16_t* __restrict__ geo,
-                              const uint16_t* __restrict__ attr, int W, int H, int M, int attr_count,
+                              const uint16_t* __restrict__ attr, int gW, int gH, int gM, int aux, int attr_count,
                               short4* __restrict__ pos, ushort4* __restrict__ col, uint32_t* __restrict__ pix,
                               uint32_t* __restrict__ part, RbFrameInfo* __restrict__ finfo ) {
   const RawDesc d     = descs[blockIdx.y];
-  const size_t  plane = (size_t)W * H;
-  const uint16_t* g   = geo + ( (size_t)d.frame * M ) * plane;
+  const size_t  plane = (size_t)gW * gH;
+  const uint16_t* g   = geo + ( (size_t)d.frame * gM ) * plane;
   const int64_t dst   = layout[d.frame].off + layout[d.frame].regular + layout[d.frame].eom + d.dst;
   int           maxc  = 0;
   for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x ) {
@@ -1063,7 +1065,7 @@ __global__ void k_raw_points( const RawDesc* __restrict__ descs, const FrameLayo
     for ( int k = 0; k < 3; k++ ) {
       const int64_t t = (int64_t)k * d.n + i;  // numRawPointsAdded (:913-928): X || Y || Z runs
       const int     u = (int)( t % d.sizeU ), v = (int)( t / d.sizeU );
-      const int     val = g[(size_t)( d.v0 + v ) * W + d.u0 + u];
+      const int     val = g[(size_t)( d.v0 + v ) * gW + d.u0 + u];
       Q[k]              = (int16_t)( val + ( k == 0 ? d.u1 : ( k == 1 ? d.v1 : d.d1 ) ) );
     }
     const int u = i % d.sizeU, v = i / d.sizeU;  // :930-941
@@ -1071,8 +1073,9 @@ __global__ void k_raw_points( const RawDesc* __restrict__ descs, const FrameLayo
     pos[dst + i] = make_short4( Q[0], Q[1], Q[2], 0 );
     ushort4 cv   = make_ushort4( 0, 0, 0, 0 );
     if ( attr_count > 0 ) {
-      const size_t fb = ( (size_t)d.frame * M ) * 3 * plane, o = (size_t)y * W + x;
+      const size_t fb = ( (size_t)d.frame * gM ) * 3 * plane, o = (size_t)y * gW + x;
       cv              = make_ushort4( attr[fb + o], attr[fb + plane + o], attr[fb + 2 * plane + o], 0 );
+      if ( aux ) { cv.x &= 0xFFu, cv.y &= 0xFFu, cv.z &= 0xFFu; }
     }
     col[dst + i]  = cv;
     pix[dst + i]  = (uint32_t)x | ( (uint32_t)y << 16 );
@@ -1458,9 +1461,12 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
                c->M, c->bmWords, P.attribute_count, a.pos, a.col, a.pix, a.part, c->d_frame_info.as<RbFrameInfo>() );
   }
   if ( !raws.empty() ) {
+    const bool aux = P.use_aux_separate_video != 0;
     RB_LAUNCH( "raw_points", k_raw_points, dim3( 64, (unsigned)raws.size() ), 256, 0, (const RawDesc*)( dS + oRaw ),
-               (const FrameLayout*)( dS + oLayout ), (const int32_t*)( dS + oPc ), c->d_geometry.as<uint16_t>(),
-               c->d_attribute.as<uint16_t>(), c->W, c->H, c->M, P.attribute_count, a.pos, a.col, a.pix, a.part,
+               (const FrameLayout*)( dS + oLayout ), (const int32_t*)( dS + oPc ),
+               aux ? c->d_aux_geo.as<uint16_t>() : c->d_geometry.as<uint16_t>(),
+               aux ? c->d_aux_attr.as<uint16_t>() : c->d_attribute.as<uint16_t>(), aux ? P.aux_width : c->W,
+               aux ? P.aux_height : c->H, aux ? 1 : c->M, aux ? 1 : 0, P.attribute_count, a.pos, a.col, a.pix, a.part,
                c->d_frame_info.as<RbFrameInfo>() );
   }
   if ( classify && ( eom || ilv ) ) {

@@ -111,7 +111,7 @@ struct Gof {  // the GOF currently resident on the GPU
   size_t                          thresholdLossyOM = 0;
   size_t                          currentFrame     = 0;
   // pinned staging: the planes going up, and per stage the fields coming down (whole GOF, frame after frame)
-  Pinned inOcc, inGeo, inAtt;
+  Pinned inOcc, inGeo, inAtt, inAuxGeo, inAuxAtt;
   Pinned pos[2], typ[2];  // after reconstruction / after geometry smoothing
   Pinned col[3];          // colours16 after reconstruction / attribute re-transfer / colour smoothing
   Pinned part, p2p;
@@ -149,7 +149,9 @@ void checkSupported( PCCContext& context, const GeneratePointCloudParameters& p,
     unsupported( "occupancy synthesis (PCCCodec.cpp:541-554) together with EOM, pixel interleaving, point local reconstruction or "
                  "patch size quantisation" );
   }
-  if ( p.useAuxSeperateVideo_ ) { unsupported( "raw / EOM points in an auxiliary video (PCCCodec.cpp:1451-1582)" ); }
+  if ( p.useAuxSeperateVideo_ && p.enhancedOccupancyMapCode_ ) {
+    unsupported( "EOM attributes in the auxiliary video (PCCCodec.cpp:1551-1580)" );
+  }
   if ( p.mapCountMinus1_ > 1 ) { unsupported( "more than two maps" ); }
   if ( p.occupancyResolution_ != 16 ) { unsupported( "an occupancy resolution other than 16" ); }
   if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
@@ -161,7 +163,9 @@ void checkSupported( PCCContext& context, const GeneratePointCloudParameters& p,
     if ( context[f].getNumTilesInAtlasFrame() != 1 ) { unsupported( "an atlas frame with several tiles (PCCDecoder.cpp:356-381)" ); }
     auto& tile = context[f].getTile( 0 );
     if ( tile.getLeftTopXInFrame() != 0 || tile.getLeftTopYInFrame() != 0 ) { unsupported( "a tile that does not start at (0, 0)" ); }
-    if ( tile.getUseRawPointsSeparateVideo() ) { unsupported( "raw points in a separate video" ); }
+    if ( tile.getUseRawPointsSeparateVideo() != p.useAuxSeperateVideo_ ) {
+      unsupported( "a tile whose auxiliary-video flag differs from the sequence's (PCCCodec.cpp:606 vs :880)" );
+    }
   }
 }
 
@@ -245,7 +249,26 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   }
   rb200::AtlasTables tables;  // the atlas layer's patches as flat rows (rb200_atlas_export.h)
   rb200::exportAtlas( context, tables );
-  rb200_frames fr{occ, geo, att};
+  rb200_frames fr{occ, geo, att, nullptr, nullptr};
+  if ( gp.useAuxSeperateVideo_ && gp.useAdditionalPointsPatch_ ) {
+    // raw points in the auxiliary video: channel 0 of context.getVideoRawPointsGeometry(), the three channels of
+    // getVideoRawPointsAttribute() (PCCCodec.cpp:895-897, :1524-1549)
+    auto&        rawGeo = context.getVideoRawPointsGeometry();
+    const size_t Wa = rawGeo.getFrame( 0 ).getWidth(), Ha = rawGeo.getFrame( 0 ).getHeight();
+    p.use_aux_separate_video = 1;
+    p.aux_width = (int)Wa, p.aux_height = (int)Ha;
+    uint16_t* ag = g.inAuxGeo.get<uint16_t>( F * Wa * Ha );
+    for ( size_t f = 0; f < F; f++ ) { std::memcpy( &ag[f * Wa * Ha], rawGeo.getFrame( f ).getChannel( 0 ).data(), Wa * Ha * 2 ); }
+    fr.aux_geometry = ag;
+    if ( hasAttr ) {
+      auto&     rawAtt = context.getVideoRawPointsAttribute();
+      uint16_t* aa     = g.inAuxAtt.get<uint16_t>( F * 3 * Wa * Ha );
+      for ( size_t f = 0; f < F; f++ ) {
+        for ( int c = 0; c < 3; c++ ) { std::memcpy( &aa[( f * 3 + c ) * Wa * Ha], rawAtt.getFrame( f ).getChannel( c ).data(), Wa * Ha * 2 ); }
+      }
+      fr.aux_attribute = aa;
+    }
+  }
   rb200_atlas  at = tables.view();
   ensureContext();
   RB( rb200_gof_begin( g.ctx, &p, (int)F ) );

@@ -67,6 +67,8 @@ class SyntheticGOF:
         self.eom_members = None
         self.raw_patches = None
         self.raw_offset = None
+        self.aux_geometry = None   # u16 [F][aux_height][aux_width]     (params.use_aux_separate_video, make_aux_video)
+        self.aux_attribute = None  # u16 [F][3][aux_height][aux_width]
         self.plr = None         # point local reconstruction tables (make_plr)
         self.sources = []       # per frame: dict(positions i16[n,3], colors u8[n,3], normals f32[n,3])
 
@@ -75,6 +77,8 @@ class SyntheticGOF:
         f.occupancy = abi.ptr(self.occupancy)
         f.geometry = abi.ptr(self.geometry)
         f.attribute = abi.ptr(self.attribute) if self.attribute is not None else None
+        f.aux_geometry = abi.ptr(self.aux_geometry) if self.aux_geometry is not None else None
+        f.aux_attribute = abi.ptr(self.aux_attribute) if self.aux_attribute is not None else None
         return f
 
     def atlas_struct(self):
@@ -702,6 +706,32 @@ def make_plr(gof, seed=0):
         blk[gof_modes[blk, 0] != 0] = 4
     gof.plr = dict(modes=gof_modes, block_mode=bm, block_offset=off)
     p.point_local_reconstruction = 1
+    return gof
+
+
+def make_aux_video(gof, seed=0):
+    """Moves the raw patches of a GOF generated with raw_points into an auxiliary video (asps.getAuxiliaryVideoEnabledFlag:
+    PCCCodec.cpp:895-897 reads their coordinates from context.getVideoRawPointsGeometry(), :1436-1439 their colours from
+    the auxiliary attribute video through 8-bit PCCColor3B values).  The auxiliary frames are 64-aligned as the syntax
+    requires (auxiliaryVideoTileRowWidthMinus1 / RowHeight in units of 64, PCCDecoder.cpp:1820-1824); the attribute
+    samples carry high bits so that the truncation shows."""
+    assert gof.raw_patches is not None and len(gof.raw_patches)
+    p, R = gof.params, gof.params.occupancy_resolution
+    rng = np.random.default_rng(seed + 4242)
+    F, M, W = gof.n_frames, p.map_count_minus1 + 1, p.width
+    geo = gof.geometry.reshape(F, M, p.height, W)
+    Wa = -(-W // 64) * 64
+    Ha = -(-int(max(r["size_v0"] for r in gof.raw_patches) * R + R) // 64) * 64  # one raw patch per frame, placed at block row 1
+    gof.aux_geometry = rng.integers(0, 1 << 10, size=(F, Ha, Wa)).astype(np.uint16)
+    gof.aux_attribute = rng.integers(0, 1 << 16, size=(F, 3, Ha, Wa)).astype(np.uint16)
+    for f in range(F):
+        for k in range(int(gof.raw_offset[f]), int(gof.raw_offset[f + 1])):
+            r = gof.raw_patches[k]
+            rows = int(r["size_v0"]) * R
+            src = geo[f, 0, int(r["v0"]) * R:int(r["v0"]) * R + rows, int(r["u0"]) * R:(int(r["u0"]) + int(r["size_u0"])) * R]
+            gof.aux_geometry[f, R:R + rows, :src.shape[1]] = src
+            gof.raw_patches[k]["u0"], gof.raw_patches[k]["v0"] = 0, 1
+    p.use_aux_separate_video, p.aux_width, p.aux_height = 1, Wa, Ha
     return gof
 
 

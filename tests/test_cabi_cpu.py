@@ -29,8 +29,8 @@ def test_header_symbols_exported(rb, lib):
 def test_struct_sizes_match_header(rb):
     # sizes computed from the header layout (all int32 / double / pointer fields, natural alignment)
     assert C.sizeof(rb.abi.Patch) == 17 * 4
-    assert C.sizeof(rb.abi.Params) == 32 * 4 + 4 * 8 + 4 * 4 + 2 * 8
-    assert C.sizeof(rb.abi.Frames) == 3 * 8
+    assert C.sizeof(rb.abi.Params) == 32 * 4 + 4 * 8 + 4 * 4 + 2 * 8 + 4 * 4
+    assert C.sizeof(rb.abi.Frames) == 5 * 8
     assert C.sizeof(rb.abi.Atlas) == 7 * 8
     assert C.sizeof(rb.abi.CloudHost) == 6 * 8
     assert C.sizeof(rb.abi.FrameCounts) == 6 * 8

@@ -65,6 +65,11 @@ def test_dropin_eom_and_raw(rb, backends):
     compare(rb, backends, "raw", raw_points=700, transfer_filter=0, seed=74)
 
 
+def test_dropin_raw_points_in_the_auxiliary_video(rb, backends):
+    g, want = compare(rb, backends, "aux raw", make=lambda g: rb.synthetic.make_aux_video(g, seed=79), raw_points=600, seed=79)
+    assert want.counts(0).raw == 600
+
+
 def test_dropin_occupancy_synthesis(rb, backends):
     """Rec-2 through the shim: the decoder skips generateOccupancyMap and the re-transfer (PCCDecoder.cpp:362, :445), the
     patch border filter and the points' boundary types run on the GPU"""

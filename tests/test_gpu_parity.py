@@ -200,6 +200,31 @@ def test_raw_points(rb, codec, checker_backend):
     run_stages(codec, small(rb, raw_points=1000, seed=19), checker_backend, what="raw")
 
 
+def test_raw_points_in_the_auxiliary_video(rb, codec, checker_backend):
+    """asps.getAuxiliaryVideoEnabledFlag: the raw patches address context.getVideoRawPointsGeometry() (PCCCodec.cpp:895-897)
+    and their colours come from the auxiliary attribute video through 8-bit PCCColor3B values (:1524-1549, :1436-1439)"""
+    g = rb.synthetic.make_aux_video(small(rb, raw_points=1000, seed=21), seed=21)
+    ref = run_stages(codec, g, checker_backend, what="aux raw")
+    c = ref.cloud(0, "reconstruct")
+    n = ref.counts(0).raw
+    assert n == 1000 and (c["colors16"][-n:] < 256).all() and (c["colors16"][-n:] > 0).any()
+    # the whole decoder sequence (Rec-1) and without attributes
+    g = rb.synthetic.make_aux_video(small(rb, raw_points=333, seed=22, transfer_filter=1), seed=22)
+    run_stages(codec, g, checker_backend, stages=ALL_STAGES, what="aux raw rec-1")
+    g = rb.synthetic.make_aux_video(small(rb, raw_points=50, seed=23, color_smoothing=False), seed=23)
+    g.params.attribute_count = 0
+    ref = checker_backend.run_gof(g, keep=("reconstruct",))
+    codec.uploadGof(g)
+    codec.generatePointCloud()
+    for f in range(g.n_frames):
+        assert np.array_equal(codec.getPointCloud(f, fields=("positions",))["positions"], ref.cloud(f, "reconstruct")["positions"])
+    # EOM together with the auxiliary video is refused, not approximated
+    g = small(rb, eom=True, geometry_smoothing=False, color_smoothing=False, seed=24)
+    g.params.use_aux_separate_video = 1
+    with pytest.raises(rb.codec.RabbitError):
+        codec.uploadGof(g)
+
+
 def test_no_attributes(rb, codec, checker_backend):
     g = small(rb, seed=20, color_smoothing=False)
     g.params.attribute_count = 0
