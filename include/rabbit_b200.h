@@ -133,8 +133,9 @@ typedef struct rb200_params {
   /* raw (missed) points carried in the auxiliary video (asps.getAuxiliaryVideoEnabledFlag, PCCDecoder.cpp:783;
    * tile.getUseRawPointsSeparateVideo, PCCCodec.cpp:606, :895-897, :1334, :1436-1439): the raw patches address the
    * auxiliary frames (rb200_frames.aux_geometry / aux_attribute) instead of the atlas; their colours are the low 8
-   * bits of the auxiliary attribute samples (they pass through PCCColor3B, PCCCodec.cpp:1541-1543).  Not together
-   * with EOM (EOM attributes in the auxiliary video, :1551-1580, are not implemented). */
+   * bits of the auxiliary attribute samples (they pass through PCCColor3B, PCCCodec.cpp:1541-1543).  With EOM the
+   * colours of the EOM points come from the auxiliary attribute video as well (:1551-1580), their synthetic pixel
+   * addresses start at (0, 0) and the occupancy map is not marked (:852-853, :880). */
   int32_t use_aux_separate_video;
   int32_t aux_width, aux_height;      /* size of the auxiliary video frames                               */
   int32_t reserved0;

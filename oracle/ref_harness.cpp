@@ -244,7 +244,7 @@ static void fillPatchTables( PCCContext& context, const rb200_params& p, int nFr
         e.v0_                  = s.v0;
         e.sizeU_               = 0;
         e.sizeV_               = 0;
-        e.isPatchInAuxVideo_   = false;
+        e.isPatchInAuxVideo_   = p.use_aux_separate_video != 0;
         e.tileIndex_           = 0;
         e.frameIndex_          = f;
         e.eomCount_            = s.eom_count;
@@ -276,6 +276,11 @@ static void fillPatchTables( PCCContext& context, const rb200_params& p, int nFr
     }
     // PCCDecoder::createPatchFrameDataStructure sets this from the syntax (PCCDecoder.cpp:1150-1238)
     tile.setTotalNumberOfRawPoints( p.use_additional_points_patch ? totalRaw : 0 );
+    {  // ... and the EOM total (:1237): generateRawPointsAttributefromVideo sizes the EOM colours with it before the frame is built
+      size_t totalEom = 0;
+      for ( auto& e : tile.getEomPatches() ) { totalEom += e.eomCount_; }
+      tile.setTotalNumberOfEOMPoints( p.enhanced_occupancy_map_code ? totalEom : 0 );
+    }
   }
 
 }
@@ -359,7 +364,7 @@ ref_gof* ref_gof_run( const rb200_params* pp,
     for ( int f = 0; f < nFrames; f++ ) {
       auto& g = rawGeo.getFrame( f );
       g.resize( Wa, Ha, PCCCOLORFORMAT::YUV444 );
-      std::memcpy( g.getChannel( 0 ).data(), fr->aux_geometry + (size_t)f * Wa * Ha, Wa * Ha * 2 );
+      if ( fr->aux_geometry ) { std::memcpy( g.getChannel( 0 ).data(), fr->aux_geometry + (size_t)f * Wa * Ha, Wa * Ha * 2 ); }
     }
     if ( p.attribute_count > 0 ) {
       auto& rawAtt = context.getVideoRawPointsAttribute();
@@ -409,7 +414,7 @@ ref_gof* ref_gof_run( const rb200_params* pp,
       codec.generateBlockToPatchFromOccupancyMapVideo( context, tile, f, occVideo.getFrame( f ),
                                                        p.occupancy_resolution, P );
       if ( p.use_aux_separate_video ) {  // PCCDecoder.cpp:330-343 (the per-tile forms: the frame loop here runs frame-parallel)
-        codec.generateRawPointsGeometryfromVideo( context, tile, f );
+        if ( p.use_additional_points_patch ) { codec.generateRawPointsGeometryfromVideo( context, tile, f ); }
         if ( p.attribute_count > 0 ) { codec.generateRawPointsAttributefromVideo( context, tile, f ); }
       }
       PCCPointSet3 tileRec;

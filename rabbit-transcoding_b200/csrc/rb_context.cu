@@ -307,10 +307,7 @@ int rb200_gof_begin( rb200_ctx* c, const rb200_params* p, int nFrames ) {
     return rb_fail( c, RB200_ERR_UNSUPPORTED, "relative_t1 together with EOM or raw patches is not implemented" );
   }
   if ( p->use_aux_separate_video ) {
-    if ( p->enhanced_occupancy_map_code ) {
-      return rb_fail( c, RB200_ERR_UNSUPPORTED, "EOM attributes in the auxiliary video (PCCCodec.cpp:1551-1580) are not implemented" );
-    }
-    if ( p->use_additional_points_patch && ( p->aux_width < p->occupancy_resolution || p->aux_height < p->occupancy_resolution ||
+    if ( ( p->use_additional_points_patch || p->enhanced_occupancy_map_code ) && ( p->aux_width < p->occupancy_resolution || p->aux_height < p->occupancy_resolution ||
                                             p->aux_width % p->occupancy_resolution || p->aux_height % p->occupancy_resolution ||
                                             p->aux_width > 16384 || p->aux_height > 16384 ) ) {
       return rb_fail( c, RB200_ERR_INVALID, "use_aux_separate_video needs aux_width / aux_height (multiples of the occupancy resolution)" );
@@ -504,14 +501,16 @@ static int gof_upload_common( rb200_ctx* c, const rb200_frames* fr, const rb200_
   const size_t occBytes = F * (size_t)c->oW * c->oH;
   const size_t geoBytes = F * c->M * (size_t)c->W * c->H * 2;
   const size_t attBytes = c->P.attribute_count > 0 ? F * c->M * 3 * (size_t)c->W * c->H * 2 : 0;
-  if ( c->P.use_aux_separate_video && c->P.use_additional_points_patch ) {
-    if ( !fr || !fr->aux_geometry || ( c->P.attribute_count > 0 && !fr->aux_attribute ) ) {
+  if ( c->P.use_aux_separate_video && ( c->P.use_additional_points_patch || c->P.enhanced_occupancy_map_code ) ) {
+    if ( !fr || ( c->P.use_additional_points_patch && !fr->aux_geometry ) || ( c->P.attribute_count > 0 && !fr->aux_attribute ) ) {
       return rb_fail( c, RB200_ERR_UNSUPPORTED, "gof_upload: the auxiliary video planes are taken through rb200_gof_upload (aux_geometry / aux_attribute)" );
     }
     const size_t ap = (size_t)c->P.aux_width * c->P.aux_height;
-    RB_CUDA( c->d_aux_geo.ensure( F * ap * 2 ) );
-    RB_CUDA( cudaMemcpyAsync( c->d_aux_geo.p, fr->aux_geometry, F * ap * 2, cudaMemcpyDefault, c->stream ) );
-    c->stats.h2d_bytes += (int64_t)( F * ap * 2 );
+    if ( fr->aux_geometry ) {
+      RB_CUDA( c->d_aux_geo.ensure( F * ap * 2 ) );
+      RB_CUDA( cudaMemcpyAsync( c->d_aux_geo.p, fr->aux_geometry, F * ap * 2, cudaMemcpyDefault, c->stream ) );
+      c->stats.h2d_bytes += (int64_t)( F * ap * 2 );
+    }
     if ( c->P.attribute_count > 0 ) {
       RB_CUDA( c->d_aux_attr.ensure( F * ap * 6 ) );
       RB_CUDA( cudaMemcpyAsync( c->d_aux_attr.p, fr->aux_attribute, F * ap * 6, cudaMemcpyDefault, c->stream ) );

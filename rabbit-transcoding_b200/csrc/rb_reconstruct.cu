@@ -947,8 +947,8 @@ struct EomSeg {
   int32_t patch;       // global patch index whose staged EOM points are copied
   int32_t eom_patch;   // index of the EOM patch inside the frame (restarts the synthetic pixel counter)
   int32_t first_in_eom_patch;
-  int32_t u0, v0;      // EOM patch origin in pixels
-  int32_t pad[2];
+  int32_t u0, v0;      // origin of the synthetic pixel addresses (the EOM patch's; 0 with the auxiliary video, :852-853)
+  int32_t cu0, cv0;    // auxiliary video: origin of the colour addresses (the EOM patch's, :1556-1557)
 };
 
 // per-patch staged EOM range = [wi_eom_base[firstWI(patch)], wi_eom_base[firstWI(patch)+nblocks))
@@ -1010,6 +1010,7 @@ __global__ void k_eom_append( const EomSeg* __restrict__ segs, const int32_t* __
                               const short4* __restrict__ stage, const FrameLayout* __restrict__ layout,
                               const int32_t* __restrict__ patch_count_of_frame, const uint16_t* __restrict__ attr,
                               uint32_t* __restrict__ bitmap, int W, int H, int Wb, int M, int words, int attr_count,
+                              const uint16_t* __restrict__ aux_attr, int auxW, int auxH, int aux,
                               short4* __restrict__ pos, ushort4* __restrict__ col, uint32_t* __restrict__ pix,
                               uint32_t* __restrict__ part, RbFrameInfo* __restrict__ finfo ) {
   const int     s = blockIdx.x;
@@ -1027,7 +1028,23 @@ __global__ void k_eom_append( const EomSeg* __restrict__ segs, const int32_t* __
     P.w               = 0;
     pos[dst + i]      = P;
     ushort4 cv        = make_ushort4( 0, 0, 0, 0 );
-    if ( attr_count > 0 && uu < W && vv < H ) {
+    if ( aux ) {
+      // generateRawPointsAttributefromVideo (:1551-1580): block of the EOM patch from the point's index k inside the patch,
+      // pixel inside the block from a counter that runs over ALL EOM points of the tile (it is not reset per patch), in
+      // the auxiliary attribute video; the values pass through 8-bit PCCColor3B (:1574-1576, :1437)
+      if ( attr_count > 0 ) {
+        const int     wbA = auxW / 16;
+        const int64_t npx = ( seg_dst[s] + i ) % 256;
+        const int     xx  = g.cu0 + (int)( blk % wbA ) * 16 + (int)( npx % 16 );
+        const int     yy  = g.cv0 + (int)( blk / wbA ) * 16 + (int)( npx / 16 );
+        // (getValue( c, xx, yy ) is channel[yy * width + xx] without a range check, PCCImage.h:205-212: a block row that
+        // runs past the right edge continues in the next pixel row, as in the reference; past the plane: 0)
+        const size_t plane = (size_t)auxW * auxH, o = (size_t)yy * auxW + xx, fb = (size_t)g.frame * 3 * plane;
+        if ( o < plane ) {
+          cv = make_ushort4( aux_attr[fb + o] & 0xFFu, aux_attr[fb + plane + o] & 0xFFu, aux_attr[fb + 2 * plane + o] & 0xFFu, 0 );
+        }
+      }
+    } else if ( attr_count > 0 && uu < W && vv < H ) {
       const size_t plane = (size_t)W * H;
       const size_t o     = (size_t)vv * W + uu;
       const size_t fb    = ( (size_t)g.frame * M ) * 3 * plane;
@@ -1036,7 +1053,7 @@ __global__ void k_eom_append( const EomSeg* __restrict__ segs, const int32_t* __
     col[dst + i]  = cv;
     pix[dst + i]  = (uint32_t)uu | ( (uint32_t)vv << 16 );
     part[dst + i] = (uint32_t)patch_count_of_frame[g.frame];  // partition = patches.size() (:843,877)
-    if ( uu < W && vv < H ) { atomicOr( &bitmap[( (size_t)g.frame * H + vv ) * words + ( uu >> 5 )], 1u << ( uu & 31 ) ); }  // :880
+    if ( !aux && uu < W && vv < H ) { atomicOr( &bitmap[( (size_t)g.frame * H + vv ) * words + ( uu >> 5 )], 1u << ( uu & 31 ) ); }  // :880
     maxc = max( maxc, max( (int)P.x, max( (int)P.y, (int)P.z ) ) );
   }
   if ( maxc > 0 ) { atomicMax( &finfo[g.frame].max_coord, maxc ); }
@@ -1305,8 +1322,11 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
           s.patch              = pb + m;
           s.eom_patch          = j - c->h_eom_off[f];
           s.first_in_eom_patch = ( k == 0 );
-          s.u0                 = e.u0 * c->R;
-          s.v0                 = e.v0 * c->R;
+          const bool auxEom    = P.use_aux_separate_video != 0;
+          s.u0                 = auxEom ? 0 : e.u0 * c->R;
+          s.v0                 = auxEom ? 0 : e.v0 * c->R;
+          s.cu0                = e.u0 * c->R;
+          s.cv0                = e.v0 * c->R;
           segs.push_back( s );
         }
       }
@@ -1451,6 +1471,18 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
       runF += segSize[s];
       runP += segSize[s];
     }
+    if ( P.use_aux_separate_video ) {
+      // the colours are addressed by the signalled eomCount_ of the patches (:1561): it must be what the patches produce
+      for ( int s = 0; s < nSeg; ) {
+        int64_t   got = 0;
+        const int f = segs[s].frame, j = segs[s].eom_patch;
+        for ( ; s < nSeg && segs[s].frame == f && segs[s].eom_patch == j; s++ ) { got += segSize[s]; }
+        if ( got != c->h_eom[c->h_eom_off[f] + j].eom_count ) {
+          return rb_fail( c, RB200_ERR_INVALID, "EOM patch %d of frame %d signals %d points but its member patches produce %lld", j, f,
+                          c->h_eom[c->h_eom_off[f] + j].eom_count, (long long)got );
+        }
+      }
+    }
     RB_CUDA( cudaMemcpyAsync( dS + oSegDst, segDst.data(), nSeg * 8, cudaMemcpyHostToDevice, c->stream ) );
     RB_CUDA( cudaMemcpyAsync( dS + oSegPix, segPix.data(), nSeg * 8, cudaMemcpyHostToDevice, c->stream ) );
     RB_CUDA( cudaStreamSynchronize( c->stream ) );
@@ -1458,7 +1490,8 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
                (const int64_t*)( dS + oSegDst ), (const int64_t*)( dS + oSegPix ), (const int32_t*)( dS + oPfw ),
                c->d_wi_eom_base.as<int64_t>(), c->d_scratch[1].as<short4>(), (const FrameLayout*)( dS + oLayout ),
                (const int32_t*)( dS + oPc ), c->d_attribute.as<uint16_t>(), c->d_bitmap.as<uint32_t>(), c->W, c->H, c->Wb,
-               c->M, c->bmWords, P.attribute_count, a.pos, a.col, a.pix, a.part, c->d_frame_info.as<RbFrameInfo>() );
+               c->M, c->bmWords, P.attribute_count, c->d_aux_attr.as<uint16_t>(), P.aux_width, P.aux_height,
+               P.use_aux_separate_video ? 1 : 0, a.pos, a.col, a.pix, a.part, c->d_frame_info.as<RbFrameInfo>() );
   }
   if ( !raws.empty() ) {
     const bool aux = P.use_aux_separate_video != 0;

@@ -725,7 +725,7 @@ int rb_smooth_radius_impl( rb200_ctx* c ) {
   const double   r2      = P.radius2_smoothing;
   const double   rad     = sqrt( r2 ) + 1.0;
   const int      cap     = std::max( 256, 2 * (int)( 4.19 * rad * rad * rad ) );
-  const int      threads = (int)std::min<int64_t>( 148 * 4 * 128, ( ( N + 127 ) / 128 ) * 128 );
+  const int      threads = (int)std::min<int64_t>( 148 * 2 * 128, ( ( N + 127 ) / 128 ) * 128 );  // (49 KB of list per thread at r2 = 64)
   RB_CUDA( S->candKey.ensure( (size_t)threads * cap * 8 ) );
   RB_CUDA( S->small.ensure( 64 ) );
   RB_CUDA( cudaMemsetAsync( S->small.p, 0, 64, c->stream ) );

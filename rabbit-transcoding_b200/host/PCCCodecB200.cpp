@@ -149,9 +149,6 @@ void checkSupported( PCCContext& context, const GeneratePointCloudParameters& p,
     unsupported( "occupancy synthesis (PCCCodec.cpp:541-554) together with EOM, pixel interleaving, point local reconstruction or "
                  "patch size quantisation" );
   }
-  if ( p.useAuxSeperateVideo_ && p.enhancedOccupancyMapCode_ ) {
-    unsupported( "EOM attributes in the auxiliary video (PCCCodec.cpp:1551-1580)" );
-  }
   if ( p.mapCountMinus1_ > 1 ) { unsupported( "more than two maps" ); }
   if ( p.occupancyResolution_ != 16 ) { unsupported( "an occupancy resolution other than 16" ); }
   if ( ( p.pointLocalReconstruction_ || p.singleMapPixelInterleaving_ ) &&
@@ -250,18 +247,22 @@ void reconstructGof( PCCContext& context, const GeneratePointCloudParameters& gp
   rb200::AtlasTables tables;  // the atlas layer's patches as flat rows (rb200_atlas_export.h)
   rb200::exportAtlas( context, tables );
   rb200_frames fr{occ, geo, att, nullptr, nullptr};
-  if ( gp.useAuxSeperateVideo_ && gp.useAdditionalPointsPatch_ ) {
-    // raw points in the auxiliary video: channel 0 of context.getVideoRawPointsGeometry(), the three channels of
-    // getVideoRawPointsAttribute() (PCCCodec.cpp:895-897, :1524-1549)
+  if ( gp.useAuxSeperateVideo_ && ( gp.useAdditionalPointsPatch_ || gp.enhancedOccupancyMapCode_ ) ) {
+    // raw / EOM points in the auxiliary video: channel 0 of context.getVideoRawPointsGeometry() (raw coordinates,
+    // PCCCodec.cpp:895-897), the three channels of getVideoRawPointsAttribute() (raw and EOM colours, :1524-1580)
     auto&        rawGeo = context.getVideoRawPointsGeometry();
-    const size_t Wa = rawGeo.getFrame( 0 ).getWidth(), Ha = rawGeo.getFrame( 0 ).getHeight();
+    auto&        rawAtt = context.getVideoRawPointsAttribute();
+    const bool   haveGeo = gp.useAdditionalPointsPatch_ && rawGeo.getFrameCount() >= F;
+    const size_t Wa = haveGeo ? rawGeo.getFrame( 0 ).getWidth() : rawAtt.getFrame( 0 ).getWidth(),
+                 Ha = haveGeo ? rawGeo.getFrame( 0 ).getHeight() : rawAtt.getFrame( 0 ).getHeight();
     p.use_aux_separate_video = 1;
     p.aux_width = (int)Wa, p.aux_height = (int)Ha;
-    uint16_t* ag = g.inAuxGeo.get<uint16_t>( F * Wa * Ha );
-    for ( size_t f = 0; f < F; f++ ) { std::memcpy( &ag[f * Wa * Ha], rawGeo.getFrame( f ).getChannel( 0 ).data(), Wa * Ha * 2 ); }
-    fr.aux_geometry = ag;
+    if ( haveGeo ) {
+      uint16_t* ag = g.inAuxGeo.get<uint16_t>( F * Wa * Ha );
+      for ( size_t f = 0; f < F; f++ ) { std::memcpy( &ag[f * Wa * Ha], rawGeo.getFrame( f ).getChannel( 0 ).data(), Wa * Ha * 2 ); }
+      fr.aux_geometry = ag;
+    }
     if ( hasAttr ) {
-      auto&     rawAtt = context.getVideoRawPointsAttribute();
       uint16_t* aa     = g.inAuxAtt.get<uint16_t>( F * 3 * Wa * Ha );
       for ( size_t f = 0; f < F; f++ ) {
         for ( int c = 0; c < 3; c++ ) { std::memcpy( &aa[( f * 3 + c ) * Wa * Ha], rawAtt.getFrame( f ).getChannel( c ).data(), Wa * Ha * 2 ); }

@@ -710,27 +710,34 @@ def make_plr(gof, seed=0):
 
 
 def make_aux_video(gof, seed=0):
-    """Moves the raw patches of a GOF generated with raw_points into an auxiliary video (asps.getAuxiliaryVideoEnabledFlag:
-    PCCCodec.cpp:895-897 reads their coordinates from context.getVideoRawPointsGeometry(), :1436-1439 their colours from
-    the auxiliary attribute video through 8-bit PCCColor3B values).  The auxiliary frames are 64-aligned as the syntax
-    requires (auxiliaryVideoTileRowWidthMinus1 / RowHeight in units of 64, PCCDecoder.cpp:1820-1824); the attribute
-    samples carry high bits so that the truncation shows."""
-    assert gof.raw_patches is not None and len(gof.raw_patches)
+    """Moves the raw patches (and the EOM patches' colours) of a GOF generated with raw_points / eom into an auxiliary video
+    (asps.getAuxiliaryVideoEnabledFlag: PCCCodec.cpp:895-897 reads the raw coordinates from
+    context.getVideoRawPointsGeometry(), :1524-1580 the raw and EOM colours from the auxiliary attribute video through
+    8-bit PCCColor3B values).  The auxiliary frames are 64-aligned as the syntax requires (auxiliaryVideoTileRowWidthMinus1 /
+    RowHeight in units of 64, PCCDecoder.cpp:1820-1824); the attribute samples carry high bits so that the truncation shows."""
+    have_raw = gof.raw_patches is not None and len(gof.raw_patches) > 0
+    have_eom = gof.eom_patches is not None and len(gof.eom_patches) > 0
+    assert have_raw or have_eom
     p, R = gof.params, gof.params.occupancy_resolution
     rng = np.random.default_rng(seed + 4242)
     F, M, W = gof.n_frames, p.map_count_minus1 + 1, p.width
     geo = gof.geometry.reshape(F, M, p.height, W)
     Wa = -(-W // 64) * 64
-    Ha = -(-int(max(r["size_v0"] for r in gof.raw_patches) * R + R) // 64) * 64  # one raw patch per frame, placed at block row 1
-    gof.aux_geometry = rng.integers(0, 1 << 10, size=(F, Ha, Wa)).astype(np.uint16)
+    raw_rows = int(max(r["size_v0"] for r in gof.raw_patches)) if have_raw else 0     # in blocks; raw patch at block row 1
+    eom_v0 = 1 + raw_rows + 1                                                          # EOM patch below it
+    eom_rows = -(-int(max(e["eom_count"] for e in gof.eom_patches)) // (R * R * (Wa // R))) + 1 if have_eom else 0
+    Ha = -(-((eom_v0 + eom_rows + 1) * R) // 64) * 64
+    gof.aux_geometry = rng.integers(0, 1 << 10, size=(F, Ha, Wa)).astype(np.uint16) if have_raw else None
     gof.aux_attribute = rng.integers(0, 1 << 16, size=(F, 3, Ha, Wa)).astype(np.uint16)
     for f in range(F):
-        for k in range(int(gof.raw_offset[f]), int(gof.raw_offset[f + 1])):
+        for k in range(int(gof.raw_offset[f]), int(gof.raw_offset[f + 1])) if have_raw else ():
             r = gof.raw_patches[k]
             rows = int(r["size_v0"]) * R
             src = geo[f, 0, int(r["v0"]) * R:int(r["v0"]) * R + rows, int(r["u0"]) * R:(int(r["u0"]) + int(r["size_u0"])) * R]
             gof.aux_geometry[f, R:R + rows, :src.shape[1]] = src
             gof.raw_patches[k]["u0"], gof.raw_patches[k]["v0"] = 0, 1
+        for k in range(int(gof.eom_offset[f]), int(gof.eom_offset[f + 1])) if have_eom else ():
+            gof.eom_patches[k]["u0"], gof.eom_patches[k]["v0"] = 1, eom_v0
     p.use_aux_separate_video, p.aux_width, p.aux_height = 1, Wa, Ha
     return gof
 

@@ -68,6 +68,9 @@ def test_dropin_eom_and_raw(rb, backends):
 def test_dropin_raw_points_in_the_auxiliary_video(rb, backends):
     g, want = compare(rb, backends, "aux raw", make=lambda g: rb.synthetic.make_aux_video(g, seed=79), raw_points=600, seed=79)
     assert want.counts(0).raw == 600
+    g, want = compare(rb, backends, "aux eom", make=lambda g: rb.synthetic.make_aux_video(g, seed=80), eom=True, geometry_smoothing=False,
+                      color_smoothing=False, transfer_filter=0, seed=80)
+    assert want.counts(0).eom > 0
 
 
 def test_dropin_occupancy_synthesis(rb, backends):

@@ -218,11 +218,27 @@ def test_raw_points_in_the_auxiliary_video(rb, codec, checker_backend):
     codec.generatePointCloud()
     for f in range(g.n_frames):
         assert np.array_equal(codec.getPointCloud(f, fields=("positions",))["positions"], ref.cloud(f, "reconstruct")["positions"])
-    # EOM together with the auxiliary video is refused, not approximated
-    g = small(rb, eom=True, geometry_smoothing=False, color_smoothing=False, seed=24)
-    g.params.use_aux_separate_video = 1
+    # EOM with the auxiliary video: synthetic pixel addresses from (0, 0), no occupancy marks (:852-853, :880), colours of the
+    # EOM points from the auxiliary attribute video (:1551-1580); with geometry smoothing on the boundary pass reads the
+    # occupancy map at those addresses (:964-971)
+    for seed, smooth in ((24, False), (25, True)):
+        g = rb.synthetic.make_aux_video(small(rb, eom=True, seed=seed, geometry_smoothing=smooth, color_smoothing=smooth), seed=seed)
+        if smooth:
+            g.params.flag_geometry_smoothing = g.params.apply_geo_smoothing = 1
+            g.params.flag_color_smoothing = g.params.apply_attr_smoothing = 1
+        ref = run_stages(codec, g, checker_backend, stages=None if smooth else ("reconstruct", "rgb8"), what=f"aux eom smoothing {smooth}")
+        c, n0, n = ref.cloud(0, "reconstruct"), ref.counts(0).regular, ref.counts(0).eom
+        assert n > 1000 and (c["colors16"][n0:n0 + n] < 256).all() and (c["point_to_pixel"][n0] == 0).all()
+    # EOM and raw points together
+    g = rb.synthetic.make_aux_video(small(rb, eom=True, raw_points=400, seed=26, geometry_smoothing=False, color_smoothing=False), seed=26)
+    ref = run_stages(codec, g, checker_backend, stages=("reconstruct", "rgb8"), what="aux eom + raw")
+    assert ref.counts(0).raw == 400 and ref.counts(0).eom > 0
+    # an eomCount_ that is not what the member patches produce cannot address the colours: refused
+    g = rb.synthetic.make_aux_video(small(rb, eom=True, seed=27, geometry_smoothing=False, color_smoothing=False), seed=27)
+    g.eom_patches[0]["eom_count"] += 1
+    codec.uploadGof(g)
     with pytest.raises(rb.codec.RabbitError):
-        codec.uploadGof(g)
+        codec.generatePointCloud()
 
 
 def test_no_attributes(rb, codec, checker_backend):

@@ -17,6 +17,7 @@ def assert_cloud_equal(got, want, what, fields=FIELDS):
 
 def run_stages(codec, gof, chk, stages=("reconstruct", "smooth_geometry", "smooth_color", "rgb8"), what=""):
     """run the CUDA path stage by stage and compare every stage with the checker's snapshot"""
+    stages = stages or ("reconstruct", "smooth_geometry", "smooth_color", "rgb8")
     ref = chk.run_gof(gof, keep=stages)
     codec.uploadGof(gof)
     p = gof.params
