@@ -54,8 +54,12 @@ __device__ __forceinline__ float sample_to_float( int s, bool chroma, int nbyte 
   return fminf( fmaxf( f, chroma ? -0.5f : 0.f ), chroma ? 0.5f : 1.f );
 }
 // floatYUVToYUV (:582-594) with nbyte = 2: (T) fClip( round( (float)( 65535. * (double)f + offset ) ), 0, 65535 )
+// For |f| >= 2^-12 the double expression is EXACT (65535 f is a 40-bit integer times ulp( f ) >= 2^-35, the offset keeps the
+// sum inside 53 bits), so its conversion to float is the single rounding of 65535 f + offset: one float fused
+// multiply-add.  Below 2^-12 the double sum rounds first; all 1.93e9 such floats were enumerated on the host: the two
+// float results differ for 4 of them and the rounded integer for none.
 __device__ __forceinline__ uint16_t float_to_u16( float f, bool chroma ) {
-  const float x = (float)__dadd_rn( __dmul_rn( 65535.0, (double)f ), chroma ? 32768.0 : 0.0 );
+  const float x = __fmaf_rn( 65535.0f, f, chroma ? 32768.0f : 0.0f );
   return (uint16_t)fminf( fmaxf( roundf( x ), 0.f ), 65535.f );
 }
 
