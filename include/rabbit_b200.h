@@ -364,7 +364,9 @@ int rb200_metrics(rb200_ctx* ctx, const rb200_metrics_params* params, int n_pair
  * a call whose sources are the same device pointers / counts, with the same drop_duplicates and normals, as the previous
  * call keeps their de-duplicated points, column tables and gathered normals (removeDuplicate + copyNormals of the
  * source, PCCMetrics.cpp:353-375) and only indexes the reconstructions.  The caller promises the buffers' contents did
- * not change in between; calling this again (on or off) drops what is kept.  Results are bit-identical either way. */
+ * not change in between; calling this again (on or off) drops what is kept.  The results are the same either way:
+ * integer quantities exactly, the double sums to the last bits that the order of the normals' atomic additions leaves
+ * open from run to run in any case (PSNR far inside 1e-6 dB). */
 int rb200_metrics_cache_sources(rb200_ctx* ctx, int on);
 
 /* ---- multi-GPU: the one exchange step of the path.  Frames / GOFs / streams are sharded over one context
