@@ -6,8 +6,10 @@ Every function restates one reference function (file:line relative to /root/refe
 BASELINE configs exercise: one or two maps (single stream, or multiple streams with an absolute or delta-coded second
 attribute map), singleMapPixelInterleaving and pointLocalReconstruction (their transferColorWeight colours are flagged
 exact only where they do not hinge on nanoflann's order of equidistant neighbours), no EOM / raw patches / PBF (those
-raise NotImplementedError here — the compiled reference in oracle/_ref covers them); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4
-16-bit conversion of PCCInternalColorConverter (all eight upsampling filters).
+raise NotImplementedError here — the compiled reference in oracle/_ref covers them); grid geometry smoothing and the
+non-grid smoothPointCloud (PCCCodec.cpp:1106-1157: the vendored IndexDist_Sorter orders equal distances by index, so no
+tree order is involved); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4 16-bit conversion of
+PCCInternalColorConverter (all eight upsampling filters).
 It is pinned against the unmodified reference (oracle/_ref/librabbit_ref.so) by tests/test_oracle_port_cpu.py, stage
 by stage and bit for bit, and against the golden fixtures in tests/golden/ — so it is a usable checker on a box that
 has neither /root/reference nor oracle/_ref.  Not restated here: PCCPointSet3::transferColors16bitBP (needs the
@@ -372,8 +374,10 @@ def smooth_geometry(params, cloud):
     pos = cloud["positions"].astype(np.int64)
     typ = cloud["boundary_types"].copy()
     n = len(pos)
-    if n == 0 or not params.flag_geometry_smoothing or not params.grid_smoothing:
+    if n == 0 or not params.flag_geometry_smoothing:
         return cloud
+    if not params.grid_smoothing:  # :140-142
+        return smooth_geometry_radius(params, cloud) if params.neighbor_count_smoothing > 0 and not params.pbf_enable else cloud
     w = (int(pos.max()) + g - 1) // g  # :68-79
     disth, th = max(g // 2, 1), g * w
     inside = ~((pos < disth).any(axis=1) | (th <= pos + disth).any(axis=1))  # :92-95
@@ -416,6 +420,43 @@ def smooth_geometry(params, cloud):
         if dist2 >= float(max(thr, count) * 2):  # :1094
             out[i] = np.trunc(cen / float(count) + 0.5).astype(np.int64).astype(np.int16)  # :1095-1097
             typ[i] = 3
+    res = dict(cloud)
+    res["positions"], res["boundary_types"] = out, typ
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PCCCodec::smoothPointCloud (:1106-1157), the non-grid filter.  PCCKdTree::searchRadius (PCCKdTree.cpp:69-79) is nanoflann's
+# radiusSearch (dist < radius2Smoothing) + std::sort with the vendored IndexDist_Sorter — by distance, equal distances by
+# index (dependencies/nanoflann/nanoflann.hpp:193-200): a total order, so the neighbourhood is the first
+# neighborCountSmoothing entries of the (distance, index)-sorted ball and no tree order is involved.
+# ---------------------------------------------------------------------------------------------------------------
+def smooth_geometry_radius(params, cloud):
+    from scipy.spatial import cKDTree
+    pos = cloud["positions"].astype(np.int64)
+    part = cloud["partition"].astype(np.int64)
+    typ = cloud["boundary_types"].copy()
+    out = cloud["positions"].copy()
+    r2, r2b, nmax = float(params.radius2_smoothing), float(params.radius2_boundary_detection), int(params.neighbor_count_smoothing)
+    tree = cKDTree(pos.astype(np.float64))
+    balls = tree.query_ball_point(pos.astype(np.float64), np.sqrt(r2) + 1e-9)  # superset; the exact test follows
+    for i in range(len(pos)):
+        idx = np.asarray(balls[i], np.int64)
+        d = ((pos[idx] - pos[i]) ** 2).sum(axis=1)
+        keep = d < r2  # RadiusResultSet::addPoint, :165-169
+        idx, d = idx[keep], d[keep]
+        order = np.lexsort((idx, d))[:nmax]  # sorted by distance then index, cut to num_results (PCCKdTree.cpp:75-76)
+        idx, d = idx[order], d[order]
+        cnt = len(idx)
+        if cnt == 0 or not ((d <= r2b) & (part[idx] != part[i])).any():  # otherClusterPointCount, :1126-1128
+            continue
+        if typ[i] == 1:
+            typ[i] = 2  # :1131-1133
+        centroid = pos[idx].sum(axis=0).astype(np.float64)  # sums of int16 in double: exact
+        e = centroid - float(cnt) * pos[i].astype(np.float64)
+        dist = float(np.int64((e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + cnt / 2.0)) / float(cnt)  # :1136-1137
+        if dist >= float(params.threshold_smoothing):  # :1141
+            out[i] = np.trunc((centroid + float(cnt // 2)) / float(cnt)).astype(np.int64).astype(np.int16)  # :1138-1140
     res = dict(cloud)
     res["positions"], res["boundary_types"] = out, typ
     return res
@@ -604,7 +645,7 @@ class Port:
             exact = cloud.pop("colors16_exact", None)  # pixel interleaving: colours that do not hinge on kd-tree tie order
             snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ, "colors16_exact": exact}
             if P.apply_geo_smoothing and P.flag_geometry_smoothing:
-                if P.grid_smoothing:
+                if P.grid_smoothing or P.neighbor_count_smoothing > 0:  # (> 0 without the grid: the encoder-side call)
                     cloud = smooth_geometry(P, cloud)
                 snaps["smooth_geometry"] = cloud
                 if P.attribute_count > 0 and P.attr_transfer_filter_type != 0:

@@ -58,6 +58,28 @@ def test_port_equals_reference_every_stage(rb, name):
         assert want.counts(f).smoothed > 0 and want.counts(f).recolored > 0
 
 
+def test_port_non_grid_smoothing(rb):
+    """smoothPointCloud (PCCCodec.cpp:1106-1157) restated with a plain (distance, index) ordering of the ball — the vendored
+    IndexDist_Sorter makes the 64 survivors independent of the kd-tree — equals the reference bit for bit"""
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+    kw = dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=207, transfer_filter=0)
+
+    def make():
+        g = rb.synthetic.generate_gof(**kw)
+        g.params.grid_smoothing = 0
+        g.params.neighbor_count_smoothing = 64
+        g.params.radius2_smoothing = 64.0
+        g.params.radius2_boundary_detection = 64.0
+        return g
+    want = ref_b.run_gof(make(), keep=("reconstruct", "smooth_geometry"))
+    got = oracle_np.Port().run_gof(make(), ("reconstruct", "smooth_geometry"))
+    w, c = want.cloud(0, "smooth_geometry"), dict(got[0]["smooth_geometry"])
+    c["colors"] = w["colors"]
+    assert_cloud_equal(c, w, "non-grid smoothing", FIELDS)
+    assert (w["positions"] != want.cloud(0, "reconstruct")["positions"]).any(axis=1).sum() > 50 and (w["boundary_types"] == 2).sum() > 50
+
+
 def test_port_remove_duplicates_and_d1(rb):
     from oracle import oracle_np
     checker, ref_b = _ref()
