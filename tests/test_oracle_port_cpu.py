@@ -80,6 +80,29 @@ def test_port_non_grid_smoothing(rb):
     assert (w["positions"] != want.cloud(0, "reconstruct")["positions"]).any(axis=1).sum() > 50 and (w["boundary_types"] == 2).sum() > 50
 
 
+def test_reference_auxiliary_video_properties(rb):
+    """what the unmodified reference does with raw / EOM points in the auxiliary video (the behaviour the CUDA path matches in
+    tests/test_gpu_parity.py): same positions as with in-atlas raw patches, colours truncated to 8 bits, pixel addresses in
+    the auxiliary frame (raw) or from (0, 0) (EOM)"""
+    checker, ref_b = _ref()
+    kw = dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=208, transfer_filter=0, raw_points=300)
+    inside = ref_b.run_gof(rb.synthetic.generate_gof(**kw), keep=("reconstruct",))
+    aux = ref_b.run_gof(rb.synthetic.make_aux_video(rb.synthetic.generate_gof(**kw), seed=1), keep=("reconstruct",))
+    a, b = inside.cloud(0, "reconstruct"), aux.cloud(0, "reconstruct")
+    n = aux.counts(0).raw
+    assert n == 300 == inside.counts(0).raw and np.array_equal(a["positions"], b["positions"])
+    assert np.array_equal(a["colors16"][:-n], b["colors16"][:-n]) and (b["colors16"][-n:] < 256).all()
+    assert (b["point_to_pixel"][-n:, 1] < 64).all() and (a["point_to_pixel"][-n:, 1] >= 64).all()
+    kw = dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=209, transfer_filter=0, eom=True, geometry_smoothing=False,
+              color_smoothing=False)
+    inside = ref_b.run_gof(rb.synthetic.generate_gof(**kw), keep=("reconstruct",))
+    aux = ref_b.run_gof(rb.synthetic.make_aux_video(rb.synthetic.generate_gof(**kw), seed=2), keep=("reconstruct",))
+    a, b = inside.cloud(0, "reconstruct"), aux.cloud(0, "reconstruct")
+    n0, n = aux.counts(0).regular, aux.counts(0).eom
+    assert n > 0 and np.array_equal(a["positions"], b["positions"]) and (b["colors16"][n0:n0 + n] < 256).all()
+    assert (b["point_to_pixel"][n0] == 0).all() and a["point_to_pixel"][n0, 1] > 0
+
+
 def test_port_remove_duplicates_and_d1(rb):
     from oracle import oracle_np
     checker, ref_b = _ref()
