@@ -106,6 +106,7 @@ struct rb200_ctx {
   RbBuf d_snap_pos[2], d_snap_col[3];
   bool  have_snap_pos[2] = {false, false}, have_snap_col[3] = {false, false, false};
   RbBuf d_blist, d_blist_n;  // indices of the boundary (type 1) points of the GOF + their count (device)
+  RbBuf d_moved_bits;        // one bit per point of the GOF: moved by the geometry filter (type 3); cleared by the reconstruction
   RbBuf d_pbf;               // occupancy synthesis: the patch-local maps of the GOF (rb_pbf.cu)
   RbBuf d_bnd_bitmap;        // occupancy synthesis: [F][H][bmWords] PCCPatch::isBorder of every occupied pixel
   int64_t blist_cap = 0;     // that count on the host

@@ -218,7 +218,7 @@ void rb200_destroy( rb200_ctx* c ) {
                    &c->d_plr_modes, &c->d_plr_block_mode, &c->d_plr_block_off,
                    &c->d_pos, &c->d_col, &c->d_pix, &c->d_part, &c->d_rgb, &c->d_pos_pre, &c->d_pack, &c->d_frame_off,
                    &c->d_geo_grid, &c->d_geo_cells, &c->d_geo_cell_ids, &c->d_col_grid, &c->d_col_cells,
-                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n, &c->d_pbf, &c->d_bnd_bitmap,
+                   &c->d_col_cell_ids, &c->d_col_lum, &c->d_col_lum_off, &c->d_blist, &c->d_blist_n, &c->d_moved_bits, &c->d_pbf, &c->d_bnd_bitmap,
                    &c->d_snap_pos[0], &c->d_snap_pos[1], &c->d_snap_col[0], &c->d_snap_col[1], &c->d_snap_col[2]};
   for ( auto* b : bufs ) { b->release(); }
   for ( auto& b : c->d_scratch ) { b.release(); }

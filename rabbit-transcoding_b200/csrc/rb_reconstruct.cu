@@ -1433,6 +1433,8 @@ int rb_reconstruct_impl( rb200_ctx* c ) {
   RB_CUDA( c->d_blist.ensure( cap * 4 ) );
   RB_CUDA( c->d_blist_n.ensure( 64 ) );
   RB_CUDA( cudaMemsetAsync( c->d_blist_n.p, 0, 4, c->stream ) );
+  RB_CUDA( c->d_moved_bits.ensure( ( cap / 32 + 2 ) * 4 ) );  // no point of a fresh reconstruction is of type 3
+  RB_CUDA( cudaMemsetAsync( c->d_moved_bits.p, 0, ( cap / 32 + 2 ) * 4, c->stream ) );
   a.blist   = c->d_blist.as<uint32_t>();
   a.blist_n = c->d_blist_n.as<uint32_t>();
   if ( eom ) {

@@ -85,6 +85,7 @@ struct GridArgs {
   const uint32_t* part;
   const uint32_t* blist;     // indices of the points classified as boundary (type 1) by the reconstruction
   const uint32_t* blist_n;
+  uint32_t*      moved_bits; // geometry: one bit per point, set for the points the filter moves (type 3)
 };
 
 __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F, int64_t i ) {
@@ -885,6 +886,7 @@ __device__ __forceinline__ bool filter_geo_point( const GridArgs& a, uint32_t li
     q.z      = (short)(long long)( __dadd_rn( cen[2] / dc, 0.5 ) );
     q.w      = 3;  // :1099
     a.pos[i] = q;
+    atomicOr( &a.moved_bits[i >> 5], 1u << ( i & 31 ) );  // the list of the moved points for the attribute re-transfer
     return true;
   }
   return false;
@@ -1181,6 +1183,7 @@ int rb_smooth_geometry_impl( rb200_ctx* c ) {
   a.part      = c->d_part.as<uint32_t>();
   a.blist     = c->d_blist.as<uint32_t>();
   a.blist_n   = c->d_blist_n.as<uint32_t>();
+  a.moved_bits = c->d_moved_bits.as<uint32_t>();
   GridBufs b{c->d_geo_grid, c->d_geo_cells, c->d_scratch[2], c->d_col_lum, c->d_geo_cell_ids, c->d_scratch[5]};
   for ( ;; ) {
     int r = setup_grid( c, a, b, g, wmax, false, c->geo_grow );

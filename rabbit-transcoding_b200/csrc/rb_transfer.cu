@@ -48,15 +48,25 @@ __device__ __forceinline__ int frame_of( const int64_t* __restrict__ off, int F,
   return lo;
 }
 
-__global__ void k_flag_moved( const short4* __restrict__ pos, int64_t n, uint32_t* __restrict__ flags ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i > n ) { return; }
-  flags[i] = ( i < n && pos[i].w == 3 ) ? 1u : 0u;
+// the moved (type 3) points come as one bit per point from the geometry filter (rb_smooth.cu): population count per word,
+// exclusive scan over the words, then every word writes the indices of its set bits and their ranks — 1/32 of the
+// traffic of flagging, scanning and listing the points themselves
+__global__ void k_moved_count( const uint32_t* __restrict__ bits, int64_t nWords, uint32_t* __restrict__ cnt ) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( w > nWords ) { return; }
+  cnt[w] = w < nWords ? (uint32_t)__popc( bits[w] ) : 0u;
 }
-__global__ void k_list_moved( const uint32_t* __restrict__ scan, int64_t n, uint32_t* __restrict__ moved ) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if ( i >= n ) { return; }
-  if ( scan[i + 1] != scan[i] ) { moved[scan[i]] = (uint32_t)i; }
+__global__ void k_moved_list( const uint32_t* __restrict__ bits, const uint32_t* __restrict__ scan, int64_t nWords,
+                              uint32_t* __restrict__ moved, uint32_t* __restrict__ rank ) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ( w >= nWords ) { return; }
+  uint32_t m = scan[w];
+  for ( uint32_t b = bits[w]; b; b &= b - 1 ) {
+    const uint32_t g = (uint32_t)( w * 32 ) + (uint32_t)( __ffs( b ) - 1 );
+    moved[m] = g;
+    rank[g]  = m;  // (only read for type-3 points)
+    m++;
+  }
 }
 
 struct TArgs {
@@ -789,18 +799,27 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   }
   TransferScratch* S = scratch_of( c );
   // ---- moved (type 3) points ----
-  RB_CUDA( S->flags.ensure( (size_t)( N + 8 ) * 4 ) );
-  RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( N + 1 ) ) );
-  uint32_t* flags = S->flags.as<uint32_t>();
-  RB_LAUNCH( "tr_flag_moved", k_flag_moved, rb_div_up( N + 1, TPB ), TPB, 0, c->d_pos.as<short4>(), N, flags );
-  int r = rb_scan_u32( c, flags, flags, N + 1, S->sums.as<uint32_t>() );
+  const int64_t nWords = ( N + 31 ) / 32;
+  if ( !c->d_moved_bits.p || c->d_moved_bits.cap < (size_t)nWords * 4 ) {
+    return rb_fail( c, RB200_ERR_STATE, "transfer_colors: no record of the moved points (smooth_geometry of this reconstruction did not run)" );
+  }
+  RB_CUDA( S->flags.ensure( (size_t)( N + 8 ) * 4 ) );  // rank of the moved points (written at their indices only)
+  RB_CUDA( S->candCnt.ensure( (size_t)( nWords + 8 ) * 4 ) );
+  RB_CUDA( S->sums.ensure( rb_scan_scratch_bytes( std::max<int64_t>( N + 1, nWords + 1 ) ) ) );
+  uint32_t*       flags = S->flags.as<uint32_t>();
+  uint32_t*       wcnt  = S->candCnt.as<uint32_t>();
+  const uint32_t* bits  = c->d_moved_bits.as<uint32_t>();
+  RB_LAUNCH( "tr_moved_count", k_moved_count, rb_div_up( nWords + 1, TPB ), TPB, 0, bits, nWords, wcnt );
+  int r = rb_scan_u32( c, wcnt, wcnt, nWords + 1, S->sums.as<uint32_t>() );
   if ( r ) { return r; }
   uint32_t* h = (uint32_t*)rb_pinned( c, 64 );
   if ( !h ) { return rb_fail( c, RB200_ERR_NOMEM, "pinned allocation failed" ); }
-  RB_CUDA( cudaMemcpyAsync( h, flags + N, 4, cudaMemcpyDeviceToHost, c->stream ) );
+  RB_CUDA( cudaMemcpyAsync( h, wcnt + nWords, 4, cudaMemcpyDeviceToHost, c->stream ) );
   RB_CUDA( cudaStreamSynchronize( c->stream ) );
   const uint32_t M = h[0];
   if ( M == 0 ) { return RB200_OK; }  // nothing moved: every colour stays (:1163-1164 with type != 3)
+  RB_CUDA( S->moved.ensure( (size_t)M * 4 ) );
+  RB_LAUNCH( "tr_list_moved", k_moved_list, rb_div_up( nWords, TPB ), TPB, 0, bits, wcnt, nWords, S->moved.as<uint32_t>(), flags );
   // ---- forest: trees 1..F over the pre-smoothing frames, F+1..2F over the smoothed frames ----
   std::vector<int64_t> hOff;
   std::vector<int>     treeOfS( F, -1 ), treeOfT( F, -1 );
@@ -833,7 +852,6 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   r = rb_kd_build( c, S->kd, S->pos2.as<short4>(), S->off.as<int64_t>(), hOff, 0, 0, 0 );
   if ( r ) { return r; }
   // ---- transfer ----
-  RB_CUDA( S->moved.ensure( (size_t)M * 4 ) );
   RB_CUDA( S->part.ensure( (size_t)M * KF * 4 ) );
   RB_CUDA( S->partDist.ensure( (size_t)M * KF * 4 ) );
   RB_CUDA( S->bwdT.ensure( (size_t)M * KF * 4 ) );
@@ -848,7 +866,6 @@ int rb_transfer_colors_impl( rb200_ctx* c ) {
   RB_CUDA( S->srcList.ensure( (size_t)M * KF * 4 ) );
   RB_CUDA( S->srcNN.ensure( (size_t)N * 8 ) );
   RB_CUDA( cudaMemsetAsync( S->claim.p, 0, (size_t)( N / 32 + 2 ) * 4, c->stream ) );
-  RB_LAUNCH( "tr_list_moved", k_list_moved, rb_div_up( N, TPB ), TPB, 0, flags, N, S->moved.as<uint32_t>() );
   TArgs a{};
   a.forest    = S->kd.forest;
   a.F         = F;
