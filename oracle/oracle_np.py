@@ -5,8 +5,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 Every function restates one reference function (file:line relative to /root/reference/source/lib) on the CTC branch the
 BASELINE configs exercise: one or two maps (single stream, or multiple streams with an absolute or delta-coded second
 attribute map), singleMapPixelInterleaving and pointLocalReconstruction (their transferColorWeight colours are flagged
-exact only where they do not hinge on nanoflann's order of equidistant neighbours), no EOM / raw patches / PBF (those
-raise NotImplementedError here — the compiled reference in oracle/_ref covers them); grid geometry smoothing and the
+exact only where they do not hinge on nanoflann's order of equidistant neighbours), raw patches in the atlas or in the
+auxiliary video, no EOM / PBF (those raise NotImplementedError here — the compiled reference in oracle/_ref covers them); grid geometry smoothing and the
 non-grid smoothPointCloud (PCCCodec.cpp:1106-1157: the vendored IndexDist_Sorter orders equal distances by index, so no
 tree order is involved); plus the decoder-side ingest: PCCImage::set and the 4:2:0 -> 4:4:4 16-bit conversion of
 PCCInternalColorConverter (all eight upsampling filters).
@@ -98,12 +98,16 @@ def boundary_map(occ):
 # PCCCodec::generatePointCloud (:517-978) + generatePoints (:327-515, default branch :497-513) +
 # PCCPatch::generatePoint (PCCPatch.h:177-207) + colorPointCloud (:1308-1449, single-stream branch :1418-1422)
 # ---------------------------------------------------------------------------------------------------------------
-def reconstruct_frame(params, occ_video, geometry, attribute, patches, plr=None, patch_base=0):
+def reconstruct_frame(params, occ_video, geometry, attribute, patches, plr=None, patch_base=0, raw_patches=None,
+                      aux_geometry=None, aux_attribute=None):
     """returns a dict of arrays in PCCPointSet3 layouts, in the reference's emission order; plr / patch_base: the point
-    local reconstruction tables of the GOF (rb200_plr layout) and the GOF index of this frame's first patch"""
+    local reconstruction tables of the GOF (rb200_plr layout) and the GOF index of this frame's first patch; raw_patches:
+    the frame's raw (missed-point) patches, read from the atlas or — use_aux_separate_video — from the auxiliary frames"""
     P = params
-    if P.enhanced_occupancy_map_code or P.use_additional_points_patch or P.pbf_enable or P.enable_size_quantization:
+    if P.enhanced_occupancy_map_code or P.pbf_enable or P.enable_size_quantization:
         raise NotImplementedError("oracle_np restates the default CTC branch only (see the module docstring)")
+    if P.use_additional_points_patch and (P.single_map_pixel_interleaving or P.point_local_reconstruction):
+        raise NotImplementedError("oracle_np: raw patches together with pixel interleaving / PLR")
     if P.single_map_pixel_interleaving or P.point_local_reconstruction:
         return reconstruct_frame_interleaved(params, occ_video, geometry, attribute, patches, plr, patch_base)
     R, M = P.occupancy_resolution, P.map_count_minus1 + 1
@@ -164,6 +168,29 @@ def reconstruct_frame(params, occ_video, geometry, attribute, patches, plr=None,
                 nv = np.clip(c16.astype(np.int64) - offset, -offset, offset - 1) + v0
                 c16 = np.where((lay == 1)[:, None], np.clip(nv, 0, maxv), c16).astype(np.uint16)
             col.append(c16)
+    # raw (missed-point) patches (:894-949): 3 n consecutive samples of the patch rectangle as X || Y || Z runs, read from
+    # map 0 of the atlas or from the auxiliary geometry video; pixel address = the n first pixels of the rectangle;
+    # partition = patches.size(); colours from attribute frame 0 at those addresses (:1418-1422) or, with the auxiliary
+    # video, from its attribute frames through 8-bit PCCColor3B values (:1524-1549, :1438)
+    if P.use_additional_points_patch and raw_patches is not None:
+        aux = bool(P.use_aux_separate_video)
+        src = aux_geometry if aux else geometry[0]
+        for r in raw_patches:
+            nr, su, sv = int(r["num_points"]), int(r["size_u0"]) * R, int(r["size_v0"]) * R
+            x0, y0 = int(r["u0"]) * R, int(r["v0"]) * R
+            vals = src[y0:y0 + sv, x0:x0 + su].reshape(-1)[:3 * nr].astype(np.int64)
+            q = np.stack([vals[:nr] + int(r["u1"]), vals[nr:2 * nr] + int(r["v1"]), vals[2 * nr:3 * nr] + int(r["d1"])], axis=1)
+            k = np.arange(nr)
+            px, py = x0 + k % su, y0 + k // su
+            pos.append(q.astype(np.int16))
+            typ.append(np.zeros(nr, np.uint16))
+            part.append(np.full(nr, len(patches), np.uint32))
+            p2p.append(np.stack([px, py, np.zeros(nr, np.int64)], axis=1).astype(np.uint32))
+            if P.attribute_count > 0:
+                if aux:
+                    col.append((np.stack([aux_attribute[c, py, px] for c in range(3)], axis=1) & 0xFF).astype(np.uint16))
+                else:
+                    col.append(np.stack([attribute[0, c, py, px] for c in range(3)], axis=1).astype(np.uint16))
 
     def cat(parts, shape, dt):
         return np.concatenate(parts) if parts else np.zeros(shape, dt)
@@ -640,8 +667,11 @@ class Port:
         out = []
         for f in range(gof.n_frames):
             patches = gof.patches[gof.patch_offset[f]:gof.patch_offset[f + 1]]
+            raws = gof.raw_patches[gof.raw_offset[f]:gof.raw_offset[f + 1]] if gof.raw_patches is not None else None
+            aux_g = gof.aux_geometry[f] if getattr(gof, "aux_geometry", None) is not None else None
+            aux_a = gof.aux_attribute[f] if getattr(gof, "aux_attribute", None) is not None else None
             cloud, b2p, occ = reconstruct_frame(P, gof.occupancy[f], gof.geometry[f], gof.attribute[f], patches,
-                                                getattr(gof, "plr", None), int(gof.patch_offset[f]))
+                                                getattr(gof, "plr", None), int(gof.patch_offset[f]), raws, aux_g, aux_a)
             exact = cloud.pop("colors16_exact", None)  # pixel interleaving: colours that do not hinge on kd-tree tie order
             snaps = {"reconstruct": cloud, "block_to_patch": b2p, "occupancy": occ, "colors16_exact": exact}
             if P.apply_geo_smoothing and P.flag_geometry_smoothing:

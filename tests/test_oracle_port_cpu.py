@@ -80,6 +80,27 @@ def test_port_non_grid_smoothing(rb):
     assert (w["positions"] != want.cloud(0, "reconstruct")["positions"]).any(axis=1).sum() > 50 and (w["boundary_types"] == 2).sum() > 50
 
 
+@pytest.mark.parametrize("aux", [False, True])
+def test_port_raw_patches(rb, aux):
+    """raw (missed-point) patches in the atlas and in the auxiliary video (PCCCodec.cpp:894-949, :1524-1549), every stage"""
+    from oracle import oracle_np
+    checker, ref_b = _ref()
+    kw = dict(n_frames=1, bitdepth=7, width=128, scale=0.9, seed=210, transfer_filter=0, raw_points=250)
+
+    def make():
+        g = rb.synthetic.generate_gof(**kw)
+        return rb.synthetic.make_aux_video(g, seed=3) if aux else g
+    stages = ("reconstruct", "smooth_geometry", "smooth_color", "rgb8")
+    want = ref_b.run_gof(make(), keep=stages)
+    got = oracle_np.Port().run_gof(make(), stages)
+    assert want.counts(0).raw == 250
+    for st in stages:
+        w, c = want.cloud(0, st), dict(got[0][st])
+        if st != "rgb8":
+            c["colors"] = w["colors"]
+        assert_cloud_equal(c, w, f"raw aux={aux} stage {st}", FIELDS)
+
+
 def test_reference_auxiliary_video_properties(rb):
     """what the unmodified reference does with raw / EOM points in the auxiliary video (the behaviour the CUDA path matches in
     tests/test_gpu_parity.py): same positions as with in-atlas raw patches, colours truncated to 8 bits, pixel addresses in
